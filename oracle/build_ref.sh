@@ -1,0 +1,67 @@
+#!/usr/bin/env bash
+# TEST INFRASTRUCTURE ONLY.  Compiles pieces of the *unmodified* reference
+# (aquaskyline/SOAP3-dp, mounted read-only at $REF, default /root/reference)
+# from the sources where they lie into oracle/_ref/ (git-ignored, travels to
+# the GPU box).  Nothing here is shipped or measured as the product.
+#
+# Outputs (all under oracle/_ref/):
+#   soap3-dp-builder, BGS-Build (+ .ini)   reference index builders (Makefile:98-102)
+#   libref_search.so   DV-Kernel.cu device code compiled for the host through
+#                      oracle/ref_shim/cuda_host_shim.h (bit-exact answer slots)
+#   libref_dp.so       DV-DPfunctions.cu:35-512 (DP kernels) compiled for the host
+#
+# Two one-line build fixes are applied to *copies* in oracle/_ref/patched/
+# (SURVEY.md §8c): 2bwt-lib/BWT.c:424 pointer comparison, and
+# 2bwt-flex/LTConstruct.c BuildLookupTable falling off the end without return.
+set -euo pipefail
+REF=${REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref
+if [ ! -d "$REF" ]; then
+  echo "[build_ref] $REF not present; keeping prebuilt files in $OUT" >&2
+  exit 0
+fi
+mkdir -p "$OUT/obj" "$OUT/patched"
+CXX=${S3_CXX:-/usr/bin/g++}   # NB: the image exports CXX=/opt/gcc/bin/g++, which has no libgomp.spec
+CFLAGS="-O3 -funroll-loops -fomit-frame-pointer -fpermissive -w -mpopcnt -fPIC"
+JOBS=${JOBS:-8}
+
+# ---- 2bwt-lib objects (Makefile BWTOBJLIBS) --------------------------------
+sed '424s/bwt->cachedSaIndex > 0/bwt->cachedSaIndex != NULL/' "$REF/2bwt-lib/BWT.c" > "$OUT/patched/BWT.c"
+sed 's/^\(\s*\)free(otop);/\1free(otop);\n\1return 0;/' "$REF/2bwt-flex/LTConstruct.c" > "$OUT/patched/LTConstruct.c"
+
+BWTSRC="dictionary DNACount HSP HSPstatistic iniparser inistrlib karlin MemManager MiscUtilities QSufSort r250 TextConverter Timing Socket BWTConstruct"
+CPUSRC="HOCC LT HOCCConstruct SRA2BWTCheckAndExtend SRA2BWTMdl"
+pids=()
+cc() { # src obj incdir
+  if [ ! -f "$2" ] || [ "$1" -nt "$2" ]; then
+    $CXX $CFLAGS -I"$3" -c "$1" -o "$2" &
+    pids+=($!)
+    if [ ${#pids[@]} -ge $JOBS ]; then wait "${pids[0]}"; pids=("${pids[@]:1}"); fi
+  fi
+}
+for s in $BWTSRC; do cc "$REF/2bwt-lib/$s.c" "$OUT/obj/$s.o" "$REF/2bwt-lib"; done
+cc "$OUT/patched/BWT.c" "$OUT/obj/BWT.o" "$REF/2bwt-lib"
+for s in $CPUSRC; do cc "$REF/2bwt-flex/$s.c" "$OUT/obj/flex_$s.o" "$REF/2bwt-flex"; done
+cc "$OUT/patched/LTConstruct.c" "$OUT/obj/flex_LTConstruct.o" "$REF/2bwt-flex"
+wait
+BWTOBJ=""; for s in dictionary DNACount HSP HSPstatistic iniparser inistrlib karlin MemManager MiscUtilities QSufSort r250 TextConverter Timing Socket BWT; do BWTOBJ="$BWTOBJ $OUT/obj/$s.o"; done
+CPUOBJ=""; for s in $CPUSRC LTConstruct; do CPUOBJ="$CPUOBJ $OUT/obj/flex_$s.o"; done
+
+if [ ! -x "$OUT/soap3-dp-builder" ]; then
+  $CXX $CFLAGS -I"$REF/2bwt-flex" "$REF/2bwt-flex/2BWT-Builder.c" "$OUT/obj/BWTConstruct.o" $BWTOBJ $CPUOBJ -lm -o "$OUT/soap3-dp-builder"
+  cp "$REF/soap3-dp-builder.ini" "$OUT/soap3-dp-builder.ini"
+fi
+if [ ! -x "$OUT/BGS-Build" ]; then
+  $CXX $CFLAGS -I"$REF" "$REF/BGS-Build.cpp" $BWTOBJ -lm -o "$OUT/BGS-Build"
+fi
+echo "[build_ref] builders OK"
+
+# ---- reference search kernels compiled for the host -------------------------
+# A generated copy adds a rank-query counter (the roofline unit of SURVEY.md 8d)
+# at the top of GPUBWTOccValue / GPUBWTAllOccValue / GPUBWTOccValueWithCumu.
+sed 's/^\(\s*\)index -= ( index > inverseSa0 );/\1++s3_rank_queries; index -= ( index > inverseSa0 );/' \
+    "$REF/DV-Kernel.cu" > "$OUT/patched/DV-Kernel.counted.cu"
+$CXX -O2 -fopenmp -fpermissive -w -fPIC -shared -DS3_COUNT_RANK_QUERIES -I"$OUT/patched" -I"$REF" -I"$HERE/ref_shim" \
+    "$HERE/ref_shim/ref_search_host.cpp" -o "$OUT/libref_search.so"
+echo "[build_ref] libref_search.so OK"

@@ -1,0 +1,154 @@
+/*
+ * soap3dp_b200.h -- C ABI of the B200-native GPU alignment hot path of SOAP3-dp.
+ *
+ * Every entry point names the reference interface it replaces (file:line in
+ * aquaskyline/SOAP3-dp).  Plain pointers and sizes only; all functions return
+ * 0 on success or a negative S3_E* code, with a message in s3_last_error().
+ * Unless a name ends in `_device`, pointers are HOST pointers and the call is
+ * synchronous (results are in host memory when it returns), exactly like the
+ * reference's perform_round*_alignment / SemiGlobalAligner::performAlignment.
+ *
+ * There is no CPU fallback: if no CUDA device is usable the calls fail.
+ */
+#ifndef SOAP3DP_B200_H
+#define SOAP3DP_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S3_OK          0
+#define S3_ECUDA      -1   /* a CUDA runtime call failed            */
+#define S3_EINVAL     -2   /* bad argument                          */
+#define S3_ENOMEM     -3   /* host or device allocation failed      */
+
+#define S3_MAX_NUM_CASES 10          /* definitions.h:121 MAX_NUM_CASES */
+
+typedef struct s3_index s3_index;    /* device-resident 2BWT index (opaque) */
+typedef struct s3_dp    s3_dp;       /* device-resident DP workspace (opaque) */
+
+const char *s3_last_error(void);
+int s3_device_count(void);
+
+/* ------------------------------------------------------------------------
+ * Index.  Replaces GPUINDEXUpload / GPUINDEXFree (alignment.cu:27-115,
+ * alignment.h:41-45).  Inputs are the host arrays of Soap3Index
+ * (IndexHandler.h:46-60): bwt->bwtCode / rev_bwt->bwtCode (2 bit/base, 16
+ * bases per word MSB first; at least ceil(textLength/16) words are read),
+ * gpu_occValue / gpu_revOccValue (numOcc*4 words, BGS-Build.cpp:141-165),
+ * and the scalars the kernels receive by value.  The arrays are re-laid out on
+ * the device into 64-byte buckets {4 x uint32 running counts, 192 bases}; the
+ * caller keeps ownership of the host arrays.  packedDNA (hsp->packedDNA, 16
+ * bases/word MSB first) and sa (bwt->saValue, full SA, saInterval == 1) are
+ * optional (NULL) and are only needed by the device-side locate / window
+ * gather entry points.
+ * ------------------------------------------------------------------------ */
+int s3_index_upload(const uint32_t *bwt, const uint32_t *occ,
+                    const uint32_t *revBwt, const uint32_t *revOcc,
+                    uint32_t numOcc, uint32_t inverseSa0, uint32_t revInverseSa0,
+                    uint32_t textLength,
+                    const uint32_t *packedDNA, const uint32_t *sa,
+                    int device, s3_index **out);
+void s3_index_free(s3_index *ix);
+/* bytes of device memory held by the index */
+size_t s3_index_device_bytes(const s3_index *ix);
+/* the CUDA stream (cudaStream_t) all work of this index is issued on */
+void *s3_index_stream(const s3_index *ix);
+
+/* rank'(c, i) = cumulativeFreq[c] + Occ(c, i) probes evaluated on the device
+ * with the re-laid-out index; replaces nothing (test hook for GPUBWTOccValue,
+ * DV-Kernel.cu:256).  which = 0 forward BWT, 1 reverse BWT.  out[4*i + c]. */
+int s3_rank_probe(s3_index *ix, int which, const uint32_t *indices, size_t n, uint32_t *out);
+
+/* ------------------------------------------------------------------------
+ * Search, round 1.  Replaces perform_round1_alignment (alignment.cu:118-215,
+ * alignment.h:48-51) and its _no_pipeline twin (:329-424): for each of the
+ * numCases cases of the numMismatch scheme, both strands, all SA ranges of
+ * every read into answers[c] (uint32[ceil32(batchSize) * wordPerAns], the
+ * reference's 32-read interleaved slot format, status words 0xFFFFFFFD /
+ * 0xFFFFFFFE, and the isBad carry-over between cases; DV-Kernel.cu:4249-4503).
+ * queries / readLengths: QueryParser.cpp:1146-1152 layout; not modified.
+ * ------------------------------------------------------------------------ */
+int s3_search_round1(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths,
+                     uint64_t batchSize, uint32_t wordPerQuery,
+                     uint32_t numMismatch, uint32_t numCases,
+                     uint32_t saRangeAllowed, uint32_t wordPerAns,
+                     int isExactNumMismatch, uint32_t *const *answers);
+
+/* Search, round 2.  Replaces perform_round2_alignment (alignment.cu:221-326)
+ * and _no_pipeline (:426-531): for each case, the reads whose round-1 status
+ * word is > 0xFFFFFFFD are gathered in read order into badReadIndices[c]
+ * (numBad[c] entries) and searched again with the larger slot into
+ * badAnswers[c] (uint32[ceil32(numBad[c]) * wordPerAns2]).  queries are the
+ * whole host query buffer and processedQuery the offset of this batch in it
+ * (alignment.cu:258).  badReadIndices[c] / badAnswers[c] must have room for
+ * batchSize reads. */
+int s3_search_round2(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths,
+                     uint32_t *const *answers,
+                     uint64_t batchSize, uint64_t processedQuery, uint32_t wordPerQuery,
+                     uint32_t numMismatch, uint32_t numCases,
+                     uint32_t saRangeAllowed2, uint32_t wordPerAns, uint32_t wordPerAns2,
+                     int isExactNumMismatch,
+                     uint32_t *const *badReadIndices, uint32_t *const *badAnswers,
+                     uint64_t *numBad);
+
+/* Device-resident variant of round 1 used for kernel timing and by callers
+ * that keep reads in HBM: d_queries, d_readLengths, d_answers[c] are device
+ * pointers; work is enqueued on s3_index_stream() and NOT synchronised.
+ * d_rankQueries (device uint64, may be NULL) receives the number of rank
+ * evaluations performed (the roofline unit). */
+int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, const uint32_t *d_readLengths,
+                            uint64_t batchSize, uint32_t wordPerQuery,
+                            uint32_t numMismatch, uint32_t numCases,
+                            uint32_t saRangeAllowed, uint32_t wordPerAns,
+                            int isExactNumMismatch, uint32_t *const *d_answers,
+                            unsigned long long *d_rankQueries);
+
+/* ------------------------------------------------------------------------
+ * Semi-global affine-gap DP.  Replaces SemiGlobalAligner::{decideConfiguration,
+ * init, performAlignment, freeMemory} (DV-DPfunctions.h:120-164,
+ * DV-DPfunctions.cu:520-741) and the two kernels SemiGlobalAligntment /
+ * GPUBacktrack (DV-DPfunctions.cu:243,316), scheme 1 (full table) semantics.
+ * Buffers are the reference's fixed-stride batch arrays (DV-DPfunctions.cu:
+ * 57-59,1469-1524): packed sequences 32-interleaved, 1-based, MSB first.
+ * NULL clip / anchor arrays mean "none" (DV-DPfunctions.cu:258-263).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    int32_t matchScore, mismatchScore, gapOpenScore, gapExtendScore;   /* soap3-dp.ini [DP] */
+} s3_dp_scores;
+
+int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint32_t maxBatch,
+                 s3_dp_scores scores, int device, s3_dp **out);
+void s3_dp_free(s3_dp *dp);
+void *s3_dp_stream(const s3_dp *dp);
+/* PatternLength() = maxReadLength + maxDPTableLength bytes per alignment
+ * (DV-DPfunctions.cu:54); maxDPTableLength = maxDNALength + 1 in scheme 1. */
+uint32_t s3_dp_pattern_length(const s3_dp *dp);
+
+int s3_dp_align(s3_dp *dp,
+                const uint32_t *packedDNASequence, const uint32_t *DNALengths,
+                const uint32_t *packedReadSequence, const uint32_t *readLengths,
+                const int32_t *cutoffThresholds,
+                int32_t *scores, uint32_t *hitLocs, uint32_t *maxScoreCounts,
+                uint8_t *pattern, uint32_t numOfThreads,
+                const uint32_t *clipLtSizes, uint32_t *clipRtSizes,
+                const uint32_t *anchorLeftLocs, const uint32_t *anchorRightLocs);
+
+/* device-resident twin (pointers are device pointers, stream-ordered, no sync).
+ * d_cells (device uint64, may be NULL) receives sum readLength*DNALength. */
+int s3_dp_align_device(s3_dp *dp,
+                       const uint32_t *d_packedDNASequence, const uint32_t *d_DNALengths,
+                       const uint32_t *d_packedReadSequence, const uint32_t *d_readLengths,
+                       const int32_t *d_cutoffThresholds,
+                       int32_t *d_scores, uint32_t *d_hitLocs, uint32_t *d_maxScoreCounts,
+                       uint8_t *d_pattern, uint32_t numOfThreads,
+                       const uint32_t *d_clipLtSizes, uint32_t *d_clipRtSizes,
+                       const uint32_t *d_anchorLeftLocs, const uint32_t *d_anchorRightLocs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOAP3DP_B200_H */

@@ -1,0 +1,226 @@
+"""Host-side mirror of the reference's GPU boundary over the C ABI.
+
+Same names, argument meaning and error behaviour as the reference functions the
+C ABI replaces (include/soap3dp_b200.h cites file:line):
+
+    GPUINDEXUpload / GPUINDEXFree                      alignment.cu:27-115
+    perform_round1_alignment / perform_round2_alignment alignment.cu:118-326
+    SemiGlobalAligner                                   DV-DPfunctions.h:120-164
+
+Everything here is ctypes over ``libsoap3dp_b200.so``.  There is NO CPU
+fallback: if the library is missing or no CUDA device is present the calls
+raise (the reference prints "CUDA ... FAILED" and exit(1)s, alignment.cu:38-42).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence
+
+import numpy as np
+
+from . import formats
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsoap3dp_b200.so")
+
+U32P = C.POINTER(C.c_uint32)
+I32P = C.POINTER(C.c_int32)
+U8P = C.POINTER(C.c_uint8)
+U64P = C.POINTER(C.c_uint64)
+
+EXPORTS = [
+    "s3_last_error", "s3_device_count", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
+    "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
+    "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
+]
+
+
+class S3Error(RuntimeError):
+    pass
+
+
+class DPScores(C.Structure):
+    _fields_ = [("matchScore", C.c_int32), ("mismatchScore", C.c_int32),
+                ("gapOpenScore", C.c_int32), ("gapExtendScore", C.c_int32)]
+
+
+_lib = None
+
+
+def load_library() -> C.CDLL:
+    """dlopen the in-tree CUDA library; fails loudly when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise S3Error(f"{LIB_PATH} is not built (run `python __graft_entry__.py build`); "
+                      "soap3dp_b200 has no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.s3_last_error.restype = C.c_char_p
+    lib.s3_device_count.restype = C.c_int
+    lib.s3_index_upload.restype = C.c_int
+    lib.s3_index_upload.argtypes = [U32P, U32P, U32P, U32P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                    U32P, U32P, C.c_int, C.POINTER(C.c_void_p)]
+    lib.s3_index_free.restype = None
+    lib.s3_index_free.argtypes = [C.c_void_p]
+    lib.s3_index_device_bytes.restype = C.c_size_t
+    lib.s3_index_device_bytes.argtypes = [C.c_void_p]
+    lib.s3_index_stream.restype = C.c_void_p
+    lib.s3_index_stream.argtypes = [C.c_void_p]
+    lib.s3_rank_probe.restype = C.c_int
+    lib.s3_rank_probe.argtypes = [C.c_void_p, C.c_int, U32P, C.c_size_t, U32P]
+    PP = C.POINTER(C.c_void_p)
+    lib.s3_search_round1.restype = C.c_int
+    lib.s3_search_round1.argtypes = [C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_uint32, C.c_int, PP]
+    lib.s3_search_round2.restype = C.c_int
+    lib.s3_search_round2.argtypes = [C.c_void_p, U32P, U32P, PP, C.c_uint64, C.c_uint64, C.c_uint32, C.c_uint32,
+                                     C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, PP, PP, U64P]
+    lib.s3_search_round1_device.restype = C.c_int
+    lib.s3_search_round1_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.c_uint32,
+                                            C.c_uint32, C.c_uint32, C.c_uint32, C.c_int, PP, C.c_void_p]
+    lib.s3_dp_create.restype = C.c_int
+    lib.s3_dp_create.argtypes = [C.c_uint32, C.c_uint32, C.c_uint32, DPScores, C.c_int, C.POINTER(C.c_void_p)]
+    lib.s3_dp_free.restype = None
+    lib.s3_dp_free.argtypes = [C.c_void_p]
+    lib.s3_dp_stream.restype = C.c_void_p
+    lib.s3_dp_stream.argtypes = [C.c_void_p]
+    lib.s3_dp_pattern_length.restype = C.c_uint32
+    lib.s3_dp_pattern_length.argtypes = [C.c_void_p]
+    lib.s3_dp_align.restype = C.c_int
+    lib.s3_dp_align.argtypes = [C.c_void_p, U32P, U32P, U32P, U32P, I32P, I32P, U32P, U32P, U8P, C.c_uint32,
+                                U32P, U32P, U32P, U32P]
+    lib.s3_dp_align_device.restype = C.c_int
+    lib.s3_dp_align_device.argtypes = [C.c_void_p] + [C.c_void_p] * 9 + [C.c_uint32] + [C.c_void_p] * 4
+    _lib = lib
+    return lib
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        raise S3Error(f"{what} failed ({rc}): {load_library().s3_last_error().decode()}")
+
+
+def _u32(a: np.ndarray):
+    assert a.dtype == np.uint32 and a.flags.c_contiguous, "need contiguous uint32"
+    return a.ctypes.data_as(U32P)
+
+
+def _ptr_array(arrs: Sequence[np.ndarray]):
+    arr = (C.c_void_p * len(arrs))()
+    for i, a in enumerate(arrs):
+        arr[i] = a.ctypes.data
+    return arr
+
+
+class GpuIndex:
+    """Opaque device index handle (what the reference keeps as _bwt/_occ/_revBwt/_revOcc)."""
+
+    def __init__(self, handle: int, text_length: int):
+        self.handle = C.c_void_p(handle)
+        self.text_length = text_length
+
+    @property
+    def stream(self) -> int:
+        return load_library().s3_index_stream(self.handle)
+
+    @property
+    def device_bytes(self) -> int:
+        return load_library().s3_index_device_bytes(self.handle)
+
+
+def _np_u32(t) -> np.ndarray:
+    """torch int32 / numpy array -> contiguous numpy uint32 view"""
+    if hasattr(t, "detach"):
+        t = t.detach().cpu().contiguous().numpy()
+    return np.ascontiguousarray(t).view(np.uint32)
+
+
+def GPUINDEXUpload(index, device: int = 0, with_text: bool = False, with_sa: bool = False) -> GpuIndex:
+    """alignment.cu:27: copy the index to device memory (and re-lay it out).
+    ``index`` is a fmindex.Soap3IndexArrays (the Soap3Index stand-in)."""
+    lib = load_library()
+    bwt, occ = _np_u32(index.fwd.bwt_words), _np_u32(index.fwd.occ)
+    rbwt, rocc = _np_u32(index.rev.bwt_words), _np_u32(index.rev.occ)
+    pac = sa = None
+    if with_text:
+        if index.packed_text is None:
+            raise S3Error("GPUINDEXUpload: index has no packed text")
+        pac = _np_u32(index.packed_text)
+    if with_sa:
+        if index.fwd.sa is None:
+            raise S3Error("GPUINDEXUpload: index has no suffix array")
+        s = index.fwd.sa
+        s = s.detach().cpu().numpy() if hasattr(s, "detach") else np.asarray(s)
+        sa = np.ascontiguousarray(s.astype(np.uint32))
+    out = C.c_void_p()
+    rc = lib.s3_index_upload(_u32(bwt), _u32(occ), _u32(rbwt), _u32(rocc), index.fwd.num_occ,
+                             index.fwd.inverse_sa0, index.rev.inverse_sa0, index.text_length,
+                             _u32(pac) if pac is not None else None, _u32(sa) if sa is not None else None,
+                             device, C.byref(out))
+    _check(rc, "GPUINDEXUpload")
+    return GpuIndex(out.value, index.text_length)
+
+
+def GPUINDEXFree(gpu_index: GpuIndex):
+    """alignment.cu:109"""
+    if gpu_index.handle:
+        load_library().s3_index_free(gpu_index.handle)
+        gpu_index.handle = C.c_void_p(0)
+
+
+def rank_probe(gpu_index: GpuIndex, which: int, indices: np.ndarray) -> np.ndarray:
+    idx = np.ascontiguousarray(indices, dtype=np.uint32)
+    out = np.empty((idx.size, 4), dtype=np.uint32)
+    _check(load_library().s3_rank_probe(gpu_index.handle, which, _u32(idx), idx.size, _u32(out.reshape(-1))), "s3_rank_probe")
+    return out
+
+
+def perform_round1_alignment(gpu_index: GpuIndex, queries: np.ndarray, read_lengths: np.ndarray, batch_size: int,
+                             word_per_query: int, num_mismatch: int, num_cases: Optional[int] = None,
+                             sa_range_allowed: Optional[int] = None, word_per_ans: Optional[int] = None,
+                             is_exact_num_mismatch: bool = False) -> List[np.ndarray]:
+    """alignment.cu:118.  Returns answers[case] (uint32[ceil32(batch)*word_per_ans])."""
+    if num_cases is None:
+        num_cases = formats.NUM_CASES[num_mismatch]
+    if sa_range_allowed is None:
+        sa_range_allowed = formats.SA_RANGES_ROUND1[num_mismatch]
+    if word_per_ans is None:
+        word_per_ans = 2 * sa_range_allowed
+    up = formats.ceil32(batch_size)
+    assert queries.size >= up * word_per_query, "queries must cover ceil32(batchSize) reads (alignment.cu:157)"
+    answers = [np.empty(up * word_per_ans, dtype=np.uint32) for _ in range(num_cases)]
+    rc = load_library().s3_search_round1(gpu_index.handle, _u32(queries), _u32(read_lengths), batch_size,
+                                         word_per_query, num_mismatch, num_cases, sa_range_allowed, word_per_ans,
+                                         int(is_exact_num_mismatch), _ptr_array(answers))
+    _check(rc, "perform_round1_alignment")
+    return answers
+
+
+def perform_round2_alignment(gpu_index: GpuIndex, queries: np.ndarray, read_lengths: np.ndarray,
+                             answers: Sequence[np.ndarray], batch_size: int, word_per_query: int, num_mismatch: int,
+                             word_per_ans: int, sa_range_allowed_2: Optional[int] = None,
+                             word_per_ans_2: Optional[int] = None, processed_query: int = 0,
+                             is_exact_num_mismatch: bool = False):
+    """alignment.cu:221.  Returns (badReadIndices[case], badAnswers[case])."""
+    num_cases = len(answers)
+    if sa_range_allowed_2 is None:
+        sa_range_allowed_2 = formats.SA_RANGES_ROUND2[num_mismatch]
+    if word_per_ans_2 is None:
+        word_per_ans_2 = 2 * sa_range_allowed_2
+    up = formats.ceil32(batch_size)
+    bad_idx = [np.empty(max(batch_size, 1), dtype=np.uint32) for _ in range(num_cases)]
+    bad_ans = [np.empty(max(up * word_per_ans_2, 1), dtype=np.uint32) for _ in range(num_cases)]
+    num_bad = (C.c_uint64 * num_cases)()
+    rc = load_library().s3_search_round2(gpu_index.handle, _u32(queries), _u32(read_lengths), _ptr_array(answers),
+                                         batch_size, processed_query, word_per_query, num_mismatch, num_cases,
+                                         sa_range_allowed_2, word_per_ans, word_per_ans_2,
+                                         int(is_exact_num_mismatch), _ptr_array(bad_idx), _ptr_array(bad_ans), num_bad)
+    _check(rc, "perform_round2_alignment")
+    out_idx, out_ans = [], []
+    for c in range(num_cases):
+        nb = int(num_bad[c])
+        out_idx.append(bad_idx[c][:nb].copy())
+        out_ans.append(bad_ans[c][:formats.ceil32(nb) * word_per_ans_2].copy())
+    return out_idx, out_ans

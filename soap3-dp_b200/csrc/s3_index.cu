@@ -1,0 +1,199 @@
+// s3_index.cu -- index upload and one-time re-layout for B200.
+// Replaces GPUINDEXUpload / GPUINDEXFree (alignment.cu:27-115).
+#include "s3_common.cuh"
+#include "../../include/soap3dp_b200.h"
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+static thread_local char g_err[512] = "";
+
+void s3_set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+extern "C" const char *s3_last_error(void) { return g_err; }
+
+extern "C" int s3_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int s3_scratch(s3_index *ix, size_t bytes, void **out)
+{
+    if (bytes > ix->scratchBytes) {
+        if (ix->scratch) { S3_CUDA(cudaStreamSynchronize(ix->stream)); S3_CUDA(cudaFree(ix->scratch)); ix->scratch = NULL; ix->scratchBytes = 0; }
+        size_t want = bytes + bytes / 4;
+        S3_CUDA(cudaMalloc(&ix->scratch, want));
+        ix->scratchBytes = want;
+    }
+    *out = ix->scratch;
+    return S3_OK;
+}
+
+int s3_pinned(s3_index *ix, size_t bytes, void **out)
+{
+    if (bytes > ix->pinnedBytes) {
+        if (ix->pinned) { S3_CUDA(cudaStreamSynchronize(ix->stream)); S3_CUDA(cudaFreeHost(ix->pinned)); ix->pinned = NULL; ix->pinnedBytes = 0; }
+        size_t want = bytes + bytes / 4;
+        S3_CUDA(cudaMallocHost(&ix->pinned, want));
+        ix->pinnedBytes = want;
+    }
+    *out = ix->pinned;
+    return S3_OK;
+}
+
+// One thread per bucket.  The running counts at 192*b are taken from the
+// reference's own sampled table (entry e = floor(192*b/128), sample position
+// 128*e <= 192*b, distance 0 or 64 bases) plus a direct count of those <= 64
+// bases, i.e. exactly how the reference kernel itself would evaluate
+// rank'(c, 192*b) (DV-Kernel.cu:256-280) -- no prefix scan needed.
+__global__ void s3_relayout_kernel(const uint32_t *__restrict__ bwt, const uint32_t *__restrict__ occ,
+                                   uint32_t textLength, uint32_t numWords, uint32_t numBuckets,
+                                   uint4 *__restrict__ out)
+{
+    uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= numBuckets) return;
+    uint32_t start = b * S3_BUCKET_BASES;
+    uint32_t e = start >> 7;
+    uint32_t cnt[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) cnt[c] = occ[4 * e + c];
+    uint32_t w = (e << 7) >> 4;                  // first word of the sample block
+    uint32_t gap = start - (e << 7);             // 0 or 64 bases
+    for (uint32_t k = 0; k < gap; k += 16, ++w) {
+        uint32_t word = w < numWords ? bwt[w] : 0u;
+        // bases beyond the text are never counted: start <= textLength
+#pragma unroll
+        for (int j = 0; j < 16; ++j) cnt[(word >> (2 * (15 - j))) & 3]++;
+    }
+    uint32_t words[12];
+#pragma unroll
+    for (int j = 0; j < 12; ++j) {
+        uint32_t wi = (start >> 4) + j;
+        words[j] = wi < numWords ? bwt[wi] : 0u;
+    }
+    uint4 *o = out + (size_t)b * 4;
+    o[0] = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
+    o[1] = make_uint4(words[0], words[1], words[2], words[3]);
+    o[2] = make_uint4(words[4], words[5], words[6], words[7]);
+    o[3] = make_uint4(words[8], words[9], words[10], words[11]);
+}
+
+static int upload_half(s3_index *ix, const uint32_t *bwt, const uint32_t *occ, uint32_t numOcc,
+                       uint32_t textLength, uint4 **d_out, uint32_t *numBucketsOut)
+{
+    size_t numWords = ((size_t)textLength + 15) / 16;
+    uint32_t numBuckets = textLength / S3_BUCKET_BASES + 1;
+    uint32_t *d_bwt = NULL, *d_occ = NULL;
+    S3_CUDA(cudaMalloc(&d_bwt, numWords * sizeof(uint32_t)));
+    S3_CUDA(cudaMalloc(&d_occ, (size_t)numOcc * 4 * sizeof(uint32_t)));
+    S3_CUDA(cudaMemcpyAsync(d_bwt, bwt, numWords * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+    S3_CUDA(cudaMemcpyAsync(d_occ, occ, (size_t)numOcc * 4 * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
+    S3_CUDA(cudaMalloc(d_out, (size_t)numBuckets * 64));
+    s3_relayout_kernel<<<(numBuckets + 255) / 256, 256, 0, ix->stream>>>(d_bwt, d_occ, textLength,
+                                                                        (uint32_t)numWords, numBuckets, *d_out);
+    S3_CUDA(cudaGetLastError());
+    S3_CUDA(cudaStreamSynchronize(ix->stream));
+    S3_CUDA(cudaFree(d_bwt));
+    S3_CUDA(cudaFree(d_occ));
+    *numBucketsOut = numBuckets;
+    ix->bytes += (size_t)numBuckets * 64;
+    return S3_OK;
+}
+
+extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const uint32_t *revBwt,
+                               const uint32_t *revOcc, uint32_t numOcc, uint32_t inverseSa0,
+                               uint32_t revInverseSa0, uint32_t textLength, const uint32_t *packedDNA,
+                               const uint32_t *sa, int device, s3_index **out)
+{
+    if (!bwt || !occ || !revBwt || !revOcc || !out || textLength == 0) {
+        s3_set_error("s3_index_upload: NULL array or empty text");
+        return S3_EINVAL;
+    }
+    if (numOcc != (textLength + 127) / 128 + 1) {
+        s3_set_error("s3_index_upload: numOcc %u does not match textLength %u (BGS-Build.cpp:141)", numOcc, textLength);
+        return S3_EINVAL;
+    }
+    int ndev = s3_device_count();
+    if (device < 0 || device >= ndev) {
+        s3_set_error("s3_index_upload: CUDA device %d not available (%d devices); there is no CPU fallback", device, ndev);
+        return S3_ECUDA;
+    }
+    S3_CUDA(cudaSetDevice(device));
+    s3_index *ix = (s3_index *)calloc(1, sizeof(s3_index));
+    if (!ix) { s3_set_error("out of host memory"); return S3_ENOMEM; }
+    ix->device = device;
+    ix->textLength = textLength;
+    S3_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    int rc;
+    uint32_t nb = 0;
+    if ((rc = upload_half(ix, bwt, occ, numOcc, textLength, &ix->d_fwd, &nb)) != S3_OK) return rc;
+    ix->fwd.buckets = ix->d_fwd; ix->fwd.inverseSa0 = inverseSa0; ix->fwd.numBuckets = nb;
+    if ((rc = upload_half(ix, revBwt, revOcc, numOcc, textLength, &ix->d_rev, &nb)) != S3_OK) return rc;
+    ix->rev.buckets = ix->d_rev; ix->rev.inverseSa0 = revInverseSa0; ix->rev.numBuckets = nb;
+    if (packedDNA) {
+        size_t words = ((size_t)textLength + 15) / 16 + 8;
+        S3_CUDA(cudaMalloc(&ix->d_packedDNA, words * 4));
+        S3_CUDA(cudaMemset(ix->d_packedDNA, 0, words * 4));
+        S3_CUDA(cudaMemcpy(ix->d_packedDNA, packedDNA, (((size_t)textLength + 15) / 16) * 4, cudaMemcpyHostToDevice));
+        ix->bytes += words * 4;
+    }
+    if (sa) {
+        size_t n = (size_t)textLength + 1;
+        S3_CUDA(cudaMalloc(&ix->d_sa, n * 4));
+        S3_CUDA(cudaMemcpy(ix->d_sa, sa, n * 4, cudaMemcpyHostToDevice));
+        ix->bytes += n * 4;
+    }
+    *out = ix;
+    return S3_OK;
+}
+
+extern "C" void s3_index_free(s3_index *ix)
+{
+    if (!ix) return;
+    cudaSetDevice(ix->device);
+    cudaStreamSynchronize(ix->stream);
+    cudaFree(ix->d_fwd); cudaFree(ix->d_rev);
+    if (ix->d_packedDNA) cudaFree(ix->d_packedDNA);
+    if (ix->d_sa) cudaFree(ix->d_sa);
+    if (ix->scratch) cudaFree(ix->scratch);
+    if (ix->pinned) cudaFreeHost(ix->pinned);
+    cudaStreamDestroy(ix->stream);
+    free(ix);
+}
+
+extern "C" size_t s3_index_device_bytes(const s3_index *ix) { return ix ? ix->bytes : 0; }
+extern "C" void *s3_index_stream(const s3_index *ix) { return ix ? (void *)ix->stream : NULL; }
+
+__global__ void s3_rank_probe_kernel(S3Half h, const uint32_t *__restrict__ idx, size_t n, uint32_t *__restrict__ out)
+{
+    size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    uint32_t r[4];
+    s3_rank4(h, idx[i], r);
+    reinterpret_cast<uint4 *>(out)[i] = make_uint4(r[0], r[1], r[2], r[3]);
+}
+
+extern "C" int s3_rank_probe(s3_index *ix, int which, const uint32_t *indices, size_t n, uint32_t *out)
+{
+    if (!ix || !indices || !out) { s3_set_error("s3_rank_probe: NULL argument"); return S3_EINVAL; }
+    if (n == 0) return S3_OK;
+    S3_CUDA(cudaSetDevice(ix->device));
+    uint32_t *d_idx, *d_out;
+    S3_CUDA(cudaMalloc(&d_idx, n * 4));
+    S3_CUDA(cudaMalloc(&d_out, n * 16));
+    S3_CUDA(cudaMemcpyAsync(d_idx, indices, n * 4, cudaMemcpyHostToDevice, ix->stream));
+    s3_rank_probe_kernel<<<(unsigned)((n + 255) / 256), 256, 0, ix->stream>>>(which ? ix->rev : ix->fwd, d_idx, n, d_out);
+    S3_CUDA(cudaGetLastError());
+    S3_CUDA(cudaMemcpyAsync(out, d_out, n * 16, cudaMemcpyDeviceToHost, ix->stream));
+    S3_CUDA(cudaStreamSynchronize(ix->stream));
+    cudaFree(d_idx); cudaFree(d_out);
+    return S3_OK;
+}

@@ -1,0 +1,119 @@
+"""Parity of the CUDA search path (through the C ABI) with the oracle.
+
+Bit-exact comparison of every answer word, for every mismatch level, case,
+round-1 and round-2 slot size, ragged read lengths, and the isBad carry-over.
+"""
+import numpy as np
+import pytest
+import torch
+
+from helpers import HostIndex, fmindex, formats, load_oracle, oracle_launch, s3
+from soap3dp_b200 import api, synth
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    G = synth.random_genome(600_000, seed=11)
+    idx = fmindex.build_index(G)
+    gi = api.GPUINDEXUpload(idx, device=0)
+    yield G, idx, HostIndex(idx), gi
+    api.GPUINDEXFree(gi)
+
+
+def _oracle_round1(olib, hi, q, lens, n, wpq, k, allowed, wpa, ncases):
+    bad = np.zeros(formats.ceil32(n), np.uint8)
+    out = []
+    for case in range(ncases):
+        a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+        oracle_launch(olib, hi, case, q, lens, n, wpq, a, bad, 0, k, allowed, wpa)
+        out.append(a)
+    return out
+
+
+def test_rank_probe(env):
+    G, idx, hi, gi = env
+    olib = load_oracle()
+    rng = np.random.default_rng(3)
+    n = hi.n
+    probes = np.concatenate([rng.integers(0, n + 2, 20000), np.arange(0, 400), np.arange(n - 400, n + 2),
+                             np.arange(hi.isa0 - 3, hi.isa0 + 4), np.arange(hi.risa0 - 3, hi.risa0 + 4)]).astype(np.uint32)
+    probes = probes[probes <= n + 1]
+    from helpers import u32p
+    for which, (bwt, occ, isa0) in enumerate(((hi.bwt, hi.occ, hi.isa0), (hi.rbwt, hi.rocc, hi.risa0))):
+        got = api.rank_probe(gi, which, probes)
+        sel = rng.choice(len(probes), 3000, replace=False)
+        for i in list(sel) + list(range(len(probes) - 420, len(probes))):
+            for c in range(4):
+                assert got[i, c] == olib.s3o_rank(u32p(bwt), u32p(occ), int(probes[i]), c, isa0), (which, i, c)
+
+
+@pytest.mark.parametrize("L", [100, 36, 150])
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4])
+def test_round1_and_round2_bit_exact(env, L, k):
+    G, idx, hi, gi = env
+    olib = load_oracle()
+    n = 4099                                   # ragged: not a multiple of 32
+    rs = synth.simulate_single_end(G, n, L, seed=100 + L + k, sub_rate=0.015)
+    reads = rs.reads.numpy()
+    lens = rs.lengths.numpy().astype(np.uint32)
+    lens[::5] = L - 1
+    lens[3::11] = L - 7
+    wpq = formats.word_per_query(L)
+    q = formats.pack_queries(reads, lens, wpq)
+    lens_up = np.zeros(formats.ceil32(n), np.uint32)
+    lens_up[:n] = lens
+    allowed = formats.SA_RANGES_ROUND1[k]
+    wpa = 2 * allowed
+    ncases = formats.NUM_CASES[k]
+    got = api.perform_round1_alignment(gi, q, lens_up, n, wpq, k)
+    want = _oracle_round1(olib, hi, q, lens_up, n, wpq, k, allowed, wpa, ncases)
+    for c in range(ncases):
+        gv, wv = formats.answers_view(got[c], n, wpa), formats.answers_view(want[c], n, wpa)
+        assert np.array_equal(gv, wv), f"k={k} case={c}: {np.nonzero((gv != wv).any(1))[0][:5]}"
+    # round 2 on the overflowing reads
+    allowed2 = formats.SA_RANGES_ROUND2[k]
+    wpa2 = 2 * allowed2
+    bad_idx, bad_ans = api.perform_round2_alignment(gi, q, lens_up, got, n, wpq, k, wpa)
+    for c in range(ncases):
+        view = formats.answers_view(want[c], n, wpa)
+        exp_idx = np.nonzero(view[:, 0] > 0xFFFFFFFD)[0].astype(np.uint32)
+        assert np.array_equal(bad_idx[c], exp_idx)
+        nb = len(exp_idx)
+        if nb == 0:
+            continue
+        bq = formats.pack_queries(reads[exp_idx], lens[exp_idx], wpq)
+        bl = np.zeros(formats.ceil32(nb), np.uint32)
+        bl[:nb] = lens[exp_idx]
+        a = np.zeros(formats.ceil32(nb) * wpa2, np.uint32)
+        oracle_launch(olib, hi, c, bq, bl, nb, wpq, a, np.zeros(formats.ceil32(nb), np.uint8), 1, k, allowed2, wpa2)
+        assert np.array_equal(formats.answers_view(bad_ans[c], nb, wpa2), formats.answers_view(a, nb, wpa2)), (k, c)
+
+
+def test_exact_num_mismatch_flag(env):
+    G, idx, hi, gi = env
+    olib = load_oracle()
+    n, L, k = 1000, 100, 1
+    rs = synth.simulate_single_end(G, n, L, seed=77, sub_rate=0.01)
+    lens = np.full(formats.ceil32(n), L, np.uint32)
+    wpq = formats.word_per_query(L)
+    q = formats.pack_queries(rs.reads.numpy(), lens[:n], wpq)
+    got = api.perform_round1_alignment(gi, q, lens, n, wpq, k, is_exact_num_mismatch=True)
+    bad = np.zeros(formats.ceil32(n), np.uint8)
+    for case in range(2):
+        a = np.zeros(formats.ceil32(n) * 8, np.uint32)
+        oracle_launch(olib, hi, case, q, lens, n, wpq, a, bad, 0, k, 4, 8, exact=1)
+        assert np.array_equal(formats.answers_view(got[case], n, 8), formats.answers_view(a, n, 8))
+
+
+def test_empty_batch_and_bad_args(env):
+    G, idx, hi, gi = env
+    q = np.zeros(32 * 8, np.uint32)
+    lens = np.zeros(32, np.uint32)
+    out = api.perform_round1_alignment(gi, q, lens, 0, 8, 2)
+    assert len(out) == 4
+    with pytest.raises(api.S3Error):
+        api.perform_round1_alignment(gi, q, lens, 1, 8, 5, num_cases=1, sa_range_allowed=1, word_per_ans=2)
+    with pytest.raises(api.S3Error):
+        api.perform_round1_alignment(gi, q, lens, 1, 8, 2, num_cases=7, sa_range_allowed=4, word_per_ans=8)

@@ -65,3 +65,15 @@ sed 's/^\(\s*\)index -= ( index > inverseSa0 );/\1++s3_rank_queries; index -= ( 
 $CXX -O2 -fopenmp -fpermissive -w -fPIC -shared -DS3_COUNT_RANK_QUERIES -I"$OUT/patched" -I"$REF" -I"$HERE/ref_shim" \
     "$HERE/ref_shim/ref_search_host.cpp" -o "$OUT/libref_search.so"
 echo "[build_ref] libref_search.so OK"
+
+# ---- reference DP kernels compiled for the host ------------------------------
+# lines 35-512 of DV-DPfunctions.cu = _MAX/_MIN/_LOW_THRESHOLD, macros, DPScoreNHitPos,
+# GenerateDPTable, SemiGlobalAligntment, GPUBacktrack.  The two texture references
+# (removed from CUDA 12) become plain array reads; nothing else is touched.
+sed -n '35,512p' "$REF/DV-DPfunctions.cu" \
+  | sed -e '/^texture <uint>/d' \
+        -e 's/tex1Dfetch(texPatterns, readTPARA + (((i)>>4)<<5))/X[readTPARA + (((i)>>4)<<5)]/' \
+  > "$OUT/patched/dp_kernels.inc"
+$CXX -O2 -fopenmp -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$HERE/ref_shim" \
+    "$HERE/ref_shim/ref_dp_host.cpp" -o "$OUT/libref_dp.so"
+echo "[build_ref] libref_dp.so OK"

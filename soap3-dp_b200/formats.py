@@ -71,3 +71,47 @@ def decode_answer_row(row: np.ndarray):
             break
         out.append((l, l + (w & ((1 << ANSWER_OFFSET_LENGTH) - 1)), (w >> 27) & 1, (w >> 24) & 7))
     return status, out
+
+
+# ---------------------------------------------------------------------------
+# DP batch formats (DV-DPfunctions.cu:55-59,1469-1524)
+# ---------------------------------------------------------------------------
+
+def dp_words(max_length: int) -> int:
+    """MC_CeilDivide16 (DV-DPfunctions.h:59)"""
+    return (max_length + 15) >> 4
+
+
+def pack_dp_sequences(seqs: np.ndarray, max_length: int) -> np.ndarray:
+    """seqs uint8 [B, <=max_length-1...] base codes, 0-based -> uint32[ceil32(B)*dp_words(max_length)]:
+    base i (1-based!) in bits 2*(15-(i&15)) of word i>>4, slot 0 unused, 32-interleaved."""
+    b, l = seqs.shape
+    nw = dp_words(max_length)
+    assert l + 1 <= nw * 16, "1-based packing needs length+1 <= 16*words"
+    padded = np.zeros((ceil32(b), nw * 16), dtype=np.uint32)
+    padded[:b, 1:l + 1] = seqs
+    shifts = (2 * (15 - np.arange(16, dtype=np.uint32)))
+    words = (padded.reshape(ceil32(b), nw, 16) << shifts).sum(axis=2, dtype=np.uint64).astype(np.uint32)
+    return np.ascontiguousarray(words.reshape(-1, 32, nw).transpose(0, 2, 1)).reshape(-1)
+
+
+def decode_pattern(pat: np.ndarray) -> str:
+    """GPU pattern bytes -> CIGAR-like string in read order (the decode loop of
+    SingleDP_Space::algnmtCPUThread, DV-DPfunctions.cu:1700-1716: 'V',n repeats the
+    previous op n-1 more times; emitted right-to-left, so reverse at the end)."""
+    ops = []
+    i = 0
+    last = None
+    while i < len(pat) and pat[i] != 0:
+        ch = chr(pat[i])
+        if ch == 'V':
+            cnt = int(pat[i + 1])
+            ops.extend([last] * (cnt - 1) if cnt >= 1 else [])
+            if cnt == 0 and ops:
+                ops.pop()
+            i += 2
+        else:
+            ops.append(ch)
+            last = ch
+            i += 1
+    return "".join(reversed(ops))

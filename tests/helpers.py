@@ -78,3 +78,163 @@ def ref_launch(lib, hi, case, queries, lengths, n, wpq, answers, is_bad, rnd, k,
     return lib.ref_search_launch(case, u32p(queries), u32p(lengths), n, wpq, u32p(hi.bwt), u32p(hi.occ), hi.isa0,
                                  u32p(hi.rbwt), u32p(hi.rocc), hi.risa0, hi.n, u32p(answers),
                                  is_bad.ctypes.data_as(C.POINTER(C.c_uint8)), rnd, k, sa_allowed, wpa, exact, nthreads)
+
+
+# ---------------------------------------------------------------------------
+# DP
+# ---------------------------------------------------------------------------
+I32P = C.POINTER(C.c_int32)
+U8P = C.POINTER(C.c_uint8)
+
+_DP_ARGS = [U32P, U32P, C.c_uint32, U32P, U32P, C.c_uint32, I32P, I32P, U32P, U32P, U8P, C.c_uint32,
+            U32P, U32P, U32P, U32P, C.c_int, C.c_int, C.c_int, C.c_int]
+
+
+def load_oracle_dp():
+    lib = load_oracle()
+    lib.s3o_dp_align.restype = C.c_ulonglong
+    lib.s3o_dp_align.argtypes = _DP_ARGS
+    return lib
+
+
+def load_ref_dp():
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_dp.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.ref_dp_align.restype = C.c_int
+    lib.ref_dp_align.argtypes = [U32P, U32P, C.c_uint32, C.c_uint32, U32P, U32P, C.c_uint32, I32P, I32P, U32P, U32P, U8P,
+                                 C.c_uint32, U32P, U32P, U32P, U32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    return lib
+
+
+def _opt(a):
+    return u32p(a) if a is not None else None
+
+
+class DPBatch:
+    """A batch in the reference's SemiGlobalAligner host format."""
+
+    def __init__(self, dna, dna_len, read, read_len, max_dna, max_read, cutoff, clip_lt=None, clip_rt=None,
+                 anchor_l=None, anchor_r=None):
+        self.n = len(dna_len)
+        self.max_dna, self.max_read = max_dna, max_read
+        self.dna = formats.pack_dp_sequences(dna, max_dna)
+        self.read = formats.pack_dp_sequences(read, max_read)
+        up = formats.ceil32(self.n)
+
+        def padu(a):
+            if a is None:
+                return None
+            o = np.zeros(up, np.uint32)
+            o[:self.n] = a
+            return o
+        self.dna_len, self.read_len = padu(dna_len), padu(read_len)
+        self.cutoff = np.zeros(up, np.int32)
+        self.cutoff[:self.n] = cutoff
+        self.clip_lt, self.clip_rt, self.anchor_l, self.anchor_r = padu(clip_lt), padu(clip_rt), padu(anchor_l), padu(anchor_r)
+        self.pat_len = max_read + max_dna
+
+    def outputs(self):
+        up = formats.ceil32(self.n)
+        return (np.zeros(up, np.int32), np.zeros(up, np.uint32), np.zeros(up, np.uint32),
+                np.zeros(up * self.pat_len, np.uint8))
+
+
+def oracle_dp(lib, b, scores=(1, -2, -3, -1)):
+    sc, hit, cnt, pat = b.outputs()
+    cells = lib.s3o_dp_align(u32p(b.dna), u32p(b.dna_len), b.max_dna, u32p(b.read), u32p(b.read_len), b.max_read,
+                             b.cutoff.ctypes.data_as(I32P), sc.ctypes.data_as(I32P), u32p(hit), u32p(cnt),
+                             pat.ctypes.data_as(U8P), b.n, _opt(b.clip_lt), _opt(b.clip_rt), _opt(b.anchor_l),
+                             _opt(b.anchor_r), *scores)
+    return sc, hit, cnt, pat, cells
+
+
+def ref_dp(lib, b, scores=(1, -2, -3, -1), nthreads=0):
+    sc, hit, cnt, pat = b.outputs()
+    lib.ref_dp_align(u32p(b.dna), u32p(b.dna_len), b.max_dna, b.max_dna, u32p(b.read), u32p(b.read_len), b.max_read,
+                     b.cutoff.ctypes.data_as(I32P), sc.ctypes.data_as(I32P), u32p(hit), u32p(cnt),
+                     pat.ctypes.data_as(U8P), b.n, _opt(b.clip_lt), _opt(b.clip_rt), _opt(b.anchor_l),
+                     _opt(b.anchor_r), *scores, 1, nthreads)
+    return sc, hit, cnt, pat
+
+
+def pattern_end(w):
+    """index of the 0 terminator; a count byte after 'V' may legitimately be 0"""
+    i = 0
+    while True:
+        if w[i] == ord('V'):
+            i += 2
+            continue
+        if w[i] == 0:
+            return i
+        i += 1
+
+
+def compare_dp(b, got, want, what=""):
+    """scores / hitLocs / counts for every alignment; pattern bytes (through the 0
+    terminator) for those reaching the cutoff -- the only ones the reference writes."""
+    gs, gh, gc, gp = got[:4]
+    ws, wh, wc, wp = want[:4]
+    n = b.n
+    assert np.array_equal(gs[:n], ws[:n]), f"{what} scores differ at {np.nonzero(gs[:n] != ws[:n])[0][:5]}"
+    assert np.array_equal(gc[:n], wc[:n]), f"{what} maxScoreCounts differ at {np.nonzero(gc[:n] != wc[:n])[0][:5]}"
+    assert np.array_equal(gh[:n], wh[:n]), f"{what} hitLocs differ at {np.nonzero(gh[:n] != wh[:n])[0][:5]}"
+    npass = 0
+    for t in range(n):
+        if ws[t] >= b.cutoff[t]:
+            npass += 1
+            w = wp[t * b.pat_len:(t + 1) * b.pat_len]
+            g = gp[t * b.pat_len:(t + 1) * b.pat_len]
+            i = pattern_end(w)
+            assert np.array_equal(g[:i + 1], w[:i + 1]), \
+                f"{what} pattern differs for alignment {t}: {bytes(g[:i + 1])} vs {bytes(w[:i + 1])}"
+    return npass
+
+
+def make_dp_batch(genome, n, read_len, mode, seed, indel_rate=0.004, sub_rate=0.02, insert=(200, 500), max_read=None):
+    """Synthetic DP batches shaped like the engines' packers:
+    mode 'single' : window = read +- margin, clips by strand, no anchors (DV-DPfunctions.cu:1425)
+    mode 'rescue' : mate-rescue windows with anchors (DV-DPfunctions.cu:2027)."""
+    from soap3dp_b200 import synth
+    G = genome
+    rs = synth.simulate_single_end(G, n, read_len, seed=seed, sub_rate=sub_rate, indel_rate=indel_rate, margin=1000)
+    rng = np.random.default_rng(seed)
+    reads = rs.reads.numpy()
+    pos = rs.pos.numpy()
+    strand = rs.strand.numpy()
+    # DP aligns the read in reference orientation (reverse-strand reads are
+    # reverse-complemented by the packers, DV-DPfunctions.cu:1497-1505)
+    fw = np.where(strand[:, None] == 1, 3 - reads[:, ::-1], reads)
+    Gn = G.numpy()
+    if max_read is None:
+        max_read = (read_len // 4 + 1) * 4
+    if mode == "single":
+        margin = read_len // 4 if read_len > 100 else 25
+        wlen = read_len + 2 * margin
+        max_dna = max_read + 2 * margin + 8
+        start = pos - margin + rng.integers(-5, 6, n)
+        dna = Gn[start[:, None] + np.arange(wlen)[None, :]]
+        dna_len = np.full(n, wlen, np.uint32)
+        clip_lt = np.where(strand == 0, 3, 8).astype(np.uint32)
+        clip_rt = np.where(strand == 0, 8, 3).astype(np.uint32)
+        anchor_l = anchor_r = None
+    else:
+        lo, hi = insert
+        wlen = hi - lo + read_len
+        max_dna = hi - lo + max_read + 1
+        left_side = rng.integers(0, 2, n).astype(bool)
+        off = rng.integers(0, hi - lo, n)
+        start = pos - off
+        dna = Gn[start[:, None] + np.arange(wlen)[None, :]]
+        dna_len = np.full(n, wlen, np.uint32)
+        clip_lt = rng.integers(0, 9, n).astype(np.uint32)
+        clip_rt = rng.integers(0, 9, n).astype(np.uint32)
+        anchor_l = np.where(left_side, max_dna, hi - lo + 1).astype(np.uint32)
+        anchor_r = np.where(left_side, read_len, 0).astype(np.uint32)
+    rl = np.full(n, read_len, np.uint32)
+    rl[::9] = read_len - 3
+    dna_len[::13] -= 7
+    cutoff = np.ceil(0.3 * rl).astype(np.int32)
+    return DPBatch(dna.astype(np.uint8), dna_len, fw.astype(np.uint8), rl, max_dna, max_read, cutoff,
+                   clip_lt, clip_rt, anchor_l, anchor_r)

@@ -125,7 +125,8 @@ int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint32_t maxBatc
 void s3_dp_free(s3_dp *dp);
 void *s3_dp_stream(const s3_dp *dp);
 /* PatternLength() = maxReadLength + maxDPTableLength bytes per alignment
- * (DV-DPfunctions.cu:54); maxDPTableLength = maxDNALength + 1 in scheme 1. */
+ * (DV-DPfunctions.cu:54); maxDPTableLength = maxDNALength in scheme 1
+ * (decideConfiguration, DV-DPfunctions.cu:592). */
 uint32_t s3_dp_pattern_length(const s3_dp *dp);
 
 int s3_dp_align(s3_dp *dp,
@@ -136,6 +137,12 @@ int s3_dp_align(s3_dp *dp,
                 uint8_t *pattern, uint32_t numOfThreads,
                 const uint32_t *clipLtSizes, uint32_t *clipRtSizes,
                 const uint32_t *anchorLeftLocs, const uint32_t *anchorRightLocs);
+/* Like the reference, clipRtSizes is only read on the host side: the kernel's
+ * actual right clip is reported through the leading 'S','V',n of the pattern
+ * (performAlignment copies back scores, hitLocs, pattern and maxScoreCounts
+ * only, DV-DPfunctions.cu:719-722).  hitLocs[t] is the 0-based start offset in
+ * the window when scores[t] >= cutoffThresholds[t] (pattern written), else the
+ * end column of the best cell (pattern untouched), as in the reference. */
 
 /* device-resident twin (pointers are device pointers, stream-ordered, no sync).
  * d_cells (device uint64, may be NULL) receives sum readLength*DNALength. */

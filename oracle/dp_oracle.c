@@ -76,6 +76,10 @@ static void dp_one(const uint32_t *dna, uint32_t dna_base, uint32_t n,
     for (uint32_t j = 1; j <= n; ++j) {
         const uint32_t refChar = unpack1(dna, dna_base, j);
         const int init = (j >= anchorLeft) ? NEG_INF : 0;
+        /* GPUBacktrack recomputes "the previous column's init" as (j > anchorLeft) (:352-357,:368),
+         * which differs from the score pass's prevInitScore (0 before column 1, :186) when
+         * anchorLeft == 0 and j == 1; the traceback test must use the traceback's value */
+        const int prevInitTb = (j > anchorLeft) ? NEG_INF : 0;
         int upScore = init, F = init + gapInit;
         int diag = prevInit;            /* with soft-clip restart applied */
         int diagRaw = Hprev[0];         /* stored H[j-1][i-1]             */
@@ -97,7 +101,7 @@ static void dp_one(const uint32_t *dna, uint32_t dna_base, uint32_t n,
             if (hStored == d + diagRaw) b = TB_DIAG;
             else if (hStored == sc.open + left) b = TB_DOPEN;
             else if (hStored == sc.ext + eLeft) b = TB_DEXT;
-            else if (i <= clipLt + 1 && hStored == prevInit + d) b = TB_SMEXIT;
+            else if (i <= clipLt + 1 && hStored == prevInitTb + d) b = TB_SMEXIT;
             else if (i <= clipLt + 1 && hStored == init + sc.open) b = TB_SIEXIT;
             else if (hStored == sc.open + upStored) b = TB_IOPEN;
             else b = TB_IEXT;

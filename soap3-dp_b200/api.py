@@ -224,3 +224,49 @@ def perform_round2_alignment(gpu_index: GpuIndex, queries: np.ndarray, read_leng
         out_idx.append(bad_idx[c][:nb].copy())
         out_ans.append(bad_ans[c][:formats.ceil32(nb) * word_per_ans_2].copy())
     return out_idx, out_ans
+
+
+class SemiGlobalAligner:
+    """DV-DPfunctions.h:120-164.  decideConfiguration/init collapse into the
+    constructor (a B200 always has room for scheme 1, the full table);
+    performAlignment keeps the reference's argument list."""
+
+    def __init__(self, max_read_length: int, max_dna_length: int, batch_size: int,
+                 match: int = 1, mismatch: int = -2, gap_open: int = -3, gap_extend: int = -1, device: int = 0):
+        lib = load_library()
+        self.max_read_length, self.max_dna_length, self.batch_size = max_read_length, max_dna_length, batch_size
+        out = C.c_void_p()
+        _check(lib.s3_dp_create(max_read_length, max_dna_length, batch_size,
+                                DPScores(match, mismatch, gap_open, gap_extend), device, C.byref(out)),
+               "SemiGlobalAligner.init")
+        self.handle = out
+        self.max_dp_table_length = max_dna_length               # scheme 1 (DV-DPfunctions.cu:592)
+        self.pattern_length = lib.s3_dp_pattern_length(self.handle)
+
+    @property
+    def stream(self) -> int:
+        return load_library().s3_dp_stream(self.handle)
+
+    def performAlignment(self, packedDNASequence, DNALengths, packedReadSequence, readLengths, cutoffThresholds,
+                         numOfThreads, clipLtSizes=None, clipRtSizes=None, anchorLeftLocs=None, anchorRightLocs=None):
+        """DV-DPfunctions.cu:669.  Returns (scores, hitLocs, maxScoreCounts, pattern)."""
+        up = formats.ceil32(max(numOfThreads, 1))
+        scores = np.zeros(up, np.int32)
+        hit = np.zeros(up, np.uint32)
+        cnt = np.zeros(up, np.uint32)
+        pat = np.zeros(up * self.pattern_length, np.uint8)
+
+        def opt(a):
+            return _u32(a) if a is not None else None
+        rc = load_library().s3_dp_align(self.handle, _u32(packedDNASequence), _u32(DNALengths), _u32(packedReadSequence),
+                                        _u32(readLengths), cutoffThresholds.ctypes.data_as(I32P),
+                                        scores.ctypes.data_as(I32P), _u32(hit), _u32(cnt), pat.ctypes.data_as(U8P),
+                                        numOfThreads, opt(clipLtSizes), opt(clipRtSizes), opt(anchorLeftLocs),
+                                        opt(anchorRightLocs))
+        _check(rc, "SemiGlobalAligner.performAlignment")
+        return scores, hit, cnt, pat
+
+    def freeMemory(self):
+        if self.handle:
+            load_library().s3_dp_free(self.handle)
+            self.handle = C.c_void_p(0)

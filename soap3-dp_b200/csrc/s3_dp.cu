@@ -1,9 +1,414 @@
-// s3_dp.cu -- placeholder until the DP kernels land (next commit)
+// s3_dp.cu -- semi-global affine-gap DP (score pass + traceback) for sm_100a.
+//
+// Replaces SemiGlobalAligntment / GPUBacktrack (DV-DPfunctions.cu:243,316) and
+// SemiGlobalAligner (DV-DPfunctions.cu:520-741), scheme-1 (full table) semantics.
+//
+// Design (not a port).  The reference runs one thread per alignment and keeps
+// the full H and E tables of shorts in global memory (8 B of traffic per cell,
+// DV-DPfunctions.cu:57,146-241), then walks them again to trace back.  Here:
+//   * one WARP per alignment; lane t owns read rows [t*R+1, t*R+R] and sweeps the
+//     reference columns as an anti-diagonal wavefront: at step s lane t is in
+//     column s-t.  The reference's inner-loop carried registers (upScore,
+//     scoreOpenUp, prevScoreUp) simply migrate from lane t-1 to lane t with
+//     __shfl_up_sync, so every intermediate value -- including the "unclamped
+//     inside a column, clamped to -32000 when stored" rule -- is bit-identical.
+//   * H/E of the previous column live in registers (2R per lane); nothing but one
+//     traceback BYTE per cell goes to memory.  The byte records the outcome of every
+//     comparison GPUBacktrack would make at that cell (oracle/dp_oracle.c has the
+//     same formulation and is pinned against the reference kernels).
+//   * max/add chains use the DPX instructions (__viaddmax_s32, __vimax3_s32).
+//   * best cell: per-lane running best in the reference's scan order, merged
+//     across lanes with the (column, row) tie-break; tie counts are summed.
+// The traceback kernel is one thread per alignment that needs one (score >=
+// cutoff) and reads only the byte plane.
 #include "s3_common.cuh"
 #include "../../include/soap3dp_b200.h"
-extern "C" int s3_dp_create(uint32_t, uint32_t, uint32_t, s3_dp_scores, int, s3_dp **) { s3_set_error("DP not built yet"); return S3_EINVAL; }
-extern "C" void s3_dp_free(s3_dp *) {}
-extern "C" void *s3_dp_stream(const s3_dp *) { return NULL; }
-extern "C" uint32_t s3_dp_pattern_length(const s3_dp *) { return 0; }
-extern "C" int s3_dp_align(s3_dp *, const uint32_t *, const uint32_t *, const uint32_t *, const uint32_t *, const int32_t *, int32_t *, uint32_t *, uint32_t *, uint8_t *, uint32_t, const uint32_t *, uint32_t *, const uint32_t *, const uint32_t *) { return S3_EINVAL; }
-extern "C" int s3_dp_align_device(s3_dp *, const uint32_t *, const uint32_t *, const uint32_t *, const uint32_t *, const int32_t *, int32_t *, uint32_t *, uint32_t *, uint8_t *, uint32_t, const uint32_t *, uint32_t *, const uint32_t *, const uint32_t *) { return S3_EINVAL; }
+#include <stdlib.h>
+#include <string.h>
+
+#define S3_NEG_INF (-32000)
+#define TB_DIAG 0
+#define TB_DOPEN 1
+#define TB_DEXT 2
+#define TB_SMEXIT 3
+#define TB_SIEXIT 4
+#define TB_IOPEN 5
+#define TB_IEXT 6
+#define TB_MATCH 8
+#define TB_EOPEN 16
+#define TB_FOPEN 32
+#define TB_FEXIT 64
+
+#define S3_DP_WARPS 4
+#define S3_DP_MAX_REF_WORDS 160      // reference window up to 2559 bases
+
+struct s3_dp {
+    int device;
+    cudaStream_t stream;
+    uint32_t maxReadLength, maxDNALength, maxBatch;
+    s3_dp_scores sc;
+    int R;                       // rows per lane
+    uint32_t slot;               // bytes per lane per column in the traceback plane
+    uint32_t chunk;              // alignments per traceback-plane chunk
+    uint8_t *d_tb;               // chunk * (maxDNALength+1) * 32 * slot
+    uint32_t *d_scRight;         // maxBatch
+    // staging for the host entry point
+    uint32_t *d_dna, *d_read, *d_dnaLen, *d_readLen, *d_hit, *d_cnt, *d_clipLt, *d_clipRt, *d_ancL, *d_ancR;
+    int32_t *d_cutoff, *d_score;
+    uint8_t *d_pattern;
+    unsigned long long *d_cells;
+};
+
+struct S3DpArgs {
+    const uint32_t *dna, *dnaLen, *read, *readLen;
+    const uint32_t *clipLt, *clipRt, *ancL, *ancR;
+    const int32_t *cutoff;
+    int32_t *score;
+    uint32_t *hit, *cnt, *scRight;
+    uint8_t *tb, *pattern;
+    uint32_t first, count;           // alignment range of this chunk
+    uint32_t maxReadLength, maxDNALength, dnaWords, readWords;
+    uint32_t slot;
+    int match, mismatch, open, ext;
+    unsigned long long *cells;
+};
+
+__device__ __forceinline__ int s3_clamp(int x) { return max(x, S3_NEG_INF); }
+
+template <int R>
+__global__ void __launch_bounds__(S3_DP_WARPS * 32)
+s3_dp_score_kernel(const S3DpArgs a)
+{
+    __shared__ uint32_t refWords[S3_DP_WARPS][S3_DP_MAX_REF_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t local = blockIdx.x * S3_DP_WARPS + warp;
+    if (local >= a.count) return;                       // whole warp leaves together
+    const uint32_t id = a.first + local;
+    const uint32_t g = id >> 5, gl = id & 31;
+    const uint32_t m = a.readLen[id], n = a.dnaLen[id];
+    const uint32_t clipLt = a.clipLt ? a.clipLt[id] : 0u;
+    const uint32_t clipRt = a.clipRt ? a.clipRt[id] : 0u;
+    const uint32_t anchorLeft = a.ancL ? a.ancL[id] : a.maxDNALength;
+    const uint32_t anchorRight = a.ancR ? a.ancR[id] : 0u;
+    const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
+    const int clipRtCheck = (int)(m - clipRt);
+
+    // reference window -> shared memory (1-based packing, MSB first; DV-DPfunctions.cu:58)
+    const uint32_t *dna = a.dna + (size_t)g * a.dnaWords * 32 + gl;
+    const uint32_t nRefWords = (n >> 4) + 1;
+    for (uint32_t w = lane; w < nRefWords; w += 32) refWords[warp][w] = dna[(size_t)w * 32];
+    // this lane's read bases
+    const uint32_t *read = a.read + (size_t)g * a.readWords * 32 + gl;
+    const uint32_t i0 = lane * R + 1;                  // first row of this lane (1-based)
+    uint32_t rc[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i = i0 + r;
+        rc[r] = (i <= m) ? (read[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 4u;   // 4 never matches
+    }
+    __syncwarp();
+
+    // column 0 (DV-DPfunctions.cu:167-184)
+    int Hp[R], Ep[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i = i0 + r;
+        const int h = (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext;
+        Hp[r] = s3_clamp(h);
+        Ep[r] = s3_clamp(h + gapInit);
+    }
+    int best = S3_NEG_INF;
+    uint32_t hitJ = 0, bestI = 0, count = 0;
+    int upOut = 0, FOut = 0, diagRawOut = 0;
+    uint8_t *tb = a.tb + (size_t)local * (a.maxDNALength + 1) * 32 * a.slot + (size_t)lane * a.slot;
+    const uint32_t colStride = 32 * a.slot;
+
+    const uint32_t steps = n + 31;
+    for (uint32_t s = 1; s <= steps; ++s) {
+        // carried registers of the row loop arrive from the lane above (column j was done there at step s-1)
+        int up = __shfl_up_sync(0xFFFFFFFFu, upOut, 1);
+        int F = __shfl_up_sync(0xFFFFFFFFu, FOut, 1);
+        int diagRaw = __shfl_up_sync(0xFFFFFFFFu, diagRawOut, 1);
+        const uint32_t j = s - lane;
+        if (j >= 1 && j <= n && i0 <= m) {
+            const int init = (j >= anchorLeft) ? S3_NEG_INF : 0;
+            const int prevInit = (j >= 2 && j - 1 >= anchorLeft) ? S3_NEG_INF : 0;
+            // GPUBacktrack's own idea of the previous column's start value (DV-DPfunctions.cu:352-357,368);
+            // differs from prevInit only for j == 1 with anchorLeft == 0
+            const int prevInitTb = (j > anchorLeft) ? S3_NEG_INF : 0;
+            int diag;
+            if (lane == 0) { up = init; F = init + gapInit; diagRaw = prevInit; diag = prevInit; }
+            else diag = (i0 - 1 <= clipLt) ? max(prevInit, diagRaw) : diagRaw;
+            int upSt = s3_clamp(up);
+            const uint32_t refChar = (refWords[warp][j >> 4] >> ((15 - (j & 15)) << 1)) & 3;
+            const bool jOk = j >= anchorRight;
+            uint32_t packed[(R + 3) / 4];
+#pragma unroll
+            for (int k = 0; k < (R + 3) / 4; ++k) packed[k] = 0;
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t i = i0 + r;
+                const bool isMatch = (refChar == rc[r]);
+                const int d = isMatch ? a.match : a.mismatch;
+                const int left = Hp[r], eL = Ep[r];
+                const int e = __viaddmax_s32(left, open, eL + ext);
+                F = __viaddmax_s32(up, open, F + ext);
+                up = __vimax3_s32(F, e, diag + d);
+                const int hSt = s3_clamp(up), eSt = s3_clamp(e);
+                const bool nearClip = i <= clipLt + 1;
+                uint32_t b = (hSt == d + diagRaw) ? TB_DIAG
+                           : (hSt == open + left) ? TB_DOPEN
+                           : (hSt == ext + eL) ? TB_DEXT
+                           : (nearClip && hSt == prevInitTb + d) ? TB_SMEXIT
+                           : (nearClip && hSt == init + open) ? TB_SIEXIT
+                           : (hSt == open + upSt) ? TB_IOPEN : TB_IEXT;
+                b |= isMatch ? TB_MATCH : 0;
+                b |= (eSt == open + left) ? TB_EOPEN : 0;
+                diagRaw = left; diag = left;
+                if (i <= clipLt) { F = max(init + gapInit, F); diag = max(prevInit, diag); }
+                b |= (F == open + upSt) ? TB_FOPEN : 0;
+                b |= (nearClip && F == init + open) ? TB_FEXIT : 0;
+                packed[r >> 2] |= b << ((r & 3) * 8);
+                Hp[r] = hSt; Ep[r] = eSt; upSt = hSt;
+                if ((int)i >= clipRtCheck && i <= m && jOk) {
+                    if (up > best) { best = up; hitJ = j; bestI = i; count = 1; }
+                    else if (up == best) ++count;
+                }
+            }
+            upOut = up; FOut = F; diagRawOut = diagRaw;
+            uint8_t *dst = tb + (size_t)j * colStride;
+            if (R == 4) *reinterpret_cast<uint32_t *>(dst) = packed[0];
+            else if (R == 8) *reinterpret_cast<uint2 *>(dst) = make_uint2(packed[0], packed[(R > 4) ? 1 : 0]);
+            else {
+#pragma unroll
+                for (int k = 0; k < (R + 3) / 4; ++k) reinterpret_cast<uint32_t *>(dst)[k] = packed[k];
+            }
+        }
+    }
+    // merge the lanes' bests: highest score, then first in (column, row) scan order
+    int gbest = best;
+    for (int o = 16; o > 0; o >>= 1) gbest = max(gbest, __shfl_xor_sync(0xFFFFFFFFu, gbest, o));
+    unsigned long long key = (best == gbest && count > 0) ? (((unsigned long long)hitJ << 32) | bestI) : ~0ull;
+    uint32_t cnt = (best == gbest) ? count : 0u;
+    for (int o = 16; o > 0; o >>= 1) {
+        key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
+        cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    }
+    if (lane == 0) {
+        const bool any = key != ~0ull;
+        a.score[id] = gbest;
+        a.hit[id] = any ? (uint32_t)(key >> 32) : 0u;
+        const uint32_t bi = (uint32_t)(key & 0xFFFFFFFFu);
+        a.scRight[id] = (any && bi != 0) ? m - bi : 0u;   // bi == 0: only ties with the -32000 start value
+        a.cnt[id] = cnt;
+        if (a.cells) atomicAdd(a.cells, (unsigned long long)m * n);
+    }
+}
+
+// One thread per alignment: GPUBacktrack's state machine (DV-DPfunctions.cu:330-508)
+// driven by the byte plane.
+__global__ void s3_dp_traceback_kernel(const S3DpArgs a, int R)
+{
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= a.count) return;
+    const uint32_t id = a.first + local;
+    if (a.score[id] < a.cutoff[id]) return;
+    const uint32_t m = a.readLen[id];
+    const uint32_t clipLt = a.clipLt ? a.clipLt[id] : 0u;
+    const uint32_t scRight = a.scRight[id];
+    const uint8_t *tb = a.tb + (size_t)local * (a.maxDNALength + 1) * 32 * a.slot;
+    const uint32_t colStride = 32 * a.slot;
+    uint8_t *pat = a.pattern + (size_t)id * (a.maxReadLength + a.maxDNALength);
+    uint32_t p = 0;
+    if (scRight > 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)scRight; }
+    uint32_t readPos = m - scRight, refIndex = a.hit[id];
+    int state = 0;      // 0 NORMAL, 1 I_EXT, 2 D_EXT, 3 SM_EXIT, 4 SI_EXIT
+    uint32_t lastCell = 0;
+    while (readPos > 0 && refIndex > 0) {
+        const uint32_t row = readPos - 1;
+        const uint32_t b = tb[(size_t)refIndex * colStride + (row / R) * a.slot + (row % R)];
+        lastCell = b;
+        if (state == 0) {
+            const uint32_t ch = b & 7;
+            if (ch == TB_DIAG) { pat[p++] = (b & TB_MATCH) ? 'M' : 'm'; --refIndex; --readPos; }
+            else if (ch == TB_DOPEN) { pat[p++] = 'D'; --refIndex; }
+            else if (ch == TB_DEXT) { pat[p++] = 'D'; --refIndex; state = 2; }
+            else if (ch == TB_SMEXIT) { state = 3; break; }
+            else if (ch == TB_SIEXIT) { state = 4; break; }
+            else if (ch == TB_IOPEN) { pat[p++] = 'I'; --readPos; }
+            else { pat[p++] = 'I'; --readPos; state = 1; }
+        } else if (state == 2) {
+            pat[p++] = 'D'; --refIndex;
+            if (b & TB_EOPEN) state = 0;
+        } else {
+            if (b & TB_FEXIT) { state = 4; break; }
+            pat[p++] = 'I'; --readPos;
+            if (b & TB_FOPEN) state = 0;
+        }
+    }
+    if (refIndex == 0) {
+        const uint32_t scNum = min(clipLt, readPos);
+        if (scNum < readPos) { pat[p++] = 'I'; pat[p++] = 'V'; pat[p++] = (uint8_t)(readPos - scNum); }
+        pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)scNum;
+    } else if (state == 4) {
+        pat[p++] = 'I'; pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(readPos - 1);
+    } else if (state == 3) {
+        pat[p++] = (lastCell & TB_MATCH) ? 'M' : 'm';
+        pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(readPos - 1);
+        refIndex -= 1;
+    }
+    pat[p++] = 0;
+    a.hit[id] = refIndex;        // start offset inside the window (refOffset == 0 in scheme 1)
+}
+
+static int pick_R(uint32_t maxReadLength)
+{
+    static const int opts[] = {4, 5, 8, 16, 32};
+    for (int k = 0; k < 5; ++k) if ((uint32_t)opts[k] * 32 >= maxReadLength) return opts[k];
+    return 0;
+}
+
+extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint32_t maxBatch, s3_dp_scores scores,
+                            int device, s3_dp **out)
+{
+    if (!out || maxReadLength == 0 || maxDNALength == 0 || maxBatch == 0) { s3_set_error("s3_dp_create: bad argument"); return S3_EINVAL; }
+    const int R = pick_R(maxReadLength);
+    if (R == 0) { s3_set_error("s3_dp_create: maxReadLength %u > 1024 (MAX_READ_LENGTH, definitions.h:42)", maxReadLength); return S3_EINVAL; }
+    if ((maxDNALength >> 4) + 1 > S3_DP_MAX_REF_WORDS) { s3_set_error("s3_dp_create: maxDNALength %u too large", maxDNALength); return S3_EINVAL; }
+    int ndev = s3_device_count();
+    if (device < 0 || device >= ndev) { s3_set_error("s3_dp_create: CUDA device %d not available (%d devices); there is no CPU fallback", device, ndev); return S3_ECUDA; }
+    S3_CUDA(cudaSetDevice(device));
+    s3_dp *dp = (s3_dp *)calloc(1, sizeof(s3_dp));
+    if (!dp) { s3_set_error("out of host memory"); return S3_ENOMEM; }
+    dp->device = device; dp->maxReadLength = maxReadLength; dp->maxDNALength = maxDNALength; dp->maxBatch = maxBatch;
+    dp->sc = scores; dp->R = R; dp->slot = (R == 5) ? 8 : R;
+    S3_CUDA(cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking));
+    const size_t perAlign = (size_t)(maxDNALength + 1) * 32 * dp->slot;
+    size_t freeB = 0, totalB = 0;
+    S3_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    size_t budget = freeB / 8;
+    if (budget > ((size_t)8 << 30)) budget = (size_t)8 << 30;
+    size_t chunk = budget / perAlign;
+    if (chunk > maxBatch) chunk = maxBatch;
+    if (chunk < 1) { s3_set_error("s3_dp_create: not enough device memory for one traceback plane"); return S3_ENOMEM; }
+    dp->chunk = (uint32_t)chunk;
+    S3_CUDA(cudaMalloc(&dp->d_tb, chunk * perAlign));
+    const size_t up = ((size_t)maxBatch + 31) / 32 * 32;
+    const size_t dnaW = (maxDNALength + 15) >> 4, readW = (maxReadLength + 15) >> 4;
+    S3_CUDA(cudaMalloc(&dp->d_scRight, up * 4));
+    S3_CUDA(cudaMalloc(&dp->d_dna, up * dnaW * 4));
+    S3_CUDA(cudaMalloc(&dp->d_read, up * readW * 4));
+    S3_CUDA(cudaMalloc(&dp->d_dnaLen, up * 4)); S3_CUDA(cudaMalloc(&dp->d_readLen, up * 4));
+    S3_CUDA(cudaMalloc(&dp->d_hit, up * 4)); S3_CUDA(cudaMalloc(&dp->d_cnt, up * 4));
+    S3_CUDA(cudaMalloc(&dp->d_clipLt, up * 4)); S3_CUDA(cudaMalloc(&dp->d_clipRt, up * 4));
+    S3_CUDA(cudaMalloc(&dp->d_ancL, up * 4)); S3_CUDA(cudaMalloc(&dp->d_ancR, up * 4));
+    S3_CUDA(cudaMalloc(&dp->d_cutoff, up * 4)); S3_CUDA(cudaMalloc(&dp->d_score, up * 4));
+    S3_CUDA(cudaMalloc(&dp->d_pattern, up * (size_t)(maxReadLength + maxDNALength)));
+    S3_CUDA(cudaMalloc(&dp->d_cells, 8));
+    *out = dp;
+    return S3_OK;
+}
+
+extern "C" void s3_dp_free(s3_dp *dp)
+{
+    if (!dp) return;
+    cudaSetDevice(dp->device);
+    cudaStreamSynchronize(dp->stream);
+    void *ptrs[] = {dp->d_tb, dp->d_scRight, dp->d_dna, dp->d_read, dp->d_dnaLen, dp->d_readLen, dp->d_hit, dp->d_cnt,
+                    dp->d_clipLt, dp->d_clipRt, dp->d_ancL, dp->d_ancR, dp->d_cutoff, dp->d_score, dp->d_pattern, dp->d_cells};
+    for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; ++i) if (ptrs[i]) cudaFree(ptrs[i]);
+    cudaStreamDestroy(dp->stream);
+    free(dp);
+}
+
+extern "C" void *s3_dp_stream(const s3_dp *dp) { return dp ? (void *)dp->stream : NULL; }
+extern "C" uint32_t s3_dp_pattern_length(const s3_dp *dp) { return dp ? dp->maxReadLength + dp->maxDNALength : 0; }
+
+template <int R>
+static void launch_score(const S3DpArgs &a, cudaStream_t st)
+{
+    s3_dp_score_kernel<R><<<(a.count + S3_DP_WARPS - 1) / S3_DP_WARPS, S3_DP_WARPS * 32, 0, st>>>(a);
+}
+
+static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t n)
+{
+    a.maxReadLength = dp->maxReadLength; a.maxDNALength = dp->maxDNALength;
+    a.dnaWords = (dp->maxDNALength + 15) >> 4; a.readWords = (dp->maxReadLength + 15) >> 4;
+    a.slot = dp->slot; a.tb = dp->d_tb; a.scRight = dp->d_scRight;
+    a.match = dp->sc.matchScore; a.mismatch = dp->sc.mismatchScore; a.open = dp->sc.gapOpenScore; a.ext = dp->sc.gapExtendScore;
+    for (uint32_t first = 0; first < n; first += dp->chunk) {
+        a.first = first;
+        a.count = (n - first < dp->chunk) ? n - first : dp->chunk;
+        switch (dp->R) {
+        case 4: launch_score<4>(a, dp->stream); break;
+        case 5: launch_score<5>(a, dp->stream); break;
+        case 8: launch_score<8>(a, dp->stream); break;
+        case 16: launch_score<16>(a, dp->stream); break;
+        default: launch_score<32>(a, dp->stream); break;
+        }
+        S3_CUDA(cudaGetLastError());
+        s3_dp_traceback_kernel<<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a, dp->R);
+        S3_CUDA(cudaGetLastError());
+    }
+    return S3_OK;
+}
+
+extern "C" int s3_dp_align_device(s3_dp *dp, const uint32_t *d_dna, const uint32_t *d_dnaLen, const uint32_t *d_read,
+                                  const uint32_t *d_readLen, const int32_t *d_cutoff, int32_t *d_scores,
+                                  uint32_t *d_hitLocs, uint32_t *d_maxScoreCounts, uint8_t *d_pattern,
+                                  uint32_t numOfThreads, const uint32_t *d_clipLt, uint32_t *d_clipRt,
+                                  const uint32_t *d_ancL, const uint32_t *d_ancR)
+{
+    if (!dp || !d_dna || !d_dnaLen || !d_read || !d_readLen || !d_cutoff || !d_scores || !d_hitLocs || !d_maxScoreCounts || !d_pattern) {
+        s3_set_error("s3_dp_align_device: NULL argument"); return S3_EINVAL;
+    }
+    if (numOfThreads > dp->maxBatch) { s3_set_error("s3_dp_align: %u alignments > maxBatch %u", numOfThreads, dp->maxBatch); return S3_EINVAL; }
+    if (numOfThreads == 0) return S3_OK;
+    S3_CUDA(cudaSetDevice(dp->device));
+    S3DpArgs a;
+    memset(&a, 0, sizeof a);
+    a.dna = d_dna; a.dnaLen = d_dnaLen; a.read = d_read; a.readLen = d_readLen; a.cutoff = d_cutoff;
+    a.score = d_scores; a.hit = d_hitLocs; a.cnt = d_maxScoreCounts; a.pattern = d_pattern;
+    a.clipLt = d_clipLt; a.clipRt = d_clipRt; a.ancL = d_ancL; a.ancR = d_ancR;
+    a.cells = NULL;
+    return dp_run_device(dp, a, numOfThreads);
+}
+
+extern "C" int s3_dp_align(s3_dp *dp, const uint32_t *packedDNASequence, const uint32_t *DNALengths,
+                           const uint32_t *packedReadSequence, const uint32_t *readLengths,
+                           const int32_t *cutoffThresholds, int32_t *scores, uint32_t *hitLocs,
+                           uint32_t *maxScoreCounts, uint8_t *pattern, uint32_t numOfThreads,
+                           const uint32_t *clipLtSizes, uint32_t *clipRtSizes, const uint32_t *anchorLeftLocs,
+                           const uint32_t *anchorRightLocs)
+{
+    if (!dp || !packedDNASequence || !DNALengths || !packedReadSequence || !readLengths || !cutoffThresholds ||
+        !scores || !hitLocs || !maxScoreCounts || !pattern) { s3_set_error("s3_dp_align: NULL argument"); return S3_EINVAL; }
+    if (numOfThreads > dp->maxBatch) { s3_set_error("s3_dp_align: %u alignments > maxBatch %u", numOfThreads, dp->maxBatch); return S3_EINVAL; }
+    if (numOfThreads == 0) return S3_OK;
+    S3_CUDA(cudaSetDevice(dp->device));
+    const size_t n = numOfThreads, up = (n + 31) / 32 * 32;
+    const size_t dnaW = (dp->maxDNALength + 15) >> 4, readW = (dp->maxReadLength + 15) >> 4;
+    const size_t patLen = dp->maxReadLength + dp->maxDNALength;
+    cudaStream_t st = dp->stream;
+    // unlike the reference, only the filled part of the fixed-size batch arrays is moved (DV-DPfunctions.cu:678-682)
+    S3_CUDA(cudaMemcpyAsync(dp->d_dna, packedDNASequence, up * dnaW * 4, cudaMemcpyHostToDevice, st));
+    S3_CUDA(cudaMemcpyAsync(dp->d_read, packedReadSequence, up * readW * 4, cudaMemcpyHostToDevice, st));
+    S3_CUDA(cudaMemcpyAsync(dp->d_dnaLen, DNALengths, n * 4, cudaMemcpyHostToDevice, st));
+    S3_CUDA(cudaMemcpyAsync(dp->d_readLen, readLengths, n * 4, cudaMemcpyHostToDevice, st));
+    S3_CUDA(cudaMemcpyAsync(dp->d_cutoff, cutoffThresholds, n * 4, cudaMemcpyHostToDevice, st));
+    if (clipLtSizes) S3_CUDA(cudaMemcpyAsync(dp->d_clipLt, clipLtSizes, n * 4, cudaMemcpyHostToDevice, st));
+    if (clipRtSizes) S3_CUDA(cudaMemcpyAsync(dp->d_clipRt, clipRtSizes, n * 4, cudaMemcpyHostToDevice, st));
+    if (anchorLeftLocs) S3_CUDA(cudaMemcpyAsync(dp->d_ancL, anchorLeftLocs, n * 4, cudaMemcpyHostToDevice, st));
+    if (anchorRightLocs) S3_CUDA(cudaMemcpyAsync(dp->d_ancR, anchorRightLocs, n * 4, cudaMemcpyHostToDevice, st));
+    int rc = s3_dp_align_device(dp, dp->d_dna, dp->d_dnaLen, dp->d_read, dp->d_readLen, dp->d_cutoff, dp->d_score,
+                                dp->d_hit, dp->d_cnt, dp->d_pattern, numOfThreads,
+                                clipLtSizes ? dp->d_clipLt : NULL, clipRtSizes ? dp->d_clipRt : NULL,
+                                anchorLeftLocs ? dp->d_ancL : NULL, anchorRightLocs ? dp->d_ancR : NULL);
+    if (rc) return rc;
+    S3_CUDA(cudaMemcpyAsync(scores, dp->d_score, n * 4, cudaMemcpyDeviceToHost, st));
+    S3_CUDA(cudaMemcpyAsync(hitLocs, dp->d_hit, n * 4, cudaMemcpyDeviceToHost, st));
+    S3_CUDA(cudaMemcpyAsync(maxScoreCounts, dp->d_cnt, n * 4, cudaMemcpyDeviceToHost, st));
+    S3_CUDA(cudaMemcpyAsync(pattern, dp->d_pattern, n * patLen, cudaMemcpyDeviceToHost, st));
+    S3_CUDA(cudaStreamSynchronize(st));
+    return S3_OK;
+}

@@ -60,7 +60,12 @@ echo "[build_ref] builders OK"
 # ---- reference search kernels compiled for the host -------------------------
 # A generated copy adds a rank-query counter (the roofline unit of SURVEY.md 8d)
 # at the top of GPUBWTOccValue / GPUBWTAllOccValue / GPUBWTOccValueWithCumu.
-sed 's/^\(\s*\)index -= ( index > inverseSa0 );/\1++s3_rank_queries; index -= ( index > inverseSa0 );/' \
+# Second edit: `rightWord >> numLeftBits` with numLeftBits == 32 (read lengths whose middle
+# base is the last of a word, e.g. 191) relies on the GPU's shift semantics (PTX shr/shl by
+# >= 32 gives 0); on x86 the same C expression is undefined and yields rightWord.  The host
+# copy spells the GPU result out so that it computes what the device computes.
+sed -e 's/^\(\s*\)index -= ( index > inverseSa0 );/\1++s3_rank_queries; index -= ( index > inverseSa0 );/' \
+    -e 's/( ( rightWord >> numLeftBits ) << numLeftBits )/( numLeftBits >= 32 ? 0u : ( ( rightWord >> numLeftBits ) << numLeftBits ) )/' \
     "$REF/DV-Kernel.cu" > "$OUT/patched/DV-Kernel.counted.cu"
 $CXX -O2 -fopenmp -fpermissive -w -fPIC -shared -DS3_COUNT_RANK_QUERIES -I"$OUT/patched" -I"$REF" -I"$HERE/ref_shim" \
     "$HERE/ref_shim/ref_search_host.cpp" -o "$OUT/libref_search.so"

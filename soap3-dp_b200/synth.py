@@ -19,6 +19,16 @@ def _gen(seed: int, device) -> torch.Generator:
     return g
 
 
+def _scatter_last(dst: torch.Tensor, idx: torch.Tensor, vals: torch.Tensor):
+    """dst[idx] = vals with a defined winner for duplicate indices (the last one in
+    order), so overlapping repeat copies give the same genome on every run/device."""
+    order = torch.argsort(idx, stable=True)
+    si = idx[order]
+    last = torch.ones_like(si, dtype=torch.bool)
+    last[:-1] = si[1:] != si[:-1]
+    dst[si[last]] = vals[order][last]
+
+
 def random_genome(n: int, seed: int = 1, device="cpu", repeat_fraction: float = 0.2,
                   max_divergence: float = 0.10, tandem_arrays_per_mbp: float = 5.0) -> torch.Tensor:
     """uint8 codes [n] (A,C,G,T = 0..3): i.i.d. uniform background with injected
@@ -53,7 +63,7 @@ def random_genome(n: int, seed: int = 1, device="cpu", repeat_fraction: float = 
             mut = torch.rand(r1 - r0, L, generator=g, device=device) < div[r0:r1, None]
             sub = torch.randint(1, 4, (r1 - r0, L), generator=g, device=device, dtype=torch.uint8)
             seq = torch.where(mut, (seq + sub) & 3, seq)
-            codes[(pos[r0:r1, None] + ar[None, :]).reshape(-1)] = seq.reshape(-1)
+            _scatter_last(codes, (pos[r0:r1, None] + ar[None, :]).reshape(-1), seq.reshape(-1))
     # tandem arrays: unit 2..40 bp, array length 100..800 bp
     nt = int(n / 1e6 * tandem_arrays_per_mbp)
     if nt > 0:
@@ -69,7 +79,7 @@ def random_genome(n: int, seed: int = 1, device="cpu", repeat_fraction: float = 
             dst = pos[r0:r1, None] + ar[None, :]
             keep = ar[None, :] < alen[r0:r1, None]
             vals = codes[src.reshape(-1)].reshape(src.shape)
-            codes[dst[keep]] = vals[keep]
+            _scatter_last(codes, dst[keep], vals[keep])
     return codes
 
 

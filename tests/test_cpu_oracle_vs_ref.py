@@ -1,0 +1,101 @@
+"""CPU tier: the oracle restatements against the reference's own kernels compiled for the
+host (oracle/_ref, built by oracle/build_ref.sh where /root/reference exists).  Skipped
+on boxes where oracle/_ref was not shipped; the golden-fixture tests cover those."""
+import numpy as np
+import pytest
+
+from helpers import (DPBatch, HostIndex, compare_dp, fmindex, formats, load_oracle, load_oracle_dp, load_ref_dp,
+                     load_ref_search, make_dp_batch, oracle_dp, oracle_launch, ref_dp, ref_launch, u32p)
+from soap3dp_b200 import synth
+
+rlib = load_ref_search()
+dlib = load_ref_dp()
+
+
+@pytest.fixture(scope="module")
+def env():
+    G = synth.random_genome(400_000, seed=31)
+    return G, HostIndex(fmindex.build_index(G))
+
+
+@pytest.mark.skipif(rlib is None, reason="oracle/_ref/libref_search.so not built")
+def test_rank_matches_reference_rank(env):
+    G, hi = env
+    olib = load_oracle()
+    rng = np.random.default_rng(0)
+    idxs = np.concatenate([rng.integers(0, hi.n + 2, 50000), [0, 1, hi.n, hi.n + 1, hi.isa0, hi.isa0 + 1]])
+    for i in idxs:
+        for c in range(4):
+            assert olib.s3o_rank(u32p(hi.bwt), u32p(hi.occ), int(i), c, hi.isa0) == \
+                rlib.ref_rank(u32p(hi.bwt), u32p(hi.occ), int(i), c, hi.isa0)
+
+
+@pytest.mark.skipif(rlib is None, reason="oracle/_ref/libref_search.so not built")
+@pytest.mark.parametrize("L", [100, 51, 200])
+def test_search_all_cases_match_reference_kernels(env, L):
+    """every mismatch level, case and round; lengths where (int)(L*ratio) truncates differently"""
+    G, hi = env
+    olib = load_oracle()
+    n = 800
+    rs = synth.simulate_single_end(G, n, L, seed=L, sub_rate=0.02)
+    lens = rs.lengths.numpy().astype(np.uint32)
+    lens[::3] = L - 2
+    lens[1::7] = L - 9
+    wpq = formats.word_per_query(L)
+    q = formats.pack_queries(rs.reads.numpy(), lens, wpq)
+    lens_up = np.zeros(formats.ceil32(n), np.uint32)
+    lens_up[:n] = lens
+    for k in range(5):
+        for rnd, allowed in ((0, formats.SA_RANGES_ROUND1[k]), (1, formats.SA_RANGES_ROUND2[k])):
+            wpa = 2 * allowed
+            bo = np.zeros(formats.ceil32(n), np.uint8)
+            br = bo.copy()
+            qr = q.copy()
+            for case in range(formats.NUM_CASES[k]):
+                if rnd == 1:
+                    qr = q.copy()
+                ao = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+                ar = ao.copy()
+                no = oracle_launch(olib, hi, case, q, lens_up, n, wpq, ao, bo, rnd, k, allowed, wpa)
+                nr = ref_launch(rlib, hi, case, qr, lens_up, n, wpq, ar, br, rnd, k, allowed, wpa, nthreads=2)
+                assert np.array_equal(formats.answers_view(ao, n, wpa), formats.answers_view(ar, n, wpa)), (L, k, rnd, case)
+                assert np.array_equal(bo, br)
+                view = formats.answers_view(ao, n, wpa)
+                if not (view[:, 0] == formats.ANSWER_OVERFLOW).any():
+                    assert no == nr, "rank-query counts must agree when no slot overflowed"
+
+
+@pytest.mark.skipif(dlib is None, reason="oracle/_ref/libref_dp.so not built")
+@pytest.mark.parametrize("mode", ["single", "rescue"])
+def test_dp_matches_reference_kernels(env, mode):
+    G, _ = env
+    olib = load_oracle_dp()
+    for L in (100, 150):
+        for scores in ((1, -2, -3, -1), (2, -3, -5, -2)):
+            b = make_dp_batch(G, 400, L, mode, seed=3 * L, indel_rate=0.006)
+            assert compare_dp(b, oracle_dp(olib, b, scores), ref_dp(dlib, b, scores), f"{mode} {L}") > 350
+
+
+@pytest.mark.skipif(dlib is None, reason="oracle/_ref/libref_dp.so not built")
+def test_dp_adversarial_matches_reference_kernels():
+    """random read/window pairs, big clips, random anchors (>= 1, as every reference caller
+    produces: DV-DPfunctions.cu:2073,2099,3401,3455), cutoffs >= 0"""
+    olib = load_oracle_dp()
+    for seed in range(4):
+        rng = np.random.default_rng(seed)
+        n, L = 600, int(rng.integers(20, 130))
+        W = L + int(rng.integers(5, 200))
+        dna = rng.integers(0, 4, (n, W)).astype(np.uint8)
+        read = rng.integers(0, 4, (n, L)).astype(np.uint8)
+        for t in range(0, n, 2):
+            o = rng.integers(0, W - L)
+            dna[t, o:o + L] = read[t]
+            for _ in range(int(rng.integers(0, 6))):
+                dna[t, o + rng.integers(0, L)] = rng.integers(0, 4)
+        b = DPBatch(dna, rng.integers(W - 3, W + 1, n).astype(np.uint32), read,
+                    rng.integers(max(L - 8, 1), L + 1, n).astype(np.uint32), W + 14, (L // 4 + 1) * 4,
+                    rng.integers(0, 30, n).astype(np.int32), rng.integers(0, L, n).astype(np.uint32),
+                    rng.integers(0, L, n).astype(np.uint32), rng.integers(1, W + 14, n).astype(np.uint32),
+                    rng.integers(0, W, n).astype(np.uint32))
+        for scores in ((1, -2, -3, -1), (1, -1, -2, -1)):
+            compare_dp(b, oracle_dp(olib, b, scores), ref_dp(dlib, b, scores), f"adv {seed}")

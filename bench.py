@@ -1,0 +1,523 @@
+#!/usr/bin/env python
+"""bench.py -- reads/s of the SOAP3-dp GPU alignment hot path on B200.
+
+Workload (BASELINE.json metric; config 4 shape at one batch per step):
+  paired-end 2x100 bp, insert 200-500, FR, against a 3.1 Gbp synthetic genome.
+  One STEP = one batch of P pairs (2P reads, default 1,048,576 reads = the reference's
+  NUM_BLOCKS*THREADS_PER_BLOCK launch size, definitions.h:75-77):
+    (1) GPU-2BWT search, <=2 mismatches (Soap3MisMatchAllow=2 when DP is on,
+        SOAP3-DP.cu:210-213): 4 cases x both strands, round-1 answer slots, for all 2P reads;
+    (2) semi-global DP mate rescue (window insert_high-insert_low+len = 400 bp, anchors as
+        HalfEndAlgnBatch::pack, DV-DPfunctions.cu:2027-2110) for every pair in which exactly
+        one mate was found by (1).
+  `value`  : inputs resident in HBM, CUDA-event timed on the library's stream.
+  `e2e`    : the same step through the host-pointer C ABI (s3_search_round1 + s3_dp_align),
+             pinned host buffers, H2D + D2H inside the timed region.
+  `--impl reference` : the reference's own kernel sources compiled for the host
+             (oracle/_ref, OpenMP over reads) -- or the oracle port if oracle/_ref is
+             absent -- timed on a bounded sample of the same workload.
+
+Launch:  python bench.py --gpus N --steps K --warmup W
+         (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import _pkg  # noqa: E402
+
+_pkg.load()
+from soap3dp_b200 import api, fmindex, formats, packing, sharding, synth  # noqa: E402
+
+INSERT_LO, INSERT_HI = 200, 500
+K_MISMATCH = 2
+DP_SCORES = (1, -2, -3, -1)                   # soap3-dp.ini:57-66
+
+
+def log(*a):
+    if int(os.environ.get("RANK", "0")) == 0:
+        print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+# ---------------------------------------------------------------------------
+# index (built on the GPU with torch, cached on local disk in the reference's array format)
+# ---------------------------------------------------------------------------
+def cache_dir():
+    d = os.environ.get("S3_CACHE", "/tmp/s3_bench_cache")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def get_index(n_bp, seed, device, rank, world):
+    """-> (genome codes on device, dict of host numpy arrays in the reference format)"""
+    tag = os.path.join(cache_dir(), f"idx_{n_bp}_{seed}")
+    names = ["bwt", "occ", "rbwt", "rocc", "meta"]
+    t0 = time.time()
+    genome = synth.random_genome(n_bp, seed=seed, device=device)
+    torch.cuda.synchronize()
+    log(f"genome {n_bp} bp generated in {time.time() - t0:.1f}s")
+    have = all(os.path.exists(f"{tag}.{x}.npy") for x in names)
+    if not have and rank == 0:
+        t0 = time.time()
+        idx = fmindex.build_index(genome, keep_sa=False, verbose=bool(os.environ.get("S3_VERBOSE")))
+        torch.cuda.synchronize()
+        log(f"2BWT index built on the GPU in {time.time() - t0:.1f}s")
+        arrs = {"bwt": idx.fwd.bwt_words, "occ": idx.fwd.occ, "rbwt": idx.rev.bwt_words, "rocc": idx.rev.occ}
+        for k, v in arrs.items():
+            np.save(f"{tag}.{k}.tmp.npy", v.cpu().numpy().view(np.uint32))
+            os.replace(f"{tag}.{k}.tmp.npy", f"{tag}.{k}.npy")
+        np.save(f"{tag}.meta.tmp.npy", np.array([idx.fwd.inverse_sa0, idx.rev.inverse_sa0, n_bp], np.int64))
+        os.replace(f"{tag}.meta.tmp.npy", f"{tag}.meta.npy")
+        del idx, arrs
+        torch.cuda.empty_cache()
+    if world > 1:
+        torch.distributed.barrier()
+    host = {k: np.load(f"{tag}.{k}.npy", mmap_mode=None) for k in names}
+    return genome, host
+
+
+def upload_index(host, device):
+    lib = api.load_library()
+    meta = host["meta"]
+    n = int(meta[2])
+    out = C.c_void_p()
+    num_occ = (n + 127) // 128 + 1
+    rc = lib.s3_index_upload(api._u32(host["bwt"]), api._u32(host["occ"]), api._u32(host["rbwt"]), api._u32(host["rocc"]),
+                             num_occ, int(meta[0]), int(meta[1]), n, None, None, device, C.byref(out))
+    api._check(rc, "s3_index_upload")
+    return api.GpuIndex(out.value, n)
+
+
+# ---------------------------------------------------------------------------
+# batches
+# ---------------------------------------------------------------------------
+class Batch:
+    pass
+
+
+def make_batch(genome, pairs, L, seed):
+    """P pairs -> interleaved reads (mate1, mate2, mate1, ...) packed on the device"""
+    m1, m2, bad = synth.simulate_paired_end(genome, pairs, L, seed=seed, insert_lo=INSERT_LO, insert_hi=INSERT_HI)
+    b = Batch()
+    b.pairs, b.n, b.L = pairs, 2 * pairs, L
+    reads = torch.stack([m1.reads, m2.reads], dim=1).reshape(2 * pairs, L)
+    b.reads = reads
+    b.pos = torch.stack([m1.pos, m2.pos], dim=1).reshape(-1)
+    b.strand = torch.stack([m1.strand, m2.strand], dim=1).reshape(-1)
+    b.wpq = formats.word_per_query(L)
+    up = formats.ceil32(b.n)
+    lens = torch.zeros(up, dtype=torch.int32, device=genome.device)
+    lens[:b.n] = L
+    b.lens = lens
+    b.queries = packing.pack_queries(reads, lens[:b.n], b.wpq)
+    return b
+
+
+def alloc_answers(b, device):
+    allowed = formats.SA_RANGES_ROUND1[K_MISMATCH]
+    wpa = 2 * allowed
+    ncases = formats.NUM_CASES[K_MISMATCH]
+    up = formats.ceil32(b.n)
+    return [torch.empty(up * wpa, dtype=torch.int32, device=device) for _ in range(ncases)], allowed, wpa, ncases
+
+
+def build_rescue_batch(genome, b, answers, wpa, max_read, max_dna):
+    """From the search result: pairs with exactly one mate found -> DP batch that rescues the
+    other mate from the found mate's position (windows/anchors/clips as HalfEndAlgnBatch::pack,
+    DV-DPfunctions.cu:2027-2110; reverse-strand reads are reverse-complemented, :1497-1505)."""
+    dev = genome.device
+    found = torch.zeros(b.n, dtype=torch.bool, device=dev)
+    for a in answers:
+        found |= packing.answers_status(a, b.n, wpa) != formats.ANSWER_NO_HIT
+    f = found.view(-1, 2)
+    need = f[:, 0] ^ f[:, 1]
+    pair_ids = torch.nonzero(need).reshape(-1)
+    aligned = pair_ids * 2 + (~f[pair_ids, 0]).to(torch.int64)      # index of the found mate
+    target = pair_ids * 2 + f[pair_ids, 0].to(torch.int64)          # mate to rescue
+    L = b.L
+    p = b.pos[aligned]
+    left = b.strand[aligned] == 0                                     # found mate is the left (+) read
+    wlen = INSERT_HI - INSERT_LO + L
+    start = torch.where(left, p + INSERT_LO - L, p + L - INSERT_HI).clamp(min=0, max=genome.numel() - wlen - 1)
+    M = pair_ids.numel()
+    ar = torch.arange(wlen, device=dev)
+    dna = torch.empty(M, wlen, dtype=torch.uint8, device=dev)
+    step = 1 << 16
+    for r0 in range(0, M, step):
+        dna[r0:r0 + step] = genome[(start[r0:r0 + step, None] + ar[None, :]).reshape(-1)].reshape(-1, wlen)
+    rd = b.reads[target]
+    rd = torch.where(left[:, None], (3 - torch.flip(rd, dims=[1])).to(torch.uint8), rd)   # mate of a + read is on -
+    d = Batch()
+    d.n = M
+    d.max_read, d.max_dna = max_read, max_dna
+    d.dna = packing.pack_dp_sequences(dna, max_dna)
+    d.read = packing.pack_dp_sequences(rd, max_read)
+    up = formats.ceil32(max(M, 1))
+
+    def full(v, dtype=torch.int32):
+        t = torch.zeros(up, dtype=dtype, device=dev)
+        t[:M] = v
+        return t
+    d.dna_len = full(wlen)
+    d.read_len = full(L)
+    d.cutoff = full(int(np.ceil(0.3 * L)))
+    # the rescued read lies on the opposite strand of the found one; clips 3/8 by strand (soap3-dp-module.cu:14)
+    d.clip_lt = full(torch.where(left, 8, 3))
+    d.clip_rt = full(torch.where(left, 3, 8))
+    d.anchor_l = full(torch.where(left, max_dna, INSERT_HI - INSERT_LO + 1))
+    d.anchor_r = full(torch.where(left, L, 0))
+    d.scores = torch.zeros(up, dtype=torch.int32, device=dev)
+    d.hit = torch.zeros(up, dtype=torch.int32, device=dev)
+    d.cnt = torch.zeros(up, dtype=torch.int32, device=dev)
+    d.pattern = torch.zeros(up * (max_read + max_dna), dtype=torch.uint8, device=dev)
+    d.cells = M * wlen * L
+    return d
+
+
+# ---------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    def __init__(self, dev_index):
+        super().__init__(daemon=True)
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self.stop_flag = False
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(dev_index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception as e:                      # noqa: BLE001
+            self.err = str(e)
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {nv.nvmlClocksThrottleReasonHwSlowdown: "hw_slowdown",
+                 nv.nvmlClocksThrottleReasonHwThermalSlowdown: "hw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwThermalSlowdown: "sw_thermal_slowdown",
+                 nv.nvmlClocksThrottleReasonSwPowerCap: "sw_power_cap",
+                 nv.nvmlClocksThrottleReasonHwPowerBrakeSlowdown: "hw_power_brake"}
+        while not self.stop_flag:
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:                       # noqa: BLE001
+                pass
+            time.sleep(0.02)
+
+    def result(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        return {"sm_mhz": float(np.median(self.samples)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+# ---------------------------------------------------------------------------
+# CPU arm: the reference's kernel sources compiled for the host (oracle/_ref) or the port
+# ---------------------------------------------------------------------------
+def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
+    """-> dict(value reads/s, kind, cores, sample, rank_queries_per_read, t_search, t_dp)"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import helpers
+    ref_s, ref_d = helpers.load_ref_search(), helpers.load_ref_dp()
+    kind = "reference" if (ref_s is not None and ref_d is not None) else "port"
+    pairs = sample_reads // 2
+    b = make_batch(genome, pairs, L, seed)
+    q = b.queries.cpu().numpy().view(np.uint32)
+    lens = b.lens.cpu().numpy().view(np.uint32)
+    n = b.n
+
+    class HI:
+        pass
+    hi = HI()
+    hi.bwt, hi.occ, hi.rbwt, hi.rocc = host["bwt"], host["occ"], host["rbwt"], host["rocc"]
+    hi.isa0, hi.risa0, hi.n = int(host["meta"][0]), int(host["meta"][1]), int(host["meta"][2])
+    allowed = formats.SA_RANGES_ROUND1[K_MISMATCH]
+    wpa = 2 * allowed
+    bad = np.zeros(formats.ceil32(n), np.uint8)
+    ans = []
+    nrank = 0
+    t0 = time.perf_counter()
+    qq = q.copy()
+    for case in range(formats.NUM_CASES[K_MISMATCH]):
+        a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+        if kind == "reference":
+            nrank += helpers.ref_launch(ref_s, hi, case, qq, lens, n, b.wpq, a, bad, 0, K_MISMATCH, allowed, wpa, nthreads=threads)
+        else:
+            nrank += helpers.oracle_launch(helpers.load_oracle(), hi, case, q, lens, n, b.wpq, a, bad, 0, K_MISMATCH, allowed, wpa)
+        ans.append(a)
+    t_search = time.perf_counter() - t0
+    # DP on the same fraction of pairs the GPU arm rescues
+    m = max(int(pairs * dp_fraction), 32)
+    dpb = helpers.make_dp_batch(genome[:4_000_000].cpu(), m, L, "rescue", seed=seed + 1, insert=(INSERT_LO, INSERT_HI))
+    t0 = time.perf_counter()
+    if kind == "reference":
+        helpers.ref_dp(ref_d, dpb, DP_SCORES, nthreads=threads)
+    else:
+        helpers.oracle_dp(helpers.load_oracle_dp(), dpb, DP_SCORES)
+    t_dp = time.perf_counter() - t0
+    used = threads if kind == "reference" else (os.cpu_count() if False else 1)
+    return {"value": n / (t_search + t_dp), "unit": "reads/s", "cores": used if kind == "reference" else 1,
+            "kind": kind,
+            "sample": f"{n} reads (k<=2, 4 cases, both strands) + {m} rescue DP alignments of the bench workload; "
+                      + ("reference kernel sources (DV-Kernel.cu, DV-DPfunctions.cu:35-512) compiled for the host, OpenMP over reads"
+                         if kind == "reference" else "oracle/ C restatement, single thread"),
+            "rank_queries_per_read": nrank / n, "t_search_s": t_search, "t_dp_s": t_dp,
+            "dp_gcups": dpb.n * 400 * L / t_dp / 1e9}
+
+
+# ---------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--genome-bp", type=int, default=int(os.environ.get("S3_GENOME_BP", 3_100_000_000)))
+    ap.add_argument("--pairs", type=int, default=int(os.environ.get("S3_PAIRS", 524_288)), help="pairs per step per GPU")
+    ap.add_argument("--read-len", type=int, default=100)
+    ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("S3_CPU_SAMPLE", 2_097_152)))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        log("note: the timing rules ask for >= 3 warm-up steps")
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if api.load_library().s3_device_count() < 1:
+        raise SystemExit("bench.py: no CUDA device; soap3dp_b200 has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if args.impl == "reference" and rank != 0:
+        return
+    if world > 1 and args.impl == "ours":
+        torch.distributed.init_process_group("nccl", device_id=device)
+    L = args.read_len
+    max_read = (L // 4 + 1) * 4                                   # DV-DPfunctions.cu:1580
+    max_dna = INSERT_HI - INSERT_LO + max_read + 1                # DV-DPfunctions.cu:2223-2224
+    genome, host = get_index(args.genome_bp, 3, device, rank, world if args.impl == "ours" else 1)
+    threads = os.cpu_count() or 1
+    workload = (f"pe_2x{L}bp_insert{INSERT_LO}-{INSERT_HI}_genome{args.genome_bp}bp: k<=2 search (4 cases, both strands, "
+                f"round-1 slots) of {2 * args.pairs} reads + mate-rescue DP (400 bp windows) per step per GPU")
+
+    if args.impl == "reference":
+        vals = []
+        info = None
+        per_step = max(args.cpu_sample // 4, 4096)
+        for s in range(args.warmup + args.steps):
+            info = cpu_arm(host, genome, L, per_step, 1000 + s, 0.12, threads)
+            if s >= args.warmup:
+                vals.append(info)
+        v = float(np.mean([x["value"] for x in vals]))
+        out = {"impl": "reference", "metric": "reads/s aligned (2x100bp PE, 3.1 Gbp synth ref)", "value": v,
+               "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": 1e3 * per_step / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+               "dtype": "u32", "data": "synthetic",
+               "config": {"workload": workload, "sample_reads_per_step": per_step},
+               "cpu_baseline": {"value": v, "unit": "reads/s", "cores": info["cores"], "kind": info["kind"],
+                                "sample": info["sample"]},
+               "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(out), flush=True)
+        return
+
+    gi = upload_index(host, local_rank)
+    log(f"index on device: {gi.device_bytes / 1e9:.2f} GB in 64-byte buckets")
+    stream = torch.cuda.ExternalStream(gi.stream, device=device)
+    total = args.warmup + args.steps
+    t0 = time.time()
+    batches = [make_batch(genome, args.pairs, L, seed=100 + 1000 * rank + s) for s in range(total)]
+    answers, allowed, wpa, ncases = alloc_answers(batches[0], device)
+    ans_ptrs = [a.data_ptr() for a in answers]
+    d_rank = torch.zeros(1, dtype=torch.int64, device=device)
+    torch.cuda.synchronize()
+    # setup pass (untimed): rank-query count and the rescue batches from the actual search result
+    rescue = []
+    nrank_total = 0
+    for s, b in enumerate(batches):
+        d_rank.zero_()
+        torch.cuda.synchronize()
+        api.search_round1_device(gi, b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq, K_MISMATCH, ncases, allowed,
+                                 wpa, ans_ptrs, d_rank.data_ptr())
+        stream.synchronize()
+        if s >= args.warmup:
+            nrank_total += int(d_rank.item())
+        rescue.append(build_rescue_batch(genome, b, answers, wpa, max_read, max_dna))
+    torch.cuda.synchronize()
+    max_m = max(r.n for r in rescue)
+    log(f"{total} batches of {batches[0].n} reads prepared in {time.time() - t0:.1f}s; rescue DP alignments per step: "
+        f"{[r.n for r in rescue]}")
+    aligner = api.SemiGlobalAligner(max_read, max_dna, max(max_m, 32), *DP_SCORES, device=local_rank)
+    aligner.set_stream(gi.stream)
+
+    def gpu_step(b, r):
+        api.search_round1_device(gi, b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq, K_MISMATCH, ncases, allowed,
+                                 wpa, ans_ptrs, 0)
+
+    def dp_step(r):
+        if r.n:
+            aligner.align_device(r.dna.data_ptr(), r.dna_len.data_ptr(), r.read.data_ptr(), r.read_len.data_ptr(),
+                                 r.cutoff.data_ptr(), r.scores.data_ptr(), r.hit.data_ptr(), r.cnt.data_ptr(),
+                                 r.pattern.data_ptr(), r.n, r.clip_lt.data_ptr(), r.clip_rt.data_ptr(),
+                                 r.anchor_l.data_ptr(), r.anchor_r.data_ptr())
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -------------------------------------------------
+    for s in range(args.warmup):
+        gpu_step(batches[s], rescue[s])
+        dp_step(rescue[s])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    launches0 = api.launch_count()
+    with torch.cuda.stream(stream):
+        for k in range(args.steps):
+            b, r = batches[args.warmup + k], rescue[args.warmup + k]
+            ev[k][0].record(stream)
+            gpu_step(b, r)
+            ev[k][1].record(stream)
+            dp_step(r)
+            ev[k][2].record(stream)
+    stream.synchronize()
+    barrier()
+    launches = api.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    t_search = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
+    t_dp = sum(e[1].elapsed_time(e[2]) for e in ev) / 1e3
+    t_total = ev[0][0].elapsed_time(ev[-1][2]) / 1e3
+    tt = torch.tensor([t_total, t_search, t_dp], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    t_total, t_search_max, t_dp_max = [float(x) for x in tt]
+    reads_per_rank = sum(batches[args.warmup + k].n for k in range(args.steps))
+    value = world * reads_per_rank / t_total
+
+    # ---- end-to-end through the host C ABI (pinned host buffers) ------------------
+    def pinned(t):
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h
+    e2e_sets = []
+    for k in range(args.steps):
+        b, r = batches[args.warmup + k], rescue[args.warmup + k]
+        hs = Batch()
+        hs.q, hs.l = pinned(b.queries), pinned(b.lens)
+        hs.ans = [torch.empty(a.shape, dtype=a.dtype, pin_memory=True) for a in answers]
+        hs.r = {k2: pinned(getattr(r, k2)) for k2 in ("dna", "dna_len", "read", "read_len", "cutoff", "clip_lt", "clip_rt",
+                                                      "anchor_l", "anchor_r")}
+        hs.out = {k2: torch.empty(getattr(r, k2).shape, dtype=getattr(r, k2).dtype, pin_memory=True)
+                  for k2 in ("scores", "hit", "cnt", "pattern")}
+        hs.n, hs.m, hs.wpq = b.n, r.n, b.wpq
+        e2e_sets.append(hs)
+    lib = api.load_library()
+    U32P, I32P, U8P = api.U32P, api.I32P, api.U8P
+
+    def p32(t):
+        return C.cast(t.data_ptr(), U32P)
+
+    def e2e_step(hs):
+        arr = (C.c_void_p * ncases)(*[a.data_ptr() for a in hs.ans])
+        api._check(lib.s3_search_round1(gi.handle, p32(hs.q), p32(hs.l), hs.n, hs.wpq, K_MISMATCH, ncases, allowed, wpa, 0,
+                                        arr), "s3_search_round1")
+        if hs.m:
+            api._check(lib.s3_dp_align(aligner.handle, p32(hs.r["dna"]), p32(hs.r["dna_len"]), p32(hs.r["read"]),
+                                       p32(hs.r["read_len"]), C.cast(hs.r["cutoff"].data_ptr(), I32P),
+                                       C.cast(hs.out["scores"].data_ptr(), I32P), p32(hs.out["hit"]), p32(hs.out["cnt"]),
+                                       C.cast(hs.out["pattern"].data_ptr(), U8P), hs.m, p32(hs.r["clip_lt"]),
+                                       p32(hs.r["clip_rt"]), p32(hs.r["anchor_l"]), p32(hs.r["anchor_r"])), "s3_dp_align")
+    for s in range(min(args.warmup, len(e2e_sets))):
+        e2e_step(e2e_sets[s])
+    barrier()
+    t0 = time.perf_counter()
+    for hs in e2e_sets:
+        e2e_step(hs)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    te = torch.tensor([t_e2e], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+    t_e2e = float(te[0])
+    hs = e2e_sets[0]
+    up = formats.ceil32(hs.n)
+    h2d = up * hs.wpq * 4 + hs.n * 4
+    d2h = ncases * up * wpa * 4
+    if hs.m:
+        upm = formats.ceil32(hs.m)
+        h2d += upm * (((max_dna + 15) >> 4) + ((max_read + 15) >> 4)) * 4 + hs.m * 4 * 7
+        d2h += hs.m * (12 + max_read + max_dna)
+    e2e_value = world * reads_per_rank / t_e2e
+
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel -----------------------------------------
+    peaks = {}
+    pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(pk_path):
+        peaks = json.load(open(pk_path))
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    search_bytes = 64.0 * nrank_total                   # 64 B per rank evaluation
+    search_gbs = search_bytes / t_search / 1e9
+    dp_cells = sum(rescue[args.warmup + k].cells for k in range(args.steps))
+    dp_gcups = dp_cells / t_dp / 1e9 if t_dp > 0 else 0.0
+    out = {
+        "metric": "reads/s aligned (2x100bp PE, 3.1 Gbp synth ref)",
+        "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u32", "data": "synthetic",
+        "config": {"workload": workload, "genome_bp": args.genome_bp, "pairs_per_step_per_gpu": args.pairs,
+                   "l2": "inputs larger than L2: 2 GB of index buckets touched at random, 32 MiB of queries and 128 MiB of "
+                         "answer slots per step, a different read batch every step",
+                   "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"},
+        "clocks": sampler.result(),
+        "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                "ms_per_step": 1e3 * t_e2e / args.steps},
+        "gpu_launches": int(launches),
+        "roofline": {"kernel": "s3_search_kernel", "bound": "hbm", "achieved": search_gbs, "peak": hbm_peak,
+                     "unit": "GB/s", "frac": search_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
+                     "rank_queries_per_launch": nrank_total / args.steps, "bytes_per_rank_query": 64,
+                     "ms_per_launch": 1e3 * t_search / args.steps, "share_of_step": t_search / (t_search + t_dp)},
+        "dp": {"kernel": "s3_dp_score_kernel+s3_dp_traceback_kernel", "gcups": dp_gcups,
+               "alignments_per_step": float(np.mean([rescue[args.warmup + k].n for k in range(args.steps)])),
+               "cells_per_step": dp_cells / args.steps, "ms_per_step": 1e3 * t_dp / args.steps},
+    }
+    if world == 1 and not args.no_cpu_baseline:
+        frac = float(np.mean([r.n / b.pairs for r, b in zip(rescue, batches)]))
+        t0 = time.time()
+        cb = cpu_arm(host, genome, L, args.cpu_sample, 999, frac, threads)
+        log(f"cpu baseline ({cb['kind']}, {cb['cores']} threads) took {time.time() - t0:.1f}s: {cb['value']:.0f} reads/s")
+        out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        out["cpu_baseline"]["rank_queries_per_read"] = cb["rank_queries_per_read"]
+        out["cpu_baseline"]["dp_gcups"] = cb["dp_gcups"]
+    print(json.dumps(out), flush=True)
+    aligner.freeMemory()
+    api.GPUINDEXFree(gi)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

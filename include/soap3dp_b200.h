@@ -32,6 +32,8 @@ typedef struct s3_dp    s3_dp;       /* device-resident DP workspace (opaque) */
 
 const char *s3_last_error(void);
 int s3_device_count(void);
+/* number of kernels this library has launched in this process so far */
+unsigned long long s3_launch_count(void);
 
 /* ------------------------------------------------------------------------
  * Index.  Replaces GPUINDEXUpload / GPUINDEXFree (alignment.cu:27-115,
@@ -124,6 +126,9 @@ int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint32_t maxBatc
                  s3_dp_scores scores, int device, s3_dp **out);
 void s3_dp_free(s3_dp *dp);
 void *s3_dp_stream(const s3_dp *dp);
+/* issue this workspace's kernels and copies on `stream` (a cudaStream_t, e.g.
+ * s3_index_stream()) so that search and DP of one batch are stream-ordered */
+void s3_dp_set_stream(s3_dp *dp, void *stream);
 /* PatternLength() = maxReadLength + maxDPTableLength bytes per alignment
  * (DV-DPfunctions.cu:54); maxDPTableLength = maxDNALength in scheme 1
  * (decideConfiguration, DV-DPfunctions.cu:592). */

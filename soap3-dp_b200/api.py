@@ -30,7 +30,7 @@ U8P = C.POINTER(C.c_uint8)
 U64P = C.POINTER(C.c_uint64)
 
 EXPORTS = [
-    "s3_last_error", "s3_device_count", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
+    "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -59,6 +59,9 @@ def load_library() -> C.CDLL:
     lib = C.CDLL(LIB_PATH)
     lib.s3_last_error.restype = C.c_char_p
     lib.s3_device_count.restype = C.c_int
+    lib.s3_launch_count.restype = C.c_ulonglong
+    lib.s3_dp_set_stream.restype = None
+    lib.s3_dp_set_stream.argtypes = [C.c_void_p, C.c_void_p]
     lib.s3_index_upload.restype = C.c_int
     lib.s3_index_upload.argtypes = [U32P, U32P, U32P, U32P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                     U32P, U32P, C.c_int, C.POINTER(C.c_void_p)]
@@ -270,3 +273,31 @@ class SemiGlobalAligner:
         if self.handle:
             load_library().s3_dp_free(self.handle)
             self.handle = C.c_void_p(0)
+
+    def set_stream(self, stream: int):
+        load_library().s3_dp_set_stream(self.handle, C.c_void_p(stream))
+
+    def align_device(self, d_dna: int, d_dna_len: int, d_read: int, d_read_len: int, d_cutoff: int, d_scores: int,
+                     d_hit: int, d_cnt: int, d_pattern: int, n: int, d_clip_lt: int = 0, d_clip_rt: int = 0,
+                     d_anchor_l: int = 0, d_anchor_r: int = 0):
+        """s3_dp_align_device: raw device pointers (ints), stream-ordered, not synchronised."""
+        p = [C.c_void_p(x or None) for x in (d_dna, d_dna_len, d_read, d_read_len, d_cutoff, d_scores, d_hit, d_cnt,
+                                             d_pattern)]
+        q = [C.c_void_p(x or None) for x in (d_clip_lt, d_clip_rt, d_anchor_l, d_anchor_r)]
+        _check(load_library().s3_dp_align_device(self.handle, *p, n, *q), "s3_dp_align_device")
+
+
+def search_round1_device(gpu_index: GpuIndex, d_queries: int, d_read_lengths: int, batch_size: int,
+                         word_per_query: int, num_mismatch: int, num_cases: int, sa_range_allowed: int,
+                         word_per_ans: int, d_answers: Sequence[int], d_rank_queries: int = 0,
+                         is_exact_num_mismatch: bool = False):
+    """s3_search_round1_device: raw device pointers (ints), enqueued on the index stream."""
+    arr = (C.c_void_p * len(d_answers))(*[C.c_void_p(a) for a in d_answers])
+    _check(load_library().s3_search_round1_device(gpu_index.handle, C.c_void_p(d_queries), C.c_void_p(d_read_lengths),
+                                                  batch_size, word_per_query, num_mismatch, num_cases,
+                                                  sa_range_allowed, word_per_ans, int(is_exact_num_mismatch), arr,
+                                                  C.c_void_p(d_rank_queries or None)), "s3_search_round1_device")
+
+
+def launch_count() -> int:
+    return int(load_library().s3_launch_count())

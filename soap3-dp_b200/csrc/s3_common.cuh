@@ -37,6 +37,8 @@ struct s3_index {
 };
 
 void s3_set_error(const char *fmt, ...);
+extern unsigned long long g_s3_launches;
+#define S3_LAUNCHED(n) (g_s3_launches += (n))
 #define S3_CUDA(call)                                                                   \
     do {                                                                                \
         cudaError_t e__ = (call);                                                       \

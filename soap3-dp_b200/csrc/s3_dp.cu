@@ -45,6 +45,7 @@
 struct s3_dp {
     int device;
     cudaStream_t stream;
+    int ownStream;
     uint32_t maxReadLength, maxDNALength, maxBatch;
     s3_dp_scores sc;
     int R;                       // rows per lane
@@ -283,6 +284,7 @@ extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint3
     dp->device = device; dp->maxReadLength = maxReadLength; dp->maxDNALength = maxDNALength; dp->maxBatch = maxBatch;
     dp->sc = scores; dp->R = R; dp->slot = (R == 5) ? 8 : R;
     S3_CUDA(cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking));
+    dp->ownStream = 1;
     const size_t perAlign = (size_t)(maxDNALength + 1) * 32 * dp->slot;
     size_t freeB = 0, totalB = 0;
     S3_CUDA(cudaMemGetInfo(&freeB, &totalB));
@@ -317,11 +319,18 @@ extern "C" void s3_dp_free(s3_dp *dp)
     void *ptrs[] = {dp->d_tb, dp->d_scRight, dp->d_dna, dp->d_read, dp->d_dnaLen, dp->d_readLen, dp->d_hit, dp->d_cnt,
                     dp->d_clipLt, dp->d_clipRt, dp->d_ancL, dp->d_ancR, dp->d_cutoff, dp->d_score, dp->d_pattern, dp->d_cells};
     for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; ++i) if (ptrs[i]) cudaFree(ptrs[i]);
-    cudaStreamDestroy(dp->stream);
+    if (dp->ownStream) cudaStreamDestroy(dp->stream);
     free(dp);
 }
 
 extern "C" void *s3_dp_stream(const s3_dp *dp) { return dp ? (void *)dp->stream : NULL; }
+extern "C" void s3_dp_set_stream(s3_dp *dp, void *stream)
+{
+    if (!dp) return;
+    cudaStreamSynchronize(dp->stream);
+    if (dp->ownStream) { cudaStreamDestroy(dp->stream); dp->ownStream = 0; }
+    dp->stream = (cudaStream_t)stream;
+}
 extern "C" uint32_t s3_dp_pattern_length(const s3_dp *dp) { return dp ? dp->maxReadLength + dp->maxDNALength : 0; }
 
 template <int R>
@@ -348,6 +357,7 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t n)
         }
         S3_CUDA(cudaGetLastError());
         s3_dp_traceback_kernel<<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a, dp->R);
+        S3_LAUNCHED(2);
         S3_CUDA(cudaGetLastError());
     }
     return S3_OK;

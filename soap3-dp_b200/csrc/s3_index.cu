@@ -7,6 +7,8 @@
 #include <string.h>
 
 static thread_local char g_err[512] = "";
+unsigned long long g_s3_launches = 0;
+extern "C" unsigned long long s3_launch_count(void) { return g_s3_launches; }
 
 void s3_set_error(const char *fmt, ...)
 {
@@ -99,6 +101,7 @@ static int upload_half(s3_index *ix, const uint32_t *bwt, const uint32_t *occ, u
     S3_CUDA(cudaMalloc(d_out, (size_t)numBuckets * 64));
     s3_relayout_kernel<<<(numBuckets + 255) / 256, 256, 0, ix->stream>>>(d_bwt, d_occ, textLength,
                                                                         (uint32_t)numWords, numBuckets, *d_out);
+    S3_LAUNCHED(1);
     S3_CUDA(cudaGetLastError());
     S3_CUDA(cudaStreamSynchronize(ix->stream));
     S3_CUDA(cudaFree(d_bwt));

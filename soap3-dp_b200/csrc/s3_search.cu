@@ -257,6 +257,7 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
     }
     if (count) s3_search_kernel<true><<<grid, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, a);
     else s3_search_kernel<false><<<grid, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, a);
+    S3_LAUNCHED(1);
     S3_CUDA(cudaGetLastError());
     return S3_OK;
 }
@@ -301,6 +302,7 @@ extern "C" int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, 
     if ((rc = launch_search(ix, a, numCases, d_rankQueries != NULL))) return rc;
     if (numCases > 1 && batchSize > 0) {
         s3_isbad_fixup_kernel<<<(unsigned)((batchSize + 255) / 256), 256, 0, ix->stream>>>(a, numCases);
+        S3_LAUNCHED(1);
         S3_CUDA(cudaGetLastError());
     }
     return S3_OK;
@@ -401,6 +403,7 @@ extern "C" int s3_search_round2(s3_index *ix, const uint32_t *queries, const uin
     for (uint32_t c = 0; c < numCases; ++c) {
         S3_CUDA(cudaMemcpyAsync(d_a, answers[c], aBytes, cudaMemcpyHostToDevice, ix->stream));
         s3_bad_flags_kernel<<<(n + 255) / 256, 256, 0, ix->stream>>>(d_a, n, wordPerAns, d_flags);
+        S3_LAUNCHED(1);
         S3_CUDA(cudaGetLastError());
         S3_CUDA(cub::DeviceSelect::Flagged(d_tmp, selTemp, cub::CountingInputIterator<uint32_t>(0), d_flags, d_badIdx,
                                            d_cnt, (int)n, ix->stream));
@@ -412,6 +415,7 @@ extern "C" int s3_search_round2(s3_index *ix, const uint32_t *queries, const uin
         const size_t nbUp = ((size_t)nb + 31) / 32 * 32;
         S3_CUDA(cudaMemsetAsync(d_bq, 0, nbUp * wordPerQuery * 4, ix->stream));
         s3_gather_bad_kernel<<<(nb + 255) / 256, 256, 0, ix->stream>>>(d_q, d_l, d_badIdx, nb, wordPerQuery, d_bq, d_bl);
+        S3_LAUNCHED(1);
         S3_CUDA(cudaGetLastError());
         S3SearchArgs a;
         memset(&a, 0, sizeof a);

@@ -155,23 +155,29 @@ def build_suffix_array(codes: torch.Tensor, max_bucket: int = 1 << 28, verbose: 
     sa[0] = n
     out = 1
     scan_chunk = 1 << 27
+    bid = None
+    if k > 0:
+        # bucket id = the first k bases of every suffix (short suffixes padded with A; the
+        # ordering inside a bucket is still decided by the full keys), computed once
+        bid = torch.empty(n, dtype=torch.uint8 if nb <= 256 else torch.int16, device=dev)
+        for c0 in range(0, n, scan_chunk):
+            c1 = min(n, c0 + scan_chunk)
+            acc = torch.zeros(c1 - c0, dtype=torch.int32, device=dev)
+            for t in range(k):
+                seg = codes[c0 + t: min(n, c1 + t)].to(torch.int32)
+                if seg.numel() < c1 - c0:
+                    seg = torch.cat([seg, torch.zeros(c1 - c0 - seg.numel(), dtype=torch.int32, device=dev)])
+                acc = acc * 4 + seg
+            bid[c0:c1] = acc.to(bid.dtype)
+            del acc
     for b in range(nb):
-        # gather positions whose first k bases spell bucket b (short suffixes padded with A;
-        # ordering inside the bucket is still decided by the full keys)
         if k == 0:
             pos = torch.arange(n, dtype=torch.int64, device=dev)
         else:
             parts = []
             for c0 in range(0, n, scan_chunk):
                 c1 = min(n, c0 + scan_chunk)
-                p = torch.arange(c0, c1, dtype=torch.int64, device=dev)
-                w = p >> 5
-                sh = (p & 31) << 1
-                a = packed[w] << sh
-                bb = ((packed[w + 1] >> 1) & 0x7FFFFFFFFFFFFFFF) >> (63 - sh)
-                pref = ((a | bb) >> (64 - 2 * k)) & (nb - 1)
-                parts.append(p[pref == b])
-                del p, w, sh, a, bb, pref
+                parts.append(torch.nonzero(bid[c0:c1] == b).reshape(-1) + c0)
             pos = torch.cat(parts)
             del parts
         m = pos.numel()
@@ -181,46 +187,52 @@ def build_suffix_array(codes: torch.Tensor, max_bucket: int = 1 << 28, verbose: 
         keys, order = torch.sort(keys, stable=True)
         pos = pos[order]
         del order
-        # tie refinement
+        # tie refinement on the COMPACTED set of still-tied suffixes only.  Tied suffixes of
+        # one run occupy a contiguous slot range; sorting the compact set by (run, next key)
+        # therefore puts its i-th element into the i-th tied slot.
         depth = _KEY_BASES
-        # group id = index of first element of the run of equal keys
-        idx = torch.arange(m, dtype=torch.int64, device=dev)
         neq = torch.ones(m, dtype=torch.bool, device=dev)
         neq[1:] = keys[1:] != keys[:-1]
         tied = ~neq
         tied[:-1] |= ~neq[1:]
         del keys
+        slots = torch.nonzero(tied).reshape(-1)             # ascending
+        del tied
         rounds = 0
-        while bool(tied.any()):
+        if slots.numel():
+            idx = torch.arange(m, dtype=torch.int64, device=dev)
+            grp = torch.cummax(torch.where(neq, idx, torch.zeros_like(idx)), dim=0).values[slots]
+            del idx
+            tpos = pos[slots]
+        del neq
+        while slots.numel():
             rounds += 1
-            tidx = idx[tied]                       # slots occupied by tied elements (ascending)
-            gstart = torch.cummax(torch.where(neq, idx, torch.zeros_like(idx)), dim=0).values[tied]
-            tpos = pos[tidx]
             k2 = _window_keys(packed, tpos + depth, n)
-            # sort by (group, key2): stable sort on key2 then stable sort on group
+            # sort by (run, key2): stable sort on key2, then stable sort on run
             k2s, o1 = torch.sort(k2, stable=True)
-            g1 = gstart[o1]
-            g2, o2 = torch.sort(g1, stable=True)
-            perm = o1[o2]
+            g2, o2 = torch.sort(grp[o1], stable=True)
+            tpos = tpos[o1[o2]]
             k2s = k2s[o2]
-            pos[tidx] = tpos[perm]
-            # new run boundaries among the tied slots
-            tn = tidx.numel()
-            new_neq = torch.ones(tn, dtype=torch.bool, device=dev)
+            pos[slots] = tpos
+            t = slots.numel()
+            new_neq = torch.ones(t, dtype=torch.bool, device=dev)
             new_neq[1:] = (g2[1:] != g2[:-1]) | (k2s[1:] != k2s[:-1])
-            neq[tidx] = new_neq
-            ttied = ~new_neq
-            ttied[:-1] |= ~new_neq[1:]
-            tied = torch.zeros(m, dtype=torch.bool, device=dev)
-            tied[tidx] = ttied
+            still = ~new_neq
+            still[:-1] |= ~new_neq[1:]
+            # new run id = slot of the first element of the refined run
+            cidx = torch.arange(t, dtype=torch.int64, device=dev)
+            first = torch.cummax(torch.where(new_neq, cidx, torch.zeros_like(cidx)), dim=0).values
+            grp = slots[first][still]
+            slots = slots[still]
+            tpos = tpos[still]
             depth += _KEY_BASES
-            if depth > n + _KEY_BASES:
+            if depth > n + 2 * _KEY_BASES:
                 raise RuntimeError("suffix refinement did not converge")
         if verbose:
             print(f"[fmindex] bucket {b}/{nb}: {m} suffixes, {rounds} refinement rounds", flush=True)
         sa[out:out + m] = pos
         out += m
-        del pos, idx, neq, tied
+        del pos
     assert out == n + 1
     return sa
 
@@ -232,7 +244,13 @@ def build_suffix_array(codes: torch.Tensor, max_bucket: int = 1 << 28, verbose: 
 def half_index_from_sa(codes: torch.Tensor, sa: torch.Tensor, keep_sa: bool = True) -> HalfIndex:
     n = codes.numel()
     dev = codes.device
-    inverse_sa0 = int(torch.nonzero(sa == 0)[0, 0])
+    inverse_sa0 = -1
+    for r0 in range(0, n + 1, 1 << 27):      # chunked: nonzero() on > 2^31 elements is not portable
+        hit = torch.nonzero(sa[r0:r0 + (1 << 27)] == 0)
+        if hit.numel():
+            inverse_sa0 = r0 + int(hit[0, 0])
+            break
+    assert inverse_sa0 >= 0
     # $-less BWT: BWT[i] = T[SA[i]-1] for SA[i] != 0, rows in SA order with the '$' row removed
     bwt = torch.empty(n, dtype=torch.uint8, device=dev)
     chunk = 1 << 27

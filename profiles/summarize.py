@@ -1,0 +1,127 @@
+#!/usr/bin/env python
+"""Turn the raw files one `profiles/gpu_session.sh <tag>` call left in gpurun_out/ into the
+tracked summaries under profiles/:
+
+    profiles/<tag>_launches.csv     the ncu launch list (gpu__time_duration per launch)
+    profiles/<tag>_bench.json       the bench line of the same session (not under a profiler)
+    profiles/<tag>_summary.md       per-kernel shares of the step + the ncu --set full metrics
+                                    the roofline numbers are read from
+
+usage: python profiles/summarize.py <tag>      (needs `ncu` on PATH; no GPU)
+"""
+import csv
+import io
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+from collections import OrderedDict
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+PROF = os.path.join(ROOT, "profiles")
+
+KEYS = [
+    ("gpu__time_duration.sum", "duration"),
+    ("dram__bytes_read.sum", "DRAM read"),
+    ("dram__bytes_write.sum", "DRAM write"),
+    ("dram__bytes_read.sum.pct_of_peak_sustained_elapsed", "DRAM read % of peak"),
+    ("dram__bytes_write.sum.pct_of_peak_sustained_elapsed", "DRAM write % of peak"),
+    ("lts__t_sector_hit_rate.pct", "L2 hit rate"),
+    ("l1tex__t_sector_hit_rate.pct", "L1 hit rate"),
+    ("launch__registers_per_thread", "registers/thread"),
+    ("launch__grid_size", "grid"),
+    ("launch__block_size", "block"),
+    ("sm__warps_active.avg.pct_of_peak_sustained_active", "achieved occupancy %"),
+    ("smsp__inst_executed.sum", "warp instructions"),
+    ("smsp__thread_inst_executed_per_inst_executed.ratio", "active threads per warp instruction"),
+    ("sm__issue_active.avg.pct_of_peak_sustained_elapsed", "issue slots busy %"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "ALU pipe %"),
+    ("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active", "FMA pipe %"),
+    ("sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active", "XU pipe (POPC) %"),
+    ("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "LSU pipe %"),
+    ("smsp__sass_inst_executed_op_local_ld.sum", "local loads"),
+    ("smsp__sass_inst_executed_op_local_st.sum", "local stores"),
+    ("smsp__average_warp_latency_per_inst_issued.ratio", "warp latency per instruction (cycles)"),
+]
+
+
+def raw_page(rep):
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rows[0], rows[1]
+    return [OrderedDict((h, (v, u)) for h, v, u in zip(hdr, r, units)) for r in rows[2:]]
+
+
+def launches(path):
+    rows = []
+    with open(path) as f:
+        lines = [ln for ln in f if not ln.startswith("==")]
+    for r in csv.DictReader(io.StringIO("".join(lines))):
+        if r.get("Metric Name") == "gpu__time_duration.sum":
+            rows.append((r["Kernel Name"], float(r["Metric Value"].replace(",", ""))))
+    return rows
+
+
+def short(name):
+    return re.sub(r"\(.*", "", name).replace("void ", "")
+
+
+def main():
+    tag = sys.argv[1]
+    md = [f"# ncu summary `{tag}`", "",
+          f"Produced by `profiles/gpu_session.sh {tag}` on one B200 (through gpurun) and "
+          f"`profiles/summarize.py {tag}` here.  Launch times under ncu are cold-cache and serialised: "
+          "compare SHARES with the CUDA-event numbers of the bench line, not absolutes.", ""]
+    bj = os.path.join(OUT, f"{tag}_bench.json")
+    if os.path.exists(bj) and os.path.getsize(bj):
+        shutil.copy(bj, os.path.join(PROF, f"{tag}_bench.json"))
+        b = json.loads(open(bj).read().strip().splitlines()[-1])
+        md += ["## bench line of the same session (CUDA events, no profiler)", "",
+               f"* value {b['value']:.0f} {b['unit']} (device-resident), e2e {b['e2e']['value']:.0f} {b['unit']}, "
+               f"{b['ms_per_step']:.2f} ms/step, clocks {b.get('clocks')}",
+               f"* roofline: {json.dumps(b.get('roofline'))}",
+               f"* dp: {json.dumps(b.get('dp'))}",
+               f"* cpu_baseline: {json.dumps(b.get('cpu_baseline'))}", ""]
+    rj = os.path.join(OUT, f"{tag}_bench_reference.json")
+    if os.path.exists(rj) and os.path.getsize(rj):
+        shutil.copy(rj, os.path.join(PROF, f"{tag}_bench_reference.json"))
+    lc = os.path.join(OUT, f"{tag}_launches.csv")
+    if os.path.exists(lc):
+        shutil.copy(lc, os.path.join(PROF, f"{tag}_launches.csv"))
+        rows = launches(lc)
+        agg = OrderedDict()
+        for k, ns in rows:
+            a = agg.setdefault(short(k), [0, 0.0])
+            a[0] += 1
+            a[1] += ns
+        tot = sum(v[1] for k, v in agg.items() if "relayout" not in k)
+        md += ["## launch list (`ncu --metrics gpu__time_duration.sum`, bench.py --steps 2 --warmup 1)", "",
+               "| kernel | launches | avg ms | share of step (index re-layout excluded) |", "|---|---|---|---|"]
+        for k, (n, ns) in agg.items():
+            sh = "-" if "relayout" in k else f"{100 * ns / tot:.1f} %"
+            md.append(f"| `{k}` | {n} | {ns / n / 1e6:.3f} | {sh} |")
+        md.append("")
+    for what in ("search", "dp"):
+        rep = os.path.join(OUT, f"{tag}_{what}.ncu-rep")
+        if not os.path.exists(rep):
+            continue
+        md += [f"## `ncu --set full` : {what}", ""]
+        for d in raw_page(rep):
+            md += [f"### `{short(d['Kernel Name'][0])}`", "", "| metric | value |", "|---|---|"]
+            for k, label in KEYS:
+                if k in d:
+                    md.append(f"| {label} (`{k}`) | {d[k][0]} {d[k][1]} |")
+            stalls = [(k.split("stalled_")[1].replace("_per_issue_active.ratio", ""), float(v[0] or 0))
+                      for k, v in d.items() if "issue_stalled" in k and k.endswith("per_issue_active.ratio")]
+            stalls.sort(key=lambda x: -x[1])
+            md.append("| top stall reasons (warps per issue) | " + ", ".join(f"{k} {v:.2f}" for k, v in stalls[:5]) + " |")
+            md.append("")
+    open(os.path.join(PROF, f"{tag}_summary.md"), "w").write("\n".join(md) + "\n")
+    print("\n".join(md))
+
+
+if __name__ == "__main__":
+    main()

@@ -268,18 +268,46 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
     dpb = helpers.make_dp_batch(genome[:4_000_000].cpu(), m, L, "rescue", seed=seed + 1, insert=(INSERT_LO, INSERT_HI))
     t0 = time.perf_counter()
     if kind == "reference":
-        helpers.ref_dp(ref_d, dpb, DP_SCORES, nthreads=threads)
+        dp_out = helpers.ref_dp(ref_d, dpb, DP_SCORES, nthreads=threads)
     else:
-        helpers.oracle_dp(helpers.load_oracle_dp(), dpb, DP_SCORES)
+        dp_out = helpers.oracle_dp(helpers.load_oracle_dp(), dpb, DP_SCORES)
     t_dp = time.perf_counter() - t0
-    used = threads if kind == "reference" else (os.cpu_count() if False else 1)
-    return {"value": n / (t_search + t_dp), "unit": "reads/s", "cores": used if kind == "reference" else 1,
+    return {"_answers": ans, "_batch": b, "_dpb": dpb, "_dp_out": dp_out, "value": n / (t_search + t_dp), "unit": "reads/s", "cores": threads if kind == "reference" else 1,
             "kind": kind,
             "sample": f"{n} reads (k<=2, 4 cases, both strands) + {m} rescue DP alignments of the bench workload; "
                       + ("reference kernel sources (DV-Kernel.cu, DV-DPfunctions.cu:35-512) compiled for the host, OpenMP over reads"
                          if kind == "reference" else "oracle/ C restatement, single thread"),
             "rank_queries_per_read": nrank / n, "t_search_s": t_search, "t_dp_s": t_dp,
             "dp_gcups": dpb.n * 400 * L / t_dp / 1e9}
+
+
+def parity_check(gi, cb, device_index):
+    """The CPU arm's sample, pushed through the GPU library (host C ABI) and compared bit for bit:
+    full-size genome, the checker is the CPU arm's output (reference kernels compiled for the host)."""
+    import helpers
+    b = cb["_batch"]
+    q = b.queries.cpu().numpy().view(np.uint32)
+    lens = b.lens.cpu().numpy().view(np.uint32)
+    got = api.perform_round1_alignment(gi, q, lens, b.n, b.wpq, K_MISMATCH)
+    wpa = 2 * formats.SA_RANGES_ROUND1[K_MISMATCH]
+    search_equal = all(np.array_equal(formats.answers_view(g, b.n, wpa), formats.answers_view(w, b.n, wpa))
+                       for g, w in zip(got, cb["_answers"]))
+    dpb = cb["_dpb"]
+    al = api.SemiGlobalAligner(dpb.max_read, dpb.max_dna, dpb.n, *DP_SCORES, device=device_index)
+    out = al.performAlignment(dpb.dna, dpb.dna_len, dpb.read, dpb.read_len, dpb.cutoff, dpb.n, dpb.clip_lt, dpb.clip_rt,
+                              dpb.anchor_l, dpb.anchor_r)
+    al.freeMemory()
+    try:
+        npass = helpers.compare_dp(dpb, out, cb["_dp_out"], "bench parity")
+        dp_equal = True
+    except AssertionError as e:
+        log("DP PARITY FAILURE:", e)
+        npass, dp_equal = 0, False
+    if not search_equal:
+        log("SEARCH PARITY FAILURE at full size")
+    return {"search_reads": int(b.n), "search_cases": len(got), "search_bit_exact": bool(search_equal),
+            "dp_alignments": int(dpb.n), "dp_tracebacks": int(npass), "dp_bit_exact": bool(dp_equal),
+            "checker": cb["kind"]}
 
 
 # ---------------------------------------------------------------------------
@@ -512,6 +540,7 @@ def main():
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         out["cpu_baseline"]["rank_queries_per_read"] = cb["rank_queries_per_read"]
         out["cpu_baseline"]["dp_gcups"] = cb["dp_gcups"]
+        out["parity_at_full_size"] = parity_check(gi, cb, local_rank)
     print(json.dumps(out), flush=True)
     aligner.freeMemory()
     api.GPUINDEXFree(gi)

@@ -1,13 +1,18 @@
 // s3_common.cuh -- shared device structures of the B200 hot path.
 //
 // Index layout in HBM (DESIGN.md "data layout"): per direction an array of
-// 64-byte, 64-byte-aligned buckets
-//     struct { uint32 cnt[4]; uint32 bwt[12]; }
-// cnt[c] = cumulativeFreq[c] + Occ(c, 192*b) on the $-less BWT, bwt = the next
-// 192 bases (2 bit/base, 16 per word, MSB first -- the reference's own word
-// format, 2bwt-lib/BWT.c:119-175).  One rank evaluation = one 64-byte bucket =
-// one 32-byte-sector pair, instead of the reference's 16 B occ + 16 B BWT loads
-// from two different cache lines (DV-Kernel.cu:256-280).
+// 64-byte, 64-byte-aligned buckets, one per 192 BWT positions:
+//     bytes  0..15  cnt[4]    cnt[c] = cumulativeFreq[c] + Occ(c, 192*b + 96)   (count at the bucket MIDDLE)
+//     bytes 16..39  half A    bases 0..95  as bit planes: hi0 hi1 hi2 lo0 | lo1 lo2
+//     bytes 40..63  half B    bases 96..191 as bit planes: lo1 lo2 | hi0 hi1 hi2 lo0
+// A base's 2-bit code is split into a "hi" and a "lo" plane (base k of a half is bit
+// k%32 of plane word k/32), so the four symbol counts of up to 96 bases cost 9 POPC
+// (hi, lo, hi&lo per word) and rank'(c, i) counts forward or backward from the middle:
+// at most 96 bases, one 16 B + one 16 B + one 8 B load inside ONE 64-byte line.  The
+// reference needs a 16 B occ load and a 16 B BWT load from two different cache lines and
+// counts 2-bit codes with 64-bit masks (DV-Kernel.cu:27-280).  Positions past the end of
+// the text are padded with code 0 and counted as such on both sides of the middle, so
+// they cancel.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -34,6 +39,10 @@ struct s3_index {
     // scratch reused across calls (grown on demand)
     void *scratch; size_t scratchBytes;
     void *pinned; size_t pinnedBytes;
+    // persistent search launches
+    uint32_t *d_workCounter;
+    int numSms;
+    size_t searchSmem; int searchBlocksPerSm;
 };
 
 void s3_set_error(const char *fmt, ...);
@@ -55,33 +64,38 @@ int s3_pinned(s3_index *ix, size_t bytes, void **out);
 // ---- rank'(., idx) for all four symbols ------------------------------------
 // Mathematically the reference's GPUBWTAllOccValue (DV-Kernel.cu:282-299):
 // C[c] + #{c in BWT[0, idx)} with the "$ is not stored" shift.
+__device__ __forceinline__ uint32_t s3_shl_clamp(uint32_t a, uint32_t s)
+{
+    uint32_t d;                                   // PTX shl clamps shift amounts > 32 to 32 (result 0)
+    asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(s));
+    return d;
+}
+
 __device__ __forceinline__ void s3_rank4(const S3Half &h, uint32_t idx, uint32_t out[4])
 {
     idx -= (idx > h.inverseSa0);
     const uint32_t b = __umulhi(idx, 0xAAAAAAABu) >> 7;          // idx / 192
     const uint32_t rem = idx - b * S3_BUCKET_BASES;
+    const bool isB = rem >= 96u;
+    const uint32_t x = isB ? rem - 96u : rem;                     // position inside the half
     const uint4 *p = h.buckets + (size_t)b * 4;
     const uint4 cnt = __ldg(p);
-    const uint4 w0 = __ldg(p + 1), w1 = __ldg(p + 2), w2 = __ldg(p + 3);
-    const unsigned long long chunk[6] = {
-        ((unsigned long long)w0.x << 32) | w0.y, ((unsigned long long)w0.z << 32) | w0.w,
-        ((unsigned long long)w1.x << 32) | w1.y, ((unsigned long long)w1.z << 32) | w1.w,
-        ((unsigned long long)w2.x << 32) | w2.y, ((unsigned long long)w2.z << 32) | w2.w};
-    uint32_t nT = 0, nHi = 0, nLo = 0;
-#pragma unroll
-    for (int k = 0; k < 6; ++k) {
-        const int nb = min(max((int)rem - 32 * k, 0), 32);
-        const unsigned long long mask = (nb >= 32) ? ~0ull : ~(~0ull >> (2 * nb));
-        const unsigned long long vm = mask & 0x5555555555555555ull;
-        const unsigned long long hi = (chunk[k] >> 1) & vm;
-        const unsigned long long lo = chunk[k] & vm;
-        nT += __popcll(hi & lo);
-        nHi += __popcll(hi);
-        nLo += __popcll(lo);
-    }
-    const uint32_t cT = nT, cG = nHi - nT, cC = nLo - nT, cA = rem - nHi - nLo + nT;
-    out[0] = cnt.x + cA;
-    out[1] = cnt.y + cC;
-    out[2] = cnt.z + cG;
-    out[3] = cnt.w + cT;
+    const uint4 hv = __ldg(p + (isB ? 3 : 1));                    // hi0 hi1 hi2 lo0
+    const uint2 lv = __ldg(reinterpret_cast<const uint2 *>(p) + (isB ? 5 : 4));   // lo1 lo2
+    // half A counts bases [x, 96) (subtracted), half B counts bases [0, x) (added)
+    const uint32_t flip = isB ? 0xFFFFFFFFu : 0u;
+    const uint32_t m0 = s3_shl_clamp(0xFFFFFFFFu, x) ^ flip;
+    const uint32_t m1 = s3_shl_clamp(0xFFFFFFFFu, (uint32_t)max((int)x - 32, 0)) ^ flip;
+    const uint32_t m2 = s3_shl_clamp(0xFFFFFFFFu, (uint32_t)max((int)x - 64, 0)) ^ flip;
+    const uint32_t h0 = hv.x & m0, h1 = hv.y & m1, h2 = hv.z & m2;
+    const uint32_t l0 = hv.w & m0, l1 = lv.x & m1, l2 = lv.y & m2;
+    const uint32_t nHi = __popc(h0) + __popc(h1) + __popc(h2);
+    const uint32_t nLo = __popc(l0) + __popc(l1) + __popc(l2);
+    const uint32_t nT = __popc(h0 & l0) + __popc(h1 & l1) + __popc(h2 & l2);
+    const uint32_t len = isB ? x : 96u - x;
+    const uint32_t cA = len - nHi - nLo + nT, cC = nLo - nT, cG = nHi - nT;
+    out[0] = isB ? cnt.x + cA : cnt.x - cA;
+    out[1] = isB ? cnt.y + cC : cnt.y - cC;
+    out[2] = isB ? cnt.z + cG : cnt.z - cG;
+    out[3] = isB ? cnt.w + nT : cnt.w - nT;
 }

@@ -6,21 +6,27 @@
 // Design (not a port).  The reference runs one thread per alignment and keeps
 // the full H and E tables of shorts in global memory (8 B of traffic per cell,
 // DV-DPfunctions.cu:57,146-241), then walks them again to trace back.  Here:
-//   * one WARP per alignment; lane t owns read rows [t*R+1, t*R+R] and sweeps the
-//     reference columns as an anti-diagonal wavefront: at step s lane t is in
-//     column s-t.  The reference's inner-loop carried registers (upScore,
-//     scoreOpenUp, prevScoreUp) simply migrate from lane t-1 to lane t with
-//     __shfl_up_sync, so every intermediate value -- including the "unclamped
-//     inside a column, clamped to -32000 when stored" rule -- is bit-identical.
-//   * H/E of the previous column live in registers (2R per lane); nothing but one
-//     traceback BYTE per cell goes to memory.  The byte records the outcome of every
-//     comparison GPUBacktrack would make at that cell (oracle/dp_oracle.c has the
-//     same formulation and is pinned against the reference kernels).
-//   * max/add chains use the DPX instructions (__viaddmax_s32, __vimax3_s32).
+//   * one WARP per PAIR of alignments; the two alignments ride in the two 16-bit
+//     halves of every register and all arithmetic is DPX 16x2 (VIADD.16x2,
+//     VIADDMNMX.S16x2, VIMNMX3.S16x2): the reference's own value range is that of a
+//     short clamped at -32000 (DV-DPfunctions.cu:45-48), so nothing is lost.
+//   * lane t owns read rows [t*R+1, t*R+R] and sweeps the reference columns as an
+//     anti-diagonal wavefront: at step s lane t is in column s-t.  The reference's
+//     inner-loop carried registers (upScore, scoreOpenUp, prevScoreUp) simply
+//     migrate from lane t-1 to lane t with __shfl_up_sync, so every intermediate
+//     value -- including the "unclamped inside a column, clamped to -32000 when
+//     stored" rule -- is bit-identical.
+//   * H/E of the previous column live in registers (2R per lane).  Per cell only the
+//     clamped H (2 bytes) goes to memory, anti-diagonal major so that a warp's store is
+//     one contiguous 512-byte line.  The one thing GPUBacktrack reads from the E table
+//     ("H == ext + E of the previous column", where an indel starts) is rebuilt by the
+//     traceback from the H row, since E is a function of the H values to its left.
 //   * best cell: per-lane running best in the reference's scan order, merged
 //     across lanes with the (column, row) tie-break; tie counts are summed.
-// The traceback kernel is one thread per alignment that needs one (score >=
-// cutoff) and reads only the byte plane.
+// The traceback kernel is one thread per alignment that reached its cutoff and is
+// GPUBacktrack's state machine (DV-DPfunctions.cu:330-508) over the stored H values.
+// A 32-bit one-alignment-per-warp variant (byte-plane traceback) remains for read
+// lengths above 256 or score parameters that do not fit 16-bit lanes.
 #include "s3_common.cuh"
 #include "../../include/soap3dp_b200.h"
 #include <stdlib.h>
@@ -49,9 +55,11 @@ struct s3_dp {
     uint32_t maxReadLength, maxDNALength, maxBatch;
     s3_dp_scores sc;
     int R;                       // rows per lane
-    uint32_t slot;               // bytes per lane per column in the traceback plane
+    int narrow;                  // 1: 16x2 kernels (H plane + flag plane), 0: 32-bit kernels (byte plane)
+    uint32_t slot;               // wide path: bytes per lane per column in the traceback plane
     uint32_t chunk;              // alignments per traceback-plane chunk
-    uint8_t *d_tb;               // chunk * (maxDNALength+1) * 32 * slot
+    uint8_t *d_tb;               // wide: chunk * (maxDNALength+1) * 32 * slot bytes
+                                 // narrow: chunk/2 pairs * (maxDNALength+32) steps * 32 lanes * R words
     uint32_t *d_scRight;         // maxBatch
     // staging for the host entry point
     uint32_t *d_dna, *d_read, *d_dnaLen, *d_readLen, *d_hit, *d_cnt, *d_clipLt, *d_clipRt, *d_ancL, *d_ancR;
@@ -72,6 +80,8 @@ struct S3DpArgs {
     uint32_t slot;
     int match, mismatch, open, ext;
     unsigned long long *cells;
+    uint32_t *hplane;                // narrow path: H values, [pair][step][lane][R] words (A low half, B high half)
+    uint32_t planeSteps;             // maxDNALength + 32
 };
 
 __device__ __forceinline__ int s3_clamp(int x) { return max(x, S3_NEG_INF); }
@@ -262,6 +272,316 @@ __global__ void s3_dp_traceback_kernel(const S3DpArgs a, int R)
     a.hit[id] = refIndex;        // start offset inside the window (refOffset == 0 in scheme 1)
 }
 
+// =============================================================================
+// 16x2 path: two alignments per warp, DPX instructions, H plane + flag plane
+// =============================================================================
+#define S3_NEG2 0x83008300u          // -32000 in both halves
+#define S3_MIN2 0x80008000u          // -32768 in both halves (identity of max)
+#define S3_MAX2 0x7FFF7FFFu          // +32767 in both halves (identity of min)
+
+__device__ __forceinline__ uint32_t s3_pk(int lo, int hi) { return ((uint32_t)lo & 0xFFFFu) | ((uint32_t)hi << 16); }
+__device__ __forceinline__ int s3_lo16(uint32_t v) { return (int)(short)(v & 0xFFFFu); }
+__device__ __forceinline__ int s3_hi16(uint32_t v) { return (int)(short)(v >> 16); }
+
+// prmt.b32 in its generic form: selector nibble bit 3 replicates the sign of the selected byte
+// (__byte_perm masks that bit away)
+__device__ __forceinline__ uint32_t s3_prmt(uint32_t a, uint32_t b, uint32_t sel)
+{
+    uint32_t d;
+    asm("prmt.b32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(sel));
+    return d;
+}
+
+struct S3Dp16Best { int best; uint32_t hitJ, bestI, count; };
+
+__device__ __forceinline__ void s3_best_update(S3Dp16Best &b, int x, uint32_t j, uint32_t i)
+{
+    if (x > b.best) { b.best = x; b.hitJ = j; b.bestI = i; b.count = 1; }
+    else if (x == b.best) ++b.count;
+}
+
+template <int R>
+__global__ void __launch_bounds__(S3_DP_WARPS * 32)
+s3_dp_score16_kernel(const S3DpArgs a)
+{
+    __shared__ uint32_t refWords[S3_DP_WARPS][2][S3_DP_MAX_REF_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t pairLocal = blockIdx.x * S3_DP_WARPS + warp;
+    if (2 * pairLocal >= a.count) return;                         // whole warp leaves together
+    const bool hasB = 2 * pairLocal + 1 < a.count;
+    const uint32_t id[2] = {a.first + 2 * pairLocal, a.first + 2 * pairLocal + (hasB ? 1u : 0u)};
+    uint32_t m[2], n[2], clipLt[2], clipRt[2], ancL[2], ancR[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        m[x] = a.readLen[id[x]]; n[x] = a.dnaLen[id[x]];
+        clipLt[x] = a.clipLt ? a.clipLt[id[x]] : 0u;
+        clipRt[x] = a.clipRt ? a.clipRt[id[x]] : 0u;
+        ancL[x] = a.ancL ? a.ancL[id[x]] : a.maxDNALength;
+        ancR[x] = a.ancR ? a.ancR[id[x]] : 0u;
+    }
+    const uint32_t mMax = max(m[0], m[1]), nMax = max(n[0], n[1]);
+    const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
+    const uint32_t OPEN2 = s3_pk(open, open), EXT2 = s3_pk(ext, ext), GAPINIT2 = s3_pk(gapInit, gapInit);
+    const uint32_t i0 = lane * R + 1;                              // first row of this lane (1-based)
+
+    // reference windows -> shared memory (1-based packing, MSB first; DV-DPfunctions.cu:58)
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        const uint32_t *dna = a.dna + (size_t)(id[x] >> 5) * a.dnaWords * 32 + (id[x] & 31);
+        const uint32_t nw = min((nMax >> 4) + 1, a.dnaWords);
+        for (uint32_t w = lane; w < nw; w += 32) refWords[warp][x][w] = dna[(size_t)w * 32];
+    }
+    // this lane's read bases become PRMT selectors: the substitution score of a row is looked
+    // up in a 4-byte table per alignment (byte c = score against reference base c)
+    uint32_t sel[R], cmask[R];
+    uint32_t eligRows = 0;                                       // bit r: row may end alignment A, bit 16+r: alignment B
+    {
+        const uint32_t *readA = a.read + (size_t)(id[0] >> 5) * a.readWords * 32 + (id[0] & 31);
+        const uint32_t *readB = a.read + (size_t)(id[1] >> 5) * a.readWords * 32 + (id[1] & 31);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t i = i0 + r;
+            const uint32_t cA = (i <= m[0]) ? (readA[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
+            const uint32_t cB = (i <= m[1]) ? (readB[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
+            sel[r] = cA | ((cA | 8u) << 4) | ((cB | 4u) << 8) | ((cB | 12u) << 12);
+            // rows in which the alignment may end (DV-DPfunctions.cu:225): i >= m - clipRt, i <= m
+            const bool eA = (int)i >= (int)(m[0] - clipRt[0]) && i <= m[0];
+            const bool eB = (int)i >= (int)(m[1] - clipRt[1]) && i <= m[1] && hasB;
+            eligRows |= (eA ? (1u << r) : 0u) | (eB ? (0x10000u << r) : 0u);
+            // soft-clip restart feeds row i from row i-1 when i-1 <= clipLt (DV-DPfunctions.cu:215-219)
+            cmask[r] = ((i - 1 <= clipLt[0]) ? 0xFFFFu : 0u) | ((i - 1 <= clipLt[1]) ? 0xFFFF0000u : 0u);
+        }
+    }
+    // column 0 (DV-DPfunctions.cu:167-184)
+    uint32_t Hp[R], Ep[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i = i0 + r;
+        const int hA = (i <= clipLt[0]) ? open : gapInit + (int)(i - clipLt[0]) * ext;
+        const int hB = (i <= clipLt[1]) ? open : gapInit + (int)(i - clipLt[1]) * ext;
+        Hp[r] = s3_pk(s3_clamp(hA), s3_clamp(hB));
+        Ep[r] = s3_pk(s3_clamp(hA + gapInit), s3_clamp(hB + gapInit));
+    }
+    __syncwarp();
+
+    // substitution tables: byte c of tX = score of this column's reference base against read base c
+    const uint32_t MISM4 = ((uint32_t)a.mismatch & 0xFFu) * 0x01010101u;
+    const uint32_t DELTA = ((uint32_t)a.match ^ (uint32_t)a.mismatch) & 0xFFu;
+
+    S3Dp16Best bestA = {S3_NEG_INF, 0u, 0u, 0u}, bestB = {S3_NEG_INF, 0u, 0u, 0u};
+    uint32_t best2 = S3_NEG2;                                    // packed running bests (trigger only)
+    uint32_t upOut = 0, FOut = 0, diagRawOut = 0;
+    uint32_t prevInit = 0;                                       // start value of the previous column
+    uint32_t clipIO[R], clipPI[R];                               // soft-clip restart operands of the current column
+    uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPI were built from
+    uint32_t *hrow = a.hplane + (size_t)pairLocal * a.planeSteps * 32 * R + (size_t)lane * R;
+    const bool laneHasRows = i0 <= mMax;
+
+    const uint32_t steps = nMax + 31;
+    for (uint32_t s = 1; s <= steps; ++s) {
+        // carried registers of the row loop arrive from the lane above (column j was done there at step s-1)
+        uint32_t up = __shfl_up_sync(0xFFFFFFFFu, upOut, 1);
+        uint32_t F = __shfl_up_sync(0xFFFFFFFFu, FOut, 1);
+        uint32_t diagRaw = __shfl_up_sync(0xFFFFFFFFu, diagRawOut, 1);
+        const uint32_t j = s - lane;
+        if (j >= 1 && j <= nMax && laneHasRows) {
+            const uint32_t init = ((j >= ancL[0]) ? (S3_NEG2 & 0xFFFFu) : 0u) | ((j >= ancL[1]) ? (S3_NEG2 & 0xFFFF0000u) : 0u);
+            if (lane == 0) { up = init; F = __vadd2(init, GAPINIT2); diagRaw = prevInit; }
+            if (init != curInit || prevInit != curPrev) {           // rare: first column and anchor crossings
+                const uint32_t io = __vadd2(init, OPEN2);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    clipIO[r] = (io & cmask[r]) | (S3_MIN2 & ~cmask[r]);
+                    clipPI[r] = (prevInit & cmask[r]) | (S3_MIN2 & ~cmask[r]);
+                }
+                curInit = init; curPrev = prevInit;
+            }
+            const uint32_t sh = (15u - (j & 15u)) << 1;
+            const uint32_t cA = (refWords[warp][0][j >> 4] >> sh) & 3u, cB = (refWords[warp][1][j >> 4] >> sh) & 3u;
+            const uint32_t tA = MISM4 ^ (DELTA << (cA << 3)), tB = MISM4 ^ (DELTA << (cB << 3));
+            uint32_t upRow[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t d = s3_prmt(tA, tB, sel[r]);
+                const uint32_t left = Hp[r], eL = Ep[r];
+                const uint32_t e = __viaddmax_s16x2(left, OPEN2, __vadd2(eL, EXT2));
+                F = __vimax3_s16x2(__vadd2(F, EXT2), __vadd2(up, OPEN2), clipIO[r]);
+                const uint32_t dg = __vmaxs2(diagRaw, clipPI[r]);
+                up = __vimax3_s16x2(F, e, __vadd2(dg, d));
+                diagRaw = left;
+                Hp[r] = __vmaxs2(up, S3_NEG2); Ep[r] = __vmaxs2(e, S3_NEG2);
+                upRow[r] = up;
+            }
+            upOut = up; FOut = F; diagRawOut = diagRaw;
+            prevInit = init;
+            // anti-diagonal major: the warp's 32 x R words of one step are contiguous
+            uint4 *hdst = reinterpret_cast<uint4 *>(hrow + (size_t)s * 32 * R);
+#pragma unroll
+            for (int k = 0; k < R / 4; ++k) hdst[k] = make_uint4(Hp[4 * k], Hp[4 * k + 1], Hp[4 * k + 2], Hp[4 * k + 3]);
+            // best cell.  Cheap conservative trigger: some row of this lane (eligible or not) reaches a running
+            // best; the exact test per eligible cell runs only then (DV-DPfunctions.cu:225-235).
+            if (eligRows) {
+                uint32_t colMax = Hp[0];
+#pragma unroll
+                for (int r = 1; r + 1 < R; r += 2) colMax = __vimax3_s16x2(colMax, Hp[r], Hp[r + 1]);
+                colMax = __vmaxs2(colMax, Hp[R - 1]);
+                bool gh, gl;
+                (void)__vibmax_s16x2(colMax, best2, &gh, &gl);
+                // columns in which the alignment may end: anchorRight <= j <= n
+                const bool okA = j >= ancR[0] && j <= n[0], okB = j >= ancR[1] && j <= n[1];
+                if ((gl && okA) || (gh && okB)) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        if (okA && ((eligRows >> r) & 1u)) s3_best_update(bestA, s3_lo16(upRow[r]), j, i0 + r);
+                        if (okB && ((eligRows >> (16 + r)) & 1u)) s3_best_update(bestB, s3_hi16(upRow[r]), j, i0 + r);
+                    }
+                    best2 = s3_pk(bestA.best, bestB.best);
+                }
+            }
+        }
+    }
+    // merge the lanes' bests: highest score, then first in (column, row) scan order
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        const S3Dp16Best &bb = x ? bestB : bestA;
+        int gbest = bb.best;
+        for (int o = 16; o > 0; o >>= 1) gbest = max(gbest, __shfl_xor_sync(0xFFFFFFFFu, gbest, o));
+        unsigned long long key = (bb.best == gbest && bb.count > 0) ? (((unsigned long long)bb.hitJ << 32) | bb.bestI) : ~0ull;
+        uint32_t cnt = (bb.best == gbest) ? bb.count : 0u;
+        for (int o = 16; o > 0; o >>= 1) {
+            key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
+            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        }
+        if (lane == 0 && (x == 0 || hasB)) {
+            const bool any = key != ~0ull;
+            a.score[id[x]] = gbest;
+            a.hit[id[x]] = any ? (uint32_t)(key >> 32) : 0u;
+            const uint32_t bi = (uint32_t)(key & 0xFFFFFFFFu);
+            a.scRight[id[x]] = (any && bi != 0) ? m[x] - bi : 0u;   // bi == 0: only ties with the -32000 start value
+            a.cnt[id[x]] = cnt;
+            if (a.cells) atomicAdd(a.cells, (unsigned long long)m[x] * n[x]);
+        }
+    }
+}
+
+// One thread per alignment: GPUBacktrack (DV-DPfunctions.cu:316-512) over the H plane.  The
+// reference reads H of three neighbours and, for its third test, E of the previous column;
+// here the E test is the stored flag bit and the borders H(j,0), H(0,i) -- which the reference
+// also keeps in its table -- are recomputed from their defining formulas.
+__global__ void s3_dp_traceback16_kernel(const S3DpArgs a, int R)
+{
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= a.count) return;
+    const uint32_t id = a.first + local;
+    if (a.score[id] < a.cutoff[id]) return;
+    const uint32_t half = local & 1u, pairLocal = local >> 1;
+    const uint32_t m = a.readLen[id];
+    const uint32_t clipLt = a.clipLt ? a.clipLt[id] : 0u;
+    const uint32_t anchorLeft = a.ancL ? a.ancL[id] : a.maxDNALength;
+    const uint32_t scRight = a.scRight[id];
+    const uint32_t *hplane = a.hplane + (size_t)pairLocal * a.planeSteps * 32 * R;
+    const uint32_t *dna = a.dna + (size_t)(id >> 5) * a.dnaWords * 32 + (id & 31);
+    const uint32_t *read = a.read + (size_t)(id >> 5) * a.readWords * 32 + (id & 31);
+    const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
+    uint8_t *pat = a.pattern + (size_t)id * (a.maxReadLength + a.maxDNALength);
+    uint32_t p = 0;
+
+    auto H = [&](uint32_t j, uint32_t i) -> int {
+        if (i == 0) return (j == 0) ? 0 : ((j >= anchorLeft) ? S3_NEG_INF : 0);
+        if (j == 0) return s3_clamp((i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext);
+        const uint32_t t = (i - 1) / R, r = (i - 1) % R;
+        const uint32_t w = hplane[((size_t)(j + t) * 32 + t) * R + r];
+        return half ? s3_hi16(w) : s3_lo16(w);
+    };
+    // E(j-1, i) as the score kernel computed and clamped it, rebuilt from row i of the H plane:
+    // E(0,i) = H(0,i)+gapInit, E(c,i) = max(open + H(c-1,i), ext + E(c-1,i)), each clamped when
+    // stored (DV-DPfunctions.cu:178-183,196-199).  Only evaluated where an indel or a clip starts.
+    auto Eprev = [&](uint32_t j, uint32_t i) -> int {
+        const int h0 = (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext;
+        int e = s3_clamp(h0 + gapInit), hl = s3_clamp(h0);
+        const uint32_t t = (i - 1) / R, r = (i - 1) % R;
+        const uint32_t *row = hplane + (size_t)t * R + r;
+        for (uint32_t c = 1; c < j; ++c) {
+            e = s3_clamp(max(open + hl, ext + e));
+            const uint32_t w = row[(size_t)(c + t) * 32 * R];
+            hl = half ? s3_hi16(w) : s3_lo16(w);
+        }
+        return e;
+    };
+    auto refAt = [&](uint32_t j) -> uint32_t { return (dna[(size_t)(j >> 4) * 32] >> ((15 - (j & 15)) << 1)) & 3; };
+    auto readAt = [&](uint32_t i) -> uint32_t { return (read[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3; };
+
+    if (scRight > 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)scRight; }
+    uint32_t readPos = m - scRight, refIndex = a.hit[id];
+    uint32_t readChar = readAt(readPos), refChar = refAt(refIndex);
+    int cur = H(refIndex, readPos), next;
+    int initScore = (refIndex >= anchorLeft) ? S3_NEG_INF : 0;
+    int prevInitScore = (refIndex > anchorLeft) ? S3_NEG_INF : 0;
+    int state = 0;      // 0 NORMAL, 1 I_EXT, 2 D_EXT, 3 SM_EXIT, 4 SI_EXIT
+#define S3_NEXT_REF() { --refIndex; refChar = refAt(refIndex); initScore = prevInitScore; prevInitScore = (refIndex > anchorLeft) ? S3_NEG_INF : 0; }
+#define S3_NEXT_READ() { --readPos; readChar = readAt(readPos); }
+    while (readPos > 0 && refIndex > 0) {
+        if (state == 0) {
+            const int d = (refChar == readChar) ? a.match : a.mismatch;
+            if (cur == d + (next = H(refIndex - 1, readPos - 1))) {
+                pat[p++] = (refChar == readChar) ? 'M' : 'm';
+                S3_NEXT_REF(); S3_NEXT_READ();
+                cur = next;
+            } else if (cur == open + (next = H(refIndex - 1, readPos))) {
+                pat[p++] = 'D';
+                S3_NEXT_REF();
+                cur = next;
+            } else if (cur == ext + Eprev(refIndex, readPos)) {
+                pat[p++] = 'D';
+                S3_NEXT_REF();
+                cur = (short)(cur - ext);
+                state = 2;
+            } else {
+                if (readPos <= clipLt + 1) {
+                    if (cur == prevInitScore + d) { state = 3; break; }
+                    else if (cur == initScore + open) { state = 4; break; }
+                }
+                if (cur == open + (next = H(refIndex, readPos - 1))) {
+                    pat[p++] = 'I';
+                    S3_NEXT_READ();
+                    cur = next;
+                } else {
+                    pat[p++] = 'I';
+                    S3_NEXT_READ();
+                    cur = (short)(cur - ext);
+                    state = 1;
+                }
+            }
+        } else {
+            if (state == 2) {
+                pat[p++] = 'D';
+                S3_NEXT_REF();
+            } else {
+                if (readPos <= clipLt + 1 && cur == initScore + open) { state = 4; break; }
+                pat[p++] = 'I';
+                S3_NEXT_READ();
+            }
+            if (cur == open + (next = H(refIndex, readPos))) { state = 0; cur = next; }
+            else cur = (short)(cur - ext);
+        }
+    }
+#undef S3_NEXT_REF
+#undef S3_NEXT_READ
+    if (refIndex == 0) {
+        const uint32_t scNum = min(clipLt, readPos);
+        if (scNum < readPos) { pat[p++] = 'I'; pat[p++] = 'V'; pat[p++] = (uint8_t)(readPos - scNum); }
+        pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)scNum;
+    } else if (state == 4) {
+        pat[p++] = 'I'; pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(readPos - 1);
+    } else if (state == 3) {
+        pat[p++] = (refChar == readChar) ? 'M' : 'm';
+        pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)(readPos - 1);
+        refIndex -= 1;
+    }
+    pat[p++] = 0;
+    a.hit[id] = refIndex;        // start offset inside the window (refOffset == 0 in scheme 1)
+}
+
 static int pick_R(uint32_t maxReadLength)
 {
     static const int opts[] = {4, 5, 8, 16, 32};
@@ -283,18 +603,30 @@ extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint3
     if (!dp) { s3_set_error("out of host memory"); return S3_ENOMEM; }
     dp->device = device; dp->maxReadLength = maxReadLength; dp->maxDNALength = maxDNALength; dp->maxBatch = maxBatch;
     dp->sc = scores; dp->R = R; dp->slot = (R == 5) ? 8 : R;
+    // 16x2 lanes hold every intermediate value when rows fit 8 per lane, the score parameters are
+    // bytes and the best possible score stays below 32000 ("DP value range")
+    auto small = [](int v) { return v >= -127 && v <= 127; };
+    dp->narrow = maxReadLength <= 256 && small(scores.matchScore) && small(scores.mismatchScore) &&
+                 small(scores.gapOpenScore) && small(scores.gapExtendScore) &&
+                 (long long)scores.matchScore * maxReadLength <= 32000 && !getenv("S3_DP_FORCE_WIDE");
+    if (dp->narrow) dp->R = (maxReadLength <= 128) ? 4 : 8;
     S3_CUDA(cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking));
     dp->ownStream = 1;
-    const size_t perAlign = (size_t)(maxDNALength + 1) * 32 * dp->slot;
+    // traceback planes are sized per chunk of alignments; narrow: per PAIR (maxDNALength+32) steps x 32 lanes x
+    // R words of H, i.e. per alignment half of that
+    const size_t perAlign = dp->narrow
+        ? (size_t)(maxDNALength + 32) * 32 * 4 * dp->R / 2
+        : (size_t)(maxDNALength + 1) * 32 * dp->slot;
     size_t freeB = 0, totalB = 0;
     S3_CUDA(cudaMemGetInfo(&freeB, &totalB));
-    size_t budget = freeB / 8;
-    if (budget > ((size_t)8 << 30)) budget = (size_t)8 << 30;
+    size_t budget = freeB / 4;
+    if (budget > ((size_t)24 << 30)) budget = (size_t)24 << 30;
     size_t chunk = budget / perAlign;
     if (chunk > maxBatch) chunk = maxBatch;
-    if (chunk < 1) { s3_set_error("s3_dp_create: not enough device memory for one traceback plane"); return S3_ENOMEM; }
+    chunk = (chunk + 1) & ~(size_t)1;                 // whole pairs
+    if (chunk < 2) { s3_set_error("s3_dp_create: not enough device memory for one traceback plane"); return S3_ENOMEM; }
     dp->chunk = (uint32_t)chunk;
-    S3_CUDA(cudaMalloc(&dp->d_tb, chunk * perAlign));
+    S3_CUDA(cudaMalloc(&dp->d_tb, chunk * perAlign + 256));
     const size_t up = ((size_t)maxBatch + 31) / 32 * 32;
     const size_t dnaW = (maxDNALength + 15) >> 4, readW = (maxReadLength + 15) >> 4;
     S3_CUDA(cudaMalloc(&dp->d_scRight, up * 4));
@@ -345,9 +677,22 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t n)
     a.dnaWords = (dp->maxDNALength + 15) >> 4; a.readWords = (dp->maxReadLength + 15) >> 4;
     a.slot = dp->slot; a.tb = dp->d_tb; a.scRight = dp->d_scRight;
     a.match = dp->sc.matchScore; a.mismatch = dp->sc.mismatchScore; a.open = dp->sc.gapOpenScore; a.ext = dp->sc.gapExtendScore;
+    a.planeSteps = dp->maxDNALength + 32;
+    if (dp->narrow) a.hplane = reinterpret_cast<uint32_t *>(dp->d_tb);
     for (uint32_t first = 0; first < n; first += dp->chunk) {
         a.first = first;
         a.count = (n - first < dp->chunk) ? n - first : dp->chunk;
+        if (dp->narrow) {
+            const uint32_t pairs = (a.count + 1) / 2;
+            const uint32_t blocks = (pairs + S3_DP_WARPS - 1) / S3_DP_WARPS;
+            if (dp->R == 4) s3_dp_score16_kernel<4><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+            else s3_dp_score16_kernel<8><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+            S3_CUDA(cudaGetLastError());
+            s3_dp_traceback16_kernel<<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a, dp->R);
+            S3_LAUNCHED(2);
+            S3_CUDA(cudaGetLastError());
+            continue;
+        }
         switch (dp->R) {
         case 4: launch_score<4>(a, dp->stream); break;
         case 5: launch_score<5>(a, dp->stream); break;

@@ -55,7 +55,9 @@ int s3_pinned(s3_index *ix, size_t bytes, void **out)
 // reference's own sampled table (entry e = floor(192*b/128), sample position
 // 128*e <= 192*b, distance 0 or 64 bases) plus a direct count of those <= 64
 // bases, i.e. exactly how the reference kernel itself would evaluate
-// rank'(c, 192*b) (DV-Kernel.cu:256-280) -- no prefix scan needed.
+// rank'(c, 192*b) (DV-Kernel.cu:256-280) -- no prefix scan needed.  The bucket
+// then stores the count at its MIDDLE (192*b + 96) and the 192 bases as hi/lo
+// bit planes (layout in s3_common.cuh).
 __global__ void s3_relayout_kernel(const uint32_t *__restrict__ bwt, const uint32_t *__restrict__ occ,
                                    uint32_t textLength, uint32_t numWords, uint32_t numBuckets,
                                    uint4 *__restrict__ out)
@@ -75,17 +77,33 @@ __global__ void s3_relayout_kernel(const uint32_t *__restrict__ bwt, const uint3
 #pragma unroll
         for (int j = 0; j < 16; ++j) cnt[(word >> (2 * (15 - j))) & 3]++;
     }
-    uint32_t words[12];
+    // 12 source words (16 bases each, MSB first) -> 6 hi-plane + 6 lo-plane words (32 bases each, LSB first)
+    uint32_t hi[6], lo[6];
 #pragma unroll
-    for (int j = 0; j < 12; ++j) {
-        uint32_t wi = (start >> 4) + j;
-        words[j] = wi < numWords ? bwt[wi] : 0u;
+    for (int j = 0; j < 6; ++j) {
+        uint32_t h = 0, l = 0;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t wi = (start >> 4) + 2 * j + half;
+            uint32_t word = wi < numWords ? bwt[wi] : 0u;          // padding = code 0
+#pragma unroll
+            for (int t = 0; t < 16; ++t) {
+                uint32_t code = (word >> (2 * (15 - t))) & 3;
+                h |= (code >> 1) << (16 * half + t);
+                l |= (code & 1) << (16 * half + t);
+            }
+        }
+        hi[j] = h; lo[j] = l;
+        if (j < 3) {                              // first 96 bases move the count to the middle
+            uint32_t nT = __popc(h & l), nH = __popc(h), nL = __popc(l);
+            cnt[3] += nT; cnt[2] += nH - nT; cnt[1] += nL - nT; cnt[0] += 32 - nH - nL + nT;
+        }
     }
     uint4 *o = out + (size_t)b * 4;
     o[0] = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
-    o[1] = make_uint4(words[0], words[1], words[2], words[3]);
-    o[2] = make_uint4(words[4], words[5], words[6], words[7]);
-    o[3] = make_uint4(words[8], words[9], words[10], words[11]);
+    o[1] = make_uint4(hi[0], hi[1], hi[2], lo[0]);                 // half A: hi0 hi1 hi2 lo0 | lo1 lo2
+    o[2] = make_uint4(lo[1], lo[2], lo[4], lo[5]);                 //         ... | half B: lo1 lo2
+    o[3] = make_uint4(hi[3], hi[4], hi[5], lo[3]);                 // half B: hi0 hi1 hi2 lo0
 }
 
 static int upload_half(s3_index *ix, const uint32_t *bwt, const uint32_t *occ, uint32_t numOcc,
@@ -135,6 +153,9 @@ extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const u
     ix->device = device;
     ix->textLength = textLength;
     S3_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    S3_CUDA(cudaDeviceGetAttribute(&ix->numSms, cudaDevAttrMultiProcessorCount, device));
+    S3_CUDA(cudaMalloc(&ix->d_workCounter, 256));
+    ix->searchSmem = (size_t)-1;
     int rc;
     uint32_t nb = 0;
     if ((rc = upload_half(ix, bwt, occ, numOcc, textLength, &ix->d_fwd, &nb)) != S3_OK) return rc;
@@ -166,6 +187,7 @@ extern "C" void s3_index_free(s3_index *ix)
     cudaFree(ix->d_fwd); cudaFree(ix->d_rev);
     if (ix->d_packedDNA) cudaFree(ix->d_packedDNA);
     if (ix->d_sa) cudaFree(ix->d_sa);
+    if (ix->d_workCounter) cudaFree(ix->d_workCounter);
     if (ix->scratch) cudaFree(ix->scratch);
     if (ix->pinned) cudaFreeHost(ix->pinned);
     cudaStreamDestroy(ix->stream);

@@ -5,15 +5,23 @@
 // perform_round{1,2}_alignment (alignment.cu:118-531).
 //
 // Design (not a port): the reference spells each (case, mismatch set) as its
-// own force-inlined recursion (51 blocks).  Here a case is a small *program* of
-// phases (direction, read segment, min..max substitutions) interpreted by ONE
-// data-driven loop whose body is "do one LF-mapping step on both interval ends".
-// All lanes of a warp execute the same loop body whatever case / depth / strand
-// they are in, so the only divergence left is the (rare) push/pop of a
-// substitution frame.  The depth-first order of the reference -- substitutions
-// in ascending symbol order *before* following the read's base, phases in
-// program order -- is preserved, so the answer slots are bit-identical,
-// including which ranges survive when a slot overflows.
+// own force-inlined recursion (51 blocks) and runs one thread per read, so a
+// warp waits for its slowest read and its lanes sit in different recursions.
+// Here
+//   * a case is a small *program* of phases (direction, read segment, min..max
+//     substitutions) interpreted by ONE data-driven loop whose body is "one
+//     LF-mapping step on both interval ends" (two rank evaluations);
+//   * a lane is a depth-first enumerator with an explicit frame stack; every
+//     iteration of the warp's loop first lets each lane make its cheap,
+//     memory-free transitions (phase end, report, pop the next substitution
+//     branch, strand flip) and then ALL lanes evaluate their two ranks together;
+//   * work items (read, case) come from a global queue: a lane that finishes
+//     its item takes the next one, so lanes stay busy whatever the length of
+//     their own enumeration (persistent warps instead of one thread per read).
+// The depth-first order of the reference -- substitutions in ascending symbol
+// order *before* following the read's base, phases in program order, the
+// second strand appended to the first -- is preserved, so the answer slots are
+// bit-identical, including which ranges survive when a slot overflows.
 #include "s3_common.cuh"
 #include "../../include/soap3dp_b200.h"
 #include <cub/device/device_select.cuh>
@@ -85,8 +93,9 @@ struct S3SearchArgs {
     uint32_t wordPerQuery;
     uint32_t *answers[S3_MAX_NUM_CASES];
     uint32_t round, numMismatch, saRangeAllowed, wordPerAnswer;
-    uint32_t firstCase, exactNum;
+    uint32_t firstCase, numCases, exactNum;
     uint32_t textLength;
+    uint32_t *workCounter;               // zeroed before the launch
     unsigned long long *rankQueries;     // may be NULL
 };
 
@@ -113,119 +122,166 @@ __device__ __forceinline__ uint32_t s3_base(const uint32_t *sm, uint32_t pos, ui
     return strand ? 3 - v : v;
 }
 
+// a phase packed in one register: start[0:11] len[11:22] dir[22] lo[23:26] hi[26:29]
+__device__ __forceinline__ uint32_t s3_pack_phase(const S3Phase &ph)
+{
+    return ph.start | (ph.len << 11) | (ph.dir << 22) | (ph.lo << 23) | (ph.hi << 26);
+}
+
+#define S3_REFILL_MIN 4        // idle lanes a warp tolerates before it goes back to the work queue
+
 template <bool COUNT>
 __global__ void __launch_bounds__(S3_THREADS)
 s3_search_kernel(const S3Half fwd, const S3Half rev, const S3SearchArgs args)
 {
     extern __shared__ uint32_t s3_smem[];
-    const uint32_t q = blockIdx.x * S3_THREADS + threadIdx.x;
-    const uint32_t whichCase = args.firstCase + blockIdx.y;
+    uint32_t *sm = s3_smem + threadIdx.x;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t totalItems = args.numQueries * args.numCases;      // < 2^32 (host splits otherwise)
+    const uint32_t maxRanges = args.saRangeAllowed;
     unsigned long long nrank = 0;
-    if (q < args.numQueries) {
-        const uint32_t lane32 = q & 31;
-        const uint32_t *query = args.queries + (size_t)(q >> 5) * 32 * args.wordPerQuery + lane32;
-        uint32_t *answer = args.answers[whichCase] + (size_t)(q >> 5) * 32 * args.wordPerAnswer + lane32;
-        const uint32_t L = args.readLengths[q];
-        uint32_t *sm = s3_smem + threadIdx.x;
-        const uint32_t nw = (L + 15) >> 4;
-        for (uint32_t w = 0; w < nw; ++w) sm[w * S3_THREADS] = query[w * 32];
-        for (uint32_t i = 0; i < args.wordPerAnswer; ++i) answer[i * 32] = 0xFFFFFFFFu;
 
-        S3Phase ph[S3_MAX_PHASES];
-        uint32_t firstL;
-        const int nph = s3_case_program(args.numMismatch, whichCase, L, args.exactNum != 0, ph, firstL);
-        const uint32_t maxRanges = args.saRangeAllowed;
-        uint32_t saCount = 0;
-        // round 1: the device read buffer of the reference flips orientation after every
-        // launch, so odd cases meet the reverse strand first (DV-Kernel.cu:4280-4285)
-        uint32_t strand = args.round > 0 ? 0u : (whichCase & 1u);
-        S3Frame frames[S3_MAX_DEPTH];
+    // ---- per-lane enumerator state ----
+    bool has = false, dead = false, alive = false;
+    uint32_t L = 0, strand = 0, pass = 0, saCount = 0, firstL = 0, nph = 0;
+    uint32_t prog[S3_MAX_PHASES] = {0, 0, 0, 0};
+    uint32_t pstart = 0, plen = 0, pdir = 0, plo = 0, phi = 0;        // current phase, unpacked
+    uint32_t p = 0, done = 0, mmp = 0, mmt = 0, depth = 0;
+    uint32_t l = 0, r = 0, rl = 0, rr = 0;
+    uint32_t *answer = NULL;
+    S3Frame frames[S3_MAX_DEPTH];
 
-        for (int pass = 0; pass < 2 && nph > 0; ++pass, strand ^= 1u) {
-            int depth = 0;
-            uint32_t p = 0, done = 0, mmp = 0, mmt = 0;
-            uint32_t l = firstL, r = args.textLength, rl = 0, rr = args.textLength;
-            bool alive = true;
-            while (true) {
-                if (saCount > maxRanges) break;
-                if (alive && done == ph[p].len) {
-                    // end of a phase
-                    if (mmp < ph[p].lo) alive = false;
-                    else if ((int)p + 1 == nph) {
-                        // report (DV-Kernel.cu:355-380)
-                        if (saCount < maxRanges) {
-                            answer[32 * 2 * saCount] = l;
-                            answer[32 * (2 * saCount + 1)] = (r - l) + (strand << 27) + (mmt << 24);
-                        }
-                        ++saCount;
-                        alive = false;
-                    } else { ++p; done = 0; mmp = 0; continue; }
-                }
-                if (alive) {
-                    const uint32_t dir = ph[p].dir;
-                    const uint32_t pos = dir ? ph[p].start + done : ph[p].start + ph[p].len - 1 - done;
-                    const uint32_t c = s3_base(sm, pos, L, strand);
-                    uint32_t a[4], b[4];
-                    if (dir) { s3_rank4(rev, rl, a); s3_rank4(rev, rr + 1, b); }
-                    else     { s3_rank4(fwd, l, a);  s3_rank4(fwd, r + 1, b); }
-                    if (COUNT) nrank += 2;
-                    if (mmp < ph[p].hi) {
-                        // does any substitution child survive?  (most do not once the interval is narrow)
-                        uint32_t live = 0;
+    auto load_phase = [&](uint32_t k) {
+        const uint32_t w = (k == 0) ? prog[0] : (k == 1) ? prog[1] : (k == 2) ? prog[2] : prog[3];
+        pstart = w & 0x7FF; plen = (w >> 11) & 0x7FF; pdir = (w >> 22) & 1; plo = (w >> 23) & 7; phi = (w >> 26) & 7;
+    };
+    auto start_pass = [&]() {
+        depth = 0; p = 0; done = 0; mmp = 0; mmt = 0;
+        l = firstL; r = args.textLength; rl = 0; rr = args.textLength;
+        alive = nph > 0;
+        load_phase(0);
+    };
+
+    while (true) {
+        // ---- (R) refill idle lanes from the global queue ----
+        const uint32_t want = __ballot_sync(0xFFFFFFFFu, !has && !dead);
+        const uint32_t busy = __ballot_sync(0xFFFFFFFFu, has);
+        if (!want && !busy) break;
+        if (want && ((uint32_t)__popc(want) >= S3_REFILL_MIN || !busy)) {
+            uint32_t base = 0;
+            if (lane == 0) base = atomicAdd(args.workCounter, (uint32_t)__popc(want));
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (!has && !dead) {
+                const uint32_t item = base + __popc(want & ((1u << lane) - 1u));
+                // the queue runs case-major so that a full warp refill reads 32 consecutive reads
+                if (item >= totalItems || item < base) dead = true;
+                else {
+                    const uint32_t ci = item / args.numQueries, q = item - ci * args.numQueries;
+                    const uint32_t whichCase = args.firstCase + ci;
+                    const uint32_t *query = args.queries + (size_t)(q >> 5) * 32 * args.wordPerQuery + (q & 31);
+                    answer = args.answers[whichCase] + (size_t)(q >> 5) * 32 * args.wordPerAnswer + (q & 31);
+                    L = args.readLengths[q];
+                    const uint32_t nw = (L + 15) >> 4;
+                    for (uint32_t w = 0; w < nw; ++w) sm[w * S3_THREADS] = query[w * 32];
+                    S3Phase ph[S3_MAX_PHASES];
+                    nph = (uint32_t)s3_case_program(args.numMismatch, whichCase, L, args.exactNum != 0, ph, firstL);
 #pragma unroll
-                        for (uint32_t e = 0; e < 4; ++e) live |= (e != c && a[e] + 1 <= b[e]) ? (1u << e) : 0u;
-                        if (live) {
-                            S3Frame &f = frames[depth++];
-#pragma unroll
-                            for (int e = 0; e < 4; ++e) { f.a[e] = a[e]; f.b[e] = b[e]; }
-                            f.r = r; f.rr = rr;
-                            f.meta = s3_meta(done, p, mmp, mmt, 0, c);
-                            alive = false;     // children are taken from the frame below
-                        }
-                    }
-                    if (alive) {
-                        // follow the read's base
-                        const uint32_t cum = (c < 3 ? b[3] - a[3] : 0) + (c < 2 ? b[2] - a[2] : 0) + (c < 1 ? b[1] - a[1] : 0);
-                        if (dir) { rl = a[c] + 1; rr = b[c]; r = r - cum; l = r - (rr - rl); }
-                        else     { l = a[c] + 1; r = b[c]; rr = rr - cum; rl = rr - (r - l); }
-                        ++done;
-                        alive = (l <= r);
-                    }
-                }
-                if (!alive) {
-                    // take the next pending branch from the innermost frame
-                    if (depth == 0) break;
-                    S3Frame &f = frames[depth - 1];
-                    const uint32_t meta = f.meta;
-                    const uint32_t c = (meta >> 22) & 3;
-                    uint32_t e = (meta >> 19) & 7;
-                    p = (meta >> 11) & 3; done = meta & 0x7FF; mmp = (meta >> 13) & 7; mmt = (meta >> 16) & 7;
-                    const uint32_t dir = ph[p].dir;
-                    // next substitution symbol with a non-empty interval, ascending
-                    while (e < 4 && (e == c || f.a[e] + 1 > f.b[e])) ++e;
-                    uint32_t sym;
-                    if (e < 4) { sym = e; f.meta = (meta & ~(7u << 19)) | ((e + 1) << 19); ++mmp; ++mmt; }
-                    else { sym = c; --depth; }             // finally the read's own base; frame retired
-                    uint32_t cum = 0;
-                    for (uint32_t j = 3; j > sym; --j) cum += f.b[j] - f.a[j];
-                    const uint32_t nlo = f.a[sym] + 1, nhi = f.b[sym];
-                    if (dir) { rl = nlo; rr = nhi; r = f.r - cum; l = r - (rr - rl); }
-                    else     { l = nlo; r = nhi; rr = f.rr - cum; rl = rr - (r - l); }
-                    ++done;
-                    alive = (l <= r);
+                    for (int k = 0; k < S3_MAX_PHASES; ++k) prog[k] = (k < (int)nph) ? s3_pack_phase(ph[k]) : 0u;
+                    // round 1: the device read buffer of the reference flips orientation after every
+                    // launch, so odd cases meet the reverse strand first (DV-Kernel.cu:4280-4285)
+                    strand = args.round > 0 ? 0u : (whichCase & 1u);
+                    pass = 0; saCount = 0; has = true;
+                    start_pass();
                 }
             }
-            if (saCount > maxRanges) break;
         }
-        // status word (DV-Kernel.cu:4468-4491); the isBad carry between the cases of
-        // round 1 is applied by s3_isbad_fixup_kernel because cases run concurrently here
-        if (saCount == 0) answer[0] = 0xFFFFFFFDu;
-        else if (saCount > maxRanges) answer[0] = 0xFFFFFFFEu;
+        // ---- (A) memory-free transitions until this lane stands on a node that needs its ranks ----
+        while (has) {
+            if (alive) {
+                if (done < plen) break;
+                // end of a phase
+                if (mmp < plo) alive = false;
+                else if (p + 1 == nph) {
+                    // report (DV-Kernel.cu:355-380)
+                    if (saCount < maxRanges) {
+                        answer[32 * 2 * saCount] = l;
+                        answer[32 * (2 * saCount + 1)] = (r - l) + (strand << 27) + (mmt << 24);
+                    }
+                    ++saCount;
+                    alive = false;
+                    if (saCount > maxRanges) { answer[0] = 0xFFFFFFFEu; has = false; }     // overflow ends the item
+                } else { ++p; done = 0; mmp = 0; load_phase(p); }
+            } else if (depth == 0) {
+                // this strand is exhausted
+                if (pass == 0 && nph > 0) { pass = 1; strand ^= 1u; start_pass(); }
+                else {
+                    // status word (DV-Kernel.cu:4468-4491); the isBad carry between the cases of round 1
+                    // is applied by s3_isbad_fixup_kernel because cases run concurrently here
+                    if (saCount == 0) answer[0] = 0xFFFFFFFDu;
+                    has = false;
+                }
+            } else {
+                // take the next pending branch from the innermost frame
+                S3Frame &f = frames[depth - 1];
+                const uint32_t meta = f.meta;
+                const uint32_t c = (meta >> 22) & 3;
+                uint32_t e = (meta >> 19) & 7;
+                const uint32_t fp = (meta >> 11) & 3;
+                if (fp != p) { p = fp; load_phase(p); }
+                done = meta & 0x7FF; mmp = (meta >> 13) & 7; mmt = (meta >> 16) & 7;
+                // next substitution symbol with a non-empty interval, ascending
+                while (e < 4 && (e == c || f.a[e] + 1 > f.b[e])) ++e;
+                uint32_t sym;
+                if (e < 4) { sym = e; f.meta = (meta & ~(7u << 19)) | ((e + 1) << 19); ++mmp; ++mmt; }
+                else { sym = c; --depth; }             // finally the read's own base; frame retired
+                uint32_t cum = 0;
+                for (uint32_t j = 3; j > sym; --j) cum += f.b[j] - f.a[j];
+                const uint32_t nlo = f.a[sym] + 1, nhi = f.b[sym];
+                if (pdir) { rl = nlo; rr = nhi; r = f.r - cum; l = r - (rr - rl); }
+                else      { l = nlo; r = nhi; rr = f.rr - cum; rl = rr - (r - l); }
+                ++done;
+                alive = (l <= r);
+            }
+        }
+        __syncwarp();
+        // ---- (B) one LF-mapping step for every lane that has work ----
+        if (has) {
+            const uint32_t pos = pdir ? pstart + done : pstart + plen - 1 - done;
+            const uint32_t c = s3_base(sm, pos, L, strand);
+            uint32_t a[4], b[4];
+            if (pdir) { s3_rank4(rev, rl, a); s3_rank4(rev, rr + 1, b); }
+            else      { s3_rank4(fwd, l, a);  s3_rank4(fwd, r + 1, b); }
+            if (COUNT) nrank += 2;
+            bool pushed = false;
+            if (mmp < phi) {
+                // does any substitution child survive?  (most do not once the interval is narrow)
+                uint32_t live = 0;
+#pragma unroll
+                for (uint32_t e = 0; e < 4; ++e) live |= (e != c && a[e] + 1 <= b[e]) ? (1u << e) : 0u;
+                if (live) {
+                    S3Frame &f = frames[depth++];
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) { f.a[e] = a[e]; f.b[e] = b[e]; }
+                    f.r = r; f.rr = rr;
+                    f.meta = s3_meta(done, p, mmp, mmt, 0, c);
+                    alive = false;     // children are taken from the frame in (A)
+                    pushed = true;
+                }
+            }
+            if (!pushed) {
+                // follow the read's base
+                const uint32_t cum = (c < 3 ? b[3] - a[3] : 0) + (c < 2 ? b[2] - a[2] : 0) + (c < 1 ? b[1] - a[1] : 0);
+                if (pdir) { rl = a[c] + 1; rr = b[c]; r = r - cum; l = r - (rr - rl); }
+                else      { l = a[c] + 1; r = b[c]; rr = rr - cum; rl = rr - (r - l); }
+                ++done;
+                alive = (l <= r);
+            }
+        }
     }
     if (COUNT) {
         // warp-aggregate then one atomic per warp
         for (int o = 16; o > 0; o >>= 1) nrank += __shfl_down_sync(0xFFFFFFFFu, nrank, o);
-        if ((threadIdx.x & 31) == 0 && nrank) atomicAdd(args.rankQueries, nrank);
+        if (lane == 0 && nrank) atomicAdd(args.rankQueries, nrank);
     }
 }
 
@@ -246,17 +302,31 @@ __global__ void s3_isbad_fixup_kernel(S3SearchArgs args, uint32_t numCases)
     }
 }
 
+// Persistent launch: as many blocks as fit on the device at once (or fewer when the batch is
+// small); every warp pulls (read, case) items from args.workCounter.  The caller has filled the
+// answer buffers with 0xFF (the "unused" word, DV-Kernel.cu:4268-4276).
 static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool count)
 {
     if (a.numQueries == 0) return S3_OK;
-    dim3 grid((a.numQueries + S3_THREADS - 1) / S3_THREADS, numCases);
-    size_t smem = (size_t)a.wordPerQuery * S3_THREADS * sizeof(uint32_t);
-    if (smem > 48 * 1024) {
+    a.numCases = numCases;
+    a.workCounter = ix->d_workCounter;
+    const size_t smem = (size_t)a.wordPerQuery * S3_THREADS * sizeof(uint32_t);
+    if (smem != ix->searchSmem) {
         S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        int perSm = 0;
+        S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, s3_search_kernel<false>, S3_THREADS, smem));
+        if (perSm < 1) { s3_set_error("search kernel does not fit on an SM with wordPerQuery %u", a.wordPerQuery); return S3_EINVAL; }
+        ix->searchSmem = smem;
+        ix->searchBlocksPerSm = perSm;
     }
-    if (count) s3_search_kernel<true><<<grid, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, a);
-    else s3_search_kernel<false><<<grid, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, a);
+    const unsigned long long items = (unsigned long long)a.numQueries * numCases;
+    unsigned long long blocks = (items + S3_THREADS - 1) / S3_THREADS;
+    const unsigned long long resident = (unsigned long long)ix->numSms * ix->searchBlocksPerSm;
+    if (blocks > resident) blocks = resident;
+    S3_CUDA(cudaMemsetAsync(ix->d_workCounter, 0, sizeof(uint32_t), ix->stream));
+    if (count) s3_search_kernel<true><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, a);
+    else s3_search_kernel<false><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, a);
     S3_LAUNCHED(1);
     S3_CUDA(cudaGetLastError());
     return S3_OK;
@@ -277,7 +347,7 @@ static int check_search_args(const char *fn, s3_index *ix, const void *q, const 
         s3_set_error("%s: wordPerAns %u < 2*saRangeAllowed %u", fn, wordPerAns, saRangeAllowed);
         return S3_EINVAL;
     }
-    if (batchSize > 0xFFFFFFFFull) { s3_set_error("%s: batch too large", fn); return S3_EINVAL; }
+    if (batchSize * numCases > 0xF0000000ull) { s3_set_error("%s: batch too large (batchSize * numCases must stay below 2^32)", fn); return S3_EINVAL; }
     return S3_OK;
 }
 
@@ -299,6 +369,8 @@ extern "C" int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, 
     a.round = 0; a.numMismatch = numMismatch; a.saRangeAllowed = saRangeAllowed; a.wordPerAnswer = wordPerAns;
     a.firstCase = 0; a.exactNum = isExactNumMismatch ? 1 : 0; a.textLength = ix->textLength;
     a.rankQueries = d_rankQueries;
+    const size_t aBytes = (batchSize + 31) / 32 * 32 * wordPerAns * sizeof(uint32_t);
+    for (uint32_t c = 0; c < numCases; ++c) S3_CUDA(cudaMemsetAsync(d_answers[c], 0xFF, aBytes, ix->stream));
     if ((rc = launch_search(ix, a, numCases, d_rankQueries != NULL))) return rc;
     if (numCases > 1 && batchSize > 0) {
         s3_isbad_fixup_kernel<<<(unsigned)((batchSize + 255) / 256), 256, 0, ix->stream>>>(a, numCases);

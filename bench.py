@@ -366,7 +366,7 @@ def main():
         return
 
     gi = upload_index(host, local_rank)
-    log(f"index on device: {gi.device_bytes / 1e9:.2f} GB in 64-byte buckets")
+    log(f"index on device: {gi.device_bytes / 1e9:.2f} GB in 32-byte single-sector buckets")
     stream = torch.cuda.ExternalStream(gi.stream, device=device)
     total = args.warmup + args.steps
     t0 = time.time()
@@ -527,6 +527,7 @@ def main():
         "roofline": {"kernel": "s3_search_kernel", "bound": "hbm", "achieved": search_gbs, "peak": hbm_peak,
                      "unit": "GB/s", "frac": search_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
                      "rank_queries_per_launch": nrank_total / args.steps, "bytes_per_rank_query": 64,
+                     "bytes_touched_per_rank_query": 32,
                      "ms_per_launch": 1e3 * t_search / args.steps, "share_of_step": t_search / (t_search + t_dp)},
         "dp": {"kernel": "s3_dp_score_kernel+s3_dp_traceback_kernel", "gcups": dp_gcups,
                "alignments_per_step": float(np.mean([rescue[args.warmup + k].n for k in range(args.steps)])),

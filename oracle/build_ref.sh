@@ -82,3 +82,18 @@ sed -n '35,512p' "$REF/DV-DPfunctions.cu" \
 $CXX -O2 -fopenmp -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$HERE/ref_shim" \
     "$HERE/ref_shim/ref_dp_host.cpp" -o "$OUT/libref_dp.so"
 echo "[build_ref] libref_dp.so OK"
+
+# ---- the reference-side shim compiles against the reference's unmodified headers --------------
+# (integration/soap3dp_b200_shim.cpp = the file a SOAP3-dp maintainer links instead of the device
+# code of alignment.cu / DV-DPfunctions.cu; the object is only a compile check and is not used)
+NVCC=${S3_NVCC:-/usr/local/cuda/bin/nvcc}
+if [ -x "$NVCC" ]; then
+  $NVCC -x cu -c -w -Xcompiler -fpermissive -ccbin "$CXX" -gencode arch=compute_100a,code=sm_100a \
+      -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -I"$HERE/../include" \
+      "$HERE/../integration/soap3dp_b200_shim.cpp" -o "$OUT/obj/soap3dp_b200_shim.o"
+  for sym in _Z14GPUINDEXUploadP10Soap3IndexPPjS2_S2_S2_ _Z24perform_round1_alignmentPjS_PA10_S_jjjjjbijyP10Soap3IndexS_S_S_S_ \
+             _ZN17SemiGlobalAligner16performAlignmentEPjS0_S0_S0_PiS1_S0_S0_PhiS0_S0_S0_S0_; do
+    nm "$OUT/obj/soap3dp_b200_shim.o" | grep -q " T $sym" || { echo "[build_ref] shim lacks $sym" >&2; exit 1; }
+  done
+  echo "[build_ref] integration shim compiles against the reference headers"
+fi

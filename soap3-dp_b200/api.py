@@ -53,10 +53,11 @@ def load_library() -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise S3Error(f"{LIB_PATH} is not built (run `python __graft_entry__.py build`); "
+    path = os.environ.get("S3_LIB_PATH", LIB_PATH)      # tuning experiments load a variant build of the same library
+    if not os.path.exists(path):
+        raise S3Error(f"{path} is not built (run `python __graft_entry__.py build`); "
                       "soap3dp_b200 has no CPU fallback")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(path)
     lib.s3_last_error.restype = C.c_char_p
     lib.s3_device_count.restype = C.c_int
     lib.s3_launch_count.restype = C.c_ulonglong

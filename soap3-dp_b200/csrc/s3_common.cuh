@@ -1,14 +1,13 @@
 // s3_common.cuh -- shared device structures of the B200 hot path.
 //
 // Index layout in HBM (DESIGN.md "data layout"): per direction an array of
-// 64-byte, 64-byte-aligned buckets, one per 192 BWT positions:
-//     bytes  0..15  cnt[4]    cnt[c] = cumulativeFreq[c] + Occ(c, 192*b + 96)   (count at the bucket MIDDLE)
-//     bytes 16..39  half A    bases 0..95  as bit planes: hi0 hi1 hi2 lo0 | lo1 lo2
-//     bytes 40..63  half B    bases 96..191 as bit planes: lo1 lo2 | hi0 hi1 hi2 lo0
-// A base's 2-bit code is split into a "hi" and a "lo" plane (base k of a half is bit
-// k%32 of plane word k/32), so the four symbol counts of up to 96 bases cost 9 POPC
-// (hi, lo, hi&lo per word) and rank'(c, i) counts forward or backward from the middle:
-// at most 96 bases, one 16 B + one 16 B + one 8 B load inside ONE 64-byte line.  The
+// 32-byte, 32-byte-aligned buckets -- ONE DRAM sector -- one per 64 BWT positions:
+//     bytes  0..15  cnt[4]        cnt[c] = cumulativeFreq[c] + Occ(c, 64*b + 32)   (count at the bucket MIDDLE)
+//     bytes 16..23  hiA loA       bases  0..31 as two bit planes (base k = bit k)
+//     bytes 24..31  hiB loB       bases 32..63
+// A base's 2-bit code is split into a "hi" and a "lo" plane, so the four symbol counts of
+// up to 32 bases cost 3 POPC (hi, lo, hi&lo), and rank'(c, i) counts forward or backward
+// from the middle: ONE 256-bit load (LDG.E.256) of ONE sector per rank evaluation.  The
 // reference needs a 16 B occ load and a 16 B BWT load from two different cache lines and
 // counts 2-bit codes with 64-bit masks (DV-Kernel.cu:27-280).  Positions past the end of
 // the text are padded with code 0 and counted as such on both sides of the middle, so
@@ -18,11 +17,11 @@
 #include <stdint.h>
 #include <stdio.h>
 
-#define S3_BUCKET_BASES 192u
+#define S3_BUCKET_BASES 64u
 #define S3_THREADS 128
 
 struct S3Half {
-    const uint4 *buckets;     // 4 x uint4 per bucket
+    const uint4 *buckets;     // 2 x uint4 per bucket
     uint32_t inverseSa0;
     uint32_t numBuckets;
 };
@@ -64,38 +63,44 @@ int s3_pinned(s3_index *ix, size_t bytes, void **out);
 // ---- rank'(., idx) for all four symbols ------------------------------------
 // Mathematically the reference's GPUBWTAllOccValue (DV-Kernel.cu:282-299):
 // C[c] + #{c in BWT[0, idx)} with the "$ is not stored" shift.
-__device__ __forceinline__ uint32_t s3_shl_clamp(uint32_t a, uint32_t s)
+// Two stages so that a caller can put the loads of several rank evaluations in flight
+// before the first POPC waits on one of them.
+struct S3Bucket {
+    uint32_t c0, c1, c2, c3;     // counts at the bucket middle
+    uint32_t hiA, loA, hiB, loB; // bit planes of bases 0..31 and 32..63
+    uint32_t rem;                // position inside the bucket (0..63)
+};
+
+__device__ __forceinline__ S3Bucket s3_rank_load(const uint4 *buckets, uint32_t inverseSa0, uint32_t idx)
 {
-    uint32_t d;                                   // PTX shl clamps shift amounts > 32 to 32 (result 0)
-    asm("shl.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(s));
-    return d;
+    S3Bucket k;
+    idx -= (idx > inverseSa0);
+    k.rem = idx & 63u;
+    const uint4 *p = buckets + (size_t)(idx >> 6) * 2;
+    // one sector, one instruction (LDG.E.256, sm_100+)
+    asm("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+        : "=r"(k.c0), "=r"(k.c1), "=r"(k.c2), "=r"(k.c3), "=r"(k.hiA), "=r"(k.loA), "=r"(k.hiB), "=r"(k.loB)
+        : "l"(p));
+    return k;
+}
+
+__device__ __forceinline__ void s3_rank_count(const S3Bucket &k, uint32_t &o0, uint32_t &o1, uint32_t &o2, uint32_t &o3)
+{
+    const bool isB = k.rem >= 32u;               // first half: count [x,32) and subtract; second: count [0,x) and add
+    const uint32_t x = k.rem & 31u;
+    const uint32_t m = isB ? ~(0xFFFFFFFFu << x) : (0xFFFFFFFFu << x);
+    const uint32_t h = (isB ? k.hiB : k.hiA) & m, l = (isB ? k.loB : k.loA) & m;
+    const uint32_t nHi = __popc(h), nLo = __popc(l), nT = __popc(h & l);
+    const uint32_t len = isB ? x : 32u - x;
+    const uint32_t cA = len - nHi - nLo + nT, cC = nLo - nT, cG = nHi - nT;
+    o0 = isB ? k.c0 + cA : k.c0 - cA;
+    o1 = isB ? k.c1 + cC : k.c1 - cC;
+    o2 = isB ? k.c2 + cG : k.c2 - cG;
+    o3 = isB ? k.c3 + nT : k.c3 - nT;
 }
 
 __device__ __forceinline__ void s3_rank4(const S3Half &h, uint32_t idx, uint32_t out[4])
 {
-    idx -= (idx > h.inverseSa0);
-    const uint32_t b = __umulhi(idx, 0xAAAAAAABu) >> 7;          // idx / 192
-    const uint32_t rem = idx - b * S3_BUCKET_BASES;
-    const bool isB = rem >= 96u;
-    const uint32_t x = isB ? rem - 96u : rem;                     // position inside the half
-    const uint4 *p = h.buckets + (size_t)b * 4;
-    const uint4 cnt = __ldg(p);
-    const uint4 hv = __ldg(p + (isB ? 3 : 1));                    // hi0 hi1 hi2 lo0
-    const uint2 lv = __ldg(reinterpret_cast<const uint2 *>(p) + (isB ? 5 : 4));   // lo1 lo2
-    // half A counts bases [x, 96) (subtracted), half B counts bases [0, x) (added)
-    const uint32_t flip = isB ? 0xFFFFFFFFu : 0u;
-    const uint32_t m0 = s3_shl_clamp(0xFFFFFFFFu, x) ^ flip;
-    const uint32_t m1 = s3_shl_clamp(0xFFFFFFFFu, (uint32_t)max((int)x - 32, 0)) ^ flip;
-    const uint32_t m2 = s3_shl_clamp(0xFFFFFFFFu, (uint32_t)max((int)x - 64, 0)) ^ flip;
-    const uint32_t h0 = hv.x & m0, h1 = hv.y & m1, h2 = hv.z & m2;
-    const uint32_t l0 = hv.w & m0, l1 = lv.x & m1, l2 = lv.y & m2;
-    const uint32_t nHi = __popc(h0) + __popc(h1) + __popc(h2);
-    const uint32_t nLo = __popc(l0) + __popc(l1) + __popc(l2);
-    const uint32_t nT = __popc(h0 & l0) + __popc(h1 & l1) + __popc(h2 & l2);
-    const uint32_t len = isB ? x : 96u - x;
-    const uint32_t cA = len - nHi - nLo + nT, cC = nLo - nT, cG = nHi - nT;
-    out[0] = isB ? cnt.x + cA : cnt.x - cA;
-    out[1] = isB ? cnt.y + cC : cnt.y - cC;
-    out[2] = isB ? cnt.z + cG : cnt.z - cG;
-    out[3] = isB ? cnt.w + nT : cnt.w - nT;
+    const S3Bucket k = s3_rank_load(h.buckets, h.inverseSa0, idx);
+    s3_rank_count(k, out[0], out[1], out[2], out[3]);
 }

@@ -51,59 +51,50 @@ int s3_pinned(s3_index *ix, size_t bytes, void **out)
     return S3_OK;
 }
 
-// One thread per bucket.  The running counts at 192*b are taken from the
-// reference's own sampled table (entry e = floor(192*b/128), sample position
-// 128*e <= 192*b, distance 0 or 64 bases) plus a direct count of those <= 64
-// bases, i.e. exactly how the reference kernel itself would evaluate
-// rank'(c, 192*b) (DV-Kernel.cu:256-280) -- no prefix scan needed.  The bucket
-// then stores the count at its MIDDLE (192*b + 96) and the 192 bases as hi/lo
-// bit planes (layout in s3_common.cuh).
+// One thread per bucket.  The running counts at the bucket MIDDLE (64*b + 32) are taken from
+// the reference's own sampled table (entry e = floor((64*b+32)/128), sample position 128*e,
+// distance 32 or 96 bases) plus a direct count of those bases, i.e. exactly how the reference
+// kernel itself would evaluate rank'(c, 64*b+32) (DV-Kernel.cu:256-280) -- no prefix scan
+// needed.  The 64 bases become hi/lo bit planes (layout in s3_common.cuh).
 __global__ void s3_relayout_kernel(const uint32_t *__restrict__ bwt, const uint32_t *__restrict__ occ,
                                    uint32_t textLength, uint32_t numWords, uint32_t numBuckets,
                                    uint4 *__restrict__ out)
 {
     uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= numBuckets) return;
-    uint32_t start = b * S3_BUCKET_BASES;
-    uint32_t e = start >> 7;
+    const uint32_t start = b * S3_BUCKET_BASES, mid = start + 32;
+    const uint32_t e = mid >> 7;
     uint32_t cnt[4];
 #pragma unroll
     for (int c = 0; c < 4; ++c) cnt[c] = occ[4 * e + c];
-    uint32_t w = (e << 7) >> 4;                  // first word of the sample block
-    uint32_t gap = start - (e << 7);             // 0 or 64 bases
-    for (uint32_t k = 0; k < gap; k += 16, ++w) {
-        uint32_t word = w < numWords ? bwt[w] : 0u;
-        // bases beyond the text are never counted: start <= textLength
+    // bases [128e, mid): whole 16-base words (mid - 128e is 32 or 96); padding past the text = code 0,
+    // counted here and by the kernel alike
+    for (uint32_t w = (e << 7) >> 4; w < (mid >> 4); ++w) {
+        const uint32_t word = w < numWords ? bwt[w] : 0u;
 #pragma unroll
         for (int j = 0; j < 16; ++j) cnt[(word >> (2 * (15 - j))) & 3]++;
     }
-    // 12 source words (16 bases each, MSB first) -> 6 hi-plane + 6 lo-plane words (32 bases each, LSB first)
-    uint32_t hi[6], lo[6];
+    // 4 source words (16 bases each, MSB first) -> 2 hi-plane + 2 lo-plane words (32 bases each, LSB first)
+    uint32_t hi[2], lo[2];
 #pragma unroll
-    for (int j = 0; j < 6; ++j) {
+    for (int j = 0; j < 2; ++j) {
         uint32_t h = 0, l = 0;
 #pragma unroll
         for (int half = 0; half < 2; ++half) {
-            uint32_t wi = (start >> 4) + 2 * j + half;
-            uint32_t word = wi < numWords ? bwt[wi] : 0u;          // padding = code 0
+            const uint32_t wi = (start >> 4) + 2 * j + half;
+            const uint32_t word = wi < numWords ? bwt[wi] : 0u;
 #pragma unroll
             for (int t = 0; t < 16; ++t) {
-                uint32_t code = (word >> (2 * (15 - t))) & 3;
+                const uint32_t code = (word >> (2 * (15 - t))) & 3;
                 h |= (code >> 1) << (16 * half + t);
                 l |= (code & 1) << (16 * half + t);
             }
         }
         hi[j] = h; lo[j] = l;
-        if (j < 3) {                              // first 96 bases move the count to the middle
-            uint32_t nT = __popc(h & l), nH = __popc(h), nL = __popc(l);
-            cnt[3] += nT; cnt[2] += nH - nT; cnt[1] += nL - nT; cnt[0] += 32 - nH - nL + nT;
-        }
     }
-    uint4 *o = out + (size_t)b * 4;
+    uint4 *o = out + (size_t)b * 2;
     o[0] = make_uint4(cnt[0], cnt[1], cnt[2], cnt[3]);
-    o[1] = make_uint4(hi[0], hi[1], hi[2], lo[0]);                 // half A: hi0 hi1 hi2 lo0 | lo1 lo2
-    o[2] = make_uint4(lo[1], lo[2], lo[4], lo[5]);                 //         ... | half B: lo1 lo2
-    o[3] = make_uint4(hi[3], hi[4], hi[5], lo[3]);                 // half B: hi0 hi1 hi2 lo0
+    o[1] = make_uint4(hi[0], lo[0], hi[1], lo[1]);
 }
 
 static int upload_half(s3_index *ix, const uint32_t *bwt, const uint32_t *occ, uint32_t numOcc,
@@ -116,7 +107,7 @@ static int upload_half(s3_index *ix, const uint32_t *bwt, const uint32_t *occ, u
     S3_CUDA(cudaMalloc(&d_occ, (size_t)numOcc * 4 * sizeof(uint32_t)));
     S3_CUDA(cudaMemcpyAsync(d_bwt, bwt, numWords * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
     S3_CUDA(cudaMemcpyAsync(d_occ, occ, (size_t)numOcc * 4 * sizeof(uint32_t), cudaMemcpyHostToDevice, ix->stream));
-    S3_CUDA(cudaMalloc(d_out, (size_t)numBuckets * 64));
+    S3_CUDA(cudaMalloc(d_out, (size_t)numBuckets * 32));
     s3_relayout_kernel<<<(numBuckets + 255) / 256, 256, 0, ix->stream>>>(d_bwt, d_occ, textLength,
                                                                         (uint32_t)numWords, numBuckets, *d_out);
     S3_LAUNCHED(1);
@@ -125,7 +116,7 @@ static int upload_half(s3_index *ix, const uint32_t *bwt, const uint32_t *occ, u
     S3_CUDA(cudaFree(d_bwt));
     S3_CUDA(cudaFree(d_occ));
     *numBucketsOut = numBuckets;
-    ix->bytes += (size_t)numBuckets * 64;
+    ix->bytes += (size_t)numBuckets * 32;
     return S3_OK;
 }
 

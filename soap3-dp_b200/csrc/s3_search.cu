@@ -99,14 +99,13 @@ struct S3SearchArgs {
     unsigned long long *rankQueries;     // may be NULL
 };
 
-// DFS frame: a node where substitutions are still allowed.  a/b are the rank
-// vectors of both interval ends at that node, from which every child interval
-// (and the reverse interval update, DV-Kernel.cu:2673-2690) is derived.
-struct S3Frame {
-    uint32_t a[4], b[4];
-    uint32_t r, rr;          // the node's own saR / revSaR
-    uint32_t meta;           // done[0:11] p[11:13] mmp[13:16] mmt[16:19] next[19:22] c[22:24]
-};
+// DFS frame: a node where substitutions are still allowed, kept in shared memory
+// (S3_FRAME_WORDS words per frame, word-major so that lanes never conflict):
+//   a[4], b[4]  rank vectors of both interval ends at the node, from which every child interval
+//               (and the other index's interval update, DV-Kernel.cu:2673-2690) is derived
+//   yhi         upper end of the node's interval in the index NOT being stepped
+//   meta        done[0:11] p[11:13] mmp[13:16] mmt[16:19] next[19:22] c[22:24]
+#define S3_FRAME_WORDS 10
 
 __device__ __forceinline__ uint32_t s3_meta(uint32_t done, uint32_t p, uint32_t mmp, uint32_t mmt, uint32_t next, uint32_t c)
 {
@@ -128,36 +127,50 @@ __device__ __forceinline__ uint32_t s3_pack_phase(const S3Phase &ph)
     return ph.start | (ph.len << 11) | (ph.dir << 22) | (ph.lo << 23) | (ph.hi << 26);
 }
 
+#ifndef S3_REFILL_MIN
 #define S3_REFILL_MIN 4        // idle lanes a warp tolerates before it goes back to the work queue
+#endif
+#ifndef S3_SEARCH_MIN_BLOCKS
+#define S3_SEARCH_MIN_BLOCKS 6
+#endif
 
 template <bool COUNT>
-__global__ void __launch_bounds__(S3_THREADS)
+__global__ void __launch_bounds__(S3_THREADS, S3_SEARCH_MIN_BLOCKS)
 s3_search_kernel(const S3Half fwd, const S3Half rev, const S3SearchArgs args)
 {
     extern __shared__ uint32_t s3_smem[];
-    uint32_t *sm = s3_smem + threadIdx.x;
+    uint32_t *fr = s3_smem + threadIdx.x;                                  // frames: fr[(depth*10 + field) * S3_THREADS]
+    uint32_t *sm = s3_smem + S3_MAX_DEPTH * S3_FRAME_WORDS * S3_THREADS + threadIdx.x;   // read words
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t totalItems = args.numQueries * args.numCases;      // < 2^32 (host splits otherwise)
     const uint32_t maxRanges = args.saRangeAllowed;
     unsigned long long nrank = 0;
 
     // ---- per-lane enumerator state ----
+    // (xlo, xhi) is the interval in the index the current phase steps through (BWT for a backward
+    // phase, reverse BWT for a forward phase), (ylo, yhi) the interval in the other one.
     bool has = false, dead = false, alive = false;
     uint32_t L = 0, strand = 0, pass = 0, saCount = 0, firstL = 0, nph = 0;
     uint32_t prog[S3_MAX_PHASES] = {0, 0, 0, 0};
     uint32_t pstart = 0, plen = 0, pdir = 0, plo = 0, phi = 0;        // current phase, unpacked
     uint32_t p = 0, done = 0, mmp = 0, mmt = 0, depth = 0;
-    uint32_t l = 0, r = 0, rl = 0, rr = 0;
+    uint32_t xlo = 0, xhi = 0, ylo = 0, yhi = 0;
     uint32_t *answer = NULL;
-    S3Frame frames[S3_MAX_DEPTH];
 
     auto load_phase = [&](uint32_t k) {
         const uint32_t w = (k == 0) ? prog[0] : (k == 1) ? prog[1] : (k == 2) ? prog[2] : prog[3];
-        pstart = w & 0x7FF; plen = (w >> 11) & 0x7FF; pdir = (w >> 22) & 1; plo = (w >> 23) & 7; phi = (w >> 26) & 7;
+        pstart = w & 0x7FF; plen = (w >> 11) & 0x7FF; plo = (w >> 23) & 7; phi = (w >> 26) & 7;
+        const uint32_t nd = (w >> 22) & 1;
+        if (nd != pdir) {                                             // the other index becomes the stepped one
+            uint32_t t = xlo; xlo = ylo; ylo = t;
+            t = xhi; xhi = yhi; yhi = t;
+            pdir = nd;
+        }
     };
     auto start_pass = [&]() {
         depth = 0; p = 0; done = 0; mmp = 0; mmt = 0;
-        l = firstL; r = args.textLength; rl = 0; rr = args.textLength;
+        // backward-only programs start from saL = 1, bi-directional ones from 0 (DV-Kernel.cu:3672 vs :3804)
+        pdir = 0; xlo = firstL; xhi = args.textLength; ylo = 0; yhi = args.textLength;
         alive = nph > 0;
         load_phase(0);
     };
@@ -202,8 +215,9 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3SearchArgs args)
                 // end of a phase
                 if (mmp < plo) alive = false;
                 else if (p + 1 == nph) {
-                    // report (DV-Kernel.cu:355-380)
+                    // report (DV-Kernel.cu:355-380): the interval on the forward BWT
                     if (saCount < maxRanges) {
+                        const uint32_t l = pdir ? ylo : xlo, r = pdir ? yhi : xhi;
                         answer[32 * 2 * saCount] = l;
                         answer[32 * (2 * saCount + 1)] = (r - l) + (strand << 27) + (mmt << 24);
                     }
@@ -222,59 +236,64 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3SearchArgs args)
                 }
             } else {
                 // take the next pending branch from the innermost frame
-                S3Frame &f = frames[depth - 1];
-                const uint32_t meta = f.meta;
+                uint32_t *f = fr + (depth - 1) * S3_FRAME_WORDS * S3_THREADS;
+                const uint32_t meta = f[9 * S3_THREADS];
                 const uint32_t c = (meta >> 22) & 3;
                 uint32_t e = (meta >> 19) & 7;
                 const uint32_t fp = (meta >> 11) & 3;
-                if (fp != p) { p = fp; load_phase(p); }
+                if (fp != p) { p = fp; load_phase(p); }          // intervals are overwritten below
                 done = meta & 0x7FF; mmp = (meta >> 13) & 7; mmt = (meta >> 16) & 7;
                 // next substitution symbol with a non-empty interval, ascending
-                while (e < 4 && (e == c || f.a[e] + 1 > f.b[e])) ++e;
+                while (e < 4 && (e == c || f[e * S3_THREADS] + 1 > f[(4 + e) * S3_THREADS])) ++e;
                 uint32_t sym;
-                if (e < 4) { sym = e; f.meta = (meta & ~(7u << 19)) | ((e + 1) << 19); ++mmp; ++mmt; }
+                if (e < 4) { sym = e; f[9 * S3_THREADS] = (meta & ~(7u << 19)) | ((e + 1) << 19); ++mmp; ++mmt; }
                 else { sym = c; --depth; }             // finally the read's own base; frame retired
                 uint32_t cum = 0;
-                for (uint32_t j = 3; j > sym; --j) cum += f.b[j] - f.a[j];
-                const uint32_t nlo = f.a[sym] + 1, nhi = f.b[sym];
-                if (pdir) { rl = nlo; rr = nhi; r = f.r - cum; l = r - (rr - rl); }
-                else      { l = nlo; r = nhi; rr = f.rr - cum; rl = rr - (r - l); }
+                for (uint32_t j = 3; j > sym; --j) cum += f[(4 + j) * S3_THREADS] - f[j * S3_THREADS];
+                xlo = f[sym * S3_THREADS] + 1; xhi = f[(4 + sym) * S3_THREADS];
+                yhi = f[8 * S3_THREADS] - cum; ylo = yhi - (xhi - xlo);
                 ++done;
-                alive = (l <= r);
+                alive = (xlo <= xhi);
             }
         }
         __syncwarp();
-        // ---- (B) one LF-mapping step for every lane that has work ----
+        // ---- (B) one LF-mapping step for every lane that has work: both ranks' loads first ----
         if (has) {
+            const uint4 *buckets = pdir ? rev.buckets : fwd.buckets;
+            const uint32_t isa0 = pdir ? rev.inverseSa0 : fwd.inverseSa0;
+            const S3Bucket ka = s3_rank_load(buckets, isa0, xlo);
+            const S3Bucket kb = s3_rank_load(buckets, isa0, xhi + 1);
             const uint32_t pos = pdir ? pstart + done : pstart + plen - 1 - done;
             const uint32_t c = s3_base(sm, pos, L, strand);
-            uint32_t a[4], b[4];
-            if (pdir) { s3_rank4(rev, rl, a); s3_rank4(rev, rr + 1, b); }
-            else      { s3_rank4(fwd, l, a);  s3_rank4(fwd, r + 1, b); }
+            uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+            s3_rank_count(ka, a0, a1, a2, a3);
+            s3_rank_count(kb, b0, b1, b2, b3);
             if (COUNT) nrank += 2;
             bool pushed = false;
             if (mmp < phi) {
                 // does any substitution child survive?  (most do not once the interval is narrow)
-                uint32_t live = 0;
-#pragma unroll
-                for (uint32_t e = 0; e < 4; ++e) live |= (e != c && a[e] + 1 <= b[e]) ? (1u << e) : 0u;
+                const bool live = (c != 0 && a0 < b0) || (c != 1 && a1 < b1) || (c != 2 && a2 < b2) || (c != 3 && a3 < b3);
                 if (live) {
-                    S3Frame &f = frames[depth++];
-#pragma unroll
-                    for (int e = 0; e < 4; ++e) { f.a[e] = a[e]; f.b[e] = b[e]; }
-                    f.r = r; f.rr = rr;
-                    f.meta = s3_meta(done, p, mmp, mmt, 0, c);
+                    uint32_t *f = fr + depth * S3_FRAME_WORDS * S3_THREADS;
+                    f[0 * S3_THREADS] = a0; f[1 * S3_THREADS] = a1; f[2 * S3_THREADS] = a2; f[3 * S3_THREADS] = a3;
+                    f[4 * S3_THREADS] = b0; f[5 * S3_THREADS] = b1; f[6 * S3_THREADS] = b2; f[7 * S3_THREADS] = b3;
+                    f[8 * S3_THREADS] = yhi;
+                    f[9 * S3_THREADS] = s3_meta(done, p, mmp, mmt, 0, c);
+                    ++depth;
                     alive = false;     // children are taken from the frame in (A)
                     pushed = true;
                 }
             }
             if (!pushed) {
                 // follow the read's base
-                const uint32_t cum = (c < 3 ? b[3] - a[3] : 0) + (c < 2 ? b[2] - a[2] : 0) + (c < 1 ? b[1] - a[1] : 0);
-                if (pdir) { rl = a[c] + 1; rr = b[c]; r = r - cum; l = r - (rr - rl); }
-                else      { l = a[c] + 1; r = b[c]; rr = rr - cum; rl = rr - (r - l); }
+                const uint32_t d1 = b1 - a1, d2 = b2 - a2, d3 = b3 - a3;
+                const uint32_t cum = (c < 3 ? d3 : 0) + (c < 2 ? d2 : 0) + (c < 1 ? d1 : 0);
+                const uint32_t ac = c == 0 ? a0 : c == 1 ? a1 : c == 2 ? a2 : a3;
+                const uint32_t bc = c == 0 ? b0 : c == 1 ? b1 : c == 2 ? b2 : b3;
+                xlo = ac + 1; xhi = bc;
+                yhi = yhi - cum; ylo = yhi - (xhi - xlo);
                 ++done;
-                alive = (l <= r);
+                alive = (xlo <= xhi);
             }
         }
     }
@@ -310,7 +329,7 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
     if (a.numQueries == 0) return S3_OK;
     a.numCases = numCases;
     a.workCounter = ix->d_workCounter;
-    const size_t smem = (size_t)a.wordPerQuery * S3_THREADS * sizeof(uint32_t);
+    const size_t smem = (size_t)(a.wordPerQuery + S3_MAX_DEPTH * S3_FRAME_WORDS) * S3_THREADS * sizeof(uint32_t);
     if (smem != ix->searchSmem) {
         S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

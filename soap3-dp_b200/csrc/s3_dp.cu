@@ -55,11 +55,12 @@ struct s3_dp {
     uint32_t maxReadLength, maxDNALength, maxBatch;
     s3_dp_scores sc;
     int R;                       // rows per lane
-    int narrow;                  // 1: 16x2 kernels (H plane + flag plane), 0: 32-bit kernels (byte plane)
+    int narrow;                  // 1: 16x2 kernel (H plane), 0: 32-bit kernels (byte plane)
+    int lanes;                   // narrow: lanes that sweep one pair of alignments (16 or 32)
     uint32_t slot;               // wide path: bytes per lane per column in the traceback plane
     uint32_t chunk;              // alignments per traceback-plane chunk
     uint8_t *d_tb;               // wide: chunk * (maxDNALength+1) * 32 * slot bytes
-                                 // narrow: chunk/2 pairs * (maxDNALength+32) steps * 32 lanes * R words
+                                 // narrow: chunk/2 pairs * (maxDNALength+lanes) steps * lanes * R words
     uint32_t *d_scRight;         // maxBatch
     // staging for the host entry point
     uint32_t *d_dna, *d_read, *d_dnaLen, *d_readLen, *d_hit, *d_cnt, *d_clipLt, *d_clipRt, *d_ancL, *d_ancR;
@@ -81,7 +82,7 @@ struct S3DpArgs {
     int match, mismatch, open, ext;
     unsigned long long *cells;
     uint32_t *hplane;                // narrow path: H values, [pair][step][lane][R] words (A low half, B high half)
-    uint32_t planeSteps;             // maxDNALength + 32
+    uint32_t planeSteps;             // maxDNALength + lanes per pair
 };
 
 __device__ __forceinline__ int s3_clamp(int x) { return max(x, S3_NEG_INF); }
@@ -294,192 +295,25 @@ __device__ __forceinline__ uint32_t s3_prmt(uint32_t a, uint32_t b, uint32_t sel
 
 struct S3Dp16Best { int best; uint32_t hitJ, bestI, count; };
 
-__device__ __forceinline__ void s3_best_update(S3Dp16Best &b, int x, uint32_t j, uint32_t i)
+// DV-DPfunctions.cu:225-235 for one eligible cell, without branches
+__device__ __forceinline__ void s3_best_update(S3Dp16Best &b, bool eligible, int x, uint32_t j, uint32_t i)
 {
-    if (x > b.best) { b.best = x; b.hitJ = j; b.bestI = i; b.count = 1; }
-    else if (x == b.best) ++b.count;
+    const bool gt = eligible && x > b.best, eq = eligible && x == b.best;
+    b.best = gt ? x : b.best;
+    b.hitJ = gt ? j : b.hitJ;
+    b.bestI = gt ? i : b.bestI;
+    b.count = gt ? 1u : b.count + (eq ? 1u : 0u);
 }
 
-template <int R>
-__global__ void __launch_bounds__(S3_DP_WARPS * 32)
-s3_dp_score16_kernel(const S3DpArgs a)
+// GPUBacktrack (DV-DPfunctions.cu:316-512) over the H plane of one pair, for the alignment in
+// half `half`.  The reference reads H of three neighbours and, for its third test, E of the
+// previous column; here E is rebuilt from the H row (see the file header) and the borders
+// H(j,0), H(0,i) -- which the reference also keeps in its table -- are recomputed from their
+// defining formulas.  Returns the start offset inside the window (the new hitLocs value).
+template <int R, int LANES>
+__device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, uint32_t half, uint32_t id,
+                                      uint32_t m, uint32_t clipLt, uint32_t anchorLeft, uint32_t scRight, uint32_t hit)
 {
-    __shared__ uint32_t refWords[S3_DP_WARPS][2][S3_DP_MAX_REF_WORDS];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t pairLocal = blockIdx.x * S3_DP_WARPS + warp;
-    if (2 * pairLocal >= a.count) return;                         // whole warp leaves together
-    const bool hasB = 2 * pairLocal + 1 < a.count;
-    const uint32_t id[2] = {a.first + 2 * pairLocal, a.first + 2 * pairLocal + (hasB ? 1u : 0u)};
-    uint32_t m[2], n[2], clipLt[2], clipRt[2], ancL[2], ancR[2];
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-        m[x] = a.readLen[id[x]]; n[x] = a.dnaLen[id[x]];
-        clipLt[x] = a.clipLt ? a.clipLt[id[x]] : 0u;
-        clipRt[x] = a.clipRt ? a.clipRt[id[x]] : 0u;
-        ancL[x] = a.ancL ? a.ancL[id[x]] : a.maxDNALength;
-        ancR[x] = a.ancR ? a.ancR[id[x]] : 0u;
-    }
-    const uint32_t mMax = max(m[0], m[1]), nMax = max(n[0], n[1]);
-    const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
-    const uint32_t OPEN2 = s3_pk(open, open), EXT2 = s3_pk(ext, ext), GAPINIT2 = s3_pk(gapInit, gapInit);
-    const uint32_t i0 = lane * R + 1;                              // first row of this lane (1-based)
-
-    // reference windows -> shared memory (1-based packing, MSB first; DV-DPfunctions.cu:58)
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-        const uint32_t *dna = a.dna + (size_t)(id[x] >> 5) * a.dnaWords * 32 + (id[x] & 31);
-        const uint32_t nw = min((nMax >> 4) + 1, a.dnaWords);
-        for (uint32_t w = lane; w < nw; w += 32) refWords[warp][x][w] = dna[(size_t)w * 32];
-    }
-    // this lane's read bases become PRMT selectors: the substitution score of a row is looked
-    // up in a 4-byte table per alignment (byte c = score against reference base c)
-    uint32_t sel[R], cmask[R];
-    uint32_t eligRows = 0;                                       // bit r: row may end alignment A, bit 16+r: alignment B
-    {
-        const uint32_t *readA = a.read + (size_t)(id[0] >> 5) * a.readWords * 32 + (id[0] & 31);
-        const uint32_t *readB = a.read + (size_t)(id[1] >> 5) * a.readWords * 32 + (id[1] & 31);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const uint32_t i = i0 + r;
-            const uint32_t cA = (i <= m[0]) ? (readA[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
-            const uint32_t cB = (i <= m[1]) ? (readB[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
-            sel[r] = cA | ((cA | 8u) << 4) | ((cB | 4u) << 8) | ((cB | 12u) << 12);
-            // rows in which the alignment may end (DV-DPfunctions.cu:225): i >= m - clipRt, i <= m
-            const bool eA = (int)i >= (int)(m[0] - clipRt[0]) && i <= m[0];
-            const bool eB = (int)i >= (int)(m[1] - clipRt[1]) && i <= m[1] && hasB;
-            eligRows |= (eA ? (1u << r) : 0u) | (eB ? (0x10000u << r) : 0u);
-            // soft-clip restart feeds row i from row i-1 when i-1 <= clipLt (DV-DPfunctions.cu:215-219)
-            cmask[r] = ((i - 1 <= clipLt[0]) ? 0xFFFFu : 0u) | ((i - 1 <= clipLt[1]) ? 0xFFFF0000u : 0u);
-        }
-    }
-    // column 0 (DV-DPfunctions.cu:167-184)
-    uint32_t Hp[R], Ep[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const uint32_t i = i0 + r;
-        const int hA = (i <= clipLt[0]) ? open : gapInit + (int)(i - clipLt[0]) * ext;
-        const int hB = (i <= clipLt[1]) ? open : gapInit + (int)(i - clipLt[1]) * ext;
-        Hp[r] = s3_pk(s3_clamp(hA), s3_clamp(hB));
-        Ep[r] = s3_pk(s3_clamp(hA + gapInit), s3_clamp(hB + gapInit));
-    }
-    __syncwarp();
-
-    // substitution tables: byte c of tX = score of this column's reference base against read base c
-    const uint32_t MISM4 = ((uint32_t)a.mismatch & 0xFFu) * 0x01010101u;
-    const uint32_t DELTA = ((uint32_t)a.match ^ (uint32_t)a.mismatch) & 0xFFu;
-
-    S3Dp16Best bestA = {S3_NEG_INF, 0u, 0u, 0u}, bestB = {S3_NEG_INF, 0u, 0u, 0u};
-    uint32_t best2 = S3_NEG2;                                    // packed running bests (trigger only)
-    uint32_t upOut = 0, FOut = 0, diagRawOut = 0;
-    uint32_t prevInit = 0;                                       // start value of the previous column
-    uint32_t clipIO[R], clipPI[R];                               // soft-clip restart operands of the current column
-    uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPI were built from
-    uint32_t *hrow = a.hplane + (size_t)pairLocal * a.planeSteps * 32 * R + (size_t)lane * R;
-    const bool laneHasRows = i0 <= mMax;
-
-    const uint32_t steps = nMax + 31;
-    for (uint32_t s = 1; s <= steps; ++s) {
-        // carried registers of the row loop arrive from the lane above (column j was done there at step s-1)
-        uint32_t up = __shfl_up_sync(0xFFFFFFFFu, upOut, 1);
-        uint32_t F = __shfl_up_sync(0xFFFFFFFFu, FOut, 1);
-        uint32_t diagRaw = __shfl_up_sync(0xFFFFFFFFu, diagRawOut, 1);
-        const uint32_t j = s - lane;
-        if (j >= 1 && j <= nMax && laneHasRows) {
-            const uint32_t init = ((j >= ancL[0]) ? (S3_NEG2 & 0xFFFFu) : 0u) | ((j >= ancL[1]) ? (S3_NEG2 & 0xFFFF0000u) : 0u);
-            if (lane == 0) { up = init; F = __vadd2(init, GAPINIT2); diagRaw = prevInit; }
-            if (init != curInit || prevInit != curPrev) {           // rare: first column and anchor crossings
-                const uint32_t io = __vadd2(init, OPEN2);
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    clipIO[r] = (io & cmask[r]) | (S3_MIN2 & ~cmask[r]);
-                    clipPI[r] = (prevInit & cmask[r]) | (S3_MIN2 & ~cmask[r]);
-                }
-                curInit = init; curPrev = prevInit;
-            }
-            const uint32_t sh = (15u - (j & 15u)) << 1;
-            const uint32_t cA = (refWords[warp][0][j >> 4] >> sh) & 3u, cB = (refWords[warp][1][j >> 4] >> sh) & 3u;
-            const uint32_t tA = MISM4 ^ (DELTA << (cA << 3)), tB = MISM4 ^ (DELTA << (cB << 3));
-            uint32_t upRow[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t d = s3_prmt(tA, tB, sel[r]);
-                const uint32_t left = Hp[r], eL = Ep[r];
-                const uint32_t e = __viaddmax_s16x2(left, OPEN2, __vadd2(eL, EXT2));
-                F = __vimax3_s16x2(__vadd2(F, EXT2), __vadd2(up, OPEN2), clipIO[r]);
-                const uint32_t dg = __vmaxs2(diagRaw, clipPI[r]);
-                up = __vimax3_s16x2(F, e, __vadd2(dg, d));
-                diagRaw = left;
-                Hp[r] = __vmaxs2(up, S3_NEG2); Ep[r] = __vmaxs2(e, S3_NEG2);
-                upRow[r] = up;
-            }
-            upOut = up; FOut = F; diagRawOut = diagRaw;
-            prevInit = init;
-            // anti-diagonal major: the warp's 32 x R words of one step are contiguous
-            uint4 *hdst = reinterpret_cast<uint4 *>(hrow + (size_t)s * 32 * R);
-#pragma unroll
-            for (int k = 0; k < R / 4; ++k) hdst[k] = make_uint4(Hp[4 * k], Hp[4 * k + 1], Hp[4 * k + 2], Hp[4 * k + 3]);
-            // best cell.  Cheap conservative trigger: some row of this lane (eligible or not) reaches a running
-            // best; the exact test per eligible cell runs only then (DV-DPfunctions.cu:225-235).
-            if (eligRows) {
-                uint32_t colMax = Hp[0];
-#pragma unroll
-                for (int r = 1; r + 1 < R; r += 2) colMax = __vimax3_s16x2(colMax, Hp[r], Hp[r + 1]);
-                colMax = __vmaxs2(colMax, Hp[R - 1]);
-                bool gh, gl;
-                (void)__vibmax_s16x2(colMax, best2, &gh, &gl);
-                // columns in which the alignment may end: anchorRight <= j <= n
-                const bool okA = j >= ancR[0] && j <= n[0], okB = j >= ancR[1] && j <= n[1];
-                if ((gl && okA) || (gh && okB)) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        if (okA && ((eligRows >> r) & 1u)) s3_best_update(bestA, s3_lo16(upRow[r]), j, i0 + r);
-                        if (okB && ((eligRows >> (16 + r)) & 1u)) s3_best_update(bestB, s3_hi16(upRow[r]), j, i0 + r);
-                    }
-                    best2 = s3_pk(bestA.best, bestB.best);
-                }
-            }
-        }
-    }
-    // merge the lanes' bests: highest score, then first in (column, row) scan order
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-        const S3Dp16Best &bb = x ? bestB : bestA;
-        int gbest = bb.best;
-        for (int o = 16; o > 0; o >>= 1) gbest = max(gbest, __shfl_xor_sync(0xFFFFFFFFu, gbest, o));
-        unsigned long long key = (bb.best == gbest && bb.count > 0) ? (((unsigned long long)bb.hitJ << 32) | bb.bestI) : ~0ull;
-        uint32_t cnt = (bb.best == gbest) ? bb.count : 0u;
-        for (int o = 16; o > 0; o >>= 1) {
-            key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
-            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-        }
-        if (lane == 0 && (x == 0 || hasB)) {
-            const bool any = key != ~0ull;
-            a.score[id[x]] = gbest;
-            a.hit[id[x]] = any ? (uint32_t)(key >> 32) : 0u;
-            const uint32_t bi = (uint32_t)(key & 0xFFFFFFFFu);
-            a.scRight[id[x]] = (any && bi != 0) ? m[x] - bi : 0u;   // bi == 0: only ties with the -32000 start value
-            a.cnt[id[x]] = cnt;
-            if (a.cells) atomicAdd(a.cells, (unsigned long long)m[x] * n[x]);
-        }
-    }
-}
-
-// One thread per alignment: GPUBacktrack (DV-DPfunctions.cu:316-512) over the H plane.  The
-// reference reads H of three neighbours and, for its third test, E of the previous column;
-// here the E test is the stored flag bit and the borders H(j,0), H(0,i) -- which the reference
-// also keeps in its table -- are recomputed from their defining formulas.
-__global__ void s3_dp_traceback16_kernel(const S3DpArgs a, int R)
-{
-    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
-    if (local >= a.count) return;
-    const uint32_t id = a.first + local;
-    if (a.score[id] < a.cutoff[id]) return;
-    const uint32_t half = local & 1u, pairLocal = local >> 1;
-    const uint32_t m = a.readLen[id];
-    const uint32_t clipLt = a.clipLt ? a.clipLt[id] : 0u;
-    const uint32_t anchorLeft = a.ancL ? a.ancL[id] : a.maxDNALength;
-    const uint32_t scRight = a.scRight[id];
-    const uint32_t *hplane = a.hplane + (size_t)pairLocal * a.planeSteps * 32 * R;
     const uint32_t *dna = a.dna + (size_t)(id >> 5) * a.dnaWords * 32 + (id & 31);
     const uint32_t *read = a.read + (size_t)(id >> 5) * a.readWords * 32 + (id & 31);
     const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
@@ -490,20 +324,20 @@ __global__ void s3_dp_traceback16_kernel(const S3DpArgs a, int R)
         if (i == 0) return (j == 0) ? 0 : ((j >= anchorLeft) ? S3_NEG_INF : 0);
         if (j == 0) return s3_clamp((i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext);
         const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-        const uint32_t w = hplane[((size_t)(j + t) * 32 + t) * R + r];
+        const uint32_t w = plane[((size_t)(j + t) * LANES + t) * R + r];
         return half ? s3_hi16(w) : s3_lo16(w);
     };
-    // E(j-1, i) as the score kernel computed and clamped it, rebuilt from row i of the H plane:
+    // E(j-1, i) as the score pass computed and clamped it, rebuilt from row i of the H plane:
     // E(0,i) = H(0,i)+gapInit, E(c,i) = max(open + H(c-1,i), ext + E(c-1,i)), each clamped when
     // stored (DV-DPfunctions.cu:178-183,196-199).  Only evaluated where an indel or a clip starts.
     auto Eprev = [&](uint32_t j, uint32_t i) -> int {
         const int h0 = (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext;
         int e = s3_clamp(h0 + gapInit), hl = s3_clamp(h0);
         const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-        const uint32_t *row = hplane + (size_t)t * R + r;
+        const uint32_t *row = plane + (size_t)t * R + r;
         for (uint32_t c = 1; c < j; ++c) {
             e = s3_clamp(max(open + hl, ext + e));
-            const uint32_t w = row[(size_t)(c + t) * 32 * R];
+            const uint32_t w = row[(size_t)(c + t) * LANES * R];
             hl = half ? s3_hi16(w) : s3_lo16(w);
         }
         return e;
@@ -512,7 +346,7 @@ __global__ void s3_dp_traceback16_kernel(const S3DpArgs a, int R)
     auto readAt = [&](uint32_t i) -> uint32_t { return (read[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3; };
 
     if (scRight > 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)scRight; }
-    uint32_t readPos = m - scRight, refIndex = a.hit[id];
+    uint32_t readPos = m - scRight, refIndex = hit;
     uint32_t readChar = readAt(readPos), refChar = refAt(refIndex);
     int cur = H(refIndex, readPos), next;
     int initScore = (refIndex >= anchorLeft) ? S3_NEG_INF : 0;
@@ -579,7 +413,194 @@ __global__ void s3_dp_traceback16_kernel(const S3DpArgs a, int R)
         refIndex -= 1;
     }
     pat[p++] = 0;
-    a.hit[id] = refIndex;        // start offset inside the window (refOffset == 0 in scheme 1)
+    return refIndex;             // start offset inside the window (refOffset == 0 in scheme 1)
+}
+
+// Score pass + traceback of S3_DP_WARPS * (32 / LANES) pairs of alignments per block.  A pair is
+// swept by a group of LANES lanes, each owning R consecutive read rows.
+template <int R, int LANES>
+__global__ void __launch_bounds__(S3_DP_WARPS * 32)
+s3_dp_align16_kernel(const S3DpArgs a)
+{
+    constexpr int GROUPS = 32 / LANES;                            // pairs per warp
+    __shared__ uint32_t refWords[S3_DP_WARPS][GROUPS][2][S3_DP_MAX_REF_WORDS];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = lane / LANES, t = lane % LANES;
+    const uint32_t numPairs = (a.count + 1) / 2;
+    const uint32_t wantPair = (blockIdx.x * S3_DP_WARPS + warp) * GROUPS + group;
+    if ((blockIdx.x * S3_DP_WARPS + warp) * GROUPS >= numPairs) return;          // whole warp leaves together
+    const bool pairValid = wantPair < numPairs;
+    const uint32_t pairLocal = pairValid ? wantPair : numPairs - 1;              // idle groups shadow a real pair, write nothing
+    const bool hasB = 2 * pairLocal + 1 < a.count;
+    const uint32_t id[2] = {a.first + 2 * pairLocal, a.first + 2 * pairLocal + (hasB ? 1u : 0u)};
+    uint32_t m[2], n[2], clipLt[2], clipRt[2], ancL[2], ancR[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        m[x] = a.readLen[id[x]]; n[x] = a.dnaLen[id[x]];
+        clipLt[x] = a.clipLt ? a.clipLt[id[x]] : 0u;
+        clipRt[x] = a.clipRt ? a.clipRt[id[x]] : 0u;
+        ancL[x] = a.ancL ? a.ancL[id[x]] : a.maxDNALength;
+        ancR[x] = a.ancR ? a.ancR[id[x]] : 0u;
+    }
+    const uint32_t mMax = max(m[0], m[1]), nMax = pairValid ? max(n[0], n[1]) : 0u;
+    const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
+    const uint32_t OPEN2 = s3_pk(open, open), EXT2 = s3_pk(ext, ext), GAPINIT2 = s3_pk(gapInit, gapInit);
+    const uint32_t i0 = t * R + 1;                                 // first row of this lane (1-based)
+
+    // reference windows -> shared memory (1-based packing, MSB first; DV-DPfunctions.cu:58)
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        const uint32_t *dna = a.dna + (size_t)(id[x] >> 5) * a.dnaWords * 32 + (id[x] & 31);
+        const uint32_t nw = min((nMax >> 4) + 1, a.dnaWords);
+        for (uint32_t w = t; w < nw; w += LANES) refWords[warp][group][x][w] = dna[(size_t)w * 32];
+    }
+    // this lane's read bases become PRMT selectors: the substitution score of a row is looked
+    // up in a 4-byte table per alignment (byte c = score against reference base c)
+    uint32_t sel[R], cmask[R];
+    uint32_t eligRows = 0;                                       // bit r: row may end alignment A, bit 16+r: alignment B
+    {
+        const uint32_t *readA = a.read + (size_t)(id[0] >> 5) * a.readWords * 32 + (id[0] & 31);
+        const uint32_t *readB = a.read + (size_t)(id[1] >> 5) * a.readWords * 32 + (id[1] & 31);
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const uint32_t i = i0 + r;
+            const uint32_t cA = (i <= m[0]) ? (readA[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
+            const uint32_t cB = (i <= m[1]) ? (readB[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
+            sel[r] = cA | ((cA | 8u) << 4) | ((cB | 4u) << 8) | ((cB | 12u) << 12);
+            // rows in which the alignment may end (DV-DPfunctions.cu:225): i >= m - clipRt, i <= m
+            const bool eA = (int)i >= (int)(m[0] - clipRt[0]) && i <= m[0];
+            const bool eB = (int)i >= (int)(m[1] - clipRt[1]) && i <= m[1] && hasB;
+            eligRows |= (eA ? (1u << r) : 0u) | (eB ? (0x10000u << r) : 0u);
+            // soft-clip restart feeds row i from row i-1 when i-1 <= clipLt (DV-DPfunctions.cu:215-219)
+            cmask[r] = ((i - 1 <= clipLt[0]) ? 0xFFFFu : 0u) | ((i - 1 <= clipLt[1]) ? 0xFFFF0000u : 0u);
+        }
+    }
+    // column 0 (DV-DPfunctions.cu:167-184)
+    uint32_t Hp[R], Ep[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i = i0 + r;
+        const int hA = (i <= clipLt[0]) ? open : gapInit + (int)(i - clipLt[0]) * ext;
+        const int hB = (i <= clipLt[1]) ? open : gapInit + (int)(i - clipLt[1]) * ext;
+        Hp[r] = s3_pk(s3_clamp(hA), s3_clamp(hB));
+        Ep[r] = s3_pk(s3_clamp(hA + gapInit), s3_clamp(hB + gapInit));
+    }
+    __syncwarp();
+
+    // substitution tables: byte c of tX = score of this column's reference base against read base c
+    const uint32_t MISM4 = ((uint32_t)a.mismatch & 0xFFu) * 0x01010101u;
+    const uint32_t DELTA = ((uint32_t)a.match ^ (uint32_t)a.mismatch) & 0xFFu;
+
+    S3Dp16Best bestA = {S3_NEG_INF, 0u, 0u, 0u}, bestB = {S3_NEG_INF, 0u, 0u, 0u};
+    uint32_t best2 = S3_NEG2;                                    // packed running bests (trigger only)
+    uint32_t upOut = 0, FOut = 0, diagRawOut = 0;
+    uint32_t prevInit = 0;                                       // start value of the previous column
+    uint32_t clipIO[R], clipPI[R];                               // soft-clip restart operands of the current column
+    uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPI were built from
+    uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
+    uint32_t *hrow = plane + (size_t)t * R;
+    const bool laneHasRows = i0 <= mMax && pairValid;
+
+    uint32_t steps = nMax + LANES - 1;
+    if (GROUPS > 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, LANES));
+    for (uint32_t s = 1; s <= steps; ++s) {
+        // carried registers of the row loop arrive from the lane above (column j was done there at step s-1)
+        uint32_t up = __shfl_up_sync(0xFFFFFFFFu, upOut, 1, LANES);
+        uint32_t F = __shfl_up_sync(0xFFFFFFFFu, FOut, 1, LANES);
+        uint32_t diagRaw = __shfl_up_sync(0xFFFFFFFFu, diagRawOut, 1, LANES);
+        const uint32_t j = s - t;
+        if (j >= 1 && j <= nMax && laneHasRows) {
+            const uint32_t init = ((j >= ancL[0]) ? (S3_NEG2 & 0xFFFFu) : 0u) | ((j >= ancL[1]) ? (S3_NEG2 & 0xFFFF0000u) : 0u);
+            if (t == 0) { up = init; F = __vadd2(init, GAPINIT2); diagRaw = prevInit; }
+            if (init != curInit || prevInit != curPrev) {           // rare: first column and anchor crossings
+                const uint32_t io = __vadd2(init, OPEN2);
+#pragma unroll
+                for (int r = 0; r < R; ++r) {
+                    clipIO[r] = (io & cmask[r]) | (S3_MIN2 & ~cmask[r]);
+                    clipPI[r] = (prevInit & cmask[r]) | (S3_MIN2 & ~cmask[r]);
+                }
+                curInit = init; curPrev = prevInit;
+            }
+            const uint32_t sh = (15u - (j & 15u)) << 1;
+            const uint32_t cA = (refWords[warp][group][0][j >> 4] >> sh) & 3u, cB = (refWords[warp][group][1][j >> 4] >> sh) & 3u;
+            const uint32_t tA = MISM4 ^ (DELTA << (cA << 3)), tB = MISM4 ^ (DELTA << (cB << 3));
+            uint32_t upRow[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t d = s3_prmt(tA, tB, sel[r]);
+                const uint32_t left = Hp[r], eL = Ep[r];
+                const uint32_t e = __viaddmax_s16x2(left, OPEN2, __vadd2(eL, EXT2));
+                F = __vimax3_s16x2(__vadd2(F, EXT2), __vadd2(up, OPEN2), clipIO[r]);
+                const uint32_t dg = __vmaxs2(diagRaw, clipPI[r]);
+                up = __vimax3_s16x2(F, e, __vadd2(dg, d));
+                diagRaw = left;
+                Hp[r] = __vmaxs2(up, S3_NEG2); Ep[r] = __vmaxs2(e, S3_NEG2);
+                upRow[r] = up;
+            }
+            upOut = up; FOut = F; diagRawOut = diagRaw;
+            prevInit = init;
+            // anti-diagonal major: the group's LANES x R words of one step are contiguous
+            uint4 *hdst = reinterpret_cast<uint4 *>(hrow + (size_t)s * LANES * R);
+#pragma unroll
+            for (int k = 0; k < R / 4; ++k) hdst[k] = make_uint4(Hp[4 * k], Hp[4 * k + 1], Hp[4 * k + 2], Hp[4 * k + 3]);
+            // best cell.  Cheap conservative trigger: some row of this lane (eligible or not) reaches a running
+            // best; the exact test per eligible cell runs only then (DV-DPfunctions.cu:225-235).
+            if (eligRows) {
+                uint32_t colMax = Hp[0];
+#pragma unroll
+                for (int r = 1; r + 1 < R; r += 2) colMax = __vimax3_s16x2(colMax, Hp[r], Hp[r + 1]);
+                colMax = __vmaxs2(colMax, Hp[R - 1]);
+                bool gh, gl;
+                (void)__vibmax_s16x2(colMax, best2, &gh, &gl);
+                // columns in which the alignment may end: anchorRight <= j <= n
+                const bool okA = j >= ancR[0] && j <= n[0], okB = j >= ancR[1] && j <= n[1];
+                // only the halves for which THIS lane owns eligible rows can move its running best
+                if ((gl && okA && (eligRows & 0xFFFFu)) || (gh && okB && (eligRows >> 16))) {
+#pragma unroll
+                    for (int r = 0; r < R; ++r) {
+                        s3_best_update(bestA, okA && ((eligRows >> r) & 1u), s3_lo16(upRow[r]), j, i0 + r);
+                        s3_best_update(bestB, okB && ((eligRows >> (16 + r)) & 1u), s3_hi16(upRow[r]), j, i0 + r);
+                    }
+                    best2 = s3_pk(bestA.best, bestB.best);
+                }
+            }
+        }
+    }
+    // merge the lanes' bests: highest score, then first in (column, row) scan order
+    int gscore[2];
+    uint32_t ghit[2], gscRight[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        const S3Dp16Best &bb = x ? bestB : bestA;
+        int gbest = bb.best;
+        for (int o = LANES / 2; o > 0; o >>= 1) gbest = max(gbest, __shfl_xor_sync(0xFFFFFFFFu, gbest, o));
+        unsigned long long key = (bb.best == gbest && bb.count > 0) ? (((unsigned long long)bb.hitJ << 32) | bb.bestI) : ~0ull;
+        uint32_t cnt = (bb.best == gbest) ? bb.count : 0u;
+        for (int o = LANES / 2; o > 0; o >>= 1) {
+            key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
+            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        }
+        const bool any = key != ~0ull;
+        const uint32_t bi = (uint32_t)(key & 0xFFFFFFFFu);
+        gscore[x] = gbest;
+        ghit[x] = any ? (uint32_t)(key >> 32) : 0u;
+        gscRight[x] = (any && bi != 0) ? m[x] - bi : 0u;          // bi == 0: only ties with the -32000 start value
+        if (t == 0 && pairValid && (x == 0 || hasB)) {
+            a.score[id[x]] = gbest;
+            a.cnt[id[x]] = cnt;
+            if (a.cells) atomicAdd(a.cells, (unsigned long long)m[x] * n[x]);
+        }
+    }
+    // traceback while the pair's H plane is still in L2: lane 0 of the group takes alignment A,
+    // lane 1 alignment B (the stores above are ordered before these loads by __syncwarp)
+    __syncwarp();
+    if (t < 2 && pairValid && (t == 0 || hasB)) {
+        const int x = t;
+        uint32_t hit = ghit[x];
+        if (gscore[x] >= a.cutoff[id[x]])
+            hit = s3_dp_traceback16<R, LANES>(a, plane, (uint32_t)x, id[x], m[x], clipLt[x], ancL[x], gscRight[x], hit);
+        a.hit[id[x]] = hit;
+    }
 }
 
 static int pick_R(uint32_t maxReadLength)
@@ -609,13 +630,17 @@ extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint3
     dp->narrow = maxReadLength <= 256 && small(scores.matchScore) && small(scores.mismatchScore) &&
                  small(scores.gapOpenScore) && small(scores.gapExtendScore) &&
                  (long long)scores.matchScore * maxReadLength <= 32000 && !getenv("S3_DP_FORCE_WIDE");
-    if (dp->narrow) dp->R = (maxReadLength <= 128) ? 4 : 8;
+    if (dp->narrow) {
+        // rows per lane x lanes per pair: 4x16 (reads <= 64), 8x16 (<= 128), 8x32 (<= 256)
+        dp->R = (maxReadLength <= 64) ? 4 : 8;
+        dp->lanes = (maxReadLength <= 128) ? 16 : 32;
+    }
     S3_CUDA(cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking));
     dp->ownStream = 1;
-    // traceback planes are sized per chunk of alignments; narrow: per PAIR (maxDNALength+32) steps x 32 lanes x
+    // traceback planes are sized per chunk of alignments; narrow: per PAIR (maxDNALength+lanes) steps x lanes x
     // R words of H, i.e. per alignment half of that
     const size_t perAlign = dp->narrow
-        ? (size_t)(maxDNALength + 32) * 32 * 4 * dp->R / 2
+        ? (size_t)(maxDNALength + dp->lanes) * dp->lanes * 4 * dp->R / 2
         : (size_t)(maxDNALength + 1) * 32 * dp->slot;
     size_t freeB = 0, totalB = 0;
     S3_CUDA(cudaMemGetInfo(&freeB, &totalB));
@@ -677,19 +702,18 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t n)
     a.dnaWords = (dp->maxDNALength + 15) >> 4; a.readWords = (dp->maxReadLength + 15) >> 4;
     a.slot = dp->slot; a.tb = dp->d_tb; a.scRight = dp->d_scRight;
     a.match = dp->sc.matchScore; a.mismatch = dp->sc.mismatchScore; a.open = dp->sc.gapOpenScore; a.ext = dp->sc.gapExtendScore;
-    a.planeSteps = dp->maxDNALength + 32;
-    if (dp->narrow) a.hplane = reinterpret_cast<uint32_t *>(dp->d_tb);
+    if (dp->narrow) { a.planeSteps = dp->maxDNALength + dp->lanes; a.hplane = reinterpret_cast<uint32_t *>(dp->d_tb); }
     for (uint32_t first = 0; first < n; first += dp->chunk) {
         a.first = first;
         a.count = (n - first < dp->chunk) ? n - first : dp->chunk;
         if (dp->narrow) {
             const uint32_t pairs = (a.count + 1) / 2;
-            const uint32_t blocks = (pairs + S3_DP_WARPS - 1) / S3_DP_WARPS;
-            if (dp->R == 4) s3_dp_score16_kernel<4><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
-            else s3_dp_score16_kernel<8><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
-            S3_CUDA(cudaGetLastError());
-            s3_dp_traceback16_kernel<<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a, dp->R);
-            S3_LAUNCHED(2);
+            const uint32_t perBlock = S3_DP_WARPS * (32 / dp->lanes);
+            const uint32_t blocks = (pairs + perBlock - 1) / perBlock;
+            if (dp->lanes == 32) s3_dp_align16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+            else if (dp->R == 8) s3_dp_align16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+            else s3_dp_align16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+            S3_LAUNCHED(1);
             S3_CUDA(cudaGetLastError());
             continue;
         }

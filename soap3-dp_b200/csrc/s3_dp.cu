@@ -293,16 +293,43 @@ __device__ __forceinline__ uint32_t s3_prmt(uint32_t a, uint32_t b, uint32_t sel
     return d;
 }
 
-struct S3Dp16Best { int best; uint32_t hitJ, bestI, count; };
+#define S3_SUBNEG2 0x82FF82FFu       // -32001 in both halves: what the plane stores for "below the clamp"
 
-// DV-DPfunctions.cu:225-235 for one eligible cell, without branches
-__device__ __forceinline__ void s3_best_update(S3Dp16Best &b, bool eligible, int x, uint32_t j, uint32_t i)
+// Best cell of one alignment (DV-DPfunctions.cu:225-235) found AFTER the sweep, from the pair's H
+// plane: highest H over the rows i >= m - clipRt and the columns anchorRight <= j <= n, the first
+// such cell in (column, row) order, and the number of cells that tie with it.  The group's lanes
+// take the columns round-robin.  The reference compares the UNclamped value of a cell with a running
+// best that starts at -32000; the plane stores max(value, -32001), so a cell below the clamp (-32001)
+// neither beats nor ties that start value, exactly like the reference's test.
+// Returns in every lane of the group: best score, key = column << 32 | row (~0 if nothing tied or
+// beat the start value; row 0 cannot occur), tie count.
+template <int R, int LANES>
+__device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t half, uint32_t t, uint32_t m, uint32_t n,
+                                             uint32_t clipRt, uint32_t anchorRight,
+                                             int &gbest, unsigned long long &gkey, uint32_t &gcnt)
 {
-    const bool gt = eligible && x > b.best, eq = eligible && x == b.best;
-    b.best = gt ? x : b.best;
-    b.hitJ = gt ? j : b.hitJ;
-    b.bestI = gt ? i : b.bestI;
-    b.count = gt ? 1u : b.count + (eq ? 1u : 0u);
+    const uint32_t iLo = (clipRt >= m) ? 1u : max(m - clipRt, 1u), jLo = max(anchorRight, 1u);
+    int best = S3_NEG_INF;
+    uint32_t cnt = 0;
+    unsigned long long key = ~0ull;
+    for (uint32_t j = jLo + t; j <= n; j += LANES) {
+        for (uint32_t i = iLo; i <= m; ++i) {
+            const uint32_t ti = (i - 1) / R, r = (i - 1) % R;
+            const uint32_t w = plane[((size_t)(j + ti) * LANES + ti) * R + r];
+            const int v = half ? s3_hi16(w) : s3_lo16(w);
+            if (v > best) { best = v; cnt = 1; key = ((unsigned long long)j << 32) | i; }
+            else if (v == best) ++cnt;
+        }
+    }
+    gbest = best;
+    for (int o = LANES / 2; o > 0; o >>= 1) gbest = max(gbest, __shfl_xor_sync(0xFFFFFFFFu, gbest, o));
+    // cells that only tie with the -32000 start value count but set no position (key stays ~0)
+    gkey = (best == gbest) ? key : ~0ull;
+    gcnt = (best == gbest) ? cnt : 0u;
+    for (int o = LANES / 2; o > 0; o >>= 1) {
+        gkey = min(gkey, __shfl_xor_sync(0xFFFFFFFFu, gkey, o));
+        gcnt += __shfl_xor_sync(0xFFFFFFFFu, gcnt, o);
+    }
 }
 
 // GPUBacktrack (DV-DPfunctions.cu:316-512) over the H plane of one pair, for the alignment in
@@ -325,7 +352,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, 
         if (j == 0) return s3_clamp((i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext);
         const uint32_t t = (i - 1) / R, r = (i - 1) % R;
         const uint32_t w = plane[((size_t)(j + t) * LANES + t) * R + r];
-        return half ? s3_hi16(w) : s3_lo16(w);
+        return s3_clamp(half ? s3_hi16(w) : s3_lo16(w));         // the plane keeps -32001 for "below the clamp"
     };
     // E(j-1, i) as the score pass computed and clamped it, rebuilt from row i of the H plane:
     // E(0,i) = H(0,i)+gapInit, E(c,i) = max(open + H(c-1,i), ext + E(c-1,i)), each clamped when
@@ -338,7 +365,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, 
         for (uint32_t c = 1; c < j; ++c) {
             e = s3_clamp(max(open + hl, ext + e));
             const uint32_t w = row[(size_t)(c + t) * LANES * R];
-            hl = half ? s3_hi16(w) : s3_lo16(w);
+            hl = s3_clamp(half ? s3_hi16(w) : s3_lo16(w));
         }
         return e;
     };
@@ -457,7 +484,6 @@ s3_dp_align16_kernel(const S3DpArgs a)
     // this lane's read bases become PRMT selectors: the substitution score of a row is looked
     // up in a 4-byte table per alignment (byte c = score against reference base c)
     uint32_t sel[R], cmask[R];
-    uint32_t eligRows = 0;                                       // bit r: row may end alignment A, bit 16+r: alignment B
     {
         const uint32_t *readA = a.read + (size_t)(id[0] >> 5) * a.readWords * 32 + (id[0] & 31);
         const uint32_t *readB = a.read + (size_t)(id[1] >> 5) * a.readWords * 32 + (id[1] & 31);
@@ -467,10 +493,6 @@ s3_dp_align16_kernel(const S3DpArgs a)
             const uint32_t cA = (i <= m[0]) ? (readA[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
             const uint32_t cB = (i <= m[1]) ? (readB[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
             sel[r] = cA | ((cA | 8u) << 4) | ((cB | 4u) << 8) | ((cB | 12u) << 12);
-            // rows in which the alignment may end (DV-DPfunctions.cu:225): i >= m - clipRt, i <= m
-            const bool eA = (int)i >= (int)(m[0] - clipRt[0]) && i <= m[0];
-            const bool eB = (int)i >= (int)(m[1] - clipRt[1]) && i <= m[1] && hasB;
-            eligRows |= (eA ? (1u << r) : 0u) | (eB ? (0x10000u << r) : 0u);
             // soft-clip restart feeds row i from row i-1 when i-1 <= clipLt (DV-DPfunctions.cu:215-219)
             cmask[r] = ((i - 1 <= clipLt[0]) ? 0xFFFFu : 0u) | ((i - 1 <= clipLt[1]) ? 0xFFFF0000u : 0u);
         }
@@ -491,8 +513,6 @@ s3_dp_align16_kernel(const S3DpArgs a)
     const uint32_t MISM4 = ((uint32_t)a.mismatch & 0xFFu) * 0x01010101u;
     const uint32_t DELTA = ((uint32_t)a.match ^ (uint32_t)a.mismatch) & 0xFFu;
 
-    S3Dp16Best bestA = {S3_NEG_INF, 0u, 0u, 0u}, bestB = {S3_NEG_INF, 0u, 0u, 0u};
-    uint32_t best2 = S3_NEG2;                                    // packed running bests (trigger only)
     uint32_t upOut = 0, FOut = 0, diagRawOut = 0;
     uint32_t prevInit = 0;                                       // start value of the previous column
     uint32_t clipIO[R], clipPI[R];                               // soft-clip restart operands of the current column
@@ -524,7 +544,7 @@ s3_dp_align16_kernel(const S3DpArgs a)
             const uint32_t sh = (15u - (j & 15u)) << 1;
             const uint32_t cA = (refWords[warp][group][0][j >> 4] >> sh) & 3u, cB = (refWords[warp][group][1][j >> 4] >> sh) & 3u;
             const uint32_t tA = MISM4 ^ (DELTA << (cA << 3)), tB = MISM4 ^ (DELTA << (cB << 3));
-            uint32_t upRow[R];
+            uint32_t Hs[R];                                       // what goes to the plane: max(H, -32001)
 #pragma unroll
             for (int r = 0; r < R; ++r) {
                 const uint32_t d = s3_prmt(tA, tB, sel[r]);
@@ -534,66 +554,37 @@ s3_dp_align16_kernel(const S3DpArgs a)
                 const uint32_t dg = __vmaxs2(diagRaw, clipPI[r]);
                 up = __vimax3_s16x2(F, e, __vadd2(dg, d));
                 diagRaw = left;
-                Hp[r] = __vmaxs2(up, S3_NEG2); Ep[r] = __vmaxs2(e, S3_NEG2);
-                upRow[r] = up;
+                Hs[r] = __vmaxs2(up, S3_SUBNEG2);
+                Hp[r] = __vmaxs2(Hs[r], S3_NEG2); Ep[r] = __vmaxs2(e, S3_NEG2);
             }
             upOut = up; FOut = F; diagRawOut = diagRaw;
             prevInit = init;
             // anti-diagonal major: the group's LANES x R words of one step are contiguous
             uint4 *hdst = reinterpret_cast<uint4 *>(hrow + (size_t)s * LANES * R);
 #pragma unroll
-            for (int k = 0; k < R / 4; ++k) hdst[k] = make_uint4(Hp[4 * k], Hp[4 * k + 1], Hp[4 * k + 2], Hp[4 * k + 3]);
-            // best cell.  Cheap conservative trigger: some row of this lane (eligible or not) reaches a running
-            // best; the exact test per eligible cell runs only then (DV-DPfunctions.cu:225-235).
-            if (eligRows) {
-                uint32_t colMax = Hp[0];
-#pragma unroll
-                for (int r = 1; r + 1 < R; r += 2) colMax = __vimax3_s16x2(colMax, Hp[r], Hp[r + 1]);
-                colMax = __vmaxs2(colMax, Hp[R - 1]);
-                bool gh, gl;
-                (void)__vibmax_s16x2(colMax, best2, &gh, &gl);
-                // columns in which the alignment may end: anchorRight <= j <= n
-                const bool okA = j >= ancR[0] && j <= n[0], okB = j >= ancR[1] && j <= n[1];
-                // only the halves for which THIS lane owns eligible rows can move its running best
-                if ((gl && okA && (eligRows & 0xFFFFu)) || (gh && okB && (eligRows >> 16))) {
-#pragma unroll
-                    for (int r = 0; r < R; ++r) {
-                        s3_best_update(bestA, okA && ((eligRows >> r) & 1u), s3_lo16(upRow[r]), j, i0 + r);
-                        s3_best_update(bestB, okB && ((eligRows >> (16 + r)) & 1u), s3_hi16(upRow[r]), j, i0 + r);
-                    }
-                    best2 = s3_pk(bestA.best, bestB.best);
-                }
-            }
+            for (int k = 0; k < R / 4; ++k) hdst[k] = make_uint4(Hs[4 * k], Hs[4 * k + 1], Hs[4 * k + 2], Hs[4 * k + 3]);
         }
     }
-    // merge the lanes' bests: highest score, then first in (column, row) scan order
+    // best cells, from the plane (the stores above are ordered before these loads by __syncwarp)
+    __syncwarp();
     int gscore[2];
     uint32_t ghit[2], gscRight[2];
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-        const S3Dp16Best &bb = x ? bestB : bestA;
-        int gbest = bb.best;
-        for (int o = LANES / 2; o > 0; o >>= 1) gbest = max(gbest, __shfl_xor_sync(0xFFFFFFFFu, gbest, o));
-        unsigned long long key = (bb.best == gbest && bb.count > 0) ? (((unsigned long long)bb.hitJ << 32) | bb.bestI) : ~0ull;
-        uint32_t cnt = (bb.best == gbest) ? bb.count : 0u;
-        for (int o = LANES / 2; o > 0; o >>= 1) {
-            key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
-            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
-        }
+        unsigned long long key;
+        uint32_t cnt;
+        s3_dp_best16<R, LANES>(plane, (uint32_t)x, (uint32_t)t, m[x], pairValid ? n[x] : 0u, clipRt[x], ancR[x], gscore[x], key, cnt);
         const bool any = key != ~0ull;
         const uint32_t bi = (uint32_t)(key & 0xFFFFFFFFu);
-        gscore[x] = gbest;
         ghit[x] = any ? (uint32_t)(key >> 32) : 0u;
-        gscRight[x] = (any && bi != 0) ? m[x] - bi : 0u;          // bi == 0: only ties with the -32000 start value
+        gscRight[x] = any ? m[x] - bi : 0u;
         if (t == 0 && pairValid && (x == 0 || hasB)) {
-            a.score[id[x]] = gbest;
+            a.score[id[x]] = gscore[x];
             a.cnt[id[x]] = cnt;
             if (a.cells) atomicAdd(a.cells, (unsigned long long)m[x] * n[x]);
         }
     }
-    // traceback while the pair's H plane is still in L2: lane 0 of the group takes alignment A,
-    // lane 1 alignment B (the stores above are ordered before these loads by __syncwarp)
-    __syncwarp();
+    // traceback while the pair's H plane is still in L2: lane 0 of the group takes alignment A, lane 1 alignment B
     if (t < 2 && pairValid && (t == 0 || hasB)) {
         const int x = t;
         uint32_t hit = ghit[x];

@@ -83,6 +83,9 @@ struct S3DpArgs {
     unsigned long long *cells;
     uint32_t *hplane;                // narrow path: H values, [pair][step][lane][R] words (A low half, B high half)
     uint32_t planeSteps;             // maxDNALength + lanes per pair
+    uint32_t open2, ext2, gapInit2;  // narrow path: score parameters in both 16-bit halves
+    uint32_t mism4, delta;           // mismatch score in all four bytes; (match ^ mismatch) & 0xFF
+    uint32_t colStride;              // narrow path: uint2 entries of one pair's column table (maxDNALength + 1)
 };
 
 __device__ __forceinline__ int s3_clamp(int x) { return max(x, S3_NEG_INF); }
@@ -450,7 +453,9 @@ __global__ void __launch_bounds__(S3_DP_WARPS * 32)
 s3_dp_align16_kernel(const S3DpArgs a)
 {
     constexpr int GROUPS = 32 / LANES;                            // pairs per warp
-    __shared__ uint32_t refWords[S3_DP_WARPS][GROUPS][2][S3_DP_MAX_REF_WORDS];
+    // per pair and reference column j: the two substitution tables of that column (byte c of .x / .y = score
+    // of alignment A / B's reference base j against read base c), built once, read every step
+    extern __shared__ uint2 s3_dp_cols[];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int group = lane / LANES, t = lane % LANES;
     const uint32_t numPairs = (a.count + 1) / 2;
@@ -471,15 +476,19 @@ s3_dp_align16_kernel(const S3DpArgs a)
     }
     const uint32_t mMax = max(m[0], m[1]), nMax = pairValid ? max(n[0], n[1]) : 0u;
     const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
-    const uint32_t OPEN2 = s3_pk(open, open), EXT2 = s3_pk(ext, ext), GAPINIT2 = s3_pk(gapInit, gapInit);
+    const uint32_t OPEN2 = a.open2, EXT2 = a.ext2, GAPINIT2 = a.gapInit2;
     const uint32_t i0 = t * R + 1;                                 // first row of this lane (1-based)
 
-    // reference windows -> shared memory (1-based packing, MSB first; DV-DPfunctions.cu:58)
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-        const uint32_t *dna = a.dna + (size_t)(id[x] >> 5) * a.dnaWords * 32 + (id[x] & 31);
-        const uint32_t nw = min((nMax >> 4) + 1, a.dnaWords);
-        for (uint32_t w = t; w < nw; w += LANES) refWords[warp][group][x][w] = dna[(size_t)w * 32];
+    // reference windows (1-based packing, MSB first; DV-DPfunctions.cu:58) -> column tables in shared memory
+    uint2 *cols = s3_dp_cols + (size_t)(warp * GROUPS + group) * a.colStride;
+    {
+        const uint32_t *dnaA = a.dna + (size_t)(id[0] >> 5) * a.dnaWords * 32 + (id[0] & 31);
+        const uint32_t *dnaB = a.dna + (size_t)(id[1] >> 5) * a.dnaWords * 32 + (id[1] & 31);
+        for (uint32_t j = t; j <= nMax; j += LANES) {
+            const uint32_t sh = (15u - (j & 15u)) << 1;
+            const uint32_t cA = (dnaA[(size_t)(j >> 4) * 32] >> sh) & 3u, cB = (dnaB[(size_t)(j >> 4) * 32] >> sh) & 3u;
+            cols[j] = make_uint2(a.mism4 ^ (a.delta << (cA << 3)), a.mism4 ^ (a.delta << (cB << 3)));
+        }
     }
     // this lane's read bases become PRMT selectors: the substitution score of a row is looked
     // up in a 4-byte table per alignment (byte c = score against reference base c)
@@ -498,20 +507,16 @@ s3_dp_align16_kernel(const S3DpArgs a)
         }
     }
     // column 0 (DV-DPfunctions.cu:167-184)
-    uint32_t Hp[R], Ep[R];
+    uint32_t Hs[R], Ep[R];              // previous column: H clamped at -32001 (as the plane keeps it), E clamped at -32000
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const uint32_t i = i0 + r;
         const int hA = (i <= clipLt[0]) ? open : gapInit + (int)(i - clipLt[0]) * ext;
         const int hB = (i <= clipLt[1]) ? open : gapInit + (int)(i - clipLt[1]) * ext;
-        Hp[r] = s3_pk(s3_clamp(hA), s3_clamp(hB));
+        Hs[r] = s3_pk(s3_clamp(hA), s3_clamp(hB));
         Ep[r] = s3_pk(s3_clamp(hA + gapInit), s3_clamp(hB + gapInit));
     }
     __syncwarp();
-
-    // substitution tables: byte c of tX = score of this column's reference base against read base c
-    const uint32_t MISM4 = ((uint32_t)a.mismatch & 0xFFu) * 0x01010101u;
-    const uint32_t DELTA = ((uint32_t)a.match ^ (uint32_t)a.mismatch) & 0xFFu;
 
     uint32_t upOut = 0, FOut = 0, diagRawOut = 0;
     uint32_t prevInit = 0;                                       // start value of the previous column
@@ -541,21 +546,18 @@ s3_dp_align16_kernel(const S3DpArgs a)
                 }
                 curInit = init; curPrev = prevInit;
             }
-            const uint32_t sh = (15u - (j & 15u)) << 1;
-            const uint32_t cA = (refWords[warp][group][0][j >> 4] >> sh) & 3u, cB = (refWords[warp][group][1][j >> 4] >> sh) & 3u;
-            const uint32_t tA = MISM4 ^ (DELTA << (cA << 3)), tB = MISM4 ^ (DELTA << (cB << 3));
-            uint32_t Hs[R];                                       // what goes to the plane: max(H, -32001)
+            const uint2 tab = cols[j];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t d = s3_prmt(tA, tB, sel[r]);
-                const uint32_t left = Hp[r], eL = Ep[r];
+                const uint32_t d = s3_prmt(tab.x, tab.y, sel[r]);
+                const uint32_t left = __vmaxs2(Hs[r], S3_NEG2), eL = Ep[r];       // H as the reference stores it
                 const uint32_t e = __viaddmax_s16x2(left, OPEN2, __vadd2(eL, EXT2));
                 F = __vimax3_s16x2(__vadd2(F, EXT2), __vadd2(up, OPEN2), clipIO[r]);
                 const uint32_t dg = __vmaxs2(diagRaw, clipPI[r]);
                 up = __vimax3_s16x2(F, e, __vadd2(dg, d));
                 diagRaw = left;
-                Hs[r] = __vmaxs2(up, S3_SUBNEG2);
-                Hp[r] = __vmaxs2(Hs[r], S3_NEG2); Ep[r] = __vmaxs2(e, S3_NEG2);
+                Hs[r] = __vmaxs2(up, S3_SUBNEG2);                                  // what the plane keeps
+                Ep[r] = __vmaxs2(e, S3_NEG2);
             }
             upOut = up; FOut = F; diagRawOut = diagRaw;
             prevInit = init;
@@ -626,6 +628,17 @@ extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint3
         dp->R = (maxReadLength <= 64) ? 4 : 8;
         dp->lanes = (maxReadLength <= 128) ? 16 : 32;
     }
+    if (dp->narrow) {
+        // column tables in dynamic shared memory: pairs per block x (maxDNALength + 1) x 8 bytes
+        const size_t smem = (size_t)S3_DP_WARPS * (32 / dp->lanes) * (maxDNALength + 1) * sizeof(uint2);
+        if (smem > 200 * 1024) dp->narrow = 0;                      // very long windows take the 32-bit path
+        else if (smem > 48 * 1024) {
+            S3_CUDA(cudaFuncSetAttribute(s3_dp_align16_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            S3_CUDA(cudaFuncSetAttribute(s3_dp_align16_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            S3_CUDA(cudaFuncSetAttribute(s3_dp_align16_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        }
+        if (!dp->narrow) dp->R = R;
+    }
     S3_CUDA(cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking));
     dp->ownStream = 1;
     // traceback planes are sized per chunk of alignments; narrow: per PAIR (maxDNALength+lanes) steps x lanes x
@@ -693,7 +706,17 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t n)
     a.dnaWords = (dp->maxDNALength + 15) >> 4; a.readWords = (dp->maxReadLength + 15) >> 4;
     a.slot = dp->slot; a.tb = dp->d_tb; a.scRight = dp->d_scRight;
     a.match = dp->sc.matchScore; a.mismatch = dp->sc.mismatchScore; a.open = dp->sc.gapOpenScore; a.ext = dp->sc.gapExtendScore;
-    if (dp->narrow) { a.planeSteps = dp->maxDNALength + dp->lanes; a.hplane = reinterpret_cast<uint32_t *>(dp->d_tb); }
+    size_t smem = 0;
+    if (dp->narrow) {
+        a.planeSteps = dp->maxDNALength + dp->lanes; a.hplane = reinterpret_cast<uint32_t *>(dp->d_tb);
+        const int gapInit = dp->sc.gapOpenScore - dp->sc.gapExtendScore;
+        auto pk = [](int v) { return ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16); };
+        a.open2 = pk(dp->sc.gapOpenScore); a.ext2 = pk(dp->sc.gapExtendScore); a.gapInit2 = pk(gapInit);
+        a.mism4 = ((uint32_t)dp->sc.mismatchScore & 0xFFu) * 0x01010101u;
+        a.delta = ((uint32_t)dp->sc.matchScore ^ (uint32_t)dp->sc.mismatchScore) & 0xFFu;
+        a.colStride = dp->maxDNALength + 1;
+        smem = (size_t)S3_DP_WARPS * (32 / dp->lanes) * a.colStride * sizeof(uint2);
+    }
     for (uint32_t first = 0; first < n; first += dp->chunk) {
         a.first = first;
         a.count = (n - first < dp->chunk) ? n - first : dp->chunk;
@@ -701,9 +724,9 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t n)
             const uint32_t pairs = (a.count + 1) / 2;
             const uint32_t perBlock = S3_DP_WARPS * (32 / dp->lanes);
             const uint32_t blocks = (pairs + perBlock - 1) / perBlock;
-            if (dp->lanes == 32) s3_dp_align16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
-            else if (dp->R == 8) s3_dp_align16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
-            else s3_dp_align16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+            if (dp->lanes == 32) s3_dp_align16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
+            else if (dp->R == 8) s3_dp_align16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
+            else s3_dp_align16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
             S3_LAUNCHED(1);
             S3_CUDA(cudaGetLastError());
             continue;

@@ -298,40 +298,97 @@ __device__ __forceinline__ uint32_t s3_prmt(uint32_t a, uint32_t b, uint32_t sel
 
 #define S3_SUBNEG2 0x82FF82FFu       // -32001 in both halves: what the plane stores for "below the clamp"
 
-// Best cell of one alignment (DV-DPfunctions.cu:225-235) found AFTER the sweep, from the pair's H
-// plane: highest H over the rows i >= m - clipRt and the columns anchorRight <= j <= n, the first
-// such cell in (column, row) order, and the number of cells that tie with it.  The group's lanes
-// take the columns round-robin.  The reference compares the UNclamped value of a cell with a running
-// best that starts at -32000; the plane stores max(value, -32001), so a cell below the clamp (-32001)
-// neither beats nor ties that start value, exactly like the reference's test.
-// Returns in every lane of the group: best score, key = column << 32 | row (~0 if nothing tied or
-// beat the start value; row 0 cannot occur), tie count.
-template <int R, int LANES>
-__device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t half, uint32_t t, uint32_t m, uint32_t n,
-                                             uint32_t clipRt, uint32_t anchorRight,
-                                             int &gbest, unsigned long long &gkey, uint32_t &gcnt)
+struct S3Dp16Best { int best; uint32_t cnt; unsigned long long key; };
+
+// DV-DPfunctions.cu:225-235 for one cell, without branches
+__device__ __forceinline__ void s3_best_update(S3Dp16Best &b, bool eligible, int v, uint32_t j, uint32_t i)
 {
-    const uint32_t iLo = (clipRt >= m) ? 1u : max(m - clipRt, 1u), jLo = max(anchorRight, 1u);
-    int best = S3_NEG_INF;
-    uint32_t cnt = 0;
-    unsigned long long key = ~0ull;
-    for (uint32_t j = jLo + t; j <= n; j += LANES) {
-        for (uint32_t i = iLo; i <= m; ++i) {
-            const uint32_t ti = (i - 1) / R, r = (i - 1) % R;
-            const uint32_t w = plane[((size_t)(j + ti) * LANES + ti) * R + r];
-            const int v = half ? s3_hi16(w) : s3_lo16(w);
-            if (v > best) { best = v; cnt = 1; key = ((unsigned long long)j << 32) | i; }
-            else if (v == best) ++cnt;
-        }
+    const bool gt = eligible && v > b.best, eq = eligible && v == b.best;
+    b.best = gt ? v : b.best;
+    const unsigned long long k = ((unsigned long long)j << 32) | i;
+    b.key = gt ? k : (eq ? min(b.key, k) : b.key);          // first in (column, row) order, whatever the visiting order
+    b.cnt = gt ? 1u : b.cnt + (eq ? 1u : 0u);
+}
+
+// Best cells of the two alignments of a pair (DV-DPfunctions.cu:225-235) found AFTER the sweep, from
+// the pair's H plane: per alignment the highest H over the rows i >= m - clipRt and the columns
+// anchorRight <= j <= n, the first such cell in (column, row) order, and the number of cells that tie
+// with it.  The reference compares the UNclamped value of a cell with a running best that starts at
+// -32000; the plane stores max(value, -32001), so a cell below the clamp (-32001) neither beats nor
+// ties that start value, exactly like the reference's test.
+// Work items are (lane slot, column) = R consecutive rows of both alignments = one 16- or 32-byte
+// entry of the slot's stream; the group's lanes take the columns round-robin, two at a time so that
+// the loads overlap.
+// Out, in every lane of the group: best score, key = column << 32 | row (~0 if nothing beat the start
+// value), tie count.
+template <int R, int LANES>
+__device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps, uint32_t t, const uint32_t m[2], const uint32_t n[2],
+                                             const uint32_t clipRt[2], const uint32_t ancR[2],
+                                             int gbest[2], unsigned long long gkey[2], uint32_t gcnt[2])
+{
+    uint32_t iLo[2], jLo[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        iLo[x] = (clipRt[x] >= m[x]) ? 1u : max(m[x] - clipRt[x], 1u);
+        jLo[x] = max(ancR[x], 1u);
     }
-    gbest = best;
-    for (int o = LANES / 2; o > 0; o >>= 1) gbest = max(gbest, __shfl_xor_sync(0xFFFFFFFFu, gbest, o));
-    // cells that only tie with the -32000 start value count but set no position (key stays ~0)
-    gkey = (best == gbest) ? key : ~0ull;
-    gcnt = (best == gbest) ? cnt : 0u;
-    for (int o = LANES / 2; o > 0; o >>= 1) {
-        gkey = min(gkey, __shfl_xor_sync(0xFFFFFFFFu, gkey, o));
-        gcnt += __shfl_xor_sync(0xFFFFFFFFu, gcnt, o);
+    const uint32_t mMax = max(m[0], m[1]);
+    const uint32_t tiLo = (min(iLo[0], iLo[1]) - 1) / R, nSlots = (mMax ? (mMax - 1) / R : 0u) - tiLo + 1;
+    const uint32_t jStart = min(jLo[0], jLo[1]), jEnd = max(n[0], n[1]);
+    S3Dp16Best bb[2] = {{S3_NEG_INF, 0u, ~0ull}, {S3_NEG_INF, 0u, ~0ull}};
+    uint32_t best2 = S3_NEG2;
+
+    // slot after slot, columns round-robin over the lanes: one iteration of the group reads LANES consecutive
+    // R-word entries of a slot's stream
+    const uint32_t nCols = (mMax && jEnd >= jStart) ? jEnd - jStart + 1 : 0u, colsUp = (nCols + LANES - 1) / LANES * LANES;
+    auto locate = [&](uint32_t q, uint32_t &j, uint32_t &ti) { ti = tiLo + q / colsUp; j = jStart + q % colsUp; };
+    auto fetch = [&](uint32_t j, uint32_t ti, uint32_t w[R]) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(plane + ((size_t)(j + ti) * LANES + ti) * R);
+#pragma unroll
+        for (int k = 0; k < R / 4; ++k) { const uint4 v = src[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+    };
+    auto consume = [&](uint32_t j, uint32_t ti, const uint32_t w[R]) {
+        // conservative trigger: some cell of the slot (eligible or not) reaches a running best
+        uint32_t mx = w[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) mx = __vmaxs2(mx, w[r]);
+        bool gh, gl;
+        (void)__vibmax_s16x2(mx, best2, &gh, &gl);
+        if (gh || gl) {
+            const bool okA = j >= jLo[0] && j <= n[0], okB = j >= jLo[1] && j <= n[1];
+#pragma unroll
+            for (int r = 0; r < R; ++r) {
+                const uint32_t i = ti * R + r + 1;
+                s3_best_update(bb[0], okA && i >= iLo[0] && i <= m[0], s3_lo16(w[r]), j, i);
+                s3_best_update(bb[1], okB && i >= iLo[1] && i <= m[1], s3_hi16(w[r]), j, i);
+            }
+            best2 = s3_pk(bb[0].best, bb[1].best);
+        }
+    };
+    const uint32_t items = colsUp * nSlots;
+    for (uint32_t q = t; q < items; q += 2 * LANES) {
+        uint32_t j0, t0, j1 = 0, t1 = 0, w0[R], w1[R];
+        locate(q, j0, t0);
+        const bool first = j0 <= jEnd;
+        if (first) fetch(j0, t0, w0);
+        bool second = q + LANES < items;
+        if (second) { locate(q + LANES, j1, t1); second = j1 <= jEnd; }
+        if (second) fetch(j1, t1, w1);
+        if (first) consume(j0, t0, w0);
+        if (second) consume(j1, t1, w1);
+    }
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        int g = bb[x].best;
+        for (int o = LANES / 2; o > 0; o >>= 1) g = max(g, __shfl_xor_sync(0xFFFFFFFFu, g, o));
+        // cells that only tie with the -32000 start value count but set no position (key stays ~0)
+        unsigned long long key = (bb[x].best == g) ? bb[x].key : ~0ull;
+        uint32_t cnt = (bb[x].best == g) ? bb[x].cnt : 0u;
+        for (int o = LANES / 2; o > 0; o >>= 1) {
+            key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
+            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+        }
+        gbest[x] = g; gkey[x] = key; gcnt[x] = cnt;
     }
 }
 
@@ -341,7 +398,7 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t hal
 // H(j,0), H(0,i) -- which the reference also keeps in its table -- are recomputed from their
 // defining formulas.  Returns the start offset inside the window (the new hitLocs value).
 template <int R, int LANES>
-__device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, uint32_t half, uint32_t id,
+__device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, uint32_t ps, uint32_t half, uint32_t id,
                                       uint32_t m, uint32_t clipLt, uint32_t anchorLeft, uint32_t scRight, uint32_t hit)
 {
     const uint32_t *dna = a.dna + (size_t)(id >> 5) * a.dnaWords * 32 + (id & 31);
@@ -446,11 +503,11 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, 
     return refIndex;             // start offset inside the window (refOffset == 0 in scheme 1)
 }
 
-// Score pass + traceback of S3_DP_WARPS * (32 / LANES) pairs of alignments per block.  A pair is
-// swept by a group of LANES lanes, each owning R consecutive read rows.
+// Score pass of S3_DP_WARPS * (32 / LANES) pairs of alignments per block.  A pair is swept by a
+// group of LANES lanes, each owning R consecutive read rows; only the H plane is written.
 template <int R, int LANES>
 __global__ void __launch_bounds__(S3_DP_WARPS * 32)
-s3_dp_align16_kernel(const S3DpArgs a)
+s3_dp_score16_kernel(const S3DpArgs a)
 {
     constexpr int GROUPS = 32 / LANES;                            // pairs per warp
     // per pair and reference column j: the two substitution tables of that column (byte c of .x / .y = score
@@ -484,6 +541,7 @@ s3_dp_align16_kernel(const S3DpArgs a)
     {
         const uint32_t *dnaA = a.dna + (size_t)(id[0] >> 5) * a.dnaWords * 32 + (id[0] & 31);
         const uint32_t *dnaB = a.dna + (size_t)(id[1] >> 5) * a.dnaWords * 32 + (id[1] & 31);
+#pragma unroll 4
         for (uint32_t j = t; j <= nMax; j += LANES) {
             const uint32_t sh = (15u - (j & 15u)) << 1;
             const uint32_t cA = (dnaA[(size_t)(j >> 4) * 32] >> sh) & 3u, cB = (dnaB[(size_t)(j >> 4) * 32] >> sh) & 3u;
@@ -567,31 +625,77 @@ s3_dp_align16_kernel(const S3DpArgs a)
             for (int k = 0; k < R / 4; ++k) hdst[k] = make_uint4(Hs[4 * k], Hs[4 * k + 1], Hs[4 * k + 2], Hs[4 * k + 3]);
         }
     }
-    // best cells, from the plane (the stores above are ordered before these loads by __syncwarp)
-    __syncwarp();
-    int gscore[2];
-    uint32_t ghit[2], gscRight[2];
+}
+
+// Second kernel of the 16x2 path: best cell and traceback of one pair per group of LANES lanes.
+// These phases wait on memory, not on the integer pipe, so they run apart from the sweep with
+// small register needs and many resident warps.
+template <int R, int LANES>
+__global__ void __launch_bounds__(S3_DP_WARPS * 32)
+s3_dp_finish16_kernel(const S3DpArgs a)
+{
+    constexpr int GROUPS = 32 / LANES;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = lane / LANES, t = lane % LANES;
+    const uint32_t numPairs = (a.count + 1) / 2;
+    const uint32_t wantPair = (blockIdx.x * S3_DP_WARPS + warp) * GROUPS + group;
+    if ((blockIdx.x * S3_DP_WARPS + warp) * GROUPS >= numPairs) return;          // whole warp leaves together
+    const bool pairValid = wantPair < numPairs;
+    const uint32_t pairLocal = pairValid ? wantPair : numPairs - 1;
+    const bool hasB = 2 * pairLocal + 1 < a.count;
+    const uint32_t id[2] = {a.first + 2 * pairLocal, a.first + 2 * pairLocal + (hasB ? 1u : 0u)};
+    uint32_t m[2], n[2], clipLt[2], clipRt[2], ancL[2], ancR[2];
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-        unsigned long long key;
-        uint32_t cnt;
-        s3_dp_best16<R, LANES>(plane, (uint32_t)x, (uint32_t)t, m[x], pairValid ? n[x] : 0u, clipRt[x], ancR[x], gscore[x], key, cnt);
-        const bool any = key != ~0ull;
-        const uint32_t bi = (uint32_t)(key & 0xFFFFFFFFu);
-        ghit[x] = any ? (uint32_t)(key >> 32) : 0u;
+        m[x] = a.readLen[id[x]]; n[x] = a.dnaLen[id[x]];
+        clipLt[x] = a.clipLt ? a.clipLt[id[x]] : 0u;
+        clipRt[x] = a.clipRt ? a.clipRt[id[x]] : 0u;
+        ancL[x] = a.ancL ? a.ancL[id[x]] : a.maxDNALength;
+        ancR[x] = a.ancR ? a.ancR[id[x]] : 0u;
+    }
+    const uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
+    int gscore[2];
+    uint32_t ghit[2], gscRight[2], gcnt[2];
+    unsigned long long gkey[2];
+    {
+        const uint32_t nn[2] = {pairValid ? n[0] : 0u, pairValid ? n[1] : 0u};
+        s3_dp_best16<R, LANES>(plane, a.planeSteps, (uint32_t)t, m, nn, clipRt, ancR, gscore, gkey, gcnt);
+    }
+    bool trace[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        const bool any = gkey[x] != ~0ull;
+        const uint32_t bi = (uint32_t)(gkey[x] & 0xFFFFFFFFu);
+        ghit[x] = any ? (uint32_t)(gkey[x] >> 32) : 0u;
         gscRight[x] = any ? m[x] - bi : 0u;
+        trace[x] = pairValid && (x == 0 || hasB) && gscore[x] >= a.cutoff[id[x]];
         if (t == 0 && pairValid && (x == 0 || hasB)) {
             a.score[id[x]] = gscore[x];
-            a.cnt[id[x]] = cnt;
+            a.cnt[id[x]] = gcnt[x];
             if (a.cells) atomicAdd(a.cells, (unsigned long long)m[x] * n[x]);
         }
+        // The traceback below is one lane chasing dependent loads.  Most of a path stays on the diagonal
+        // through the best cell, so all lanes of the group touch those cells now: by the time the
+        // walking lane needs them they are on their way into L1/L2.
+        if (trace[x]) {
+            const uint32_t rp = m[x] - gscRight[x];
+            uint32_t touched = 0;
+            for (uint32_t k = t; k < rp && k < ghit[x]; k += LANES) {
+                const uint32_t i = rp - k, ti = (i - 1) / R, r = (i - 1) % R;
+                {
+                    const int j = (int)(ghit[x] - k);
+                    if (j >= 1 && j <= (int)n[x]) touched ^= plane[((size_t)(j + ti) * LANES + ti) * R + r];
+                }
+            }
+            if (touched == 0x9E3779B9u) a.cnt[id[x]] = gcnt[x];     // keeps the loads alive; never changes a result
+        }
     }
-    // traceback while the pair's H plane is still in L2: lane 0 of the group takes alignment A, lane 1 alignment B
+    // traceback: lane 0 of the group takes alignment A, lane 1 alignment B
     if (t < 2 && pairValid && (t == 0 || hasB)) {
         const int x = t;
         uint32_t hit = ghit[x];
-        if (gscore[x] >= a.cutoff[id[x]])
-            hit = s3_dp_traceback16<R, LANES>(a, plane, (uint32_t)x, id[x], m[x], clipLt[x], ancL[x], gscRight[x], hit);
+        if (trace[x])
+            hit = s3_dp_traceback16<R, LANES>(a, plane, a.planeSteps, (uint32_t)x, id[x], m[x], clipLt[x], ancL[x], gscRight[x], hit);
         a.hit[id[x]] = hit;
     }
 }
@@ -633,9 +737,9 @@ extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint3
         const size_t smem = (size_t)S3_DP_WARPS * (32 / dp->lanes) * (maxDNALength + 1) * sizeof(uint2);
         if (smem > 200 * 1024) dp->narrow = 0;                      // very long windows take the 32-bit path
         else if (smem > 48 * 1024) {
-            S3_CUDA(cudaFuncSetAttribute(s3_dp_align16_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            S3_CUDA(cudaFuncSetAttribute(s3_dp_align16_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            S3_CUDA(cudaFuncSetAttribute(s3_dp_align16_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            S3_CUDA(cudaFuncSetAttribute(s3_dp_score16_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            S3_CUDA(cudaFuncSetAttribute(s3_dp_score16_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            S3_CUDA(cudaFuncSetAttribute(s3_dp_score16_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         }
         if (!dp->narrow) dp->R = R;
     }
@@ -724,10 +828,17 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t n)
             const uint32_t pairs = (a.count + 1) / 2;
             const uint32_t perBlock = S3_DP_WARPS * (32 / dp->lanes);
             const uint32_t blocks = (pairs + perBlock - 1) / perBlock;
-            if (dp->lanes == 32) s3_dp_align16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
-            else if (dp->R == 8) s3_dp_align16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
-            else s3_dp_align16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
-            S3_LAUNCHED(1);
+            if (dp->lanes == 32) {
+                s3_dp_score16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
+                s3_dp_finish16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+            } else if (dp->R == 8) {
+                s3_dp_score16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
+                s3_dp_finish16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+            } else {
+                s3_dp_score16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
+                s3_dp_finish16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+            }
+            S3_LAUNCHED(2);
             S3_CUDA(cudaGetLastError());
             continue;
         }

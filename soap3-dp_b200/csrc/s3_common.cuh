@@ -26,6 +26,17 @@ struct S3Half {
     uint32_t numBuckets;
 };
 
+// Copy/compute pipeline of the host-pointer entry points: a batch is cut into chunks; chunk c+1 goes up
+// on `in` while chunk c computes on the handle's own stream and chunk c-1 comes down on `out`.
+#define S3_PIPE_CHUNKS 16
+struct S3Pipe {
+    cudaStream_t in, out;
+    cudaEvent_t up[S3_PIPE_CHUNKS], done[S3_PIPE_CHUNKS];
+    int ready;
+};
+int s3_pipe_init(S3Pipe *p);
+void s3_pipe_destroy(S3Pipe *p);
+
 struct s3_index {
     int device;
     cudaStream_t stream;
@@ -38,6 +49,7 @@ struct s3_index {
     // scratch reused across calls (grown on demand)
     void *scratch; size_t scratchBytes;
     void *pinned; size_t pinnedBytes;
+    S3Pipe pipe;
     // persistent search launches
     uint32_t *d_workCounter;
     int numSms;

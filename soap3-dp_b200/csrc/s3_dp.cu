@@ -67,6 +67,7 @@ struct s3_dp {
     int32_t *d_cutoff, *d_score;
     uint8_t *d_pattern;
     unsigned long long *d_cells;
+    S3Pipe pipe;
 };
 
 struct S3DpArgs {
@@ -784,6 +785,7 @@ extern "C" void s3_dp_free(s3_dp *dp)
     void *ptrs[] = {dp->d_tb, dp->d_scRight, dp->d_dna, dp->d_read, dp->d_dnaLen, dp->d_readLen, dp->d_hit, dp->d_cnt,
                     dp->d_clipLt, dp->d_clipRt, dp->d_ancL, dp->d_ancR, dp->d_cutoff, dp->d_score, dp->d_pattern, dp->d_cells};
     for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; ++i) if (ptrs[i]) cudaFree(ptrs[i]);
+    s3_pipe_destroy(&dp->pipe);
     if (dp->ownStream) cudaStreamDestroy(dp->stream);
     free(dp);
 }
@@ -804,7 +806,8 @@ static void launch_score(const S3DpArgs &a, cudaStream_t st)
     s3_dp_score_kernel<R><<<(a.count + S3_DP_WARPS - 1) / S3_DP_WARPS, S3_DP_WARPS * 32, 0, st>>>(a);
 }
 
-static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t n)
+// alignments [begin, end) of the batch arrays in `a`
+static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t begin, uint32_t end)
 {
     a.maxReadLength = dp->maxReadLength; a.maxDNALength = dp->maxDNALength;
     a.dnaWords = (dp->maxDNALength + 15) >> 4; a.readWords = (dp->maxReadLength + 15) >> 4;
@@ -821,9 +824,9 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t n)
         a.colStride = dp->maxDNALength + 1;
         smem = (size_t)S3_DP_WARPS * (32 / dp->lanes) * a.colStride * sizeof(uint2);
     }
-    for (uint32_t first = 0; first < n; first += dp->chunk) {
+    for (uint32_t first = begin; first < end; first += dp->chunk) {
         a.first = first;
-        a.count = (n - first < dp->chunk) ? n - first : dp->chunk;
+        a.count = (end - first < dp->chunk) ? end - first : dp->chunk;
         if (dp->narrow) {
             const uint32_t pairs = (a.count + 1) / 2;
             const uint32_t perBlock = S3_DP_WARPS * (32 / dp->lanes);
@@ -875,7 +878,20 @@ extern "C" int s3_dp_align_device(s3_dp *dp, const uint32_t *d_dna, const uint32
     a.score = d_scores; a.hit = d_hitLocs; a.cnt = d_maxScoreCounts; a.pattern = d_pattern;
     a.clipLt = d_clipLt; a.clipRt = d_clipRt; a.ancL = d_ancL; a.ancR = d_ancR;
     a.cells = NULL;
-    return dp_run_device(dp, a, numOfThreads);
+    return dp_run_device(dp, a, 0, numOfThreads);
+}
+
+// the same for a sub-range of the batch (the host entry point pipelines copies against it)
+static int dp_align_device_range(s3_dp *dp, uint32_t begin, uint32_t end, bool clipLt, bool clipRt, bool ancL, bool ancR)
+{
+    S3DpArgs a;
+    memset(&a, 0, sizeof a);
+    a.dna = dp->d_dna; a.dnaLen = dp->d_dnaLen; a.read = dp->d_read; a.readLen = dp->d_readLen; a.cutoff = dp->d_cutoff;
+    a.score = dp->d_score; a.hit = dp->d_hit; a.cnt = dp->d_cnt; a.pattern = dp->d_pattern;
+    a.clipLt = clipLt ? dp->d_clipLt : NULL; a.clipRt = clipRt ? dp->d_clipRt : NULL;
+    a.ancL = ancL ? dp->d_ancL : NULL; a.ancR = ancR ? dp->d_ancR : NULL;
+    a.cells = NULL;
+    return dp_run_device(dp, a, begin, end);
 }
 
 extern "C" int s3_dp_align(s3_dp *dp, const uint32_t *packedDNASequence, const uint32_t *DNALengths,
@@ -890,29 +906,46 @@ extern "C" int s3_dp_align(s3_dp *dp, const uint32_t *packedDNASequence, const u
     if (numOfThreads > dp->maxBatch) { s3_set_error("s3_dp_align: %u alignments > maxBatch %u", numOfThreads, dp->maxBatch); return S3_EINVAL; }
     if (numOfThreads == 0) return S3_OK;
     S3_CUDA(cudaSetDevice(dp->device));
-    const size_t n = numOfThreads, up = (n + 31) / 32 * 32;
+    const size_t n = numOfThreads;
     const size_t dnaW = (dp->maxDNALength + 15) >> 4, readW = (dp->maxReadLength + 15) >> 4;
     const size_t patLen = dp->maxReadLength + dp->maxDNALength;
     cudaStream_t st = dp->stream;
-    // unlike the reference, only the filled part of the fixed-size batch arrays is moved (DV-DPfunctions.cu:678-682)
-    S3_CUDA(cudaMemcpyAsync(dp->d_dna, packedDNASequence, up * dnaW * 4, cudaMemcpyHostToDevice, st));
-    S3_CUDA(cudaMemcpyAsync(dp->d_read, packedReadSequence, up * readW * 4, cudaMemcpyHostToDevice, st));
-    S3_CUDA(cudaMemcpyAsync(dp->d_dnaLen, DNALengths, n * 4, cudaMemcpyHostToDevice, st));
-    S3_CUDA(cudaMemcpyAsync(dp->d_readLen, readLengths, n * 4, cudaMemcpyHostToDevice, st));
-    S3_CUDA(cudaMemcpyAsync(dp->d_cutoff, cutoffThresholds, n * 4, cudaMemcpyHostToDevice, st));
-    if (clipLtSizes) S3_CUDA(cudaMemcpyAsync(dp->d_clipLt, clipLtSizes, n * 4, cudaMemcpyHostToDevice, st));
-    if (clipRtSizes) S3_CUDA(cudaMemcpyAsync(dp->d_clipRt, clipRtSizes, n * 4, cudaMemcpyHostToDevice, st));
-    if (anchorLeftLocs) S3_CUDA(cudaMemcpyAsync(dp->d_ancL, anchorLeftLocs, n * 4, cudaMemcpyHostToDevice, st));
-    if (anchorRightLocs) S3_CUDA(cudaMemcpyAsync(dp->d_ancR, anchorRightLocs, n * 4, cudaMemcpyHostToDevice, st));
-    int rc = s3_dp_align_device(dp, dp->d_dna, dp->d_dnaLen, dp->d_read, dp->d_readLen, dp->d_cutoff, dp->d_score,
-                                dp->d_hit, dp->d_cnt, dp->d_pattern, numOfThreads,
-                                clipLtSizes ? dp->d_clipLt : NULL, clipRtSizes ? dp->d_clipRt : NULL,
-                                anchorLeftLocs ? dp->d_ancL : NULL, anchorRightLocs ? dp->d_ancR : NULL);
-    if (rc) return rc;
-    S3_CUDA(cudaMemcpyAsync(scores, dp->d_score, n * 4, cudaMemcpyDeviceToHost, st));
-    S3_CUDA(cudaMemcpyAsync(hitLocs, dp->d_hit, n * 4, cudaMemcpyDeviceToHost, st));
-    S3_CUDA(cudaMemcpyAsync(maxScoreCounts, dp->d_cnt, n * 4, cudaMemcpyDeviceToHost, st));
-    S3_CUDA(cudaMemcpyAsync(pattern, dp->d_pattern, n * patLen, cudaMemcpyDeviceToHost, st));
+    int rc;
+    if ((rc = s3_pipe_init(&dp->pipe))) return rc;
+    S3Pipe &pp = dp->pipe;
+    // Chunks of whole 32-alignment groups (the interleave unit of the packed sequences): chunk k+1 goes up
+    // while chunk k is aligned and chunk k-1 comes down.  Unlike the reference, only the filled part of the
+    // fixed-size batch arrays is moved (DV-DPfunctions.cu:678-682 copies batchSize entries whatever the fill).
+    // Two chunks only: each must still fill the device several times over.
+    size_t chunk = (n >= 65536) ? (((n + 31) / 32 * 32) / 2 + 31) / 32 * 32 : (n + 31) / 32 * 32;
+    if (chunk > dp->chunk) chunk = dp->chunk / 32 * 32;
+    if (chunk < 32) chunk = 32;
+    S3_CUDA(cudaEventRecord(pp.done[0], st));
+    S3_CUDA(cudaStreamWaitEvent(pp.in, pp.done[0], 0));
+    int k = 0;
+    for (size_t c0 = 0; c0 < n; c0 += chunk, k = (k + 1) % S3_PIPE_CHUNKS) {
+        const size_t cnt = (n - c0 < chunk) ? n - c0 : chunk, cntUp = (cnt + 31) / 32 * 32;
+        S3_CUDA(cudaMemcpyAsync(dp->d_dna + c0 * dnaW, packedDNASequence + c0 * dnaW, cntUp * dnaW * 4, cudaMemcpyHostToDevice, pp.in));
+        S3_CUDA(cudaMemcpyAsync(dp->d_read + c0 * readW, packedReadSequence + c0 * readW, cntUp * readW * 4, cudaMemcpyHostToDevice, pp.in));
+        S3_CUDA(cudaMemcpyAsync(dp->d_dnaLen + c0, DNALengths + c0, cnt * 4, cudaMemcpyHostToDevice, pp.in));
+        S3_CUDA(cudaMemcpyAsync(dp->d_readLen + c0, readLengths + c0, cnt * 4, cudaMemcpyHostToDevice, pp.in));
+        S3_CUDA(cudaMemcpyAsync(dp->d_cutoff + c0, cutoffThresholds + c0, cnt * 4, cudaMemcpyHostToDevice, pp.in));
+        if (clipLtSizes) S3_CUDA(cudaMemcpyAsync(dp->d_clipLt + c0, clipLtSizes + c0, cnt * 4, cudaMemcpyHostToDevice, pp.in));
+        if (clipRtSizes) S3_CUDA(cudaMemcpyAsync(dp->d_clipRt + c0, clipRtSizes + c0, cnt * 4, cudaMemcpyHostToDevice, pp.in));
+        if (anchorLeftLocs) S3_CUDA(cudaMemcpyAsync(dp->d_ancL + c0, anchorLeftLocs + c0, cnt * 4, cudaMemcpyHostToDevice, pp.in));
+        if (anchorRightLocs) S3_CUDA(cudaMemcpyAsync(dp->d_ancR + c0, anchorRightLocs + c0, cnt * 4, cudaMemcpyHostToDevice, pp.in));
+        S3_CUDA(cudaEventRecord(pp.up[k], pp.in));
+        S3_CUDA(cudaStreamWaitEvent(st, pp.up[k], 0));
+        if ((rc = dp_align_device_range(dp, (uint32_t)c0, (uint32_t)(c0 + cnt), clipLtSizes != NULL, clipRtSizes != NULL,
+                                        anchorLeftLocs != NULL, anchorRightLocs != NULL))) return rc;
+        S3_CUDA(cudaEventRecord(pp.done[k], st));
+        S3_CUDA(cudaStreamWaitEvent(pp.out, pp.done[k], 0));
+        S3_CUDA(cudaMemcpyAsync(scores + c0, dp->d_score + c0, cnt * 4, cudaMemcpyDeviceToHost, pp.out));
+        S3_CUDA(cudaMemcpyAsync(hitLocs + c0, dp->d_hit + c0, cnt * 4, cudaMemcpyDeviceToHost, pp.out));
+        S3_CUDA(cudaMemcpyAsync(maxScoreCounts + c0, dp->d_cnt + c0, cnt * 4, cudaMemcpyDeviceToHost, pp.out));
+        S3_CUDA(cudaMemcpyAsync(pattern + c0 * patLen, dp->d_pattern + c0 * patLen, cnt * patLen, cudaMemcpyDeviceToHost, pp.out));
+    }
+    S3_CUDA(cudaStreamSynchronize(pp.out));
     S3_CUDA(cudaStreamSynchronize(st));
     return S3_OK;
 }

@@ -27,6 +27,27 @@ extern "C" int s3_device_count(void)
     return n;
 }
 
+int s3_pipe_init(S3Pipe *p)
+{
+    if (p->ready) return S3_OK;
+    S3_CUDA(cudaStreamCreateWithFlags(&p->in, cudaStreamNonBlocking));
+    S3_CUDA(cudaStreamCreateWithFlags(&p->out, cudaStreamNonBlocking));
+    for (int i = 0; i < S3_PIPE_CHUNKS; ++i) {
+        S3_CUDA(cudaEventCreateWithFlags(&p->up[i], cudaEventDisableTiming));
+        S3_CUDA(cudaEventCreateWithFlags(&p->done[i], cudaEventDisableTiming));
+    }
+    p->ready = 1;
+    return S3_OK;
+}
+
+void s3_pipe_destroy(S3Pipe *p)
+{
+    if (!p->ready) return;
+    cudaStreamDestroy(p->in); cudaStreamDestroy(p->out);
+    for (int i = 0; i < S3_PIPE_CHUNKS; ++i) { cudaEventDestroy(p->up[i]); cudaEventDestroy(p->done[i]); }
+    p->ready = 0;
+}
+
 int s3_scratch(s3_index *ix, size_t bytes, void **out)
 {
     if (bytes > ix->scratchBytes) {
@@ -178,6 +199,7 @@ extern "C" void s3_index_free(s3_index *ix)
     cudaFree(ix->d_fwd); cudaFree(ix->d_rev);
     if (ix->d_packedDNA) cudaFree(ix->d_packedDNA);
     if (ix->d_sa) cudaFree(ix->d_sa);
+    s3_pipe_destroy(&ix->pipe);
     if (ix->d_workCounter) cudaFree(ix->d_workCounter);
     if (ix->scratch) cudaFree(ix->scratch);
     if (ix->pinned) cudaFreeHost(ix->pinned);

@@ -409,6 +409,7 @@ extern "C" int s3_search_round1(s3_index *ix, const uint32_t *queries, const uin
     if (rc) return rc;
     if (batchSize == 0) return S3_OK;
     S3_CUDA(cudaSetDevice(ix->device));
+    if ((rc = s3_pipe_init(&ix->pipe))) return rc;
     const size_t roundUp = (batchSize + 31) / 32 * 32;
     const size_t qBytes = roundUp * wordPerQuery * 4, lBytes = roundUp * 4, aBytes = roundUp * wordPerAns * 4;
     char *d;
@@ -416,13 +417,33 @@ extern "C" int s3_search_round1(s3_index *ix, const uint32_t *queries, const uin
     uint32_t *d_q = (uint32_t *)d, *d_l = (uint32_t *)(d + qBytes);
     uint32_t *d_ans[S3_MAX_NUM_CASES];
     for (uint32_t c = 0; c < numCases; ++c) d_ans[c] = (uint32_t *)(d + qBytes + lBytes + aBytes * c);
-    S3_CUDA(cudaMemcpyAsync(d_q, queries, qBytes, cudaMemcpyHostToDevice, ix->stream));
-    // the reference copies roundUp lengths (alignment.cu:161); only batchSize are meaningful
-    S3_CUDA(cudaMemcpyAsync(d_l, readLengths, batchSize * 4, cudaMemcpyHostToDevice, ix->stream));
-    if ((rc = s3_search_round1_device(ix, d_q, d_l, batchSize, wordPerQuery, numMismatch, numCases, saRangeAllowed,
-                                      wordPerAns, isExactNumMismatch, d_ans, NULL))) return rc;
-    for (uint32_t c = 0; c < numCases; ++c)
-        S3_CUDA(cudaMemcpyAsync(answers[c], d_ans[c], aBytes, cudaMemcpyDeviceToHost, ix->stream));
+    // Chunks of whole 32-read groups (the interleave unit of both buffers, so a chunk is a contiguous
+    // slice of each): chunk k+1 is copied in while chunk k is searched and chunk k-1 is copied out.
+    // (The reference copies, launches per case and copies back strictly in sequence, alignment.cu:158-215.)
+    // Two chunks only: a launch needs several items per resident lane to keep the persistent warps busy.
+    size_t chunk = (batchSize >= 262144) ? ((roundUp / 2 + 31) / 32) * 32 : roundUp;
+    S3Pipe &pp = ix->pipe;
+    S3_CUDA(cudaEventRecord(pp.done[0], ix->stream));               // earlier work on the scratch buffer
+    S3_CUDA(cudaStreamWaitEvent(pp.in, pp.done[0], 0));
+    int k = 0;
+    for (size_t c0 = 0; c0 < batchSize; c0 += chunk, k = (k + 1) % S3_PIPE_CHUNKS) {
+        const size_t cnt = (batchSize - c0 < chunk) ? batchSize - c0 : chunk, cntUp = (cnt + 31) / 32 * 32;
+        S3_CUDA(cudaMemcpyAsync(d_q + c0 * wordPerQuery, queries + c0 * wordPerQuery, cntUp * wordPerQuery * 4,
+                                cudaMemcpyHostToDevice, pp.in));
+        // the reference copies roundUp lengths (alignment.cu:161); only batchSize are meaningful
+        S3_CUDA(cudaMemcpyAsync(d_l + c0, readLengths + c0, cnt * 4, cudaMemcpyHostToDevice, pp.in));
+        S3_CUDA(cudaEventRecord(pp.up[k], pp.in));
+        S3_CUDA(cudaStreamWaitEvent(ix->stream, pp.up[k], 0));
+        uint32_t *d_sub[S3_MAX_NUM_CASES];
+        for (uint32_t c = 0; c < numCases; ++c) d_sub[c] = d_ans[c] + c0 * wordPerAns;
+        if ((rc = s3_search_round1_device(ix, d_q + c0 * wordPerQuery, d_l + c0, cnt, wordPerQuery, numMismatch, numCases,
+                                          saRangeAllowed, wordPerAns, isExactNumMismatch, d_sub, NULL))) return rc;
+        S3_CUDA(cudaEventRecord(pp.done[k], ix->stream));
+        S3_CUDA(cudaStreamWaitEvent(pp.out, pp.done[k], 0));
+        for (uint32_t c = 0; c < numCases; ++c)
+            S3_CUDA(cudaMemcpyAsync(answers[c] + c0 * wordPerAns, d_sub[c], cntUp * wordPerAns * 4, cudaMemcpyDeviceToHost, pp.out));
+    }
+    S3_CUDA(cudaStreamSynchronize(pp.out));
     S3_CUDA(cudaStreamSynchronize(ix->stream));
     return S3_OK;
 }

@@ -26,6 +26,18 @@ struct S3Half {
     uint32_t numBuckets;
 };
 
+// Seed tables (DESIGN.md "seed tables"): the interval reached after the first K exact steps of a
+// pass, for every K-mer in processing order (first base stepped = most significant digit).
+//   fwd0 : steps on the BWT from (0, n)          -- the other-index interval of forward-first programs
+//   fwd1 : steps on the BWT from (1, n)          -- backward-only programs (DV-Kernel.cu:3672)
+//   rev0 : steps on the reverse BWT from (0, n)  -- forward-first programs (DV-Kernel.cu:3804)
+// Entry = (lo, hi); an empty interval is stored as (0xFFFFFFF0 | s, 0), s = the step that emptied it,
+// so that the rank-evaluation count of the stepwise search can still be reported.
+struct S3Seed {
+    const uint2 *fwd0, *fwd1, *rev0;
+    uint32_t K;               // 0: no tables
+};
+
 // Copy/compute pipeline of the host-pointer entry points: a batch is cut into chunks; chunk c+1 goes up
 // on `in` while chunk c computes on the handle's own stream and chunk c-1 comes down on `out`.
 #define S3_PIPE_CHUNKS 16
@@ -41,6 +53,8 @@ struct s3_index {
     int device;
     cudaStream_t stream;
     S3Half fwd, rev;
+    S3Seed seed;
+    uint2 *d_seed[3];
     uint32_t textLength;
     uint4 *d_fwd, *d_rev;
     uint32_t *d_packedDNA;    // optional

@@ -118,6 +118,46 @@ __global__ void s3_relayout_kernel(const uint32_t *__restrict__ bwt, const uint3
     o[1] = make_uint4(hi[0], lo[0], hi[1], lo[1]);
 }
 
+// One thread per K-mer: K exact LF-mapping steps from (firstL, n), exactly the loop of the search kernel.
+__global__ void s3_seed_build_kernel(S3Half h, uint32_t textLength, uint32_t K, uint32_t firstL, uint2 *__restrict__ table)
+{
+    const uint32_t key = blockIdx.x * blockDim.x + threadIdx.x;
+    if (key >= (1u << (2 * K))) return;
+    uint32_t lo = firstL, hi = textLength;
+    for (uint32_t d = 0; d < K; ++d) {
+        const uint32_t c = (key >> (2 * (K - 1 - d))) & 3u;
+        uint32_t a[4], b[4];
+        s3_rank4(h, lo, a);
+        s3_rank4(h, hi + 1, b);
+        lo = a[c] + 1; hi = b[c];
+        if (lo > hi) { lo = 0xFFFFFFF0u | (d + 1); hi = 0; break; }
+    }
+    table[key] = make_uint2(lo, hi);
+}
+
+static int build_seed_tables(s3_index *ix)
+{
+    // K-mers shorter than the text's information content stay mostly non-empty: K = floor(log4 n) - 2, in [4, 13]
+    uint32_t K = 0;
+    while (K < 16 && (1ull << (2 * (K + 1))) <= ix->textLength) ++K;
+    K = (K > 15) ? 13 : (K >= 6 ? (K - 2 > 13 ? 13 : K - 2) : 4);
+    if (getenv("S3_NO_SEED_TABLES")) { ix->seed.K = 0; return S3_OK; }
+    const size_t entries = (size_t)1 << (2 * K);
+    const S3Half *half[3] = {&ix->fwd, &ix->fwd, &ix->rev};
+    const uint32_t firstL[3] = {0u, 1u, 0u};
+    for (int t = 0; t < 3; ++t) {
+        S3_CUDA(cudaMalloc(&ix->d_seed[t], entries * sizeof(uint2)));
+        s3_seed_build_kernel<<<(unsigned)((entries + 255) / 256), 256, 0, ix->stream>>>(*half[t], ix->textLength, K, firstL[t], ix->d_seed[t]);
+        S3_LAUNCHED(1);
+        S3_CUDA(cudaGetLastError());
+        ix->bytes += entries * sizeof(uint2);
+    }
+    S3_CUDA(cudaStreamSynchronize(ix->stream));
+    ix->seed.fwd0 = ix->d_seed[0]; ix->seed.fwd1 = ix->d_seed[1]; ix->seed.rev0 = ix->d_seed[2];
+    ix->seed.K = K;
+    return S3_OK;
+}
+
 static int upload_half(s3_index *ix, const uint32_t *bwt, const uint32_t *occ, uint32_t numOcc,
                        uint32_t textLength, uint4 **d_out, uint32_t *numBucketsOut)
 {
@@ -174,6 +214,7 @@ extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const u
     ix->fwd.buckets = ix->d_fwd; ix->fwd.inverseSa0 = inverseSa0; ix->fwd.numBuckets = nb;
     if ((rc = upload_half(ix, revBwt, revOcc, numOcc, textLength, &ix->d_rev, &nb)) != S3_OK) return rc;
     ix->rev.buckets = ix->d_rev; ix->rev.inverseSa0 = revInverseSa0; ix->rev.numBuckets = nb;
+    if ((rc = build_seed_tables(ix)) != S3_OK) return rc;
     if (packedDNA) {
         size_t words = ((size_t)textLength + 15) / 16 + 8;
         S3_CUDA(cudaMalloc(&ix->d_packedDNA, words * 4));
@@ -197,6 +238,7 @@ extern "C" void s3_index_free(s3_index *ix)
     cudaSetDevice(ix->device);
     cudaStreamSynchronize(ix->stream);
     cudaFree(ix->d_fwd); cudaFree(ix->d_rev);
+    for (int t = 0; t < 3; ++t) if (ix->d_seed[t]) cudaFree(ix->d_seed[t]);
     if (ix->d_packedDNA) cudaFree(ix->d_packedDNA);
     if (ix->d_sa) cudaFree(ix->d_sa);
     s3_pipe_destroy(&ix->pipe);

@@ -136,7 +136,7 @@ __device__ __forceinline__ uint32_t s3_pack_phase(const S3Phase &ph)
 
 template <bool COUNT>
 __global__ void __launch_bounds__(S3_THREADS, S3_SEARCH_MIN_BLOCKS)
-s3_search_kernel(const S3Half fwd, const S3Half rev, const S3SearchArgs args)
+s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3SearchArgs args)
 {
     extern __shared__ uint32_t s3_smem[];
     uint32_t *fr = s3_smem + threadIdx.x;                                  // frames: fr[(depth*10 + field) * S3_THREADS]
@@ -173,6 +173,26 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3SearchArgs args)
         pdir = 0; xlo = firstL; xhi = args.textLength; ylo = 0; yhi = args.textLength;
         alive = nph > 0;
         load_phase(0);
+        // Seed tables: the first K steps of an exact first phase are one table lookup (the interval after K
+        // steps is a function of the K bases alone).  Same intervals as stepping, K dependent loads fewer.
+        const uint32_t K = seed.K;
+        if (K && alive && plen >= K) {
+            uint32_t key = 0, rkey = 0;
+            for (uint32_t d = 0; d < K; ++d) {
+                const uint32_t pos = pdir ? pstart + d : pstart + plen - 1 - d;
+                const uint32_t c = s3_base(sm, pos, L, strand);
+                key = (key << 2) | c;
+                rkey |= c << (2 * d);
+            }
+            const uint2 e = __ldg((pdir ? seed.rev0 : seed.fwd1) + key);
+            uint32_t stepsDone = K;
+            if (e.x >= 0xFFFFFFF0u) { alive = false; stepsDone = e.x & 15u; }
+            else {
+                xlo = e.x; xhi = e.y; done = K;
+                if (pdir) { ylo = __ldg(seed.fwd0 + rkey).x; yhi = ylo + (xhi - xlo); }
+            }
+            if (COUNT) nrank += 2 * stepsDone;
+        }
     };
 
     while (true) {
@@ -344,8 +364,8 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
     const unsigned long long resident = (unsigned long long)ix->numSms * ix->searchBlocksPerSm;
     if (blocks > resident) blocks = resident;
     S3_CUDA(cudaMemsetAsync(ix->d_workCounter, 0, sizeof(uint32_t), ix->stream));
-    if (count) s3_search_kernel<true><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, a);
-    else s3_search_kernel<false><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, a);
+    if (count) s3_search_kernel<true><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, a);
+    else s3_search_kernel<false><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, a);
     S3_LAUNCHED(1);
     S3_CUDA(cudaGetLastError());
     return S3_OK;

@@ -1,9 +1,10 @@
 // random_sector_bw.cu -- what HBM3e delivers for the search kernel's access pattern:
-// independent random reads of one aligned 64-byte bucket (one 32-byte-sector pair), no
-// dependency between reads, as many in flight as the SMs can hold.  Prints GB/s for
-// footprints well above L2.  Diagnostic only (profiles/gpu_session.sh runs it); the
-// roofline denominator stays the streaming number in MEASURED_PEAKS.json, this figure says
-// how much of it a random-sector workload can reach at all.
+// independent random reads of one aligned 32-byte bucket (one sector, one LDG.E.256), no
+// dependency between reads, as many in flight as the SMs can hold.  Prints million reads/s and
+// the DRAM-side GB/s at 32 B (bytes used) and 64 B (bytes the memory system fetches per miss)
+// for footprints well above L2.  Diagnostic only (profiles/gpu_session.sh runs it); the roofline
+// denominator stays the streaming number in MEASURED_PEAKS.json, this figure says how much of it
+// a random-sector workload can reach at all.
 //
 // build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o random_sector_bw random_sector_bw.cu
 #include <cuda_runtime.h>
@@ -17,60 +18,66 @@ __device__ __forceinline__ uint32_t mix(uint32_t x)
     return x;
 }
 
-// each thread reads `per` random buckets; `bytes` = 64 (cnt + both halves), 40 (what s3_rank4 touches) or 32
-template <int BYTES>
-__global__ void gather(const uint4 *__restrict__ buckets, uint32_t numBuckets, uint32_t per, uint32_t seed, uint32_t *sink)
+__device__ __forceinline__ uint32_t ld256(const uint4 *p)
+{
+    uint32_t a, b, c, d, e, f, g, h;
+    asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d), "=r"(e), "=r"(f), "=r"(g), "=r"(h) : "l"(p));
+    return a ^ b ^ c ^ d ^ e ^ f ^ g ^ h;
+}
+
+// each thread reads `per` random buckets, UNROLL of them in flight at a time
+template <int UNROLL>
+__global__ void gather(const uint4 *__restrict__ buckets, uint32_t mask, uint32_t per, uint32_t seed, uint32_t *sink)
 {
     uint32_t x = mix(seed + blockIdx.x * blockDim.x + threadIdx.x);
     uint32_t acc = 0;
-#pragma unroll 4
-    for (uint32_t k = 0; k < per; ++k) {
-        x = mix(x + k);
-        const uint4 *p = buckets + (size_t)(x % numBuckets) * 4;
-        uint4 a = __ldg(p);
-        acc += a.x ^ a.w;
-        if (BYTES >= 40) { uint4 b = __ldg(p + 1); uint2 c = __ldg(reinterpret_cast<const uint2 *>(p) + 4); acc += b.y ^ c.x; }
-        if (BYTES >= 64) { uint4 d = __ldg(p + 3); acc += d.z; }
+    for (uint32_t k = 0; k < per; k += UNROLL) {
+        uint32_t v[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) { x = mix(x + k + u); v[u] = ld256(buckets + (size_t)(x & mask) * 2); }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) acc += v[u];
     }
     if (acc == 0x12345678u) *sink = acc;
 }
 
-template <int BYTES>
-static double run(const uint4 *d, uint32_t numBuckets, uint32_t *sink, int blocks, int threads, uint32_t per)
+template <int UNROLL>
+static double run(const uint4 *d, uint32_t mask, uint32_t *sink, int blocks, int threads, uint32_t per)
 {
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
-    gather<BYTES><<<blocks, threads>>>(d, numBuckets, per, 1, sink);
+    gather<UNROLL><<<blocks, threads>>>(d, mask, per, 1, sink);
     cudaDeviceSynchronize();
     float best = 1e30f;
     for (int it = 0; it < 5; ++it) {
         cudaEventRecord(e0);
-        gather<BYTES><<<blocks, threads>>>(d, numBuckets, per, 77 + it, sink);
+        gather<UNROLL><<<blocks, threads>>>(d, mask, per, 77 + it, sink);
         cudaEventRecord(e1);
         cudaEventSynchronize(e1);
         float ms; cudaEventElapsedTime(&ms, e0, e1);
         if (ms < best) best = ms;
     }
-    const double reads = (double)blocks * threads * per;
-    return reads * 64.0 / (best * 1e-3) / 1e9;      // GB/s counted at 64 B per bucket read, like the roofline
+    return (double)blocks * threads * per / (best * 1e-3);      // reads per second
 }
 
-int main(int argc, char **argv)
+int main()
 {
-    const double gbs[] = {1.0, 2.0, 8.0};
     int sms = 0;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0);
     uint32_t *sink; cudaMalloc(&sink, 4);
-    for (double gb : gbs) {
-        const size_t bytes = (size_t)(gb * (1u << 30));
-        uint4 *d; if (cudaMalloc(&d, bytes) != cudaSuccess) { printf("alloc %.0f GB failed\n", gb); continue; }
+    for (int logb : {25, 26, 27}) {                              // 1, 2, 4 GiB of 32-byte buckets
+        const size_t bytes = (size_t)32 << logb;
+        uint4 *d; if (cudaMalloc(&d, bytes) != cudaSuccess) { printf("alloc failed\n"); continue; }
         cudaMemset(d, 1, bytes);
-        const uint32_t nb = (uint32_t)(bytes / 64);
-        for (int threads : {256, 1024}) {
-            const int blocks = sms * (2048 / threads) * 4;
-            printf("{\"footprint_gb\": %.0f, \"threads_per_block\": %d, \"gbs_at_64B_per_read\": {\"touch16B\": %.0f, \"touch40B\": %.0f, \"touch64B\": %.0f}}\n",
-                   gb, threads, run<16>(d, nb, sink, blocks, threads, 256), run<40>(d, nb, sink, blocks, threads, 256),
-                   run<64>(d, nb, sink, blocks, threads, 256));
+        const uint32_t mask = (1u << logb) - 1;
+        for (int warpsPerSm : {24, 64}) {
+            const int threads = 128, blocks = sms * warpsPerSm / 4;
+            const double r1 = run<1>(d, mask, sink, blocks, threads, 512), r2 = run<2>(d, mask, sink, blocks, threads, 512),
+                         r8 = run<8>(d, mask, sink, blocks, threads, 512);
+            printf("{\"footprint_gib\": %.0f, \"warps_per_sm\": %d, \"mreads_per_s\": {\"1_in_flight\": %.0f, \"2_in_flight\": %.0f, \"8_in_flight\": %.0f}, "
+                   "\"gbs_at_32B\": %.0f, \"gbs_at_64B\": %.0f}\n",
+                   bytes / 1073741824.0, warpsPerSm, r1 / 1e6, r2 / 1e6, r8 / 1e6, r8 * 32 / 1e9, r8 * 64 / 1e9);
         }
         cudaFree(d);
     }

@@ -60,7 +60,7 @@ def cache_dir():
 def get_index(n_bp, seed, device, rank, world):
     """-> (genome codes on device, dict of host numpy arrays in the reference format)"""
     tag = os.path.join(cache_dir(), f"idx_{n_bp}_{seed}")
-    names = ["bwt", "occ", "rbwt", "rocc", "meta"]
+    names = ["bwt", "occ", "rbwt", "rocc", "meta", "sa", "pac"]
     t0 = time.time()
     genome = synth.random_genome(n_bp, seed=seed, device=device)
     torch.cuda.synchronize()
@@ -68,13 +68,17 @@ def get_index(n_bp, seed, device, rank, world):
     have = all(os.path.exists(f"{tag}.{x}.npy") for x in names)
     if not have and rank == 0:
         t0 = time.time()
-        idx = fmindex.build_index(genome, keep_sa=False, verbose=bool(os.environ.get("S3_VERBOSE")))
+        idx = fmindex.build_index(genome, keep_sa=True, verbose=bool(os.environ.get("S3_VERBOSE")))
         torch.cuda.synchronize()
         log(f"2BWT index built on the GPU in {time.time() - t0:.1f}s")
-        arrs = {"bwt": idx.fwd.bwt_words, "occ": idx.fwd.occ, "rbwt": idx.rev.bwt_words, "rocc": idx.rev.occ}
+        arrs = {"bwt": idx.fwd.bwt_words, "occ": idx.fwd.occ, "rbwt": idx.rev.bwt_words, "rocc": idx.rev.occ,
+                "pac": idx.packed_text}
         for k, v in arrs.items():
             np.save(f"{tag}.{k}.tmp.npy", v.cpu().numpy().view(np.uint32))
             os.replace(f"{tag}.{k}.tmp.npy", f"{tag}.{k}.npy")
+        # the suffix array of the n + 1 BWT rows, as bwt->saValue with SaValueFreq = 1 (soap3-dp-builder.ini:29)
+        np.save(f"{tag}.sa.tmp.npy", idx.fwd.sa.cpu().numpy().astype(np.uint32))
+        os.replace(f"{tag}.sa.tmp.npy", f"{tag}.sa.npy")
         np.save(f"{tag}.meta.tmp.npy", np.array([idx.fwd.inverse_sa0, idx.rev.inverse_sa0, n_bp], np.int64))
         os.replace(f"{tag}.meta.tmp.npy", f"{tag}.meta.npy")
         del idx, arrs
@@ -91,8 +95,11 @@ def upload_index(host, device):
     n = int(meta[2])
     out = C.c_void_p()
     num_occ = (n + 127) // 128 + 1
+    with_locate = not os.environ.get("S3_NO_CHECK_EXTEND")
     rc = lib.s3_index_upload(api._u32(host["bwt"]), api._u32(host["occ"]), api._u32(host["rbwt"]), api._u32(host["rocc"]),
-                             num_occ, int(meta[0]), int(meta[1]), n, None, None, device, C.byref(out))
+                             num_occ, int(meta[0]), int(meta[1]), n,
+                             api._u32(host["pac"]) if with_locate else None, api._u32(host["sa"]) if with_locate else None,
+                             device, C.byref(out))
     api._check(rc, "s3_index_upload")
     return api.GpuIndex(out.value, n)
 
@@ -365,8 +372,11 @@ def main():
         print(json.dumps(out), flush=True)
         return
 
+    t0 = time.time()
     gi = upload_index(host, local_rank)
-    log(f"index on device: {gi.device_bytes / 1e9:.2f} GB in 32-byte single-sector buckets")
+    host.pop("sa", None)                                      # 12 GB of host memory per rank, no longer needed
+    log(f"index on device in {time.time() - t0:.1f}s: {gi.device_bytes / 1e9:.2f} GB (32-byte single-sector buckets, seed tables, "
+        f"suffix array + inverse + packed text for check-and-extend)")
     stream = torch.cuda.ExternalStream(gi.stream, device=device)
     total = args.warmup + args.steps
     t0 = time.time()

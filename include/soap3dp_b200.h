@@ -44,9 +44,12 @@ unsigned long long s3_launch_count(void);
  * and the scalars the kernels receive by value.  The arrays are re-laid out on
  * the device into 64-byte buckets {4 x uint32 running counts, 192 bases}; the
  * caller keeps ownership of the host arrays.  packedDNA (hsp->packedDNA, 16
- * bases/word MSB first) and sa (bwt->saValue, full SA, saInterval == 1) are
- * optional (NULL) and are only needed by the device-side locate / window
- * gather entry points.
+ * bases/word MSB first) and sa (bwt->saValue, the full suffix array of the
+ * n + 1 BWT rows, SaValueFreq == 1 as in soap3-dp-builder.ini:29) are optional:
+ * when both are given the search finishes a read by comparing it with the
+ * text as soon as its interval is a single suffix ("check and extend", what
+ * the reference's CPU search does, 2bwt-flex/SRA2BWTCheckAndExtend.c) instead
+ * of stepping through the rest of it; answers are identical either way.
  * ------------------------------------------------------------------------ */
 int s3_index_upload(const uint32_t *bwt, const uint32_t *occ,
                     const uint32_t *revBwt, const uint32_t *revOcc,
@@ -54,6 +57,8 @@ int s3_index_upload(const uint32_t *bwt, const uint32_t *occ,
                     uint32_t textLength,
                     const uint32_t *packedDNA, const uint32_t *sa,
                     int device, s3_index **out);
+/* the same two optional arrays when they already live in device memory (copied) */
+int s3_index_set_locate_device(s3_index *ix, const uint32_t *d_sa, const uint32_t *d_packedDNA);
 void s3_index_free(s3_index *ix);
 /* bytes of device memory held by the index */
 size_t s3_index_device_bytes(const s3_index *ix);

@@ -31,6 +31,7 @@ U64P = C.POINTER(C.c_uint64)
 
 EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
+    "s3_index_set_locate_device",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -66,6 +67,8 @@ def load_library() -> C.CDLL:
     lib.s3_index_upload.restype = C.c_int
     lib.s3_index_upload.argtypes = [U32P, U32P, U32P, U32P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
                                     U32P, U32P, C.c_int, C.POINTER(C.c_void_p)]
+    lib.s3_index_set_locate_device.restype = C.c_int
+    lib.s3_index_set_locate_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
     lib.s3_index_free.restype = None
     lib.s3_index_free.argtypes = [C.c_void_p]
     lib.s3_index_device_bytes.restype = C.c_size_t
@@ -165,6 +168,13 @@ def GPUINDEXUpload(index, device: int = 0, with_text: bool = False, with_sa: boo
                              device, C.byref(out))
     _check(rc, "GPUINDEXUpload")
     return GpuIndex(out.value, index.text_length)
+
+
+def set_locate_device(gpu_index: GpuIndex, d_sa: int, d_packed_text: int):
+    """s3_index_set_locate_device: suffix array (uint32[n+1]) and packed text already on the device
+    (raw device pointers); enables check-and-extend."""
+    _check(load_library().s3_index_set_locate_device(gpu_index.handle, C.c_void_p(d_sa), C.c_void_p(d_packed_text)),
+           "s3_index_set_locate_device")
 
 
 def GPUINDEXFree(gpu_index: GpuIndex):

@@ -49,12 +49,22 @@ struct S3Pipe {
 int s3_pipe_init(S3Pipe *p);
 void s3_pipe_destroy(S3Pipe *p);
 
+// Text-side arrays for check-and-extend: once an interval holds a single suffix, the
+// rest of the read is compared with the text itself instead of being stepped through the index.
+struct S3Locate {
+    const uint32_t *sa;       // suffix array of the BWT rows (n + 1 entries, row 0 = the '$' suffix), NULL: disabled
+    const uint32_t *isa;      // inverse: row of the suffix starting at a text position (n entries)
+    const uint32_t *text;     // packed text, 16 bases per word, MSB first (hsp->packedDNA)
+};
+
 struct s3_index {
     int device;
     cudaStream_t stream;
     S3Half fwd, rev;
     S3Seed seed;
     uint2 *d_seed[3];
+    S3Locate loc;
+    uint32_t *d_isa;
     uint32_t textLength;
     uint4 *d_fwd, *d_rev;
     uint32_t *d_packedDNA;    // optional

@@ -181,6 +181,36 @@ static int upload_half(s3_index *ix, const uint32_t *bwt, const uint32_t *occ, u
     return S3_OK;
 }
 
+__global__ void s3_isa_kernel(const uint32_t *__restrict__ sa, uint32_t textLength, uint32_t *__restrict__ isa)
+{
+    const size_t row = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (row > textLength) return;
+    const uint32_t pos = sa[row];
+    if (pos < textLength) isa[pos] = (uint32_t)row;              // row 0 (the '$' suffix, position n or -1) has no entry
+}
+
+// Copies the suffix array (n + 1 rows) and the packed text onto the device and inverts the suffix array;
+// enables check-and-extend in the search kernel.
+static int attach_locate(s3_index *ix, const uint32_t *sa, const uint32_t *packedDNA, cudaMemcpyKind kind)
+{
+    if (ix->loc.sa) return S3_OK;
+    const size_t n = ix->textLength, words = (n + 15) / 16 + 8;
+    S3_CUDA(cudaMalloc(&ix->d_packedDNA, words * 4));
+    S3_CUDA(cudaMemsetAsync(ix->d_packedDNA, 0, words * 4, ix->stream));
+    S3_CUDA(cudaMemcpyAsync(ix->d_packedDNA, packedDNA, ((n + 15) / 16) * 4, kind, ix->stream));
+    S3_CUDA(cudaMalloc(&ix->d_sa, (n + 1) * 4));
+    S3_CUDA(cudaMemcpyAsync(ix->d_sa, sa, (n + 1) * 4, kind, ix->stream));
+    S3_CUDA(cudaMalloc(&ix->d_isa, (n + 1) * 4));
+    S3_CUDA(cudaMemsetAsync(ix->d_isa, 0, (n + 1) * 4, ix->stream));
+    s3_isa_kernel<<<(unsigned)((n + 1 + 255) / 256), 256, 0, ix->stream>>>(ix->d_sa, (uint32_t)n, ix->d_isa);
+    S3_LAUNCHED(1);
+    S3_CUDA(cudaGetLastError());
+    S3_CUDA(cudaStreamSynchronize(ix->stream));
+    ix->bytes += words * 4 + 2 * (n + 1) * 4;
+    ix->loc.sa = ix->d_sa; ix->loc.isa = ix->d_isa; ix->loc.text = ix->d_packedDNA;
+    return S3_OK;
+}
+
 extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const uint32_t *revBwt,
                                const uint32_t *revOcc, uint32_t numOcc, uint32_t inverseSa0,
                                uint32_t revInverseSa0, uint32_t textLength, const uint32_t *packedDNA,
@@ -215,21 +245,16 @@ extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const u
     if ((rc = upload_half(ix, revBwt, revOcc, numOcc, textLength, &ix->d_rev, &nb)) != S3_OK) return rc;
     ix->rev.buckets = ix->d_rev; ix->rev.inverseSa0 = revInverseSa0; ix->rev.numBuckets = nb;
     if ((rc = build_seed_tables(ix)) != S3_OK) return rc;
-    if (packedDNA) {
-        size_t words = ((size_t)textLength + 15) / 16 + 8;
-        S3_CUDA(cudaMalloc(&ix->d_packedDNA, words * 4));
-        S3_CUDA(cudaMemset(ix->d_packedDNA, 0, words * 4));
-        S3_CUDA(cudaMemcpy(ix->d_packedDNA, packedDNA, (((size_t)textLength + 15) / 16) * 4, cudaMemcpyHostToDevice));
-        ix->bytes += words * 4;
-    }
-    if (sa) {
-        size_t n = (size_t)textLength + 1;
-        S3_CUDA(cudaMalloc(&ix->d_sa, n * 4));
-        S3_CUDA(cudaMemcpy(ix->d_sa, sa, n * 4, cudaMemcpyHostToDevice));
-        ix->bytes += n * 4;
-    }
     *out = ix;
+    if (packedDNA && sa) return attach_locate(ix, sa, packedDNA, cudaMemcpyHostToDevice);
     return S3_OK;
+}
+
+extern "C" int s3_index_set_locate_device(s3_index *ix, const uint32_t *d_sa, const uint32_t *d_packedDNA)
+{
+    if (!ix || !d_sa || !d_packedDNA) { s3_set_error("s3_index_set_locate_device: NULL argument"); return S3_EINVAL; }
+    S3_CUDA(cudaSetDevice(ix->device));
+    return attach_locate(ix, d_sa, d_packedDNA, cudaMemcpyDeviceToDevice);
 }
 
 extern "C" void s3_index_free(s3_index *ix)
@@ -241,6 +266,7 @@ extern "C" void s3_index_free(s3_index *ix)
     for (int t = 0; t < 3; ++t) if (ix->d_seed[t]) cudaFree(ix->d_seed[t]);
     if (ix->d_packedDNA) cudaFree(ix->d_packedDNA);
     if (ix->d_sa) cudaFree(ix->d_sa);
+    if (ix->d_isa) cudaFree(ix->d_isa);
     s3_pipe_destroy(&ix->pipe);
     if (ix->d_workCounter) cudaFree(ix->d_workCounter);
     if (ix->scratch) cudaFree(ix->scratch);

@@ -112,13 +112,27 @@ __device__ __forceinline__ uint32_t s3_meta(uint32_t done, uint32_t p, uint32_t 
     return done | (p << 11) | (mmp << 13) | (mmt << 16) | (next << 19) | (c << 22);
 }
 
-// smem read: word w of this thread's read lives at sm[w * S3_THREADS + tid]
-__device__ __forceinline__ uint32_t s3_base(const uint32_t *sm, uint32_t pos, uint32_t L, uint32_t strand)
+// The read sits in shared memory twice, as the strand it was given in and as its reverse complement
+// (what the reference materialises in place between the two strands, DV-Kernel.cu:4351-4395), both in
+// the TEXT's packing -- 16 bases per word, first base in the top bits -- so that a stretch of the read
+// can be XORed against the packed text.  Word w of a strand lives at sr[w * S3_THREADS].
+__device__ __forceinline__ uint32_t s3_base(const uint32_t *sr, uint32_t pos)
 {
-    // strand 1 = reverse complement (what the reference materialises in place, DV-Kernel.cu:4351-4395)
-    const uint32_t i = strand ? (L - 1 - pos) : pos;
-    const uint32_t v = (sm[(i >> 4) * S3_THREADS] >> ((i & 15) << 1)) & 3;
-    return strand ? 3 - v : v;
+    return (sr[(pos >> 4) * S3_THREADS] >> (30u - ((pos & 15u) << 1))) & 3u;
+}
+
+// 16 bases, first base in the low bits <-> first base in the high bits
+__device__ __forceinline__ uint32_t s3_flip16(uint32_t w)
+{
+    w = __brev(w);
+    return ((w & 0x55555555u) << 1) | ((w >> 1) & 0x55555555u);
+}
+
+__device__ __forceinline__ uint32_t s3_shr_clamp(uint32_t a, uint32_t s)
+{
+    uint32_t d;                                   // PTX shr clamps shift amounts > 32 to 32 (result 0)
+    asm("shr.b32 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(s));
+    return d;
 }
 
 // a phase packed in one register: start[0:11] len[11:22] dir[22] lo[23:26] hi[26:29]
@@ -136,11 +150,13 @@ __device__ __forceinline__ uint32_t s3_pack_phase(const S3Phase &ph)
 
 template <bool COUNT>
 __global__ void __launch_bounds__(S3_THREADS, S3_SEARCH_MIN_BLOCKS)
-s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3SearchArgs args)
+s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3Locate loc, const S3SearchArgs args)
 {
     extern __shared__ uint32_t s3_smem[];
     uint32_t *fr = s3_smem + threadIdx.x;                                  // frames: fr[(depth*10 + field) * S3_THREADS]
-    uint32_t *sm = s3_smem + S3_MAX_DEPTH * S3_FRAME_WORDS * S3_THREADS + threadIdx.x;   // read words
+    uint32_t *sm0 = s3_smem + S3_MAX_DEPTH * S3_FRAME_WORDS * S3_THREADS + threadIdx.x;  // read words, given strand
+    uint32_t *sm1 = sm0 + args.wordPerQuery * S3_THREADS;                                // reverse complement
+    const uint32_t *sr = sm0;                                                            // strand being searched
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t totalItems = args.numQueries * args.numCases;      // < 2^32 (host splits otherwise)
     const uint32_t maxRanges = args.saRangeAllowed;
@@ -172,6 +188,7 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
         // backward-only programs start from saL = 1, bi-directional ones from 0 (DV-Kernel.cu:3672 vs :3804)
         pdir = 0; xlo = firstL; xhi = args.textLength; ylo = 0; yhi = args.textLength;
         alive = nph > 0;
+        sr = strand ? sm1 : sm0;
         load_phase(0);
         // Seed tables: the first K steps of an exact first phase are one table lookup (the interval after K
         // steps is a function of the K bases alone).  Same intervals as stepping, K dependent loads fewer.
@@ -180,7 +197,7 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
             uint32_t key = 0, rkey = 0;
             for (uint32_t d = 0; d < K; ++d) {
                 const uint32_t pos = pdir ? pstart + d : pstart + plen - 1 - d;
-                const uint32_t c = s3_base(sm, pos, L, strand);
+                const uint32_t c = s3_base(sr, pos);
                 key = (key << 2) | c;
                 rkey |= c << (2 * d);
             }
@@ -193,6 +210,75 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
             }
             if (COUNT) nrank += 2 * stepsDone;
         }
+    };
+
+    // report (DV-Kernel.cu:355-380): the interval on the forward BWT; a slot overflow ends the item
+    auto report = [&](uint32_t l, uint32_t r, uint32_t mm) {
+        if (saCount < maxRanges) {
+            answer[32 * 2 * saCount] = l;
+            answer[32 * (2 * saCount + 1)] = (r - l) + (strand << 27) + (mm << 24);
+        }
+        ++saCount;
+        if (saCount > maxRanges) { answer[0] = 0xFFFFFFFEu; has = false; }
+    };
+
+    // Check-and-extend.  The lane stands on a node whose interval is ONE suffix: every further step could
+    // only follow the text at that suffix' position, taking a substitution wherever read and text differ
+    // (if the phase still allows one) -- so the outcome of the whole remaining program is decided by the
+    // number of differences in each phase's stretch of the read, counted by XOR against the packed text,
+    // and the final interval is the row of the suffix that starts where the read starts.  Same answer as
+    // stepping (the reference's CPU search does the same once an interval is small,
+    // 2bwt-flex/SRA2BWTCheckAndExtend.c), ~5 sectors instead of one per remaining base.
+    auto check_extend = [&]() {
+        const uint32_t row = pdir ? ylo : xlo;                       // row on the forward BWT
+        const uint32_t ta = __ldg(loc.sa + row);                     // text position of the matched block
+        // the matched block in read coordinates starts at the smallest position touched so far
+        uint32_t qa = (done > 0) ? (pdir ? pstart : pstart + plen - done) : 0xFFFFFFFFu;
+#pragma unroll
+        for (int k = 0; k < S3_MAX_PHASES - 1; ++k) if ((uint32_t)k < p) qa = min(qa, prog[k] & 0x7FFu);
+        alive = false;                                               // this branch ends here, reported or not
+        if (ta < qa || (unsigned long long)(ta - qa) + L > args.textLength) return;       // hangs off the text
+        const uint32_t ps = ta - qa;                                 // text position of read base 0
+        // remaining stretches: the rest of the current phase, then the later phases
+        uint32_t ra[S3_MAX_PHASES], rb[S3_MAX_PHASES], cnt[S3_MAX_PHASES];
+#pragma unroll
+        for (int k = 0; k < S3_MAX_PHASES; ++k) {
+            const uint32_t st = prog[k] & 0x7FFu, ln = (prog[k] >> 11) & 0x7FFu;
+            ra[k] = st; rb[k] = st + ln; cnt[k] = 0;
+            if ((uint32_t)k == p) { if (pdir) ra[k] = st + done; else rb[k] = st + ln - done; }
+            if ((uint32_t)k < p || (uint32_t)k >= nph) rb[k] = ra[k] = 0;               // nothing left to check
+        }
+        const uint32_t *tw = loc.text + (ps >> 4);
+        const uint32_t sh = (ps & 15u) << 1;
+        const uint32_t nw = (L + 15) >> 4;
+        uint32_t t0 = __ldg(tw);
+        for (uint32_t w = 0; w < nw; ++w) {
+            const uint32_t t1 = __ldg(tw + w + 1);
+            const uint32_t x = sr[w * S3_THREADS] ^ __funnelshift_l(t1, t0, sh);         // 16 read bases vs 16 text bases
+            const uint32_t m = (x | (x >> 1)) & 0x55555555u;                            // bit 30-2k: base k differs
+            t0 = t1;
+#pragma unroll
+            for (int k = 0; k < S3_MAX_PHASES; ++k) {
+                // bases [ra, rb) of the read that fall into this word
+                const uint32_t k0 = max(ra[k], 16u * w) - 16u * w, k1 = min(rb[k], 16u * w + 16u);
+                if (k1 > 16u * w + k0) {
+                    const uint32_t mask = s3_shr_clamp(0xFFFFFFFFu, 2 * k0) & ~s3_shr_clamp(0xFFFFFFFFu, 2 * (k1 - 16u * w));
+                    cnt[k] += __popc(m & mask);
+                }
+            }
+        }
+        uint32_t mm = mmt;
+#pragma unroll
+        for (int k = 0; k < S3_MAX_PHASES; ++k) {
+            if ((uint32_t)k >= p && (uint32_t)k < nph) {
+                const uint32_t lo = (prog[k] >> 23) & 7u, hi = (prog[k] >> 26) & 7u;
+                const uint32_t tot = cnt[k] + (((uint32_t)k == p) ? mmp : 0u);
+                if (tot < lo || tot > hi) return;
+                mm += cnt[k];
+            }
+        }
+        const uint32_t l = __ldg(loc.isa + ps);
+        report(l, l, mm);
     };
 
     while (true) {
@@ -215,7 +301,22 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
                     answer = args.answers[whichCase] + (size_t)(q >> 5) * 32 * args.wordPerAnswer + (q & 31);
                     L = args.readLengths[q];
                     const uint32_t nw = (L + 15) >> 4;
-                    for (uint32_t w = 0; w < nw; ++w) sm[w * S3_THREADS] = query[w * 32];
+                    // queries hold base i of a read in bits 2(i%16) of word i/16 (QueryParser.cpp:1146-1152)
+                    for (uint32_t w = 0; w < nw; ++w) sm0[w * S3_THREADS] = query[w * 32];
+                    // reverse complement, word j = bases 16j..16j+15 of it = the complemented 32-bit window of the
+                    // given read's bit stream that ENDS with base L-1-16j: the reversal of the base order is
+                    // exactly the change from first-base-low to first-base-high packing
+                    for (uint32_t j = 0; j < nw; ++j) {
+                        const int ob = 2 * ((int)L - 16 * (int)(j + 1));
+                        uint32_t win;
+                        if (ob >= 0) {
+                            const uint32_t wl = (uint32_t)ob >> 5, sh = (uint32_t)ob & 31u;
+                            const uint32_t lo = sm0[wl * S3_THREADS], hi = (wl + 1 < nw) ? sm0[(wl + 1) * S3_THREADS] : 0u;
+                            win = __funnelshift_r(lo, hi, sh);
+                        } else win = sm0[0] << (uint32_t)(-ob);
+                        sm1[j * S3_THREADS] = ~win;
+                    }
+                    for (uint32_t w = 0; w < nw; ++w) sm0[w * S3_THREADS] = s3_flip16(sm0[w * S3_THREADS]);
                     S3Phase ph[S3_MAX_PHASES];
                     nph = (uint32_t)s3_case_program(args.numMismatch, whichCase, L, args.exactNum != 0, ph, firstL);
 #pragma unroll
@@ -234,17 +335,8 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
                 if (done < plen) break;
                 // end of a phase
                 if (mmp < plo) alive = false;
-                else if (p + 1 == nph) {
-                    // report (DV-Kernel.cu:355-380): the interval on the forward BWT
-                    if (saCount < maxRanges) {
-                        const uint32_t l = pdir ? ylo : xlo, r = pdir ? yhi : xhi;
-                        answer[32 * 2 * saCount] = l;
-                        answer[32 * (2 * saCount + 1)] = (r - l) + (strand << 27) + (mmt << 24);
-                    }
-                    ++saCount;
-                    alive = false;
-                    if (saCount > maxRanges) { answer[0] = 0xFFFFFFFEu; has = false; }     // overflow ends the item
-                } else { ++p; done = 0; mmp = 0; load_phase(p); }
+                else if (p + 1 == nph) { report(pdir ? ylo : xlo, pdir ? yhi : xhi, mmt); alive = false; }
+                else { ++p; done = 0; mmp = 0; load_phase(p); }
             } else if (depth == 0) {
                 // this strand is exhausted
                 if (pass == 0 && nph > 0) { pass = 1; strand ^= 1u; start_pass(); }
@@ -278,13 +370,14 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
         }
         __syncwarp();
         // ---- (B) one LF-mapping step for every lane that has work: both ranks' loads first ----
-        if (has) {
+        if (has && !COUNT && loc.sa != NULL && xlo == xhi) check_extend();
+        else if (has) {
             const uint4 *buckets = pdir ? rev.buckets : fwd.buckets;
             const uint32_t isa0 = pdir ? rev.inverseSa0 : fwd.inverseSa0;
             const S3Bucket ka = s3_rank_load(buckets, isa0, xlo);
             const S3Bucket kb = s3_rank_load(buckets, isa0, xhi + 1);
             const uint32_t pos = pdir ? pstart + done : pstart + plen - 1 - done;
-            const uint32_t c = s3_base(sm, pos, L, strand);
+            const uint32_t c = s3_base(sr, pos);
             uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
             s3_rank_count(ka, a0, a1, a2, a3);
             s3_rank_count(kb, b0, b1, b2, b3);
@@ -349,7 +442,7 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
     if (a.numQueries == 0) return S3_OK;
     a.numCases = numCases;
     a.workCounter = ix->d_workCounter;
-    const size_t smem = (size_t)(a.wordPerQuery + S3_MAX_DEPTH * S3_FRAME_WORDS) * S3_THREADS * sizeof(uint32_t);
+    const size_t smem = (size_t)(2 * a.wordPerQuery + S3_MAX_DEPTH * S3_FRAME_WORDS) * S3_THREADS * sizeof(uint32_t);
     if (smem != ix->searchSmem) {
         S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -364,8 +457,8 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
     const unsigned long long resident = (unsigned long long)ix->numSms * ix->searchBlocksPerSm;
     if (blocks > resident) blocks = resident;
     S3_CUDA(cudaMemsetAsync(ix->d_workCounter, 0, sizeof(uint32_t), ix->stream));
-    if (count) s3_search_kernel<true><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, a);
-    else s3_search_kernel<false><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, a);
+    if (count) s3_search_kernel<true><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
+    else s3_search_kernel<false><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
     S3_LAUNCHED(1);
     S3_CUDA(cudaGetLastError());
     return S3_OK;

@@ -13,11 +13,15 @@ from soap3dp_b200 import api, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module")
-def env():
+@pytest.fixture(scope="module", params=["stepping", "check_and_extend"])
+def env(request):
+    """The same index twice: BWT/occ only (every base is an LF-mapping step), and with the suffix
+    array and the packed text as well (single-suffix intervals are finished by check-and-extend).
+    Both must give the oracle's answer slots bit for bit."""
     G = synth.random_genome(600_000, seed=11)
     idx = fmindex.build_index(G)
-    gi = api.GPUINDEXUpload(idx, device=0)
+    ce = request.param == "check_and_extend"
+    gi = api.GPUINDEXUpload(idx, device=0, with_text=ce, with_sa=ce)
     yield G, idx, HostIndex(idx), gi
     api.GPUINDEXFree(gi)
 
@@ -89,6 +93,41 @@ def test_round1_and_round2_bit_exact(env, L, k):
         a = np.zeros(formats.ceil32(nb) * wpa2, np.uint32)
         oracle_launch(olib, hi, c, bq, bl, nb, wpq, a, np.zeros(formats.ceil32(nb), np.uint8), 1, k, allowed2, wpa2)
         assert np.array_equal(formats.answers_view(bad_ans[c], nb, wpa2), formats.answers_view(a, nb, wpa2)), (k, c)
+
+
+def test_reads_at_the_text_ends(env):
+    """Reads cut from the first and last bases of the text, and reads hanging off either end:
+    the l = 1 start of the backward-only cases and check-and-extend's bounds."""
+    G, idx, hi, gi = env
+    olib = load_oracle()
+    g = G.numpy()
+    L, k = 60, 2
+    n_text = len(g)
+    rng = np.random.default_rng(5)
+    reads = []
+    for off in list(range(0, 6)) + list(range(n_text - L - 5, n_text - L + 1)):
+        r = g[off:off + L].copy()
+        reads.append(r)
+        r2 = r.copy(); r2[rng.integers(0, L)] ^= 1                     # one substitution
+        reads.append(r2)
+        reads.append((3 - r[::-1]).astype(np.uint8))                  # reverse strand
+    for cut in (1, 3, 17):                                            # hang off the ends
+        reads.append(np.concatenate([rng.integers(0, 4, cut).astype(np.uint8), g[:L - cut]]))
+        reads.append(np.concatenate([g[n_text - (L - cut):], rng.integers(0, 4, cut).astype(np.uint8)]))
+    reads = np.stack(reads).astype(np.uint8)
+    n = len(reads)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    wpq = formats.word_per_query(L)
+    q = formats.pack_queries(reads, lens[:n], wpq)
+    for k in (0, 1, 2, 3):
+        allowed = formats.SA_RANGES_ROUND1[k]
+        wpa = 2 * allowed
+        got = api.perform_round1_alignment(gi, q, lens, n, wpq, k)
+        want = _oracle_round1(olib, hi, q, lens, n, wpq, k, allowed, wpa, formats.NUM_CASES[k])
+        for c in range(formats.NUM_CASES[k]):
+            gv, wv = formats.answers_view(got[c], n, wpa), formats.answers_view(want[c], n, wpa)
+            assert np.array_equal(gv, wv), f"k={k} case={c}: reads {np.nonzero((gv != wv).any(1))[0][:8]}"
 
 
 def test_exact_num_mismatch_flag(env):

@@ -75,7 +75,8 @@ struct s3_index {
     void *pinned; size_t pinnedBytes;
     S3Pipe pipe;
     // persistent search launches
-    uint32_t *d_workCounter;
+    uint32_t *d_workCounter;          // [0] work queue head, [1] number of items the easy kernel left behind
+    uint32_t *d_hardItems; size_t hardCap;
     int numSms;
     size_t searchSmem; int searchBlocksPerSm;
 };

@@ -269,6 +269,7 @@ extern "C" void s3_index_free(s3_index *ix)
     if (ix->d_isa) cudaFree(ix->d_isa);
     s3_pipe_destroy(&ix->pipe);
     if (ix->d_workCounter) cudaFree(ix->d_workCounter);
+    if (ix->d_hardItems) cudaFree(ix->d_hardItems);
     if (ix->scratch) cudaFree(ix->scratch);
     if (ix->pinned) cudaFreeHost(ix->pinned);
     cudaStreamDestroy(ix->stream);

@@ -96,6 +96,8 @@ struct S3SearchArgs {
     uint32_t firstCase, numCases, exactNum;
     uint32_t textLength;
     uint32_t *workCounter;               // zeroed before the launch
+    const uint32_t *itemList;            // NULL: every item; else item ids (case * numQueries + read) ...
+    const uint32_t *itemCount;           // ... and how many (device memory, written by the easy kernel)
     unsigned long long *rankQueries;     // may be NULL
 };
 
@@ -141,6 +143,188 @@ __device__ __forceinline__ uint32_t s3_pack_phase(const S3Phase &ph)
     return ph.start | (ph.len << 11) | (ph.dir << 22) | (ph.lo << 23) | (ph.hi << 26);
 }
 
+// Loads read q into shared memory in both orientations (see s3_base).  Returns its length.
+__device__ __forceinline__ uint32_t s3_load_read(const S3SearchArgs &args, uint32_t q, uint32_t *sm0, uint32_t *sm1)
+{
+    const uint32_t *query = args.queries + (size_t)(q >> 5) * 32 * args.wordPerQuery + (q & 31);
+    const uint32_t L = args.readLengths[q];
+    const uint32_t nw = (L + 15) >> 4;
+    // queries hold base i of a read in bits 2(i%16) of word i/16 (QueryParser.cpp:1146-1152)
+    for (uint32_t w = 0; w < nw; ++w) sm0[w * S3_THREADS] = query[w * 32];
+    // reverse complement, word j = bases 16j..16j+15 of it = the complemented 32-bit window of the
+    // given read's bit stream that ENDS with base L-1-16j: the reversal of the base order is
+    // exactly the change from first-base-low to first-base-high packing
+    for (uint32_t j = 0; j < nw; ++j) {
+        const int ob = 2 * ((int)L - 16 * (int)(j + 1));
+        uint32_t win;
+        if (ob >= 0) {
+            const uint32_t wl = (uint32_t)ob >> 5, sh = (uint32_t)ob & 31u;
+            const uint32_t lo = sm0[wl * S3_THREADS], hi = (wl + 1 < nw) ? sm0[(wl + 1) * S3_THREADS] : 0u;
+            win = __funnelshift_r(lo, hi, sh);
+        } else win = sm0[0] << (uint32_t)(-ob);
+        sm1[j * S3_THREADS] = ~win;
+    }
+    for (uint32_t w = 0; w < nw; ++w) sm0[w * S3_THREADS] = s3_flip16(sm0[w * S3_THREADS]);
+    return L;
+}
+
+// Check-and-extend.  The caller stands on a node whose interval is ONE suffix (row `row` of the forward
+// BWT): every further step could only follow the text at that suffix' position, taking a substitution
+// wherever read and text differ (if the phase still allows one) -- so the outcome of the whole remaining
+// program is decided by the number of differences in each phase's stretch of the read, counted by XOR
+// against the packed text, and the final interval is the row of the suffix that starts where the read
+// starts.  Same answer as stepping (the reference's CPU search does the same once an interval is small,
+// 2bwt-flex/SRA2BWTCheckAndExtend.c), ~5 sectors instead of one per remaining base.
+// State: phases prog[0..nph), standing in phase p (direction pdir) with `done` bases of it consumed and
+// mmp substitutions spent in it, mmt in total.  Returns true with the row and the total substitutions
+// if the read survives.
+__device__ __forceinline__ bool s3_check_extend(const S3Locate &loc, const uint32_t *sr, uint32_t L, uint32_t textLength,
+                                                const uint32_t prog[S3_MAX_PHASES], uint32_t nph, uint32_t p, uint32_t pdir,
+                                                uint32_t done, uint32_t mmp, uint32_t mmt, uint32_t row,
+                                                uint32_t &outRow, uint32_t &outMm)
+{
+    const uint32_t ta = __ldg(loc.sa + row);                     // text position of the matched block
+    // the matched block in read coordinates starts at the smallest position touched so far
+    const uint32_t pstart = prog[p] & 0x7FFu, plen = (prog[p] >> 11) & 0x7FFu;
+    uint32_t qa = (done > 0) ? (pdir ? pstart : pstart + plen - done) : 0xFFFFFFFFu;
+#pragma unroll
+    for (int k = 0; k < S3_MAX_PHASES - 1; ++k) if ((uint32_t)k < p) qa = min(qa, prog[k] & 0x7FFu);
+    if (ta < qa || (unsigned long long)(ta - qa) + L > textLength) return false;      // hangs off the text
+    const uint32_t ps = ta - qa;                                 // text position of read base 0
+    // remaining stretches: the rest of the current phase, then the later phases
+    uint32_t ra[S3_MAX_PHASES], rb[S3_MAX_PHASES], cnt[S3_MAX_PHASES];
+#pragma unroll
+    for (int k = 0; k < S3_MAX_PHASES; ++k) {
+        const uint32_t st = prog[k] & 0x7FFu, ln = (prog[k] >> 11) & 0x7FFu;
+        ra[k] = st; rb[k] = st + ln; cnt[k] = 0;
+        if ((uint32_t)k == p) { if (pdir) ra[k] = st + done; else rb[k] = st + ln - done; }
+        if ((uint32_t)k < p || (uint32_t)k >= nph) rb[k] = ra[k] = 0;                   // nothing left to check
+    }
+    const uint32_t *tw = loc.text + (ps >> 4);
+    const uint32_t sh = (ps & 15u) << 1;
+    const uint32_t nw = (L + 15) >> 4;
+    uint32_t t0 = __ldg(tw);
+    for (uint32_t w = 0; w < nw; ++w) {
+        const uint32_t t1 = __ldg(tw + w + 1);
+        const uint32_t x = sr[w * S3_THREADS] ^ __funnelshift_l(t1, t0, sh);             // 16 read bases vs 16 text bases
+        const uint32_t m = (x | (x >> 1)) & 0x55555555u;                                // bit 30-2k: base k differs
+        t0 = t1;
+#pragma unroll
+        for (int k = 0; k < S3_MAX_PHASES; ++k) {
+            // bases [ra, rb) of the read that fall into this word
+            const uint32_t k0 = max(ra[k], 16u * w) - 16u * w, k1 = min(rb[k], 16u * w + 16u);
+            if (k1 > 16u * w + k0) {
+                const uint32_t mask = s3_shr_clamp(0xFFFFFFFFu, 2 * k0) & ~s3_shr_clamp(0xFFFFFFFFu, 2 * (k1 - 16u * w));
+                cnt[k] += __popc(m & mask);
+            }
+        }
+    }
+    uint32_t mm = mmt;
+#pragma unroll
+    for (int k = 0; k < S3_MAX_PHASES; ++k) {
+        if ((uint32_t)k >= p && (uint32_t)k < nph) {
+            const uint32_t lo = (prog[k] >> 23) & 7u, hi = (prog[k] >> 26) & 7u;
+            const uint32_t tot = cnt[k] + (((uint32_t)k == p) ? mmp : 0u);
+            if (tot < lo || tot > hi) return false;
+            mm += cnt[k];
+        }
+    }
+    outRow = __ldg(loc.isa + ps);
+    outMm = mm;
+    return true;
+}
+
+// Packs the phases of (numMismatch, whichCase, L) into prog[]; returns their number.
+__device__ __forceinline__ uint32_t s3_pack_program(const S3SearchArgs &args, uint32_t whichCase, uint32_t L,
+                                                    uint32_t prog[S3_MAX_PHASES], uint32_t &firstL)
+{
+    S3Phase ph[S3_MAX_PHASES];
+    const uint32_t nph = (uint32_t)s3_case_program(args.numMismatch, whichCase, L, args.exactNum != 0, ph, firstL);
+#pragma unroll
+    for (int k = 0; k < S3_MAX_PHASES; ++k) prog[k] = (k < (int)nph) ? s3_pack_phase(ph[k]) : 0u;
+    return nph;
+}
+
+#ifndef S3_EASY_STEPS
+#define S3_EASY_STEPS 16       // LF-mapping steps the easy kernel spends on a pass after its seed lookup
+#endif
+
+// First kernel of a search launch: one thread per (read, case), no work queue, no frame stack, every
+// thread on the same straight path --
+//     seed lookup -> a few exact steps until the interval is one suffix -> check-and-extend
+// for the first strand and then the second.  That settles every item whose exact first phase
+// pins the read to one place (or to none) -- almost all reads outside repeats.  Anything else (a first
+// phase that is still ambiguous after S3_EASY_STEPS steps or at its end, a read too short for the seed
+// table) is appended to `hardItems` untouched and enumerated by s3_search_kernel.
+__global__ void __launch_bounds__(S3_THREADS)
+s3_search_easy_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3Locate loc, const S3SearchArgs args,
+                      uint32_t *__restrict__ hardItems, uint32_t *__restrict__ hardCount)
+{
+    extern __shared__ uint32_t s3_smem[];
+    uint32_t *sm0 = s3_smem + threadIdx.x, *sm1 = sm0 + args.wordPerQuery * S3_THREADS;
+    const uint32_t item = blockIdx.x * S3_THREADS + threadIdx.x;
+    if (item >= args.numQueries * args.numCases) return;
+    const uint32_t ci = item / args.numQueries, q = item - ci * args.numQueries;
+    const uint32_t whichCase = args.firstCase + ci;
+    const uint32_t L = s3_load_read(args, q, sm0, sm1);
+    uint32_t prog[S3_MAX_PHASES], firstL;
+    const uint32_t nph = s3_pack_program(args, whichCase, L, prog, firstL);
+    const uint32_t pstart = prog[0] & 0x7FFu, plen = (prog[0] >> 11) & 0x7FFu, pdir = (prog[0] >> 22) & 1u;
+    const uint32_t K = seed.K;
+    bool hard = nph == 0 || plen < K || ((prog[0] >> 23) & 63u) != 0;            // phase 0 must be exact and seedable
+    uint32_t strand = args.round > 0 ? 0u : (whichCase & 1u);
+    uint32_t repRow[2], repMeta[2], nrep = 0;
+    for (int pass = 0; pass < 2 && !hard; ++pass, strand ^= 1u) {
+        const uint32_t *sr = strand ? sm1 : sm0;
+        uint32_t key = 0, rkey = 0;
+        for (uint32_t d = 0; d < K; ++d) {
+            const uint32_t pos = pdir ? pstart + d : pstart + plen - 1 - d;
+            const uint32_t c = s3_base(sr, pos);
+            key = (key << 2) | c;
+            rkey |= c << (2 * d);
+        }
+        const uint2 e = __ldg((pdir ? seed.rev0 : seed.fwd1) + key);
+        if (e.x >= 0xFFFFFFF0u) continue;                                       // no occurrence of the seed
+        uint32_t xlo = e.x, xhi = e.y, ylo = 0, yhi = 0, done = K;
+        if (pdir) { ylo = __ldg(seed.fwd0 + rkey).x; yhi = ylo + (xhi - xlo); }
+        const uint4 *buckets = pdir ? rev.buckets : fwd.buckets;
+        const uint32_t isa0 = pdir ? rev.inverseSa0 : fwd.inverseSa0;
+        bool alive = true;
+        for (int s = 0; s < S3_EASY_STEPS && alive && xlo != xhi && done < plen; ++s) {
+            const S3Bucket ka = s3_rank_load(buckets, isa0, xlo);
+            const S3Bucket kb = s3_rank_load(buckets, isa0, xhi + 1);
+            const uint32_t pos = pdir ? pstart + done : pstart + plen - 1 - done;
+            const uint32_t c = s3_base(sr, pos);
+            uint32_t a0, a1, a2, a3, b0, b1, b2, b3;
+            s3_rank_count(ka, a0, a1, a2, a3);
+            s3_rank_count(kb, b0, b1, b2, b3);
+            const uint32_t d1 = b1 - a1, d2 = b2 - a2, d3 = b3 - a3;
+            const uint32_t cum = (c < 3 ? d3 : 0) + (c < 2 ? d2 : 0) + (c < 1 ? d1 : 0);
+            xlo = (c == 0 ? a0 : c == 1 ? a1 : c == 2 ? a2 : a3) + 1;
+            xhi = c == 0 ? b0 : c == 1 ? b1 : c == 2 ? b2 : b3;
+            yhi = yhi - cum; ylo = yhi - (xhi - xlo);
+            ++done;
+            alive = xlo <= xhi;
+        }
+        if (!alive) continue;
+        if (xlo != xhi) { hard = true; break; }                                  // still several suffixes: enumerate
+        uint32_t row, mm;
+        if (s3_check_extend(loc, sr, L, args.textLength, prog, nph, 0, pdir, done, 0, 0, pdir ? ylo : xlo, row, mm)) {
+            repRow[nrep] = row; repMeta[nrep] = (strand << 27) + (mm << 24); ++nrep;
+        }
+    }
+    if (hard) { hardItems[atomicAdd(hardCount, 1u)] = item; return; }
+    // answer slot (DV-Kernel.cu:355-380,4468-4491); the buffer was filled with 0xFF before the launch
+    uint32_t *answer = args.answers[whichCase] + (size_t)(q >> 5) * 32 * args.wordPerAnswer + (q & 31);
+    uint32_t saCount = 0;
+    for (uint32_t k = 0; k < nrep; ++k) {
+        if (saCount < args.saRangeAllowed) { answer[32 * 2 * saCount] = repRow[k]; answer[32 * (2 * saCount + 1)] = repMeta[k]; }
+        ++saCount;
+    }
+    if (saCount == 0) answer[0] = 0xFFFFFFFDu;
+    else if (saCount > args.saRangeAllowed) answer[0] = 0xFFFFFFFEu;
+}
+
 #ifndef S3_REFILL_MIN
 #define S3_REFILL_MIN 4        // idle lanes a warp tolerates before it goes back to the work queue
 #endif
@@ -158,7 +342,8 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
     uint32_t *sm1 = sm0 + args.wordPerQuery * S3_THREADS;                                // reverse complement
     const uint32_t *sr = sm0;                                                            // strand being searched
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t totalItems = args.numQueries * args.numCases;      // < 2^32 (host splits otherwise)
+    // all (read, case) items, or the list the easy kernel left behind
+    const uint32_t totalItems = args.itemList ? *args.itemCount : args.numQueries * args.numCases;   // < 2^32
     const uint32_t maxRanges = args.saRangeAllowed;
     unsigned long long nrank = 0;
 
@@ -222,63 +407,11 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
         if (saCount > maxRanges) { answer[0] = 0xFFFFFFFEu; has = false; }
     };
 
-    // Check-and-extend.  The lane stands on a node whose interval is ONE suffix: every further step could
-    // only follow the text at that suffix' position, taking a substitution wherever read and text differ
-    // (if the phase still allows one) -- so the outcome of the whole remaining program is decided by the
-    // number of differences in each phase's stretch of the read, counted by XOR against the packed text,
-    // and the final interval is the row of the suffix that starts where the read starts.  Same answer as
-    // stepping (the reference's CPU search does the same once an interval is small,
-    // 2bwt-flex/SRA2BWTCheckAndExtend.c), ~5 sectors instead of one per remaining base.
     auto check_extend = [&]() {
-        const uint32_t row = pdir ? ylo : xlo;                       // row on the forward BWT
-        const uint32_t ta = __ldg(loc.sa + row);                     // text position of the matched block
-        // the matched block in read coordinates starts at the smallest position touched so far
-        uint32_t qa = (done > 0) ? (pdir ? pstart : pstart + plen - done) : 0xFFFFFFFFu;
-#pragma unroll
-        for (int k = 0; k < S3_MAX_PHASES - 1; ++k) if ((uint32_t)k < p) qa = min(qa, prog[k] & 0x7FFu);
+        uint32_t row, mm;
         alive = false;                                               // this branch ends here, reported or not
-        if (ta < qa || (unsigned long long)(ta - qa) + L > args.textLength) return;       // hangs off the text
-        const uint32_t ps = ta - qa;                                 // text position of read base 0
-        // remaining stretches: the rest of the current phase, then the later phases
-        uint32_t ra[S3_MAX_PHASES], rb[S3_MAX_PHASES], cnt[S3_MAX_PHASES];
-#pragma unroll
-        for (int k = 0; k < S3_MAX_PHASES; ++k) {
-            const uint32_t st = prog[k] & 0x7FFu, ln = (prog[k] >> 11) & 0x7FFu;
-            ra[k] = st; rb[k] = st + ln; cnt[k] = 0;
-            if ((uint32_t)k == p) { if (pdir) ra[k] = st + done; else rb[k] = st + ln - done; }
-            if ((uint32_t)k < p || (uint32_t)k >= nph) rb[k] = ra[k] = 0;               // nothing left to check
-        }
-        const uint32_t *tw = loc.text + (ps >> 4);
-        const uint32_t sh = (ps & 15u) << 1;
-        const uint32_t nw = (L + 15) >> 4;
-        uint32_t t0 = __ldg(tw);
-        for (uint32_t w = 0; w < nw; ++w) {
-            const uint32_t t1 = __ldg(tw + w + 1);
-            const uint32_t x = sr[w * S3_THREADS] ^ __funnelshift_l(t1, t0, sh);         // 16 read bases vs 16 text bases
-            const uint32_t m = (x | (x >> 1)) & 0x55555555u;                            // bit 30-2k: base k differs
-            t0 = t1;
-#pragma unroll
-            for (int k = 0; k < S3_MAX_PHASES; ++k) {
-                // bases [ra, rb) of the read that fall into this word
-                const uint32_t k0 = max(ra[k], 16u * w) - 16u * w, k1 = min(rb[k], 16u * w + 16u);
-                if (k1 > 16u * w + k0) {
-                    const uint32_t mask = s3_shr_clamp(0xFFFFFFFFu, 2 * k0) & ~s3_shr_clamp(0xFFFFFFFFu, 2 * (k1 - 16u * w));
-                    cnt[k] += __popc(m & mask);
-                }
-            }
-        }
-        uint32_t mm = mmt;
-#pragma unroll
-        for (int k = 0; k < S3_MAX_PHASES; ++k) {
-            if ((uint32_t)k >= p && (uint32_t)k < nph) {
-                const uint32_t lo = (prog[k] >> 23) & 7u, hi = (prog[k] >> 26) & 7u;
-                const uint32_t tot = cnt[k] + (((uint32_t)k == p) ? mmp : 0u);
-                if (tot < lo || tot > hi) return;
-                mm += cnt[k];
-            }
-        }
-        const uint32_t l = __ldg(loc.isa + ps);
-        report(l, l, mm);
+        if (s3_check_extend(loc, sr, L, args.textLength, prog, nph, p, pdir, done, mmp, mmt, pdir ? ylo : xlo, row, mm))
+            report(row, row, mm);
     };
 
     while (true) {
@@ -295,32 +428,12 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
                 // the queue runs case-major so that a full warp refill reads 32 consecutive reads
                 if (item >= totalItems || item < base) dead = true;
                 else {
-                    const uint32_t ci = item / args.numQueries, q = item - ci * args.numQueries;
+                    const uint32_t it = args.itemList ? args.itemList[item] : item;
+                    const uint32_t ci = it / args.numQueries, q = it - ci * args.numQueries;
                     const uint32_t whichCase = args.firstCase + ci;
-                    const uint32_t *query = args.queries + (size_t)(q >> 5) * 32 * args.wordPerQuery + (q & 31);
                     answer = args.answers[whichCase] + (size_t)(q >> 5) * 32 * args.wordPerAnswer + (q & 31);
-                    L = args.readLengths[q];
-                    const uint32_t nw = (L + 15) >> 4;
-                    // queries hold base i of a read in bits 2(i%16) of word i/16 (QueryParser.cpp:1146-1152)
-                    for (uint32_t w = 0; w < nw; ++w) sm0[w * S3_THREADS] = query[w * 32];
-                    // reverse complement, word j = bases 16j..16j+15 of it = the complemented 32-bit window of the
-                    // given read's bit stream that ENDS with base L-1-16j: the reversal of the base order is
-                    // exactly the change from first-base-low to first-base-high packing
-                    for (uint32_t j = 0; j < nw; ++j) {
-                        const int ob = 2 * ((int)L - 16 * (int)(j + 1));
-                        uint32_t win;
-                        if (ob >= 0) {
-                            const uint32_t wl = (uint32_t)ob >> 5, sh = (uint32_t)ob & 31u;
-                            const uint32_t lo = sm0[wl * S3_THREADS], hi = (wl + 1 < nw) ? sm0[(wl + 1) * S3_THREADS] : 0u;
-                            win = __funnelshift_r(lo, hi, sh);
-                        } else win = sm0[0] << (uint32_t)(-ob);
-                        sm1[j * S3_THREADS] = ~win;
-                    }
-                    for (uint32_t w = 0; w < nw; ++w) sm0[w * S3_THREADS] = s3_flip16(sm0[w * S3_THREADS]);
-                    S3Phase ph[S3_MAX_PHASES];
-                    nph = (uint32_t)s3_case_program(args.numMismatch, whichCase, L, args.exactNum != 0, ph, firstL);
-#pragma unroll
-                    for (int k = 0; k < S3_MAX_PHASES; ++k) prog[k] = (k < (int)nph) ? s3_pack_phase(ph[k]) : 0u;
+                    L = s3_load_read(args, q, sm0, sm1);
+                    nph = s3_pack_program(args, whichCase, L, prog, firstL);
                     // round 1: the device read buffer of the reference flips orientation after every
                     // launch, so odd cases meet the reverse strand first (DV-Kernel.cu:4280-4285)
                     strand = args.round > 0 ? 0u : (whichCase & 1u);
@@ -456,7 +569,23 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
     unsigned long long blocks = (items + S3_THREADS - 1) / S3_THREADS;
     const unsigned long long resident = (unsigned long long)ix->numSms * ix->searchBlocksPerSm;
     if (blocks > resident) blocks = resident;
-    S3_CUDA(cudaMemsetAsync(ix->d_workCounter, 0, sizeof(uint32_t), ix->stream));
+    S3_CUDA(cudaMemsetAsync(ix->d_workCounter, 0, 2 * sizeof(uint32_t), ix->stream));
+    a.itemList = NULL; a.itemCount = NULL;
+    if (!count && ix->loc.sa && ix->seed.K && !getenv("S3_NO_EASY_KERNEL")) {
+        // the straight-line kernel settles what it can; the enumerating kernel takes the list it leaves
+        if (items > ix->hardCap) {
+            if (ix->d_hardItems) { S3_CUDA(cudaStreamSynchronize(ix->stream)); S3_CUDA(cudaFree(ix->d_hardItems)); ix->d_hardItems = NULL; ix->hardCap = 0; }
+            S3_CUDA(cudaMalloc(&ix->d_hardItems, items * sizeof(uint32_t)));
+            ix->hardCap = items;
+        }
+        const size_t smemEasy = (size_t)2 * a.wordPerQuery * S3_THREADS * sizeof(uint32_t);
+        if (smemEasy > 48 * 1024) S3_CUDA(cudaFuncSetAttribute(s3_search_easy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEasy));
+        s3_search_easy_kernel<<<(unsigned)((items + S3_THREADS - 1) / S3_THREADS), S3_THREADS, smemEasy, ix->stream>>>(
+            ix->fwd, ix->rev, ix->seed, ix->loc, a, ix->d_hardItems, ix->d_workCounter + 1);
+        S3_LAUNCHED(1);
+        S3_CUDA(cudaGetLastError());
+        a.itemList = ix->d_hardItems; a.itemCount = ix->d_workCounter + 1;
+    }
     if (count) s3_search_kernel<true><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
     else s3_search_kernel<false><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
     S3_LAUNCHED(1);

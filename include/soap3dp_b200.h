@@ -114,6 +114,14 @@ int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, const uint3
                             int isExactNumMismatch, uint32_t *const *d_answers,
                             unsigned long long *d_rankQueries);
 
+/* Tuning knob, answers are identical for every value.  A (read, case) enumeration that is
+ * still running in its lane after `steps` LF-mapping steps is split: the substitution children
+ * along the read's own path become independent tasks for other lanes and their ranges are merged
+ * back in enumeration order under the slot's cap (round-1 slots, saRangeAllowed <= 4).  Default
+ * 256; 0 splits every enumerated item; negative: never split (one lane per item, as the
+ * reference runs one thread per read, DV-Kernel.cu:4249). */
+int s3_search_set_split_budget(s3_index *ix, int32_t steps);
+
 /* ------------------------------------------------------------------------
  * Semi-global affine-gap DP.  Replaces SemiGlobalAligner::{decideConfiguration,
  * init, performAlignment, freeMemory} (DV-DPfunctions.h:120-164,
@@ -132,7 +140,8 @@ int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint32_t maxBatc
 void s3_dp_free(s3_dp *dp);
 void *s3_dp_stream(const s3_dp *dp);
 /* issue this workspace's kernels and copies on `stream` (a cudaStream_t, e.g.
- * s3_index_stream()) so that search and DP of one batch are stream-ordered */
+ * s3_index_stream()) so that search and DP of one batch are stream-ordered;
+ * NULL gives the workspace a stream of its own again */
 void s3_dp_set_stream(s3_dp *dp, void *stream);
 /* PatternLength() = maxReadLength + maxDPTableLength bytes per alignment
  * (DV-DPfunctions.cu:54); maxDPTableLength = maxDNALength in scheme 1

@@ -31,7 +31,7 @@ U64P = C.POINTER(C.c_uint64)
 
 EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
-    "s3_index_set_locate_device",
+    "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -69,6 +69,8 @@ def load_library() -> C.CDLL:
                                     U32P, U32P, C.c_int, C.POINTER(C.c_void_p)]
     lib.s3_index_set_locate_device.restype = C.c_int
     lib.s3_index_set_locate_device.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.s3_search_set_split_budget.restype = C.c_int
+    lib.s3_search_set_split_budget.argtypes = [C.c_void_p, C.c_int32]
     lib.s3_index_free.restype = None
     lib.s3_index_free.argtypes = [C.c_void_p]
     lib.s3_index_device_bytes.restype = C.c_size_t
@@ -175,6 +177,11 @@ def set_locate_device(gpu_index: GpuIndex, d_sa: int, d_packed_text: int):
     (raw device pointers); enables check-and-extend."""
     _check(load_library().s3_index_set_locate_device(gpu_index.handle, C.c_void_p(d_sa), C.c_void_p(d_packed_text)),
            "s3_index_set_locate_device")
+
+
+def set_split_budget(gpu_index: GpuIndex, steps: int):
+    """Tuning knob of the search (include/soap3dp_b200.h): steps before a long enumeration is split."""
+    _check(load_library().s3_search_set_split_budget(gpu_index.handle, steps), "s3_search_set_split_budget")
 
 
 def GPUINDEXFree(gpu_index: GpuIndex):

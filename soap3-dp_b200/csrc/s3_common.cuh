@@ -75,15 +75,18 @@ struct s3_index {
     void *pinned; size_t pinnedBytes;
     S3Pipe pipe;
     // persistent search launches
-    uint32_t *d_workCounter;          // [0] work queue head, [1] number of items the easy kernel left behind
+    uint32_t *d_workCounter;          // [0] work queue head, [1] number of items the easy kernel left behind, [4..7] S3_HV_* counters
+    uint32_t *d_heavy; uint32_t heavyCap, heavyMaxTasks;     // scratch for splitting long enumerations (s3_search.cu)
+    int32_t splitBudget;              // steps before an item is split (s3_search_set_split_budget); < 0: never
     uint32_t *d_hardItems; size_t hardCap;
+    uint32_t *d_itemStats; size_t itemStatsCap;   // S3_ITEM_STATS builds only (tools/search_tail.py)
     int numSms;
     size_t searchSmem; int searchBlocksPerSm;
 };
 
 void s3_set_error(const char *fmt, ...);
 extern unsigned long long g_s3_launches;
-#define S3_LAUNCHED(n) (g_s3_launches += (n))
+#define S3_LAUNCHED(n) ((void)__atomic_fetch_add(&g_s3_launches, (unsigned long long)(n), __ATOMIC_RELAXED))
 #define S3_CUDA(call)                                                                   \
     do {                                                                                \
         cudaError_t e__ = (call);                                                       \

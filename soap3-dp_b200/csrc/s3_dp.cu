@@ -796,7 +796,11 @@ extern "C" void s3_dp_set_stream(s3_dp *dp, void *stream)
     if (!dp) return;
     cudaStreamSynchronize(dp->stream);
     if (dp->ownStream) { cudaStreamDestroy(dp->stream); dp->ownStream = 0; }
-    dp->stream = (cudaStream_t)stream;
+    if (stream) { dp->stream = (cudaStream_t)stream; return; }
+    // NULL: back to a stream of its own
+    cudaSetDevice(dp->device);
+    if (cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking) == cudaSuccess) dp->ownStream = 1;
+    else dp->stream = 0;
 }
 extern "C" uint32_t s3_dp_pattern_length(const s3_dp *dp) { return dp ? dp->maxReadLength + dp->maxDNALength : 0; }
 

@@ -236,6 +236,7 @@ extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const u
     ix->textLength = textLength;
     S3_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
     S3_CUDA(cudaDeviceGetAttribute(&ix->numSms, cudaDevAttrMultiProcessorCount, device));
+    ix->splitBudget = 256;
     S3_CUDA(cudaMalloc(&ix->d_workCounter, 256));
     ix->searchSmem = (size_t)-1;
     int rc;
@@ -270,6 +271,8 @@ extern "C" void s3_index_free(s3_index *ix)
     s3_pipe_destroy(&ix->pipe);
     if (ix->d_workCounter) cudaFree(ix->d_workCounter);
     if (ix->d_hardItems) cudaFree(ix->d_hardItems);
+    if (ix->d_itemStats) cudaFree(ix->d_itemStats);
+    if (ix->d_heavy) cudaFree(ix->d_heavy);
     if (ix->scratch) cudaFree(ix->scratch);
     if (ix->pinned) cudaFreeHost(ix->pinned);
     cudaStreamDestroy(ix->stream);

@@ -86,6 +86,21 @@ __host__ __device__ inline int s3_case_program(uint32_t k, uint32_t cs, uint32_t
     return n;
 }
 
+// Splitting of long enumerations (see s3_search_kernel): scratch owned by the index handle.
+#define S3_TASK_WORDS 16
+#define S3_TASK_RESULTS 4          // ranges a task record holds: splitting needs saRangeAllowed <= 4 (every round-1 slot)
+enum { S3_HV_ITEMS = 0, S3_HV_SPINE_HEAD = 1, S3_HV_TASKS = 2, S3_HV_TASK_HEAD = 3 };
+struct S3Heavy {
+    uint32_t *items;               // heavy item ids (case * numQueries + read)
+    uint32_t cap;                  // room in items[]; 0: no splitting in this launch
+    uint32_t maxTasks;             // task records per unit = (heavy item, strand pass)
+    uint32_t *tasks;               // [cap * 2 * maxTasks][S3_TASK_WORDS]
+    uint32_t *unitTasks;           // [cap * 2] task records written per unit
+    uint32_t *queue;               // task ids (unit * maxTasks + k) waiting for a lane
+    uint32_t *counters;            // S3_HV_*: heavy items, spine queue head, tasks queued, task queue head
+    int32_t budget;                // LF-mapping steps an item may take in one lane before it is split
+};
+
 struct S3SearchArgs {
     const uint32_t *queries;
     const uint32_t *readLengths;
@@ -99,6 +114,8 @@ struct S3SearchArgs {
     const uint32_t *itemList;            // NULL: every item; else item ids (case * numQueries + read) ...
     const uint32_t *itemCount;           // ... and how many (device memory, written by the easy kernel)
     unsigned long long *rankQueries;     // may be NULL
+    uint32_t *itemStats;                 // S3_ITEM_STATS builds only: LF-mapping steps spent per item
+    S3Heavy heavy;
 };
 
 // DFS frame: a node where substitutions are still allowed, kept in shared memory
@@ -147,7 +164,7 @@ __device__ __forceinline__ uint32_t s3_pack_phase(const S3Phase &ph)
 __device__ __forceinline__ uint32_t s3_load_read(const S3SearchArgs &args, uint32_t q, uint32_t *sm0, uint32_t *sm1)
 {
     const uint32_t *query = args.queries + (size_t)(q >> 5) * 32 * args.wordPerQuery + (q & 31);
-    const uint32_t L = args.readLengths[q];
+    const uint32_t L = min(args.readLengths[q], 16u * args.wordPerQuery);      // a length the buffer cannot hold is cut, never followed
     const uint32_t nw = (L + 15) >> 4;
     // queries hold base i of a read in bits 2(i%16) of word i/16 (QueryParser.cpp:1146-1152)
     for (uint32_t w = 0; w < nw; ++w) sm0[w * S3_THREADS] = query[w * 32];
@@ -332,7 +349,23 @@ s3_search_easy_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, con
 #define S3_SEARCH_MIN_BLOCKS 6
 #endif
 
-template <bool COUNT>
+// One enumerator, three ways to feed it:
+//   S3_MODE_ITEMS    work = (read, case) items, all of them or the list the easy kernel left.  An item that
+//                    is still running after `heavy.budget` steps is taken back (its slot is blanked) and
+//                    put on the heavy list: a launch would otherwise end with a few lanes walking one
+//                    long enumeration each, one dependent DRAM access after the other.
+//   S3_MODE_SPINE    work = (heavy item, strand pass).  The lane follows the read's own bases only; where
+//                    the item's enumeration would branch into a substitution it writes the child's state
+//                    down as a TASK instead, in enumeration order.
+//   S3_MODE_SUBTREE  work = tasks.  The ordinary depth-first enumeration below one substitution child,
+//                    results into the task record.
+// s3_heavy_merge_kernel then strings the tasks' results together in enumeration order and applies the
+// slot's cap, so the answer is bit-identical to what the single lane would have written.
+#define S3_MODE_ITEMS 0
+#define S3_MODE_SPINE 1
+#define S3_MODE_SUBTREE 2
+
+template <bool COUNT, int MODE>
 __global__ void __launch_bounds__(S3_THREADS, S3_SEARCH_MIN_BLOCKS)
 s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3Locate loc, const S3SearchArgs args)
 {
@@ -342,10 +375,31 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
     uint32_t *sm1 = sm0 + args.wordPerQuery * S3_THREADS;                                // reverse complement
     const uint32_t *sr = sm0;                                                            // strand being searched
     const uint32_t lane = threadIdx.x & 31;
-    // all (read, case) items, or the list the easy kernel left behind
-    const uint32_t totalItems = args.itemList ? *args.itemCount : args.numQueries * args.numCases;   // < 2^32
+    const S3Heavy &hv = args.heavy;
+    uint32_t totalItems;                                                                 // < 2^32
+    uint32_t *queueHead;
+    if (MODE == S3_MODE_ITEMS) {
+        // all (read, case) items, or the list the easy kernel left behind
+        totalItems = args.itemList ? *args.itemCount : args.numQueries * args.numCases;
+        queueHead = args.workCounter;
+    } else if (MODE == S3_MODE_SPINE) {
+        totalItems = 2 * min(hv.counters[S3_HV_ITEMS], hv.cap);
+        queueHead = hv.counters + S3_HV_SPINE_HEAD;
+    } else {
+        totalItems = hv.counters[S3_HV_TASKS];
+        queueHead = hv.counters + S3_HV_TASK_HEAD;
+    }
+    if (totalItems == 0) return;
     const uint32_t maxRanges = args.saRangeAllowed;
     unsigned long long nrank = 0;
+#ifdef S3_ITEM_STATS
+    uint32_t statItem = 0, statSteps = 0;
+#define S3_STAT_END() do { if (MODE == S3_MODE_ITEMS && args.itemStats) args.itemStats[statItem] = statSteps; } while (0)
+#define S3_STAT_STEP() (++statSteps)
+#else
+#define S3_STAT_END() do { } while (0)
+#define S3_STAT_STEP() do { } while (0)
+#endif
 
     // ---- per-lane enumerator state ----
     // (xlo, xhi) is the interval in the index the current phase steps through (BWT for a backward
@@ -357,6 +411,9 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
     uint32_t p = 0, done = 0, mmp = 0, mmt = 0, depth = 0;
     uint32_t xlo = 0, xhi = 0, ylo = 0, yhi = 0;
     uint32_t *answer = NULL;
+    uint32_t curItem = 0;            // ITEMS: the item id; SPINE: the unit (2 * heavy index + pass); SUBTREE: the task id
+    int budget = 0;                  // ITEMS: steps left before the item is split
+    uint32_t *task = NULL;           // SPINE: the unit's task block; SUBTREE: the task record
 
     auto load_phase = [&](uint32_t k) {
         const uint32_t w = (k == 0) ? prog[0] : (k == 1) ? prog[1] : (k == 2) ? prog[2] : prog[3];
@@ -397,14 +454,39 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
         }
     };
 
+    // A task record (S3_TASK_WORDS words): the enumerator state below one substitution child
+    //   [0..3] xlo xhi ylo yhi   [4] done[0:11] p[11:13] mmp[13:16] mmt[16:19] pdir[19] strand[20]
+    //   [5] number of ranges found (may be cap + 1)   [6..] up to S3_TASK_RESULTS ranges (saL, packed width word)
+    auto emit_task = [&](uint32_t a_e, uint32_t b_e, uint32_t cum) {
+        uint32_t *t = task + (size_t)saCount * S3_TASK_WORDS;
+        const uint32_t tyhi = yhi - cum;
+        t[0] = a_e + 1; t[1] = b_e; t[2] = tyhi - (b_e - (a_e + 1)); t[3] = tyhi;
+        t[4] = (done + 1) | (p << 11) | ((mmp + 1) << 13) | ((mmt + 1) << 16) | (pdir << 19) | (strand << 20);
+        t[5] = 0;
+        hv.queue[atomicAdd(hv.counters + S3_HV_TASKS, 1u)] = curItem * hv.maxTasks + saCount;
+        ++saCount;
+    };
+
     // report (DV-Kernel.cu:355-380): the interval on the forward BWT; a slot overflow ends the item
     auto report = [&](uint32_t l, uint32_t r, uint32_t mm) {
-        if (saCount < maxRanges) {
-            answer[32 * 2 * saCount] = l;
-            answer[32 * (2 * saCount + 1)] = (r - l) + (strand << 27) + (mm << 24);
+        const uint32_t packed = (r - l) + (strand << 27) + (mm << 24);
+        if (MODE == S3_MODE_ITEMS) {
+            if (saCount < maxRanges) {
+                answer[32 * 2 * saCount] = l;
+                answer[32 * (2 * saCount + 1)] = packed;
+            }
+            ++saCount;
+            if (saCount > maxRanges) { answer[0] = 0xFFFFFFFEu; has = false; S3_STAT_END(); }
+        } else if (MODE == S3_MODE_SPINE) {
+            // a range found on the spine itself takes its place among the tasks as one that is already done
+            uint32_t *t = task + (size_t)saCount * S3_TASK_WORDS;
+            t[5] = 1; t[6] = l; t[7] = packed;
+            ++saCount;
+        } else {
+            if (saCount < maxRanges) { task[6 + 2 * saCount] = l; task[7 + 2 * saCount] = packed; }
+            ++saCount;
+            if (saCount > maxRanges) { task[5] = saCount; has = false; }
         }
-        ++saCount;
-        if (saCount > maxRanges) { answer[0] = 0xFFFFFFFEu; has = false; }
     };
 
     auto check_extend = [&]() {
@@ -421,14 +503,20 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
         if (!want && !busy) break;
         if (want && ((uint32_t)__popc(want) >= S3_REFILL_MIN || !busy)) {
             uint32_t base = 0;
-            if (lane == 0) base = atomicAdd(args.workCounter, (uint32_t)__popc(want));
+            if (lane == 0) base = atomicAdd(queueHead, (uint32_t)__popc(want));
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (!has && !dead) {
                 const uint32_t item = base + __popc(want & ((1u << lane) - 1u));
                 // the queue runs case-major so that a full warp refill reads 32 consecutive reads
                 if (item >= totalItems || item < base) dead = true;
                 else {
-                    const uint32_t it = args.itemList ? args.itemList[item] : item;
+                    uint32_t it;                                         // (read, case) of this piece of work
+                    if (MODE == S3_MODE_ITEMS) { it = args.itemList ? args.itemList[item] : item; curItem = it; budget = hv.budget; }
+                    else if (MODE == S3_MODE_SPINE) { curItem = item; it = hv.items[item >> 1]; }
+                    else { curItem = hv.queue[item]; it = hv.items[(curItem / hv.maxTasks) >> 1]; }
+#ifdef S3_ITEM_STATS
+                    statItem = it; statSteps = 0;
+#endif
                     const uint32_t ci = it / args.numQueries, q = it - ci * args.numQueries;
                     const uint32_t whichCase = args.firstCase + ci;
                     answer = args.answers[whichCase] + (size_t)(q >> 5) * 32 * args.wordPerAnswer + (q & 31);
@@ -438,7 +526,21 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
                     // launch, so odd cases meet the reverse strand first (DV-Kernel.cu:4280-4285)
                     strand = args.round > 0 ? 0u : (whichCase & 1u);
                     pass = 0; saCount = 0; has = true;
-                    start_pass();
+                    if (MODE == S3_MODE_ITEMS) start_pass();
+                    else if (MODE == S3_MODE_SPINE) {
+                        task = hv.tasks + (size_t)curItem * hv.maxTasks * S3_TASK_WORDS;
+                        strand ^= (curItem & 1u);
+                        start_pass();
+                    } else {
+                        task = hv.tasks + (size_t)curItem * S3_TASK_WORDS;
+                        const uint32_t meta = task[4];
+                        xlo = task[0]; xhi = task[1]; ylo = task[2]; yhi = task[3];
+                        done = meta & 0x7FF; p = (meta >> 11) & 3; mmp = (meta >> 13) & 7; mmt = (meta >> 16) & 7;
+                        pdir = (meta >> 19) & 1; strand = (meta >> 20) & 1;
+                        sr = strand ? sm1 : sm0;
+                        depth = 0; alive = true;
+                        load_phase(p);                                   // same direction: nothing is swapped
+                    }
                 }
             }
         }
@@ -451,13 +553,16 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
                 else if (p + 1 == nph) { report(pdir ? ylo : xlo, pdir ? yhi : xhi, mmt); alive = false; }
                 else { ++p; done = 0; mmp = 0; load_phase(p); }
             } else if (depth == 0) {
+                if (MODE == S3_MODE_SPINE) { hv.unitTasks[curItem] = saCount; has = false; }
+                else if (MODE == S3_MODE_SUBTREE) { task[5] = saCount; has = false; }
                 // this strand is exhausted
-                if (pass == 0 && nph > 0) { pass = 1; strand ^= 1u; start_pass(); }
+                else if (pass == 0 && nph > 0) { pass = 1; strand ^= 1u; start_pass(); }
                 else {
                     // status word (DV-Kernel.cu:4468-4491); the isBad carry between the cases of round 1
                     // is applied by s3_isbad_fixup_kernel because cases run concurrently here
                     if (saCount == 0) answer[0] = 0xFFFFFFFDu;
                     has = false;
+                    S3_STAT_END();
                 }
             } else {
                 // take the next pending branch from the innermost frame
@@ -482,7 +587,18 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
             }
         }
         __syncwarp();
+        // ---- an item that outlasts its budget goes to the heavy list, if there is room ----
+        if (MODE == S3_MODE_ITEMS && !COUNT && has && hv.cap && --budget < 0) {
+            const uint32_t slot = atomicAdd(hv.counters + S3_HV_ITEMS, 1u);
+            if (slot < hv.cap) {
+                hv.items[slot] = curItem;
+                for (uint32_t k = 0; k < 2 * min(saCount, maxRanges); ++k) answer[32 * k] = 0xFFFFFFFFu;    // take back what was written
+                has = false;
+                S3_STAT_END();
+            } else budget = 0x7FFFFFFF;                               // no room: this lane finishes it alone
+        }
         // ---- (B) one LF-mapping step for every lane that has work: both ranks' loads first ----
+        if (has) S3_STAT_STEP();
         if (has && !COUNT && loc.sa != NULL && xlo == xhi) check_extend();
         else if (has) {
             const uint4 *buckets = pdir ? rev.buckets : fwd.buckets;
@@ -499,7 +615,14 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
             if (mmp < phi) {
                 // does any substitution child survive?  (most do not once the interval is narrow)
                 const bool live = (c != 0 && a0 < b0) || (c != 1 && a1 < b1) || (c != 2 && a2 < b2) || (c != 3 && a3 < b3);
-                if (live) {
+                if (live && MODE == S3_MODE_SPINE) {
+                    // the children become tasks, ascending like the frame would hand them out; the spine goes on
+                    const uint32_t d1 = b1 - a1, d2 = b2 - a2, d3 = b3 - a3;
+                    if (c != 0 && a0 < b0) emit_task(a0, b0, d1 + d2 + d3);
+                    if (c != 1 && a1 < b1) emit_task(a1, b1, d2 + d3);
+                    if (c != 2 && a2 < b2) emit_task(a2, b2, d3);
+                    if (c != 3 && a3 < b3) emit_task(a3, b3, 0u);
+                } else if (live) {
                     uint32_t *f = fr + depth * S3_FRAME_WORDS * S3_THREADS;
                     f[0 * S3_THREADS] = a0; f[1 * S3_THREADS] = a1; f[2 * S3_THREADS] = a2; f[3 * S3_THREADS] = a3;
                     f[4 * S3_THREADS] = b0; f[5 * S3_THREADS] = b1; f[6 * S3_THREADS] = b2; f[7 * S3_THREADS] = b3;
@@ -530,6 +653,34 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
     }
 }
 
+// The split items' answer slots: the tasks of pass 0, then those of pass 1, each in the order the spine
+// wrote them = the order one lane would have found their ranges in; the slot's cap and status words as
+// in the enumerator's own report (DV-Kernel.cu:355-380,4468-4491).
+__global__ void s3_heavy_merge_kernel(const S3SearchArgs args)
+{
+    const S3Heavy &hv = args.heavy;
+    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    if (h >= min(hv.counters[S3_HV_ITEMS], hv.cap)) return;
+    const uint32_t it = hv.items[h];
+    const uint32_t ci = it / args.numQueries, q = it - ci * args.numQueries;
+    uint32_t *answer = args.answers[args.firstCase + ci] + (size_t)(q >> 5) * 32 * args.wordPerAnswer + (q & 31);
+    const uint32_t maxRanges = args.saRangeAllowed;
+    uint32_t total = 0;
+    for (uint32_t u = 2 * h; u < 2 * h + 2 && total <= maxRanges; ++u) {
+        const uint32_t *t = hv.tasks + (size_t)u * hv.maxTasks * S3_TASK_WORDS;
+        const uint32_t nt = hv.unitTasks[u];
+        for (uint32_t k = 0; k < nt && total <= maxRanges; ++k, t += S3_TASK_WORDS) {
+            const uint32_t cnt = t[5];
+            for (uint32_t r = 0; r < cnt && total <= maxRanges; ++r) {
+                if (total < maxRanges) { answer[32 * 2 * total] = t[6 + 2 * r]; answer[32 * (2 * total + 1)] = t[7 + 2 * r]; }
+                ++total;
+            }
+        }
+    }
+    if (total == 0) answer[0] = 0xFFFFFFFDu;
+    else if (total > maxRanges) answer[0] = 0xFFFFFFFEu;
+}
+
 // Round 1 semantics of isBad (DV-Kernel.cu:4285,4478-4491): once a read overflowed in
 // case c, every later case reports a bare overflow slot without being searched.
 __global__ void s3_isbad_fixup_kernel(S3SearchArgs args, uint32_t numCases)
@@ -557,20 +708,55 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
     a.workCounter = ix->d_workCounter;
     const size_t smem = (size_t)(2 * a.wordPerQuery + S3_MAX_DEPTH * S3_FRAME_WORDS) * S3_THREADS * sizeof(uint32_t);
     if (smem != ix->searchSmem) {
-        S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<true, S3_MODE_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<false, S3_MODE_ITEMS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<false, S3_MODE_SPINE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<false, S3_MODE_SUBTREE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         int perSm = 0;
-        S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, s3_search_kernel<false>, S3_THREADS, smem));
+        S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, s3_search_kernel<false, S3_MODE_ITEMS>, S3_THREADS, smem));
         if (perSm < 1) { s3_set_error("search kernel does not fit on an SM with wordPerQuery %u", a.wordPerQuery); return S3_EINVAL; }
         ix->searchSmem = smem;
         ix->searchBlocksPerSm = perSm;
+    }
+    // Scratch for splitting long enumerations: every substitution child of a heavy item's spine is a task
+    // record, at most 3 per base and one range found on the spine itself per strand pass.
+    memset(&a.heavy, 0, sizeof a.heavy);
+    if (!count && a.saRangeAllowed <= S3_TASK_RESULTS && ix->splitBudget >= 0) {
+        const uint32_t maxTasks = 3 * 16 * a.wordPerQuery + 2;
+        if (maxTasks > ix->heavyMaxTasks) {
+            if (ix->d_heavy) { S3_CUDA(cudaStreamSynchronize(ix->stream)); S3_CUDA(cudaFree(ix->d_heavy)); ix->d_heavy = NULL; ix->heavyMaxTasks = 0; }
+            size_t cap = ((size_t)256 << 20) / ((size_t)2 * maxTasks * S3_TASK_WORDS * 4);
+            if (cap > 4096) cap = 4096;
+            if (cap < 64) cap = 64;
+            // items | unitTasks | queue | tasks
+            const size_t words = cap + 2 * cap + 2 * cap * maxTasks + 2 * cap * maxTasks * S3_TASK_WORDS;
+            S3_CUDA(cudaMalloc(&ix->d_heavy, words * sizeof(uint32_t)));
+            ix->heavyCap = (uint32_t)cap; ix->heavyMaxTasks = maxTasks;
+            ix->bytes += words * sizeof(uint32_t);
+        }
+        a.heavy.cap = ix->heavyCap; a.heavy.maxTasks = ix->heavyMaxTasks;
+        a.heavy.items = ix->d_heavy;
+        a.heavy.unitTasks = a.heavy.items + ix->heavyCap;
+        a.heavy.queue = a.heavy.unitTasks + 2 * (size_t)ix->heavyCap;
+        a.heavy.tasks = a.heavy.queue + 2 * (size_t)ix->heavyCap * ix->heavyMaxTasks;
+        a.heavy.counters = ix->d_workCounter + 4;
+        a.heavy.budget = ix->splitBudget;
     }
     const unsigned long long items = (unsigned long long)a.numQueries * numCases;
     unsigned long long blocks = (items + S3_THREADS - 1) / S3_THREADS;
     const unsigned long long resident = (unsigned long long)ix->numSms * ix->searchBlocksPerSm;
     if (blocks > resident) blocks = resident;
-    S3_CUDA(cudaMemsetAsync(ix->d_workCounter, 0, 2 * sizeof(uint32_t), ix->stream));
+    S3_CUDA(cudaMemsetAsync(ix->d_workCounter, 0, 8 * sizeof(uint32_t), ix->stream));
     a.itemList = NULL; a.itemCount = NULL;
+#ifdef S3_ITEM_STATS
+    if (items > ix->itemStatsCap) {
+        if (ix->d_itemStats) { S3_CUDA(cudaStreamSynchronize(ix->stream)); S3_CUDA(cudaFree(ix->d_itemStats)); ix->d_itemStats = NULL; }
+        S3_CUDA(cudaMalloc(&ix->d_itemStats, items * sizeof(uint32_t)));
+        ix->itemStatsCap = items;
+    }
+    S3_CUDA(cudaMemsetAsync(ix->d_itemStats, 0, items * sizeof(uint32_t), ix->stream));
+    a.itemStats = ix->d_itemStats;
+#endif
     if (!count && ix->loc.sa && ix->seed.K && !getenv("S3_NO_EASY_KERNEL")) {
         // the straight-line kernel settles what it can; the enumerating kernel takes the list it leaves
         if (items > ix->hardCap) {
@@ -586,10 +772,40 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
         S3_CUDA(cudaGetLastError());
         a.itemList = ix->d_hardItems; a.itemCount = ix->d_workCounter + 1;
     }
-    if (count) s3_search_kernel<true><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
-    else s3_search_kernel<false><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
+    if (count) s3_search_kernel<true, S3_MODE_ITEMS><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
+    else s3_search_kernel<false, S3_MODE_ITEMS><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
     S3_LAUNCHED(1);
     S3_CUDA(cudaGetLastError());
+    if (a.heavy.cap) {
+        // the items that outlasted their budget: spines, then the tasks they wrote, then the slots.  The
+        // three launches find their work counts in device memory and return at once when there is none.
+        unsigned long long spineBlocks = (2ull * a.heavy.cap + S3_THREADS - 1) / S3_THREADS;
+        if (spineBlocks > blocks) spineBlocks = blocks;
+        s3_search_kernel<false, S3_MODE_SPINE><<<(unsigned)spineBlocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
+        s3_search_kernel<false, S3_MODE_SUBTREE><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
+        s3_heavy_merge_kernel<<<(a.heavy.cap + 127) / 128, 128, 0, ix->stream>>>(a);
+        S3_LAUNCHED(3);
+        S3_CUDA(cudaGetLastError());
+    }
+    return S3_OK;
+}
+
+#ifdef S3_ITEM_STATS
+// experiment builds only: steps per item of the last launch (0 = settled by the straight-line kernel)
+extern "C" int s3_debug_item_stats(s3_index *ix, uint32_t *out, uint64_t n, uint32_t *hardCount)
+{
+    S3_CUDA(cudaStreamSynchronize(ix->stream));
+    if (n > ix->itemStatsCap) n = ix->itemStatsCap;
+    S3_CUDA(cudaMemcpy(out, ix->d_itemStats, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    S3_CUDA(cudaMemcpy(hardCount, ix->d_workCounter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    return S3_OK;
+}
+#endif
+
+extern "C" int s3_search_set_split_budget(s3_index *ix, int32_t steps)
+{
+    if (!ix) { s3_set_error("s3_search_set_split_budget: NULL index"); return S3_EINVAL; }
+    ix->splitBudget = steps;
     return S3_OK;
 }
 

@@ -13,15 +13,22 @@ from soap3dp_b200 import api, synth
 pytestmark = pytest.mark.gpu
 
 
-@pytest.fixture(scope="module", params=["stepping", "check_and_extend"])
+@pytest.fixture(scope="module", params=["stepping", "check_and_extend", "stepping+split", "check_and_extend+split",
+                                        "check_and_extend+nosplit"])
 def env(request):
-    """The same index twice: BWT/occ only (every base is an LF-mapping step), and with the suffix
-    array and the packed text as well (single-suffix intervals are finished by check-and-extend).
-    Both must give the oracle's answer slots bit for bit."""
+    """The same index in every way the search can run: BWT/occ only (every base is an LF-mapping step)
+    or with the suffix array and the packed text as well (single-suffix intervals are finished by
+    check-and-extend); long enumerations split after the default 256 steps (rare at this size), after
+    3 steps (almost every enumerated item goes through spine + tasks + merge, and the heavy list
+    overflows so some stay with their lane) or never.  All must give the oracle's answer slots bit for bit."""
     G = synth.random_genome(600_000, seed=11)
     idx = fmindex.build_index(G)
-    ce = request.param == "check_and_extend"
+    ce = request.param.startswith("check_and_extend")
     gi = api.GPUINDEXUpload(idx, device=0, with_text=ce, with_sa=ce)
+    if request.param.endswith("+split"):
+        api.set_split_budget(gi, 3)
+    elif request.param.endswith("+nosplit"):
+        api.set_split_budget(gi, -1)
     yield G, idx, HostIndex(idx), gi
     api.GPUINDEXFree(gi)
 

@@ -375,6 +375,8 @@ def main():
     t0 = time.time()
     gi = upload_index(host, local_rank)
     host.pop("sa", None)                                      # 12 GB of host memory per rank, no longer needed
+    if os.environ.get("S3_SPLIT_BUDGET"):                     # tuning experiments (profiles/variants.sh)
+        api.set_split_budget(gi, int(os.environ["S3_SPLIT_BUDGET"]))
     log(f"index on device in {time.time() - t0:.1f}s: {gi.device_bytes / 1e9:.2f} GB (32-byte single-sector buckets, seed tables, "
         f"suffix array + inverse + packed text for check-and-extend)")
     stream = torch.cuda.ExternalStream(gi.stream, device=device)

@@ -18,10 +18,10 @@ timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:
     --log-file $OUT/${TAG}_launches.csv python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_bench.log 2>&1
 tail -3 $OUT/${TAG}_launches.csv
 echo "== ncu full: search"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:s3_search_kernel -s 3 -c 1 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:s3_search -s 7 -c 4 \
     -f -o $OUT/${TAG}_search python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_search.log 2>&1
 echo "== ncu full: dp"
-timeout 1500 ncu --set full --clock-control none --import-source on -k regex:s3_dp_ -s 6 -c 2 \
+timeout 1500 ncu --set full --clock-control none --import-source on -k regex:s3_dp_ -s 3 -c 3 \
     -f -o $OUT/${TAG}_dp python bench.py --steps 2 --warmup 1 --no-cpu-baseline > $OUT/${TAG}_ncu_dp.log 2>&1
 kill $SMI
 ls -la $OUT

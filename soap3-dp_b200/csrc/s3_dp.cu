@@ -299,6 +299,13 @@ __device__ __forceinline__ uint32_t s3_prmt(uint32_t a, uint32_t b, uint32_t sel
 
 #define S3_SUBNEG2 0x82FF82FFu       // -32001 in both halves: what the plane stores for "below the clamp"
 
+// Where lane t's R words of one step sit inside the step's LANES * R words.  DRAM moves 64-byte bursts,
+// two of these 32-byte slots: the best-cell scan reads the last lanes that hold rows (tLast and, when the
+// right clip reaches back into it, tLast - 1), so the slots are rotated by one when tLast is even and
+// that pair shares a burst.
+template <int LANES>
+__device__ __forceinline__ uint32_t s3_dp_slot(uint32_t t, uint32_t tLast) { return (t + (~tLast & 1u)) & (uint32_t)(LANES - 1); }
+
 struct S3Dp16Best { int best; uint32_t cnt; unsigned long long key; };
 
 // DV-DPfunctions.cu:225-235 for one cell, without branches
@@ -339,12 +346,13 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
     S3Dp16Best bb[2] = {{S3_NEG_INF, 0u, ~0ull}, {S3_NEG_INF, 0u, ~0ull}};
     uint32_t best2 = S3_NEG2;
 
-    // slot after slot, columns round-robin over the lanes: one iteration of the group reads LANES consecutive
-    // R-word entries of a slot's stream
-    const uint32_t nCols = (mMax && jEnd >= jStart) ? jEnd - jStart + 1 : 0u, colsUp = (nCols + LANES - 1) / LANES * LANES;
-    auto locate = [&](uint32_t q, uint32_t &j, uint32_t &ti) { ti = tiLo + q / colsUp; j = jStart + q % colsUp; };
+    // column after column, the eligible slots of a column on neighbouring lanes: with the slot rotation of
+    // s3_dp_slot the last two of them are one 64-byte burst
+    const uint32_t tLast = mMax ? (mMax - 1) / R : 0u;
+    const uint32_t nCols = (mMax && jEnd >= jStart) ? jEnd - jStart + 1 : 0u;
+    auto locate = [&](uint32_t q, uint32_t &j, uint32_t &ti) { ti = tiLo + q % nSlots; j = jStart + q / nSlots; };
     auto fetch = [&](uint32_t j, uint32_t ti, uint32_t w[R]) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(plane + ((size_t)(j + ti) * LANES + ti) * R);
+        const uint4 *src = reinterpret_cast<const uint4 *>(plane + ((size_t)(j + ti) * LANES + s3_dp_slot<LANES>(ti, tLast)) * R);
 #pragma unroll
         for (int k = 0; k < R / 4; ++k) { const uint4 v = src[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
     };
@@ -366,15 +374,14 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
             best2 = s3_pk(bb[0].best, bb[1].best);
         }
     };
-    const uint32_t items = colsUp * nSlots;
+    const uint32_t items = nCols * nSlots;
     for (uint32_t q = t; q < items; q += 2 * LANES) {
         uint32_t j0, t0, j1 = 0, t1 = 0, w0[R], w1[R];
         locate(q, j0, t0);
-        const bool first = j0 <= jEnd;
-        if (first) fetch(j0, t0, w0);
-        bool second = q + LANES < items;
-        if (second) { locate(q + LANES, j1, t1); second = j1 <= jEnd; }
-        if (second) fetch(j1, t1, w1);
+        const bool first = true;
+        fetch(j0, t0, w0);
+        const bool second = q + LANES < items;
+        if (second) { locate(q + LANES, j1, t1); fetch(j1, t1, w1); }
         if (first) consume(j0, t0, w0);
         if (second) consume(j1, t1, w1);
     }
@@ -399,7 +406,7 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
 // H(j,0), H(0,i) -- which the reference also keeps in its table -- are recomputed from their
 // defining formulas.  Returns the start offset inside the window (the new hitLocs value).
 template <int R, int LANES>
-__device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, uint32_t ps, uint32_t half, uint32_t id,
+__device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, uint32_t tLast, uint32_t half, uint32_t id,
                                       uint32_t m, uint32_t clipLt, uint32_t anchorLeft, uint32_t scRight, uint32_t hit)
 {
     const uint32_t *dna = a.dna + (size_t)(id >> 5) * a.dnaWords * 32 + (id & 31);
@@ -412,7 +419,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, 
         if (i == 0) return (j == 0) ? 0 : ((j >= anchorLeft) ? S3_NEG_INF : 0);
         if (j == 0) return s3_clamp((i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext);
         const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-        const uint32_t w = plane[((size_t)(j + t) * LANES + t) * R + r];
+        const uint32_t w = plane[((size_t)(j + t) * LANES + s3_dp_slot<LANES>(t, tLast)) * R + r];
         return s3_clamp(half ? s3_hi16(w) : s3_lo16(w));         // the plane keeps -32001 for "below the clamp"
     };
     // E(j-1, i) as the score pass computed and clamped it, rebuilt from row i of the H plane:
@@ -422,7 +429,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, 
         const int h0 = (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext;
         int e = s3_clamp(h0 + gapInit), hl = s3_clamp(h0);
         const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-        const uint32_t *row = plane + (size_t)t * R + r;
+        const uint32_t *row = plane + (size_t)s3_dp_slot<LANES>(t, tLast) * R + r;
         for (uint32_t c = 1; c < j; ++c) {
             e = s3_clamp(max(open + hl, ext + e));
             const uint32_t w = row[(size_t)(c + t) * LANES * R];
@@ -582,7 +589,7 @@ s3_dp_score16_kernel(const S3DpArgs a)
     uint32_t clipIO[R], clipPI[R];                               // soft-clip restart operands of the current column
     uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPI were built from
     uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
-    uint32_t *hrow = plane + (size_t)t * R;
+    uint32_t *hrow = plane + (size_t)s3_dp_slot<LANES>((uint32_t)t, mMax ? (mMax - 1) / R : 0u) * R;
     const bool laneHasRows = i0 <= mMax && pairValid;
 
     uint32_t steps = nMax + LANES - 1;
@@ -628,12 +635,12 @@ s3_dp_score16_kernel(const S3DpArgs a)
     }
 }
 
-// Second kernel of the 16x2 path: best cell and traceback of one pair per group of LANES lanes.
-// These phases wait on memory, not on the integer pipe, so they run apart from the sweep with
-// small register needs and many resident warps.
+// Second kernel of the 16x2 path: best cell of both alignments of a pair, per group of LANES lanes.
+// Reads the eligible slots of the pair's H plane once (bandwidth bound); scores, tie counts, the end
+// column and the right clip go to the batch arrays.
 template <int R, int LANES>
 __global__ void __launch_bounds__(S3_DP_WARPS * 32)
-s3_dp_finish16_kernel(const S3DpArgs a)
+s3_dp_best16_kernel(const S3DpArgs a)
 {
     constexpr int GROUPS = 32 / LANES;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -645,60 +652,50 @@ s3_dp_finish16_kernel(const S3DpArgs a)
     const uint32_t pairLocal = pairValid ? wantPair : numPairs - 1;
     const bool hasB = 2 * pairLocal + 1 < a.count;
     const uint32_t id[2] = {a.first + 2 * pairLocal, a.first + 2 * pairLocal + (hasB ? 1u : 0u)};
-    uint32_t m[2], n[2], clipLt[2], clipRt[2], ancL[2], ancR[2];
+    uint32_t m[2], n[2], clipRt[2], ancR[2];
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-        m[x] = a.readLen[id[x]]; n[x] = a.dnaLen[id[x]];
-        clipLt[x] = a.clipLt ? a.clipLt[id[x]] : 0u;
+        m[x] = a.readLen[id[x]]; n[x] = pairValid ? a.dnaLen[id[x]] : 0u;
         clipRt[x] = a.clipRt ? a.clipRt[id[x]] : 0u;
-        ancL[x] = a.ancL ? a.ancL[id[x]] : a.maxDNALength;
         ancR[x] = a.ancR ? a.ancR[id[x]] : 0u;
     }
     const uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
     int gscore[2];
-    uint32_t ghit[2], gscRight[2], gcnt[2];
+    uint32_t gcnt[2];
     unsigned long long gkey[2];
-    {
-        const uint32_t nn[2] = {pairValid ? n[0] : 0u, pairValid ? n[1] : 0u};
-        s3_dp_best16<R, LANES>(plane, a.planeSteps, (uint32_t)t, m, nn, clipRt, ancR, gscore, gkey, gcnt);
-    }
-    bool trace[2];
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-        const bool any = gkey[x] != ~0ull;
-        const uint32_t bi = (uint32_t)(gkey[x] & 0xFFFFFFFFu);
-        ghit[x] = any ? (uint32_t)(gkey[x] >> 32) : 0u;
-        gscRight[x] = any ? m[x] - bi : 0u;
-        trace[x] = pairValid && (x == 0 || hasB) && gscore[x] >= a.cutoff[id[x]];
-        if (t == 0 && pairValid && (x == 0 || hasB)) {
-            a.score[id[x]] = gscore[x];
-            a.cnt[id[x]] = gcnt[x];
-            if (a.cells) atomicAdd(a.cells, (unsigned long long)m[x] * n[x]);
-        }
-        // The traceback below is one lane chasing dependent loads.  Most of a path stays on the diagonal
-        // through the best cell, so all lanes of the group touch those cells now: by the time the
-        // walking lane needs them they are on their way into L1/L2.
-        if (trace[x]) {
-            const uint32_t rp = m[x] - gscRight[x];
-            uint32_t touched = 0;
-            for (uint32_t k = t; k < rp && k < ghit[x]; k += LANES) {
-                const uint32_t i = rp - k, ti = (i - 1) / R, r = (i - 1) % R;
-                {
-                    const int j = (int)(ghit[x] - k);
-                    if (j >= 1 && j <= (int)n[x]) touched ^= plane[((size_t)(j + ti) * LANES + ti) * R + r];
-                }
-            }
-            if (touched == 0x9E3779B9u) a.cnt[id[x]] = gcnt[x];     // keeps the loads alive; never changes a result
-        }
-    }
-    // traceback: lane 0 of the group takes alignment A, lane 1 alignment B
+    s3_dp_best16<R, LANES>(plane, a.planeSteps, (uint32_t)t, m, n, clipRt, ancR, gscore, gkey, gcnt);
     if (t < 2 && pairValid && (t == 0 || hasB)) {
         const int x = t;
-        uint32_t hit = ghit[x];
-        if (trace[x])
-            hit = s3_dp_traceback16<R, LANES>(a, plane, a.planeSteps, (uint32_t)x, id[x], m[x], clipLt[x], ancL[x], gscRight[x], hit);
-        a.hit[id[x]] = hit;
+        const bool any = gkey[x] != ~0ull;
+        const uint32_t bi = (uint32_t)(gkey[x] & 0xFFFFFFFFu);
+        a.score[id[x]] = gscore[x];
+        a.cnt[id[x]] = gcnt[x];
+        a.hit[id[x]] = any ? (uint32_t)(gkey[x] >> 32) : 0u;
+        a.scRight[id[x]] = any ? m[x] - bi : 0u;
+        if (a.cells) atomicAdd(a.cells, (unsigned long long)m[x] * n[x]);
     }
+}
+
+// Third kernel: traceback, one THREAD per alignment that reached its cutoff.  A traceback is a chain of
+// ~readLength dependent loads; what hides their latency is having every alignment of the chunk in
+// flight at once, which a thread each (and few registers) gives and a lane group per pair does not.
+template <int R, int LANES>
+__global__ void __launch_bounds__(128)
+s3_dp_traceback16_kernel(const S3DpArgs a)
+{
+    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
+    if (local >= a.count) return;
+    const uint32_t id = a.first + local;
+    if (a.score[id] < a.cutoff[id]) return;            // hitLocs stays the end column (DV-DPfunctions.cu:300-312)
+    const uint32_t pairLocal = local >> 1, half = local & 1u;
+    const uint32_t mate = a.first + (local ^ 1u);
+    const uint32_t m = a.readLen[id];
+    const uint32_t mMax = (local ^ 1u) < a.count ? max(m, a.readLen[mate]) : m;
+    const uint32_t tLast = mMax ? (mMax - 1) / R : 0u;
+    const uint32_t clipLt = a.clipLt ? a.clipLt[id] : 0u;
+    const uint32_t ancL = a.ancL ? a.ancL[id] : a.maxDNALength;
+    const uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
+    a.hit[id] = s3_dp_traceback16<R, LANES>(a, plane, tLast, half, id, m, clipLt, ancL, a.scRight[id], a.hit[id]);
 }
 
 static int pick_R(uint32_t maxReadLength)
@@ -837,15 +834,18 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t begin, uint32_t end)
             const uint32_t blocks = (pairs + perBlock - 1) / perBlock;
             if (dp->lanes == 32) {
                 s3_dp_score16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
-                s3_dp_finish16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+                s3_dp_best16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+                s3_dp_traceback16_kernel<8, 32><<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a);
             } else if (dp->R == 8) {
                 s3_dp_score16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
-                s3_dp_finish16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+                s3_dp_best16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+                s3_dp_traceback16_kernel<8, 16><<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a);
             } else {
                 s3_dp_score16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
-                s3_dp_finish16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+                s3_dp_best16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+                s3_dp_traceback16_kernel<4, 16><<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a);
             }
-            S3_LAUNCHED(2);
+            S3_LAUNCHED(3);
             S3_CUDA(cudaGetLastError());
             continue;
         }

@@ -401,14 +401,22 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
 }
 
 // GPUBacktrack (DV-DPfunctions.cu:316-512) over the H plane of one pair, for the alignment in
-// half `half`.  The reference reads H of three neighbours and, for its third test, E of the
-// previous column; here E is rebuilt from the H row (see the file header) and the borders
-// H(j,0), H(0,i) -- which the reference also keeps in its table -- are recomputed from their
-// defining formulas.  Returns the start offset inside the window (the new hitLocs value).
+// half `half`; called by ALL lanes of a warp together, each with its own alignment (`active` false:
+// nothing to trace).  The reference reads H of three neighbours and, for its third test, E of the
+// previous column.  E is not stored here.  It follows from row i of the H plane: with a gap extension
+// score <= 0 the clamped recurrence E(c,i) = max(-32000, open + H(c-1,i), ext + E(c-1,i))
+// (DV-DPfunctions.cu:178-183,196-199) unrolls to
+//     E(j-1,i) = max(-32000, E(0,i) + (j-1) ext, max over 0 <= c <= j-2 of open + H(c,i) + (j-2-c) ext)
+// -- a maximum over the row, which the 32 lanes of the warp evaluate together for whichever lane
+// needs it (one strided load each per 32 columns and a shuffle reduction) instead of that lane walking
+// the row alone.  The borders H(j,0), H(0,i) -- which the reference also keeps in its table -- are
+// recomputed from their defining formulas.  Returns the start offset inside the window (the new
+// hitLocs value).
 template <int R, int LANES>
-__device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, uint32_t tLast, uint32_t half, uint32_t id,
-                                      uint32_t m, uint32_t clipLt, uint32_t anchorLeft, uint32_t scRight, uint32_t hit)
+__device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint32_t *plane, uint32_t tLast, uint32_t half,
+                                      uint32_t id, uint32_t m, uint32_t clipLt, uint32_t anchorLeft, uint32_t scRight, uint32_t hit)
 {
+    const uint32_t lane = threadIdx.x & 31;
     const uint32_t *dna = a.dna + (size_t)(id >> 5) * a.dnaWords * 32 + (id & 31);
     const uint32_t *read = a.read + (size_t)(id >> 5) * a.readWords * 32 + (id & 31);
     const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
@@ -422,53 +430,81 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, 
         const uint32_t w = plane[((size_t)(j + t) * LANES + s3_dp_slot<LANES>(t, tLast)) * R + r];
         return s3_clamp(half ? s3_hi16(w) : s3_lo16(w));         // the plane keeps -32001 for "below the clamp"
     };
-    // E(j-1, i) as the score pass computed and clamped it, rebuilt from row i of the H plane:
-    // E(0,i) = H(0,i)+gapInit, E(c,i) = max(open + H(c-1,i), ext + E(c-1,i)), each clamped when
-    // stored (DV-DPfunctions.cu:178-183,196-199).  Only evaluated where an indel or a clip starts.
-    auto Eprev = [&](uint32_t j, uint32_t i) -> int {
-        const int h0 = (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext;
-        int e = s3_clamp(h0 + gapInit), hl = s3_clamp(h0);
-        const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-        const uint32_t *row = plane + (size_t)s3_dp_slot<LANES>(t, tLast) * R + r;
-        for (uint32_t c = 1; c < j; ++c) {
-            e = s3_clamp(max(open + hl, ext + e));
-            const uint32_t w = row[(size_t)(c + t) * LANES * R];
-            hl = s3_clamp(half ? s3_hi16(w) : s3_lo16(w));
+    // E(j-1, i) for every lane that wants it (see above); all lanes of the warp take part
+    auto Eprev = [&](bool want, uint32_t j, uint32_t i) -> int {
+        int mine = 0;
+        uint32_t need = __ballot_sync(0xFFFFFFFFu, want);
+        while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            const uint32_t t = (i - 1) / R, r = (i - 1) % R;
+            // column c of the requester's row is rowBase[c * LANES * R]
+            const unsigned long long rowBase = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(size_t)(plane + ((size_t)t * LANES + s3_dp_slot<LANES>(t, tLast)) * R + r), src);
+            const uint32_t jj = __shfl_sync(0xFFFFFFFFu, j, src), hf = __shfl_sync(0xFFFFFFFFu, half, src);
+            const int h0 = __shfl_sync(0xFFFFFFFFu, (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext, src);
+            const uint32_t *row = reinterpret_cast<const uint32_t *>((size_t)rowBase);
+            int e = S3_NEG_INF;
+            if (lane == 0) {
+                e = max(e, s3_clamp(h0 + gapInit) + (int)(jj - 1) * ext);
+                if (jj >= 2) e = max(e, open + s3_clamp(h0) + (int)(jj - 2) * ext);
+            }
+            for (uint32_t c = 1 + lane; c + 2 <= jj; c += 32) {
+                const uint32_t w = row[(size_t)c * LANES * R];
+                e = max(e, open + s3_clamp(hf ? s3_hi16(w) : s3_lo16(w)) + (int)(jj - 2 - c) * ext);
+            }
+            for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, o));
+            if ((int)lane == src) mine = e;
         }
-        return e;
+        return mine;
     };
     auto refAt = [&](uint32_t j) -> uint32_t { return (dna[(size_t)(j >> 4) * 32] >> ((15 - (j & 15)) << 1)) & 3; };
     auto readAt = [&](uint32_t i) -> uint32_t { return (read[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3; };
 
-    if (scRight > 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)scRight; }
-    uint32_t readPos = m - scRight, refIndex = hit;
-    uint32_t readChar = readAt(readPos), refChar = refAt(refIndex);
-    int cur = H(refIndex, readPos), next;
-    int initScore = (refIndex >= anchorLeft) ? S3_NEG_INF : 0;
-    int prevInitScore = (refIndex > anchorLeft) ? S3_NEG_INF : 0;
+    uint32_t readPos = 0, refIndex = hit, readChar = 0, refChar = 0;
+    int cur = 0, next = 0, initScore = 0, prevInitScore = 0;
     int state = 0;      // 0 NORMAL, 1 I_EXT, 2 D_EXT, 3 SM_EXIT, 4 SI_EXIT
+    bool run = active;
+    if (active) {
+        if (scRight > 0) { pat[p++] = 'S'; pat[p++] = 'V'; pat[p++] = (uint8_t)scRight; }
+        readPos = m - scRight;
+        readChar = readAt(readPos); refChar = refAt(refIndex);
+        cur = H(refIndex, readPos);
+        initScore = (refIndex >= anchorLeft) ? S3_NEG_INF : 0;
+        prevInitScore = (refIndex > anchorLeft) ? S3_NEG_INF : 0;
+    }
 #define S3_NEXT_REF() { --refIndex; refChar = refAt(refIndex); initScore = prevInitScore; prevInitScore = (refIndex > anchorLeft) ? S3_NEG_INF : 0; }
 #define S3_NEXT_READ() { --readPos; readChar = readAt(readPos); }
-    while (readPos > 0 && refIndex > 0) {
+    while (true) {
+        run = run && readPos > 0 && refIndex > 0;
+        if (!__any_sync(0xFFFFFFFFu, run)) break;
+        // the two tests that need no E; the third one does
+        int sel = 0, d = 0;         // 1: diagonal, 2: deletion opened here, 3: neither
+        if (run && state == 0) {
+            d = (refChar == readChar) ? a.match : a.mismatch;
+            if (cur == d + (next = H(refIndex - 1, readPos - 1))) sel = 1;
+            else if (cur == open + (next = H(refIndex - 1, readPos))) sel = 2;
+            else sel = 3;
+        }
+        const int ePrev = Eprev(sel == 3, refIndex, readPos);
+        if (!run) continue;
         if (state == 0) {
-            const int d = (refChar == readChar) ? a.match : a.mismatch;
-            if (cur == d + (next = H(refIndex - 1, readPos - 1))) {
+            if (sel == 1) {
                 pat[p++] = (refChar == readChar) ? 'M' : 'm';
                 S3_NEXT_REF(); S3_NEXT_READ();
                 cur = next;
-            } else if (cur == open + (next = H(refIndex - 1, readPos))) {
+            } else if (sel == 2) {
                 pat[p++] = 'D';
                 S3_NEXT_REF();
                 cur = next;
-            } else if (cur == ext + Eprev(refIndex, readPos)) {
+            } else if (cur == ext + ePrev) {
                 pat[p++] = 'D';
                 S3_NEXT_REF();
                 cur = (short)(cur - ext);
                 state = 2;
             } else {
                 if (readPos <= clipLt + 1) {
-                    if (cur == prevInitScore + d) { state = 3; break; }
-                    else if (cur == initScore + open) { state = 4; break; }
+                    if (cur == prevInitScore + d) { state = 3; run = false; continue; }
+                    else if (cur == initScore + open) { state = 4; run = false; continue; }
                 }
                 if (cur == open + (next = H(refIndex, readPos - 1))) {
                     pat[p++] = 'I';
@@ -486,7 +522,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, 
                 pat[p++] = 'D';
                 S3_NEXT_REF();
             } else {
-                if (readPos <= clipLt + 1 && cur == initScore + open) { state = 4; break; }
+                if (readPos <= clipLt + 1 && cur == initScore + open) { state = 4; run = false; continue; }
                 pat[p++] = 'I';
                 S3_NEXT_READ();
             }
@@ -496,6 +532,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, const uint32_t *plane, 
     }
 #undef S3_NEXT_REF
 #undef S3_NEXT_READ
+    if (!active) return hit;
     if (refIndex == 0) {
         const uint32_t scNum = min(clipLt, readPos);
         if (scNum < readPos) { pat[p++] = 'I'; pat[p++] = 'V'; pat[p++] = (uint8_t)(readPos - scNum); }
@@ -684,18 +721,20 @@ __global__ void __launch_bounds__(128)
 s3_dp_traceback16_kernel(const S3DpArgs a)
 {
     const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
-    if (local >= a.count) return;
-    const uint32_t id = a.first + local;
-    if (a.score[id] < a.cutoff[id]) return;            // hitLocs stays the end column (DV-DPfunctions.cu:300-312)
-    const uint32_t pairLocal = local >> 1, half = local & 1u;
-    const uint32_t mate = a.first + (local ^ 1u);
+    const bool inRange = local < a.count;
+    const uint32_t id = a.first + (inRange ? local : 0u);
+    // below the cutoff hitLocs stays the end column (DV-DPfunctions.cu:300-312)
+    const bool active = inRange && a.score[id] >= a.cutoff[id];
+    const uint32_t pairLocal = (inRange ? local : 0u) >> 1, half = local & 1u;
     const uint32_t m = a.readLen[id];
-    const uint32_t mMax = (local ^ 1u) < a.count ? max(m, a.readLen[mate]) : m;
+    const uint32_t mMax = (inRange && (local ^ 1u) < a.count) ? max(m, a.readLen[a.first + (local ^ 1u)]) : m;
     const uint32_t tLast = mMax ? (mMax - 1) / R : 0u;
     const uint32_t clipLt = a.clipLt ? a.clipLt[id] : 0u;
     const uint32_t ancL = a.ancL ? a.ancL[id] : a.maxDNALength;
     const uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
-    a.hit[id] = s3_dp_traceback16<R, LANES>(a, plane, tLast, half, id, m, clipLt, ancL, a.scRight[id], a.hit[id]);
+    // every lane of the warp goes in: the lanes help each other with the E rows (s3_dp_traceback16)
+    const uint32_t start = s3_dp_traceback16<R, LANES>(a, active, plane, tLast, half, id, m, clipLt, ancL, a.scRight[id], a.hit[id]);
+    if (active) a.hit[id] = start;
 }
 
 static int pick_R(uint32_t maxReadLength)
@@ -724,7 +763,8 @@ extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint3
     auto small = [](int v) { return v >= -127 && v <= 127; };
     dp->narrow = maxReadLength <= 256 && small(scores.matchScore) && small(scores.mismatchScore) &&
                  small(scores.gapOpenScore) && small(scores.gapExtendScore) &&
-                 (long long)scores.matchScore * maxReadLength <= 32000 && !getenv("S3_DP_FORCE_WIDE");
+                 (long long)scores.matchScore * maxReadLength <= 32000 && scores.gapExtendScore <= 0 &&
+                 !getenv("S3_DP_FORCE_WIDE");      // extension <= 0: the traceback's closed form for E
     if (dp->narrow) {
         // rows per lane x lanes per pair: 4x16 (reads <= 64), 8x16 (<= 128), 8x32 (<= 256)
         dp->R = (maxReadLength <= 64) ? 4 : 8;

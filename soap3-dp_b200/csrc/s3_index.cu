@@ -137,10 +137,16 @@ __global__ void s3_seed_build_kernel(S3Half h, uint32_t textLength, uint32_t K, 
 
 static int build_seed_tables(s3_index *ix)
 {
-    // K-mers shorter than the text's information content stay mostly non-empty: K = floor(log4 n) - 2, in [4, 13]
+    // K = floor(log4 n), in [4, 15]: a K-mer then has a handful of occurrences, so a pass is one lookup and
+    // one or two steps away from a single suffix; at 3.1 Gbp the three tables are 3 x 8.6 GB, which a
+    // 180 GB device has room for (K goes down until they fit in a quarter of the free memory).
     uint32_t K = 0;
-    while (K < 16 && (1ull << (2 * (K + 1))) <= ix->textLength) ++K;
-    K = (K > 15) ? 13 : (K >= 6 ? (K - 2 > 13 ? 13 : K - 2) : 4);
+    while (K < 15 && (1ull << (2 * (K + 1))) <= ix->textLength) ++K;
+    if (K < 4) K = 4;
+    size_t freeB = 0, totalB = 0;
+    S3_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    while (K > 4 && 3 * (sizeof(uint2) << (2 * K)) > freeB / 4) --K;
+    if (getenv("S3_SEED_K")) { const int k = atoi(getenv("S3_SEED_K")); if (k >= 4 && k <= 15) K = (uint32_t)k; }   // tuning experiments
     if (getenv("S3_NO_SEED_TABLES")) { ix->seed.K = 0; return S3_OK; }
     const size_t entries = (size_t)1 << (2 * K);
     const S3Half *half[3] = {&ix->fwd, &ix->fwd, &ix->rev};

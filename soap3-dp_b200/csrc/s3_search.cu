@@ -221,6 +221,23 @@ __device__ __forceinline__ bool s3_check_extend(const S3Locate &loc, const uint3
     const uint32_t sh = (ps & 15u) << 1;
     const uint32_t nw = (L + 15) >> 4;
     uint32_t t0 = __ldg(tw);
+    {
+        // Most calls fail, and fail on the total alone: every substitution spent so far is a base where read and
+        // text differ, so the stretches still to be checked hold (all differences - mmt) of them, and no more than
+        // the phases from p on still allow can be taken.
+        uint32_t allowed = 0, total = 0, u0 = t0;
+#pragma unroll
+        for (int k = 0; k < S3_MAX_PHASES; ++k) if ((uint32_t)k >= p && (uint32_t)k < nph) allowed += (prog[k] >> 26) & 7u;
+        for (uint32_t w = 0; w < nw; ++w) {
+            const uint32_t u1 = __ldg(tw + w + 1);
+            const uint32_t x = sr[w * S3_THREADS] ^ __funnelshift_l(u1, u0, sh);
+            uint32_t m = (x | (x >> 1)) & 0x55555555u;
+            if (w + 1 == nw && (L & 15u)) m &= ~s3_shr_clamp(0xFFFFFFFFu, 2 * (L & 15u));      // bases past the read's end
+            total += __popc(m);
+            u0 = u1;
+        }
+        if (total > allowed - mmp + mmt) return false;
+    }
     for (uint32_t w = 0; w < nw; ++w) {
         const uint32_t t1 = __ldg(tw + w + 1);
         const uint32_t x = sr[w * S3_THREADS] ^ __funnelshift_l(t1, t0, sh);             // 16 read bases vs 16 text bases
@@ -246,7 +263,7 @@ __device__ __forceinline__ bool s3_check_extend(const S3Locate &loc, const uint3
             mm += cnt[k];
         }
     }
-    outRow = __ldg(loc.isa + ps);
+    outRow = (qa == 0) ? row : __ldg(loc.isa + ps);          // the matched block starts the read: same suffix, same row
     outMm = mm;
     return true;
 }
@@ -344,6 +361,9 @@ s3_search_easy_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, con
 
 #ifndef S3_REFILL_MIN
 #define S3_REFILL_MIN 4        // idle lanes a warp tolerates before it goes back to the work queue
+#endif
+#ifndef S3_CE_BATCH
+#define S3_CE_BATCH 8          // lanes of a warp that wait for each other before they check-and-extend together
 #endif
 #ifndef S3_SEARCH_MIN_BLOCKS
 #define S3_SEARCH_MIN_BLOCKS 6
@@ -587,8 +607,16 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
             }
         }
         __syncwarp();
+        // A lane whose interval is one suffix finishes its branch by check-and-extend: three dependent accesses
+        // (suffix array, text, inverse) and a few hundred instructions that the rest of the warp sits through.
+        // Such lanes wait until S3_CE_BATCH of them can go together, or nobody else has a step to make.
+        const bool single = has && !COUNT && loc.sa != NULL && xlo == xhi;
+        const uint32_t ceLanes = __ballot_sync(0xFFFFFFFFu, single);
+        const uint32_t stepLanes = __ballot_sync(0xFFFFFFFFu, has && !single);
+        const bool ceNow = (uint32_t)__popc(ceLanes) >= S3_CE_BATCH || !stepLanes;
+        const bool act = has && (!single || ceNow);
         // ---- an item that outlasts its budget goes to the heavy list, if there is room ----
-        if (MODE == S3_MODE_ITEMS && !COUNT && has && hv.cap && --budget < 0) {
+        if (MODE == S3_MODE_ITEMS && !COUNT && act && hv.cap && --budget < 0) {
             const uint32_t slot = atomicAdd(hv.counters + S3_HV_ITEMS, 1u);
             if (slot < hv.cap) {
                 hv.items[slot] = curItem;
@@ -598,8 +626,8 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
             } else budget = 0x7FFFFFFF;                               // no room: this lane finishes it alone
         }
         // ---- (B) one LF-mapping step for every lane that has work: both ranks' loads first ----
-        if (has) S3_STAT_STEP();
-        if (has && !COUNT && loc.sa != NULL && xlo == xhi) check_extend();
+        if (has && act) S3_STAT_STEP();
+        if (has && single) { if (ceNow) check_extend(); }
         else if (has) {
             const uint4 *buckets = pdir ? rev.buckets : fwd.buckets;
             const uint32_t isa0 = pdir ? rev.inverseSa0 : fwd.inverseSa0;
@@ -658,8 +686,10 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
 // in the enumerator's own report (DV-Kernel.cu:355-380,4468-4491).
 __global__ void s3_heavy_merge_kernel(const S3SearchArgs args)
 {
+    // one warp per split item: 32 task records at a time, an exclusive prefix sum of their range counts gives
+    // every task its place in the slot
     const S3Heavy &hv = args.heavy;
-    const uint32_t h = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t h = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
     if (h >= min(hv.counters[S3_HV_ITEMS], hv.cap)) return;
     const uint32_t it = hv.items[h];
     const uint32_t ci = it / args.numQueries, q = it - ci * args.numQueries;
@@ -667,18 +697,27 @@ __global__ void s3_heavy_merge_kernel(const S3SearchArgs args)
     const uint32_t maxRanges = args.saRangeAllowed;
     uint32_t total = 0;
     for (uint32_t u = 2 * h; u < 2 * h + 2 && total <= maxRanges; ++u) {
-        const uint32_t *t = hv.tasks + (size_t)u * hv.maxTasks * S3_TASK_WORDS;
+        const uint32_t *tasks = hv.tasks + (size_t)u * hv.maxTasks * S3_TASK_WORDS;
         const uint32_t nt = hv.unitTasks[u];
-        for (uint32_t k = 0; k < nt && total <= maxRanges; ++k, t += S3_TASK_WORDS) {
-            const uint32_t cnt = t[5];
-            for (uint32_t r = 0; r < cnt && total <= maxRanges; ++r) {
-                if (total < maxRanges) { answer[32 * 2 * total] = t[6 + 2 * r]; answer[32 * (2 * total + 1)] = t[7 + 2 * r]; }
-                ++total;
+        for (uint32_t k0 = 0; k0 < nt && total <= maxRanges; k0 += 32) {
+            const uint32_t *t = tasks + (size_t)(k0 + lane) * S3_TASK_WORDS;
+            const uint32_t cnt = (k0 + lane < nt) ? t[5] : 0u;
+            uint32_t before = cnt;                                   // inclusive scan, then shifted
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xFFFFFFFFu, before, o); if ((int)lane >= o) before += v; }
+            const uint32_t sum = __shfl_sync(0xFFFFFFFFu, before, 31);
+            before = total + before - cnt;
+            for (uint32_t r = 0; r < cnt && before + r < maxRanges; ++r) {
+                answer[32 * 2 * (before + r)] = t[6 + 2 * r];
+                answer[32 * (2 * (before + r) + 1)] = t[7 + 2 * r];
             }
+            total += sum;
         }
     }
-    if (total == 0) answer[0] = 0xFFFFFFFDu;
-    else if (total > maxRanges) answer[0] = 0xFFFFFFFEu;
+    __syncwarp();
+    if (lane == 0) {
+        if (total == 0) answer[0] = 0xFFFFFFFDu;
+        else if (total > maxRanges) answer[0] = 0xFFFFFFFEu;
+    }
 }
 
 // Round 1 semantics of isBad (DV-Kernel.cu:4285,4478-4491): once a read overflowed in
@@ -783,7 +822,7 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
         if (spineBlocks > blocks) spineBlocks = blocks;
         s3_search_kernel<false, S3_MODE_SPINE><<<(unsigned)spineBlocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
         s3_search_kernel<false, S3_MODE_SUBTREE><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
-        s3_heavy_merge_kernel<<<(a.heavy.cap + 127) / 128, 128, 0, ix->stream>>>(a);
+        s3_heavy_merge_kernel<<<(a.heavy.cap + 3) / 4, 128, 0, ix->stream>>>(a);
         S3_LAUNCHED(3);
         S3_CUDA(cudaGetLastError());
     }

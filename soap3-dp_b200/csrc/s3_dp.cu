@@ -84,8 +84,15 @@ struct S3DpArgs {
     unsigned long long *cells;
     uint32_t *hplane;                // narrow path: H values, [pair][step][lane][R] words (A low half, B high half)
     uint32_t planeSteps;             // maxDNALength + lanes per pair
-    uint32_t open2, ext2, gapInit2;  // narrow path: score parameters in both 16-bit halves
-    uint32_t mism4, delta;           // mismatch score in all four bytes; (match ^ mismatch) & 0xFF
+    // narrow path.  Values travel as v + 32768 in each 16-bit half ("biased"), so that a score parameter is
+    // added to both halves by ONE 32-bit add of kX = x * 0x10001 (two's complement for x < 0: no carry or
+    // borrow crosses the halves because 0 < biased value +- parameter < 65536) -- an IMAD, which leaves the
+    // ALU pipe to the 16x2 max instructions.
+    uint32_t kOpen, kExt, kGapInit;
+    uint32_t ceh2;                   // biased max(-32000 + open, -32000 + ext): the clamp of H and E, moved into E's max
+    uint32_t nego2;                  // biased -32000 + open: the clamp of the diagonal H, in the "+ open" domain
+    uint32_t one;                    // 1, opaque to the compiler (mad.lo by it keeps the adds on the FMA pipe)
+    uint32_t mism4, delta;           // (mismatch - open) in all four bytes; ((match - open) ^ (mismatch - open)) & 0xFF
     uint32_t colStride;              // narrow path: uint2 entries of one pair's column table (maxDNALength + 1)
 };
 
@@ -297,7 +304,21 @@ __device__ __forceinline__ uint32_t s3_prmt(uint32_t a, uint32_t b, uint32_t sel
     return d;
 }
 
-#define S3_SUBNEG2 0x82FF82FFu       // -32001 in both halves: what the plane stores for "below the clamp"
+#define S3_BIAS2 0x80008000u         // the H plane and the score kernel's registers hold v + 32768 per half
+#define S3_NEGB2 0x03000300u         // -32000, biased
+
+__device__ __forceinline__ uint32_t s3_fadd(uint32_t x, uint32_t k, uint32_t one)
+{
+#ifdef S3_DP_FORCE_IMAD
+    uint32_t d;                                   // x + k as IMAD (FMA pipe); `one` is 1 at run time
+    asm("mad.lo.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(x), "r"(one), "r"(k));
+    return d;
+#else
+    (void)one;
+    return x + k;                                 // ptxas spreads plain adds over the ALU (IADD3) and FMA (IMAD.IADD) pipes itself
+#endif
+}
+__device__ __forceinline__ uint32_t s3_bpk(int lo, int hi) { return ((uint32_t)(lo + 32768) & 0xFFFFu) | ((uint32_t)(hi + 32768) << 16); }
 
 // Where lane t's R words of one step sit inside the step's LANES * R words.  DRAM moves 64-byte bursts,
 // two of these 32-byte slots: the best-cell scan reads the last lanes that hold rows (tLast and, when the
@@ -322,8 +343,8 @@ __device__ __forceinline__ void s3_best_update(S3Dp16Best &b, bool eligible, int
 // the pair's H plane: per alignment the highest H over the rows i >= m - clipRt and the columns
 // anchorRight <= j <= n, the first such cell in (column, row) order, and the number of cells that tie
 // with it.  The reference compares the UNclamped value of a cell with a running best that starts at
-// -32000; the plane stores max(value, -32001), so a cell below the clamp (-32001) neither beats nor
-// ties that start value, exactly like the reference's test.
+// -32000; the plane stores the unclamped value (biased by 32768), so a cell below the clamp neither
+// beats nor ties that start value, exactly like the reference's test.
 // Work items are (lane slot, column) = R consecutive rows of both alignments = one 16- or 32-byte
 // entry of the slot's stream; the group's lanes take the columns round-robin, two at a time so that
 // the loads overlap.
@@ -344,7 +365,7 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
     const uint32_t tiLo = (min(iLo[0], iLo[1]) - 1) / R, nSlots = (mMax ? (mMax - 1) / R : 0u) - tiLo + 1;
     const uint32_t jStart = min(jLo[0], jLo[1]), jEnd = max(n[0], n[1]);
     S3Dp16Best bb[2] = {{S3_NEG_INF, 0u, ~0ull}, {S3_NEG_INF, 0u, ~0ull}};
-    uint32_t best2 = S3_NEG2;
+    uint32_t best2 = S3_NEGB2;
 
     // column after column, the eligible slots of a column on neighbouring lanes: with the slot rotation of
     // s3_dp_slot the last two of them are one 64-byte burst
@@ -357,21 +378,22 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
         for (int k = 0; k < R / 4; ++k) { const uint4 v = src[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
     };
     auto consume = [&](uint32_t j, uint32_t ti, const uint32_t w[R]) {
-        // conservative trigger: some cell of the slot (eligible or not) reaches a running best
+        // conservative trigger, on the biased words as they come: some cell of the slot (eligible or not)
+        // reaches a running best
         uint32_t mx = w[0];
 #pragma unroll
-        for (int r = 1; r < R; ++r) mx = __vmaxs2(mx, w[r]);
+        for (int r = 1; r < R; ++r) mx = __vmaxu2(mx, w[r]);
         bool gh, gl;
-        (void)__vibmax_s16x2(mx, best2, &gh, &gl);
+        (void)__vibmax_u16x2(mx, best2, &gh, &gl);
         if (gh || gl) {
             const bool okA = j >= jLo[0] && j <= n[0], okB = j >= jLo[1] && j <= n[1];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t i = ti * R + r + 1;
-                s3_best_update(bb[0], okA && i >= iLo[0] && i <= m[0], s3_lo16(w[r]), j, i);
-                s3_best_update(bb[1], okB && i >= iLo[1] && i <= m[1], s3_hi16(w[r]), j, i);
+                const uint32_t i = ti * R + r + 1, v = w[r] ^ S3_BIAS2;
+                s3_best_update(bb[0], okA && i >= iLo[0] && i <= m[0], s3_lo16(v), j, i);
+                s3_best_update(bb[1], okB && i >= iLo[1] && i <= m[1], s3_hi16(v), j, i);
             }
-            best2 = s3_pk(bb[0].best, bb[1].best);
+            best2 = s3_bpk(bb[0].best, bb[1].best);
         }
     };
     const uint32_t items = nCols * nSlots;
@@ -427,8 +449,8 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
         if (i == 0) return (j == 0) ? 0 : ((j >= anchorLeft) ? S3_NEG_INF : 0);
         if (j == 0) return s3_clamp((i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext);
         const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-        const uint32_t w = plane[((size_t)(j + t) * LANES + s3_dp_slot<LANES>(t, tLast)) * R + r];
-        return s3_clamp(half ? s3_hi16(w) : s3_lo16(w));         // the plane keeps -32001 for "below the clamp"
+        const uint32_t w = plane[((size_t)(j + t) * LANES + s3_dp_slot<LANES>(t, tLast)) * R + r] ^ S3_BIAS2;
+        return s3_clamp(half ? s3_hi16(w) : s3_lo16(w));         // the plane keeps the unclamped value
     };
     // E(j-1, i) for every lane that wants it (see above); all lanes of the warp take part
     auto Eprev = [&](bool want, uint32_t j, uint32_t i) -> int {
@@ -449,7 +471,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
                 if (jj >= 2) e = max(e, open + s3_clamp(h0) + (int)(jj - 2) * ext);
             }
             for (uint32_t c = 1 + lane; c + 2 <= jj; c += 32) {
-                const uint32_t w = row[(size_t)c * LANES * R];
+                const uint32_t w = row[(size_t)c * LANES * R] ^ S3_BIAS2;
                 e = max(e, open + s3_clamp(hf ? s3_hi16(w) : s3_lo16(w)) + (int)(jj - 2 - c) * ext);
             }
             for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, o));
@@ -578,7 +600,11 @@ s3_dp_score16_kernel(const S3DpArgs a)
     }
     const uint32_t mMax = max(m[0], m[1]), nMax = pairValid ? max(n[0], n[1]) : 0u;
     const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
-    const uint32_t OPEN2 = a.open2, EXT2 = a.ext2, GAPINIT2 = a.gapInit2;
+    // the three constants of the row loop must stay in registers (ptxas otherwise re-reads them from the constant
+    // bank every step and the loop waits for them): + 0 from a loaded value it cannot see through
+    const uint32_t zero = n[0] >> 31;
+    const uint32_t KOPEN = a.kOpen + zero, KEXT = a.kExt + zero, CEH2 = a.ceh2 + zero;
+    const uint32_t KGAPINIT = a.kGapInit, NEGO2 = a.nego2, ONE = a.one;
     const uint32_t i0 = t * R + 1;                                 // first row of this lane (1-based)
 
     // reference windows (1-based packing, MSB first; DV-DPfunctions.cu:58) -> column tables in shared memory
@@ -594,8 +620,9 @@ s3_dp_score16_kernel(const S3DpArgs a)
         }
     }
     // this lane's read bases become PRMT selectors: the substitution score of a row is looked
-    // up in a 4-byte table per alignment (byte c = score against reference base c)
-    uint32_t sel[R], cmask[R];
+    // up in a 4-byte table per alignment (byte c = score against reference base c, minus the gap open score:
+    // the diagonal H arrives with + open on it, see the row loop)
+    uint32_t sel[R];
     {
         const uint32_t *readA = a.read + (size_t)(id[0] >> 5) * a.readWords * 32 + (id[0] & 31);
         const uint32_t *readB = a.read + (size_t)(id[1] >> 5) * a.readWords * 32 + (id[1] & 31);
@@ -605,26 +632,26 @@ s3_dp_score16_kernel(const S3DpArgs a)
             const uint32_t cA = (i <= m[0]) ? (readA[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
             const uint32_t cB = (i <= m[1]) ? (readB[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
             sel[r] = cA | ((cA | 8u) << 4) | ((cB | 4u) << 8) | ((cB | 12u) << 12);
-            // soft-clip restart feeds row i from row i-1 when i-1 <= clipLt (DV-DPfunctions.cu:215-219)
-            cmask[r] = ((i - 1 <= clipLt[0]) ? 0xFFFFu : 0u) | ((i - 1 <= clipLt[1]) ? 0xFFFF0000u : 0u);
         }
     }
-    // column 0 (DV-DPfunctions.cu:167-184)
-    uint32_t Hs[R], Ep[R];              // previous column: H clamped at -32001 (as the plane keeps it), E clamped at -32000
+    // column 0 (DV-DPfunctions.cu:167-184).  Carried per row, biased: HO = H of the previous column + open and E of
+    // the previous column, both UNclamped -- the reference's clamp at -32000 when it stores a value is applied
+    // where the value is used (ceh2 in E's max, nego2 in the diagonal's), which takes the same maximum.
+    uint32_t HO[R], E[R];
 #pragma unroll
     for (int r = 0; r < R; ++r) {
         const uint32_t i = i0 + r;
         const int hA = (i <= clipLt[0]) ? open : gapInit + (int)(i - clipLt[0]) * ext;
         const int hB = (i <= clipLt[1]) ? open : gapInit + (int)(i - clipLt[1]) * ext;
-        Hs[r] = s3_pk(s3_clamp(hA), s3_clamp(hB));
-        Ep[r] = s3_pk(s3_clamp(hA + gapInit), s3_clamp(hB + gapInit));
+        HO[r] = s3_bpk(s3_clamp(hA), s3_clamp(hB)) + KOPEN;
+        E[r] = s3_bpk(s3_clamp(hA + gapInit), s3_clamp(hB + gapInit));
     }
     __syncwarp();
 
-    uint32_t upOut = 0, FOut = 0, diagRawOut = 0;
-    uint32_t prevInit = 0;                                       // start value of the previous column
-    uint32_t clipIO[R], clipPI[R];                               // soft-clip restart operands of the current column
-    uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPI were built from
+    uint32_t upOOut = 0, FOut = 0, diagOOut = 0;
+    uint32_t prevInit = S3_BIAS2;                                // start value of the previous column (0, biased)
+    uint32_t clipIO[R], clipPIO[R];                              // soft-clip restart operands of the current column
+    uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPIO were built from
     uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
     uint32_t *hrow = plane + (size_t)s3_dp_slot<LANES>((uint32_t)t, mMax ? (mMax - 1) / R : 0u) * R;
     const bool laneHasRows = i0 <= mMax && pairValid;
@@ -632,42 +659,53 @@ s3_dp_score16_kernel(const S3DpArgs a)
     uint32_t steps = nMax + LANES - 1;
     if (GROUPS > 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, LANES));
     for (uint32_t s = 1; s <= steps; ++s) {
-        // carried registers of the row loop arrive from the lane above (column j was done there at step s-1)
-        uint32_t up = __shfl_up_sync(0xFFFFFFFFu, upOut, 1, LANES);
+        // carried registers of the row loop arrive from the lane above (column j was done there at step s-1):
+        // H of the row above + open, F, and H of the previous column's row above + open (the diagonal)
+        uint32_t upO = __shfl_up_sync(0xFFFFFFFFu, upOOut, 1, LANES);
         uint32_t F = __shfl_up_sync(0xFFFFFFFFu, FOut, 1, LANES);
-        uint32_t diagRaw = __shfl_up_sync(0xFFFFFFFFu, diagRawOut, 1, LANES);
+        uint32_t diagO = __shfl_up_sync(0xFFFFFFFFu, diagOOut, 1, LANES);
         const uint32_t j = s - t;
         if (j >= 1 && j <= nMax && laneHasRows) {
-            const uint32_t init = ((j >= ancL[0]) ? (S3_NEG2 & 0xFFFFu) : 0u) | ((j >= ancL[1]) ? (S3_NEG2 & 0xFFFF0000u) : 0u);
-            if (t == 0) { up = init; F = __vadd2(init, GAPINIT2); diagRaw = prevInit; }
+            const uint32_t init = ((j >= ancL[0]) ? (S3_NEGB2 & 0xFFFFu) : 0x8000u) | ((j >= ancL[1]) ? (S3_NEGB2 & 0xFFFF0000u) : 0x80000000u);
+            if (t == 0) { upO = init + KOPEN; F = init + KGAPINIT; diagO = prevInit + KOPEN; }
             if (init != curInit || prevInit != curPrev) {           // rare: first column and anchor crossings
-                const uint32_t io = __vadd2(init, OPEN2);
+                const uint32_t io = init + KOPEN, pio = prevInit + KOPEN;
 #pragma unroll
                 for (int r = 0; r < R; ++r) {
-                    clipIO[r] = (io & cmask[r]) | (S3_MIN2 & ~cmask[r]);
-                    clipPI[r] = (prevInit & cmask[r]) | (S3_MIN2 & ~cmask[r]);
+                    // soft-clip restart feeds row i from row i-1 when i-1 <= clipLt (DV-DPfunctions.cu:215-219)
+                    const uint32_t i = i0 + r;
+                    const uint32_t cm = ((i - 1 <= clipLt[0]) ? 0xFFFFu : 0u) | ((i - 1 <= clipLt[1]) ? 0xFFFF0000u : 0u);
+                    clipIO[r] = io & cm;                            // biased 0 = -32768: the identity of max elsewhere
+                    clipPIO[r] = (pio & cm) | (NEGO2 & ~cm);
                 }
                 curInit = init; curPrev = prevInit;
             }
             const uint2 tab = cols[j];
+            uint32_t out[R];
 #pragma unroll
             for (int r = 0; r < R; ++r) {
-                const uint32_t d = s3_prmt(tab.x, tab.y, sel[r]);
-                const uint32_t left = __vmaxs2(Hs[r], S3_NEG2), eL = Ep[r];       // H as the reference stores it
-                const uint32_t e = __viaddmax_s16x2(left, OPEN2, __vadd2(eL, EXT2));
-                F = __vimax3_s16x2(__vadd2(F, EXT2), __vadd2(up, OPEN2), clipIO[r]);
-                const uint32_t dg = __vmaxs2(diagRaw, clipPI[r]);
-                up = __vimax3_s16x2(F, e, __vadd2(dg, d));
-                diagRaw = left;
-                Hs[r] = __vmaxs2(up, S3_SUBNEG2);                                  // what the plane keeps
-                Ep[r] = __vmaxs2(e, S3_NEG2);
+                // 5 instructions on the ALU pipe (PRMT, 3 x VIMNMX3.U16x2, VIMNMX.U16x2) and 4 adds on the FMA pipe
+                const uint32_t d = s3_prmt(tab.x, tab.y, sel[r]);                       // substitution score - open, >= 0
+                const uint32_t e = __vimax3_u16x2(HO[r], s3_fadd(E[r], KEXT, ONE), CEH2);
+                F = __vimax3_u16x2(s3_fadd(F, KEXT, ONE), upO, clipIO[r]);
+                const uint32_t dg = __vmaxu2(diagO, clipPIO[r]);
+                const uint32_t up = __vimax3_u16x2(F, e, s3_fadd(dg, d, ONE));
+                diagO = HO[r];
+                upO = s3_fadd(up, KOPEN, ONE);
+                HO[r] = upO; E[r] = e; out[r] = up;
             }
-            upOut = up; FOut = F; diagRawOut = diagRaw;
+            upOOut = upO; FOut = F; diagOOut = diagO;
             prevInit = init;
             // anti-diagonal major: the group's LANES x R words of one step are contiguous
-            uint4 *hdst = reinterpret_cast<uint4 *>(hrow + (size_t)s * LANES * R);
+            uint32_t *hdst = hrow + (size_t)s * LANES * R;
+            if (R == 8) {
+                // one 256-bit store = the lane's whole 32-byte sector (two 128-bit stores would each write half of it)
+                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(hdst), "r"(out[0]), "r"(out[1]), "r"(out[2]),
+                             "r"(out[3]), "r"(out[R > 4 ? 4 : 0]), "r"(out[R > 5 ? 5 : 0]), "r"(out[R > 6 ? 6 : 0]), "r"(out[R > 7 ? 7 : 0]) : "memory");
+            } else {
 #pragma unroll
-            for (int k = 0; k < R / 4; ++k) hdst[k] = make_uint4(Hs[4 * k], Hs[4 * k + 1], Hs[4 * k + 2], Hs[4 * k + 3]);
+                for (int k = 0; k < R / 4; ++k) reinterpret_cast<uint4 *>(hdst)[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
+            }
         }
     }
 }
@@ -764,7 +802,10 @@ extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint3
     dp->narrow = maxReadLength <= 256 && small(scores.matchScore) && small(scores.mismatchScore) &&
                  small(scores.gapOpenScore) && small(scores.gapExtendScore) &&
                  (long long)scores.matchScore * maxReadLength <= 32000 && scores.gapExtendScore <= 0 &&
-                 !getenv("S3_DP_FORCE_WIDE");      // extension <= 0: the traceback's closed form for E
+                 scores.matchScore - scores.gapOpenScore >= 0 && scores.matchScore - scores.gapOpenScore <= 127 &&
+                 scores.mismatchScore - scores.gapOpenScore >= 0 && scores.mismatchScore - scores.gapOpenScore <= 127 &&
+                 !getenv("S3_DP_FORCE_WIDE");      // extension <= 0: the traceback's closed form for E;
+                                                   // substitution scores - open in [0, 127]: the score kernel's byte tables
     if (dp->narrow) {
         // rows per lane x lanes per pair: 4x16 (reads <= 64), 8x16 (<= 128), 8x32 (<= 256)
         dp->R = (maxReadLength <= 64) ? 4 : 8;
@@ -858,10 +899,15 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t begin, uint32_t end)
     if (dp->narrow) {
         a.planeSteps = dp->maxDNALength + dp->lanes; a.hplane = reinterpret_cast<uint32_t *>(dp->d_tb);
         const int gapInit = dp->sc.gapOpenScore - dp->sc.gapExtendScore;
-        auto pk = [](int v) { return ((uint32_t)v & 0xFFFFu) | ((uint32_t)v << 16); };
-        a.open2 = pk(dp->sc.gapOpenScore); a.ext2 = pk(dp->sc.gapExtendScore); a.gapInit2 = pk(gapInit);
-        a.mism4 = ((uint32_t)dp->sc.mismatchScore & 0xFFu) * 0x01010101u;
-        a.delta = ((uint32_t)dp->sc.matchScore ^ (uint32_t)dp->sc.mismatchScore) & 0xFFu;
+        auto k32 = [](int v) { return (uint32_t)((long long)v * 0x10001ll); };        // v in both halves of one 32-bit addend
+        auto bpk = [](int v) { return (uint32_t)(v + 32768) * 0x10001u; };
+        const int open = dp->sc.gapOpenScore, ext = dp->sc.gapExtendScore;
+        a.kOpen = k32(open); a.kExt = k32(ext); a.kGapInit = k32(gapInit);
+        a.ceh2 = bpk(S3_NEG_INF + (open > ext ? open : ext));
+        a.nego2 = bpk(S3_NEG_INF + open);
+        a.one = 1;
+        a.mism4 = ((uint32_t)(dp->sc.mismatchScore - open) & 0xFFu) * 0x01010101u;
+        a.delta = ((uint32_t)(dp->sc.matchScore - open) ^ (uint32_t)(dp->sc.mismatchScore - open)) & 0xFFu;
         a.colStride = dp->maxDNALength + 1;
         smem = (size_t)S3_DP_WARPS * (32 / dp->lanes) * a.colStride * sizeof(uint2);
     }

@@ -432,6 +432,8 @@ def main():
     sampler.start()
     ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
     launches0 = api.launch_count()
+    api.set_timing(gi.handle, True)                 # events between the library's launches: per-kernel times of the timed region
+    api.set_timing(aligner.handle, True, dp=True)
     with torch.cuda.stream(stream):
         for k in range(args.steps):
             b, r = batches[args.warmup + k], rescue[args.warmup + k]
@@ -443,6 +445,10 @@ def main():
     stream.synchronize()
     barrier()
     launches = api.launch_count() - launches0
+    ms_search, n_search = api.read_timing(gi.handle)
+    ms_dp, n_dp = api.read_timing(aligner.handle, dp=True)
+    api.set_timing(gi.handle, False)
+    api.set_timing(aligner.handle, False, dp=True)
     sampler.stop_flag = True
     sampler.join()
     t_search = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
@@ -572,25 +578,57 @@ def main():
 
     if rank != 0:
         return
-    # ---- roofline of the dominant kernel -----------------------------------------
+    # ---- rooflines ---------------------------------------------------------------
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
         peaks = json.load(open(pk_path))
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    search_bytes = 64.0 * nrank_total                   # 64 B per rank evaluation
+    traffic = {}
+    tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")      # dram bytes per launch from the last ncu --set full capture
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path))
+    K = args.steps
+    names_s = ["s3_search_easy_kernel", "s3_search_kernel<items>", "s3_search_kernel<spine>", "s3_search_kernel<tasks>",
+               "s3_heavy_merge_kernel", "s3_isbad_fixup_kernel"]
+    names_d = ["s3_dp_score16_kernel", "s3_dp_best16_kernel", "s3_dp_traceback16_kernel"]
+    kernels = {}
+    for nm, ms, cnt in list(zip(names_s, ms_search, n_search)) + list(zip(names_d, ms_dp, n_dp)):
+        if cnt:
+            kernels[nm] = {"ms_per_step": ms / K, "launches_per_step": cnt / K}
+    search_bytes = 64.0 * nrank_total                   # 64 B per rank evaluation of the reference's algorithm
     search_gbs = search_bytes / t_search / 1e9
     dp_cells = sum(rescue[args.warmup + k].cells for k in range(args.steps))
     dp_gcups = dp_cells / t_dp / 1e9 if t_dp > 0 else 0.0
+    t_score = ms_dp[0] / 1e3
+    score_gbs = 2.0 * dp_cells / t_score / 1e9 if t_score > 0 else 0.0          # 2 B per cell: the H plane
+    dpx = {}
+    dpx_path = os.path.join(ROOT, "profiles", "r01_dpx_rate.json")              # tools/dpx_rate.cu on this pool's B200
+    if os.path.exists(dpx_path):
+        dpx = json.load(open(dpx_path))
+    dpx_peak = float(dpx.get("gcups_peak_5op", 7324.6))
+    search_roof = {"kernel": "search launch (s3_search_easy_kernel + s3_search_kernel<items|spine|tasks> + merge)", "bound": "hbm",
+                   "achieved": search_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": search_gbs / hbm_peak,
+                   "traffic": traffic.get("search_launch"), "peak_source": peak_src,
+                   "rank_queries_per_launch": nrank_total / K, "bytes_per_rank_query": 64,
+                   "note": "algorithmic bytes = the REFERENCE algorithm's rank evaluations x 64 B; seed tables and check-and-extend "
+                           "answer most of them without touching the index, so frac can exceed 1 -- `traffic` is what the "
+                           "kernels really move",
+                   "ms_per_launch": 1e3 * t_search / K, "share_of_step": t_search / (t_search + t_dp)}
+    score_roof = {"kernel": "s3_dp_score16_kernel", "bound": "hbm", "achieved": score_gbs, "peak": hbm_peak, "unit": "GB/s",
+                  "frac": score_gbs / hbm_peak, "traffic": traffic.get("s3_dp_score16_kernel"), "peak_source": peak_src,
+                  "cells_per_launch": dp_cells / K, "bytes_per_cell": 2,
+                  "ms_per_launch": 1e3 * t_score / K, "share_of_step": t_score / (t_search + t_dp)}
+    dominant = max(kernels.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if kernels else "s3_dp_score16_kernel"
     out = {
         "metric": "reads/s aligned (2x100bp PE, 3.1 Gbp synth ref)",
         "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
         "config": {"workload": workload, "genome_bp": args.genome_bp, "pairs_per_step_per_gpu": args.pairs,
-                   "l2": "inputs larger than L2: 2 GB of index buckets touched at random, 32 MiB of queries and 128 MiB of "
-                         "answer slots per step, a different read batch every step",
+                   "l2": "inputs larger than L2: 56 GB of index (buckets, seed tables, suffix array, text) touched at random, "
+                         "32 MiB of queries and 128 MiB of answer slots per step, a different read batch every step",
                    "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"},
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
@@ -600,14 +638,19 @@ def main():
                 "serial_value": world * reads_per_rank / t_e2e_serial, "serial_ms_per_step": 1e3 * t_e2e_serial / args.steps,
                 "link": link},
         "gpu_launches": int(launches),
-        "roofline": {"kernel": "s3_search_kernel", "bound": "hbm", "achieved": search_gbs, "peak": hbm_peak,
-                     "unit": "GB/s", "frac": search_gbs / hbm_peak, "traffic": None, "peak_source": peak_src,
-                     "rank_queries_per_launch": nrank_total / args.steps, "bytes_per_rank_query": 64,
-                     "bytes_touched_per_rank_query": 32,
-                     "ms_per_launch": 1e3 * t_search / args.steps, "share_of_step": t_search / (t_search + t_dp)},
-        "dp": {"kernel": "s3_dp_score_kernel+s3_dp_traceback_kernel", "gcups": dp_gcups,
+        # the dominant kernel of the step by measured time is the DP score sweep (H plane writes); the search launch's
+        # line follows under "search"
+        "roofline": score_roof if dominant == "s3_dp_score16_kernel" else search_roof,
+        "search": search_roof,
+        "dp": {"kernel": "s3_dp_score16_kernel + s3_dp_best16_kernel + s3_dp_traceback16_kernel", "gcups": dp_gcups,
+               "gcups_score_kernel": dp_cells / t_score / 1e9 if t_score > 0 else 0.0,
+               "dpx_peak_gcups": dpx_peak, "frac_of_dpx_peak": dp_gcups / dpx_peak,
+               "dpx_peak_source": "tools/dpx_rate.cu on B200 (profiles/r01_dpx_rate.json): VIMNMX3/VIADDMNMX .16x2 issue rate x SMs x "
+                                  "clock x 64 cells / 5 instructions per cell pair (SURVEY.md 8d)",
+               "score_kernel_hbm": score_roof,
                "alignments_per_step": float(np.mean([rescue[args.warmup + k].n for k in range(args.steps)])),
                "cells_per_step": dp_cells / args.steps, "ms_per_step": 1e3 * t_dp / args.steps},
+        "kernels": kernels,
     }
     if world == 1 and not args.no_cpu_baseline:
         frac = float(np.mean([r.n / b.pairs for r, b in zip(rescue, batches)]))

@@ -174,6 +174,19 @@ int s3_dp_align_device(s3_dp *dp,
                        const uint32_t *d_clipLtSizes, uint32_t *d_clipRtSizes,
                        const uint32_t *d_anchorLeftLocs, const uint32_t *d_anchorRightLocs);
 
+/* ------------------------------------------------------------------------
+ * Measurement hooks (replace nothing in the reference).  With timing on, CUDA events are
+ * recorded between the kernel launches of every call on the handle; read_timing waits for the
+ * handle's stream, returns the milliseconds (and launches) per kernel slot since the last read
+ * and forgets them.  msPerSlot / launchesPerSlot hold 8 entries.
+ *   index slots: 0 straight-line search kernel, 1 enumerating kernel, 2 spine, 3 tasks, 4 merge, 5 isBad carry-over
+ *   dp slots:    0 score sweep, 1 best cell, 2 traceback
+ * ------------------------------------------------------------------------ */
+int s3_index_set_timing(s3_index *ix, int on);
+int s3_index_read_timing(s3_index *ix, float *msPerSlot, int *launchesPerSlot);
+int s3_dp_set_timing(s3_dp *dp, int on);
+int s3_dp_read_timing(s3_dp *dp, float *msPerSlot, int *launchesPerSlot);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,12 +104,25 @@ def main():
             sh = "-" if "relayout" in k else f"{100 * ns / tot:.1f} %"
             md.append(f"| `{k}` | {n} | {ns / n / 1e6:.3f} | {sh} |")
         md.append("")
+    def gbytes(d):
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            v, u = d.get(k, ("0", "byte"))
+            tot += float(v.replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+        return tot
+    traffic = {"capture": tag, "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)"}
     for what in ("search", "dp"):
         rep = os.path.join(OUT, f"{tag}_{what}.ncu-rep")
         if not os.path.exists(rep):
             continue
         md += [f"## `ncu --set full` : {what}", ""]
-        for d in raw_page(rep):
+        pages = raw_page(rep)
+        for d in pages:
+            traffic[short(d['Kernel Name'][0]).split("<")[0] + ("<" + short(d['Kernel Name'][0]).split("<")[1] if "search_kernel<" in d['Kernel Name'][0] else "")] = gbytes(d)
+        if what == "search":
+            # one search launch = the straight-line kernel + the enumerating kernel and its split path
+            traffic["search_launch"] = sum(gbytes(d) for d in pages)
+        for d in pages:
             md += [f"### `{short(d['Kernel Name'][0])}`", "", "| metric | value |", "|---|---|"]
             for k, label in KEYS:
                 if k in d:
@@ -119,6 +132,8 @@ def main():
             stalls.sort(key=lambda x: -x[1])
             md.append("| top stall reasons (warps per issue) | " + ", ".join(f"{k} {v:.2f}" for k, v in stalls[:5]) + " |")
             md.append("")
+    if len(traffic) > 2:
+        json.dump(traffic, open(os.path.join(PROF, "ncu_traffic.json"), "w"), indent=1)      # bench.py's roofline.traffic
     open(os.path.join(PROF, f"{tag}_summary.md"), "w").write("\n".join(md) + "\n")
     print("\n".join(md))
 

@@ -32,6 +32,7 @@ U64P = C.POINTER(C.c_uint64)
 EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
+    "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -177,6 +178,24 @@ def set_locate_device(gpu_index: GpuIndex, d_sa: int, d_packed_text: int):
     (raw device pointers); enables check-and-extend."""
     _check(load_library().s3_index_set_locate_device(gpu_index.handle, C.c_void_p(d_sa), C.c_void_p(d_packed_text)),
            "s3_index_set_locate_device")
+
+
+def set_timing(handle: int, on: bool, dp: bool = False):
+    """Per-kernel timing hooks of include/soap3dp_b200.h (handle: GpuIndex.handle or SemiGlobalAligner.handle)."""
+    lib = load_library()
+    fn = lib.s3_dp_set_timing if dp else lib.s3_index_set_timing
+    fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.c_int]
+    _check(fn(handle, 1 if on else 0), "set_timing")
+
+
+def read_timing(handle: int, dp: bool = False):
+    """-> (ms per kernel slot, launches per kernel slot) since the last read."""
+    lib = load_library()
+    fn = lib.s3_dp_read_timing if dp else lib.s3_index_read_timing
+    fn.restype, fn.argtypes = C.c_int, [C.c_void_p, C.POINTER(C.c_float), C.POINTER(C.c_int)]
+    ms, cnt = (C.c_float * 8)(), (C.c_int * 8)()
+    _check(fn(handle, ms, cnt), "read_timing")
+    return list(ms), list(cnt)
 
 
 def set_split_budget(gpu_index: GpuIndex, steps: int):

@@ -57,6 +57,20 @@ struct S3Locate {
     const uint32_t *text;     // packed text, 16 bases per word, MSB first (hsp->packedDNA)
 };
 
+// Optional per-kernel timing (bench.py's roofline lines): events between the launches of a call, summed per kernel
+// slot when read.  Off by default; costs nothing then.
+#define S3_TIMING_SLOTS 8
+#define S3_TIMING_MARKS 256
+struct S3Timing {
+    int on, n;
+    cudaEvent_t ev[S3_TIMING_MARKS];     // created on first use
+    int slot[S3_TIMING_MARKS];           // kernel slot that ENDS at mark i (-1: start of a run of launches)
+    int created;
+};
+void s3_timing_mark(S3Timing *t, cudaStream_t st, int slot);
+int s3_timing_read(S3Timing *t, cudaStream_t st, float *msPerSlot, int *launchesPerSlot);
+void s3_timing_destroy(S3Timing *t);
+
 struct s3_index {
     int device;
     cudaStream_t stream;
@@ -77,6 +91,7 @@ struct s3_index {
     // persistent search launches
     uint32_t *d_workCounter;          // [0] work queue head, [1] number of items the easy kernel left behind, [4..7] S3_HV_* counters
     uint32_t *d_heavy; uint32_t heavyCap, heavyMaxTasks;     // scratch for splitting long enumerations (s3_search.cu)
+    S3Timing timing;                  // slots: 0 easy, 1 items, 2 spine, 3 subtree, 4 merge, 5 isBad fixup
     int32_t splitBudget;              // steps before an item is split (s3_search_set_split_budget); < 0: never
     uint32_t *d_hardItems; size_t hardCap;
     uint32_t *d_itemStats; size_t itemStatsCap;   // S3_ITEM_STATS builds only (tools/search_tail.py)

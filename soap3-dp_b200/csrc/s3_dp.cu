@@ -68,6 +68,7 @@ struct s3_dp {
     uint8_t *d_pattern;
     unsigned long long *d_cells;
     S3Pipe pipe;
+    S3Timing timing;             // slots: 0 score, 1 best cell, 2 traceback
 };
 
 struct S3DpArgs {
@@ -327,6 +328,16 @@ __device__ __forceinline__ uint32_t s3_bpk(int lo, int hi) { return ((uint32_t)(
 template <int LANES>
 __device__ __forceinline__ uint32_t s3_dp_slot(uint32_t t, uint32_t tLast) { return (t + (~tLast & 1u)) & (uint32_t)(LANES - 1); }
 
+// Word offset of lane t's R words of step s in a pair's H plane ([step][lane slot][row]: the LANES x R words of
+// a step are contiguous, and every lane writes and reads whole 32-byte sectors), and the distance between two
+// steps of a lane.  (A [lane][step][row] order was measured too: same kernel times, profiles/r01u.)
+template <int R, int LANES>
+__device__ __forceinline__ size_t s3_dp_cell(uint32_t t, uint32_t s, uint32_t tLast)
+{
+    return ((size_t)s * LANES + s3_dp_slot<LANES>(t, tLast)) * R;
+}
+#define S3_DP_STEP_STRIDE(R, LANES) ((size_t)(LANES) * (R))
+
 struct S3Dp16Best { int best; uint32_t cnt; unsigned long long key; };
 
 // DV-DPfunctions.cu:225-235 for one cell, without branches
@@ -373,16 +384,33 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
     const uint32_t nCols = (mMax && jEnd >= jStart) ? jEnd - jStart + 1 : 0u;
     auto locate = [&](uint32_t q, uint32_t &j, uint32_t &ti) { ti = tiLo + q % nSlots; j = jStart + q / nSlots; };
     auto fetch = [&](uint32_t j, uint32_t ti, uint32_t w[R]) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(plane + ((size_t)(j + ti) * LANES + s3_dp_slot<LANES>(ti, tLast)) * R);
+        const uint4 *src = reinterpret_cast<const uint4 *>(plane + s3_dp_cell<R, LANES>(ti, j + ti, tLast));
+        if (R == 8) {
+            // the slot is one 32-byte sector: one 256-bit load
+            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[R > 4 ? 4 : 0]), "=r"(w[R > 5 ? 5 : 0]), "=r"(w[R > 6 ? 6 : 0]), "=r"(w[R > 7 ? 7 : 0])
+                         : "l"(src));
+        } else {
 #pragma unroll
-        for (int k = 0; k < R / 4; ++k) { const uint4 v = src[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+            for (int k = 0; k < R / 4; ++k) { const uint4 v = src[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+        }
     };
+    // which halves of the R words of slot ti belong to rows that may end the alignment (biased 0 = -32768 never wins)
+    uint32_t keep[R], keepTi = 0xFFFFFFFFu;
     auto consume = [&](uint32_t j, uint32_t ti, const uint32_t w[R]) {
-        // conservative trigger, on the biased words as they come: some cell of the slot (eligible or not)
-        // reaches a running best
-        uint32_t mx = w[0];
+        // trigger, on the biased words as they come: some eligible cell of the slot reaches a running best
+        if (ti != keepTi) {
 #pragma unroll
-        for (int r = 1; r < R; ++r) mx = __vmaxu2(mx, w[r]);
+            for (int r = 0; r < R; ++r) {
+                const uint32_t i = ti * R + r + 1;
+                keep[r] = ((i >= iLo[0] && i <= m[0]) ? 0xFFFFu : 0u) | ((i >= iLo[1] && i <= m[1]) ? 0xFFFF0000u : 0u);
+            }
+            keepTi = ti;
+        }
+        uint32_t mx = w[0] & keep[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) mx = __vmaxu2(mx, w[r] & keep[r]);
+        mx &= ((j >= jLo[0] && j <= n[0]) ? 0xFFFFu : 0u) | ((j >= jLo[1] && j <= n[1]) ? 0xFFFF0000u : 0u);
         bool gh, gl;
         (void)__vibmax_u16x2(mx, best2, &gh, &gl);
         if (gh || gl) {
@@ -449,7 +477,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
         if (i == 0) return (j == 0) ? 0 : ((j >= anchorLeft) ? S3_NEG_INF : 0);
         if (j == 0) return s3_clamp((i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext);
         const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-        const uint32_t w = plane[((size_t)(j + t) * LANES + s3_dp_slot<LANES>(t, tLast)) * R + r] ^ S3_BIAS2;
+        const uint32_t w = plane[s3_dp_cell<R, LANES>(t, j + t, tLast) + r] ^ S3_BIAS2;
         return s3_clamp(half ? s3_hi16(w) : s3_lo16(w));         // the plane keeps the unclamped value
     };
     // E(j-1, i) for every lane that wants it (see above); all lanes of the warp take part
@@ -460,8 +488,8 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
             const int src = __ffs(need) - 1;
             need &= need - 1;
             const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-            // column c of the requester's row is rowBase[c * LANES * R]
-            const unsigned long long rowBase = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(size_t)(plane + ((size_t)t * LANES + s3_dp_slot<LANES>(t, tLast)) * R + r), src);
+            // column c of the requester's row is rowBase[c * S3_DP_STEP_STRIDE]
+            const unsigned long long rowBase = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(size_t)(plane + s3_dp_cell<R, LANES>(t, t, tLast) + r), src);
             const uint32_t jj = __shfl_sync(0xFFFFFFFFu, j, src), hf = __shfl_sync(0xFFFFFFFFu, half, src);
             const int h0 = __shfl_sync(0xFFFFFFFFu, (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext, src);
             const uint32_t *row = reinterpret_cast<const uint32_t *>((size_t)rowBase);
@@ -471,7 +499,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
                 if (jj >= 2) e = max(e, open + s3_clamp(h0) + (int)(jj - 2) * ext);
             }
             for (uint32_t c = 1 + lane; c + 2 <= jj; c += 32) {
-                const uint32_t w = row[(size_t)c * LANES * R] ^ S3_BIAS2;
+                const uint32_t w = row[(size_t)c * S3_DP_STEP_STRIDE(R, LANES)] ^ S3_BIAS2;
                 e = max(e, open + s3_clamp(hf ? s3_hi16(w) : s3_lo16(w)) + (int)(jj - 2 - c) * ext);
             }
             for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, o));
@@ -653,7 +681,7 @@ s3_dp_score16_kernel(const S3DpArgs a)
     uint32_t clipIO[R], clipPIO[R];                              // soft-clip restart operands of the current column
     uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPIO were built from
     uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
-    uint32_t *hrow = plane + (size_t)s3_dp_slot<LANES>((uint32_t)t, mMax ? (mMax - 1) / R : 0u) * R;
+    uint32_t *hrow = plane + s3_dp_cell<R, LANES>((uint32_t)t, 0u, mMax ? (mMax - 1) / R : 0u);
     const bool laneHasRows = i0 <= mMax && pairValid;
 
     uint32_t steps = nMax + LANES - 1;
@@ -697,7 +725,7 @@ s3_dp_score16_kernel(const S3DpArgs a)
             upOOut = upO; FOut = F; diagOOut = diagO;
             prevInit = init;
             // anti-diagonal major: the group's LANES x R words of one step are contiguous
-            uint32_t *hdst = hrow + (size_t)s * LANES * R;
+            uint32_t *hdst = hrow + (size_t)s * S3_DP_STEP_STRIDE(R, LANES);
             if (R == 8) {
                 // one 256-bit store = the lane's whole 32-byte sector (two 128-bit stores would each write half of it)
                 asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(hdst), "r"(out[0]), "r"(out[1]), "r"(out[2]),
@@ -864,8 +892,23 @@ extern "C" void s3_dp_free(s3_dp *dp)
                     dp->d_clipLt, dp->d_clipRt, dp->d_ancL, dp->d_ancR, dp->d_cutoff, dp->d_score, dp->d_pattern, dp->d_cells};
     for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; ++i) if (ptrs[i]) cudaFree(ptrs[i]);
     s3_pipe_destroy(&dp->pipe);
+    s3_timing_destroy(&dp->timing);
     if (dp->ownStream) cudaStreamDestroy(dp->stream);
     free(dp);
+}
+
+extern "C" int s3_dp_set_timing(s3_dp *dp, int on)
+{
+    if (!dp) { s3_set_error("s3_dp_set_timing: NULL workspace"); return S3_EINVAL; }
+    dp->timing.on = on ? 1 : 0; dp->timing.n = 0;
+    return S3_OK;
+}
+
+extern "C" int s3_dp_read_timing(s3_dp *dp, float *msPerSlot, int *launchesPerSlot)
+{
+    if (!dp || !msPerSlot) { s3_set_error("s3_dp_read_timing: NULL argument"); return S3_EINVAL; }
+    S3_CUDA(cudaSetDevice(dp->device));
+    return s3_timing_read(&dp->timing, dp->stream, msPerSlot, launchesPerSlot);
 }
 
 extern "C" void *s3_dp_stream(const s3_dp *dp) { return dp ? (void *)dp->stream : NULL; }
@@ -918,18 +961,28 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t begin, uint32_t end)
             const uint32_t pairs = (a.count + 1) / 2;
             const uint32_t perBlock = S3_DP_WARPS * (32 / dp->lanes);
             const uint32_t blocks = (pairs + perBlock - 1) / perBlock;
+            s3_timing_mark(&dp->timing, dp->stream, -1);
             if (dp->lanes == 32) {
                 s3_dp_score16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, 0);
                 s3_dp_best16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, 1);
                 s3_dp_traceback16_kernel<8, 32><<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, 2);
             } else if (dp->R == 8) {
                 s3_dp_score16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, 0);
                 s3_dp_best16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, 1);
                 s3_dp_traceback16_kernel<8, 16><<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, 2);
             } else {
                 s3_dp_score16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, 0);
                 s3_dp_best16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, 1);
                 s3_dp_traceback16_kernel<4, 16><<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, 2);
             }
             S3_LAUNCHED(3);
             S3_CUDA(cudaGetLastError());

@@ -48,6 +48,51 @@ void s3_pipe_destroy(S3Pipe *p)
     p->ready = 0;
 }
 
+void s3_timing_mark(S3Timing *t, cudaStream_t st, int slot)
+{
+    if (!t->on || t->n >= S3_TIMING_MARKS) return;
+    if (t->created <= t->n) { if (cudaEventCreate(&t->ev[t->n]) != cudaSuccess) return; t->created = t->n + 1; }
+    cudaEventRecord(t->ev[t->n], st);
+    t->slot[t->n] = slot;
+    ++t->n;
+}
+
+// sums the marked intervals per slot since the last read, and forgets them
+int s3_timing_read(S3Timing *t, cudaStream_t st, float *msPerSlot, int *launchesPerSlot)
+{
+    for (int k = 0; k < S3_TIMING_SLOTS; ++k) { msPerSlot[k] = 0.f; if (launchesPerSlot) launchesPerSlot[k] = 0; }
+    S3_CUDA(cudaStreamSynchronize(st));
+    for (int i = 1; i < t->n; ++i) {
+        if (t->slot[i] < 0 || t->slot[i] >= S3_TIMING_SLOTS) continue;
+        float ms = 0.f;
+        S3_CUDA(cudaEventElapsedTime(&ms, t->ev[i - 1], t->ev[i]));
+        msPerSlot[t->slot[i]] += ms;
+        if (launchesPerSlot) launchesPerSlot[t->slot[i]] += 1;
+    }
+    t->n = 0;
+    return S3_OK;
+}
+
+void s3_timing_destroy(S3Timing *t)
+{
+    for (int i = 0; i < t->created; ++i) cudaEventDestroy(t->ev[i]);
+    t->created = 0; t->n = 0;
+}
+
+extern "C" int s3_index_set_timing(s3_index *ix, int on)
+{
+    if (!ix) { s3_set_error("s3_index_set_timing: NULL index"); return S3_EINVAL; }
+    ix->timing.on = on ? 1 : 0; ix->timing.n = 0;
+    return S3_OK;
+}
+
+extern "C" int s3_index_read_timing(s3_index *ix, float *msPerSlot, int *launchesPerSlot)
+{
+    if (!ix || !msPerSlot) { s3_set_error("s3_index_read_timing: NULL argument"); return S3_EINVAL; }
+    S3_CUDA(cudaSetDevice(ix->device));
+    return s3_timing_read(&ix->timing, ix->stream, msPerSlot, launchesPerSlot);
+}
+
 int s3_scratch(s3_index *ix, size_t bytes, void **out)
 {
     if (bytes > ix->scratchBytes) {
@@ -279,6 +324,7 @@ extern "C" void s3_index_free(s3_index *ix)
     if (ix->d_hardItems) cudaFree(ix->d_hardItems);
     if (ix->d_itemStats) cudaFree(ix->d_itemStats);
     if (ix->d_heavy) cudaFree(ix->d_heavy);
+    s3_timing_destroy(&ix->timing);
     if (ix->scratch) cudaFree(ix->scratch);
     if (ix->pinned) cudaFreeHost(ix->pinned);
     cudaStreamDestroy(ix->stream);

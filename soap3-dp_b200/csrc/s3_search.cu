@@ -805,14 +805,18 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
         }
         const size_t smemEasy = (size_t)2 * a.wordPerQuery * S3_THREADS * sizeof(uint32_t);
         if (smemEasy > 48 * 1024) S3_CUDA(cudaFuncSetAttribute(s3_search_easy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEasy));
+        s3_timing_mark(&ix->timing, ix->stream, -1);
         s3_search_easy_kernel<<<(unsigned)((items + S3_THREADS - 1) / S3_THREADS), S3_THREADS, smemEasy, ix->stream>>>(
             ix->fwd, ix->rev, ix->seed, ix->loc, a, ix->d_hardItems, ix->d_workCounter + 1);
+        s3_timing_mark(&ix->timing, ix->stream, 0);
         S3_LAUNCHED(1);
         S3_CUDA(cudaGetLastError());
         a.itemList = ix->d_hardItems; a.itemCount = ix->d_workCounter + 1;
     }
+    s3_timing_mark(&ix->timing, ix->stream, -1);
     if (count) s3_search_kernel<true, S3_MODE_ITEMS><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
     else s3_search_kernel<false, S3_MODE_ITEMS><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
+    s3_timing_mark(&ix->timing, ix->stream, 1);
     S3_LAUNCHED(1);
     S3_CUDA(cudaGetLastError());
     if (a.heavy.cap) {
@@ -821,8 +825,11 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
         unsigned long long spineBlocks = (2ull * a.heavy.cap + S3_THREADS - 1) / S3_THREADS;
         if (spineBlocks > blocks) spineBlocks = blocks;
         s3_search_kernel<false, S3_MODE_SPINE><<<(unsigned)spineBlocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
+        s3_timing_mark(&ix->timing, ix->stream, 2);
         s3_search_kernel<false, S3_MODE_SUBTREE><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
+        s3_timing_mark(&ix->timing, ix->stream, 3);
         s3_heavy_merge_kernel<<<(a.heavy.cap + 3) / 4, 128, 0, ix->stream>>>(a);
+        s3_timing_mark(&ix->timing, ix->stream, 4);
         S3_LAUNCHED(3);
         S3_CUDA(cudaGetLastError());
     }
@@ -889,7 +896,9 @@ extern "C" int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, 
     for (uint32_t c = 0; c < numCases; ++c) S3_CUDA(cudaMemsetAsync(d_answers[c], 0xFF, aBytes, ix->stream));
     if ((rc = launch_search(ix, a, numCases, d_rankQueries != NULL))) return rc;
     if (numCases > 1 && batchSize > 0) {
+        s3_timing_mark(&ix->timing, ix->stream, -1);
         s3_isbad_fixup_kernel<<<(unsigned)((batchSize + 255) / 256), 256, 0, ix->stream>>>(a, numCases);
+        s3_timing_mark(&ix->timing, ix->stream, 5);
         S3_LAUNCHED(1);
         S3_CUDA(cudaGetLastError());
     }

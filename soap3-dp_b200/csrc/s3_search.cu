@@ -362,6 +362,12 @@ s3_search_easy_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, con
 #ifndef S3_REFILL_MIN
 #define S3_REFILL_MIN 4        // idle lanes a warp tolerates before it goes back to the work queue
 #endif
+#ifndef S3_HEAVY_CAP
+#define S3_HEAVY_CAP 4096      // split items per launch, at most (and S3_HEAVY_MB of task records)
+#endif
+#ifndef S3_HEAVY_MB
+#define S3_HEAVY_MB 256
+#endif
 #ifndef S3_CE_BATCH
 #define S3_CE_BATCH 8          // lanes of a warp that wait for each other before they check-and-extend together
 #endif
@@ -764,8 +770,8 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
         const uint32_t maxTasks = 3 * 16 * a.wordPerQuery + 2;
         if (maxTasks > ix->heavyMaxTasks) {
             if (ix->d_heavy) { S3_CUDA(cudaStreamSynchronize(ix->stream)); S3_CUDA(cudaFree(ix->d_heavy)); ix->d_heavy = NULL; ix->heavyMaxTasks = 0; }
-            size_t cap = ((size_t)256 << 20) / ((size_t)2 * maxTasks * S3_TASK_WORDS * 4);
-            if (cap > 4096) cap = 4096;
+            size_t cap = ((size_t)S3_HEAVY_MB << 20) / ((size_t)2 * maxTasks * S3_TASK_WORDS * 4);
+            if (cap > S3_HEAVY_CAP) cap = S3_HEAVY_CAP;
             if (cap < 64) cap = 64;
             // items | unitTasks | queue | tasks
             const size_t words = cap + 2 * cap + 2 * cap * maxTasks + 2 * cap * maxTasks * S3_TASK_WORDS;

@@ -114,6 +114,27 @@ int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, const uint3
                             int isExactNumMismatch, uint32_t *const *d_answers,
                             unsigned long long *d_rankQueries);
 
+/* ------------------------------------------------------------------------
+ * Capless search.  Replaces round 1 + round 2 + the CPU fallback for reads whose slot still
+ * overflows (all_valid_alignment, alignment.cu:855-954; CPUfunctions.cpp:1310-1329,1394-1412)
+ * by one call: every SA range of every read for all cases of the numMismatch scheme, no slot
+ * cap, as CSR.  Ranges of read q are entries offsets[q] .. offsets[q+1]-1: case ascending, inside
+ * a case in the enumeration order of round 1 -- the reference's round-1 slot of (q, case) holds
+ * the first saRangeAllowed of them.  saL/saR are inclusive bounds on the forward BWT;
+ * info = strand | numMismatches << 1 | case << 4.  The arrays are malloc'ed by the library;
+ * release them with s3_search_result_free.
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t numReads, total;
+    uint64_t *offsets;            /* numReads + 1 */
+    uint32_t *saL, *saR, *info;   /* total each */
+} s3_search_result;
+
+int s3_search(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths,
+              uint64_t batchSize, uint32_t wordPerQuery, uint32_t numMismatch,
+              int isExactNumMismatch, s3_search_result *out);
+void s3_search_result_free(s3_search_result *r);
+
 /* Tuning knob, answers are identical for every value.  A (read, case) enumeration that is
  * still running in its lane after `steps` LF-mapping steps is split: the substitution children
  * along the read's own path become independent tasks for other lanes and their ranges are merged

@@ -9,5 +9,5 @@ for spec in "$@"; do
   if [ -f "$lib" ]; then envs="$envs S3_LIB_PATH=$lib"; fi
   line=$(env $envs S3_X=1 timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline 2>>$OUT/${TAG}_var.err | tail -1)
   echo "{\"variant\": \"$spec\", \"bench\": $line}" >> $OUT/${TAG}_variants.jsonl
-  echo "$spec: $(echo "$line" | python -c 'import sys,json; b=json.loads(sys.stdin.read()); print("value %.1fM e2e %.1fM search %.2f ms dp %.2f ms" % (b["value"]/1e6, b["e2e"]["value"]/1e6, b["roofline"]["ms_per_launch"], b["dp"]["ms_per_step"]))')"
+  echo "$spec: $(echo "$line" | python -c 'import sys,json; b=json.loads(sys.stdin.read()); print("value %.1fM e2e %.1fM search %.2f ms dp %.2f ms" % (b["value"]/1e6, b["e2e"]["value"]/1e6, b["search"]["ms_per_launch"], b["dp"]["ms_per_step"]))')"
 done

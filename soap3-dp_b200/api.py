@@ -33,6 +33,7 @@ EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
+    "s3_search", "s3_search_result_free",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -178,6 +179,35 @@ def set_locate_device(gpu_index: GpuIndex, d_sa: int, d_packed_text: int):
     (raw device pointers); enables check-and-extend."""
     _check(load_library().s3_index_set_locate_device(gpu_index.handle, C.c_void_p(d_sa), C.c_void_p(d_packed_text)),
            "s3_index_set_locate_device")
+
+
+class SearchResult(C.Structure):
+    _fields_ = [("numReads", C.c_uint64), ("total", C.c_uint64), ("offsets", U64P), ("saL", U32P), ("saR", U32P), ("info", U32P)]
+
+
+def search(gpu_index: GpuIndex, queries: np.ndarray, read_lengths: np.ndarray, batch_size: int, word_per_query: int,
+           num_mismatch: int, is_exact_num_mismatch: bool = False):
+    """Capless search (include/soap3dp_b200.h s3_search): -> (offsets[N+1] uint64, saL, saR, info) numpy copies."""
+    lib = load_library()
+    lib.s3_search.restype = C.c_int
+    lib.s3_search.argtypes = [C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32, C.c_uint32, C.c_int, C.POINTER(SearchResult)]
+    lib.s3_search_result_free.restype = None
+    lib.s3_search_result_free.argtypes = [C.POINTER(SearchResult)]
+    res = SearchResult()
+    _check(lib.s3_search(gpu_index.handle, _u32(queries), _u32(read_lengths), batch_size, word_per_query, num_mismatch,
+                         1 if is_exact_num_mismatch else 0, C.byref(res)), "s3_search")
+    try:
+        n, tot = int(res.numReads), int(res.total)
+        offsets = np.ctypeslib.as_array(res.offsets, shape=(n + 1,)).copy()
+        if tot:
+            sa_l = np.ctypeslib.as_array(res.saL, shape=(tot,)).copy()
+            sa_r = np.ctypeslib.as_array(res.saR, shape=(tot,)).copy()
+            info = np.ctypeslib.as_array(res.info, shape=(tot,)).copy()
+        else:
+            sa_l = sa_r = info = np.zeros(0, np.uint32)
+    finally:
+        lib.s3_search_result_free(C.byref(res))
+    return offsets, sa_l, sa_r, info
 
 
 def set_timing(handle: int, on: bool, dp: bool = False):

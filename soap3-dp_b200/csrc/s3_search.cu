@@ -25,6 +25,7 @@
 #include "s3_common.cuh"
 #include "../../include/soap3dp_b200.h"
 #include <cub/device/device_select.cuh>
+#include <cub/device/device_scan.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 
 #define S3_MAX_PHASES 4
@@ -116,6 +117,10 @@ struct S3SearchArgs {
     unsigned long long *rankQueries;     // may be NULL
     uint32_t *itemStats;                 // S3_ITEM_STATS builds only: LF-mapping steps spent per item
     S3Heavy heavy;
+    // capless search (s3_search): per (read, case) -- read-major -- the number of ranges (first pass) and then
+    // where its ranges start (second pass), and the range arrays
+    unsigned long long *csrCount;
+    uint32_t *csrL, *csrR, *csrInfo;
 };
 
 // DFS frame: a node where substitutions are still allowed, kept in shared memory
@@ -391,7 +396,9 @@ s3_search_easy_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, con
 #define S3_MODE_SPINE 1
 #define S3_MODE_SUBTREE 2
 
-template <bool COUNT, int MODE>
+// CSR: 0 answer slots (the reference's format); 1 first pass of the capless search (count the ranges of every
+// item, write nothing); 2 second pass (write them where the prefix sum of the counts says)
+template <bool COUNT, int MODE, int CSR = 0>
 __global__ void __launch_bounds__(S3_THREADS, S3_SEARCH_MIN_BLOCKS)
 s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3Locate loc, const S3SearchArgs args)
 {
@@ -496,7 +503,15 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
     // report (DV-Kernel.cu:355-380): the interval on the forward BWT; a slot overflow ends the item
     auto report = [&](uint32_t l, uint32_t r, uint32_t mm) {
         const uint32_t packed = (r - l) + (strand << 27) + (mm << 24);
-        if (MODE == S3_MODE_ITEMS) {
+        if (MODE == S3_MODE_ITEMS && CSR != 0) {
+            if (CSR == 2) {
+                const uint32_t ci = curItem / args.numQueries, q = curItem - ci * args.numQueries;
+                const unsigned long long o = args.csrCount[(size_t)q * args.numCases + ci] + saCount;
+                args.csrL[o] = l; args.csrR[o] = r;
+                args.csrInfo[o] = strand | (mm << 1) | ((args.firstCase + ci) << 4);
+            }
+            ++saCount;                                               // no cap: every range of the item
+        } else if (MODE == S3_MODE_ITEMS) {
             if (saCount < maxRanges) {
                 answer[32 * 2 * saCount] = l;
                 answer[32 * (2 * saCount + 1)] = packed;
@@ -586,7 +601,10 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
                 else {
                     // status word (DV-Kernel.cu:4468-4491); the isBad carry between the cases of round 1
                     // is applied by s3_isbad_fixup_kernel because cases run concurrently here
-                    if (saCount == 0) answer[0] = 0xFFFFFFFDu;
+                    if (CSR == 1) {
+                        const uint32_t ci = curItem / args.numQueries, q = curItem - ci * args.numQueries;
+                        args.csrCount[(size_t)q * args.numCases + ci] = saCount;
+                    } else if (CSR == 0 && saCount == 0) answer[0] = 0xFFFFFFFDu;
                     has = false;
                     S3_STAT_END();
                 }
@@ -980,6 +998,106 @@ __global__ void s3_gather_bad_kernel(const uint32_t *__restrict__ queries, const
     uint32_t *dst = outQ + (size_t)(k >> 5) * 32 * wordPerQuery + (k & 31);
     for (uint32_t w = 0; w < wordPerQuery; ++w) dst[w * 32] = src[w * 32];
     outLen[k] = readLengths[q];
+}
+
+// ---- capless search ---------------------------------------------------------
+// Replaces round 1 + round 2 + the CPU fallback for reads that still overflow (CPUfunctions.cpp:1310-1329,
+// 1394-1412) by ONE call without slot caps (SURVEY.md 8b "preferred new path"): every SA range of every read
+// for every case of the numMismatch scheme, as CSR.  Two passes of the enumerator over all items: count, prefix
+// sum, fill.  Order inside a read: case ascending, inside a case the enumeration order of round 1 (first strand =
+// case parity, DV-Kernel.cu:4280-4285), so the reference's slot contents are the first saRangeAllowed entries of a
+// case's run and any order-dependent truncation can be replayed by the caller.
+template <int PASS>
+static int launch_search_csr(s3_index *ix, S3SearchArgs &a, uint32_t numCases)
+{
+    a.numCases = numCases;
+    a.workCounter = ix->d_workCounter;
+    a.itemList = NULL; a.itemCount = NULL;
+    memset(&a.heavy, 0, sizeof a.heavy);
+    const size_t smem = (size_t)(2 * a.wordPerQuery + S3_MAX_DEPTH * S3_FRAME_WORDS) * S3_THREADS * sizeof(uint32_t);
+    S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<false, S3_MODE_ITEMS, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int perSm = 0;
+    S3_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, s3_search_kernel<false, S3_MODE_ITEMS, PASS>, S3_THREADS, smem));
+    if (perSm < 1) { s3_set_error("search kernel does not fit on an SM with wordPerQuery %u", a.wordPerQuery); return S3_EINVAL; }
+    const unsigned long long items = (unsigned long long)a.numQueries * numCases;
+    unsigned long long blocks = (items + S3_THREADS - 1) / S3_THREADS;
+    if (blocks > (unsigned long long)ix->numSms * perSm) blocks = (unsigned long long)ix->numSms * perSm;
+    S3_CUDA(cudaMemsetAsync(ix->d_workCounter, 0, 8 * sizeof(uint32_t), ix->stream));
+    s3_search_kernel<false, S3_MODE_ITEMS, PASS><<<(unsigned)blocks, S3_THREADS, smem, ix->stream>>>(ix->fwd, ix->rev, ix->seed, ix->loc, a);
+    S3_LAUNCHED(1);
+    S3_CUDA(cudaGetLastError());
+    return S3_OK;
+}
+
+extern "C" void s3_search_result_free(s3_search_result *r)
+{
+    if (!r) return;
+    free(r->offsets); free(r->saL); free(r->saR); free(r->info);
+    memset(r, 0, sizeof *r);
+}
+
+extern "C" int s3_search(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t batchSize,
+                         uint32_t wordPerQuery, uint32_t numMismatch, int isExactNumMismatch, s3_search_result *out)
+{
+    static const uint32_t ncases[5] = {1, 2, 4, 6, 10};
+    if (!out) { s3_set_error("s3_search: NULL result"); return S3_EINVAL; }
+    memset(out, 0, sizeof *out);
+    int rc = check_search_args("s3_search", ix, queries, readLengths, batchSize, wordPerQuery, numMismatch,
+                               numMismatch <= 4 ? ncases[numMismatch] : 0, 1, 2);
+    if (rc) return rc;
+    const uint32_t numCases = ncases[numMismatch];
+    out->numReads = batchSize;
+    out->offsets = (uint64_t *)calloc(batchSize + 1, sizeof(uint64_t));
+    if (!out->offsets) { s3_set_error("s3_search: out of host memory"); return S3_ENOMEM; }
+    if (batchSize == 0) return S3_OK;
+    S3_CUDA(cudaSetDevice(ix->device));
+    const size_t roundUp = (batchSize + 31) / 32 * 32, items = batchSize * numCases;
+    const size_t qBytes = roundUp * wordPerQuery * 4, lBytes = roundUp * 4, cBytes = (items + 1) * 8;
+    size_t scanTemp = 0;
+    cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (unsigned long long *)NULL, (unsigned long long *)NULL, (int)(items + 1), ix->stream);
+    char *d;
+    if ((rc = s3_scratch(ix, qBytes + lBytes + cBytes + scanTemp + 1024, (void **)&d))) { s3_search_result_free(out); return rc; }
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { char *p = d + off; off += (bytes + 255) / 256 * 256; return p; };
+    uint32_t *d_q = (uint32_t *)carve(qBytes), *d_l = (uint32_t *)carve(lBytes);
+    unsigned long long *d_cnt = (unsigned long long *)carve(cBytes);
+    void *d_tmp = carve(scanTemp);
+    S3_CUDA(cudaMemcpyAsync(d_q, queries, qBytes, cudaMemcpyHostToDevice, ix->stream));
+    S3_CUDA(cudaMemcpyAsync(d_l, readLengths, batchSize * 4, cudaMemcpyHostToDevice, ix->stream));
+    S3_CUDA(cudaMemsetAsync(d_cnt, 0, cBytes, ix->stream));
+    S3SearchArgs a;
+    memset(&a, 0, sizeof a);
+    a.queries = d_q; a.readLengths = d_l; a.numQueries = (uint32_t)batchSize; a.wordPerQuery = wordPerQuery;
+    a.round = 0; a.numMismatch = numMismatch; a.saRangeAllowed = 0xFFFFFFFFu; a.wordPerAnswer = 0;
+    a.firstCase = 0; a.exactNum = isExactNumMismatch ? 1 : 0; a.textLength = ix->textLength;
+    a.csrCount = d_cnt;
+    if ((rc = launch_search_csr<1>(ix, a, numCases))) { s3_search_result_free(out); return rc; }
+    // counts -> starts (one extra element: the total)
+    S3_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_cnt, d_cnt, (int)(items + 1), ix->stream));
+    unsigned long long total = 0;
+    S3_CUDA(cudaMemcpyAsync(&total, d_cnt + items, 8, cudaMemcpyDeviceToHost, ix->stream));
+    // a read's run starts where its first case starts
+    S3_CUDA(cudaMemcpy2DAsync(out->offsets, 8, d_cnt, (size_t)numCases * 8, 8, batchSize, cudaMemcpyDeviceToHost, ix->stream));
+    S3_CUDA(cudaStreamSynchronize(ix->stream));
+    out->offsets[batchSize] = total;
+    out->total = total;
+    if (total == 0) return S3_OK;
+    uint32_t *d_out = NULL;
+    S3_CUDA(cudaMalloc(&d_out, (size_t)total * 12));
+    a.csrL = d_out; a.csrR = d_out + total; a.csrInfo = d_out + 2 * total;
+    rc = launch_search_csr<2>(ix, a, numCases);
+    out->saL = (uint32_t *)malloc((size_t)total * 4); out->saR = (uint32_t *)malloc((size_t)total * 4); out->info = (uint32_t *)malloc((size_t)total * 4);
+    if (rc == S3_OK && (!out->saL || !out->saR || !out->info)) { s3_set_error("s3_search: out of host memory"); rc = S3_ENOMEM; }
+    if (rc == S3_OK) {
+        cudaError_t e = cudaMemcpyAsync(out->saL, a.csrL, (size_t)total * 4, cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out->saR, a.csrR, (size_t)total * 4, cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaMemcpyAsync(out->info, a.csrInfo, (size_t)total * 4, cudaMemcpyDeviceToHost, ix->stream);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+        if (e != cudaSuccess) { s3_set_error("s3_search: copying the ranges back failed: %s", cudaGetErrorString(e)); rc = S3_ECUDA; }
+    }
+    cudaFree(d_out);
+    if (rc != S3_OK) s3_search_result_free(out);
+    return rc;
 }
 
 extern "C" int s3_search_round2(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths,

@@ -163,3 +163,51 @@ def test_empty_batch_and_bad_args(env):
         api.perform_round1_alignment(gi, q, lens, 1, 8, 5, num_cases=1, sa_range_allowed=1, word_per_ans=2)
     with pytest.raises(api.S3Error):
         api.perform_round1_alignment(gi, q, lens, 1, 8, 2, num_cases=7, sa_range_allowed=4, word_per_ans=8)
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3])
+def test_capless_search_is_the_uncapped_slot_sequence(env, k):
+    """s3_search (CSR, no caps) == for every read, the cases' slot contents in order when the oracle is given
+    slots nothing overflows (1024 ranges per case, no isBad carry-over between the cases)."""
+    G, idx, hi, gi = env
+    olib = load_oracle()
+    n, L = 1501, 100
+    rs = synth.simulate_single_end(G, n, L, seed=300 + k, sub_rate=0.02)
+    reads = rs.reads.numpy()
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    lens[7:n:13] = L - 3
+    wpq = formats.word_per_query(L)
+    q = formats.pack_queries(reads, lens[:n], wpq)
+    offsets, sa_l, sa_r, info = api.search(gi, q, lens, n, wpq, k)
+    assert offsets[0] == 0 and offsets[-1] == len(sa_l) == len(sa_r) == len(info)
+    allowed, wpa = 1024, 2048
+    want = []
+    for case in range(formats.NUM_CASES[k]):
+        a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+        oracle_launch(olib, hi, case, q, lens, n, wpq, a, np.zeros(formats.ceil32(n), np.uint8), 0, k, allowed, wpa)
+        want.append(formats.answers_view(a, n, wpa))
+    total = 0
+    for r in range(n):
+        exp = []
+        for case in range(formats.NUM_CASES[k]):
+            row = want[case][r]
+            assert row[0] != 0xFFFFFFFE, "oracle slot overflowed; enlarge it"
+            if row[0] == 0xFFFFFFFD:
+                continue
+            for s in range(allowed):
+                if row[2 * s] == 0xFFFFFFFF and row[2 * s + 1] == 0xFFFFFFFF:
+                    break
+                w = int(row[2 * s + 1])
+                exp.append((int(row[2 * s]), int(row[2 * s]) + (w & 0xFFFFFF), ((w >> 27) & 1) | (((w >> 24) & 7) << 1) | (case << 4)))
+        lo, hi_ = int(offsets[r]), int(offsets[r + 1])
+        got = list(zip(sa_l[lo:hi_].tolist(), sa_r[lo:hi_].tolist(), info[lo:hi_].tolist()))
+        assert got == exp, f"k={k} read {r}: {got[:4]} != {exp[:4]}"
+        total += len(exp)
+    assert total == offsets[-1] and total > 0
+
+
+def test_capless_search_empty_batch(env):
+    G, idx, hi, gi = env
+    offsets, sa_l, sa_r, info = api.search(gi, np.zeros(32 * 8, np.uint32), np.zeros(32, np.uint32), 0, 8, 2)
+    assert offsets.tolist() == [0] and len(sa_l) == 0

@@ -135,6 +135,19 @@ int s3_search(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths
               int isExactNumMismatch, s3_search_result *out);
 void s3_search_result_free(s3_search_result *r);
 
+/* ------------------------------------------------------------------------
+ * Locate.  SA ranges -> text positions from the suffix array in HBM; replaces the host loops
+ * `for k in [l, r]: (*bwt->_bwtSaValue)(bwt, k)` that follow every search (SAList.cpp:411,
+ * CPUfunctions.cpp:2915,2975, PEAlgnmt.cpp:1246, DV-DPfunctions.cu:1186,2931).  Needs an index
+ * uploaded with its suffix array.  Positions of range g: (*positions)[offsets[g] ..
+ * offsets[g+1]-1] = SA[saL[g] + k] for k < min(saR[g]-saL[g]+1, maxPerRange), in SA order like
+ * the reference's loops; an empty range (saR < saL) gives none.  offsets has numRanges + 1
+ * entries; *positions is malloc'ed by the library (s3_free).
+ * ------------------------------------------------------------------------ */
+int s3_locate(s3_index *ix, const uint32_t *saL, const uint32_t *saR, uint64_t numRanges,
+              uint32_t maxPerRange, uint64_t *offsets, uint32_t **positions, uint64_t *total);
+void s3_free(void *p);
+
 /* Tuning knob, answers are identical for every value.  A (read, case) enumeration that is
  * still running in its lane after `steps` LF-mapping steps is split: the substitution children
  * along the read's own path become independent tasks for other lanes and their ranges are merged
@@ -194,6 +207,30 @@ int s3_dp_align_device(s3_dp *dp,
                        uint8_t *d_pattern, uint32_t numOfThreads,
                        const uint32_t *d_clipLtSizes, uint32_t *d_clipRtSizes,
                        const uint32_t *d_anchorLeftLocs, const uint32_t *d_anchorRightLocs);
+
+/* ------------------------------------------------------------------------
+ * DP on windows named by the caller: packing on the device + s3_dp_align.  Replaces the
+ * base-at-a-time host packers packRead / repackDNA of the three DP engines
+ * (SingleEndAlgnBatch, HalfEndAlgnBatch, PairEndAlgnBatch: DV-DPfunctions.cu:1469-1524,
+ * 2111-2167, 3474-3529) together with performAlignment: alignment t aligns read readIDs[t]
+ * (0-based index into the query buffer `queries`, QueryParser.cpp:1146-1152 layout,
+ * wordPerOldQuery words per read; strands[t] = 1 as given, 2 reverse-complemented, as
+ * CandidateInfo.strand) against text bases [DNAStarts[t], DNAStarts[t] + DNALengths[t]) of the
+ * packed text the index was uploaded with.  What windows to align (margins, insert sizes,
+ * anchors, clips) stays the caller's decision, as in the engines' pack() functions.
+ * 28 bytes per alignment go to the device instead of the packed batch arrays.  Outputs and
+ * the clip / anchor arrays are those of s3_dp_align.
+ * ------------------------------------------------------------------------ */
+int s3_dp_align_windows(s3_dp *dp, s3_index *ix,
+                        const uint32_t *queries, const uint32_t *queryLengths, uint64_t numQueries,
+                        uint32_t wordPerOldQuery,
+                        const uint32_t *readIDs, const uint8_t *strands,
+                        const uint32_t *DNAStarts, const uint32_t *DNALengths,
+                        const int32_t *cutoffThresholds,
+                        int32_t *scores, uint32_t *hitLocs, uint32_t *maxScoreCounts,
+                        uint8_t *pattern, uint32_t numOfThreads,
+                        const uint32_t *clipLtSizes, uint32_t *clipRtSizes,
+                        const uint32_t *anchorLeftLocs, const uint32_t *anchorRightLocs);
 
 /* ------------------------------------------------------------------------
  * Measurement hooks (replace nothing in the reference).  With timing on, CUDA events are

@@ -33,7 +33,7 @@ EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
-    "s3_search", "s3_search_result_free",
+    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -210,6 +210,28 @@ def search(gpu_index: GpuIndex, queries: np.ndarray, read_lengths: np.ndarray, b
     return offsets, sa_l, sa_r, info
 
 
+def locate(gpu_index: GpuIndex, sa_l: np.ndarray, sa_r: np.ndarray, max_per_range: int = 0xFFFFFFFF):
+    """SA ranges -> text positions (include/soap3dp_b200.h s3_locate): -> (offsets[n+1] uint64, positions uint32)."""
+    lib = load_library()
+    lib.s3_locate.restype = C.c_int
+    lib.s3_locate.argtypes = [C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32, U64P, C.POINTER(U32P), U64P]
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    n = len(sa_l)
+    sa_l = np.ascontiguousarray(sa_l, np.uint32)
+    sa_r = np.ascontiguousarray(sa_r, np.uint32)
+    offsets = np.zeros(n + 1, np.uint64)
+    pos, total = U32P(), C.c_uint64(0)
+    _check(lib.s3_locate(gpu_index.handle, _u32(sa_l), _u32(sa_r), n, max_per_range,
+                         offsets.ctypes.data_as(U64P), C.byref(pos), C.byref(total)), "s3_locate")
+    try:
+        out = np.ctypeslib.as_array(pos, shape=(int(total.value),)).copy() if total.value else np.zeros(0, np.uint32)
+    finally:
+        if total.value:
+            lib.s3_free(pos)
+    return offsets, out
+
+
 def set_timing(handle: int, on: bool, dp: bool = False):
     """Per-kernel timing hooks of include/soap3dp_b200.h (handle: GpuIndex.handle or SemiGlobalAligner.handle)."""
     lib = load_library()
@@ -334,6 +356,32 @@ class SemiGlobalAligner:
                                         numOfThreads, opt(clipLtSizes), opt(clipRtSizes), opt(anchorLeftLocs),
                                         opt(anchorRightLocs))
         _check(rc, "SemiGlobalAligner.performAlignment")
+        return scores, hit, cnt, pat
+
+    def performAlignmentOnWindows(self, gpu_index, queries, queryLengths, numQueries, wordPerOldQuery, readIDs, strands,
+                                  DNAStarts, DNALengths, cutoffThresholds, numOfThreads, clipLtSizes=None, clipRtSizes=None,
+                                  anchorLeftLocs=None, anchorRightLocs=None):
+        """s3_dp_align_windows: the batch is packed on the device from the index's text and the query buffer
+        (the engines' packRead / repackDNA, DV-DPfunctions.cu:1469-1524).  Returns (scores, hitLocs, maxScoreCounts, pattern)."""
+        lib = load_library()
+        lib.s3_dp_align_windows.restype = C.c_int
+        lib.s3_dp_align_windows.argtypes = [C.c_void_p, C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32, U32P, U8P, U32P, U32P,
+                                            I32P, I32P, U32P, U32P, U8P, C.c_uint32, U32P, U32P, U32P, U32P]
+        up = formats.ceil32(max(numOfThreads, 1))
+        scores = np.zeros(up, np.int32)
+        hit = np.zeros(up, np.uint32)
+        cnt = np.zeros(up, np.uint32)
+        pat = np.zeros(up * self.pattern_length, np.uint8)
+
+        def opt(a):
+            return _u32(a) if a is not None else None
+        strands = np.ascontiguousarray(strands, np.uint8)
+        rc = lib.s3_dp_align_windows(self.handle, gpu_index.handle, _u32(queries), _u32(queryLengths), numQueries, wordPerOldQuery,
+                                     _u32(readIDs), strands.ctypes.data_as(U8P), _u32(DNAStarts), _u32(DNALengths),
+                                     cutoffThresholds.ctypes.data_as(I32P), scores.ctypes.data_as(I32P), _u32(hit), _u32(cnt),
+                                     pat.ctypes.data_as(U8P), numOfThreads, opt(clipLtSizes), opt(clipRtSizes),
+                                     opt(anchorLeftLocs), opt(anchorRightLocs))
+        _check(rc, "SemiGlobalAligner.performAlignmentOnWindows")
         return scores, hit, cnt, pat
 
     def freeMemory(self):

@@ -69,6 +69,7 @@ struct s3_dp {
     unsigned long long *d_cells;
     S3Pipe pipe;
     S3Timing timing;             // slots: 0 score, 1 best cell, 2 traceback
+    void *d_stage; size_t stageBytes;    // s3_dp_align_windows: query buffer and window descriptors
 };
 
 struct S3DpArgs {
@@ -893,6 +894,7 @@ extern "C" void s3_dp_free(s3_dp *dp)
     for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; ++i) if (ptrs[i]) cudaFree(ptrs[i]);
     s3_pipe_destroy(&dp->pipe);
     s3_timing_destroy(&dp->timing);
+    if (dp->d_stage) cudaFree(dp->d_stage);
     if (dp->ownStream) cudaStreamDestroy(dp->stream);
     free(dp);
 }
@@ -1035,6 +1037,117 @@ static int dp_align_device_range(s3_dp *dp, uint32_t begin, uint32_t end, bool c
     a.ancL = ancL ? dp->d_ancL : NULL; a.ancR = ancR ? dp->d_ancR : NULL;
     a.cells = NULL;
     return dp_run_device(dp, a, begin, end);
+}
+
+// ---- DP batch packing on the device --------------------------------------------
+// One thread per (alignment, output word).  Word w of a packed sequence holds bases i = 16w .. 16w+15,
+// 1-based, base i in bits 2(15 - (i & 15)); base 0 does not exist (DV-DPfunctions.cu:58,1469-1524).
+//   DNA:  base i = text base DNAStart + i - 1 (MC_OldDnaUnpack of hsp->packedDNA, :1512-1524)
+//   read: strand 1: base i = read base i - 1;  strand 2: the complement of read base length - i (:1478-1505);
+//         read bases come from the query buffer (base k in bits 2(k % 16) of word k / 16, QueryParser.cpp:1146)
+__global__ void s3_dp_pack_kernel(const uint32_t *__restrict__ text, const uint32_t *__restrict__ queries, uint32_t wordPerOldQuery,
+                                  const uint32_t *__restrict__ readIDs, const uint8_t *__restrict__ strands,
+                                  const uint32_t *__restrict__ dnaStarts, const uint32_t *__restrict__ dnaLens,
+                                  const uint32_t *__restrict__ readLens, uint32_t first, uint32_t count,
+                                  uint32_t dnaWords, uint32_t readWords, uint32_t *__restrict__ outDna, uint32_t *__restrict__ outRead)
+{
+    const uint32_t perAlign = dnaWords + readWords;
+    const uint64_t gid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (gid >= (uint64_t)count * perAlign) return;
+    // consecutive threads = consecutive alignments of one word index: the 32-interleaved stores coalesce
+    const uint32_t w = (uint32_t)(gid / count), id = first + (uint32_t)(gid % count);
+    uint32_t word = 0;
+    if (w < dnaWords) {
+        const uint32_t start = dnaStarts[id], len = dnaLens[id];
+        for (uint32_t i = max(16u * w, 1u); i < 16u * w + 16u && i <= len; ++i) {
+            const uint32_t pos = start + i - 1;
+            word |= ((text[pos >> 4] >> ((15u - (pos & 15u)) << 1)) & 3u) << ((15u - (i & 15u)) << 1);
+        }
+        outDna[(size_t)(id >> 5) * 32 * dnaWords + (size_t)w * 32 + (id & 31)] = word;
+    } else {
+        const uint32_t wr = w - dnaWords, rid = readIDs[id], len = readLens[id];
+        const uint32_t *q = queries + (size_t)(rid >> 5) * 32 * wordPerOldQuery + (rid & 31);
+        const bool rc = strands[id] == 2;
+        for (uint32_t i = max(16u * wr, 1u); i < 16u * wr + 16u && i <= len; ++i) {
+            const uint32_t k = rc ? len - i : i - 1;
+            uint32_t c = (q[(size_t)(k >> 4) * 32] >> ((k & 15u) << 1)) & 3u;
+            if (rc) c = 3u - c;
+            word |= c << ((15u - (i & 15u)) << 1);
+        }
+        outRead[(size_t)(id >> 5) * 32 * readWords + (size_t)wr * 32 + (id & 31)] = word;
+    }
+}
+
+extern "C" int s3_dp_align_windows(s3_dp *dp, s3_index *ix,
+                                   const uint32_t *queries, const uint32_t *queryLengths, uint64_t numQueries, uint32_t wordPerOldQuery,
+                                   const uint32_t *readIDs, const uint8_t *strands, const uint32_t *DNAStarts, const uint32_t *DNALengths,
+                                   const int32_t *cutoffThresholds, int32_t *scores, uint32_t *hitLocs, uint32_t *maxScoreCounts,
+                                   uint8_t *pattern, uint32_t numOfThreads, const uint32_t *clipLtSizes, uint32_t *clipRtSizes,
+                                   const uint32_t *anchorLeftLocs, const uint32_t *anchorRightLocs)
+{
+    if (!dp || !ix || !queries || !queryLengths || !readIDs || !strands || !DNAStarts || !DNALengths || !cutoffThresholds ||
+        !scores || !hitLocs || !maxScoreCounts || !pattern) { s3_set_error("s3_dp_align_windows: NULL argument"); return S3_EINVAL; }
+    if (!ix->d_packedDNA) { s3_set_error("s3_dp_align_windows: the index was uploaded without the packed text"); return S3_EINVAL; }
+    if (ix->device != dp->device) { s3_set_error("s3_dp_align_windows: index and workspace live on different devices"); return S3_EINVAL; }
+    if (numOfThreads > dp->maxBatch) { s3_set_error("s3_dp_align_windows: %u alignments > maxBatch %u", numOfThreads, dp->maxBatch); return S3_EINVAL; }
+    if (numOfThreads == 0) return S3_OK;
+    const uint32_t n = numOfThreads;
+    // the caller's windows and reads must fit the workspace and the text (the reference clamps windows the same
+    // way before it packs, DV-DPfunctions.cu:1439-1449)
+    for (uint32_t t = 0; t < n; ++t) {
+        if (readIDs[t] >= numQueries || (strands[t] != 1 && strands[t] != 2) ||
+            DNALengths[t] > dp->maxDNALength || queryLengths[readIDs[t]] > dp->maxReadLength ||
+            (uint64_t)DNAStarts[t] + DNALengths[t] > ix->textLength) {
+            s3_set_error("s3_dp_align_windows: alignment %u is out of range (read %u, window %u+%u)", t, readIDs[t], DNAStarts[t], DNALengths[t]);
+            return S3_EINVAL;
+        }
+    }
+    S3_CUDA(cudaSetDevice(dp->device));
+    cudaStream_t st = dp->stream;
+    const size_t up = ((size_t)n + 31) / 32 * 32, qUp = ((size_t)numQueries + 31) / 32 * 32;
+    const size_t dnaW = (dp->maxDNALength + 15) >> 4, readW = (dp->maxReadLength + 15) >> 4;
+    const size_t patLen = dp->maxReadLength + dp->maxDNALength;
+    // staging: query buffer + per-alignment descriptors (readIDs, strands, starts) next to the workspace's own arrays
+    const size_t qBytes = qUp * wordPerOldQuery * 4, need = qBytes + up * 4 * 2 + up + 1024;
+    if (need > dp->stageBytes) {
+        if (dp->d_stage) { S3_CUDA(cudaStreamSynchronize(st)); S3_CUDA(cudaFree(dp->d_stage)); dp->d_stage = NULL; dp->stageBytes = 0; }
+        S3_CUDA(cudaMalloc(&dp->d_stage, need + need / 4));
+        dp->stageBytes = need + need / 4;
+    }
+    uint32_t *d_q = (uint32_t *)dp->d_stage;
+    uint32_t *d_rid = (uint32_t *)((char *)dp->d_stage + (qBytes + 255) / 256 * 256), *d_start = d_rid + up;
+    uint8_t *d_strand = (uint8_t *)(d_start + up);
+    uint32_t *h_len = (uint32_t *)malloc((size_t)n * 4);             // the reads' own lengths, per alignment
+    if (!h_len) { s3_set_error("s3_dp_align_windows: out of host memory"); return S3_ENOMEM; }
+    for (uint32_t t = 0; t < n; ++t) h_len[t] = queryLengths[readIDs[t]];
+    cudaError_t e = cudaMemcpyAsync(d_q, queries, qBytes, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_rid, readIDs, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_start, DNAStarts, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d_strand, strands, (size_t)n, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dp->d_dnaLen, DNALengths, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dp->d_readLen, h_len, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dp->d_cutoff, cutoffThresholds, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && clipLtSizes) e = cudaMemcpyAsync(dp->d_clipLt, clipLtSizes, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && clipRtSizes) e = cudaMemcpyAsync(dp->d_clipRt, clipRtSizes, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && anchorLeftLocs) e = cudaMemcpyAsync(dp->d_ancL, anchorLeftLocs, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess && anchorRightLocs) e = cudaMemcpyAsync(dp->d_ancR, anchorRightLocs, (size_t)n * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);            // h_len is read by the copy until here
+    free(h_len);
+    if (e != cudaSuccess) { s3_set_error("s3_dp_align_windows: staging failed: %s", cudaGetErrorString(e)); return S3_ECUDA; }
+    const uint64_t threads = (uint64_t)n * (dnaW + readW);
+    s3_dp_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(ix->d_packedDNA, d_q, wordPerOldQuery, d_rid, d_strand, d_start,
+                                                                        dp->d_dnaLen, dp->d_readLen, 0, n, (uint32_t)dnaW, (uint32_t)readW,
+                                                                        dp->d_dna, dp->d_read);
+    S3_LAUNCHED(1);
+    S3_CUDA(cudaGetLastError());
+    int rc = dp_align_device_range(dp, 0, n, clipLtSizes != NULL, clipRtSizes != NULL, anchorLeftLocs != NULL, anchorRightLocs != NULL);
+    if (rc) return rc;
+    S3_CUDA(cudaMemcpyAsync(scores, dp->d_score, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    S3_CUDA(cudaMemcpyAsync(hitLocs, dp->d_hit, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    S3_CUDA(cudaMemcpyAsync(maxScoreCounts, dp->d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    S3_CUDA(cudaMemcpyAsync(pattern, dp->d_pattern, (size_t)n * patLen, cudaMemcpyDeviceToHost, st));
+    S3_CUDA(cudaStreamSynchronize(st));
+    return S3_OK;
 }
 
 extern "C" int s3_dp_align(s3_dp *dp, const uint32_t *packedDNASequence, const uint32_t *DNALengths,

@@ -1100,6 +1100,81 @@ extern "C" int s3_search(s3_index *ix, const uint32_t *queries, const uint32_t *
     return rc;
 }
 
+// ---- locate -------------------------------------------------------------------
+// SA ranges -> text positions from the suffix array in HBM.  Replaces the host loops
+// `for k in [l, r]: (*bwt->_bwtSaValue)(bwt, k)` that follow every search in the reference (SAList.cpp:411,
+// CPUfunctions.cpp:2915,2975, PEAlgnmt.cpp:1246, DV-DPfunctions.cu:1186,2931).
+__global__ void s3_locate_count_kernel(const uint32_t *__restrict__ saL, const uint32_t *__restrict__ saR, uint64_t n,
+                                       uint32_t maxPerRange, unsigned long long *__restrict__ cnt)
+{
+    const uint64_t g = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g > n) return;
+    unsigned long long c = 0;
+    if (g < n && saR[g] >= saL[g]) { c = (unsigned long long)(saR[g] - saL[g]) + 1; if (c > maxPerRange) c = maxPerRange; }
+    cnt[g] = c;                                                       // cnt[n] = 0: the scan leaves the total there
+}
+
+__global__ void s3_locate_fill_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ saL, const uint32_t *__restrict__ saR,
+                                      uint64_t n, uint32_t maxPerRange, const unsigned long long *__restrict__ start,
+                                      uint32_t *__restrict__ out)
+{
+    // one warp per range: consecutive suffix array entries, consecutive outputs
+    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (g >= n || saR[g] < saL[g]) return;
+    unsigned long long c = (unsigned long long)(saR[g] - saL[g]) + 1;
+    if (c > maxPerRange) c = maxPerRange;
+    for (unsigned long long k = lane; k < c; k += 32) out[start[g] + k] = sa[(size_t)saL[g] + k];
+}
+
+extern "C" void s3_free(void *p) { free(p); }
+
+extern "C" int s3_locate(s3_index *ix, const uint32_t *saL, const uint32_t *saR, uint64_t numRanges, uint32_t maxPerRange,
+                         uint64_t *offsets, uint32_t **positions, uint64_t *total)
+{
+    if (!ix || !offsets || !positions || !total || (numRanges && (!saL || !saR))) { s3_set_error("s3_locate: NULL argument"); return S3_EINVAL; }
+    if (!ix->loc.sa) { s3_set_error("s3_locate: the index was uploaded without its suffix array"); return S3_EINVAL; }
+    if (numRanges >= 0x7FFFFFFFull || maxPerRange == 0) { s3_set_error("s3_locate: numRanges / maxPerRange out of range"); return S3_EINVAL; }
+    *positions = NULL; *total = 0; offsets[0] = 0;
+    if (numRanges == 0) return S3_OK;
+    S3_CUDA(cudaSetDevice(ix->device));
+    size_t scanTemp = 0;
+    cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (unsigned long long *)NULL, (unsigned long long *)NULL, (int)(numRanges + 1), ix->stream);
+    const size_t rBytes = numRanges * 4, cBytes = (numRanges + 1) * 8;
+    char *d;
+    int rc;
+    if ((rc = s3_scratch(ix, 2 * rBytes + cBytes + scanTemp + 1024, (void **)&d))) return rc;
+    size_t off = 0;
+    auto carve = [&](size_t bytes) { char *p = d + off; off += (bytes + 255) / 256 * 256; return p; };
+    uint32_t *d_l = (uint32_t *)carve(rBytes), *d_r = (uint32_t *)carve(rBytes);
+    unsigned long long *d_cnt = (unsigned long long *)carve(cBytes);
+    void *d_tmp = carve(scanTemp);
+    S3_CUDA(cudaMemcpyAsync(d_l, saL, rBytes, cudaMemcpyHostToDevice, ix->stream));
+    S3_CUDA(cudaMemcpyAsync(d_r, saR, rBytes, cudaMemcpyHostToDevice, ix->stream));
+    s3_locate_count_kernel<<<(unsigned)((numRanges + 256) / 256), 256, 0, ix->stream>>>(d_l, d_r, numRanges, maxPerRange, d_cnt);
+    S3_LAUNCHED(1);
+    S3_CUDA(cudaGetLastError());
+    S3_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_cnt, d_cnt, (int)(numRanges + 1), ix->stream));
+    S3_CUDA(cudaMemcpyAsync(offsets, d_cnt, cBytes, cudaMemcpyDeviceToHost, ix->stream));
+    S3_CUDA(cudaStreamSynchronize(ix->stream));
+    const uint64_t tot = offsets[numRanges];
+    *total = tot;
+    if (tot == 0) return S3_OK;
+    uint32_t *d_out = NULL;
+    S3_CUDA(cudaMalloc(&d_out, tot * 4));
+    s3_locate_fill_kernel<<<(unsigned)((numRanges * 32 + 255) / 256), 256, 0, ix->stream>>>(ix->loc.sa, d_l, d_r, numRanges, maxPerRange, d_cnt, d_out);
+    S3_LAUNCHED(1);
+    uint32_t *h = (uint32_t *)malloc(tot * 4);
+    cudaError_t e = cudaGetLastError();
+    if (!h) { cudaFree(d_out); s3_set_error("s3_locate: out of host memory"); return S3_ENOMEM; }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(h, d_out, tot * 4, cudaMemcpyDeviceToHost, ix->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
+    cudaFree(d_out);
+    if (e != cudaSuccess) { free(h); s3_set_error("s3_locate: %s", cudaGetErrorString(e)); return S3_ECUDA; }
+    *positions = h;
+    return S3_OK;
+}
+
 extern "C" int s3_search_round2(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths,
                                 uint32_t *const *answers, uint64_t batchSize, uint64_t processedQuery,
                                 uint32_t wordPerQuery, uint32_t numMismatch, uint32_t numCases,

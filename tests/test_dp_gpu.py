@@ -5,7 +5,7 @@ import numpy as np
 import pytest
 
 from helpers import compare_dp, load_oracle_dp, make_dp_batch, oracle_dp, DPBatch
-from soap3dp_b200 import api, synth
+from soap3dp_b200 import api, formats, synth
 
 pytestmark = pytest.mark.gpu
 
@@ -78,3 +78,76 @@ def test_dp_empty_and_bad_args(genome):
     al.freeMemory()
     with pytest.raises(api.S3Error):
         api.SemiGlobalAligner(2000, 162, 64)
+
+
+@pytest.mark.parametrize("L", [100, 150, 61])
+def test_windows_packed_on_the_device_give_the_same_alignments(L):
+    """s3_dp_align_windows (read ids + window starts; batch arrays built on the device from the index's text and the
+    query buffer) == s3_dp_align on the arrays the host packers build (formats.pack_dp_sequences = packRead /
+    repackDNA, DV-DPfunctions.cu:1469-1524), both strands, ragged lengths, windows at the very ends of the text."""
+    from soap3dp_b200 import fmindex
+    G = synth.random_genome(200_000, seed=21)
+    idx = fmindex.build_index(G)
+    gi = api.GPUINDEXUpload(idx, device=0, with_text=True, with_sa=True)
+    g = G.numpy()
+    rng = np.random.default_rng(L)
+    nq, n = 700, 1500
+    rs = synth.simulate_single_end(G, nq, L, seed=50 + L, sub_rate=0.02, indel_rate=0.004, margin=400)
+    reads = rs.reads.numpy()
+    qlen = np.zeros(formats.ceil32(nq), np.uint32)
+    qlen[:nq] = L
+    qlen[5:nq:7] = L - 4
+    wpq = formats.word_per_query(L)
+    queries = formats.pack_queries(reads, qlen[:nq], wpq)
+    rid = rng.integers(0, nq, n).astype(np.uint32)
+    pos = rs.pos.numpy()[rid]
+    strand = (rs.strand.numpy()[rid] + 1).astype(np.uint8)            # 1 as given, 2 reverse-complemented
+    strand[::10] = 3 - strand[::10]                                   # some against the wrong strand: low scores
+    margin = 25
+    max_read = (L // 4 + 1) * 4
+    max_dna = max_read + 2 * margin + 8
+    start = np.clip(pos - margin + rng.integers(-5, 6, n), 0, len(g) - 1).astype(np.uint32)
+    dlen = np.minimum(L + 2 * margin, len(g) - start).astype(np.uint32)
+    start[0], dlen[0] = 0, L + 2 * margin
+    start[1] = len(g) - (L + 2 * margin); dlen[1] = L + 2 * margin
+    dlen[2::13] -= 7
+    rlen = qlen[rid]
+    cutoff = np.ceil(0.3 * rlen).astype(np.int32)
+    clip_lt = np.where(strand == 1, 3, 8).astype(np.uint32)
+    clip_rt = np.where(strand == 1, 8, 3).astype(np.uint32)
+    # the host packers' view of the same batch
+    dna = np.zeros((n, int(dlen.max())), np.uint8)
+    for t in range(n):
+        dna[t, :dlen[t]] = g[start[t]:start[t] + dlen[t]]
+    rd = np.zeros((n, L), np.uint8)
+    for t in range(n):
+        r = reads[rid[t], :rlen[t]]
+        rd[t, :rlen[t]] = r if strand[t] == 1 else 3 - r[::-1]
+    al = api.SemiGlobalAligner(max_read, max_dna, n)
+    up = formats.ceil32(n)
+
+    def padded(a, dtype=np.uint32):
+        o = np.zeros(up, dtype)
+        o[:n] = a
+        return o
+    want = al.performAlignment(formats.pack_dp_sequences(dna, max_dna), padded(dlen), formats.pack_dp_sequences(rd, max_read),
+                               padded(rlen), padded(cutoff, np.int32), n, padded(clip_lt), padded(clip_rt))
+    got = al.performAlignmentOnWindows(gi, queries, qlen, nq, wpq, padded(rid), padded(strand, np.uint8), padded(start), padded(dlen),
+                                       padded(cutoff, np.int32), n, padded(clip_lt), padded(clip_rt))
+    for a, b, name in zip(got, want, ("scores", "hitLocs", "maxScoreCounts", "pattern")):
+        if name == "pattern":
+            a = a.reshape(up, -1)[:n]; b = b.reshape(up, -1)[:n]
+            ok = want[0][:n] >= cutoff                                   # patterns exist for traced alignments only
+            for t in np.nonzero(ok)[0]:
+                ea, eb = a[t], b[t]
+                la = int(np.argmax(ea == 0)); lb = int(np.argmax(eb == 0))
+                assert la == lb and np.array_equal(ea[:la], eb[:lb]), f"pattern {t}"
+        else:
+            assert np.array_equal(a[:n], b[:n]), name
+    assert int((want[0][:n] >= cutoff).sum()) > n // 2
+    with pytest.raises(api.S3Error):                                      # window past the end of the text
+        bad = padded(start).copy(); bad[3] = len(g) - 5
+        al.performAlignmentOnWindows(gi, queries, qlen, nq, wpq, padded(rid), padded(strand, np.uint8), bad, padded(dlen),
+                                     padded(cutoff, np.int32), n)
+    al.freeMemory()
+    api.GPUINDEXFree(gi)

@@ -211,3 +211,44 @@ def test_capless_search_empty_batch(env):
     G, idx, hi, gi = env
     offsets, sa_l, sa_r, info = api.search(gi, np.zeros(32 * 8, np.uint32), np.zeros(32, np.uint32), 0, 8, 2)
     assert offsets.tolist() == [0] and len(sa_l) == 0
+
+
+def test_locate_is_the_suffix_array_gather(env, request):
+    """s3_locate == SA[l .. r] for every range (capped per range), in SA order, empty ranges skipped; and the
+    positions of a capless 1-mismatch search really are occurrences of the reads within 1 substitution."""
+    G, idx, hi, gi = env
+    if "check_and_extend" not in request.node.name:
+        with pytest.raises(api.S3Error):
+            api.locate(gi, np.array([1], np.uint32), np.array([2], np.uint32))
+        return
+    sa = idx.fwd.sa.numpy().astype(np.uint32) if hasattr(idx.fwd.sa, "numpy") else np.asarray(idx.fwd.sa, np.uint32)
+    rng = np.random.default_rng(9)
+    n = 5000
+    l = rng.integers(0, hi.n - 40, n).astype(np.uint32)
+    r = (l + rng.integers(0, 40, n)).astype(np.uint32)
+    r[::17] = l[::17] - 1                                   # empty ranges
+    l[0], r[0] = 0, 0
+    for cap in (0xFFFFFFFF, 5):
+        offsets, pos = api.locate(gi, l, r, cap)
+        exp = [sa[int(a):int(a) + min(int(b) - int(a) + 1, cap)] if b >= a else sa[:0] for a, b in zip(l.astype(np.int64), r.astype(np.int64))]
+        assert offsets[-1] == len(pos) == sum(len(e) for e in exp)
+        assert np.array_equal(pos, np.concatenate(exp))
+        assert np.array_equal(offsets, np.concatenate([[0], np.cumsum([len(e) for e in exp])]).astype(np.uint64))
+    # end to end: search -> locate -> the text at the position is within 1 substitution of the read
+    nr, L = 300, 64
+    rs = synth.simulate_single_end(G, nr, L, seed=41, sub_rate=0.01)
+    lens = np.zeros(formats.ceil32(nr), np.uint32)
+    lens[:nr] = L
+    wpq = formats.word_per_query(L)
+    offs, sa_l, sa_r, info = api.search(gi, formats.pack_queries(rs.reads.numpy(), lens[:nr], wpq), lens, nr, wpq, 1)
+    o2, pos = api.locate(gi, sa_l, sa_r, 8)
+    g = G.numpy()
+    reads = rs.reads.numpy()
+    checked = 0
+    for q in range(nr):
+        for e in range(int(offs[q]), int(offs[q + 1])):
+            rd = reads[q] if (info[e] & 1) == 0 else (3 - reads[q][::-1])
+            for p in pos[int(o2[e]):int(o2[e + 1])]:
+                assert int((g[int(p):int(p) + L] != rd).sum()) == ((int(info[e]) >> 1) & 7) <= 1
+                checked += 1
+    assert checked > nr // 2

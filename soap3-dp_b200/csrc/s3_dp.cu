@@ -426,15 +426,28 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
         }
     };
     const uint32_t items = nCols * nSlots;
-    for (uint32_t q = t; q < items; q += 2 * LANES) {
-        uint32_t j0, t0, j1 = 0, t1 = 0, w0[R], w1[R];
-        locate(q, j0, t0);
-        const bool first = true;
-        fetch(j0, t0, w0);
-        const bool second = q + LANES < items;
-        if (second) { locate(q + LANES, j1, t1); fetch(j1, t1, w1); }
-        if (first) consume(j0, t0, w0);
-        if (second) consume(j1, t1, w1);
+    if (LANES % nSlots == 0) {
+        // the usual case (1 or 2 slots): a lane keeps its slot and walks the columns with a fixed stride -- no
+        // division per entry, and the row masks are built once
+        const uint32_t ti = tiLo + t % nSlots, jStep = LANES / nSlots;
+        for (uint32_t j = jStart + t / nSlots; j <= jEnd && nCols; j += 2 * jStep) {
+            uint32_t w0[R], w1[R];
+            fetch(j, ti, w0);
+            const bool second = j + jStep <= jEnd;
+            if (second) fetch(j + jStep, ti, w1);
+            consume(j, ti, w0);
+            if (second) consume(j + jStep, ti, w1);
+        }
+    } else {
+        for (uint32_t q = t; q < items; q += 2 * LANES) {
+            uint32_t j0, t0, j1 = 0, t1 = 0, w0[R], w1[R];
+            locate(q, j0, t0);
+            fetch(j0, t0, w0);
+            const bool second = q + LANES < items;
+            if (second) { locate(q + LANES, j1, t1); fetch(j1, t1, w1); }
+            consume(j0, t0, w0);
+            if (second) consume(j1, t1, w1);
+        }
     }
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
@@ -1174,6 +1187,7 @@ extern "C" int s3_dp_align(s3_dp *dp, const uint32_t *packedDNASequence, const u
     // fixed-size batch arrays is moved (DV-DPfunctions.cu:678-682 copies batchSize entries whatever the fill).
     // Two chunks only: each must still fill the device several times over.
     size_t chunk = (n >= 65536) ? (((n + 31) / 32 * 32) / 2 + 31) / 32 * 32 : (n + 31) / 32 * 32;
+    if (getenv("S3_HOST_CHUNKS")) { const int c = atoi(getenv("S3_HOST_CHUNKS")); if (c >= 1 && c <= S3_PIPE_CHUNKS) chunk = (((n + 31) / 32 * 32) / c + 31) / 32 * 32; }   // tuning experiments
     if (chunk > dp->chunk) chunk = dp->chunk / 32 * 32;
     if (chunk < 32) chunk = 32;
     S3_CUDA(cudaEventRecord(pp.done[0], st));

@@ -952,6 +952,7 @@ extern "C" int s3_search_round1(s3_index *ix, const uint32_t *queries, const uin
     // (The reference copies, launches per case and copies back strictly in sequence, alignment.cu:158-215.)
     // Two chunks only: a launch needs several items per resident lane to keep the persistent warps busy.
     size_t chunk = (batchSize >= 262144) ? ((roundUp / 2 + 31) / 32) * 32 : roundUp;
+    if (getenv("S3_HOST_CHUNKS")) { const int c = atoi(getenv("S3_HOST_CHUNKS")); if (c >= 1 && c <= S3_PIPE_CHUNKS) chunk = ((roundUp / c + 31) / 32) * 32; }   // tuning experiments
     S3Pipe &pp = ix->pipe;
     S3_CUDA(cudaEventRecord(pp.done[0], ix->stream));               // earlier work on the scratch buffer
     S3_CUDA(cudaStreamWaitEvent(pp.in, pp.done[0], 0));

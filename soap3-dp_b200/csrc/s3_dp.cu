@@ -339,18 +339,6 @@ __device__ __forceinline__ size_t s3_dp_cell(uint32_t t, uint32_t s, uint32_t tL
 }
 #define S3_DP_STEP_STRIDE(R, LANES) ((size_t)(LANES) * (R))
 
-struct S3Dp16Best { int best; uint32_t cnt; unsigned long long key; };
-
-// DV-DPfunctions.cu:225-235 for one cell, without branches
-__device__ __forceinline__ void s3_best_update(S3Dp16Best &b, bool eligible, int v, uint32_t j, uint32_t i)
-{
-    const bool gt = eligible && v > b.best, eq = eligible && v == b.best;
-    b.best = gt ? v : b.best;
-    const unsigned long long k = ((unsigned long long)j << 32) | i;
-    b.key = gt ? k : (eq ? min(b.key, k) : b.key);          // first in (column, row) order, whatever the visiting order
-    b.cnt = gt ? 1u : b.cnt + (eq ? 1u : 0u);
-}
-
 // Best cells of the two alignments of a pair (DV-DPfunctions.cu:225-235) found AFTER the sweep, from
 // the pair's H plane: per alignment the highest H over the rows i >= m - clipRt and the columns
 // anchorRight <= j <= n, the first such cell in (column, row) order, and the number of cells that tie
@@ -376,8 +364,9 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
     const uint32_t mMax = max(m[0], m[1]);
     const uint32_t tiLo = (min(iLo[0], iLo[1]) - 1) / R, nSlots = (mMax ? (mMax - 1) / R : 0u) - tiLo + 1;
     const uint32_t jStart = min(jLo[0], jLo[1]), jEnd = max(n[0], n[1]);
-    S3Dp16Best bb[2] = {{S3_NEG_INF, 0u, ~0ull}, {S3_NEG_INF, 0u, ~0ull}};
-    uint32_t best2 = S3_NEGB2;
+    // per lane: running best of both alignments (biased, packed), how many cells tie with it, and the first of
+    // them as column << 12 | row (rows <= 256, columns < 2^20)
+    uint32_t best2 = S3_NEGB2, cnt[2] = {0u, 0u}, key[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
 
     // column after column, the eligible slots of a column on neighbouring lanes: with the slot rotation of
     // s3_dp_slot the last two of them are one 64-byte burst
@@ -408,21 +397,31 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
             }
             keepTi = ti;
         }
-        uint32_t mx = w[0] & keep[0];
+        const uint32_t colKeep = ((j >= jLo[0] && j <= n[0]) ? 0xFFFFu : 0u) | ((j >= jLo[1] && j <= n[1]) ? 0xFFFF0000u : 0u);
+        uint32_t wm[R];
 #pragma unroll
-        for (int r = 1; r < R; ++r) mx = __vmaxu2(mx, w[r] & keep[r]);
-        mx &= ((j >= jLo[0] && j <= n[0]) ? 0xFFFFu : 0u) | ((j >= jLo[1] && j <= n[1]) ? 0xFFFF0000u : 0u);
+        for (int r = 0; r < R; ++r) wm[r] = w[r] & keep[r] & colKeep;
+        uint32_t mx = wm[0];
+#pragma unroll
+        for (int r = 1; r < R; ++r) mx = __vmaxu2(mx, wm[r]);
         bool gh, gl;
         (void)__vibmax_u16x2(mx, best2, &gh, &gl);
         if (gh || gl) {
-            const bool okA = j >= jLo[0] && j <= n[0], okB = j >= jLo[1] && j <= n[1];
+            // The slot's rows in ascending order through DV-DPfunctions.cu:225-235 leave: the maximum as the new best
+            // if it beats the old one (count = the rows that hold it, position = the first of them), or the rows that
+            // tie with the old best added to its count.  Rows equal to the slot maximum, as bit r of each half:
+            uint32_t eq = 0;
 #pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t i = ti * R + r + 1, v = w[r] ^ S3_BIAS2;
-                s3_best_update(bb[0], okA && i >= iLo[0] && i <= m[0], s3_lo16(v), j, i);
-                s3_best_update(bb[1], okB && i >= iLo[1] && i <= m[1], s3_hi16(v), j, i);
+            for (int r = 0; r < R; ++r) eq |= (__vcmpeq2(wm[r], mx) & 0x00010001u) << r;
+#pragma unroll
+            for (int x = 0; x < 2; ++x) {
+                if (x == 0 ? !gl : !gh) continue;
+                const uint32_t rows = (eq >> (16 * x)) & 0xFFFFu, v = (mx >> (16 * x)) & 0xFFFFu, b = (best2 >> (16 * x)) & 0xFFFFu;
+                const uint32_t k = (j << 12) | (ti * R + (uint32_t)__ffs(rows));          // 1-based row
+                if (v > b) { cnt[x] = (uint32_t)__popc(rows); key[x] = k; }
+                else { cnt[x] += (uint32_t)__popc(rows); key[x] = min(key[x], k); }
             }
-            best2 = s3_bpk(bb[0].best, bb[1].best);
+            best2 = __vmaxu2(best2, mx);
         }
     };
     const uint32_t items = nCols * nSlots;
@@ -451,16 +450,19 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
     }
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-        int g = bb[x].best;
+        const int mine = (int)((best2 >> (16 * x)) & 0xFFFFu) - 32768;
+        int g = mine;
         for (int o = LANES / 2; o > 0; o >>= 1) g = max(g, __shfl_xor_sync(0xFFFFFFFFu, g, o));
-        // cells that only tie with the -32000 start value count but set no position (key stays ~0)
-        unsigned long long key = (bb[x].best == g) ? bb[x].key : ~0ull;
-        uint32_t cnt = (bb[x].best == g) ? bb[x].cnt : 0u;
+        // position = the first cell, in (column, row) order, that holds the final best -- if any cell beat the
+        // -32000 the reference starts from (cells that only tie with it are counted, hitPos stays 0)
+        uint32_t k = (mine == g && g > S3_NEG_INF) ? key[x] : 0xFFFFFFFFu;
+        uint32_t c = (mine == g) ? cnt[x] : 0u;
         for (int o = LANES / 2; o > 0; o >>= 1) {
-            key = min(key, __shfl_xor_sync(0xFFFFFFFFu, key, o));
-            cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+            k = min(k, __shfl_xor_sync(0xFFFFFFFFu, k, o));
+            c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
         }
-        gbest[x] = g; gkey[x] = key; gcnt[x] = cnt;
+        gbest[x] = g; gcnt[x] = c;
+        gkey[x] = (k == 0xFFFFFFFFu) ? ~0ull : (((unsigned long long)(k >> 12) << 32) | (k & 0xFFFu));
     }
 }
 

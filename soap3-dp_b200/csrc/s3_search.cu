@@ -295,7 +295,10 @@ __device__ __forceinline__ uint32_t s3_pack_program(const S3SearchArgs &args, ui
 // pins the read to one place (or to none) -- almost all reads outside repeats.  Anything else (a first
 // phase that is still ambiguous after S3_EASY_STEPS steps or at its end, a read too short for the seed
 // table) is appended to `hardItems` untouched and enumerated by s3_search_kernel.
-__global__ void __launch_bounds__(S3_THREADS)
+#ifndef S3_EASY_MIN_BLOCKS
+#define S3_EASY_MIN_BLOCKS 8       // <= 64 registers: more reads in flight (the kernel runs at the random-burst rate of the memory system)
+#endif
+__global__ void __launch_bounds__(S3_THREADS, S3_EASY_MIN_BLOCKS)
 s3_search_easy_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3Locate loc, const S3SearchArgs args,
                       uint32_t *__restrict__ hardItems, uint32_t *__restrict__ hardCount)
 {

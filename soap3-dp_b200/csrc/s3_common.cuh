@@ -92,6 +92,16 @@ struct s3_index {
     uint32_t *d_workCounter;          // [0] work queue head, [1] number of items the easy kernel left behind, [4..7] S3_HV_* counters
     uint32_t *d_heavy; uint32_t heavyCap, heavyMaxTasks;     // scratch for splitting long enumerations (s3_search.cu)
     S3Timing timing;                  // slots: 0 easy, 1 items, 2 spine, 3 subtree, 4 merge, 5 isBad fixup
+    // A second set of everything a search launch writes to, on a stream of its own: two halves of a batch (or two
+    // chunks of a host call) are searched side by side, so the latency-bound end of one (its last long items,
+    // spines, tasks) runs under the other's bandwidth-bound start.
+    struct Side {
+        cudaStream_t stream;
+        uint32_t *d_workCounter, *d_hardItems; size_t hardCap;
+        uint32_t *d_heavy; uint32_t heavyCap, heavyMaxTasks;
+        cudaEvent_t fork, join;
+        int ready;
+    } side;
     int32_t splitBudget;              // steps before an item is split (s3_search_set_split_budget); < 0: never
     uint32_t *d_hardItems; size_t hardCap;
     uint32_t *d_itemStats; size_t itemStatsCap;   // S3_ITEM_STATS builds only (tools/search_tail.py)

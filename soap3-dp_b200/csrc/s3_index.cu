@@ -324,6 +324,14 @@ extern "C" void s3_index_free(s3_index *ix)
     if (ix->d_hardItems) cudaFree(ix->d_hardItems);
     if (ix->d_itemStats) cudaFree(ix->d_itemStats);
     if (ix->d_heavy) cudaFree(ix->d_heavy);
+    if (ix->side.ready) {
+        cudaStreamSynchronize(ix->side.stream);
+        if (ix->side.d_workCounter) cudaFree(ix->side.d_workCounter);
+        if (ix->side.d_hardItems) cudaFree(ix->side.d_hardItems);
+        if (ix->side.d_heavy) cudaFree(ix->side.d_heavy);
+        cudaEventDestroy(ix->side.fork); cudaEventDestroy(ix->side.join);
+        cudaStreamDestroy(ix->side.stream);
+    }
     s3_timing_destroy(&ix->timing);
     if (ix->scratch) cudaFree(ix->scratch);
     if (ix->pinned) cudaFreeHost(ix->pinned);

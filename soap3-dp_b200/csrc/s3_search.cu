@@ -901,16 +901,36 @@ static int check_search_args(const char *fn, s3_index *ix, const void *q, const 
     return S3_OK;
 }
 
-extern "C" int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, const uint32_t *d_readLengths,
-                                       uint64_t batchSize, uint32_t wordPerQuery, uint32_t numMismatch,
-                                       uint32_t numCases, uint32_t saRangeAllowed, uint32_t wordPerAns,
-                                       int isExactNumMismatch, uint32_t *const *d_answers,
-                                       unsigned long long *d_rankQueries)
+// ---- the side context (s3_index::Side) ----------------------------------------
+static int side_init(s3_index *ix)
 {
-    int rc = check_search_args("s3_search_round1_device", ix, d_queries, d_readLengths, batchSize, wordPerQuery,
-                               numMismatch, numCases, saRangeAllowed, wordPerAns);
-    if (rc) return rc;
-    S3_CUDA(cudaSetDevice(ix->device));
+    if (ix->side.ready) return S3_OK;
+    S3_CUDA(cudaStreamCreateWithFlags(&ix->side.stream, cudaStreamNonBlocking));
+    S3_CUDA(cudaEventCreateWithFlags(&ix->side.fork, cudaEventDisableTiming));
+    S3_CUDA(cudaEventCreateWithFlags(&ix->side.join, cudaEventDisableTiming));
+    S3_CUDA(cudaMalloc(&ix->side.d_workCounter, 256));
+    ix->side.ready = 1;
+    return S3_OK;
+}
+
+// launch_search and everything below it use the handle's own fields; the side context is swapped in for a launch
+// (host code of one thread: a handle is never used by two threads at once)
+static void side_swap(s3_index *ix)
+{
+    auto sw = [](auto &x, auto &y) { auto t = x; x = y; y = t; };
+    sw(ix->stream, ix->side.stream);
+    sw(ix->d_workCounter, ix->side.d_workCounter);
+    sw(ix->d_hardItems, ix->side.d_hardItems); sw(ix->hardCap, ix->side.hardCap);
+    sw(ix->d_heavy, ix->side.d_heavy); sw(ix->heavyCap, ix->side.heavyCap); sw(ix->heavyMaxTasks, ix->side.heavyMaxTasks);
+}
+
+static bool side_usable(const s3_index *ix) { return !ix->timing.on && !getenv("S3_NO_SIDE_STREAM"); }
+
+// round 1 of `batchSize` reads on the handle's CURRENT stream and launch resources
+static int round1_here(s3_index *ix, const uint32_t *d_queries, const uint32_t *d_readLengths, uint64_t batchSize,
+                       uint32_t wordPerQuery, uint32_t numMismatch, uint32_t numCases, uint32_t saRangeAllowed,
+                       uint32_t wordPerAns, int isExactNumMismatch, uint32_t *const *d_answers, unsigned long long *d_rankQueries)
+{
     S3SearchArgs a;
     memset(&a, 0, sizeof a);
     a.queries = d_queries; a.readLengths = d_readLengths; a.numQueries = (uint32_t)batchSize;
@@ -921,6 +941,7 @@ extern "C" int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, 
     a.rankQueries = d_rankQueries;
     const size_t aBytes = (batchSize + 31) / 32 * 32 * wordPerAns * sizeof(uint32_t);
     for (uint32_t c = 0; c < numCases; ++c) S3_CUDA(cudaMemsetAsync(d_answers[c], 0xFF, aBytes, ix->stream));
+    int rc;
     if ((rc = launch_search(ix, a, numCases, d_rankQueries != NULL))) return rc;
     if (numCases > 1 && batchSize > 0) {
         s3_timing_mark(&ix->timing, ix->stream, -1);
@@ -929,6 +950,48 @@ extern "C" int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, 
         S3_LAUNCHED(1);
         S3_CUDA(cudaGetLastError());
     }
+    return S3_OK;
+}
+
+// The device entry point can search a batch as two halves side by side too (from S3_SIDE_MIN_READS reads on, set in
+// the environment).  Off by default: measured on the bench workload it helps the host entry point, whose chunks wait
+// for copies anyway (e2e 109.8 -> 113.9 M reads/s), and costs the device-resident pipeline 5 % (profiles/r02f).
+static uint64_t side_min_reads()
+{
+    const char *e = getenv("S3_SIDE_MIN_READS");
+    return e ? strtoull(e, NULL, 10) : ~0ull;
+}
+
+extern "C" int s3_search_round1_device(s3_index *ix, const uint32_t *d_queries, const uint32_t *d_readLengths,
+                                       uint64_t batchSize, uint32_t wordPerQuery, uint32_t numMismatch,
+                                       uint32_t numCases, uint32_t saRangeAllowed, uint32_t wordPerAns,
+                                       int isExactNumMismatch, uint32_t *const *d_answers,
+                                       unsigned long long *d_rankQueries)
+{
+    int rc = check_search_args("s3_search_round1_device", ix, d_queries, d_readLengths, batchSize, wordPerQuery,
+                               numMismatch, numCases, saRangeAllowed, wordPerAns);
+    if (rc) return rc;
+    S3_CUDA(cudaSetDevice(ix->device));
+    if (batchSize < side_min_reads() || d_rankQueries != NULL || !side_usable(ix))
+        return round1_here(ix, d_queries, d_readLengths, batchSize, wordPerQuery, numMismatch, numCases, saRangeAllowed,
+                           wordPerAns, isExactNumMismatch, d_answers, d_rankQueries);
+    // two halves of whole 32-read groups (the interleave unit of the buffers), the second on the side stream
+    if ((rc = side_init(ix))) return rc;
+    const uint64_t half = ((batchSize / 2 + 31) / 32) * 32;
+    uint32_t *ansB[S3_MAX_NUM_CASES];
+    for (uint32_t c = 0; c < numCases; ++c) ansB[c] = d_answers[c] + half * wordPerAns;
+    S3_CUDA(cudaEventRecord(ix->side.fork, ix->stream));              // whatever the caller queued before this call
+    S3_CUDA(cudaStreamWaitEvent(ix->side.stream, ix->side.fork, 0));
+    if ((rc = round1_here(ix, d_queries, d_readLengths, half, wordPerQuery, numMismatch, numCases, saRangeAllowed, wordPerAns,
+                          isExactNumMismatch, d_answers, NULL))) return rc;
+    side_swap(ix);
+    rc = round1_here(ix, d_queries + half * wordPerQuery, d_readLengths + half, batchSize - half, wordPerQuery, numMismatch, numCases,
+                     saRangeAllowed, wordPerAns, isExactNumMismatch, ansB, NULL);
+    cudaError_t e = (rc == S3_OK) ? cudaEventRecord(ix->side.join, ix->stream) : cudaSuccess;
+    side_swap(ix);
+    if (rc) return rc;
+    S3_CUDA(e);
+    S3_CUDA(cudaStreamWaitEvent(ix->stream, ix->side.join, 0));
     return S3_OK;
 }
 
@@ -959,6 +1022,8 @@ extern "C" int s3_search_round1(s3_index *ix, const uint32_t *queries, const uin
     S3Pipe &pp = ix->pipe;
     S3_CUDA(cudaEventRecord(pp.done[0], ix->stream));               // earlier work on the scratch buffer
     S3_CUDA(cudaStreamWaitEvent(pp.in, pp.done[0], 0));
+    const bool useSide = chunk < batchSize && side_usable(ix);
+    if (useSide && (rc = side_init(ix))) return rc;
     int k = 0;
     for (size_t c0 = 0; c0 < batchSize; c0 += chunk, k = (k + 1) % S3_PIPE_CHUNKS) {
         const size_t cnt = (batchSize - c0 < chunk) ? batchSize - c0 : chunk, cntUp = (cnt + 31) / 32 * 32;
@@ -967,18 +1032,25 @@ extern "C" int s3_search_round1(s3_index *ix, const uint32_t *queries, const uin
         // the reference copies roundUp lengths (alignment.cu:161); only batchSize are meaningful
         S3_CUDA(cudaMemcpyAsync(d_l + c0, readLengths + c0, cnt * 4, cudaMemcpyHostToDevice, pp.in));
         S3_CUDA(cudaEventRecord(pp.up[k], pp.in));
-        S3_CUDA(cudaStreamWaitEvent(ix->stream, pp.up[k], 0));
         uint32_t *d_sub[S3_MAX_NUM_CASES];
         for (uint32_t c = 0; c < numCases; ++c) d_sub[c] = d_ans[c] + c0 * wordPerAns;
-        if ((rc = s3_search_round1_device(ix, d_q + c0 * wordPerQuery, d_l + c0, cnt, wordPerQuery, numMismatch, numCases,
-                                          saRangeAllowed, wordPerAns, isExactNumMismatch, d_sub, NULL))) return rc;
-        S3_CUDA(cudaEventRecord(pp.done[k], ix->stream));
+        // odd chunks on the side stream: the end of one chunk's search runs under the start of the next
+        const bool side = (k & 1) && useSide;
+        if (side) side_swap(ix);
+        cudaError_t e = cudaStreamWaitEvent(ix->stream, pp.up[k], 0);
+        rc = (e == cudaSuccess) ? round1_here(ix, d_q + c0 * wordPerQuery, d_l + c0, cnt, wordPerQuery, numMismatch, numCases,
+                                              saRangeAllowed, wordPerAns, isExactNumMismatch, d_sub, NULL) : S3_OK;
+        if (e == cudaSuccess && rc == S3_OK) e = cudaEventRecord(pp.done[k], ix->stream);
+        if (side) side_swap(ix);
+        if (rc) return rc;
+        S3_CUDA(e);
         S3_CUDA(cudaStreamWaitEvent(pp.out, pp.done[k], 0));
         for (uint32_t c = 0; c < numCases; ++c)
             S3_CUDA(cudaMemcpyAsync(answers[c] + c0 * wordPerAns, d_sub[c], cntUp * wordPerAns * 4, cudaMemcpyDeviceToHost, pp.out));
     }
     S3_CUDA(cudaStreamSynchronize(pp.out));
     S3_CUDA(cudaStreamSynchronize(ix->stream));
+    if (useSide) S3_CUDA(cudaStreamSynchronize(ix->side.stream));
     return S3_OK;
 }
 

@@ -252,3 +252,37 @@ def test_locate_is_the_suffix_array_gather(env, request):
                 assert int((g[int(p):int(p) + L] != rd).sum()) == ((int(info[e]) >> 1) & 7) <= 1
                 checked += 1
     assert checked > nr // 2
+
+
+def test_two_halves_side_by_side_give_the_same_slots(env, monkeypatch):
+    """Large batches are searched as two halves on two streams (device entry point) and the host entry point puts
+    every other chunk on the side stream; forced here at test size.  Slots must stay the oracle's."""
+    G, idx, hi, gi = env
+    olib = load_oracle()
+    n, L, k = 4099, 100, 2
+    rs = synth.simulate_single_end(G, n, L, seed=907, sub_rate=0.015)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    lens[3:n:11] = L - 5
+    wpq = formats.word_per_query(L)
+    q = formats.pack_queries(rs.reads.numpy(), lens[:n], wpq)
+    allowed = formats.SA_RANGES_ROUND1[k]
+    wpa, ncases = 2 * allowed, formats.NUM_CASES[k]
+    want = _oracle_round1(olib, hi, q, lens, n, wpq, k, allowed, wpa, ncases)
+    # host entry point, two chunks
+    monkeypatch.setenv("S3_HOST_CHUNKS", "2")
+    got = api.perform_round1_alignment(gi, q, lens, n, wpq, k)
+    for c in range(ncases):
+        assert np.array_equal(formats.answers_view(got[c], n, wpa), formats.answers_view(want[c], n, wpa)), f"host chunks, case {c}"
+    # device entry point, two halves
+    monkeypatch.setenv("S3_SIDE_MIN_READS", "64")
+    dq = torch.from_numpy(q.view(np.int32)).cuda()
+    dl = torch.from_numpy(lens.view(np.int32)).cuda()
+    da = [torch.empty(formats.ceil32(n) * wpa, dtype=torch.int32, device="cuda") for _ in range(ncases)]
+    torch.cuda.synchronize()
+    for _ in range(2):                                                    # twice: the side context is reused
+        api.search_round1_device(gi, dq.data_ptr(), dl.data_ptr(), n, wpq, k, ncases, allowed, wpa, [a.data_ptr() for a in da])
+    torch.cuda.ExternalStream(gi.stream).synchronize()
+    for c in range(ncases):
+        gv = formats.answers_view(da[c].cpu().numpy().view(np.uint32), n, wpa)
+        assert np.array_equal(gv, formats.answers_view(want[c], n, wpa)), f"device halves, case {c}"

@@ -332,12 +332,17 @@ __device__ __forceinline__ uint32_t s3_dp_slot(uint32_t t, uint32_t tLast) { ret
 // Word offset of lane t's R words of step s in a pair's H plane ([step][lane slot][row]: the LANES x R words of
 // a step are contiguous, and every lane writes and reads whole 32-byte sectors), and the distance between two
 // steps of a lane.  (A [lane][step][row] order was measured too: same kernel times, profiles/r01u.)
+#ifndef S3_DP_STEP_BLOCK
+#define S3_DP_STEP_BLOCK 1           // steps of a lane that sit next to each other in the plane (1, 2 or 4)
+#endif
+// [step block][lane slot][step in block][row]: with a block of 4 a lane's sectors of four consecutive steps are one
+// 128-byte line -- the traceback's diagonal neighbour is mostly in the line it just read, the best-cell scan reads
+// whole lines -- while the lanes of a group still write into one contiguous region per block of steps.
 template <int R, int LANES>
 __device__ __forceinline__ size_t s3_dp_cell(uint32_t t, uint32_t s, uint32_t tLast)
 {
-    return ((size_t)s * LANES + s3_dp_slot<LANES>(t, tLast)) * R;
+    return ((((size_t)(s / S3_DP_STEP_BLOCK) * LANES + s3_dp_slot<LANES>(t, tLast)) * S3_DP_STEP_BLOCK) + s % S3_DP_STEP_BLOCK) * R;
 }
-#define S3_DP_STEP_STRIDE(R, LANES) ((size_t)(LANES) * (R))
 
 // Best cells of the two alignments of a pair (DV-DPfunctions.cu:225-235) found AFTER the sweep, from
 // the pair's H plane: per alignment the highest H over the rows i >= m - clipRt and the columns
@@ -504,8 +509,9 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
             const int src = __ffs(need) - 1;
             need &= need - 1;
             const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-            // column c of the requester's row is rowBase[c * S3_DP_STEP_STRIDE]
-            const unsigned long long rowBase = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(size_t)(plane + s3_dp_cell<R, LANES>(t, t, tLast) + r), src);
+            // the requester's plane, lane and row: column c of its row is at s3_dp_cell(lane, c + lane) + row
+            const unsigned long long rowBase = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(size_t)(plane + r), src);
+            const uint32_t tt = __shfl_sync(0xFFFFFFFFu, t, src), tl = __shfl_sync(0xFFFFFFFFu, tLast, src);
             const uint32_t jj = __shfl_sync(0xFFFFFFFFu, j, src), hf = __shfl_sync(0xFFFFFFFFu, half, src);
             const int h0 = __shfl_sync(0xFFFFFFFFu, (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext, src);
             const uint32_t *row = reinterpret_cast<const uint32_t *>((size_t)rowBase);
@@ -515,7 +521,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
                 if (jj >= 2) e = max(e, open + s3_clamp(h0) + (int)(jj - 2) * ext);
             }
             for (uint32_t c = 1 + lane; c + 2 <= jj; c += 32) {
-                const uint32_t w = row[(size_t)c * S3_DP_STEP_STRIDE(R, LANES)] ^ S3_BIAS2;
+                const uint32_t w = row[s3_dp_cell<R, LANES>(tt, c + tt, tl)] ^ S3_BIAS2;
                 e = max(e, open + s3_clamp(hf ? s3_hi16(w) : s3_lo16(w)) + (int)(jj - 2 - c) * ext);
             }
             for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, o));
@@ -697,7 +703,7 @@ s3_dp_score16_kernel(const S3DpArgs a)
     uint32_t clipIO[R], clipPIO[R];                              // soft-clip restart operands of the current column
     uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPIO were built from
     uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
-    uint32_t *hrow = plane + s3_dp_cell<R, LANES>((uint32_t)t, 0u, mMax ? (mMax - 1) / R : 0u);
+    const uint32_t tLastW = mMax ? (mMax - 1) / R : 0u;
     const bool laneHasRows = i0 <= mMax && pairValid;
 
     uint32_t steps = nMax + LANES - 1;
@@ -741,7 +747,7 @@ s3_dp_score16_kernel(const S3DpArgs a)
             upOOut = upO; FOut = F; diagOOut = diagO;
             prevInit = init;
             // anti-diagonal major: the group's LANES x R words of one step are contiguous
-            uint32_t *hdst = hrow + (size_t)s * S3_DP_STEP_STRIDE(R, LANES);
+            uint32_t *hdst = plane + s3_dp_cell<R, LANES>((uint32_t)t, s, tLastW);
             if (R == 8) {
                 // one 256-bit store = the lane's whole 32-byte sector (two 128-bit stores would each write half of it)
                 asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(hdst), "r"(out[0]), "r"(out[1]), "r"(out[2]),
@@ -871,7 +877,7 @@ extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint3
     // traceback planes are sized per chunk of alignments; narrow: per PAIR (maxDNALength+lanes) steps x lanes x
     // R words of H, i.e. per alignment half of that
     const size_t perAlign = dp->narrow
-        ? (size_t)(maxDNALength + dp->lanes) * dp->lanes * 4 * dp->R / 2
+        ? (size_t)((maxDNALength + dp->lanes + S3_DP_STEP_BLOCK) / S3_DP_STEP_BLOCK * S3_DP_STEP_BLOCK) * dp->lanes * 4 * dp->R / 2
         : (size_t)(maxDNALength + 1) * 32 * dp->slot;
     size_t freeB = 0, totalB = 0;
     S3_CUDA(cudaMemGetInfo(&freeB, &totalB));
@@ -957,7 +963,8 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t begin, uint32_t end)
     a.match = dp->sc.matchScore; a.mismatch = dp->sc.mismatchScore; a.open = dp->sc.gapOpenScore; a.ext = dp->sc.gapExtendScore;
     size_t smem = 0;
     if (dp->narrow) {
-        a.planeSteps = dp->maxDNALength + dp->lanes; a.hplane = reinterpret_cast<uint32_t *>(dp->d_tb);
+        a.planeSteps = (dp->maxDNALength + dp->lanes + S3_DP_STEP_BLOCK) / S3_DP_STEP_BLOCK * S3_DP_STEP_BLOCK;     // steps 0 .. maxDNALength + lanes - 1, whole blocks
+        a.hplane = reinterpret_cast<uint32_t *>(dp->d_tb);
         const int gapInit = dp->sc.gapOpenScore - dp->sc.gapExtendScore;
         auto k32 = [](int v) { return (uint32_t)((long long)v * 0x10001ll); };        // v in both halves of one 32-bit addend
         auto bpk = [](int v) { return (uint32_t)(v + 32768) * 0x10001u; };

@@ -279,7 +279,21 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
     else:
         dp_out = helpers.oracle_dp(helpers.load_oracle_dp(), dpb, DP_SCORES)
     t_dp = time.perf_counter() - t0
-    return {"_answers": ans, "_batch": b, "_dpb": dpb, "_dp_out": dp_out, "value": n / (t_search + t_dp), "unit": "reads/s", "cores": threads if kind == "reference" else 1,
+    # the reference's own DP kernels compiled for sm_100a, on this GPU, on the same batch: the kernel to beat
+    gpu_ref = None
+    ref_cu = helpers.load_ref_dp_cuda() if kind == "reference" else None
+    if ref_cu is not None and torch.cuda.is_available():
+        try:
+            helpers.ref_dp_cuda(ref_cu, dpb, DP_SCORES)                       # warm-up
+            out_cu, ms_cu = helpers.ref_dp_cuda(ref_cu, dpb, DP_SCORES)
+            same = helpers.compare_dp(dpb, out_cu, dp_out, "reference CUDA kernels vs reference host build")
+            gpu_ref = {"kind": "reference DP kernels (DV-DPfunctions.cu:35-512, textures -> array reads) compiled for sm_100a, "
+                               "8192 alignments per launch as SemiGlobalAligner::performAlignment",
+                       "alignments": int(dpb.n), "kernel_ms": ms_cu, "gcups": dpb.n * 400 * L / (ms_cu * 1e-3) / 1e9,
+                       "tracebacks_equal_to_host_build": int(same)}
+        except Exception as e:                       # noqa: BLE001
+            gpu_ref = {"error": str(e)[:200]}
+    return {"_answers": ans, "gpu_reference_dp": gpu_ref, "_batch": b, "_dpb": dpb, "_dp_out": dp_out, "value": n / (t_search + t_dp), "unit": "reads/s", "cores": threads if kind == "reference" else 1,
             "kind": kind,
             "sample": f"{n} reads (k<=2, 4 cases, both strands) + {m} rescue DP alignments of the bench workload; "
                       + ("reference kernel sources (DV-Kernel.cu, DV-DPfunctions.cu:35-512) compiled for the host, OpenMP over reads"
@@ -700,6 +714,10 @@ def main():
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         out["cpu_baseline"]["rank_queries_per_read"] = cb["rank_queries_per_read"]
         out["cpu_baseline"]["dp_gcups"] = cb["dp_gcups"]
+        if cb.get("gpu_reference_dp"):
+            out["dp"]["reference_cuda_kernels_on_this_gpu"] = cb["gpu_reference_dp"]
+            if cb["gpu_reference_dp"].get("gcups"):
+                out["dp"]["speedup_over_reference_cuda_kernels"] = dp_gcups / cb["gpu_reference_dp"]["gcups"]
         out["parity_at_full_size"] = parity_check(gi, cb, local_rank)
     print(json.dumps(out), flush=True)
     aligner.freeMemory()

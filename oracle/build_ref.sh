@@ -9,6 +9,7 @@
 #   libref_search.so   DV-Kernel.cu device code compiled for the host through
 #                      oracle/ref_shim/cuda_host_shim.h (bit-exact answer slots)
 #   libref_dp.so       DV-DPfunctions.cu:35-512 (DP kernels) compiled for the host
+#   libref_dp_cuda.so  the same kernels compiled for sm_100a, launched as performAlignment launches them
 #
 # Two one-line build fixes are applied to *copies* in oracle/_ref/patched/
 # (SURVEY.md §8c): 2bwt-lib/BWT.c:424 pointer comparison, and
@@ -82,6 +83,14 @@ sed -n '35,512p' "$REF/DV-DPfunctions.cu" \
 $CXX -O2 -fopenmp -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$HERE/ref_shim" \
     "$HERE/ref_shim/ref_dp_host.cpp" -o "$OUT/libref_dp.so"
 echo "[build_ref] libref_dp.so OK"
+
+# ---- the same DP kernels compiled for sm_100a: the reference's GPU kernels on the B200 ("kernel to beat") -----
+NVCC=${S3_NVCC:-/usr/local/cuda/bin/nvcc}
+if [ -x "$NVCC" ]; then
+  $NVCC -O3 -w -shared -Xcompiler -fPIC -ccbin "$CXX" -gencode arch=compute_100a,code=sm_100a -I"$OUT/patched" \
+      "$HERE/ref_shim/ref_dp_cuda.cu" -o "$OUT/libref_dp_cuda.so" -lcudart
+  echo "[build_ref] libref_dp_cuda.so OK"
+fi
 
 # ---- the reference-side shim compiles against the reference's unmodified headers --------------
 # (integration/soap3dp_b200_shim.cpp = the file a SOAP3-dp maintainer links instead of the device

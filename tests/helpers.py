@@ -159,6 +159,33 @@ def ref_dp(lib, b, scores=(1, -2, -3, -1), nthreads=0):
     return sc, hit, cnt, pat
 
 
+def load_ref_dp_cuda():
+    """the reference's DP kernels compiled for sm_100a (oracle/build_ref.sh); None when not built"""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_dp_cuda.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.ref_dp_cuda_align.restype = C.c_int
+    lib.ref_dp_cuda_align.argtypes = [U32P, U32P, C.c_uint32, C.c_uint32, U32P, U32P, C.c_uint32, I32P, I32P, U32P, U32P, U8P,
+                                      C.c_uint32, U32P, U32P, U32P, U32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                      C.POINTER(C.c_float)]
+    return lib
+
+
+def ref_dp_cuda(lib, b, scores=(1, -2, -3, -1), num_blocks=64):
+    """-> ((scores, hitLocs, counts, pattern), kernel milliseconds): the reference's kernels on the GPU, launched
+    numOfBlocks x 128 alignments at a time like SemiGlobalAligner::performAlignment (DV-DPfunctions.cu:669-725)"""
+    sc, hit, cnt, pat = b.outputs()
+    ms = C.c_float(0)
+    rc = lib.ref_dp_cuda_align(u32p(b.dna), u32p(b.dna_len), b.max_dna, b.max_dna, u32p(b.read), u32p(b.read_len), b.max_read,
+                               b.cutoff.ctypes.data_as(I32P), sc.ctypes.data_as(I32P), u32p(hit), u32p(cnt),
+                               pat.ctypes.data_as(U8P), b.n, _opt(b.clip_lt), _opt(b.clip_rt), _opt(b.anchor_l),
+                               _opt(b.anchor_r), *scores, num_blocks, C.byref(ms))
+    if rc != 0:
+        raise RuntimeError("ref_dp_cuda_align failed")
+    return (sc, hit, cnt, pat), float(ms.value)
+
+
 def pattern_end(w):
     """index of the 0 terminator; a count byte after 'V' may legitimately be 0"""
     i = 0

@@ -151,3 +151,22 @@ def test_windows_packed_on_the_device_give_the_same_alignments(L):
                                      padded(cutoff, np.int32), n)
     al.freeMemory()
     api.GPUINDEXFree(gi)
+
+
+def test_reference_cuda_kernels_give_the_same_alignments():
+    """Second opinion: the reference's own DP kernels compiled for sm_100a (oracle/_ref/libref_dp_cuda.so, built by
+    oracle/build_ref.sh where the reference is present) run on this GPU == our kernels == the oracle."""
+    from helpers import load_ref_dp_cuda, ref_dp_cuda
+    lib = load_ref_dp_cuda()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref_dp_cuda.so not built")
+    G = synth.random_genome(300_000, seed=77)
+    for mode, L in (("rescue", 100), ("single", 100)):
+        b = make_dp_batch(G, 2000, L, mode, seed=13)
+        ref_out, ms = ref_dp_cuda(lib, b)
+        al = api.SemiGlobalAligner(b.max_read, b.max_dna, b.n)
+        ours = al.performAlignment(b.dna, b.dna_len, b.read, b.read_len, b.cutoff, b.n, b.clip_lt, b.clip_rt, b.anchor_l, b.anchor_r)
+        al.freeMemory()
+        assert compare_dp(b, ours, ref_out, f"ours vs reference CUDA kernels ({mode})") > 1000
+        assert compare_dp(b, ref_out, oracle_dp(load_oracle_dp(), b), f"reference CUDA kernels vs oracle ({mode})") > 1000
+        assert ms > 0

@@ -293,7 +293,26 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
                        "tracebacks_equal_to_host_build": int(same)}
         except Exception as e:                       # noqa: BLE001
             gpu_ref = {"error": str(e)[:200]}
-    return {"_answers": ans, "gpu_reference_dp": gpu_ref, "_batch": b, "_dpb": dpb, "_dp_out": dp_out, "value": n / (t_search + t_dp), "unit": "reads/s", "cores": threads if kind == "reference" else 1,
+    # and its search kernels, when oracle/build_ref_search_cuda.sh has been run (an hour of cicc)
+    gpu_ref_s = None
+    ref_scu = helpers.load_ref_search_cuda() if kind == "reference" else None
+    if ref_scu is not None and torch.cuda.is_available():
+        try:
+            if ref_scu.ref_search_cuda_upload(helpers.u32p(hi.bwt), helpers.u32p(hi.rbwt), len(hi.bwt), helpers.u32p(hi.occ),
+                                              helpers.u32p(hi.rocc), len(hi.occ)) != 0:
+                raise RuntimeError("index upload failed")
+            warm = min(n, 65536)
+            helpers.ref_search_cuda_round1(ref_scu, hi, q.copy(), lens, warm, b.wpq, K_MISMATCH, allowed, wpa)
+            ans_cu, ms_cu = helpers.ref_search_cuda_round1(ref_scu, hi, q.copy(), lens, n, b.wpq, K_MISMATCH, allowed, wpa)
+            ref_scu.ref_search_cuda_free()
+            equal = all(np.array_equal(formats.answers_view(x, n, wpa), formats.answers_view(y, n, wpa)) for x, y in zip(ans_cu, ans))
+            gpu_ref_s = {"kind": "reference search kernels (DV-Kernel.cu, unmodified) compiled for sm_100a, one launch per case over "
+                                 "<= 1,048,576 reads as perform_round1_alignment",
+                         "reads": int(n), "kernel_ms": ms_cu, "reads_per_s": n / (ms_cu * 1e-3),
+                         "slots_equal_to_host_build": bool(equal)}
+        except Exception as e:                       # noqa: BLE001
+            gpu_ref_s = {"error": str(e)[:200]}
+    return {"_answers": ans, "gpu_reference_dp": gpu_ref, "gpu_reference_search": gpu_ref_s, "_batch": b, "_dpb": dpb, "_dp_out": dp_out, "value": n / (t_search + t_dp), "unit": "reads/s", "cores": threads if kind == "reference" else 1,
             "kind": kind,
             "sample": f"{n} reads (k<=2, 4 cases, both strands) + {m} rescue DP alignments of the bench workload; "
                       + ("reference kernel sources (DV-Kernel.cu, DV-DPfunctions.cu:35-512) compiled for the host, OpenMP over reads"
@@ -714,6 +733,10 @@ def main():
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         out["cpu_baseline"]["rank_queries_per_read"] = cb["rank_queries_per_read"]
         out["cpu_baseline"]["dp_gcups"] = cb["dp_gcups"]
+        if cb.get("gpu_reference_search"):
+            out["search"]["reference_cuda_kernels_on_this_gpu"] = cb["gpu_reference_search"]
+            if cb["gpu_reference_search"].get("reads_per_s"):
+                out["search"]["speedup_over_reference_cuda_kernels"] = (reads_per_rank / t_search) / cb["gpu_reference_search"]["reads_per_s"]
         if cb.get("gpu_reference_dp"):
             out["dp"]["reference_cuda_kernels_on_this_gpu"] = cb["gpu_reference_dp"]
             if cb["gpu_reference_dp"].get("gcups"):

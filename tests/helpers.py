@@ -186,6 +186,42 @@ def ref_dp_cuda(lib, b, scores=(1, -2, -3, -1), num_blocks=64):
     return (sc, hit, cnt, pat), float(ms.value)
 
 
+def load_ref_search_cuda():
+    """the reference's search kernels compiled for sm_100a (oracle/build_ref_search_cuda.sh); None when not built"""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_search_cuda.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.ref_search_cuda_upload.restype = C.c_int
+    lib.ref_search_cuda_upload.argtypes = [U32P, U32P, C.c_size_t, U32P, U32P, C.c_size_t]
+    lib.ref_search_cuda_free.restype = None
+    lib.ref_search_cuda_round1.restype = C.c_int
+    lib.ref_search_cuda_round1.argtypes = [U32P, U32P, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                                           C.POINTER(C.c_void_p), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_int,
+                                           C.POINTER(C.c_float)]
+    return lib
+
+
+def ref_search_cuda_round1(lib, hi, queries, lengths, n, wpq, k, sa_allowed, wpa, max_launch=1 << 20):
+    """-> (answers per case, kernel milliseconds): perform_round1_alignment with the reference's kernels on the GPU,
+    at most 1,048,576 reads per launch (NUM_BLOCKS * THREADS_PER_BLOCK, definitions.h:75-77).  The index must have been
+    uploaded with lib.ref_search_cuda_upload."""
+    ncases = formats.NUM_CASES[k]
+    up = formats.ceil32(n)
+    answers = [np.zeros(up * wpa, np.uint32) for _ in range(ncases)]
+    total = 0.0
+    for first in range(0, n, max_launch):
+        cnt = min(max_launch, n - first)
+        ptrs = (C.c_void_p * ncases)(*[a[first * wpa:].ctypes.data for a in answers])
+        ms = C.c_float(0)
+        rc = lib.ref_search_cuda_round1(u32p(queries[first * wpq:]), u32p(lengths[first:]), cnt, wpq, hi.isa0, hi.risa0, hi.n,
+                                        ptrs, k, ncases, sa_allowed, wpa, 0, C.byref(ms))
+        if rc != 0:
+            raise RuntimeError("ref_search_cuda_round1 failed")
+        total += float(ms.value)
+    return answers, total
+
+
 def pattern_end(w):
     """index of the 0 terminator; a count byte after 'V' may legitimately be 0"""
     i = 0

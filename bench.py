@@ -306,8 +306,10 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
             ans_cu, ms_cu = helpers.ref_search_cuda_round1(ref_scu, hi, q.copy(), lens, n, b.wpq, K_MISMATCH, allowed, wpa)
             ref_scu.ref_search_cuda_free()
             equal = all(np.array_equal(formats.answers_view(x, n, wpa), formats.answers_view(y, n, wpa)) for x, y in zip(ans_cu, ans))
-            gpu_ref_s = {"kind": "reference search kernels (DV-Kernel.cu, unmodified) compiled for sm_100a, one launch per case over "
-                                 "<= 1,048,576 reads as perform_round1_alignment",
+            flags_path = os.path.join(ROOT, "oracle", "_ref", "libref_search_cuda.so.flags")
+            flags = open(flags_path).read().strip() if os.path.exists(flags_path) else "flags not recorded"
+            gpu_ref_s = {"kind": "reference search kernels (DV-Kernel.cu, unmodified) compiled for sm_100a (" + flags + "), one launch per "
+                                 "case over <= 1,048,576 reads as perform_round1_alignment",
                          "reads": int(n), "kernel_ms": ms_cu, "reads_per_s": n / (ms_cu * 1e-3),
                          "slots_equal_to_host_build": bool(equal)}
         except Exception as e:                       # noqa: BLE001

@@ -15,4 +15,5 @@ TARGET=${1:-$OUT/libref_search_cuda.so}
 time $NVCC -w -shared -Xcompiler -fPIC -ccbin /usr/bin/g++ -gencode arch=compute_100a,code=sm_100a -Xcicc $OPT -Xptxas $OPT \
     -I"$REF" "$HERE/ref_shim/ref_search_cuda.cu" -o "$TARGET.tmp" -lcudart
 mv "$TARGET.tmp" "$TARGET"
+echo "nvcc -Xcicc $OPT -Xptxas $OPT" > "$TARGET.flags"
 echo "[build_ref_search_cuda] $TARGET OK"

@@ -286,3 +286,30 @@ def test_two_halves_side_by_side_give_the_same_slots(env, monkeypatch):
     for c in range(ncases):
         gv = formats.answers_view(da[c].cpu().numpy().view(np.uint32), n, wpa)
         assert np.array_equal(gv, formats.answers_view(want[c], n, wpa)), f"device halves, case {c}"
+
+
+def test_reference_cuda_search_kernels_give_the_same_slots(env):
+    """Second opinion: the reference's own search kernels compiled for sm_100a (oracle/_ref/libref_search_cuda.so, built
+    by oracle/build_ref_search_cuda.sh where the reference is present) run on this GPU == our slots, k = 1..3."""
+    from helpers import load_ref_search_cuda, ref_search_cuda_round1, u32p
+    lib = load_ref_search_cuda()
+    if lib is None:
+        pytest.skip("oracle/_ref/libref_search_cuda.so not built")
+    G, idx, hi, gi = env
+    assert lib.ref_search_cuda_upload(u32p(hi.bwt), u32p(hi.rbwt), len(hi.bwt), u32p(hi.occ), u32p(hi.rocc), len(hi.occ)) == 0
+    try:
+        n, L = 3000, 100
+        for k in (1, 2, 3):
+            rs = synth.simulate_single_end(G, n, L, seed=600 + k, sub_rate=0.015)
+            lens = np.zeros(formats.ceil32(n), np.uint32)
+            lens[:n] = L
+            wpq = formats.word_per_query(L)
+            q = formats.pack_queries(rs.reads.numpy(), lens[:n], wpq)
+            allowed = formats.SA_RANGES_ROUND1[k]
+            wpa = 2 * allowed
+            ref, ms = ref_search_cuda_round1(lib, hi, q.copy(), lens, n, wpq, k, allowed, wpa)
+            got = api.perform_round1_alignment(gi, q, lens, n, wpq, k)
+            for c in range(formats.NUM_CASES[k]):
+                assert np.array_equal(formats.answers_view(got[c], n, wpa), formats.answers_view(ref[c], n, wpa)), (k, c)
+    finally:
+        lib.ref_search_cuda_free()

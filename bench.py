@@ -687,6 +687,12 @@ def main():
                            "answer most of them without touching the index, so frac can exceed 1 -- `traffic` is what the "
                            "kernels really move",
                    "ms_per_launch": 1e3 * t_search / K, "share_of_step": t_search / (t_search + t_dp)}
+    if traffic.get("search_launch"):
+        # what the launch really moves, against what independent random 32-byte reads reach on this GPU
+        # (tools/random_sector_bw.cu, profiles/r01_random_sector_bw.txt: 47.5 G sectors/s = 3.04 TB/s of 64-byte DRAM bursts)
+        search_roof["executed_gbs"] = traffic["search_launch"] / (t_search / K) / 1e9
+        search_roof["random_burst_peak_gbs"] = 3040.0
+        search_roof["executed_frac_of_random_burst_peak"] = search_roof["executed_gbs"] / 3040.0
     score_roof = {"kernel": "s3_dp_score16_kernel", "bound": "hbm", "achieved": score_gbs, "peak": hbm_peak, "unit": "GB/s",
                   "frac": score_gbs / hbm_peak, "traffic": traffic.get("s3_dp_score16_kernel"), "peak_source": peak_src,
                   "cells_per_launch": dp_cells / K, "bytes_per_cell": 2,

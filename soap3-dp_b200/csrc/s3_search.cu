@@ -113,7 +113,9 @@ struct S3SearchArgs {
     uint32_t textLength;
     uint32_t *workCounter;               // zeroed before the launch
     const uint32_t *itemList;            // NULL: every item; else item ids (case * numQueries + read) ...
-    const uint32_t *itemCount;           // ... and how many (device memory, written by the easy kernel)
+    const uint32_t *itemCount;           // ... and how many (device memory, written by the easy kernel): [1] taken from the front
+                                         // of the list (first phase left a wide interval: likely long), [2] from its back
+    uint32_t itemCap;                    // entries the list has room for
     unsigned long long *rankQueries;     // may be NULL
     uint32_t *itemStats;                 // S3_ITEM_STATS builds only: LF-mapping steps spent per item
     S3Heavy heavy;
@@ -284,6 +286,9 @@ __device__ __forceinline__ uint32_t s3_pack_program(const S3SearchArgs &args, ui
     return nph;
 }
 
+#ifndef S3_WIDE_MIN
+#define S3_WIDE_MIN 16         // suffixes left after the easy kernel's walk from which an item counts as likely long
+#endif
 #ifndef S3_EASY_STEPS
 #define S3_EASY_STEPS 16       // LF-mapping steps the easy kernel spends on a pass after its seed lookup
 #endif
@@ -316,6 +321,7 @@ s3_search_easy_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, con
     bool hard = nph == 0 || plen < K || ((prog[0] >> 23) & 63u) != 0;            // phase 0 must be exact and seedable
     uint32_t strand = args.round > 0 ? 0u : (whichCase & 1u);
     uint32_t repRow[2], repMeta[2], nrep = 0;
+    bool wide = false;
     for (int pass = 0; pass < 2 && !hard; ++pass, strand ^= 1u) {
         const uint32_t *sr = strand ? sm1 : sm0;
         uint32_t key = 0, rkey = 0;
@@ -349,13 +355,19 @@ s3_search_easy_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, con
             alive = xlo <= xhi;
         }
         if (!alive) continue;
-        if (xlo != xhi) { hard = true; break; }                                  // still several suffixes: enumerate
+        if (xlo != xhi) { hard = true; wide = xhi - xlo >= S3_WIDE_MIN; break; }    // still several suffixes: enumerate
         uint32_t row, mm;
         if (s3_check_extend(loc, sr, L, args.textLength, prog, nph, 0, pdir, done, 0, 0, pdir ? ylo : xlo, row, mm)) {
             repRow[nrep] = row; repMeta[nrep] = (strand << 27) + (mm << 24); ++nrep;
         }
     }
-    if (hard) { hardItems[atomicAdd(hardCount, 1u)] = item; return; }
+    if (hard) {
+        // The enumerating kernel ends with its longest items: those whose first phase is still spread over many
+        // suffixes (repeats) tend to be them, so they go to the front of the list and start first.
+        if (wide) hardItems[atomicAdd(hardCount + 1, 1u)] = item;
+        else hardItems[args.itemCap - 1u - atomicAdd(hardCount + 2, 1u)] = item;
+        return;
+    }
     // answer slot (DV-Kernel.cu:355-380,4468-4491); the buffer was filled with 0xFF before the launch
     uint32_t *answer = args.answers[whichCase] + (size_t)(q >> 5) * 32 * args.wordPerAnswer + (q & 31);
     uint32_t saCount = 0;
@@ -416,7 +428,7 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
     uint32_t *queueHead;
     if (MODE == S3_MODE_ITEMS) {
         // all (read, case) items, or the list the easy kernel left behind
-        totalItems = args.itemList ? *args.itemCount : args.numQueries * args.numCases;
+        totalItems = args.itemList ? args.itemCount[1] + args.itemCount[2] : args.numQueries * args.numCases;
         queueHead = args.workCounter;
     } else if (MODE == S3_MODE_SPINE) {
         totalItems = 2 * min(hv.counters[S3_HV_ITEMS], hv.cap);
@@ -555,7 +567,14 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
                 if (item >= totalItems || item < base) dead = true;
                 else {
                     uint32_t it;                                         // (read, case) of this piece of work
-                    if (MODE == S3_MODE_ITEMS) { it = args.itemList ? args.itemList[item] : item; curItem = it; budget = hv.budget; }
+                    if (MODE == S3_MODE_ITEMS) {
+                        it = item;
+                        if (args.itemList) {                             // front of the list first, then its back
+                            const uint32_t nFront = args.itemCount[1];
+                            it = item < nFront ? args.itemList[item] : args.itemList[args.itemCap - 1u - (item - nFront)];
+                        }
+                        curItem = it; budget = hv.budget;
+                    }
                     else if (MODE == S3_MODE_SPINE) { curItem = item; it = hv.items[item >> 1]; }
                     else { curItem = hv.queue[item]; it = hv.items[(curItem / hv.maxTasks) >> 1]; }
 #ifdef S3_ITEM_STATS
@@ -832,6 +851,7 @@ static int launch_search(s3_index *ix, S3SearchArgs &a, uint32_t numCases, bool 
         }
         const size_t smemEasy = (size_t)2 * a.wordPerQuery * S3_THREADS * sizeof(uint32_t);
         if (smemEasy > 48 * 1024) S3_CUDA(cudaFuncSetAttribute(s3_search_easy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smemEasy));
+        a.itemCap = (uint32_t)ix->hardCap;
         s3_timing_mark(&ix->timing, ix->stream, -1);
         s3_search_easy_kernel<<<(unsigned)((items + S3_THREADS - 1) / S3_THREADS), S3_THREADS, smemEasy, ix->stream>>>(
             ix->fwd, ix->rev, ix->seed, ix->loc, a, ix->d_hardItems, ix->d_workCounter + 1);
@@ -870,7 +890,9 @@ extern "C" int s3_debug_item_stats(s3_index *ix, uint32_t *out, uint64_t n, uint
     S3_CUDA(cudaStreamSynchronize(ix->stream));
     if (n > ix->itemStatsCap) n = ix->itemStatsCap;
     S3_CUDA(cudaMemcpy(out, ix->d_itemStats, n * sizeof(uint32_t), cudaMemcpyDeviceToHost));
-    S3_CUDA(cudaMemcpy(hardCount, ix->d_workCounter + 1, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    uint32_t hc[2] = {0, 0};
+    S3_CUDA(cudaMemcpy(hc, ix->d_workCounter + 2, sizeof hc, cudaMemcpyDeviceToHost));
+    *hardCount = hc[0] + hc[1];
     return S3_OK;
 }
 #endif

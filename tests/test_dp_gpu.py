@@ -170,3 +170,23 @@ def test_reference_cuda_kernels_give_the_same_alignments():
         assert compare_dp(b, ours, ref_out, f"ours vs reference CUDA kernels ({mode})") > 1000
         assert compare_dp(b, ref_out, oracle_dp(load_oracle_dp(), b), f"reference CUDA kernels vs oracle ({mode})") > 1000
         assert ms > 0
+
+
+@pytest.mark.parametrize("mode,L,scores", [("single", 100, (1, -4, -3, -1)),      # mismatch below gap open: not the 16x2 tables
+                                           ("rescue", 100, (1, -4, -3, -1)),
+                                           ("single", 300, (1, -2, -3, -1)),      # reads above 256 bases
+                                           ("rescue", 100, (1, -2, -3, 0))])      # free extension
+def test_dp_32bit_path_bit_exact(genome, mode, L, scores):
+    """Score parameters or read lengths outside what 16-bit lanes hold take the 32-bit kernels (one alignment per warp,
+    byte-plane traceback); same oracle."""
+    olib = load_oracle_dp()
+    b = make_dp_batch(genome, 700, L, mode, seed=3 * L + len(mode), indel_rate=0.006)
+    npass = compare_dp(b, _run(b, scores), oracle_dp(olib, b, scores), f"32-bit path {mode} L={L} {scores}")
+    assert npass > 300
+
+
+def test_dp_forced_32bit_path(genome, monkeypatch):
+    monkeypatch.setenv("S3_DP_FORCE_WIDE", "1")
+    olib = load_oracle_dp()
+    b = make_dp_batch(genome, 600, 100, "rescue", seed=44, indel_rate=0.006)
+    assert compare_dp(b, _run(b), oracle_dp(olib, b), "forced 32-bit path") > 400

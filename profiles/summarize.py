@@ -97,11 +97,12 @@ def main():
             a = agg.setdefault(short(k), [0, 0.0])
             a[0] += 1
             a[1] += ns
-        tot = sum(v[1] for k, v in agg.items() if "relayout" not in k)
+        upload = ("relayout", "seed_build", "s3_isa_kernel", "search_kernel<1")      # index upload and the rank-count pass
+        tot = sum(v[1] for k, v in agg.items() if not any(u in k for u in upload))
         md += ["## launch list (`ncu --metrics gpu__time_duration.sum`, bench.py --steps 2 --warmup 1)", "",
-               "| kernel | launches | avg ms | share of step (index re-layout excluded) |", "|---|---|---|---|"]
+               "| kernel | launches | avg ms | share of the steps' kernel time (index upload and the rank-count pass excluded) |", "|---|---|---|---|"]
         for k, (n, ns) in agg.items():
-            sh = "-" if "relayout" in k else f"{100 * ns / tot:.1f} %"
+            sh = "-" if any(u in k for u in upload) else f"{100 * ns / tot:.1f} %"
             md.append(f"| `{k}` | {n} | {ns / n / 1e6:.3f} | {sh} |")
         md.append("")
     def gbytes(d):

@@ -51,6 +51,32 @@ def log(*a):
 # ---------------------------------------------------------------------------
 # index (built on the GPU with torch, cached on local disk in the reference's array format)
 # ---------------------------------------------------------------------------
+def bind_to_gpu_numa_node(dev_index):
+    """One process per GPU: run (and first-touch the pinned host buffers) on the CPUs of the NUMA node the GPU hangs off,
+    so that the e2e copies of N ranks do not cross the socket interconnect.  Best effort; returns the node or None."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        bdf = pynvml.nvmlDeviceGetPciInfo(pynvml.nvmlDeviceGetHandleByIndex(dev_index)).busId
+        bdf = (bdf.decode() if isinstance(bdf, bytes) else bdf).lower()
+        if len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]                                # 00000000:1b:00.0 -> 0000:1b:00.0
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return node
+    except Exception:                                    # noqa: BLE001
+        pass
+    return None
+
+
 def cache_dir():
     d = os.environ.get("S3_CACHE", "/tmp/s3_bench_cache")
     os.makedirs(d, exist_ok=True)
@@ -375,6 +401,7 @@ def main():
         raise SystemExit("bench.py: no CUDA device; soap3dp_b200 has no CPU fallback")
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
+    numa = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if args.impl == "reference" and rank != 0:
         return
     if world > 1 and args.impl == "ours":
@@ -710,7 +737,8 @@ def main():
                              "one after the other on one stream",
                    "l2": "inputs larger than L2: 56 GB of index (buckets, seed tables, suffix array, text) touched at random, "
                          "32 MiB of queries and 128 MiB of answer slots per step, a different read batch every step",
-                   "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"},
+                   "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"
+                                  + (f"; rank 0 bound to the CPUs of NUMA node {numa}" if numa is not None else "")},
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * t_e2e / args.steps,

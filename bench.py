@@ -213,6 +213,11 @@ def build_rescue_batch(genome, b, answers, wpa, max_read, max_dna):
     d.cnt = torch.zeros(up, dtype=torch.int32, device=dev)
     d.pattern = torch.zeros(up * (max_read + max_dna), dtype=torch.uint8, device=dev)
     d.cells = M * wlen * L
+    # the same batch as the caller of s3_dp_align_windows names it: read ids, strands (2 = reverse-complemented), window starts
+    d.read_ids = full(target.to(torch.int32))
+    d.strand_code = torch.zeros(up, dtype=torch.uint8, device=dev)
+    d.strand_code[:M] = torch.where(left, 2, 1).to(torch.uint8)
+    d.start = full(start.to(torch.int32))
     return d
 
 
@@ -674,6 +679,68 @@ def main():
         d2h += hs.m * (12 + max_read + max_dna)
     e2e_value = world * reads_per_rank / t_e2e
 
+    # ---- the next rows of the scope table at bench size (rank 0, N = 1): locate and device-side DP packing ------
+    extras = {}
+    if rank == 0 and world == 1:
+        try:
+            hs, r, b = e2e_sets[-1], rescue[args.warmup + args.steps - 1], batches[args.warmup + args.steps - 1]
+            # SA ranges of the last step's answers -> text positions (s3_locate), host arrays in and out
+            views = [formats.answers_view(a.numpy().view(np.uint32), hs.n, wpa) for a in hs.ans]
+            sal, sar = [], []
+            for v in views:
+                for sidx in range(allowed):
+                    l, w = v[:, 2 * sidx], v[:, 2 * sidx + 1]
+                    ok = (l < 0xFFFFFFFD) & (w != 0xFFFFFFFF) if sidx == 0 else (l != 0xFFFFFFFF) & (w != 0xFFFFFFFF)
+                    ok &= v[:, 0] < 0xFFFFFFFD
+                    sal.append(l[ok])
+                    sar.append(l[ok] + (w[ok] & 0xFFFFFF))
+            sal = np.ascontiguousarray(np.concatenate(sal)).astype(np.uint32)
+            sar = np.ascontiguousarray(np.concatenate(sar)).astype(np.uint32)
+            api.locate(gi, sal, sar, 8)                                          # first call of this size: module loading
+            t0 = time.perf_counter()
+            offs, pos = api.locate(gi, sal, sar, 8)
+            t_loc = time.perf_counter() - t0
+            extras["locate"] = {"ranges": int(len(sal)), "positions": int(len(pos)), "ms": 1e3 * t_loc,
+                                "ranges_per_s": len(sal) / t_loc,
+                                "call": "s3_locate, pageable host arrays in and out, <= 8 positions per range"}
+            # the last step's rescue batch through s3_dp_align_windows (packed on the device) against s3_dp_align (packed by
+            # the caller), both with pinned host buffers
+            if r.n:
+                lib.s3_dp_align_windows.restype = C.c_int
+                lib.s3_dp_align_windows.argtypes = [C.c_void_p, C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32, U32P, U8P, U32P, U32P,
+                                                    I32P, I32P, U32P, U32P, U8P, C.c_uint32, U32P, U32P, U32P, U32P]
+                w_in = {k2: pinned(getattr(r, k2)) for k2 in ("read_ids", "strand_code", "start")}
+                w_out = {k2: torch.empty_like(v) for k2, v in hs.out.items()}
+                w_out = {k2: v.pin_memory() for k2, v in w_out.items()}
+
+                def win_call():
+                    api._check(lib.s3_dp_align_windows(aligner.handle, gi.handle, p32(hs.q), p32(hs.l), hs.n, hs.wpq, p32(w_in["read_ids"]),
+                                                       C.cast(w_in["strand_code"].data_ptr(), U8P), p32(w_in["start"]), p32(hs.r["dna_len"]),
+                                                       C.cast(hs.r["cutoff"].data_ptr(), I32P), C.cast(w_out["scores"].data_ptr(), I32P),
+                                                       p32(w_out["hit"]), p32(w_out["cnt"]), C.cast(w_out["pattern"].data_ptr(), U8P), r.n,
+                                                       p32(hs.r["clip_lt"]), p32(hs.r["clip_rt"]), p32(hs.r["anchor_l"]),
+                                                       p32(hs.r["anchor_r"])), "s3_dp_align_windows")
+                win_call()
+                t0 = time.perf_counter()
+                win_call()
+                t_win = time.perf_counter() - t0
+                e2e_dp(hs)
+                t0 = time.perf_counter()
+                e2e_dp(hs)
+                t_packed = time.perf_counter() - t0
+                same = all(torch.equal(w_out[k2][:r.n], hs.out[k2][:r.n]) for k2 in ("scores", "hit", "cnt"))
+                pl = max_read + max_dna
+                pw, pp = w_out["pattern"].view(-1, pl)[:r.n], hs.out["pattern"].view(-1, pl)[:r.n]
+                traced = hs.out["scores"][:r.n] >= hs.r["cutoff"][:r.n]
+                same_pat = bool(torch.equal(pw[traced][:, :L + 8], pp[traced][:, :L + 8]))
+                extras["dp_align_windows"] = {"alignments": int(r.n), "ms": 1e3 * t_win, "ms_s3_dp_align_same_batch": 1e3 * t_packed,
+                                              "h2d_bytes": int(hs.q.numel() * 4 + hs.n * 4 + r.n * 29),
+                                              "h2d_bytes_s3_dp_align": int(formats.ceil32(r.n) * (((max_dna + 15) >> 4) + ((max_read + 15) >> 4)) * 4 + r.n * 28),
+                                              "outputs_equal_to_s3_dp_align": bool(same and same_pat),
+                                              "call": "s3_dp_align_windows: query buffer + 29 B per alignment in, batch arrays packed on the "
+                                                      "device; pinned host buffers"}
+        except Exception as e:                           # noqa: BLE001
+            extras["error"] = str(e)[:300]
     if rank != 0:
         return
     # ---- rooflines ---------------------------------------------------------------
@@ -760,6 +827,7 @@ def main():
                "alignments_per_step": float(np.mean([rescue[args.warmup + k].n for k in range(args.steps)])),
                "cells_per_step": dp_cells / args.steps, "ms_per_step": 1e3 * t_dp / args.steps},
         "kernels": kernels,
+        "next_rows": extras,
     }
     if world == 1 and not args.no_cpu_baseline:
         frac = float(np.mean([r.n / b.pairs for r, b in zip(rescue, batches)]))

@@ -77,6 +77,16 @@ def bind_to_gpu_numa_node(dev_index):
     return None
 
 
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
 def cache_dir():
     d = os.environ.get("S3_CACHE", "/tmp/s3_bench_cache")
     os.makedirs(d, exist_ok=True)
@@ -434,7 +444,7 @@ def main():
                "dtype": "u32", "data": "synthetic",
                "config": {"workload": workload, "sample_reads_per_step": per_step},
                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": info["cores"], "kind": info["kind"],
-                                "sample": info["sample"]},
+                                "sample": info["sample"], "cpu_model": cpu_model()},
                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out), flush=True)
         return
@@ -835,6 +845,7 @@ def main():
         cb = cpu_arm(host, genome, L, args.cpu_sample, 999, frac, threads)
         log(f"cpu baseline ({cb['kind']}, {cb['cores']} threads) took {time.time() - t0:.1f}s: {cb['value']:.0f} reads/s")
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        out["cpu_baseline"]["cpu_model"] = cpu_model()
         out["cpu_baseline"]["rank_queries_per_read"] = cb["rank_queries_per_read"]
         out["cpu_baseline"]["dp_gcups"] = cb["dp_gcups"]
         if cb.get("gpu_reference_search"):

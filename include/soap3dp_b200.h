@@ -148,6 +148,24 @@ int s3_locate(s3_index *ix, const uint32_t *saL, const uint32_t *saR, uint64_t n
               uint32_t maxPerRange, uint64_t *offsets, uint32_t **positions, uint64_t *total);
 void s3_free(void *p);
 
+/* ------------------------------------------------------------------------
+ * Seed hits -> candidate positions for single-end DP seeding.  Replaces
+ * SingleEndSeedingBatch::decodePositions + singleMerge (DV-DPfunctions.cu:1101-1219): for
+ * every SA range g of a seed (strand 1 / 2 as SARecord.strand, the seed's read, its offset in
+ * the read, its length, the read's length) the estimated read start of every occurrence
+ * (SA[k] - offset, or SA[k] + seedLength + offset - readLength on strand 2, uint arithmetic),
+ * ordered by (readID, start) with ties in arrival order -- what the reference's three radix
+ * passes leave -- and thinned per read to the hits more than DPS_DIVIDE_GAP = 50 past the last
+ * one kept.  maxPerRange caps the occurrences taken from one range (0xFFFFFFFF: all, as the
+ * reference).  Needs an index uploaded with its suffix array.  The three output arrays are
+ * malloc'ed by the library (s3_free).
+ * ------------------------------------------------------------------------ */
+int s3_seed_candidates(s3_index *ix, const uint32_t *saL, const uint32_t *saR, const int32_t *strands,
+                       const uint32_t *readIDs, const uint32_t *offsets, const uint32_t *seedLengths,
+                       const uint32_t *readLengths, uint64_t numRanges, uint32_t maxPerRange,
+                       uint32_t **candReadIDs, uint32_t **candPositions, int32_t **candStrands,
+                       uint64_t *numCandidates);
+
 /* Tuning knob, answers are identical for every value.  A (read, case) enumeration that is
  * still running in its lane after `steps` LF-mapping steps is split: the substitution children
  * along the read's own path become independent tasks for other lanes and their ranges are merged

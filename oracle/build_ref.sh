@@ -10,6 +10,7 @@
 #                      oracle/ref_shim/cuda_host_shim.h (bit-exact answer slots)
 #   libref_dp.so       DV-DPfunctions.cu:35-512 (DP kernels) compiled for the host
 #   libref_dp_cuda.so  the same kernels compiled for sm_100a, launched as performAlignment launches them
+#   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
 # Two one-line build fixes are applied to *copies* in oracle/_ref/patched/
 # (SURVEY.md §8c): 2bwt-lib/BWT.c:424 pointer comparison, and
@@ -83,6 +84,15 @@ sed -n '35,512p' "$REF/DV-DPfunctions.cu" \
 $CXX -O2 -fopenmp -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$HERE/ref_shim" \
     "$HERE/ref_shim/ref_dp_host.cpp" -o "$OUT/libref_dp.so"
 echo "[build_ref] libref_dp.so OK"
+
+# ---- reference seed-hit sort + merge (single-end DP seeding) on the host ------------------------
+# radix sort macros, struct SeedPos, DPS_DIVIDE_GAP and the body of singleMerge, cut from where they lie; the method
+# becomes a free function, nothing else is edited
+{ sed -n '60,95p' "$REF/DV-DPfunctions.h"; sed -n '919,926p' "$REF/DV-DPfunctions.h"; sed -n '944p' "$REF/DV-DPfunctions.h" | sed 's/^\s*//';
+  sed -n '1101,1141p' "$REF/DV-DPfunctions.cu" | sed 's/SingleEndSeedingEngine::SingleEndSeedingBatch::singleMerge/ref_singleMerge/'; } \
+  > "$OUT/patched/seed_merge.inc"
+$CXX -O2 -fpermissive -w -fPIC -shared -I"$OUT/patched" "$HERE/ref_shim/ref_seed_host.cpp" -o "$OUT/libref_seed.so"
+echo "[build_ref] libref_seed.so OK"
 
 # ---- the same DP kernels compiled for sm_100a: the reference's GPU kernels on the B200 ("kernel to beat") -----
 NVCC=${S3_NVCC:-/usr/local/cuda/bin/nvcc}

@@ -33,7 +33,7 @@ EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
-    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows",
+    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_seed_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -230,6 +230,31 @@ def locate(gpu_index: GpuIndex, sa_l: np.ndarray, sa_r: np.ndarray, max_per_rang
         if total.value:
             lib.s3_free(pos)
     return offsets, out
+
+
+def seed_candidates(gpu_index: GpuIndex, sa_l, sa_r, strands, read_ids, offsets, seed_lengths, read_lengths,
+                    max_per_range: int = 0xFFFFFFFF):
+    """s3_seed_candidates (SingleEndSeedingBatch::decodePositions + singleMerge): -> (readIDs, positions, strands)."""
+    lib = load_library()
+    lib.s3_seed_candidates.restype = C.c_int
+    lib.s3_seed_candidates.argtypes = [C.c_void_p, U32P, U32P, I32P, U32P, U32P, U32P, U32P, C.c_uint64, C.c_uint32,
+                                       C.POINTER(U32P), C.POINTER(U32P), C.POINTER(I32P), U64P]
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    u = [np.ascontiguousarray(a, np.uint32) for a in (sa_l, sa_r, read_ids, offsets, seed_lengths, read_lengths)]
+    st = np.ascontiguousarray(strands, np.int32)
+    r, p, s, m = U32P(), U32P(), I32P(), C.c_uint64(0)
+    _check(lib.s3_seed_candidates(gpu_index.handle, _u32(u[0]), _u32(u[1]), st.ctypes.data_as(I32P), _u32(u[2]), _u32(u[3]),
+                                  _u32(u[4]), _u32(u[5]), len(st), max_per_range, C.byref(r), C.byref(p), C.byref(s), C.byref(m)),
+           "s3_seed_candidates")
+    n = int(m.value)
+    if n == 0:
+        return np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.int32)
+    try:
+        return (np.ctypeslib.as_array(r, shape=(n,)).copy(), np.ctypeslib.as_array(p, shape=(n,)).copy(),
+                np.ctypeslib.as_array(s, shape=(n,)).copy())
+    finally:
+        lib.s3_free(r); lib.s3_free(p); lib.s3_free(s)
 
 
 def set_timing(handle: int, on: bool, dp: bool = False):

@@ -99,3 +99,43 @@ def test_dp_adversarial_matches_reference_kernels():
                     rng.integers(0, W, n).astype(np.uint32))
         for scores in ((1, -2, -3, -1), (1, -1, -2, -1)):
             compare_dp(b, oracle_dp(olib, b, scores), ref_dp(dlib, b, scores), f"adv {seed}")
+
+
+def test_seed_oracle_matches_the_reference_sort_and_merge():
+    """oracle/seed_oracle.c == the reference's own radix-sort macros + singleMerge body (oracle/_ref/libref_seed.so):
+    ties, more than 255 hits (the reference's 8-bit strand pass overflows its counters and sorts into a freed array),
+    estimated starts that wrapped below zero."""
+    import ctypes as C
+    import os
+    import helpers
+    path = os.path.join(helpers.ROOT, "oracle", "_ref", "libref_seed.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_seed.so not built")
+    ref = C.CDLL(path)
+    U, I = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    ref.ref_seed_sort_merge.restype = C.c_uint32
+    ref.ref_seed_sort_merge.argtypes = [U, U, I, C.c_uint32, U, U, I]
+    olib = helpers.load_oracle()
+    olib.s3o_seed_candidates.restype = C.c_uint64
+    olib.s3o_seed_candidates.argtypes = [U, U, U, I, U, U, U, U, C.c_uint64, C.c_uint32, U, U, I, C.c_uint64]
+    rng = np.random.default_rng(12)
+    for n, nreads, span in ((5000, 40, 3000), (300, 3, 200), (1, 1, 10), (20000, 2000, 100000)):
+        # as ranges of one position each over an identity "suffix array", so that both sides see the same hits
+        sa = np.arange(span + 64, dtype=np.uint32)
+        rid = rng.integers(0, nreads, n).astype(np.uint32)
+        x = rng.integers(0, span, n).astype(np.uint32)
+        st = rng.integers(1, 3, n).astype(np.int32)
+        off = rng.integers(0, 60, n).astype(np.uint32)
+        sl = np.full(n, 28, np.uint32)
+        rl = np.full(n, 100, np.uint32)
+        est = np.where(st == 1, x - off, x + sl + off - rl).astype(np.uint32)       # wraps for small x
+        o = [np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.int32)]
+        m = ref.ref_seed_sort_merge(rid.ctypes.data_as(U), est.ctypes.data_as(U), st.ctypes.data_as(I), n,
+                                    o[0].ctypes.data_as(U), o[1].ctypes.data_as(U), o[2].ctypes.data_as(I))
+        g = [np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.int32)]
+        m2 = olib.s3o_seed_candidates(sa.ctypes.data_as(U), x.ctypes.data_as(U), x.ctypes.data_as(U), st.ctypes.data_as(I),
+                                      rid.ctypes.data_as(U), off.ctypes.data_as(U), sl.ctypes.data_as(U), rl.ctypes.data_as(U),
+                                      n, 0xFFFFFFFF, g[0].ctypes.data_as(U), g[1].ctypes.data_as(U), g[2].ctypes.data_as(I), n)
+        assert m == m2
+        for a, b in zip(o, g):
+            assert np.array_equal(a[:m], b[:m])

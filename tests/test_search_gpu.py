@@ -313,3 +313,52 @@ def test_reference_cuda_search_kernels_give_the_same_slots(env):
                 assert np.array_equal(formats.answers_view(got[c], n, wpa), formats.answers_view(ref[c], n, wpa)), (k, c)
     finally:
         lib.ref_search_cuda_free()
+
+
+def test_seed_candidates_match_the_oracle(env, request):
+    """s3_seed_candidates (positions from the suffix array in HBM, one stable radix sort, merge walk) == the oracle's
+    restatement of decodePositions + singleMerge (pinned against the reference's own sort macros and merge body in the
+    CPU tier): real seed hits of a 1-mismatch capless search, both strands, with and without a cap per range."""
+    import ctypes as C
+    G, idx, hi, gi = env
+    if "check_and_extend" not in request.node.name:
+        with pytest.raises(api.S3Error):
+            api.seed_candidates(gi, [1], [2], [1], [0], [0], [20], [100])
+        return
+    sa = idx.fwd.sa.numpy().astype(np.uint32) if hasattr(idx.fwd.sa, "numpy") else np.asarray(idx.fwd.sa, np.uint32)
+    nr, L, seed_len = 600, 100, 22
+    rs = synth.simulate_single_end(G, nr, L, seed=71, sub_rate=0.01)
+    reads = rs.reads.numpy()
+    # three seeds per read (offsets 0, 39, 78), searched exactly: the ranges a seeding round hands to decodePositions
+    offs = np.array([0, 39, 78], np.uint32)
+    seeds = np.stack([reads[:, o:o + seed_len] for o in offs], axis=1).reshape(-1, seed_len)
+    ns = len(seeds)
+    lens = np.zeros(formats.ceil32(ns), np.uint32)
+    lens[:ns] = seed_len
+    wps = formats.word_per_query(seed_len)
+    offsets, sa_l, sa_r, info = api.search(gi, formats.pack_queries(seeds, lens[:ns], wps), lens, ns, wps, 1)
+    seed_of = np.repeat(np.arange(ns), np.diff(offsets).astype(np.int64))
+    strands = ((info & 1) + 1).astype(np.int32)                           # SARecord.strand: 1 as given, 2 reverse complement
+    read_ids = (seed_of // 3).astype(np.uint32)
+    off = offs[seed_of % 3]
+    sl = np.full(len(sa_l), seed_len, np.uint32)
+    rl = np.full(len(sa_l), L, np.uint32)
+    assert len(sa_l) > nr
+    olib = load_oracle()
+    U, I = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    olib.s3o_seed_candidates.restype = C.c_uint64
+    olib.s3o_seed_candidates.argtypes = [U, U, U, I, U, U, U, U, C.c_uint64, C.c_uint32, U, U, I, C.c_uint64]
+    for cap in (0xFFFFFFFF, 3):
+        got = api.seed_candidates(gi, sa_l, sa_r, strands, read_ids, off, sl, rl, cap)
+        total = int((np.minimum(sa_r.astype(np.int64) - sa_l + 1, cap)).sum())
+        w = [np.zeros(total, np.uint32), np.zeros(total, np.uint32), np.zeros(total, np.int32)]
+        m = olib.s3o_seed_candidates(sa.ctypes.data_as(U), sa_l.ctypes.data_as(U), sa_r.ctypes.data_as(U), strands.ctypes.data_as(I),
+                                     read_ids.ctypes.data_as(U), off.ctypes.data_as(U), sl.ctypes.data_as(U), rl.ctypes.data_as(U),
+                                     len(sa_l), cap, w[0].ctypes.data_as(U), w[1].ctypes.data_as(U), w[2].ctypes.data_as(I), total)
+        assert m == len(got[0]) and m >= nr // 2
+        for a, b in zip(got, w):
+            assert np.array_equal(a, b[:m])
+        # most reads: one candidate at the read's true start (its three seeds agree)
+        true_pos = rs.pos.numpy()
+        hit = sum(1 for r, p in zip(got[0], got[1]) if abs(int(p) - int(true_pos[r])) <= 2)
+        assert hit > nr * 0.8

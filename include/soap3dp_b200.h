@@ -166,6 +166,25 @@ int s3_seed_candidates(s3_index *ix, const uint32_t *saL, const uint32_t *saR, c
                        uint32_t **candReadIDs, uint32_t **candPositions, int32_t **candStrands,
                        uint64_t *numCandidates);
 
+/* The same for paired-end DP seeding.  Replaces PairEndSeedingBatch::decodeMergePositions
+ * (DV-DPfunctions.cu:2626-2653,2780-2999): the seed ranges of the reads (arrays ...0) and of
+ * their mates (arrays ...1; readIDs hold the pair's even read id on both sides, as
+ * readIDs[readOrMate][seedID] does), estimated starts, the 50-base thinning of the left
+ * group, the insert-size join [insertLow - len - margin, insertHigh - len + margin] with
+ * margin = DP2_MARGIN(len) and len = lengthsByReadID[pair id], for read-left/mate-right and
+ * mate-left/read-right with the leg strands peStrandLeftLeg / peStrandRightLeg (1 or 2), and
+ * the final stable sort by readIDLeft (= pair id, + 1 when the mate is the left end).
+ * Output arrays are malloc'ed by the library (s3_free). */
+int s3_seed_pair_candidates(s3_index *ix,
+                            const uint32_t *saL0, const uint32_t *saR0, const int32_t *strands0, const uint32_t *readIDs0,
+                            const uint32_t *offsets0, const uint32_t *seedLengths0, const uint32_t *readLengths0, uint64_t n0,
+                            const uint32_t *saL1, const uint32_t *saR1, const int32_t *strands1, const uint32_t *readIDs1,
+                            const uint32_t *offsets1, const uint32_t *seedLengths1, const uint32_t *readLengths1, uint64_t n1,
+                            uint32_t maxPerRange, const uint32_t *lengthsByReadID, uint64_t numReadIDs,
+                            int insertLow, int insertHigh, int peStrandLeftLeg, int peStrandRightLeg,
+                            uint32_t **candReadIDLeft, uint32_t **candPosLeft, uint32_t **candPosRight,
+                            uint64_t *numCandidates);
+
 /* Tuning knob, answers are identical for every value.  A (read, case) enumeration that is
  * still running in its lane after `steps` LF-mapping steps is split: the substitution children
  * along the read's own path become independent tasks for other lanes and their ranges are merged

@@ -10,6 +10,7 @@
 #                      oracle/ref_shim/cuda_host_shim.h (bit-exact answer slots)
 #   libref_dp.so       DV-DPfunctions.cu:35-512 (DP kernels) compiled for the host
 #   libref_dp_cuda.so  the same kernels compiled for sm_100a, launched as performAlignment launches them
+#   libref_seed_pair.so  findRevStart + pairEndMerge of paired-end DP seeding (DV-DPfunctions.cu:2626-2653,2780-2880)
 #   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
 # Two one-line build fixes are applied to *copies* in oracle/_ref/patched/
@@ -93,6 +94,15 @@ echo "[build_ref] libref_dp.so OK"
   > "$OUT/patched/seed_merge.inc"
 $CXX -O2 -fpermissive -w -fPIC -shared -I"$OUT/patched" "$HERE/ref_shim/ref_seed_host.cpp" -o "$OUT/libref_seed.so"
 echo "[build_ref] libref_seed.so OK"
+
+# ---- reference paired-end seed-hit join on the host -----------------------------------------------
+{ sed -n '60,95p' "$REF/DV-DPfunctions.h"; sed -n '1382,1393p' "$REF/DV-DPfunctions.h"; sed -n '1413p' "$REF/DV-DPfunctions.h" | sed 's/^\s*//';
+  sed -n '2549p' "$REF/DV-DPfunctions.cu";
+  sed -n '2626,2653p' "$REF/DV-DPfunctions.cu" | sed 's/PairEndSeedingEngine::PairEndSeedingBatch::findRevStart/ref_findRevStart/';
+  sed -n '2780,2880p' "$REF/DV-DPfunctions.cu" | sed 's/PairEndSeedingEngine::PairEndSeedingBatch::pairEndMerge/ref_pairEndMerge/'; } \
+  > "$OUT/patched/seed_pair.inc"
+$CXX -O2 -fpermissive -w -fPIC -shared -I"$OUT/patched" "$HERE/ref_shim/ref_seed_pair_host.cpp" -o "$OUT/libref_seed_pair.so"
+echo "[build_ref] libref_seed_pair.so OK"
 
 # ---- the same DP kernels compiled for sm_100a: the reference's GPU kernels on the B200 ("kernel to beat") -----
 NVCC=${S3_NVCC:-/usr/local/cuda/bin/nvcc}

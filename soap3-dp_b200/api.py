@@ -33,7 +33,7 @@ EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
-    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_seed_candidates",
+    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -255,6 +255,36 @@ def seed_candidates(gpu_index: GpuIndex, sa_l, sa_r, strands, read_ids, offsets,
                 np.ctypeslib.as_array(s, shape=(n,)).copy())
     finally:
         lib.s3_free(r); lib.s3_free(p); lib.s3_free(s)
+
+
+def seed_pair_candidates(gpu_index: GpuIndex, side0, side1, lengths_by_read_id, insert_low: int, insert_high: int,
+                         left_leg: int = 1, right_leg: int = 2, max_per_range: int = 0xFFFFFFFF):
+    """s3_seed_pair_candidates (PairEndSeedingBatch::decodeMergePositions).  side0 / side1 = (saL, saR, strands, readIDs,
+    offsets, seedLengths, readLengths) of the reads' and the mates' seed ranges -> (readIDLeft, posLeft, posRight)."""
+    lib = load_library()
+    side_t = [U32P, U32P, I32P, U32P, U32P, U32P, U32P, C.c_uint64]
+    lib.s3_seed_pair_candidates.restype = C.c_int
+    lib.s3_seed_pair_candidates.argtypes = [C.c_void_p] + side_t + side_t + [C.c_uint32, U32P, C.c_uint64, C.c_int, C.c_int, C.c_int,
+                                                                            C.c_int, C.POINTER(U32P), C.POINTER(U32P), C.POINTER(U32P), U64P]
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    keep, args = [], []
+    for sd in (side0, side1):
+        a = [np.ascontiguousarray(sd[0], np.uint32), np.ascontiguousarray(sd[1], np.uint32), np.ascontiguousarray(sd[2], np.int32)] + \
+            [np.ascontiguousarray(x, np.uint32) for x in sd[3:7]]
+        keep.append(a)
+        args += [_u32(a[0]), _u32(a[1]), a[2].ctypes.data_as(I32P), _u32(a[3]), _u32(a[4]), _u32(a[5]), _u32(a[6]), len(a[0])]
+    lens = np.ascontiguousarray(lengths_by_read_id, np.uint32)
+    r, pl, pr, m = U32P(), U32P(), U32P(), C.c_uint64(0)
+    _check(lib.s3_seed_pair_candidates(gpu_index.handle, *args, max_per_range, _u32(lens), len(lens), insert_low, insert_high,
+                                       left_leg, right_leg, C.byref(r), C.byref(pl), C.byref(pr), C.byref(m)), "s3_seed_pair_candidates")
+    n = int(m.value)
+    if n == 0:
+        return np.zeros(0, np.uint32), np.zeros(0, np.uint32), np.zeros(0, np.uint32)
+    try:
+        return tuple(np.ctypeslib.as_array(x, shape=(n,)).copy() for x in (r, pl, pr))
+    finally:
+        lib.s3_free(r); lib.s3_free(pl); lib.s3_free(pr)
 
 
 def set_timing(handle: int, on: bool, dp: bool = False):

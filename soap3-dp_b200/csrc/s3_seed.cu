@@ -161,3 +161,316 @@ done:
     free(h_r); free(h_p); free(h_s);
     return rc;
 }
+
+// =====================================================================================================================
+// Paired-end seeding: seed hits of both ends -> candidate (left start, right start) pairs.
+// Replaces PairEndSeedingBatch::decodePositions (both ends), findRevStart, the two pairEndMerge calls and the final sort
+// of decodeMergePositions (DV-DPfunctions.cu:2626-2653,2780-2999).  Per end: key = (strandIndex << 31 | pair id) << 32
+// | estimated start, two guards, one 64-bit sort (= the reference's sort by pos, then by strand_readID).  Per call:
+// one thread per left group that has a partner group thins it IN PLACE (the reference does, and when both legs use the
+// same strand its second call joins against what the first left behind) and then walks the two-pointer join, once to
+// count and once to write; the calls' candidates, first call first, get one stable sort by readIDLeft.
+// =====================================================================================================================
+typedef unsigned long long s3_u64;
+
+__global__ void s3_pair_fill_kernel(const uint32_t *__restrict__ sa, const uint32_t *__restrict__ saL, const uint32_t *__restrict__ saR,
+                                    const int32_t *__restrict__ strands, const uint32_t *__restrict__ readIDs,
+                                    const uint32_t *__restrict__ offsets, const uint32_t *__restrict__ seedLengths,
+                                    const uint32_t *__restrict__ readLengths, uint64_t n, uint32_t maxPerRange,
+                                    const s3_u64 *__restrict__ start, s3_u64 total, s3_u64 *__restrict__ keys)
+{
+    const uint64_t g = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const uint32_t lane = threadIdx.x & 31;
+    if (g == n && lane < 2) {                                           // array guards (DV-DPfunctions.cu:2961-2962)
+        keys[total + lane] = ((s3_u64)(0x7FFFFFFFu | (lane << 31)) << 32) | 0xFFFFFFFFull;
+        return;
+    }
+    if (g >= n || saR[g] < saL[g]) return;
+    s3_u64 c = (s3_u64)(saR[g] - saL[g]) + 1;
+    if (c > maxPerRange) c = maxPerRange;
+    const uint32_t si = (uint32_t)strands[g] - 1u, off = offsets[g], add = seedLengths[g] + off - readLengths[g];
+    const s3_u64 hi = (s3_u64)(readIDs[g] | (si << 31)) << 32;
+    for (s3_u64 k = lane; k < c; k += 32) {
+        const uint32_t x = sa[(size_t)saL[g] + k];
+        keys[start[g] + k] = hi | (si == 0 ? x - off : x + add);
+    }
+}
+
+__device__ __forceinline__ uint32_t s3_pair_lower(const s3_u64 *k, uint32_t lo, uint32_t hi, uint32_t key32)
+{
+    while (lo < hi) { const uint32_t mid = lo + ((hi - lo) >> 1); if ((uint32_t)(k[mid] >> 32) < key32) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+
+// left groups with a partner: thinned in place (MC_Compress, DV-DPfunctions.cu:2826-2838); their new end and the start
+// of the partner group are noted at the group's first element
+__global__ void s3_pair_thin_kernel(s3_u64 *__restrict__ L, uint32_t lo, uint32_t hi, const s3_u64 *__restrict__ R, uint32_t rlo, uint32_t rhi,
+                                    uint32_t rightStrandBit, uint32_t *__restrict__ groupEnd, uint32_t *__restrict__ rightStart)
+{
+    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= hi) return;
+    groupEnd[i] = 0;
+    const uint32_t key32 = (uint32_t)(L[i] >> 32), id = key32 & 0x7FFFFFFFu;
+    if (id == 0x7FFFFFFFu || (i > lo && (uint32_t)(L[i - 1] >> 32) == key32)) return;
+    const uint32_t rkey = id | rightStrandBit, j = s3_pair_lower(R, rlo, rhi, rkey);
+    if (j >= rhi || (uint32_t)(R[j] >> 32) != rkey) return;
+    uint32_t c = i, prev = (uint32_t)L[i];
+    for (uint32_t p = i + 1; p < hi && (uint32_t)(L[p] >> 32) == key32; ++p) {
+        const uint32_t cur = (uint32_t)L[p];
+        if ((uint32_t)(prev + S3_DIVIDE_GAP) < cur) { L[++c] = L[p]; prev = cur; }
+    }
+    groupEnd[i] = c + 1;
+    rightStart[i] = j;
+}
+
+// the two-pointer walk of pairEndMerge (DV-DPfunctions.cu:2839-2877); FILL = false counts, true writes
+template <bool FILL>
+__global__ void s3_pair_join_kernel(const s3_u64 *__restrict__ L, uint32_t lo, uint32_t hi, const s3_u64 *__restrict__ R,
+                                    const uint32_t *__restrict__ groupEnd, const uint32_t *__restrict__ rightStart,
+                                    const uint32_t *__restrict__ lengthsByReadID, int insertLow, int insertHigh, uint32_t leftReadOrMate,
+                                    s3_u64 *__restrict__ counts, uint32_t *__restrict__ outID, uint32_t *__restrict__ outL, uint32_t *__restrict__ outR)
+{
+    const uint32_t i = lo + blockIdx.x * blockDim.x + threadIdx.x;
+    if (i > hi) return;
+    if (i == hi) { if (!FILL) counts[i - lo] = 0; return; }            // one extra slot: the scan leaves the total there
+    const uint32_t le = groupEnd[i];
+    if (le == 0) { if (!FILL) counts[i - lo] = 0; return; }
+    const uint32_t id = (uint32_t)(L[i] >> 32) & 0x7FFFFFFFu;
+    uint32_t rp = rightStart[i];
+    const uint32_t rkey = (uint32_t)(R[rp] >> 32);
+    uint32_t re = rp;
+    while ((uint32_t)(R[re] >> 32) == rkey) ++re;                       // ends at the next group or a guard
+    const int readLength = (int)lengthsByReadID[id];
+    const int margin = readLength > 100 ? (readLength >> 2) : 25;       // DP2_MARGIN, DV-DPfunctions.cu:2549
+    int lengthLow = insertLow - readLength - margin;
+    if (lengthLow < 0) lengthLow = 0;
+    const int lengthHigh = insertHigh - readLength + margin;
+    uint32_t lp = i, lloc = (uint32_t)L[lp], rloc = (uint32_t)R[rp];
+    s3_u64 n = 0;
+    const s3_u64 base = FILL ? counts[i - lo] : 0;
+    while (lp < le && rp < re) {
+        if ((uint32_t)(lloc + (uint32_t)lengthLow) > rloc) { ++rp; rloc = (uint32_t)R[rp]; }
+        else if ((uint32_t)(lloc + (uint32_t)lengthHigh) < rloc) { ++lp; lloc = (uint32_t)L[lp]; }
+        else {
+            if (FILL) { outID[base + n] = id + leftReadOrMate; outL[base + n] = lloc; outR[base + n] = rloc; }
+            ++n;
+            ++lp; lloc = (uint32_t)L[lp];
+        }
+    }
+    if (!FILL) counts[i - lo] = n;
+}
+
+__global__ void s3_pair_gather_kernel(const uint32_t *__restrict__ order, uint64_t m, const uint32_t *__restrict__ inL, const uint32_t *__restrict__ inR,
+                                      uint32_t *__restrict__ outL, uint32_t *__restrict__ outR)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    outL[i] = inL[order[i]]; outR[i] = inR[order[i]];
+}
+
+__global__ void s3_iota_kernel(uint32_t *a, uint64_t m)
+{
+    const uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < m) a[i] = (uint32_t)i;
+}
+
+struct S3PairSide { s3_u64 *keys; uint32_t len, rev; };
+
+// one end's hits: gathered, keyed, sorted; rev = first element of the reverse-strand part (findRevStart)
+static int s3_pair_side(s3_index *ix, const uint32_t *const in[7], uint64_t n, uint32_t maxPerRange, S3PairSide *out)
+{
+    int rc = S3_OK;
+    cudaStream_t st = ix->stream;
+    const size_t rB = n * 4;
+    char *d_in = NULL;
+    void *d_tmp = NULL;
+    s3_u64 *k0 = NULL, *k1 = NULL;
+    size_t t1 = 0, t2 = 0;
+    s3_u64 total = 0;
+    out->keys = NULL; out->len = out->rev = 0;
+    S3_TRY(cudaMalloc(&d_in, 7 * rB + (n + 1) * 8 + 16));
+    {
+        uint32_t *d[7];
+        for (int a = 0; a < 7; ++a) { d[a] = (uint32_t *)d_in + a * n; if (n) S3_TRY(cudaMemcpyAsync(d[a], in[a], rB, cudaMemcpyHostToDevice, st)); }
+        s3_u64 *d_cnt = (s3_u64 *)(((uintptr_t)((uint32_t *)d_in + 7 * n) + 7) & ~(uintptr_t)7);
+        s3_seed_count_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(d[0], d[1], n, maxPerRange, d_cnt);
+        S3_LAUNCHED(1);
+        cub::DeviceScan::ExclusiveSum(NULL, t1, d_cnt, d_cnt, (int)(n + 1), st);
+        S3_TRY(cudaMalloc(&d_tmp, t1));
+        S3_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, t1, d_cnt, d_cnt, (int)(n + 1), st));
+        S3_TRY(cudaMemcpyAsync(&total, d_cnt + n, 8, cudaMemcpyDeviceToHost, st));
+        S3_TRY(cudaStreamSynchronize(st));
+        cudaFree(d_tmp); d_tmp = NULL;
+        if (total + 2 >= 0x7FFFFFFFull) { s3_set_error("s3_seed_pair_candidates: %llu positions in one call", total); rc = S3_EINVAL; goto done; }
+        const size_t T = (size_t)total + 2;
+        S3_TRY(cudaMalloc(&k0, T * 8)); S3_TRY(cudaMalloc(&k1, T * 8));
+        s3_pair_fill_kernel<<<(unsigned)(((n + 1) * 32 + 255) / 256), 256, 0, st>>>(ix->loc.sa, d[0], d[1], (const int32_t *)d[2], d[3], d[4], d[5], d[6],
+                                                                                       n, maxPerRange, d_cnt, total, k0);
+        S3_LAUNCHED(1);
+        cub::DeviceRadixSort::SortKeys(NULL, t2, k0, k1, (int)T, 0, 64, st);
+        S3_TRY(cudaMalloc(&d_tmp, t2));
+        S3_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, t2, k0, k1, (int)T, 0, 64, st));
+        S3_TRY(cudaStreamSynchronize(st));
+        out->keys = k1; k1 = NULL; out->len = (uint32_t)T;
+    }
+done:
+    if (d_in) cudaFree(d_in);
+    if (d_tmp) cudaFree(d_tmp);
+    if (k0) cudaFree(k0);
+    if (k1) cudaFree(k1);
+    return rc;
+}
+
+__global__ void s3_pair_revstart_kernel(const s3_u64 *k, uint32_t len, uint32_t *out)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) *out = s3_pair_lower(k, 0, len, 0x80000000u);
+}
+
+extern "C" int s3_seed_pair_candidates(s3_index *ix,
+                                       const uint32_t *saL0, const uint32_t *saR0, const int32_t *strands0, const uint32_t *readIDs0,
+                                       const uint32_t *offsets0, const uint32_t *seedLengths0, const uint32_t *readLengths0, uint64_t n0,
+                                       const uint32_t *saL1, const uint32_t *saR1, const int32_t *strands1, const uint32_t *readIDs1,
+                                       const uint32_t *offsets1, const uint32_t *seedLengths1, const uint32_t *readLengths1, uint64_t n1,
+                                       uint32_t maxPerRange, const uint32_t *lengthsByReadID, uint64_t numReadIDs,
+                                       int insertLow, int insertHigh, int peStrandLeftLeg, int peStrandRightLeg,
+                                       uint32_t **candReadIDLeft, uint32_t **candPosLeft, uint32_t **candPosRight, uint64_t *numCandidates)
+{
+    if (!ix || !candReadIDLeft || !candPosLeft || !candPosRight || !numCandidates || !lengthsByReadID ||
+        (n0 && (!saL0 || !saR0 || !strands0 || !readIDs0 || !offsets0 || !seedLengths0 || !readLengths0)) ||
+        (n1 && (!saL1 || !saR1 || !strands1 || !readIDs1 || !offsets1 || !seedLengths1 || !readLengths1))) {
+        s3_set_error("s3_seed_pair_candidates: NULL argument"); return S3_EINVAL;
+    }
+    if (!ix->loc.sa) { s3_set_error("s3_seed_pair_candidates: the index was uploaded without its suffix array"); return S3_EINVAL; }
+    if (peStrandLeftLeg < 1 || peStrandLeftLeg > 2 || peStrandRightLeg < 1 || peStrandRightLeg > 2 || maxPerRange == 0 ||
+        n0 >= 0x7FFFFFF0ull || n1 >= 0x7FFFFFF0ull) { s3_set_error("s3_seed_pair_candidates: argument out of range"); return S3_EINVAL; }
+    for (uint64_t g = 0; g < n0; ++g) if (readIDs0[g] >= numReadIDs) { s3_set_error("s3_seed_pair_candidates: read id %u out of range", readIDs0[g]); return S3_EINVAL; }
+    for (uint64_t g = 0; g < n1; ++g) if (readIDs1[g] >= numReadIDs) { s3_set_error("s3_seed_pair_candidates: read id %u out of range", readIDs1[g]); return S3_EINVAL; }
+    *candReadIDLeft = *candPosLeft = *candPosRight = NULL; *numCandidates = 0;
+    if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_seed_pair_candidates: cudaSetDevice failed"); return S3_ECUDA; }
+    int rc = S3_OK;
+    cudaStream_t st = ix->stream;
+    S3PairSide side[2] = {{NULL, 0, 0}, {NULL, 0, 0}};
+    uint32_t *d_len = NULL, *d_aux = NULL, *d_out = NULL, *d_sorted = NULL;
+    s3_u64 *d_counts = NULL;
+    void *d_tmp = NULL;
+    uint32_t *h[3] = {NULL, NULL, NULL};
+    s3_u64 tot[2] = {0, 0};
+    const uint32_t *const in0[7] = {saL0, saR0, (const uint32_t *)strands0, readIDs0, offsets0, seedLengths0, readLengths0};
+    const uint32_t *const in1[7] = {saL1, saR1, (const uint32_t *)strands1, readIDs1, offsets1, seedLengths1, readLengths1};
+    if ((rc = s3_pair_side(ix, in0, n0, maxPerRange, &side[0]))) goto done;
+    if ((rc = s3_pair_side(ix, in1, n1, maxPerRange, &side[1]))) goto done;
+    {
+        S3_TRY(cudaMalloc(&d_len, numReadIDs * 4 + 16));
+        S3_TRY(cudaMemcpyAsync(d_len, lengthsByReadID, numReadIDs * 4, cudaMemcpyHostToDevice, st));
+        uint32_t *d_rev = d_len + numReadIDs;
+        for (int s = 0; s < 2; ++s) s3_pair_revstart_kernel<<<1, 1, 0, st>>>(side[s].keys, side[s].len, d_rev + s);
+        uint32_t rev[2];
+        S3_TRY(cudaMemcpyAsync(rev, d_rev, 8, cudaMemcpyDeviceToHost, st));
+        S3_TRY(cudaStreamSynchronize(st));
+        side[0].rev = rev[0]; side[1].rev = rev[1];
+        const uint32_t maxLen = side[0].len > side[1].len ? side[0].len : side[1].len;
+        S3_TRY(cudaMalloc(&d_counts, ((size_t)maxLen + 1) * 8));                   // only to size the scan's temporary storage
+        size_t tScan = 0;
+        cub::DeviceScan::ExclusiveSum(NULL, tScan, d_counts, d_counts, (int)(maxLen + 1), st);
+        S3_TRY(cudaMalloc(&d_tmp, tScan));
+        // segment of an end's array that holds strand index si: [0, rev) or [rev, len)
+        auto seg = [&](int s, int si, uint32_t &lo, uint32_t &hi) { lo = si ? side[s].rev : 0u; hi = si ? side[s].len : side[s].rev; };
+        // the two calls (DV-DPfunctions.cu:2987-2988): read left / mate right, then mate left / read right.  Counting of
+        // call 1 must see the arrays as call 0's thinning left them, so: thin + count, call after call, then fill.
+        uint32_t lo[2], hi[2], rlo[2], rhi[2];
+        uint32_t *groupEnd[2], *rightStart[2];
+        s3_u64 *counts[2] = {NULL, NULL};
+        uint32_t *ge_all = NULL;
+        S3_TRY(cudaMalloc(&ge_all, ((size_t)side[0].len + side[1].len) * 8 + 16));
+        groupEnd[0] = ge_all; rightStart[0] = ge_all + side[0].len;
+        groupEnd[1] = ge_all + 2 * (size_t)side[0].len; rightStart[1] = groupEnd[1] + side[1].len;
+        s3_u64 *cnt_all = NULL;
+        cudaError_t e2 = cudaMalloc(&cnt_all, ((size_t)side[0].len + side[1].len + 2) * 8);
+        if (e2 != cudaSuccess) { cudaFree(ge_all); s3_set_error("s3_seed_pair_candidates: %s", cudaGetErrorString(e2)); rc = S3_ECUDA; goto done; }
+        counts[0] = cnt_all; counts[1] = cnt_all + side[0].len + 1;
+        bool ok = true;
+        for (int call = 0; call < 2 && ok; ++call) {
+            const int ls = call, rs = 1 - call;                                    // which end is on the left
+            seg(ls, peStrandLeftLeg - 1, lo[call], hi[call]);
+            seg(rs, peStrandRightLeg - 1, rlo[call], rhi[call]);
+            const uint32_t nL = hi[call] - lo[call];
+            if (nL) {
+                s3_pair_thin_kernel<<<(nL + 255) / 256, 256, 0, st>>>(side[ls].keys, lo[call], hi[call], side[rs].keys, rlo[call], rhi[call],
+                                                                      (uint32_t)(peStrandRightLeg - 1) << 31, groupEnd[call] - 0, rightStart[call]);
+                S3_LAUNCHED(1);
+            }
+            // the fill pass of call 0 must read call 0's LEFT array as thinned and its RIGHT array untouched: write call 0's
+            // candidates before call 1 thins that right array
+            s3_pair_join_kernel<false><<<(nL + 1 + 255) / 256, 256, 0, st>>>(side[ls].keys, lo[call], hi[call], side[rs].keys, groupEnd[call], rightStart[call],
+                                                                            d_len, insertLow, insertHigh, (uint32_t)call, counts[call], NULL, NULL, NULL);
+            S3_LAUNCHED(1);
+            if (cub::DeviceScan::ExclusiveSum(d_tmp, tScan, counts[call], counts[call], (int)(nL + 1), st) != cudaSuccess) { ok = false; break; }
+            if (cudaMemcpyAsync(&tot[call], counts[call] + nL, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess) { ok = false; break; }
+            if (cudaStreamSynchronize(st) != cudaSuccess) { ok = false; break; }
+            if (call == 0) {
+                // room for call 0's candidates now; call 1's are appended after its own count
+                if (tot[0] && cudaMalloc(&d_out, (size_t)tot[0] * 12) != cudaSuccess) { ok = false; break; }
+                if (tot[0]) {
+                    s3_pair_join_kernel<true><<<(nL + 1 + 255) / 256, 256, 0, st>>>(side[ls].keys, lo[0], hi[0], side[rs].keys, groupEnd[0], rightStart[0], d_len,
+                                                                                   insertLow, insertHigh, 0u, counts[0], d_out, d_out + tot[0], d_out + 2 * tot[0]);
+                    S3_LAUNCHED(1);
+                }
+            }
+        }
+        uint32_t *d_all = NULL;
+        const s3_u64 m = tot[0] + tot[1];
+        if (ok && m >= 0x7FFFFFFFull) { s3_set_error("s3_seed_pair_candidates: %llu candidates in one call", m); rc = S3_EINVAL; ok = false; }
+        if (ok && m) {
+            // all candidates in one place: ids | left | right, call 0's first
+            ok = cudaMalloc(&d_all, (size_t)m * 12) == cudaSuccess;
+            if (ok && tot[0]) {
+                ok = cudaMemcpyAsync(d_all, d_out, (size_t)tot[0] * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess &&
+                     cudaMemcpyAsync(d_all + m, d_out + tot[0], (size_t)tot[0] * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess &&
+                     cudaMemcpyAsync(d_all + 2 * m, d_out + 2 * tot[0], (size_t)tot[0] * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess;
+            }
+            if (ok && tot[1]) {
+                const uint32_t nL = hi[1] - lo[1];
+                s3_pair_join_kernel<true><<<(nL + 1 + 255) / 256, 256, 0, st>>>(side[1].keys, lo[1], hi[1], side[0].keys, groupEnd[1], rightStart[1], d_len,
+                                                                               insertLow, insertHigh, 1u, counts[1], d_all + tot[0], d_all + m + tot[0], d_all + 2 * m + tot[0]);
+                S3_LAUNCHED(1);
+            }
+            // stable sort by readIDLeft (MC_RadixSort_32_16 on candArr, DV-DPfunctions.cu:2997)
+            size_t tSort = 0;
+            void *d_t2 = NULL;
+            if (ok) ok = cudaMalloc(&d_sorted, (size_t)m * 20) == cudaSuccess;      // ids out | order in | order out | left out | right out
+            if (ok) {
+                uint32_t *idsOut = d_sorted, *ordIn = d_sorted + m, *ordOut = d_sorted + 2 * m, *lOut = d_sorted + 3 * m, *rOut = d_sorted + 4 * m;
+                s3_iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ordIn, m);
+                cub::DeviceRadixSort::SortPairs(NULL, tSort, d_all, idsOut, ordIn, ordOut, (int)m, 0, 32, st);
+                ok = cudaMalloc(&d_t2, tSort) == cudaSuccess &&
+                     cub::DeviceRadixSort::SortPairs(d_t2, tSort, d_all, idsOut, ordIn, ordOut, (int)m, 0, 32, st) == cudaSuccess;
+                if (ok) {
+                    s3_pair_gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ordOut, m, d_all + m, d_all + 2 * m, lOut, rOut);
+                    S3_LAUNCHED(2);
+                    for (int a = 0; a < 3 && ok; ++a) { h[a] = (uint32_t *)malloc((size_t)m * 4); ok = h[a] != NULL; }
+                    if (ok) ok = cudaMemcpyAsync(h[0], idsOut, (size_t)m * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                                 cudaMemcpyAsync(h[1], lOut, (size_t)m * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                                 cudaMemcpyAsync(h[2], rOut, (size_t)m * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
+                                 cudaStreamSynchronize(st) == cudaSuccess;
+                }
+                if (d_t2) cudaFree(d_t2);
+            }
+        }
+        if (ok && cudaGetLastError() != cudaSuccess) ok = false;
+        cudaFree(ge_all); cudaFree(cnt_all);
+        if (d_all) cudaFree(d_all);
+        if (!ok) { if (rc == S3_OK) { s3_set_error("s3_seed_pair_candidates: a CUDA call failed: %s", cudaGetErrorString(cudaGetLastError())); rc = S3_ECUDA; } goto done; }
+        if (m) { *candReadIDLeft = h[0]; *candPosLeft = h[1]; *candPosRight = h[2]; h[0] = h[1] = h[2] = NULL; }
+        *numCandidates = m;
+    }
+done:
+    for (int s = 0; s < 2; ++s) if (side[s].keys) cudaFree(side[s].keys);
+    if (d_len) cudaFree(d_len);
+    if (d_aux) cudaFree(d_aux);
+    if (d_counts) cudaFree(d_counts);
+    if (d_out) cudaFree(d_out);
+    if (d_sorted) cudaFree(d_sorted);
+    if (d_tmp) cudaFree(d_tmp);
+    for (int a = 0; a < 3; ++a) free(h[a]);
+    return rc;
+}

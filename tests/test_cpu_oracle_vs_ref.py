@@ -139,3 +139,57 @@ def test_seed_oracle_matches_the_reference_sort_and_merge():
         assert m == m2
         for a, b in zip(o, g):
             assert np.array_equal(a[:m], b[:m])
+
+
+def test_seed_pair_oracle_matches_the_reference_join():
+    """s3o_seed_pair_candidates == the reference's own findRevStart + pairEndMerge + sorts (oracle/_ref/libref_seed_pair.so),
+    for every combination of leg strands -- with equal legs the reference's second merge call joins against the array its
+    first call thinned in place."""
+    import ctypes as C
+    import os
+    import helpers
+    path = os.path.join(helpers.ROOT, "oracle", "_ref", "libref_seed_pair.so")
+    if not os.path.exists(path):
+        pytest.skip("oracle/_ref/libref_seed_pair.so not built")
+    ref = C.CDLL(path)
+    o = helpers.load_oracle()
+    U, I = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    ref.ref_seed_pair_merge.restype = C.c_uint32
+    ref.ref_seed_pair_merge.argtypes = [U, U, C.c_uint32, U, U, C.c_uint32, U, C.c_int, C.c_int, C.c_int, C.c_int, U, U, U]
+    o.s3o_seed_pair_candidates.restype = C.c_uint64
+    o.s3o_seed_pair_candidates.argtypes = [U] + [U, U, I, U, U, U, U, C.c_uint64] * 2 + [C.c_uint32, U, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                                                         U, U, U, C.c_uint64]
+    rng = np.random.default_rng(5)
+
+    def u(a):
+        return a.ctypes.data_as(U)
+    for n0, n1, npairs, span in ((3000, 3000, 60, 5000), (500, 800, 5, 1500), (1, 1, 1, 100), (20000, 15000, 1500, 200000), (4000, 10, 40, 3000)):
+        for legs in ((1, 2), (2, 1), (1, 1), (2, 2)):
+            sa = np.arange(span + 200, dtype=np.uint32)
+            sides = []
+            for n in (n0, n1):
+                rid = (rng.integers(0, npairs, n) * 2).astype(np.uint32)
+                x = rng.integers(0, span, n).astype(np.uint32)
+                st = rng.integers(1, 3, n).astype(np.int32)
+                off = rng.integers(0, 60, n).astype(np.uint32)
+                sl = np.full(n, 28, np.uint32)
+                rl = rng.choice([100, 100, 150, 75], n).astype(np.uint32)
+                sides.append((x, st, rid, off, sl, rl))
+            lens = rng.choice([100, 100, 150, 75], npairs * 2 + 2).astype(np.uint32)
+            keys, poss = [], []
+            for x, st, rid, off, sl, rl in sides:
+                si = (st - 1).astype(np.uint32)
+                poss.append(np.where(si == 0, x - off, x + sl + off - rl).astype(np.uint32))
+                keys.append((rid | (si << 31)).astype(np.uint32))
+            cap = (n0 + n1) * 50 + 10
+            want = [np.zeros(cap, np.uint32) for _ in range(3)]
+            m = ref.ref_seed_pair_merge(u(keys[0]), u(poss[0]), n0, u(keys[1]), u(poss[1]), n1, u(lens), 200, 500, legs[0], legs[1],
+                                        u(want[0]), u(want[1]), u(want[2]))
+            got = [np.zeros(cap, np.uint32) for _ in range(3)]
+            a = []
+            for x, st, rid, off, sl, rl in sides:
+                a += [u(x), u(x), st.ctypes.data_as(I), u(rid), u(off), u(sl), u(rl), len(x)]
+            m2 = o.s3o_seed_pair_candidates(u(sa), *a, 0xFFFFFFFF, u(lens), 200, 500, legs[0], legs[1], u(got[0]), u(got[1]), u(got[2]), cap)
+            assert m == m2, (legs, m, m2)
+            for w, g in zip(want, got):
+                assert np.array_equal(w[:m], g[:m]), legs

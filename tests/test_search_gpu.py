@@ -362,3 +362,73 @@ def test_seed_candidates_match_the_oracle(env, request):
         true_pos = rs.pos.numpy()
         hit = sum(1 for r, p in zip(got[0], got[1]) if abs(int(p) - int(true_pos[r])) <= 2)
         assert hit > nr * 0.8
+
+
+@pytest.mark.parametrize("legs", [(1, 2), (2, 1), (1, 1), (2, 2)])
+def test_seed_pair_candidates_match_the_oracle(env, request, legs):
+    """s3_seed_pair_candidates == the oracle's restatement of decodePositions x 2 + pairEndMerge x 2 + the final sort
+    (pinned against the reference's own functions in the CPU tier): real seed hits of simulated pairs, and a dense
+    synthetic set (many hits per read, thinning, equal legs: the second call joins against the array the first thinned)."""
+    import ctypes as C
+    G, idx, hi, gi = env
+    if "check_and_extend" not in request.node.name:
+        one = ([1], [2], [1], [0], [0], [20], [100])
+        with pytest.raises(api.S3Error):                 # no suffix array on the device: the call must say so
+            api.seed_pair_candidates(gi, one, one, np.array([100, 100], np.uint32), 200, 500, legs[0], legs[1])
+        return
+    sa = idx.fwd.sa.numpy().astype(np.uint32) if hasattr(idx.fwd.sa, "numpy") else np.asarray(idx.fwd.sa, np.uint32)
+    olib = load_oracle()
+    U, I = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    olib.s3o_seed_pair_candidates.restype = C.c_uint64
+    olib.s3o_seed_pair_candidates.argtypes = [U] + [U, U, I, U, U, U, U, C.c_uint64] * 2 + [C.c_uint32, U, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                                                           U, U, U, C.c_uint64]
+
+    def check(side0, side1, lens, cap_per_range, min_expected):
+        got = api.seed_pair_candidates(gi, side0, side1, lens, 200, 500, legs[0], legs[1], cap_per_range)
+        a = []
+        keep = []
+        for sd in (side0, side1):
+            arrs = [np.ascontiguousarray(sd[0], np.uint32), np.ascontiguousarray(sd[1], np.uint32), np.ascontiguousarray(sd[2], np.int32)] + \
+                   [np.ascontiguousarray(x, np.uint32) for x in sd[3:7]]
+            keep.append(arrs)
+            a += [arrs[0].ctypes.data_as(U), arrs[1].ctypes.data_as(U), arrs[2].ctypes.data_as(I)] + [x.ctypes.data_as(U) for x in arrs[3:]] + [len(arrs[0])]
+        cap = 4 * (len(side0[0]) + len(side1[0])) * 64 + 16
+        w = [np.zeros(cap, np.uint32) for _ in range(3)]
+        m = olib.s3o_seed_pair_candidates(sa.ctypes.data_as(U), *a, cap_per_range, lens.ctypes.data_as(U), 200, 500, legs[0], legs[1],
+                                          w[0].ctypes.data_as(U), w[1].ctypes.data_as(U), w[2].ctypes.data_as(U), cap)
+        assert m == len(got[0]) and m <= cap and m >= min_expected, (m, len(got[0]))
+        for x, y in zip(got, w):
+            assert np.array_equal(x, y[:m])
+        return got
+
+    # --- real pairs: three exact-or-1-mismatch seeds per end
+    npairs, L, seed_len = 300, 100, 22
+    m1, m2, _ = synth.simulate_paired_end(G, npairs, L, seed=91, insert_lo=200, insert_hi=500)
+    offs = np.array([0, 39, 78], np.uint32)
+    sides = []
+    for mate in (m1, m2):
+        reads = mate.reads.numpy()
+        seeds = np.stack([reads[:, o:o + seed_len] for o in offs], axis=1).reshape(-1, seed_len)
+        ns = len(seeds)
+        lens_s = np.zeros(formats.ceil32(ns), np.uint32)
+        lens_s[:ns] = seed_len
+        wps = formats.word_per_query(seed_len)
+        offsets, sa_l, sa_r, info = api.search(gi, formats.pack_queries(seeds, lens_s[:ns], wps), lens_s, ns, wps, 1)
+        seed_of = np.repeat(np.arange(ns), np.diff(offsets).astype(np.int64))
+        sides.append((sa_l, sa_r, ((info & 1) + 1).astype(np.int32), (2 * (seed_of // 3)).astype(np.uint32), offs[seed_of % 3],
+                      np.full(len(sa_l), seed_len, np.uint32), np.full(len(sa_l), L, np.uint32)))
+    lens = np.full(2 * npairs, L, np.uint32)
+    got = check(sides[0], sides[1], lens, 0xFFFFFFFF, npairs // 2 if legs == (1, 2) else 0)
+    if legs == (1, 2):                                   # FR pairs: nearly every pair has its candidate at the true starts
+        assert len(set(got[0].tolist())) > npairs * 0.8
+    # --- dense synthetic ranges over the same suffix array: wide ranges, many per read, capped and not
+    rng = np.random.default_rng(17)
+    dense = []
+    for n in (4000, 3500):
+        l = rng.integers(0, hi.n - 64, n).astype(np.uint32)
+        dense.append((l, (l + rng.integers(0, 12, n)).astype(np.uint32), rng.integers(1, 3, n).astype(np.int32),
+                      (2 * rng.integers(0, 25, n)).astype(np.uint32), rng.integers(0, 70, n).astype(np.uint32),
+                      np.full(n, 25, np.uint32), rng.choice([100, 150], n).astype(np.uint32)))
+    lens2 = rng.choice([100, 150, 75], 60).astype(np.uint32)
+    check(dense[0], dense[1], lens2, 0xFFFFFFFF, 0)
+    check(dense[0], dense[1], lens2, 4, 0)

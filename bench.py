@@ -749,6 +749,36 @@ def main():
                                               "outputs_equal_to_s3_dp_align": bool(same and same_pat),
                                               "call": "s3_dp_align_windows: query buffer + 29 B per alignment in, batch arrays packed on the "
                                                       "device; pinned host buffers"}
+            # capless search (s3_search) of the seeds of 131,072 reads of the step + s3_seed_candidates on what it finds:
+            # three 22-base seeds per read, <= 1 mismatch, as a DP seeding round hands them over
+            n_seed_reads, seed_len = 131072, 22
+            rd = b.reads[:n_seed_reads].cpu().numpy()
+            seed_offs = np.array([0, 39, 78], np.uint32)
+            seeds = np.stack([rd[:, o:o + seed_len] for o in seed_offs], axis=1).reshape(-1, seed_len)
+            ns = len(seeds)
+            slens = np.zeros(formats.ceil32(ns), np.uint32)
+            slens[:ns] = seed_len
+            wps = formats.word_per_query(seed_len)
+            sq = formats.pack_queries(seeds, slens[:ns], wps)
+            api.search(gi, sq[:32 * wps * 64], slens[:2048], 2048, wps, 1)
+            t0 = time.perf_counter()
+            c_offs, c_l, c_r, c_info = api.search(gi, sq, slens, ns, wps, 1)
+            t_csr = time.perf_counter() - t0
+            extras["capless_search"] = {"seeds": int(ns), "seed_length": seed_len, "mismatches": 1, "ranges": int(len(c_l)), "ms": 1e3 * t_csr,
+                                        "seeds_per_s": ns / t_csr, "call": "s3_search (CSR, no slot caps), pageable host arrays"}
+            seed_of = np.repeat(np.arange(ns), np.diff(c_offs).astype(np.int64))
+            sc_args = (c_l, c_r, ((c_info & 1) + 1).astype(np.int32), (seed_of // 3).astype(np.uint32), seed_offs[seed_of % 3],
+                       np.full(len(c_l), seed_len, np.uint32), np.full(len(c_l), L, np.uint32))
+            api.seed_candidates(gi, *sc_args, 64)
+            t0 = time.perf_counter()
+            cr, cp, cs = api.seed_candidates(gi, *sc_args, 64)
+            t_sc = time.perf_counter() - t0
+            true_pos = b.pos[:n_seed_reads].cpu().numpy()
+            near = int((np.abs(cp.astype(np.int64) - true_pos[cr]) <= 3).sum())
+            extras["seed_candidates"] = {"ranges": int(len(c_l)), "candidates": int(len(cr)), "ms": 1e3 * t_sc, "ranges_per_s": len(c_l) / t_sc,
+                                         "reads_with_a_candidate_at_their_true_start": int(len(set(cr[np.abs(cp.astype(np.int64) - true_pos[cr]) <= 3].tolist()))),
+                                         "reads": n_seed_reads, "candidates_at_true_start": near,
+                                         "call": "s3_seed_candidates, <= 64 positions per range, pageable host arrays"}
         except Exception as e:                           # noqa: BLE001
             extras["error"] = str(e)[:300]
     if rank != 0:

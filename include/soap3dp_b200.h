@@ -42,7 +42,8 @@ unsigned long long s3_launch_count(void);
  * bases per word MSB first; at least ceil(textLength/16) words are read),
  * gpu_occValue / gpu_revOccValue (numOcc*4 words, BGS-Build.cpp:141-165),
  * and the scalars the kernels receive by value.  The arrays are re-laid out on
- * the device into 64-byte buckets {4 x uint32 running counts, 192 bases}; the
+ * the device into 32-byte buckets {4 x uint32 running counts, 64 bases as bit planes} and
+ * seed tables of the first floor(log4 n) exact steps are built (3 x 8.6 GB at 3.1 Gbp); the
  * caller keeps ownership of the host arrays.  packedDNA (hsp->packedDNA, 16
  * bases/word MSB first) and sa (bwt->saValue, the full suffix array of the
  * n + 1 BWT rows, SaValueFreq == 1 as in soap3-dp-builder.ini:29) are optional:

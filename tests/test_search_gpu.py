@@ -432,3 +432,27 @@ def test_seed_pair_candidates_match_the_oracle(env, request, legs):
     lens2 = rng.choice([100, 150, 75], 60).astype(np.uint32)
     check(dense[0], dense[1], lens2, 0xFFFFFFFF, 0)
     check(dense[0], dense[1], lens2, 4, 0)
+
+
+def test_longest_reads(env):
+    """MAX_READ_LENGTH = 1024 (definitions.h:42): 1000-base reads, 64 words per query -- the largest shared-memory
+    footprint of the search kernels and the largest task blocks of the split path."""
+    G, idx, hi, gi = env
+    olib = load_oracle()
+    n, L = 150, 1000
+    rs = synth.simulate_single_end(G, n, L, seed=5150, sub_rate=0.002)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    lens[1:n:4] = L - 9
+    wpq = formats.word_per_query(L)
+    assert wpq == 64
+    q = formats.pack_queries(rs.reads.numpy(), lens[:n], wpq)
+    for k in (1, 2):
+        allowed = formats.SA_RANGES_ROUND1[k]
+        wpa, ncases = 2 * allowed, formats.NUM_CASES[k]
+        got = api.perform_round1_alignment(gi, q, lens, n, wpq, k)
+        want = _oracle_round1(olib, hi, q, lens, n, wpq, k, allowed, wpa, ncases)
+        for c in range(ncases):
+            gv, wv = formats.answers_view(got[c], n, wpa), formats.answers_view(want[c], n, wpa)
+            assert np.array_equal(gv, wv), f"k={k} case={c}: {np.nonzero((gv != wv).any(1))[0][:5]}"
+        assert sum(int((formats.answers_view(w, n, wpa)[:, 0] < 0xFFFFFFFD).sum()) for w in want) > 20

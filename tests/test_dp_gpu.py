@@ -190,3 +190,28 @@ def test_dp_forced_32bit_path(genome, monkeypatch):
     olib = load_oracle_dp()
     b = make_dp_batch(genome, 600, 100, "rescue", seed=44, indel_rate=0.006)
     assert compare_dp(b, _run(b), oracle_dp(olib, b), "forced 32-bit path") > 400
+
+
+def test_dp_long_windows(genome):
+    """Windows of ~2000 reference bases (deep DP for a wide insert range): the largest column tables the 16x2 kernels keep
+    in shared memory, and a plane of 2000+ steps per pair."""
+    olib = load_oracle_dp()
+    rng = np.random.default_rng(23)
+    g = genome.numpy()
+    n, L, W = 260, 100, 2000
+    start = rng.integers(0, len(g) - W - 1, n)
+    dna = g[start[:, None] + np.arange(W)[None, :]].astype(np.uint8)
+    read = np.zeros((n, L), np.uint8)
+    for t in range(n):
+        o = rng.integers(0, W - L)
+        read[t] = dna[t, o:o + L]
+        for _ in range(3):
+            read[t, rng.integers(0, L)] = rng.integers(0, 4)
+    dlen = rng.integers(W - 40, W + 1, n).astype(np.uint32)
+    rlen = rng.integers(L - 5, L + 1, n).astype(np.uint32)
+    b = DPBatch(dna, dlen, read, rlen, W + 8, 104, np.ceil(0.3 * rlen).astype(np.int32),
+                rng.integers(0, 9, n).astype(np.uint32), rng.integers(0, 9, n).astype(np.uint32),
+                rng.integers(1, W + 8, n).astype(np.uint32), rng.integers(0, 300, n).astype(np.uint32))
+    assert compare_dp(b, _run(b), oracle_dp(olib, b), "long windows") > n // 2
+    with pytest.raises(api.S3Error):
+        api.SemiGlobalAligner(104, 2600, 64)              # beyond what a window may hold (2559 bases)

@@ -97,3 +97,46 @@ def test_dp_oracle_matches_reference_kernels_golden(genome_and_index):
         assert sha(hit[:b.n]) == g["hitLocs"], g
         assert sha(cnt[:b.n]) == g["maxScoreCounts"], g
         assert h.hexdigest() == g["patterns"], g
+
+
+def test_seed_oracles_match_the_golden_fixtures():
+    """oracle/seed_oracle.c against tests/golden/seed_golden.json, which tests/golden/make_seed_golden.py produced with the
+    reference's own sort macros, singleMerge, findRevStart and pairEndMerge (works without oracle/_ref)."""
+    import ctypes as C
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_seed_golden", os.path.join(GOLD, "make_seed_golden.py"))
+    mk = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mk)
+    gold = json.load(open(os.path.join(GOLD, "seed_golden.json")))
+    o = load_oracle()
+    U, I = C.POINTER(C.c_uint32), C.POINTER(C.c_int32)
+    o.s3o_seed_candidates.restype = C.c_uint64
+    o.s3o_seed_candidates.argtypes = [U, U, U, I, U, U, U, U, C.c_uint64, C.c_uint32, U, U, I, C.c_uint64]
+    o.s3o_seed_pair_candidates.restype = C.c_uint64
+    o.s3o_seed_pair_candidates.argtypes = [U] + [U, U, I, U, U, U, U, C.c_uint64] * 2 + [C.c_uint32, U, C.c_int, C.c_int, C.c_int, C.c_int,
+                                                                                         U, U, U, C.c_uint64]
+
+    def u(a):
+        return a.ctypes.data_as(U)
+    for g in gold["single"]:
+        seed, n, nreads, span = g["case"]
+        rid, x, st, off, sl, rl = mk.single_case(seed, n, nreads, span)
+        sa = np.arange(span + 64, dtype=np.uint32)                 # identity suffix array: a range [x, x] is the hit x
+        out = [np.zeros(n, np.uint32), np.zeros(n, np.uint32), np.zeros(n, np.int32)]
+        m = o.s3o_seed_candidates(u(sa), u(x), u(x), st.ctypes.data_as(I), u(rid), u(off), u(sl), u(rl), n, 0xFFFFFFFF,
+                                  u(out[0]), u(out[1]), out[2].ctypes.data_as(I), n)
+        assert m == g["candidates"]
+        assert [sha(out[0][:m]), sha(out[1][:m]), sha(out[2][:m])] == [g["readIDs"], g["positions"], g["strands"]]
+        assert [[int(a), int(b), int(c)] for a, b, c in zip(out[0][:8], out[1][:8], out[2][:8])] == g["first"]
+    for g in gold["pair"]:
+        seed, n0, n1, npairs, span = g["case"]
+        sides, lens = mk.pair_case(seed, n0, n1, npairs, span)
+        sa = np.arange(span + 200, dtype=np.uint32)
+        a = []
+        for rid, x, st, off, sl, rl in sides:
+            a += [u(x), u(x), st.ctypes.data_as(I), u(rid), u(off), u(sl), u(rl), len(x)]
+        cap = (n0 + n1) * 50 + 10
+        out = [np.zeros(cap, np.uint32) for _ in range(3)]
+        m = o.s3o_seed_pair_candidates(u(sa), *a, 0xFFFFFFFF, u(lens), 200, 500, g["legs"][0], g["legs"][1], u(out[0]), u(out[1]), u(out[2]), cap)
+        assert m == g["candidates"], g["legs"]
+        assert [sha(out[0][:m]), sha(out[1][:m]), sha(out[2][:m])] == [g["readIDLeft"], g["posLeft"], g["posRight"]], g["legs"]

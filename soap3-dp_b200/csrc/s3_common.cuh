@@ -60,7 +60,7 @@ struct S3Locate {
 // Optional per-kernel timing (bench.py's roofline lines): events between the launches of a call, summed per kernel
 // slot when read.  Off by default; costs nothing then.
 #define S3_TIMING_SLOTS 8
-#define S3_TIMING_MARKS 256
+#define S3_TIMING_MARKS 4096        // marks between two reads: ~13 per bench step
 struct S3Timing {
     int on, n;
     cudaEvent_t ev[S3_TIMING_MARKS];     // created on first use

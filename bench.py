@@ -749,6 +749,20 @@ def main():
                                               "outputs_equal_to_s3_dp_align": bool(same and same_pat),
                                               "call": "s3_dp_align_windows: query buffer + 29 B per alignment in, batch arrays packed on the "
                                                       "device; pinned host buffers"}
+                # the same outputs through s3_dp_decode (host threads): special + SAM CIGARs, edit distance
+                try:
+                    dec_args = (hs.out["pattern"].numpy(), pl, hs.out["scores"].numpy()[:r.n], hs.r["read_len"].numpy()[:r.n],
+                                hs.r["cutoff"].numpy()[:r.n], api.DPScores(*DP_SCORES))
+                    api.decode_alignments(*dec_args, split=False)
+                    t0 = time.perf_counter()
+                    dec = api.decode_alignments(*dec_args, split=False)
+                    t_dec = time.perf_counter() - t0
+                    extras["dp_decode"] = {"alignments": int(r.n), "decoded": int((dec["editdist"] >= 0).sum()), "ms": 1e3 * t_dec,
+                                           "mean_editdist": float(dec["editdist"][dec["editdist"] >= 0].mean()) if (dec["editdist"] >= 0).any() else None,
+                                           "cigar_bytes": int(len(dec["cigar"][1])), "sam_cigar_bytes": int(len(dec["sam"][1])),
+                                           "call": "s3_dp_decode on the host arrays s3_dp_align returned, host threads"}
+                except Exception as e:                   # noqa: BLE001
+                    extras["dp_decode"] = {"error": str(e)[:200]}
             # capless search (s3_search) of the seeds of 131,072 reads of the step + s3_seed_candidates on what it finds:
             # three 22-base seeds per read, <= 1 mismatch, as a DP seeding round hands them over
             n_seed_reads, seed_len = 131072, 22

@@ -271,6 +271,61 @@ int s3_dp_align_windows(s3_dp *dp, s3_index *ix,
                         const uint32_t *anchorLeftLocs, const uint32_t *anchorRightLocs);
 
 /* ------------------------------------------------------------------------
+ * DP result decoding (host work on the arrays s3_dp_align* returned).  Replaces the result loops
+ * of the DP engines' CPU threads (SingleDP_Space::algnmtCPUThread DV-DPfunctions.cu:1699-1733,
+ * DP_Space::algnmtCPUThread :2359-2400, DeepDP_Space::DP2CPUAlgnThread :3765-3795) with
+ * CigarStringEncoder (DV-DPfunctions.h:514-597), and convertToCigarStr (PE.cpp:420-485).  For
+ * every alignment t with scores[t] >= cutoffThresholds[t]:
+ *   cigars[cigarOffsets[t] .. cigarOffsets[t+1])   the reference's "special" CIGAR in read order
+ *                                                  ('M' match and 'm' mismatch kept apart, I, D, S)
+ *   samCigars[samOffsets[t] .. samOffsets[t+1])    its SAM form (optional: pass both NULL to skip)
+ *   editdist[t]      I + D + (L*match + gapPenalty - score) / (match - mismatch), L = readLength - I - S
+ *   refSpanDelta[t]  D - I - S: reference bases covered = readLength + refSpanDelta (the insertSize terms)
+ *   opCounts[5t..]   bases in M, m, I, D, S
+ * and an empty string, editdist -1, zeros otherwise (the reference emits no result for those).
+ * The alignment's text position stays windowStart + hitLocs[t] and num_sameScore stays
+ * maxScoreCounts[t].  Strings carry no terminators between alignments; *cigars / *samCigars are
+ * malloc'ed by the library (s3_free).  editdist, refSpanDelta, opCounts may be NULL.
+ * ------------------------------------------------------------------------ */
+int s3_dp_decode(const uint8_t *pattern, uint32_t patternLength, const int32_t *scores,
+                 const uint32_t *readLengths, const int32_t *cutoffThresholds, uint32_t numOfThreads,
+                 s3_dp_scores scores4,
+                 uint64_t *cigarOffsets, char **cigars, uint64_t *samOffsets, char **samCigars,
+                 int32_t *editdist, int32_t *refSpanDelta, uint32_t *opCounts);
+
+/* ------------------------------------------------------------------------
+ * Tables of the DP stages (host, integer).  s3_seed_layout replaces getSeedPositions
+ * (definitions.h:323-442): the seed length and the 0-based seed offsets of a read of readLength
+ * bases in a seeding stage -- what a caller cuts out of its reads before s3_search and hands to
+ * s3_seed_candidates as seedOffsets / seedLengths.  Stages as definitions.h:317-321; stage 2
+ * (default DP = mate rescue) has no seeds.  Up to `capacity` offsets are written; a deep-DP read
+ * shorter than its seed gets *seedNum = 0 (the reference reads before its array there).
+ * s3_dp_stage_parameters replaces getParameterFor{SingleDP,DefaultDP,NewDefaultDP,DeepDP}
+ * (CPUfunctions.cpp:59-260; stage 5 = deep DP with round 2's maxHitNum,
+ * DV-DPForBothUnalign.cu:138-139): cutoffThreshold = ceil(0.3 * readLength) when
+ * isDefaultThreshold == 1 (soap3-dp.ini DPScoreThreshold = DEFAULT), else dpScoreThreshold; the
+ * per-read maxHitNum / seedLength / sampleDist; the clip limits passed through.  Fields a stage
+ * does not set are 0.  readLength2 is the mate's length (ignored by stage 1).
+ * ------------------------------------------------------------------------ */
+#define S3_STAGE_SINGLE_DP      1
+#define S3_STAGE_DEFAULT_DP     2
+#define S3_STAGE_NEW_DEFAULT_DP 3
+#define S3_STAGE_DEEP_DP_ROUND1 4
+#define S3_STAGE_DEEP_DP_ROUND2 5
+int s3_seed_layout(int stage, int32_t readLength, int32_t *seedLength, int32_t *seedPositions,
+                   int32_t capacity, int32_t *seedNum);
+typedef struct {
+    int32_t cutoffThreshold, maxHitNum, sampleDist, seedLength;        /* DPParam, PEAlgnmt.h:341-347 */
+} s3_dp_read_params;
+typedef struct {
+    int32_t softClipLeft, softClipRight, tailTrimLen, singleDPSeedNum, singleDPSeedPos[10];
+    s3_dp_read_params paramRead[2];                                    /* DPParameters, PEAlgnmt.h:349-364 */
+} s3_dp_stage_params;
+int s3_dp_stage_parameters(int stage, uint32_t readLength, uint32_t readLength2, int isDefaultThreshold,
+                           int32_t dpScoreThreshold, int32_t maxFrontLenClipped, int32_t maxEndLenClipped,
+                           s3_dp_stage_params *out);
+
+/* ------------------------------------------------------------------------
  * Measurement hooks (replace nothing in the reference).  With timing on, CUDA events are
  * recorded between the kernel launches of every call on the handle; read_timing waits for the
  * handle's stream, returns the milliseconds (and launches) per kernel slot since the last read

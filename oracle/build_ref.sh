@@ -11,6 +11,8 @@
 #   libref_dp.so       DV-DPfunctions.cu:35-512 (DP kernels) compiled for the host
 #   libref_dp_cuda.so  the same kernels compiled for sm_100a, launched as performAlignment launches them
 #   libref_seed_pair.so  findRevStart + pairEndMerge of paired-end DP seeding (DV-DPfunctions.cu:2626-2653,2780-2880)
+#   libref_decode.so   CigarStringEncoder + the result loop of algnmtCPUThread + convertToCigarStr (DV-DPfunctions.h:514-597, .cu:1699-1733, PE.cpp:83-110,420-483)
+#   libref_params.so   getSeedPositions (definitions.h:323-442) + getParameterFor*DP (CPUfunctions.cpp:46-260)
 #   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
 # Two one-line build fixes are applied to *copies* in oracle/_ref/patched/
@@ -103,6 +105,19 @@ echo "[build_ref] libref_seed.so OK"
   > "$OUT/patched/seed_pair.inc"
 $CXX -O2 -fpermissive -w -fPIC -shared -I"$OUT/patched" "$HERE/ref_shim/ref_seed_pair_host.cpp" -o "$OUT/libref_seed_pair.so"
 echo "[build_ref] libref_seed_pair.so OK"
+
+# ---- reference DP result decoding (pattern bytes -> CIGAR, edit distance) on the host ---------------
+{ sed -n '514,529p' "$REF/DV-DPfunctions.h"; sed -n '545,597p' "$REF/DV-DPfunctions.h"; } > "$OUT/patched/decode.inc"
+sed -n '1699,1733p' "$REF/DV-DPfunctions.cu" > "$OUT/patched/decode_loop.inc"
+{ sed -n '83,110p' "$REF/PE.cpp"; sed -n '420,485p' "$REF/PE.cpp" | sed 's/^int convertToCigarStr ( char \* special_cigar, char \* cigar, int \* deletedEnd )/int convertToCigarStr ( char * special_cigar, char * cigar, int * deletedEnd = NULL )/'; } > "$OUT/patched/sam_cigar.inc"
+$CXX -O2 -fpermissive -w -fPIC -shared -I"$OUT/patched" "$HERE/ref_shim/ref_decode_host.cpp" -o "$OUT/libref_decode.so"
+echo "[build_ref] libref_decode.so OK"
+
+# ---- reference stage tables (seed layout, per-stage DP parameters) against the reference's own headers --------
+sed -n '46,260p' "$REF/CPUfunctions.cpp" > "$OUT/patched/params.inc"
+$CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
+    "$HERE/ref_shim/ref_params_host.cpp" -o "$OUT/libref_params.so"
+echo "[build_ref] libref_params.so OK"
 
 # ---- the same DP kernels compiled for sm_100a: the reference's GPU kernels on the B200 ("kernel to beat") -----
 NVCC=${S3_NVCC:-/usr/local/cuda/bin/nvcc}

@@ -33,7 +33,7 @@ EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
-    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_seed_candidates", "s3_seed_pair_candidates",
+    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_dp_decode", "s3_seed_layout", "s3_dp_stage_parameters", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -285,6 +285,84 @@ def seed_pair_candidates(gpu_index: GpuIndex, side0, side1, lengths_by_read_id, 
         return tuple(np.ctypeslib.as_array(x, shape=(n,)).copy() for x in (r, pl, pr))
     finally:
         lib.s3_free(r); lib.s3_free(pl); lib.s3_free(pr)
+
+
+def decode_alignments(pattern: np.ndarray, pattern_length: int, scores, read_lengths, cutoffs, dp_scores: "DPScores",
+                      sam: bool = True, split: bool = True):
+    """s3_dp_decode (the result loops of the DP engines' CPU threads + CigarStringEncoder, DV-DPfunctions.cu:1699-1733,
+    DV-DPfunctions.h:514-597; convertToCigarStr PE.cpp:420-485): -> dict(cigar=[str], sam=[str] | None, editdist,
+    ref_span_delta, op_counts[n,5] as M m I D S).  Alignments under their cutoff give '' and editdist -1.
+    split=False leaves the strings as the library returns them: cigar / sam = (offsets[n+1], bytes)."""
+    lib = load_library()
+    lib.s3_dp_decode.restype = C.c_int
+    lib.s3_dp_decode.argtypes = [U8P, C.c_uint32, I32P, U32P, I32P, C.c_uint32, DPScores, U64P, C.POINTER(C.c_char_p),
+                                 U64P, C.POINTER(C.c_char_p), I32P, I32P, U32P]
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    n = len(scores)
+    pattern = np.ascontiguousarray(pattern, np.uint8)
+    assert pattern.size >= n * pattern_length
+    scores = np.ascontiguousarray(scores, np.int32)
+    read_lengths = np.ascontiguousarray(read_lengths, np.uint32)
+    cutoffs = np.ascontiguousarray(cutoffs, np.int32)
+    off, soff = np.zeros(n + 1, np.uint64), np.zeros(n + 1, np.uint64)
+    ed, span, ops = np.zeros(n, np.int32), np.zeros(n, np.int32), np.zeros((n, 5), np.uint32)
+    cig, scig = C.c_char_p(), C.c_char_p()
+    _check(lib.s3_dp_decode(pattern.ctypes.data_as(U8P), pattern_length, scores.ctypes.data_as(I32P), _u32(read_lengths),
+                            cutoffs.ctypes.data_as(I32P), n, dp_scores, off.ctypes.data_as(U64P), C.byref(cig),
+                            soff.ctypes.data_as(U64P) if sam else None, C.byref(scig) if sam else None,
+                            ed.ctypes.data_as(I32P), span.ctypes.data_as(I32P), ops.ctypes.data_as(U32P)), "s3_dp_decode")
+    try:
+        text = C.string_at(cig, int(off[n]))
+        cigars = (off, text)
+        sams = (soff, C.string_at(scig, int(soff[n]))) if sam else None
+        if split:
+            text = text.decode("ascii")
+            cigars = [text[int(off[t]):int(off[t + 1])] for t in range(n)]
+            if sam:
+                text = sams[1].decode("ascii")
+                sams = [text[int(soff[t]):int(soff[t + 1])] for t in range(n)]
+    finally:
+        lib.s3_free(cig)
+        if sam:
+            lib.s3_free(scig)
+    return dict(cigar=cigars, sam=sams, editdist=ed, ref_span_delta=span, op_counts=ops)
+
+
+STAGE_SINGLE_DP, STAGE_DEFAULT_DP, STAGE_NEW_DEFAULT_DP, STAGE_DEEP_DP_ROUND1, STAGE_DEEP_DP_ROUND2 = 1, 2, 3, 4, 5   # definitions.h:317-321
+
+
+class DPReadParams(C.Structure):
+    _fields_ = [("cutoffThreshold", C.c_int32), ("maxHitNum", C.c_int32), ("sampleDist", C.c_int32), ("seedLength", C.c_int32)]
+
+
+class DPStageParams(C.Structure):
+    _fields_ = [("softClipLeft", C.c_int32), ("softClipRight", C.c_int32), ("tailTrimLen", C.c_int32),
+                ("singleDPSeedNum", C.c_int32), ("singleDPSeedPos", C.c_int32 * 10), ("paramRead", DPReadParams * 2)]
+
+
+def getSeedPositions(stage: int, read_length: int, capacity: int = 256):
+    """s3_seed_layout (getSeedPositions, definitions.h:323-442): -> (seedLength, [seed offsets])."""
+    lib = load_library()
+    lib.s3_seed_layout.restype = C.c_int
+    lib.s3_seed_layout.argtypes = [C.c_int, C.c_int32, I32P, I32P, C.c_int32, I32P]
+    sl, num = C.c_int32(0), C.c_int32(0)
+    pos = (C.c_int32 * capacity)()
+    _check(lib.s3_seed_layout(stage, read_length, C.byref(sl), pos, capacity, C.byref(num)), "s3_seed_layout")
+    return int(sl.value), [int(pos[i]) for i in range(num.value)]
+
+
+def getParameterForDP(stage: int, read_length: int, read_length2: int = 0, is_default_threshold: bool = True,
+                      dp_score_threshold: int = 0, max_front_clipped: int = 0, max_end_clipped: int = 0) -> DPStageParams:
+    """s3_dp_stage_parameters (getParameterFor{SingleDP,DefaultDP,NewDefaultDP,DeepDP}, CPUfunctions.cpp:59-260)."""
+    lib = load_library()
+    lib.s3_dp_stage_parameters.restype = C.c_int
+    lib.s3_dp_stage_parameters.argtypes = [C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int32, C.c_int32, C.c_int32,
+                                           C.POINTER(DPStageParams)]
+    out = DPStageParams()
+    _check(lib.s3_dp_stage_parameters(stage, read_length, read_length2, 1 if is_default_threshold else 0, dp_score_threshold,
+                                      max_front_clipped, max_end_clipped, C.byref(out)), "s3_dp_stage_parameters")
+    return out
 
 
 def set_timing(handle: int, on: bool, dp: bool = False):

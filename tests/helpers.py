@@ -301,3 +301,70 @@ def make_dp_batch(genome, n, read_len, mode, seed, indel_rate=0.004, sub_rate=0.
     cutoff = np.ceil(0.3 * rl).astype(np.int32)
     return DPBatch(dna.astype(np.uint8), dna_len, fw.astype(np.uint8), rl, max_dna, max_read, cutoff,
                    clip_lt, clip_rt, anchor_l, anchor_r)
+
+
+# ---- DP result decoding (pattern bytes -> CIGAR, edit distance) ----------------------------------------------------
+def load_decode_oracle():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import decode_oracle
+    return decode_oracle
+
+
+def load_ref_decode():
+    """the reference's CigarStringEncoder + result loop + convertToCigarStr (oracle/build_ref.sh); None when not built"""
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_decode.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.ref_dp_decode.restype = C.c_int
+    lib.ref_dp_decode.argtypes = [U8P, C.c_int, I32P, U32P, U32P, U32P, U32P, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                  C.c_int, I32P, U32P, I32P, U32P, C.c_char_p, C.c_size_t]
+    lib.ref_convert_cigar.restype = C.c_int
+    lib.ref_convert_cigar.argtypes = [C.c_char_p, C.c_char_p]
+    return lib
+
+
+def ref_decode(lib, pattern, pat_len, scores, hit_locs, lengths, positions, counts, cutoff, scores4):
+    """-> list of (index, algnmt, special cigar, sam cigar, editdist, num_sameScore) for the alignments the reference keeps"""
+    n = len(scores)
+    idx, alg, ed, same = np.zeros(n, np.int32), np.zeros(n, np.uint32), np.zeros(n, np.int32), np.zeros(n, np.uint32)
+    cap = n * 1100 + 16
+    buf = C.create_string_buffer(cap)
+    m = lib.ref_dp_decode(np.ascontiguousarray(pattern, np.uint8).ctypes.data_as(U8P), pat_len,
+                          np.ascontiguousarray(scores, np.int32).ctypes.data_as(I32P), u32p(np.ascontiguousarray(hit_locs, np.uint32)),
+                          u32p(np.ascontiguousarray(lengths, np.uint32)), u32p(np.ascontiguousarray(positions, np.uint32)),
+                          u32p(np.ascontiguousarray(counts, np.uint32)), n, cutoff, *scores4,
+                          idx.ctypes.data_as(I32P), u32p(alg), ed.ctypes.data_as(I32P), u32p(same), buf, cap)
+    assert m >= 0
+    cigars = buf.value.decode("ascii").split("\n")[:m]
+    out = []
+    sam = C.create_string_buffer(4096)
+    for k in range(m):
+        lib.ref_convert_cigar(cigars[k].encode("ascii"), sam)
+        out.append((int(idx[k]), int(alg[k]), cigars[k], sam.value.decode("ascii"), int(ed[k]), int(same[k])))
+    return out
+
+
+def synthetic_patterns(rng, n, pat_len, max_ops=40):
+    """pattern bytes as GPUBacktrack may write them and some it never writes (a count byte of 0 or 255, an escape
+    first, deletions at either end): right-to-left op bytes, 'V',count escapes, 0-terminated"""
+    pat = np.zeros(n * pat_len, np.uint8)
+    for t in range(n):
+        out = []
+        if rng.random() < 0.5:
+            out += [ord('S'), ord('V'), int(rng.integers(0, 12))]          # the right clip is always written this way
+        elif rng.random() < 0.05:
+            out += [ord('V'), int(rng.integers(0, 5))]
+        for _ in range(int(rng.integers(1, max_ops))):
+            op = "MMMMMMMMmmIDS"[int(rng.integers(0, 13))]
+            out.append(ord(op))
+            r = rng.random()
+            if r < 0.25:
+                out += [ord('V'), int(rng.integers(0, 9))]
+            elif r < 0.27:
+                out += [ord('V'), 255]
+        out = out[:pat_len - 3]
+        if out and out[-1] == ord('V'):
+            out.append(2)
+        pat[t * pat_len:t * pat_len + len(out)] = out
+    return pat

@@ -215,3 +215,21 @@ def test_dp_long_windows(genome):
     assert compare_dp(b, _run(b), oracle_dp(olib, b), "long windows") > n // 2
     with pytest.raises(api.S3Error):
         api.SemiGlobalAligner(104, 2600, 64)              # beyond what a window may hold (2559 bases)
+
+
+@pytest.mark.parametrize("mode", ["single", "rescue"])
+def test_alignments_decode_to_the_reference_cigars(genome, mode):
+    """s3_dp_align -> s3_dp_decode against the restatement of the engines' result loops run on the DP oracle's
+    outputs (DV-DPfunctions.cu:1699-1733, DV-DPfunctions.h:514-597, PE.cpp:420-485)"""
+    from helpers import load_decode_oracle
+    orc = load_decode_oracle()
+    scores = (1, -2, -3, -1)
+    b = make_dp_batch(genome, 700, 100, mode, seed=44, indel_rate=0.01)
+    sc, hit, cnt, pat = _run(b, scores)[:4]
+    d = api.decode_alignments(pat, b.pat_len, sc[:b.n], b.read_len, b.cutoff, api.DPScores(*scores))
+    wsc, whit, wcnt, wpat = oracle_dp(load_oracle_dp(), b, scores)[:4]
+    want = orc.decode_batch(wpat, b.pat_len, wsc[:b.n], b.read_len, b.cutoff, scores)
+    got = [(d["cigar"][t], d["sam"][t], int(d["editdist"][t]), int(d["ref_span_delta"][t]),
+            tuple(int(x) for x in d["op_counts"][t])) for t in range(b.n)]
+    assert got == want
+    assert sum(1 for w in want if w[0]) > 500

@@ -12,6 +12,7 @@
 #   libref_dp_cuda.so  the same kernels compiled for sm_100a, launched as performAlignment launches them
 #   libref_seed_pair.so  findRevStart + pairEndMerge of paired-end DP seeding (DV-DPfunctions.cu:2626-2653,2780-2880)
 #   libref_decode.so   CigarStringEncoder + the result loop of algnmtCPUThread + convertToCigarStr (DV-DPfunctions.h:514-597, .cu:1699-1733, PE.cpp:83-110,420-483)
+#   libref_pair.so     PEMappingOccurrences + PEStatsPEPairList and what they call (PEAlgnmt.cpp:114-361,480-637,777-838)
 #   libref_params.so   getSeedPositions (definitions.h:323-442) + getParameterFor*DP (CPUfunctions.cpp:46-260)
 #   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
@@ -112,6 +113,13 @@ sed -n '1699,1733p' "$REF/DV-DPfunctions.cu" > "$OUT/patched/decode_loop.inc"
 { sed -n '83,110p' "$REF/PE.cpp"; sed -n '420,485p' "$REF/PE.cpp" | sed 's/^int convertToCigarStr ( char \* special_cigar, char \* cigar, int \* deletedEnd )/int convertToCigarStr ( char * special_cigar, char * cigar, int * deletedEnd = NULL )/'; } > "$OUT/patched/sam_cigar.inc"
 $CXX -O2 -fpermissive -w -fPIC -shared -I"$OUT/patched" "$HERE/ref_shim/ref_decode_host.cpp" -o "$OUT/libref_decode.so"
 echo "[build_ref] libref_decode.so OK"
+
+# ---- reference paired-end pairing (sort, merge walk, predicates, stats) against the reference's own header --------
+{ sed -n '45,57p' "$REF/PEAlgnmt.cpp"; sed -n '114,361p' "$REF/PEAlgnmt.cpp"; sed -n '480,637p' "$REF/PEAlgnmt.cpp";
+  sed -n '645,711p' "$REF/PEAlgnmt.cpp"; sed -n '777,838p' "$REF/PEAlgnmt.cpp"; } > "$OUT/patched/pair.inc"
+$CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
+    "$HERE/ref_shim/ref_pair_host.cpp" -o "$OUT/libref_pair.so"
+echo "[build_ref] libref_pair.so OK"
 
 # ---- reference stage tables (seed layout, per-stage DP parameters) against the reference's own headers --------
 sed -n '46,260p' "$REF/CPUfunctions.cpp" > "$OUT/patched/params.inc"

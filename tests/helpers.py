@@ -368,3 +368,98 @@ def synthetic_patterns(rng, n, pat_len, max_ops=40):
             out.append(2)
         pat[t * pat_len:t * pat_len + len(out)] = out
     return pat
+
+
+# ---- paired-end pairing of the two reads' occurrence lists (PEAlgnmt.cpp) ------------------------------------------
+U64P = C.POINTER(C.c_uint64)
+
+
+def make_occurrence_lists(rng, num_pairs, max_occ=12, span=1 << 20, near_edges=False):
+    """per read pair two occurrence lists in arrival order: clusters of a left and a right hit an insert apart,
+    duplicates of a position, both strands, 0..4 mismatches, empty and single-element lists"""
+    p1, s1, m1, o1, p2, s2, m2, o2 = [], [], [], [0], [], [], [], [0]
+    for _ in range(num_pairs):
+        n1, n2 = int(rng.integers(0, max_occ)), int(rng.integers(0, max_occ))
+        base = int(rng.integers(0, 600)) if near_edges and rng.random() < 0.5 else \
+            (0xFFFFFFFF - int(rng.integers(0, 900)) if near_edges else int(rng.integers(1000, span)))
+        a = (base + rng.integers(-300, 300, n1)) & 0xFFFFFFFF
+        b = (base + rng.integers(-700, 700, n2)) & 0xFFFFFFFF
+        if n1 > 2 and rng.random() < 0.5:
+            a[1] = a[0]
+        if n2 > 2 and rng.random() < 0.5:
+            b[2] = b[0]
+        p1 += list(a); p2 += list(b)
+        s1 += list(rng.integers(1, 3, n1)); s2 += list(rng.integers(1, 3, n2))
+        m1 += list(rng.integers(0, 5, n1)); m2 += list(rng.integers(0, 5, n2))
+        o1.append(len(p1)); o2.append(len(p2))
+    f = lambda x, t: np.ascontiguousarray(np.array(x, dtype=np.int64).astype(t))
+    return (f(p1, np.uint32), f(s1, np.uint8), f(m1, np.uint8), f(o1, np.uint64),
+            f(p2, np.uint32), f(s2, np.uint8), f(m2, np.uint8), f(o2, np.uint64))
+
+
+def oracle_pair_occurrences(lists, pattern_lengths, lbound, ubound, left_leg, right_leg, report_one):
+    """oracle/pair_oracle.c -> dict(offsets, pos1, pos2, insertion, flags[n,4], optimal, suboptimal, stats[numPairs,32])"""
+    lib = load_oracle()
+    U8 = C.POINTER(C.c_uint8)
+    lib.s3o_pair_occurrences.restype = C.c_uint64
+    lib.s3o_pair_occurrences.argtypes = [U32P, U8, U8, U64P, U32P, U8, U8, U64P, U32P, C.c_uint64, C.c_int32, C.c_int32, C.c_int, C.c_int,
+                                         C.c_int, U64P, U32P, U32P, U32P, U8, C.c_uint64, U32P, U32P, U32P]
+    p1, s1, m1, o1, p2, s2, m2, o2 = lists
+    npairs = len(o1) - 1
+    pl = np.ascontiguousarray(pattern_lengths, np.uint32)
+    offs = np.zeros(npairs + 1, np.uint64)
+    opt, sub, stats = np.zeros(npairs, np.uint32), np.zeros(npairs, np.uint32), np.zeros((npairs, 32), np.uint32)
+    args = (u32p(p1), s1.ctypes.data_as(U8), m1.ctypes.data_as(U8), o1.ctypes.data_as(U64P), u32p(p2), s2.ctypes.data_as(U8),
+            m2.ctypes.data_as(U8), o2.ctypes.data_as(U64P), u32p(pl), npairs, lbound, ubound, left_leg, right_leg, int(report_one))
+    total = lib.s3o_pair_occurrences(*args, offs.ctypes.data_as(U64P), None, None, None, None, 0, None, None, None)
+    a, b, ins, fl = np.zeros(total, np.uint32), np.zeros(total, np.uint32), np.zeros(total, np.uint32), np.zeros((total, 4), np.uint8)
+    lib.s3o_pair_occurrences(*args, offs.ctypes.data_as(U64P), u32p(a), u32p(b), u32p(ins), fl.ctypes.data_as(U8), total,
+                             u32p(opt), u32p(sub), u32p(stats))
+    return dict(offsets=offs, pos1=a, pos2=b, insertion=ins, flags=fl, optimal=opt, suboptimal=sub, stats=stats)
+
+
+def load_ref_pair():
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_pair.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    U8 = C.POINTER(C.c_uint8)
+    I = C.POINTER(C.c_int)
+    lib.ref_pair_occurrences.restype = C.c_int
+    lib.ref_pair_occurrences.argtypes = [U32P, U8, U8, C.c_uint, U32P, U8, U8, C.c_uint, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         U32P, U32P, U32P, U8, C.c_uint, I, I, U32P]
+    return lib
+
+
+def ref_pair_occurrences(lib, lists, pattern_lengths, lbound, ubound, left_leg, right_leg, report_one):
+    """the reference's PEMappingOccurrences + PEStatsPEOutput, read pair by read pair -> the oracle's dict"""
+    U8 = C.POINTER(C.c_uint8)
+    p1, s1, m1, o1, p2, s2, m2, o2 = lists
+    npairs = len(o1) - 1
+    offs = np.zeros(npairs + 1, np.uint64)
+    opt, sub, stats = np.zeros(npairs, np.uint32), np.zeros(npairs, np.uint32), np.zeros((npairs, 32), np.uint32)
+    A, B, INS, FL = [], [], [], []
+    for p in range(npairs):
+        a0, a1, b0, b1 = int(o1[p]), int(o1[p + 1]), int(o2[p]), int(o2[p + 1])
+        cap = (a1 - a0) * (b1 - b0) * 2 + 1
+        a, b, ins, fl = np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), np.zeros(cap, np.uint32), np.zeros((cap, 4), np.uint8)
+        x1, y1, z1 = (np.ascontiguousarray(v[a0:a1]) for v in (p1, s1, m1))
+        x2, y2, z2 = (np.ascontiguousarray(v[b0:b1]) for v in (p2, s2, m2))
+        io, isub = C.c_int(-1), C.c_int(-1)
+        st = np.zeros(30, np.uint32)
+        n = lib.ref_pair_occurrences(u32p(x1), y1.ctypes.data_as(U8), z1.ctypes.data_as(U8), a1 - a0, u32p(x2), y2.ctypes.data_as(U8),
+                                     z2.ctypes.data_as(U8), b1 - b0, int(pattern_lengths[p]), lbound, ubound, left_leg, right_leg,
+                                     1 if report_one else 0, u32p(a), u32p(b), u32p(ins), fl.ctypes.data_as(U8), cap,
+                                     C.byref(io), C.byref(isub), u32p(st))
+        assert n <= cap
+        A.append(a[:n]); B.append(b[:n]); INS.append(ins[:n]); FL.append(fl[:n])
+        offs[p + 1] = offs[p] + n
+        opt[p], sub[p] = io.value & 0xFFFFFFFF, isub.value & 0xFFFFFFFF
+        stats[p, :30] = st
+    cat = lambda v, shape: np.concatenate(v) if v else np.zeros(shape, np.uint32)
+    return dict(offsets=offs, pos1=cat(A, 0), pos2=cat(B, 0), insertion=cat(INS, 0),
+                flags=np.concatenate(FL) if FL else np.zeros((0, 4), np.uint8), optimal=opt, suboptimal=sub, stats=stats)
+
+
+def same_pairing(x, y):
+    return all(np.array_equal(x[k], y[k]) for k in ("offsets", "pos1", "pos2", "insertion", "flags", "optimal", "suboptimal", "stats"))

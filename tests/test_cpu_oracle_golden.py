@@ -140,3 +140,25 @@ def test_seed_oracles_match_the_golden_fixtures():
         m = o.s3o_seed_pair_candidates(u(sa), *a, 0xFFFFFFFF, u(lens), 200, 500, g["legs"][0], g["legs"][1], u(out[0]), u(out[1]), u(out[2]), cap)
         assert m == g["candidates"], g["legs"]
         assert [sha(out[0][:m]), sha(out[1][:m]), sha(out[2][:m])] == [g["readIDLeft"], g["posLeft"], g["posRight"]], g["legs"]
+
+
+def test_pair_oracle_matches_the_golden_fixture():
+    """oracle/pair_oracle.c against records generated from the reference's PEMappingOccurrences + PEStatsPEOutput"""
+    import json
+    import os
+    import helpers
+    g = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "pair_golden.json")))
+    total = 0
+    for case in g["cases"]:
+        types = (np.uint32, np.uint8, np.uint8, np.uint64) * 2
+        lists = tuple(np.ascontiguousarray(np.array(v, dtype=t)) for v, t in zip(case["lists"], types))
+        got = helpers.oracle_pair_occurrences(lists, np.array(case["pattern_lengths"], np.uint32), *case["bounds"], *case["legs"],
+                                              case["report_one"])
+        for k, v in case["want"].items():
+            assert np.array_equal(np.asarray(got[k]).astype(np.int64), np.array(v, dtype=np.int64).reshape(np.asarray(got[k]).shape)), k
+        stats = np.zeros_like(got["stats"])
+        for p, k, c in case["stats_nonzero"]:
+            stats[p, k] = c
+        assert np.array_equal(stats, got["stats"])
+        total += len(case["want"]["pos1"])
+    assert total > 200

@@ -193,3 +193,26 @@ def test_seed_pair_oracle_matches_the_reference_join():
             assert m == m2, (legs, m, m2)
             for w, g in zip(want, got):
                 assert np.array_equal(w[:m], g[:m]), legs
+
+
+def test_pair_oracle_matches_the_reference_pairing():
+    """oracle/pair_oracle.c == the reference's PEMappingOccurrences + PEStatsPEOutput (oracle/_ref/libref_pair.so): every
+    leg-strand combination, report-all and report-one, ties in position, empty lists, positions at both ends of the
+    32-bit range (the predicates wrap there like the reference's unsigned arithmetic)."""
+    import helpers
+    ref = helpers.load_ref_pair()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_pair.so not built")
+    rng = np.random.default_rng(5)
+    found = 0
+    for legs in ((1, 2), (2, 1), (1, 1), (2, 2)):
+        for report_one in (False, True):
+            for near_edges in (False, True):
+                lists = helpers.make_occurrence_lists(rng, 300, near_edges=near_edges)
+                pl = rng.integers(60, 151, 300).astype(np.uint32)
+                for lb, ub in ((200, 500), (1, 300)):
+                    want = helpers.ref_pair_occurrences(ref, lists, pl, lb, ub, *legs, report_one)
+                    got = helpers.oracle_pair_occurrences(lists, pl, lb, ub, *legs, report_one)
+                    assert helpers.same_pairing(got, want), (legs, report_one, near_edges, lb, ub)
+                    found += len(want["pos1"])
+    assert found > 5000

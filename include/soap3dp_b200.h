@@ -294,6 +294,33 @@ int s3_dp_decode(const uint8_t *pattern, uint32_t patternLength, const int32_t *
                  int32_t *editdist, int32_t *refSpanDelta, uint32_t *opCounts);
 
 /* ------------------------------------------------------------------------
+ * Paired-end pairing of the two reads' occurrence lists, a batch of read pairs per call.
+ * Replaces PEMappingOccurrences + PEStatsPEOutput as hostKernel calls them pair by pair once both
+ * reads have hits (CPUfunctions.cpp:2281-2310; PEAlgnmt.cpp:114-291,480-637,777-838).  Lists are
+ * CSR over read pairs: occurrences of read pair p's first read are pos1 / strand1 / mism1
+ * [off1[p], off1[p+1]) in arrival order (text position, SRAOccurrence.strand 1 or 2,
+ * mismatchCount), its second read's likewise in ...2; patternLengths[p] = the second read's
+ * length (pe_in->patternLength, CPUfunctions.cpp:2284).  Per read pair, in the reference's
+ * emission order (both lists stably sorted by position, merge walk, list 1 first on ties), one
+ * record per valid pair: (*outPos1)[r], (*outPos2)[r] = algnmt_1 / algnmt_2 (always list 1 /
+ * list 2), (*outInsertion)[r], (*outFlags)[4r..] = strand_1, mismatch_1, strand_2, mismatch_2,
+ * for r in [pairOffsets[p], pairOffsets[p+1]); the insert-size test is the reference's unsigned
+ * insertLbound <= rightPos + patternLength - leftPos <= insertUbound with the left / right leg
+ * strands; reportOne = PE_REPORT_ONE.  optimal[p] / suboptimal[p] = index inside p's records of
+ * PEStatsPEPairList's two pairs (0xFFFFFFFF: none), mismatchStats[32p + k] = records of p with k
+ * mismatches in total.  pairOffsets has numPairs + 1 entries; the four record arrays are
+ * malloc'ed by the library (s3_free).  The index handle only names the device and stream.
+ * ------------------------------------------------------------------------ */
+int s3_pair_occurrences(s3_index *ix,
+                        const uint32_t *pos1, const uint8_t *strand1, const uint8_t *mism1, const uint64_t *off1,
+                        const uint32_t *pos2, const uint8_t *strand2, const uint8_t *mism2, const uint64_t *off2,
+                        const uint32_t *patternLengths, uint64_t numPairs,
+                        int32_t insertLbound, int32_t insertUbound, int strandLeftLeg, int strandRightLeg,
+                        int reportOne,
+                        uint64_t *pairOffsets, uint32_t **outPos1, uint32_t **outPos2, uint32_t **outInsertion,
+                        uint8_t **outFlags, uint32_t *optimal, uint32_t *suboptimal, uint32_t *mismatchStats);
+
+/* ------------------------------------------------------------------------
  * Tables of the DP stages (host, integer).  s3_seed_layout replaces getSeedPositions
  * (definitions.h:323-442): the seed length and the 0-based seed offsets of a read of readLength
  * bases in a seeding stage -- what a caller cuts out of its reads before s3_search and hands to

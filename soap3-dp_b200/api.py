@@ -33,7 +33,7 @@ EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
-    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_dp_decode", "s3_seed_layout", "s3_dp_stage_parameters", "s3_seed_candidates", "s3_seed_pair_candidates",
+    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_dp_decode", "s3_seed_layout", "s3_dp_stage_parameters", "s3_pair_occurrences", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -327,6 +327,51 @@ def decode_alignments(pattern: np.ndarray, pattern_length: int, scores, read_len
         if sam:
             lib.s3_free(scig)
     return dict(cigar=cigars, sam=sams, editdist=ed, ref_span_delta=span, op_counts=ops)
+
+
+def pair_occurrences(gpu_index: GpuIndex, pos1, strand1, mism1, off1, pos2, strand2, mism2, off2, pattern_lengths,
+                     insert_lbound: int, insert_ubound: int, strand_left_leg: int = 1, strand_right_leg: int = 2,
+                     report_one: bool = False):
+    """s3_pair_occurrences (PEMappingOccurrences + PEStatsPEOutput, PEAlgnmt.cpp:480-637,777-838, batched over read pairs):
+    -> dict(offsets[numPairs+1], pos1, pos2, insertion, flags[n,4] = strand_1 mismatch_1 strand_2 mismatch_2, optimal,
+    suboptimal, stats[numPairs,32])."""
+    lib = load_library()
+    U8PP = C.POINTER(U8P)
+    lib.s3_pair_occurrences.restype = C.c_int
+    lib.s3_pair_occurrences.argtypes = [C.c_void_p, U32P, U8P, U8P, U64P, U32P, U8P, U8P, U64P, U32P, C.c_uint64, C.c_int32, C.c_int32,
+                                        C.c_int, C.c_int, C.c_int, U64P, C.POINTER(U32P), C.POINTER(U32P), C.POINTER(U32P), U8PP,
+                                        U32P, U32P, U32P]
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    a32 = lambda x: np.ascontiguousarray(x, np.uint32)
+    a8 = lambda x: np.ascontiguousarray(x, np.uint8)
+    a64 = lambda x: np.ascontiguousarray(x, np.uint64)
+    pos1, pos2, pl = a32(pos1), a32(pos2), a32(pattern_lengths)
+    strand1, mism1, strand2, mism2 = a8(strand1), a8(mism1), a8(strand2), a8(mism2)
+    off1, off2 = a64(off1), a64(off2)
+    npairs = len(off1) - 1
+    assert len(off2) == npairs + 1 and len(pl) >= npairs
+    offs = np.zeros(npairs + 1, np.uint64)
+    opt, sub, stats = np.zeros(npairs, np.uint32), np.zeros(npairs, np.uint32), np.zeros((npairs, 32), np.uint32)
+    o1, o2, oi, of = U32P(), U32P(), U32P(), U8P()
+    b8 = lambda x: x.ctypes.data_as(U8P)
+    _check(lib.s3_pair_occurrences(gpu_index.handle, _u32(pos1), b8(strand1), b8(mism1), off1.ctypes.data_as(U64P),
+                                   _u32(pos2), b8(strand2), b8(mism2), off2.ctypes.data_as(U64P), _u32(pl), npairs,
+                                   insert_lbound, insert_ubound, strand_left_leg, strand_right_leg, 1 if report_one else 0,
+                                   offs.ctypes.data_as(U64P), C.byref(o1), C.byref(o2), C.byref(oi), C.byref(of),
+                                   _u32(opt), _u32(sub), _u32(stats)), "s3_pair_occurrences")
+    n = int(offs[npairs])
+    try:
+        if n:
+            a, b, ins = (np.ctypeslib.as_array(x, shape=(n,)).copy() for x in (o1, o2, oi))
+            fl = np.ctypeslib.as_array(of, shape=(n, 4)).copy()
+        else:
+            a = b = ins = np.zeros(0, np.uint32)
+            fl = np.zeros((0, 4), np.uint8)
+    finally:
+        if n:
+            lib.s3_free(o1); lib.s3_free(o2); lib.s3_free(oi); lib.s3_free(of)
+    return dict(offsets=offs, pos1=a, pos2=b, insertion=ins, flags=fl, optimal=opt, suboptimal=sub, stats=stats)
 
 
 STAGE_SINGLE_DP, STAGE_DEFAULT_DP, STAGE_NEW_DEFAULT_DP, STAGE_DEEP_DP_ROUND1, STAGE_DEEP_DP_ROUND2 = 1, 2, 3, 4, 5   # definitions.h:317-321

@@ -1,0 +1,54 @@
+"""GPU tier, last file of the run on purpose: s3_pair_occurrences (paired-end pairing of two occurrence lists, batched
+over read pairs) against the pairing oracle.
+
+The per-read-pair walk both kernels run is checked on the CPU tier from the same source (tests/test_cpu_pair_walk.py),
+and the oracle is pinned against the reference's PEMappingOccurrences / PEStatsPEPairList.  What only a GPU can check --
+the key kernel, the two device sorts, the scan and the buffer layout of csrc/s3_pair.cu -- was written after this
+round's GPU minutes were spent, so these tests have not run on hardware yet: they are xfail(strict=False) until the
+first GPU session that sees them pass, and run after every other GPU test so that a fault here cannot mask one there."""
+import numpy as np
+import pytest
+
+import helpers
+from soap3dp_b200 import api, fmindex, synth
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
+              pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; not yet run on hardware")]
+
+
+@pytest.fixture(scope="module")
+def gi():
+    idx = fmindex.build_index(synth.random_genome(50_000, seed=3))
+    h = api.GPUINDEXUpload(idx, device=0)
+    yield h
+    try:
+        api.GPUINDEXFree(h)
+    except Exception:          # noqa: BLE001 -- a fault in the entry under test must not turn into a teardown error
+        pass
+
+
+@pytest.mark.parametrize("legs", [(1, 2), (2, 1), (1, 1)])
+@pytest.mark.parametrize("report_one", [False, True])
+def test_pairs_match_the_oracle(gi, legs, report_one):
+    rng = np.random.default_rng(23 + legs[0] * 2 + legs[1] + int(report_one))
+    for near_edges, npairs in ((False, 3000), (True, 500)):
+        lists = helpers.make_occurrence_lists(rng, npairs, max_occ=16, near_edges=near_edges)
+        pl = rng.integers(60, 151, npairs).astype(np.uint32)
+        got = api.pair_occurrences(gi, *lists, pl, 200, 500, *legs, report_one)
+        want = helpers.oracle_pair_occurrences(lists, pl, 200, 500, *legs, report_one)
+        assert helpers.same_pairing(got, want)
+        assert len(want["pos1"]) > 0
+
+
+def test_pairs_of_empty_lists_and_batches(gi):
+    z32, z8 = np.zeros(0, np.uint32), np.zeros(0, np.uint8)
+    got = api.pair_occurrences(gi, z32, z8, z8, np.zeros(1, np.uint64), z32, z8, z8, np.zeros(1, np.uint64), z32, 200, 500)
+    assert got["offsets"].tolist() == [0] and len(got["pos1"]) == 0
+    z64 = np.zeros(4, np.uint64)
+    got = api.pair_occurrences(gi, z32, z8, z8, z64, z32, z8, z8, z64, np.full(3, 100, np.uint32), 200, 500)
+    assert got["offsets"].tolist() == [0, 0, 0, 0] and (got["optimal"] == 0xFFFFFFFF).all()
+    rng = np.random.default_rng(2)
+    lists = list(helpers.make_occurrence_lists(rng, 200))
+    lists[4:] = [z32, z8, z8, np.zeros(201, np.uint64)]                      # the second reads have no hits at all
+    got = api.pair_occurrences(gi, *lists, np.full(200, 100, np.uint32), 200, 500)
+    assert int(got["offsets"][-1]) == 0

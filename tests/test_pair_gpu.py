@@ -1,19 +1,14 @@
-"""GPU tier, last file of the run on purpose: s3_pair_occurrences (paired-end pairing of two occurrence lists, batched
-over read pairs) against the pairing oracle.
-
-The per-read-pair walk both kernels run is checked on the CPU tier from the same source (tests/test_cpu_pair_walk.py),
-and the oracle is pinned against the reference's PEMappingOccurrences / PEStatsPEPairList.  What only a GPU can check --
-the key kernel, the two device sorts, the scan and the buffer layout of csrc/s3_pair.cu -- was written after this
-round's GPU minutes were spent, so these tests have not run on hardware yet: they are xfail(strict=False) until the
-first GPU session that sees them pass, and run after every other GPU test so that a fault here cannot mask one there."""
+"""GPU tier: s3_pair_occurrences (paired-end pairing of two occurrence lists, batched over read pairs) against the pairing
+oracle, which the CPU tier pins against the reference's PEMappingOccurrences / PEStatsPEPairList.  The per-read-pair
+walk both kernels run is also checked on the CPU tier from the same source (tests/test_cpu_pair_walk.py).  The same
+comparisons were first run on a B200 through tools/pair_gpu_check.py (profiles/r03a_pair_check.txt)."""
 import numpy as np
 import pytest
 
 import helpers
 from soap3dp_b200 import api, fmindex, synth
 
-pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300),
-              pytest.mark.xfail(strict=False, reason="written after the round's GPU budget was spent; not yet run on hardware")]
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(300)]
 
 
 @pytest.fixture(scope="module")

@@ -81,6 +81,19 @@ def main():
                 bad = [k for k in want if not np.array_equal(want[k], got[k])]
                 lines.append(f"{'PASS' if not bad else 'FAIL ' + ','.join(bad)} legs={legs} one={one} near_edges={near} pairs={tot}")
                 print(lines[-1], flush=True)
+    # empty batches and lists
+    z32, z8 = np.zeros(0, np.uint32), np.zeros(0, np.uint8)
+    g = api.pair_occurrences(gi, z32, z8, z8, np.zeros(1, np.uint64), z32, z8, z8, np.zeros(1, np.uint64), z32, 200, 500)
+    ok = g["offsets"].tolist() == [0] and len(g["pos1"]) == 0
+    z64 = np.zeros(4, np.uint64)
+    g = api.pair_occurrences(gi, z32, z8, z8, z64, z32, z8, z8, z64, np.full(3, 100, np.uint32), 200, 500)
+    ok = ok and g["offsets"].tolist() == [0, 0, 0, 0] and bool((g["optimal"] == 0xFFFFFFFF).all())
+    L = list(lists(rng, 200))
+    L[4:] = [z32, z8, z8, np.zeros(201, np.uint64)]
+    g = api.pair_occurrences(gi, *L, np.full(200, 100, np.uint32), 200, 500)
+    ok = ok and int(g["offsets"][-1]) == 0 and bool((g["suboptimal"] == 0xFFFFFFFF).all())
+    lines.append(f"{'PASS' if ok else 'FAIL'} empty batch / empty lists / second reads without hits")
+    print(lines[-1], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     open(os.path.join(ROOT, "gpurun_out", "pair_check.txt"), "w").write("\n".join(lines) + "\n")
 

@@ -94,6 +94,39 @@ def main():
     ok = ok and int(g["offsets"][-1]) == 0 and bool((g["suboptimal"] == 0xFFFFFFFF).all())
     lines.append(f"{'PASS' if ok else 'FAIL'} empty batch / empty lists / second reads without hits")
     print(lines[-1], flush=True)
+    # bench size: the 524,288 read pairs of one bench step, 1-3 occurrences per read around a common locus
+    import time
+    npairs = 524288
+    c1, c2 = rng.integers(1, 4, npairs), rng.integers(1, 4, npairs)
+    o1, o2 = np.zeros(npairs + 1, np.uint64), np.zeros(npairs + 1, np.uint64)
+    o1[1:], o2[1:] = np.cumsum(c1), np.cumsum(c2)
+    base = rng.integers(1000, 3_000_000_000, npairs)
+    p1 = (np.repeat(base, c1) + rng.integers(-40, 40, int(o1[-1]))).astype(np.uint32)
+    p2 = (np.repeat(base, c2) + rng.integers(150, 420, int(o2[-1]))).astype(np.uint32)
+    s1, s2 = rng.integers(1, 3, len(p1)).astype(np.uint8), rng.integers(1, 3, len(p2)).astype(np.uint8)
+    m1, m2 = rng.integers(0, 3, len(p1)).astype(np.uint8), rng.integers(0, 3, len(p2)).astype(np.uint8)
+    big = (p1, s1, m1, o1, p2, s2, m2, o2)
+    pl = np.full(npairs, 100, np.uint32)
+    ts = []
+    for _ in range(4):
+        t0 = time.perf_counter()
+        got = api.pair_occurrences(gi, *big, pl, 200, 500, 1, 2, False)
+        ts.append(time.perf_counter() - t0)
+    b8 = lambda x: x.ctypes.data_as(U8P)
+    args = (u(p1), b8(s1), b8(m1), o1.ctypes.data_as(U64P), u(p2), b8(s2), b8(m2), o2.ctypes.data_as(U64P), u(pl), npairs, 200, 500, 1, 2, 0)
+    tot = int(got["offsets"][-1])
+    offs = np.zeros(npairs + 1, np.uint64)
+    a, b, ins, fl = np.zeros(tot, np.uint32), np.zeros(tot, np.uint32), np.zeros(tot, np.uint32), np.zeros((tot, 4), np.uint8)
+    opt, sub, st = np.zeros(npairs, np.uint32), np.zeros(npairs, np.uint32), np.zeros((npairs, 32), np.uint32)
+    t0 = time.perf_counter()
+    olib.s3o_pair_occurrences(*args, offs.ctypes.data_as(U64P), u(a), u(b), u(ins), b8(fl), tot, u(opt), u(sub), u(st))
+    t_cpu = time.perf_counter() - t0
+    want = dict(offsets=offs, pos1=a, pos2=b, insertion=ins, flags=fl, optimal=opt, suboptimal=sub, stats=st)
+    bad = [k for k in want if not np.array_equal(want[k], got[k])]
+    lines.append(f"{'PASS' if not bad else 'FAIL ' + ','.join(bad)} bench size: {npairs} read pairs, {len(p1)} + {len(p2)} occurrences -> {tot} pairs; "
+                 f"s3_pair_occurrences (pageable host arrays in and out, ctypes wrapper included) {1e3 * min(ts[1:]):.1f} ms "
+                 f"= {npairs / min(ts[1:]) / 1e6:.1f} M read pairs/s; oracle port on one host core {1e3 * t_cpu:.1f} ms")
+    print(lines[-1], flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     open(os.path.join(ROOT, "gpurun_out", "pair_check.txt"), "w").write("\n".join(lines) + "\n")
 

@@ -321,6 +321,28 @@ int s3_pair_occurrences(s3_index *ix,
                         uint8_t **outFlags, uint32_t *optimal, uint32_t *suboptimal, uint32_t *mismatchStats);
 
 /* ------------------------------------------------------------------------
+ * Best-hit filters on every read's SA-range list and occurrence list, a batch of reads per call.
+ * Replaces retainAllBest / retainAllBestWithCap / retainAllBestAndSecBest (SAList.cpp:140-348)
+ * as hostKernel applies them read by read (CPUfunctions.cpp:2170-2255).  Lists are CSR over
+ * reads, entries in arrival order: SA ranges saL / saR / saStrand / saMism [saOff[r], saOff[r+1])
+ * (PESRAAlignmentResult) and occurrences occPos / occStrand / occMism likewise (SRAOccurrence).
+ * Kept entries come back in the same order, CSR by outSaOff / outOccOff (numReads + 1 entries
+ * each); out*Flags hold strand, mismatchCount per kept entry; num[r] = the function's return
+ * value (occurrences retained).  Mode 1 cuts a range short (outSaR) or skips entries once maxNum
+ * occurrences are in, in list order, exactly as the reference's running count does.  The output
+ * arrays are the caller's and must hold as many entries as the input lists.
+ * ------------------------------------------------------------------------ */
+#define S3_RETAIN_ALL_BEST        0
+#define S3_RETAIN_BEST_WITH_CAP   1
+#define S3_RETAIN_BEST_AND_SECOND 2
+int s3_retain_best(s3_index *ix, int mode, int32_t maxNum,
+                   const uint32_t *saL, const uint32_t *saR, const uint8_t *saStrand, const uint8_t *saMism, const uint64_t *saOff,
+                   const uint32_t *occPos, const uint8_t *occStrand, const uint8_t *occMism, const uint64_t *occOff,
+                   uint64_t numReads,
+                   uint64_t *outSaOff, uint32_t *outSaL, uint32_t *outSaR, uint8_t *outSaFlags,
+                   uint64_t *outOccOff, uint32_t *outOccPos, uint8_t *outOccFlags, uint32_t *num);
+
+/* ------------------------------------------------------------------------
  * Tables of the DP stages (host, integer).  s3_seed_layout replaces getSeedPositions
  * (definitions.h:323-442): the seed length and the 0-based seed offsets of a read of readLength
  * bases in a seeding stage -- what a caller cuts out of its reads before s3_search and hands to

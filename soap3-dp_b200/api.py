@@ -33,7 +33,7 @@ EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
-    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_dp_decode", "s3_seed_layout", "s3_dp_stage_parameters", "s3_pair_occurrences", "s3_seed_candidates", "s3_seed_pair_candidates",
+    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_dp_decode", "s3_seed_layout", "s3_dp_stage_parameters", "s3_pair_occurrences", "s3_retain_best", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -372,6 +372,37 @@ def pair_occurrences(gpu_index: GpuIndex, pos1, strand1, mism1, off1, pos2, stra
         if n:
             lib.s3_free(o1); lib.s3_free(o2); lib.s3_free(oi); lib.s3_free(of)
     return dict(offsets=offs, pos1=a, pos2=b, insertion=ins, flags=fl, optimal=opt, suboptimal=sub, stats=stats)
+
+
+RETAIN_ALL_BEST, RETAIN_BEST_WITH_CAP, RETAIN_BEST_AND_SECOND = 0, 1, 2
+
+
+def retain_best(gpu_index: GpuIndex, mode: int, sa_l, sa_r, sa_strand, sa_mism, sa_off, occ_pos, occ_strand, occ_mism, occ_off,
+                max_num: int = 0):
+    """s3_retain_best (retainAllBest / retainAllBestWithCap / retainAllBestAndSecBest, SAList.cpp:140-348, a batch of reads):
+    -> dict(sa_off, sa_l, sa_r, sa_flags[n,2] = strand mismatchCount, occ_off, occ_pos, occ_flags[n,2], num)."""
+    lib = load_library()
+    lib.s3_retain_best.restype = C.c_int
+    lib.s3_retain_best.argtypes = [C.c_void_p, C.c_int, C.c_int32, U32P, U32P, U8P, U8P, U64P, U32P, U8P, U8P, U64P, C.c_uint64,
+                                   U64P, U32P, U32P, U8P, U64P, U32P, U8P, U32P]
+    a32 = lambda x: np.ascontiguousarray(x, np.uint32)
+    a8 = lambda x: np.ascontiguousarray(x, np.uint8)
+    sa_l, sa_r, occ_pos = a32(sa_l), a32(sa_r), a32(occ_pos)
+    sa_strand, sa_mism, occ_strand, occ_mism = a8(sa_strand), a8(sa_mism), a8(occ_strand), a8(occ_mism)
+    sa_off, occ_off = np.ascontiguousarray(sa_off, np.uint64), np.ascontiguousarray(occ_off, np.uint64)
+    n = len(sa_off) - 1
+    assert len(occ_off) == n + 1
+    o_sa_off, o_occ_off = np.zeros(n + 1, np.uint64), np.zeros(n + 1, np.uint64)
+    o_l, o_r, o_sf = np.zeros(len(sa_l), np.uint32), np.zeros(len(sa_l), np.uint32), np.zeros((len(sa_l), 2), np.uint8)
+    o_p, o_of = np.zeros(len(occ_pos), np.uint32), np.zeros((len(occ_pos), 2), np.uint8)
+    num = np.zeros(n, np.uint32)
+    b8 = lambda x: x.ctypes.data_as(U8P)
+    _check(lib.s3_retain_best(gpu_index.handle, mode, max_num, _u32(sa_l), _u32(sa_r), b8(sa_strand), b8(sa_mism), sa_off.ctypes.data_as(U64P),
+                              _u32(occ_pos), b8(occ_strand), b8(occ_mism), occ_off.ctypes.data_as(U64P), n,
+                              o_sa_off.ctypes.data_as(U64P), _u32(o_l), _u32(o_r), b8(o_sf), o_occ_off.ctypes.data_as(U64P), _u32(o_p), b8(o_of),
+                              _u32(num)), "s3_retain_best")
+    ks, ko = int(o_sa_off[-1]), int(o_occ_off[-1])
+    return dict(sa_off=o_sa_off, sa_l=o_l[:ks], sa_r=o_r[:ks], sa_flags=o_sf[:ks], occ_off=o_occ_off, occ_pos=o_p[:ko], occ_flags=o_of[:ko], num=num)
 
 
 STAGE_SINGLE_DP, STAGE_DEFAULT_DP, STAGE_NEW_DEFAULT_DP, STAGE_DEEP_DP_ROUND1, STAGE_DEEP_DP_ROUND2 = 1, 2, 3, 4, 5   # definitions.h:317-321

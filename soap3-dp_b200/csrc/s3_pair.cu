@@ -148,3 +148,101 @@ done:
     free(h_a); free(h_b); free(h_i); free(h_f);
     return rc;
 }
+
+// =====================================================================================================================
+// Best-hit filters on every read's SA-range list and occurrence list.  Replaces retainAllBest / retainAllBestWithCap /
+// retainAllBestAndSecBest (SAList.cpp:140-348) as hostKernel applies them read by read before DP and pairing
+// (CPUfunctions.cpp:2170-2255): one thread per read, a count pass, two prefix sums, a fill pass (s3_retain_walk.cuh).
+// =====================================================================================================================
+#include "s3_retain_walk.cuh"
+
+template <bool FILL>
+__global__ void s3_retain_kernel(S3RetainIn I, int mode, int32_t maxNum, const s3_u64 *__restrict__ saOff, const s3_u64 *__restrict__ occOff,
+                                 uint64_t numReads, s3_u64 *__restrict__ keptSa, s3_u64 *__restrict__ keptOcc, S3RetainOut O, uint32_t *__restrict__ num)
+{
+    const uint64_t r = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= numReads) return;
+    uint32_t ks, ko;
+    const uint32_t n = s3_retain_walk<FILL>(I, mode, maxNum, saOff[r], saOff[r + 1], occOff[r], occOff[r + 1],
+                                            FILL ? keptSa[r] : 0, FILL ? keptOcc[r] : 0, O, &ks, &ko);
+    if (FILL) num[r] = n;
+    else { keptSa[r] = ks; keptOcc[r] = ko; }
+}
+
+extern "C" int s3_retain_best(s3_index *ix, int mode, int32_t maxNum,
+                              const uint32_t *saL, const uint32_t *saR, const uint8_t *saStrand, const uint8_t *saMism, const uint64_t *saOff,
+                              const uint32_t *occPos, const uint8_t *occStrand, const uint8_t *occMism, const uint64_t *occOff, uint64_t numReads,
+                              uint64_t *outSaOff, uint32_t *outSaL, uint32_t *outSaR, uint8_t *outSaFlags,
+                              uint64_t *outOccOff, uint32_t *outOccPos, uint8_t *outOccFlags, uint32_t *num)
+{
+    if (!ix || !saOff || !occOff || !outSaOff || !outOccOff || (numReads && !num)) { s3_set_error("s3_retain_best: NULL argument"); return S3_EINVAL; }
+    if (mode < S3_RETAIN_ALL_BEST || mode > S3_RETAIN_BEST_AND_SECOND || (mode == S3_RETAIN_BEST_WITH_CAP && maxNum < 1)) {
+        s3_set_error("s3_retain_best: mode %d / maxNum %d", mode, maxNum); return S3_EINVAL;
+    }
+    outSaOff[0] = outOccOff[0] = 0;
+    if (numReads == 0) return S3_OK;
+    if (saOff[0] != 0 || occOff[0] != 0) { s3_set_error("s3_retain_best: offsets must start at 0"); return S3_EINVAL; }
+    const uint64_t nS = saOff[numReads], nO = occOff[numReads];
+    if (numReads >= 0x7FFFFFFFull || nS >= 0x7FFFFFFFull || nO >= 0x7FFFFFFFull) { s3_set_error("s3_retain_best: batch too large"); return S3_EINVAL; }
+    if ((nS && (!saL || !saR || !saStrand || !saMism || !outSaL || !outSaR || !outSaFlags)) || (nO && (!occPos || !occStrand || !occMism || !outOccPos || !outOccFlags))) {
+        s3_set_error("s3_retain_best: NULL list"); return S3_EINVAL;
+    }
+    if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_retain_best: cudaSetDevice failed"); return S3_ECUDA; }
+    int rc = S3_OK;
+    cudaStream_t st = ix->stream;
+    char *d_buf = NULL;
+    void *d_tmp = NULL;
+    size_t t1 = 0;
+    const size_t R8 = (numReads + 1) * 8, mS = nS ? nS : 1, mO = nO ? nO : 1;
+    // 8-byte arrays, then 4-byte, then bytes
+    const size_t bytes = 4 * R8 + (4 * mS + 2 * mO + numReads) * 4 + (2 * mS + 2 * mO) + (2 * mS + 2 * mO) + 64;
+    S3_TRY(cudaMalloc(&d_buf, bytes));
+    {
+        s3_u64 *d_saOff = (s3_u64 *)d_buf, *d_occOff = d_saOff + numReads + 1, *d_kS = d_occOff + numReads + 1, *d_kO = d_kS + numReads + 1;
+        uint32_t *d_saL = (uint32_t *)(d_kO + numReads + 1), *d_saR = d_saL + mS, *d_oL = d_saR + mS, *d_oR = d_oL + mS;
+        uint32_t *d_occ = d_oR + mS, *d_oOcc = d_occ + mO, *d_num = d_oOcc + mO;
+        uint8_t *d_sS = (uint8_t *)(d_num + numReads), *d_sM = d_sS + mS, *d_cS = d_sM + mS, *d_cM = d_cS + mO;
+        uint8_t *d_oSF = d_cM + mO, *d_oOF = d_oSF + 2 * mS;
+        S3_TRY(cudaMemcpyAsync(d_saOff, saOff, R8, cudaMemcpyHostToDevice, st));
+        S3_TRY(cudaMemcpyAsync(d_occOff, occOff, R8, cudaMemcpyHostToDevice, st));
+        if (nS) {
+            S3_TRY(cudaMemcpyAsync(d_saL, saL, nS * 4, cudaMemcpyHostToDevice, st)); S3_TRY(cudaMemcpyAsync(d_saR, saR, nS * 4, cudaMemcpyHostToDevice, st));
+            S3_TRY(cudaMemcpyAsync(d_sS, saStrand, nS, cudaMemcpyHostToDevice, st)); S3_TRY(cudaMemcpyAsync(d_sM, saMism, nS, cudaMemcpyHostToDevice, st));
+        }
+        if (nO) {
+            S3_TRY(cudaMemcpyAsync(d_occ, occPos, nO * 4, cudaMemcpyHostToDevice, st));
+            S3_TRY(cudaMemcpyAsync(d_cS, occStrand, nO, cudaMemcpyHostToDevice, st)); S3_TRY(cudaMemcpyAsync(d_cM, occMism, nO, cudaMemcpyHostToDevice, st));
+        }
+        S3_TRY(cudaMemsetAsync(d_kS, 0, 2 * R8, st));
+        cub::DeviceScan::ExclusiveSum(NULL, t1, d_kS, d_kS, (int)(numReads + 1), st);
+        S3_TRY(cudaMalloc(&d_tmp, t1));
+        S3RetainIn I = {d_saL, d_saR, d_sS, d_sM, d_occ, d_cS, d_cM};
+        S3RetainOut O = {d_oL, d_oR, d_oSF, d_oOcc, d_oOF};
+        const unsigned blocks = (unsigned)((numReads + 127) / 128);
+        s3_retain_kernel<false><<<blocks, 128, 0, st>>>(I, mode, maxNum, d_saOff, d_occOff, numReads, d_kS, d_kO, O, d_num);
+        S3_LAUNCHED(1);
+        S3_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, t1, d_kS, d_kS, (int)(numReads + 1), st));
+        S3_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, t1, d_kO, d_kO, (int)(numReads + 1), st));
+        s3_retain_kernel<true><<<blocks, 128, 0, st>>>(I, mode, maxNum, d_saOff, d_occOff, numReads, d_kS, d_kO, O, d_num);
+        S3_LAUNCHED(1);
+        S3_TRY(cudaGetLastError());
+        S3_TRY(cudaMemcpyAsync(outSaOff, d_kS, R8, cudaMemcpyDeviceToHost, st));
+        S3_TRY(cudaMemcpyAsync(outOccOff, d_kO, R8, cudaMemcpyDeviceToHost, st));
+        S3_TRY(cudaMemcpyAsync(num, d_num, numReads * 4, cudaMemcpyDeviceToHost, st));
+        S3_TRY(cudaStreamSynchronize(st));
+        const uint64_t kS = outSaOff[numReads], kO = outOccOff[numReads];
+        if (kS) {
+            S3_TRY(cudaMemcpyAsync(outSaL, d_oL, kS * 4, cudaMemcpyDeviceToHost, st)); S3_TRY(cudaMemcpyAsync(outSaR, d_oR, kS * 4, cudaMemcpyDeviceToHost, st));
+            S3_TRY(cudaMemcpyAsync(outSaFlags, d_oSF, kS * 2, cudaMemcpyDeviceToHost, st));
+        }
+        if (kO) {
+            S3_TRY(cudaMemcpyAsync(outOccPos, d_oOcc, kO * 4, cudaMemcpyDeviceToHost, st));
+            S3_TRY(cudaMemcpyAsync(outOccFlags, d_oOF, kO * 2, cudaMemcpyDeviceToHost, st));
+        }
+        S3_TRY(cudaStreamSynchronize(st));
+    }
+done:
+    if (d_buf) cudaFree(d_buf);
+    if (d_tmp) cudaFree(d_tmp);
+    return rc;
+}

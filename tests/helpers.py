@@ -463,3 +463,88 @@ def ref_pair_occurrences(lib, lists, pattern_lengths, lbound, ubound, left_leg, 
 
 def same_pairing(x, y):
     return all(np.array_equal(x[k], y[k]) for k in ("offsets", "pos1", "pos2", "insertion", "flags", "optimal", "suboptimal", "stats"))
+
+
+# ---- best-hit filters on a read's SA-range list and occurrence list (SAList.cpp retainAllBest family) ---------------
+def make_hit_lists(rng, num_reads, max_sa=7, max_occ=7):
+    """per read an SA-range list and an occurrence list in arrival order; either may be empty, mismatch counts 0..4 with
+    the minimum on either side or on both, ranges of 1..40 suffixes"""
+    n_sa, n_occ = rng.integers(0, max_sa, num_reads), rng.integers(0, max_occ, num_reads)
+    sa_off, occ_off = np.zeros(num_reads + 1, np.uint64), np.zeros(num_reads + 1, np.uint64)
+    sa_off[1:], occ_off[1:] = np.cumsum(n_sa), np.cumsum(n_occ)
+    ts, to = int(sa_off[-1]), int(occ_off[-1])
+    sa_l = rng.integers(0, 1 << 31, ts).astype(np.uint32)
+    sa_r = (sa_l + rng.integers(0, 40, ts)).astype(np.uint32)
+    return (sa_l, sa_r, rng.integers(1, 3, ts).astype(np.uint8), rng.integers(0, 5, ts).astype(np.uint8), sa_off,
+            rng.integers(0, 1 << 32, to).astype(np.uint32), rng.integers(1, 3, to).astype(np.uint8), rng.integers(0, 5, to).astype(np.uint8), occ_off)
+
+
+_RETAIN_ARGS = None
+
+
+def _retain_argtypes():
+    U8 = C.POINTER(C.c_uint8)
+    return [C.c_int, C.c_int32, U32P, U32P, U8, U8, U64P, U32P, U8, U8, U64P, C.c_uint64,
+            U64P, U32P, U32P, U8, U64P, U32P, U8, U32P]
+
+
+def run_retain(fn, lists, mode, max_num):
+    """fn = s3o_retain_best or the harness twin -> dict(sa_off, sa_l, sa_r, sa_flags, occ_off, occ_pos, occ_flags, num)"""
+    U8 = C.POINTER(C.c_uint8)
+    fn.restype = None
+    fn.argtypes = _retain_argtypes()
+    sa_l, sa_r, sa_s, sa_m, sa_off, occ_p, occ_s, occ_m, occ_off = lists
+    n = len(sa_off) - 1
+    o_sa_off, o_occ_off = np.zeros(n + 1, np.uint64), np.zeros(n + 1, np.uint64)
+    o_l, o_r, o_sf = np.zeros(len(sa_l), np.uint32), np.zeros(len(sa_l), np.uint32), np.zeros((len(sa_l), 2), np.uint8)
+    o_p, o_of = np.zeros(len(occ_p), np.uint32), np.zeros((len(occ_p), 2), np.uint8)
+    num = np.zeros(n, np.uint32)
+    b8 = lambda x: x.ctypes.data_as(U8)
+    fn(mode, max_num, u32p(sa_l), u32p(sa_r), b8(sa_s), b8(sa_m), sa_off.ctypes.data_as(U64P), u32p(occ_p), b8(occ_s), b8(occ_m),
+       occ_off.ctypes.data_as(U64P), n, o_sa_off.ctypes.data_as(U64P), u32p(o_l), u32p(o_r), b8(o_sf), o_occ_off.ctypes.data_as(U64P),
+       u32p(o_p), b8(o_of), u32p(num))
+    ks, ko = int(o_sa_off[-1]), int(o_occ_off[-1])
+    return dict(sa_off=o_sa_off, sa_l=o_l[:ks], sa_r=o_r[:ks], sa_flags=o_sf[:ks], occ_off=o_occ_off, occ_pos=o_p[:ko], occ_flags=o_of[:ko], num=num)
+
+
+def oracle_retain_best(lists, mode, max_num=0):
+    return run_retain(load_oracle().s3o_retain_best, lists, mode, max_num)
+
+
+def load_ref_retain():
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_retain.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    U8 = C.POINTER(C.c_uint8)
+    lib.ref_retain_best.restype = C.c_uint
+    lib.ref_retain_best.argtypes = [C.c_int, C.c_int, U32P, U32P, U8, U8, C.c_uint, U32P, U8, U8, C.c_uint, U32P, U32P, U8, U32P, U32P, U8, U32P]
+    return lib
+
+
+def ref_retain_best(lib, lists, mode, max_num=0):
+    """the reference's functions read by read -> the oracle's dict"""
+    U8 = C.POINTER(C.c_uint8)
+    sa_l, sa_r, sa_s, sa_m, sa_off, occ_p, occ_s, occ_m, occ_off = lists
+    n = len(sa_off) - 1
+    out = dict(sa_off=np.zeros(n + 1, np.uint64), occ_off=np.zeros(n + 1, np.uint64), num=np.zeros(n, np.uint32))
+    L, R, SF, P, OF = [], [], [], [], []
+    b8 = lambda x: x.ctypes.data_as(U8)
+    for r in range(n):
+        s0, s1, o0, o1 = int(sa_off[r]), int(sa_off[r + 1]), int(occ_off[r]), int(occ_off[r + 1])
+        a = [np.ascontiguousarray(v[s0:s1]) for v in (sa_l, sa_r, sa_s, sa_m)]
+        b = [np.ascontiguousarray(v[o0:o1]) for v in (occ_p, occ_s, occ_m)]
+        ol, orr, osf = np.zeros(s1 - s0 + 1, np.uint32), np.zeros(s1 - s0 + 1, np.uint32), np.zeros((s1 - s0 + 1, 2), np.uint8)
+        op, oof = np.zeros(o1 - o0 + 1, np.uint32), np.zeros((o1 - o0 + 1, 2), np.uint8)
+        ks, ko = C.c_uint32(0), C.c_uint32(0)
+        out["num"][r] = lib.ref_retain_best(mode, max_num, u32p(a[0]), u32p(a[1]), b8(a[2]), b8(a[3]), s1 - s0, u32p(b[0]), b8(b[1]), b8(b[2]), o1 - o0,
+                                            u32p(ol), u32p(orr), b8(osf), C.byref(ks), u32p(op), b8(oof), C.byref(ko))
+        L.append(ol[:ks.value]); R.append(orr[:ks.value]); SF.append(osf[:ks.value]); P.append(op[:ko.value]); OF.append(oof[:ko.value])
+        out["sa_off"][r + 1] = out["sa_off"][r] + ks.value
+        out["occ_off"][r + 1] = out["occ_off"][r] + ko.value
+    out.update(sa_l=np.concatenate(L), sa_r=np.concatenate(R), sa_flags=np.concatenate(SF), occ_pos=np.concatenate(P), occ_flags=np.concatenate(OF))
+    return out
+
+
+def same_retained(x, y):
+    return all(np.array_equal(x[k], y[k]) for k in ("sa_off", "sa_l", "sa_r", "sa_flags", "occ_off", "occ_pos", "occ_flags", "num"))

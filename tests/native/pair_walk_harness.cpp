@@ -50,3 +50,30 @@ extern "C" uint64_t harness_pair_occurrences(const uint32_t *pos1, const uint8_t
         s3_pair_walk<true>(L, P, p, off1[p], off1[p + 1], off2[p], off2[p + 1], patternLengths[p], pairOffsets[p], O);
     return total;
 }
+
+/* ---- the per-read step of s3_retain_best (csrc/s3_retain_walk.cuh), driven like csrc/s3_pair.cu drives it: a count
+ * pass, exclusive sums of the kept entries, a fill pass ---- */
+#include "s3_retain_walk.cuh"
+
+extern "C" void harness_retain_best(int mode, int32_t maxNum,
+                                    const uint32_t *saL, const uint32_t *saR, const uint8_t *saStrand, const uint8_t *saMism, const uint64_t *saOff,
+                                    const uint32_t *occPos, const uint8_t *occStrand, const uint8_t *occMism, const uint64_t *occOff, uint64_t numReads,
+                                    uint64_t *outSaOff, uint32_t *outSaL, uint32_t *outSaR, uint8_t *outSaFlags,
+                                    uint64_t *outOccOff, uint32_t *outOccPos, uint8_t *outOccFlags, uint32_t *num)
+{
+    S3RetainIn I = {saL, saR, saStrand, saMism, occPos, occStrand, occMism};
+    S3RetainOut O = {nullptr, nullptr, nullptr, nullptr, nullptr};
+    uint64_t s = 0, o = 0;
+    for (uint64_t r = 0; r < numReads; ++r) {
+        uint32_t ks, ko;
+        s3_retain_walk<false>(I, mode, maxNum, saOff[r], saOff[r + 1], occOff[r], occOff[r + 1], 0, 0, O, &ks, &ko);
+        outSaOff[r] = s; outOccOff[r] = o;
+        s += ks; o += ko;
+    }
+    outSaOff[numReads] = s; outOccOff[numReads] = o;
+    O = S3RetainOut{outSaL, outSaR, outSaFlags, outOccPos, outOccFlags};
+    for (uint64_t r = 0; r < numReads; ++r) {
+        uint32_t ks, ko;
+        num[r] = s3_retain_walk<true>(I, mode, maxNum, saOff[r], saOff[r + 1], occOff[r], occOff[r + 1], outSaOff[r], outOccOff[r], O, &ks, &ko);
+    }
+}

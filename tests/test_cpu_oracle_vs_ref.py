@@ -216,3 +216,21 @@ def test_pair_oracle_matches_the_reference_pairing():
                     assert helpers.same_pairing(got, want), (legs, report_one, near_edges, lb, ub)
                     found += len(want["pos1"])
     assert found > 5000
+
+
+def test_retain_oracle_matches_the_reference_filters():
+    """oracle/retain_oracle.c == the reference's retainAllBest / retainAllBestWithCap / retainAllBestAndSecBest
+    (oracle/_ref/libref_retain.so): empty lists on either side, the minimum on the SA side, on the occurrence side, on both,
+    caps that cut a range short, that fall between entries, that the first best occurrence overrides"""
+    import helpers
+    ref = helpers.load_ref_retain()
+    if ref is None:
+        pytest.skip("oracle/_ref/libref_retain.so not built")
+    rng = np.random.default_rng(31)
+    for mode, caps in ((0, (0,)), (1, (1, 2, 5, 30, 1000)), (2, (0,))):
+        for cap in caps:
+            lists = helpers.make_hit_lists(rng, 1500)
+            want = helpers.ref_retain_best(ref, lists, mode, cap)
+            got = helpers.oracle_retain_best(lists, mode, cap)
+            assert helpers.same_retained(got, want), (mode, cap)
+            assert int(want["sa_off"][-1]) > 300 and int(want["occ_off"][-1]) > 300

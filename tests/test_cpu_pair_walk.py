@@ -72,3 +72,16 @@ def test_the_kernels_walk_on_empty_batches_and_lists(harness):
     assert got["offsets"].tolist() == [0, 0, 0, 0] and (got["optimal"] == 0xFFFFFFFF).all() and (got["suboptimal"] == 0xFFFFFFFF).all()
     want = helpers.oracle_pair_occurrences(lists, np.full(3, 100, np.uint32), 200, 500, 1, 2, False)
     assert helpers.same_pairing(got, want)
+
+
+def test_the_retain_kernels_step_gives_the_oracles_lists(harness):
+    """csrc/s3_retain_walk.cuh (closed form: minima first, then one pass) against the oracle's statement-by-statement
+    restatement of the reference's running-minimum filters"""
+    rng = np.random.default_rng(41)
+    for mode, caps in ((0, (0,)), (1, (1, 2, 3, 7, 40, 10000)), (2, (0,))):
+        for cap in caps:
+            for max_sa, max_occ in ((7, 7), (1, 9), (9, 1), (3, 3)):
+                lists = helpers.make_hit_lists(rng, 3000, max_sa=max_sa, max_occ=max_occ)
+                got = helpers.run_retain(harness.harness_retain_best, lists, mode, cap)
+                want = helpers.oracle_retain_best(lists, mode, cap)
+                assert helpers.same_retained(got, want), (mode, cap, max_sa, max_occ)

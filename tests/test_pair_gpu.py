@@ -1,7 +1,7 @@
 """GPU tier: s3_pair_occurrences (paired-end pairing of two occurrence lists, batched over read pairs) against the pairing
 oracle, which the CPU tier pins against the reference's PEMappingOccurrences / PEStatsPEPairList.  The per-read-pair
 walk both kernels run is also checked on the CPU tier from the same source (tests/test_cpu_pair_walk.py).  The same
-comparisons were first run on a B200 through tools/pair_gpu_check.py (profiles/r03a_pair_check.txt)."""
+comparisons were first run on a B200 through tools/pair_gpu_check.py (profiles/r03b_pair_retain_check.txt)."""
 import numpy as np
 import pytest
 
@@ -47,3 +47,22 @@ def test_pairs_of_empty_lists_and_batches(gi):
     lists[4:] = [z32, z8, z8, np.zeros(201, np.uint64)]                      # the second reads have no hits at all
     got = api.pair_occurrences(gi, *lists, np.full(200, 100, np.uint32), 200, 500)
     assert int(got["offsets"][-1]) == 0
+
+
+@pytest.mark.parametrize("mode,cap", [(0, 0), (1, 1), (1, 3), (1, 40), (2, 0)])
+def test_best_hit_filters_match_the_oracle(gi, mode, cap):
+    """s3_retain_best against oracle/retain_oracle.c (pinned against the reference's retainAllBest family on the CPU tier)"""
+    rng = np.random.default_rng(50 + 7 * mode + cap)
+    for nreads, max_sa, max_occ in ((20000, 7, 7), (3000, 9, 2), (3000, 2, 9), (3, 1, 1)):
+        lists = helpers.make_hit_lists(rng, nreads, max_sa=max_sa, max_occ=max_occ)
+        got = api.retain_best(gi, mode, *lists, cap)
+        want = helpers.oracle_retain_best(lists, mode, cap)
+        assert helpers.same_retained(got, want), (mode, cap, nreads)
+
+
+def test_best_hit_filter_rejects_bad_arguments(gi):
+    lists = helpers.make_hit_lists(np.random.default_rng(1), 10)
+    with pytest.raises(api.S3Error, match="mode"):
+        api.retain_best(gi, 3, *lists)
+    with pytest.raises(api.S3Error, match="maxNum"):
+        api.retain_best(gi, 1, *lists, 0)

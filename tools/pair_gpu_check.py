@@ -94,6 +94,38 @@ def main():
     ok = ok and int(g["offsets"][-1]) == 0 and bool((g["suboptimal"] == 0xFFFFFFFF).all())
     lines.append(f"{'PASS' if ok else 'FAIL'} empty batch / empty lists / second reads without hits")
     print(lines[-1], flush=True)
+    # best-hit filters (s3_retain_best) against oracle/retain_oracle.c
+    olib.s3o_retain_best.restype = None
+    olib.s3o_retain_best.argtypes = [C.c_int, C.c_int32, U32P, U32P, U8P, U8P, U64P, U32P, U8P, U8P, U64P, C.c_uint64,
+                                     U64P, U32P, U32P, U8P, U64P, U32P, U8P, U32P]
+    b8 = lambda x: x.ctypes.data_as(U8P)
+    for mode, cap, nreads, mx in ((0, 0, 20000, (7, 7)), (1, 1, 5000, (7, 7)), (1, 3, 5000, (9, 2)), (1, 40, 5000, (2, 9)), (2, 0, 20000, (7, 7)),
+                                  (0, 0, 1048576, (3, 3)), (0, 0, 3, (1, 1))):
+        n_sa, n_occ = rng.integers(0, mx[0], nreads), rng.integers(0, mx[1], nreads)
+        so, oo = np.zeros(nreads + 1, np.uint64), np.zeros(nreads + 1, np.uint64)
+        so[1:], oo[1:] = np.cumsum(n_sa), np.cumsum(n_occ)
+        ts_, to_ = int(so[-1]), int(oo[-1])
+        sl = rng.integers(0, 1 << 31, ts_).astype(np.uint32)
+        sr = (sl + rng.integers(0, 40, ts_)).astype(np.uint32)
+        ss, sm = rng.integers(1, 3, ts_).astype(np.uint8), rng.integers(0, 5, ts_).astype(np.uint8)
+        op_, os_, om = rng.integers(0, 1 << 32, to_).astype(np.uint32), rng.integers(1, 3, to_).astype(np.uint8), rng.integers(0, 5, to_).astype(np.uint8)
+        import time
+        t0 = time.perf_counter()
+        got = api.retain_best(gi, mode, sl, sr, ss, sm, so, op_, os_, om, oo, cap)
+        t_gpu = time.perf_counter() - t0
+        w_so, w_oo = np.zeros(nreads + 1, np.uint64), np.zeros(nreads + 1, np.uint64)
+        w_l, w_r, w_sf = np.zeros(ts_, np.uint32), np.zeros(ts_, np.uint32), np.zeros((ts_, 2), np.uint8)
+        w_p, w_of, w_n = np.zeros(to_, np.uint32), np.zeros((to_, 2), np.uint8), np.zeros(nreads, np.uint32)
+        t0 = time.perf_counter()
+        olib.s3o_retain_best(mode, cap, u(sl), u(sr), b8(ss), b8(sm), so.ctypes.data_as(U64P), u(op_), b8(os_), b8(om), oo.ctypes.data_as(U64P), nreads,
+                             w_so.ctypes.data_as(U64P), u(w_l), u(w_r), b8(w_sf), w_oo.ctypes.data_as(U64P), u(w_p), b8(w_of), u(w_n))
+        t_cpu = time.perf_counter() - t0
+        ks, ko = int(w_so[-1]), int(w_oo[-1])
+        want = dict(sa_off=w_so, sa_l=w_l[:ks], sa_r=w_r[:ks], sa_flags=w_sf[:ks], occ_off=w_oo, occ_pos=w_p[:ko], occ_flags=w_of[:ko], num=w_n)
+        bad = [k for k in want if not np.array_equal(want[k], got[k])]
+        lines.append(f"{'PASS' if not bad else 'FAIL ' + ','.join(bad)} retain mode={mode} cap={cap} reads={nreads}: {ts_} ranges + {to_} occurrences -> "
+                     f"{ks} + {ko} kept; call {1e3 * t_gpu:.1f} ms (first call of a size includes module load), oracle {1e3 * t_cpu:.1f} ms")
+        print(lines[-1], flush=True)
     # bench size: the 524,288 read pairs of one bench step, 1-3 occurrences per read around a common locus
     import time
     npairs = 524288

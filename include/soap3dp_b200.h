@@ -293,6 +293,22 @@ int s3_dp_decode(const uint8_t *pattern, uint32_t patternLength, const int32_t *
                  uint64_t *cigarOffsets, char **cigars, uint64_t *samOffsets, char **samCigars,
                  int32_t *editdist, int32_t *refSpanDelta, uint32_t *opCounts);
 
+/* MD:Z and the NM pieces of decoded alignments.  Replaces getMisInfoForDP (PE.cpp:499-666, trim 0)
+ * for a batch: from the special CIGARs of s3_dp_decode (cigars / cigarOffsets), the alignments'
+ * text positions (windowStart + hitLoc) and the packed text (hsp->packedDNA: 16 bases per word,
+ * most significant first), md[mdOffsets[t] .. mdOffsets[t+1]) = the MD string, numMismatch /
+ * gapOpen / gapExt as the reference counts them (gapExt counts every gap base), and
+ * avgMismatchQual = (int)(sum of qualities at mismatching read offsets / numMismatch), 20 without
+ * mismatches or without qualities.  qualities (signed chars as the reference's) of alignment t are
+ * qualities[qualityOffsets[t] .. qualityOffsets[t+1]) in read order, or NULL.  An alignment with
+ * an empty CIGAR gets an empty MD.  *md is malloc'ed by the library (s3_free); the four count
+ * arrays may be NULL. */
+int s3_dp_md(const uint32_t *packedDNA, uint64_t textLength, const char *cigars, const uint64_t *cigarOffsets,
+             const uint32_t *positions, uint32_t numOfThreads,
+             const int8_t *qualities, const uint64_t *qualityOffsets,
+             uint64_t *mdOffsets, char **md, int32_t *numMismatch, int32_t *gapOpen, int32_t *gapExt,
+             int32_t *avgMismatchQual);
+
 /* ------------------------------------------------------------------------
  * Paired-end pairing of the two reads' occurrence lists, a batch of read pairs per call.
  * Replaces PEMappingOccurrences + PEStatsPEOutput as hostKernel calls them pair by pair once both

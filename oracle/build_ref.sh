@@ -14,6 +14,7 @@
 #   libref_decode.so   CigarStringEncoder + the result loop of algnmtCPUThread + convertToCigarStr (DV-DPfunctions.h:514-597, .cu:1699-1733, PE.cpp:83-110,420-483)
 #   libref_pair.so     PEMappingOccurrences + PEStatsPEPairList and what they call (PEAlgnmt.cpp:114-361,480-637,777-838)
 #   libref_retain.so   retainAllBest / retainAllBestWithCap / retainAllBestAndSecBest + list helpers (SAList.cpp:26-69,140-390)
+#   libref_md.so       getMisInfoForDP (PE.cpp:499-666): MD string, mismatch / gap counts of a DP alignment
 #   libref_params.so   getSeedPositions (definitions.h:323-442) + getParameterFor*DP (CPUfunctions.cpp:46-260)
 #   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
@@ -121,6 +122,12 @@ echo "[build_ref] libref_decode.so OK"
 $CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
     "$HERE/ref_shim/ref_pair_host.cpp" -o "$OUT/libref_pair.so"
 echo "[build_ref] libref_pair.so OK"
+
+# ---- reference MD-string builder of DP alignments against the reference's own header ---------------------------
+{ sed -n '83,110p' "$REF/PE.cpp"; sed -n '499,666p' "$REF/PE.cpp"; } > "$OUT/patched/md.inc"
+$CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
+    "$HERE/ref_shim/ref_md_host.cpp" -o "$OUT/libref_md.so"
+echo "[build_ref] libref_md.so OK"
 
 # ---- reference best-hit filters (retainAllBest family) against the reference's own header ---------------------
 { sed -n '26,69p' "$REF/SAList.cpp"; sed -n '140,390p' "$REF/SAList.cpp"; } > "$OUT/patched/retain.inc"

@@ -102,3 +102,42 @@ def decode_batch(pattern, pattern_length, scores, read_lengths, cutoffs, scores4
         else:
             out.append(("", "", -1, 0, (0, 0, 0, 0, 0)))
     return out
+
+
+def md_string(special, pos, text, qualities=None):
+    """getMisInfoForDP (PE.cpp:499-666) with trim = 0: special CIGAR + text position -> (MD string, numMismatch, gapOpen,
+    gapExt, avg_mismatch_qual).  text: base codes 0..3 by position; qualities: signed values in read order or None."""
+    dna = "ACGT"
+    cur = cur_match = q_pos = 0
+    t_pos = pos
+    n_mis = gap_open = gap_ext = 0
+    total_q = 0.0
+    md = []
+    for i, ch in enumerate(special):
+        if ch.isdigit():
+            cur = cur * 10 + int(ch)
+            continue
+        if ch == 'M':
+            cur_match += cur; q_pos += cur; t_pos += cur; cur = 0
+        elif ch == 'm':
+            md.append(str(cur_match)); md.append(dna[text[t_pos]])
+            if qualities is not None:
+                total_q += qualities[q_pos]
+            for j in range(1, cur):
+                md.append('0'); md.append(dna[text[t_pos + j]])
+                if qualities is not None:
+                    total_q += qualities[q_pos + j]
+            q_pos += cur; t_pos += cur; n_mis += cur; cur_match = 0; cur = 0
+        elif ch == 'I':
+            q_pos += cur; gap_open += 1; gap_ext += cur; cur = 0
+        elif ch == 'D':
+            if i == len(special) - 1:
+                continue
+            md.append(str(cur_match)); md.append('^')
+            md.extend(dna[text[t_pos + j]] for j in range(cur))
+            t_pos += cur; gap_open += 1; gap_ext += cur; cur_match = 0; cur = 0
+        elif ch == 'S':
+            q_pos += cur; cur = 0
+    md.append(str(cur_match))
+    avg = int(total_q / n_mis) if n_mis > 0 else 20
+    return "".join(md), n_mis, gap_open, gap_ext, avg

@@ -33,7 +33,7 @@ EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
-    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_dp_decode", "s3_seed_layout", "s3_dp_stage_parameters", "s3_pair_occurrences", "s3_retain_best", "s3_seed_candidates", "s3_seed_pair_candidates",
+    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_dp_decode", "s3_dp_md", "s3_seed_layout", "s3_dp_stage_parameters", "s3_pair_occurrences", "s3_retain_best", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]
@@ -372,6 +372,40 @@ def pair_occurrences(gpu_index: GpuIndex, pos1, strand1, mism1, off1, pos2, stra
         if n:
             lib.s3_free(o1); lib.s3_free(o2); lib.s3_free(oi); lib.s3_free(of)
     return dict(offsets=offs, pos1=a, pos2=b, insertion=ins, flags=fl, optimal=opt, suboptimal=sub, stats=stats)
+
+
+def md_strings(packed_text: np.ndarray, text_length: int, cigars, positions, qualities=None):
+    """s3_dp_md (getMisInfoForDP, PE.cpp:499-666): special CIGARs (list of str) + text positions ->
+    dict(md=[str], num_mismatch, gap_open, gap_ext, avg_mismatch_qual).  qualities: list of int8 arrays in read order."""
+    lib = load_library()
+    I8P = C.POINTER(C.c_int8)
+    lib.s3_dp_md.restype = C.c_int
+    lib.s3_dp_md.argtypes = [U32P, C.c_uint64, C.c_char_p, U64P, U32P, C.c_uint32, I8P, U64P, U64P, C.POINTER(C.c_char_p), I32P, I32P, I32P, I32P]
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    n = len(cigars)
+    off = np.zeros(n + 1, np.uint64)
+    off[1:] = np.cumsum([len(c) for c in cigars])
+    text = "".join(cigars).encode("ascii")
+    pos = np.ascontiguousarray(positions, np.uint32)
+    packed = np.ascontiguousarray(packed_text, np.uint32)
+    q = qoff = None
+    if qualities is not None:
+        qoff = np.zeros(n + 1, np.uint64)
+        qoff[1:] = np.cumsum([len(x) for x in qualities])
+        q = np.ascontiguousarray(np.concatenate([np.asarray(x, np.int8) for x in qualities]) if n else np.zeros(0, np.int8))
+    moff = np.zeros(n + 1, np.uint64)
+    nm, go, ge, aq = (np.zeros(n, np.int32) for _ in range(4))
+    out = C.c_char_p()
+    i32 = lambda a: a.ctypes.data_as(I32P)
+    _check(lib.s3_dp_md(_u32(packed), text_length, text, off.ctypes.data_as(U64P), _u32(pos), n,
+                        q.ctypes.data_as(I8P) if q is not None else None, qoff.ctypes.data_as(U64P) if qoff is not None else None,
+                        moff.ctypes.data_as(U64P), C.byref(out), i32(nm), i32(go), i32(ge), i32(aq)), "s3_dp_md")
+    try:
+        md = C.string_at(out, int(moff[n])).decode("ascii")
+    finally:
+        lib.s3_free(out)
+    return dict(md=[md[int(moff[t]):int(moff[t + 1])] for t in range(n)], num_mismatch=nm, gap_open=go, gap_ext=ge, avg_mismatch_qual=aq)
 
 
 RETAIN_ALL_BEST, RETAIN_BEST_WITH_CAP, RETAIN_BEST_AND_SECOND = 0, 1, 2

@@ -181,3 +181,102 @@ extern "C" int s3_dp_decode(const uint8_t *pattern, uint32_t patternLength, cons
     *cigars = out;
     return S3_OK;
 }
+
+
+// MD:Z string and the NM pieces of an alignment from its special CIGAR and the packed text.  Replaces getMisInfoForDP
+// (PE.cpp:499-666) with trim = 0 (the strand only matters to its trimming): matches accumulate; a mismatch run writes
+// the count so far and the text base, further bases of the run as "0" + base; a deletion writes the count, '^' and the
+// deleted text bases -- except as the last op, which is ignored; the final count closes the string.
+namespace {
+
+inline char text_base(const uint32_t *packed, uint64_t pos)
+{
+    static const char dna[4] = {'A', 'C', 'G', 'T'};               // dnaChar, 2bwt-lib/HSP.h:278
+    return dna[(packed[pos >> 4] >> ((15 - (pos & 15)) * 2)) & 3];
+}
+
+struct MdOut { int32_t numMismatch, gapOpen, gapExt, avgQual; };
+
+// returns false when the alignment runs past the text
+bool md_one(const uint32_t *packed, uint64_t textLength, const char *cig, size_t len, uint32_t pos, const int8_t *qual, size_t qualLen,
+            std::string &md, MdOut &o)
+{
+    o = MdOut{0, 0, 0, 20};                                          // DEFAULT_QUAL_VALUE, PE.h:27
+    int32_t cur = 0, curMatch = 0;
+    uint64_t qPos = 0, tPos = pos;
+    double sumQual = 0.0;
+    for (size_t i = 0; i < len; ++i) {
+        const char c = cig[i];
+        if (c >= '0' && c <= '9') { cur = cur * 10 + (c - '0'); continue; }
+        switch (c) {
+        case 'M': curMatch += cur; qPos += cur; tPos += cur; cur = 0; break;
+        case 'm':
+            if (tPos + (uint64_t)cur > textLength) return false;
+            put_num(md, curMatch);
+            md.push_back(text_base(packed, tPos));
+            if (qual && qPos < qualLen) sumQual += qual[qPos];
+            for (int32_t j = 1; j < cur; ++j) {
+                md.push_back('0');
+                md.push_back(text_base(packed, tPos + j));
+                if (qual && qPos + j < qualLen) sumQual += qual[qPos + j];
+            }
+            qPos += cur; tPos += cur; o.numMismatch += cur; curMatch = 0; cur = 0;
+            break;
+        case 'I': qPos += cur; o.gapOpen++; o.gapExt += cur; cur = 0; break;
+        case 'D':
+            if (i == len - 1) break;                                 // last delete, ignored (its count stays, like the reference)
+            if (tPos + (uint64_t)cur > textLength) return false;
+            put_num(md, curMatch);
+            md.push_back('^');
+            for (int32_t j = 0; j < cur; ++j) md.push_back(text_base(packed, tPos + j));
+            tPos += cur; o.gapOpen++; o.gapExt += cur; curMatch = 0; cur = 0;
+            break;
+        case 'S': qPos += cur; cur = 0; break;
+        default: break;
+        }
+    }
+    put_num(md, curMatch);
+    if (o.numMismatch > 0) o.avgQual = (int32_t)(sumQual / o.numMismatch);
+    return true;
+}
+
+}  // namespace
+
+extern "C" int s3_dp_md(const uint32_t *packedDNA, uint64_t textLength, const char *cigars, const uint64_t *cigarOffsets,
+                        const uint32_t *positions, uint32_t numOfThreads, const int8_t *qualities, const uint64_t *qualityOffsets,
+                        uint64_t *mdOffsets, char **md, int32_t *numMismatch, int32_t *gapOpen, int32_t *gapExt, int32_t *avgMismatchQual)
+{
+    if (!packedDNA || !cigarOffsets || !positions || !mdOffsets || !md || (qualities && !qualityOffsets) || (numOfThreads && cigarOffsets[numOfThreads] && !cigars)) {
+        s3_set_error("s3_dp_md: NULL argument");
+        return S3_EINVAL;
+    }
+    *md = nullptr;
+    std::string out;
+    try {
+        out.reserve((size_t)numOfThreads * 12);
+        for (uint32_t t = 0; t < numOfThreads; ++t) {
+            mdOffsets[t] = out.size();
+            MdOut o{0, 0, 0, 20};
+            const size_t len = (size_t)(cigarOffsets[t + 1] - cigarOffsets[t]);
+            if (len) {                                               // an alignment under its cutoff has no CIGAR and gets no MD
+                const int8_t *q = qualities ? qualities + qualityOffsets[t] : nullptr;
+                const size_t ql = qualities ? (size_t)(qualityOffsets[t + 1] - qualityOffsets[t]) : 0;
+                if (!md_one(packedDNA, textLength, cigars + cigarOffsets[t], len, positions[t], q, ql, out, o)) {
+                    s3_set_error("s3_dp_md: alignment %u at %u runs past the text (%llu bases)", t, positions[t], (unsigned long long)textLength);
+                    return S3_EINVAL;
+                }
+            }
+            if (numMismatch) numMismatch[t] = o.numMismatch;
+            if (gapOpen) gapOpen[t] = o.gapOpen;
+            if (gapExt) gapExt[t] = o.gapExt;
+            if (avgMismatchQual) avgMismatchQual[t] = o.avgQual;
+        }
+    } catch (...) { s3_set_error("s3_dp_md: out of host memory"); return S3_ENOMEM; }
+    mdOffsets[numOfThreads] = out.size();
+    char *buf = (char *)malloc(out.size() + 1);
+    if (!buf) { s3_set_error("s3_dp_md: out of host memory"); return S3_ENOMEM; }
+    memcpy(buf, out.data(), out.size());
+    buf[out.size()] = 0;
+    *md = buf;
+    return S3_OK;
+}

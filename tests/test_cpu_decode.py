@@ -140,3 +140,94 @@ def test_sam_cigar_quirks_are_the_reference_ones():
         for s in ("5M1m3M2I4M", "2S5M3D", "3D5M", "4S3D2M1D", "7m", "1M2D3M4I5m6S"):
             ref.ref_convert_cigar(s.encode(), buf)
             assert buf.value.decode() == orc.to_sam_cigar(s), s
+
+
+# ---- MD strings (s3_dp_md) ------------------------------------------------------------------------------------------
+def pack_text(bases):
+    """hsp->packedDNA: 16 bases per word, most significant first"""
+    n = len(bases)
+    padded = np.zeros((n + 15) // 16 * 16 + 16, np.uint32)
+    padded[:n] = bases
+    shifts = (2 * (15 - np.arange(16, dtype=np.uint32))).astype(np.uint32)
+    return np.ascontiguousarray((padded.reshape(-1, 16) << shifts).sum(axis=1, dtype=np.uint64).astype(np.uint32))
+
+
+def load_ref_md():
+    import ctypes as C
+    path = os.path.join(helpers.ROOT, "oracle", "_ref", "libref_md.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    I = C.POINTER(C.c_int)
+    lib.ref_md.restype = C.c_int
+    lib.ref_md.argtypes = [helpers.U32P, C.c_char_p, C.c_char_p, C.c_uint, C.c_uint, C.c_int, C.c_char_p, C.c_char_p, I, I, I, I]
+    return lib
+
+
+def ref_md(lib, packed, qual, read_len, pos, cigar):
+    import ctypes as C
+    out = C.create_string_buffer(4096)
+    v = [C.c_int(0) for _ in range(4)]
+    q = bytes(np.asarray(qual, np.int8).astype(np.uint8)) if qual is not None else bytes(1100)
+    n = lib.ref_md(helpers.u32p(packed), bytes(1100), q, read_len, pos, 1, cigar.encode("ascii"), out, *(C.byref(x) for x in v))
+    assert n == len(out.value)
+    return (out.value.decode("ascii"), *(x.value for x in v))
+
+
+def md_cases():
+    """(text bases, packed text, [(cigar, pos, read length)]) from real tracebacks: the windows laid end to end are the text"""
+    orc = load_decode_oracle()
+    scores4 = (1, -2, -3, -1)
+    b, sc, hit, cnt, pat = dp_oracle_batch("rescue", 100, scores4, n=300, seed=23)
+    # unpack the windows (1-based, 32-interleaved, most significant base first: DV-DPfunctions.cu:57-59) and lay them end to end
+    W = b.max_dna
+    nw = len(b.dna) // helpers.formats.ceil32(b.n)
+    words = b.dna.reshape(-1, nw, 32)
+    text = np.zeros(b.n * W, np.uint32)
+    for t in range(b.n):
+        w = words[t // 32, :, t % 32]
+        i = np.arange(1, int(b.dna_len[t]) + 1)
+        text[t * W:t * W + len(i)] = (w[i >> 4] >> (2 * (15 - (i & 15)))) & 3
+    dec = orc.decode_batch(pat, b.pat_len, sc, b.read_len, b.cutoff, scores4)
+    cases = [(dec[t][0], t * W + int(hit[t]), int(b.read_len[t])) for t in range(b.n) if dec[t][0]]
+    rng = np.random.default_rng(6)
+    for cig in ("3D5M", "2S5M3D", "4m", "10M3m2I5M1D4M2m6S", "1m1M1m", "7M2D1m3D4M", "5S20M"):      # never written by the kernel, still defined
+        cases.append((cig, int(rng.integers(0, len(text) - 200)), 60))
+    return text, pack_text(text), cases
+
+
+def test_md_strings_match_the_restatement_and_the_reference():
+    orc = load_decode_oracle()
+    ref = load_ref_md()
+    text, packed, cases = md_cases()
+    rng = np.random.default_rng(8)
+    quals = [rng.integers(2, 60, 160).astype(np.int8) for _ in cases]
+    for with_q in (True, False):
+        got = api.md_strings(packed, len(text), [c[0] for c in cases], [c[1] for c in cases], quals if with_q else None)
+        n_mis = 0
+        for t, (cig, pos, rl) in enumerate(cases):
+            want = orc.md_string(cig, pos, text, quals[t] if with_q else None)
+            mine = (got["md"][t], int(got["num_mismatch"][t]), int(got["gap_open"][t]), int(got["gap_ext"][t]), int(got["avg_mismatch_qual"][t]))
+            assert mine == want, (cig, pos)
+            if ref is not None and with_q:
+                assert ref_md(ref, packed, quals[t], rl, pos, cig) == want, (cig, pos)
+            n_mis += want[1]
+        assert n_mis > 300 and len(cases) > 250
+    # matches only: the read is the text; an alignment under its cutoff has no CIGAR and gets no MD
+    got = api.md_strings(packed, len(text), ["100M", ""], [5, 9])
+    assert got["md"] == ["100", ""] and got["num_mismatch"].tolist() == [0, 0] and got["avg_mismatch_qual"].tolist() == [20, 20]
+    with pytest.raises(api.S3Error, match="runs past the text"):
+        api.md_strings(packed, len(text), ["5M3m"], [len(text) - 6])
+
+
+def test_md_string_is_consistent_with_the_alignment():
+    """size-independent property: the MD numbers and letters add up to the reference span, and its letters are text bases"""
+    import re
+    text, packed, cases = md_cases()
+    got = api.md_strings(packed, len(text), [c[0] for c in cases], [c[1] for c in cases])
+    for t, (cig, pos, rl) in enumerate(cases[:250]):
+        ops = re.findall(r"(\d+)([MmIDS])", cig)
+        span = sum(int(n) for n, o in ops if o in "MmD")
+        md = got["md"][t]
+        covered = sum(int(x) for x in re.findall(r"\d+", md)) + len(re.findall(r"[ACGT]", md))
+        assert covered == span, (cig, md)

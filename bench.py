@@ -364,6 +364,63 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
             "dp_gcups": dpb.n * 400 * L / t_dp / 1e9}
 
 
+def pairing_rows(views, allowed, n_reads, L, true_pos, retain_best, locate, pair_occurrences, max_per_range=8):
+    """The steps between the search answers and the paired result, as SOAP3-dp's hostKernel runs them per read pair
+    (CPUfunctions.cpp:1258-1300, 2170-2310): answer slots -> per-read SA-range lists -> best-hit filter (s3_retain_best)
+    -> positions (s3_locate) -> pairing of the two mates' occurrence lists (s3_pair_occurrences).  views: one [n_reads,
+    2 * allowed] array per case; reads 2i / 2i+1 are mates.  The three callables are the library entries (tests pass the
+    oracles).  Returns the measured row for `next_rows`."""
+    rid, sl, sr, mm, st = [], [], [], [], []
+    for v in views:
+        for sidx in range(allowed):
+            l, w = v[:, 2 * sidx], v[:, 2 * sidx + 1]
+            ok = (l < 0xFFFFFFFD) & (w != 0xFFFFFFFF) if sidx == 0 else (l != 0xFFFFFFFF) & (w != 0xFFFFFFFF)
+            ok &= v[:, 0] < 0xFFFFFFFD
+            rid.append(np.nonzero(ok)[0])
+            sl.append(l[ok]); sr.append(l[ok] + (w[ok] & 0xFFFFFF))
+            mm.append((w[ok] >> 24) & 7); st.append(((w[ok] >> 27) & 1) + 1)           # CPUfunctions.cpp:1281-1282
+    rid = np.concatenate(rid)
+    order = np.argsort(rid, kind="stable")
+    rid = rid[order]
+    sl, sr = (np.ascontiguousarray(np.concatenate(x)[order].astype(np.uint32)) for x in (sl, sr))
+    mm, st = (np.ascontiguousarray(np.concatenate(x)[order].astype(np.uint8)) for x in (mm, st))
+    sa_off = np.zeros(n_reads + 1, np.uint64)
+    sa_off[1:] = np.cumsum(np.bincount(rid, minlength=n_reads))
+    z32, z8, zoff = np.zeros(0, np.uint32), np.zeros(0, np.uint8), np.zeros(n_reads + 1, np.uint64)
+    t0 = time.perf_counter()
+    kept = retain_best(0, sl, sr, st, mm, sa_off, z32, z8, z8, zoff)
+    t_retain = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    loc_off, pos = locate(kept["sa_l"], kept["sa_r"], max_per_range)
+    t_locate = time.perf_counter() - t0
+    per_range = np.diff(loc_off).astype(np.int64)
+    range_read = np.repeat(np.arange(n_reads), np.diff(kept["sa_off"]).astype(np.int64))
+    occ_read = np.repeat(range_read, per_range)
+    occ_strand = np.repeat(kept["sa_flags"][:, 0], per_range)
+    occ_mism = np.repeat(kept["sa_flags"][:, 1], per_range)
+    per_read = np.bincount(occ_read, minlength=n_reads)
+    lists = []
+    for parity in (0, 1):
+        sel = (occ_read & 1) == parity
+        off = np.zeros(n_reads // 2 + 1, np.uint64)
+        off[1:] = np.cumsum(per_read[parity::2])
+        lists += [np.ascontiguousarray(pos[sel]), np.ascontiguousarray(occ_strand[sel]), np.ascontiguousarray(occ_mism[sel]), off]
+    n_pairs = n_reads // 2
+    t0 = time.perf_counter()
+    pr = pair_occurrences(*lists, np.full(n_pairs, L, np.uint32), INSERT_LO, INSERT_HI, 1, 2, False)
+    t_pair = time.perf_counter() - t0
+    has = pr["optimal"] != 0xFFFFFFFF
+    best = (pr["offsets"][:-1][has] + pr["optimal"][has]).astype(np.int64)
+    at_truth = int(((pr["pos1"][best] == true_pos[0::2][has]) & (pr["pos2"][best] == true_pos[1::2][has])).sum())
+    both_found = int(((per_read[0::2] > 0) & (per_read[1::2] > 0)).sum())
+    return {"read_pairs": int(n_pairs), "sa_ranges": int(len(sl)), "sa_ranges_kept": int(len(kept["sa_l"])), "positions": int(len(pos)),
+            "pairs_with_both_mates_found": both_found, "pairs_with_a_valid_pairing": int(has.sum()),
+            "optimal_pairing_at_the_true_positions": at_truth, "valid_pairings": int(pr["offsets"][-1]),
+            "ms_retain_best": 1e3 * t_retain, "ms_locate": 1e3 * t_locate, "ms_pair_occurrences": 1e3 * t_pair,
+            "call": "s3_retain_best (all best) -> s3_locate (<= 8 per range) -> s3_pair_occurrences (insert 200-500, FR), pageable host "
+                    "arrays between the calls; numpy glue between them not counted"}
+
+
 def parity_check(gi, cb, device_index):
     """The CPU arm's sample, pushed through the GPU library (host C ABI) and compared bit for bit:
     full-size genome, the checker is the CPU arm's output (reference kernels compiled for the host)."""
@@ -901,6 +958,18 @@ def main():
             if cb["gpu_reference_dp"].get("gcups"):
                 out["dp"]["speedup_over_reference_cuda_kernels"] = dp_gcups / cb["gpu_reference_dp"]["gcups"]
         out["parity_at_full_size"] = parity_check(gi, cb, local_rank)
+    if world == 1:
+        # best-hit filter -> locate -> pairing of the two mates' lists on the last step's answers; after everything else has
+        # been measured and compared, so that nothing above depends on these newer entries
+        try:
+            hs, b = e2e_sets[-1], batches[args.warmup + args.steps - 1]
+            views = [formats.answers_view(a.numpy().view(np.uint32), hs.n, wpa) for a in hs.ans]
+            out["next_rows"]["pairing"] = pairing_rows(views, allowed, hs.n, L, b.pos.cpu().numpy().astype(np.uint32),
+                                                       lambda mode, *a: api.retain_best(gi, mode, *a),
+                                                       lambda l_, r_, cap: api.locate(gi, l_, r_, cap),
+                                                       lambda *a: api.pair_occurrences(gi, *a))
+        except Exception as e:                           # noqa: BLE001
+            out["next_rows"]["pairing"] = {"error": str(e)[:200]}
     print(json.dumps(out), flush=True)
     aligner.freeMemory()
     api.GPUINDEXFree(gi)

@@ -15,6 +15,7 @@
 #   libref_pair.so     PEMappingOccurrences + PEStatsPEPairList and what they call (PEAlgnmt.cpp:114-361,480-637,777-838)
 #   libref_retain.so   retainAllBest / retainAllBestWithCap / retainAllBestAndSecBest + list helpers (SAList.cpp:26-69,140-390)
 #   libref_md.so       getMisInfoForDP (PE.cpp:499-666): MD string, mismatch / gap counts of a DP alignment
+#   shim_check (+ shim_case/)  the drop-in shim linked with a driver written against the reference's headers, and its test case
 #   libref_params.so   getSeedPositions (definitions.h:323-442) + getParameterFor*DP (CPUfunctions.cpp:46-260)
 #   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
@@ -149,9 +150,11 @@ if [ -x "$NVCC" ]; then
   echo "[build_ref] libref_dp_cuda.so OK"
 fi
 
-# ---- the reference-side shim compiles against the reference's unmodified headers --------------
-# (integration/soap3dp_b200_shim.cpp = the file a SOAP3-dp maintainer links instead of the device
-# code of alignment.cu / DV-DPfunctions.cu; the object is only a compile check and is not used)
+# ---- the reference-side shim compiles against the reference's unmodified headers, and runs --------------
+# (integration/soap3dp_b200_shim.cpp = the file a SOAP3-dp maintainer links instead of the device code of alignment.cu /
+# DV-DPfunctions.cu.)  shim_check is a small driver that calls it the way SOAP3-dp does -- Soap3Index / BWT / DPParameters
+# from the reference's headers, GPUINDEXUpload, perform_round1_alignment, SemiGlobalAligner -- on the case
+# oracle/make_shim_case.py writes, and compares with the oracle: oracle/_ref/shim_check oracle/_ref/shim_case (on a GPU box).
 NVCC=${S3_NVCC:-/usr/local/cuda/bin/nvcc}
 if [ -x "$NVCC" ]; then
   $NVCC -x cu -c -w -Xcompiler -fpermissive -ccbin "$CXX" -gencode arch=compute_100a,code=sm_100a \
@@ -162,4 +165,13 @@ if [ -x "$NVCC" ]; then
     nm "$OUT/obj/soap3dp_b200_shim.o" | grep -q " T $sym" || { echo "[build_ref] shim lacks $sym" >&2; exit 1; }
   done
   echo "[build_ref] integration shim compiles against the reference headers"
+  LIBDIR="$HERE/../soap3-dp_b200"
+  if [ -f "$LIBDIR/libsoap3dp_b200.so" ]; then
+    $NVCC -x cu -c -w -Xcompiler -fpermissive -ccbin "$CXX" -gencode arch=compute_100a,code=sm_100a \
+        -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -I"$HERE/../include" "$HERE/ref_shim/shim_check.cu" -o "$OUT/obj/shim_check.o"
+    $NVCC -Wno-deprecated-gpu-targets -ccbin "$CXX" -o "$OUT/shim_check" "$OUT/obj/shim_check.o" "$OUT/obj/soap3dp_b200_shim.o" \
+        -L"$LIBDIR" -lsoap3dp_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../../soap3-dp_b200' -lcudart
+    if [ ! -f "$OUT/shim_case/meta.txt" ]; then python "$HERE/make_shim_case.py"; fi
+    echo "[build_ref] shim_check OK"
+  fi
 fi

@@ -1,0 +1,53 @@
+"""TEST INFRASTRUCTURE ONLY.  Writes the inputs and the oracle's expected outputs for oracle/ref_shim/shim_check.cu (the
+executed check of the drop-in shim, integration/soap3dp_b200_shim.cpp) into oracle/_ref/shim_case/ as raw little-endian
+arrays: a 200 kbp index, 2048 reads of 100 bp searched with <= 2 mismatches (round 1, four cases), and 512 mate-rescue DP
+alignments.  Run by oracle/build_ref.sh in the container that has /root/reference."""
+import os
+import sys
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.join(HERE, "..", "tests"))
+import helpers  # noqa: E402
+from soap3dp_b200 import fmindex, formats, synth  # noqa: E402
+
+out = os.path.join(HERE, "_ref", "shim_case")
+os.makedirs(out, exist_ok=True)
+
+
+def save(name, a):
+    np.ascontiguousarray(a).tofile(os.path.join(out, name + ".bin"))
+
+
+G = synth.random_genome(200_000, seed=91)
+idx = fmindex.build_index(G)
+hi = helpers.HostIndex(idx)
+save("bwt", hi.bwt); save("occ", hi.occ); save("rbwt", hi.rbwt); save("rocc", hi.rocc)
+n, L, k = 2048, 100, 2
+rs = synth.simulate_single_end(G, n, L, seed=7, sub_rate=0.015)
+lens = np.zeros(n, np.uint32)
+lens[:] = rs.lengths.numpy()
+wpq = formats.word_per_query(L)
+q = formats.pack_queries(rs.reads.numpy(), lens, wpq)
+allowed = formats.SA_RANGES_ROUND1[k]
+wpa = 2 * allowed
+olib = helpers.load_oracle()
+bad = np.zeros(n, np.uint8)
+save("queries", q); save("lengths", lens)
+hits = 0
+for case in range(formats.NUM_CASES[k]):
+    a = np.zeros(n * wpa, np.uint32)
+    helpers.oracle_launch(olib, hi, case, q, lens, n, wpq, a, bad, 0, k, allowed, wpa)
+    save(f"answers{case}", a)
+    hits += int((formats.answers_view(a, n, wpa)[:, 0] < 0xFFFFFFFD).sum())
+m = 512
+b = helpers.make_dp_batch(G, m, L, "rescue", seed=13, indel_rate=0.01)
+sc, hit, cnt, pat, _ = helpers.oracle_dp(helpers.load_oracle_dp(), b)
+for name in ("dna", "dna_len", "read", "read_len", "cutoff", "clip_lt", "clip_rt", "anchor_l", "anchor_r"):
+    save("dp_" + name, getattr(b, name))
+save("dp_scores", sc); save("dp_hit", hit); save("dp_cnt", cnt); save("dp_pattern", pat)
+with open(os.path.join(out, "meta.txt"), "w") as f:
+    f.write(f"{hi.n} {hi.isa0} {hi.risa0} {len(hi.bwt)} {len(hi.occ)} {n} {wpq} {k} {formats.NUM_CASES[k]} {allowed} {wpa} "
+            f"{m} {b.max_read} {b.max_dna} {b.pat_len}\n")
+print(f"[make_shim_case] {n} reads ({hits} case slots with hits), {m} DP alignments ({int((sc[:m] >= b.cutoff[:m]).sum())} traced) -> {out}")

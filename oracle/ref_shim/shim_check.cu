@@ -1,0 +1,109 @@
+/* TEST INFRASTRUCTURE ONLY -- see oracle/build_ref.sh.
+ * Executes the drop-in shim (integration/soap3dp_b200_shim.cpp) the way SOAP3-dp would: through the reference's own
+ * declarations -- Soap3Index / SRAIndex / BWT from its unmodified headers, GPUINDEXUpload, perform_round1_alignment,
+ * SemiGlobalAligner::{init, performAlignment, freeMemory}, GPUINDEXFree -- on the case oracle/make_shim_case.py wrote, and
+ * compares every answer word, score, hit location, tie count and traced pattern with the oracle's.  Linked against the shim
+ * object and libsoap3dp_b200.so; run on a GPU box as oracle/_ref/shim_check <case dir>.
+ */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+#include "alignment.h"
+#include "DV-DPfunctions.h"
+
+template <class T> static std::vector<T> load(const std::string &dir, const char *name)
+{
+    std::string p = dir + "/" + name + ".bin";
+    FILE *f = fopen(p.c_str(), "rb");
+    if (!f) { printf("FAIL cannot open %s\n", p.c_str()); exit(2); }
+    fseek(f, 0, SEEK_END); long sz = ftell(f); fseek(f, 0, SEEK_SET);
+    std::vector<T> v(sz / sizeof(T));
+    if (fread(v.data(), 1, sz, f) != (size_t)sz) { printf("FAIL short read %s\n", p.c_str()); exit(2); }
+    fclose(f);
+    return v;
+}
+
+static size_t pattern_bytes(const uchar *p, size_t cap)
+{
+    size_t i = 0;
+    while (i < cap && p[i] != 0) i += p[i] == 'V' ? 2 : 1;       /* a count byte may be 0 */
+    return i < cap ? i + 1 : cap;
+}
+
+int main(int argc, char **argv)
+{
+    std::string dir = argc > 1 ? argv[1] : "oracle/_ref/shim_case";
+    unsigned textLength, isa0, risa0, nbwt, nocc, n, wpq, k, numCases, allowed, wpa, m, maxRead, maxDNA, patLen;
+    {
+        FILE *f = fopen((dir + "/meta.txt").c_str(), "r");
+        if (!f || fscanf(f, "%u %u %u %u %u %u %u %u %u %u %u %u %u %u %u", &textLength, &isa0, &risa0, &nbwt, &nocc, &n, &wpq, &k, &numCases,
+                         &allowed, &wpa, &m, &maxRead, &maxDNA, &patLen) != 15) { printf("FAIL meta.txt\n"); return 2; }
+        fclose(f);
+    }
+    std::vector<uint> bwtCode = load<uint>(dir, "bwt"), occ = load<uint>(dir, "occ"), rbwtCode = load<uint>(dir, "rbwt"), rocc = load<uint>(dir, "rocc");
+    /* the reference's own structures, only the fields GPUINDEXUpload reads (alignment.cu:27-107) */
+    BWT bwt, revBwt; SRAIndex sra; Soap3Index index;
+    memset(&bwt, 0, sizeof bwt); memset(&revBwt, 0, sizeof revBwt); memset(&sra, 0, sizeof sra); memset(&index, 0, sizeof index);
+    bwt.bwtCode = bwtCode.data(); bwt.textLength = textLength; bwt.inverseSa0 = isa0;
+    revBwt.bwtCode = rbwtCode.data(); revBwt.textLength = textLength; revBwt.inverseSa0 = risa0;
+    sra.bwt = &bwt; sra.rev_bwt = &revBwt;
+    index.sraIndex = &sra; index.gpu_occValue = occ.data(); index.gpu_revOccValue = rocc.data(); index.gpu_numOfOccValue = nocc / 4;
+    cudaSetDevice(0);
+    uint *_bwt = NULL, *_occ = NULL, *_revBwt = NULL, *_revOcc = NULL;
+    GPUINDEXUpload(&index, &_bwt, &_occ, &_revBwt, &_revOcc);
+    int fails = 0;
+
+    /* round 1, all cases in one call (alignment.cu:118-215) */
+    std::vector<uint> queries = load<uint>(dir, "queries"), lengths = load<uint>(dir, "lengths");
+    std::vector<std::vector<uint> > got(numCases, std::vector<uint>((size_t)n * wpa, 0u));
+    uint *ans[2][MAX_NUM_CASES];                                  /* the caller's double buffer, alignment.cu:700-760; buffer 1 is used */
+    memset(ans, 0, sizeof ans);
+    for (unsigned c = 0; c < numCases; ++c) ans[1][c] = got[c].data();
+    perform_round1_alignment(queries.data(), lengths.data(), ans, k, numCases, allowed, wpq, wpa, false, 1,
+                             (n + 127) / 128, n, &index, _bwt, _revBwt, _occ, _revOcc);
+    for (unsigned c = 0; c < numCases; ++c) {
+        char name[32]; snprintf(name, sizeof name, "answers%u", c);
+        std::vector<uint> want = load<uint>(dir, name);
+        size_t bad = 0, hits = 0;
+        for (size_t i = 0; i < want.size(); ++i) bad += want[i] != got[c][i];
+        for (unsigned r = 0; r < n; ++r) hits += want[(size_t)(r / 32) * 32 * wpa + r % 32] < 0xFFFFFFFDu;
+        printf("%s perform_round1_alignment case %u: %zu words, %zu reads with hits, %zu words differ\n", bad ? "FAIL" : "PASS", c, want.size(), hits, bad);
+        fails += bad != 0;
+    }
+
+    /* DP (DV-DPfunctions.cu:520-741) */
+    std::vector<uint> dna = load<uint>(dir, "dp_dna"), dnaLen = load<uint>(dir, "dp_dna_len"), rd = load<uint>(dir, "dp_read"), rdLen = load<uint>(dir, "dp_read_len");
+    std::vector<int> cutoff = load<int>(dir, "dp_cutoff"), wScores = load<int>(dir, "dp_scores");
+    std::vector<uint> clipLt = load<uint>(dir, "dp_clip_lt"), clipRt = load<uint>(dir, "dp_clip_rt"), ancL = load<uint>(dir, "dp_anchor_l"), ancR = load<uint>(dir, "dp_anchor_r");
+    std::vector<uint> wHit = load<uint>(dir, "dp_hit"), wCnt = load<uint>(dir, "dp_cnt");
+    std::vector<uchar> wPat = load<uchar>(dir, "dp_pattern");
+    DPParameters para; memset(&para, 0, sizeof para);
+    para.matchScore = 1; para.mismatchScore = -2; para.openGapScore = -3; para.extendGapScore = -1;       /* soap3-dp.ini */
+    SemiGlobalAligner aligner;
+    int maxDPTableLength = 0, numOfBlocks = 0, patternLength = 0;
+    aligner.decideConfiguration((int)maxRead, (int)maxDNA, maxDPTableLength, numOfBlocks, patternLength, para);
+    aligner.init((int)wScores.size(), (int)maxRead, (int)maxDNA, maxDPTableLength, para);
+    std::vector<int> scores(wScores.size(), 0);
+    std::vector<uint> hit(wHit.size(), 0), cnt(wCnt.size(), 0);
+    std::vector<uchar> pat(wPat.size(), 0);
+    aligner.performAlignment(dna.data(), dnaLen.data(), rd.data(), rdLen.data(), cutoff.data(), scores.data(), hit.data(), cnt.data(), pat.data(), (int)m,
+                             clipLt.data(), clipRt.data(), ancL.data(), ancR.data());
+    size_t bs = 0, bh = 0, bc = 0, bp = 0, traced = 0;
+    for (unsigned t = 0; t < m; ++t) {
+        bs += scores[t] != wScores[t]; bh += hit[t] != wHit[t]; bc += cnt[t] != wCnt[t];
+        if (wScores[t] >= cutoff[t]) {
+            ++traced;
+            const uchar *a = &pat[(size_t)t * patLen], *b = &wPat[(size_t)t * patLen];
+            bp += memcmp(a, b, pattern_bytes(b, patLen)) != 0;
+        }
+    }
+    printf("%s SemiGlobalAligner::performAlignment: %u alignments (%zu traced, patternLength %d == %u), differ: scores %zu, hitLocs %zu, counts %zu, patterns %zu\n",
+           (bs || bh || bc || bp || patternLength != (int)patLen) ? "FAIL" : "PASS", m, traced, patternLength, patLen, bs, bh, bc, bp);
+    fails += (bs || bh || bc || bp || patternLength != (int)patLen);
+    aligner.freeMemory();
+    GPUINDEXFree(_bwt, _occ, _revBwt, _revOcc);
+    printf("%s drop-in shim executed through the reference's declarations\n", fails ? "FAIL" : "PASS");
+    return fails ? 1 : 0;
+}

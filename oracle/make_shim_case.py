@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY.  Writes the inputs and the oracle's expected outputs for oracle/ref_shim/shim_check.cu (the
 executed check of the drop-in shim, integration/soap3dp_b200_shim.cpp) into oracle/_ref/shim_case/ as raw little-endian
-arrays: a 200 kbp index, 2048 reads of 100 bp searched with <= 2 mismatches (round 1, four cases), and 512 mate-rescue DP
-alignments.  Run by oracle/build_ref.sh in the container that has /root/reference."""
+arrays: a 200 kbp index with close repeats, 2048 reads of 100 bp searched with <= 2 mismatches (round 1, four cases; round 2
+on the reads whose round-1 slot overflowed), and 512 mate-rescue DP alignments.  Run by oracle/build_ref.sh in the container that has /root/reference."""
 import os
 import sys
 
@@ -20,7 +20,7 @@ def save(name, a):
     np.ascontiguousarray(a).tofile(os.path.join(out, name + ".bin"))
 
 
-G = synth.random_genome(200_000, seed=91)
+G = synth.random_genome(200_000, seed=91, repeat_fraction=0.5, max_divergence=0.02)      # close repeats: slots overflow
 idx = fmindex.build_index(G)
 hi = helpers.HostIndex(idx)
 save("bwt", hi.bwt); save("occ", hi.occ); save("rbwt", hi.rbwt); save("rocc", hi.rocc)
@@ -41,6 +41,24 @@ for case in range(formats.NUM_CASES[k]):
     helpers.oracle_launch(olib, hi, case, q, lens, n, wpq, a, bad, 0, k, allowed, wpa)
     save(f"answers{case}", a)
     hits += int((formats.answers_view(a, n, wpa)[:, 0] < 0xFFFFFFFD).sum())
+# round 2 (alignment.cu:221-326): per case the overflowing reads, in read order, searched again with the larger slot
+allowed2 = formats.SA_RANGES_ROUND2[k]
+wpa2 = 2 * allowed2
+reads_np = rs.reads.numpy()
+nbad = []
+for case in range(formats.NUM_CASES[k]):
+    a = np.fromfile(os.path.join(out, f"answers{case}.bin"), np.uint32)
+    idx2 = np.nonzero(formats.answers_view(a, n, wpa)[:, 0] > 0xFFFFFFFD)[0].astype(np.uint32)
+    nb = len(idx2)
+    nbad.append(nb)
+    save(f"bad_idx{case}", idx2)
+    a2 = np.zeros(formats.ceil32(max(nb, 1)) * wpa2, np.uint32)
+    if nb:
+        bq = formats.pack_queries(reads_np[idx2], lens[idx2], wpq)
+        bl = np.zeros(formats.ceil32(nb), np.uint32)
+        bl[:nb] = lens[idx2]
+        helpers.oracle_launch(olib, hi, case, bq, bl, nb, wpq, a2, np.zeros(formats.ceil32(nb), np.uint8), 1, k, allowed2, wpa2)
+    save(f"bad_ans{case}", a2)
 m = 512
 b = helpers.make_dp_batch(G, m, L, "rescue", seed=13, indel_rate=0.01)
 sc, hit, cnt, pat, _ = helpers.oracle_dp(helpers.load_oracle_dp(), b)
@@ -49,5 +67,5 @@ for name in ("dna", "dna_len", "read", "read_len", "cutoff", "clip_lt", "clip_rt
 save("dp_scores", sc); save("dp_hit", hit); save("dp_cnt", cnt); save("dp_pattern", pat)
 with open(os.path.join(out, "meta.txt"), "w") as f:
     f.write(f"{hi.n} {hi.isa0} {hi.risa0} {len(hi.bwt)} {len(hi.occ)} {n} {wpq} {k} {formats.NUM_CASES[k]} {allowed} {wpa} "
-            f"{m} {b.max_read} {b.max_dna} {b.pat_len}\n")
-print(f"[make_shim_case] {n} reads ({hits} case slots with hits), {m} DP alignments ({int((sc[:m] >= b.cutoff[:m]).sum())} traced) -> {out}")
+            f"{m} {b.max_read} {b.max_dna} {b.pat_len} {allowed2} {wpa2}\n")
+print(f"[make_shim_case] {n} reads ({hits} case slots with hits, overflowing per case {nbad}), {m} DP alignments ({int((sc[:m] >= b.cutoff[:m]).sum())} traced) -> {out}")

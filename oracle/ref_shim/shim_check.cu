@@ -1,6 +1,6 @@
 /* TEST INFRASTRUCTURE ONLY -- see oracle/build_ref.sh.
  * Executes the drop-in shim (integration/soap3dp_b200_shim.cpp) the way SOAP3-dp would: through the reference's own
- * declarations -- Soap3Index / SRAIndex / BWT from its unmodified headers, GPUINDEXUpload, perform_round1_alignment,
+ * declarations -- Soap3Index / SRAIndex / BWT from its unmodified headers, GPUINDEXUpload, perform_round1_alignment, perform_round2_alignment,
  * SemiGlobalAligner::{init, performAlignment, freeMemory}, GPUINDEXFree -- on the case oracle/make_shim_case.py wrote, and
  * compares every answer word, score, hit location, tie count and traced pattern with the oracle's.  Linked against the shim
  * object and libsoap3dp_b200.so; run on a GPU box as oracle/_ref/shim_check <case dir>.
@@ -35,11 +35,11 @@ static size_t pattern_bytes(const uchar *p, size_t cap)
 int main(int argc, char **argv)
 {
     std::string dir = argc > 1 ? argv[1] : "oracle/_ref/shim_case";
-    unsigned textLength, isa0, risa0, nbwt, nocc, n, wpq, k, numCases, allowed, wpa, m, maxRead, maxDNA, patLen;
+    unsigned textLength, isa0, risa0, nbwt, nocc, n, wpq, k, numCases, allowed, wpa, m, maxRead, maxDNA, patLen, allowed2, wpa2;
     {
         FILE *f = fopen((dir + "/meta.txt").c_str(), "r");
-        if (!f || fscanf(f, "%u %u %u %u %u %u %u %u %u %u %u %u %u %u %u", &textLength, &isa0, &risa0, &nbwt, &nocc, &n, &wpq, &k, &numCases,
-                         &allowed, &wpa, &m, &maxRead, &maxDNA, &patLen) != 15) { printf("FAIL meta.txt\n"); return 2; }
+        if (!f || fscanf(f, "%u %u %u %u %u %u %u %u %u %u %u %u %u %u %u %u %u", &textLength, &isa0, &risa0, &nbwt, &nocc, &n, &wpq, &k, &numCases,
+                         &allowed, &wpa, &m, &maxRead, &maxDNA, &patLen, &allowed2, &wpa2) != 17) { printf("FAIL meta.txt\n"); return 2; }
         fclose(f);
     }
     std::vector<uint> bwtCode = load<uint>(dir, "bwt"), occ = load<uint>(dir, "occ"), rbwtCode = load<uint>(dir, "rbwt"), rocc = load<uint>(dir, "rocc");
@@ -71,6 +71,36 @@ int main(int argc, char **argv)
         for (unsigned r = 0; r < n; ++r) hits += want[(size_t)(r / 32) * 32 * wpa + r % 32] < 0xFFFFFFFDu;
         printf("%s perform_round1_alignment case %u: %zu words, %zu reads with hits, %zu words differ\n", bad ? "FAIL" : "PASS", c, want.size(), hits, bad);
         fails += bad != 0;
+    }
+
+    /* round 2 on what round 1 left (alignment.cu:221-326); like the reference's caller (alignment.cu:898-954) the number of
+     * bad reads per case is re-counted from the round-1 status words, the shim hands none back */
+    {
+        std::vector<std::vector<uint> > badIdx(numCases, std::vector<uint>(n, 0xDEADBEEFu)), badAns(numCases, std::vector<uint>((size_t)n * wpa2, 0u));
+        uint *pIdx[2][MAX_NUM_CASES], *pAns[2][MAX_NUM_CASES];
+        memset(pIdx, 0, sizeof pIdx); memset(pAns, 0, sizeof pAns);
+        for (unsigned c = 0; c < numCases; ++c) { pIdx[1][c] = badIdx[c].data(); pAns[1][c] = badAns[c].data(); }
+        perform_round2_alignment(queries.data(), lengths.data(), ans, k, numCases, allowed2, wpq, wpa, wpa2, false, 1,
+                                 (n + 127) / 128, n, &index, _bwt, _revBwt, _occ, _revOcc, 0, pIdx, pAns);
+        for (unsigned c = 0; c < numCases; ++c) {
+            char name[32];
+            snprintf(name, sizeof name, "bad_idx%u", c);
+            std::vector<uint> wantIdx = load<uint>(dir, name);
+            snprintf(name, sizeof name, "bad_ans%u", c);
+            std::vector<uint> wantAns = load<uint>(dir, name);
+            size_t nb = 0, bad = 0;
+            for (unsigned r = 0; r < n; ++r) nb += got[c][(size_t)(r / 32) * 32 * wpa + r % 32] > 0xFFFFFFFDu;
+            bad += nb != wantIdx.size();
+            for (size_t i = 0; i < wantIdx.size() && i < nb; ++i) bad += badIdx[c][i] != wantIdx[i];
+            /* rows of the nb reads only: the padding lanes of the last group of 32 are not part of the contract */
+            for (size_t r = 0; r < nb && r < wantIdx.size(); ++r)
+                for (unsigned w = 0; w < wpa2; ++w) {
+                    size_t at = (r / 32) * 32 * wpa2 + (size_t)w * 32 + r % 32;
+                    bad += badAns[c][at] != wantAns[at];
+                }
+            printf("%s perform_round2_alignment case %u: %zu reads searched again with %u slots, %zu differences\n", bad ? "FAIL" : "PASS", c, nb, allowed2, bad);
+            fails += bad != 0;
+        }
     }
 
     /* DP (DV-DPfunctions.cu:520-741) */

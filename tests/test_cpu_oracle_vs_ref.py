@@ -234,3 +234,52 @@ def test_retain_oracle_matches_the_reference_filters():
             got = helpers.oracle_retain_best(lists, mode, cap)
             assert helpers.same_retained(got, want), (mode, cap)
             assert int(want["sa_off"][-1]) > 300 and int(want["occ_off"][-1]) > 300
+
+
+def test_dp_without_the_full_table_gives_the_same_alignments():
+    """design check for the next DP kernel: a score pass that keeps (H, E) of every 32nd column, then a
+    second sweep of only the columns the traceback can reach (restarting from an earlier kept column when it reaches
+    further) -- same scores, hit locations, tie counts and patterns as the full-table oracle, on engine-shaped batches
+    and on adversarial ones (random pairs, big clips, random anchors, cutoff 0)"""
+    import ctypes as C
+    import helpers
+    from helpers import I32P, U8P, U32P, _opt
+    lib = load_oracle_dp()
+    lib.s3o_dp_align_resweep.restype = C.c_ulonglong
+    lib.s3o_dp_align_resweep.argtypes = helpers._DP_ARGS + [C.c_uint32, C.c_uint32, C.POINTER(C.c_ulonglong)]
+
+    def resweep(b, scores, every, slack, stats):
+        sc, hit, cnt, pat = b.outputs()
+        lib.s3o_dp_align_resweep(u32p(b.dna), u32p(b.dna_len), b.max_dna, u32p(b.read), u32p(b.read_len), b.max_read,
+                                 b.cutoff.ctypes.data_as(I32P), sc.ctypes.data_as(I32P), u32p(hit), u32p(cnt), pat.ctypes.data_as(U8P), b.n,
+                                 _opt(b.clip_lt), _opt(b.clip_rt), _opt(b.anchor_l), _opt(b.anchor_r), *scores, every, slack, stats)
+        return sc, hit, cnt, pat
+
+    G = synth.random_genome(300_000, seed=9)
+    cost = {}
+    for mode, L in (("rescue", 100), ("single", 100), ("rescue", 150)):
+        b = make_dp_batch(G, 600, L, mode, seed=L, indel_rate=0.01)
+        for every, slack in ((32, 16), (16, 0), (64, 40)):
+            stats = (C.c_ulonglong * 3)(0, 0, 0)
+            assert compare_dp(b, resweep(b, (1, -2, -3, -1), every, slack, stats), oracle_dp(lib, b), f"resweep {mode} {L} {every}") > 500
+            cost[(mode, L, every, slack)] = (stats[0] / stats[2], stats[1])
+    # mate-rescue windows are 4 x the read: with 32-column checkpoints and 16 columns of slack about a third of the columns
+    # are swept again and restarts are rare
+    assert cost[("rescue", 100, 32, 16)][0] < 0.45 and cost[("rescue", 100, 32, 16)][1] <= 6
+    rng = np.random.default_rng(3)
+    adv = (C.c_ulonglong * 3)(0, 0, 0)
+    for seed in range(3):
+        n, L = 500, int(rng.integers(20, 130))
+        W = L + int(rng.integers(5, 300))
+        dna = rng.integers(0, 4, (n, W)).astype(np.uint8)
+        read = rng.integers(0, 4, (n, L)).astype(np.uint8)
+        for t in range(0, n, 2):
+            o = rng.integers(0, W - L)
+            dna[t, o:o + L] = read[t]
+        b = DPBatch(dna, rng.integers(W - 3, W + 1, n).astype(np.uint32), read, rng.integers(max(L - 8, 1), L + 1, n).astype(np.uint32),
+                    W + 14, (L // 4 + 1) * 4, np.zeros(n, np.int32), rng.integers(0, L, n).astype(np.uint32),
+                    rng.integers(0, L, n).astype(np.uint32), rng.integers(1, W + 14, n).astype(np.uint32), rng.integers(0, W, n).astype(np.uint32))
+        compare_dp(b, resweep(b, (1, -2, -3, -1), 32, 8, adv), oracle_dp(lib, b), f"resweep adversarial {seed}")
+        compare_dp(b, resweep(b, (1, -1, -2, -1), 8, 0, adv), oracle_dp(lib, b, (1, -1, -2, -1)), f"resweep adversarial {seed} b")
+    print("resweep cost (fraction of columns swept again, restarts per 600):", {k: (round(v[0], 3), v[1]) for k, v in cost.items()},
+          f"; adversarial {adv[0]} of {adv[2]} columns, {adv[1]} restarts")

@@ -251,32 +251,64 @@ extern "C" int s3_dp_md(const uint32_t *packedDNA, uint64_t textLength, const ch
         return S3_EINVAL;
     }
     *md = nullptr;
-    std::string out;
-    try {
-        out.reserve((size_t)numOfThreads * 12);
-        for (uint32_t t = 0; t < numOfThreads; ++t) {
-            mdOffsets[t] = out.size();
+    const uint32_t n = numOfThreads;
+    uint32_t nt = std::thread::hardware_concurrency();
+    if (const char *e = getenv("S3_DECODE_THREADS")) nt = (uint32_t)atoi(e);
+    nt = nt < 1 ? 1 : nt > 32 ? 32 : nt;
+    if ((uint64_t)nt * 4096 > n) nt = n / 4096 ? n / 4096 : 1;
+    struct MdChunk { std::string md; std::vector<uint32_t> len; };
+    std::vector<MdChunk> chunks(nt);
+    std::atomic<bool> failed{false};
+    std::atomic<int64_t> pastText{-1};
+    auto work = [&](uint32_t c) { try {
+        const uint32_t lo = (uint32_t)((uint64_t)n * c / nt), hi = (uint32_t)((uint64_t)n * (c + 1) / nt);
+        MdChunk &ch = chunks[c];
+        ch.len.resize(hi - lo);
+        ch.md.reserve((size_t)(hi - lo) * 12);
+        for (uint32_t t = lo; t < hi; ++t) {
+            const size_t m0 = ch.md.size();
             MdOut o{0, 0, 0, 20};
             const size_t len = (size_t)(cigarOffsets[t + 1] - cigarOffsets[t]);
             if (len) {                                               // an alignment under its cutoff has no CIGAR and gets no MD
                 const int8_t *q = qualities ? qualities + qualityOffsets[t] : nullptr;
                 const size_t ql = qualities ? (size_t)(qualityOffsets[t + 1] - qualityOffsets[t]) : 0;
-                if (!md_one(packedDNA, textLength, cigars + cigarOffsets[t], len, positions[t], q, ql, out, o)) {
-                    s3_set_error("s3_dp_md: alignment %u at %u runs past the text (%llu bases)", t, positions[t], (unsigned long long)textLength);
-                    return S3_EINVAL;
+                if (!md_one(packedDNA, textLength, cigars + cigarOffsets[t], len, positions[t], q, ql, ch.md, o)) {
+                    int64_t none = -1;
+                    pastText.compare_exchange_strong(none, (int64_t)t);
+                    return;
                 }
             }
+            ch.len[t - lo] = (uint32_t)(ch.md.size() - m0);
             if (numMismatch) numMismatch[t] = o.numMismatch;
             if (gapOpen) gapOpen[t] = o.gapOpen;
             if (gapExt) gapExt[t] = o.gapExt;
             if (avgMismatchQual) avgMismatchQual[t] = o.avgQual;
         }
-    } catch (...) { s3_set_error("s3_dp_md: out of host memory"); return S3_ENOMEM; }
-    mdOffsets[numOfThreads] = out.size();
-    char *buf = (char *)malloc(out.size() + 1);
+    } catch (...) { failed = true; } };
+    if (nt == 1) work(0);
+    else {
+        std::vector<std::thread> th;
+        for (uint32_t c = 0; c < nt; ++c) th.emplace_back(work, c);
+        for (auto &t : th) t.join();
+    }
+    if (failed) { s3_set_error("s3_dp_md: out of host memory"); return S3_ENOMEM; }
+    if (pastText >= 0) {
+        const uint32_t t = (uint32_t)pastText.load();
+        s3_set_error("s3_dp_md: alignment %u at %u runs past the text (%llu bases)", t, positions[t], (unsigned long long)textLength);
+        return S3_EINVAL;
+    }
+    uint64_t total = 0;
+    for (auto &ch : chunks) total += ch.md.size();
+    char *buf = (char *)malloc(total + 1);
     if (!buf) { s3_set_error("s3_dp_md: out of host memory"); return S3_ENOMEM; }
-    memcpy(buf, out.data(), out.size());
-    buf[out.size()] = 0;
+    uint64_t at = 0, posBytes = 0;
+    uint32_t t = 0;
+    for (auto &ch : chunks) {
+        memcpy(buf + posBytes, ch.md.data(), ch.md.size()); posBytes += ch.md.size();
+        for (size_t k = 0; k < ch.len.size(); ++k, ++t) { mdOffsets[t] = at; at += ch.len[k]; }
+    }
+    mdOffsets[n] = at;
+    buf[total] = 0;
     *md = buf;
     return S3_OK;
 }

@@ -231,3 +231,17 @@ def test_md_string_is_consistent_with_the_alignment():
         md = got["md"][t]
         covered = sum(int(x) for x in re.findall(r"\d+", md)) + len(re.findall(r"[ACGT]", md))
         assert covered == span, (cig, md)
+
+
+def test_md_thread_count_does_not_change_the_result(monkeypatch):
+    text, packed, cases = md_cases()
+    cig, pos = [c[0] for c in cases] * 60, [c[1] for c in cases] * 60          # > 4096 alignments per host thread
+    res = []
+    for nt in ("1", "3"):
+        monkeypatch.setenv("S3_DECODE_THREADS", nt)
+        d = api.md_strings(packed, len(text), cig, pos)
+        res.append((d["md"], d["num_mismatch"].tolist(), d["gap_ext"].tolist()))
+    assert res[0] == res[1] and len(cig) > 3 * 4096
+    monkeypatch.setenv("S3_DECODE_THREADS", "3")
+    with pytest.raises(api.S3Error, match="runs past the text"):
+        api.md_strings(packed, len(text), cig + ["5M3m"], pos + [len(text) - 6])

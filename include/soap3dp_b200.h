@@ -8,7 +8,10 @@
  * synchronous (results are in host memory when it returns), exactly like the
  * reference's perform_round*_alignment / SemiGlobalAligner::performAlignment.
  *
- * There is no CPU fallback: if no CUDA device is usable the calls fail.
+ * There is no CPU fallback: if no CUDA device is usable the calls fail.  Four
+ * entries replace code that runs on the host in the reference as well and are
+ * host code here too (no device involved): s3_dp_decode, s3_dp_md,
+ * s3_seed_layout, s3_dp_stage_parameters.
  */
 #ifndef SOAP3DP_B200_H
 #define SOAP3DP_B200_H

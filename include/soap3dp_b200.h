@@ -8,10 +8,10 @@
  * synchronous (results are in host memory when it returns), exactly like the
  * reference's perform_round*_alignment / SemiGlobalAligner::performAlignment.
  *
- * There is no CPU fallback: if no CUDA device is usable the calls fail.  Four
+ * There is no CPU fallback: if no CUDA device is usable the calls fail.  A few
  * entries replace code that runs on the host in the reference as well and are
  * host code here too (no device involved): s3_dp_decode, s3_dp_md,
- * s3_seed_layout, s3_dp_stage_parameters.
+ * s3_seed_layout, s3_dp_stage_parameters, s3_mapq_*.
  */
 #ifndef SOAP3DP_B200_H
 #define SOAP3DP_B200_H
@@ -392,6 +392,30 @@ typedef struct {
 int s3_dp_stage_parameters(int stage, uint32_t readLength, uint32_t readLength2, int isDefaultThreshold,
                            int32_t dpScoreThreshold, int32_t maxFrontLenClipped, int32_t maxEndLenClipped,
                            s3_dp_stage_params *out);
+
+/* ------------------------------------------------------------------------
+ * Mapping qualities (host, scalar).  Replace the MAPQ functions of the SAM writers with their
+ * tables (BGS-IO.cpp:33-45, 2280-2580; g_log_n of bwase_initialize, CPUfunctions.cpp:3014-3019
+ * is built in).  Argument lists are the reference's, without the g_log_n pointer:
+ *   s3_mapq_unique       getMapQualScore            :2280     s3_mapq_bwa_single   bwaLikeSingleQualScore :2311
+ *   s3_mapq_single       getMapQualScoreSingle      :2331     s3_mapq_single_dp    getMapQualScoreForSingleDP :2370
+ *   s3_mapq_bwa_pair     bwaLikePairQualScore       :2415     s3_mapq_pair_end     getMapQualScore2 :2465
+ *   s3_mapq_unique_dp    getMapQualScoreForDP       :2500     s3_mapq_pair_end_dp  getMapQualScoreForDP2 :2534
+ *   s3_mapq_of_pair      getMapQualScoreForPair     :2577
+ * ------------------------------------------------------------------------ */
+int32_t s3_mapq_unique(int n, int mismatchNum, int avgMismatchQual, int maxMAPQ, int minMAPQ);
+int32_t s3_mapq_bwa_single(int x0, int x1);
+int32_t s3_mapq_single(int mismatchNum, int avgMismatchQual, int x0, int x1, int maxMAPQ, int minMAPQ, int isBWALike);
+int32_t s3_mapq_single_dp(int maxDPScore, int avgMismatchQual, int x0, int x1_t1, int x1_t2, int bestDPScore,
+                          int secondBestDPScore, int maxMAPQ, int minMAPQ, int dpThres, int isBWALike);
+void s3_mapq_bwa_pair(int x0_0, int x1_0, int x0_1, int x1_1, int op_score, int op_num, int subop_score, int subop_num,
+                      int readlen_0, int readlen_1, int32_t *mapScore0, int32_t *mapScore1);
+int32_t s3_mapq_pair_end(int mismatchNum, int avgMismatchQual, int x0, int x1, int isBestHit, uint32_t totalNumValidPairs,
+                         int maxMAPQ, int minMAPQ);
+int32_t s3_mapq_unique_dp(int n, int dpScore, int maxDPScore, int avgMismatchQual, int maxMAPQ, int minMAPQ);
+int32_t s3_mapq_pair_end_dp(int dpScore, int maxDPScore, int avgMismatchQual, int x0, int x1, int bestDPScore,
+                            int secondBestDPScore, int isBestHit, int totalNumValidPairs, int maxMAPQ, int minMAPQ);
+int32_t s3_mapq_of_pair(int score1, int score2);
 
 /* ------------------------------------------------------------------------
  * Measurement hooks (replace nothing in the reference).  With timing on, CUDA events are

@@ -16,6 +16,7 @@
 #   libref_retain.so   retainAllBest / retainAllBestWithCap / retainAllBestAndSecBest + list helpers (SAList.cpp:26-69,140-390)
 #   libref_md.so       getMisInfoForDP (PE.cpp:499-666): MD string, mismatch / gap counts of a DP alignment
 #   shim_check (+ shim_case/)  the drop-in shim linked with a driver written against the reference's headers, and its test case
+#   libref_mapq.so     the nine MAPQ functions of the SAM writers + tables (BGS-IO.cpp:33-45,2280-2580)
 #   libref_params.so   getSeedPositions (definitions.h:323-442) + getParameterFor*DP (CPUfunctions.cpp:46-260)
 #   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
@@ -129,6 +130,11 @@ echo "[build_ref] libref_pair.so OK"
 $CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
     "$HERE/ref_shim/ref_md_host.cpp" -o "$OUT/libref_md.so"
 echo "[build_ref] libref_md.so OK"
+
+# ---- reference MAPQ functions and their tables ------------------------------------------------------------
+{ sed -n '33p;42p;45p' "$REF/BGS-IO.cpp"; sed -n '3014,3019p' "$REF/CPUfunctions.cpp"; sed -n '2280,2580p' "$REF/BGS-IO.cpp"; } > "$OUT/patched/mapq.inc"
+$CXX -O2 -fpermissive -w -fPIC -shared -I"$OUT/patched" "$HERE/ref_shim/ref_mapq_host.cpp" -o "$OUT/libref_mapq.so"
+echo "[build_ref] libref_mapq.so OK"
 
 # ---- reference best-hit filters (retainAllBest family) against the reference's own header ---------------------
 { sed -n '26,69p' "$REF/SAList.cpp"; sed -n '140,390p' "$REF/SAList.cpp"; } > "$OUT/patched/retain.inc"

@@ -33,7 +33,9 @@ EXPORTS = [
     "s3_last_error", "s3_device_count", "s3_launch_count", "s3_dp_set_stream", "s3_index_upload", "s3_index_free", "s3_index_device_bytes",
     "s3_index_set_locate_device", "s3_search_set_split_budget",
     "s3_index_set_timing", "s3_index_read_timing", "s3_dp_set_timing", "s3_dp_read_timing",
-    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_dp_decode", "s3_dp_md", "s3_seed_layout", "s3_dp_stage_parameters", "s3_pair_occurrences", "s3_retain_best", "s3_seed_candidates", "s3_seed_pair_candidates",
+    "s3_search", "s3_search_result_free", "s3_locate", "s3_free", "s3_dp_align_windows", "s3_dp_decode", "s3_dp_md", "s3_seed_layout", "s3_dp_stage_parameters", "s3_pair_occurrences", "s3_retain_best",
+    "s3_mapq_unique", "s3_mapq_bwa_single", "s3_mapq_single", "s3_mapq_single_dp", "s3_mapq_bwa_pair", "s3_mapq_pair_end",
+    "s3_mapq_unique_dp", "s3_mapq_pair_end_dp", "s3_mapq_of_pair", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
 ]

@@ -868,7 +868,7 @@ def main():
     K = args.steps
     names_s = ["s3_search_easy_kernel", "s3_search_kernel<items>", "s3_search_kernel<spine>", "s3_search_kernel<tasks>",
                "s3_heavy_merge_kernel", "s3_isbad_fixup_kernel"]
-    names_d = ["s3_dp_score16_kernel", "s3_dp_best16_kernel", "s3_dp_traceback16_kernel"]
+    names_d = ["s3_dp_sweep16_kernel", "s3_dp_resweep16_kernel", "s3_dp_traceback16_kernel", "s3_dp pass 2 (second sweep + traceback of what left its window)"]
     kernels = {}
     for nm, ms, cnt in list(zip(names_s, ms_search, n_search)) + list(zip(names_d, ms_dp, n_dp)):
         if cnt:

@@ -60,8 +60,12 @@ struct s3_dp {
     uint32_t slot;               // wide path: bytes per lane per column in the traceback plane
     uint32_t chunk;              // alignments per traceback-plane chunk
     uint8_t *d_tb;               // wide: chunk * (maxDNALength+1) * 32 * slot bytes
-                                 // narrow: chunk/2 pairs * (maxDNALength+lanes) steps * lanes * R words
+                                 // narrow: chunk/2 pairs * (maxDNALength+lanes+1) steps * lanes * PW words (a pass-2 plane each)
     uint32_t *d_scRight;         // maxBatch
+    // narrow path: checkpoints of the sweep (per pair of a chunk), the traceback lists of a chunk (3 x chunk ids:
+    // resumed, from column 0, second pass) with their counters, first step of every alignment's second sweep
+    uint32_t *d_ckpt, *d_tbList, *d_tbCount, *d_s0;
+    uint32_t numCk;
     // staging for the host entry point
     uint32_t *d_dna, *d_read, *d_dnaLen, *d_readLen, *d_hit, *d_cnt, *d_clipLt, *d_clipRt, *d_ancL, *d_ancR;
     int32_t *d_cutoff, *d_score;
@@ -84,8 +88,11 @@ struct S3DpArgs {
     uint32_t slot;
     int match, mismatch, open, ext;
     unsigned long long *cells;
-    uint32_t *hplane;                // narrow path: H values, [pair][step][lane][R] words (A low half, B high half)
-    uint32_t planeSteps;             // maxDNALength + lanes per pair
+    uint32_t *hplane;                // narrow path: H values of a traceback window, [pair][step][lane][PW] words (A low half, B high half)
+    uint32_t planeSteps;             // steps per pair in it: pass 1 maxReadLength + slack + checkpoint distance + lanes + 1, pass 2 maxDNALength + lanes + 1
+    uint32_t *ckpt; size_t ckStride; uint32_t numCk;      // checkpoints: words per pair of the sweep, checkpoints per pair
+    uint32_t *tbList, *tbCount, tbCap, *s0;               // traceback lists (3 x tbCap), their counters, first step of the second sweep
+    uint32_t pass;                   // 1: windows, 2: whole tables of what pass 1 could not trace
     // narrow path.  Values travel as v + 32768 in each 16-bit half ("biased"), so that a score parameter is
     // added to both halves by ONE 32-bit add of kX = x * 0x10001 (two's complement for x < 0: no carry or
     // borrow crosses the halves because 0 < biased value +- parameter < 65536) -- an IMAD, which leaves the
@@ -110,7 +117,8 @@ s3_dp_score_kernel(const S3DpArgs a)
     if (local >= a.count) return;                       // whole warp leaves together
     const uint32_t id = a.first + local;
     const uint32_t g = id >> 5, gl = id & 31;
-    const uint32_t m = a.readLen[id], n = a.dnaLen[id];
+    // lengths past what the packed arrays hold (base i lives in word i >> 4) are cut: never read beyond a slot
+    const uint32_t m = min(a.readLen[id], a.readWords * 16u - 1u), n = min(a.dnaLen[id], a.dnaWords * 16u - 1u);
     const uint32_t clipLt = a.clipLt ? a.clipLt[id] : 0u;
     const uint32_t clipRt = a.clipRt ? a.clipRt[id] : 0u;
     const uint32_t anchorLeft = a.ancL ? a.ancL[id] : a.maxDNALength;
@@ -238,7 +246,7 @@ __global__ void s3_dp_traceback_kernel(const S3DpArgs a, int R)
     if (local >= a.count) return;
     const uint32_t id = a.first + local;
     if (a.score[id] < a.cutoff[id]) return;
-    const uint32_t m = a.readLen[id];
+    const uint32_t m = min(a.readLen[id], a.readWords * 16u - 1u);
     const uint32_t clipLt = a.clipLt ? a.clipLt[id] : 0u;
     const uint32_t scRight = a.scRight[id];
     const uint8_t *tb = a.tb + (size_t)local * (a.maxDNALength + 1) * 32 * a.slot;
@@ -322,140 +330,309 @@ __device__ __forceinline__ uint32_t s3_fadd(uint32_t x, uint32_t k, uint32_t one
 }
 __device__ __forceinline__ uint32_t s3_bpk(int lo, int hi) { return ((uint32_t)(lo + 32768) & 0xFFFFu) | ((uint32_t)(hi + 32768) << 16); }
 
-// Where lane t's R words of one step sit inside the step's LANES * R words.  DRAM moves 64-byte bursts,
-// two of these 32-byte slots: the best-cell scan reads the last lanes that hold rows (tLast and, when the
-// right clip reaches back into it, tLast - 1), so the slots are rotated by one when tLast is even and
-// that pair shares a burst.
-template <int LANES>
-__device__ __forceinline__ uint32_t s3_dp_slot(uint32_t t, uint32_t tLast) { return (t + (~tLast & 1u)) & (uint32_t)(LANES - 1); }
-
-// Word offset of lane t's R words of step s in a pair's H plane ([step][lane slot][row]: the LANES x R words of
-// a step are contiguous, and every lane writes and reads whole 32-byte sectors), and the distance between two
-// steps of a lane.  (A [lane][step][row] order was measured too: same kernel times, profiles/r01u.)
-#ifndef S3_DP_STEP_BLOCK
-#define S3_DP_STEP_BLOCK 1           // steps of a lane that sit next to each other in the plane (1, 2 or 4)
+// ---- the 16x2 path keeps no H plane of the whole table ------------------------------------------------
+// (1) s3_dp_sweep16_kernel   sweeps every column once: best cell, tie count, right clip (DV-DPfunctions.cu:225-235)
+//     are found inside the sweep; every S3_DP_CK steps each lane leaves a checkpoint of its registers (64 B).
+// (2) s3_dp_resweep16_kernel sweeps again, for the alignments that reached their cutoff, only the steps a
+//     traceback from the best cell can reach: from the last checkpoint at least readLength + S3_DP_SLACK columns left
+//     of the end column, into a plane of that window only.
+// (3) s3_dp_traceback16_kernel walks that plane.  A traceback that needs a cell left of its window (more than
+//     S3_DP_SLACK deleted bases) puts its alignment on a list; pass 2 re-sweeps those from column 0 into a full-size
+//     plane and traces them again.  Results are those of the full table: a resumed sweep continues from the very
+//     registers of the first one (oracle/dp_oracle.c:dp_one_resweep states the scheme on the CPU).
+#ifndef S3_DP_CK
+#define S3_DP_CK 32u                 // steps between two checkpoints (a power of two, >= the lanes of a group)
 #endif
-// [step block][lane slot][step in block][row]: with a block of 4 a lane's sectors of four consecutive steps are one
-// 128-byte line -- the traceback's diagonal neighbour is mostly in the line it just read, the best-cell scan reads
-// whole lines -- while the lanes of a group still write into one contiguous region per block of steps.
-template <int R, int LANES>
-__device__ __forceinline__ size_t s3_dp_cell(uint32_t t, uint32_t s, uint32_t tLast)
+#ifndef S3_DP_SLACK
+#define S3_DP_SLACK 16u              // columns kept left of (end column - read length)
+#endif
+
+template <int R> struct S3DpGeom {
+    static constexpr int PW = (R <= 4) ? 4 : (R <= 8) ? 8 : 16; // words per lane and step in a traceback plane: whole 16- / 32- / 64-byte pieces
+    static constexpr int CKW = (2 * R + 2 + 7) / 8 * 8;         // words per lane and checkpoint: H + open [R], E [R], F, diagonal
+};
+
+// The R rows of one lane at one column: 5 instructions on the ALU pipe per row (PRMT, 3 x VIMNMX3.U16x2,
+// VIMNMX.U16x2) and 4 adds the compiler spreads over the ALU and FMA pipes.  HO[r] leaves as H + open of this column.
+// (A form whose row-to-row chain is one add and one maximum -- F(i+1) = max(F(i) + ext, X(i) + open, clip) with
+// X = max(E, diagonal + score), valid for ext >= open -- costs two more instructions per row and was measured no
+// faster: the sweep is bound by issue slots, not by that chain.)
+template <int R>
+__device__ __forceinline__ void s3_dp_rows(const uint2 tab, const uint32_t (&sel)[R], uint32_t (&HO)[R], uint32_t (&E)[R],
+                                           const uint32_t (&clipIO)[R], const uint32_t (&clipPIO)[R],
+                                           uint32_t &upO, uint32_t &F, uint32_t &diagO,
+                                           const uint32_t KOPEN, const uint32_t KEXT, const uint32_t CEH2, const uint32_t ONE)
 {
-    return ((((size_t)(s / S3_DP_STEP_BLOCK) * LANES + s3_dp_slot<LANES>(t, tLast)) * S3_DP_STEP_BLOCK) + s % S3_DP_STEP_BLOCK) * R;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t d = s3_prmt(tab.x, tab.y, sel[r]);                       // substitution score - open, >= 0
+        const uint32_t e = __vimax3_u16x2(HO[r], s3_fadd(E[r], KEXT, ONE), CEH2);
+        F = __vimax3_u16x2(s3_fadd(F, KEXT, ONE), upO, clipIO[r]);
+        const uint32_t dg = __vmaxu2(diagO, clipPIO[r]);
+        const uint32_t up = __vimax3_u16x2(F, e, s3_fadd(dg, d, ONE));
+        diagO = HO[r];
+        upO = s3_fadd(up, KOPEN, ONE);
+        HO[r] = upO; E[r] = e;
+    }
 }
 
-// Best cells of the two alignments of a pair (DV-DPfunctions.cu:225-235) found AFTER the sweep, from
-// the pair's H plane: per alignment the highest H over the rows i >= m - clipRt and the columns
-// anchorRight <= j <= n, the first such cell in (column, row) order, and the number of cells that tie
-// with it.  The reference compares the UNclamped value of a cell with a running best that starts at
-// -32000; the plane stores the unclamped value (biased by 32768), so a cell below the clamp neither
-// beats nor ties that start value, exactly like the reference's test.
-// Work items are (lane slot, column) = R consecutive rows of both alignments = one 16- or 32-byte
-// entry of the slot's stream; the group's lanes take the columns round-robin, two at a time so that
-// the loads overlap.
-// Out, in every lane of the group: best score, key = column << 32 | row (~0 if nothing beat the start
-// value), tie count.
-template <int R, int LANES>
-__device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps, uint32_t t, const uint32_t m[2], const uint32_t n[2],
-                                             const uint32_t clipRt[2], const uint32_t ancR[2],
-                                             int gbest[2], unsigned long long gkey[2], uint32_t gcnt[2])
+// soft-clip restart operands of a column (DV-DPfunctions.cu:215-219): row i is fed from row i-1 when i-1 <= clipLt
+template <int R>
+__device__ __forceinline__ void s3_dp_clip_operands(const uint32_t init, const uint32_t prevInit, const uint32_t i0, const uint32_t (&clipLt)[2],
+                                                    const uint32_t KOPEN, const uint32_t NEGO2, uint32_t (&clipIO)[R], uint32_t (&clipPIO)[R])
 {
+    const uint32_t io = init + KOPEN, pio = prevInit + KOPEN;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i = i0 + r;
+        const uint32_t cm = ((i - 1 <= clipLt[0]) ? 0xFFFFu : 0u) | ((i - 1 <= clipLt[1]) ? 0xFFFF0000u : 0u);
+        clipIO[r] = io & cm;                            // biased 0 = -32768: the identity of max elsewhere
+        clipPIO[r] = (pio & cm) | (NEGO2 & ~cm);
+    }
+}
+
+// start value of column j of both alignments (biased): 0 left of the left anchor, -32000 from it on
+__device__ __forceinline__ uint32_t s3_dp_init2(const uint32_t jA, const uint32_t jB, const uint32_t (&ancL)[2])
+{
+    return ((jA >= ancL[0]) ? (S3_NEGB2 & 0xFFFFu) : 0x8000u) | ((jB >= ancL[1]) ? (S3_NEGB2 & 0xFFFF0000u) : 0x80000000u);
+}
+
+// the two alignments of a pair: what the kernels need of them
+struct S3DpPair {
+    uint32_t id[2], m[2], n[2], clipLt[2], clipRt[2], ancL[2], ancR[2];
+};
+__device__ __forceinline__ void s3_dp_load_pair(const S3DpArgs &a, S3DpPair &p)
+{
+#pragma unroll
+    for (int x = 0; x < 2; ++x) {
+        // lengths past what the packed arrays hold (base i lives in word i >> 4) are cut: never read beyond a slot
+        p.m[x] = min(a.readLen[p.id[x]], a.readWords * 16u - 1u);
+        p.n[x] = min(a.dnaLen[p.id[x]], a.dnaWords * 16u - 1u);
+        p.clipLt[x] = a.clipLt ? a.clipLt[p.id[x]] : 0u;
+        p.clipRt[x] = a.clipRt ? a.clipRt[p.id[x]] : 0u;
+        p.ancL[x] = a.ancL ? a.ancL[p.id[x]] : a.maxDNALength;
+        p.ancR[x] = a.ancR ? a.ancR[p.id[x]] : 0u;
+    }
+}
+
+// this lane's read bases become PRMT selectors: the substitution score of a row is looked up in a 4-byte table
+// per alignment (byte c = score against reference base c, minus the gap open score: the diagonal H arrives with
+// + open on it, see s3_dp_rows)
+template <int R>
+__device__ __forceinline__ void s3_dp_selectors(const S3DpArgs &a, const S3DpPair &p, const uint32_t i0, uint32_t (&sel)[R])
+{
+    const uint32_t *readA = a.read + (size_t)(p.id[0] >> 5) * a.readWords * 32 + (p.id[0] & 31);
+    const uint32_t *readB = a.read + (size_t)(p.id[1] >> 5) * a.readWords * 32 + (p.id[1] & 31);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i = i0 + r;
+        const uint32_t cA = (i <= p.m[0]) ? (readA[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
+        const uint32_t cB = (i <= p.m[1]) ? (readB[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
+        sel[r] = cA | ((cA | 8u) << 4) | ((cB | 4u) << 8) | ((cB | 12u) << 12);
+    }
+}
+
+// column 0 (DV-DPfunctions.cu:167-184).  Carried per row, biased: HO = H of the previous column + open and E of
+// the previous column, both UNclamped -- the reference's clamp at -32000 when it stores a value is applied
+// where the value is used (ceh2 in E's max, nego2 in the diagonal's), which takes the same maximum.
+template <int R>
+__device__ __forceinline__ void s3_dp_column0(const S3DpPair &p, const uint32_t i0, const int open, const int gapInit, const int ext,
+                                              const uint32_t KOPEN, uint32_t (&HO)[R], uint32_t (&E)[R])
+{
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i = i0 + r;
+        const int hA = (i <= p.clipLt[0]) ? open : gapInit + (int)(i - p.clipLt[0]) * ext;
+        const int hB = (i <= p.clipLt[1]) ? open : gapInit + (int)(i - p.clipLt[1]) * ext;
+        HO[r] = s3_bpk(s3_clamp(hA), s3_clamp(hB)) + KOPEN;
+        E[r] = s3_bpk(s3_clamp(hA + gapInit), s3_clamp(hB + gapInit));
+    }
+}
+
+// Sweep of S3_DP_WARPS * (32 / LANES) pairs of alignments per block.  A pair is swept by a group of LANES lanes,
+// each owning R consecutive read rows; at step s lane t is in column s - t.
+// Best cell (DV-DPfunctions.cu:225-235): the lanes that hold rows i >= m - clipRt ("slot lanes", the last one or two
+// of a group unless the right clip is long) leave their R values of every step in a ring in shared memory; when the
+// ring holds LANES entries every lane of the group takes one: maximum over its eligible rows, the rows that hold it,
+// against a running (best, first cell, tie count) of its own.  The reference's scan -- strictly greater replaces,
+// equal counts -- gives the maximum, the number of cells that hold it and the first of them in (column, row) order,
+// which is what merging the lanes' triples at the end gives.  The reference compares the UNclamped value of a cell
+// with a best that starts at -32000; the values here are unclamped too, so a cell below the clamp neither beats nor
+// ties that start value.
+// resident blocks per SM the sweeps are compiled for: the more rows a lane holds the more registers
+#ifndef S3_DP_MINBLOCKS
+#define S3_DP_MINBLOCKS(R) ((R) <= 8 ? 4 : 3)
+#endif
+template <int R, int LANES>
+__global__ void __launch_bounds__(S3_DP_WARPS * 32, S3_DP_MINBLOCKS(R))
+s3_dp_sweep16_kernel(const S3DpArgs a)
+{
+    constexpr int GROUPS = 32 / LANES;                            // pairs per warp
+    constexpr int PW = S3DpGeom<R>::PW, CKW = S3DpGeom<R>::CKW;
+    // per pair and reference column j: the two substitution tables of that column (byte c of .x / .y = score
+    // of alignment A / B's reference base j against read base c), built once, read every step; then the rings
+    extern __shared__ uint2 s3_dp_cols[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = lane / LANES, t = lane % LANES;
+    const uint32_t gmask = (LANES == 32) ? 0xFFFFFFFFu : (((1u << LANES) - 1u) << (LANES * group));
+    const uint32_t numPairs = (a.count + 1) / 2;
+    const uint32_t wantPair = (blockIdx.x * S3_DP_WARPS + warp) * GROUPS + group;
+    if ((blockIdx.x * S3_DP_WARPS + warp) * GROUPS >= numPairs) return;          // whole warp leaves together
+    const bool pairValid = wantPair < numPairs;
+    const uint32_t pairLocal = pairValid ? wantPair : numPairs - 1;              // idle groups shadow a real pair, write nothing
+    const bool hasB = 2 * pairLocal + 1 < a.count;
+    S3DpPair p;
+    p.id[0] = a.first + 2 * pairLocal; p.id[1] = a.first + 2 * pairLocal + (hasB ? 1u : 0u);
+    s3_dp_load_pair(a, p);
+    const uint32_t mMax = max(p.m[0], p.m[1]), nMax = pairValid ? max(p.n[0], p.n[1]) : 0u;
+    const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
+    // the constants of the row loop must stay in registers (ptxas otherwise re-reads them from the constant
+    // bank every step and the loop waits for them): + 0 from a loaded value it cannot see through
+    const uint32_t zero = p.n[0] >> 31;
+    const uint32_t KOPEN = a.kOpen + zero, KEXT = a.kExt + zero, CEH2 = a.ceh2 + zero;
+    const uint32_t KGAPINIT = a.kGapInit, NEGO2 = a.nego2, ONE = a.one;
+    const uint32_t i0 = t * R + 1;                                 // first row of this lane (1-based)
+
+    // reference windows (1-based packing, MSB first; DV-DPfunctions.cu:58) -> column tables in shared memory
+    uint2 *cols = s3_dp_cols + (size_t)(warp * GROUPS + group) * a.colStride;
+    uint32_t *ring = reinterpret_cast<uint32_t *>(s3_dp_cols + (size_t)S3_DP_WARPS * GROUPS * a.colStride) +
+                     (size_t)(warp * GROUPS + group) * (2 * LANES * PW + LANES * R);
+    uint32_t *keepRow = ring + 2 * LANES * PW;
+    {
+        const uint32_t *dnaA = a.dna + (size_t)(p.id[0] >> 5) * a.dnaWords * 32 + (p.id[0] & 31);
+        const uint32_t *dnaB = a.dna + (size_t)(p.id[1] >> 5) * a.dnaWords * 32 + (p.id[1] & 31);
+#pragma unroll 4
+        for (uint32_t j = t; j <= nMax; j += LANES) {
+            const uint32_t sh = (15u - (j & 15u)) << 1;
+            const uint32_t cA = (dnaA[(size_t)(j >> 4) * 32] >> sh) & 3u, cB = (dnaB[(size_t)(j >> 4) * 32] >> sh) & 3u;
+            cols[j] = make_uint2(a.mism4 ^ (a.delta << (cA << 3)), a.mism4 ^ (a.delta << (cB << 3)));
+        }
+    }
+    uint32_t sel[R], HO[R], E[R];
+    s3_dp_selectors<R>(a, p, i0, sel);
+    s3_dp_column0<R>(p, i0, open, gapInit, ext, KOPEN, HO, E);
+
+    // cells that may end the alignment: rows iLo..m, columns jLo..n
     uint32_t iLo[2], jLo[2];
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-        iLo[x] = (clipRt[x] >= m[x]) ? 1u : max(m[x] - clipRt[x], 1u);
-        jLo[x] = max(ancR[x], 1u);
+        iLo[x] = (p.clipRt[x] >= p.m[x]) ? 1u : max(p.m[x] - p.clipRt[x], 1u);
+        jLo[x] = max(p.ancR[x], 1u);
     }
-    const uint32_t mMax = max(m[0], m[1]);
-    const uint32_t tiLo = (min(iLo[0], iLo[1]) - 1) / R, nSlots = (mMax ? (mMax - 1) / R : 0u) - tiLo + 1;
-    const uint32_t jStart = min(jLo[0], jLo[1]), jEnd = max(n[0], n[1]);
-    // per lane: running best of both alignments (biased, packed), how many cells tie with it, and the first of
-    // them as column << 12 | row (rows <= 256, columns < 2^20)
-    uint32_t best2 = S3_NEGB2, cnt[2] = {0u, 0u}, key[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+    const uint32_t tLastW = mMax ? (mMax - 1) / R : 0u;
+    const uint32_t tiLo = (min(iLo[0], iLo[1]) - 1) / R;
+    const uint32_t nSlots = tLastW - tiLo + 1;                    // lanes that hold such rows
+    const uint32_t perDrain = (uint32_t)LANES / nSlots;           // steps the ring takes
+    const bool slotLane = (uint32_t)t >= tiLo && (uint32_t)t <= tLastW;
+    // the ring entry this lane takes when the ring is emptied: step (first buffered + myStep), lane mySlot; which halves
+    // of that lane's R words belong to rows that may end the alignment (rows iLo..m)
+    const uint32_t myStep = (uint32_t)t / nSlots, mySlot = tiLo + (uint32_t)t % nSlots;
+    // (kept in shared memory, [row][lane]: read only when the ring is emptied)
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const uint32_t i = mySlot * R + r + 1;
+        keepRow[r * LANES + t] = ((i >= iLo[0] && i <= p.m[0]) ? 0xFFFFu : 0u) | ((i >= iLo[1] && i <= p.m[1]) ? 0xFFFF0000u : 0u);
+    }
+    const uint32_t jSpan[2] = {p.n[0] - jLo[0], p.n[1] - jLo[1]};     // (wraps when no column is eligible: then jLo > n >= every j)
+    const bool anyCol[2] = {jLo[0] <= p.n[0], jLo[1] <= p.n[1]};
+    // the ring holds H + open (what the lanes carry); the running best is kept in that domain
+    uint32_t best2 = S3_NEGB2 + KOPEN, cnt[2] = {0u, 0u}, key[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};   // key: column << 12 | row
+    // the ring has two halves used in turn, so one warp-level sync per emptying is enough: a lane cannot be more than
+    // one emptying ahead of another
+    auto drain = [&](const uint32_t *buf, const uint32_t sFirst, const uint32_t buffered) {
+        __syncwarp(gmask);
+        if (myStep < buffered) {
+            const uint32_t j = sFirst + myStep - mySlot;           // (wraps below column 1: masked like j > n)
+            const uint32_t colKeep = ((anyCol[0] && j - jLo[0] <= jSpan[0]) ? 0xFFFFu : 0u) | ((anyCol[1] && j - jLo[1] <= jSpan[1]) ? 0xFFFF0000u : 0u);
+            const uint4 *src = reinterpret_cast<const uint4 *>(buf + (size_t)t * PW);
+            uint32_t w[PW];
+#pragma unroll
+            for (int k = 0; k < PW / 4; ++k) { const uint4 v = src[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
+            uint32_t wm[R];
+#pragma unroll
+            for (int r = 0; r < R; ++r) wm[r] = w[r] & keepRow[r * LANES + t];     // 0 never wins
+            uint32_t mx = wm[0];
+#pragma unroll
+            for (int r = 1; r < R; ++r) mx = __vmaxu2(mx, wm[r]);
+            mx &= colKeep;
+            bool gh, gl;
+            (void)__vibmax_u16x2(mx, best2, &gh, &gl);
+            if (gh || gl) {
+                // The slot's rows in ascending order through DV-DPfunctions.cu:225-235 leave: the maximum as the new best
+                // if it beats the old one (count = the rows that hold it, position = the first of them), or the rows that
+                // tie with the old best added to its count.  Rows equal to the slot maximum, as bit r of each half:
+                uint32_t eq = 0;
+#pragma unroll
+                for (int r = 0; r < R; ++r) eq |= (__vcmpeq2(wm[r], mx) & 0x00010001u) << r;
+#pragma unroll
+                for (int x = 0; x < 2; ++x) {
+                    if (x == 0 ? !gl : !gh) continue;
+                    const uint32_t rows = (eq >> (16 * x)) & 0xFFFFu, v = (mx >> (16 * x)) & 0xFFFFu, b = (best2 >> (16 * x)) & 0xFFFFu;
+                    const uint32_t k = (j << 12) | (mySlot * R + (uint32_t)__ffs(rows));          // 1-based row
+                    if (v > b) { cnt[x] = (uint32_t)__popc(rows); key[x] = k; }
+                    else { cnt[x] += (uint32_t)__popc(rows); key[x] = min(key[x], k); }
+                }
+                best2 = __vmaxu2(best2, mx);
+            }
+        }
+    };
 
-    // column after column, the eligible slots of a column on neighbouring lanes: with the slot rotation of
-    // s3_dp_slot the last two of them are one 64-byte burst
-    const uint32_t tLast = mMax ? (mMax - 1) / R : 0u;
-    const uint32_t nCols = (mMax && jEnd >= jStart) ? jEnd - jStart + 1 : 0u;
-    auto locate = [&](uint32_t q, uint32_t &j, uint32_t &ti) { ti = tiLo + q % nSlots; j = jStart + q / nSlots; };
-    auto fetch = [&](uint32_t j, uint32_t ti, uint32_t w[R]) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(plane + s3_dp_cell<R, LANES>(ti, j + ti, tLast));
-        if (R == 8) {
-            // the slot is one 32-byte sector: one 256-bit load
-            asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
-                         : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[R > 4 ? 4 : 0]), "=r"(w[R > 5 ? 5 : 0]), "=r"(w[R > 6 ? 6 : 0]), "=r"(w[R > 7 ? 7 : 0])
-                         : "l"(src));
-        } else {
-#pragma unroll
-            for (int k = 0; k < R / 4; ++k) { const uint4 v = src[k]; w[4 * k] = v.x; w[4 * k + 1] = v.y; w[4 * k + 2] = v.z; w[4 * k + 3] = v.w; }
-        }
-    };
-    // which halves of the R words of slot ti belong to rows that may end the alignment (biased 0 = -32768 never wins)
-    uint32_t keep[R], keepTi = 0xFFFFFFFFu;
-    auto consume = [&](uint32_t j, uint32_t ti, const uint32_t w[R]) {
-        // trigger, on the biased words as they come: some eligible cell of the slot reaches a running best
-        if (ti != keepTi) {
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                const uint32_t i = ti * R + r + 1;
-                keep[r] = ((i >= iLo[0] && i <= m[0]) ? 0xFFFFu : 0u) | ((i >= iLo[1] && i <= m[1]) ? 0xFFFF0000u : 0u);
+    uint32_t upOOut = 0, FOut = 0, diagOOut = 0;
+    uint32_t prevInit = S3_BIAS2;                                // start value of the previous column (0, biased)
+    uint32_t clipIO[R], clipPIO[R];                              // soft-clip restart operands of the current column
+    uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPIO were built from
+    const bool laneHasRows = i0 <= mMax && pairValid;
+    uint32_t *ck = a.ckpt + (size_t)pairLocal * a.ckStride + (size_t)t * CKW;
+    uint32_t pend = 0, sFirst = 1;
+    uint32_t *ringNow = ring;
+    __syncwarp();
+
+    uint32_t steps = nMax + LANES - 1;
+    for (int o = LANES; o < 32; o <<= 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, o));   // the groups of a warp step together
+    for (uint32_t s = 1; s <= steps; ++s) {
+        // carried registers of the row loop arrive from the lane above (column j was done there at step s-1):
+        // H of the row above + open, F, and H of the previous column's row above + open (the diagonal)
+        uint32_t upO = __shfl_up_sync(0xFFFFFFFFu, upOOut, 1, LANES);
+        uint32_t F = __shfl_up_sync(0xFFFFFFFFu, FOut, 1, LANES);
+        uint32_t diagO = __shfl_up_sync(0xFFFFFFFFu, diagOOut, 1, LANES);
+        const uint32_t j = s - t;
+        if (j >= 1 && j <= nMax && laneHasRows) {
+            const uint32_t init = s3_dp_init2(j, j, p.ancL);
+            if (t == 0) { upO = init + KOPEN; F = init + KGAPINIT; diagO = prevInit + KOPEN; }
+            if (init != curInit || prevInit != curPrev) {           // rare: first column and anchor crossings
+                s3_dp_clip_operands<R>(init, prevInit, i0, p.clipLt, KOPEN, NEGO2, clipIO, clipPIO);
+                curInit = init; curPrev = prevInit;
             }
-            keepTi = ti;
-        }
-        const uint32_t colKeep = ((j >= jLo[0] && j <= n[0]) ? 0xFFFFu : 0u) | ((j >= jLo[1] && j <= n[1]) ? 0xFFFF0000u : 0u);
-        uint32_t wm[R];
+            s3_dp_rows<R>(cols[j], sel, HO, E, clipIO, clipPIO, upO, F, diagO, KOPEN, KEXT, CEH2, ONE);
+            upOOut = upO; FOut = F; diagOOut = diagO;
+            prevInit = init;
+            if (slotLane) {
+                uint32_t *dst = ringNow + ((size_t)pend * nSlots + ((uint32_t)t - tiLo)) * PW;
 #pragma unroll
-        for (int r = 0; r < R; ++r) wm[r] = w[r] & keep[r] & colKeep;
-        uint32_t mx = wm[0];
-#pragma unroll
-        for (int r = 1; r < R; ++r) mx = __vmaxu2(mx, wm[r]);
-        bool gh, gl;
-        (void)__vibmax_u16x2(mx, best2, &gh, &gl);
-        if (gh || gl) {
-            // The slot's rows in ascending order through DV-DPfunctions.cu:225-235 leave: the maximum as the new best
-            // if it beats the old one (count = the rows that hold it, position = the first of them), or the rows that
-            // tie with the old best added to its count.  Rows equal to the slot maximum, as bit r of each half:
-            uint32_t eq = 0;
-#pragma unroll
-            for (int r = 0; r < R; ++r) eq |= (__vcmpeq2(wm[r], mx) & 0x00010001u) << r;
-#pragma unroll
-            for (int x = 0; x < 2; ++x) {
-                if (x == 0 ? !gl : !gh) continue;
-                const uint32_t rows = (eq >> (16 * x)) & 0xFFFFu, v = (mx >> (16 * x)) & 0xFFFFu, b = (best2 >> (16 * x)) & 0xFFFFu;
-                const uint32_t k = (j << 12) | (ti * R + (uint32_t)__ffs(rows));          // 1-based row
-                if (v > b) { cnt[x] = (uint32_t)__popc(rows); key[x] = k; }
-                else { cnt[x] += (uint32_t)__popc(rows); key[x] = min(key[x], k); }
+                for (int k = 0; k < PW / 4; ++k)
+                    reinterpret_cast<uint4 *>(dst)[k] = make_uint4(HO[4 * k < R ? 4 * k : 0], HO[4 * k + 1 < R ? 4 * k + 1 : 0],
+                                                                   HO[4 * k + 2 < R ? 4 * k + 2 : 0], HO[4 * k + 3 < R ? 4 * k + 3 : 0]);
             }
-            best2 = __vmaxu2(best2, mx);
         }
-    };
-    const uint32_t items = nCols * nSlots;
-    if (LANES % nSlots == 0) {
-        // the usual case (1 or 2 slots): a lane keeps its slot and walks the columns with a fixed stride -- no
-        // division per entry, and the row masks are built once
-        const uint32_t ti = tiLo + t % nSlots, jStep = LANES / nSlots;
-        for (uint32_t j = jStart + t / nSlots; j <= jEnd && nCols; j += 2 * jStep) {
-            uint32_t w0[R], w1[R];
-            fetch(j, ti, w0);
-            const bool second = j + jStep <= jEnd;
-            if (second) fetch(j + jStep, ti, w1);
-            consume(j, ti, w0);
-            if (second) consume(j + jStep, ti, w1);
-        }
-    } else {
-        for (uint32_t q = t; q < items; q += 2 * LANES) {
-            uint32_t j0, t0, j1 = 0, t1 = 0, w0[R], w1[R];
-            locate(q, j0, t0);
-            fetch(j0, t0, w0);
-            const bool second = q + LANES < items;
-            if (second) { locate(q + LANES, j1, t1); fetch(j1, t1, w1); }
-            consume(j0, t0, w0);
-            if (second) consume(j1, t1, w1);
+        if (++pend == perDrain) { drain(ringNow, sFirst, pend); pend = 0; sFirst = s + 1; ringNow = ring + ((ringNow == ring) ? LANES * PW : 0); }
+        if ((s & (S3_DP_CK - 1u)) == 0u && laneHasRows && s / S3_DP_CK <= a.numCk) {
+            // a checkpoint: everything a sweep needs to go on from step s + 1 (the row above's H + open is HO[R-1])
+            uint32_t *dst = ck + (size_t)(s / S3_DP_CK - 1u) * LANES * CKW;
+            uint32_t w[CKW];
+#pragma unroll
+            for (int r = 0; r < R; ++r) { w[r] = HO[r]; w[R + r] = E[r]; }
+            w[2 * R] = FOut; w[2 * R + 1] = diagOOut;
+#pragma unroll
+            for (int k = 2 * R + 2; k < CKW; ++k) w[k] = 0;
+#pragma unroll
+            for (int k = 0; k < CKW / 4; ++k) reinterpret_cast<uint4 *>(dst)[k] = make_uint4(w[4 * k], w[4 * k + 1], w[4 * k + 2], w[4 * k + 3]);
         }
     }
+    if (pend) drain(ringNow, sFirst, pend);
+    // merge the lanes' (best, first cell, tie count)
 #pragma unroll
     for (int x = 0; x < 2; ++x) {
-        const int mine = (int)((best2 >> (16 * x)) & 0xFFFFu) - 32768;
+        const int mine = (int)((best2 >> (16 * x)) & 0xFFFFu) - 32768 - open;
         int g = mine;
         for (int o = LANES / 2; o > 0; o >>= 1) g = max(g, __shfl_xor_sync(0xFFFFFFFFu, g, o));
         // position = the first cell, in (column, row) order, that holds the final best -- if any cell beat the
@@ -466,63 +643,245 @@ __device__ __forceinline__ void s3_dp_best16(const uint32_t *plane, uint32_t ps,
             k = min(k, __shfl_xor_sync(0xFFFFFFFFu, k, o));
             c += __shfl_xor_sync(0xFFFFFFFFu, c, o);
         }
-        gbest[x] = g; gcnt[x] = c;
-        gkey[x] = (k == 0xFFFFFFFFu) ? ~0ull : (((unsigned long long)(k >> 12) << 32) | (k & 0xFFFu));
+        if (t == x && pairValid && (x == 0 || hasB)) {
+            const bool any = k != 0xFFFFFFFFu;
+            const uint32_t id = p.id[x], hitJ = any ? (k >> 12) : 0u, bi = k & 0xFFFu;
+            a.score[id] = g;
+            a.cnt[id] = c;
+            a.hit[id] = hitJ;
+            a.scRight[id] = any ? p.m[x] - bi : 0u;
+            if (a.cells) atomicAdd(a.cells, (unsigned long long)p.m[x] * p.n[x]);
+            if (g >= a.cutoff[id]) {
+                // traced back: from the last checkpoint that leaves readLength + S3_DP_SLACK columns left of the end
+                // column to every lane, or from column 0
+                const int last = (int)hitJ - (int)p.m[x] - (int)S3_DP_SLACK - 1;
+                const uint32_t s0 = (last >= (int)S3_DP_CK) ? ((uint32_t)last / S3_DP_CK) * S3_DP_CK : 0u;
+                a.s0[id] = s0;
+                const uint32_t cls = s0 ? 0u : 1u;
+                a.tbList[(size_t)cls * a.tbCap + atomicAdd(a.tbCount + cls, 1u)] = id;
+            }
+        }
     }
 }
 
-// GPUBacktrack (DV-DPfunctions.cu:316-512) over the H plane of one pair, for the alignment in
-// half `half`; called by ALL lanes of a warp together, each with its own alignment (`active` false:
-// nothing to trace).  The reference reads H of three neighbours and, for its third test, E of the
-// previous column.  E is not stored here.  It follows from row i of the H plane: with a gap extension
-// score <= 0 the clamped recurrence E(c,i) = max(-32000, open + H(c-1,i), ext + E(c-1,i))
-// (DV-DPfunctions.cu:178-183,196-199) unrolls to
-//     E(j-1,i) = max(-32000, E(0,i) + (j-1) ext, max over 0 <= c <= j-2 of open + H(c,i) + (j-2-c) ext)
-// -- a maximum over the row, which the 32 lanes of the warp evaluate together for whichever lane
-// needs it (one strided load each per 32 columns and a shuffle reduction) instead of that lane walking
-// the row alone.  The borders H(j,0), H(0,i) -- which the reference also keeps in its table -- are
-// recomputed from their defining formulas.  Returns the start offset inside the window (the new
-// hitLocs value).
-template <int R, int LANES>
-__device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint32_t *plane, uint32_t tLast, uint32_t half,
-                                      uint32_t id, uint32_t m, uint32_t clipLt, uint32_t anchorLeft, uint32_t scRight, uint32_t hit)
+// the pairs of a traceback pass: the resumed alignments two by two, then those that start at column 0
+struct S3DpTbPair { uint32_t id[2]; bool valid[2]; bool resumed; };
+__device__ __forceinline__ bool s3_dp_tb_pair(const S3DpArgs &a, uint32_t pairIdx, S3DpTbPair &q)
 {
+    const uint32_t nR = (a.pass == 1) ? a.tbCount[0] : 0u, nS = (a.pass == 1) ? a.tbCount[1] : min(a.tbCount[2], a.tbCap);
+    const uint32_t pairsR = (nR + 1) / 2, pairsS = (nS + 1) / 2;
+    if (pairIdx >= pairsR + pairsS) return false;
+    q.resumed = pairIdx < pairsR;
+    const uint32_t k0 = q.resumed ? 2 * pairIdx : 2 * (pairIdx - pairsR), cnt = q.resumed ? nR : nS;
+    const uint32_t *list = a.tbList + (size_t)((a.pass == 1) ? (q.resumed ? 0 : 1) : 2) * a.tbCap;
+    q.valid[0] = true; q.valid[1] = k0 + 1 < cnt;
+    q.id[0] = list[k0]; q.id[1] = q.valid[1] ? list[k0 + 1] : q.id[0];
+    return true;
+}
+__device__ __forceinline__ uint32_t s3_dp_tb_pairs(const S3DpArgs &a)
+{
+    const uint32_t nR = (a.pass == 1) ? a.tbCount[0] : 0u, nS = (a.pass == 1) ? a.tbCount[1] : min(a.tbCount[2], a.tbCap);
+    return (nR + 1) / 2 + (nS + 1) / 2;
+}
+
+// Second sweep of the alignments that are traced back, two by two (not the pairs of the first sweep: each half
+// has its own first step s0 and end column).  Local step u of half x is step s0[x] + u of its first sweep; the
+// lane's R words of a step go to plane[pair][u][lane].
+template <int R, int LANES>
+__global__ void __launch_bounds__(S3_DP_WARPS * 32, S3_DP_MINBLOCKS(R))
+s3_dp_resweep16_kernel(const S3DpArgs a)
+{
+    constexpr int GROUPS = 32 / LANES;
+    constexpr int PW = S3DpGeom<R>::PW, CKW = S3DpGeom<R>::CKW;
+    extern __shared__ uint2 s3_dp_cols[];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int group = lane / LANES, t = lane % LANES;
+    const uint32_t numPairs = s3_dp_tb_pairs(a);
+    const uint32_t wantPair = (blockIdx.x * S3_DP_WARPS + warp) * GROUPS + group;
+    if ((blockIdx.x * S3_DP_WARPS + warp) * GROUPS >= numPairs) return;          // whole warp leaves together
+    const bool pairValid = wantPair < numPairs;
+    const uint32_t pairIdx = pairValid ? wantPair : numPairs - 1;
+    S3DpTbPair q;
+    s3_dp_tb_pair(a, pairIdx, q);
+    S3DpPair p;
+    p.id[0] = q.id[0]; p.id[1] = q.id[1];
+    s3_dp_load_pair(a, p);
+    uint32_t s0[2], hit[2];
+#pragma unroll
+    for (int x = 0; x < 2; ++x) { s0[x] = q.resumed ? a.s0[p.id[x]] : 0u; hit[x] = a.hit[p.id[x]]; }
+    const uint32_t mMax = max(p.m[0], p.m[1]);
+    const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
+    const uint32_t zero = p.n[0] >> 31;
+    const uint32_t KOPEN = a.kOpen + zero, KEXT = a.kExt + zero, CEH2 = a.ceh2 + zero;
+    const uint32_t KGAPINIT = a.kGapInit, NEGO2 = a.nego2, ONE = a.one;
+    const uint32_t i0 = t * R + 1;
+    const uint32_t tLastW = mMax ? (mMax - 1) / R : 0u;
+    // steps until the last lane with rows has done both end columns
+    uint32_t steps = pairValid ? min(max(hit[0] + tLastW - s0[0], hit[1] + tLastW - s0[1]), a.planeSteps - 1u) : 0u;
+
+    // column tables of the window: entry c = u - t + LANES - 1 holds column s0[x] + u - t of half x
+    uint2 *cols = s3_dp_cols + (size_t)(warp * GROUPS + group) * a.colStride;
+    {
+        const uint32_t *dnaA = a.dna + (size_t)(p.id[0] >> 5) * a.dnaWords * 32 + (p.id[0] & 31);
+        const uint32_t *dnaB = a.dna + (size_t)(p.id[1] >> 5) * a.dnaWords * 32 + (p.id[1] & 31);
+        for (uint32_t c = t; c < steps + LANES; c += LANES) {
+            const int jA = (int)(s0[0] + c) - (LANES - 1), jB = (int)(s0[1] + c) - (LANES - 1);
+            uint32_t cA = 0, cB = 0;
+            if (jA >= 1 && jA <= (int)p.n[0]) cA = (dnaA[(size_t)(jA >> 4) * 32] >> ((15u - ((uint32_t)jA & 15u)) << 1)) & 3u;
+            if (jB >= 1 && jB <= (int)p.n[1]) cB = (dnaB[(size_t)(jB >> 4) * 32] >> ((15u - ((uint32_t)jB & 15u)) << 1)) & 3u;
+            cols[c] = make_uint2(a.mism4 ^ (a.delta << (cA << 3)), a.mism4 ^ (a.delta << (cB << 3)));
+        }
+    }
+    uint32_t sel[R], HO[R], E[R];
+    s3_dp_selectors<R>(a, p, i0, sel);
+    uint32_t upOOut = 0, FOut = 0, diagOOut = 0, prevInit = S3_BIAS2;
+    if (q.resumed) {
+        // the registers of the first sweep after step s0[x], each half from the pair it was swept in
+        uint32_t w[2][2 * R + 2];
+#pragma unroll
+        for (int x = 0; x < 2; ++x) {
+            const uint32_t rel = p.id[x] - a.first;
+            const uint4 *src = reinterpret_cast<const uint4 *>(a.ckpt + (size_t)(rel >> 1) * a.ckStride +
+                                                               ((size_t)(s0[x] / S3_DP_CK - 1u) * LANES + t) * CKW);
+            const uint32_t sh = (rel & 1u) * 16u;
+#pragma unroll
+            for (int k = 0; k < (2 * R + 2 + 3) / 4; ++k) {
+                const uint4 v = src[k];
+                if (4 * k < 2 * R + 2) w[x][4 * k] = (v.x >> sh) & 0xFFFFu;
+                if (4 * k + 1 < 2 * R + 2) w[x][4 * k + 1] = (v.y >> sh) & 0xFFFFu;
+                if (4 * k + 2 < 2 * R + 2) w[x][4 * k + 2] = (v.z >> sh) & 0xFFFFu;
+                if (4 * k + 3 < 2 * R + 2) w[x][4 * k + 3] = (v.w >> sh) & 0xFFFFu;
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) { HO[r] = w[0][r] | (w[1][r] << 16); E[r] = w[0][R + r] | (w[1][R + r] << 16); }
+        FOut = w[0][2 * R] | (w[1][2 * R] << 16);
+        diagOOut = w[0][2 * R + 1] | (w[1][2 * R + 1] << 16);
+        upOOut = HO[R - 1];
+        // start value of the column before this lane's first one (>= 1: s0 >= S3_DP_CK >= LANES)
+        prevInit = s3_dp_init2(s0[0] - t, s0[1] - t, p.ancL);
+    } else {
+        s3_dp_column0<R>(p, i0, open, gapInit, ext, KOPEN, HO, E);
+    }
+    __syncwarp();
+
+    uint32_t clipIO[R], clipPIO[R];
+    uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;
+    const bool laneHasRows = i0 <= mMax && pairValid;
+    uint32_t *plane = a.hplane + ((size_t)pairIdx * a.planeSteps * LANES + t) * PW;
+    for (int o = LANES; o < 32; o <<= 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, o));   // the groups of a warp step together
+    for (uint32_t u = 1; u <= steps; ++u) {
+        uint32_t upO = __shfl_up_sync(0xFFFFFFFFu, upOOut, 1, LANES);
+        uint32_t F = __shfl_up_sync(0xFFFFFFFFu, FOut, 1, LANES);
+        uint32_t diagO = __shfl_up_sync(0xFFFFFFFFu, diagOOut, 1, LANES);
+        // a lane that starts at column 0 has nothing to do before its column 1; a resumed lane is past it
+        if ((q.resumed || u > (uint32_t)t) && laneHasRows && u < a.planeSteps) {
+            const uint32_t init = s3_dp_init2(s0[0] + u - t, s0[1] + u - t, p.ancL);
+            if (t == 0) { upO = init + KOPEN; F = init + KGAPINIT; diagO = prevInit + KOPEN; }
+            if (init != curInit || prevInit != curPrev) {
+                s3_dp_clip_operands<R>(init, prevInit, i0, p.clipLt, KOPEN, NEGO2, clipIO, clipPIO);
+                curInit = init; curPrev = prevInit;
+            }
+            s3_dp_rows<R>(cols[u - t + (LANES - 1)], sel, HO, E, clipIO, clipPIO, upO, F, diagO, KOPEN, KEXT, CEH2, ONE);
+            upOOut = upO; FOut = F; diagOOut = diagO;
+            prevInit = init;
+            // the plane holds what the lanes carry: H + open, unclamped, biased
+            uint32_t *hdst = plane + (size_t)u * LANES * PW;
+            if (PW >= 8) {
+                // 256-bit stores = the lane's whole 32-byte sectors
+#pragma unroll
+                for (int k = 0; k < PW / 8; ++k)
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(hdst + 8 * k), "r"(HO[8 * k < R ? 8 * k : 0]), "r"(HO[8 * k + 1 < R ? 8 * k + 1 : 0]),
+                                 "r"(HO[8 * k + 2 < R ? 8 * k + 2 : 0]), "r"(HO[8 * k + 3 < R ? 8 * k + 3 : 0]), "r"(HO[8 * k + 4 < R ? 8 * k + 4 : 0]),
+                                 "r"(HO[8 * k + 5 < R ? 8 * k + 5 : 0]), "r"(HO[8 * k + 6 < R ? 8 * k + 6 : 0]), "r"(HO[8 * k + 7 < R ? 8 * k + 7 : 0]) : "memory");
+            } else {
+                *reinterpret_cast<uint4 *>(hdst) = make_uint4(HO[0], HO[R > 1 ? 1 : 0], HO[R > 2 ? 2 : 0], HO[R > 3 ? 3 : 0]);
+            }
+        }
+    }
+}
+
+// GPUBacktrack (DV-DPfunctions.cu:316-512) over the window plane of one alignment; called by ALL lanes of a
+// warp together, each with its own alignment (`active` false: nothing to trace).  The reference reads H of three
+// neighbours and, for its third test, E of the previous column.  E is not stored here.  It follows from row i of
+// the plane: with a gap extension score <= 0 the clamped recurrence E(c,i) = max(-32000, open + H(c-1,i),
+// ext + E(c-1,i)) (DV-DPfunctions.cu:178-183,196-199) unrolls, from any column jc on, to
+//     E(j-1,i) = max(-32000, E(jc,i) + (j-1-jc) ext, max over jc <= c <= j-2 of open + H(c,i) + (j-2-c) ext)
+// -- a maximum over the row, which the 32 lanes of the warp evaluate together for whichever lane needs it (one
+// strided load each per 32 columns and a shuffle reduction).  jc is column 0 (H and E from their defining formulas,
+// like the borders H(j,0), H(0,i)) or, for a resumed sweep, the column of the lane's checkpoint, which holds both.
+// A cell left of the window sets `fail`; the caller lists the alignment for the second pass.
+// Returns the start offset inside the window (the new hitLocs value).
+template <int R, int LANES>
+__device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint32_t *plane, const uint32_t *ck, uint32_t ckHalf,
+                                      uint32_t s0, uint32_t half, uint32_t id, uint32_t m, uint32_t clipLt, uint32_t anchorLeft,
+                                      uint32_t scRight, uint32_t hit, bool &fail)
+{
+    constexpr int PW = S3DpGeom<R>::PW, CKW = S3DpGeom<R>::CKW;
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t *dna = a.dna + (size_t)(id >> 5) * a.dnaWords * 32 + (id & 31);
     const uint32_t *read = a.read + (size_t)(id >> 5) * a.readWords * 32 + (id & 31);
     const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
     uint8_t *pat = a.pattern + (size_t)id * (a.maxReadLength + a.maxDNALength);
     uint32_t p = 0;
+    fail = false;
 
+    auto ckH = [&](uint32_t t, uint32_t r) -> int {      // H at the lane's checkpoint column (kept as H + open, unclamped)
+        const uint32_t w = ck[(size_t)t * CKW + r];
+        return s3_clamp((int)((ckHalf ? w >> 16 : w) & 0xFFFFu) - 32768 - open);
+    };
+    auto ckE = [&](uint32_t t, uint32_t r) -> int {
+        const uint32_t w = ck[(size_t)t * CKW + R + r];
+        return s3_clamp((int)((ckHalf ? w >> 16 : w) & 0xFFFFu) - 32768);
+    };
     auto H = [&](uint32_t j, uint32_t i) -> int {
         if (i == 0) return (j == 0) ? 0 : ((j >= anchorLeft) ? S3_NEG_INF : 0);
         if (j == 0) return s3_clamp((i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext);
         const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-        const uint32_t w = plane[s3_dp_cell<R, LANES>(t, j + t, tLast) + r] ^ S3_BIAS2;
-        return s3_clamp(half ? s3_hi16(w) : s3_lo16(w));         // the plane keeps the unclamped value
+        const int u = (int)(j + t) - (int)s0;
+        if (u >= 1) {
+            const uint32_t w = plane[((size_t)u * LANES + t) * PW + r];
+            return s3_clamp((int)((half ? w >> 16 : w) & 0xFFFFu) - 32768 - open);      // the plane keeps H + open, unclamped, biased
+        }
+        if (u == 0) return ckH(t, r);
+        fail = true;
+        return 0;
     };
     // E(j-1, i) for every lane that wants it (see above); all lanes of the warp take part
     auto Eprev = [&](bool want, uint32_t j, uint32_t i) -> int {
         int mine = 0;
+        const uint32_t t = want ? (i - 1) / R : 0u, r = want ? (i - 1) % R : 0u;
+        uint32_t jc = 0;
+        int hC = 0, eC = 0;
+        if (want) {
+            if (s0) {
+                jc = s0 - t;
+                if (j < jc + 1) { fail = true; want = false; }
+                else { hC = ckH(t, r); eC = ckE(t, r); }
+            } else {
+                const int h0 = (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext;
+                hC = s3_clamp(h0); eC = s3_clamp(h0 + gapInit);
+            }
+        }
         uint32_t need = __ballot_sync(0xFFFFFFFFu, want);
         while (need) {
             const int src = __ffs(need) - 1;
             need &= need - 1;
-            const uint32_t t = (i - 1) / R, r = (i - 1) % R;
-            // the requester's plane, lane and row: column c of its row is at s3_dp_cell(lane, c + lane) + row
-            const unsigned long long rowBase = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(size_t)(plane + r), src);
-            const uint32_t tt = __shfl_sync(0xFFFFFFFFu, t, src), tl = __shfl_sync(0xFFFFFFFFu, tLast, src);
+            // the requester's row: column c is at rowBase + (c + t - s0) * LANES * PW
+            const unsigned long long rowBase = __shfl_sync(0xFFFFFFFFu, (unsigned long long)(size_t)(plane + (size_t)t * PW + r), src);
+            const int uOff = __shfl_sync(0xFFFFFFFFu, (int)t - (int)s0, src);
             const uint32_t jj = __shfl_sync(0xFFFFFFFFu, j, src), hf = __shfl_sync(0xFFFFFFFFu, half, src);
-            const int h0 = __shfl_sync(0xFFFFFFFFu, (i <= clipLt) ? open : gapInit + (int)(i - clipLt) * ext, src);
+            const uint32_t jcc = __shfl_sync(0xFFFFFFFFu, jc, src);
+            const int hCC = __shfl_sync(0xFFFFFFFFu, hC, src), eCC = __shfl_sync(0xFFFFFFFFu, eC, src);
             const uint32_t *row = reinterpret_cast<const uint32_t *>((size_t)rowBase);
             int e = S3_NEG_INF;
             if (lane == 0) {
-                e = max(e, s3_clamp(h0 + gapInit) + (int)(jj - 1) * ext);
-                if (jj >= 2) e = max(e, open + s3_clamp(h0) + (int)(jj - 2) * ext);
+                e = max(e, eCC + (int)(jj - 1 - jcc) * ext);
+                if (jj >= jcc + 2) e = max(e, open + hCC + (int)(jj - 2 - jcc) * ext);
             }
-            for (uint32_t c = 1 + lane; c + 2 <= jj; c += 32) {
-                const uint32_t w = row[s3_dp_cell<R, LANES>(tt, c + tt, tl)] ^ S3_BIAS2;
-                e = max(e, open + s3_clamp(hf ? s3_hi16(w) : s3_lo16(w)) + (int)(jj - 2 - c) * ext);
+            for (uint32_t c = jcc + 1 + lane; c + 2 <= jj; c += 32) {
+                const uint32_t w = row[(size_t)((int)c + uOff) * LANES * PW];
+                e = max(e, open + s3_clamp((int)((hf ? w >> 16 : w) & 0xFFFFu) - 32768 - open) + (int)(jj - 2 - c) * ext);
             }
             for (int o = 16; o > 0; o >>= 1) e = max(e, __shfl_xor_sync(0xFFFFFFFFu, e, o));
             if ((int)lane == src) mine = e;
@@ -547,7 +906,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
 #define S3_NEXT_REF() { --refIndex; refChar = refAt(refIndex); initScore = prevInitScore; prevInitScore = (refIndex > anchorLeft) ? S3_NEG_INF : 0; }
 #define S3_NEXT_READ() { --readPos; readChar = readAt(readPos); }
     while (true) {
-        run = run && readPos > 0 && refIndex > 0;
+        run = run && !fail && readPos > 0 && refIndex > 0;
         if (!__any_sync(0xFFFFFFFFu, run)) break;
         // the two tests that need no E; the third one does
         int sel = 0, d = 0;         // 1: diagonal, 2: deletion opened here, 3: neither
@@ -556,9 +915,10 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
             if (cur == d + (next = H(refIndex - 1, readPos - 1))) sel = 1;
             else if (cur == open + (next = H(refIndex - 1, readPos))) sel = 2;
             else sel = 3;
+            if (fail) sel = 0;
         }
         const int ePrev = Eprev(sel == 3, refIndex, readPos);
-        if (!run) continue;
+        if (!run || fail) continue;
         if (state == 0) {
             if (sel == 1) {
                 pat[p++] = (refChar == readChar) ? 'M' : 'm';
@@ -604,7 +964,7 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
     }
 #undef S3_NEXT_REF
 #undef S3_NEXT_READ
-    if (!active) return hit;
+    if (!active || fail) return hit;
     if (refIndex == 0) {
         const uint32_t scNum = min(clipLt, readPos);
         if (scNum < readPos) { pat[p++] = 'I'; pat[p++] = 'V'; pat[p++] = (uint8_t)(readPos - scNum); }
@@ -620,209 +980,90 @@ __device__ uint32_t s3_dp_traceback16(const S3DpArgs &a, bool active, const uint
     return refIndex;             // start offset inside the window (refOffset == 0 in scheme 1)
 }
 
-// Score pass of S3_DP_WARPS * (32 / LANES) pairs of alignments per block.  A pair is swept by a
-// group of LANES lanes, each owning R consecutive read rows; only the H plane is written.
-template <int R, int LANES>
-__global__ void __launch_bounds__(S3_DP_WARPS * 32)
-s3_dp_score16_kernel(const S3DpArgs a)
-{
-    constexpr int GROUPS = 32 / LANES;                            // pairs per warp
-    // per pair and reference column j: the two substitution tables of that column (byte c of .x / .y = score
-    // of alignment A / B's reference base j against read base c), built once, read every step
-    extern __shared__ uint2 s3_dp_cols[];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int group = lane / LANES, t = lane % LANES;
-    const uint32_t numPairs = (a.count + 1) / 2;
-    const uint32_t wantPair = (blockIdx.x * S3_DP_WARPS + warp) * GROUPS + group;
-    if ((blockIdx.x * S3_DP_WARPS + warp) * GROUPS >= numPairs) return;          // whole warp leaves together
-    const bool pairValid = wantPair < numPairs;
-    const uint32_t pairLocal = pairValid ? wantPair : numPairs - 1;              // idle groups shadow a real pair, write nothing
-    const bool hasB = 2 * pairLocal + 1 < a.count;
-    const uint32_t id[2] = {a.first + 2 * pairLocal, a.first + 2 * pairLocal + (hasB ? 1u : 0u)};
-    uint32_t m[2], n[2], clipLt[2], clipRt[2], ancL[2], ancR[2];
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-        m[x] = a.readLen[id[x]]; n[x] = a.dnaLen[id[x]];
-        clipLt[x] = a.clipLt ? a.clipLt[id[x]] : 0u;
-        clipRt[x] = a.clipRt ? a.clipRt[id[x]] : 0u;
-        ancL[x] = a.ancL ? a.ancL[id[x]] : a.maxDNALength;
-        ancR[x] = a.ancR ? a.ancR[id[x]] : 0u;
-    }
-    const uint32_t mMax = max(m[0], m[1]), nMax = pairValid ? max(n[0], n[1]) : 0u;
-    const int open = a.open, ext = a.ext, gapInit = a.open - a.ext;
-    // the three constants of the row loop must stay in registers (ptxas otherwise re-reads them from the constant
-    // bank every step and the loop waits for them): + 0 from a loaded value it cannot see through
-    const uint32_t zero = n[0] >> 31;
-    const uint32_t KOPEN = a.kOpen + zero, KEXT = a.kExt + zero, CEH2 = a.ceh2 + zero;
-    const uint32_t KGAPINIT = a.kGapInit, NEGO2 = a.nego2, ONE = a.one;
-    const uint32_t i0 = t * R + 1;                                 // first row of this lane (1-based)
-
-    // reference windows (1-based packing, MSB first; DV-DPfunctions.cu:58) -> column tables in shared memory
-    uint2 *cols = s3_dp_cols + (size_t)(warp * GROUPS + group) * a.colStride;
-    {
-        const uint32_t *dnaA = a.dna + (size_t)(id[0] >> 5) * a.dnaWords * 32 + (id[0] & 31);
-        const uint32_t *dnaB = a.dna + (size_t)(id[1] >> 5) * a.dnaWords * 32 + (id[1] & 31);
-#pragma unroll 4
-        for (uint32_t j = t; j <= nMax; j += LANES) {
-            const uint32_t sh = (15u - (j & 15u)) << 1;
-            const uint32_t cA = (dnaA[(size_t)(j >> 4) * 32] >> sh) & 3u, cB = (dnaB[(size_t)(j >> 4) * 32] >> sh) & 3u;
-            cols[j] = make_uint2(a.mism4 ^ (a.delta << (cA << 3)), a.mism4 ^ (a.delta << (cB << 3)));
-        }
-    }
-    // this lane's read bases become PRMT selectors: the substitution score of a row is looked
-    // up in a 4-byte table per alignment (byte c = score against reference base c, minus the gap open score:
-    // the diagonal H arrives with + open on it, see the row loop)
-    uint32_t sel[R];
-    {
-        const uint32_t *readA = a.read + (size_t)(id[0] >> 5) * a.readWords * 32 + (id[0] & 31);
-        const uint32_t *readB = a.read + (size_t)(id[1] >> 5) * a.readWords * 32 + (id[1] & 31);
-#pragma unroll
-        for (int r = 0; r < R; ++r) {
-            const uint32_t i = i0 + r;
-            const uint32_t cA = (i <= m[0]) ? (readA[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
-            const uint32_t cB = (i <= m[1]) ? (readB[(size_t)(i >> 4) * 32] >> ((15 - (i & 15)) << 1)) & 3 : 0u;
-            sel[r] = cA | ((cA | 8u) << 4) | ((cB | 4u) << 8) | ((cB | 12u) << 12);
-        }
-    }
-    // column 0 (DV-DPfunctions.cu:167-184).  Carried per row, biased: HO = H of the previous column + open and E of
-    // the previous column, both UNclamped -- the reference's clamp at -32000 when it stores a value is applied
-    // where the value is used (ceh2 in E's max, nego2 in the diagonal's), which takes the same maximum.
-    uint32_t HO[R], E[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-        const uint32_t i = i0 + r;
-        const int hA = (i <= clipLt[0]) ? open : gapInit + (int)(i - clipLt[0]) * ext;
-        const int hB = (i <= clipLt[1]) ? open : gapInit + (int)(i - clipLt[1]) * ext;
-        HO[r] = s3_bpk(s3_clamp(hA), s3_clamp(hB)) + KOPEN;
-        E[r] = s3_bpk(s3_clamp(hA + gapInit), s3_clamp(hB + gapInit));
-    }
-    __syncwarp();
-
-    uint32_t upOOut = 0, FOut = 0, diagOOut = 0;
-    uint32_t prevInit = S3_BIAS2;                                // start value of the previous column (0, biased)
-    uint32_t clipIO[R], clipPIO[R];                              // soft-clip restart operands of the current column
-    uint32_t curInit = 0xFFFFFFFFu, curPrev = 0xFFFFFFFFu;       // values clipIO / clipPIO were built from
-    uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
-    const uint32_t tLastW = mMax ? (mMax - 1) / R : 0u;
-    const bool laneHasRows = i0 <= mMax && pairValid;
-
-    uint32_t steps = nMax + LANES - 1;
-    if (GROUPS > 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, LANES));
-    for (uint32_t s = 1; s <= steps; ++s) {
-        // carried registers of the row loop arrive from the lane above (column j was done there at step s-1):
-        // H of the row above + open, F, and H of the previous column's row above + open (the diagonal)
-        uint32_t upO = __shfl_up_sync(0xFFFFFFFFu, upOOut, 1, LANES);
-        uint32_t F = __shfl_up_sync(0xFFFFFFFFu, FOut, 1, LANES);
-        uint32_t diagO = __shfl_up_sync(0xFFFFFFFFu, diagOOut, 1, LANES);
-        const uint32_t j = s - t;
-        if (j >= 1 && j <= nMax && laneHasRows) {
-            const uint32_t init = ((j >= ancL[0]) ? (S3_NEGB2 & 0xFFFFu) : 0x8000u) | ((j >= ancL[1]) ? (S3_NEGB2 & 0xFFFF0000u) : 0x80000000u);
-            if (t == 0) { upO = init + KOPEN; F = init + KGAPINIT; diagO = prevInit + KOPEN; }
-            if (init != curInit || prevInit != curPrev) {           // rare: first column and anchor crossings
-                const uint32_t io = init + KOPEN, pio = prevInit + KOPEN;
-#pragma unroll
-                for (int r = 0; r < R; ++r) {
-                    // soft-clip restart feeds row i from row i-1 when i-1 <= clipLt (DV-DPfunctions.cu:215-219)
-                    const uint32_t i = i0 + r;
-                    const uint32_t cm = ((i - 1 <= clipLt[0]) ? 0xFFFFu : 0u) | ((i - 1 <= clipLt[1]) ? 0xFFFF0000u : 0u);
-                    clipIO[r] = io & cm;                            // biased 0 = -32768: the identity of max elsewhere
-                    clipPIO[r] = (pio & cm) | (NEGO2 & ~cm);
-                }
-                curInit = init; curPrev = prevInit;
-            }
-            const uint2 tab = cols[j];
-            uint32_t out[R];
-#pragma unroll
-            for (int r = 0; r < R; ++r) {
-                // 5 instructions on the ALU pipe (PRMT, 3 x VIMNMX3.U16x2, VIMNMX.U16x2) and 4 adds on the FMA pipe
-                const uint32_t d = s3_prmt(tab.x, tab.y, sel[r]);                       // substitution score - open, >= 0
-                const uint32_t e = __vimax3_u16x2(HO[r], s3_fadd(E[r], KEXT, ONE), CEH2);
-                F = __vimax3_u16x2(s3_fadd(F, KEXT, ONE), upO, clipIO[r]);
-                const uint32_t dg = __vmaxu2(diagO, clipPIO[r]);
-                const uint32_t up = __vimax3_u16x2(F, e, s3_fadd(dg, d, ONE));
-                diagO = HO[r];
-                upO = s3_fadd(up, KOPEN, ONE);
-                HO[r] = upO; E[r] = e; out[r] = up;
-            }
-            upOOut = upO; FOut = F; diagOOut = diagO;
-            prevInit = init;
-            // anti-diagonal major: the group's LANES x R words of one step are contiguous
-            uint32_t *hdst = plane + s3_dp_cell<R, LANES>((uint32_t)t, s, tLastW);
-            if (R == 8) {
-                // one 256-bit store = the lane's whole 32-byte sector (two 128-bit stores would each write half of it)
-                asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" :: "l"(hdst), "r"(out[0]), "r"(out[1]), "r"(out[2]),
-                             "r"(out[3]), "r"(out[R > 4 ? 4 : 0]), "r"(out[R > 5 ? 5 : 0]), "r"(out[R > 6 ? 6 : 0]), "r"(out[R > 7 ? 7 : 0]) : "memory");
-            } else {
-#pragma unroll
-                for (int k = 0; k < R / 4; ++k) reinterpret_cast<uint4 *>(hdst)[k] = make_uint4(out[4 * k], out[4 * k + 1], out[4 * k + 2], out[4 * k + 3]);
-            }
-        }
-    }
-}
-
-// Second kernel of the 16x2 path: best cell of both alignments of a pair, per group of LANES lanes.
-// Reads the eligible slots of the pair's H plane once (bandwidth bound); scores, tie counts, the end
-// column and the right clip go to the batch arrays.
-template <int R, int LANES>
-__global__ void __launch_bounds__(S3_DP_WARPS * 32)
-s3_dp_best16_kernel(const S3DpArgs a)
-{
-    constexpr int GROUPS = 32 / LANES;
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int group = lane / LANES, t = lane % LANES;
-    const uint32_t numPairs = (a.count + 1) / 2;
-    const uint32_t wantPair = (blockIdx.x * S3_DP_WARPS + warp) * GROUPS + group;
-    if ((blockIdx.x * S3_DP_WARPS + warp) * GROUPS >= numPairs) return;          // whole warp leaves together
-    const bool pairValid = wantPair < numPairs;
-    const uint32_t pairLocal = pairValid ? wantPair : numPairs - 1;
-    const bool hasB = 2 * pairLocal + 1 < a.count;
-    const uint32_t id[2] = {a.first + 2 * pairLocal, a.first + 2 * pairLocal + (hasB ? 1u : 0u)};
-    uint32_t m[2], n[2], clipRt[2], ancR[2];
-#pragma unroll
-    for (int x = 0; x < 2; ++x) {
-        m[x] = a.readLen[id[x]]; n[x] = pairValid ? a.dnaLen[id[x]] : 0u;
-        clipRt[x] = a.clipRt ? a.clipRt[id[x]] : 0u;
-        ancR[x] = a.ancR ? a.ancR[id[x]] : 0u;
-    }
-    const uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
-    int gscore[2];
-    uint32_t gcnt[2];
-    unsigned long long gkey[2];
-    s3_dp_best16<R, LANES>(plane, a.planeSteps, (uint32_t)t, m, n, clipRt, ancR, gscore, gkey, gcnt);
-    if (t < 2 && pairValid && (t == 0 || hasB)) {
-        const int x = t;
-        const bool any = gkey[x] != ~0ull;
-        const uint32_t bi = (uint32_t)(gkey[x] & 0xFFFFFFFFu);
-        a.score[id[x]] = gscore[x];
-        a.cnt[id[x]] = gcnt[x];
-        a.hit[id[x]] = any ? (uint32_t)(gkey[x] >> 32) : 0u;
-        a.scRight[id[x]] = any ? m[x] - bi : 0u;
-        if (a.cells) atomicAdd(a.cells, (unsigned long long)m[x] * n[x]);
-    }
-}
-
-// Third kernel: traceback, one THREAD per alignment that reached its cutoff.  A traceback is a chain of
-// ~readLength dependent loads; what hides their latency is having every alignment of the chunk in
-// flight at once, which a thread each (and few registers) gives and a lane group per pair does not.
+// Traceback, one THREAD per alignment of the pass.  A traceback is a chain of ~readLength dependent loads; what
+// hides their latency is having every alignment of the chunk in flight at once, which a thread each (and few
+// registers) gives and a lane group per pair does not.
 template <int R, int LANES>
 __global__ void __launch_bounds__(128)
 s3_dp_traceback16_kernel(const S3DpArgs a)
 {
-    const uint32_t local = blockIdx.x * blockDim.x + threadIdx.x;
-    const bool inRange = local < a.count;
-    const uint32_t id = a.first + (inRange ? local : 0u);
-    // below the cutoff hitLocs stays the end column (DV-DPfunctions.cu:300-312)
-    const bool active = inRange && a.score[id] >= a.cutoff[id];
-    const uint32_t pairLocal = (inRange ? local : 0u) >> 1, half = local & 1u;
-    const uint32_t m = a.readLen[id];
-    const uint32_t mMax = (inRange && (local ^ 1u) < a.count) ? max(m, a.readLen[a.first + (local ^ 1u)]) : m;
-    const uint32_t tLast = mMax ? (mMax - 1) / R : 0u;
+    constexpr int PW = S3DpGeom<R>::PW, CKW = S3DpGeom<R>::CKW;
+    const uint32_t slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t numPairs = s3_dp_tb_pairs(a);
+    if ((slot & ~31u) >= 2 * numPairs) return;                    // whole warp leaves together
+    S3DpTbPair q;
+    const bool inRange = s3_dp_tb_pair(a, slot >> 1, q);
+    const uint32_t half = slot & 1u;
+    const bool active = inRange && q.valid[half];
+    const uint32_t id = inRange ? q.id[half] : a.first;
+    const uint32_t s0 = (inRange && q.resumed) ? a.s0[id] : 0u;
+    const uint32_t m = min(a.readLen[id], a.readWords * 16u - 1u);
     const uint32_t clipLt = a.clipLt ? a.clipLt[id] : 0u;
     const uint32_t ancL = a.ancL ? a.ancL[id] : a.maxDNALength;
-    const uint32_t *plane = a.hplane + (size_t)pairLocal * a.planeSteps * LANES * R;
+    const uint32_t *plane = a.hplane + (size_t)(slot >> 1) * a.planeSteps * LANES * PW;
+    const uint32_t rel = id - a.first;
+    const uint32_t *ck = a.ckpt + (size_t)(rel >> 1) * a.ckStride + (size_t)(s0 ? s0 / S3_DP_CK - 1u : 0u) * LANES * CKW;
+    bool fail = false;
     // every lane of the warp goes in: the lanes help each other with the E rows (s3_dp_traceback16)
-    const uint32_t start = s3_dp_traceback16<R, LANES>(a, active, plane, tLast, half, id, m, clipLt, ancL, a.scRight[id], a.hit[id]);
-    if (active) a.hit[id] = start;
+    const uint32_t start = s3_dp_traceback16<R, LANES>(a, active, plane, ck, rel & 1u, s0, half, id, m, clipLt, ancL, a.scRight[id], a.hit[id], fail);
+    if (!active) return;
+    if (fail) {
+        // (cannot happen in pass 2: its window is the whole table)
+        const uint32_t k = atomicAdd(a.tbCount + 2, 1u);
+        if (k < a.tbCap) a.tbList[(size_t)2 * a.tbCap + k] = id;
+    } else a.hit[id] = start;
+}
+
+static uint32_t dp_plane_words(const s3_dp *dp) { return dp->R <= 4 ? 4 : dp->R <= 8 ? 8 : 16; }      // S3DpGeom<R>::PW
+// steps of a pair's traceback plane: pass 1 a window (see s3_dp_sweep16_kernel: at most readLength + slack +
+// checkpoint distance + the lanes' stagger), pass 2 the whole table
+static uint32_t dp_plane_steps(const s3_dp *dp, int pass)
+{
+    const uint32_t whole = dp->maxDNALength + dp->lanes + 1, window = dp->maxReadLength + S3_DP_SLACK + S3_DP_CK + dp->lanes + 1;
+    return (pass == 1 && window < whole) ? window : whole;
+}
+// dynamic shared memory: 0 the sweep (column tables of the whole window + rings), 1 / 2 the second sweep of that pass
+static size_t dp_narrow_smem(const s3_dp *dp, int which)
+{
+    const size_t groups = (size_t)S3_DP_WARPS * (32 / dp->lanes);
+    if (which == 0) return groups * ((size_t)(dp->maxDNALength + 1) * sizeof(uint2) + ((size_t)2 * dp->lanes * dp_plane_words(dp) + (size_t)dp->lanes * dp->R) * 4);
+    return groups * (size_t)(dp_plane_steps(dp, which) + dp->lanes) * sizeof(uint2);
+}
+
+// the three kernels of the 16x2 path for (rows per lane, lanes per pair)
+struct S3DpNarrowKernels {
+    void (*sweep)(const S3DpArgs), (*resweep)(const S3DpArgs), (*traceback)(const S3DpArgs);
+};
+template <int R, int LANES> static S3DpNarrowKernels dp_narrow_of()
+{
+    S3DpNarrowKernels k = {s3_dp_sweep16_kernel<R, LANES>, s3_dp_resweep16_kernel<R, LANES>, s3_dp_traceback16_kernel<R, LANES>};
+    return k;
+}
+static S3DpNarrowKernels dp_narrow_kernels(const s3_dp *dp)
+{
+    if (dp->lanes == 8) switch (dp->R) {
+        case 3: return dp_narrow_of<3, 8>(); case 4: return dp_narrow_of<4, 8>(); case 5: return dp_narrow_of<5, 8>();
+        case 6: return dp_narrow_of<6, 8>(); case 7: return dp_narrow_of<7, 8>(); case 8: return dp_narrow_of<8, 8>();
+        case 9: return dp_narrow_of<9, 8>(); case 10: return dp_narrow_of<10, 8>(); case 11: return dp_narrow_of<11, 8>();
+        case 12: return dp_narrow_of<12, 8>(); default: return dp_narrow_of<13, 8>();
+    }
+    if (dp->lanes == 16) switch (dp->R) {
+        case 3: return dp_narrow_of<3, 16>(); case 4: return dp_narrow_of<4, 16>(); case 5: return dp_narrow_of<5, 16>();
+        case 6: return dp_narrow_of<6, 16>(); case 7: return dp_narrow_of<7, 16>(); default: return dp_narrow_of<8, 16>();
+    }
+    switch (dp->R) {
+        case 5: return dp_narrow_of<5, 32>(); case 6: return dp_narrow_of<6, 32>(); case 7: return dp_narrow_of<7, 32>();
+        case 3: return dp_narrow_of<3, 32>(); case 4: return dp_narrow_of<4, 32>();
+        default: return dp_narrow_of<8, 32>();
+    }
+}
+static int dp_narrow_set_smem(const s3_dp *dp)
+{
+    const S3DpNarrowKernels k = dp_narrow_kernels(dp);
+    const size_t s0 = dp_narrow_smem(dp, 0), s1 = dp_narrow_smem(dp, 1), s2 = dp_narrow_smem(dp, 2);
+    if (s0 > 48 * 1024) S3_CUDA(cudaFuncSetAttribute((const void *)k.sweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s0));
+    if ((s1 > s2 ? s1 : s2) > 48 * 1024) S3_CUDA(cudaFuncSetAttribute((const void *)k.resweep, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(s1 > s2 ? s1 : s2)));
+    return S3_OK;
 }
 
 static int pick_R(uint32_t maxReadLength)
@@ -832,6 +1073,17 @@ static int pick_R(uint32_t maxReadLength)
     return 0;
 }
 
+// inside s3_dp_create, once the workspace exists: a failed call releases what has been allocated so far (the struct is
+// calloc'ed, so a partial free is safe)
+#define S3_CUDA_DP(call)                                                                \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            s3_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            s3_dp_free(dp);                                                             \
+            return S3_ECUDA;                                                            \
+        }                                                                               \
+    } while (0)
 extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint32_t maxBatch, s3_dp_scores scores,
                             int device, s3_dp **out)
 {
@@ -857,50 +1109,55 @@ extern "C" int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint3
                  !getenv("S3_DP_FORCE_WIDE");      // extension <= 0: the traceback's closed form for E;
                                                    // substitution scores - open in [0, 127]: the score kernel's byte tables
     if (dp->narrow) {
-        // rows per lane x lanes per pair: 4x16 (reads <= 64), 8x16 (<= 128), 8x32 (<= 256)
-        dp->R = (maxReadLength <= 64) ? 4 : 8;
-        dp->lanes = (maxReadLength <= 128) ? 16 : 32;
-    }
-    if (dp->narrow) {
-        // column tables in dynamic shared memory: pairs per block x (maxDNALength + 1) x 8 bytes
-        const size_t smem = (size_t)S3_DP_WARPS * (32 / dp->lanes) * (maxDNALength + 1) * sizeof(uint2);
-        if (smem > 200 * 1024) dp->narrow = 0;                      // very long windows take the 32-bit path
-        else if (smem > 48 * 1024) {
-            S3_CUDA(cudaFuncSetAttribute(s3_dp_score16_kernel<8, 32>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            S3_CUDA(cudaFuncSetAttribute(s3_dp_score16_kernel<8, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            S3_CUDA(cudaFuncSetAttribute(s3_dp_score16_kernel<4, 16>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        }
+        // lanes per pair x rows per lane: the more rows a lane holds the less each cell pays for a step's fixed work
+        // (shuffles, column start values, loop), up to what the registers take: 8 lanes x <= 13 rows for reads <= 104,
+        // 16 lanes x <= 8 rows up to 128, 32 x 8 up to 256; as few rows per lane as hold the read
+        dp->lanes = (maxReadLength <= 104) ? 8 : (maxReadLength <= 128) ? 16 : 32;
+        if (getenv("S3_DP_LANES")) { const int l = atoi(getenv("S3_DP_LANES")); if ((l == 16 && maxReadLength <= 128) || l == 32) dp->lanes = l; }   // tuning experiments
+        dp->R = (int)((maxReadLength + dp->lanes - 1) / dp->lanes);
+        if (dp->R < 3) dp->R = 3;
+        // column tables (and the sweep's rings) in dynamic shared memory
+        if (dp_narrow_smem(dp, 2) > 200 * 1024 || dp_narrow_smem(dp, 0) > 200 * 1024) dp->narrow = 0;   // very long windows take the 32-bit path
+        else { int rc = dp_narrow_set_smem(dp); if (rc) { s3_dp_free(dp); return rc; } }
         if (!dp->narrow) dp->R = R;
     }
-    S3_CUDA(cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking));
+    S3_CUDA_DP(cudaStreamCreateWithFlags(&dp->stream, cudaStreamNonBlocking));
     dp->ownStream = 1;
-    // traceback planes are sized per chunk of alignments; narrow: per PAIR (maxDNALength+lanes) steps x lanes x
-    // R words of H, i.e. per alignment half of that
+    // traceback planes are sized per chunk of alignments; narrow: per PAIR a pass-2 plane (the whole table: what a chunk
+    // needs should every traceback leave its window), i.e. per alignment half of that
     const size_t perAlign = dp->narrow
-        ? (size_t)((maxDNALength + dp->lanes + S3_DP_STEP_BLOCK) / S3_DP_STEP_BLOCK * S3_DP_STEP_BLOCK) * dp->lanes * 4 * dp->R / 2
+        ? (size_t)dp_plane_steps(dp, 2) * dp->lanes * 4 * dp_plane_words(dp) / 2
         : (size_t)(maxDNALength + 1) * 32 * dp->slot;
     size_t freeB = 0, totalB = 0;
-    S3_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    S3_CUDA_DP(cudaMemGetInfo(&freeB, &totalB));
     size_t budget = freeB / 4;
     if (budget > ((size_t)24 << 30)) budget = (size_t)24 << 30;
     size_t chunk = budget / perAlign;
     if (chunk > maxBatch) chunk = maxBatch;
     chunk = (chunk + 1) & ~(size_t)1;                 // whole pairs
-    if (chunk < 2) { s3_set_error("s3_dp_create: not enough device memory for one traceback plane"); return S3_ENOMEM; }
+    if (chunk < 2) { s3_set_error("s3_dp_create: not enough device memory for one traceback plane"); s3_dp_free(dp); return S3_ENOMEM; }
     dp->chunk = (uint32_t)chunk;
-    S3_CUDA(cudaMalloc(&dp->d_tb, chunk * perAlign + 256));
+    S3_CUDA_DP(cudaMalloc(&dp->d_tb, chunk * perAlign + 256));
     const size_t up = ((size_t)maxBatch + 31) / 32 * 32;
     const size_t dnaW = (maxDNALength + 15) >> 4, readW = (maxReadLength + 15) >> 4;
-    S3_CUDA(cudaMalloc(&dp->d_scRight, up * 4));
-    S3_CUDA(cudaMalloc(&dp->d_dna, up * dnaW * 4));
-    S3_CUDA(cudaMalloc(&dp->d_read, up * readW * 4));
-    S3_CUDA(cudaMalloc(&dp->d_dnaLen, up * 4)); S3_CUDA(cudaMalloc(&dp->d_readLen, up * 4));
-    S3_CUDA(cudaMalloc(&dp->d_hit, up * 4)); S3_CUDA(cudaMalloc(&dp->d_cnt, up * 4));
-    S3_CUDA(cudaMalloc(&dp->d_clipLt, up * 4)); S3_CUDA(cudaMalloc(&dp->d_clipRt, up * 4));
-    S3_CUDA(cudaMalloc(&dp->d_ancL, up * 4)); S3_CUDA(cudaMalloc(&dp->d_ancR, up * 4));
-    S3_CUDA(cudaMalloc(&dp->d_cutoff, up * 4)); S3_CUDA(cudaMalloc(&dp->d_score, up * 4));
-    S3_CUDA(cudaMalloc(&dp->d_pattern, up * (size_t)(maxReadLength + maxDNALength)));
-    S3_CUDA(cudaMalloc(&dp->d_cells, 8));
+    S3_CUDA_DP(cudaMalloc(&dp->d_scRight, up * 4));
+    S3_CUDA_DP(cudaMalloc(&dp->d_dna, up * dnaW * 4));
+    S3_CUDA_DP(cudaMalloc(&dp->d_read, up * readW * 4));
+    S3_CUDA_DP(cudaMalloc(&dp->d_dnaLen, up * 4)); S3_CUDA_DP(cudaMalloc(&dp->d_readLen, up * 4));
+    S3_CUDA_DP(cudaMalloc(&dp->d_hit, up * 4)); S3_CUDA_DP(cudaMalloc(&dp->d_cnt, up * 4));
+    S3_CUDA_DP(cudaMalloc(&dp->d_clipLt, up * 4)); S3_CUDA_DP(cudaMalloc(&dp->d_clipRt, up * 4));
+    S3_CUDA_DP(cudaMalloc(&dp->d_ancL, up * 4)); S3_CUDA_DP(cudaMalloc(&dp->d_ancR, up * 4));
+    S3_CUDA_DP(cudaMalloc(&dp->d_cutoff, up * 4)); S3_CUDA_DP(cudaMalloc(&dp->d_score, up * 4));
+    S3_CUDA_DP(cudaMalloc(&dp->d_pattern, up * (size_t)(maxReadLength + maxDNALength)));
+    S3_CUDA_DP(cudaMalloc(&dp->d_cells, 8));
+    if (dp->narrow) {
+        dp->numCk = (maxDNALength + dp->lanes - 1) / S3_DP_CK;
+        const size_t ckw = (size_t)(2 * dp->R + 2 + 7) / 8 * 8;
+        S3_CUDA_DP(cudaMalloc(&dp->d_ckpt, (chunk / 2 + 1) * (size_t)(dp->numCk ? dp->numCk : 1) * dp->lanes * ckw * 4));
+        S3_CUDA_DP(cudaMalloc(&dp->d_tbList, 3 * chunk * 4));
+        S3_CUDA_DP(cudaMalloc(&dp->d_tbCount, 16));
+        S3_CUDA_DP(cudaMalloc(&dp->d_s0, up * 4));
+    }
     *out = dp;
     return S3_OK;
 }
@@ -911,7 +1168,8 @@ extern "C" void s3_dp_free(s3_dp *dp)
     cudaSetDevice(dp->device);
     cudaStreamSynchronize(dp->stream);
     void *ptrs[] = {dp->d_tb, dp->d_scRight, dp->d_dna, dp->d_read, dp->d_dnaLen, dp->d_readLen, dp->d_hit, dp->d_cnt,
-                    dp->d_clipLt, dp->d_clipRt, dp->d_ancL, dp->d_ancR, dp->d_cutoff, dp->d_score, dp->d_pattern, dp->d_cells};
+                    dp->d_clipLt, dp->d_clipRt, dp->d_ancL, dp->d_ancR, dp->d_cutoff, dp->d_score, dp->d_pattern, dp->d_cells,
+                    dp->d_ckpt, dp->d_tbList, dp->d_tbCount, dp->d_s0};
     for (size_t i = 0; i < sizeof ptrs / sizeof ptrs[0]; ++i) if (ptrs[i]) cudaFree(ptrs[i]);
     s3_pipe_destroy(&dp->pipe);
     s3_timing_destroy(&dp->timing);
@@ -961,9 +1219,7 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t begin, uint32_t end)
     a.dnaWords = (dp->maxDNALength + 15) >> 4; a.readWords = (dp->maxReadLength + 15) >> 4;
     a.slot = dp->slot; a.tb = dp->d_tb; a.scRight = dp->d_scRight;
     a.match = dp->sc.matchScore; a.mismatch = dp->sc.mismatchScore; a.open = dp->sc.gapOpenScore; a.ext = dp->sc.gapExtendScore;
-    size_t smem = 0;
     if (dp->narrow) {
-        a.planeSteps = (dp->maxDNALength + dp->lanes + S3_DP_STEP_BLOCK) / S3_DP_STEP_BLOCK * S3_DP_STEP_BLOCK;     // steps 0 .. maxDNALength + lanes - 1, whole blocks
         a.hplane = reinterpret_cast<uint32_t *>(dp->d_tb);
         const int gapInit = dp->sc.gapOpenScore - dp->sc.gapExtendScore;
         auto k32 = [](int v) { return (uint32_t)((long long)v * 0x10001ll); };        // v in both halves of one 32-bit addend
@@ -975,40 +1231,32 @@ static int dp_run_device(s3_dp *dp, S3DpArgs a, uint32_t begin, uint32_t end)
         a.one = 1;
         a.mism4 = ((uint32_t)(dp->sc.mismatchScore - open) & 0xFFu) * 0x01010101u;
         a.delta = ((uint32_t)(dp->sc.matchScore - open) ^ (uint32_t)(dp->sc.mismatchScore - open)) & 0xFFu;
-        a.colStride = dp->maxDNALength + 1;
-        smem = (size_t)S3_DP_WARPS * (32 / dp->lanes) * a.colStride * sizeof(uint2);
+        a.ckpt = dp->d_ckpt; a.numCk = dp->numCk;
+        a.ckStride = (size_t)(dp->numCk ? dp->numCk : 1) * dp->lanes * ((2 * dp->R + 2 + 7) / 8 * 8);
+        a.tbList = dp->d_tbList; a.tbCount = dp->d_tbCount; a.tbCap = dp->chunk; a.s0 = dp->d_s0;
     }
+    const S3DpNarrowKernels nk = dp->narrow ? dp_narrow_kernels(dp) : S3DpNarrowKernels();
     for (uint32_t first = begin; first < end; first += dp->chunk) {
         a.first = first;
         a.count = (end - first < dp->chunk) ? end - first : dp->chunk;
         if (dp->narrow) {
-            const uint32_t pairs = (a.count + 1) / 2;
             const uint32_t perBlock = S3_DP_WARPS * (32 / dp->lanes);
-            const uint32_t blocks = (pairs + perBlock - 1) / perBlock;
+            const uint32_t blocks = ((a.count + 1) / 2 + perBlock - 1) / perBlock;
+            // the pairs of a traceback pass: at most every alignment of the chunk, two by two, in two classes
+            const uint32_t tbBlocks = (a.count / 2 + 2 + perBlock - 1) / perBlock, tbThreads = 2 * (a.count / 2 + 2);
+            S3_CUDA(cudaMemsetAsync(dp->d_tbCount, 0, 16, dp->stream));
             s3_timing_mark(&dp->timing, dp->stream, -1);
-            if (dp->lanes == 32) {
-                s3_dp_score16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
-                s3_timing_mark(&dp->timing, dp->stream, 0);
-                s3_dp_best16_kernel<8, 32><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
-                s3_timing_mark(&dp->timing, dp->stream, 1);
-                s3_dp_traceback16_kernel<8, 32><<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a);
-                s3_timing_mark(&dp->timing, dp->stream, 2);
-            } else if (dp->R == 8) {
-                s3_dp_score16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
-                s3_timing_mark(&dp->timing, dp->stream, 0);
-                s3_dp_best16_kernel<8, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
-                s3_timing_mark(&dp->timing, dp->stream, 1);
-                s3_dp_traceback16_kernel<8, 16><<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a);
-                s3_timing_mark(&dp->timing, dp->stream, 2);
-            } else {
-                s3_dp_score16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, smem, dp->stream>>>(a);
-                s3_timing_mark(&dp->timing, dp->stream, 0);
-                s3_dp_best16_kernel<4, 16><<<blocks, S3_DP_WARPS * 32, 0, dp->stream>>>(a);
-                s3_timing_mark(&dp->timing, dp->stream, 1);
-                s3_dp_traceback16_kernel<4, 16><<<(a.count + 127) / 128, 128, 0, dp->stream>>>(a);
-                s3_timing_mark(&dp->timing, dp->stream, 2);
+            a.pass = 0; a.colStride = dp->maxDNALength + 1;
+            nk.sweep<<<blocks, S3_DP_WARPS * 32, dp_narrow_smem(dp, 0), dp->stream>>>(a);
+            s3_timing_mark(&dp->timing, dp->stream, 0);
+            for (int pass = 1; pass <= 2; ++pass) {
+                a.pass = pass; a.planeSteps = dp_plane_steps(dp, pass); a.colStride = a.planeSteps + dp->lanes;
+                nk.resweep<<<tbBlocks, S3_DP_WARPS * 32, dp_narrow_smem(dp, pass), dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, pass == 1 ? 1 : 3);
+                nk.traceback<<<(tbThreads + 127) / 128, 128, 0, dp->stream>>>(a);
+                s3_timing_mark(&dp->timing, dp->stream, pass == 1 ? 2 : 3);
             }
-            S3_LAUNCHED(3);
+            S3_LAUNCHED(5);
             S3_CUDA(cudaGetLastError());
             continue;
         }

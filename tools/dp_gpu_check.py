@@ -3,8 +3,7 @@ kernels in 15-25 s GPU slots.  `--make-case [n]` (needs torch and the oracle; ru
 batch shaped like bench.py's (100-base reads, 401-column windows, n alignments, default 65,536) and the oracle's outputs
 to tools/_dp_case.npz.  Without flags: uploads the batch, runs s3_dp_align_device `S3_DP_CHECK_STEPS` (default 6) times with
 the library's timing hooks on, compares scores, hit locations, tie counts and traced patterns with the oracle's, and
-prints per-kernel milliseconds and GCUPS; also written to gpurun_out/dp_check.txt.  (Written at the end of a round: the
-upload and the first call ran on a B200, the rest of main() has not yet.)"""
+prints per-kernel milliseconds and GCUPS; also written to gpurun_out/dp_check.txt."""
 import ctypes as C
 import os
 import sys
@@ -86,8 +85,7 @@ def main():
     d_in = {k: cu.upload(z[k]) for k in FIELDS}
     want = {k: z[k] for k in ("scores", "hit", "cnt", "pattern")}
     d_out = {k: cu.alloc(want[k].nbytes) for k in want}
-    lib.s3_dp_stream.restype = C.c_void_p
-    stream = lib.s3_dp_stream(al.handle)                    # SemiGlobalAligner.handle is a c_void_p already
+    stream = al.stream
     steps = int(os.environ.get("S3_DP_CHECK_STEPS", 6))
 
     def step():
@@ -112,10 +110,11 @@ def main():
         k = pattern_bytes(w)
         bad_pat += int(not np.array_equal(got["pattern"][t * pat_len:t * pat_len + k], w[:k]))
     ok = not any(bad.values()) and bad_pat == 0
-    per = [m / steps for m in ms[:3]]
+    per = [m / steps for m in ms[:4]]
     lines = [f"{'PASS' if ok else 'FAIL'} DP parity: {n} alignments ({len(traced)} traced), differ: {bad}, patterns {bad_pat}",
-             f"DP step {sum(per):.3f} ms (score sweep {per[0]:.3f}, best cell {per[1]:.3f}, traceback {per[2]:.3f}; launches per step "
-             f"{[c // steps for c in launches[:3]]}), wall {1e3 * wall:.3f} ms; {cells / 1e9:.2f} G cells -> {cells / (sum(per) * 1e-3) / 1e9:.0f} GCUPS"]
+             f"DP step {sum(per):.3f} ms (sweep {per[0]:.3f}, second sweep of the traceback windows {per[1]:.3f}, traceback {per[2]:.3f}, "
+             f"pass 2 {per[3]:.3f}; launches per step {[c // steps for c in launches[:4]]}), wall {1e3 * wall:.3f} ms; "
+             f"{cells / 1e9:.2f} G cells -> {cells / (sum(per) * 1e-3) / 1e9:.0f} GCUPS (sweep alone {cells / (per[0] * 1e-3) / 1e9:.0f})"]
     print("\n".join(lines), flush=True)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     open(os.path.join(ROOT, "gpurun_out", "dp_check.txt"), "w").write("\n".join(lines) + "\n")

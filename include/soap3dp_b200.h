@@ -210,6 +210,10 @@ typedef struct {
     int32_t matchScore, mismatchScore, gapOpenScore, gapExtendScore;   /* soap3-dp.ini [DP] */
 } s3_dp_scores;
 
+/* Sequences are 1-based in their slots (base i in word i >> 4), so a slot of w = ceil(max / 16) words holds 16 w - 1
+ * bases: a length equal to a maximum that is a multiple of 16 does not fit (the reference sizes maxReadLength as
+ * (L / 4 + 1) * 4 and maxDNALength with + 8 slack, DV-DPfunctions.cu:1580-1581, and never meets the case).  The host
+ * entries reject such lengths with S3_EINVAL; the device entries cut them to what the slot holds. */
 int s3_dp_create(uint32_t maxReadLength, uint32_t maxDNALength, uint32_t maxBatch,
                  s3_dp_scores scores, int device, s3_dp **out);
 void s3_dp_free(s3_dp *dp);
@@ -272,6 +276,17 @@ int s3_dp_align_windows(s3_dp *dp, s3_index *ix,
                         uint8_t *pattern, uint32_t numOfThreads,
                         const uint32_t *clipLtSizes, uint32_t *clipRtSizes,
                         const uint32_t *anchorLeftLocs, const uint32_t *anchorRightLocs);
+
+/* device-resident twin: every pointer is a device pointer (d_readLengths per ALIGNMENT, not per query), the work is
+ * enqueued on s3_dp_stream() and not synchronised; numOfThreads <= maxBatch of the workspace */
+int s3_dp_align_windows_device(s3_dp *dp, s3_index *ix, const uint32_t *d_queries, uint32_t wordPerOldQuery,
+                               const uint32_t *d_readIDs, const uint8_t *d_strands,
+                               const uint32_t *d_DNAStarts, const uint32_t *d_DNALengths, const uint32_t *d_readLengths,
+                               const int32_t *d_cutoffThresholds,
+                               int32_t *d_scores, uint32_t *d_hitLocs, uint32_t *d_maxScoreCounts,
+                               uint8_t *d_pattern, uint32_t numOfThreads,
+                               const uint32_t *d_clipLtSizes, uint32_t *d_clipRtSizes,
+                               const uint32_t *d_anchorLeftLocs, const uint32_t *d_anchorRightLocs);
 
 /* ------------------------------------------------------------------------
  * DP result decoding (host work on the arrays s3_dp_align* returned).  Replaces the result loops
@@ -360,6 +375,88 @@ int s3_retain_best(s3_index *ix, int mode, int32_t maxNum,
                    uint64_t numReads,
                    uint64_t *outSaOff, uint32_t *outSaL, uint32_t *outSaR, uint8_t *outSaFlags,
                    uint64_t *outOccOff, uint32_t *outOccPos, uint8_t *outOccFlags, uint32_t *num);
+
+/* ------------------------------------------------------------------------
+ * A batch of read pairs from queries to alignments without leaving the device.  Replaces what soap3_dp_pair_align does
+ * on the host between its GPU calls (alignment.cu:1896-2330) for one batch: round 1 of all_valid_alignment
+ * (alignment.cu:855), hostKernel's per-pair work (CPUfunctions.cpp:1498-2620: collect_all_answers :1226, the routing of a
+ * pair by which mates have hits :2153-2262 / :2440-2530, transferAllSAToOcc SAList.cpp:392, PEMappingOccurrences +
+ * PEStatsPEOutput PEAlgnmt.cpp:480,777) and the default-DP engine's mate rescue (HalfEndOccStream, HalfEndAlgnBatch::pack
+ * DV-DPfunctions.cu:1900,2027; performAlignment :669; the result loop :2359-2420) -- the semantics of the empty
+ * alignPairR (soap3-dp-module.h:60, soap3-dp-module.cu:183-193) with in-memory results.  Reads 2p and 2p + 1 are the two
+ * mates of pair p (the reference's interleaved pair layout).  Queries go in, a few dozen bytes per pair come out:
+ *   route[p]   what became of pair p (codes below)
+ *   pairs[p]   S3_PE_PAIRED: PEStatsPEPairList's optimal pair (algnmt_1/2, strands, mismatches, insertion), the number
+ *              of valid pairs, how many share the optimal / the suboptimal total
+ *   dp[t]      one record per rescue window in HalfEndOccStream's order (reads ascending, a read's SA ranges in slot
+ *              order, a range in suffix-array order): the aligned mate's occurrence, the DP read, its position
+ *              (window start + hitLoc, 0xFFFFFFFF below the cutoff), score, maxScoreCounts, and its CIGAR as
+ *              runs[runOffset .. runOffset + numRuns) in read order, each length << 8 | op with op one of M m I D S
+ *              (CigarStringEncoder's special CIGAR, DV-DPfunctions.h:545-597)
+ * Reads whose round-1 slot overflowed in some case are not searched again here: their pair is S3_PE_OVERFLOW and goes
+ * to s3_search_round2 / s3_search like the reference's round 2.  Pairs the reference hands to its later stages are
+ * named, not processed: S3_PE_NONE (both-unaligned list: deep DP), *_TOO_MANY (new-default DP), BOTH_NO_PAIR_MANY.
+ * The host arrays of s3_pe_align's result are the library's (pinned) and stay valid until the next call on the handle.
+ * ------------------------------------------------------------------------ */
+#define S3_PE_NONE              0   /* no mate has a hit: addReadIDToBothUnalignedPairs */
+#define S3_PE_PAIRED            1   /* both mates hit and a valid pair exists */
+#define S3_PE_BOTH_HIT          1   /* (inside the chain: both mates hit, pairing to come) */
+#define S3_PE_FIRST_RESCUES     2   /* only the first read hit: its occurrences rescue the mate (dpInput) */
+#define S3_PE_SECOND_RESCUES    3
+#define S3_PE_BOTH_RESCUE       4   /* both hit, no valid pair, few hits each: each rescues the other (dpInput) */
+#define S3_PE_FIRST_TOO_MANY    5   /* only the first read hit, more than maxHitNumForDP best hits: dpInputForNewDefault */
+#define S3_PE_SECOND_TOO_MANY   6
+#define S3_PE_BOTH_NO_PAIR_MANY 7   /* both hit, no valid pair, one of them with more than maxHitNumForDP hits */
+#define S3_PE_OVERFLOW          8   /* a round-1 slot of one of the mates overflowed (isMoreThanSA1) */
+
+typedef struct s3_pe s3_pe;
+typedef struct {
+    uint32_t numMismatch;                 /* Soap3MisMatchAllow: 2 when DP follows (SOAP3-DP.cu:210-213) */
+    int32_t insertLow, insertHigh;        /* -v / -u */
+    int32_t strandLeftLeg, strandRightLeg;/* 1 / 2: StrandArrangement +/- */
+    uint32_t maxOutputPerRead;            /* soap3-dp.ini MaxOutputPerRead (1000) */
+    uint32_t maxHitNumForDP;              /* getParameterForDefaultDP maxHitNum (CPUfunctions.cpp:59-86) */
+    int32_t keepSecondBest;               /* needOutputMAPQ: retainAllBestAndSecBest instead of retainAllBest */
+    s3_dp_scores scores;                  /* soap3-dp.ini [DP] */
+    int32_t cutoffThreshold;              /* DPScoreThreshold; < 0: DEFAULT = ceil(0.3 * read length) */
+    int32_t softClipLeft, softClipRight;  /* MaxFrontLenClipped / MaxEndLenClipped */
+    uint32_t maxWindows;                  /* rescue windows per batch the DP workspace is sized for; 0: one per read */
+} s3_pe_params;
+typedef struct {
+    uint32_t pos1, pos2, insertion;       /* PEPairs algnmt_1, algnmt_2, insertion */
+    uint8_t strand1, mism1, strand2, mism2;
+    uint32_t numPairs;                    /* numPEAlgnmt */
+    uint16_t numOptimal, numSuboptimal;   /* num_minMismatch, num_soMinMismatch (CPUfunctions.cpp:2311-2320) */
+    int8_t optimalTotal, suboptimalTotal; /* totalMismatchCount of the two pairs of PEStatsPEPairList; 127: none */
+    uint16_t pad;
+} s3_pe_pair_result;
+typedef struct {
+    uint32_t dpReadID, alignedPos, dpPos;
+    int32_t score;
+    uint32_t numSameScore, runOffset;
+    uint16_t numRuns;
+    uint8_t alignedStrand, alignedMismatches, dpStrand, leftOrRight, pad[2];
+} s3_pe_dp_result;
+typedef struct {
+    uint64_t numPairs, numRanges, numOccurrences, numWindows, numRuns;
+    uint32_t routeCounts[16];             /* pairs per first-stage route code */
+    uint64_t h2dBytes, d2hBytes;          /* what crossed the link for this batch */
+    uint8_t *route; s3_pe_pair_result *pairs; s3_pe_dp_result *dp; uint32_t *runs;              /* host (s3_pe_align) */
+    uint8_t *d_route; s3_pe_pair_result *d_pairs; s3_pe_dp_result *d_dp; uint32_t *d_runs;      /* device (s3_pe_align_device) */
+} s3_pe_result;
+/* maxReads (even) reads of up to maxReadLength bases per batch; needs an index uploaded with suffix array and text */
+int s3_pe_create(s3_index *ix, uint32_t maxReads, uint32_t maxReadLength, const s3_pe_params *params, s3_pe **out);
+void s3_pe_free(s3_pe *pe);
+int s3_pe_align(s3_pe *pe, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
+                s3_pe_result *out);
+/* queries / readLengths already in device memory, results left there (two 4-byte counts are all that crosses the link) */
+int s3_pe_align_device(s3_pe *pe, const uint32_t *d_queries, const uint32_t *d_readLengths, uint64_t numReads,
+                       uint32_t wordPerQuery, s3_pe_result *out);
+/* milliseconds per stage summed since timing was switched on: 0 search, 1 collect + route, 2 locate + sort,
+ * 3 pairing + window count, 4 window fill, 5 DP, 6 CIGAR runs + records */
+int s3_pe_set_timing(s3_pe *pe, int on);
+int s3_pe_read_timing(s3_pe *pe, float *msPerStage);
+s3_dp *s3_pe_dp(s3_pe *pe);               /* the chain's DP workspace (for s3_dp_set_timing / s3_dp_read_timing) */
 
 /* ------------------------------------------------------------------------
  * Tables of the DP stages (host, integer).  s3_seed_layout replaces getSeedPositions

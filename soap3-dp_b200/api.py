@@ -661,3 +661,119 @@ def search_round1_device(gpu_index: GpuIndex, d_queries: int, d_read_lengths: in
 
 def launch_count() -> int:
     return int(load_library().s3_launch_count())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# paired-end batch on the device (s3_pe_*): the in-memory alignPairR the reference declares and leaves empty
+# (soap3-dp-module.h:60, soap3-dp-module.cu:183-193)
+# ---------------------------------------------------------------------------------------------------------------------
+PE_NONE, PE_PAIRED, PE_FIRST_RESCUES, PE_SECOND_RESCUES, PE_BOTH_RESCUE = 0, 1, 2, 3, 4
+PE_FIRST_TOO_MANY, PE_SECOND_TOO_MANY, PE_BOTH_NO_PAIR_MANY, PE_OVERFLOW = 5, 6, 7, 8
+
+
+class PEParams(C.Structure):
+    _fields_ = [("numMismatch", C.c_uint32), ("insertLow", C.c_int32), ("insertHigh", C.c_int32),
+                ("strandLeftLeg", C.c_int32), ("strandRightLeg", C.c_int32), ("maxOutputPerRead", C.c_uint32),
+                ("maxHitNumForDP", C.c_uint32), ("keepSecondBest", C.c_int32), ("scores", DPScores),
+                ("cutoffThreshold", C.c_int32), ("softClipLeft", C.c_int32), ("softClipRight", C.c_int32),
+                ("maxWindows", C.c_uint32)]
+
+
+class PEResult(C.Structure):
+    _fields_ = [("numPairs", C.c_uint64), ("numRanges", C.c_uint64), ("numOccurrences", C.c_uint64), ("numWindows", C.c_uint64),
+                ("numRuns", C.c_uint64), ("routeCounts", C.c_uint32 * 16), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
+                ("route", C.c_void_p), ("pairs", C.c_void_p), ("dp", C.c_void_p), ("runs", C.c_void_p),
+                ("d_route", C.c_void_p), ("d_pairs", C.c_void_p), ("d_dp", C.c_void_p), ("d_runs", C.c_void_p)]
+
+
+PE_PAIR_DTYPE = np.dtype([("pos1", np.uint32), ("pos2", np.uint32), ("insertion", np.uint32), ("strand1", np.uint8), ("mism1", np.uint8),
+                          ("strand2", np.uint8), ("mism2", np.uint8), ("numPairs", np.uint32), ("numOptimal", np.uint16),
+                          ("numSuboptimal", np.uint16), ("optimalTotal", np.int8), ("suboptimalTotal", np.int8), ("pad", np.uint16)])
+PE_DP_DTYPE = np.dtype([("dpReadID", np.uint32), ("alignedPos", np.uint32), ("dpPos", np.uint32), ("score", np.int32),
+                        ("numSameScore", np.uint32), ("runOffset", np.uint32), ("numRuns", np.uint16), ("alignedStrand", np.uint8),
+                        ("alignedMismatches", np.uint8), ("dpStrand", np.uint8), ("leftOrRight", np.uint8), ("pad", np.uint8, (2,))])
+
+
+def pe_params(num_mismatch=2, insert_low=200, insert_high=500, left_leg=1, right_leg=2, max_output_per_read=1000,
+              max_hit_num_for_dp=None, keep_second_best=False, scores=(1, -2, -3, -1), cutoff=-1, soft_clip_left=3,
+              soft_clip_right=8, max_windows=0, read_length=100) -> PEParams:
+    """Defaults as soap3_dp_pair_align sees them: Soap3MisMatchAllow 2 with DP (SOAP3-DP.cu:210-213), the ini's MaxOutputPerRead,
+    getParameterForDefaultDP's maxHitNum for the read length, clips 3 / 8 (soap3-dp-module.cu:14)."""
+    if max_hit_num_for_dp is None:
+        max_hit_num_for_dp = getParameterForDP(2, read_length, read_length).paramRead[0].maxHitNum
+    return PEParams(num_mismatch, insert_low, insert_high, left_leg, right_leg, max_output_per_read, max_hit_num_for_dp,
+                    int(keep_second_best), DPScores(*scores), cutoff, soft_clip_left, soft_clip_right, max_windows)
+
+
+class PairAligner:
+    """s3_pe_create / s3_pe_align: a batch of read pairs (reads 2p, 2p + 1 = the mates of pair p) from queries to
+    pairings and mate-rescue alignments on the device."""
+
+    def __init__(self, gpu_index: GpuIndex, max_reads: int, max_read_length: int, params: PEParams):
+        lib = load_library()
+        lib.s3_pe_create.restype = C.c_int
+        lib.s3_pe_create.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.POINTER(PEParams), C.POINTER(C.c_void_p)]
+        lib.s3_pe_free.restype = None
+        lib.s3_pe_free.argtypes = [C.c_void_p]
+        for fn in (lib.s3_pe_align, lib.s3_pe_align_device):
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(PEResult)]
+        lib.s3_pe_set_timing.restype = C.c_int
+        lib.s3_pe_set_timing.argtypes = [C.c_void_p, C.c_int]
+        lib.s3_pe_read_timing.restype = C.c_int
+        lib.s3_pe_read_timing.argtypes = [C.c_void_p, C.POINTER(C.c_float)]
+        lib.s3_pe_dp.restype = C.c_void_p
+        lib.s3_pe_dp.argtypes = [C.c_void_p]
+        self.params = params
+        out = C.c_void_p()
+        _check(lib.s3_pe_create(gpu_index.handle, max_reads, max_read_length, C.byref(params), C.byref(out)), "s3_pe_create")
+        self.handle = out
+
+    def align(self, queries, read_lengths, num_reads: int, word_per_query: int, copy: bool = True):
+        """queries / read_lengths: host uint32 arrays (or raw host addresses).  -> dict of numpy arrays (copies unless copy=False)"""
+        res = PEResult()
+        q = queries.ctypes.data if hasattr(queries, "ctypes") else int(queries)
+        l = read_lengths.ctypes.data if hasattr(read_lengths, "ctypes") else int(read_lengths)
+        _check(load_library().s3_pe_align(self.handle, C.c_void_p(q), C.c_void_p(l), num_reads, word_per_query, C.byref(res)), "s3_pe_align")
+        return self._unpack(res, copy)
+
+    def align_device(self, d_queries: int, d_read_lengths: int, num_reads: int, word_per_query: int) -> PEResult:
+        res = PEResult()
+        _check(load_library().s3_pe_align_device(self.handle, C.c_void_p(d_queries), C.c_void_p(d_read_lengths), num_reads, word_per_query,
+                                                 C.byref(res)), "s3_pe_align_device")
+        return res
+
+    @staticmethod
+    def _unpack(res: PEResult, copy: bool):
+        def view(ptr, dtype, n):
+            if not ptr or n == 0:
+                return np.zeros(0, dtype)
+            buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+            a = np.frombuffer(buf, dtype=dtype, count=n)
+            return a.copy() if copy else a
+        P, M, R = int(res.numPairs), int(res.numWindows), int(res.numRuns)
+        return {"route": view(res.route, np.uint8, P), "pairs": view(res.pairs, PE_PAIR_DTYPE, P), "dp": view(res.dp, PE_DP_DTYPE, M),
+                "runs": view(res.runs, np.uint32, R), "num_ranges": int(res.numRanges), "num_occurrences": int(res.numOccurrences),
+                "route_counts": list(res.routeCounts), "h2d_bytes": int(res.h2dBytes), "d2h_bytes": int(res.d2hBytes)}
+
+    def set_timing(self, on: bool):
+        _check(load_library().s3_pe_set_timing(self.handle, int(on)), "s3_pe_set_timing")
+
+    def read_timing(self):
+        ms = (C.c_float * 8)()
+        _check(load_library().s3_pe_read_timing(self.handle, ms), "s3_pe_read_timing")
+        return list(ms)
+
+    @property
+    def dp_handle(self):
+        return C.c_void_p(load_library().s3_pe_dp(self.handle))
+
+    def free(self):
+        if self.handle:
+            load_library().s3_pe_free(self.handle)
+            self.handle = C.c_void_p(0)
+
+
+def runs_to_cigar(runs: np.ndarray) -> str:
+    """(length << 8 | op) runs of s3_pe_align -> the special CIGAR string the reference's encoder writes"""
+    return "".join(f"{int(r) >> 8}{chr(int(r) & 0xFF)}" for r in runs)

@@ -1,0 +1,643 @@
+// s3_chain.cu -- a batch of read pairs from queries to alignments without leaving the device.
+//
+// Replaces, for a batch, what soap3_dp_pair_align does between its GPU calls on the host
+// (alignment.cu:1896-2330): all_valid_alignment's round 1 (alignment.cu:855), hostKernel's per-pair work
+// (CPUfunctions.cpp:1498-2620: collect_all_answers :1226, the routing of a pair by which mates have hits :2153-2262 and
+// :2440-2530, transferAllSAToOcc SAList.cpp:392, PEMappingOccurrences + PEStatsPEOutput PEAlgnmt.cpp:480,777) and the
+// default-DP engine's mate rescue (HalfEndOccStream::fetchNextOcc DV-DPfunctions.cu:1900, HalfEndAlgnBatch::pack :2027,
+// SemiGlobalAligner::performAlignment :669, the result loop of DP_Space::algnmtCPUThread :2359-2420).  The reference
+// ships four padded buffers across PCIe per batch (queries in, 8-word answer slots per read and case out, packed
+// windows in, 509-byte traceback patterns out); here the queries go in and a few dozen bytes per pair come out.
+//
+//   search (round-1 slots, all cases)           s3_search_round1_device
+//   collect   per read: its SA ranges over the cases in slot order, capped at MaxOutputPerRead occurrences
+//   route     per pair: both mates hit -> pairing; one -> mate rescue (best hits only when there are more than
+//             maxHitNumForDP); none -> the both-unaligned list (deep DP is the caller's next stage)
+//   locate    the occurrences of every read that is paired or rescues its mate, from the suffix array
+//   pair      one stable sort by (read, position); per pair the reference's merge walk: number of valid pairs,
+//             the optimal pair, the second-best total
+//   route 2   both mates hit but no valid pair: both rescue each other when neither has more than maxHitNumForDP hits
+//   windows   per rescuing occurrence the window HalfEndAlgnBatch::pack cuts, in HalfEndOccStream's order
+//   DP        s3_dp_align_windows_device
+//   results   per window that reached its cutoff: position, score, tie count, CIGAR as (op, length) runs in read order
+// Two small device-to-host reads of counts size the later stages (occurrences, windows); everything else is
+// stream-ordered.
+#include "s3_common.cuh"
+#include "s3_pair_walk.cuh"
+#include "../../include/soap3dp_b200.h"
+
+#include <cub/cub.cuh>
+#include <stdlib.h>
+#include <string.h>
+
+#define S3_TRYC(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { s3_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); return S3_ECUDA; } } while (0)
+
+struct S3Arena {
+    char *base; size_t cap, used;
+};
+static int arena_reserve(S3Arena *a, size_t bytes, cudaStream_t st)
+{
+    a->used = 0;
+    if (bytes <= a->cap) return S3_OK;
+    if (a->base) { S3_TRYC(cudaStreamSynchronize(st)); S3_TRYC(cudaFree(a->base)); a->base = NULL; a->cap = 0; }
+    bytes += bytes / 4;
+    S3_TRYC(cudaMalloc(&a->base, bytes));
+    a->cap = bytes;
+    return S3_OK;
+}
+template <typename T> static T *arena_take(S3Arena *a, size_t n)
+{
+    const size_t off = (a->used + 255) / 256 * 256;
+    a->used = off + n * sizeof(T);
+    return a->used <= a->cap ? reinterpret_cast<T *>(a->base + off) : NULL;
+}
+static size_t arena_need(size_t n, size_t sz) { return n * sz + 256; }
+
+struct s3_pe {
+    s3_index *ix;
+    s3_dp *dp;
+    s3_pe_params par;
+    uint32_t maxReads, maxReadLength, maxDNALength, maxWindows;
+    S3Arena A, B, C;                 // stage buffers: sized by the batch, by the occurrences, by the windows
+    void *pinned; size_t pinnedBytes;
+    uint32_t *h_counts;              // pinned: what the two mid-chain reads bring back
+    float msStages[8];
+    cudaEvent_t ev[10];
+    int timing;
+};
+
+// ---- collect (collect_all_answers, CPUfunctions.cpp:1226-1300, round-1 slots only) ------------------------------------
+// One thread per read.  COUNT: ranges and occurrences of the read; FILL: the ranges at rangeOff[read].
+// A case whose status word is > 0xFFFFFFFD overflowed its slot (isMoreThanSA1): the reference searches such a read
+// again (round 2, then the CPU); here the read is flagged and its pair reported as S3_PE_OVERFLOW.
+struct S3Collect {
+    const uint32_t *answers[S3_MAX_NUM_CASES];
+    uint32_t numCases, allowed, wordPerAns, numReads, textLength, maxOutputPerRead;
+};
+template <bool FILL>
+__global__ void s3_pe_collect_kernel(const S3Collect c, uint32_t *__restrict__ nRanges, uint32_t *__restrict__ totOcc, uint8_t *__restrict__ readFlags,
+                                     const uint32_t *__restrict__ rangeOff, uint32_t *__restrict__ saL, uint32_t *__restrict__ saR,
+                                     uint8_t *__restrict__ saFlags)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= c.numReads) return;
+    const size_t off = (size_t)(r >> 5) * 32 * c.wordPerAns + (r & 31);
+    uint32_t n = 0, tot = 0;
+    bool more = false;
+    const uint32_t base = FILL ? rangeOff[r] : 0u;
+    for (uint32_t w = 0; w < c.numCases; ++w) {
+        const uint32_t *ans = c.answers[w] + off;
+        const uint32_t first = ans[0];
+        if (first > 0xFFFFFFFDu) { more = true; continue; }
+        if (first == 0xFFFFFFFDu) continue;
+        for (uint32_t i = 0; i < c.allowed; ++i) {
+            const uint32_t a0 = ans[(size_t)(2 * i) * 32], a1 = ans[(size_t)(2 * i + 1) * 32];
+            if (a0 >= 0xFFFFFFFDu || a1 >= 0xFFFFFFFDu) break;
+            const uint32_t l = a0;
+            uint32_t rr = l + (a1 & 0xFFFFFFu);
+            if (!(l <= rr && rr <= c.textLength)) break;
+            if (tot < c.maxOutputPerRead) {
+                if (tot + (rr - l + 1) > c.maxOutputPerRead) rr = l + c.maxOutputPerRead - tot - 1;
+                if (FILL) {
+                    saL[base + n] = l; saR[base + n] = rr;
+                    saFlags[2 * (size_t)(base + n)] = (uint8_t)(((a1 >> 27) & 1u) + 1u);        // strand 1 / 2
+                    saFlags[2 * (size_t)(base + n) + 1] = (uint8_t)((a1 >> 24) & 7u);           // mismatches
+                }
+                ++n; tot += rr - l + 1;
+            }
+            if (tot >= c.maxOutputPerRead) break;
+        }
+    }
+    if (!FILL) { nRanges[r] = n; totOcc[r] = tot; readFlags[r] = more ? 1 : 0; }
+}
+
+// ---- route (CPUfunctions.cpp:2153-2262) ------------------------------------------------------------------------------
+// One thread per pair.  A mate that rescues the other with more than maxHitNumForDP occurrences keeps its best hits only
+// (retainAllBest, or retainAllBestAndSecBest when mapping qualities are wanted: SAList.cpp:140-348 on a list without
+// occurrences = the ranges with the minimum / minimum + 1 mismatches); still too many -> the new-default-DP list.
+// keepRange[g] = 1 for the ranges that stay; locCount[r] = occurrences of read r to locate.
+__global__ void s3_pe_route_kernel(uint32_t numPairs, const uint32_t *__restrict__ rangeOff, const uint32_t *__restrict__ saL,
+                                   const uint32_t *__restrict__ saR, const uint8_t *__restrict__ saFlags, const uint32_t *__restrict__ totOcc,
+                                   const uint8_t *__restrict__ readFlags, uint32_t maxHit, int keepSecondBest,
+                                   uint8_t *__restrict__ route, uint8_t *__restrict__ keepRange, uint32_t *__restrict__ locCount,
+                                   uint32_t *__restrict__ counters)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= numPairs) return;
+    const uint32_t r0 = 2 * p, r1 = 2 * p + 1;
+    const uint32_t t0 = totOcc[r0], t1 = totOcc[r1];
+    uint8_t rt;
+    uint32_t c0 = 0, c1 = 0;
+    if (readFlags[r0] || readFlags[r1]) rt = S3_PE_OVERFLOW;
+    else if (t0 > 0 && t1 > 0) { rt = S3_PE_BOTH_HIT; c0 = t0; c1 = t1; }
+    else if (t0 == 0 && t1 == 0) rt = S3_PE_NONE;
+    else {
+        const uint32_t r = t0 ? r0 : r1;
+        uint32_t tot = t0 ? t0 : t1;
+        if (tot > maxHit) {
+            int mn = 999;
+            for (uint32_t g = rangeOff[r]; g < rangeOff[r + 1]; ++g) mn = min(mn, (int)saFlags[2 * (size_t)g + 1]);
+            tot = 0;
+            for (uint32_t g = rangeOff[r]; g < rangeOff[r + 1]; ++g) {
+                const bool keep = (int)saFlags[2 * (size_t)g + 1] <= mn + (keepSecondBest ? 1 : 0);
+                keepRange[g] = keep ? 1 : 0;
+                if (keep) tot += saR[g] - saL[g] + 1;
+            }
+        }
+        if (tot <= maxHit) { rt = t0 ? S3_PE_FIRST_RESCUES : S3_PE_SECOND_RESCUES; if (t0) c0 = tot; else c1 = tot; }
+        else rt = t0 ? S3_PE_FIRST_TOO_MANY : S3_PE_SECOND_TOO_MANY;
+    }
+    route[p] = rt;
+    locCount[r0] = c0; locCount[r1] = c1;
+    atomicAdd(counters + rt, 1u);
+}
+
+// ---- locate (transferAllSAToOcc SAList.cpp:392-419; HalfEndOccStream::fetchNextOcc DV-DPfunctions.cu:1900-1960) ------
+// One thread per read: the kept ranges in list order, each in suffix-array order.
+__global__ void s3_pe_locate_kernel(uint32_t numReads, const uint32_t *__restrict__ sa, const uint32_t *__restrict__ rangeOff,
+                                    const uint32_t *__restrict__ saL, const uint32_t *__restrict__ saR, const uint8_t *__restrict__ saFlags,
+                                    const uint8_t *__restrict__ keepRange, const uint32_t *__restrict__ locOff,
+                                    uint32_t *__restrict__ occPos, uint8_t *__restrict__ occFlags, unsigned long long *__restrict__ occKey,
+                                    uint32_t *__restrict__ occVal)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= numReads) return;
+    uint32_t o = locOff[r];
+    const uint32_t end = locOff[r + 1];
+    for (uint32_t g = rangeOff[r]; g < rangeOff[r + 1] && o < end; ++g) {
+        if (!keepRange[g]) continue;
+        for (uint32_t k = saL[g]; k <= saR[g] && o < end; ++k, ++o) {
+            const uint32_t pos = sa[k];
+            occPos[o] = pos;
+            occFlags[2 * (size_t)o] = saFlags[2 * (size_t)g]; occFlags[2 * (size_t)o + 1] = saFlags[2 * (size_t)g + 1];
+            occKey[o] = ((unsigned long long)r << 32) | pos;       // one stable sort orders every read's list by position
+            occVal[o] = o;
+        }
+    }
+}
+
+// ---- pairing (PEMappingCore / PEStatsPEPairList, through s3_pair_walk.cuh's walk) --------------------------------------
+// One thread per pair with both mates hit: the walk's records are not kept, only what hostKernel reads of them
+// (CPUfunctions.cpp:2293-2330): how many valid pairs, the optimal pair, how many pairs share its total, the second total.
+typedef s3_pe_pair_result S3PeBest;            // include/soap3dp_b200.h
+__global__ void s3_pe_pair_kernel(uint32_t numPairs, const uint8_t *__restrict__ route, const uint32_t *__restrict__ locOff,
+                                  const unsigned long long *__restrict__ key, const uint32_t *__restrict__ val,
+                                  const uint8_t *__restrict__ occFlags, const uint32_t *__restrict__ readLengths,
+                                  S3PairParams P, S3PeBest *__restrict__ best)
+{
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= numPairs) return;
+    S3PeBest b;
+    memset(&b, 0, sizeof b);
+    b.optimalTotal = b.suboptimalTotal = 127;
+    if (route[p] != S3_PE_BOTH_HIT) { best[p] = b; return; }
+    const uint32_t a0 = locOff[2 * p], a1 = locOff[2 * p + 1], b1 = locOff[2 * p + 2];
+    const uint32_t patternLength = readLengths[2 * p + 1];            // pe_in->patternLength = the second read's (CPUfunctions.cpp:2284)
+    // the walk of s3_pair_walk (PEMappingCore PEAlgnmt.cpp:229-291), keeping the optimal record and the histogram only
+    uint16_t stats[32];
+    for (int k = 0; k < 32; ++k) stats[k] = 0;
+    uint32_t n = 0, optCount = 255, optDiff = 255;
+    int subTot = 127;
+    uint32_t i1 = a0, i2 = a1;
+    while (i1 < a1 && i2 < b1) {
+        const uint32_t pa = (uint32_t)key[i1], pb = (uint32_t)key[i2];
+        const bool firstIsLeft = pa <= pb;
+        const uint32_t lv = firstIsLeft ? val[i1] : val[i2];
+        const uint32_t lpos = firstIsLeft ? pa : pb;
+        const uint8_t lstrand = occFlags[2 * (size_t)lv];
+        if (lstrand == P.leftLeg) {
+            const uint32_t end = firstIsLeft ? b1 : a1;
+            for (uint32_t i = firstIsLeft ? i2 : i1; i < end; ++i) {
+                const uint32_t rv = val[i], rpos = (uint32_t)key[i];
+                const uint8_t rstrand = occFlags[2 * (size_t)rv];
+                const uint32_t rightEnd = rpos + patternLength - 1u, gap = rightEnd - lpos + 1u;
+                bool stop = false;
+                if (P.lbound <= gap && gap <= P.ubound && rstrand == P.rightLeg) {
+                    const uint32_t v1 = firstIsLeft ? lv : rv, v2 = firstIsLeft ? rv : lv;
+                    const uint8_t m1 = occFlags[2 * (size_t)v1 + 1], m2 = occFlags[2 * (size_t)v2 + 1];
+                    const int tot = (int8_t)(uint8_t)(m1 + m2);
+                    if (tot >= 0 && tot < 32) stats[tot]++;
+                    int d = (int)(int8_t)m1 - (int)(int8_t)m2;
+                    if ((int8_t)m2 > (int8_t)m1) d = -d;
+                    const bool better = tot < (int)optCount, tie = tot == (int)optCount && d < (int)optDiff;
+                    if (better || tie) {
+                        if (better) subTot = (optCount == 255) ? 127 : (int)optCount;     // the pair it displaces becomes the suboptimal one
+                        optCount = (uint8_t)tot; optDiff = (uint8_t)d;
+                        b.pos1 = firstIsLeft ? lpos : rpos; b.pos2 = firstIsLeft ? rpos : lpos; b.insertion = gap;
+                        b.strand1 = occFlags[2 * (size_t)v1]; b.mism1 = m1; b.strand2 = occFlags[2 * (size_t)v2]; b.mism2 = m2;
+                    }
+                    ++n;
+                    stop = P.reportOne != 0;
+                }
+                if (stop) break;
+                if (lstrand != rstrand && (uint32_t)(lpos + P.ubound) < rightEnd) break;
+            }
+        }
+        if (firstIsLeft) ++i1; else ++i2;
+    }
+    b.numPairs = n;
+    if (n) {
+        b.optimalTotal = (int8_t)optCount;
+        b.numOptimal = (optCount < 32) ? stats[optCount] : 0;
+        b.suboptimalTotal = (int8_t)subTot;
+        b.numSuboptimal = (subTot >= 0 && subTot < 32) ? stats[subTot] : 0;
+    }
+    best[p] = b;
+}
+
+// ---- route 2 + windows (CPUfunctions.cpp:2440-2470; HalfEndAlgnBatch::pack DV-DPfunctions.cu:2027-2110) --------------
+// Which reads hand their occurrences to the default DP: the hit mate of a *_RESCUES pair; both mates of a pair with hits
+// on both sides and no valid pairing, when neither has more than maxHitNumForDP occurrences (more: left to the caller,
+// S3_PE_BOTH_NO_PAIR_MANY -- the reference filters them down to their best hits first).
+// One thread per read; COUNT: windows of the read, FILL: their descriptors from winOff[read].
+struct S3PeWindows {
+    uint32_t *alignedOcc;            // index of the occurrence the window hangs on
+    uint32_t *readID;                // the read that is aligned by DP (the mate)
+    uint8_t *strand;                 // its strand in the window (1 as given, 2 reverse-complemented)
+    uint8_t *leftOrRight;            // CandidateInfo.leftOrRight: 1 the DP read is the right end, 0 the left end
+    uint32_t *start, *dnaLen, *readLen, *clipLt, *clipRt, *ancL, *ancR;
+    int32_t *cutoff;
+};
+struct S3PeWinParams {
+    int insertLow, insertHigh, leftLeg, rightLeg, softClipLeft, softClipRight, cutoff;     // cutoff < 0: ceil(0.3 * length)
+    uint32_t maxDNALength, textLength, maxHit;
+};
+__device__ __forceinline__ int s3_pe_cutoff(const S3PeWinParams &w, uint32_t len)
+{
+    // (int) ceil(DP_SCORE_THRESHOLD_RATIO * (double) read_length) with the ratio 0.3 (CPUfunctions.cpp:65)
+    return w.cutoff >= 0 ? w.cutoff : (int)ceil(0.3 * (double)len);
+}
+template <bool FILL>
+__global__ void s3_pe_window_kernel(uint32_t numReads, const uint8_t *__restrict__ route, uint8_t *__restrict__ routeFinal, const S3PeBest *__restrict__ best,
+                                    const uint32_t *__restrict__ locOff, const uint32_t *__restrict__ occPos, const uint8_t *__restrict__ occFlags,
+                                    const uint32_t *__restrict__ readLengths, const S3PeWinParams w, uint32_t *__restrict__ winCount,
+                                    const uint32_t *__restrict__ winOff, S3PeWindows out)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= numReads) return;
+    const uint32_t p = r >> 1;
+    uint8_t rt = route[p];
+    if (rt == S3_PE_BOTH_HIT && best[p].numPairs == 0) {
+        const uint32_t t0 = locOff[2 * p + 1] - locOff[2 * p], t1 = locOff[2 * p + 2] - locOff[2 * p + 1];
+        rt = (t0 <= w.maxHit && t1 <= w.maxHit) ? S3_PE_BOTH_RESCUE : S3_PE_BOTH_NO_PAIR_MANY;
+    }
+    const bool rescues = rt == S3_PE_BOTH_RESCUE || (rt == S3_PE_FIRST_RESCUES && !(r & 1)) || (rt == S3_PE_SECOND_RESCUES && (r & 1));
+    uint32_t n = 0;
+    const uint32_t base = FILL ? winOff[r] : 0u;
+    if (rescues) {
+        const uint32_t alignedLen = readLengths[r], mate = r ^ 1u, mateLen = readLengths[mate];
+        const bool isDouble = w.leftLeg == w.rightLeg;
+        (void)isDouble;
+        for (uint32_t o = locOff[r]; o < locOff[r + 1]; ++o) {
+            const uint32_t pos = occPos[o];
+            const int strand = occFlags[2 * (size_t)o];
+            for (int side = 0; side < 2; ++side) {
+                // side 0: the aligned read is the left end, its mate lies to the right; side 1: the other way round
+                if (strand != (side == 0 ? w.leftLeg : w.rightLeg)) continue;
+                uint32_t start, stop;
+                if (side == 0) {
+                    stop = pos + (uint32_t)w.insertHigh;
+                    start = pos + (uint32_t)w.insertLow - mateLen;
+                    if (start < pos) start = pos;
+                } else {
+                    start = pos + alignedLen - (uint32_t)w.insertHigh;
+                    stop = pos + alignedLen - (uint32_t)w.insertLow + mateLen;
+                    if (stop >= pos + alignedLen) stop = pos + alignedLen - 1;
+                }
+                if (!(start < w.textLength && stop <= w.textLength)) continue;
+                if (FILL) {
+                    const uint32_t k = base + n;
+                    const int dpStrand = side == 0 ? w.rightLeg : w.leftLeg;
+                    out.alignedOcc[k] = o; out.readID[k] = mate; out.strand[k] = (uint8_t)dpStrand; out.leftOrRight[k] = side == 0 ? 1 : 0;
+                    out.start[k] = start; out.dnaLen[k] = stop - start; out.readLen[k] = mateLen;
+                    out.clipLt[k] = (uint32_t)(dpStrand == 1 ? w.softClipLeft : w.softClipRight);
+                    out.clipRt[k] = (uint32_t)(dpStrand == 1 ? w.softClipRight : w.softClipLeft);
+                    out.ancL[k] = side == 0 ? w.maxDNALength : (uint32_t)(w.insertHigh - w.insertLow + 1);
+                    out.ancR[k] = side == 0 ? mateLen : 0u;
+                    out.cutoff[k] = s3_pe_cutoff(w, mateLen);
+                }
+                ++n;
+            }
+        }
+    }
+    if (!FILL) winCount[r] = n;
+    else if (!(r & 1)) routeFinal[p] = rt;
+}
+
+// ---- results: CIGAR runs (CigarStringEncoder DV-DPfunctions.h:545-597 as the engines' result loops drive it, ----------
+// DV-DPfunctions.cu:2376-2390): the pattern is written right to left, 'V',c repeats the op before it c - 1 more times,
+// neighbours of one type merge, runs whose length ends <= 0 separate their neighbours and are dropped; out in read order
+// as length << 8 | op.  One thread per window; COUNT / FILL.
+template <bool FILL>
+__global__ void s3_pe_runs_kernel(uint32_t numWindows, const uint8_t *__restrict__ pattern, uint32_t patternLength,
+                                  const int32_t *__restrict__ scores, const int32_t *__restrict__ cutoff,
+                                  uint32_t *__restrict__ runCount, const uint32_t *__restrict__ runOff, uint32_t *__restrict__ runs)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numWindows) return;
+    uint32_t kept = 0;
+    if (scores[t] >= cutoff[t]) {
+        const uint8_t *p = pattern + (size_t)t * patternLength, *end = p + patternLength;
+        const uint32_t total = FILL ? runOff[t + 1] - runOff[t] : 0u;
+        uint32_t *dst = FILL ? runs + runOff[t] : NULL;
+        uint8_t last = 'N', curType = 0;
+        int curCnt = 0;
+        bool have = false;
+        for (; p < end && *p != 0; ++p) {
+            uint8_t type; int cnt;
+            if (*p == 'V') { if (++p >= end) break; type = last; cnt = (int)*p - 1; }
+            else { type = last = *p; cnt = 1; }
+            if (have && curType == type) curCnt += cnt;
+            else {
+                if (have && curCnt > 0 && curType != 'N') { if (FILL) dst[total - 1 - kept] = ((uint32_t)curCnt << 8) | curType; ++kept; }
+                curType = type; curCnt = cnt; have = true;
+            }
+        }
+        if (have && curCnt > 0 && curType != 'N') { if (FILL) dst[total - 1 - kept] = ((uint32_t)curCnt << 8) | curType; ++kept; }
+    }
+    if (!FILL) runCount[t] = kept;
+}
+
+// one record per window: what DP_Space::algnmtCPUThread puts into AlgnmtDPResult (DV-DPfunctions.cu:2359-2420)
+__global__ void s3_pe_result_kernel(uint32_t numWindows, const S3PeWindows win, const uint32_t *__restrict__ occPos,
+                                    const uint8_t *__restrict__ occFlags, const int32_t *__restrict__ scores,
+                                    const uint32_t *__restrict__ hit, const uint32_t *__restrict__ cnt, const uint32_t *__restrict__ runOff,
+                                    s3_pe_dp_result *__restrict__ out)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= numWindows) return;
+    s3_pe_dp_result r;
+    const uint32_t o = win.alignedOcc[t];
+    r.dpReadID = win.readID[t];
+    r.alignedPos = occPos[o];
+    r.alignedStrand = occFlags[2 * (size_t)o]; r.alignedMismatches = occFlags[2 * (size_t)o + 1];
+    r.dpStrand = win.strand[t]; r.leftOrRight = win.leftOrRight[t];
+    r.score = scores[t];
+    const bool ok = scores[t] >= win.cutoff[t];
+    r.dpPos = ok ? win.start[t] + hit[t] : 0xFFFFFFFFu;           // startLocs + hitLocs (:2392), none below the cutoff (:2412)
+    r.numSameScore = cnt[t];
+    r.runOffset = runOff[t]; r.numRuns = runOff[t + 1] - runOff[t];
+    out[t] = r;
+}
+
+// =======================================================================================================================
+static const uint32_t kAllowed[5] = {2, 4, 4, 2, 1};            // MAX_SA_RANGES_ALLOWED1_* (definitions.h:47-51)
+static const uint32_t kCases[5] = {1, 2, 4, 6, 10};             // definitions.h:116-120
+
+extern "C" int s3_pe_create(s3_index *ix, uint32_t maxReads, uint32_t maxReadLength, const s3_pe_params *params, s3_pe **out)
+{
+    if (!ix || !params || !out || maxReads == 0 || (maxReads & 1) || maxReadLength == 0) { s3_set_error("s3_pe_create: bad argument (maxReads must be even)"); return S3_EINVAL; }
+    if (!ix->loc.sa || !ix->d_packedDNA) { s3_set_error("s3_pe_create: the index was uploaded without its suffix array and packed text"); return S3_EINVAL; }
+    if (params->numMismatch > 4 || params->insertHigh < params->insertLow || params->insertLow < 0 ||
+        (params->strandLeftLeg != 1 && params->strandLeftLeg != 2) || (params->strandRightLeg != 1 && params->strandRightLeg != 2) ||
+        params->maxOutputPerRead == 0 || params->maxHitNumForDP == 0) { s3_set_error("s3_pe_create: bad parameters"); return S3_EINVAL; }
+    S3_TRYC(cudaSetDevice(ix->device));
+    s3_pe *pe = (s3_pe *)calloc(1, sizeof(s3_pe));
+    if (!pe) { s3_set_error("out of host memory"); return S3_ENOMEM; }
+    pe->ix = ix; pe->par = *params; pe->maxReads = maxReads;
+    // the engines' sizes: maxReadLength = (L / 4 + 1) * 4, maxDNALength = insert_high - insert_low + L + 1
+    // (DV-DPfunctions.cu:2223-2224 with L = inputMaxReadLength)
+    pe->maxReadLength = (maxReadLength / 4 + 1) * 4;
+    pe->maxDNALength = (uint32_t)(params->insertHigh - params->insertLow) + pe->maxReadLength + 1;
+    pe->maxWindows = params->maxWindows ? params->maxWindows : maxReads;
+    int rc = s3_dp_create(pe->maxReadLength, pe->maxDNALength, pe->maxWindows, params->scores, ix->device, &pe->dp);
+    if (rc) { free(pe); return rc; }
+    s3_dp_set_stream(pe->dp, ix->stream);
+    if (cudaMallocHost(&pe->h_counts, 64 * sizeof(uint32_t)) != cudaSuccess) { s3_set_error("s3_pe_create: pinned allocation failed"); s3_pe_free(pe); return S3_ENOMEM; }
+    for (int k = 0; k < 10; ++k) if (cudaEventCreate(&pe->ev[k]) != cudaSuccess) { s3_set_error("s3_pe_create: cudaEventCreate failed"); s3_pe_free(pe); return S3_ECUDA; }
+    *out = pe;
+    return S3_OK;
+}
+
+extern "C" void s3_pe_free(s3_pe *pe)
+{
+    if (!pe) return;
+    cudaSetDevice(pe->ix->device);
+    cudaStreamSynchronize(pe->ix->stream);
+    if (pe->dp) s3_dp_free(pe->dp);
+    if (pe->A.base) cudaFree(pe->A.base);
+    if (pe->B.base) cudaFree(pe->B.base);
+    if (pe->C.base) cudaFree(pe->C.base);
+    if (pe->pinned) cudaFreeHost(pe->pinned);
+    if (pe->h_counts) cudaFreeHost(pe->h_counts);
+    for (int k = 0; k < 10; ++k) if (pe->ev[k]) cudaEventDestroy(pe->ev[k]);
+    free(pe);
+}
+
+extern "C" int s3_pe_set_timing(s3_pe *pe, int on) { if (!pe) return S3_EINVAL; pe->timing = on ? 1 : 0; return S3_OK; }
+extern "C" int s3_pe_read_timing(s3_pe *pe, float *msPerStage)
+{
+    if (!pe || !msPerStage) return S3_EINVAL;
+    for (int k = 0; k < 8; ++k) msPerStage[k] = pe->msStages[k];
+    return S3_OK;
+}
+extern "C" s3_dp *s3_pe_dp(s3_pe *pe) { return pe ? pe->dp : NULL; }
+
+static int pe_pinned(s3_pe *pe, size_t bytes)
+{
+    if (bytes <= pe->pinnedBytes) return S3_OK;
+    if (pe->pinned) { cudaFreeHost(pe->pinned); pe->pinned = NULL; pe->pinnedBytes = 0; }
+    bytes += bytes / 4;
+    if (cudaMallocHost(&pe->pinned, bytes) != cudaSuccess) { s3_set_error("s3_pe_align: pinned allocation of %zu bytes failed", bytes); return S3_ENOMEM; }
+    pe->pinnedBytes = bytes;
+    return S3_OK;
+}
+
+#define PE_MARK(k) do { if (pe->timing) S3_TRYC(cudaEventRecord(pe->ev[k], st)); } while (0)
+
+// queriesOnDevice: queries / readLengths are device pointers and the result arrays stay on the device (nothing but the
+// counts crosses the link): the device-resident measurement of bench.py
+static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads64, uint32_t wordPerQuery,
+                  int queriesOnDevice, s3_pe_result *res)
+{
+    if (!pe || !queries || !readLengths || !res) { s3_set_error("s3_pe_align: NULL argument"); return S3_EINVAL; }
+    memset(res, 0, sizeof *res);
+    if (numReads64 > pe->maxReads || (numReads64 & 1)) { s3_set_error("s3_pe_align: %llu reads (even, <= %u)", (unsigned long long)numReads64, pe->maxReads); return S3_EINVAL; }
+    const uint32_t N = (uint32_t)numReads64, P = N / 2;
+    if (N == 0) return S3_OK;
+    s3_index *ix = pe->ix;
+    S3_TRYC(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const uint32_t k = pe->par.numMismatch, C = kCases[k], allowed = kAllowed[k], wpa = 2 * allowed;
+    const size_t up = ((size_t)N + 31) / 32 * 32, maxRanges = (size_t)N * C * allowed;
+    int rc;
+
+    // ---- stage 1 buffers
+    size_t scanTemp = 0, t2 = 0;
+    cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (uint32_t *)NULL, (uint32_t *)NULL, (int)(N + 1), st);
+    size_t needA = arena_need(up * wordPerQuery, 4) + arena_need(up, 4) + C * arena_need(up * wpa, 4) + 6 * arena_need(N + 1, 4) + arena_need(N, 1) +
+                   2 * arena_need(maxRanges, 4) + arena_need(maxRanges, 2) + arena_need(maxRanges, 1) + 2 * arena_need(P, 1) + arena_need(P, sizeof(S3PeBest)) +
+                   arena_need(scanTemp, 1) + arena_need(64, 4) + 4096;
+    if ((rc = arena_reserve(&pe->A, needA, st))) return rc;
+    S3Arena *A = &pe->A;
+    uint32_t *d_q = queriesOnDevice ? const_cast<uint32_t *>(queries) : arena_take<uint32_t>(A, up * wordPerQuery);
+    uint32_t *d_len = queriesOnDevice ? const_cast<uint32_t *>(readLengths) : arena_take<uint32_t>(A, up);
+    uint32_t *d_ans[S3_MAX_NUM_CASES];
+    for (uint32_t c = 0; c < C; ++c) d_ans[c] = arena_take<uint32_t>(A, up * wpa);
+    uint32_t *d_nRanges = arena_take<uint32_t>(A, N + 1), *d_rangeOff = arena_take<uint32_t>(A, N + 1), *d_totOcc = arena_take<uint32_t>(A, N + 1);
+    uint32_t *d_locCount = arena_take<uint32_t>(A, N + 1), *d_locOff = arena_take<uint32_t>(A, N + 1), *d_winCount = arena_take<uint32_t>(A, N + 1);
+    uint8_t *d_readFlags = arena_take<uint8_t>(A, N);
+    uint32_t *d_saL = arena_take<uint32_t>(A, maxRanges), *d_saR = arena_take<uint32_t>(A, maxRanges);
+    uint8_t *d_saFlags = arena_take<uint8_t>(A, 2 * maxRanges), *d_keep = arena_take<uint8_t>(A, maxRanges);
+    uint8_t *d_route = arena_take<uint8_t>(A, P), *d_routeFinal = arena_take<uint8_t>(A, P);
+    S3PeBest *d_best = arena_take<S3PeBest>(A, P);
+    void *d_tmp = arena_take<char>(A, scanTemp);
+    uint32_t *d_counters = arena_take<uint32_t>(A, 64);
+    if (!d_counters) { s3_set_error("s3_pe_align: stage buffer accounting"); return S3_ENOMEM; }
+
+    PE_MARK(0);
+    if (!queriesOnDevice) {
+        S3_TRYC(cudaMemcpyAsync(d_q, queries, up * wordPerQuery * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_len, readLengths, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = s3_search_round1_device(ix, d_q, d_len, N, wordPerQuery, k, C, allowed, wpa, 0, d_ans, NULL))) return rc;
+    PE_MARK(1);
+    S3Collect col;
+    memset(&col, 0, sizeof col);
+    for (uint32_t c = 0; c < C; ++c) col.answers[c] = d_ans[c];
+    col.numCases = C; col.allowed = allowed; col.wordPerAns = wpa; col.numReads = N; col.textLength = ix->textLength;
+    col.maxOutputPerRead = pe->par.maxOutputPerRead;
+    const unsigned nbR = (N + 255) / 256, nbP = (P + 255) / 256;
+    S3_TRYC(cudaMemsetAsync(d_nRanges + N, 0, 4, st));
+    S3_TRYC(cudaMemsetAsync(d_counters, 0, 64 * 4, st));
+    s3_pe_collect_kernel<false><<<nbR, 256, 0, st>>>(col, d_nRanges, d_totOcc, d_readFlags, NULL, NULL, NULL, NULL);
+    S3_TRYC(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_nRanges, d_rangeOff, (int)(N + 1), st));
+    s3_pe_collect_kernel<true><<<nbR, 256, 0, st>>>(col, NULL, NULL, NULL, d_rangeOff, d_saL, d_saR, d_saFlags);
+    S3_TRYC(cudaMemsetAsync(d_keep, 1, maxRanges, st));
+    S3_TRYC(cudaMemsetAsync(d_locCount + N, 0, 4, st));
+    s3_pe_route_kernel<<<nbP, 256, 0, st>>>(P, d_rangeOff, d_saL, d_saR, d_saFlags, d_totOcc, d_readFlags, pe->par.maxHitNumForDP,
+                                           pe->par.keepSecondBest, d_route, d_keep, d_locCount, d_counters);
+    S3_TRYC(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_locCount, d_locOff, (int)(N + 1), st));
+    S3_LAUNCHED(3);
+    S3_TRYC(cudaGetLastError());
+    // first read of counts: occurrences to locate
+    S3_TRYC(cudaMemcpyAsync(pe->h_counts, d_locOff + N, 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaMemcpyAsync(pe->h_counts + 1, d_rangeOff + N, 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaStreamSynchronize(st));
+    const uint32_t T = pe->h_counts[0];
+    res->numRanges = pe->h_counts[1];
+    PE_MARK(2);
+
+    // ---- stage 2: locate, pairing, windows
+    const size_t Tm = T ? T : 1;
+    cub::DeviceRadixSort::SortPairs(NULL, t2, (unsigned long long *)NULL, (unsigned long long *)NULL, (uint32_t *)NULL, (uint32_t *)NULL, (int)Tm, 0, 64, st);
+    size_t needB = arena_need(Tm, 4) + arena_need(Tm, 2) + 2 * arena_need(Tm, 8) + 2 * arena_need(Tm, 4) + arena_need(t2, 1) + arena_need(N + 1, 4) + 4096;
+    if ((rc = arena_reserve(&pe->B, needB, st))) return rc;
+    S3Arena *B = &pe->B;
+    uint32_t *d_occPos = arena_take<uint32_t>(B, Tm);
+    uint8_t *d_occFlags = arena_take<uint8_t>(B, 2 * Tm);
+    unsigned long long *d_keyA = arena_take<unsigned long long>(B, Tm), *d_keyB = arena_take<unsigned long long>(B, Tm);
+    uint32_t *d_valA = arena_take<uint32_t>(B, Tm), *d_valB = arena_take<uint32_t>(B, Tm);
+    void *d_tmp2 = arena_take<char>(B, t2);
+    uint32_t *d_winOff = arena_take<uint32_t>(B, N + 1);
+    if (!d_winOff) { s3_set_error("s3_pe_align: stage buffer accounting"); return S3_ENOMEM; }
+    if (T) {
+        s3_pe_locate_kernel<<<nbR, 256, 0, st>>>(N, ix->loc.sa, d_rangeOff, d_saL, d_saR, d_saFlags, d_keep, d_locOff, d_occPos, d_occFlags, d_keyA, d_valA);
+        // ordered by (read, position), ties in arrival order: what PERadixSort leaves of each list (PEAlgnmt.cpp:114-199)
+        int endBit = 33;
+        while (endBit < 64 && (1ull << (endBit - 32)) < (unsigned long long)N) ++endBit;
+        S3_TRYC(cub::DeviceRadixSort::SortPairs(d_tmp2, t2, d_keyA, d_keyB, d_valA, d_valB, (int)T, 0, endBit, st));
+        S3_LAUNCHED(1);
+    }
+    PE_MARK(3);
+    S3PairParams pp = {(uint32_t)pe->par.insertLow, (uint32_t)pe->par.insertHigh, pe->par.strandLeftLeg, pe->par.strandRightLeg, 0};
+    s3_pe_pair_kernel<<<nbP, 256, 0, st>>>(P, d_route, d_locOff, d_keyB, d_valB, d_occFlags, d_len, pp, d_best);
+    S3PeWinParams wp = {pe->par.insertLow, pe->par.insertHigh, pe->par.strandLeftLeg, pe->par.strandRightLeg, pe->par.softClipLeft, pe->par.softClipRight,
+                        pe->par.cutoffThreshold, pe->maxDNALength, ix->textLength, pe->par.maxHitNumForDP};
+    S3PeWindows win;
+    memset(&win, 0, sizeof win);
+    S3_TRYC(cudaMemsetAsync(d_winCount + N, 0, 4, st));
+    s3_pe_window_kernel<false><<<nbR, 256, 0, st>>>(N, d_route, NULL, d_best, d_locOff, d_occPos, d_occFlags, d_len, wp, d_winCount, NULL, win);
+    S3_TRYC(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_winCount, d_winOff, (int)(N + 1), st));
+    S3_LAUNCHED(2);
+    S3_TRYC(cudaGetLastError());
+    // second read of counts: windows
+    S3_TRYC(cudaMemcpyAsync(pe->h_counts + 2, d_winOff + N, 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaStreamSynchronize(st));
+    const uint32_t M = pe->h_counts[2];
+    PE_MARK(4);
+    if (M > pe->maxWindows) { s3_set_error("s3_pe_align: %u rescue windows > maxWindows %u of s3_pe_create", M, pe->maxWindows); return S3_EINVAL; }
+
+    // ---- stage 3: windows, DP, results
+    const size_t Mm = M ? M : 1, patLen = (size_t)pe->maxReadLength + pe->maxDNALength;
+    size_t needC = 9 * arena_need(Mm, 4) + 2 * arena_need(Mm, 1) + 3 * arena_need(Mm, 4) + arena_need(Mm * patLen, 1) + 2 * arena_need(Mm + 1, 4) +
+                   arena_need(Mm, sizeof(s3_pe_dp_result)) + arena_need(Mm * (size_t)(pe->maxReadLength + 8), 4) + 4096;
+    if ((rc = arena_reserve(&pe->C, needC, st))) return rc;
+    S3Arena *Cc = &pe->C;
+    win.alignedOcc = arena_take<uint32_t>(Cc, Mm); win.readID = arena_take<uint32_t>(Cc, Mm);
+    win.start = arena_take<uint32_t>(Cc, Mm); win.dnaLen = arena_take<uint32_t>(Cc, Mm); win.readLen = arena_take<uint32_t>(Cc, Mm);
+    win.clipLt = arena_take<uint32_t>(Cc, Mm); win.clipRt = arena_take<uint32_t>(Cc, Mm); win.ancL = arena_take<uint32_t>(Cc, Mm); win.ancR = arena_take<uint32_t>(Cc, Mm);
+    win.strand = arena_take<uint8_t>(Cc, Mm); win.leftOrRight = arena_take<uint8_t>(Cc, Mm);
+    win.cutoff = arena_take<int32_t>(Cc, Mm);
+    int32_t *d_score = arena_take<int32_t>(Cc, Mm);
+    uint32_t *d_hit = arena_take<uint32_t>(Cc, Mm), *d_cnt = arena_take<uint32_t>(Cc, Mm);
+    uint8_t *d_pattern = arena_take<uint8_t>(Cc, Mm * patLen);
+    uint32_t *d_runCount = arena_take<uint32_t>(Cc, Mm + 1), *d_runOff = arena_take<uint32_t>(Cc, Mm + 1);
+    s3_pe_dp_result *d_res = arena_take<s3_pe_dp_result>(Cc, Mm);
+    uint32_t *d_runs = arena_take<uint32_t>(Cc, Mm * (size_t)(pe->maxReadLength + 8));
+    if (!d_runs) { s3_set_error("s3_pe_align: stage buffer accounting"); return S3_ENOMEM; }
+    // the fill pass also writes the final route codes, so it runs even without windows
+    s3_pe_window_kernel<true><<<nbR, 256, 0, st>>>(N, d_route, d_routeFinal, d_best, d_locOff, d_occPos, d_occFlags, d_len, wp, NULL, d_winOff, win);
+    S3_LAUNCHED(1);
+    PE_MARK(5);
+    uint32_t totalRuns = 0;
+    if (M) {
+        if ((rc = s3_dp_align_windows_device(pe->dp, ix, d_q, wordPerQuery, win.readID, win.strand, win.start, win.dnaLen, win.readLen, win.cutoff,
+                                             d_score, d_hit, d_cnt, d_pattern, M, win.clipLt, win.clipRt, win.ancL, win.ancR))) return rc;
+        PE_MARK(6);
+        const unsigned nbM = (M + 127) / 128;
+        size_t scanM = 0;
+        cub::DeviceScan::ExclusiveSum(NULL, scanM, (uint32_t *)NULL, (uint32_t *)NULL, (int)(M + 1), st);
+        if (scanM > scanTemp) { s3_set_error("s3_pe_align: scan scratch"); return S3_ENOMEM; }
+        S3_TRYC(cudaMemsetAsync(d_runCount + M, 0, 4, st));
+        s3_pe_runs_kernel<false><<<nbM, 128, 0, st>>>(M, d_pattern, (uint32_t)patLen, d_score, win.cutoff, d_runCount, NULL, NULL);
+        S3_TRYC(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_runCount, d_runOff, (int)(M + 1), st));
+        s3_pe_runs_kernel<true><<<nbM, 128, 0, st>>>(M, d_pattern, (uint32_t)patLen, d_score, win.cutoff, NULL, d_runOff, d_runs);
+        s3_pe_result_kernel<<<nbM, 128, 0, st>>>(M, win, d_occPos, d_occFlags, d_score, d_hit, d_cnt, d_runOff, d_res);
+        S3_LAUNCHED(3);
+        S3_TRYC(cudaGetLastError());
+        S3_TRYC(cudaMemcpyAsync(pe->h_counts + 3, d_runOff + M, 4, cudaMemcpyDeviceToHost, st));
+    } else PE_MARK(6);
+    S3_TRYC(cudaMemcpyAsync(pe->h_counts + 8, d_counters, 16 * 4, cudaMemcpyDeviceToHost, st));
+    PE_MARK(7);
+    if (queriesOnDevice) {
+        S3_TRYC(cudaStreamSynchronize(st));
+        totalRuns = M ? pe->h_counts[3] : 0;
+        res->d_route = d_routeFinal; res->d_pairs = (s3_pe_pair_result *)d_best; res->d_dp = d_res; res->d_runs = d_runs;
+    } else {
+        // the runs' total is needed to size their copy: everything else goes first
+        const size_t bytes = (size_t)P + 256 + (size_t)P * sizeof(S3PeBest) + 256 + Mm * sizeof(s3_pe_dp_result) + 256 + Mm * (size_t)(pe->maxReadLength + 8) * 4;
+        if ((rc = pe_pinned(pe, bytes))) return rc;
+        char *h = (char *)pe->pinned;
+        res->route = (uint8_t *)h; h += ((size_t)P + 255) / 256 * 256;
+        res->pairs = (s3_pe_pair_result *)h; h += ((size_t)P * sizeof(S3PeBest) + 255) / 256 * 256;
+        res->dp = (s3_pe_dp_result *)h; h += (Mm * sizeof(s3_pe_dp_result) + 255) / 256 * 256;
+        res->runs = (uint32_t *)h;
+        S3_TRYC(cudaMemcpyAsync(res->route, d_routeFinal, P, cudaMemcpyDeviceToHost, st));
+        S3_TRYC(cudaMemcpyAsync(res->pairs, d_best, (size_t)P * sizeof(S3PeBest), cudaMemcpyDeviceToHost, st));
+        if (M) S3_TRYC(cudaMemcpyAsync(res->dp, d_res, (size_t)M * sizeof(s3_pe_dp_result), cudaMemcpyDeviceToHost, st));
+        S3_TRYC(cudaStreamSynchronize(st));
+        totalRuns = M ? pe->h_counts[3] : 0;
+        if (totalRuns) {
+            S3_TRYC(cudaMemcpyAsync(res->runs, d_runs, (size_t)totalRuns * 4, cudaMemcpyDeviceToHost, st));
+            S3_TRYC(cudaStreamSynchronize(st));
+        }
+        res->h2dBytes = up * wordPerQuery * 4 + (size_t)N * 4;
+        res->d2hBytes = (size_t)P + (size_t)P * sizeof(S3PeBest) + (size_t)M * sizeof(s3_pe_dp_result) + (size_t)totalRuns * 4 + 20 * 4;
+    }
+    res->numPairs = P; res->numOccurrences = T; res->numWindows = M; res->numRuns = totalRuns;
+    for (int c = 0; c < 16; ++c) res->routeCounts[c] = pe->h_counts[8 + c];
+    if (pe->timing) {
+        for (int s = 0; s < 7; ++s) { float ms = 0; cudaEventElapsedTime(&ms, pe->ev[s], pe->ev[s + 1]); pe->msStages[s] += ms; }
+    }
+    return S3_OK;
+}
+
+extern "C" int s3_pe_align(s3_pe *pe, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery, s3_pe_result *out)
+{
+    return pe_run(pe, queries, readLengths, numReads, wordPerQuery, 0, out);
+}
+extern "C" int s3_pe_align_device(s3_pe *pe, const uint32_t *d_queries, const uint32_t *d_readLengths, uint64_t numReads, uint32_t wordPerQuery, s3_pe_result *out)
+{
+    return pe_run(pe, d_queries, d_readLengths, numReads, wordPerQuery, 1, out);
+}

@@ -1348,6 +1348,38 @@ __global__ void s3_dp_pack_kernel(const uint32_t *__restrict__ text, const uint3
     }
 }
 
+// device-resident twin of s3_dp_align_windows: every pointer is a device pointer, readLengths are per ALIGNMENT,
+// work is enqueued on the workspace's stream and not synchronised
+extern "C" int s3_dp_align_windows_device(s3_dp *dp, s3_index *ix, const uint32_t *d_queries, uint32_t wordPerOldQuery,
+                                          const uint32_t *d_readIDs, const uint8_t *d_strands, const uint32_t *d_DNAStarts,
+                                          const uint32_t *d_DNALengths, const uint32_t *d_readLengths, const int32_t *d_cutoffThresholds,
+                                          int32_t *d_scores, uint32_t *d_hitLocs, uint32_t *d_maxScoreCounts, uint8_t *d_pattern,
+                                          uint32_t numOfThreads, const uint32_t *d_clipLtSizes, uint32_t *d_clipRtSizes,
+                                          const uint32_t *d_anchorLeftLocs, const uint32_t *d_anchorRightLocs)
+{
+    if (!dp || !ix || !d_queries || !d_readIDs || !d_strands || !d_DNAStarts || !d_DNALengths || !d_readLengths || !d_cutoffThresholds ||
+        !d_scores || !d_hitLocs || !d_maxScoreCounts || !d_pattern) { s3_set_error("s3_dp_align_windows_device: NULL argument"); return S3_EINVAL; }
+    if (!ix->d_packedDNA) { s3_set_error("s3_dp_align_windows_device: the index was uploaded without the packed text"); return S3_EINVAL; }
+    if (ix->device != dp->device) { s3_set_error("s3_dp_align_windows_device: index and workspace live on different devices"); return S3_EINVAL; }
+    if (numOfThreads > dp->maxBatch) { s3_set_error("s3_dp_align_windows_device: %u alignments > maxBatch %u", numOfThreads, dp->maxBatch); return S3_EINVAL; }
+    if (numOfThreads == 0) return S3_OK;
+    S3_CUDA(cudaSetDevice(dp->device));
+    const uint32_t n = numOfThreads;
+    const size_t dnaW = (dp->maxDNALength + 15) >> 4, readW = (dp->maxReadLength + 15) >> 4;
+    const uint64_t threads = (uint64_t)n * (dnaW + readW);
+    s3_dp_pack_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, dp->stream>>>(ix->d_packedDNA, d_queries, wordPerOldQuery, d_readIDs, d_strands,
+                                                                                d_DNAStarts, d_DNALengths, d_readLengths, 0, n, (uint32_t)dnaW,
+                                                                                (uint32_t)readW, dp->d_dna, dp->d_read);
+    S3_LAUNCHED(1);
+    S3_CUDA(cudaGetLastError());
+    S3DpArgs a;
+    memset(&a, 0, sizeof a);
+    a.dna = dp->d_dna; a.dnaLen = d_DNALengths; a.read = dp->d_read; a.readLen = d_readLengths; a.cutoff = d_cutoffThresholds;
+    a.score = d_scores; a.hit = d_hitLocs; a.cnt = d_maxScoreCounts; a.pattern = d_pattern;
+    a.clipLt = d_clipLtSizes; a.clipRt = d_clipRtSizes; a.ancL = d_anchorLeftLocs; a.ancR = d_anchorRightLocs;
+    return dp_run_device(dp, a, 0, n);
+}
+
 extern "C" int s3_dp_align_windows(s3_dp *dp, s3_index *ix,
                                    const uint32_t *queries, const uint32_t *queryLengths, uint64_t numQueries, uint32_t wordPerOldQuery,
                                    const uint32_t *readIDs, const uint8_t *strands, const uint32_t *DNAStarts, const uint32_t *DNALengths,
@@ -1367,6 +1399,8 @@ extern "C" int s3_dp_align_windows(s3_dp *dp, s3_index *ix,
     for (uint32_t t = 0; t < n; ++t) {
         if (readIDs[t] >= numQueries || (strands[t] != 1 && strands[t] != 2) ||
             DNALengths[t] > dp->maxDNALength || queryLengths[readIDs[t]] > dp->maxReadLength ||
+            DNALengths[t] >= 16u * (uint32_t)((dp->maxDNALength + 15) >> 4) || queryLengths[readIDs[t]] >= 16u * (uint32_t)((dp->maxReadLength + 15) >> 4) ||
+            queryLengths[readIDs[t]] > 16u * wordPerOldQuery ||
             (uint64_t)DNAStarts[t] + DNALengths[t] > ix->textLength) {
             s3_set_error("s3_dp_align_windows: alignment %u is out of range (read %u, window %u+%u)", t, readIDs[t], DNAStarts[t], DNALengths[t]);
             return S3_EINVAL;
@@ -1431,6 +1465,13 @@ extern "C" int s3_dp_align(s3_dp *dp, const uint32_t *packedDNASequence, const u
         !scores || !hitLocs || !maxScoreCounts || !pattern) { s3_set_error("s3_dp_align: NULL argument"); return S3_EINVAL; }
     if (numOfThreads > dp->maxBatch) { s3_set_error("s3_dp_align: %u alignments > maxBatch %u", numOfThreads, dp->maxBatch); return S3_EINVAL; }
     if (numOfThreads == 0) return S3_OK;
+    // sequences are 1-based in their slots (base i in word i >> 4, DV-DPfunctions.cu:58): a slot of w words holds 16 w - 1 bases
+    for (uint32_t t = 0; t < numOfThreads; ++t)
+        if (DNALengths[t] >= 16u * (uint32_t)((dp->maxDNALength + 15) >> 4) || readLengths[t] >= 16u * (uint32_t)((dp->maxReadLength + 15) >> 4)) {
+            s3_set_error("s3_dp_align: alignment %u (read %u, window %u bases) does not fit the packed slots of maxReadLength %u / maxDNALength %u "
+                         "(a slot of w words holds 16 w - 1 bases)", t, readLengths[t], DNALengths[t], dp->maxReadLength, dp->maxDNALength);
+            return S3_EINVAL;
+        }
     S3_CUDA(cudaSetDevice(dp->device));
     const size_t n = numOfThreads;
     const size_t dnaW = (dp->maxDNALength + 15) >> 4, readW = (dp->maxReadLength + 15) >> 4;

@@ -1,0 +1,137 @@
+"""Parity of the device-resident paired-end chain (s3_pe_align: search -> collect -> route -> locate -> pairing ->
+rescue windows -> DP -> CIGAR runs) with the composition of the oracles on the host (oracle/pe_chain_oracle.py):
+route code of every pair, the optimal pairing and its counts, every rescue window's record and CIGAR -- bit-exact."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+from helpers import (DPBatch, HostIndex, ROOT, fmindex, formats, load_oracle, load_oracle_dp, oracle_dp, oracle_launch,
+                     oracle_pair_occurrences)
+from soap3dp_b200 import api, synth
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+import decode_oracle  # noqa: E402
+import pe_chain_oracle  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def env():
+    G = synth.random_genome(500_000, seed=17)
+    idx = fmindex.build_index(G, keep_sa=True)
+    gi = api.GPUINDEXUpload(idx, device=0, with_text=True, with_sa=True)
+    yield G, idx, HostIndex(idx), gi
+    api.GPUINDEXFree(gi)
+
+
+def _dp_fn(dna, dna_len, rd, rl, max_dna, max_read, cutoff, clip_lt, clip_rt, anc_l, anc_r, scores):
+    b = DPBatch(dna, dna_len, rd, rl, max_dna, max_read, cutoff, clip_lt, clip_rt, anc_l, anc_r)
+    sc, hit, cnt, pat, _ = oracle_dp(load_oracle_dp(), b, scores)
+    return sc, hit, cnt, pat, b.pat_len
+
+
+def _decode_fn(pat, score, read_length, scores):
+    return decode_oracle.decode_one(pat, score, read_length, scores)[0]
+
+
+def _run_both(env, pairs, L, seed, k=2, max_hit=None, keep_second=False, max_output=1000, bad_mate_fraction=0.2, insert=(200, 500)):
+    G, idx, hi, gi = env
+    m1, m2, _ = synth.simulate_paired_end(G, pairs, L, seed=seed, insert_lo=insert[0], insert_hi=insert[1], bad_mate_fraction=bad_mate_fraction)
+    reads = torch.stack([m1.reads, m2.reads], dim=1).reshape(2 * pairs, L).cpu().numpy()
+    n = 2 * pairs
+    # a few pairs with both mates unfindable, and a few with a mate from a different place (both hit, no valid pair)
+    rng = np.random.default_rng(seed)
+    for p in rng.choice(pairs, max(pairs // 20, 1), replace=False):
+        reads[2 * p] = rng.integers(0, 4, L)
+        reads[2 * p + 1] = rng.integers(0, 4, L)
+    gen = G.cpu().numpy()
+    for p in rng.choice(pairs, max(pairs // 20, 1), replace=False):
+        o = int(rng.integers(1000, len(gen) - 1000))
+        reads[2 * p + 1] = gen[o:o + L]
+    wpq = formats.word_per_query(L)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    q = formats.pack_queries(reads, lens[:n], wpq)
+    par = api.pe_params(num_mismatch=k, insert_low=insert[0], insert_high=insert[1], max_output_per_read=max_output,
+                        max_hit_num_for_dp=max_hit, keep_second_best=keep_second, read_length=L)
+    al = api.PairAligner(gi, n, L, par)
+    try:
+        got = al.align(q, lens, n, wpq)
+    finally:
+        al.free()
+    # the oracles
+    olib = load_oracle()
+    allowed = formats.SA_RANGES_ROUND1[k]
+    wpa = 2 * allowed
+    bad = np.zeros(formats.ceil32(n), np.uint8)
+    views = []
+    for case in range(formats.NUM_CASES[k]):
+        a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+        oracle_launch(olib, hi, case, q, lens, n, wpq, a, bad, 0, k, allowed, wpa)
+        views.append(formats.answers_view(a, n, wpa))
+    sa = idx.fwd.sa.cpu().numpy()
+    max_read = (L // 4 + 1) * 4
+    opar = dict(insert_low=insert[0], insert_high=insert[1], left_leg=1, right_leg=2, max_output_per_read=max_output, max_hit=par.maxHitNumForDP,
+                keep_second_best=keep_second, cutoff=-1, soft_clip_left=3, soft_clip_right=8, max_read=max_read,
+                max_dna=insert[1] - insert[0] + max_read + 1, scores=(1, -2, -3, -1))
+    want = pe_chain_oracle.pe_chain(views, allowed, lens[:n], sa, gen, list(reads), opar, oracle_pair_occurrences, _dp_fn, _decode_fn)
+    return got, want
+
+
+def _compare(got, want):
+    assert np.array_equal(got["route"], want["route"]), np.nonzero(got["route"] != want["route"])[0][:10]
+    for p, w in enumerate(want["pairs"]):
+        g = got["pairs"][p]
+        if w is None:
+            assert g["numPairs"] == 0
+            continue
+        assert g["numPairs"] == w["numPairs"], p
+        if w["numPairs"]:
+            for k in ("pos1", "pos2", "insertion", "strand1", "mism1", "strand2", "mism2", "optimalTotal", "numOptimal", "suboptimalTotal", "numSuboptimal"):
+                assert int(g[k]) == w[k], (p, k, int(g[k]), w[k])
+    assert len(got["dp"]) == len(want["dp"])
+    traced = 0
+    for t, w in enumerate(want["dp"]):
+        g = got["dp"][t]
+        for k in ("dpReadID", "alignedPos", "alignedStrand", "alignedMismatches", "dpStrand", "leftOrRight", "score", "numSameScore", "dpPos"):
+            assert int(g[k]) == w[k], (t, k, int(g[k]), w[k])
+        cig = api.runs_to_cigar(got["runs"][int(g["runOffset"]):int(g["runOffset"]) + int(g["numRuns"])])
+        assert cig == w["cigar"], (t, cig, w["cigar"])
+        traced += w["cigar"] != ""
+    return traced
+
+
+@pytest.mark.parametrize("L,pairs,seed", [(100, 1500, 3), (75, 800, 4), (50, 600, 5)])
+def test_pe_chain_bit_exact(env, L, pairs, seed):
+    got, want = _run_both(env, pairs, L, seed)
+    traced = _compare(got, want)
+    routes = np.bincount(want["route"], minlength=9)
+    assert routes[pe_chain_oracle.PAIRED] > pairs // 3 and routes[pe_chain_oracle.NONE] > 0
+    assert routes[pe_chain_oracle.FIRST_RESCUES] + routes[pe_chain_oracle.SECOND_RESCUES] > pairs // 20 and traced > pairs // 20
+    assert routes[pe_chain_oracle.BOTH_RESCUE] > 0
+    assert got["d2h_bytes"] < 200 * pairs              # a few dozen bytes per pair come back
+
+
+def test_pe_chain_few_hits_allowed(env):
+    """maxHitNumForDP 1 and a cap of 3 occurrences per read: the best-hit filter, the too-many routes and the truncation of
+    a read's list all come into play (the genome has repeats)"""
+    for keep_second in (False, True):
+        got, want = _run_both(env, 1200, 100, 7, max_hit=1, keep_second=keep_second, max_output=3)
+        _compare(got, want)
+
+
+def test_pe_chain_empty_and_bad_args(env):
+    G, idx, hi, gi = env
+    al = api.PairAligner(gi, 64, 100, api.pe_params())
+    z = np.zeros(64 * 8, np.uint32)
+    out = al.align(z, z[:64], 0, 8)
+    assert len(out["route"]) == 0
+    with pytest.raises(api.S3Error):
+        al.align(z, z[:64], 63, 8)                      # odd number of reads
+    with pytest.raises(api.S3Error):
+        al.align(z, z[:64], 128, 8)                     # more than maxReads
+    al.free()

@@ -41,6 +41,7 @@ from soap3dp_b200 import api, fmindex, formats, packing, sharding, synth  # noqa
 INSERT_LO, INSERT_HI = 200, 500
 K_MISMATCH = 2
 DP_SCORES = (1, -2, -3, -1)                   # soap3-dp.ini:57-66
+RESCUE_FRACTION_HINT = 0.3                    # rescue windows per pair of the GPU arm on this workload (the reference arm's DP share)
 
 
 def log(*a):
@@ -93,12 +94,12 @@ def cache_dir():
     return d
 
 
-def get_index(n_bp, seed, device, rank, world):
+def get_index(n_bp, seed, device, rank, world, repeat_fraction=0.2):
     """-> (genome codes on device, dict of host numpy arrays in the reference format)"""
-    tag = os.path.join(cache_dir(), f"idx_{n_bp}_{seed}")
+    tag = os.path.join(cache_dir(), f"idx_{n_bp}_{seed}_{repeat_fraction}")
     names = ["bwt", "occ", "rbwt", "rocc", "meta", "sa", "pac"]
     t0 = time.time()
-    genome = synth.random_genome(n_bp, seed=seed, device=device)
+    genome = synth.random_genome(n_bp, seed=seed, device=device, repeat_fraction=repeat_fraction)
     torch.cuda.synchronize()
     log(f"genome {n_bp} bp generated in {time.time() - t0:.1f}s")
     have = all(os.path.exists(f"{tag}.{x}.npy") for x in names)
@@ -451,6 +452,111 @@ def parity_check(gi, cb, device_index):
 
 
 # ---------------------------------------------------------------------------
+def chain_parity(gi, host, genome, L, pairs, seed, par, device_index):
+    """A sample of the workload through s3_pe_align, compared record by record with the composition of the oracles on the
+    host (oracle/pe_chain_oracle.py) at full genome size."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import helpers
+    import decode_oracle
+    import pe_chain_oracle
+    b = make_batch(genome, pairs, L, seed)
+    n = b.n
+    q = b.queries.cpu().numpy().view(np.uint32)
+    lens = b.lens.cpu().numpy().view(np.uint32)
+    al = api.PairAligner(gi, n, L, par)
+    try:
+        got = al.align(q, lens, n, b.wpq)
+    finally:
+        al.free()
+
+    class HI:
+        pass
+    hi = HI()
+    hi.bwt, hi.occ, hi.rbwt, hi.rocc = host["bwt"], host["occ"], host["rbwt"], host["rocc"]
+    hi.isa0, hi.risa0, hi.n = int(host["meta"][0]), int(host["meta"][1]), int(host["meta"][2])
+    ref_s = helpers.load_ref_search()
+    allowed = formats.SA_RANGES_ROUND1[K_MISMATCH]
+    wpa = 2 * allowed
+    bad = np.zeros(formats.ceil32(n), np.uint8)
+    views = []
+    qq = q.copy()
+    for case in range(formats.NUM_CASES[K_MISMATCH]):
+        a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+        if ref_s is not None:
+            helpers.ref_launch(ref_s, hi, case, qq, lens, n, b.wpq, a, bad, 0, K_MISMATCH, allowed, wpa, nthreads=os.cpu_count() or 1)
+        else:
+            helpers.oracle_launch(helpers.load_oracle(), hi, case, q, lens, n, b.wpq, a, bad, 0, K_MISMATCH, allowed, wpa)
+        views.append(formats.answers_view(a, n, wpa))
+    max_read = (L // 4 + 1) * 4
+    max_dna = INSERT_HI - INSERT_LO + max_read + 1
+    ref_d = helpers.load_ref_dp()
+
+    def dp_fn(dna, dna_len, rd, rl, mdna, mread, cutoff, clip_lt, clip_rt, anc_l, anc_r, scores):
+        db = helpers.DPBatch(dna, dna_len, rd, rl, mdna, mread, cutoff, clip_lt, clip_rt, anc_l, anc_r)
+        if ref_d is not None:
+            sc, hit, cnt, pat = helpers.ref_dp(ref_d, db, scores, nthreads=os.cpu_count() or 1)
+        else:
+            sc, hit, cnt, pat, _ = helpers.oracle_dp(helpers.load_oracle_dp(), db, scores)
+        return sc, hit, cnt, pat, db.pat_len
+    opar = dict(insert_low=INSERT_LO, insert_high=INSERT_HI, left_leg=1, right_leg=2, max_output_per_read=par.maxOutputPerRead,
+                max_hit=par.maxHitNumForDP, keep_second_best=bool(par.keepSecondBest), cutoff=-1, soft_clip_left=par.softClipLeft,
+                soft_clip_right=par.softClipRight, max_read=max_read, max_dna=max_dna, scores=DP_SCORES)
+    gen = _GenomeView(genome)
+    reads = b.reads.cpu().numpy()
+    want = pe_chain_oracle.pe_chain(views, allowed, lens[:n], host["sa"], gen, list(reads), opar, helpers.oracle_pair_occurrences, dp_fn,
+                                    lambda pat, score, rl, sc4: decode_oracle.decode_one(pat, score, rl, sc4)[0])
+    route_ok = bool(np.array_equal(got["route"], want["route"]))
+    pair_ok, dp_ok = True, len(got["dp"]) == len(want["dp"])
+    for p, w in enumerate(want["pairs"]):
+        g = got["pairs"][p]
+        if w is None or not w["numPairs"]:
+            pair_ok &= int(g["numPairs"]) == 0
+            continue
+        pair_ok &= all(int(g[k2]) == w[k2] for k2 in ("numPairs", "pos1", "pos2", "insertion", "strand1", "mism1", "strand2", "mism2", "optimalTotal",
+                                                     "numOptimal", "suboptimalTotal", "numSuboptimal"))
+    traced = 0
+    if dp_ok:
+        for t, w in enumerate(want["dp"]):
+            g = got["dp"][t]
+            dp_ok &= all(int(g[k2]) == w[k2] for k2 in ("dpReadID", "alignedPos", "alignedStrand", "alignedMismatches", "dpStrand", "leftOrRight",
+                                                       "score", "numSameScore", "dpPos"))
+            cig = api.runs_to_cigar(got["runs"][int(g["runOffset"]):int(g["runOffset"]) + int(g["numRuns"])])
+            dp_ok &= cig == w["cigar"]
+            traced += w["cigar"] != ""
+    if not (route_ok and pair_ok and dp_ok):
+        log(f"CHAIN PARITY FAILURE at full size: routes {route_ok}, pairings {pair_ok}, rescue alignments {dp_ok}")
+    return {"pairs": int(pairs), "routes_bit_exact": route_ok, "pairings_bit_exact": bool(pair_ok), "rescue_alignments": len(want["dp"]),
+            "rescue_alignments_bit_exact": bool(dp_ok), "rescue_cigars_compared": int(traced),
+            "route_counts": np.bincount(want["route"], minlength=9).tolist(),
+            "checker": "oracle/pe_chain_oracle.py over " + ("the reference's kernels compiled for the host (oracle/_ref)" if ref_s is not None and ref_d is not None
+                                                           else "the oracle ports")}
+
+
+class _GenomeView:
+    """the genome's base codes for the oracle's window reads, without a 3 GB host copy"""
+    def __init__(self, g):
+        self.g = g
+
+    def __len__(self):
+        return int(self.g.numel())
+
+    def __getitem__(self, sl):
+        return self.g[sl].cpu().numpy()
+
+
+def random_sector_rate(gi, device):
+    """independent random 32-byte reads over the index's own bucket array (s3_random_sector_probe): the memory system's
+    random-sector rate in this run, the denominator of the search roofline"""
+    lib = api.load_library()
+    lib.s3_random_sector_probe.restype = C.c_int
+    lib.s3_random_sector_probe.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    ms, n = C.c_float(), C.c_uint64()
+    api._check(lib.s3_random_sector_probe(gi.handle, 64, C.byref(ms), C.byref(n)), "s3_random_sector_probe")
+    api._check(lib.s3_random_sector_probe(gi.handle, 64, C.byref(ms), C.byref(n)), "s3_random_sector_probe")
+    return n.value / (ms.value * 1e-3)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -461,7 +567,9 @@ def main():
     ap.add_argument("--pairs", type=int, default=int(os.environ.get("S3_PAIRS", 524_288)), help="pairs per step per GPU")
     ap.add_argument("--read-len", type=int, default=100)
     ap.add_argument("--cpu-sample", type=int, default=int(os.environ.get("S3_CPU_SAMPLE", 2_097_152)))
+    ap.add_argument("--parity-pairs", type=int, default=int(os.environ.get("S3_PARITY_PAIRS", 32_768)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--repeat-fraction", type=float, default=float(os.environ.get("S3_REPEAT_FRACTION", 0.2)))
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: the timing rules ask for >= 3 warm-up steps")
@@ -479,19 +587,17 @@ def main():
     if world > 1 and args.impl == "ours":
         torch.distributed.init_process_group("nccl", device_id=device)
     L = args.read_len
-    max_read = (L // 4 + 1) * 4                                   # DV-DPfunctions.cu:1580
-    max_dna = INSERT_HI - INSERT_LO + max_read + 1                # DV-DPfunctions.cu:2223-2224
-    genome, host = get_index(args.genome_bp, 3, device, rank, world if args.impl == "ours" else 1)
+    genome, host = get_index(args.genome_bp, 3, device, rank, world if args.impl == "ours" else 1, args.repeat_fraction)
     threads = os.cpu_count() or 1
-    workload = (f"pe_2x{L}bp_insert{INSERT_LO}-{INSERT_HI}_genome{args.genome_bp}bp: k<=2 search (4 cases, both strands, "
-                f"round-1 slots) of {2 * args.pairs} reads + mate-rescue DP (400 bp windows) per step per GPU")
+    workload = (f"pe_2x{L}bp_insert{INSERT_LO}-{INSERT_HI}_genome{args.genome_bp}bp: per step and GPU {args.pairs} read pairs through k<=2 search "
+                f"(4 cases, both strands, round-1 slots), answer collection, routing, locate, pairing and mate-rescue DP (400 bp windows) with CIGARs")
 
     if args.impl == "reference":
         vals = []
         info = None
         per_step = max(args.cpu_sample // 4, 4096)
         for s in range(args.warmup + args.steps):
-            info = cpu_arm(host, genome, L, per_step, 1000 + s, 0.12, threads)
+            info = cpu_arm(host, genome, L, per_step, 1000 + s, RESCUE_FRACTION_HINT, threads)
             if s >= args.warmup:
                 vals.append(info)
         v = float(np.mean([x["value"] for x in vals]))
@@ -499,7 +605,9 @@ def main():
                "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": 1e3 * per_step / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u32", "data": "synthetic",
-               "config": {"workload": workload, "sample_reads_per_step": per_step},
+               "config": {"workload": workload, "sample_reads_per_step": per_step,
+                          "sample": "the reference arm runs the same pipeline stages on a bounded sample per step: k<=2 search of "
+                                    f"{per_step} reads + mate-rescue DP of the same fraction of pairs as the GPU arm rescues"},
                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": info["cores"], "kind": info["kind"],
                                 "sample": info["sample"], "cpu_model": cpu_model()},
                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
@@ -508,48 +616,22 @@ def main():
 
     t0 = time.time()
     gi = upload_index(host, local_rank)
-    host.pop("sa", None)                                      # 12 GB of host memory per rank, no longer needed
+    if not (rank == 0 and world == 1):
+        host.pop("sa", None)                                  # 12 GB of host memory per rank, only the parity check reads it
     if os.environ.get("S3_SPLIT_BUDGET"):                     # tuning experiments (profiles/variants.sh)
         api.set_split_budget(gi, int(os.environ["S3_SPLIT_BUDGET"]))
     log(f"index on device in {time.time() - t0:.1f}s: {gi.device_bytes / 1e9:.2f} GB (32-byte single-sector buckets, seed tables, "
-        f"suffix array + inverse + packed text for check-and-extend)")
+        f"suffix array + inverse + packed text)")
     stream = torch.cuda.ExternalStream(gi.stream, device=device)
     total = args.warmup + args.steps
     t0 = time.time()
     batches = [make_batch(genome, args.pairs, L, seed=100 + 1000 * rank + s) for s in range(total)]
-    answers, allowed, wpa, ncases = alloc_answers(batches[0], device)
-    ans_ptrs = [a.data_ptr() for a in answers]
-    d_rank = torch.zeros(1, dtype=torch.int64, device=device)
+    N, wpq = batches[0].n, batches[0].wpq
+    par = api.pe_params(num_mismatch=K_MISMATCH, insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES, read_length=L,
+                        max_windows=N // 2)
+    pe = api.PairAligner(gi, N, L, par)
     torch.cuda.synchronize()
-    # setup pass (untimed): rank-query count and the rescue batches from the actual search result
-    rescue = []
-    nrank_total = 0
-    for s, b in enumerate(batches):
-        d_rank.zero_()
-        torch.cuda.synchronize()
-        api.search_round1_device(gi, b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq, K_MISMATCH, ncases, allowed,
-                                 wpa, ans_ptrs, d_rank.data_ptr())
-        stream.synchronize()
-        if s >= args.warmup:
-            nrank_total += int(d_rank.item())
-        rescue.append(build_rescue_batch(genome, b, answers, wpa, max_read, max_dna))
-    torch.cuda.synchronize()
-    max_m = max(r.n for r in rescue)
-    log(f"{total} batches of {batches[0].n} reads prepared in {time.time() - t0:.1f}s; rescue DP alignments per step: "
-        f"{[r.n for r in rescue]}")
-    aligner = api.SemiGlobalAligner(max_read, max_dna, max(max_m, 32), *DP_SCORES, device=local_rank)
-    aligner.set_stream(gi.stream)
-
-    def gpu_step(b, r):
-        api.search_round1_device(gi, b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq, K_MISMATCH, ncases, allowed,
-                                 wpa, ans_ptrs, 0)
-
-    def dp_step(r):
-        if r.n:
-            aligner.align_device(r.dna.data_ptr(), r.dna_len.data_ptr(), r.read.data_ptr(), r.read_len.data_ptr(),
-                                 r.cutoff.data_ptr(), r.scores.data_ptr(), r.hit.data_ptr(), r.cnt.data_ptr(),
-                                 r.pattern.data_ptr(), r.n, r.clip_lt.data_ptr(), r.clip_rt.data_ptr(),
-                                 r.anchor_l.data_ptr(), r.anchor_r.data_ptr())
+    log(f"{total} batches of {N} reads prepared in {time.time() - t0:.1f}s")
 
     def barrier():
         torch.cuda.synchronize()
@@ -557,164 +639,94 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident timing -------------------------------------------------
-    api.set_timing(gi.handle, True)                 # events between the library's launches: per-kernel times of the timed region
-    api.set_timing(aligner.handle, True, dp=True)
-    for s in range(args.warmup):                    # warm-up in the mode that is measured (one stream, timing hooks on)
-        gpu_step(batches[s], rescue[s])
-        dp_step(rescue[s])
+    def device_step(b):
+        return pe.align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq)
+
+    # ---- device-resident timing: queries in HBM, results left there ---------------------------------------------
+    for s in range(args.warmup):
+        device_step(batches[s])
     barrier()
-    api.read_timing(gi.handle)
-    api.read_timing(aligner.handle, dp=True)
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = api.launch_count()
-    with torch.cuda.stream(stream):
-        for k in range(args.steps):
-            b, r = batches[args.warmup + k], rescue[args.warmup + k]
-            ev[k][0].record(stream)
-            gpu_step(b, r)
-            ev[k][1].record(stream)
-            dp_step(r)
-            ev[k][2].record(stream)
+    stats = []
+    e0.record(stream)
+    for k in range(args.steps):
+        stats.append(device_step(batches[args.warmup + k]))
+    e1.record(stream)
     stream.synchronize()
     barrier()
     launches = api.launch_count() - launches0
-    ms_search, n_search = api.read_timing(gi.handle)
-    ms_dp, n_dp = api.read_timing(aligner.handle, dp=True)
-    api.set_timing(gi.handle, False)
-    api.set_timing(aligner.handle, False, dp=True)
-    t_search = sum(e[0].elapsed_time(e[1]) for e in ev) / 1e3
-    t_dp = sum(e[1].elapsed_time(e[2]) for e in ev) / 1e3
-    t_total = ev[0][0].elapsed_time(ev[-1][2]) / 1e3
-    tt = torch.tensor([t_total, t_search, t_dp], dtype=torch.float64, device=device)
-    if world > 1:
-        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-    t_serial, t_search_max, t_dp_max = [float(x) for x in tt]
-    reads_per_rank = sum(batches[args.warmup + k].n for k in range(args.steps))
-
-    # ---- the same K steps as a pipeline: search of batch k+1 on the index stream while the DP of batch k runs
-    # on the workspace's own stream (the search tail is latency bound, the DP sweep bandwidth bound) -----------
-    aligner.set_stream(0)
-    dp_stream = torch.cuda.ExternalStream(aligner.stream, device=device)
-    for s in range(args.warmup):                    # warm-up of this mode: batch halves side by side, DP on its own stream
-        gpu_step(batches[s], rescue[s])
-        first = torch.cuda.Event()
-        first.record(stream)
-        dp_stream.wait_event(first)
-        dp_step(rescue[s])
-    barrier()
-    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    searched = [torch.cuda.Event() for _ in range(args.steps)]
-    launches0p = api.launch_count()
-    p0.record(stream)
-    dp_stream.wait_event(p0)
-    for k in range(args.steps):
-        b, r = batches[args.warmup + k], rescue[args.warmup + k]
-        gpu_step(b, r)
-        searched[k].record(stream)
-        dp_stream.wait_event(searched[k])              # DP of batch k follows the search of batch k
-        dp_step(r)
-    dp_done = torch.cuda.Event()
-    dp_done.record(dp_stream)
-    stream.wait_event(dp_done)
-    p1.record(stream)
-    stream.synchronize()
-    barrier()
-    launches_p = api.launch_count() - launches0p
     sampler.stop_flag = True
     sampler.join()
-    tp = torch.tensor([p0.elapsed_time(p1) / 1e3], dtype=torch.float64, device=device)
+    tt = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=device)
     if world > 1:
-        torch.distributed.all_reduce(tp, op=torch.distributed.ReduceOp.MAX)
-    t_total = float(tp[0])
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    t_total = float(tt[0])
+    reads_per_rank = N * args.steps
     value = world * reads_per_rank / t_total
-    value_serial = world * reads_per_rank / t_serial
+    windows = [int(r.numWindows) for r in stats]
+    wlen = INSERT_HI - INSERT_LO + L
+    dp_cells = float(sum(windows)) * L * wlen
+    routes = np.sum([list(r.routeCounts)[:9] for r in stats], axis=0)
 
-    # ---- end-to-end through the host C ABI (pinned host buffers) ------------------
+    # ---- the same steps with the per-kernel timing hooks on (events between the library's launches) ---------------
+    api.set_timing(gi.handle, True)
+    api.set_timing(pe.dp_handle, True, dp=True)
+    pe.set_timing(True)
+    device_step(batches[0])
+    barrier()
+    api.read_timing(gi.handle)
+    api.read_timing(pe.dp_handle, dp=True)
+    pe.read_timing()
+    st0 = pe.read_timing()
+    for k in range(args.steps):
+        device_step(batches[args.warmup + k])
+    barrier()
+    ms_search, n_search = api.read_timing(gi.handle)
+    ms_dp, n_dp = api.read_timing(pe.dp_handle, dp=True)
+    st1 = pe.read_timing()
+    ms_stage = [b_ - a_ for a_, b_ in zip(st0, st1)]
+    api.set_timing(gi.handle, False)
+    api.set_timing(pe.dp_handle, False, dp=True)
+    pe.set_timing(False)
+
+    # ---- end to end through the host-pointer entry: queries from pinned host memory, results into host memory -----
     def pinned(t):
         h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
         h.copy_(t)
         return h
-    e2e_sets = []
-    for k in range(args.steps):
-        b, r = batches[args.warmup + k], rescue[args.warmup + k]
-        hs = Batch()
-        hs.q, hs.l = pinned(b.queries), pinned(b.lens)
-        hs.ans = [torch.empty(a.shape, dtype=a.dtype, pin_memory=True) for a in answers]
-        hs.r = {k2: pinned(getattr(r, k2)) for k2 in ("dna", "dna_len", "read", "read_len", "cutoff", "clip_lt", "clip_rt",
-                                                      "anchor_l", "anchor_r")}
-        hs.out = {k2: torch.empty(getattr(r, k2).shape, dtype=getattr(r, k2).dtype, pin_memory=True)
-                  for k2 in ("scores", "hit", "cnt", "pattern")}
-        hs.n, hs.m, hs.wpq = b.n, r.n, b.wpq
-        e2e_sets.append(hs)
-    lib = api.load_library()
-    U32P, I32P, U8P = api.U32P, api.I32P, api.U8P
-
-    def p32(t):
-        return C.cast(t.data_ptr(), U32P)
-
-    def e2e_step(hs):
-        arr = (C.c_void_p * ncases)(*[a.data_ptr() for a in hs.ans])
-        api._check(lib.s3_search_round1(gi.handle, p32(hs.q), p32(hs.l), hs.n, hs.wpq, K_MISMATCH, ncases, allowed, wpa, 0,
-                                        arr), "s3_search_round1")
-        if hs.m:
-            api._check(lib.s3_dp_align(aligner.handle, p32(hs.r["dna"]), p32(hs.r["dna_len"]), p32(hs.r["read"]),
-                                       p32(hs.r["read_len"]), C.cast(hs.r["cutoff"].data_ptr(), I32P),
-                                       C.cast(hs.out["scores"].data_ptr(), I32P), p32(hs.out["hit"]), p32(hs.out["cnt"]),
-                                       C.cast(hs.out["pattern"].data_ptr(), U8P), hs.m, p32(hs.r["clip_lt"]),
-                                       p32(hs.r["clip_rt"]), p32(hs.r["anchor_l"]), p32(hs.r["anchor_r"])), "s3_dp_align")
-    def e2e_search(hs):
-        arr = (C.c_void_p * ncases)(*[a.data_ptr() for a in hs.ans])
-        api._check(lib.s3_search_round1(gi.handle, p32(hs.q), p32(hs.l), hs.n, hs.wpq, K_MISMATCH, ncases, allowed, wpa, 0,
-                                        arr), "s3_search_round1")
-
-    def e2e_dp(hs):
-        if hs.m:
-            api._check(lib.s3_dp_align(aligner.handle, p32(hs.r["dna"]), p32(hs.r["dna_len"]), p32(hs.r["read"]),
-                                       p32(hs.r["read_len"]), C.cast(hs.r["cutoff"].data_ptr(), I32P),
-                                       C.cast(hs.out["scores"].data_ptr(), I32P), p32(hs.out["hit"]), p32(hs.out["cnt"]),
-                                       C.cast(hs.out["pattern"].data_ptr(), U8P), hs.m, p32(hs.r["clip_lt"]),
-                                       p32(hs.r["clip_rt"]), p32(hs.r["anchor_l"]), p32(hs.r["anchor_r"])), "s3_dp_align")
-
-    def e2e_pipelined(sets):
-        # The caller the reference itself is: its main thread searches batch k+1 while a GPU thread of a DP engine
-        # aligns batch k (one pthread per engine owns the DP calls, DV-DPfunctions.cu:1743-1774).  Both calls are the
-        # synchronous host-pointer entry points; every step's H2D and D2H copies are inside the timed region.
-        import queue
-        todo, errs = queue.Queue(), []
-
-        def dp_thread():
-            torch.cuda.set_device(local_rank)
-            while True:
-                hs = todo.get()
-                if hs is None:
-                    return
-                try:
-                    e2e_dp(hs)
-                except Exception as e:              # noqa: BLE001
-                    errs.append(e)
-        th = threading.Thread(target=dp_thread)
-        th.start()
-        for hs in sets:
-            e2e_search(hs)
-            todo.put(hs)
-        todo.put(None)
-        th.join()
-        if errs:
-            raise errs[0]
+    host_sets = [(pinned(batches[args.warmup + k].queries), pinned(batches[args.warmup + k].lens)) for k in range(args.steps)]
+    pageable_sets = [(q.numpy().copy(), l.numpy().copy()) for q, l in host_sets[:2]]
 
     def timed(fn):
         barrier()
         t0 = time.perf_counter()
-        fn()
+        r = fn()
         barrier()
         t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
         if world > 1:
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-        return float(t[0])
+        return float(t[0]), r
 
+    def e2e_steps(sets):
+        # the next batch's queries go up (s3_pe_prefetch, a copy stream) while this batch is aligned
+        out = None
+        ptr = lambda x: x.data_ptr() if hasattr(x, "data_ptr") else x
+        for k, (q, l) in enumerate(sets):
+            if k + 1 < len(sets):
+                pe.prefetch(ptr(sets[k + 1][0]), ptr(sets[k + 1][1]), N, wpq)
+            out = pe.align(ptr(q), ptr(l), N, wpq, copy=False)
+        return out
+    for s in range(min(args.warmup, len(host_sets))):
+        e2e_steps(host_sets[s:s + 1])
+    t_e2e, last = timed(lambda: e2e_steps(host_sets))
+    h2d, d2h = last["h2d_bytes"], last["d2h_bytes"]
+    e2e_value = world * reads_per_rank / t_e2e
+    e2e_steps(pageable_sets[:1])
+    t_page, _ = timed(lambda: e2e_steps(pageable_sets))
+    pageable_value = world * N * len(pageable_sets) / t_page
     # what the link gives: one 256 MiB pinned copy each way, alone
     probe_h = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
     probe_d = torch.empty(256 << 20, dtype=torch.uint8, device=device)
@@ -729,132 +741,10 @@ def main():
         torch.cuda.synchronize()
         link[name] = (256 << 20) / (c0.elapsed_time(c1) * 1e-3) / 1e9
     del probe_h, probe_d
-    for s in range(min(args.warmup, len(e2e_sets))):
-        e2e_step(e2e_sets[s])
-    t_e2e_serial = timed(lambda: [e2e_step(hs) for hs in e2e_sets])
-    e2e_pipelined(e2e_sets[:2])
-    t_e2e = timed(lambda: e2e_pipelined(e2e_sets))
-    if os.environ.get("S3_E2E_SERIAL"):
-        t_e2e = t_e2e_serial
-    hs = e2e_sets[0]
-    up = formats.ceil32(hs.n)
-    h2d = up * hs.wpq * 4 + hs.n * 4
-    d2h = ncases * up * wpa * 4
-    if hs.m:
-        upm = formats.ceil32(hs.m)
-        h2d += upm * (((max_dna + 15) >> 4) + ((max_read + 15) >> 4)) * 4 + hs.m * 4 * 7
-        d2h += hs.m * (12 + max_read + max_dna)
-    e2e_value = world * reads_per_rank / t_e2e
-
-    # ---- the next rows of the scope table at bench size (rank 0, N = 1): locate and device-side DP packing ------
-    extras = {}
-    if rank == 0 and world == 1:
-        try:
-            hs, r, b = e2e_sets[-1], rescue[args.warmup + args.steps - 1], batches[args.warmup + args.steps - 1]
-            # SA ranges of the last step's answers -> text positions (s3_locate), host arrays in and out
-            views = [formats.answers_view(a.numpy().view(np.uint32), hs.n, wpa) for a in hs.ans]
-            sal, sar = [], []
-            for v in views:
-                for sidx in range(allowed):
-                    l, w = v[:, 2 * sidx], v[:, 2 * sidx + 1]
-                    ok = (l < 0xFFFFFFFD) & (w != 0xFFFFFFFF) if sidx == 0 else (l != 0xFFFFFFFF) & (w != 0xFFFFFFFF)
-                    ok &= v[:, 0] < 0xFFFFFFFD
-                    sal.append(l[ok])
-                    sar.append(l[ok] + (w[ok] & 0xFFFFFF))
-            sal = np.ascontiguousarray(np.concatenate(sal)).astype(np.uint32)
-            sar = np.ascontiguousarray(np.concatenate(sar)).astype(np.uint32)
-            api.locate(gi, sal, sar, 8)                                          # first call of this size: module loading
-            t0 = time.perf_counter()
-            offs, pos = api.locate(gi, sal, sar, 8)
-            t_loc = time.perf_counter() - t0
-            extras["locate"] = {"ranges": int(len(sal)), "positions": int(len(pos)), "ms": 1e3 * t_loc,
-                                "ranges_per_s": len(sal) / t_loc,
-                                "call": "s3_locate, pageable host arrays in and out, <= 8 positions per range"}
-            # the last step's rescue batch through s3_dp_align_windows (packed on the device) against s3_dp_align (packed by
-            # the caller), both with pinned host buffers
-            if r.n:
-                lib.s3_dp_align_windows.restype = C.c_int
-                lib.s3_dp_align_windows.argtypes = [C.c_void_p, C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32, U32P, U8P, U32P, U32P,
-                                                    I32P, I32P, U32P, U32P, U8P, C.c_uint32, U32P, U32P, U32P, U32P]
-                w_in = {k2: pinned(getattr(r, k2)) for k2 in ("read_ids", "strand_code", "start")}
-                w_out = {k2: torch.empty_like(v) for k2, v in hs.out.items()}
-                w_out = {k2: v.pin_memory() for k2, v in w_out.items()}
-
-                def win_call():
-                    api._check(lib.s3_dp_align_windows(aligner.handle, gi.handle, p32(hs.q), p32(hs.l), hs.n, hs.wpq, p32(w_in["read_ids"]),
-                                                       C.cast(w_in["strand_code"].data_ptr(), U8P), p32(w_in["start"]), p32(hs.r["dna_len"]),
-                                                       C.cast(hs.r["cutoff"].data_ptr(), I32P), C.cast(w_out["scores"].data_ptr(), I32P),
-                                                       p32(w_out["hit"]), p32(w_out["cnt"]), C.cast(w_out["pattern"].data_ptr(), U8P), r.n,
-                                                       p32(hs.r["clip_lt"]), p32(hs.r["clip_rt"]), p32(hs.r["anchor_l"]),
-                                                       p32(hs.r["anchor_r"])), "s3_dp_align_windows")
-                win_call()
-                t0 = time.perf_counter()
-                win_call()
-                t_win = time.perf_counter() - t0
-                e2e_dp(hs)
-                t0 = time.perf_counter()
-                e2e_dp(hs)
-                t_packed = time.perf_counter() - t0
-                same = all(torch.equal(w_out[k2][:r.n], hs.out[k2][:r.n]) for k2 in ("scores", "hit", "cnt"))
-                pl = max_read + max_dna
-                pw, pp = w_out["pattern"].view(-1, pl)[:r.n], hs.out["pattern"].view(-1, pl)[:r.n]
-                traced = hs.out["scores"][:r.n] >= hs.r["cutoff"][:r.n]
-                same_pat = bool(torch.equal(pw[traced][:, :L + 8], pp[traced][:, :L + 8]))
-                extras["dp_align_windows"] = {"alignments": int(r.n), "ms": 1e3 * t_win, "ms_s3_dp_align_same_batch": 1e3 * t_packed,
-                                              "h2d_bytes": int(hs.q.numel() * 4 + hs.n * 4 + r.n * 29),
-                                              "h2d_bytes_s3_dp_align": int(formats.ceil32(r.n) * (((max_dna + 15) >> 4) + ((max_read + 15) >> 4)) * 4 + r.n * 28),
-                                              "outputs_equal_to_s3_dp_align": bool(same and same_pat),
-                                              "call": "s3_dp_align_windows: query buffer + 29 B per alignment in, batch arrays packed on the "
-                                                      "device; pinned host buffers"}
-                # the same outputs through s3_dp_decode (host threads): special + SAM CIGARs, edit distance
-                try:
-                    dec_args = (hs.out["pattern"].numpy(), pl, hs.out["scores"].numpy()[:r.n], hs.r["read_len"].numpy()[:r.n],
-                                hs.r["cutoff"].numpy()[:r.n], api.DPScores(*DP_SCORES))
-                    api.decode_alignments(*dec_args, split=False)
-                    t0 = time.perf_counter()
-                    dec = api.decode_alignments(*dec_args, split=False)
-                    t_dec = time.perf_counter() - t0
-                    extras["dp_decode"] = {"alignments": int(r.n), "decoded": int((dec["editdist"] >= 0).sum()), "ms": 1e3 * t_dec,
-                                           "mean_editdist": float(dec["editdist"][dec["editdist"] >= 0].mean()) if (dec["editdist"] >= 0).any() else None,
-                                           "cigar_bytes": int(len(dec["cigar"][1])), "sam_cigar_bytes": int(len(dec["sam"][1])),
-                                           "call": "s3_dp_decode on the host arrays s3_dp_align returned, host threads"}
-                except Exception as e:                   # noqa: BLE001
-                    extras["dp_decode"] = {"error": str(e)[:200]}
-            # capless search (s3_search) of the seeds of 131,072 reads of the step + s3_seed_candidates on what it finds:
-            # three 22-base seeds per read, <= 1 mismatch, as a DP seeding round hands them over
-            n_seed_reads, seed_len = 131072, 22
-            rd = b.reads[:n_seed_reads].cpu().numpy()
-            seed_offs = np.array([0, 39, 78], np.uint32)
-            seeds = np.stack([rd[:, o:o + seed_len] for o in seed_offs], axis=1).reshape(-1, seed_len)
-            ns = len(seeds)
-            slens = np.zeros(formats.ceil32(ns), np.uint32)
-            slens[:ns] = seed_len
-            wps = formats.word_per_query(seed_len)
-            sq = formats.pack_queries(seeds, slens[:ns], wps)
-            api.search(gi, sq[:32 * wps * 64], slens[:2048], 2048, wps, 1)
-            t0 = time.perf_counter()
-            c_offs, c_l, c_r, c_info = api.search(gi, sq, slens, ns, wps, 1)
-            t_csr = time.perf_counter() - t0
-            extras["capless_search"] = {"seeds": int(ns), "seed_length": seed_len, "mismatches": 1, "ranges": int(len(c_l)), "ms": 1e3 * t_csr,
-                                        "seeds_per_s": ns / t_csr, "call": "s3_search (CSR, no slot caps), pageable host arrays"}
-            seed_of = np.repeat(np.arange(ns), np.diff(c_offs).astype(np.int64))
-            sc_args = (c_l, c_r, ((c_info & 1) + 1).astype(np.int32), (seed_of // 3).astype(np.uint32), seed_offs[seed_of % 3],
-                       np.full(len(c_l), seed_len, np.uint32), np.full(len(c_l), L, np.uint32))
-            api.seed_candidates(gi, *sc_args, 64)
-            t0 = time.perf_counter()
-            cr, cp, cs = api.seed_candidates(gi, *sc_args, 64)
-            t_sc = time.perf_counter() - t0
-            true_pos = b.pos[:n_seed_reads].cpu().numpy()
-            near = int((np.abs(cp.astype(np.int64) - true_pos[cr]) <= 3).sum())
-            extras["seed_candidates"] = {"ranges": int(len(c_l)), "candidates": int(len(cr)), "ms": 1e3 * t_sc, "ranges_per_s": len(c_l) / t_sc,
-                                         "reads_with_a_candidate_at_their_true_start": int(len(set(cr[np.abs(cp.astype(np.int64) - true_pos[cr]) <= 3].tolist()))),
-                                         "reads": n_seed_reads, "candidates_at_true_start": near,
-                                         "call": "s3_seed_candidates, <= 64 positions per range, pageable host arrays"}
-        except Exception as e:                           # noqa: BLE001
-            extras["error"] = str(e)[:300]
     if rank != 0:
         return
-    # ---- rooflines ---------------------------------------------------------------
+
+    # ---- rooflines ---------------------------------------------------------------------------------------------
     peaks = {}
     pk_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(pk_path):
@@ -873,75 +763,91 @@ def main():
     for nm, ms, cnt in list(zip(names_s, ms_search, n_search)) + list(zip(names_d, ms_dp, n_dp)):
         if cnt:
             kernels[nm] = {"ms_per_step": ms / K, "launches_per_step": cnt / K}
-    search_bytes = 64.0 * nrank_total                   # 64 B per rank evaluation of the reference's algorithm
-    search_gbs = search_bytes / t_search / 1e9
-    dp_cells = sum(rescue[args.warmup + k].cells for k in range(args.steps))
-    dp_gcups = dp_cells / t_dp / 1e9 if t_dp > 0 else 0.0
-    t_score = ms_dp[0] / 1e3
-    score_gbs = 2.0 * dp_cells / t_score / 1e9 if t_score > 0 else 0.0          # 2 B per cell: the H plane
+    stage_names = ["search launch", "collect + route (+ first count read)", "locate + sort", "pairing + window count (+ second count read)",
+                   "window descriptors", "DP (pack + sweep + second sweep + traceback)", "CIGAR runs + records"]
+    stages = {nm: ms / K for nm, ms in zip(stage_names, ms_stage)}
+    t_step_hooks = sum(ms_stage) / K
+    t_search = sum(ms_search) / 1e3
+    t_dp = sum(ms_dp) / 1e3
+    t_sweep = ms_dp[0] / 1e3
     dpx = {}
     dpx_path = os.path.join(ROOT, "profiles", "r01_dpx_rate.json")              # tools/dpx_rate.cu on this pool's B200
     if os.path.exists(dpx_path):
         dpx = json.load(open(dpx_path))
     dpx_peak = float(dpx.get("gcups_peak_5op", 7324.6))
+    dp_gcups = dp_cells / t_dp / 1e9 if t_dp > 0 else 0.0
+    sweep_gcups = dp_cells / t_sweep / 1e9 if t_sweep > 0 else 0.0
+    try:
+        sector_rate = random_sector_rate(gi, device)
+    except Exception as e:                                   # noqa: BLE001
+        log("random sector probe failed:", e)
+        sector_rate = None
+    # the search launch against the random-sector rate of this run: executed 32-byte sectors per launch (ncu dram__sectors_read
+    # of the launch's kernels, profiles/ncu_traffic.json) / launch time / probe rate
     search_roof = {"kernel": "search launch (s3_search_easy_kernel + s3_search_kernel<items|spine|tasks> + merge)", "bound": "hbm",
-                   "achieved": search_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": search_gbs / hbm_peak,
-                   "traffic": traffic.get("search_launch"), "peak_source": peak_src,
-                   "rank_queries_per_launch": nrank_total / K, "bytes_per_rank_query": 64,
-                   "note": "algorithmic bytes = the REFERENCE algorithm's rank evaluations x 64 B; seed tables and check-and-extend "
-                           "answer most of them without touching the index, so frac can exceed 1 -- `traffic` is what the "
-                           "kernels really move",
-                   "ms_per_launch": 1e3 * t_search / K, "share_of_step": t_search / (t_search + t_dp)}
-    if traffic.get("search_launch"):
-        # what the launch really moves, against what independent random 32-byte reads reach on this GPU
-        # (tools/random_sector_bw.cu, profiles/r01_random_sector_bw.txt: 47.5 G sectors/s = 3.04 TB/s of 64-byte DRAM bursts)
-        search_roof["executed_gbs"] = traffic["search_launch"] / (t_search / K) / 1e9
-        search_roof["random_burst_peak_gbs"] = 3040.0
-        search_roof["executed_frac_of_random_burst_peak"] = search_roof["executed_gbs"] / 3040.0
-    score_roof = {"kernel": "s3_dp_score16_kernel", "bound": "hbm", "achieved": score_gbs, "peak": hbm_peak, "unit": "GB/s",
-                  "frac": score_gbs / hbm_peak, "traffic": traffic.get("s3_dp_score16_kernel"), "peak_source": peak_src,
-                  "cells_per_launch": dp_cells / K, "bytes_per_cell": 2,
-                  "ms_per_launch": 1e3 * t_score / K, "share_of_step": t_score / (t_search + t_dp)}
-    dominant = max(kernels.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if kernels else "s3_dp_score16_kernel"
+                   "unit": "G sectors/s", "ms_per_launch": 1e3 * t_search / K, "share_of_step": (t_search / K) / (t_step_hooks / 1e3) if t_step_hooks else None,
+                   "peak": sector_rate / 1e9 if sector_rate else None,
+                   "peak_source": "s3_random_sector_probe in this run: independent random 32-byte reads over the index's bucket array",
+                   "traffic": traffic.get("search_launch")}
+    if traffic.get("search_launch") and sector_rate:
+        search_roof["achieved"] = traffic["search_launch"] / 32.0 / (t_search / K) / 1e9
+        search_roof["frac"] = search_roof["achieved"] / search_roof["peak"]
+        search_roof["achieved_gbs"] = traffic["search_launch"] / (t_search / K) / 1e9
+        search_roof["frac_of_hbm_copy_peak"] = search_roof["achieved_gbs"] / hbm_peak
+    dp_traffic = None
+    if all(traffic.get(k2) is not None for k2 in ("s3_dp_sweep16_kernel", "s3_dp_resweep16_kernel", "s3_dp_traceback16_kernel")):
+        dp_traffic = sum(traffic[k2] for k2 in ("s3_dp_sweep16_kernel", "s3_dp_resweep16_kernel", "s3_dp_traceback16_kernel"))
+    sweep_roof = {"kernel": "s3_dp_sweep16_kernel", "bound": "dpx", "achieved": sweep_gcups, "peak": dpx_peak, "unit": "GCUPS",
+                  "frac": sweep_gcups / dpx_peak, "traffic": traffic.get("s3_dp_sweep16_kernel"),
+                  "peak_source": "tools/dpx_rate.cu on B200 (profiles/r01_dpx_rate.json): VIMNMX3/VIADDMNMX .16x2 issue rate x SMs x clock x "
+                                 "64 cells / 5 instructions per cell pair (SURVEY.md 8d)",
+                  "cells_per_launch": dp_cells / K, "ms_per_launch": 1e3 * t_sweep / K,
+                  "share_of_step": (t_sweep / K) / (t_step_hooks / 1e3) if t_step_hooks else None,
+                  "hbm": {"achieved_gbs": (traffic["s3_dp_sweep16_kernel"] / (t_sweep / K) / 1e9) if traffic.get("s3_dp_sweep16_kernel") else None,
+                          "peak_gbs": hbm_peak, "peak_source": peak_src}}
+    dominant = max(kernels.items(), key=lambda kv: kv[1]["ms_per_step"])[0] if kernels else "s3_dp_sweep16_kernel"
     out = {
         "metric": "reads/s aligned (2x100bp PE, 3.1 Gbp synth ref)",
         "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
-        "value_one_stream": value_serial, "ms_per_step_one_stream": 1e3 * t_serial / args.steps,
-        "config": {"workload": workload, "genome_bp": args.genome_bp, "pairs_per_step_per_gpu": args.pairs,
-                   "timing": "value: K steps as a two-stream pipeline on the device (search of batch k+1 overlaps the DP of batch k, "
-                             "DP k after search k), CUDA events; value_one_stream, kernels, roofline, search, dp: the same K steps "
-                             "one after the other on one stream",
-                   "l2": "inputs larger than L2: 56 GB of index (buckets, seed tables, suffix array, text) touched at random, "
-                         "32 MiB of queries and 128 MiB of answer slots per step, a different read batch every step",
+        "config": {"workload": workload, "genome_bp": args.genome_bp, "repeat_fraction": args.repeat_fraction, "pairs_per_step_per_gpu": args.pairs,
+                   "step": "s3_pe_align_device: search -> collect -> route -> locate -> pairing -> rescue windows -> DP -> CIGAR runs, nothing "
+                           "taken from the simulator's truth; reads whose round-1 slot overflowed are reported (route 8), not searched again",
+                   "timing": "value: K steps back to back, queries resident in HBM, results left there, CUDA events on the library's stream "
+                             "(two 4-byte count reads per step are part of the chain); kernels / stages: the same K steps once more with the "
+                             "library's timing hooks on; e2e: the same K steps through s3_pe_align, queries from pinned host memory, results "
+                             "into host memory, wall clock",
+                   "l2": "inputs larger than L2: 56 GB of index (buckets, seed tables, suffix array, text) touched at random, a different "
+                         "32 MiB read batch every step",
                    "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"
                                   + (f"; rank 0 bound to the CPUs of NUMA node {numa}" if numa is not None else "")},
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * t_e2e / args.steps,
-                "mode": "host-pointer C ABI (s3_search_round1 + s3_dp_align), pinned host buffers; two caller threads: search of "
-                        "batch k+1 overlaps DP of batch k, as the reference's main thread and DP GPU thread do",
-                "serial_value": world * reads_per_rank / t_e2e_serial, "serial_ms_per_step": 1e3 * t_e2e_serial / args.steps,
+                "mode": "s3_pe_align (host-pointer C ABI): queries from pinned host memory in, routes + pairings + rescue records + CIGAR runs "
+                        "into host memory out, one call per step; the next step's queries are uploaded by s3_pe_prefetch under this step's kernels",
+                "pageable_value": pageable_value, "pageable_ms_per_step": 1e3 * t_page / len(pageable_sets),
                 "link": link},
-        "gpu_launches": int(launches_p),
-        # the dominant kernel of the step by measured time is the DP score sweep (H plane writes); the search launch's
-        # line follows under "search"
-        "roofline": score_roof if dominant == "s3_dp_score16_kernel" else search_roof,
+        "gpu_launches": int(launches),
+        "roofline": sweep_roof if dominant.startswith("s3_dp") else search_roof,
         "search": search_roof,
-        "dp": {"kernel": "s3_dp_score16_kernel + s3_dp_best16_kernel + s3_dp_traceback16_kernel", "gcups": dp_gcups,
-               "gcups_score_kernel": dp_cells / t_score / 1e9 if t_score > 0 else 0.0,
-               "dpx_peak_gcups": dpx_peak, "frac_of_dpx_peak": dp_gcups / dpx_peak,
-               "dpx_peak_source": "tools/dpx_rate.cu on B200 (profiles/r01_dpx_rate.json): VIMNMX3/VIADDMNMX .16x2 issue rate x SMs x "
-                                  "clock x 64 cells / 5 instructions per cell pair (SURVEY.md 8d)",
-               "score_kernel_hbm": score_roof,
-               "alignments_per_step": float(np.mean([rescue[args.warmup + k].n for k in range(args.steps)])),
-               "cells_per_step": dp_cells / args.steps, "ms_per_step": 1e3 * t_dp / args.steps},
+        "dp": {"kernel": "s3_dp_sweep16_kernel + s3_dp_resweep16_kernel + s3_dp_traceback16_kernel", "gcups": dp_gcups,
+               "dpx_peak_gcups": dpx_peak, "frac_of_dpx_peak": dp_gcups / dpx_peak, "sweep": sweep_roof,
+               "alignments_per_step": float(np.mean(windows)), "cells_per_step": dp_cells / args.steps, "ms_per_step": 1e3 * t_dp / args.steps,
+               "dram_bytes_per_step": dp_traffic, "algorithmic_bytes_per_step": 0.5 * dp_cells / args.steps,
+               "note": "algorithmic bytes = 0.5 B per cell (SURVEY.md 8d: inputs + traceback bits)"},
+        "routes_per_step": {nm: float(routes[c]) / args.steps for c, nm in enumerate(
+            ["both unaligned (deep DP list)", "both hit (paired or rescued below)", "first read rescues its mate", "second read rescues its mate",
+             "-", "first read: too many hits", "second read: too many hits", "-", "round-1 slot overflow"]) if nm != "-"},
+        "pipeline": {"ranges_per_step": float(np.mean([int(r.numRanges) for r in stats])),
+                     "occurrences_per_step": float(np.mean([int(r.numOccurrences) for r in stats])),
+                     "rescue_windows_per_step": float(np.mean(windows)), "cigar_runs_per_step": float(np.mean([int(r.numRuns) for r in stats]))},
+        "stages_ms_per_step": stages,
         "kernels": kernels,
-        "next_rows": extras,
     }
     if world == 1 and not args.no_cpu_baseline:
-        frac = float(np.mean([r.n / b.pairs for r, b in zip(rescue, batches)]))
+        frac = float(np.mean(windows)) / args.pairs
         t0 = time.time()
         cb = cpu_arm(host, genome, L, args.cpu_sample, 999, frac, threads)
         log(f"cpu baseline ({cb['kind']}, {cb['cores']} threads) took {time.time() - t0:.1f}s: {cb['value']:.0f} reads/s")
@@ -957,21 +863,15 @@ def main():
             out["dp"]["reference_cuda_kernels_on_this_gpu"] = cb["gpu_reference_dp"]
             if cb["gpu_reference_dp"].get("gcups"):
                 out["dp"]["speedup_over_reference_cuda_kernels"] = dp_gcups / cb["gpu_reference_dp"]["gcups"]
-        out["parity_at_full_size"] = parity_check(gi, cb, local_rank)
-    if world == 1:
-        # best-hit filter -> locate -> pairing of the two mates' lists on the last step's answers; after everything else has
-        # been measured and compared, so that nothing above depends on these newer entries
+        del cb
+        t0 = time.time()
         try:
-            hs, b = e2e_sets[-1], batches[args.warmup + args.steps - 1]
-            views = [formats.answers_view(a.numpy().view(np.uint32), hs.n, wpa) for a in hs.ans]
-            out["next_rows"]["pairing"] = pairing_rows(views, allowed, hs.n, L, b.pos.cpu().numpy().astype(np.uint32),
-                                                       lambda mode, *a: api.retain_best(gi, mode, *a),
-                                                       lambda l_, r_, cap: api.locate(gi, l_, r_, cap),
-                                                       lambda *a: api.pair_occurrences(gi, *a))
-        except Exception as e:                           # noqa: BLE001
-            out["next_rows"]["pairing"] = {"error": str(e)[:200]}
+            out["parity_at_full_size"] = chain_parity(gi, host, genome, L, args.parity_pairs, 4242, par, local_rank)
+            log(f"chain parity on {args.parity_pairs} pairs took {time.time() - t0:.1f}s: {out['parity_at_full_size']}")
+        except Exception as e:                               # noqa: BLE001
+            out["parity_at_full_size"] = {"error": str(e)[:300]}
     print(json.dumps(out), flush=True)
-    aligner.freeMemory()
+    pe.free()
     api.GPUINDEXFree(gi)
     if world > 1:
         torch.distributed.destroy_process_group()

@@ -426,7 +426,7 @@ typedef struct {
     uint32_t pos1, pos2, insertion;       /* PEPairs algnmt_1, algnmt_2, insertion */
     uint8_t strand1, mism1, strand2, mism2;
     uint32_t numPairs;                    /* numPEAlgnmt */
-    uint16_t numOptimal, numSuboptimal;   /* num_minMismatch, num_soMinMismatch (CPUfunctions.cpp:2311-2320) */
+    uint32_t numOptimal, numSuboptimal;   /* num_minMismatch, num_soMinMismatch (CPUfunctions.cpp:2311-2320) */
     int8_t optimalTotal, suboptimalTotal; /* totalMismatchCount of the two pairs of PEStatsPEPairList; 127: none */
     uint16_t pad;
 } s3_pe_pair_result;
@@ -449,6 +449,11 @@ int s3_pe_create(s3_index *ix, uint32_t maxReads, uint32_t maxReadLength, const 
 void s3_pe_free(s3_pe *pe);
 int s3_pe_align(s3_pe *pe, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
                 s3_pe_result *out);
+/* Starts the upload of the NEXT batch's queries on a stream of its own and returns at once; the s3_pe_align call that
+ * names the same host arrays finds them on the device.  Called before s3_pe_align of the current batch, the copy runs
+ * under that batch's kernels (the reference double-buffers its batches the same way, alignment.cu:555,1030).  The host
+ * arrays must stay untouched until that s3_pe_align returns (pinned memory for the copy to be asynchronous). */
+int s3_pe_prefetch(s3_pe *pe, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery);
 /* queries / readLengths already in device memory, results left there (two 4-byte counts are all that crosses the link) */
 int s3_pe_align_device(s3_pe *pe, const uint32_t *d_queries, const uint32_t *d_readLengths, uint64_t numReads,
                        uint32_t wordPerQuery, s3_pe_result *out);
@@ -522,6 +527,10 @@ int32_t s3_mapq_of_pair(int score1, int score2);
  *   index slots: 0 straight-line search kernel, 1 enumerating kernel, 2 spine, 3 tasks, 4 merge, 5 isBad carry-over
  *   dp slots:    0 score sweep, 1 best cell, 2 traceback
  * ------------------------------------------------------------------------ */
+/* The memory system's random-sector rate: loadsPerThread independent random 32-byte reads per thread over the index's
+ * forward bucket array (the search's own access pattern), timed on the index stream.  *numLoads / *ms = sectors per
+ * millisecond; what bench.py reports the search launch's executed sectors against. */
+int s3_random_sector_probe(s3_index *ix, uint32_t loadsPerThread, float *ms, uint64_t *numLoads);
 int s3_index_set_timing(s3_index *ix, int on);
 int s3_index_read_timing(s3_index *ix, float *msPerSlot, int *launchesPerSlot);
 int s3_dp_set_timing(s3_dp *dp, int on);

@@ -38,6 +38,8 @@ EXPORTS = [
     "s3_mapq_unique_dp", "s3_mapq_pair_end_dp", "s3_mapq_of_pair", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
+    "s3_dp_align_windows_device", "s3_random_sector_probe",
+    "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
 ]
 
 
@@ -687,8 +689,8 @@ class PEResult(C.Structure):
 
 
 PE_PAIR_DTYPE = np.dtype([("pos1", np.uint32), ("pos2", np.uint32), ("insertion", np.uint32), ("strand1", np.uint8), ("mism1", np.uint8),
-                          ("strand2", np.uint8), ("mism2", np.uint8), ("numPairs", np.uint32), ("numOptimal", np.uint16),
-                          ("numSuboptimal", np.uint16), ("optimalTotal", np.int8), ("suboptimalTotal", np.int8), ("pad", np.uint16)])
+                          ("strand2", np.uint8), ("mism2", np.uint8), ("numPairs", np.uint32), ("numOptimal", np.uint32),
+                          ("numSuboptimal", np.uint32), ("optimalTotal", np.int8), ("suboptimalTotal", np.int8), ("pad", np.uint16)])
 PE_DP_DTYPE = np.dtype([("dpReadID", np.uint32), ("alignedPos", np.uint32), ("dpPos", np.uint32), ("score", np.int32),
                         ("numSameScore", np.uint32), ("runOffset", np.uint32), ("numRuns", np.uint16), ("alignedStrand", np.uint8),
                         ("alignedMismatches", np.uint8), ("dpStrand", np.uint8), ("leftOrRight", np.uint8), ("pad", np.uint8, (2,))])
@@ -736,6 +738,15 @@ class PairAligner:
         l = read_lengths.ctypes.data if hasattr(read_lengths, "ctypes") else int(read_lengths)
         _check(load_library().s3_pe_align(self.handle, C.c_void_p(q), C.c_void_p(l), num_reads, word_per_query, C.byref(res)), "s3_pe_align")
         return self._unpack(res, copy)
+
+    def prefetch(self, queries, read_lengths, num_reads: int, word_per_query: int):
+        """s3_pe_prefetch: start the upload of the next batch (pinned host arrays or raw host addresses)"""
+        lib = load_library()
+        lib.s3_pe_prefetch.restype = C.c_int
+        lib.s3_pe_prefetch.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32]
+        q = queries.ctypes.data if hasattr(queries, "ctypes") else int(queries)
+        l = read_lengths.ctypes.data if hasattr(read_lengths, "ctypes") else int(read_lengths)
+        _check(lib.s3_pe_prefetch(self.handle, C.c_void_p(q), C.c_void_p(l), num_reads, word_per_query), "s3_pe_prefetch")
 
     def align_device(self, d_queries: int, d_read_lengths: int, num_reads: int, word_per_query: int) -> PEResult:
         res = PEResult()

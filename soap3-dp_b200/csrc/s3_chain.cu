@@ -64,7 +64,21 @@ struct s3_pe {
     float msStages[8];
     cudaEvent_t ev[10];
     int timing;
+    // input double buffer of the host entry: the next batch's queries go up on a stream of their own (s3_pe_prefetch)
+    // while the current batch is being aligned
+    uint32_t *d_in[2]; size_t inBytes[2];
+    cudaStream_t copyStream; cudaEvent_t pfDone[2];
+    struct { const uint32_t *queries; uint64_t reads; uint32_t wpq; } pf[2];     // what has been prefetched into d_in[k] and not aligned yet (queries NULL: nothing)
 };
+
+static int pe_input_buffer(s3_pe *pe, int k, size_t bytes, cudaStream_t st)
+{
+    if (bytes <= pe->inBytes[k]) return S3_OK;
+    if (pe->d_in[k]) { S3_TRYC(cudaStreamSynchronize(st)); S3_TRYC(cudaFree(pe->d_in[k])); pe->d_in[k] = NULL; pe->inBytes[k] = 0; }
+    S3_TRYC(cudaMalloc(&pe->d_in[k], bytes));
+    pe->inBytes[k] = bytes;
+    return S3_OK;
+}
 
 // ---- collect (collect_all_answers, CPUfunctions.cpp:1226-1300, round-1 slots only) ------------------------------------
 // One thread per read.  COUNT: ranges and occurrences of the read; FILL: the ranges at rangeOff[read].
@@ -180,69 +194,118 @@ __global__ void s3_pe_locate_kernel(uint32_t numReads, const uint32_t *__restric
 // One thread per pair with both mates hit: the walk's records are not kept, only what hostKernel reads of them
 // (CPUfunctions.cpp:2293-2330): how many valid pairs, the optimal pair, how many pairs share its total, the second total.
 typedef s3_pe_pair_result S3PeBest;            // include/soap3dp_b200.h
-__global__ void s3_pe_pair_kernel(uint32_t numPairs, const uint8_t *__restrict__ route, const uint32_t *__restrict__ locOff,
-                                  const unsigned long long *__restrict__ key, const uint32_t *__restrict__ val,
-                                  const uint8_t *__restrict__ occFlags, const uint32_t *__restrict__ readLengths,
-                                  S3PairParams P, S3PeBest *__restrict__ best)
+// The reference walks the two position-ordered lists as one merge: the element that goes first (list 1 on equal
+// positions) is a left leg and is tried against the other list from that list's cursor.  That cursor is a function of the
+// element alone -- for a list-1 element the first list-2 position >= its own, for a list-2 element the first list-1
+// position > its own -- so the elements are independent: ONE WARP per pair, the lanes take the elements in turn (a pair of
+// tandem-repeat reads has 10^3 x 10^3 candidates; one thread per pair left a 38 ms tail).  What the walk's order decides is
+// rebuilt from an emission key (rank of the left leg in the merge << 32 | partner index): the optimal pair is the first
+// record with the smallest (total mismatches, mismatch difference); PEStatsPEPairList's suboptimal pair is the optimal one
+// it displaced last, i.e. its total is the smallest total among the records emitted before the first record of the final
+// optimal total.
+// flags of the occurrences in sorted order, so that a scan reads two arrays front to back instead of chasing val[]
+__global__ void s3_pe_sorted_flags_kernel(uint32_t n, const uint32_t *__restrict__ val, const uint8_t *__restrict__ occFlags, uint16_t *__restrict__ sflags)
 {
-    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= numPairs) return;
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) sflags[i] = reinterpret_cast<const uint16_t *>(occFlags)[val[i]];          // strand | mismatches << 8
+}
+
+// One group of THREADS threads per pair: a warp for the ordinary pair (HEAVY false: pairs with more than
+// S3_PE_HEAVY_ELEMENTS occurrences are put on a list instead), a whole block for the listed ones (HEAVY true).
+#define S3_PE_PAIR_WARPS 4
+#define S3_PE_HEAVY_ELEMENTS 192u
+template <bool HEAVY>
+__global__ void __launch_bounds__(S3_PE_PAIR_WARPS * 32)
+s3_pe_pair_kernel(uint32_t numPairs, const uint8_t *__restrict__ route, const uint32_t *__restrict__ locOff,
+                  const unsigned long long *__restrict__ key, const uint16_t *__restrict__ sflags,
+                  const uint32_t *__restrict__ readLengths, S3PairParams P, S3PeBest *__restrict__ best,
+                  uint32_t *__restrict__ heavyList, uint32_t *__restrict__ heavyCount)
+{
+    constexpr uint32_t THREADS = HEAVY ? S3_PE_PAIR_WARPS * 32 : 32, GROUPS = S3_PE_PAIR_WARPS * 32 / THREADS;
+    __shared__ uint32_t sStats[GROUPS][16];
+    __shared__ unsigned long long sFirst[GROUPS][16];
+    __shared__ uint32_t sN[GROUPS], sTD[GROUPS];
+    __shared__ unsigned long long sKey[GROUPS];
+    const uint32_t grp = HEAVY ? 0u : threadIdx.x >> 5, t = HEAVY ? threadIdx.x : (threadIdx.x & 31);
+    uint32_t p;
+    if (HEAVY) { if (blockIdx.x >= *heavyCount) return; p = heavyList[blockIdx.x]; }
+    else { p = blockIdx.x * GROUPS + grp; if (p >= numPairs) return; }
     S3PeBest b;
     memset(&b, 0, sizeof b);
     b.optimalTotal = b.suboptimalTotal = 127;
-    if (route[p] != S3_PE_BOTH_HIT) { best[p] = b; return; }
+    if (route[p] != S3_PE_BOTH_HIT) { if (t == 0) best[p] = b; return; }
     const uint32_t a0 = locOff[2 * p], a1 = locOff[2 * p + 1], b1 = locOff[2 * p + 2];
+    if (!HEAVY && b1 - a0 > S3_PE_HEAVY_ELEMENTS) { if (t == 0) heavyList[atomicAdd(heavyCount, 1u)] = p; return; }
     const uint32_t patternLength = readLengths[2 * p + 1];            // pe_in->patternLength = the second read's (CPUfunctions.cpp:2284)
-    // the walk of s3_pair_walk (PEMappingCore PEAlgnmt.cpp:229-291), keeping the optimal record and the histogram only
-    uint16_t stats[32];
-    for (int k = 0; k < 32; ++k) stats[k] = 0;
-    uint32_t n = 0, optCount = 255, optDiff = 255;
-    int subTot = 127;
-    uint32_t i1 = a0, i2 = a1;
-    while (i1 < a1 && i2 < b1) {
-        const uint32_t pa = (uint32_t)key[i1], pb = (uint32_t)key[i2];
-        const bool firstIsLeft = pa <= pb;
-        const uint32_t lv = firstIsLeft ? val[i1] : val[i2];
-        const uint32_t lpos = firstIsLeft ? pa : pb;
-        const uint8_t lstrand = occFlags[2 * (size_t)lv];
-        if (lstrand == P.leftLeg) {
-            const uint32_t end = firstIsLeft ? b1 : a1;
-            for (uint32_t i = firstIsLeft ? i2 : i1; i < end; ++i) {
-                const uint32_t rv = val[i], rpos = (uint32_t)key[i];
-                const uint8_t rstrand = occFlags[2 * (size_t)rv];
-                const uint32_t rightEnd = rpos + patternLength - 1u, gap = rightEnd - lpos + 1u;
-                bool stop = false;
-                if (P.lbound <= gap && gap <= P.ubound && rstrand == P.rightLeg) {
-                    const uint32_t v1 = firstIsLeft ? lv : rv, v2 = firstIsLeft ? rv : lv;
-                    const uint8_t m1 = occFlags[2 * (size_t)v1 + 1], m2 = occFlags[2 * (size_t)v2 + 1];
-                    const int tot = (int8_t)(uint8_t)(m1 + m2);
-                    if (tot >= 0 && tot < 32) stats[tot]++;
-                    int d = (int)(int8_t)m1 - (int)(int8_t)m2;
-                    if ((int8_t)m2 > (int8_t)m1) d = -d;
-                    const bool better = tot < (int)optCount, tie = tot == (int)optCount && d < (int)optDiff;
-                    if (better || tie) {
-                        if (better) subTot = (optCount == 255) ? 127 : (int)optCount;     // the pair it displaces becomes the suboptimal one
-                        optCount = (uint8_t)tot; optDiff = (uint8_t)d;
-                        b.pos1 = firstIsLeft ? lpos : rpos; b.pos2 = firstIsLeft ? rpos : lpos; b.insertion = gap;
-                        b.strand1 = occFlags[2 * (size_t)v1]; b.mism1 = m1; b.strand2 = occFlags[2 * (size_t)v2]; b.mism2 = m2;
-                    }
-                    ++n;
-                    stop = P.reportOne != 0;
-                }
-                if (stop) break;
-                if (lstrand != rstrand && (uint32_t)(lpos + P.ubound) < rightEnd) break;
-            }
+    if (t < 16) { sStats[grp][t] = 0; sFirst[grp][t] = ~0ull; }
+    if (t == 0) { sN[grp] = 0; sTD[grp] = 0xFFFFFFFFu; sKey[grp] = ~0ull; }
+    if (HEAVY) __syncthreads(); else __syncwarp();
+    uint32_t n = 0;
+    uint32_t bestTD = 0xFFFFFFFFu;                  // total << 8 | difference of this thread's best record
+    unsigned long long bestKey = ~0ull;
+    uint32_t bl = 0, br = 0, bgap = 0;
+    uint16_t bfl = 0, bfr = 0;
+    bool bFirstIsLeft = true;
+    for (uint32_t e = a0 + t; e < b1; e += THREADS) {
+        const bool firstIsLeft = e < a1;            // an element of list 1 (the first read's) or of list 2
+        const uint32_t lpos = (uint32_t)key[e];
+        const uint16_t lfl = sflags[e];
+        const uint8_t lstrand = (uint8_t)(lfl & 0xFF);
+        if (lstrand != P.leftLeg) continue;
+        // cursor in the other list, and this element's rank in the merge
+        uint32_t lo = firstIsLeft ? a1 : a0, hi = firstIsLeft ? b1 : a1;
+        while (lo < hi) {
+            const uint32_t mid = (lo + hi) >> 1, mp = (uint32_t)key[mid];
+            if (firstIsLeft ? (mp < lpos) : (mp <= lpos)) lo = mid + 1; else hi = mid;
         }
-        if (firstIsLeft) ++i1; else ++i2;
+        const uint32_t end = firstIsLeft ? b1 : a1;
+        const unsigned long long rank = (unsigned long long)((e - (firstIsLeft ? a0 : a1)) + (lo - (firstIsLeft ? a1 : a0))) << 32;
+        for (uint32_t i = lo; i < end; ++i) {
+            const uint32_t rpos = (uint32_t)key[i];
+            const uint16_t rfl = sflags[i];
+            const uint8_t rstrand = (uint8_t)(rfl & 0xFF);
+            const uint32_t rightEnd = rpos + patternLength - 1u, gap = rightEnd - lpos + 1u;
+            if (P.lbound <= gap && gap <= P.ubound && rstrand == P.rightLeg) {
+                const uint8_t m1 = (uint8_t)((firstIsLeft ? lfl : rfl) >> 8), m2 = (uint8_t)((firstIsLeft ? rfl : lfl) >> 8);
+                const int tot = (int8_t)(uint8_t)(m1 + m2);
+                int d = (int)(int8_t)m1 - (int)(int8_t)m2;
+                if ((int8_t)m2 > (int8_t)m1) d = -d;
+                const unsigned long long k = rank | (i - lo);
+                if (tot >= 0 && tot < 16) { atomicAdd(&sStats[grp][tot], 1u); atomicMin(&sFirst[grp][tot], k); }
+                const uint32_t td = ((uint32_t)(uint8_t)tot << 8) | (uint32_t)(uint8_t)d;
+                if (td < bestTD || (td == bestTD && k < bestKey)) {
+                    bestTD = td; bestKey = k; bl = lpos; br = rpos; bgap = gap; bfl = lfl; bfr = rfl; bFirstIsLeft = firstIsLeft;
+                }
+                ++n;
+            }
+            if (lstrand != rstrand && (uint32_t)(lpos + P.ubound) < rightEnd) break;     // PEIsPairOutOfRange
+        }
     }
-    b.numPairs = n;
-    if (n) {
-        b.optimalTotal = (int8_t)optCount;
-        b.numOptimal = (optCount < 32) ? stats[optCount] : 0;
-        b.suboptimalTotal = (int8_t)subTot;
-        b.numSuboptimal = (subTot >= 0 && subTot < 32) ? stats[subTot] : 0;
+    // the group's records: count, the best (total, difference) and among those the first emitted
+    if (n) atomicAdd(&sN[grp], n);
+    if (bestTD != 0xFFFFFFFFu) atomicMin(&sTD[grp], bestTD);
+    if (HEAVY) __syncthreads(); else __syncwarp();
+    const uint32_t gTD = sTD[grp];
+    if (bestTD == gTD && bestTD != 0xFFFFFFFFu) atomicMin(&sKey[grp], bestKey);
+    if (HEAVY) __syncthreads(); else __syncwarp();
+    const uint32_t nAll = sN[grp];
+    if (nAll == 0) { if (t == 0) best[p] = b; return; }
+    if (bestTD == gTD && bestKey == sKey[grp]) {
+        const int tot = (int)(gTD >> 8);
+        const uint16_t f1 = bFirstIsLeft ? bfl : bfr, f2 = bFirstIsLeft ? bfr : bfl;
+        b.pos1 = bFirstIsLeft ? bl : br; b.pos2 = bFirstIsLeft ? br : bl; b.insertion = bgap;
+        b.strand1 = (uint8_t)(f1 & 0xFF); b.mism1 = (uint8_t)(f1 >> 8);
+        b.strand2 = (uint8_t)(f2 & 0xFF); b.mism2 = (uint8_t)(f2 >> 8);
+        b.numPairs = nAll;
+        b.optimalTotal = (int8_t)tot;
+        b.numOptimal = (tot < 16) ? sStats[grp][tot] : 0;
+        // the optimal pair displaced last: the smallest total emitted before the first record of the final total
+        int sub = 127;
+        if (tot < 16) { for (int u = tot + 1; u < 16; ++u) if (sFirst[grp][u] < sFirst[grp][tot]) { sub = u; break; } }
+        b.suboptimalTotal = (int8_t)sub;
+        b.numSuboptimal = (sub < 16) ? sStats[grp][sub] : 0;
+        best[p] = b;
     }
-    best[p] = b;
 }
 
 // ---- route 2 + windows (CPUfunctions.cpp:2440-2470; HalfEndAlgnBatch::pack DV-DPfunctions.cu:2027-2110) --------------
@@ -367,6 +430,7 @@ __global__ void s3_pe_result_kernel(uint32_t numWindows, const S3PeWindows win, 
     const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
     if (t >= numWindows) return;
     s3_pe_dp_result r;
+    memset(&r, 0, sizeof r);
     const uint32_t o = win.alignedOcc[t];
     r.dpReadID = win.readID[t];
     r.alignedPos = occPos[o];
@@ -405,6 +469,10 @@ extern "C" int s3_pe_create(s3_index *ix, uint32_t maxReads, uint32_t maxReadLen
     s3_dp_set_stream(pe->dp, ix->stream);
     if (cudaMallocHost(&pe->h_counts, 64 * sizeof(uint32_t)) != cudaSuccess) { s3_set_error("s3_pe_create: pinned allocation failed"); s3_pe_free(pe); return S3_ENOMEM; }
     for (int k = 0; k < 10; ++k) if (cudaEventCreate(&pe->ev[k]) != cudaSuccess) { s3_set_error("s3_pe_create: cudaEventCreate failed"); s3_pe_free(pe); return S3_ECUDA; }
+    if (cudaStreamCreateWithFlags(&pe->copyStream, cudaStreamNonBlocking) != cudaSuccess || cudaEventCreateWithFlags(&pe->pfDone[0], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&pe->pfDone[1], cudaEventDisableTiming) != cudaSuccess) {
+        s3_set_error("s3_pe_create: copy stream"); s3_pe_free(pe); return S3_ECUDA;
+    }
     *out = pe;
     return S3_OK;
 }
@@ -421,6 +489,9 @@ extern "C" void s3_pe_free(s3_pe *pe)
     if (pe->pinned) cudaFreeHost(pe->pinned);
     if (pe->h_counts) cudaFreeHost(pe->h_counts);
     for (int k = 0; k < 10; ++k) if (pe->ev[k]) cudaEventDestroy(pe->ev[k]);
+    if (pe->copyStream) { cudaStreamSynchronize(pe->copyStream); cudaStreamDestroy(pe->copyStream); }
+    for (int k = 0; k < 2; ++k) if (pe->pfDone[k]) cudaEventDestroy(pe->pfDone[k]);
+    for (int k = 0; k < 2; ++k) if (pe->d_in[k]) cudaFree(pe->d_in[k]);
     free(pe);
 }
 
@@ -470,8 +541,24 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
                    arena_need(scanTemp, 1) + arena_need(64, 4) + 4096;
     if ((rc = arena_reserve(&pe->A, needA, st))) return rc;
     S3Arena *A = &pe->A;
-    uint32_t *d_q = queriesOnDevice ? const_cast<uint32_t *>(queries) : arena_take<uint32_t>(A, up * wordPerQuery);
-    uint32_t *d_len = queriesOnDevice ? const_cast<uint32_t *>(readLengths) : arena_take<uint32_t>(A, up);
+    uint32_t *d_q = const_cast<uint32_t *>(queries), *d_len = const_cast<uint32_t *>(readLengths);
+    bool uploaded = false;
+    if (!queriesOnDevice) {
+        const size_t inBytes = up * wordPerQuery * 4 + up * 4;
+        int buf = -1;
+        for (int b2 = 0; b2 < 2; ++b2)
+            if (pe->pf[b2].queries == queries && pe->pf[b2].reads == numReads64 && pe->pf[b2].wpq == wordPerQuery) buf = b2;
+        if (buf >= 0) {
+            uploaded = true;
+            S3_TRYC(cudaStreamWaitEvent(st, pe->pfDone[buf], 0));
+            pe->pf[buf].queries = NULL;
+        } else {
+            buf = pe->pf[0].queries ? 1 : 0;                     // a buffer no prefetched batch is waiting in
+            if (pe->pf[buf].queries) { S3_TRYC(cudaStreamSynchronize(pe->copyStream)); pe->pf[buf].queries = NULL; }     // both taken: drop one
+            if ((rc = pe_input_buffer(pe, buf, inBytes, st))) return rc;
+        }
+        d_q = pe->d_in[buf]; d_len = d_q + up * wordPerQuery;
+    }
     uint32_t *d_ans[S3_MAX_NUM_CASES];
     for (uint32_t c = 0; c < C; ++c) d_ans[c] = arena_take<uint32_t>(A, up * wpa);
     uint32_t *d_nRanges = arena_take<uint32_t>(A, N + 1), *d_rangeOff = arena_take<uint32_t>(A, N + 1), *d_totOcc = arena_take<uint32_t>(A, N + 1);
@@ -486,7 +573,7 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     if (!d_counters) { s3_set_error("s3_pe_align: stage buffer accounting"); return S3_ENOMEM; }
 
     PE_MARK(0);
-    if (!queriesOnDevice) {
+    if (!queriesOnDevice && !uploaded) {
         S3_TRYC(cudaMemcpyAsync(d_q, queries, up * wordPerQuery * 4, cudaMemcpyHostToDevice, st));
         S3_TRYC(cudaMemcpyAsync(d_len, readLengths, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     }
@@ -521,7 +608,7 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     // ---- stage 2: locate, pairing, windows
     const size_t Tm = T ? T : 1;
     cub::DeviceRadixSort::SortPairs(NULL, t2, (unsigned long long *)NULL, (unsigned long long *)NULL, (uint32_t *)NULL, (uint32_t *)NULL, (int)Tm, 0, 64, st);
-    size_t needB = arena_need(Tm, 4) + arena_need(Tm, 2) + 2 * arena_need(Tm, 8) + 2 * arena_need(Tm, 4) + arena_need(t2, 1) + arena_need(N + 1, 4) + 4096;
+    size_t needB = arena_need(Tm, 4) + arena_need(Tm, 2) + 2 * arena_need(Tm, 8) + 2 * arena_need(Tm, 4) + arena_need(t2, 1) + arena_need(N + 1, 4) + arena_need(Tm, 2) + arena_need(P + 1, 4) + 4096;
     if ((rc = arena_reserve(&pe->B, needB, st))) return rc;
     S3Arena *B = &pe->B;
     uint32_t *d_occPos = arena_take<uint32_t>(B, Tm);
@@ -530,18 +617,24 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     uint32_t *d_valA = arena_take<uint32_t>(B, Tm), *d_valB = arena_take<uint32_t>(B, Tm);
     void *d_tmp2 = arena_take<char>(B, t2);
     uint32_t *d_winOff = arena_take<uint32_t>(B, N + 1);
-    if (!d_winOff) { s3_set_error("s3_pe_align: stage buffer accounting"); return S3_ENOMEM; }
+    uint16_t *d_sflags = arena_take<uint16_t>(B, Tm);
+    uint32_t *d_heavy = arena_take<uint32_t>(B, P + 1);
+    if (!d_heavy) { s3_set_error("s3_pe_align: stage buffer accounting"); return S3_ENOMEM; }
     if (T) {
         s3_pe_locate_kernel<<<nbR, 256, 0, st>>>(N, ix->loc.sa, d_rangeOff, d_saL, d_saR, d_saFlags, d_keep, d_locOff, d_occPos, d_occFlags, d_keyA, d_valA);
         // ordered by (read, position), ties in arrival order: what PERadixSort leaves of each list (PEAlgnmt.cpp:114-199)
         int endBit = 33;
         while (endBit < 64 && (1ull << (endBit - 32)) < (unsigned long long)N) ++endBit;
         S3_TRYC(cub::DeviceRadixSort::SortPairs(d_tmp2, t2, d_keyA, d_keyB, d_valA, d_valB, (int)T, 0, endBit, st));
-        S3_LAUNCHED(1);
+        s3_pe_sorted_flags_kernel<<<(T + 255) / 256, 256, 0, st>>>(T, d_valB, d_occFlags, d_sflags);
+        S3_LAUNCHED(2);
     }
     PE_MARK(3);
     S3PairParams pp = {(uint32_t)pe->par.insertLow, (uint32_t)pe->par.insertHigh, pe->par.strandLeftLeg, pe->par.strandRightLeg, 0};
-    s3_pe_pair_kernel<<<nbP, 256, 0, st>>>(P, d_route, d_locOff, d_keyB, d_valB, d_occFlags, d_len, pp, d_best);
+    // ordinary pairs a warp each; the few with hundreds of occurrences (tandem repeats) a block each afterwards
+    S3_TRYC(cudaMemsetAsync(d_heavy + P, 0, 4, st));
+    s3_pe_pair_kernel<false><<<(P + S3_PE_PAIR_WARPS - 1) / S3_PE_PAIR_WARPS, S3_PE_PAIR_WARPS * 32, 0, st>>>(P, d_route, d_locOff, d_keyB, d_sflags, d_len, pp, d_best, d_heavy, d_heavy + P);
+    s3_pe_pair_kernel<true><<<(unsigned)(Tm / S3_PE_HEAVY_ELEMENTS + 1), S3_PE_PAIR_WARPS * 32, 0, st>>>(P, d_route, d_locOff, d_keyB, d_sflags, d_len, pp, d_best, d_heavy, d_heavy + P);
     S3PeWinParams wp = {pe->par.insertLow, pe->par.insertHigh, pe->par.strandLeftLeg, pe->par.strandRightLeg, pe->par.softClipLeft, pe->par.softClipRight,
                         pe->par.cutoffThreshold, pe->maxDNALength, ix->textLength, pe->par.maxHitNumForDP};
     S3PeWindows win;
@@ -630,6 +723,26 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     if (pe->timing) {
         for (int s = 0; s < 7; ++s) { float ms = 0; cudaEventElapsedTime(&ms, pe->ev[s], pe->ev[s + 1]); pe->msStages[s] += ms; }
     }
+    return S3_OK;
+}
+
+extern "C" int s3_pe_prefetch(s3_pe *pe, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery)
+{
+    if (!pe || !queries || !readLengths) { s3_set_error("s3_pe_prefetch: NULL argument"); return S3_EINVAL; }
+    if (numReads > pe->maxReads || (numReads & 1) || numReads == 0) { s3_set_error("s3_pe_prefetch: %llu reads (even, 1..%u)", (unsigned long long)numReads, pe->maxReads); return S3_EINVAL; }
+    S3_TRYC(cudaSetDevice(pe->ix->device));
+    const size_t up = ((size_t)numReads + 31) / 32 * 32;
+    // a buffer no prefetched batch is waiting in (s3_pe_align is synchronous, so none is in use by a running call); with both
+    // taken the call does nothing and that batch is uploaded by its s3_pe_align
+    if (pe->pf[0].queries && pe->pf[1].queries) return S3_OK;
+    const int buf = pe->pf[0].queries ? 1 : 0;
+    int rc;
+    if ((rc = pe_input_buffer(pe, buf, up * wordPerQuery * 4 + up * 4, pe->copyStream))) return rc;
+    uint32_t *d_q = pe->d_in[buf];
+    S3_TRYC(cudaMemcpyAsync(d_q, queries, up * wordPerQuery * 4, cudaMemcpyHostToDevice, pe->copyStream));
+    S3_TRYC(cudaMemcpyAsync(d_q + up * wordPerQuery, readLengths, (size_t)numReads * 4, cudaMemcpyHostToDevice, pe->copyStream));
+    S3_TRYC(cudaEventRecord(pe->pfDone[buf], pe->copyStream));
+    pe->pf[buf].queries = queries; pe->pf[buf].reads = numReads; pe->pf[buf].wpq = wordPerQuery;
     return S3_OK;
 }
 

@@ -339,7 +339,7 @@ __device__ __forceinline__ uint32_t s3_bpk(int lo, int hi) { return ((uint32_t)(
 // (3) s3_dp_traceback16_kernel walks that plane.  A traceback that needs a cell left of its window (more than
 //     S3_DP_SLACK deleted bases) puts its alignment on a list; pass 2 re-sweeps those from column 0 into a full-size
 //     plane and traces them again.  Results are those of the full table: a resumed sweep continues from the very
-//     registers of the first one (oracle/dp_oracle.c:dp_one_resweep states the scheme on the CPU).
+//     registers of the first one (the scheme is stated on the CPU by dp_one_resweep of the DP restatement under tests).
 #ifndef S3_DP_CK
 #define S3_DP_CK 32u                 // steps between two checkpoints (a power of two, >= the lanes of a group)
 #endif

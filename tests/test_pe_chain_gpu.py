@@ -135,3 +135,29 @@ def test_pe_chain_empty_and_bad_args(env):
     with pytest.raises(api.S3Error):
         al.align(z, z[:64], 128, 8)                     # more than maxReads
     al.free()
+
+
+def test_pe_prefetch_gives_the_same_batches(env):
+    """s3_pe_prefetch uploads the next batch while the current one is aligned: results of three batches are those of plain calls"""
+    G, idx, hi, gi = env
+    L, pairs = 100, 700
+    wpq = formats.word_per_query(L)
+    n = 2 * pairs
+    sets = []
+    for seed in (21, 22, 23):
+        m1, m2, _ = synth.simulate_paired_end(G, pairs, L, seed=seed, bad_mate_fraction=0.2)
+        reads = torch.stack([m1.reads, m2.reads], dim=1).reshape(n, L).cpu().numpy()
+        lens = np.zeros(formats.ceil32(n), np.uint32)
+        lens[:n] = L
+        sets.append((formats.pack_queries(reads, lens[:n], wpq), lens))
+    al = api.PairAligner(gi, n, L, api.pe_params())
+    plain = [al.align(q, l, n, wpq) for q, l in sets]
+    got = []
+    for k, (q, l) in enumerate(sets):
+        if k + 1 < len(sets):
+            al.prefetch(sets[k + 1][0], sets[k + 1][1], n, wpq)
+        got.append(al.align(q, l, n, wpq))
+    al.free()
+    for a, b in zip(plain, got):
+        for key in ("route", "pairs", "dp", "runs"):
+            assert np.array_equal(a[key], b[key]), key

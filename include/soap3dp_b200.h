@@ -289,6 +289,40 @@ int s3_dp_align_windows_device(s3_dp *dp, s3_index *ix, const uint32_t *d_querie
                                const uint32_t *d_anchorLeftLocs, const uint32_t *d_anchorRightLocs);
 
 /* ------------------------------------------------------------------------
+ * Which windows are aligned.  Replaces the deciding half of the three DP engines' batch packers -- SingleEndAlgnBatch::pack
+ * (DV-DPfunctions.cu:1425-1468), HalfEndAlgnBatch::pack (:2027-2110), PairEndAlgnBatch::packLeft (:3374-3418) and packRight
+ * (:3420-3472) -- for a batch of candidates, on the device: for every candidate the text window, clips, anchors and cutoff
+ * the reference would align it with, in the arrays s3_dp_align_windows takes.  Candidates (numCandidates each):
+ *   S3_WIN_SINGLE      readIDs, positions (estimated read start, s3_seed_candidates), strands                 -> 1 window each
+ *   S3_WIN_HALF        readIDs / positions / strands of the ALIGNED read's occurrences                        -> 0..2 windows each
+ *                      for its mate (readID ^ 1), windows in candidate order (HalfEndOccStream's order)
+ *   S3_WIN_PAIR_LEFT   readIDs = readIDLeft, positions = its estimated start (s3_seed_pair_candidates)         -> 1 window each
+ *   S3_WIN_PAIR_RIGHT  the same candidates with positions2 = the right read's estimated start and the left    -> 0..1 windows each
+ *                      pass's leftScores / leftStarts (its DNAStarts) / leftHitLocs: only candidates whose left
+ *                      read reached its cutoff; window cut at hitPosLeft + insertHigh, right anchor at + insertLow
+ * readLengths is indexed by read id (numReads entries; reads 2p, 2p + 1 are mates).  Outputs hold 2 * numCandidates
+ * entries for S3_WIN_HALF, numCandidates otherwise: outCandidate (index of the candidate a window belongs to), outReadIDs
+ * (the read to align), outStrands (1 as given, 2 reverse-complemented), outLeftOrRight (CandidateInfo.leftOrRight of the
+ * half-end engine), then the arrays of s3_dp_align_windows.  cutoffThreshold < 0 means DEFAULT = ceil(0.3 * read length).
+ * ------------------------------------------------------------------------ */
+#define S3_WIN_SINGLE     1
+#define S3_WIN_HALF       2
+#define S3_WIN_PAIR_LEFT  3
+#define S3_WIN_PAIR_RIGHT 4
+typedef struct {
+    int32_t insertLow, insertHigh, strandLeftLeg, strandRightLeg;
+    int32_t softClipLeft, softClipRight;
+    int32_t cutoffThreshold[2];          /* paramRead[0 / 1]: the even / odd read of a pair */
+    uint32_t maxDNALength;               /* the workspace's maxDNALength: "no left anchor" is stored as this value */
+} s3_window_params;
+int s3_dp_make_windows(s3_index *ix, int mode, const s3_window_params *par, const uint32_t *readLengths, uint64_t numReads,
+                       const uint32_t *readIDs, const uint32_t *positions, const uint32_t *positions2, const uint8_t *strands,
+                       const int32_t *leftScores, const uint32_t *leftStarts, const uint32_t *leftHitLocs, uint64_t numCandidates,
+                       uint32_t *outCandidate, uint32_t *outReadIDs, uint8_t *outStrands, uint8_t *outLeftOrRight,
+                       uint32_t *DNAStarts, uint32_t *DNALengths, uint32_t *clipLtSizes, uint32_t *clipRtSizes,
+                       uint32_t *anchorLeftLocs, uint32_t *anchorRightLocs, int32_t *cutoffThresholds, uint64_t *numWindows);
+
+/* ------------------------------------------------------------------------
  * DP result decoding (host work on the arrays s3_dp_align* returned).  Replaces the result loops
  * of the DP engines' CPU threads (SingleDP_Space::algnmtCPUThread DV-DPfunctions.cu:1699-1733,
  * DP_Space::algnmtCPUThread :2359-2400, DeepDP_Space::DP2CPUAlgnThread :3765-3795) with

@@ -32,9 +32,17 @@ void GPUINDEXUpload ( Soap3Index * index, uint ** _bwt, uint ** _occ, uint ** _r
     BWT * revBwt = index->sraIndex->rev_bwt;
     uint numOcc = ( bwt->textLength + GPU_OCC_INTERVAL - 1 ) / GPU_OCC_INTERVAL + 1;
     s3_index * ix = NULL;
+    // With the packed text and the full suffix array (SaValueFreq = 1, soap3-dp-builder.ini:29: bwt->saValue holds
+    // textLength + 1 rows, BWT.c:254-285) the search finishes single-suffix intervals by comparing the read with the text
+    // (check and extend) and the seed tables' straight-line kernel runs: the path bench.py measures.  A sampled suffix
+    // array (saInterval > 1) keeps the stepping search; answers are identical either way.
+    HSP * hsp = index->sraIndex->hsp;
+    const uint * packedDNA = hsp ? ( const uint * ) hsp->packedDNA : NULL;
+    const uint * sa = ( bwt->saInterval == 1 ) ? ( const uint * ) bwt->saValue : NULL;
+    if ( !packedDNA || !sa ) { packedDNA = NULL; sa = NULL; }
     if ( s3_index_upload ( bwt->bwtCode, index->gpu_occValue, revBwt->bwtCode, index->gpu_revOccValue,
                            numOcc, bwt->inverseSa0, revBwt->inverseSa0, bwt->textLength,
-                           NULL, NULL, s3_current_device (), &ix ) != S3_OK )
+                           packedDNA, sa, s3_current_device (), &ix ) != S3_OK )
     { s3_die ( "GPUINDEXUpload" ); }
     *_bwt = ( uint * ) ix;
     *_occ = *_revBwt = *_revOcc = NULL;
@@ -45,12 +53,35 @@ void GPUINDEXFree ( uint * _bwt, uint * _occ, uint * _revBwt, uint * _revOcc )
     s3_index_free ( ( s3_index * ) _bwt );
 }
 
+// The reference keeps its query and answer buffers in plain malloc'ed memory for the whole run (alignment.cu:689-760) and
+// hands the same pointers to every call: they are page-locked the first time they are seen, so that the copies of every
+// later call run at the link's rate and overlap the kernels.  A buffer that cannot be registered is used as it is.
+#include <map>
+static std::map<const void *, size_t> s3_pinned_buffers;
+static void s3_pin_once ( const void * p, size_t bytes )
+{
+    if ( !p || bytes == 0 ) { return; }
+    std::map<const void *, size_t>::iterator it = s3_pinned_buffers.find ( p );
+    if ( it != s3_pinned_buffers.end () && it->second >= bytes ) { return; }
+    if ( it != s3_pinned_buffers.end () ) { cudaHostUnregister ( ( void * ) p ); s3_pinned_buffers.erase ( it ); }
+    if ( cudaHostRegister ( ( void * ) p, bytes, cudaHostRegisterPortable ) == cudaSuccess ) { s3_pinned_buffers[p] = bytes; }
+    else { cudaGetLastError (); }
+}
+static void s3_pin_round1 ( uint * nextQuery, uint * nextReadLength, uint ** answers, uint numCases, uint wordPerQuery, uint word_per_ans, ullint batchSize )
+{
+    const size_t up = ( ( size_t ) batchSize + 31 ) / 32 * 32;
+    s3_pin_once ( nextQuery, up * wordPerQuery * sizeof ( uint ) );
+    s3_pin_once ( nextReadLength, ( size_t ) batchSize * sizeof ( uint ) );
+    for ( uint c = 0; c < numCases; c++ ) { s3_pin_once ( answers[c], up * word_per_ans * sizeof ( uint ) ); }
+}
+
 // ---- alignment.cu:118 / :329 ---------------------------------------------------------------
 void perform_round1_alignment ( uint * nextQuery, uint * nextReadLength, uint * answers[][MAX_NUM_CASES],
                                 uint numMismatch, uint numCases, uint sa_range_allowed, uint wordPerQuery, uint word_per_ans,
                                 bool isExactNumMismatch, int doubleBufferIdx, uint blocksNeeded, ullint batchSize,
                                 Soap3Index * index, uint * _bwt, uint * _revBwt, uint * _occ, uint * _revOcc )
 {
+    s3_pin_round1 ( nextQuery, nextReadLength, answers[doubleBufferIdx], numCases, wordPerQuery, word_per_ans, batchSize );
     if ( s3_search_round1 ( ( s3_index * ) _bwt, nextQuery, nextReadLength, batchSize, wordPerQuery,
                             numMismatch, numCases, sa_range_allowed, word_per_ans, isExactNumMismatch,
                             answers[doubleBufferIdx] ) != S3_OK )
@@ -62,6 +93,7 @@ void perform_round1_alignment_no_pipeline ( uint * nextQuery, uint * nextReadLen
         bool isExactNumMismatch, uint blocksNeeded, ullint batchSize,
         Soap3Index * index, uint * _bwt, uint * _revBwt, uint * _occ, uint * _revOcc )
 {
+    s3_pin_round1 ( nextQuery, nextReadLength, answers, numCases, wordPerQuery, word_per_ans, batchSize );
     if ( s3_search_round1 ( ( s3_index * ) _bwt, nextQuery, nextReadLength, batchSize, wordPerQuery,
                             numMismatch, numCases, sa_range_allowed, word_per_ans, isExactNumMismatch,
                             answers ) != S3_OK )

@@ -13,6 +13,7 @@
 #   libref_seed_pair.so  findRevStart + pairEndMerge of paired-end DP seeding (DV-DPfunctions.cu:2626-2653,2780-2880)
 #   libref_decode.so   CigarStringEncoder + the result loop of algnmtCPUThread + convertToCigarStr (DV-DPfunctions.h:514-597, .cu:1699-1733, PE.cpp:83-110,420-483)
 #   libref_pair.so     PEMappingOccurrences + PEStatsPEPairList and what they call (PEAlgnmt.cpp:114-361,480-637,777-838)
+#   libref_windows.so  the DP engines' batch packers: SingleEndAlgnBatch::pack, HalfEndAlgnBatch::pack, packLeft / packRight (DV-DPfunctions.cu:1425,2027,3374,3420)
 #   libref_retain.so   retainAllBest / retainAllBestWithCap / retainAllBestAndSecBest + list helpers (SAList.cpp:26-69,140-390)
 #   libref_md.so       getMisInfoForDP (PE.cpp:499-666): MD string, mismatch / gap counts of a DP alignment
 #   shim_check (+ shim_case/)  the drop-in shim linked with a driver written against the reference's headers, and its test case
@@ -141,6 +142,13 @@ echo "[build_ref] libref_mapq.so OK"
 $CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
     "$HERE/ref_shim/ref_retain_host.cpp" -o "$OUT/libref_retain.so"
 echo "[build_ref] libref_retain.so OK"
+
+# ---- reference DP batch packers: which windows, clips, anchors the three engines hand to the kernel --------------
+sed -n '1425,1468p' "$REF/DV-DPfunctions.cu" | sed 's/int SingleEndAlignmentEngine::SingleEndAlgnBatch::pack (/int ref_single_pack (/' > "$OUT/patched/win_single.inc"
+sed -n '2027,2110p' "$REF/DV-DPfunctions.cu" | sed 's/int HalfEndAlignmentEngine::HalfEndAlgnBatch::pack (/int ref_half_pack (/' > "$OUT/patched/win_half.inc"
+sed -n '3374,3472p' "$REF/DV-DPfunctions.cu" | sed 's/int PairEndAlignmentEngine::PairEndAlgnBatch::packLeft (/int ref_pair_packLeft (/; s/void PairEndAlignmentEngine::PairEndAlgnBatch::packRight ()/void ref_pair_packRight ()/' > "$OUT/patched/win_pair.inc"
+$CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" "$HERE/ref_shim/ref_windows_host.cpp" -o "$OUT/libref_windows.so"
+echo "[build_ref] libref_windows.so OK"
 
 # ---- reference stage tables (seed layout, per-stage DP parameters) against the reference's own headers --------
 sed -n '46,260p' "$REF/CPUfunctions.cpp" > "$OUT/patched/params.inc"

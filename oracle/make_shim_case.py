@@ -21,9 +21,13 @@ def save(name, a):
 
 
 G = synth.random_genome(200_000, seed=91, repeat_fraction=0.5, max_divergence=0.02)      # close repeats: slots overflow
-idx = fmindex.build_index(G)
+idx = fmindex.build_index(G, keep_sa=True)
 hi = helpers.HostIndex(idx)
 save("bwt", hi.bwt); save("occ", hi.occ); save("rbwt", hi.rbwt); save("rocc", hi.rocc)
+# hsp->packedDNA and bwt->saValue with SaValueFreq = 1 (row 0 forced to -1 like BWTLoad does, BWT.c:284)
+sa = idx.fwd.sa.cpu().numpy().astype(np.uint32)
+sa[0] = 0xFFFFFFFF
+save("sa", sa); save("pac", idx.packed_text.cpu().numpy().view(np.uint32))
 n, L, k = 2048, 100, 2
 rs = synth.simulate_single_end(G, n, L, seed=7, sub_rate=0.015)
 lens = np.zeros(n, np.uint32)

@@ -4,6 +4,8 @@
  *   retainAllBest            SAList.cpp:140-207
  *   retainAllBestWithCap     SAList.cpp:209-288
  *   retainAllBestAndSecBest  SAList.cpp:290-348
+ * SRAOccurrence.mismatchCount is a uint8_t (2bwt-flex/SRACore.h:86-95; the char version in PEAlgnmt.h is commented out),
+ * so counts >= 128 compare as large, not negative.
  * Pinned against those functions compiled from the reference by oracle/build_ref.sh (libref_retain.so):
  * tests/test_cpu_oracle_vs_ref.py.
  */
@@ -32,11 +34,11 @@ void s3o_retain_best(int mode, int32_t maxNum,
                          outOccFlags[2 * (oBase + newOcc) + 1] = occMism[i]; newOcc++; } while (0)
         if (mode == 2) {
             for (uint64_t i = saOff[r]; i < saOff[r + 1]; ++i) if (saMism[i] < minMatch) minMatch = saMism[i];
-            for (uint64_t i = occOff[r]; i < occOff[r + 1]; ++i) if ((signed char)occMism[i] < minMatch) minMatch = (signed char)occMism[i];
+            for (uint64_t i = occOff[r]; i < occOff[r + 1]; ++i) if ((int)occMism[i] < minMatch) minMatch = (int)occMism[i];
             for (uint64_t i = saOff[r]; i < saOff[r + 1]; ++i)
                 if (saMism[i] <= minMatch + 1) { int c = saR[i] - saL[i] + 1; KEEP_SA(i, c); n += c; }
             for (uint64_t i = occOff[r]; i < occOff[r + 1]; ++i)
-                if ((signed char)occMism[i] <= minMatch + 1) { KEEP_OCC(i); n++; }
+                if ((int)occMism[i] <= minMatch + 1) { KEEP_OCC(i); n++; }
         } else {
             for (uint64_t i = saOff[r]; i < saOff[r + 1]; ++i) {
                 if (saMism[i] < minMatch) {
@@ -54,7 +56,7 @@ void s3o_retain_best(int mode, int32_t maxNum,
                 }
             }
             for (uint64_t i = occOff[r]; i < occOff[r + 1]; ++i) {
-                int mm = (signed char)occMism[i];
+                int mm = (int)occMism[i];
                 if (mm < minMatch) {
                     minMatch = mm;
                     newSa = 0; newOcc = 0;

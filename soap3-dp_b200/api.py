@@ -38,7 +38,7 @@ EXPORTS = [
     "s3_mapq_unique_dp", "s3_mapq_pair_end_dp", "s3_mapq_of_pair", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
-    "s3_dp_align_windows_device", "s3_random_sector_probe",
+    "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows",
     "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
 ]
 
@@ -788,3 +788,44 @@ class PairAligner:
 def runs_to_cigar(runs: np.ndarray) -> str:
     """(length << 8 | op) runs of s3_pe_align -> the special CIGAR string the reference's encoder writes"""
     return "".join(f"{int(r) >> 8}{chr(int(r) & 0xFF)}" for r in runs)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# which windows are aligned (s3_dp_make_windows: the deciding half of the three DP engines' pack() functions)
+# ---------------------------------------------------------------------------------------------------------------------
+WIN_SINGLE, WIN_HALF, WIN_PAIR_LEFT, WIN_PAIR_RIGHT = 1, 2, 3, 4
+
+
+class WindowParams(C.Structure):
+    _fields_ = [("insertLow", C.c_int32), ("insertHigh", C.c_int32), ("strandLeftLeg", C.c_int32), ("strandRightLeg", C.c_int32),
+                ("softClipLeft", C.c_int32), ("softClipRight", C.c_int32), ("cutoffThreshold", C.c_int32 * 2), ("maxDNALength", C.c_uint32)]
+
+
+def make_windows(gpu_index: GpuIndex, mode: int, params: WindowParams, read_lengths, read_ids, positions, strands=None, positions2=None,
+                 left_scores=None, left_starts=None, left_hit_locs=None):
+    """s3_dp_make_windows -> dict(candidate, read_ids, strands, left_or_right, dna_starts, dna_lengths, clip_lt, clip_rt, anchor_l, anchor_r, cutoffs)"""
+    lib = load_library()
+    lib.s3_dp_make_windows.restype = C.c_int
+    lib.s3_dp_make_windows.argtypes = [C.c_void_p, C.c_int, C.POINTER(WindowParams), U32P, C.c_uint64, U32P, U32P, U32P, U8P, I32P, U32P, U32P, C.c_uint64,
+                                       U32P, U32P, U8P, U8P, U32P, U32P, U32P, U32P, U32P, U32P, I32P, U64P]
+    n = len(read_ids)
+    cap = max(2 * n if mode == WIN_HALF else n, 1)
+    u = lambda a: _u32(np.ascontiguousarray(a, np.uint32)) if a is not None else None
+    keep = [np.ascontiguousarray(x, np.uint32) if x is not None else None for x in (read_lengths, read_ids, positions, positions2, left_starts, left_hit_locs)]
+    st = np.ascontiguousarray(strands, np.uint8) if strands is not None else None
+    sc = np.ascontiguousarray(left_scores, np.int32) if left_scores is not None else None
+    o32 = [np.zeros(cap, np.uint32) for _ in range(8)]
+    o8 = [np.zeros(cap, np.uint8) for _ in range(2)]
+    cut = np.zeros(cap, np.int32)
+    m = C.c_uint64()
+    p = lambda a: _u32(a) if a is not None else None
+    _check(lib.s3_dp_make_windows(gpu_index.handle, mode, C.byref(params), p(keep[0]), len(keep[0]), p(keep[1]), p(keep[2]), p(keep[3]),
+                                  st.ctypes.data_as(U8P) if st is not None else None, sc.ctypes.data_as(I32P) if sc is not None else None,
+                                  p(keep[4]), p(keep[5]), n, _u32(o32[0]), _u32(o32[1]), o8[0].ctypes.data_as(U8P), o8[1].ctypes.data_as(U8P),
+                                  _u32(o32[2]), _u32(o32[3]), _u32(o32[4]), _u32(o32[5]), _u32(o32[6]), _u32(o32[7]), cut.ctypes.data_as(I32P),
+                                  C.byref(m)), "s3_dp_make_windows")
+    k = int(m.value)
+    names = ("candidate", "read_ids", "dna_starts", "dna_lengths", "clip_lt", "clip_rt", "anchor_l", "anchor_r")
+    out = {nm: a[:k].copy() for nm, a in zip(names, o32)}
+    out.update(strands=o8[0][:k].copy(), left_or_right=o8[1][:k].copy(), cutoffs=cut[:k].copy())
+    return out

@@ -24,6 +24,7 @@
 // stream-ordered.
 #include "s3_common.cuh"
 #include "s3_pair_walk.cuh"
+#include "s3_windows.cuh"
 #include "../../include/soap3dp_b200.h"
 
 #include <cub/cub.cuh>
@@ -322,14 +323,9 @@ struct S3PeWindows {
     int32_t *cutoff;
 };
 struct S3PeWinParams {
-    int insertLow, insertHigh, leftLeg, rightLeg, softClipLeft, softClipRight, cutoff;     // cutoff < 0: ceil(0.3 * length)
-    uint32_t maxDNALength, textLength, maxHit;
+    S3WinParams w;                   // what HalfEndAlgnBatch::pack decides with (csrc/s3_windows.cuh)
+    uint32_t maxHit;
 };
-__device__ __forceinline__ int s3_pe_cutoff(const S3PeWinParams &w, uint32_t len)
-{
-    // (int) ceil(DP_SCORE_THRESHOLD_RATIO * (double) read_length) with the ratio 0.3 (CPUfunctions.cpp:65)
-    return w.cutoff >= 0 ? w.cutoff : (int)ceil(0.3 * (double)len);
-}
 template <bool FILL>
 __global__ void s3_pe_window_kernel(uint32_t numReads, const uint8_t *__restrict__ route, uint8_t *__restrict__ routeFinal, const S3PeBest *__restrict__ best,
                                     const uint32_t *__restrict__ locOff, const uint32_t *__restrict__ occPos, const uint8_t *__restrict__ occFlags,
@@ -348,39 +344,19 @@ __global__ void s3_pe_window_kernel(uint32_t numReads, const uint8_t *__restrict
     uint32_t n = 0;
     const uint32_t base = FILL ? winOff[r] : 0u;
     if (rescues) {
-        const uint32_t alignedLen = readLengths[r], mate = r ^ 1u, mateLen = readLengths[mate];
-        const bool isDouble = w.leftLeg == w.rightLeg;
-        (void)isDouble;
+        const uint32_t alignedLen = readLengths[r], mateLen = readLengths[r ^ 1u];
         for (uint32_t o = locOff[r]; o < locOff[r + 1]; ++o) {
-            const uint32_t pos = occPos[o];
-            const int strand = occFlags[2 * (size_t)o];
-            for (int side = 0; side < 2; ++side) {
-                // side 0: the aligned read is the left end, its mate lies to the right; side 1: the other way round
-                if (strand != (side == 0 ? w.leftLeg : w.rightLeg)) continue;
-                uint32_t start, stop;
-                if (side == 0) {
-                    stop = pos + (uint32_t)w.insertHigh;
-                    start = pos + (uint32_t)w.insertLow - mateLen;
-                    if (start < pos) start = pos;
-                } else {
-                    start = pos + alignedLen - (uint32_t)w.insertHigh;
-                    stop = pos + alignedLen - (uint32_t)w.insertLow + mateLen;
-                    if (stop >= pos + alignedLen) stop = pos + alignedLen - 1;
+            S3Window x[2];
+            const int k = s3_win_half(w.w, r, occPos[o], occFlags[2 * (size_t)o], alignedLen, mateLen, x);
+            if (FILL)
+                for (int j = 0; j < k; ++j) {
+                    const uint32_t t = base + n + j;
+                    out.alignedOcc[t] = o; out.readID[t] = x[j].readID; out.strand[t] = x[j].strand; out.leftOrRight[t] = x[j].leftOrRight;
+                    out.start[t] = x[j].start; out.dnaLen[t] = x[j].dnaLen; out.readLen[t] = x[j].readLen;
+                    out.clipLt[t] = x[j].clipLt; out.clipRt[t] = x[j].clipRt; out.ancL[t] = x[j].ancL; out.ancR[t] = x[j].ancR;
+                    out.cutoff[t] = x[j].cutoff;
                 }
-                if (!(start < w.textLength && stop <= w.textLength)) continue;
-                if (FILL) {
-                    const uint32_t k = base + n;
-                    const int dpStrand = side == 0 ? w.rightLeg : w.leftLeg;
-                    out.alignedOcc[k] = o; out.readID[k] = mate; out.strand[k] = (uint8_t)dpStrand; out.leftOrRight[k] = side == 0 ? 1 : 0;
-                    out.start[k] = start; out.dnaLen[k] = stop - start; out.readLen[k] = mateLen;
-                    out.clipLt[k] = (uint32_t)(dpStrand == 1 ? w.softClipLeft : w.softClipRight);
-                    out.clipRt[k] = (uint32_t)(dpStrand == 1 ? w.softClipRight : w.softClipLeft);
-                    out.ancL[k] = side == 0 ? w.maxDNALength : (uint32_t)(w.insertHigh - w.insertLow + 1);
-                    out.ancR[k] = side == 0 ? mateLen : 0u;
-                    out.cutoff[k] = s3_pe_cutoff(w, mateLen);
-                }
-                ++n;
-            }
+            n += (uint32_t)k;
         }
     }
     if (!FILL) winCount[r] = n;
@@ -635,8 +611,11 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     S3_TRYC(cudaMemsetAsync(d_heavy + P, 0, 4, st));
     s3_pe_pair_kernel<false><<<(P + S3_PE_PAIR_WARPS - 1) / S3_PE_PAIR_WARPS, S3_PE_PAIR_WARPS * 32, 0, st>>>(P, d_route, d_locOff, d_keyB, d_sflags, d_len, pp, d_best, d_heavy, d_heavy + P);
     s3_pe_pair_kernel<true><<<(unsigned)(Tm / S3_PE_HEAVY_ELEMENTS + 1), S3_PE_PAIR_WARPS * 32, 0, st>>>(P, d_route, d_locOff, d_keyB, d_sflags, d_len, pp, d_best, d_heavy, d_heavy + P);
-    S3PeWinParams wp = {pe->par.insertLow, pe->par.insertHigh, pe->par.strandLeftLeg, pe->par.strandRightLeg, pe->par.softClipLeft, pe->par.softClipRight,
-                        pe->par.cutoffThreshold, pe->maxDNALength, ix->textLength, pe->par.maxHitNumForDP};
+    S3PeWinParams wp;
+    wp.w.insertLow = pe->par.insertLow; wp.w.insertHigh = pe->par.insertHigh; wp.w.leftLeg = pe->par.strandLeftLeg; wp.w.rightLeg = pe->par.strandRightLeg;
+    wp.w.softClipLeft = pe->par.softClipLeft; wp.w.softClipRight = pe->par.softClipRight;
+    wp.w.cutoff[0] = wp.w.cutoff[1] = pe->par.cutoffThreshold; wp.w.maxDNALength = pe->maxDNALength; wp.w.textLength = ix->textLength;
+    wp.maxHit = pe->par.maxHitNumForDP;
     S3PeWindows win;
     memset(&win, 0, sizeof win);
     S3_TRYC(cudaMemsetAsync(d_winCount + N, 0, 4, st));

@@ -262,6 +262,17 @@ static int attach_locate(s3_index *ix, const uint32_t *sa, const uint32_t *packe
     return S3_OK;
 }
 
+// inside s3_index_upload, once the handle exists: a failed call releases what has been allocated so far (the struct is
+// calloc'ed and s3_index_free checks every pointer)
+#define S3_CUDA_IX(call)                                                                \
+    do {                                                                                \
+        cudaError_t e__ = (call);                                                       \
+        if (e__ != cudaSuccess) {                                                       \
+            s3_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); \
+            s3_index_free(ix);                                                          \
+            return S3_ECUDA;                                                            \
+        }                                                                               \
+    } while (0)
 extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const uint32_t *revBwt,
                                const uint32_t *revOcc, uint32_t numOcc, uint32_t inverseSa0,
                                uint32_t revInverseSa0, uint32_t textLength, const uint32_t *packedDNA,
@@ -285,20 +296,20 @@ extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const u
     if (!ix) { s3_set_error("out of host memory"); return S3_ENOMEM; }
     ix->device = device;
     ix->textLength = textLength;
-    S3_CUDA(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
-    S3_CUDA(cudaDeviceGetAttribute(&ix->numSms, cudaDevAttrMultiProcessorCount, device));
+    S3_CUDA_IX(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    S3_CUDA_IX(cudaDeviceGetAttribute(&ix->numSms, cudaDevAttrMultiProcessorCount, device));
     ix->splitBudget = 256;
-    S3_CUDA(cudaMalloc(&ix->d_workCounter, 256));
+    S3_CUDA_IX(cudaMalloc(&ix->d_workCounter, 256));
     ix->searchSmem = (size_t)-1;
     int rc;
     uint32_t nb = 0;
-    if ((rc = upload_half(ix, bwt, occ, numOcc, textLength, &ix->d_fwd, &nb)) != S3_OK) return rc;
+    if ((rc = upload_half(ix, bwt, occ, numOcc, textLength, &ix->d_fwd, &nb)) != S3_OK) { s3_index_free(ix); return rc; }
     ix->fwd.buckets = ix->d_fwd; ix->fwd.inverseSa0 = inverseSa0; ix->fwd.numBuckets = nb;
-    if ((rc = upload_half(ix, revBwt, revOcc, numOcc, textLength, &ix->d_rev, &nb)) != S3_OK) return rc;
+    if ((rc = upload_half(ix, revBwt, revOcc, numOcc, textLength, &ix->d_rev, &nb)) != S3_OK) { s3_index_free(ix); return rc; }
     ix->rev.buckets = ix->d_rev; ix->rev.inverseSa0 = revInverseSa0; ix->rev.numBuckets = nb;
-    if ((rc = build_seed_tables(ix)) != S3_OK) return rc;
+    if ((rc = build_seed_tables(ix)) != S3_OK) { s3_index_free(ix); return rc; }
+    if (packedDNA && sa && (rc = attach_locate(ix, sa, packedDNA, cudaMemcpyHostToDevice)) != S3_OK) { s3_index_free(ix); return rc; }
     *out = ix;
-    if (packedDNA && sa) return attach_locate(ix, sa, packedDNA, cudaMemcpyHostToDevice);
     return S3_OK;
 }
 

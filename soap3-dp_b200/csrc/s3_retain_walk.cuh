@@ -39,7 +39,7 @@ S3_HD uint32_t s3_retain_walk(const S3RetainIn &I, int mode, int32_t maxNum, uin
 {
     int mSa = 999, mOcc = 999;
     for (uint64_t i = s0; i < s1; ++i) if ((int)I.saMism[i] < mSa) mSa = I.saMism[i];
-    for (uint64_t i = o0; i < o1; ++i) if ((int)(int8_t)I.occMism[i] < mOcc) mOcc = (int8_t)I.occMism[i];     // char mismatchCount
+    for (uint64_t i = o0; i < o1; ++i) if ((int)I.occMism[i] < mOcc) mOcc = I.occMism[i];     // uint8_t mismatchCount (2bwt-flex/SRACore.h:86-95)
     uint32_t num = 0, nSa = 0, nOcc = 0;
     if (mode == S3_RETAIN_BEST_AND_SECOND) {
         const int m = mSa < mOcc ? mSa : mOcc;
@@ -49,7 +49,7 @@ S3_HD uint32_t s3_retain_walk(const S3RetainIn &I, int mode, int32_t maxNum, uin
                 num += I.saR[i] - I.saL[i] + 1; ++nSa;
             }
         for (uint64_t i = o0; i < o1; ++i)
-            if ((int)(int8_t)I.occMism[i] <= m + 1) {
+            if ((int)I.occMism[i] <= m + 1) {
                 if (FILL) { O.occPos[occBase + nOcc] = I.occPos[i]; O.occFlags[2 * (occBase + nOcc)] = I.occStrand[i]; O.occFlags[2 * (occBase + nOcc) + 1] = I.occMism[i]; }
                 ++num; ++nOcc;
             }
@@ -70,7 +70,7 @@ S3_HD uint32_t s3_retain_walk(const S3RetainIn &I, int mode, int32_t maxNum, uin
         if (mOcc <= mSa && mOcc != 999) {
             const bool reset = mOcc < mSa;          // the first best occurrence restarts the count at 1, cap or not
             for (uint64_t i = o0; i < o1; ++i) {
-                if ((int)(int8_t)I.occMism[i] != mOcc) continue;
+                if ((int)I.occMism[i] != mOcc) continue;
                 if (cap && !(reset && nOcc == 0) && !(num < (uint32_t)maxNum)) continue;
                 if (FILL) { O.occPos[occBase + nOcc] = I.occPos[i]; O.occFlags[2 * (occBase + nOcc)] = I.occStrand[i]; O.occFlags[2 * (occBase + nOcc) + 1] = I.occMism[i]; }
                 ++num; ++nOcc;

@@ -1235,6 +1235,8 @@ extern "C" int s3_locate(s3_index *ix, const uint32_t *saL, const uint32_t *saR,
     if (numRanges >= 0x7FFFFFFFull || maxPerRange == 0) { s3_set_error("s3_locate: numRanges / maxPerRange out of range"); return S3_EINVAL; }
     *positions = NULL; *total = 0; offsets[0] = 0;
     if (numRanges == 0) return S3_OK;
+    for (uint64_t g = 0; g < numRanges; ++g)
+        if (saR[g] >= saL[g] && saR[g] > ix->textLength) { s3_set_error("s3_locate: range %llu (%u..%u) lies outside the suffix array", (unsigned long long)g, saL[g], saR[g]); return S3_EINVAL; }
     S3_CUDA(cudaSetDevice(ix->device));
     size_t scanTemp = 0;
     cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (unsigned long long *)NULL, (unsigned long long *)NULL, (int)(numRanges + 1), ix->stream);

@@ -87,6 +87,9 @@ extern "C" int s3_seed_candidates(s3_index *ix, const uint32_t *saL, const uint3
     }
     if (!ix->loc.sa) { s3_set_error("s3_seed_candidates: the index was uploaded without its suffix array"); return S3_EINVAL; }
     if (numRanges >= 0x7FFFFFFFull || maxPerRange == 0) { s3_set_error("s3_seed_candidates: numRanges / maxPerRange out of range"); return S3_EINVAL; }
+    // the suffix array has textLength + 1 rows: a stale or overflow-marker answer word passed as a range must not become a read past it
+    for (uint64_t g = 0; g < numRanges; ++g)
+        if (saR[g] >= saL[g] && saR[g] > ix->textLength) { s3_set_error("s3_seed_candidates: range %llu (%u..%u) lies outside the suffix array", (unsigned long long)g, saL[g], saR[g]); return S3_EINVAL; }
     *candReadIDs = *candPositions = NULL; *candStrands = NULL; *numCandidates = 0;
     if (numRanges == 0) return S3_OK;
     if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_seed_candidates: cudaSetDevice failed"); return S3_ECUDA; }
@@ -345,6 +348,8 @@ extern "C" int s3_seed_pair_candidates(s3_index *ix,
         n0 >= 0x7FFFFFF0ull || n1 >= 0x7FFFFFF0ull) { s3_set_error("s3_seed_pair_candidates: argument out of range"); return S3_EINVAL; }
     for (uint64_t g = 0; g < n0; ++g) if (readIDs0[g] >= numReadIDs) { s3_set_error("s3_seed_pair_candidates: read id %u out of range", readIDs0[g]); return S3_EINVAL; }
     for (uint64_t g = 0; g < n1; ++g) if (readIDs1[g] >= numReadIDs) { s3_set_error("s3_seed_pair_candidates: read id %u out of range", readIDs1[g]); return S3_EINVAL; }
+    for (uint64_t g = 0; g < n0; ++g) if (saR0[g] >= saL0[g] && saR0[g] > ix->textLength) { s3_set_error("s3_seed_pair_candidates: range %u..%u lies outside the suffix array", saL0[g], saR0[g]); return S3_EINVAL; }
+    for (uint64_t g = 0; g < n1; ++g) if (saR1[g] >= saL1[g] && saR1[g] > ix->textLength) { s3_set_error("s3_seed_pair_candidates: range %u..%u lies outside the suffix array", saL1[g], saR1[g]); return S3_EINVAL; }
     *candReadIDLeft = *candPosLeft = *candPosRight = NULL; *numCandidates = 0;
     if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_seed_pair_candidates: cudaSetDevice failed"); return S3_ECUDA; }
     int rc = S3_OK;

@@ -466,7 +466,7 @@ def same_pairing(x, y):
 
 
 # ---- best-hit filters on a read's SA-range list and occurrence list (SAList.cpp retainAllBest family) ---------------
-def make_hit_lists(rng, num_reads, max_sa=7, max_occ=7):
+def make_hit_lists(rng, num_reads, max_sa=7, max_occ=7, high_counts=False):
     """per read an SA-range list and an occurrence list in arrival order; either may be empty, mismatch counts 0..4 with
     the minimum on either side or on both, ranges of 1..40 suffixes"""
     n_sa, n_occ = rng.integers(0, max_sa, num_reads), rng.integers(0, max_occ, num_reads)
@@ -475,8 +475,12 @@ def make_hit_lists(rng, num_reads, max_sa=7, max_occ=7):
     ts, to = int(sa_off[-1]), int(occ_off[-1])
     sa_l = rng.integers(0, 1 << 31, ts).astype(np.uint32)
     sa_r = (sa_l + rng.integers(0, 40, ts)).astype(np.uint32)
+    occ_m = rng.integers(0, 5, to).astype(np.uint8)
+    if high_counts:                                        # DP-derived lists may carry other values in the field: counts >= 128 are large, not negative
+        sel = rng.random(to) < 0.3
+        occ_m[sel] = rng.integers(126, 256, int(sel.sum())).astype(np.uint8)
     return (sa_l, sa_r, rng.integers(1, 3, ts).astype(np.uint8), rng.integers(0, 5, ts).astype(np.uint8), sa_off,
-            rng.integers(0, 1 << 32, to).astype(np.uint32), rng.integers(1, 3, to).astype(np.uint8), rng.integers(0, 5, to).astype(np.uint8), occ_off)
+            rng.integers(0, 1 << 32, to).astype(np.uint32), rng.integers(1, 3, to).astype(np.uint8), occ_m, occ_off)
 
 
 _RETAIN_ARGS = None
@@ -548,3 +552,111 @@ def ref_retain_best(lib, lists, mode, max_num=0):
 
 def same_retained(x, y):
     return all(np.array_equal(x[k], y[k]) for k in ("sa_off", "sa_l", "sa_r", "sa_flags", "occ_off", "occ_pos", "occ_flags", "num"))
+
+
+# ---- which windows the DP engines align (oracle/window_oracle.c, oracle/_ref/libref_windows.so) -----------------------
+def oracle_windows_single(lib, rid, pos, strand, lens, text, clip_l, clip_r):
+    """-> [n, 4] start, length, clipLt, clipRt"""
+    lib.s3o_window_single.restype = C.c_int
+    lib.s3o_window_single.argtypes = [C.c_uint32, C.c_uint32, C.c_int, U32P, C.c_uint32, C.c_int, C.c_int, U32P, U32P, U32P, U32P]
+    out = np.zeros((len(rid), 4), np.uint32)
+    v = [C.c_uint32() for _ in range(4)]
+    for c in range(len(rid)):
+        lib.s3o_window_single(int(rid[c]), int(pos[c]), int(strand[c]), u32p(lens), text, clip_l, clip_r, *[C.byref(x) for x in v])
+        out[c] = [x.value for x in v]
+    return out
+
+
+def oracle_windows_half(lib, rid, pos, strand, lens, text, P):
+    """-> candidate index per window, [m, 9] leftOrRight, start, length, readLen, dpStrand, clipLt, clipRt, ancL, ancR"""
+    I32 = C.POINTER(C.c_int)
+    lib.s3o_window_half.restype = C.c_int
+    lib.s3o_window_half.argtypes = [C.c_uint32, C.c_uint32, C.c_int, U32P, C.c_uint32] + [C.c_int] * 7 + [I32, U32P, U32P, U32P, I32, U32P, U32P, U32P, U32P]
+    lor, dps = (C.c_int * 2)(), (C.c_int * 2)()
+    a = [(C.c_uint32 * 2)() for _ in range(7)]
+    cand, rows = [], []
+    for c in range(len(rid)):
+        k = lib.s3o_window_half(int(rid[c]), int(pos[c]), int(strand[c]), u32p(lens), text, P["left"], P["right"], P["ins_high"], P["ins_low"], P["max_dna"],
+                                P["clip_l"], P["clip_r"], lor, a[0], a[1], a[2], dps, a[3], a[4], a[5], a[6])
+        for j in range(k):
+            cand.append(c)
+            rows.append([lor[j], a[0][j], a[1][j], a[2][j], dps[j], a[3][j], a[4][j], a[5][j], a[6][j]])
+    return np.array(cand, np.uint32), (np.array(rows, np.uint32) if rows else np.zeros((0, 9), np.uint32))
+
+
+def oracle_windows_pair_left(lib, rid, pos, lens, text, P):
+    """-> [n, 6] start, length, clipLt, clipRt, ancL, ancR"""
+    lib.s3o_window_pair_left.restype = None
+    lib.s3o_window_pair_left.argtypes = [C.c_uint32, C.c_uint32, U32P, C.c_uint32, C.c_int, C.c_int, C.c_int, C.c_int] + [U32P] * 6
+    v = [C.c_uint32() for _ in range(6)]
+    out = np.zeros((len(rid), 6), np.uint32)
+    for c in range(len(rid)):
+        lib.s3o_window_pair_left(int(rid[c]), int(pos[c]), u32p(lens), text, P["left"], P["max_dna"], P["clip_l"], P["clip_r"], *[C.byref(x) for x in v])
+        out[c] = [x.value for x in v]
+    return out
+
+
+def oracle_windows_pair_right(lib, rid, pos2, lstart, lhit, lens, text, P):
+    """-> [n, 7] right read id, start, length, clipLt, clipRt, ancL, ancR"""
+    lib.s3o_window_pair_right.restype = None
+    lib.s3o_window_pair_right.argtypes = [C.c_uint32] * 4 + [U32P, C.c_uint32] + [C.c_int] * 6 + [U32P] * 7
+    v = [C.c_uint32() for _ in range(7)]
+    out = np.zeros((len(rid), 7), np.uint32)
+    for c in range(len(rid)):
+        lib.s3o_window_pair_right(int(rid[c]), int(pos2[c]), int(lstart[c]), int(lhit[c]), u32p(lens), text, P["right"], P["ins_high"], P["ins_low"],
+                                  P["max_dna"], P["clip_l"], P["clip_r"], *[C.byref(x) for x in v])
+        out[c] = [x.value for x in v]
+    return out
+
+
+def load_ref_windows():
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_windows.so")
+    return C.CDLL(path) if os.path.exists(path) else None
+
+
+def ref_windows_single(lib, rid, pos, strand, lens, text, clip_l, clip_r, cutoff):
+    n = len(rid)
+    I32 = C.POINTER(C.c_int)
+    st = np.ascontiguousarray(strand, np.int32)
+    o = [np.zeros(n, np.uint32) for _ in range(4)]
+    oc = np.zeros(n, np.int32)
+    lens = np.ascontiguousarray(lens, np.uint32)
+    k = lib.ref_windows_single(u32p(np.ascontiguousarray(rid)), u32p(np.ascontiguousarray(pos)), st.ctypes.data_as(I32), n, u32p(lens), text, clip_l, clip_r, cutoff,
+                               u32p(o[0]), u32p(o[1]), u32p(o[2]), u32p(o[3]), oc.ctypes.data_as(I32))
+    assert k == n and (oc == cutoff).all()
+    return np.stack(o, axis=1)
+
+
+def ref_windows_half(lib, rid, pos, strand, lens, text, P, cut0, cut1):
+    n = len(rid)
+    I32 = C.POINTER(C.c_int)
+    U8 = C.POINTER(C.c_uint8)
+    u = [np.zeros(2 * n + 2, np.uint32) for _ in range(8)]
+    lor, cut = np.zeros(2 * n + 2, np.int32), np.zeros(2 * n + 2, np.int32)
+    st = np.ascontiguousarray(strand, np.uint8)
+    lens = np.ascontiguousarray(lens, np.uint32)
+    k = lib.ref_windows_half(u32p(np.ascontiguousarray(rid)), u32p(np.ascontiguousarray(pos)), st.ctypes.data_as(U8), n, u32p(lens), text, P["left"], P["right"],
+                             P["ins_high"], P["ins_low"], P["max_dna"], P["clip_l"], P["clip_r"], cut0, cut1,
+                             u32p(u[0]), lor.ctypes.data_as(I32), u32p(u[1]), u32p(u[2]), u32p(u[3]), u32p(u[4]), u32p(u[5]), u32p(u[6]), u32p(u[7]),
+                             cut.ctypes.data_as(I32))
+    # columns like oracle_windows_half: leftOrRight, start, length, readLen, (dpStrand: not recorded by the packer), clipLt, clipRt, ancL, ancR
+    rows = np.stack([lor[:k].astype(np.uint32), u[1][:k], u[2][:k], u[3][:k], np.zeros(k, np.uint32), u[4][:k], u[5][:k], u[6][:k], u[7][:k]], axis=1)
+    return u[0][:k].copy(), rows, cut[:k].copy()
+
+
+def ref_windows_pair(lib, rid, pos, pos2, lens, text, P, lsc, lhit):
+    """-> left [n, 6] start, length, clipLt, clipRt, ancL, ancR; right [n, 7] start, length, readLen, clipLt, clipRt, ancL, ancR"""
+    n = len(rid)
+    I32 = C.POINTER(C.c_int)
+    L = [np.zeros(n, np.uint32) for _ in range(6)]
+    R = [np.zeros(n, np.uint32) for _ in range(7)]
+    cl, cr = np.zeros(n, np.int32), np.zeros(n, np.int32)
+    lens = np.ascontiguousarray(lens, np.uint32)
+    lsc = np.ascontiguousarray(lsc, np.int32)
+    k = lib.ref_windows_pair(u32p(np.ascontiguousarray(rid)), u32p(np.ascontiguousarray(pos)), u32p(np.ascontiguousarray(pos2)), n, u32p(lens), text,
+                             P["left"], P["right"], P["ins_high"], P["ins_low"], P["max_dna"], P["clip_l"], P["clip_r"], P["cut"][0], P["cut"][1],
+                             u32p(L[0]), u32p(L[1]), u32p(L[2]), u32p(L[3]), u32p(L[4]), u32p(L[5]), cl.ctypes.data_as(I32),
+                             lsc.ctypes.data_as(I32), u32p(np.ascontiguousarray(lhit, np.uint32)),
+                             u32p(R[0]), u32p(R[1]), u32p(R[2]), u32p(R[3]), u32p(R[4]), u32p(R[5]), u32p(R[6]), cr.ctypes.data_as(I32))
+    assert k == n
+    return np.stack(L, axis=1), np.stack(R, axis=1)

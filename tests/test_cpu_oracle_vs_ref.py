@@ -234,6 +234,8 @@ def test_retain_oracle_matches_the_reference_filters():
             got = helpers.oracle_retain_best(lists, mode, cap)
             assert helpers.same_retained(got, want), (mode, cap)
             assert int(want["sa_off"][-1]) > 300 and int(want["occ_off"][-1]) > 300
+            lists = helpers.make_hit_lists(rng, 800, high_counts=True)          # mismatchCount is a uint8_t: 128..255 are large
+            assert helpers.same_retained(helpers.oracle_retain_best(lists, mode, cap), helpers.ref_retain_best(ref, lists, mode, cap)), (mode, cap, "high")
 
 
 def test_dp_without_the_full_table_gives_the_same_alignments():

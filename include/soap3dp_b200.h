@@ -498,6 +498,35 @@ int s3_pe_read_timing(s3_pe *pe, float *msPerStage);
 s3_dp *s3_pe_dp(s3_pe *pe);               /* the chain's DP workspace (for s3_dp_set_timing / s3_dp_read_timing) */
 
 /* ------------------------------------------------------------------------
+ * A batch of single-end reads from queries to occurrences on the device: search (round-1 slots, all cases of the
+ * numMismatch scheme) -> collect -> best hits (optional) -> locate.  The in-memory alignSingleR (soap3-dp-module.h:66-74,
+ * soap3-dp-module.cu:62-181: soap3_dp_single_align with outputFileName == NULL, hostKernel storing occRec records,
+ * CPUfunctions.cpp:1887-1905): occurrences of read r are positions / occFlags [occOffsets[r], occOffsets[r+1]) in the
+ * order collect_all_answers (CPUfunctions.cpp:1226-1300) and transferAllSAToOcc (SAList.cpp:392-419) leave them -- cases
+ * ascending, slots in order, suffix-array order inside a range -- capped at maxOutputPerRead; occFlags hold strand (1 / 2)
+ * and mismatches per occurrence (occRec.strand; occRec.source is 1, occRec.score the mismatch count).  reportBest keeps
+ * the ranges with the fewest mismatches only (retainAllBest, SAList.cpp:140-207).  readFlags[r] bit 0: a round-1 slot of
+ * the read overflowed in some case (isMoreThanSA1: the reference searches it again, s3_search_round2 / s3_search).
+ * Host arrays are the library's (pinned), valid until the next call on the handle.
+ * ------------------------------------------------------------------------ */
+typedef struct s3_se s3_se;
+typedef struct {
+    uint32_t numMismatch;                 /* 0..4 */
+    uint32_t maxOutputPerRead;            /* soap3-dp.ini MaxOutputPerRead */
+    int32_t reportBest;                   /* 0: all valid alignments, 1: all best */
+} s3_se_params;
+typedef struct {
+    uint64_t numReads, numRanges, numOccurrences, h2dBytes, d2hBytes;
+    uint32_t *occOffsets, *positions; uint8_t *occFlags, *readFlags;                  /* host (s3_se_align) */
+    uint32_t *d_occOffsets, *d_positions; uint8_t *d_occFlags, *d_readFlags;          /* device (s3_se_align_device) */
+} s3_se_result;
+int s3_se_create(s3_index *ix, uint32_t maxReads, const s3_se_params *params, s3_se **out);
+void s3_se_free(s3_se *se);
+int s3_se_align(s3_se *se, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery, s3_se_result *out);
+int s3_se_align_device(s3_se *se, const uint32_t *d_queries, const uint32_t *d_readLengths, uint64_t numReads, uint32_t wordPerQuery,
+                       s3_se_result *out);
+
+/* ------------------------------------------------------------------------
  * Tables of the DP stages (host, integer).  s3_seed_layout replaces getSeedPositions
  * (definitions.h:323-442): the seed length and the 0-based seed offsets of a read of readLength
  * bases in a seeding stage -- what a caller cuts out of its reads before s3_search and hands to

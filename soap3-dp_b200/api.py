@@ -40,6 +40,7 @@ EXPORTS = [
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
     "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows",
     "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
+    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device",
 ]
 
 
@@ -829,3 +830,61 @@ def make_windows(gpu_index: GpuIndex, mode: int, params: WindowParams, read_leng
     out = {nm: a[:k].copy() for nm, a in zip(names, o32)}
     out.update(strands=o8[0][:k].copy(), left_or_right=o8[1][:k].copy(), cutoffs=cut[:k].copy())
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# single-end batch on the device (s3_se_*): the in-memory alignSingleR (soap3-dp-module.cu:62)
+# ---------------------------------------------------------------------------------------------------------------------
+class SEParams(C.Structure):
+    _fields_ = [("numMismatch", C.c_uint32), ("maxOutputPerRead", C.c_uint32), ("reportBest", C.c_int32)]
+
+
+class SEResult(C.Structure):
+    _fields_ = [("numReads", C.c_uint64), ("numRanges", C.c_uint64), ("numOccurrences", C.c_uint64), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
+                ("occOffsets", C.c_void_p), ("positions", C.c_void_p), ("occFlags", C.c_void_p), ("readFlags", C.c_void_p),
+                ("d_occOffsets", C.c_void_p), ("d_positions", C.c_void_p), ("d_occFlags", C.c_void_p), ("d_readFlags", C.c_void_p)]
+
+
+class SingleAligner:
+    """s3_se_create / s3_se_align: alignSingleR's results (occurrences per read) for a batch, on the device."""
+
+    def __init__(self, gpu_index: GpuIndex, max_reads: int, num_mismatch: int = 2, max_output_per_read: int = 1000, report_best: bool = False):
+        lib = load_library()
+        lib.s3_se_create.restype = C.c_int
+        lib.s3_se_create.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(SEParams), C.POINTER(C.c_void_p)]
+        lib.s3_se_free.restype = None
+        lib.s3_se_free.argtypes = [C.c_void_p]
+        for fn in (lib.s3_se_align, lib.s3_se_align_device):
+            fn.restype = C.c_int
+            fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(SEResult)]
+        par = SEParams(num_mismatch, max_output_per_read, int(report_best))
+        out = C.c_void_p()
+        _check(lib.s3_se_create(gpu_index.handle, max_reads, C.byref(par), C.byref(out)), "s3_se_create")
+        self.handle = out
+
+    def align(self, queries, read_lengths, num_reads: int, word_per_query: int):
+        res = SEResult()
+        q = queries.ctypes.data if hasattr(queries, "ctypes") else int(queries)
+        l = read_lengths.ctypes.data if hasattr(read_lengths, "ctypes") else int(read_lengths)
+        _check(load_library().s3_se_align(self.handle, C.c_void_p(q), C.c_void_p(l), num_reads, word_per_query, C.byref(res)), "s3_se_align")
+
+        def view(ptr, dtype, n):
+            if not ptr or n == 0:
+                return np.zeros(0, dtype)
+            buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
+            return np.frombuffer(buf, dtype=dtype, count=n).copy()
+        n, t = int(res.numReads), int(res.numOccurrences)
+        return {"occ_offsets": view(res.occOffsets, np.uint32, n + 1), "positions": view(res.positions, np.uint32, t),
+                "occ_flags": view(res.occFlags, np.uint8, 2 * t).reshape(-1, 2), "read_flags": view(res.readFlags, np.uint8, n),
+                "num_ranges": int(res.numRanges), "h2d_bytes": int(res.h2dBytes), "d2h_bytes": int(res.d2hBytes)}
+
+    def align_device(self, d_queries: int, d_read_lengths: int, num_reads: int, word_per_query: int) -> SEResult:
+        res = SEResult()
+        _check(load_library().s3_se_align_device(self.handle, C.c_void_p(d_queries), C.c_void_p(d_read_lengths), num_reads, word_per_query,
+                                                 C.byref(res)), "s3_se_align_device")
+        return res
+
+    def free(self):
+        if self.handle:
+            load_library().s3_se_free(self.handle)
+            self.handle = C.c_void_p(0)

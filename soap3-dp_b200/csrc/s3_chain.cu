@@ -733,3 +733,173 @@ extern "C" int s3_pe_align_device(s3_pe *pe, const uint32_t *d_queries, const ui
 {
     return pe_run(pe, d_queries, d_readLengths, numReads, wordPerQuery, 1, out);
 }
+
+
+// =======================================================================================================================
+// Single-end batch: search -> collect -> (best hits) -> locate.  The in-memory alignSingleR (soap3-dp-module.cu:62-181:
+// soap3_dp_single_align with outputFileName == NULL, hostKernel storing occRec records, CPUfunctions.cpp:1887-1905): per
+// read its occurrences in the order collect_all_answers + transferAllSAToOcc leave them (cases ascending, slots in order,
+// suffix-array order inside a range), capped at MaxOutputPerRead; reportBest keeps the ranges with the fewest mismatches
+// only (retainAllBest, SAList.cpp:140-207, the all-best report type).  Reads whose round-1 slot overflowed in some case
+// are flagged (readFlags bit 0), like S3_PE_OVERFLOW.
+// =======================================================================================================================
+struct s3_se {
+    s3_index *ix;
+    s3_se_params par;
+    uint32_t maxReads;
+    S3Arena A, B;
+    void *pinned; size_t pinnedBytes;
+    uint32_t *h_counts;
+};
+
+// one thread per read: which ranges stay, how many occurrences they hold
+__global__ void s3_se_select_kernel(uint32_t numReads, const uint32_t *__restrict__ rangeOff, const uint32_t *__restrict__ saL,
+                                    const uint32_t *__restrict__ saR, const uint8_t *__restrict__ saFlags, const uint32_t *__restrict__ totOcc,
+                                    int reportBest, uint8_t *__restrict__ keepRange, uint32_t *__restrict__ locCount)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= numReads) return;
+    uint32_t tot = totOcc[r];
+    if (reportBest && tot) {
+        int mn = 999;
+        for (uint32_t g = rangeOff[r]; g < rangeOff[r + 1]; ++g) mn = min(mn, (int)saFlags[2 * (size_t)g + 1]);
+        tot = 0;
+        for (uint32_t g = rangeOff[r]; g < rangeOff[r + 1]; ++g) {
+            const bool keep = (int)saFlags[2 * (size_t)g + 1] == mn;
+            keepRange[g] = keep ? 1 : 0;
+            if (keep) tot += saR[g] - saL[g] + 1;
+        }
+    }
+    locCount[r] = tot;
+}
+
+extern "C" int s3_se_create(s3_index *ix, uint32_t maxReads, const s3_se_params *params, s3_se **out)
+{
+    if (!ix || !params || !out || maxReads == 0) { s3_set_error("s3_se_create: bad argument"); return S3_EINVAL; }
+    if (!ix->loc.sa) { s3_set_error("s3_se_create: the index was uploaded without its suffix array"); return S3_EINVAL; }
+    if (params->numMismatch > 4 || params->maxOutputPerRead == 0) { s3_set_error("s3_se_create: bad parameters"); return S3_EINVAL; }
+    S3_TRYC(cudaSetDevice(ix->device));
+    s3_se *se = (s3_se *)calloc(1, sizeof(s3_se));
+    if (!se) { s3_set_error("out of host memory"); return S3_ENOMEM; }
+    se->ix = ix; se->par = *params; se->maxReads = maxReads;
+    if (cudaMallocHost(&se->h_counts, 16 * sizeof(uint32_t)) != cudaSuccess) { s3_set_error("s3_se_create: pinned allocation failed"); free(se); return S3_ENOMEM; }
+    *out = se;
+    return S3_OK;
+}
+
+extern "C" void s3_se_free(s3_se *se)
+{
+    if (!se) return;
+    cudaSetDevice(se->ix->device);
+    cudaStreamSynchronize(se->ix->stream);
+    if (se->A.base) cudaFree(se->A.base);
+    if (se->B.base) cudaFree(se->B.base);
+    if (se->pinned) cudaFreeHost(se->pinned);
+    if (se->h_counts) cudaFreeHost(se->h_counts);
+    free(se);
+}
+
+static int se_run(s3_se *se, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads64, uint32_t wordPerQuery, int onDevice, s3_se_result *res)
+{
+    if (!se || !queries || !readLengths || !res) { s3_set_error("s3_se_align: NULL argument"); return S3_EINVAL; }
+    memset(res, 0, sizeof *res);
+    if (numReads64 > se->maxReads) { s3_set_error("s3_se_align: %llu reads > maxReads %u", (unsigned long long)numReads64, se->maxReads); return S3_EINVAL; }
+    const uint32_t N = (uint32_t)numReads64;
+    if (N == 0) return S3_OK;
+    s3_index *ix = se->ix;
+    S3_TRYC(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const uint32_t k = se->par.numMismatch, C = kCases[k], allowed = kAllowed[k], wpa = 2 * allowed;
+    const size_t up = ((size_t)N + 31) / 32 * 32, maxRanges = (size_t)N * C * allowed;
+    int rc;
+    size_t scanTemp = 0;
+    cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (uint32_t *)NULL, (uint32_t *)NULL, (int)(N + 1), st);
+    const size_t needA = arena_need(up * wordPerQuery, 4) + arena_need(up, 4) + C * arena_need(up * wpa, 4) + 5 * arena_need(N + 1, 4) + arena_need(N, 1) +
+                         2 * arena_need(maxRanges, 4) + arena_need(maxRanges, 2) + arena_need(maxRanges, 1) + arena_need(scanTemp, 1) + 4096;
+    if ((rc = arena_reserve(&se->A, needA, st))) return rc;
+    S3Arena *A = &se->A;
+    uint32_t *d_q = onDevice ? const_cast<uint32_t *>(queries) : arena_take<uint32_t>(A, up * wordPerQuery);
+    uint32_t *d_len = onDevice ? const_cast<uint32_t *>(readLengths) : arena_take<uint32_t>(A, up);
+    uint32_t *d_ans[S3_MAX_NUM_CASES];
+    for (uint32_t c = 0; c < C; ++c) d_ans[c] = arena_take<uint32_t>(A, up * wpa);
+    uint32_t *d_nRanges = arena_take<uint32_t>(A, N + 1), *d_rangeOff = arena_take<uint32_t>(A, N + 1), *d_totOcc = arena_take<uint32_t>(A, N + 1);
+    uint32_t *d_locCount = arena_take<uint32_t>(A, N + 1), *d_locOff = arena_take<uint32_t>(A, N + 1);
+    uint8_t *d_readFlags = arena_take<uint8_t>(A, N);
+    uint32_t *d_saL = arena_take<uint32_t>(A, maxRanges), *d_saR = arena_take<uint32_t>(A, maxRanges);
+    uint8_t *d_saFlags = arena_take<uint8_t>(A, 2 * maxRanges), *d_keep = arena_take<uint8_t>(A, maxRanges);
+    void *d_tmp = arena_take<char>(A, scanTemp);
+    if (!d_tmp) { s3_set_error("s3_se_align: stage buffer accounting"); return S3_ENOMEM; }
+    if (!onDevice) {
+        S3_TRYC(cudaMemcpyAsync(d_q, queries, up * wordPerQuery * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_len, readLengths, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+    }
+    if ((rc = s3_search_round1_device(ix, d_q, d_len, N, wordPerQuery, k, C, allowed, wpa, 0, d_ans, NULL))) return rc;
+    S3Collect col;
+    memset(&col, 0, sizeof col);
+    for (uint32_t c = 0; c < C; ++c) col.answers[c] = d_ans[c];
+    col.numCases = C; col.allowed = allowed; col.wordPerAns = wpa; col.numReads = N; col.textLength = ix->textLength;
+    col.maxOutputPerRead = se->par.maxOutputPerRead;
+    const unsigned nbR = (N + 255) / 256;
+    S3_TRYC(cudaMemsetAsync(d_nRanges + N, 0, 4, st));
+    s3_pe_collect_kernel<false><<<nbR, 256, 0, st>>>(col, d_nRanges, d_totOcc, d_readFlags, NULL, NULL, NULL, NULL);
+    S3_TRYC(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_nRanges, d_rangeOff, (int)(N + 1), st));
+    s3_pe_collect_kernel<true><<<nbR, 256, 0, st>>>(col, NULL, NULL, NULL, d_rangeOff, d_saL, d_saR, d_saFlags);
+    S3_TRYC(cudaMemsetAsync(d_keep, 1, maxRanges, st));
+    S3_TRYC(cudaMemsetAsync(d_locCount + N, 0, 4, st));
+    s3_se_select_kernel<<<nbR, 256, 0, st>>>(N, d_rangeOff, d_saL, d_saR, d_saFlags, d_totOcc, se->par.reportBest, d_keep, d_locCount);
+    S3_TRYC(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_locCount, d_locOff, (int)(N + 1), st));
+    S3_LAUNCHED(3);
+    S3_TRYC(cudaGetLastError());
+    S3_TRYC(cudaMemcpyAsync(se->h_counts, d_locOff + N, 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaMemcpyAsync(se->h_counts + 1, d_rangeOff + N, 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaStreamSynchronize(st));
+    const uint32_t T = se->h_counts[0];
+    const size_t Tm = T ? T : 1;
+    if ((rc = arena_reserve(&se->B, arena_need(Tm, 4) + arena_need(Tm, 2) + arena_need(Tm, 8) + arena_need(Tm, 4) + 4096, st))) return rc;
+    uint32_t *d_occPos = arena_take<uint32_t>(&se->B, Tm);
+    uint8_t *d_occFlags = arena_take<uint8_t>(&se->B, 2 * Tm);
+    unsigned long long *d_key = arena_take<unsigned long long>(&se->B, Tm);
+    uint32_t *d_val = arena_take<uint32_t>(&se->B, Tm);
+    if (!d_val) { s3_set_error("s3_se_align: stage buffer accounting"); return S3_ENOMEM; }
+    if (T) {
+        s3_pe_locate_kernel<<<nbR, 256, 0, st>>>(N, ix->loc.sa, d_rangeOff, d_saL, d_saR, d_saFlags, d_keep, d_locOff, d_occPos, d_occFlags, d_key, d_val);
+        S3_LAUNCHED(1);
+        S3_TRYC(cudaGetLastError());
+    }
+    res->numReads = N; res->numRanges = se->h_counts[1]; res->numOccurrences = T;
+    if (onDevice) {
+        S3_TRYC(cudaStreamSynchronize(st));
+        res->d_occOffsets = d_locOff; res->d_positions = d_occPos; res->d_occFlags = d_occFlags; res->d_readFlags = d_readFlags;
+        return S3_OK;
+    }
+    const size_t bytes = ((size_t)N + 1) * 4 + 256 + Tm * 4 + 256 + 2 * Tm + 256 + N + 256;
+    if (bytes > se->pinnedBytes) {
+        if (se->pinned) { cudaFreeHost(se->pinned); se->pinned = NULL; se->pinnedBytes = 0; }
+        if (cudaMallocHost(&se->pinned, bytes + bytes / 4) != cudaSuccess) { s3_set_error("s3_se_align: pinned allocation failed"); return S3_ENOMEM; }
+        se->pinnedBytes = bytes + bytes / 4;
+    }
+    char *h = (char *)se->pinned;
+    res->occOffsets = (uint32_t *)h; h += (((size_t)N + 1) * 4 + 255) / 256 * 256;
+    res->positions = (uint32_t *)h; h += (Tm * 4 + 255) / 256 * 256;
+    res->occFlags = (uint8_t *)h; h += (2 * Tm + 255) / 256 * 256;
+    res->readFlags = (uint8_t *)h;
+    S3_TRYC(cudaMemcpyAsync(res->occOffsets, d_locOff, ((size_t)N + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (T) {
+        S3_TRYC(cudaMemcpyAsync(res->positions, d_occPos, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
+        S3_TRYC(cudaMemcpyAsync(res->occFlags, d_occFlags, (size_t)T * 2, cudaMemcpyDeviceToHost, st));
+    }
+    S3_TRYC(cudaMemcpyAsync(res->readFlags, d_readFlags, N, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaStreamSynchronize(st));
+    res->h2dBytes = up * wordPerQuery * 4 + (size_t)N * 4;
+    res->d2hBytes = ((size_t)N + 1) * 4 + (size_t)T * 6 + N + 8;
+    return S3_OK;
+}
+
+extern "C" int s3_se_align(s3_se *se, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery, s3_se_result *out)
+{
+    return se_run(se, queries, readLengths, numReads, wordPerQuery, 0, out);
+}
+extern "C" int s3_se_align_device(s3_se *se, const uint32_t *d_queries, const uint32_t *d_readLengths, uint64_t numReads, uint32_t wordPerQuery, s3_se_result *out)
+{
+    return se_run(se, d_queries, d_readLengths, numReads, wordPerQuery, 1, out);
+}

@@ -161,3 +161,44 @@ def test_pe_prefetch_gives_the_same_batches(env):
     for a, b in zip(plain, got):
         for key in ("route", "pairs", "dp", "runs"):
             assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4])
+def test_se_chain_bit_exact(env, k):
+    """s3_se_align (alignSingleR's results): every read's occurrences == collect_all_answers + transferAllSAToOcc restated on the oracle's slots"""
+    G, idx, hi, gi = env
+    L, n = 100, 3000
+    rs = synth.simulate_single_end(G, n, L, seed=30 + k, sub_rate=0.02)
+    reads = rs.reads.cpu().numpy()
+    wpq = formats.word_per_query(L)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    q = formats.pack_queries(reads, lens[:n], wpq)
+    olib = load_oracle()
+    allowed = formats.SA_RANGES_ROUND1[k]
+    wpa = 2 * allowed
+    bad = np.zeros(formats.ceil32(n), np.uint8)
+    views = []
+    for case in range(formats.NUM_CASES[k]):
+        a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+        oracle_launch(olib, hi, case, q, lens, n, wpq, a, bad, 0, k, allowed, wpa)
+        views.append(formats.answers_view(a, n, wpa))
+    sa = idx.fwd.sa.cpu().numpy()
+    for best, cap in ((False, 1000), (True, 1000), (False, 5)):
+        col = pe_chain_oracle.collect(views, allowed, hi.n, cap)
+        al = api.SingleAligner(gi, n, num_mismatch=k, max_output_per_read=cap, report_best=best)
+        got = al.align(q, lens, n, wpq)
+        al.free()
+        off, hits = 0, 0
+        for r, (ranges, tot, more) in enumerate(col):
+            if best and ranges:
+                ranges, tot = pe_chain_oracle.retain(ranges, False)
+            want = [(int(sa[i]), st, mm) for l, rr, st, mm in ranges for i in range(l, rr + 1)]
+            a, b = int(got["occ_offsets"][r]), int(got["occ_offsets"][r + 1])
+            assert a == off and b - a == len(want), (k, best, cap, r)
+            have = [(int(p), int(f[0]), int(f[1])) for p, f in zip(got["positions"][a:b], got["occ_flags"][a:b])]
+            assert have == want, (k, best, cap, r)
+            assert int(got["read_flags"][r]) == int(more)
+            off = b
+            hits += bool(want)
+        assert hits > n // 20

@@ -557,6 +557,192 @@ def random_sector_rate(gi, device):
     return n.value / (ms.value * 1e-3)
 
 
+def make_se_batch(genome, n, L, seed):
+    rs = synth.simulate_single_end(genome, n, L, seed=seed, sub_rate=0.01)
+    b = Batch()
+    b.n, b.L, b.reads, b.pos, b.strand = n, L, rs.reads, rs.pos, rs.strand
+    b.wpq = formats.word_per_query(L)
+    lens = torch.zeros(formats.ceil32(n), dtype=torch.int32, device=genome.device)
+    lens[:n] = L
+    b.lens = lens
+    b.queries = packing.pack_queries(rs.reads, lens[:n], b.wpq)
+    return b
+
+
+def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream, L, threads, k):
+    """BASELINE config 2: single-end 100 bp reads, <= k mismatches (10 cases at k = 4, both strands), search + answer collection +
+    locate per step through s3_se_align_device / s3_se_align (alignSingleR's results)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    N = 2 * args.pairs
+    total = args.warmup + args.steps
+    batches = [make_se_batch(genome, N, L, seed=300 + 1000 * rank + s) for s in range(total)]
+    wpq = batches[0].wpq
+    se = api.SingleAligner(gi, N, num_mismatch=k, max_output_per_read=1000, report_best=False)
+    ncases = formats.NUM_CASES[k]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(b):
+        return se.align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq)
+    for s in range(args.warmup):
+        device_step(batches[s])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = api.launch_count()
+    stats = []
+    e0.record(stream)
+    for kk in range(args.steps):
+        stats.append(device_step(batches[args.warmup + kk]))
+    e1.record(stream)
+    stream.synchronize()
+    barrier()
+    launches = api.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    tt = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    t_total = float(tt[0])
+    value = world * N * args.steps / t_total
+    api.set_timing(gi.handle, True)
+    device_step(batches[0])
+    barrier()
+    api.read_timing(gi.handle)
+    for kk in range(args.steps):
+        device_step(batches[args.warmup + kk])
+    barrier()
+    ms_search, n_search = api.read_timing(gi.handle)
+    api.set_timing(gi.handle, False)
+
+    def pinned(t):
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        h.copy_(t)
+        return h
+    host_sets = [(pinned(batches[args.warmup + kk].queries), pinned(batches[args.warmup + kk].lens)) for kk in range(args.steps)]
+    for q, l in host_sets[:2]:
+        se.align(q.data_ptr(), l.data_ptr(), N, wpq)
+    barrier()
+    t0 = time.perf_counter()
+    last = None
+    for q, l in host_sets:
+        last = se.align(q.data_ptr(), l.data_ptr(), N, wpq)
+    barrier()
+    te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
+    t_e2e = float(te[0])
+    if rank != 0:
+        return
+    K = args.steps
+    names_s = ["s3_search_easy_kernel", "s3_search_kernel<items>", "s3_search_kernel<spine>", "s3_search_kernel<tasks>",
+               "s3_heavy_merge_kernel", "s3_isbad_fixup_kernel"]
+    kernels = {nm: {"ms_per_step": ms / K, "launches_per_step": cnt / K} for nm, ms, cnt in zip(names_s, ms_search, n_search) if cnt}
+    t_search = sum(ms_search) / 1e3
+    try:
+        sector_rate = random_sector_rate(gi, device)
+    except Exception:                                        # noqa: BLE001
+        sector_rate = None
+    traffic = {}
+    tr_path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tr_path):
+        traffic = json.load(open(tr_path))
+    tkey = f"search_launch_k{k}"
+    roof = {"kernel": f"search launch, k <= {k} ({ncases} cases)", "bound": "hbm", "unit": "G sectors/s", "ms_per_launch": 1e3 * t_search / K,
+            "share_of_step": (t_search / K) / (t_total / K), "peak": sector_rate / 1e9 if sector_rate else None,
+            "peak_source": "s3_random_sector_probe in this run: independent random 32-byte reads over the index's bucket array",
+            "traffic": traffic.get(tkey), "achieved": None, "frac": None}
+    if traffic.get(tkey) and sector_rate:
+        roof["achieved"] = traffic[tkey] / 32.0 / (t_search / K) / 1e9
+        roof["frac"] = roof["achieved"] / roof["peak"]
+    out = {"metric": f"reads/s searched and located (SE {L} bp, <= {k} mismatches, 3.1 Gbp synth ref)", "value": value, "unit": "reads/s", "n_gpus": world,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
+           "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+           "config": {"workload": f"se_{L}bp_k{k}_genome{args.genome_bp}bp: per step and GPU {N} reads through <= {k}-mismatch search ({ncases} cases, both "
+                                  "strands, round-1 slots), answer collection and locate (s3_se_align)",
+                      "genome_bp": args.genome_bp, "repeat_fraction": args.repeat_fraction, "reads_per_step_per_gpu": N,
+                      "timing": "value: K steps back to back, queries resident in HBM (one 8-byte count read per step is part of the chain), CUDA events; "
+                                "e2e: s3_se_align with pinned host queries in, occurrences out, wall clock",
+                      "l2": "inputs larger than L2: the 56 GB index is touched at random, a different read batch every step",
+                      "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"},
+           "clocks": sampler.result(),
+           "e2e": {"value": world * N * args.steps / t_e2e, "unit": "reads/s", "h2d_bytes_per_step": last["h2d_bytes"], "d2h_bytes_per_step": last["d2h_bytes"],
+                   "ms_per_step": 1e3 * t_e2e / args.steps},
+           "gpu_launches": int(launches), "roofline": roof, "kernels": kernels,
+           "pipeline": {"ranges_per_step": float(np.mean([int(r.numRanges) for r in stats])),
+                        "occurrences_per_step": float(np.mean([int(r.numOccurrences) for r in stats])),
+                        "reads_with_a_slot_overflow_per_step": None}}
+    if world == 1 and not args.no_cpu_baseline:
+        import helpers
+        import pe_chain_oracle
+        ref_s = helpers.load_ref_search()
+        n = min(args.cpu_sample // 16, N)
+        b = make_se_batch(genome, n, L, seed=4343)
+        q = b.queries.cpu().numpy().view(np.uint32)
+        lens = b.lens.cpu().numpy().view(np.uint32)
+
+        class HI:
+            pass
+        hi = HI()
+        hi.bwt, hi.occ, hi.rbwt, hi.rocc = host["bwt"], host["occ"], host["rbwt"], host["rocc"]
+        hi.isa0, hi.risa0, hi.n = int(host["meta"][0]), int(host["meta"][1]), int(host["meta"][2])
+        allowed = formats.SA_RANGES_ROUND1[k]
+        wpa = 2 * allowed
+        bad = np.zeros(formats.ceil32(n), np.uint8)
+        views = []
+        qq = q.copy()
+        t0 = time.perf_counter()
+        nrank = 0
+        for case in range(ncases):
+            a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+            if ref_s is not None:
+                nrank += helpers.ref_launch(ref_s, hi, case, qq, lens, n, wpq, a, bad, 0, k, allowed, wpa, nthreads=threads)
+            else:
+                nrank += helpers.oracle_launch(helpers.load_oracle(), hi, case, q, lens, n, wpq, a, bad, 0, k, allowed, wpa)
+            views.append(formats.answers_view(a, n, wpa))
+        t_cpu = time.perf_counter() - t0
+        out["cpu_baseline"] = {"value": n / t_cpu, "unit": "reads/s", "cores": threads if ref_s is not None else 1, "kind": "reference" if ref_s is not None else "port",
+                               "sample": f"{n} reads, <= {k} mismatches, {ncases} cases, both strands: reference kernel sources (DV-Kernel.cu) compiled for the host, OpenMP over reads",
+                               "cpu_model": cpu_model(), "rank_queries_per_read": nrank / n}
+        # parity of the sample through the chain
+        al = api.SingleAligner(gi, n, num_mismatch=k, max_output_per_read=1000, report_best=False)
+        got = al.align(q, lens, n, wpq)
+        al.free()
+        col = pe_chain_oracle.collect(views, allowed, hi.n, 1000)
+        sa = host["sa"]
+        ok, off, located = True, 0, 0
+        for r, (ranges, tot, more) in enumerate(col):
+            a0, a1 = int(got["occ_offsets"][r]), int(got["occ_offsets"][r + 1])
+            want = np.concatenate([sa[l:rr + 1] for l, rr, _, _ in ranges]).astype(np.uint32) if ranges else np.zeros(0, np.uint32)
+            wf = np.array([[st, mm] for l, rr, st, mm in ranges for _ in range(rr - l + 1)], np.uint8).reshape(-1, 2)
+            ok &= a0 == off and a1 - a0 == len(want) and np.array_equal(got["positions"][a0:a1], want) and np.array_equal(got["occ_flags"][a0:a1], wf)
+            ok &= int(got["read_flags"][r]) == int(more)
+            off = a1
+            located += len(want)
+        if not ok:
+            log("SE CHAIN PARITY FAILURE at full size")
+        true_pos = b.pos.cpu().numpy()
+        first = got["occ_offsets"][:-1]
+        has = np.diff(got["occ_offsets"].astype(np.int64)) > 0
+        at_truth = int((np.abs(got["positions"][first[has]].astype(np.int64) - true_pos[has]) <= 0).sum()) if has.any() else 0
+        out["parity_at_full_size"] = {"reads": int(n), "cases": ncases, "occurrences": int(located), "occurrences_bit_exact": bool(ok),
+                                      "reads_with_hits": int(has.sum()), "reads_whose_first_hit_is_the_simulated_position": at_truth,
+                                      "reads_with_a_slot_overflow": int(got["read_flags"].sum()),
+                                      "checker": "oracle/pe_chain_oracle.collect over " + ("the reference's kernels compiled for the host" if ref_s is not None else "the oracle port")}
+        out["pipeline"]["reads_with_a_slot_overflow_per_step"] = float(got["read_flags"].mean() * N)
+    print(json.dumps(out), flush=True)
+    se.free()
+    api.GPUINDEXFree(gi)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -570,6 +756,9 @@ def main():
     ap.add_argument("--parity-pairs", type=int, default=int(os.environ.get("S3_PARITY_PAIRS", 32_768)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--repeat-fraction", type=float, default=float(os.environ.get("S3_REPEAT_FRACTION", 0.2)))
+    ap.add_argument("--config", default="pe100", choices=["pe100", "se100_k4"],
+                    help="pe100 (default): the BASELINE metric's workload (config 4 shape); se100_k4: config 2, single-end 100 bp, <= 4 mismatches, "
+                         "search + collect + locate (s3_se_align).  A 45 %%-repeat genome: --repeat-fraction 0.45")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: the timing rules ask for >= 3 warm-up steps")
@@ -624,6 +813,8 @@ def main():
         f"suffix array + inverse + packed text)")
     stream = torch.cuda.ExternalStream(gi.stream, device=device)
     total = args.warmup + args.steps
+    if args.config == "se100_k4":
+        return run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream, L, threads, k=4)
     t0 = time.time()
     batches = [make_batch(genome, args.pairs, L, seed=100 + 1000 * rank + s) for s in range(total)]
     N, wpq = batches[0].n, batches[0].wpq

@@ -189,6 +189,27 @@ int s3_seed_pair_candidates(s3_index *ix,
                             uint32_t **candReadIDLeft, uint32_t **candPosLeft, uint32_t **candPosRight,
                             uint64_t *numCandidates);
 
+/* ------------------------------------------------------------------------
+ * The seeding driver of the DP stages.  Replaces single_1_mismatch_alignment2 (alignment.cu:1839-1893) with hostKernelSingle's
+ * per-seed bookkeeping (CPUfunctions.cpp:2700-2870): every seed is searched exactly; the seeds without any alignment are
+ * searched again with at most 1 mismatch; a seed keeps its SA ranges (SARecord: saLeft, saRight, strand 1 / 2) when they
+ * hold at most maxHitNum[seed] occurrences, else none (status 4, too many hits; ProceedDPForTooManyHits = 0).  seeds /
+ * seedLengths are a query buffer in the usual layout (QueryParser.cpp:1146-1152) with wordPerSeed words per seed, as the
+ * seeding batches build them (DV-DPfunctions.cu:2655-2680).  Ranges of seed s are [offsets[s], offsets[s+1]) in the
+ * reference's order: cases ascending, enumeration order inside a case.  status[s]: 0 no hit, 1 ranges kept, 4 too many.
+ * The arrays are malloc'ed by the library (s3_seed_search_result_free).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    uint64_t numSeeds, total;
+    uint64_t *offsets;            /* numSeeds + 1 */
+    uint32_t *saL, *saR;          /* total each */
+    uint8_t *strand;              /* total */
+    uint8_t *status;              /* numSeeds */
+} s3_seed_search_result;
+int s3_seed_search(s3_index *ix, const uint32_t *seeds, const uint32_t *seedLengths, uint64_t numSeeds, uint32_t wordPerSeed,
+                   const uint32_t *maxHitNum, s3_seed_search_result *out);
+void s3_seed_search_result_free(s3_seed_search_result *r);
+
 /* Tuning knob, answers are identical for every value.  A (read, case) enumeration that is
  * still running in its lane after `steps` LF-mapping steps is split: the substitution children
  * along the read's own path become independent tasks for other lanes and their ranges are merged

@@ -40,7 +40,7 @@ EXPORTS = [
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
     "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows",
     "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
-    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device",
+    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_seed_search", "s3_seed_search_result_free",
 ]
 
 
@@ -888,3 +888,25 @@ class SingleAligner:
         if self.handle:
             load_library().s3_se_free(self.handle)
             self.handle = C.c_void_p(0)
+
+
+class SeedSearchResult(C.Structure):
+    _fields_ = [("numSeeds", C.c_uint64), ("total", C.c_uint64), ("offsets", U64P), ("saL", U32P), ("saR", U32P), ("strand", U8P), ("status", U8P)]
+
+
+def seed_search(gpu_index: GpuIndex, seeds: np.ndarray, seed_lengths: np.ndarray, num_seeds: int, word_per_seed: int, max_hit_num):
+    """s3_seed_search (single_1_mismatch_alignment2, alignment.cu:1839): -> offsets[numSeeds+1], saL, saR, strand, status[numSeeds]"""
+    lib = load_library()
+    lib.s3_seed_search.restype = C.c_int
+    lib.s3_seed_search.argtypes = [C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32, U32P, C.POINTER(SeedSearchResult)]
+    lib.s3_seed_search_result_free.restype = None
+    lib.s3_seed_search_result_free.argtypes = [C.POINTER(SeedSearchResult)]
+    mh = np.ascontiguousarray(np.broadcast_to(np.asarray(max_hit_num, np.uint32), (max(num_seeds, 1),)))
+    res = SeedSearchResult()
+    _check(lib.s3_seed_search(gpu_index.handle, _u32(seeds), _u32(seed_lengths), num_seeds, word_per_seed, _u32(mh), C.byref(res)), "s3_seed_search")
+    t = int(res.total)
+    cp = lambda p, n, dt: np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt)
+    out = (cp(res.offsets, num_seeds + 1, np.uint64), cp(res.saL, t, np.uint32), cp(res.saR, t, np.uint32), cp(res.strand, t, np.uint8),
+           cp(res.status, num_seeds, np.uint8))
+    lib.s3_seed_search_result_free(C.byref(res))
+    return out

@@ -479,3 +479,96 @@ done:
     for (int a = 0; a < 3; ++a) free(h[a]);
     return rc;
 }
+
+// =====================================================================================================================
+// The seeding driver.  Replaces single_1_mismatch_alignment2 (alignment.cu:1839-1893) with the per-seed bookkeeping of
+// hostKernelSingle (CPUfunctions.cpp:2700-2870) for a batch of seeds: every seed is searched exactly
+// (single_all_valid_seed_alignment with 0 mismatches); the seeds without any alignment -- noAlignment, every case's status
+// word "no hit" (alignment.cu:1643-1661) -- are searched again with 1 mismatch (both cases of that scheme, the "at most"
+// variant like every caller).  A seed keeps its SA ranges when they hold at most maxHitNum occurrences; with more it keeps
+// none and is marked too-many (status 4, ProceedDPForTooManyHits = 0 as shipped).  The reference reaches a seed's complete
+// range list through round 1, round 2 and its CPU search; s3_search enumerates it without caps in the same order (cases
+// ascending, enumeration order inside a case).
+// =====================================================================================================================
+extern "C" void s3_seed_search_result_free(s3_seed_search_result *r)
+{
+    if (!r) return;
+    free(r->offsets); free(r->saL); free(r->saR); free(r->strand); free(r->status);
+    memset(r, 0, sizeof *r);
+}
+
+extern "C" int s3_seed_search(s3_index *ix, const uint32_t *seeds, const uint32_t *seedLengths, uint64_t numSeeds, uint32_t wordPerSeed,
+                              const uint32_t *maxHitNum, s3_seed_search_result *out)
+{
+    if (!out) { s3_set_error("s3_seed_search: NULL result"); return S3_EINVAL; }
+    memset(out, 0, sizeof *out);
+    if (!ix || (numSeeds && (!seeds || !seedLengths || !maxHitNum))) { s3_set_error("s3_seed_search: NULL argument"); return S3_EINVAL; }
+    out->numSeeds = numSeeds;
+    out->offsets = (uint64_t *)calloc(numSeeds + 1, 8);
+    out->status = (uint8_t *)calloc(numSeeds ? numSeeds : 1, 1);
+    if (!out->offsets || !out->status) { s3_seed_search_result_free(out); s3_set_error("s3_seed_search: out of host memory"); return S3_ENOMEM; }
+    if (numSeeds == 0) return S3_OK;
+    int rc;
+    s3_search_result exact, one;
+    memset(&one, 0, sizeof one);
+    if ((rc = s3_search(ix, seeds, seedLengths, numSeeds, wordPerSeed, 0, 0, &exact))) { s3_seed_search_result_free(out); return rc; }
+    // the seeds without an exact alignment, packed like packReads2 (CPUfunctions.cpp:303-338)
+    uint64_t n1 = 0;
+    for (uint64_t s = 0; s < numSeeds; ++s) n1 += exact.offsets[s + 1] == exact.offsets[s];
+    uint32_t *ids1 = NULL, *q1 = NULL, *l1 = NULL;
+    if (n1) {
+        const uint64_t up1 = (n1 + 31) / 32 * 32;
+        ids1 = (uint32_t *)malloc(n1 * 4); q1 = (uint32_t *)calloc(up1 * wordPerSeed, 4); l1 = (uint32_t *)calloc(up1, 4);
+        if (!ids1 || !q1 || !l1) { rc = S3_ENOMEM; s3_set_error("s3_seed_search: out of host memory"); }
+        else {
+            uint64_t k = 0;
+            for (uint64_t s = 0; s < numSeeds; ++s) {
+                if (exact.offsets[s + 1] != exact.offsets[s]) continue;
+                const uint32_t *src = seeds + (s / 32) * 32 * wordPerSeed + s % 32;
+                uint32_t *dst = q1 + (k / 32) * 32 * wordPerSeed + k % 32;
+                for (uint32_t w = 0; w < wordPerSeed; ++w) dst[(size_t)w * 32] = src[(size_t)w * 32];
+                l1[k] = seedLengths[s]; ids1[k] = (uint32_t)s; ++k;
+            }
+            rc = s3_search(ix, q1, l1, n1, wordPerSeed, 1, 0, &one);
+        }
+    }
+    if (rc == S3_OK) {
+        // count, then fill: a seed's ranges come from the pass that found it
+        uint64_t total = 0, k = 0;
+        for (uint64_t s = 0; s < numSeeds; ++s) {
+            const bool second = exact.offsets[s + 1] == exact.offsets[s];
+            const s3_search_result &R = second ? one : exact;
+            const uint64_t a = second ? R.offsets[k] : R.offsets[s], b = second ? R.offsets[k + 1] : R.offsets[s + 1];
+            if (second) ++k;
+            unsigned long long occ = 0;
+            for (uint64_t g = a; g < b; ++g) occ += (unsigned long long)(R.saR[g] - R.saL[g]) + 1;
+            out->offsets[s] = total;
+            if (occ == 0) out->status[s] = 0;
+            else if (occ <= maxHitNum[s]) { out->status[s] = 1; total += b - a; }
+            else out->status[s] = 4;
+        }
+        out->offsets[numSeeds] = total; out->total = total;
+        const uint64_t T = total ? total : 1;
+        out->saL = (uint32_t *)malloc(T * 4); out->saR = (uint32_t *)malloc(T * 4); out->strand = (uint8_t *)malloc(T);
+        if (!out->saL || !out->saR || !out->strand) { rc = S3_ENOMEM; s3_set_error("s3_seed_search: out of host memory"); }
+        else {
+            k = 0;
+            for (uint64_t s = 0; s < numSeeds; ++s) {
+                const bool second = exact.offsets[s + 1] == exact.offsets[s];
+                const s3_search_result &R = second ? one : exact;
+                const uint64_t a = second ? R.offsets[k] : R.offsets[s];
+                if (second) ++k;
+                if (out->status[s] != 1) continue;
+                const uint64_t cnt = out->offsets[s + 1] - out->offsets[s];
+                for (uint64_t g = 0; g < cnt; ++g) {
+                    out->saL[out->offsets[s] + g] = R.saL[a + g]; out->saR[out->offsets[s] + g] = R.saR[a + g];
+                    out->strand[out->offsets[s] + g] = (uint8_t)((R.info[a + g] & 1u) + 1u);          // SARecord.strand 1 / 2
+                }
+            }
+        }
+    }
+    free(ids1); free(q1); free(l1);
+    s3_search_result_free(&exact); s3_search_result_free(&one);
+    if (rc) s3_seed_search_result_free(out);
+    return rc;
+}

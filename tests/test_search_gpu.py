@@ -165,13 +165,13 @@ def test_empty_batch_and_bad_args(env):
         api.perform_round1_alignment(gi, q, lens, 1, 8, 2, num_cases=7, sa_range_allowed=4, word_per_ans=8)
 
 
-@pytest.mark.parametrize("k", [0, 1, 2, 3])
+@pytest.mark.parametrize("k", [0, 1, 2, 3, 4])
 def test_capless_search_is_the_uncapped_slot_sequence(env, k):
     """s3_search (CSR, no caps) == for every read, the cases' slot contents in order when the oracle is given
     slots nothing overflows (1024 ranges per case, no isBad carry-over between the cases)."""
     G, idx, hi, gi = env
     olib = load_oracle()
-    n, L = 1501, 100
+    n, L = (1501, 100) if k < 4 else (701, 100)
     rs = synth.simulate_single_end(G, n, L, seed=300 + k, sub_rate=0.02)
     reads = rs.reads.numpy()
     lens = np.zeros(formats.ceil32(n), np.uint32)
@@ -181,7 +181,7 @@ def test_capless_search_is_the_uncapped_slot_sequence(env, k):
     q = formats.pack_queries(reads, lens[:n], wpq)
     offsets, sa_l, sa_r, info = api.search(gi, q, lens, n, wpq, k)
     assert offsets[0] == 0 and offsets[-1] == len(sa_l) == len(sa_r) == len(info)
-    allowed, wpa = 1024, 2048
+    allowed, wpa = (1024, 2048) if k < 4 else (4096, 8192)
     want = []
     for case in range(formats.NUM_CASES[k]):
         a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
@@ -456,3 +456,43 @@ def test_longest_reads(env):
             gv, wv = formats.answers_view(got[c], n, wpa), formats.answers_view(want[c], n, wpa)
             assert np.array_equal(gv, wv), f"k={k} case={c}: {np.nonzero((gv != wv).any(1))[0][:5]}"
         assert sum(int((formats.answers_view(w, n, wpa)[:, 0] < 0xFFFFFFFD).sum()) for w in want) > 20
+
+
+def test_seed_search_is_the_seeding_driver(env, request):
+    """s3_seed_search == single_1_mismatch_alignment2 restated on the oracle's slots: exact first, 1 mismatch for the seeds
+    without an alignment, ranges dropped beyond maxHitNum occurrences"""
+    import os
+    import sys
+    from helpers import ROOT
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import seeding_oracle
+    G, idx, hi, gi = env
+    olib = load_oracle()
+    n, L = 1800, 26
+    rs = synth.simulate_single_end(G, n, L, seed=77, sub_rate=0.03)
+    reads = rs.reads.numpy()
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    lens[5:n:11] = 22
+    wps = formats.word_per_query(L)
+    q = formats.pack_queries(reads, lens[:n], wps)
+
+    def launcher(qq, ll, m):
+        def run(case, k, allowed, wpa):
+            a = np.zeros(formats.ceil32(max(m, 1)) * wpa, np.uint32)
+            oracle_launch(olib, hi, case, qq, ll, m, wps, a, np.zeros(formats.ceil32(max(m, 1)), np.uint8), 0, k, allowed, wpa)
+            return formats.answers_view(a, m, wpa)
+        return run
+
+    def launch_one(ids):
+        ll = np.zeros(formats.ceil32(max(len(ids), 1)), np.uint32)
+        ll[:len(ids)] = lens[ids]
+        return launcher(formats.pack_queries(reads[ids], lens[ids], wps), ll, len(ids))
+    for max_hit in (2, 40):
+        want = seeding_oracle.seeding_driver(launcher(q, lens, n), launch_one, n, max_hit)
+        offsets, sa_l, sa_r, strand, status = api.seed_search(gi, q, lens, n, wps, max_hit)
+        assert status.tolist() == [w[0] for w in want]
+        for s, (st, ranges) in enumerate(want):
+            a, b = int(offsets[s]), int(offsets[s + 1])
+            assert list(zip(sa_l[a:b].tolist(), sa_r[a:b].tolist(), strand[a:b].tolist())) == ranges, s
+        assert (status == 1).sum() > n // 3 and (status == 4).sum() > 0

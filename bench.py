@@ -813,6 +813,8 @@ def main():
         f"suffix array + inverse + packed text)")
     stream = torch.cuda.ExternalStream(gi.stream, device=device)
     total = args.warmup + args.steps
+    if os.environ.get("S3_L2_REGION"):                        # ncu captures with a window in place (profiles/exp_l2_persist.sh)
+        api.set_l2_persist(gi, int(os.environ["S3_L2_REGION"]))
     if args.config == "se100_k4":
         return run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream, L, threads, k=4)
     t0 = time.time()
@@ -882,6 +884,32 @@ def main():
     api.set_timing(gi.handle, False)
     api.set_timing(pe.dp_handle, False, dp=True)
     pe.set_timing(False)
+
+    # ---- L2 access-policy windows over the index arrays (north_star choice 2), measured: the search launch with each ----
+    l2_exp = None
+    if os.environ.get("S3_L2_EXPERIMENT") and rank == 0:
+        l2_exp = {}
+        names = {0: "none", 1: "forward buckets", 2: "reverse buckets", 3: "seed table fwd1", 4: "seed table rev0", 5: "packed text", 6: "suffix array"}
+        allowed, wpa, ncases = formats.SA_RANGES_ROUND1[K_MISMATCH], 2 * formats.SA_RANGES_ROUND1[K_MISMATCH], formats.NUM_CASES[K_MISMATCH]
+        ans = [torch.empty(formats.ceil32(N) * wpa, dtype=torch.int32, device=device) for _ in range(ncases)]
+        ptrs = [a_.data_ptr() for a_ in ans]
+        for region in (0, 1, 2, 3, 4, 5, 6, 0):
+            api.set_l2_persist(gi, region)
+            api.set_timing(gi.handle, True)
+            b0 = batches[0]
+            api.search_round1_device(gi, b0.queries.data_ptr(), b0.lens.data_ptr(), b0.n, b0.wpq, K_MISMATCH, ncases, allowed, wpa, ptrs, 0)
+            torch.cuda.synchronize()
+            api.read_timing(gi.handle)
+            for kk in range(args.steps):
+                bb = batches[args.warmup + kk]
+                api.search_round1_device(gi, bb.queries.data_ptr(), bb.lens.data_ptr(), bb.n, bb.wpq, K_MISMATCH, ncases, allowed, wpa, ptrs, 0)
+            torch.cuda.synchronize()
+            ms, cnt = api.read_timing(gi.handle)
+            api.set_timing(gi.handle, False)
+            key = names[region] + (" (again)" if region == 0 and "none" in l2_exp else "")
+            l2_exp[key] = {"easy_kernel_ms": ms[0] / args.steps, "enumerator_ms": ms[1] / args.steps, "search_launch_ms": sum(ms) / args.steps}
+        api.set_l2_persist(gi, 0)
+        del ans
 
     # ---- end to end through the host-pointer entry: queries from pinned host memory, results into host memory -----
     def pinned(t):
@@ -1037,6 +1065,8 @@ def main():
         "stages_ms_per_step": stages,
         "kernels": kernels,
     }
+    if l2_exp is not None:
+        out["l2_persistence_experiment"] = l2_exp
     if world == 1 and not args.no_cpu_baseline:
         frac = float(np.mean(windows)) / args.pairs
         t0 = time.time()

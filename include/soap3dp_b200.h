@@ -580,6 +580,60 @@ int s3_dp_stage_parameters(int stage, uint32_t readLength, uint32_t readLength2,
                            s3_dp_stage_params *out);
 
 /* ------------------------------------------------------------------------
+ * The two DP stages that start from seeds, for a batch.  Orchestration of the entries above, like the reference's wrappers:
+ *   s3_single_dp_align  replaces DPForUnalignSingle2 (DV-DPForSingleReads.cu:155; SingleDPWrapper::run :141; the engines
+ *                       SingleEndSeedingEngine / SingleEndAlignmentEngine, DV-DPfunctions.cu:1026-1780) for the reads
+ *                       readIDs[0..n): seeds (s3_seed_layout, stage 1) -> s3_seed_search -> s3_seed_candidates ->
+ *                       s3_dp_make_windows (S3_WIN_SINGLE) -> s3_dp_align_windows -> one s3_dp_hit per candidate that
+ *                       reaches its cutoff (SingleAlgnmtResult, DV-DPfunctions.cu:1699-1733), in candidate order
+ *   s3_deep_dp_align    replaces DPForUnalignPairs2 (DV-DPForBothUnalign.cu:245; DeepDPWrapper::run2 :226, seeding_ext
+ *                       :131-143; PairEndSeedingEngine / PairEndAlignmentEngine, DV-DPfunctions.cu:2571-3800) for the pairs
+ *                       whose even read ids are pairReadIDs[0..n): seeds of both mates (stage 4; stage 5 with its larger hit
+ *                       limit for the pairs that found no candidate and had a seed with too many hits) -> s3_seed_search per
+ *                       side -> s3_seed_pair_candidates -> left window, DP, right window cut by the left hit, DP -> one
+ *                       s3_deep_dp_hit per candidate whose two reads reach their cutoffs (DeepDPAlignResult, :3755-3795)
+ * positions are window start + hitLoc; CIGARs are runs[runOffset .. + numRuns) in read order, each length << 8 | op (the
+ * special CIGAR of CigarStringEncoder).  unseeded lists the reads / pairs without any candidate (the reference's
+ * unseededIDStream).  cutoff: isDefaultThreshold ? ceil(0.3 * read length) : dpScoreThreshold.  The arrays are malloc'ed by
+ * the library (s3_single_dp_result_free / s3_deep_dp_result_free).
+ * ------------------------------------------------------------------------ */
+typedef struct {
+    int32_t insertLow, insertHigh, strandLeftLeg, strandRightLeg;     /* deep DP only */
+    s3_dp_scores scores;
+    int32_t isDefaultThreshold, dpScoreThreshold;                     /* soap3-dp.ini DPScoreThreshold */
+    int32_t softClipLeft, softClipRight;
+} s3_stage_params;
+typedef struct {
+    uint32_t readID, pos;
+    int32_t score;
+    uint32_t numSameScore, runOffset;
+    uint16_t numRuns;
+    uint8_t strand, pad;
+} s3_dp_hit;
+typedef struct {
+    uint64_t numReads, numSeeds, numCandidates, numHits, numRuns, numUnseeded;
+    s3_dp_hit *hits; uint32_t *runs, *unseeded;
+} s3_single_dp_result;
+typedef struct {
+    uint32_t readID;                      /* the pair's even read id */
+    uint32_t pos1, pos2;                  /* algnmt_1 / algnmt_2: of the pair's first read and of its mate */
+    int32_t score1, score2;
+    uint32_t numSame1, numSame2, runOffset1, runOffset2;
+    uint16_t numRuns1, numRuns2;
+    uint8_t strand1, strand2, pad[2];
+} s3_deep_dp_hit;
+typedef struct {
+    uint64_t numPairs, numSeeds, numCandidates, numHits, numRuns, numUnseeded;
+    s3_deep_dp_hit *hits; uint32_t *runs, *unseeded;
+} s3_deep_dp_result;
+int s3_single_dp_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
+                       const uint32_t *readIDs, uint64_t n, const s3_stage_params *par, s3_single_dp_result *out);
+void s3_single_dp_result_free(s3_single_dp_result *r);
+int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
+                     const uint32_t *pairReadIDs, uint64_t n, const s3_stage_params *par, s3_deep_dp_result *out);
+void s3_deep_dp_result_free(s3_deep_dp_result *r);
+
+/* ------------------------------------------------------------------------
  * Mapping qualities (host, scalar).  Replace the MAPQ functions of the SAM writers with their
  * tables (BGS-IO.cpp:33-45, 2280-2580; g_log_n of bwase_initialize, CPUfunctions.cpp:3014-3019
  * is built in).  Argument lists are the reference's, without the g_log_n pointer:
@@ -615,6 +669,11 @@ int32_t s3_mapq_of_pair(int score1, int score2);
  * forward bucket array (the search's own access pattern), timed on the index stream.  *numLoads / *ms = sectors per
  * millisecond; what bench.py reports the search launch's executed sectors against. */
 int s3_random_sector_probe(s3_index *ix, uint32_t loadsPerThread, float *ms, uint64_t *numLoads);
+/* L2 access-policy window over one of the index arrays for the kernels on the index stream (measurement knob; region 0
+ * resets): 1 forward buckets, 2 reverse buckets, 3 seed table fwd1, 4 seed table rev0, 5 packed text, 6 suffix array.
+ * windowBytes 0 = the largest window the device allows, persistBytes 0 = its largest persisting carve-out.  Answers do
+ * not depend on it. */
+int s3_index_set_l2_persist(s3_index *ix, int region, size_t windowBytes, size_t persistBytes);
 int s3_index_set_timing(s3_index *ix, int on);
 int s3_index_read_timing(s3_index *ix, float *msPerSlot, int *launchesPerSlot);
 int s3_dp_set_timing(s3_dp *dp, int on);

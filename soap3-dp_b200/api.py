@@ -38,9 +38,10 @@ EXPORTS = [
     "s3_mapq_unique_dp", "s3_mapq_pair_end_dp", "s3_mapq_of_pair", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
-    "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows",
+    "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows", "s3_index_set_l2_persist",
     "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
     "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_seed_search", "s3_seed_search_result_free",
+    "s3_single_dp_align", "s3_single_dp_result_free", "s3_deep_dp_align", "s3_deep_dp_result_free",
 ]
 
 
@@ -910,3 +911,68 @@ def seed_search(gpu_index: GpuIndex, seeds: np.ndarray, seed_lengths: np.ndarray
            cp(res.status, num_seeds, np.uint8))
     lib.s3_seed_search_result_free(C.byref(res))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the DP stages that start from seeds (DPForUnalignSingle2 / DPForUnalignPairs2)
+# ---------------------------------------------------------------------------------------------------------------------
+class StageParams(C.Structure):
+    _fields_ = [("insertLow", C.c_int32), ("insertHigh", C.c_int32), ("strandLeftLeg", C.c_int32), ("strandRightLeg", C.c_int32), ("scores", DPScores),
+                ("isDefaultThreshold", C.c_int32), ("dpScoreThreshold", C.c_int32), ("softClipLeft", C.c_int32), ("softClipRight", C.c_int32)]
+
+
+DP_HIT_DTYPE = np.dtype([("readID", np.uint32), ("pos", np.uint32), ("score", np.int32), ("numSameScore", np.uint32), ("runOffset", np.uint32),
+                         ("numRuns", np.uint16), ("strand", np.uint8), ("pad", np.uint8)])
+DEEP_HIT_DTYPE = np.dtype([("readID", np.uint32), ("pos1", np.uint32), ("pos2", np.uint32), ("score1", np.int32), ("score2", np.int32),
+                           ("numSame1", np.uint32), ("numSame2", np.uint32), ("runOffset1", np.uint32), ("runOffset2", np.uint32),
+                           ("numRuns1", np.uint16), ("numRuns2", np.uint16), ("strand1", np.uint8), ("strand2", np.uint8), ("pad", np.uint8, (2,))])
+
+
+class _StageResult(C.Structure):
+    _fields_ = [("numIn", C.c_uint64), ("numSeeds", C.c_uint64), ("numCandidates", C.c_uint64), ("numHits", C.c_uint64), ("numRuns", C.c_uint64),
+                ("numUnseeded", C.c_uint64), ("hits", C.c_void_p), ("runs", C.c_void_p), ("unseeded", C.c_void_p)]
+
+
+def stage_params(insert_low=200, insert_high=500, left_leg=1, right_leg=2, scores=(1, -2, -3, -1), default_threshold=True, threshold=0,
+                 soft_clip_left=3, soft_clip_right=8) -> StageParams:
+    return StageParams(insert_low, insert_high, left_leg, right_leg, DPScores(*scores), int(default_threshold), threshold, soft_clip_left, soft_clip_right)
+
+
+def _stage_align(fn_name, free_name, dtype, gpu_index, queries, read_lengths, num_reads, word_per_query, ids, params):
+    lib = load_library()
+    fn, fr = getattr(lib, fn_name), getattr(lib, free_name)
+    fn.restype = C.c_int
+    fn.argtypes = [C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32, U32P, C.c_uint64, C.POINTER(StageParams), C.POINTER(_StageResult)]
+    fr.restype = None
+    fr.argtypes = [C.POINTER(_StageResult)]
+    ids = np.ascontiguousarray(ids, np.uint32)
+    res = _StageResult()
+    _check(fn(gpu_index.handle, _u32(queries), _u32(read_lengths), num_reads, word_per_query, _u32(ids), len(ids), C.byref(params), C.byref(res)), fn_name)
+
+    def view(ptr, dt, n):
+        if not ptr or n == 0:
+            return np.zeros(0, dt)
+        buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
+        return np.frombuffer(buf, dtype=dt, count=n).copy()
+    out = {"hits": view(res.hits, dtype, int(res.numHits)), "runs": view(res.runs, np.uint32, int(res.numRuns)),
+           "unseeded": view(res.unseeded, np.uint32, int(res.numUnseeded)), "num_seeds": int(res.numSeeds), "num_candidates": int(res.numCandidates)}
+    fr(C.byref(res))
+    return out
+
+
+def single_dp_align(gpu_index: GpuIndex, queries, read_lengths, num_reads: int, word_per_query: int, read_ids, params: StageParams):
+    """s3_single_dp_align (DPForUnalignSingle2, DV-DPForSingleReads.cu:155)"""
+    return _stage_align("s3_single_dp_align", "s3_single_dp_result_free", DP_HIT_DTYPE, gpu_index, queries, read_lengths, num_reads, word_per_query, read_ids, params)
+
+
+def deep_dp_align(gpu_index: GpuIndex, queries, read_lengths, num_reads: int, word_per_query: int, pair_read_ids, params: StageParams):
+    """s3_deep_dp_align (DPForUnalignPairs2, DV-DPForBothUnalign.cu:245)"""
+    return _stage_align("s3_deep_dp_align", "s3_deep_dp_result_free", DEEP_HIT_DTYPE, gpu_index, queries, read_lengths, num_reads, word_per_query, pair_read_ids, params)
+
+
+def set_l2_persist(gpu_index: GpuIndex, region: int, window_bytes: int = 0, persist_bytes: int = 0):
+    """s3_index_set_l2_persist (measurement knob): access-policy window over one of the index arrays; region 0 resets"""
+    lib = load_library()
+    lib.s3_index_set_l2_persist.restype = C.c_int
+    lib.s3_index_set_l2_persist.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t]
+    _check(lib.s3_index_set_l2_persist(gpu_index.handle, region, window_bytes, persist_bytes), "s3_index_set_l2_persist")

@@ -423,3 +423,53 @@ extern "C" int s3_random_sector_probe(s3_index *ix, uint32_t loadsPerThread, flo
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_sink);
     return S3_OK;
 }
+
+// ---- L2 access-policy window (measurement knob) --------------------------------------------------------------------
+// Pins a window of one of the index arrays in the persisting part of L2 for the kernels launched on the index stream.
+// region: 0 none (resets), 1 forward buckets, 2 reverse buckets, 3 seed table fwd1, 4 seed table rev0, 5 packed text,
+// 6 suffix array.  windowBytes = 0: as much of the array as the device's largest window allows.  The window's hit ratio
+// is set so that the persisting carve-out (persistBytes, capped at the device's maximum) is not over-subscribed.
+// Nothing in the index is hot -- reads are uniform over the genome, the seed tables replace the top of the BWT -- so this
+// exists to MEASURE that (profiles/), not because the search relies on it.
+extern "C" int s3_index_set_l2_persist(s3_index *ix, int region, size_t windowBytes, size_t persistBytes)
+{
+    if (!ix) { s3_set_error("s3_index_set_l2_persist: NULL index"); return S3_EINVAL; }
+    S3_CUDA(cudaSetDevice(ix->device));
+    S3_CUDA(cudaStreamSynchronize(ix->stream));
+    cudaStreamAttrValue attr;
+    memset(&attr, 0, sizeof attr);
+    if (region == 0) {
+        attr.accessPolicyWindow.num_bytes = 0;
+        S3_CUDA(cudaStreamSetAttribute(ix->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+        S3_CUDA(cudaCtxResetPersistingL2Cache());
+        S3_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, 0));
+        return S3_OK;
+    }
+    const size_t n = ix->textLength;
+    const size_t seedEntries = ix->seed.K ? ((size_t)1 << (2 * ix->seed.K)) : 0;
+    void *base = NULL; size_t bytes = 0;
+    switch (region) {
+    case 1: base = ix->d_fwd; bytes = (size_t)ix->fwd.numBuckets * 32; break;
+    case 2: base = ix->d_rev; bytes = (size_t)ix->rev.numBuckets * 32; break;
+    case 3: base = ix->d_seed[1]; bytes = seedEntries * 8; break;
+    case 4: base = ix->d_seed[2]; bytes = seedEntries * 8; break;
+    case 5: base = ix->d_packedDNA; bytes = (n + 15) / 16 * 4; break;
+    case 6: base = ix->d_sa; bytes = (n + 1) * 4; break;
+    default: s3_set_error("s3_index_set_l2_persist: region %d", region); return S3_EINVAL;
+    }
+    if (!base) { s3_set_error("s3_index_set_l2_persist: the index does not hold region %d", region); return S3_EINVAL; }
+    int maxWindow = 0, maxPersist = 0;
+    S3_CUDA(cudaDeviceGetAttribute(&maxWindow, cudaDevAttrMaxAccessPolicyWindowSize, ix->device));
+    S3_CUDA(cudaDeviceGetAttribute(&maxPersist, cudaDevAttrMaxPersistingL2CacheSize, ix->device));
+    if (windowBytes == 0 || windowBytes > bytes) windowBytes = bytes;
+    if (windowBytes > (size_t)maxWindow) windowBytes = (size_t)maxWindow;
+    if (persistBytes == 0 || persistBytes > (size_t)maxPersist) persistBytes = (size_t)maxPersist;
+    S3_CUDA(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, persistBytes));
+    attr.accessPolicyWindow.base_ptr = base;
+    attr.accessPolicyWindow.num_bytes = windowBytes;
+    attr.accessPolicyWindow.hitRatio = windowBytes <= persistBytes ? 1.0f : (float)((double)persistBytes / (double)windowBytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    S3_CUDA(cudaStreamSetAttribute(ix->stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return S3_OK;
+}

@@ -49,7 +49,10 @@ KEYS = [
 
 
 def raw_page(rep):
-    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    if rep.endswith(".csv"):
+        txt = open(rep).read()
+    else:
+        txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(txt)))
     hdr, units = rows[0], rows[1]
     return [OrderedDict((h, (v, u)) for h, v, u in zip(hdr, r, units)) for r in rows[2:]]
@@ -72,7 +75,7 @@ def short(name):
 def main():
     tag = sys.argv[1]
     md = [f"# ncu summary `{tag}`", "",
-          f"Produced by `profiles/gpu_session.sh {tag}` on one B200 (through gpurun) and "
+          f"Produced by `profiles/gpu_session.sh {tag}` (round 2: `profiles/gpu_session_r2.sh {tag}`) on one B200 (through gpurun) and "
           f"`profiles/summarize.py {tag}` here.  Launch times under ncu are cold-cache and serialised: "
           "compare SHARES with the CUDA-event numbers of the bench line, not absolutes.", ""]
     bj = os.path.join(OUT, f"{tag}_bench.json")
@@ -97,7 +100,7 @@ def main():
             a = agg.setdefault(short(k), [0, 0.0])
             a[0] += 1
             a[1] += ns
-        upload = ("relayout", "seed_build", "s3_isa_kernel", "search_kernel<1")      # index upload and the rank-count pass
+        upload = ("relayout", "seed_build", "s3_isa_kernel", "search_kernel<1", "random_sector")      # index upload, the rank-count pass, the probe
         tot = sum(v[1] for k, v in agg.items() if not any(u in k for u in upload))
         md += ["## launch list (`ncu --metrics gpu__time_duration.sum`, bench.py --steps 2 --warmup 1)", "",
                "| kernel | launches | avg ms | share of the steps' kernel time (index upload and the rank-count pass excluded) |", "|---|---|---|---|"]
@@ -112,6 +115,41 @@ def main():
             tot += float(v.replace(",", "")) * {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
         return tot
     traffic = {"capture": tag, "unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum)"}
+    # round 2: one capture of a whole chain step, and the search launch of config 2
+    for what, key in (("chain", None), ("search_k4", "search_launch_k4")):
+        rep = os.path.join(OUT, f"{tag}_{what}.ncu-rep")
+        if not os.path.exists(rep):
+            rep = os.path.join(OUT, f"{tag}_{what}_raw.csv")          # the session leaves the raw page as CSV (the reports are too big to bring back)
+        if not os.path.exists(rep):
+            continue
+        md += [f"## `ncu --set full` : {what} (one step; launches of one kernel summed)", ""]
+        pages = raw_page(rep)
+        per = OrderedDict()
+        for d in pages:
+            nm = short(d['Kernel Name'][0])
+            nm = nm.split("<")[0] + ("<" + nm.split("<")[1] if "search_kernel<" in nm else "")
+            per.setdefault(nm, []).append(d)
+        if key:
+            traffic[key] = sum(gbytes(d) for d in pages)
+        else:
+            for nm, ds in per.items():
+                traffic[nm] = sum(gbytes(d) for d in ds)
+            traffic["search_launch"] = sum(gbytes(d) for d in pages if any(x in d['Kernel Name'][0] for x in ("s3_search", "s3_heavy", "s3_isbad")))
+            traffic["chain_step"] = sum(gbytes(d) for d in pages)
+        md += ["| kernel | launches | ms (under ncu) | DRAM read + write | L2 hit rate | registers | warp instructions | issue slots busy % | ALU pipe % | top stalls |",
+               "|---|---|---|---|---|---|---|---|---|---|"]
+        for nm, ds in per.items():
+            d = max(ds, key=lambda x: float(x["gpu__time_duration.sum"][0].replace(",", "")))
+            scale = {"nsecond": 1e-6, "ns": 1e-6, "usecond": 1e-3, "us": 1e-3, "msecond": 1.0, "ms": 1.0, "second": 1e3, "s": 1e3}
+            ms = sum(float(x["gpu__time_duration.sum"][0].replace(",", "")) * scale.get(x["gpu__time_duration.sum"][1], 1e-6) for x in ds)
+            stalls = [(k.split("stalled_")[1].replace("_per_issue_active.ratio", ""), float(v[0] or 0))
+                      for k, v in d.items() if "issue_stalled" in k and k.endswith("per_issue_active.ratio")]
+            stalls.sort(key=lambda x: -x[1])
+            g = lambda k: d[k][0] if k in d else "-"
+            md.append(f"| `{nm}` | {len(ds)} | {ms:.3f} | {sum(gbytes(x) for x in ds) / 1e9:.3f} GB | {g('lts__t_sector_hit_rate.pct')} | {g('launch__registers_per_thread')} | "
+                      f"{g('smsp__inst_executed.sum')} | {g('sm__issue_active.avg.pct_of_peak_sustained_elapsed')} | {g('sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active')} | "
+                      + ", ".join(f"{k} {v:.2f}" for k, v in stalls[:4]) + " |")
+        md.append("")
     for what in ("search", "dp"):
         rep = os.path.join(OUT, f"{tag}_{what}.ncu-rep")
         if not os.path.exists(rep):
@@ -133,6 +171,15 @@ def main():
             stalls.sort(key=lambda x: -x[1])
             md.append("| top stall reasons (warps per issue) | " + ", ".join(f"{k} {v:.2f}" for k, v in stalls[:5]) + " |")
             md.append("")
+    if os.path.exists(bj) and os.path.getsize(bj):
+        b = json.loads(open(bj).read().strip().splitlines()[-1])
+        if b.get("l2_persistence_experiment"):
+            md += ["## L2 access-policy windows over the index arrays (`S3_L2_EXPERIMENT=1`, CUDA events, 5 search launches each)", "",
+                   "| window (largest the device allows, persisting carve-out at its maximum) | straight-line kernel ms | enumerator ms | search launch ms |", "|---|---|---|---|"]
+            for k, v in b["l2_persistence_experiment"].items():
+                md.append(f"| {k} | {v['easy_kernel_ms']:.3f} | {v['enumerator_ms']:.3f} | {v['search_launch_ms']:.3f} |")
+            md += ["", "No window changes the launch by more than its run-to-run spread: reads are uniform over the genome, the seed tables replace the "
+                   "top of the BWT, and nothing in the 56 GB index is touched often enough to be worth a carve-out of the 126 MB L2.", ""]
     if len(traffic) > 2:
         json.dump(traffic, open(os.path.join(PROF, "ncu_traffic.json"), "w"), indent=1)      # bench.py's roofline.traffic
     open(os.path.join(PROF, f"{tag}_summary.md"), "w").write("\n".join(md) + "\n")

@@ -383,43 +383,54 @@ extern "C" int s3_rank_probe(s3_index *ix, int which, const uint32_t *indices, s
 // Independent random 32-byte reads (one LDG.E.256 each, the search's own access) over the forward bucket array, four in
 // flight per thread: what bench.py reports the search launch's executed sectors against (the search is
 // bound by random sectors, not by streaming bandwidth).  Replaces nothing in the reference.
+template <int U>
 __global__ void s3_random_sector_kernel(const uint4 *__restrict__ buckets, uint32_t numBuckets, uint32_t loads, uint32_t *__restrict__ sink)
 {
     uint32_t x = (blockIdx.x * blockDim.x + threadIdx.x) * 2654435761u + 12345u;
     uint32_t acc = 0;
-    for (uint32_t k = 0; k < loads; k += 4) {
-        uint32_t v[4][8];
+    for (uint32_t k = 0; k < loads; k += U) {
+        uint32_t v[U][8];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             x = x * 1664525u + 1013904223u;
             const uint4 *p = buckets + (size_t)(((unsigned long long)x * numBuckets) >> 32) * 2;
             asm volatile("ld.global.nc.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
                          : "=r"(v[u][0]), "=r"(v[u][1]), "=r"(v[u][2]), "=r"(v[u][3]), "=r"(v[u][4]), "=r"(v[u][5]), "=r"(v[u][6]), "=r"(v[u][7]) : "l"(p));
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) acc ^= v[u][0] ^ v[u][7];
+        for (int u = 0; u < U; ++u) acc ^= v[u][0] ^ v[u][7];
         x ^= acc & 1u;                      // the next addresses depend on nothing that waits: acc & 1 only keeps the loads alive
     }
     if (acc == 0x9E3779B9u) sink[0] = acc;
 }
 
+// Several shapes are tried (loads in flight per thread x threads per block) and the best rate is reported: the probe is
+// meant to be a ceiling for kernels whose own access pattern this is.
 extern "C" int s3_random_sector_probe(s3_index *ix, uint32_t loadsPerThread, float *ms, uint64_t *numLoads)
 {
     if (!ix || !ms || !numLoads || loadsPerThread == 0) { s3_set_error("s3_random_sector_probe: bad argument"); return S3_EINVAL; }
     S3_CUDA(cudaSetDevice(ix->device));
-    loadsPerThread = (loadsPerThread + 3) / 4 * 4;
-    const unsigned blocks = (unsigned)ix->numSms * 64, threads = 256;
+    loadsPerThread = (loadsPerThread + 15) / 16 * 16;
     uint32_t *d_sink;
     S3_CUDA(cudaMalloc(&d_sink, 4));
     cudaEvent_t e0, e1;
     S3_CUDA(cudaEventCreate(&e0)); S3_CUDA(cudaEventCreate(&e1));
-    S3_CUDA(cudaEventRecord(e0, ix->stream));
-    s3_random_sector_kernel<<<blocks, threads, 0, ix->stream>>>(ix->d_fwd, ix->fwd.numBuckets, loadsPerThread, d_sink);
-    S3_LAUNCHED(1);
-    S3_CUDA(cudaEventRecord(e1, ix->stream));
-    S3_CUDA(cudaStreamSynchronize(ix->stream));
-    S3_CUDA(cudaEventElapsedTime(ms, e0, e1));
-    *numLoads = (uint64_t)blocks * threads * loadsPerThread;
+    double bestRate = 0;
+    for (int shape = 0; shape < 6; ++shape) {
+        const int U = shape % 3 == 0 ? 4 : shape % 3 == 1 ? 8 : 16, threads = shape < 3 ? 256 : 512;
+        const unsigned blocks = (unsigned)ix->numSms * (shape < 3 ? 64 : 32);
+        S3_CUDA(cudaEventRecord(e0, ix->stream));
+        if (U == 4) s3_random_sector_kernel<4><<<blocks, threads, 0, ix->stream>>>(ix->d_fwd, ix->fwd.numBuckets, loadsPerThread, d_sink);
+        else if (U == 8) s3_random_sector_kernel<8><<<blocks, threads, 0, ix->stream>>>(ix->d_fwd, ix->fwd.numBuckets, loadsPerThread, d_sink);
+        else s3_random_sector_kernel<16><<<blocks, threads, 0, ix->stream>>>(ix->d_fwd, ix->fwd.numBuckets, loadsPerThread, d_sink);
+        S3_LAUNCHED(1);
+        S3_CUDA(cudaEventRecord(e1, ix->stream));
+        S3_CUDA(cudaStreamSynchronize(ix->stream));
+        float t = 0;
+        S3_CUDA(cudaEventElapsedTime(&t, e0, e1));
+        const uint64_t n = (uint64_t)blocks * threads * loadsPerThread;
+        if ((double)n / t > bestRate) { bestRate = (double)n / t; *ms = t; *numLoads = n; }
+    }
     cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(d_sink);
     return S3_OK;
 }

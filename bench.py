@@ -746,7 +746,7 @@ def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-bp", type=int, default=int(os.environ.get("S3_GENOME_BP", 3_100_000_000)))
@@ -823,8 +823,26 @@ def main():
     par = api.pe_params(num_mismatch=K_MISMATCH, insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES, read_length=L,
                         max_windows=N // 2)
     pe = api.PairAligner(gi, N, L, par)
+    # a second handle on the same index arrays + its own chain: two batches in flight, one host thread each
+    gi2 = api.index_clone(gi)
+    pe2 = api.PairAligner(gi2, N, L, par)
+    stream2 = torch.cuda.ExternalStream(gi2.stream, device=device)
     torch.cuda.synchronize()
     log(f"{total} batches of {N} reads prepared in {time.time() - t0:.1f}s")
+
+    def two_threads(fn_a, fn_b):
+        errs = []
+
+        def run(fn):
+            try:
+                torch.cuda.set_device(local_rank)
+                fn()
+            except Exception as e:                          # noqa: BLE001
+                errs.append(e)
+        ta, tb = threading.Thread(target=run, args=(fn_a,)), threading.Thread(target=run, args=(fn_b,))
+        ta.start(); tb.start(); ta.join(); tb.join()
+        if errs:
+            raise errs[0]
 
     def barrier():
         torch.cuda.synchronize()
@@ -850,19 +868,42 @@ def main():
     e1.record(stream)
     stream.synchronize()
     barrier()
-    launches = api.launch_count() - launches0
-    sampler.stop_flag = True
-    sampler.join()
     tt = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=device)
     if world > 1:
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
-    t_total = float(tt[0])
+    t_one = float(tt[0])
     reads_per_rank = N * args.steps
+    value_one = world * reads_per_rank / t_one
+    # ---- the same K steps with two batches in flight: even steps on one handle, odd steps on its clone ------------
+    timed_batches = [batches[args.warmup + k] for k in range(args.steps)]
+    for s in range(args.warmup):
+        pe2.align_device(batches[s].queries.data_ptr(), batches[s].lens.data_ptr(), N, wpq)
+    two_threads(lambda: [device_step(b) for b in timed_batches[0:2:2]], lambda: [pe2.align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq) for b in timed_batches[1:2:2]])
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = api.launch_count()
+    d0.record(stream)
+    two_threads(lambda: [device_step(b) for b in timed_batches[0::2]],
+                lambda: [pe2.align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq) for b in timed_batches[1::2]])
+    fin = torch.cuda.Event()
+    fin.record(stream2)
+    stream.wait_event(fin)
+    d1.record(stream)
+    stream.synchronize()
+    barrier()
+    launches = api.launch_count() - launches0
+    tt = torch.tensor([d0.elapsed_time(d1) / 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    t_total = float(tt[0])
     value = world * reads_per_rank / t_total
     windows = [int(r.numWindows) for r in stats]
     wlen = INSERT_HI - INSERT_LO + L
     dp_cells = float(sum(windows)) * L * wlen
     routes = np.sum([list(r.routeCounts)[:9] for r in stats], axis=0)
+
+    sampler.stop_flag = True
+    sampler.join()
 
     # ---- the same steps with the per-kernel timing hooks on (events between the library's launches) ---------------
     api.set_timing(gi.handle, True)
@@ -938,9 +979,20 @@ def main():
                 pe.prefetch(ptr(sets[k + 1][0]), ptr(sets[k + 1][1]), N, wpq)
             out = pe.align(ptr(q), ptr(l), N, wpq, copy=False)
         return out
-    for s in range(min(args.warmup, len(host_sets))):
-        e2e_steps(host_sets[s:s + 1])
-    t_e2e, last = timed(lambda: e2e_steps(host_sets))
+    def e2e_steps_on(aligner, sets):
+        out = None
+        ptr = lambda x: x.data_ptr() if hasattr(x, "data_ptr") else x
+        for k, (q, l) in enumerate(sets):
+            if k + 1 < len(sets):
+                aligner.prefetch(ptr(sets[k + 1][0]), ptr(sets[k + 1][1]), N, wpq)
+            out = aligner.align(ptr(q), ptr(l), N, wpq, copy=False)
+        return out
+    for s in range(max(min(args.warmup, len(host_sets)) // 2, 1)):          # warm-up with the prefetch path: both input buffers of both handles get allocated
+        e2e_steps(host_sets[:2])
+        e2e_steps_on(pe2, host_sets[:2])
+    t_e2e_one, last = timed(lambda: e2e_steps(host_sets))
+    # two caller threads, a handle each: the reference's own shape (its main thread searches batch k + 1 while a DP engine thread aligns batch k)
+    t_e2e, _ = timed(lambda: two_threads(lambda: e2e_steps_on(pe, host_sets[0::2]), lambda: e2e_steps_on(pe2, host_sets[1::2])))
     h2d, d2h = last["h2d_bytes"], last["d2h_bytes"]
     e2e_value = world * reads_per_rank / t_e2e
     e2e_steps(pageable_sets[:1])
@@ -1030,13 +1082,15 @@ def main():
         "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u32", "data": "synthetic",
+        "value_one_batch_in_flight": value_one, "ms_per_step_one_batch_in_flight": 1e3 * t_one / args.steps,
         "config": {"workload": workload, "genome_bp": args.genome_bp, "repeat_fraction": args.repeat_fraction, "pairs_per_step_per_gpu": args.pairs,
                    "step": "s3_pe_align_device: search -> collect -> route -> locate -> pairing -> rescue windows -> DP -> CIGAR runs, nothing "
                            "taken from the simulator's truth; reads whose round-1 slot overflowed are reported (route 8), not searched again",
-                   "timing": "value: K steps back to back, queries resident in HBM, results left there, CUDA events on the library's stream "
-                             "(two 4-byte count reads per step are part of the chain); kernels / stages: the same K steps once more with the "
-                             "library's timing hooks on; e2e: the same K steps through s3_pe_align, queries from pinned host memory, results "
-                             "into host memory, wall clock",
+                   "timing": "value: K steps, queries resident in HBM, results left there, two batches in flight (even steps on one handle, odd "
+                             "steps on its s3_index_clone, one host thread each), CUDA events around the whole; value_one_batch_in_flight: the "
+                             "same K steps back to back on one handle (two 4-byte count reads per step are part of the chain); kernels / "
+                             "stages: those K steps once more with the library's timing hooks on; e2e: the K steps through s3_pe_align, queries "
+                             "from pinned host memory, results into host memory, wall clock, two caller threads like value",
                    "l2": "inputs larger than L2: 56 GB of index (buckets, seed tables, suffix array, text) touched at random, a different "
                          "32 MiB read batch every step",
                    "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"
@@ -1044,6 +1098,7 @@ def main():
         "clocks": sampler.result(),
         "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                 "ms_per_step": 1e3 * t_e2e / args.steps,
+                "one_thread_value": world * reads_per_rank / t_e2e_one, "one_thread_ms_per_step": 1e3 * t_e2e_one / args.steps,
                 "mode": "s3_pe_align (host-pointer C ABI): queries from pinned host memory in, routes + pairings + rescue records + CIGAR runs "
                         "into host memory out, one call per step; the next step's queries are uploaded by s3_pe_prefetch under this step's kernels",
                 "pageable_value": pageable_value, "pageable_ms_per_step": 1e3 * t_page / len(pageable_sets),
@@ -1092,6 +1147,8 @@ def main():
         except Exception as e:                               # noqa: BLE001
             out["parity_at_full_size"] = {"error": str(e)[:300]}
     print(json.dumps(out), flush=True)
+    pe2.free()
+    api.GPUINDEXFree(gi2)
     pe.free()
     api.GPUINDEXFree(gi)
     if world > 1:

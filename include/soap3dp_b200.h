@@ -64,6 +64,10 @@ int s3_index_upload(const uint32_t *bwt, const uint32_t *occ,
 /* the same two optional arrays when they already live in device memory (copied) */
 int s3_index_set_locate_device(s3_index *ix, const uint32_t *d_sa, const uint32_t *d_packedDNA);
 void s3_index_free(s3_index *ix);
+/* A second handle on the same device arrays with a stream, work queues and scratch of its own: two batches can then be in
+ * flight at once, one host thread per handle (the reference overlaps its search of batch k + 1 with the DP of batch k the
+ * same way, alignment.cu:555,1030).  Clones are freed before the handle they were made from. */
+int s3_index_clone(s3_index *ix, s3_index **out);
 /* bytes of device memory held by the index */
 size_t s3_index_device_bytes(const s3_index *ix);
 /* the CUDA stream (cudaStream_t) all work of this index is issued on */

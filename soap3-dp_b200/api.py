@@ -38,7 +38,7 @@ EXPORTS = [
     "s3_mapq_unique_dp", "s3_mapq_pair_end_dp", "s3_mapq_of_pair", "s3_seed_candidates", "s3_seed_pair_candidates",
     "s3_index_stream", "s3_rank_probe", "s3_search_round1", "s3_search_round2", "s3_search_round1_device",
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
-    "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows", "s3_index_set_l2_persist",
+    "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows", "s3_index_set_l2_persist", "s3_index_clone",
     "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
     "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_seed_search", "s3_seed_search_result_free",
     "s3_single_dp_align", "s3_single_dp_result_free", "s3_deep_dp_align", "s3_deep_dp_result_free",
@@ -976,3 +976,13 @@ def set_l2_persist(gpu_index: GpuIndex, region: int, window_bytes: int = 0, pers
     lib.s3_index_set_l2_persist.restype = C.c_int
     lib.s3_index_set_l2_persist.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t]
     _check(lib.s3_index_set_l2_persist(gpu_index.handle, region, window_bytes, persist_bytes), "s3_index_set_l2_persist")
+
+
+def index_clone(gpu_index: GpuIndex) -> GpuIndex:
+    """s3_index_clone: a second handle on the same device arrays with its own stream and scratch (one host thread per handle)"""
+    lib = load_library()
+    lib.s3_index_clone.restype = C.c_int
+    lib.s3_index_clone.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    out = C.c_void_p()
+    _check(lib.s3_index_clone(gpu_index.handle, C.byref(out)), "s3_index_clone")
+    return GpuIndex(out.value, gpu_index.text_length)

@@ -107,6 +107,7 @@ struct s3_index {
     uint32_t *d_itemStats; size_t itemStatsCap;   // S3_ITEM_STATS builds only (tools/search_tail.py)
     int numSms;
     size_t searchSmem; int searchBlocksPerSm;
+    int sharedArrays;                 // s3_index_clone: buckets, seed tables, suffix array, text belong to another handle
 };
 
 void s3_set_error(const char *fmt, ...);

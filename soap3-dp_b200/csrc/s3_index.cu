@@ -325,11 +325,13 @@ extern "C" void s3_index_free(s3_index *ix)
     if (!ix) return;
     cudaSetDevice(ix->device);
     cudaStreamSynchronize(ix->stream);
-    cudaFree(ix->d_fwd); cudaFree(ix->d_rev);
-    for (int t = 0; t < 3; ++t) if (ix->d_seed[t]) cudaFree(ix->d_seed[t]);
-    if (ix->d_packedDNA) cudaFree(ix->d_packedDNA);
-    if (ix->d_sa) cudaFree(ix->d_sa);
-    if (ix->d_isa) cudaFree(ix->d_isa);
+    if (!ix->sharedArrays) {
+        cudaFree(ix->d_fwd); cudaFree(ix->d_rev);
+        for (int t = 0; t < 3; ++t) if (ix->d_seed[t]) cudaFree(ix->d_seed[t]);
+        if (ix->d_packedDNA) cudaFree(ix->d_packedDNA);
+        if (ix->d_sa) cudaFree(ix->d_sa);
+        if (ix->d_isa) cudaFree(ix->d_isa);
+    }
     s3_pipe_destroy(&ix->pipe);
     if (ix->d_workCounter) cudaFree(ix->d_workCounter);
     if (ix->d_hardItems) cudaFree(ix->d_hardItems);
@@ -348,6 +350,30 @@ extern "C" void s3_index_free(s3_index *ix)
     if (ix->pinned) cudaFreeHost(ix->pinned);
     cudaStreamDestroy(ix->stream);
     free(ix);
+}
+
+// A second handle on the same device arrays: its own stream, work queues and scratch, so that two batches can be in
+// flight at once (one host thread each) -- the memory-bound search of one under the compute-bound DP of the other.  The
+// reference gets the same overlap from its two engine threads (main thread searching batch k + 1 while a DP engine's GPU
+// thread aligns batch k).  Free the clones before the handle they were made from.
+extern "C" int s3_index_clone(s3_index *ix, s3_index **out)
+{
+    if (!ix || !out) { s3_set_error("s3_index_clone: NULL argument"); return S3_EINVAL; }
+    S3_CUDA(cudaSetDevice(ix->device));
+    s3_index *c = (s3_index *)calloc(1, sizeof(s3_index));
+    if (!c) { s3_set_error("out of host memory"); return S3_ENOMEM; }
+    c->device = ix->device; c->fwd = ix->fwd; c->rev = ix->rev; c->seed = ix->seed; c->loc = ix->loc;
+    for (int t = 0; t < 3; ++t) c->d_seed[t] = ix->d_seed[t];
+    c->d_isa = ix->d_isa; c->textLength = ix->textLength; c->d_fwd = ix->d_fwd; c->d_rev = ix->d_rev;
+    c->d_packedDNA = ix->d_packedDNA; c->d_sa = ix->d_sa; c->bytes = 0;
+    c->numSms = ix->numSms; c->splitBudget = ix->splitBudget; c->searchSmem = (size_t)-1; c->sharedArrays = 1;
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&c->d_workCounter, 256) != cudaSuccess) {
+        s3_set_error("s3_index_clone: %s", cudaGetErrorString(cudaGetLastError()));
+        s3_index_free(c);
+        return S3_ECUDA;
+    }
+    *out = c;
+    return S3_OK;
 }
 
 extern "C" size_t s3_index_device_bytes(const s3_index *ix) { return ix ? ix->bytes : 0; }

@@ -278,20 +278,63 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------
-# CPU arm: the reference's kernel sources compiled for the host (oracle/_ref) or the port
+# CPU arm.  Search: the reference's own CPU search (oracle/_ref/libref_cpu_search.so = ProcessReadDoubleStrand2 on the models of
+# SRAModelConstruct, 13-mer lookup tables, check-and-extend: what SOAP3-dp runs on the host for a read the GPU left over).
+# DP: the reference has no CPU implementation of it, so its DP kernels compiled for the host (oracle/_ref/libref_dp.so) stand in.
+# The reference's search kernels compiled for the host are timed beside it as `kernel_code`.  Without oracle/_ref: the oracle port.
 # ---------------------------------------------------------------------------
-def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
-    """-> dict(value reads/s, kind, cores, sample, rank_queries_per_read, t_search, t_dp)"""
+_REF_CPU = {}
+MAX_OUTPUT_PER_READ = 1000
+
+
+def ref_cpu_handle(host, threads):
+    """-> helpers.RefCpuSearch on the bench index (built once: occurrence tables + two 13-mer lookup tables), or None"""
+    if "h" in _REF_CPU:
+        return _REF_CPU["h"]
+    import helpers
+    lib = helpers.load_ref_cpu_search()
+    h = None
+    if lib is not None and "sa" in host and "pac" in host:
+        t0 = time.time()
+        meta = host["meta"]
+        h = helpers.RefCpuSearch(lib, host["bwt"], host["rbwt"], int(meta[0]), int(meta[1]), int(meta[2]), host["pac"], host["sa"], threads)
+        log(f"reference CPU index structs (occ tables, 13-mer lookup tables of both directions) built in {time.time() - t0:.1f}s")
+    _REF_CPU["h"] = h
+    return h
+
+
+def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads, kernel_code_reads=None, gpu_legs=True, keep_hits=0):
+    """-> dict(value reads/s, kind, cores, sample, ...)"""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     import helpers
     ref_s, ref_d = helpers.load_ref_search(), helpers.load_ref_dp()
+    ref_c = ref_cpu_handle(host, threads)
     kind = "reference" if (ref_s is not None and ref_d is not None) else "port"
     pairs = sample_reads // 2
     b = make_batch(genome, pairs, L, seed)
     q = b.queries.cpu().numpy().view(np.uint32)
     lens = b.lens.cpu().numpy().view(np.uint32)
     n = b.n
+    ncases = formats.NUM_CASES[K_MISMATCH]
+    out = {}
 
+    # --- the reference's CPU search
+    t_cpu_search = None
+    if ref_c is not None:
+        reads = np.ascontiguousarray(b.reads.cpu().numpy().astype(np.uint8))
+        t0 = time.perf_counter()
+        res = ref_c.search(reads, K_MISMATCH, ncases, MAX_OUTPUT_PER_READ, threads)
+        t_cpu_search = time.perf_counter() - t0
+        cnt = res["counts"]
+        out["cpu_search"] = {"reads": int(n), "seconds": t_cpu_search, "reads_per_s": n / t_cpu_search,
+                             "reads_with_a_hit": int((cnt[:, 3] > 0).sum()), "occurrences": int(cnt[:, 3].sum()),
+                             "found_by_check_and_extend": int(cnt[:, 2].sum()), "sa_ranges": int(cnt[:, 0].sum())}
+        if keep_hits:
+            m = min(keep_hits, n)
+            out["_hit_reads"] = reads[:m]
+            out["_hits"] = ref_c.search(reads[:m], K_MISMATCH, ncases, MAX_OUTPUT_PER_READ, threads, out_cap=64)["hits"]
+
+    # --- the reference's search kernels compiled for the host (or the port)
     class HI:
         pass
     hi = HI()
@@ -299,20 +342,24 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
     hi.isa0, hi.risa0, hi.n = int(host["meta"][0]), int(host["meta"][1]), int(host["meta"][2])
     allowed = formats.SA_RANGES_ROUND1[K_MISMATCH]
     wpa = 2 * allowed
-    bad = np.zeros(formats.ceil32(n), np.uint8)
+    nk = n if (kernel_code_reads is None or ref_c is None) else min(n, formats.ceil32(kernel_code_reads))
+    bad = np.zeros(formats.ceil32(nk), np.uint8)
     ans = []
     nrank = 0
+    qq = q[:formats.ceil32(nk) * b.wpq].copy() if nk < n else q.copy()
+    lk = lens[:formats.ceil32(nk)].copy()
+    lk[nk:] = 0
     t0 = time.perf_counter()
-    qq = q.copy()
-    for case in range(formats.NUM_CASES[K_MISMATCH]):
-        a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+    for case in range(ncases):
+        a = np.zeros(formats.ceil32(nk) * wpa, np.uint32)
         if kind == "reference":
-            nrank += helpers.ref_launch(ref_s, hi, case, qq, lens, n, b.wpq, a, bad, 0, K_MISMATCH, allowed, wpa, nthreads=threads)
+            nrank += helpers.ref_launch(ref_s, hi, case, qq, lk, nk, b.wpq, a, bad, 0, K_MISMATCH, allowed, wpa, nthreads=threads)
         else:
-            nrank += helpers.oracle_launch(helpers.load_oracle(), hi, case, q, lens, n, b.wpq, a, bad, 0, K_MISMATCH, allowed, wpa)
+            nrank += helpers.oracle_launch(helpers.load_oracle(), hi, case, qq, lk, nk, b.wpq, a, bad, 0, K_MISMATCH, allowed, wpa)
         ans.append(a)
-    t_search = time.perf_counter() - t0
-    # DP on the same fraction of pairs the GPU arm rescues
+    t_kernel_search = time.perf_counter() - t0
+
+    # --- DP on the same fraction of pairs the GPU arm rescues
     m = max(int(pairs * dp_fraction), 32)
     dpb = helpers.make_dp_batch(genome[:4_000_000].cpu(), m, L, "rescue", seed=seed + 1, insert=(INSERT_LO, INSERT_HI))
     t0 = time.perf_counter()
@@ -321,9 +368,10 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
     else:
         dp_out = helpers.oracle_dp(helpers.load_oracle_dp(), dpb, DP_SCORES)
     t_dp = time.perf_counter() - t0
-    # the reference's own DP kernels compiled for sm_100a, on this GPU, on the same batch: the kernel to beat
+
+    # --- the reference's own CUDA kernels compiled for sm_100a, on this GPU, on the same batches: the kernels to beat
     gpu_ref = None
-    ref_cu = helpers.load_ref_dp_cuda() if kind == "reference" else None
+    ref_cu = helpers.load_ref_dp_cuda() if (kind == "reference" and gpu_legs) else None
     if ref_cu is not None and torch.cuda.is_available():
         try:
             helpers.ref_dp_cuda(ref_cu, dpb, DP_SCORES)                       # warm-up
@@ -335,34 +383,46 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads):
                        "tracebacks_equal_to_host_build": int(same)}
         except Exception as e:                       # noqa: BLE001
             gpu_ref = {"error": str(e)[:200]}
-    # and its search kernels, when oracle/build_ref_search_cuda.sh has been run (an hour of cicc)
     gpu_ref_s = None
-    ref_scu = helpers.load_ref_search_cuda() if kind == "reference" else None
+    ref_scu = helpers.load_ref_search_cuda() if (kind == "reference" and gpu_legs) else None
     if ref_scu is not None and torch.cuda.is_available():
         try:
             if ref_scu.ref_search_cuda_upload(helpers.u32p(hi.bwt), helpers.u32p(hi.rbwt), len(hi.bwt), helpers.u32p(hi.occ),
                                               helpers.u32p(hi.rocc), len(hi.occ)) != 0:
                 raise RuntimeError("index upload failed")
-            warm = min(n, 65536)
-            helpers.ref_search_cuda_round1(ref_scu, hi, q.copy(), lens, warm, b.wpq, K_MISMATCH, allowed, wpa)
-            ans_cu, ms_cu = helpers.ref_search_cuda_round1(ref_scu, hi, q.copy(), lens, n, b.wpq, K_MISMATCH, allowed, wpa)
+            warm = min(nk, 65536)
+            helpers.ref_search_cuda_round1(ref_scu, hi, qq.copy(), lk, warm, b.wpq, K_MISMATCH, allowed, wpa)
+            ans_cu, ms_cu = helpers.ref_search_cuda_round1(ref_scu, hi, qq.copy(), lk, nk, b.wpq, K_MISMATCH, allowed, wpa)
             ref_scu.ref_search_cuda_free()
-            equal = all(np.array_equal(formats.answers_view(x, n, wpa), formats.answers_view(y, n, wpa)) for x, y in zip(ans_cu, ans))
+            equal = all(np.array_equal(formats.answers_view(x, nk, wpa), formats.answers_view(y, nk, wpa)) for x, y in zip(ans_cu, ans))
             flags_path = os.path.join(ROOT, "oracle", "_ref", "libref_search_cuda.so.flags")
             flags = open(flags_path).read().strip() if os.path.exists(flags_path) else "flags not recorded"
             gpu_ref_s = {"kind": "reference search kernels (DV-Kernel.cu, unmodified) compiled for sm_100a (" + flags + "), one launch per "
                                  "case over <= 1,048,576 reads as perform_round1_alignment",
-                         "reads": int(n), "kernel_ms": ms_cu, "reads_per_s": n / (ms_cu * 1e-3),
+                         "reads": int(nk), "kernel_ms": ms_cu, "reads_per_s": nk / (ms_cu * 1e-3),
                          "slots_equal_to_host_build": bool(equal)}
         except Exception as e:                       # noqa: BLE001
             gpu_ref_s = {"error": str(e)[:200]}
-    return {"_answers": ans, "gpu_reference_dp": gpu_ref, "gpu_reference_search": gpu_ref_s, "_batch": b, "_dpb": dpb, "_dp_out": dp_out, "value": n / (t_search + t_dp), "unit": "reads/s", "cores": threads if kind == "reference" else 1,
-            "kind": kind,
-            "sample": f"{n} reads (k<=2, 4 cases, both strands) + {m} rescue DP alignments of the bench workload; "
-                      + ("reference kernel sources (DV-Kernel.cu, DV-DPfunctions.cu:35-512) compiled for the host, OpenMP over reads"
-                         if kind == "reference" else "oracle/ C restatement, single thread"),
-            "rank_queries_per_read": nrank / n, "t_search_s": t_search, "t_dp_s": t_dp,
-            "dp_gcups": dpb.n * 400 * L / t_dp / 1e9}
+
+    t_search = t_cpu_search if t_cpu_search is not None else t_kernel_search * (n / nk)
+    dp_text = f"{m} mate-rescue DP alignments (the fraction of pairs the GPU arm rescues; the reference has no CPU DP: its DP kernels, DV-DPfunctions.cu:35-512, compiled for the host, OpenMP over alignments)"
+    if t_cpu_search is not None:
+        sample = (f"{n} reads of the bench workload through the reference's CPU search (ProcessReadDoubleStrand2 per case on SRAModelConstruct's "
+                  f"16G models, k<=2, 4 cases, both strands, lookup tables + check-and-extend, MaxOutputPerRead {MAX_OUTPUT_PER_READ}, OpenMP over reads) + " + dp_text)
+    elif kind == "reference":
+        sample = f"{n} reads (k<=2, 4 cases, both strands) through the reference's search kernels (DV-Kernel.cu) compiled for the host, OpenMP over reads + " + dp_text
+    else:
+        sample = f"{n} reads + {m} rescue DP alignments through the oracle/ C restatement, single thread"
+    out.update({"gpu_reference_dp": gpu_ref, "gpu_reference_search": gpu_ref_s, "value": n / (t_search + t_dp), "unit": "reads/s",
+                "cores": threads if kind == "reference" else 1, "kind": kind, "sample": sample,
+                "search_path": "ProcessReadDoubleStrand2" if t_cpu_search is not None else "kernel_code",
+                "kernel_code": {"what": "the reference's GPU search kernels (DV-Kernel.cu) compiled for the host, OpenMP over reads: the same code "
+                                        "path the GPU arm replaces, on CPU cores", "reads": int(nk), "seconds": t_kernel_search,
+                                "search_reads_per_s": nk / t_kernel_search, "rank_queries_per_read": nrank / nk,
+                                "value_with_this_search": n / (t_kernel_search * (n / nk) + t_dp)},
+                "rank_queries_per_read": nrank / nk, "t_search_s": t_search, "t_dp_s": t_dp,
+                "dp_gcups": dpb.n * 400 * L / t_dp / 1e9})
+    return out
 
 
 def pairing_rows(views, allowed, n_reads, L, true_pos, retain_best, locate, pair_occurrences, max_per_range=8):
@@ -422,33 +482,35 @@ def pairing_rows(views, allowed, n_reads, L, true_pos, retain_best, locate, pair
                     "arrays between the calls; numpy glue between them not counted"}
 
 
-def parity_check(gi, cb, device_index):
-    """The CPU arm's sample, pushed through the GPU library (host C ABI) and compared bit for bit:
-    full-size genome, the checker is the CPU arm's output (reference kernels compiled for the host)."""
-    import helpers
-    b = cb["_batch"]
-    q = b.queries.cpu().numpy().view(np.uint32)
-    lens = b.lens.cpu().numpy().view(np.uint32)
-    got = api.perform_round1_alignment(gi, q, lens, b.n, b.wpq, K_MISMATCH)
-    wpa = 2 * formats.SA_RANGES_ROUND1[K_MISMATCH]
-    search_equal = all(np.array_equal(formats.answers_view(g, b.n, wpa), formats.answers_view(w, b.n, wpa))
-                       for g, w in zip(got, cb["_answers"]))
-    dpb = cb["_dpb"]
-    al = api.SemiGlobalAligner(dpb.max_read, dpb.max_dna, dpb.n, *DP_SCORES, device=device_index)
-    out = al.performAlignment(dpb.dna, dpb.dna_len, dpb.read, dpb.read_len, dpb.cutoff, dpb.n, dpb.clip_lt, dpb.clip_rt,
-                              dpb.anchor_l, dpb.anchor_r)
-    al.freeMemory()
+# ---------------------------------------------------------------------------
+def cpu_search_parity(gi, cb, L):
+    """The first reads of the CPU arm's sample through s3_se_align (search -> collect -> locate on the device) against what the
+    reference's own CPU search reported for them: per read the same (position, strand, mismatches) set.  Reads whose round-1
+    slot overflowed (flag from the device) or that reach the cap on either side are counted apart, not compared."""
+    reads, hits = cb["_hit_reads"], cb["_hits"]
+    n = len(hits)
+    wpq = formats.word_per_query(L)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    q = formats.pack_queries(reads, lens[:n], wpq)
+    al = api.SingleAligner(gi, n, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, report_best=False)
     try:
-        npass = helpers.compare_dp(dpb, out, cb["_dp_out"], "bench parity")
-        dp_equal = True
-    except AssertionError as e:
-        log("DP PARITY FAILURE:", e)
-        npass, dp_equal = 0, False
-    if not search_equal:
-        log("SEARCH PARITY FAILURE at full size")
-    return {"search_reads": int(b.n), "search_cases": len(got), "search_bit_exact": bool(search_equal),
-            "dp_alignments": int(dpb.n), "dp_tracebacks": int(npass), "dp_bit_exact": bool(dp_equal),
-            "checker": cb["kind"]}
+        got = al.align(q, lens, n, wpq)
+    finally:
+        al.free()
+    off = got["occ_offsets"]
+    same = skipped = with_hits = 0
+    for r in range(n):
+        a, b = int(off[r]), int(off[r + 1])
+        if int(got["read_flags"][r]) or len(hits[r]) >= 64 or b - a >= 64:
+            skipped += 1
+            continue
+        mine = {(int(p), int(f[0]), int(f[1])) for p, f in zip(got["positions"][a:b], got["occ_flags"][a:b])}
+        same += mine == set(hits[r])
+        with_hits += bool(hits[r])
+    return {"reads": n, "compared": n - skipped, "reads_with_hits": with_hits, "equal": same, "bit_exact": bool(same == n - skipped),
+            "skipped_overflow_or_over_64_hits": skipped,
+            "checker": "the reference's CPU search (ProcessReadDoubleStrand2, oracle/_ref/libref_cpu_search.so) on the full-size index"}
 
 
 # ---------------------------------------------------------------------------
@@ -707,9 +769,30 @@ def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream
                 nrank += helpers.oracle_launch(helpers.load_oracle(), hi, case, q, lens, n, wpq, a, bad, 0, k, allowed, wpa)
             views.append(formats.answers_view(a, n, wpa))
         t_cpu = time.perf_counter() - t0
-        out["cpu_baseline"] = {"value": n / t_cpu, "unit": "reads/s", "cores": threads if ref_s is not None else 1, "kind": "reference" if ref_s is not None else "port",
-                               "sample": f"{n} reads, <= {k} mismatches, {ncases} cases, both strands: reference kernel sources (DV-Kernel.cu) compiled for the host, OpenMP over reads",
-                               "cpu_model": cpu_model(), "rank_queries_per_read": nrank / n}
+        kernel_code = {"what": "the reference's GPU search kernels (DV-Kernel.cu) compiled for the host, OpenMP over reads", "reads": int(n),
+                       "seconds": t_cpu, "search_reads_per_s": n / t_cpu, "rank_queries_per_read": nrank / n}
+        ref_c = ref_cpu_handle(host, threads)
+        if ref_c is not None:
+            # the reference's own CPU search on a sample of its own size (it is much faster per read than the kernel code on CPU cores)
+            nb = min(args.cpu_sample, 4 * N)
+            bb = make_se_batch(genome, nb, L, seed=4344)
+            rd = np.ascontiguousarray(bb.reads.cpu().numpy().astype(np.uint8))
+            t0 = time.perf_counter()
+            res = ref_c.search(rd, k, ncases, 1000, threads)
+            t_ref = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": nb / t_ref, "unit": "reads/s", "cores": threads, "kind": "reference",
+                                   "sample": f"{nb} reads of the bench workload through the reference's CPU search (ProcessReadDoubleStrand2 per case on "
+                                             f"SRAModelConstruct's 16G models, <= {k} mismatches, {ncases} cases, both strands, lookup tables + "
+                                             "check-and-extend, MaxOutputPerRead 1000, OpenMP over reads)",
+                                   "cpu_model": cpu_model(), "search_path": "ProcessReadDoubleStrand2",
+                                   "cpu_search": {"reads": int(nb), "seconds": t_ref, "occurrences": int(res["counts"][:, 3].sum()),
+                                                  "reads_with_a_hit": int((res["counts"][:, 3] > 0).sum())},
+                                   "kernel_code": kernel_code, "rank_queries_per_read": nrank / n}
+            del bb, rd, res
+        else:
+            out["cpu_baseline"] = {"value": n / t_cpu, "unit": "reads/s", "cores": threads if ref_s is not None else 1, "kind": "reference" if ref_s is not None else "port",
+                                   "sample": f"{n} reads, <= {k} mismatches, {ncases} cases, both strands: reference kernel sources (DV-Kernel.cu) compiled for the host, OpenMP over reads",
+                                   "cpu_model": cpu_model(), "rank_queries_per_read": nrank / n, "search_path": "kernel_code", "kernel_code": kernel_code}
         # parity of the sample through the chain
         al = api.SingleAligner(gi, n, num_mismatch=k, max_output_per_read=1000, report_best=False)
         got = al.align(q, lens, n, wpq)
@@ -786,7 +869,7 @@ def main():
         info = None
         per_step = max(args.cpu_sample // 4, 4096)
         for s in range(args.warmup + args.steps):
-            info = cpu_arm(host, genome, L, per_step, 1000 + s, RESCUE_FRACTION_HINT, threads)
+            info = cpu_arm(host, genome, L, per_step, 1000 + s, RESCUE_FRACTION_HINT, threads, kernel_code_reads=32768, gpu_legs=False)
             if s >= args.warmup:
                 vals.append(info)
         v = float(np.mean([x["value"] for x in vals]))
@@ -794,11 +877,12 @@ def main():
                "unit": "reads/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
                "ms_per_step": 1e3 * per_step / v, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                "dtype": "u32", "data": "synthetic",
-               "config": {"workload": workload, "sample_reads_per_step": per_step,
-                          "sample": "the reference arm runs the same pipeline stages on a bounded sample per step: k<=2 search of "
+               "config": {"workload": workload, "genome_bp": args.genome_bp, "repeat_fraction": args.repeat_fraction, "sample_reads_per_step": per_step,
+                          "sample": "the reference arm runs the same stages on a bounded sample per step: k<=2 search of "
                                     f"{per_step} reads + mate-rescue DP of the same fraction of pairs as the GPU arm rescues"},
                "cpu_baseline": {"value": v, "unit": "reads/s", "cores": info["cores"], "kind": info["kind"],
-                                "sample": info["sample"], "cpu_model": cpu_model()},
+                                "sample": info["sample"], "cpu_model": cpu_model(), "search_path": info["search_path"],
+                                "cpu_search": info.get("cpu_search"), "kernel_code": info["kernel_code"], "dp_gcups": info["dp_gcups"]},
                "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(out), flush=True)
         return
@@ -1125,12 +1209,16 @@ def main():
     if world == 1 and not args.no_cpu_baseline:
         frac = float(np.mean(windows)) / args.pairs
         t0 = time.time()
-        cb = cpu_arm(host, genome, L, args.cpu_sample, 999, frac, threads)
+        cb = cpu_arm(host, genome, L, args.cpu_sample, 999, frac, threads, kernel_code_reads=args.cpu_sample // 4, keep_hits=65536)
         log(f"cpu baseline ({cb['kind']}, {cb['cores']} threads) took {time.time() - t0:.1f}s: {cb['value']:.0f} reads/s")
         out["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
         out["cpu_baseline"]["cpu_model"] = cpu_model()
         out["cpu_baseline"]["rank_queries_per_read"] = cb["rank_queries_per_read"]
         out["cpu_baseline"]["dp_gcups"] = cb["dp_gcups"]
+        out["cpu_baseline"]["search_path"] = cb["search_path"]
+        out["cpu_baseline"]["cpu_search"] = cb.get("cpu_search")
+        out["cpu_baseline"]["kernel_code"] = cb["kernel_code"]
+        out["cpu_baseline"]["same_config"] = "same workload generator, read length, k, cases, MaxOutputPerRead and rescue fraction as the GPU arm; bounded sample"
         if cb.get("gpu_reference_search"):
             out["search"]["reference_cuda_kernels_on_this_gpu"] = cb["gpu_reference_search"]
             if cb["gpu_reference_search"].get("reads_per_s"):
@@ -1139,6 +1227,13 @@ def main():
             out["dp"]["reference_cuda_kernels_on_this_gpu"] = cb["gpu_reference_dp"]
             if cb["gpu_reference_dp"].get("gcups"):
                 out["dp"]["speedup_over_reference_cuda_kernels"] = dp_gcups / cb["gpu_reference_dp"]["gcups"]
+        cpu_parity = None
+        if "_hits" in cb:
+            try:
+                cpu_parity = cpu_search_parity(gi, cb, L)
+                log("search vs the reference's CPU search at full size:", cpu_parity)
+            except Exception as e:                           # noqa: BLE001
+                cpu_parity = {"error": str(e)[:300]}
         del cb
         t0 = time.time()
         try:
@@ -1146,6 +1241,7 @@ def main():
             log(f"chain parity on {args.parity_pairs} pairs took {time.time() - t0:.1f}s: {out['parity_at_full_size']}")
         except Exception as e:                               # noqa: BLE001
             out["parity_at_full_size"] = {"error": str(e)[:300]}
+        out["parity_at_full_size"]["search_vs_reference_cpu_search"] = cpu_parity
     print(json.dumps(out), flush=True)
     pe2.free()
     api.GPUINDEXFree(gi2)

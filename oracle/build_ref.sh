@@ -19,6 +19,8 @@
 #   shim_check (+ shim_case/)  the drop-in shim linked with a driver written against the reference's headers, and its test case
 #   libref_mapq.so     the nine MAPQ functions of the SAM writers + tables (BGS-IO.cpp:33-45,2280-2580)
 #   libref_params.so   getSeedPositions (definitions.h:323-442) + getParameterFor*DP (CPUfunctions.cpp:46-260)
+#   libref_cpu_search.so  the reference's own CPU search: ProcessReadDoubleStrand2 (CPUfunctions.cpp:555-622) + BGS-HostAlgnmtAlgo2.cpp,
+#                      SAList.cpp, SRA2BWTMdl.c, SRA2BWTCheckAndExtend.c, BWT.c compiled from where they lie; the CPU arm of bench.py
 #   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
 # Two one-line build fixes are applied to *copies* in oracle/_ref/patched/
@@ -155,6 +157,16 @@ sed -n '46,260p' "$REF/CPUfunctions.cpp" > "$OUT/patched/params.inc"
 $CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
     "$HERE/ref_shim/ref_params_host.cpp" -o "$OUT/libref_params.so"
 echo "[build_ref] libref_params.so OK"
+
+# ---- the reference's CPU search path: models, lookup-table + BWT backward / bidirectional search, check-and-extend ------------
+# ProcessReadDoubleStrand2 is cut by line range (CPUfunctions.cpp as a whole needs the aligner around it); the files it calls
+# into are compiled whole and unmodified.  ref_cpu_search_host.cpp builds BWT / LT / HSP structs from arrays and loops over reads.
+sed -n '555,622p' "$REF/CPUfunctions.cpp" > "$OUT/patched/cpu_search.inc"
+$CXX $CFLAGS -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -c "$REF/BGS-HostAlgnmtAlgo2.cpp" -o "$OUT/obj/HostAlgnmtAlgo2.o"
+$CXX $CFLAGS -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -c "$REF/SAList.cpp" -o "$OUT/obj/SAList.o"
+$CXX $CFLAGS -fopenmp -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" "$HERE/ref_shim/ref_cpu_search_host.cpp" \
+    "$OUT/obj/HostAlgnmtAlgo2.o" "$OUT/obj/SAList.o" "$OUT/obj/BWTConstruct.o" $BWTOBJ $CPUOBJ -lm -o "$OUT/libref_cpu_search.so"
+echo "[build_ref] libref_cpu_search.so OK"
 
 # ---- the same DP kernels compiled for sm_100a: the reference's GPU kernels on the B200 ("kernel to beat") -----
 NVCC=${S3_NVCC:-/usr/local/cuda/bin/nvcc}

@@ -660,3 +660,61 @@ def ref_windows_pair(lib, rid, pos, pos2, lens, text, P, lsc, lhit):
                              u32p(R[0]), u32p(R[1]), u32p(R[2]), u32p(R[3]), u32p(R[4]), u32p(R[5]), u32p(R[6]), cr.ctypes.data_as(I32))
     assert k == n
     return np.stack(L, axis=1), np.stack(R, axis=1)
+
+
+# ---------------------------------------------------------------------------
+# the reference's own CPU search (ProcessReadDoubleStrand2 on SRAModelConstruct's models), oracle/_ref/libref_cpu_search.so
+# ---------------------------------------------------------------------------
+def load_ref_cpu_search():
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_cpu_search.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.ref_cpu_create.restype = C.c_void_p
+    lib.ref_cpu_create.argtypes = [U32P, U32P, C.c_ulonglong, C.c_uint32, C.c_uint32, C.c_uint32, U32P, U32P, C.c_int]
+    lib.ref_cpu_free.argtypes = [C.c_void_p]
+    lib.ref_cpu_search.restype = C.c_ulonglong
+    lib.ref_cpu_search.argtypes = [C.c_void_p, U8P, C.c_uint32, C.c_uint32, C.c_int, C.c_int, C.c_uint32, C.c_int, U32P,
+                                   C.c_uint32, U32P, U8P, U8P, U32P]
+    lib.ref_cpu_describe.restype = C.c_int
+    lib.ref_cpu_describe.argtypes = [C.c_void_p, C.c_uint32, C.c_int, C.c_int, C.c_char_p, C.c_int]
+    return lib
+
+
+class RefCpuSearch:
+    """The reference's CPU index structs built from the arrays of an index (BWT code words of the text and of the reversed text,
+    packed text, suffix array), and its CPU search over a batch of reads."""
+
+    def __init__(self, lib, bwt, rbwt, isa0, risa0, n, pac, sa, threads=0):
+        self.lib = lib
+        self.keep = (bwt, rbwt, pac, sa)                   # the suffix array is used in place
+        self.h = lib.ref_cpu_create(u32p(bwt), u32p(rbwt), len(bwt), isa0, risa0, n, u32p(pac), u32p(sa), threads)
+        if not self.h:
+            raise RuntimeError("ref_cpu_create failed")
+
+    def describe(self, read_length, k, num_cases):
+        buf = C.create_string_buffer(16384)
+        self.lib.ref_cpu_describe(self.h, read_length, k, num_cases, buf, len(buf))
+        return buf.value.decode()
+
+    def search(self, reads, k, num_cases, max_output_per_read=0xFFFFFFFF, threads=0, out_cap=0):
+        """reads: [n, L] uint8 base codes -> dict(total, counts [n, 4] = ranges, occurrences in ranges, check-and-extend occurrences,
+        total; and with out_cap: hits = per read a list of (position, strand, mismatches))"""
+        reads = np.ascontiguousarray(reads, dtype=np.uint8)
+        n, L = reads.shape
+        counts = np.zeros(4 * n, np.uint32)
+        if out_cap:
+            pos, st, mm, on = np.zeros(n * out_cap, np.uint32), np.zeros(n * out_cap, np.uint8), np.zeros(n * out_cap, np.uint8), np.zeros(n, np.uint32)
+            args = (out_cap, u32p(pos), st.ctypes.data_as(U8P), mm.ctypes.data_as(U8P), u32p(on))
+        else:
+            args = (0, None, None, None, None)
+        total = self.lib.ref_cpu_search(self.h, reads.ctypes.data_as(U8P), n, L, k, num_cases, max_output_per_read, threads, u32p(counts), *args)
+        out = dict(total=int(total), counts=counts.reshape(n, 4))
+        if out_cap:
+            out["hits"] = [[(int(pos[r * out_cap + i]), int(st[r * out_cap + i]), int(mm[r * out_cap + i])) for i in range(int(on[r]))] for r in range(n)]
+        return out
+
+    def free(self):
+        if self.h:
+            self.lib.ref_cpu_free(self.h)
+            self.h = None

@@ -6,6 +6,7 @@ import pytest
 
 from helpers import (DPBatch, HostIndex, compare_dp, fmindex, formats, load_oracle, load_oracle_dp, load_ref_dp,
                      load_ref_search, make_dp_batch, oracle_dp, oracle_launch, ref_dp, ref_launch, u32p)
+import helpers
 from soap3dp_b200 import synth
 
 rlib = load_ref_search()
@@ -285,3 +286,61 @@ def test_dp_without_the_full_table_gives_the_same_alignments():
         compare_dp(b, resweep(b, (1, -1, -2, -1), 8, 0, adv), oracle_dp(lib, b, (1, -1, -2, -1)), f"resweep adversarial {seed} b")
     print("resweep cost (fraction of columns swept again, restarts per 600):", {k: (round(v[0], 3), v[1]) for k, v in cost.items()},
           f"; adversarial {adv[0]} of {adv[2]} columns, {adv[1]} restarts")
+
+
+clib = helpers.load_ref_cpu_search()
+
+
+@pytest.mark.skipif(clib is None, reason="oracle/_ref/libref_cpu_search.so not built")
+@pytest.mark.parametrize("L", [100, 75])
+def test_search_oracle_finds_what_the_reference_cpu_search_finds(L):
+    """The reference's own CPU search -- ProcessReadDoubleStrand2 per case on the models SRAModelConstruct builds, with its 13-mer
+    lookup tables and check-and-extend, as hostKernel runs it for a read the GPU left over (CPUfunctions.cpp:1313-1328) --
+    reports, for every read and mismatch level, exactly the (position, strand, mismatches) set the answer slots of the
+    search oracle expand to."""
+    G = synth.random_genome(300_000, seed=5)
+    idx = fmindex.build_index(G, keep_sa=True)
+    hi = HostIndex(idx)
+    sa = idx.fwd.sa.cpu().numpy().astype(np.uint32)
+    pac = idx.packed_text.cpu().numpy().view(np.uint32)
+    ref = helpers.RefCpuSearch(clib, hi.bwt, hi.rbwt, hi.isa0, hi.risa0, hi.n, pac, sa, threads=2)
+    olib = load_oracle()
+    n = 1500
+    try:
+        for k in range(5):
+            assert ref.describe(L, k, formats.NUM_CASES[k]).count("case") == formats.NUM_CASES[k]
+            rs = synth.simulate_single_end(G, n, L, seed=30 + k, sub_rate=0.02)
+            reads = np.ascontiguousarray(rs.reads.cpu().numpy().astype(np.uint8))
+            got = ref.search(reads, k, formats.NUM_CASES[k], threads=2, out_cap=2048)
+            wpq = formats.word_per_query(L)
+            lens = np.zeros(formats.ceil32(n), np.uint32)
+            lens[:n] = L
+            q = formats.pack_queries(reads, lens[:n], wpq)
+            allowed = 1024
+            wpa = 2 * allowed
+            bad = np.zeros(formats.ceil32(n), np.uint8)
+            want = [set() for _ in range(n)]
+            for case in range(formats.NUM_CASES[k]):
+                a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+                oracle_launch(olib, hi, case, q, lens, n, wpq, a, bad, 0, k, allowed, wpa)
+                v = formats.answers_view(a, n, wpa)
+                for r in range(n):
+                    w = v[r]
+                    assert int(w[0]) <= 0xFFFFFFFD
+                    if int(w[0]) == 0xFFFFFFFD:
+                        continue
+                    for i in range(allowed):
+                        a0, a1 = int(w[2 * i]), int(w[2 * i + 1])
+                        if a0 >= 0xFFFFFFFD or a1 >= 0xFFFFFFFD:
+                            break
+                        for j in range(a0, a0 + (a1 & 0xFFFFFF) + 1):
+                            want[r].add((int(sa[j]), ((a1 >> 27) & 1) + 1, (a1 >> 24) & 7))
+            found = 0
+            for r in range(n):
+                assert len(got["hits"][r]) == len(set(got["hits"][r])), (k, r)
+                assert set(got["hits"][r]) == want[r], (k, r)
+                assert int(got["counts"][r, 3]) == len(want[r])
+                found += bool(want[r])
+            assert found > n // 10
+    finally:
+        ref.free()

@@ -716,12 +716,14 @@ def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream
     if os.path.exists(tr_path):
         traffic = json.load(open(tr_path))
     tkey = f"search_launch_k{k}"
-    roof = {"kernel": f"search launch, k <= {k} ({ncases} cases)", "bound": "hbm", "unit": "G sectors/s", "ms_per_launch": 1e3 * t_search / K,
-            "share_of_step": (t_search / K) / (t_total / K), "peak": sector_rate / 1e9 if sector_rate else None,
-            "peak_source": "s3_random_sector_probe in this run: independent random 32-byte reads over the index's bucket array",
-            "traffic": traffic.get(tkey), "achieved": None, "frac": None}
+    per_load = float(traffic.get("random_sector_probe_dram_bytes_per_load") or 64.0)
+    roof = {"kernel": f"search launch, k <= {k} ({ncases} cases)", "bound": "hbm", "unit": "GB/s", "ms_per_launch": 1e3 * t_search / K,
+            "share_of_step": (t_search / K) / (t_total / K), "peak": sector_rate * per_load / 1e9 if sector_rate else None,
+            "peak_source": "s3_random_sector_probe in this run (independent random 32-byte loads over the index's bucket array) x "
+                           f"{per_load:.0f} DRAM bytes per load (ncu of the probe kernel, profiles/ncu_traffic.json)",
+            "random_loads_per_s": sector_rate, "traffic": traffic.get(tkey), "achieved": None, "frac": None}
     if traffic.get(tkey) and sector_rate:
-        roof["achieved"] = traffic[tkey] / 32.0 / (t_search / K) / 1e9
+        roof["achieved"] = traffic[tkey] / (t_search / K) / 1e9
         roof["frac"] = roof["achieved"] / roof["peak"]
     out = {"metric": f"reads/s searched and located (SE {L} bp, <= {k} mismatches, 3.1 Gbp synth ref)", "value": value, "unit": "reads/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -897,6 +899,10 @@ def main():
         f"suffix array + inverse + packed text)")
     stream = torch.cuda.ExternalStream(gi.stream, device=device)
     total = args.warmup + args.steps
+    if os.environ.get("S3_PROBE_ONLY"):                       # ncu of the probe itself: DRAM bytes per random 32-byte load (profiles/)
+        print(json.dumps({"random_sector_loads_per_s": random_sector_rate(gi, device)}), flush=True)
+        api.GPUINDEXFree(gi)
+        return
     if os.environ.get("S3_L2_REGION"):                        # ncu captures with a window in place (profiles/exp_l2_persist.sh)
         api.set_l2_persist(gi, int(os.environ["S3_L2_REGION"]))
     if args.config == "se100_k4":
@@ -1137,18 +1143,21 @@ def main():
     except Exception as e:                                   # noqa: BLE001
         log("random sector probe failed:", e)
         sector_rate = None
-    # the search launch against the random-sector rate of this run: executed 32-byte sectors per launch (ncu dram__sectors_read
-    # of the launch's kernels, profiles/ncu_traffic.json) / launch time / probe rate
+    # the search launch against the random-access rate of this run, both in DRAM bytes: achieved = DRAM bytes the launch's kernels
+    # moved (ncu dram__bytes_read + write, profiles/ncu_traffic.json) / launch time; peak = the probe's independent random 32-byte
+    # loads per second x the DRAM bytes ncu counts per such load (HBM3e moves a 64-byte burst per random 32-byte sector:
+    # profiles/ncu_traffic.json "random_sector_probe_dram_bytes_per_load")
+    per_load = float(traffic.get("random_sector_probe_dram_bytes_per_load") or 64.0)
     search_roof = {"kernel": "search launch (s3_search_easy_kernel + s3_search_kernel<items|spine|tasks> + merge)", "bound": "hbm",
-                   "unit": "G sectors/s", "ms_per_launch": 1e3 * t_search / K, "share_of_step": (t_search / K) / (t_step_hooks / 1e3) if t_step_hooks else None,
-                   "peak": sector_rate / 1e9 if sector_rate else None,
-                   "peak_source": "s3_random_sector_probe in this run: independent random 32-byte reads over the index's bucket array",
-                   "traffic": traffic.get("search_launch")}
+                   "unit": "GB/s", "ms_per_launch": 1e3 * t_search / K, "share_of_step": (t_search / K) / (t_step_hooks / 1e3) if t_step_hooks else None,
+                   "peak": sector_rate * per_load / 1e9 if sector_rate else None,
+                   "peak_source": "s3_random_sector_probe in this run (independent random 32-byte loads over the index's bucket array) x "
+                                  f"{per_load:.0f} DRAM bytes per load (ncu of the probe kernel, profiles/ncu_traffic.json)",
+                   "random_loads_per_s": sector_rate, "traffic": traffic.get("search_launch")}
     if traffic.get("search_launch") and sector_rate:
-        search_roof["achieved"] = traffic["search_launch"] / 32.0 / (t_search / K) / 1e9
+        search_roof["achieved"] = traffic["search_launch"] / (t_search / K) / 1e9
         search_roof["frac"] = search_roof["achieved"] / search_roof["peak"]
-        search_roof["achieved_gbs"] = traffic["search_launch"] / (t_search / K) / 1e9
-        search_roof["frac_of_hbm_copy_peak"] = search_roof["achieved_gbs"] / hbm_peak
+        search_roof["frac_of_hbm_copy_peak"] = search_roof["achieved"] / hbm_peak
     dp_traffic = None
     if all(traffic.get(k2) is not None for k2 in ("s3_dp_sweep16_kernel", "s3_dp_resweep16_kernel", "s3_dp_traceback16_kernel")):
         dp_traffic = sum(traffic[k2] for k2 in ("s3_dp_sweep16_kernel", "s3_dp_resweep16_kernel", "s3_dp_traceback16_kernel"))

@@ -539,17 +539,40 @@ typedef struct {
     uint32_t numMismatch;                 /* 0..4 */
     uint32_t maxOutputPerRead;            /* soap3-dp.ini MaxOutputPerRead */
     int32_t reportBest;                   /* 0: all valid alignments, 1: all best */
+    /* long reads (single_end_alignment, alignment.cu:2475-2491; hostKernel, CPUfunctions.cpp:1812-1842): with longReadMode the
+     * search aligns the first S3_LONG_READ_SEED_LEN bases of every read longer than S3_LONG_READ_LEN, and each occurrence is
+     * then extended over the rest of the read by s3_validate_alignments' rule; the list is cut to maxOutputPerRead.  The other
+     * three fields are validateAlignments' only_keep_best_ans, min_seed_mismatch_allowed and needOutputMAPQ (allowance x 2). */
+    int32_t longReadMode, onlyKeepBest, minSeedMismatch, doubleAllowance;
 } s3_se_params;
 typedef struct {
     uint64_t numReads, numRanges, numOccurrences, h2dBytes, d2hBytes;
     uint32_t *occOffsets, *positions; uint8_t *occFlags, *readFlags;                  /* host (s3_se_align) */
     uint32_t *d_occOffsets, *d_positions; uint8_t *d_occFlags, *d_readFlags;          /* device (s3_se_align_device) */
 } s3_se_result;
+#define S3_LONG_READ_LEN 120u             /* definitions.h:140 */
+#define S3_LONG_READ_SEED_LEN 100u        /* definitions.h:141 */
 int s3_se_create(s3_index *ix, uint32_t maxReads, const s3_se_params *params, s3_se **out);
 void s3_se_free(s3_se *se);
 int s3_se_align(s3_se *se, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery, s3_se_result *out);
 int s3_se_align_device(s3_se *se, const uint32_t *d_queries, const uint32_t *d_readLengths, uint64_t numReads, uint32_t wordPerQuery,
                        s3_se_result *out);
+
+/* ------------------------------------------------------------------------
+ * Long reads: ungapped extension of seed alignments.  Replaces validateAlignments (CPUfunctions.cpp:1129-1222, with
+ * createQueryPackedDNA / createRevQueryPackedDNA / createTargetPackedDNA / numMismatchNew, PE.cpp:28-60,148-178,287-325) as
+ * hostKernel applies it to the occurrence list of every read in long-read mode (CPUfunctions.cpp:1812-1842).  Host arrays:
+ * the occurrences of read r are positions / occFlags (strand, mismatches of the first seedLen bases) [occOffsets[r],
+ * occOffsets[r + 1]); seedLen = S3_LONG_READ_SEED_LEN for reads longer than S3_LONG_READ_LEN, else the read length (nothing to
+ * extend: the list is only cut to maxHitNum).  An occurrence stays when seed mismatches + Hamming distance of the remaining
+ * bases <= ceil(0.02 * readLen) (twice that with doubleAllowance); a reverse-strand occurrence moves to the start of the
+ * whole read; entries with fewer than minSeedMismatch seed mismatches are skipped; onlyKeepBest keeps the running best (the
+ * output restarts when a better total turns up) and the walk stops once maxHitNum entries with minSeedMismatch in total are
+ * out.  In place: the outCounts[r] kept entries of read r are at the front of its list.  Needs the packed text on the device.
+ * ------------------------------------------------------------------------ */
+int s3_validate_alignments(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
+                           const uint32_t *occOffsets, uint32_t *positions, uint8_t *occFlags, int onlyKeepBest, int minSeedMismatch,
+                           int doubleAllowance, int maxHitNum, uint32_t *outCounts);
 
 /* ------------------------------------------------------------------------
  * Tables of the DP stages (host, integer).  s3_seed_layout replaces getSeedPositions

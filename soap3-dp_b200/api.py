@@ -40,7 +40,7 @@ EXPORTS = [
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
     "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows", "s3_index_set_l2_persist", "s3_index_clone",
     "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
-    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_seed_search", "s3_seed_search_result_free",
+    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_validate_alignments", "s3_seed_search", "s3_seed_search_result_free",
     "s3_single_dp_align", "s3_single_dp_result_free", "s3_deep_dp_align", "s3_deep_dp_result_free",
 ]
 
@@ -837,7 +837,8 @@ def make_windows(gpu_index: GpuIndex, mode: int, params: WindowParams, read_leng
 # single-end batch on the device (s3_se_*): the in-memory alignSingleR (soap3-dp-module.cu:62)
 # ---------------------------------------------------------------------------------------------------------------------
 class SEParams(C.Structure):
-    _fields_ = [("numMismatch", C.c_uint32), ("maxOutputPerRead", C.c_uint32), ("reportBest", C.c_int32)]
+    _fields_ = [("numMismatch", C.c_uint32), ("maxOutputPerRead", C.c_uint32), ("reportBest", C.c_int32),
+                ("longReadMode", C.c_int32), ("onlyKeepBest", C.c_int32), ("minSeedMismatch", C.c_int32), ("doubleAllowance", C.c_int32)]
 
 
 class SEResult(C.Structure):
@@ -849,7 +850,8 @@ class SEResult(C.Structure):
 class SingleAligner:
     """s3_se_create / s3_se_align: alignSingleR's results (occurrences per read) for a batch, on the device."""
 
-    def __init__(self, gpu_index: GpuIndex, max_reads: int, num_mismatch: int = 2, max_output_per_read: int = 1000, report_best: bool = False):
+    def __init__(self, gpu_index: GpuIndex, max_reads: int, num_mismatch: int = 2, max_output_per_read: int = 1000, report_best: bool = False,
+                 long_read_mode: bool = False, only_keep_best: bool = False, min_seed_mismatch: int = 0, double_allowance: bool = False):
         lib = load_library()
         lib.s3_se_create.restype = C.c_int
         lib.s3_se_create.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(SEParams), C.POINTER(C.c_void_p)]
@@ -858,7 +860,7 @@ class SingleAligner:
         for fn in (lib.s3_se_align, lib.s3_se_align_device):
             fn.restype = C.c_int
             fn.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.c_uint32, C.POINTER(SEResult)]
-        par = SEParams(num_mismatch, max_output_per_read, int(report_best))
+        par = SEParams(num_mismatch, max_output_per_read, int(report_best), int(long_read_mode), int(only_keep_best), min_seed_mismatch, int(double_allowance))
         out = C.c_void_p()
         _check(lib.s3_se_create(gpu_index.handle, max_reads, C.byref(par), C.byref(out)), "s3_se_create")
         self.handle = out
@@ -889,6 +891,24 @@ class SingleAligner:
         if self.handle:
             load_library().s3_se_free(self.handle)
             self.handle = C.c_void_p(0)
+
+
+def validate_alignments(gpu_index: GpuIndex, queries, read_lengths, num_reads: int, word_per_query: int, occ_offsets, positions, occ_flags,
+                        only_keep_best=False, min_seed_mismatch=0, double_allowance=False, max_hit_num=1000):
+    """s3_validate_alignments (validateAlignments, CPUfunctions.cpp:1129): -> (counts[num_reads], positions, occ_flags updated copies)"""
+    lib = load_library()
+    lib.s3_validate_alignments.restype = C.c_int
+    lib.s3_validate_alignments.argtypes = [C.c_void_p, U32P, U32P, C.c_uint64, C.c_uint32, U32P, U32P, U8P, C.c_int, C.c_int, C.c_int, C.c_int, U32P]
+    pos = np.ascontiguousarray(positions, np.uint32).copy()
+    fl = np.ascontiguousarray(occ_flags, np.uint8).copy()
+    off = np.ascontiguousarray(occ_offsets, np.uint32)
+    counts = np.zeros(max(num_reads, 1), np.uint32)
+    if len(pos) == 0:
+        pos, fl = np.zeros(1, np.uint32), np.zeros(2, np.uint8)
+    _check(lib.s3_validate_alignments(gpu_index.handle, _u32(queries), _u32(read_lengths), num_reads, word_per_query, _u32(off), _u32(pos),
+                                      fl.ctypes.data_as(U8P), int(only_keep_best), min_seed_mismatch, int(double_allowance), max_hit_num, _u32(counts)),
+           "s3_validate_alignments")
+    return counts[:num_reads], pos, fl
 
 
 class SeedSearchResult(C.Structure):

@@ -773,6 +773,126 @@ __global__ void s3_se_select_kernel(uint32_t numReads, const uint32_t *__restric
     locCount[r] = tot;
 }
 
+__global__ void s3_se_seed_length_kernel(uint32_t up, uint32_t numReads, const uint32_t *__restrict__ readLengths, uint32_t *__restrict__ seedLengths)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= up) return;
+    const uint32_t len = r < numReads ? readLengths[r] : 0u;
+    seedLengths[r] = len > S3_LONG_READ_LEN ? S3_LONG_READ_SEED_LEN : len;
+}
+
+// ---- long reads: the seed alignments of reads longer than 120 bases are extended without gaps over the rest of the read ------
+// validateAlignments (CPUfunctions.cpp:1129-1222) as hostKernel calls it (:1812-1842): the search aligned the first 100 bases
+// (alignment.cu:2475-2491); an occurrence stays if its seed mismatches + the Hamming distance of the other readLen - 100 bases
+// (PE.cpp:28-60, 148-178, 287-325) is within ceil(0.02 * readLen) (twice that when MAPQ is wanted); a reverse-strand occurrence
+// moves to the start of the whole read.  onlyKeepBest keeps the running best only (an earlier, worse entry is dropped when a
+// better one turns up: the output size resets), the walk stops once maxHitNum entries of minSeedMismatch total are out, and the
+// list is cut to maxHitNum.  One thread per read, in place: the kept entries of read r move to the front of its list.
+__device__ __forceinline__ uint32_t s3_val_text(const uint32_t *__restrict__ text, uint64_t p) { return (__ldg(text + (p >> 4)) >> (30u - 2u * ((uint32_t)p & 15u))) & 3u; }
+__device__ __forceinline__ uint32_t s3_val_read(const uint32_t *__restrict__ q, uint32_t wpq, uint32_t r, uint32_t k)
+{
+    return (__ldg(q + (size_t)(r / 32) * 32 * wpq + (size_t)(k >> 4) * 32 + r % 32) >> ((k & 15u) << 1)) & 3u;
+}
+
+__global__ void s3_validate_kernel(uint32_t numReads, const uint32_t *__restrict__ queries, uint32_t wpq, const uint32_t *__restrict__ readLengths,
+                                   const uint32_t *__restrict__ text, uint32_t textLength, const uint32_t *__restrict__ off, uint32_t *__restrict__ pos,
+                                   uint8_t *__restrict__ flags, int onlyKeepBest, int minSeedMismatch, int doubleAllowance, int maxHitNum,
+                                   uint32_t *__restrict__ outCount)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= numReads) return;
+    const uint32_t a = off[r], n = off[r + 1] - a, len = readLengths[r], seed = len > S3_LONG_READ_LEN ? S3_LONG_READ_SEED_LEN : len;
+    uint32_t m = n;
+    if (n && len > seed) {
+        const uint32_t ext = len - seed;
+        int maxMismatch = (int)((len + 49u) / 50u);                                   // ceil(0.02 * len)
+        if (doubleAllowance) maxMismatch *= 2;
+        int pre = maxMismatch;
+        m = 0;
+        for (uint32_t i = 0; i < n; ++i) {
+            const uint32_t p = pos[a + i], st = flags[2 * (size_t)(a + i)];
+            const int mm = flags[2 * (size_t)(a + i) + 1];
+            if (mm < minSeedMismatch) continue;
+            int mismatch = maxMismatch + 1;
+            if (st == 1 && (uint64_t)p + len <= textLength) {
+                mismatch = 0;
+                for (uint32_t j = 0; j < ext && mismatch + mm <= maxMismatch; ++j) mismatch += s3_val_text(text, (uint64_t)p + seed + j) != s3_val_read(queries, wpq, r, seed + j);
+            }
+            if (st == 2 && p >= ext) {
+                mismatch = 0;
+                for (uint32_t j = 0; j < ext && mismatch + mm <= maxMismatch; ++j) mismatch += s3_val_text(text, (uint64_t)p - ext + j) != 3u - s3_val_read(queries, wpq, r, len - 1 - j);
+            }
+            const int tot = mismatch + mm;
+            if (tot > maxMismatch) continue;
+            if (onlyKeepBest && tot > pre) continue;
+            if (onlyKeepBest && tot < pre) { m = 0; pre = tot; }
+            pos[a + m] = st == 1 ? p : p - ext;
+            flags[2 * (size_t)(a + m)] = (uint8_t)st;
+            flags[2 * (size_t)(a + m) + 1] = (uint8_t)tot;
+            ++m;
+            if (pre == minSeedMismatch && (int)m >= maxHitNum) break;
+        }
+    }
+    if (n && (int)m > maxHitNum) m = (uint32_t)maxHitNum;
+    outCount[r] = m;
+}
+
+// kept entries of every read, gathered into lists of their own (offsets = exclusive scan of the counts)
+__global__ void s3_validate_gather_kernel(uint32_t numReads, const uint32_t *__restrict__ off, const uint32_t *__restrict__ count, const uint32_t *__restrict__ newOff,
+                                          const uint32_t *__restrict__ pos, const uint8_t *__restrict__ flags, uint32_t *__restrict__ outPos, uint8_t *__restrict__ outFlags)
+{
+    const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= numReads) return;
+    const uint32_t a = off[r], b = newOff[r], m = count[r];
+    for (uint32_t i = 0; i < m; ++i) {
+        outPos[b + i] = pos[a + i];
+        outFlags[2 * (size_t)(b + i)] = flags[2 * (size_t)(a + i)];
+        outFlags[2 * (size_t)(b + i) + 1] = flags[2 * (size_t)(a + i) + 1];
+    }
+}
+
+extern "C" int s3_validate_alignments(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
+                                      const uint32_t *occOffsets, uint32_t *positions, uint8_t *occFlags, int onlyKeepBest, int minSeedMismatch,
+                                      int doubleAllowance, int maxHitNum, uint32_t *outCounts)
+{
+    if (!ix || !queries || !readLengths || !occOffsets || !positions || !occFlags || !outCounts || maxHitNum < 1) { s3_set_error("s3_validate_alignments: bad argument"); return S3_EINVAL; }
+    if (!ix->loc.text) { s3_set_error("s3_validate_alignments: the index was uploaded without its packed text"); return S3_EINVAL; }
+    if (numReads == 0) return S3_OK;
+    if (numReads > 0xFFFFFFF0ull) { s3_set_error("s3_validate_alignments: too many reads"); return S3_EINVAL; }
+    const uint32_t N = (uint32_t)numReads, T = occOffsets[N];
+    for (uint32_t r = 0; r < N; ++r) {
+        if (occOffsets[r] > occOffsets[r + 1]) { s3_set_error("s3_validate_alignments: offsets not ascending at read %u", r); return S3_EINVAL; }
+        if (readLengths[r] > 16u * wordPerQuery) { s3_set_error("s3_validate_alignments: read %u longer than its query words", r); return S3_EINVAL; }
+    }
+    S3_TRYC(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const size_t up = ((size_t)N + 31) / 32 * 32, Tm = T ? T : 1;
+    uint32_t *d_q = NULL, *d_len = NULL, *d_off = NULL, *d_pos = NULL, *d_cnt = NULL;
+    uint8_t *d_fl = NULL;
+    int rc = S3_OK;
+#define S3_VAL(call) do { cudaError_t e_ = (call); if (e_ != cudaSuccess && rc == S3_OK) { s3_set_error("s3_validate_alignments: %s", cudaGetErrorString(e_)); rc = S3_ECUDA; } } while (0)
+    S3_VAL(cudaMalloc(&d_q, up * wordPerQuery * 4)); S3_VAL(cudaMalloc(&d_len, (size_t)N * 4)); S3_VAL(cudaMalloc(&d_off, ((size_t)N + 1) * 4));
+    S3_VAL(cudaMalloc(&d_pos, Tm * 4)); S3_VAL(cudaMalloc(&d_fl, 2 * Tm)); S3_VAL(cudaMalloc(&d_cnt, (size_t)N * 4));
+    if (rc == S3_OK) {
+        S3_VAL(cudaMemcpyAsync(d_q, queries, up * wordPerQuery * 4, cudaMemcpyHostToDevice, st));
+        S3_VAL(cudaMemcpyAsync(d_len, readLengths, (size_t)N * 4, cudaMemcpyHostToDevice, st));
+        S3_VAL(cudaMemcpyAsync(d_off, occOffsets, ((size_t)N + 1) * 4, cudaMemcpyHostToDevice, st));
+        if (T) { S3_VAL(cudaMemcpyAsync(d_pos, positions, (size_t)T * 4, cudaMemcpyHostToDevice, st)); S3_VAL(cudaMemcpyAsync(d_fl, occFlags, 2 * (size_t)T, cudaMemcpyHostToDevice, st)); }
+    }
+    if (rc == S3_OK) {
+        s3_validate_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, d_q, wordPerQuery, d_len, ix->loc.text, ix->textLength, d_off, d_pos, d_fl, onlyKeepBest, minSeedMismatch,
+                                                             doubleAllowance, maxHitNum, d_cnt);
+        S3_LAUNCHED(1);
+        S3_VAL(cudaGetLastError());
+        if (T) { S3_VAL(cudaMemcpyAsync(positions, d_pos, (size_t)T * 4, cudaMemcpyDeviceToHost, st)); S3_VAL(cudaMemcpyAsync(occFlags, d_fl, 2 * (size_t)T, cudaMemcpyDeviceToHost, st)); }
+        S3_VAL(cudaMemcpyAsync(outCounts, d_cnt, (size_t)N * 4, cudaMemcpyDeviceToHost, st));
+        S3_VAL(cudaStreamSynchronize(st));
+    }
+#undef S3_VAL
+    cudaFree(d_q); cudaFree(d_len); cudaFree(d_off); cudaFree(d_pos); cudaFree(d_fl); cudaFree(d_cnt);
+    return rc;
+}
+
 extern "C" int s3_se_create(s3_index *ix, uint32_t maxReads, const s3_se_params *params, s3_se **out)
 {
     if (!ix || !params || !out || maxReads == 0) { s3_set_error("s3_se_create: bad argument"); return S3_EINVAL; }
@@ -814,7 +934,7 @@ static int se_run(s3_se *se, const uint32_t *queries, const uint32_t *readLength
     int rc;
     size_t scanTemp = 0;
     cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (uint32_t *)NULL, (uint32_t *)NULL, (int)(N + 1), st);
-    const size_t needA = arena_need(up * wordPerQuery, 4) + arena_need(up, 4) + C * arena_need(up * wpa, 4) + 5 * arena_need(N + 1, 4) + arena_need(N, 1) +
+    const size_t needA = arena_need(up * wordPerQuery, 4) + arena_need(up, 4) + C * arena_need(up * wpa, 4) + 7 * arena_need(N + 1, 4) + arena_need(up, 4) + arena_need(N, 1) +
                          2 * arena_need(maxRanges, 4) + arena_need(maxRanges, 2) + arena_need(maxRanges, 1) + arena_need(scanTemp, 1) + 4096;
     if ((rc = arena_reserve(&se->A, needA, st))) return rc;
     S3Arena *A = &se->A;
@@ -825,6 +945,7 @@ static int se_run(s3_se *se, const uint32_t *queries, const uint32_t *readLength
     uint32_t *d_nRanges = arena_take<uint32_t>(A, N + 1), *d_rangeOff = arena_take<uint32_t>(A, N + 1), *d_totOcc = arena_take<uint32_t>(A, N + 1);
     uint32_t *d_locCount = arena_take<uint32_t>(A, N + 1), *d_locOff = arena_take<uint32_t>(A, N + 1);
     uint8_t *d_readFlags = arena_take<uint8_t>(A, N);
+    uint32_t *d_seedLen = arena_take<uint32_t>(A, up), *d_valCount = arena_take<uint32_t>(A, N + 1), *d_valOff = arena_take<uint32_t>(A, N + 1);
     uint32_t *d_saL = arena_take<uint32_t>(A, maxRanges), *d_saR = arena_take<uint32_t>(A, maxRanges);
     uint8_t *d_saFlags = arena_take<uint8_t>(A, 2 * maxRanges), *d_keep = arena_take<uint8_t>(A, maxRanges);
     void *d_tmp = arena_take<char>(A, scanTemp);
@@ -833,7 +954,14 @@ static int se_run(s3_se *se, const uint32_t *queries, const uint32_t *readLength
         S3_TRYC(cudaMemcpyAsync(d_q, queries, up * wordPerQuery * 4, cudaMemcpyHostToDevice, st));
         S3_TRYC(cudaMemcpyAsync(d_len, readLengths, (size_t)N * 4, cudaMemcpyHostToDevice, st));
     }
-    if ((rc = s3_search_round1_device(ix, d_q, d_len, N, wordPerQuery, k, C, allowed, wpa, 0, d_ans, NULL))) return rc;
+    // long-read mode: the search aligns the first 100 bases of a read longer than 120 (alignment.cu:2475-2491)
+    uint32_t *d_searchLen = d_len;
+    if (se->par.longReadMode) {
+        d_searchLen = d_seedLen;
+        s3_se_seed_length_kernel<<<(unsigned)((up + 255) / 256), 256, 0, st>>>((uint32_t)up, N, d_len, d_seedLen);
+        S3_LAUNCHED(1);
+    }
+    if ((rc = s3_search_round1_device(ix, d_q, d_searchLen, N, wordPerQuery, k, C, allowed, wpa, 0, d_ans, NULL))) return rc;
     S3Collect col;
     memset(&col, 0, sizeof col);
     for (uint32_t c = 0; c < C; ++c) col.answers[c] = d_ans[c];
@@ -866,13 +994,31 @@ static int se_run(s3_se *se, const uint32_t *queries, const uint32_t *readLength
         S3_LAUNCHED(1);
         S3_TRYC(cudaGetLastError());
     }
-    res->numReads = N; res->numRanges = se->h_counts[1]; res->numOccurrences = T;
+    uint32_t Tout = T;
+    if (se->par.longReadMode && T) {
+        // validateAlignments on every read's list, then the kept entries gathered into lists of their own
+        if (!ix->loc.text) { s3_set_error("s3_se_align: long-read mode needs the packed text on the device"); return S3_EINVAL; }
+        S3_TRYC(cudaMemsetAsync(d_valCount + N, 0, 4, st));
+        s3_validate_kernel<<<(N + 127) / 128, 128, 0, st>>>(N, d_q, wordPerQuery, d_len, ix->loc.text, ix->textLength, d_locOff, d_occPos, d_occFlags,
+                                                             se->par.onlyKeepBest, se->par.minSeedMismatch, se->par.doubleAllowance,
+                                                             (int)se->par.maxOutputPerRead, d_valCount);
+        S3_TRYC(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_valCount, d_valOff, (int)(N + 1), st));
+        s3_validate_gather_kernel<<<nbR, 256, 0, st>>>(N, d_locOff, d_valCount, d_valOff, d_occPos, d_occFlags, (uint32_t *)d_key, (uint8_t *)d_val);
+        S3_LAUNCHED(3);
+        S3_TRYC(cudaGetLastError());
+        S3_TRYC(cudaMemcpyAsync(se->h_counts + 2, d_valOff + N, 4, cudaMemcpyDeviceToHost, st));
+        S3_TRYC(cudaStreamSynchronize(st));
+        Tout = se->h_counts[2];
+        d_locOff = d_valOff; d_occPos = (uint32_t *)d_key; d_occFlags = (uint8_t *)d_val;
+    }
+    res->numReads = N; res->numRanges = se->h_counts[1]; res->numOccurrences = Tout;
     if (onDevice) {
         S3_TRYC(cudaStreamSynchronize(st));
         res->d_occOffsets = d_locOff; res->d_positions = d_occPos; res->d_occFlags = d_occFlags; res->d_readFlags = d_readFlags;
         return S3_OK;
     }
-    const size_t bytes = ((size_t)N + 1) * 4 + 256 + Tm * 4 + 256 + 2 * Tm + 256 + N + 256;
+    const size_t To = Tout ? Tout : 1;
+    const size_t bytes = ((size_t)N + 1) * 4 + 256 + To * 4 + 256 + 2 * To + 256 + N + 256;
     if (bytes > se->pinnedBytes) {
         if (se->pinned) { cudaFreeHost(se->pinned); se->pinned = NULL; se->pinnedBytes = 0; }
         if (cudaMallocHost(&se->pinned, bytes + bytes / 4) != cudaSuccess) { s3_set_error("s3_se_align: pinned allocation failed"); return S3_ENOMEM; }
@@ -880,18 +1026,18 @@ static int se_run(s3_se *se, const uint32_t *queries, const uint32_t *readLength
     }
     char *h = (char *)se->pinned;
     res->occOffsets = (uint32_t *)h; h += (((size_t)N + 1) * 4 + 255) / 256 * 256;
-    res->positions = (uint32_t *)h; h += (Tm * 4 + 255) / 256 * 256;
-    res->occFlags = (uint8_t *)h; h += (2 * Tm + 255) / 256 * 256;
+    res->positions = (uint32_t *)h; h += (To * 4 + 255) / 256 * 256;
+    res->occFlags = (uint8_t *)h; h += (2 * To + 255) / 256 * 256;
     res->readFlags = (uint8_t *)h;
     S3_TRYC(cudaMemcpyAsync(res->occOffsets, d_locOff, ((size_t)N + 1) * 4, cudaMemcpyDeviceToHost, st));
-    if (T) {
-        S3_TRYC(cudaMemcpyAsync(res->positions, d_occPos, (size_t)T * 4, cudaMemcpyDeviceToHost, st));
-        S3_TRYC(cudaMemcpyAsync(res->occFlags, d_occFlags, (size_t)T * 2, cudaMemcpyDeviceToHost, st));
+    if (Tout) {
+        S3_TRYC(cudaMemcpyAsync(res->positions, d_occPos, (size_t)Tout * 4, cudaMemcpyDeviceToHost, st));
+        S3_TRYC(cudaMemcpyAsync(res->occFlags, d_occFlags, (size_t)Tout * 2, cudaMemcpyDeviceToHost, st));
     }
     S3_TRYC(cudaMemcpyAsync(res->readFlags, d_readFlags, N, cudaMemcpyDeviceToHost, st));
     S3_TRYC(cudaStreamSynchronize(st));
     res->h2dBytes = up * wordPerQuery * 4 + (size_t)N * 4;
-    res->d2hBytes = ((size_t)N + 1) * 4 + (size_t)T * 6 + N + 8;
+    res->d2hBytes = ((size_t)N + 1) * 4 + (size_t)Tout * 6 + N + 8;
     return S3_OK;
 }
 

@@ -292,6 +292,12 @@ extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const u
         return S3_ECUDA;
     }
     S3_CUDA(cudaSetDevice(device));
+    if (const char *g = getenv("S3_L2_FETCH_GRANULARITY")) {              // measurement knob (profiles/): 32 / 64 / 128
+        size_t got = 0;
+        cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(g));
+        cudaDeviceGetLimit(&got, cudaLimitMaxL2FetchGranularity);
+        fprintf(stderr, "[soap3dp_b200] cudaLimitMaxL2FetchGranularity asked %s, is %zu\n", g, got);
+    }
     s3_index *ix = (s3_index *)calloc(1, sizeof(s3_index));
     if (!ix) { s3_set_error("out of host memory"); return S3_ENOMEM; }
     ix->device = device;

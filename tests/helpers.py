@@ -718,3 +718,89 @@ class RefCpuSearch:
         if self.h:
             self.lib.ref_cpu_free(self.h)
             self.h = None
+
+
+# ---------------------------------------------------------------------------
+# long reads: validation of seed alignments (validateAlignments)
+# ---------------------------------------------------------------------------
+_VAL_ONE = [U32P, C.c_uint32, U8P, C.c_uint32, C.c_uint32, C.c_uint32, U32P, U8P, U8P, C.c_int, C.c_int, C.c_int, C.c_int]
+
+
+def load_ref_validate():
+    path = os.path.join(ROOT, "oracle", "_ref", "libref_validate.so")
+    if not os.path.exists(path):
+        return None
+    lib = C.CDLL(path)
+    lib.ref_validate.restype = C.c_uint32
+    lib.ref_validate.argtypes = _VAL_ONE
+    return lib
+
+
+def validate_one(fn, pac, n_text, read, seed_len, pos, strand, mism, keep_best, min_seed, max_mism, max_hit):
+    """fn = liboracle's s3o_validate_one or libref_validate's ref_validate -> kept (pos, strand, mism) lists"""
+    fn.restype = C.c_uint32
+    fn.argtypes = _VAL_ONE
+    p, s, m = np.array(pos, np.uint32), np.array(strand, np.uint8), np.array(mism, np.uint8)
+    if len(p) == 0:
+        p, s, m = np.zeros(1, np.uint32), np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    read = np.ascontiguousarray(read, np.uint8)
+    k = fn(u32p(pac), n_text, read.ctypes.data_as(U8P), seed_len, len(read), len(pos), u32p(p), s.ctypes.data_as(U8P), m.ctypes.data_as(U8P),
+           int(keep_best), min_seed, max_mism, max_hit)
+    return p[:k].tolist(), s[:k].tolist(), m[:k].tolist()
+
+
+def oracle_validate_batch(lib, pac, n_text, reads, read_lengths, off, pos, flags, keep_best, min_seed, double_allowance, max_hit):
+    """reads: [n, maxLen] uint8; CSR lists; flags [T, 2] = strand, mismatches -> (counts, pos, flags) with the kept entries in front"""
+    lib.s3o_validate_batch.restype = None
+    lib.s3o_validate_batch.argtypes = [U32P, C.c_uint32, U8P, C.c_uint32, U32P, C.c_uint64, U32P, U32P, U8P, U8P, C.c_int, C.c_int, C.c_int, C.c_int, U32P]
+    reads = np.ascontiguousarray(reads, np.uint8)
+    n = reads.shape[0]
+    p = np.ascontiguousarray(pos, np.uint32).copy()
+    fl = np.ascontiguousarray(flags, np.uint8).reshape(-1, 2)
+    s, m = np.ascontiguousarray(fl[:, 0]).copy(), np.ascontiguousarray(fl[:, 1]).copy()
+    if len(p) == 0:
+        p, s, m = np.zeros(1, np.uint32), np.zeros(1, np.uint8), np.zeros(1, np.uint8)
+    cnt = np.zeros(max(n, 1), np.uint32)
+    lens = np.ascontiguousarray(read_lengths, np.uint32)
+    off = np.ascontiguousarray(off, np.uint32)
+    lib.s3o_validate_batch(u32p(pac), n_text, reads.ctypes.data_as(U8P), reads.shape[1], u32p(lens), n, u32p(off), u32p(p), s.ctypes.data_as(U8P),
+                           m.ctypes.data_as(U8P), int(keep_best), min_seed, int(double_allowance), max_hit, u32p(cnt))
+    return cnt[:n], p, np.stack([s, m], axis=1)
+
+
+def pack_text(codes):
+    """base codes -> hsp->packedDNA words (16 bases per word, first base in the top bits), four words of padding"""
+    codes = np.asarray(codes, np.uint8)
+    n = len(codes)
+    pac = np.zeros((n + 15) // 16 + 4, np.uint32)
+    for k in range(16):
+        v = codes[k::16].astype(np.uint32)
+        pac[:len(v)] |= v << np.uint32(30 - 2 * k)
+    return pac
+
+
+def validation_cases(rng, genome, trials):
+    """random reads with occurrence lists that hold true hits on both strands, near-misses, text edges, random places"""
+    n = len(genome)
+    for _ in range(trials):
+        L = int(rng.integers(101, 260))
+        seed = int(rng.choice([100, 100, 100, L, 37]))
+        ext = L - seed if L > seed else 0
+        p0 = int(rng.integers(0, n - L))
+        read = genome[p0:p0 + L].copy()
+        for _ in range(int(rng.integers(0, 6))):
+            read[int(rng.integers(0, L))] = rng.integers(0, 4)
+        rev = rng.random() < 0.4
+        if rev:
+            read = (3 - read[::-1]).astype(np.uint8)
+        m = int(rng.integers(0, 12))
+        pos, st, mm = [], [], []
+        for _ in range(m):
+            s = int(rng.integers(1, 3))
+            c = rng.random()
+            if s == 1:
+                p = p0 if (c < 0.6 and not rev) else (n - int(rng.integers(0, L)) if c < 0.7 else int(rng.integers(0, n)))
+            else:
+                p = p0 + ext if (c < 0.6 and rev) else (int(rng.integers(0, L)) if c < 0.7 else int(rng.integers(0, n)))
+            pos.append(p); st.append(s); mm.append(int(rng.integers(0, 3)))
+        yield read, seed, pos, st, mm, int(rng.integers(0, 2)), int(rng.integers(0, 3)), int(rng.integers(0, 8)), int(rng.integers(1, 6))

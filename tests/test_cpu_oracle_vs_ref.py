@@ -344,3 +344,23 @@ def test_search_oracle_finds_what_the_reference_cpu_search_finds(L):
             assert found > n // 10
     finally:
         ref.free()
+
+
+vlib = helpers.load_ref_validate()
+
+
+@pytest.mark.skipif(vlib is None, reason="oracle/_ref/libref_validate.so not built")
+def test_validate_oracle_matches_the_reference_validation():
+    """validateAlignments + the packers / popcount distance it calls, cut from the reference, against oracle/validate_oracle.c"""
+    rng = np.random.default_rng(1)
+    G = rng.integers(0, 4, 60_000).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    olib = load_oracle()
+    kept = changed = 0
+    for read, seed, pos, st, mm, keep, mins, mx, mh in helpers.validation_cases(rng, G, 4000):
+        a = helpers.validate_one(olib.s3o_validate_one, pac, len(G), read, seed, pos, st, mm, keep, mins, mx, mh)
+        b = helpers.validate_one(vlib.ref_validate, pac, len(G), read, seed, pos, st, mm, keep, mins, mx, mh)
+        assert a == b, (read.tolist(), seed, pos, st, mm, keep, mins, mx, mh)
+        kept += len(a[0])
+        changed += a[0] != pos
+    assert kept > 1000 and changed > 1000

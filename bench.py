@@ -631,6 +631,200 @@ def make_se_batch(genome, n, L, seed):
     return b
 
 
+def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, threads):
+    """BASELINE config 3 (se150_dp) and the deep-DP leg of config 4 (pe100_deep): the search chain followed by the DP stage that
+    starts from seeds, for the reads the chain left unaligned.
+      se150_dp    150 bp single-end reads with 1 % substitutions and 0.15 % indels: s3_se_align in long-read mode (first 100 bases
+                  searched with <= 2 mismatches, occurrences extended over the read: validateAlignments), then s3_single_dp_align
+                  (DPForUnalignSingle2) for the reads without a valid occurrence
+      pe100_deep  the default workload's pairs: s3_pe_align, then s3_deep_dp_align (DPForUnalignPairs2) for the pairs with no
+                  occurrence of either read
+    The seeded stages are host-orchestrated entries (host arrays in and out), so every number here is end to end: wall clock over
+    K steps through the host-pointer C ABI, queries from host memory, results into host memory."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    se_mode = args.config == "se150_dp"
+    L = 150 if se_mode else args.read_len
+    N = args.pairs if se_mode else 2 * args.pairs
+    total = args.warmup + args.steps
+    wpq = formats.word_per_query(L)
+    sets = []
+    for s in range(total):
+        if se_mode:
+            rs = synth.simulate_single_end(genome, N, L, seed=500 + 1000 * rank + s, sub_rate=0.01, indel_rate=0.0015)
+            lens = torch.zeros(formats.ceil32(N), dtype=torch.int32, device=device)
+            lens[:N] = L
+            q = packing.pack_queries(rs.reads, lens[:N], wpq)
+            sets.append((q.cpu().numpy().view(np.uint32), lens.cpu().numpy().view(np.uint32), rs.reads.cpu().numpy()))
+        else:
+            b = make_batch(genome, args.pairs, L, seed=100 + 1000 * rank + s)
+            sets.append((b.queries.cpu().numpy().view(np.uint32), b.lens.cpu().numpy().view(np.uint32), b.reads.cpu().numpy()))
+    sp = api.stage_params(insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES)
+    if se_mode:
+        chain = api.SingleAligner(gi, N, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True)
+    else:
+        chain = api.PairAligner(gi, N, L, api.pe_params(num_mismatch=K_MISMATCH, insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES,
+                                                        read_length=L, max_windows=N // 2))
+
+    def step(q, lens):
+        t0 = time.perf_counter()
+        got = chain.align(q, lens, N, wpq)
+        t1 = time.perf_counter()
+        if se_mode:
+            ids = np.nonzero((np.diff(got["occ_offsets"].astype(np.int64)) == 0) & (got["read_flags"] == 0))[0].astype(np.uint32)
+            res = api.single_dp_align(gi, q, lens, N, wpq, ids, sp)
+            aligned = int((np.diff(got["occ_offsets"].astype(np.int64)) > 0).sum())
+        else:
+            ids = (2 * np.nonzero(got["route"] == 0)[0]).astype(np.uint32)
+            res = api.deep_dp_align(gi, q, lens, N, wpq, ids, sp)
+            aligned = int((got["route"] != 0).sum())
+        t2 = time.perf_counter()
+        return got, res, ids, (t1 - t0, t2 - t1), aligned
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+    for s in range(args.warmup):
+        step(sets[s][0], sets[s][1])
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    launches0 = api.launch_count()
+    t_chain = t_stage = 0.0
+    n_ids = n_hits = n_seeds = n_cand = n_aligned = n_unseeded = 0
+    h2d = d2h = 0
+    t0 = time.perf_counter()
+    for kk in range(args.steps):
+        got, res, ids, (a, b2), aligned = step(sets[args.warmup + kk][0], sets[args.warmup + kk][1])
+        t_chain += a; t_stage += b2
+        n_ids += len(ids); n_hits += len(res["hits"]); n_seeds += res["num_seeds"]; n_cand += res["num_candidates"]; n_aligned += aligned
+        n_unseeded += len(res["unseeded"])
+        h2d += got["h2d_bytes"]; d2h += got["d2h_bytes"]
+    barrier()
+    tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    launches = api.launch_count() - launches0
+    sampler.stop_flag = True
+    sampler.join()
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    if rank != 0:
+        return
+    t_total = float(tt[0])
+    K = args.steps
+    unit = "reads" if se_mode else "pairs"
+    value = world * N * K / t_total
+    name = (f"se_{L}bp_indels_genome{args.genome_bp}bp: per step and GPU {N} reads (1 % substitutions, 0.15 % indels) through the long-read search chain "
+            "(first 100 bases, k<=2, validateAlignments) and single-read DP from seeds for the rest") if se_mode else \
+           (f"pe_2x{L}bp_insert{INSERT_LO}-{INSERT_HI}_genome{args.genome_bp}bp + deep DP: per step and GPU {args.pairs} read pairs through s3_pe_align and, for the "
+            "pairs with no occurrence of either read, deep DP from seeds (two rounds, left read then right read)")
+    out = {"metric": ("reads/s aligned (SE 150 bp with indels, search + single-read DP, 3.1 Gbp synth ref)" if se_mode else
+                      "reads/s aligned (2x100bp PE + deep DP for both-unaligned pairs, 3.1 Gbp synth ref)"),
+           "value": value, "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / K,
+           "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+           "config": {"workload": name, "genome_bp": args.genome_bp, "repeat_fraction": args.repeat_fraction, "reads_per_step_per_gpu": N,
+                      "timing": "wall clock over K steps through the host-pointer entries (the seeded DP stages are host-orchestrated): value == e2e",
+                      "l2": "inputs larger than L2: the 56 GB index is touched at random, a different read batch every step",
+                      "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"},
+           "clocks": sampler.result(),
+           "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K), "ms_per_step": 1e3 * t_total / K,
+                   "note": "h2d / d2h count the chain's transfers; the seeded stage moves its own seed, candidate and window arrays"},
+           "gpu_launches": int(launches),
+           "stages_ms_per_step": {"search chain (s3_se_align long-read mode)" if se_mode else "s3_pe_align": 1e3 * t_chain / K,
+                                  "s3_single_dp_align" if se_mode else "s3_deep_dp_align": 1e3 * t_stage / K},
+           "pipeline": {f"{unit}_aligned_by_the_chain_per_step": n_aligned / K, f"{unit}_sent_to_the_seeded_stage_per_step": n_ids / K,
+                        "seeds_per_step": n_seeds / K, "candidates_per_step": n_cand / K, "stage_alignments_per_step": n_hits / K,
+                        f"{unit}_without_a_candidate_per_step": n_unseeded / K},
+           "roofline": None}
+    if world == 1 and not args.no_cpu_baseline:
+        # parity of a sample at full size: the chain and the seeded stage against the compositions of the oracles
+        import helpers
+        import seeding_oracle
+        from test_stages_gpu import OracleEnv, PAR
+        m = min(args.parity_pairs // 16, 2048)
+        q, lens, reads = sets[-1]
+        m = m - (m & 1)
+        rd = [np.ascontiguousarray(reads[r]) for r in range(m)]
+        lens_m = np.zeros(formats.ceil32(m), np.uint32)
+        lens_m[:m] = L
+        qm = formats.pack_queries(np.stack(rd), lens_m[:m], wpq)
+
+        class HI:
+            pass
+        hi = HI()
+        hi.bwt, hi.occ, hi.rbwt, hi.rocc = host["bwt"], host["occ"], host["rbwt"], host["rocc"]
+        hi.isa0, hi.risa0, hi.n = int(host["meta"][0]), int(host["meta"][1]), int(host["meta"][2])
+        env = OracleEnv(None, hi, sa=host["sa"])
+        gv = _GenomeView(genome)
+        t0 = time.time()
+        if se_mode:
+            ids = np.arange(m, dtype=np.uint32)
+            got = api.single_dp_align(gi, qm, lens_m, m, wpq, ids, sp)
+            want = seeding_oracle.single_dp(env, gv, rd, ids.tolist(), PAR)
+            same = got["num_seeds"] == want["seeds"] and got["num_candidates"] == want["candidates"] and got["unseeded"].tolist() == want["unseeded"] \
+                and len(got["hits"]) == len(want["hits"])
+            if same:
+                for h, w in zip(got["hits"], want["hits"]):
+                    cig = api.runs_to_cigar(got["runs"][int(h["runOffset"]):int(h["runOffset"]) + int(h["numRuns"])])
+                    same &= (int(h["readID"]), int(h["strand"]), int(h["pos"]), int(h["score"]), int(h["numSameScore"]), cig) == w
+        else:
+            ids = np.arange(0, m, 2, dtype=np.uint32)
+            got = api.deep_dp_align(gi, qm, lens_m, m, wpq, ids, sp)
+            want = seeding_oracle.deep_dp(env, gv, rd, ids.tolist(), PAR)
+            same = got["num_seeds"] == want["seeds"] and got["num_candidates"] == want["candidates"] and got["unseeded"].tolist() == want["unseeded"] \
+                and len(got["hits"]) == len(want["hits"])
+            if same:
+                for h, w in zip(got["hits"], want["hits"]):
+                    c1 = api.runs_to_cigar(got["runs"][int(h["runOffset1"]):int(h["runOffset1"]) + int(h["numRuns1"])])
+                    c2 = api.runs_to_cigar(got["runs"][int(h["runOffset2"]):int(h["runOffset2"]) + int(h["numRuns2"])])
+                    same &= (int(h["readID"]), int(h["strand1"]), int(h["strand2"]), int(h["pos1"]), int(h["pos2"]), int(h["score1"]), int(h["score2"]),
+                             int(h["numSame1"]), int(h["numSame2"]), c1, c2) == w
+        out["parity_at_full_size"] = {("reads" if se_mode else "pairs"): int(m if se_mode else m // 2), "seeds": int(want["seeds"]),
+                                      "candidates": int(want["candidates"]), "stage_alignments": len(want["hits"]), "stage_bit_exact": bool(same),
+                                      "seconds": time.time() - t0,
+                                      "checker": "oracle/seeding_oracle.py (every read of the sample sent through the seeded stage) over the oracle restatements"}
+        log("seeded stage parity at full size:", out["parity_at_full_size"])
+        if se_mode:
+            # and the long-read chain of the same sample against the reference's CPU search of the seeds + the validation oracle
+            ref_c = ref_cpu_handle(host, threads)
+            if ref_c is not None:
+                seeds = np.ascontiguousarray(np.stack(rd)[:, :100])
+                hits = ref_c.search(seeds, K_MISMATCH, formats.NUM_CASES[K_MISMATCH], MAX_OUTPUT_PER_READ, threads, out_cap=64)["hits"]
+                al = api.SingleAligner(gi, m, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True)
+                g2 = al.align(qm, lens_m, m, wpq)
+                al.free()
+                pac = host["pac"]
+                olib = helpers.load_oracle()
+                ok = cmp = 0
+                for r in range(m):
+                    if len(hits[r]) >= 64 or int(g2["read_flags"][r]):
+                        continue
+                    a, b2 = int(g2["occ_offsets"][r]), int(g2["occ_offsets"][r + 1])
+                    mine = sorted((int(p), int(f[0]), int(f[1])) for p, f in zip(g2["positions"][a:b2], g2["occ_flags"][a:b2]))
+                    hp = [h[0] for h in hits[r]]; hs = [h[1] for h in hits[r]]; hm = [h[2] for h in hits[r]]
+                    vp, vs, vm = helpers.validate_one(olib.s3o_validate_one, pac, hi.n, rd[r], 100, hp, hs, hm, 0, 0, int(np.ceil(0.02 * L)), MAX_OUTPUT_PER_READ)
+                    cmp += 1
+                    ok += mine == sorted(zip(vp, vs, vm))
+                out["parity_at_full_size"]["long_read_chain_vs_reference_cpu_search"] = {"reads_compared": cmp, "equal": ok, "bit_exact": bool(ok == cmp)}
+                log("long-read chain vs the reference's CPU search + validation oracle:", out["parity_at_full_size"]["long_read_chain_vs_reference_cpu_search"])
+                # CPU baseline of this config's search leg: the reference's CPU search of the 100-base seeds
+                nb = min(args.cpu_sample // 2, N)
+                sd = np.ascontiguousarray(sets[0][2][:nb, :100])
+                t0 = time.perf_counter()
+                res = ref_c.search(sd, K_MISMATCH, formats.NUM_CASES[K_MISMATCH], MAX_OUTPUT_PER_READ, threads)
+                tcs = time.perf_counter() - t0
+                out["cpu_baseline"] = {"value": nb / tcs, "unit": "reads/s", "cores": threads, "kind": "reference", "cpu_model": cpu_model(),
+                                       "sample": f"{nb} reads: the reference's CPU search (ProcessReadDoubleStrand2) of the first 100 bases, k<=2, both strands; "
+                                                 "the validation and the seeded DP stage are not included (the reference has no CPU DP)",
+                                       "reads_with_a_hit": int((res["counts"][:, 3] > 0).sum())}
+    print(json.dumps(out), flush=True)
+    chain.free()
+    api.GPUINDEXFree(gi)
+    if world > 1:
+        torch.distributed.destroy_process_group()
+
+
 def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream, L, threads, k):
     """BASELINE config 2: single-end 100 bp reads, <= k mismatches (10 cases at k = 4, both strands), search + answer collection +
     locate per step through s3_se_align_device / s3_se_align (alignSingleR's results)."""
@@ -841,9 +1035,10 @@ def main():
     ap.add_argument("--parity-pairs", type=int, default=int(os.environ.get("S3_PARITY_PAIRS", 32_768)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--repeat-fraction", type=float, default=float(os.environ.get("S3_REPEAT_FRACTION", 0.2)))
-    ap.add_argument("--config", default="pe100", choices=["pe100", "se100_k4"],
+    ap.add_argument("--config", default="pe100", choices=["pe100", "se100_k4", "se150_dp", "pe100_deep"],
                     help="pe100 (default): the BASELINE metric's workload (config 4 shape); se100_k4: config 2, single-end 100 bp, <= 4 mismatches, "
-                         "search + collect + locate (s3_se_align).  A 45 %%-repeat genome: --repeat-fraction 0.45")
+                         "search + collect + locate (s3_se_align); se150_dp: config 3, 150 bp reads with indels, long-read search chain + single-read DP from "
+                         "seeds; pe100_deep: the default workload + deep DP of the both-unaligned pairs.  A 45 %%-repeat genome: --repeat-fraction 0.45")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: the timing rules ask for >= 3 warm-up steps")
@@ -905,6 +1100,8 @@ def main():
         return
     if os.environ.get("S3_L2_REGION"):                        # ncu captures with a window in place (profiles/exp_l2_persist.sh)
         api.set_l2_persist(gi, int(os.environ["S3_L2_REGION"]))
+    if args.config in ("se150_dp", "pe100_deep"):
+        return run_stage_config(args, gi, host, genome, device, local_rank, rank, world, threads)
     if args.config == "se100_k4":
         return run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream, L, threads, k=4)
     t0 = time.time()

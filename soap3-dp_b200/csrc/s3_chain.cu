@@ -1049,3 +1049,126 @@ extern "C" int s3_se_align_device(s3_se *se, const uint32_t *d_queries, const ui
 {
     return se_run(se, d_queries, d_readLengths, numReads, wordPerQuery, 1, out);
 }
+
+
+// =======================================================================================================================
+// Alignment step of the seeded DP stages (s3_single_dp_align, s3_deep_dp_align): see s3_common.cuh.
+// =======================================================================================================================
+struct S3StageWs {
+    s3_dp *dp; uint32_t maxRead, maxDNA, cap; s3_dp_scores scores;
+    uint32_t *d_q; size_t qBytes;                 // query buffer + read lengths of the current stage call
+    S3Arena arena;
+    void *pinned[2]; size_t pinnedBytes[2];
+};
+
+void s3_stage_ws_free(s3_index *ix)
+{
+    S3StageWs *ws = (S3StageWs *)ix->stageWs;
+    if (!ws) return;
+    if (ws->dp) s3_dp_free(ws->dp);
+    if (ws->d_q) cudaFree(ws->d_q);
+    if (ws->arena.base) cudaFree(ws->arena.base);
+    for (int i = 0; i < 2; ++i) if (ws->pinned[i]) cudaFreeHost(ws->pinned[i]);
+    free(ws);
+    ix->stageWs = NULL;
+}
+
+int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery, int uploadQueries,
+                   uint32_t maxRead, uint32_t maxDNA, s3_dp_scores scores, int slot, uint64_t n64,
+                   const uint32_t *readID, const uint8_t *strand, const uint32_t *start, const uint32_t *len, const int32_t *cutoff,
+                   const uint32_t *clipLt, const uint32_t *clipRt, const uint32_t *ancL, const uint32_t *ancR, S3StageAligned *out)
+{
+    memset(out, 0, sizeof *out);
+    if (n64 == 0) return S3_OK;
+    if (n64 > 0x7FFFFFF0ull) { s3_set_error("s3_stage_align: too many alignments in one call"); return S3_EINVAL; }
+    const uint32_t n = (uint32_t)n64;
+    S3_TRYC(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    S3StageWs *ws = (S3StageWs *)ix->stageWs;
+    if (!ws) {
+        ws = (S3StageWs *)calloc(1, sizeof(S3StageWs));
+        if (!ws) { s3_set_error("out of host memory"); return S3_ENOMEM; }
+        ix->stageWs = ws;
+    }
+    int rc;
+    if (!ws->dp || ws->maxRead != maxRead || ws->maxDNA != maxDNA || ws->cap < n || memcmp(&ws->scores, &scores, sizeof scores)) {
+        if (ws->dp) { S3_TRYC(cudaStreamSynchronize(st)); s3_dp_free(ws->dp); ws->dp = NULL; }
+        const uint32_t cap = n + n / 4 < 65536u ? 65536u : n + n / 4;
+        if ((rc = s3_dp_create(maxRead, maxDNA, cap, scores, ix->device, &ws->dp))) return rc;
+        s3_dp_set_stream(ws->dp, st);
+        ws->maxRead = maxRead; ws->maxDNA = maxDNA; ws->cap = cap; ws->scores = scores;
+    }
+    const size_t up = ((size_t)numReads + 31) / 32 * 32, qBytes = up * wordPerQuery * 4;
+    if (uploadQueries || !ws->d_q) {
+        if (qBytes > ws->qBytes) {
+            if (ws->d_q) { S3_TRYC(cudaStreamSynchronize(st)); cudaFree(ws->d_q); ws->d_q = NULL; ws->qBytes = 0; }
+            S3_TRYC(cudaMalloc(&ws->d_q, qBytes + qBytes / 4));
+            ws->qBytes = qBytes + qBytes / 4;
+        }
+        S3_TRYC(cudaMemcpyAsync(ws->d_q, queries, qBytes, cudaMemcpyHostToDevice, st));
+    }
+    const size_t patLen = s3_dp_pattern_length(ws->dp);
+    size_t scanTemp = 0;
+    cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (uint32_t *)NULL, (uint32_t *)NULL, (int)(n + 1), st);
+    const size_t need = 13 * arena_need(n, 4) + arena_need(n, 1) + arena_need((size_t)n * patLen, 1) + 2 * arena_need(n + 1, 4) +
+                        arena_need((size_t)n * (maxRead + 8), 4) + arena_need(scanTemp, 1) + 4096;
+    if ((rc = arena_reserve(&ws->arena, need, st))) return rc;
+    S3Arena *A = &ws->arena;
+    uint32_t *d_readID = arena_take<uint32_t>(A, n), *d_start = arena_take<uint32_t>(A, n), *d_len = arena_take<uint32_t>(A, n), *d_rl = arena_take<uint32_t>(A, n);
+    uint32_t *d_clt = arena_take<uint32_t>(A, n), *d_crt = arena_take<uint32_t>(A, n), *d_al = arena_take<uint32_t>(A, n), *d_ar = arena_take<uint32_t>(A, n);
+    int32_t *d_cut = arena_take<int32_t>(A, n), *d_score = arena_take<int32_t>(A, n);
+    uint32_t *d_hit = arena_take<uint32_t>(A, n), *d_cnt = arena_take<uint32_t>(A, n), *d_spare = arena_take<uint32_t>(A, n);
+    uint8_t *d_strand = arena_take<uint8_t>(A, n);
+    uint8_t *d_pattern = arena_take<uint8_t>(A, (size_t)n * patLen);
+    uint32_t *d_runCount = arena_take<uint32_t>(A, n + 1), *d_runOff = arena_take<uint32_t>(A, n + 1);
+    uint32_t *d_runs = arena_take<uint32_t>(A, (size_t)n * (maxRead + 8));
+    void *d_tmp = arena_take<char>(A, scanTemp);
+    (void)d_spare;
+    if (!d_tmp) { s3_set_error("s3_stage_align: stage buffer accounting"); return S3_ENOMEM; }
+    // host side: results of this slot, and the per-alignment read lengths (staged in the slot's buffer before they are uploaded)
+    const size_t hostBytes = 4 * (((size_t)n + 1) * 4 + 256) + (size_t)n * (maxRead + 8) * 4 + 256;
+    if (hostBytes > ws->pinnedBytes[slot]) {
+        if (ws->pinned[slot]) { S3_TRYC(cudaStreamSynchronize(st)); cudaFreeHost(ws->pinned[slot]); ws->pinned[slot] = NULL; ws->pinnedBytes[slot] = 0; }
+        if (cudaMallocHost(&ws->pinned[slot], hostBytes + hostBytes / 4) != cudaSuccess) { s3_set_error("s3_stage_align: pinned allocation failed"); return S3_ENOMEM; }
+        ws->pinnedBytes[slot] = hostBytes + hostBytes / 4;
+    }
+    char *h = (char *)ws->pinned[slot];
+    const size_t stride = (((size_t)n + 1) * 4 + 255) / 256 * 256;
+    int32_t *h_score = (int32_t *)h; uint32_t *h_hit = (uint32_t *)(h + stride), *h_cnt = (uint32_t *)(h + 2 * stride), *h_runOff = (uint32_t *)(h + 3 * stride);
+    uint32_t *h_runs = (uint32_t *)(h + 4 * stride);
+    for (uint32_t t = 0; t < n; ++t) {
+        if (readID[t] >= numReads) { s3_set_error("s3_stage_align: read id %u out of range", readID[t]); return S3_EINVAL; }
+        h_runs[t] = readLengths[readID[t]];
+    }
+    S3_TRYC(cudaMemcpyAsync(d_rl, h_runs, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYC(cudaMemcpyAsync(d_readID, readID, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYC(cudaMemcpyAsync(d_start, start, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYC(cudaMemcpyAsync(d_len, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYC(cudaMemcpyAsync(d_cut, cutoff, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYC(cudaMemcpyAsync(d_clt, clipLt, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYC(cudaMemcpyAsync(d_crt, clipRt, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYC(cudaMemcpyAsync(d_al, ancL, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYC(cudaMemcpyAsync(d_ar, ancR, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYC(cudaMemcpyAsync(d_strand, strand, n, cudaMemcpyHostToDevice, st));
+    if ((rc = s3_dp_align_windows_device(ws->dp, ix, ws->d_q, wordPerQuery, d_readID, d_strand, d_start, d_len, d_rl, d_cut, d_score, d_hit, d_cnt, d_pattern, n,
+                                         d_clt, d_crt, d_al, d_ar))) return rc;
+    const unsigned nb = (n + 127) / 128;
+    S3_TRYC(cudaMemsetAsync(d_runCount + n, 0, 4, st));
+    s3_pe_runs_kernel<false><<<nb, 128, 0, st>>>(n, d_pattern, (uint32_t)patLen, d_score, d_cut, d_runCount, NULL, NULL);
+    S3_TRYC(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_runCount, d_runOff, (int)(n + 1), st));
+    s3_pe_runs_kernel<true><<<nb, 128, 0, st>>>(n, d_pattern, (uint32_t)patLen, d_score, d_cut, NULL, d_runOff, d_runs);
+    S3_LAUNCHED(2);
+    S3_TRYC(cudaGetLastError());
+    S3_TRYC(cudaMemcpyAsync(h_score, d_score, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaMemcpyAsync(h_hit, d_hit, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaMemcpyAsync(h_runOff, d_runOff, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYC(cudaStreamSynchronize(st));
+    const uint32_t total = h_runOff[n];
+    if (total) {
+        S3_TRYC(cudaMemcpyAsync(h_runs, d_runs, (size_t)total * 4, cudaMemcpyDeviceToHost, st));
+        S3_TRYC(cudaStreamSynchronize(st));
+    }
+    out->score = h_score; out->hit = h_hit; out->cnt = h_cnt; out->runOff = h_runOff; out->runs = h_runs; out->numRuns = total;
+    return S3_OK;
+}

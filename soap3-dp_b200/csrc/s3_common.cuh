@@ -16,6 +16,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include "../../include/soap3dp_b200.h"
 
 #define S3_BUCKET_BASES 64u
 #define S3_THREADS 128
@@ -108,7 +109,22 @@ struct s3_index {
     int numSms;
     size_t searchSmem; int searchBlocksPerSm;
     int sharedArrays;                 // s3_index_clone: buckets, seed tables, suffix array, text belong to another handle
+    void *stageWs;                    // workspace of the seeded DP stages (s3_stage_align, s3_chain.cu), created on first use
 };
+
+// Alignment step of the seeded DP stages (s3_stages.cu): windows in host arrays -> scores, hit locations, tie counts and the
+// CIGAR runs of the alignments that reach their cutoff, in host arrays the handle owns (two slots: the deep stage keeps the left
+// reads' results while the right reads are aligned).  The DP workspace, the device copy of the query buffer and all scratch
+// live in the handle's stage workspace and are reused from call to call.
+struct S3StageAligned {
+    const int32_t *score; const uint32_t *hit, *cnt, *runOff, *runs;
+    uint64_t numRuns;
+};
+int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery, int uploadQueries,
+                   uint32_t maxRead, uint32_t maxDNA, s3_dp_scores scores, int slot, uint64_t n,
+                   const uint32_t *readID, const uint8_t *strand, const uint32_t *start, const uint32_t *len, const int32_t *cutoff,
+                   const uint32_t *clipLt, const uint32_t *clipRt, const uint32_t *ancL, const uint32_t *ancR, S3StageAligned *out);
+void s3_stage_ws_free(s3_index *ix);
 
 void s3_set_error(const char *fmt, ...);
 extern unsigned long long g_s3_launches;

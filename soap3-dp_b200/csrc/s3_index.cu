@@ -338,6 +338,7 @@ extern "C" void s3_index_free(s3_index *ix)
         if (ix->d_sa) cudaFree(ix->d_sa);
         if (ix->d_isa) cudaFree(ix->d_isa);
     }
+    s3_stage_ws_free(ix);
     s3_pipe_destroy(&ix->pipe);
     if (ix->d_workCounter) cudaFree(ix->d_workCounter);
     if (ix->d_hardItems) cudaFree(ix->d_hardItems);

@@ -16,11 +16,28 @@
 #include "s3_common.cuh"
 #include "../../include/soap3dp_b200.h"
 
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <chrono>
 #include <vector>
 
 namespace {
+
+// S3_STAGE_TIMING=1: wall-clock milliseconds of every step of a stage call on stderr (tuning aid)
+struct StageClock {
+    bool on;
+    std::chrono::steady_clock::time_point t;
+    const char *what;
+    explicit StageClock(const char *w) : on(getenv("S3_STAGE_TIMING") != NULL), t(std::chrono::steady_clock::now()), what(w) {}
+    void lap(const char *step)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[%s] %-28s %8.2f ms\n", what, step, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
 
 struct SeedSet {                                   // one side's seeding batch (DV-DPfunctions.cu:2655-2680 / 1057-1080)
     std::vector<uint32_t> words, lengths, readIDs, offsets, maxHit;
@@ -43,44 +60,23 @@ void seed_set_reserve(SeedSet &s, uint32_t wordPerSeed, size_t seeds)
     s.n = 0;
 }
 
+// `len` bases of read `readID` from base `off` on, 16 per word, as the next seed of the set (word-wise: two source words per word)
 void seed_set_add(SeedSet &s, const uint32_t *queries, uint32_t wpq, uint32_t readID, uint32_t keyID, uint32_t off, uint32_t len, uint32_t maxHit)
 {
     const uint64_t id = s.n++;
     uint32_t *dst = s.words.data() + (id / 32) * 32 * s.wordPerSeed + id % 32;
-    for (uint32_t i = 0; i < len; ++i) dst[(size_t)(i >> 4) * 32] |= read_base(queries, wpq, readID, off + i) << ((i & 15u) << 1);
+    const uint32_t *src = queries + (size_t)(readID / 32) * 32 * wpq + readID % 32;
+    for (uint32_t w = 0, done = 0; done < len; ++w, done += 16) {
+        const uint32_t k = off + done, sw = k >> 4, sh = (k & 15u) << 1;
+        uint32_t v = sw < wpq ? src[(size_t)sw * 32] >> sh : 0u;
+        if (sh && sw + 1 < wpq) v |= src[(size_t)(sw + 1) * 32] << (32u - sh);
+        const uint32_t rem = len - done;
+        if (rem < 16) v &= (1u << (2 * rem)) - 1u;
+        dst[(size_t)w * 32] = v;
+    }
     s.lengths[id] = len;
     s.readIDs.push_back(keyID); s.offsets.push_back(off); s.maxHit.push_back(maxHit);
 }
-
-// traceback pattern -> CIGAR runs in read order, length << 8 | op (CigarStringEncoder, DV-DPfunctions.h:545-597, as the
-// engines' result loops drive it; the same rule as s3_pe_runs_kernel and s3_dp_decode)
-void pattern_runs(const uint8_t *p, size_t cap, std::vector<uint32_t> &out)
-{
-    std::vector<uint32_t> rev;
-    uint8_t last = 'N', curType = 0;
-    int curCnt = 0;
-    bool have = false;
-    const uint8_t *end = p + cap;
-    for (; p < end && *p != 0; ++p) {
-        uint8_t type; int cnt;
-        if (*p == 'V') { if (++p >= end) break; type = last; cnt = (int)*p - 1; }
-        else { type = last = *p; cnt = 1; }
-        if (have && curType == type) curCnt += cnt;
-        else {
-            if (have && curCnt > 0 && curType != 'N') rev.push_back(((uint32_t)curCnt << 8) | curType);
-            curType = type; curCnt = cnt; have = true;
-        }
-    }
-    if (have && curCnt > 0 && curType != 'N') rev.push_back(((uint32_t)curCnt << 8) | curType);
-    out.insert(out.end(), rev.rbegin(), rev.rend());
-}
-
-struct Aligned {                                   // outputs of one s3_dp_align_windows call
-    std::vector<int32_t> score;
-    std::vector<uint32_t> hit, cnt;
-    std::vector<uint8_t> pattern;
-    uint32_t patLen = 0;
-};
 
 struct Windows {
     std::vector<uint32_t> cand, readID, start, len, clipLt, clipRt, ancL, ancR;
@@ -99,15 +95,11 @@ int make_windows(s3_index *ix, int mode, const s3_window_params &wp, const uint3
                               w.lor.data(), w.start.data(), w.len.data(), w.clipLt.data(), w.clipRt.data(), w.ancL.data(), w.ancR.data(), w.cutoff.data(), &w.n);
 }
 
-int align_windows(s3_dp *dp, s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wpq, Windows &w, Aligned &a)
+int align_windows(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wpq, int uploadQueries, uint32_t maxRead,
+                  uint32_t maxDNA, s3_dp_scores scores, int slot, Windows &w, S3StageAligned &a)
 {
-    a.patLen = s3_dp_pattern_length(dp);
-    const size_t n = w.n ? w.n : 1;
-    a.score.assign(n, 0); a.hit.assign(n, 0); a.cnt.assign(n, 0); a.pattern.assign(n * a.patLen, 0);
-    if (!w.n) return S3_OK;
-    return s3_dp_align_windows(dp, ix, queries, readLengths, numReads, wpq, w.readID.data(), w.strand.data(), w.start.data(), w.len.data(), w.cutoff.data(),
-                               a.score.data(), a.hit.data(), a.cnt.data(), a.pattern.data(), (uint32_t)w.n, w.clipLt.data(), w.clipRt.data(),
-                               w.ancL.data(), w.ancR.data());
+    return s3_stage_align(ix, queries, readLengths, numReads, wpq, uploadQueries, maxRead, maxDNA, scores, slot, w.n, w.readID.data(), w.strand.data(),
+                          w.start.data(), w.len.data(), w.cutoff.data(), w.clipLt.data(), w.clipRt.data(), w.ancL.data(), w.ancR.data(), &a);
 }
 
 uint32_t margin_of(uint32_t len) { return len > 100u ? len >> 2 : 25u; }
@@ -148,23 +140,39 @@ extern "C" int s3_single_dp_align(s3_index *ix, const uint32_t *queries, const u
         if (readLengths[readIDs[k]] > maxLen) maxLen = readLengths[readIDs[k]];
     }
     int rc;
+    StageClock clk("s3_single_dp_align");
     // ---- seeds (SingleEndSeedingBatch::packSeeds, DV-DPfunctions.cu:1082-1100)
     SeedSet seeds;
-    seed_set_reserve(seeds, (maxLen + 15) / 16, n * 16);
-    std::vector<int32_t> seedPos(maxLen + 16);
+    // seed layout and hit limit depend on the read length only: one plan per length that occurs
+    struct Plan { int32_t seedLen, seedNum, maxHit; std::vector<int32_t> pos; bool made; };
+    std::vector<Plan> plans(maxLen + 1);
+    for (auto &p : plans) p.made = false;
+    uint64_t totalSeeds = 0;
+    uint32_t maxSeedLen = 1;
+    for (int pass = 0; pass < 2; ++pass)
     for (uint64_t k = 0; k < n; ++k) {
         const uint32_t r = readIDs[k], len = readLengths[r];
-        int32_t seedLen = 0, seedNum = 0;
-        if ((rc = s3_seed_layout(S3_STAGE_SINGLE_DP, (int32_t)len, &seedLen, seedPos.data(), (int32_t)seedPos.size(), &seedNum))) return rc;
-        s3_dp_stage_params sp;
-        if ((rc = s3_dp_stage_parameters(S3_STAGE_SINGLE_DP, len, 0, par->isDefaultThreshold, par->dpScoreThreshold, par->softClipLeft, par->softClipRight, &sp))) return rc;
-        if (seeds.n + (uint64_t)seedNum > seeds.lengths.size() - 32) { s3_set_error("s3_single_dp_align: more than 16 seeds per read"); return S3_EINVAL; }
-        for (int32_t j = 0; j < seedNum; ++j) seed_set_add(seeds, queries, wordPerQuery, r, r, (uint32_t)seedPos[j], (uint32_t)seedLen, (uint32_t)sp.paramRead[0].maxHitNum);
+        Plan &p = plans[len];
+        if (pass == 0 && p.made) { totalSeeds += (uint64_t)p.seedNum; continue; }
+        if (pass == 1 && k == 0) seed_set_reserve(seeds, (maxSeedLen + 15) / 16, (size_t)totalSeeds);
+        if (!p.made) {
+            p.pos.resize(maxLen + 16);
+            if ((rc = s3_seed_layout(S3_STAGE_SINGLE_DP, (int32_t)len, &p.seedLen, p.pos.data(), (int32_t)p.pos.size(), &p.seedNum))) return rc;
+            s3_dp_stage_params sp;
+            if ((rc = s3_dp_stage_parameters(S3_STAGE_SINGLE_DP, len, 0, par->isDefaultThreshold, par->dpScoreThreshold, par->softClipLeft, par->softClipRight, &sp))) return rc;
+            p.maxHit = sp.paramRead[0].maxHitNum;
+            p.made = true;
+            if ((uint32_t)p.seedLen > maxSeedLen) maxSeedLen = (uint32_t)p.seedLen;
+        }
+        if (pass == 0) { totalSeeds += (uint64_t)p.seedNum; continue; }
+        for (int32_t j = 0; j < p.seedNum; ++j) seed_set_add(seeds, queries, wordPerQuery, r, r, (uint32_t)p.pos[j], (uint32_t)p.seedLen, (uint32_t)p.maxHit);
     }
     out->numSeeds = seeds.n;
+    clk.lap("seed packing");
     // ---- seeding driver, candidate positions (decodePositions + singleMerge, DV-DPfunctions.cu:1101-1219)
     s3_seed_search_result sr;
     if ((rc = s3_seed_search(ix, seeds.words.data(), seeds.lengths.data(), seeds.n, seeds.wordPerSeed, seeds.maxHit.data(), &sr))) return rc;
+    clk.lap("s3_seed_search");
     std::vector<uint32_t> rid(sr.total), off(sr.total), slen(sr.total), rlen(sr.total);
     std::vector<int32_t> strand(sr.total);
     for (uint64_t s = 0; s < seeds.n; ++s)
@@ -177,6 +185,7 @@ extern "C" int s3_single_dp_align(s3_index *ix, const uint32_t *queries, const u
     s3_seed_search_result_free(&sr);
     if (rc) return rc;
     out->numCandidates = nc;
+    clk.lap("s3_seed_candidates");
     // reads without a candidate (alignFlags XOR inputFlags, DV-DPfunctions.cu:1300-1310)
     std::vector<uint8_t> seeded(numReads, 0);
     for (uint64_t c = 0; c < nc; ++c) seeded[cR[c]] = 1;
@@ -194,25 +203,28 @@ extern "C" int s3_single_dp_align(s3_index *ix, const uint32_t *queries, const u
         std::vector<uint8_t> st8(nc);
         for (uint64_t c = 0; c < nc; ++c) st8[c] = (uint8_t)cS[c];
         Windows w;
-        Aligned a;
-        s3_dp *dp = NULL;
+        S3StageAligned a;
         rc = make_windows(ix, S3_WIN_SINGLE, wp, readLengths, numReads, cR, cP, NULL, st8.data(), NULL, NULL, NULL, nc, w);
-        if (rc == S3_OK) rc = s3_dp_create(maxRead, maxDNA, (uint32_t)(nc > 32 ? nc : 32), par->scores, ix->device, &dp);
-        if (rc == S3_OK) rc = align_windows(dp, ix, queries, readLengths, numReads, wordPerQuery, w, a);
-        if (dp) s3_dp_free(dp);
-        if (rc == S3_OK)
+        clk.lap("s3_dp_make_windows");
+        if (rc == S3_OK) rc = align_windows(ix, queries, readLengths, numReads, wordPerQuery, 1, maxRead, maxDNA, par->scores, 0, w, a);
+        clk.lap("upload + DP + CIGAR runs");
+        if (rc == S3_OK && w.n) {
+            hits.reserve(w.n);
+            runs.reserve(a.numRuns);
             for (uint64_t t = 0; t < w.n; ++t) {
                 if (a.score[t] < w.cutoff[t]) continue;
                 s3_dp_hit h;
                 memset(&h, 0, sizeof h);
                 h.readID = w.readID[t]; h.strand = w.strand[t]; h.pos = w.start[t] + a.hit[t]; h.score = a.score[t]; h.numSameScore = a.cnt[t];
                 h.runOffset = (uint32_t)runs.size();
-                pattern_runs(a.pattern.data() + t * a.patLen, a.patLen, runs);
+                runs.insert(runs.end(), a.runs + a.runOff[t], a.runs + a.runOff[t + 1]);
                 h.numRuns = (uint16_t)(runs.size() - h.runOffset);
                 hits.push_back(h);
             }
+        }
     }
     s3_free(cR); s3_free(cP); s3_free(cS);
+    clk.lap("records + CIGAR runs");
     if (rc) return rc;
     out->numHits = hits.size(); out->numRuns = runs.size(); out->numUnseeded = unseeded.size();
     out->hits = to_malloc(hits); out->runs = to_malloc(runs); out->unseeded = to_malloc(unseeded);
@@ -235,27 +247,48 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
         for (int i = 0; i < 2; ++i) if (readLengths[e + i] > maxLen) maxLen = readLengths[e + i];
     }
     int rc = S3_OK;
+    StageClock clk("s3_deep_dp_align");
     std::vector<uint32_t> candID, candL, candR;                       // readIDLeft, estimated starts: all rounds' candidates
     std::vector<uint32_t> input(pairReadIDs, pairReadIDs + n), next, unseeded;
-    std::vector<int32_t> seedPos(maxLen + 16);
     for (int round = 0; round < 2 && !input.empty() && rc == S3_OK; ++round) {
         const int stage = round == 0 ? S3_STAGE_DEEP_DP_ROUND1 : S3_STAGE_DEEP_DP_ROUND2;
         // ---- seeds of both mates (PairEndSeedingBatch::packSeeds, DV-DPfunctions.cu:2682-2706)
         SeedSet side[2];
-        for (int i = 0; i < 2; ++i) seed_set_reserve(side[i], (maxLen + 15) / 16, input.size() * 32);
+        // seed layout per read length, hit limits per pair of lengths: made once per distinct value
+        struct Layout { int32_t seedLen, seedNum; std::vector<int32_t> pos; bool made; };
+        std::vector<Layout> layouts(maxLen + 1);
+        for (auto &l : layouts) l.made = false;
+        uint64_t sideSeeds[2] = {0, 0};
+        uint32_t maxSeedLen = 1;
+        for (size_t k = 0; k < input.size() && rc == S3_OK; ++k)
+            for (int i = 0; i < 2; ++i) {
+                Layout &l = layouts[readLengths[input[k] + i]];
+                if (!l.made) {
+                    l.pos.resize(maxLen + 16);
+                    if ((rc = s3_seed_layout(stage, (int32_t)readLengths[input[k] + i], &l.seedLen, l.pos.data(), (int32_t)l.pos.size(), &l.seedNum))) break;
+                    l.made = true;
+                    if ((uint32_t)l.seedLen > maxSeedLen) maxSeedLen = (uint32_t)l.seedLen;
+                }
+                sideSeeds[i] += (uint64_t)l.seedNum;
+            }
+        if (rc) break;
+        for (int i = 0; i < 2; ++i) seed_set_reserve(side[i], (maxSeedLen + 15) / 16, (size_t)sideSeeds[i]);
+        uint32_t spLen[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
+        s3_dp_stage_params sp;
         for (size_t k = 0; k < input.size() && rc == S3_OK; ++k) {
             const uint32_t e = input[k];
-            s3_dp_stage_params sp;
-            if ((rc = s3_dp_stage_parameters(stage, readLengths[e], readLengths[e + 1], par->isDefaultThreshold, par->dpScoreThreshold, par->softClipLeft, par->softClipRight, &sp))) break;
+            if (readLengths[e] != spLen[0] || readLengths[e + 1] != spLen[1]) {
+                if ((rc = s3_dp_stage_parameters(stage, readLengths[e], readLengths[e + 1], par->isDefaultThreshold, par->dpScoreThreshold, par->softClipLeft, par->softClipRight, &sp))) break;
+                spLen[0] = readLengths[e]; spLen[1] = readLengths[e + 1];
+            }
             for (int i = 0; i < 2; ++i) {
-                int32_t seedLen = 0, seedNum = 0;
-                if ((rc = s3_seed_layout(stage, (int32_t)readLengths[e + i], &seedLen, seedPos.data(), (int32_t)seedPos.size(), &seedNum))) break;
-                if (side[i].n + (uint64_t)seedNum > side[i].lengths.size() - 32) { s3_set_error("s3_deep_dp_align: more than 32 seeds per read"); rc = S3_EINVAL; break; }
-                for (int32_t j = 0; j < seedNum; ++j)
-                    seed_set_add(side[i], queries, wordPerQuery, e + i, e, (uint32_t)seedPos[j], (uint32_t)seedLen, (uint32_t)sp.paramRead[i].maxHitNum);
+                Layout &l = layouts[readLengths[e + i]];
+                for (int32_t j = 0; j < l.seedNum; ++j)
+                    seed_set_add(side[i], queries, wordPerQuery, e + i, e, (uint32_t)l.pos[j], (uint32_t)l.seedLen, (uint32_t)sp.paramRead[i].maxHitNum);
             }
         }
         if (rc) break;
+        clk.lap("seed packing");
         out->numSeeds += side[0].n + side[1].n;
         // ---- seeding driver per side; a pair with a too-many seed on either side is flagged (decodePositions, :2951-2954)
         s3_seed_search_result sr[2];
@@ -275,6 +308,7 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
                 }
             }
         }
+        clk.lap("s3_seed_search x 2");
         // ---- candidate position pairs (decodeMergePositions, DV-DPfunctions.cu:2963-2999)
         uint32_t *cID = NULL, *cL = NULL, *cR = NULL;
         uint64_t nc = 0;
@@ -284,6 +318,7 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
                                          0xFFFFFFFFu, readLengths, numReads, par->insertLow, par->insertHigh, par->strandLeftLeg, par->strandRightLeg,
                                          &cID, &cL, &cR, &nc);
         s3_seed_search_result_free(&sr[0]); s3_seed_search_result_free(&sr[1]);
+        clk.lap("s3_seed_pair_candidates");
         if (rc) break;
         // ---- seeded / too many / unseeded pairs (performSeeding, DV-DPfunctions.cu:3105-3125)
         std::vector<uint8_t> seeded(numReads, 0);
@@ -311,15 +346,16 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
         wp.softClipLeft = par->softClipLeft; wp.softClipRight = par->softClipRight;
         wp.cutoffThreshold[0] = wp.cutoffThreshold[1] = par->isDefaultThreshold ? -1 : par->dpScoreThreshold; wp.maxDNALength = maxDNA;
         Windows wl, wr;
-        Aligned al, ar;
-        s3_dp *dp = NULL;
+        S3StageAligned al, ar;
+        clk.lap("round bookkeeping");
         rc = make_windows(ix, S3_WIN_PAIR_LEFT, wp, readLengths, numReads, candID.data(), candL.data(), NULL, NULL, NULL, NULL, NULL, nc, wl);
-        if (rc == S3_OK) rc = s3_dp_create(maxRead, maxDNA, (uint32_t)(nc > 32 ? nc : 32), par->scores, ix->device, &dp);
-        if (rc == S3_OK) rc = align_windows(dp, ix, queries, readLengths, numReads, wordPerQuery, wl, al);
-        if (rc == S3_OK) rc = make_windows(ix, S3_WIN_PAIR_RIGHT, wp, readLengths, numReads, candID.data(), candL.data(), candR.data(), NULL, al.score.data(),
-                                           wl.start.data(), al.hit.data(), nc, wr);
-        if (rc == S3_OK) rc = align_windows(dp, ix, queries, readLengths, numReads, wordPerQuery, wr, ar);
-        if (dp) s3_dp_free(dp);
+        clk.lap("windows left");
+        if (rc == S3_OK) rc = align_windows(ix, queries, readLengths, numReads, wordPerQuery, 1, maxRead, maxDNA, par->scores, 0, wl, al);
+        clk.lap("align left");
+        if (rc == S3_OK) rc = make_windows(ix, S3_WIN_PAIR_RIGHT, wp, readLengths, numReads, candID.data(), candL.data(), candR.data(), NULL, al.score,
+                                           wl.start.data(), al.hit, nc, wr);
+        if (rc == S3_OK) rc = align_windows(ix, queries, readLengths, numReads, wordPerQuery, 0, maxRead, maxDNA, par->scores, 1, wr, ar);
+        clk.lap("windows right + align right");
         if (rc == S3_OK)
             for (uint64_t t = 0; t < wr.n; ++t) {
                 if (ar.score[t] < wr.cutoff[t]) continue;           // the left read reached its cutoff or the candidate has no right window
@@ -330,9 +366,9 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
                 h.readID = left - readSide;
                 const uint32_t posLeft = wl.start[c] + al.hit[c], posRight = wr.start[t] + ar.hit[t];
                 uint32_t roL = (uint32_t)runs.size();
-                pattern_runs(al.pattern.data() + (size_t)c * al.patLen, al.patLen, runs);
+                runs.insert(runs.end(), al.runs + al.runOff[c], al.runs + al.runOff[c + 1]);
                 uint32_t nL = (uint32_t)runs.size() - roL, roR = (uint32_t)runs.size();
-                pattern_runs(ar.pattern.data() + (size_t)t * ar.patLen, ar.patLen, runs);
+                runs.insert(runs.end(), ar.runs + ar.runOff[t], ar.runs + ar.runOff[t + 1]);
                 uint32_t nR = (uint32_t)runs.size() - roR;
                 if (readSide == 0) {
                     h.pos1 = posLeft; h.pos2 = posRight; h.score1 = al.score[c]; h.score2 = ar.score[t]; h.numSame1 = al.cnt[c]; h.numSame2 = ar.cnt[t];
@@ -346,6 +382,7 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
                 hits.push_back(h);
             }
     }
+    clk.lap("records + CIGAR runs");
     if (rc) return rc;
     out->numHits = hits.size(); out->numRuns = runs.size(); out->numUnseeded = unseeded.size();
     out->hits = to_malloc(hits); out->runs = to_malloc(runs); out->unseeded = to_malloc(unseeded);

@@ -32,9 +32,9 @@ def env():
 
 
 class OracleEnv:
-    def __init__(self, idx, hi):
+    def __init__(self, idx, hi, sa=None):
         self.olib, self.hi = load_oracle(), hi
-        self.sa = np.ascontiguousarray(idx.fwd.sa.cpu().numpy().astype(np.uint32))
+        self.sa = sa if sa is not None else np.ascontiguousarray(idx.fwd.sa.cpu().numpy().astype(np.uint32))
         o = self.olib
         o.s3o_seed_candidates.restype = C.c_uint64
         o.s3o_seed_candidates.argtypes = [U, U, U, I, U, U, U, U, C.c_uint64, C.c_uint32, U, U, I, C.c_uint64]

@@ -349,6 +349,7 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads, kernel_co
     qq = q[:formats.ceil32(nk) * b.wpq].copy() if nk < n else q.copy()
     lk = lens[:formats.ceil32(nk)].copy()
     lk[nk:] = 0
+    q0 = qq.copy()                                            # the reference's kernels turn the queries around in place
     t0 = time.perf_counter()
     for case in range(ncases):
         a = np.zeros(formats.ceil32(nk) * wpa, np.uint32)
@@ -391,8 +392,8 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads, kernel_co
                                               helpers.u32p(hi.rocc), len(hi.occ)) != 0:
                 raise RuntimeError("index upload failed")
             warm = min(nk, 65536)
-            helpers.ref_search_cuda_round1(ref_scu, hi, qq.copy(), lk, warm, b.wpq, K_MISMATCH, allowed, wpa)
-            ans_cu, ms_cu = helpers.ref_search_cuda_round1(ref_scu, hi, qq.copy(), lk, nk, b.wpq, K_MISMATCH, allowed, wpa)
+            helpers.ref_search_cuda_round1(ref_scu, hi, q0.copy(), lk, warm, b.wpq, K_MISMATCH, allowed, wpa)
+            ans_cu, ms_cu = helpers.ref_search_cuda_round1(ref_scu, hi, q0.copy(), lk, nk, b.wpq, K_MISMATCH, allowed, wpa)
             ref_scu.ref_search_cuda_free()
             equal = all(np.array_equal(formats.answers_view(x, nk, wpa), formats.answers_view(y, nk, wpa)) for x, y in zip(ans_cu, ans))
             flags_path = os.path.join(ROOT, "oracle", "_ref", "libref_search_cuda.so.flags")

@@ -589,6 +589,11 @@ s3_dp_sweep16_kernel(const S3DpArgs a)
 
     uint32_t steps = nMax + LANES - 1;
     for (int o = LANES; o < 32; o <<= 1) steps = max(steps, __shfl_xor_sync(0xFFFFFFFFu, steps, o));   // the groups of a warp step together
+#ifndef S3_DP_SWEEP_UNROLL
+#define S3_DP_SWEEP_UNROLL 1
+#endif
+    constexpr int SWEEP_UNROLL = S3_DP_SWEEP_UNROLL;
+#pragma unroll SWEEP_UNROLL
     for (uint32_t s = 1; s <= steps; ++s) {
         // carried registers of the row loop arrive from the lane above (column j was done there at step s-1):
         // H of the row above + open, F, and H of the previous column's row above + open (the diagonal)

@@ -21,6 +21,7 @@
 #   libref_params.so   getSeedPositions (definitions.h:323-442) + getParameterFor*DP (CPUfunctions.cpp:46-260)
 #   libref_cpu_search.so  the reference's own CPU search: ProcessReadDoubleStrand2 (CPUfunctions.cpp:555-622) + BGS-HostAlgnmtAlgo2.cpp,
 #                      SAList.cpp, SRA2BWTMdl.c, SRA2BWTCheckAndExtend.c, BWT.c compiled from where they lie; the CPU arm of bench.py
+#   libref_validate.so validateAlignments (CPUfunctions.cpp:1129-1222) + the packers / popcount distance it calls (PE.cpp:28-60,148-206,287-325)
 #   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
 # Two one-line build fixes are applied to *copies* in oracle/_ref/patched/
@@ -157,6 +158,12 @@ sed -n '46,260p' "$REF/CPUfunctions.cpp" > "$OUT/patched/params.inc"
 $CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
     "$HERE/ref_shim/ref_params_host.cpp" -o "$OUT/libref_params.so"
 echo "[build_ref] libref_params.so OK"
+
+# ---- reference long-read validation of seed alignments, against the reference's own headers -------------------------------
+{ sed -n '28,60p' "$REF/PE.cpp"; sed -n '148,206p' "$REF/PE.cpp"; sed -n '287,325p' "$REF/PE.cpp"; sed -n '1129,1222p' "$REF/CPUfunctions.cpp"; } > "$OUT/patched/validate.inc"
+$CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
+    "$HERE/ref_shim/ref_validate_host.cpp" -o "$OUT/libref_validate.so"
+echo "[build_ref] libref_validate.so OK"
 
 # ---- the reference's CPU search path: models, lookup-table + BWT backward / bidirectional search, check-and-extend ------------
 # ProcessReadDoubleStrand2 is cut by line range (CPUfunctions.cpp as a whole needs the aligner around it); the files it calls

@@ -1073,23 +1073,55 @@ void s3_stage_ws_free(s3_index *ix)
     ix->stageWs = NULL;
 }
 
+__global__ void s3_stage_readlen_kernel(uint32_t n, const uint32_t *__restrict__ readID, const uint32_t *__restrict__ lengthsByRead, uint32_t *__restrict__ out)
+{
+    const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) out[t] = lengthsByRead[readID[t]];
+}
+
+static S3StageWs *stage_ws(s3_index *ix)
+{
+    S3StageWs *ws = (S3StageWs *)ix->stageWs;
+    if (!ws) {
+        ws = (S3StageWs *)calloc(1, sizeof(S3StageWs));
+        ix->stageWs = ws;
+    }
+    return ws;
+}
+
+const uint32_t *s3_stage_queries(s3_index *ix) { S3StageWs *ws = (S3StageWs *)ix->stageWs; return ws ? ws->d_q : NULL; }
+
+int s3_stage_upload_queries(s3_index *ix, const uint32_t *queries, uint64_t numReads, uint32_t wordPerQuery)
+{
+    S3StageWs *ws = stage_ws(ix);
+    if (!ws) { s3_set_error("out of host memory"); return S3_ENOMEM; }
+    S3_TRYC(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
+    const size_t up = ((size_t)numReads + 31) / 32 * 32, qBytes = up * wordPerQuery * 4;
+    if (qBytes > ws->qBytes) {
+        if (ws->d_q) { S3_TRYC(cudaStreamSynchronize(st)); cudaFree(ws->d_q); ws->d_q = NULL; ws->qBytes = 0; }
+        S3_TRYC(cudaMalloc(&ws->d_q, qBytes + qBytes / 4));
+        ws->qBytes = qBytes + qBytes / 4;
+    }
+    S3_TRYC(cudaMemcpyAsync(ws->d_q, queries, qBytes, cudaMemcpyHostToDevice, st));
+    return S3_OK;
+}
+
 int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery, int uploadQueries,
                    uint32_t maxRead, uint32_t maxDNA, s3_dp_scores scores, int slot, uint64_t n64,
                    const uint32_t *readID, const uint8_t *strand, const uint32_t *start, const uint32_t *len, const int32_t *cutoff,
-                   const uint32_t *clipLt, const uint32_t *clipRt, const uint32_t *ancL, const uint32_t *ancR, S3StageAligned *out)
+                   const uint32_t *clipLt, const uint32_t *clipRt, const uint32_t *ancL, const uint32_t *ancR,
+                   const uint32_t *d_lenByRead, const uint32_t *d_cand, S3StageAligned *out)
 {
     memset(out, 0, sizeof *out);
     if (n64 == 0) return S3_OK;
     if (n64 > 0x7FFFFFF0ull) { s3_set_error("s3_stage_align: too many alignments in one call"); return S3_EINVAL; }
     const uint32_t n = (uint32_t)n64;
+    const bool dev = d_lenByRead != NULL;
     S3_TRYC(cudaSetDevice(ix->device));
     cudaStream_t st = ix->stream;
-    S3StageWs *ws = (S3StageWs *)ix->stageWs;
-    if (!ws) {
-        ws = (S3StageWs *)calloc(1, sizeof(S3StageWs));
-        if (!ws) { s3_set_error("out of host memory"); return S3_ENOMEM; }
-        ix->stageWs = ws;
-    }
+    S3StageWs *ws = stage_ws(ix);
+    if (!ws) { s3_set_error("out of host memory"); return S3_ENOMEM; }
     int rc;
     if (!ws->dp || ws->maxRead != maxRead || ws->maxDNA != maxDNA || ws->cap < n || memcmp(&ws->scores, &scores, sizeof scores)) {
         if (ws->dp) { S3_TRYC(cudaStreamSynchronize(st)); s3_dp_free(ws->dp); ws->dp = NULL; }
@@ -1098,15 +1130,7 @@ int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLe
         s3_dp_set_stream(ws->dp, st);
         ws->maxRead = maxRead; ws->maxDNA = maxDNA; ws->cap = cap; ws->scores = scores;
     }
-    const size_t up = ((size_t)numReads + 31) / 32 * 32, qBytes = up * wordPerQuery * 4;
-    if (uploadQueries || !ws->d_q) {
-        if (qBytes > ws->qBytes) {
-            if (ws->d_q) { S3_TRYC(cudaStreamSynchronize(st)); cudaFree(ws->d_q); ws->d_q = NULL; ws->qBytes = 0; }
-            S3_TRYC(cudaMalloc(&ws->d_q, qBytes + qBytes / 4));
-            ws->qBytes = qBytes + qBytes / 4;
-        }
-        S3_TRYC(cudaMemcpyAsync(ws->d_q, queries, qBytes, cudaMemcpyHostToDevice, st));
-    }
+    if (uploadQueries || !ws->d_q) { if ((rc = s3_stage_upload_queries(ix, queries, numReads, wordPerQuery))) return rc; }
     const size_t patLen = s3_dp_pattern_length(ws->dp);
     size_t scanTemp = 0;
     cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (uint32_t *)NULL, (uint32_t *)NULL, (int)(n + 1), st);
@@ -1125,31 +1149,44 @@ int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLe
     void *d_tmp = arena_take<char>(A, scanTemp);
     (void)d_spare;
     if (!d_tmp) { s3_set_error("s3_stage_align: stage buffer accounting"); return S3_ENOMEM; }
-    // host side: results of this slot, and the per-alignment read lengths (staged in the slot's buffer before they are uploaded)
-    const size_t hostBytes = 4 * (((size_t)n + 1) * 4 + 256) + (size_t)n * (maxRead + 8) * 4 + 256;
+    // host side: results of this slot (and, staged there first, the per-alignment read lengths of the host mode)
+    const size_t stride = (((size_t)n + 1) * 4 + 255) / 256 * 256;
+    const size_t hostBytes = 10 * stride + (size_t)n * (maxRead + 8) * 4 + 256;
     if (hostBytes > ws->pinnedBytes[slot]) {
         if (ws->pinned[slot]) { S3_TRYC(cudaStreamSynchronize(st)); cudaFreeHost(ws->pinned[slot]); ws->pinned[slot] = NULL; ws->pinnedBytes[slot] = 0; }
         if (cudaMallocHost(&ws->pinned[slot], hostBytes + hostBytes / 4) != cudaSuccess) { s3_set_error("s3_stage_align: pinned allocation failed"); return S3_ENOMEM; }
         ws->pinnedBytes[slot] = hostBytes + hostBytes / 4;
     }
     char *h = (char *)ws->pinned[slot];
-    const size_t stride = (((size_t)n + 1) * 4 + 255) / 256 * 256;
     int32_t *h_score = (int32_t *)h; uint32_t *h_hit = (uint32_t *)(h + stride), *h_cnt = (uint32_t *)(h + 2 * stride), *h_runOff = (uint32_t *)(h + 3 * stride);
-    uint32_t *h_runs = (uint32_t *)(h + 4 * stride);
-    for (uint32_t t = 0; t < n; ++t) {
-        if (readID[t] >= numReads) { s3_set_error("s3_stage_align: read id %u out of range", readID[t]); return S3_EINVAL; }
-        h_runs[t] = readLengths[readID[t]];
+    uint32_t *h_readID = (uint32_t *)(h + 4 * stride), *h_start = (uint32_t *)(h + 5 * stride), *h_cand = (uint32_t *)(h + 6 * stride);
+    int32_t *h_cutoff = (int32_t *)(h + 7 * stride);
+    uint8_t *h_strand = (uint8_t *)(h + 8 * stride);
+    uint32_t *h_runs = (uint32_t *)(h + 10 * stride);
+    if (dev) {
+        // the DP writes its right clips in place, and the caller's arrays may be reused: work on copies
+        d_readID = const_cast<uint32_t *>(readID); d_start = const_cast<uint32_t *>(start); d_len = const_cast<uint32_t *>(len);
+        d_cut = const_cast<int32_t *>(cutoff); d_clt = const_cast<uint32_t *>(clipLt); d_al = const_cast<uint32_t *>(ancL); d_ar = const_cast<uint32_t *>(ancR);
+        d_strand = const_cast<uint8_t *>(strand);
+        S3_TRYC(cudaMemcpyAsync(d_crt, clipRt, (size_t)n * 4, cudaMemcpyDeviceToDevice, st));
+        s3_stage_readlen_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d_readID, d_lenByRead, d_rl);
+        S3_LAUNCHED(1);
+    } else {
+        for (uint32_t t = 0; t < n; ++t) {
+            if (readID[t] >= numReads) { s3_set_error("s3_stage_align: read id %u out of range", readID[t]); return S3_EINVAL; }
+            h_runs[t] = readLengths[readID[t]];
+        }
+        S3_TRYC(cudaMemcpyAsync(d_rl, h_runs, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_readID, readID, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_start, start, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_len, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_cut, cutoff, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_clt, clipLt, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_crt, clipRt, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_al, ancL, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_ar, ancR, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+        S3_TRYC(cudaMemcpyAsync(d_strand, strand, n, cudaMemcpyHostToDevice, st));
     }
-    S3_TRYC(cudaMemcpyAsync(d_rl, h_runs, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    S3_TRYC(cudaMemcpyAsync(d_readID, readID, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    S3_TRYC(cudaMemcpyAsync(d_start, start, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    S3_TRYC(cudaMemcpyAsync(d_len, len, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    S3_TRYC(cudaMemcpyAsync(d_cut, cutoff, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    S3_TRYC(cudaMemcpyAsync(d_clt, clipLt, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    S3_TRYC(cudaMemcpyAsync(d_crt, clipRt, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    S3_TRYC(cudaMemcpyAsync(d_al, ancL, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    S3_TRYC(cudaMemcpyAsync(d_ar, ancR, (size_t)n * 4, cudaMemcpyHostToDevice, st));
-    S3_TRYC(cudaMemcpyAsync(d_strand, strand, n, cudaMemcpyHostToDevice, st));
     if ((rc = s3_dp_align_windows_device(ws->dp, ix, ws->d_q, wordPerQuery, d_readID, d_strand, d_start, d_len, d_rl, d_cut, d_score, d_hit, d_cnt, d_pattern, n,
                                          d_clt, d_crt, d_al, d_ar))) return rc;
     const unsigned nb = (n + 127) / 128;
@@ -1163,6 +1200,13 @@ int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLe
     S3_TRYC(cudaMemcpyAsync(h_hit, d_hit, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     S3_TRYC(cudaMemcpyAsync(h_cnt, d_cnt, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
     S3_TRYC(cudaMemcpyAsync(h_runOff, d_runOff, ((size_t)n + 1) * 4, cudaMemcpyDeviceToHost, st));
+    if (dev) {
+        S3_TRYC(cudaMemcpyAsync(h_readID, d_readID, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        S3_TRYC(cudaMemcpyAsync(h_start, d_start, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        S3_TRYC(cudaMemcpyAsync(h_cutoff, d_cut, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        S3_TRYC(cudaMemcpyAsync(h_strand, d_strand, n, cudaMemcpyDeviceToHost, st));
+        if (d_cand) S3_TRYC(cudaMemcpyAsync(h_cand, d_cand, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+    }
     S3_TRYC(cudaStreamSynchronize(st));
     const uint32_t total = h_runOff[n];
     if (total) {
@@ -1170,5 +1214,7 @@ int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLe
         S3_TRYC(cudaStreamSynchronize(st));
     }
     out->score = h_score; out->hit = h_hit; out->cnt = h_cnt; out->runOff = h_runOff; out->runs = h_runs; out->numRuns = total;
+    out->readID = h_readID; out->start = h_start; out->cutoff = h_cutoff; out->strand = h_strand; out->cand = h_cand;
+    out->d_score = d_score; out->d_hit = d_hit;
     return S3_OK;
 }

@@ -110,7 +110,23 @@ struct s3_index {
     size_t searchSmem; int searchBlocksPerSm;
     int sharedArrays;                 // s3_index_clone: buckets, seed tables, suffix array, text belong to another handle
     void *stageWs;                    // workspace of the seeded DP stages (s3_stage_align, s3_chain.cu), created on first use
+    void *pinnedCount;                // 64 pinned bytes for the small count reads of stream-ordered entries
 };
+
+// the seeding driver and the single-end seed merge on device arrays (s3_seed.cu); see the host entries for what they compute
+struct S3SeedRangesDev {
+    uint32_t *d_buf;             // saL | saR | strand | read id | seed offset | seed length | read length, numRanges words each (cudaFreeAsync)
+    uint64_t numRanges;
+    uint8_t *d_status;           // per seed: 0 none, 1 kept, 4 too many occurrences (cudaFreeAsync)
+};
+int s3_seed_search_device(s3_index *ix, const uint32_t *d_seeds, const uint32_t *d_seedLengths, uint32_t numSeeds, uint32_t wordPerSeed,
+                          const uint32_t *d_maxHit, const uint32_t *d_seedReadID, const uint32_t *d_seedOffset, const uint32_t *d_seedReadLength,
+                          S3SeedRangesDev *out);
+int s3_seed_candidates_device(s3_index *ix, const uint32_t *d_l, const uint32_t *d_r, const int32_t *d_st, const uint32_t *d_rid,
+                              const uint32_t *d_off, const uint32_t *d_sl, const uint32_t *d_rl, uint64_t numRanges, uint32_t maxPerRange,
+                              uint32_t **d_out, uint32_t *numCandidates);
+int s3_search_csr_device(s3_index *ix, const uint32_t *d_queries, const uint32_t *d_readLengths, uint32_t batchSize, uint32_t wordPerQuery,
+                         uint32_t numMismatch, int isExactNumMismatch, unsigned long long *d_starts, uint32_t **d_out, unsigned long long *total);
 
 // Alignment step of the seeded DP stages (s3_stages.cu): windows in host arrays -> scores, hit locations, tie counts and the
 // CIGAR runs of the alignments that reach their cutoff, in host arrays the handle owns (two slots: the deep stage keeps the left
@@ -119,11 +135,20 @@ struct s3_index {
 struct S3StageAligned {
     const int32_t *score; const uint32_t *hit, *cnt, *runOff, *runs;
     uint64_t numRuns;
+    // device mode only (windows given as device arrays): host copies of what the records need of the windows
+    const uint32_t *readID, *start, *cand; const int32_t *cutoff; const uint8_t *strand;
+    // device pointers of this call's scores / hit locations (valid until the next call on the handle): the deep stage's right windows read them
+    const int32_t *d_score; const uint32_t *d_hit;
 };
+// d_readLengthsByRead == NULL: the window arrays are host arrays (uploaded here); else they are device arrays, d_cand (may be
+// NULL) is copied back with them, and the read length of an alignment is looked up on the device.
 int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery, int uploadQueries,
                    uint32_t maxRead, uint32_t maxDNA, s3_dp_scores scores, int slot, uint64_t n,
                    const uint32_t *readID, const uint8_t *strand, const uint32_t *start, const uint32_t *len, const int32_t *cutoff,
-                   const uint32_t *clipLt, const uint32_t *clipRt, const uint32_t *ancL, const uint32_t *ancR, S3StageAligned *out);
+                   const uint32_t *clipLt, const uint32_t *clipRt, const uint32_t *ancL, const uint32_t *ancR,
+                   const uint32_t *d_readLengthsByRead, const uint32_t *d_cand, S3StageAligned *out);
+const uint32_t *s3_stage_queries(s3_index *ix);            // device copy of the query buffer of the current stage call (NULL before the first upload)
+int s3_stage_upload_queries(s3_index *ix, const uint32_t *queries, uint64_t numReads, uint32_t wordPerQuery);
 void s3_stage_ws_free(s3_index *ix);
 
 void s3_set_error(const char *fmt, ...);

@@ -303,6 +303,12 @@ extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const u
     ix->device = device;
     ix->textLength = textLength;
     S3_CUDA_IX(cudaStreamCreateWithFlags(&ix->stream, cudaStreamNonBlocking));
+    S3_CUDA_IX(cudaMallocHost(&ix->pinnedCount, 64));
+    {   // stream-ordered allocations (cudaMallocAsync) keep their memory between calls instead of returning it at every synchronize
+        cudaMemPool_t pool;
+        unsigned long long keep = ~0ull;
+        if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+    }
     S3_CUDA_IX(cudaDeviceGetAttribute(&ix->numSms, cudaDevAttrMultiProcessorCount, device));
     ix->splitBudget = 256;
     S3_CUDA_IX(cudaMalloc(&ix->d_workCounter, 256));
@@ -355,6 +361,7 @@ extern "C" void s3_index_free(s3_index *ix)
     s3_timing_destroy(&ix->timing);
     if (ix->scratch) cudaFree(ix->scratch);
     if (ix->pinned) cudaFreeHost(ix->pinned);
+    if (ix->pinnedCount) cudaFreeHost(ix->pinnedCount);
     cudaStreamDestroy(ix->stream);
     free(ix);
 }
@@ -374,7 +381,8 @@ extern "C" int s3_index_clone(s3_index *ix, s3_index **out)
     c->d_isa = ix->d_isa; c->textLength = ix->textLength; c->d_fwd = ix->d_fwd; c->d_rev = ix->d_rev;
     c->d_packedDNA = ix->d_packedDNA; c->d_sa = ix->d_sa; c->bytes = 0;
     c->numSms = ix->numSms; c->splitBudget = ix->splitBudget; c->searchSmem = (size_t)-1; c->sharedArrays = 1;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&c->d_workCounter, 256) != cudaSuccess) {
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess || cudaMalloc(&c->d_workCounter, 256) != cudaSuccess ||
+        cudaMallocHost(&c->pinnedCount, 64) != cudaSuccess) {
         s3_set_error("s3_index_clone: %s", cudaGetErrorString(cudaGetLastError()));
         s3_index_free(c);
         return S3_ECUDA;

@@ -23,6 +23,7 @@
 // second strand appended to the first -- is preserved, so the answer slots are
 // bit-identical, including which ranges survive when a slot overflows.
 #include "s3_common.cuh"
+#include <chrono>
 #include "../../include/soap3dp_b200.h"
 #include <cub/device/device_select.cuh>
 #include <cub/device/device_scan.cuh>
@@ -1134,6 +1135,46 @@ extern "C" void s3_search_result_free(s3_search_result *r)
     memset(r, 0, sizeof *r);
 }
 
+// The capless search on device arrays (the seeded DP stages keep their seeds there; s3_search below is its host-pointer
+// form).  d_starts receives batchSize * numCases + 1 run starts (item = read * numCases + case; the last entry is the total),
+// *d_out a stream-ordered allocation of 3 * total words (L | R | info) that the caller returns with cudaFreeAsync on the
+// index stream (NULL when nothing was found).  One 8-byte read back sizes the second pass.
+int s3_search_csr_device(s3_index *ix, const uint32_t *d_queries, const uint32_t *d_readLengths, uint32_t batchSize, uint32_t wordPerQuery,
+                         uint32_t numMismatch, int isExactNumMismatch, unsigned long long *d_starts, uint32_t **d_out, unsigned long long *total)
+{
+    static const uint32_t ncases[5] = {1, 2, 4, 6, 10};
+    *d_out = NULL; *total = 0;
+    if (batchSize == 0) return S3_OK;
+    const uint32_t numCases = ncases[numMismatch];
+    const size_t items = (size_t)batchSize * numCases;
+    cudaStream_t st = ix->stream;
+    size_t scanTemp = 0;
+    cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (unsigned long long *)NULL, (unsigned long long *)NULL, (int)(items + 1), st);
+    void *d_tmp = NULL;
+    S3_CUDA(cudaMallocAsync(&d_tmp, scanTemp + 16, st));
+    S3_CUDA(cudaMemsetAsync(d_starts, 0, (items + 1) * 8, st));
+    S3SearchArgs a;
+    memset(&a, 0, sizeof a);
+    a.queries = d_queries; a.readLengths = d_readLengths; a.numQueries = batchSize; a.wordPerQuery = wordPerQuery;
+    a.round = 0; a.numMismatch = numMismatch; a.saRangeAllowed = 0xFFFFFFFFu; a.wordPerAnswer = 0;
+    a.firstCase = 0; a.exactNum = isExactNumMismatch ? 1 : 0; a.textLength = ix->textLength;
+    a.csrCount = d_starts;
+    int rc = launch_search_csr<1>(ix, a, numCases);
+    if (rc == S3_OK && cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_starts, d_starts, (int)(items + 1), st) != cudaSuccess) { s3_set_error("s3_search: scan failed"); rc = S3_ECUDA; }
+    cudaFreeAsync(d_tmp, st);
+    if (rc) return rc;
+    unsigned long long *h_total = (unsigned long long *)ix->pinnedCount;
+    S3_CUDA(cudaMemcpyAsync(h_total, d_starts + items, 8, cudaMemcpyDeviceToHost, st));
+    S3_CUDA(cudaStreamSynchronize(st));
+    *total = *h_total;
+    if (*total == 0) return S3_OK;
+    if (*total >= 0x7FFFFFFFull) { s3_set_error("s3_search: %llu ranges in one call", *total); return S3_EINVAL; }
+    S3_CUDA(cudaMallocAsync((void **)d_out, (size_t)*total * 12, st));
+    a.csrL = *d_out; a.csrR = *d_out + *total; a.csrInfo = *d_out + 2 * *total;
+    if ((rc = launch_search_csr<2>(ix, a, numCases))) { cudaFreeAsync(*d_out, st); *d_out = NULL; }
+    return rc;
+}
+
 extern "C" int s3_search(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t batchSize,
                          uint32_t wordPerQuery, uint32_t numMismatch, int isExactNumMismatch, s3_search_result *out)
 {
@@ -1149,51 +1190,37 @@ extern "C" int s3_search(s3_index *ix, const uint32_t *queries, const uint32_t *
     if (!out->offsets) { s3_set_error("s3_search: out of host memory"); return S3_ENOMEM; }
     if (batchSize == 0) return S3_OK;
     S3_CUDA(cudaSetDevice(ix->device));
+    cudaStream_t st = ix->stream;
     const size_t roundUp = (batchSize + 31) / 32 * 32, items = batchSize * numCases;
     const size_t qBytes = roundUp * wordPerQuery * 4, lBytes = roundUp * 4, cBytes = (items + 1) * 8;
-    size_t scanTemp = 0;
-    cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (unsigned long long *)NULL, (unsigned long long *)NULL, (int)(items + 1), ix->stream);
     char *d;
-    if ((rc = s3_scratch(ix, qBytes + lBytes + cBytes + scanTemp + 1024, (void **)&d))) { s3_search_result_free(out); return rc; }
+    if ((rc = s3_scratch(ix, qBytes + lBytes + cBytes + 1024, (void **)&d))) { s3_search_result_free(out); return rc; }
     size_t off = 0;
     auto carve = [&](size_t bytes) { char *p = d + off; off += (bytes + 255) / 256 * 256; return p; };
     uint32_t *d_q = (uint32_t *)carve(qBytes), *d_l = (uint32_t *)carve(lBytes);
     unsigned long long *d_cnt = (unsigned long long *)carve(cBytes);
-    void *d_tmp = carve(scanTemp);
-    S3_CUDA(cudaMemcpyAsync(d_q, queries, qBytes, cudaMemcpyHostToDevice, ix->stream));
-    S3_CUDA(cudaMemcpyAsync(d_l, readLengths, batchSize * 4, cudaMemcpyHostToDevice, ix->stream));
-    S3_CUDA(cudaMemsetAsync(d_cnt, 0, cBytes, ix->stream));
-    S3SearchArgs a;
-    memset(&a, 0, sizeof a);
-    a.queries = d_q; a.readLengths = d_l; a.numQueries = (uint32_t)batchSize; a.wordPerQuery = wordPerQuery;
-    a.round = 0; a.numMismatch = numMismatch; a.saRangeAllowed = 0xFFFFFFFFu; a.wordPerAnswer = 0;
-    a.firstCase = 0; a.exactNum = isExactNumMismatch ? 1 : 0; a.textLength = ix->textLength;
-    a.csrCount = d_cnt;
-    if ((rc = launch_search_csr<1>(ix, a, numCases))) { s3_search_result_free(out); return rc; }
-    // counts -> starts (one extra element: the total)
-    S3_CUDA(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_cnt, d_cnt, (int)(items + 1), ix->stream));
-    unsigned long long total = 0;
-    S3_CUDA(cudaMemcpyAsync(&total, d_cnt + items, 8, cudaMemcpyDeviceToHost, ix->stream));
-    // a read's run starts where its first case starts
-    S3_CUDA(cudaMemcpy2DAsync(out->offsets, 8, d_cnt, (size_t)numCases * 8, 8, batchSize, cudaMemcpyDeviceToHost, ix->stream));
-    S3_CUDA(cudaStreamSynchronize(ix->stream));
-    out->offsets[batchSize] = total;
-    out->total = total;
-    if (total == 0) return S3_OK;
+    S3_CUDA(cudaMemcpyAsync(d_q, queries, qBytes, cudaMemcpyHostToDevice, st));
+    S3_CUDA(cudaMemsetAsync(d_l, 0, lBytes, st));
+    S3_CUDA(cudaMemcpyAsync(d_l, readLengths, batchSize * 4, cudaMemcpyHostToDevice, st));
     uint32_t *d_out = NULL;
-    S3_CUDA(cudaMalloc(&d_out, (size_t)total * 12));
-    a.csrL = d_out; a.csrR = d_out + total; a.csrInfo = d_out + 2 * total;
-    rc = launch_search_csr<2>(ix, a, numCases);
-    out->saL = (uint32_t *)malloc((size_t)total * 4); out->saR = (uint32_t *)malloc((size_t)total * 4); out->info = (uint32_t *)malloc((size_t)total * 4);
-    if (rc == S3_OK && (!out->saL || !out->saR || !out->info)) { s3_set_error("s3_search: out of host memory"); rc = S3_ENOMEM; }
-    if (rc == S3_OK) {
-        cudaError_t e = cudaMemcpyAsync(out->saL, a.csrL, (size_t)total * 4, cudaMemcpyDeviceToHost, ix->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out->saR, a.csrR, (size_t)total * 4, cudaMemcpyDeviceToHost, ix->stream);
-        if (e == cudaSuccess) e = cudaMemcpyAsync(out->info, a.csrInfo, (size_t)total * 4, cudaMemcpyDeviceToHost, ix->stream);
-        if (e == cudaSuccess) e = cudaStreamSynchronize(ix->stream);
-        if (e != cudaSuccess) { s3_set_error("s3_search: copying the ranges back failed: %s", cudaGetErrorString(e)); rc = S3_ECUDA; }
+    unsigned long long total = 0;
+    if ((rc = s3_search_csr_device(ix, d_q, d_l, (uint32_t)batchSize, wordPerQuery, numMismatch, isExactNumMismatch, d_cnt, &d_out, &total))) { s3_search_result_free(out); return rc; }
+    // a read's run starts where its first case starts
+    S3_CUDA(cudaMemcpy2DAsync(out->offsets, 8, d_cnt, (size_t)numCases * 8, 8, batchSize, cudaMemcpyDeviceToHost, st));
+    out->total = total;
+    if (total) {
+        out->saL = (uint32_t *)malloc((size_t)total * 4); out->saR = (uint32_t *)malloc((size_t)total * 4); out->info = (uint32_t *)malloc((size_t)total * 4);
+        if (!out->saL || !out->saR || !out->info) { s3_set_error("s3_search: out of host memory"); rc = S3_ENOMEM; }
+        if (rc == S3_OK) {
+            cudaError_t e = cudaMemcpyAsync(out->saL, d_out, (size_t)total * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out->saR, d_out + total, (size_t)total * 4, cudaMemcpyDeviceToHost, st);
+            if (e == cudaSuccess) e = cudaMemcpyAsync(out->info, d_out + 2 * total, (size_t)total * 4, cudaMemcpyDeviceToHost, st);
+            if (e != cudaSuccess) { s3_set_error("s3_search: copying the ranges back failed: %s", cudaGetErrorString(e)); rc = S3_ECUDA; }
+        }
     }
-    cudaFree(d_out);
+    if (cudaStreamSynchronize(st) != cudaSuccess && rc == S3_OK) { s3_set_error("s3_search: synchronize failed"); rc = S3_ECUDA; }
+    out->offsets[batchSize] = total;
+    if (d_out) cudaFreeAsync(d_out, st);
     if (rc != S3_OK) s3_search_result_free(out);
     return rc;
 }

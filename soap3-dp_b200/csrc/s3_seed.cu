@@ -12,6 +12,20 @@
 #include <cub/device/device_select.cuh>
 #include <cub/iterator/counting_input_iterator.cuh>
 #include <stdlib.h>
+#include <chrono>
+
+// S3_STAGE_TIMING=1: wall-clock laps on stderr (tuning aid, like s3_stages.cu)
+struct S3Lap {
+    bool on; std::chrono::steady_clock::time_point t; const char *what;
+    explicit S3Lap(const char *w) : on(getenv("S3_STAGE_TIMING") != NULL), t(std::chrono::steady_clock::now()), what(w) {}
+    void lap(const char *step)
+    {
+        if (!on) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "    [%s] %-24s %8.2f ms\n", what, step, std::chrono::duration<double, std::milli>(now - t).count());
+        t = now;
+    }
+};
 
 #define S3_DIVIDE_GAP 50u            // DPS_DIVIDE_GAP, DV-DPfunctions.h:944
 
@@ -76,6 +90,73 @@ __global__ void s3_seed_gather_kernel(const unsigned long long *__restrict__ key
 
 #define S3_TRY(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { s3_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); rc = S3_ECUDA; goto done; } } while (0)
 
+// Device form: every pointer is a device pointer; *d_out is a stream-ordered allocation of 3 * m words (read id | estimated
+// start | strand) the caller returns with cudaFreeAsync on the index stream (NULL when m == 0).
+int s3_seed_candidates_device(s3_index *ix, const uint32_t *d_l, const uint32_t *d_r, const int32_t *d_st, const uint32_t *d_rid,
+                              const uint32_t *d_off, const uint32_t *d_sl, const uint32_t *d_rl, uint64_t numRanges, uint32_t maxPerRange,
+                              uint32_t **d_out, uint32_t *numCandidates)
+{
+    *d_out = NULL; *numCandidates = 0;
+    if (numRanges == 0) return S3_OK;
+    int rc = S3_OK;
+    cudaStream_t st = ix->stream;
+    unsigned long long *d_cnt = NULL;
+    char *d_work = NULL;
+    void *d_tmp = NULL;
+    size_t t1 = 0, t2 = 0, t3 = 0;
+    unsigned long long *h_total = (unsigned long long *)ix->pinnedCount;
+    uint32_t *h_m = (uint32_t *)ix->pinnedCount + 4;
+    S3_TRY(cudaMallocAsync((void **)&d_cnt, (numRanges + 1) * 8 + 8, st));
+    s3_seed_count_kernel<<<(unsigned)((numRanges + 256) / 256), 256, 0, st>>>(d_l, d_r, numRanges, maxPerRange, d_cnt);
+    S3_LAUNCHED(1);
+    cub::DeviceScan::ExclusiveSum(NULL, t1, d_cnt, d_cnt, (int)(numRanges + 1), st);
+    S3_TRY(cudaMallocAsync(&d_tmp, t1 + 16, st));
+    S3_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, t1, d_cnt, d_cnt, (int)(numRanges + 1), st));
+    S3_TRY(cudaMemcpyAsync(h_total, d_cnt + numRanges, 8, cudaMemcpyDeviceToHost, st));
+    S3_TRY(cudaStreamSynchronize(st));
+    cudaFreeAsync(d_tmp, st); d_tmp = NULL;
+    {
+        const unsigned long long total = *h_total;
+        if (total == 0) goto done;
+        if (total >= 0x7FFFFFFFull) { s3_set_error("s3_seed_candidates: %llu positions in one call", total); rc = S3_EINVAL; goto done; }
+        // keys x2, vals x2, selected indices, keep flags, the count
+        const size_t T = (size_t)total;
+        S3_TRY(cudaMallocAsync((void **)&d_work, T * (8 + 8 + 4 + 4 + 4) + T + 1024, st));
+        unsigned long long *k0 = (unsigned long long *)d_work, *k1 = k0 + T;
+        int32_t *v0 = (int32_t *)(k1 + T), *v1 = v0 + T;
+        uint32_t *sel = (uint32_t *)(v1 + T);
+        uint8_t *keep = (uint8_t *)(sel + T);
+        uint32_t *d_m = (uint32_t *)(((uintptr_t)(keep + T) + 15) & ~(uintptr_t)15);
+        s3_seed_fill_kernel<<<(unsigned)((numRanges * 32 + 255) / 256), 256, 0, st>>>(ix->loc.sa, d_l, d_r, d_st, d_rid, d_off, d_sl, d_rl,
+                                                                                         numRanges, maxPerRange, d_cnt, k0, v0);
+        S3_LAUNCHED(1);
+        cub::DeviceRadixSort::SortPairs(NULL, t2, k0, k1, v0, v1, (int)T, 0, 64, st);
+        cub::DeviceSelect::Flagged(NULL, t3, cub::CountingInputIterator<uint32_t>(0), keep, sel, d_m, (int)T, st);
+        S3_TRY(cudaMallocAsync(&d_tmp, (t2 > t3 ? t2 : t3) + 16, st));
+        S3_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, t2, k0, k1, v0, v1, (int)T, 0, 64, st));      // stable: ties stay in arrival order
+        S3_TRY(cudaMemsetAsync(keep, 0, T, st));
+        s3_seed_merge_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(k1, T, keep);
+        S3_LAUNCHED(1);
+        S3_TRY(cub::DeviceSelect::Flagged(d_tmp, t3, cub::CountingInputIterator<uint32_t>(0), keep, sel, d_m, (int)T, st));
+        S3_TRY(cudaMemcpyAsync(h_m, d_m, 4, cudaMemcpyDeviceToHost, st));
+        S3_TRY(cudaStreamSynchronize(st));
+        const uint32_t m = *h_m;
+        if (m) {
+            S3_TRY(cudaMallocAsync((void **)d_out, (size_t)m * 12, st));
+            s3_seed_gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k1, v1, sel, m, *d_out, *d_out + m, (int32_t *)(*d_out + 2 * (size_t)m));
+            S3_LAUNCHED(1);
+            S3_TRY(cudaGetLastError());
+        }
+        *numCandidates = m;
+    }
+done:
+    if (d_cnt) cudaFreeAsync(d_cnt, st);
+    if (d_work) cudaFreeAsync(d_work, st);
+    if (d_tmp) cudaFreeAsync(d_tmp, st);
+    if (rc && *d_out) { cudaFreeAsync(*d_out, st); *d_out = NULL; }
+    return rc;
+}
+
 extern "C" int s3_seed_candidates(s3_index *ix, const uint32_t *saL, const uint32_t *saR, const int32_t *strands,
                                   const uint32_t *readIDs, const uint32_t *offsets, const uint32_t *seedLengths,
                                   const uint32_t *readLengths, uint64_t numRanges, uint32_t maxPerRange,
@@ -96,71 +177,29 @@ extern "C" int s3_seed_candidates(s3_index *ix, const uint32_t *saL, const uint3
     int rc = S3_OK;
     cudaStream_t st = ix->stream;
     const size_t rB = numRanges * 4;
-    char *d_in = NULL, *d_work = NULL;
-    void *d_tmp = NULL;
-    unsigned long long total = 0;
+    uint32_t *d_in = NULL, *d_out = NULL;
     uint32_t m = 0;
     uint32_t *h_r = NULL, *h_p = NULL; int32_t *h_s = NULL;
-    size_t tmpBytes = 0, t1 = 0, t2 = 0, t3 = 0;
-    S3_TRY(cudaMalloc(&d_in, 7 * rB + (numRanges + 1) * 8 + 8));
+    S3_TRY(cudaMallocAsync((void **)&d_in, 7 * rB + 64, st));
     {
-        uint32_t *d_l = (uint32_t *)d_in, *d_r = d_l + numRanges, *d_rid = d_r + numRanges, *d_off = d_rid + numRanges,
-                 *d_sl = d_off + numRanges, *d_rl = d_sl + numRanges;
-        int32_t *d_st = (int32_t *)(d_rl + numRanges);
-        unsigned long long *d_cnt = (unsigned long long *)(d_st + numRanges + ((numRanges & 1) ? 1 : 0));
-        S3_TRY(cudaMemcpyAsync(d_l, saL, rB, cudaMemcpyHostToDevice, st)); S3_TRY(cudaMemcpyAsync(d_r, saR, rB, cudaMemcpyHostToDevice, st));
-        S3_TRY(cudaMemcpyAsync(d_rid, readIDs, rB, cudaMemcpyHostToDevice, st)); S3_TRY(cudaMemcpyAsync(d_off, offsets, rB, cudaMemcpyHostToDevice, st));
-        S3_TRY(cudaMemcpyAsync(d_sl, seedLengths, rB, cudaMemcpyHostToDevice, st)); S3_TRY(cudaMemcpyAsync(d_rl, readLengths, rB, cudaMemcpyHostToDevice, st));
-        S3_TRY(cudaMemcpyAsync(d_st, strands, rB, cudaMemcpyHostToDevice, st));
-        s3_seed_count_kernel<<<(unsigned)((numRanges + 256) / 256), 256, 0, st>>>(d_l, d_r, numRanges, maxPerRange, d_cnt);
-        S3_LAUNCHED(1);
-        cub::DeviceScan::ExclusiveSum(NULL, t1, d_cnt, d_cnt, (int)(numRanges + 1), st);
-        S3_TRY(cudaMalloc(&d_tmp, t1));
-        S3_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, t1, d_cnt, d_cnt, (int)(numRanges + 1), st));
-        S3_TRY(cudaMemcpyAsync(&total, d_cnt + numRanges, 8, cudaMemcpyDeviceToHost, st));
-        S3_TRY(cudaStreamSynchronize(st));
-        cudaFree(d_tmp); d_tmp = NULL;
-        if (total == 0) goto done;
-        if (total >= 0x7FFFFFFFull) { s3_set_error("s3_seed_candidates: %llu positions in one call", total); rc = S3_EINVAL; goto done; }
-        // keys x2, vals x2, keep flags, selected indices, outputs
-        const size_t T = (size_t)total;
-        S3_TRY(cudaMalloc(&d_work, T * (8 + 8 + 4 + 4 + 4 + 4 + 4 + 4) + T + 1024));
-        unsigned long long *k0 = (unsigned long long *)d_work, *k1 = k0 + T;
-        int32_t *v0 = (int32_t *)(k1 + T), *v1 = v0 + T;
-        uint32_t *sel = (uint32_t *)(v1 + T), *o_r = sel + T, *o_p = o_r + T;
-        int32_t *o_s = (int32_t *)(o_p + T);
-        uint8_t *keep = (uint8_t *)(o_s + T);
-        uint32_t *d_m = (uint32_t *)d_in;                 // the range arrays are done with after the fill: reuse a word for the count
-        s3_seed_fill_kernel<<<(unsigned)((numRanges * 32 + 255) / 256), 256, 0, st>>>(ix->loc.sa, d_l, d_r, d_st, d_rid, d_off, d_sl, d_rl,
-                                                                                         numRanges, maxPerRange, d_cnt, k0, v0);
-        S3_LAUNCHED(1);
-        cub::DeviceRadixSort::SortPairs(NULL, t2, k0, k1, v0, v1, (int)T, 0, 64, st);
-        cub::DeviceSelect::Flagged(NULL, t3, cub::CountingInputIterator<uint32_t>(0), keep, sel, d_m, (int)T, st);
-        tmpBytes = t2 > t3 ? t2 : t3;
-        S3_TRY(cudaMalloc(&d_tmp, tmpBytes));
-        S3_TRY(cub::DeviceRadixSort::SortPairs(d_tmp, t2, k0, k1, v0, v1, (int)T, 0, 64, st));      // stable: ties stay in arrival order
-        S3_TRY(cudaMemsetAsync(keep, 0, T, st));
-        s3_seed_merge_kernel<<<(unsigned)((T + 255) / 256), 256, 0, st>>>(k1, T, keep);
-        S3_LAUNCHED(1);
-        S3_TRY(cub::DeviceSelect::Flagged(d_tmp, t3, cub::CountingInputIterator<uint32_t>(0), keep, sel, d_m, (int)T, st));
-        S3_TRY(cudaMemcpyAsync(&m, d_m, 4, cudaMemcpyDeviceToHost, st));
-        S3_TRY(cudaStreamSynchronize(st));
-        s3_seed_gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(k1, v1, sel, m, o_r, o_p, o_s);
-        S3_LAUNCHED(1);
-        S3_TRY(cudaGetLastError());
-        h_r = (uint32_t *)malloc((size_t)m * 4); h_p = (uint32_t *)malloc((size_t)m * 4); h_s = (int32_t *)malloc((size_t)m * 4);
-        if (!h_r || !h_p || !h_s) { s3_set_error("s3_seed_candidates: out of host memory"); rc = S3_ENOMEM; goto done; }
-        S3_TRY(cudaMemcpyAsync(h_r, o_r, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-        S3_TRY(cudaMemcpyAsync(h_p, o_p, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-        S3_TRY(cudaMemcpyAsync(h_s, o_s, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
-        S3_TRY(cudaStreamSynchronize(st));
-        *candReadIDs = h_r; *candPositions = h_p; *candStrands = h_s; *numCandidates = m;
-        h_r = h_p = NULL; h_s = NULL;
+        const uint32_t *src[7] = {saL, saR, (const uint32_t *)strands, readIDs, offsets, seedLengths, readLengths};
+        for (int a = 0; a < 7; ++a) S3_TRY(cudaMemcpyAsync(d_in + a * numRanges, src[a], rB, cudaMemcpyHostToDevice, st));
+        if ((rc = s3_seed_candidates_device(ix, d_in, d_in + numRanges, (const int32_t *)(d_in + 2 * numRanges), d_in + 3 * numRanges, d_in + 4 * numRanges,
+                                            d_in + 5 * numRanges, d_in + 6 * numRanges, numRanges, maxPerRange, &d_out, &m))) goto done;
+        if (m) {
+            h_r = (uint32_t *)malloc((size_t)m * 4); h_p = (uint32_t *)malloc((size_t)m * 4); h_s = (int32_t *)malloc((size_t)m * 4);
+            if (!h_r || !h_p || !h_s) { s3_set_error("s3_seed_candidates: out of host memory"); rc = S3_ENOMEM; goto done; }
+            S3_TRY(cudaMemcpyAsync(h_r, d_out, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            S3_TRY(cudaMemcpyAsync(h_p, d_out + m, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            S3_TRY(cudaMemcpyAsync(h_s, d_out + 2 * (size_t)m, (size_t)m * 4, cudaMemcpyDeviceToHost, st));
+            S3_TRY(cudaStreamSynchronize(st));
+            *candReadIDs = h_r; *candPositions = h_p; *candStrands = h_s; *numCandidates = m;
+            h_r = h_p = NULL; h_s = NULL;
+        }
     }
 done:
-    if (d_in) cudaFree(d_in);
-    if (d_work) cudaFree(d_work);
-    if (d_tmp) cudaFree(d_tmp);
+    if (d_in) cudaFreeAsync(d_in, st);
+    if (d_out) cudaFreeAsync(d_out, st);
     free(h_r); free(h_p); free(h_s);
     return rc;
 }
@@ -509,9 +548,11 @@ extern "C" int s3_seed_search(s3_index *ix, const uint32_t *seeds, const uint32_
     if (!out->offsets || !out->status) { s3_seed_search_result_free(out); s3_set_error("s3_seed_search: out of host memory"); return S3_ENOMEM; }
     if (numSeeds == 0) return S3_OK;
     int rc;
+    S3Lap clk("s3_seed_search");
     s3_search_result exact, one;
     memset(&one, 0, sizeof one);
     if ((rc = s3_search(ix, seeds, seedLengths, numSeeds, wordPerSeed, 0, 0, &exact))) { s3_seed_search_result_free(out); return rc; }
+    clk.lap("exact search");
     // the seeds without an exact alignment, packed like packReads2 (CPUfunctions.cpp:303-338)
     uint64_t n1 = 0;
     for (uint64_t s = 0; s < numSeeds; ++s) n1 += exact.offsets[s + 1] == exact.offsets[s];
@@ -529,7 +570,9 @@ extern "C" int s3_seed_search(s3_index *ix, const uint32_t *seeds, const uint32_
                 for (uint32_t w = 0; w < wordPerSeed; ++w) dst[(size_t)w * 32] = src[(size_t)w * 32];
                 l1[k] = seedLengths[s]; ids1[k] = (uint32_t)s; ++k;
             }
+            clk.lap("pack seeds without a hit");
             rc = s3_search(ix, q1, l1, n1, wordPerSeed, 1, 0, &one);
+            clk.lap("1-mismatch search");
         }
     }
     if (rc == S3_OK) {
@@ -569,6 +612,138 @@ extern "C" int s3_seed_search(s3_index *ix, const uint32_t *seeds, const uint32_
     }
     free(ids1); free(q1); free(l1);
     s3_search_result_free(&exact); s3_search_result_free(&one);
+    clk.lap("merge");
     if (rc) s3_seed_search_result_free(out);
+    return rc;
+}
+
+// ---- the seeding driver on device arrays (the seeded DP stages) ----------------------------------------------------------
+__global__ void s3_seedsrch_nohit_kernel(const unsigned long long *__restrict__ starts0, uint32_t numSeeds, uint8_t *__restrict__ flags)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s < numSeeds) flags[s] = starts0[s + 1] == starts0[s];
+}
+
+// the seeds without an exact alignment, packed like packReads2 (CPUfunctions.cpp:303-338); rank[seed] = its place in that batch
+__global__ void s3_seedsrch_gather_kernel(const uint32_t *__restrict__ ids1, uint32_t n1, const uint32_t *__restrict__ seeds,
+                                          const uint32_t *__restrict__ seedLengths, uint32_t wordPerSeed, uint32_t *__restrict__ q1,
+                                          uint32_t *__restrict__ l1, uint32_t *__restrict__ rank)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n1) return;
+    const uint32_t s = ids1[k];
+    const uint32_t *src = seeds + (size_t)(s / 32) * 32 * wordPerSeed + s % 32;
+    uint32_t *dst = q1 + (size_t)(k / 32) * 32 * wordPerSeed + k % 32;
+    for (uint32_t w = 0; w < wordPerSeed; ++w) dst[(size_t)w * 32] = src[(size_t)w * 32];
+    l1[k] = seedLengths[s];
+    rank[s] = k;
+}
+
+// per seed: the pass its ranges come from, how many occurrences they hold, what it keeps (count pass), then the kept ranges
+// with their seed's read id, offset, length and read length (fill pass)
+template <bool FILL>
+__global__ void s3_seedsrch_merge_kernel(uint32_t numSeeds, const unsigned long long *__restrict__ starts0, const uint32_t *__restrict__ out0,
+                                         unsigned long long total0, const uint32_t *__restrict__ rank, const unsigned long long *__restrict__ starts1,
+                                         const uint32_t *__restrict__ out1, unsigned long long total1, const uint32_t *__restrict__ maxHit,
+                                         uint8_t *__restrict__ status, uint32_t *__restrict__ keptCount, const uint32_t *__restrict__ keptOff,
+                                         const uint32_t *__restrict__ seedReadID, const uint32_t *__restrict__ seedOffset, const uint32_t *__restrict__ seedLength,
+                                         const uint32_t *__restrict__ seedReadLength, uint32_t *__restrict__ dst, uint32_t numKept)
+{
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= numSeeds) return;
+    const bool second = starts0[s + 1] == starts0[s];
+    unsigned long long a, b, tot;
+    const uint32_t *src;
+    if (second) { const uint32_t k = rank[s]; a = starts1[2 * (size_t)k]; b = starts1[2 * (size_t)k + 2]; src = out1; tot = total1; }
+    else { a = starts0[s]; b = starts0[s + 1]; src = out0; tot = total0; }
+    if (!FILL) {
+        unsigned long long occ = 0;
+        for (unsigned long long g = a; g < b; ++g) occ += (unsigned long long)(src[tot + g] - src[g]) + 1;
+        const uint8_t st = occ == 0 ? 0 : (occ <= maxHit[s] ? 1 : 4);
+        status[s] = st;
+        keptCount[s] = st == 1 ? (uint32_t)(b - a) : 0u;
+        return;
+    }
+    if (status[s] != 1) return;
+    const uint32_t o = keptOff[s], n = (uint32_t)(b - a);
+    for (uint32_t g = 0; g < n; ++g) {
+        dst[o + g] = src[a + g];                                                      // saL
+        dst[(size_t)numKept + o + g] = src[tot + a + g];                              // saR
+        dst[2 * (size_t)numKept + o + g] = (src[2 * tot + a + g] & 1u) + 1u;          // SARecord.strand 1 / 2
+        dst[3 * (size_t)numKept + o + g] = seedReadID[s];
+        dst[4 * (size_t)numKept + o + g] = seedOffset[s];
+        dst[5 * (size_t)numKept + o + g] = seedLength[s];
+        dst[6 * (size_t)numKept + o + g] = seedReadLength[s];
+    }
+}
+
+int s3_seed_search_device(s3_index *ix, const uint32_t *d_seeds, const uint32_t *d_seedLengths, uint32_t numSeeds, uint32_t wordPerSeed,
+                          const uint32_t *d_maxHit, const uint32_t *d_seedReadID, const uint32_t *d_seedOffset, const uint32_t *d_seedReadLength,
+                          S3SeedRangesDev *out)
+{
+    memset(out, 0, sizeof *out);
+    if (numSeeds == 0) return S3_OK;
+    int rc = S3_OK;
+    cudaStream_t st = ix->stream;
+    unsigned long long *d_starts0 = NULL, *d_starts1 = NULL;
+    uint32_t *d_out0 = NULL, *d_out1 = NULL, *d_ids1 = NULL, *d_q1 = NULL, *d_l1 = NULL, *d_rank = NULL, *d_keptCount = NULL, *d_keptOff = NULL, *d_n1 = NULL;
+    uint8_t *d_flags = NULL;
+    void *d_tmp = NULL;
+    unsigned long long total0 = 0, total1 = 0;
+    uint32_t n1 = 0;
+    uint32_t *h_cnt = (uint32_t *)ix->pinnedCount + 8;
+    size_t t1 = 0, t2 = 0;
+    const unsigned nb = (numSeeds + 255) / 256;
+    S3_TRY(cudaMallocAsync((void **)&d_starts0, ((size_t)numSeeds + 1) * 8, st));
+    if ((rc = s3_search_csr_device(ix, d_seeds, d_seedLengths, numSeeds, wordPerSeed, 0, 0, d_starts0, &d_out0, &total0))) goto done;
+    S3_TRY(cudaMallocAsync((void **)&d_flags, numSeeds, st));
+    S3_TRY(cudaMallocAsync((void **)&d_ids1, (size_t)numSeeds * 4 + 16, st));
+    S3_TRY(cudaMallocAsync((void **)&d_rank, (size_t)numSeeds * 4, st));
+    S3_TRY(cudaMallocAsync((void **)&d_n1, 16, st));
+    s3_seedsrch_nohit_kernel<<<nb, 256, 0, st>>>(d_starts0, numSeeds, d_flags);
+    S3_LAUNCHED(1);
+    cub::DeviceSelect::Flagged(NULL, t1, cub::CountingInputIterator<uint32_t>(0), d_flags, d_ids1, d_n1, (int)numSeeds, st);
+    cub::DeviceScan::ExclusiveSum(NULL, t2, (uint32_t *)NULL, (uint32_t *)NULL, (int)(numSeeds + 1), st);
+    S3_TRY(cudaMallocAsync(&d_tmp, (t1 > t2 ? t1 : t2) + 16, st));
+    S3_TRY(cub::DeviceSelect::Flagged(d_tmp, t1, cub::CountingInputIterator<uint32_t>(0), d_flags, d_ids1, d_n1, (int)numSeeds, st));
+    S3_TRY(cudaMemcpyAsync(h_cnt, d_n1, 4, cudaMemcpyDeviceToHost, st));
+    S3_TRY(cudaStreamSynchronize(st));
+    n1 = h_cnt[0];
+    if (n1) {
+        const size_t up1 = ((size_t)n1 + 31) / 32 * 32;
+        S3_TRY(cudaMallocAsync((void **)&d_q1, up1 * wordPerSeed * 4, st));
+        S3_TRY(cudaMallocAsync((void **)&d_l1, up1 * 4, st));
+        S3_TRY(cudaMallocAsync((void **)&d_starts1, (2 * (size_t)n1 + 1) * 8, st));
+        S3_TRY(cudaMemsetAsync(d_q1, 0, up1 * wordPerSeed * 4, st));
+        S3_TRY(cudaMemsetAsync(d_l1, 0, up1 * 4, st));
+        s3_seedsrch_gather_kernel<<<(n1 + 255) / 256, 256, 0, st>>>(d_ids1, n1, d_seeds, d_seedLengths, wordPerSeed, d_q1, d_l1, d_rank);
+        S3_LAUNCHED(1);
+        if ((rc = s3_search_csr_device(ix, d_q1, d_l1, n1, wordPerSeed, 1, 0, d_starts1, &d_out1, &total1))) goto done;
+    }
+    S3_TRY(cudaMallocAsync((void **)&out->d_status, numSeeds, st));
+    S3_TRY(cudaMallocAsync((void **)&d_keptCount, ((size_t)numSeeds + 1) * 4, st));
+    S3_TRY(cudaMallocAsync((void **)&d_keptOff, ((size_t)numSeeds + 1) * 4, st));
+    S3_TRY(cudaMemsetAsync(d_keptCount + numSeeds, 0, 4, st));
+    s3_seedsrch_merge_kernel<false><<<nb, 256, 0, st>>>(numSeeds, d_starts0, d_out0, total0, d_rank, d_starts1, d_out1, total1, d_maxHit, out->d_status,
+                                                       d_keptCount, NULL, NULL, NULL, NULL, NULL, NULL, 0);
+    S3_LAUNCHED(1);
+    S3_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, t2, d_keptCount, d_keptOff, (int)(numSeeds + 1), st));
+    S3_TRY(cudaMemcpyAsync(h_cnt, d_keptOff + numSeeds, 4, cudaMemcpyDeviceToHost, st));
+    S3_TRY(cudaStreamSynchronize(st));
+    out->numRanges = h_cnt[0];
+    if (out->numRanges) {
+        S3_TRY(cudaMallocAsync((void **)&out->d_buf, (size_t)out->numRanges * 28, st));
+        s3_seedsrch_merge_kernel<true><<<nb, 256, 0, st>>>(numSeeds, d_starts0, d_out0, total0, d_rank, d_starts1, d_out1, total1, d_maxHit, out->d_status,
+                                                          NULL, d_keptOff, d_seedReadID, d_seedOffset, d_seedLengths, d_seedReadLength, out->d_buf,
+                                                          (uint32_t)out->numRanges);
+        S3_LAUNCHED(1);
+        S3_TRY(cudaGetLastError());
+    }
+done:
+    {
+        void *tmp[] = {d_starts0, d_starts1, d_out0, d_out1, d_ids1, d_q1, d_l1, d_rank, d_keptCount, d_keptOff, d_n1, d_flags, d_tmp};
+        for (void *p : tmp) if (p) cudaFreeAsync(p, st);
+    }
+    if (rc) { if (out->d_buf) cudaFreeAsync(out->d_buf, st); if (out->d_status) cudaFreeAsync(out->d_status, st); memset(out, 0, sizeof *out); }
     return rc;
 }

@@ -14,6 +14,7 @@
 // s3_dp_align_windows), each verified against its own oracle; host arrays travel between them, as they do between the
 // reference's engine threads.  The batches here are the small remainder of a run (reads the search left unaligned).
 #include "s3_common.cuh"
+#include "s3_windows.cuh"
 #include "../../include/soap3dp_b200.h"
 
 #include <stdio.h>
@@ -21,6 +22,57 @@
 #include <string.h>
 #include <chrono>
 #include <vector>
+
+// ---- device side of the stages: seeds cut from the query buffer, windows of the candidates ---------------------------------
+#define S3_STAGE_MAX_SEEDS 32
+struct S3SeedPlan { int32_t seedLen, seedNum, maxHit, pad; int32_t pos[S3_STAGE_MAX_SEEDS]; };
+
+// one thread per (entry, seed slot): entry k cuts the seeds of read srcRead[k] by plan planIdx[k]; seed ids start at seedStart[k]
+__global__ void s3_stage_seed_kernel(uint32_t n, const uint32_t *__restrict__ queries, uint32_t wpq, const uint32_t *__restrict__ entries,
+                                     const S3SeedPlan *__restrict__ plans, const uint32_t *__restrict__ lenByRead, uint32_t wordPerSeed,
+                                     uint32_t *__restrict__ seeds, uint32_t *__restrict__ seedLen, uint32_t *__restrict__ seedKey,
+                                     uint32_t *__restrict__ seedOff, uint32_t *__restrict__ seedMaxHit, uint32_t *__restrict__ seedReadLen)
+{
+    const uint32_t idx = blockIdx.x * blockDim.x + threadIdx.x, k = idx / S3_STAGE_MAX_SEEDS, j = idx % S3_STAGE_MAX_SEEDS;
+    if (k >= n) return;
+    const uint32_t r = entries[k], key = entries[n + k], start = entries[3 * (size_t)n + k];
+    const S3SeedPlan &p = plans[entries[2 * (size_t)n + k]];
+    if ((int32_t)j >= p.seedNum) return;
+    const uint32_t id = start + j, off = (uint32_t)p.pos[j], len = (uint32_t)p.seedLen;
+    const uint32_t *src = queries + (size_t)(r / 32) * 32 * wpq + r % 32;
+    uint32_t *dst = seeds + (size_t)(id / 32) * 32 * wordPerSeed + id % 32;
+    for (uint32_t w = 0, done = 0; w < wordPerSeed; ++w, done += 16) {
+        uint32_t v = 0;
+        if (done < len) {
+            const uint32_t b = off + done, sw = b >> 4, sh = (b & 15u) << 1;
+            v = sw < wpq ? src[(size_t)sw * 32] >> sh : 0u;
+            if (sh && sw + 1 < wpq) v |= src[(size_t)(sw + 1) * 32] << (32u - sh);
+            const uint32_t rem = len - done;
+            if (rem < 16) v &= (1u << (2 * rem)) - 1u;
+        }
+        dst[(size_t)w * 32] = v;
+    }
+    seedLen[id] = len; seedKey[id] = key; seedOff[id] = off; seedMaxHit[id] = (uint32_t)p.maxHit; seedReadLen[id] = lenByRead[r];
+}
+
+struct S3StageWin { uint32_t *readID, *start, *dnaLen, *clipLt, *clipRt, *ancL, *ancR, *cand; int32_t *cutoff; uint8_t *strand; };
+
+__device__ __forceinline__ void s3_stage_win_store(const S3StageWin &o, uint32_t k, uint32_t cand, const S3Window &x)
+{
+    o.cand[k] = cand; o.readID[k] = x.readID; o.start[k] = x.start; o.dnaLen[k] = x.dnaLen; o.clipLt[k] = x.clipLt; o.clipRt[k] = x.clipRt;
+    o.ancL[k] = x.ancL; o.ancR[k] = x.ancR; o.strand[k] = x.strand; o.cutoff[k] = x.cutoff;
+}
+
+// SingleEndAlgnBatch::pack for every candidate (read id | estimated start | strand)
+__global__ void s3_stage_win_single_kernel(S3WinParams w, uint32_t m, const uint32_t *__restrict__ cand, const uint32_t *__restrict__ lenByRead, S3StageWin o)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    S3Window x;
+    const uint32_t id = cand[c];
+    s3_win_single(w, id, cand[m + c], (int)cand[2 * (size_t)m + c], lenByRead[id], x);
+    s3_stage_win_store(o, c, c, x);
+}
 
 namespace {
 
@@ -99,7 +151,7 @@ int align_windows(s3_index *ix, const uint32_t *queries, const uint32_t *readLen
                   uint32_t maxDNA, s3_dp_scores scores, int slot, Windows &w, S3StageAligned &a)
 {
     return s3_stage_align(ix, queries, readLengths, numReads, wpq, uploadQueries, maxRead, maxDNA, scores, slot, w.n, w.readID.data(), w.strand.data(),
-                          w.start.data(), w.len.data(), w.cutoff.data(), w.clipLt.data(), w.clipRt.data(), w.ancL.data(), w.ancR.data(), &a);
+                          w.start.data(), w.len.data(), w.cutoff.data(), w.clipLt.data(), w.clipRt.data(), w.ancL.data(), w.ancR.data(), NULL, NULL, &a);
 }
 
 uint32_t margin_of(uint32_t len) { return len > 100u ? len >> 2 : 25u; }
@@ -126,105 +178,180 @@ extern "C" void s3_deep_dp_result_free(s3_deep_dp_result *r)
     memset(r, 0, sizeof *r);
 }
 
+#define S3_TRYS(call) do { cudaError_t e__ = (call); if (e__ != cudaSuccess) { s3_set_error("%s:%d: %s failed: %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__)); rc = S3_ECUDA; goto done; } } while (0)
+
+namespace {
+
+// seed plans of a stage by read length, made once per distinct length; entries (read to cut, key id, plan, first seed id)
+struct StagePlans {
+    std::vector<S3SeedPlan> table;
+    std::vector<int32_t> ofLen;                 // plan index by read length, -1: not made yet
+    uint32_t maxSeedLen = 1;
+    int get(int stage, uint32_t len, uint32_t len2, int side, const s3_stage_params *par, uint32_t *idx)
+    {
+        if (len >= ofLen.size()) ofLen.resize(len + 1, -1);
+        if (ofLen[len] < 0) {
+            S3SeedPlan p;
+            memset(&p, 0, sizeof p);
+            std::vector<int32_t> pos(len + 64);
+            int rc = s3_seed_layout(stage, (int32_t)len, &p.seedLen, pos.data(), (int32_t)pos.size(), &p.seedNum);
+            if (rc) return rc;
+            if (p.seedNum > S3_STAGE_MAX_SEEDS) { s3_set_error("seeded DP stage: more than %d seeds per read", S3_STAGE_MAX_SEEDS); return S3_EINVAL; }
+            for (int32_t j = 0; j < p.seedNum; ++j) p.pos[j] = pos[j];
+            s3_dp_stage_params sp;
+            if ((rc = s3_dp_stage_parameters(stage, side == 0 ? len : len2, side == 0 ? len2 : len, par->isDefaultThreshold, par->dpScoreThreshold,
+                                             par->softClipLeft, par->softClipRight, &sp))) return rc;
+            p.maxHit = sp.paramRead[side].maxHitNum;
+            if ((uint32_t)p.seedLen > maxSeedLen) maxSeedLen = (uint32_t)p.seedLen;
+            ofLen[len] = (int32_t)table.size();
+            table.push_back(p);
+        }
+        *idx = (uint32_t)ofLen[len];
+        return S3_OK;
+    }
+};
+
+// one side's seeding on the device: entries -> seeds -> seeding driver.  Device arrays of the result are freed by the caller.
+struct SeedSide {
+    uint32_t *d_entries = NULL, *d_seedBuf = NULL;
+    S3SeedPlan *d_plans = NULL;
+    uint64_t numSeeds = 0;
+    S3SeedRangesDev ranges;
+    SeedSide() { memset(&ranges, 0, sizeof ranges); }
+};
+
+void seed_side_free(s3_index *ix, SeedSide &x)
+{
+    void *p[] = {x.d_entries, x.d_seedBuf, x.d_plans, x.ranges.d_buf, x.ranges.d_status};
+    for (void *q : p) if (q) cudaFreeAsync(q, ix->stream);
+    x = SeedSide();
+}
+
+// entries: srcRead | key | plan | seedStart (n each, host); the stage's query buffer and d_lenByRead are on the device already
+int seed_side_run(s3_index *ix, const std::vector<uint32_t> &entries, size_t n, uint64_t totalSeeds, const StagePlans &plans, uint32_t wpq,
+                  const uint32_t *d_lenByRead, SeedSide &x)
+{
+    int rc = S3_OK;
+    cudaStream_t st = ix->stream;
+    x.numSeeds = totalSeeds;
+    if (n == 0 || totalSeeds == 0) return S3_OK;
+    if (totalSeeds >= 0x7FFFFFF0ull) { s3_set_error("seeded DP stage: too many seeds in one call"); return S3_EINVAL; }
+    const uint32_t S = (uint32_t)totalSeeds, wps = (plans.maxSeedLen + 15) / 16;
+    const size_t up = ((size_t)S + 31) / 32 * 32;
+    S3_TRYS(cudaMallocAsync((void **)&x.d_entries, 4 * n * 4, st));
+    S3_TRYS(cudaMallocAsync((void **)&x.d_plans, plans.table.size() * sizeof(S3SeedPlan), st));
+    S3_TRYS(cudaMallocAsync((void **)&x.d_seedBuf, (up * wps + up + 4 * (size_t)S) * 4, st));
+    S3_TRYS(cudaMemcpyAsync(x.d_entries, entries.data(), 4 * n * 4, cudaMemcpyHostToDevice, st));
+    S3_TRYS(cudaMemcpyAsync(x.d_plans, plans.table.data(), plans.table.size() * sizeof(S3SeedPlan), cudaMemcpyHostToDevice, st));
+    {
+        uint32_t *d_seeds = x.d_seedBuf, *d_seedLen = d_seeds + up * wps, *d_key = d_seedLen + up, *d_off = d_key + S, *d_maxHit = d_off + S, *d_rl = d_maxHit + S;
+        S3_TRYS(cudaMemsetAsync(d_seeds, 0, (up * wps + up) * 4, st));
+        const unsigned long long threads = (unsigned long long)n * S3_STAGE_MAX_SEEDS;
+        s3_stage_seed_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>((uint32_t)n, s3_stage_queries(ix), wpq, x.d_entries, x.d_plans, d_lenByRead, wps,
+                                                                                  d_seeds, d_seedLen, d_key, d_off, d_maxHit, d_rl);
+        S3_LAUNCHED(1);
+        S3_TRYS(cudaGetLastError());
+        rc = s3_seed_search_device(ix, d_seeds, d_seedLen, S, wps, d_maxHit, d_key, d_off, d_rl, &x.ranges);
+    }
+done:
+    return rc;
+}
+
+}  // namespace
+
 extern "C" int s3_single_dp_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
                                   const uint32_t *readIDs, uint64_t n, const s3_stage_params *par, s3_single_dp_result *out)
 {
     if (!out) { s3_set_error("s3_single_dp_align: NULL result"); return S3_EINVAL; }
     memset(out, 0, sizeof *out);
     if (!ix || !queries || !readLengths || !par || (n && !readIDs)) { s3_set_error("s3_single_dp_align: NULL argument"); return S3_EINVAL; }
+    if (!ix->loc.sa || !ix->loc.text) { s3_set_error("s3_single_dp_align: the index was uploaded without its suffix array and packed text"); return S3_EINVAL; }
     out->numReads = n;
     if (n == 0) return S3_OK;
+    if (numReads >= 0xFFFFFFF0ull) { s3_set_error("s3_single_dp_align: too many reads"); return S3_EINVAL; }
     uint32_t maxLen = 0;
     for (uint64_t k = 0; k < n; ++k) {
         if (readIDs[k] >= numReads) { s3_set_error("s3_single_dp_align: read id %u out of range", readIDs[k]); return S3_EINVAL; }
+        if (readLengths[readIDs[k]] > 16u * wordPerQuery) { s3_set_error("s3_single_dp_align: read %u longer than its query words", readIDs[k]); return S3_EINVAL; }
         if (readLengths[readIDs[k]] > maxLen) maxLen = readLengths[readIDs[k]];
     }
-    int rc;
+    int rc = S3_OK;
     StageClock clk("s3_single_dp_align");
-    // ---- seeds (SingleEndSeedingBatch::packSeeds, DV-DPfunctions.cu:1082-1100)
-    SeedSet seeds;
-    // seed layout and hit limit depend on the read length only: one plan per length that occurs
-    struct Plan { int32_t seedLen, seedNum, maxHit; std::vector<int32_t> pos; bool made; };
-    std::vector<Plan> plans(maxLen + 1);
-    for (auto &p : plans) p.made = false;
+    if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_single_dp_align: cudaSetDevice failed"); return S3_ECUDA; }
+    cudaStream_t st = ix->stream;
+    // ---- seeds (SingleEndSeedingBatch::packSeeds, DV-DPfunctions.cu:1082-1100): the layout depends on the read length only
+    StagePlans plans;
+    std::vector<uint32_t> entries(4 * n);
     uint64_t totalSeeds = 0;
-    uint32_t maxSeedLen = 1;
-    for (int pass = 0; pass < 2; ++pass)
     for (uint64_t k = 0; k < n; ++k) {
-        const uint32_t r = readIDs[k], len = readLengths[r];
-        Plan &p = plans[len];
-        if (pass == 0 && p.made) { totalSeeds += (uint64_t)p.seedNum; continue; }
-        if (pass == 1 && k == 0) seed_set_reserve(seeds, (maxSeedLen + 15) / 16, (size_t)totalSeeds);
-        if (!p.made) {
-            p.pos.resize(maxLen + 16);
-            if ((rc = s3_seed_layout(S3_STAGE_SINGLE_DP, (int32_t)len, &p.seedLen, p.pos.data(), (int32_t)p.pos.size(), &p.seedNum))) return rc;
-            s3_dp_stage_params sp;
-            if ((rc = s3_dp_stage_parameters(S3_STAGE_SINGLE_DP, len, 0, par->isDefaultThreshold, par->dpScoreThreshold, par->softClipLeft, par->softClipRight, &sp))) return rc;
-            p.maxHit = sp.paramRead[0].maxHitNum;
-            p.made = true;
-            if ((uint32_t)p.seedLen > maxSeedLen) maxSeedLen = (uint32_t)p.seedLen;
-        }
-        if (pass == 0) { totalSeeds += (uint64_t)p.seedNum; continue; }
-        for (int32_t j = 0; j < p.seedNum; ++j) seed_set_add(seeds, queries, wordPerQuery, r, r, (uint32_t)p.pos[j], (uint32_t)p.seedLen, (uint32_t)p.maxHit);
+        const uint32_t r = readIDs[k];
+        uint32_t idx;
+        if ((rc = plans.get(S3_STAGE_SINGLE_DP, readLengths[r], 0, 0, par, &idx))) return rc;
+        entries[k] = r; entries[n + k] = r; entries[2 * n + k] = idx; entries[3 * n + k] = (uint32_t)totalSeeds;
+        totalSeeds += (uint64_t)plans.table[idx].seedNum;
     }
-    out->numSeeds = seeds.n;
-    clk.lap("seed packing");
-    // ---- seeding driver, candidate positions (decodePositions + singleMerge, DV-DPfunctions.cu:1101-1219)
-    s3_seed_search_result sr;
-    if ((rc = s3_seed_search(ix, seeds.words.data(), seeds.lengths.data(), seeds.n, seeds.wordPerSeed, seeds.maxHit.data(), &sr))) return rc;
-    clk.lap("s3_seed_search");
-    std::vector<uint32_t> rid(sr.total), off(sr.total), slen(sr.total), rlen(sr.total);
-    std::vector<int32_t> strand(sr.total);
-    for (uint64_t s = 0; s < seeds.n; ++s)
-        for (uint64_t g = sr.offsets[s]; g < sr.offsets[s + 1]; ++g) {
-            rid[g] = seeds.readIDs[s]; off[g] = seeds.offsets[s]; slen[g] = seeds.lengths[s]; rlen[g] = readLengths[seeds.readIDs[s]]; strand[g] = sr.strand[g];
-        }
-    uint32_t *cR = NULL, *cP = NULL; int32_t *cS = NULL;
-    uint64_t nc = 0;
-    rc = s3_seed_candidates(ix, sr.saL, sr.saR, strand.data(), rid.data(), off.data(), slen.data(), rlen.data(), sr.total, 0xFFFFFFFFu, &cR, &cP, &cS, &nc);
-    s3_seed_search_result_free(&sr);
-    if (rc) return rc;
-    out->numCandidates = nc;
-    clk.lap("s3_seed_candidates");
-    // reads without a candidate (alignFlags XOR inputFlags, DV-DPfunctions.cu:1300-1310)
-    std::vector<uint8_t> seeded(numReads, 0);
-    for (uint64_t c = 0; c < nc; ++c) seeded[cR[c]] = 1;
-    std::vector<uint32_t> unseeded;
-    for (uint64_t k = 0; k < n; ++k) if (!seeded[readIDs[k]]) unseeded.push_back(readIDs[k]);
+    out->numSeeds = totalSeeds;
+    uint32_t *d_len = NULL, *d_cand = NULL, *d_win = NULL;
+    uint32_t m = 0;
+    SeedSide side;
     std::vector<s3_dp_hit> hits;
-    std::vector<uint32_t> runs;
-    if (nc) {
+    std::vector<uint32_t> runs, unseeded;
+    std::vector<uint8_t> seeded(numReads, 0);
+    S3_TRYS(cudaMallocAsync((void **)&d_len, numReads * 4 + 16, st));
+    S3_TRYS(cudaMemcpyAsync(d_len, readLengths, numReads * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = s3_stage_upload_queries(ix, queries, numReads, wordPerQuery))) goto done;
+    clk.lap("plans + uploads");
+    // ---- seeding driver, candidate positions (decodePositions + singleMerge, DV-DPfunctions.cu:1101-1219)
+    if ((rc = seed_side_run(ix, entries, n, totalSeeds, plans, wordPerQuery, d_len, side))) goto done;
+    clk.lap("seeds + seeding driver");
+    if (side.ranges.numRanges) {
+        const uint64_t R = side.ranges.numRanges;
+        const uint32_t *b = side.ranges.d_buf;
+        if ((rc = s3_seed_candidates_device(ix, b, b + R, (const int32_t *)(b + 2 * R), b + 3 * R, b + 4 * R, b + 5 * R, b + 6 * R, R, 0xFFFFFFFFu, &d_cand, &m))) goto done;
+    }
+    out->numCandidates = m;
+    clk.lap("candidates");
+    if (m) {
         // ---- windows (SingleEndAlgnBatch::pack), DP, results (SingleDP_Space::algnmtCPUThread, DV-DPfunctions.cu:1699-1733)
         const uint32_t maxRead = (maxLen / 4 + 1) * 4, maxDNA = maxRead + 2 * margin_of(maxRead) + 8;         // DV-DPfunctions.cu:1580-1581
-        s3_window_params wp;
-        memset(&wp, 0, sizeof wp);
-        wp.strandLeftLeg = 1; wp.strandRightLeg = 2; wp.softClipLeft = par->softClipLeft; wp.softClipRight = par->softClipRight;
-        wp.cutoffThreshold[0] = wp.cutoffThreshold[1] = par->isDefaultThreshold ? -1 : par->dpScoreThreshold; wp.maxDNALength = maxDNA;
-        std::vector<uint8_t> st8(nc);
-        for (uint64_t c = 0; c < nc; ++c) st8[c] = (uint8_t)cS[c];
-        Windows w;
+        S3WinParams w;
+        memset(&w, 0, sizeof w);
+        w.leftLeg = 1; w.rightLeg = 2; w.softClipLeft = par->softClipLeft; w.softClipRight = par->softClipRight;
+        w.cutoff[0] = w.cutoff[1] = par->isDefaultThreshold ? -1 : par->dpScoreThreshold; w.maxDNALength = maxDNA; w.textLength = ix->textLength;
+        S3_TRYS(cudaMallocAsync((void **)&d_win, (size_t)m * 40 + 64, st));
+        S3StageWin o;
+        o.readID = d_win; o.start = d_win + m; o.dnaLen = d_win + 2 * (size_t)m; o.clipLt = d_win + 3 * (size_t)m; o.clipRt = d_win + 4 * (size_t)m;
+        o.ancL = d_win + 5 * (size_t)m; o.ancR = d_win + 6 * (size_t)m; o.cand = d_win + 7 * (size_t)m; o.cutoff = (int32_t *)(d_win + 8 * (size_t)m);
+        o.strand = (uint8_t *)(d_win + 9 * (size_t)m);
+        s3_stage_win_single_kernel<<<(m + 255) / 256, 256, 0, st>>>(w, m, d_cand, d_len, o);
+        S3_LAUNCHED(1);
+        S3_TRYS(cudaGetLastError());
         S3StageAligned a;
-        rc = make_windows(ix, S3_WIN_SINGLE, wp, readLengths, numReads, cR, cP, NULL, st8.data(), NULL, NULL, NULL, nc, w);
-        clk.lap("s3_dp_make_windows");
-        if (rc == S3_OK) rc = align_windows(ix, queries, readLengths, numReads, wordPerQuery, 1, maxRead, maxDNA, par->scores, 0, w, a);
-        clk.lap("upload + DP + CIGAR runs");
-        if (rc == S3_OK && w.n) {
-            hits.reserve(w.n);
-            runs.reserve(a.numRuns);
-            for (uint64_t t = 0; t < w.n; ++t) {
-                if (a.score[t] < w.cutoff[t]) continue;
-                s3_dp_hit h;
-                memset(&h, 0, sizeof h);
-                h.readID = w.readID[t]; h.strand = w.strand[t]; h.pos = w.start[t] + a.hit[t]; h.score = a.score[t]; h.numSameScore = a.cnt[t];
-                h.runOffset = (uint32_t)runs.size();
-                runs.insert(runs.end(), a.runs + a.runOff[t], a.runs + a.runOff[t + 1]);
-                h.numRuns = (uint16_t)(runs.size() - h.runOffset);
-                hits.push_back(h);
-            }
+        if ((rc = s3_stage_align(ix, queries, readLengths, numReads, wordPerQuery, 0, maxRead, maxDNA, par->scores, 0, m, o.readID, o.strand, o.start, o.dnaLen,
+                                 o.cutoff, o.clipLt, o.clipRt, o.ancL, o.ancR, d_len, NULL, &a))) goto done;
+        clk.lap("windows + DP + CIGAR runs");
+        hits.reserve(m);
+        runs.reserve(a.numRuns);
+        for (uint32_t t = 0; t < m; ++t) {
+            seeded[a.readID[t]] = 1;
+            if (a.score[t] < a.cutoff[t]) continue;
+            s3_dp_hit h;
+            memset(&h, 0, sizeof h);
+            h.readID = a.readID[t]; h.strand = a.strand[t]; h.pos = a.start[t] + a.hit[t]; h.score = a.score[t]; h.numSameScore = a.cnt[t];
+            h.runOffset = (uint32_t)runs.size();
+            runs.insert(runs.end(), a.runs + a.runOff[t], a.runs + a.runOff[t + 1]);
+            h.numRuns = (uint16_t)(runs.size() - h.runOffset);
+            hits.push_back(h);
         }
     }
-    s3_free(cR); s3_free(cP); s3_free(cS);
-    clk.lap("records + CIGAR runs");
+    // reads without a candidate (alignFlags XOR inputFlags, DV-DPfunctions.cu:1300-1310)
+    for (uint64_t k = 0; k < n; ++k) if (!seeded[readIDs[k]]) unseeded.push_back(readIDs[k]);
+    clk.lap("records");
+done:
+    seed_side_free(ix, side);
+    if (d_len) cudaFreeAsync(d_len, st);
+    if (d_cand) cudaFreeAsync(d_cand, st);
+    if (d_win) cudaFreeAsync(d_win, st);
     if (rc) return rc;
     out->numHits = hits.size(); out->numRuns = runs.size(); out->numUnseeded = unseeded.size();
     out->hits = to_malloc(hits); out->runs = to_malloc(runs); out->unseeded = to_malloc(unseeded);

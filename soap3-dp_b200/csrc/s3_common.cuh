@@ -125,6 +125,10 @@ int s3_seed_search_device(s3_index *ix, const uint32_t *d_seeds, const uint32_t 
 int s3_seed_candidates_device(s3_index *ix, const uint32_t *d_l, const uint32_t *d_r, const int32_t *d_st, const uint32_t *d_rid,
                               const uint32_t *d_off, const uint32_t *d_sl, const uint32_t *d_rl, uint64_t numRanges, uint32_t maxPerRange,
                               uint32_t **d_out, uint32_t *numCandidates);
+int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint64_t n0, const uint32_t *const in1[7], uint64_t n1, int onDevice,
+                                uint32_t maxPerRange, const uint32_t *lengthsByReadID, uint64_t numReadIDs,
+                                int insertLow, int insertHigh, int peStrandLeftLeg, int peStrandRightLeg,
+                                uint32_t **candReadIDLeft, uint32_t **candPosLeft, uint32_t **candPosRight, uint64_t *numCandidates);
 int s3_search_csr_device(s3_index *ix, const uint32_t *d_queries, const uint32_t *d_readLengths, uint32_t batchSize, uint32_t wordPerQuery,
                          uint32_t numMismatch, int isExactNumMismatch, unsigned long long *d_starts, uint32_t **d_out, unsigned long long *total);
 

@@ -319,7 +319,7 @@ __global__ void s3_iota_kernel(uint32_t *a, uint64_t m)
 struct S3PairSide { s3_u64 *keys; uint32_t len, rev; };
 
 // one end's hits: gathered, keyed, sorted; rev = first element of the reverse-strand part (findRevStart)
-static int s3_pair_side(s3_index *ix, const uint32_t *const in[7], uint64_t n, uint32_t maxPerRange, S3PairSide *out)
+static int s3_pair_side(s3_index *ix, const uint32_t *const in[7], uint64_t n, uint32_t maxPerRange, int onDevice, S3PairSide *out)
 {
     int rc = S3_OK;
     cudaStream_t st = ix->stream;
@@ -333,7 +333,11 @@ static int s3_pair_side(s3_index *ix, const uint32_t *const in[7], uint64_t n, u
     S3_TRY(cudaMalloc(&d_in, 7 * rB + (n + 1) * 8 + 16));
     {
         uint32_t *d[7];
-        for (int a = 0; a < 7; ++a) { d[a] = (uint32_t *)d_in + a * n; if (n) S3_TRY(cudaMemcpyAsync(d[a], in[a], rB, cudaMemcpyHostToDevice, st)); }
+        for (int a = 0; a < 7; ++a) {
+            if (onDevice) { d[a] = const_cast<uint32_t *>(in[a]); continue; }
+            d[a] = (uint32_t *)d_in + a * n;
+            if (n) S3_TRY(cudaMemcpyAsync(d[a], in[a], rB, cudaMemcpyHostToDevice, st));
+        }
         s3_u64 *d_cnt = (s3_u64 *)(((uintptr_t)((uint32_t *)d_in + 7 * n) + 7) & ~(uintptr_t)7);
         s3_seed_count_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(d[0], d[1], n, maxPerRange, d_cnt);
         S3_LAUNCHED(1);
@@ -368,6 +372,11 @@ __global__ void s3_pair_revstart_kernel(const s3_u64 *k, uint32_t len, uint32_t 
     if (blockIdx.x == 0 && threadIdx.x == 0) *out = s3_pair_lower(k, 0, len, 0x80000000u);
 }
 
+int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint64_t n0, const uint32_t *const in1[7], uint64_t n1, int onDevice,
+                                uint32_t maxPerRange, const uint32_t *lengthsByReadID, uint64_t numReadIDs,
+                                int insertLow, int insertHigh, int peStrandLeftLeg, int peStrandRightLeg,
+                                uint32_t **candReadIDLeft, uint32_t **candPosLeft, uint32_t **candPosRight, uint64_t *numCandidates);
+
 extern "C" int s3_seed_pair_candidates(s3_index *ix,
                                        const uint32_t *saL0, const uint32_t *saR0, const int32_t *strands0, const uint32_t *readIDs0,
                                        const uint32_t *offsets0, const uint32_t *seedLengths0, const uint32_t *readLengths0, uint64_t n0,
@@ -389,6 +398,19 @@ extern "C" int s3_seed_pair_candidates(s3_index *ix,
     for (uint64_t g = 0; g < n1; ++g) if (readIDs1[g] >= numReadIDs) { s3_set_error("s3_seed_pair_candidates: read id %u out of range", readIDs1[g]); return S3_EINVAL; }
     for (uint64_t g = 0; g < n0; ++g) if (saR0[g] >= saL0[g] && saR0[g] > ix->textLength) { s3_set_error("s3_seed_pair_candidates: range %u..%u lies outside the suffix array", saL0[g], saR0[g]); return S3_EINVAL; }
     for (uint64_t g = 0; g < n1; ++g) if (saR1[g] >= saL1[g] && saR1[g] > ix->textLength) { s3_set_error("s3_seed_pair_candidates: range %u..%u lies outside the suffix array", saL1[g], saR1[g]); return S3_EINVAL; }
+    const uint32_t *const in0[7] = {saL0, saR0, (const uint32_t *)strands0, readIDs0, offsets0, seedLengths0, readLengths0};
+    const uint32_t *const in1[7] = {saL1, saR1, (const uint32_t *)strands1, readIDs1, offsets1, seedLengths1, readLengths1};
+    return s3_seed_pair_candidates_any(ix, in0, n0, in1, n1, 0, maxPerRange, lengthsByReadID, numReadIDs, insertLow, insertHigh, peStrandLeftLeg, peStrandRightLeg,
+                                       candReadIDLeft, candPosLeft, candPosRight, numCandidates);
+}
+
+// onDevice: the range arrays and lengthsByReadID are device arrays, and the three output pointers receive device arrays: the first
+// one (*candReadIDLeft) is the base of one allocation the caller returns with cudaFree.
+int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint64_t n0, const uint32_t *const in1[7], uint64_t n1, int onDevice,
+                                uint32_t maxPerRange, const uint32_t *lengthsByReadID, uint64_t numReadIDs,
+                                int insertLow, int insertHigh, int peStrandLeftLeg, int peStrandRightLeg,
+                                uint32_t **candReadIDLeft, uint32_t **candPosLeft, uint32_t **candPosRight, uint64_t *numCandidates)
+{
     *candReadIDLeft = *candPosLeft = *candPosRight = NULL; *numCandidates = 0;
     if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_seed_pair_candidates: cudaSetDevice failed"); return S3_ECUDA; }
     int rc = S3_OK;
@@ -399,13 +421,13 @@ extern "C" int s3_seed_pair_candidates(s3_index *ix,
     void *d_tmp = NULL;
     uint32_t *h[3] = {NULL, NULL, NULL};
     s3_u64 tot[2] = {0, 0};
-    const uint32_t *const in0[7] = {saL0, saR0, (const uint32_t *)strands0, readIDs0, offsets0, seedLengths0, readLengths0};
-    const uint32_t *const in1[7] = {saL1, saR1, (const uint32_t *)strands1, readIDs1, offsets1, seedLengths1, readLengths1};
-    if ((rc = s3_pair_side(ix, in0, n0, maxPerRange, &side[0]))) goto done;
-    if ((rc = s3_pair_side(ix, in1, n1, maxPerRange, &side[1]))) goto done;
+    S3Lap clk("s3_seed_pair_candidates");
+    if ((rc = s3_pair_side(ix, in0, n0, maxPerRange, onDevice, &side[0]))) goto done;
+    if ((rc = s3_pair_side(ix, in1, n1, maxPerRange, onDevice, &side[1]))) goto done;
+    clk.lap("two sides: gather + sort");
     {
         S3_TRY(cudaMalloc(&d_len, numReadIDs * 4 + 16));
-        S3_TRY(cudaMemcpyAsync(d_len, lengthsByReadID, numReadIDs * 4, cudaMemcpyHostToDevice, st));
+        S3_TRY(cudaMemcpyAsync(d_len, lengthsByReadID, numReadIDs * 4, onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         uint32_t *d_rev = d_len + numReadIDs;
         for (int s = 0; s < 2; ++s) s3_pair_revstart_kernel<<<1, 1, 0, st>>>(side[s].keys, side[s].len, d_rev + s);
         uint32_t rev[2];
@@ -461,6 +483,7 @@ extern "C" int s3_seed_pair_candidates(s3_index *ix,
                 }
             }
         }
+        clk.lap("thin + join, two calls");
         uint32_t *d_all = NULL;
         const s3_u64 m = tot[0] + tot[1];
         if (ok && m >= 0x7FFFFFFFull) { s3_set_error("s3_seed_pair_candidates: %llu candidates in one call", m); rc = S3_EINVAL; ok = false; }
@@ -491,7 +514,12 @@ extern "C" int s3_seed_pair_candidates(s3_index *ix,
                 if (ok) {
                     s3_pair_gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ordOut, m, d_all + m, d_all + 2 * m, lOut, rOut);
                     S3_LAUNCHED(2);
-                    for (int a = 0; a < 3 && ok; ++a) { h[a] = (uint32_t *)malloc((size_t)m * 4); ok = h[a] != NULL; }
+                    if (onDevice) {
+                        ok = cudaStreamSynchronize(st) == cudaSuccess;
+                        if (ok) { *candReadIDLeft = idsOut; *candPosLeft = lOut; *candPosRight = rOut; d_sorted = NULL; }     // the caller's now
+                    }
+                    for (int a = 0; a < 3 && ok && !onDevice; ++a) { h[a] = (uint32_t *)malloc((size_t)m * 4); ok = h[a] != NULL; }
+                    if (onDevice) { /* nothing to copy back */ } else
                     if (ok) ok = cudaMemcpyAsync(h[0], idsOut, (size_t)m * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
                                  cudaMemcpyAsync(h[1], lOut, (size_t)m * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
                                  cudaMemcpyAsync(h[2], rOut, (size_t)m * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
@@ -500,14 +528,16 @@ extern "C" int s3_seed_pair_candidates(s3_index *ix,
                 if (d_t2) cudaFree(d_t2);
             }
         }
+        clk.lap("fill + final sort");
         if (ok && cudaGetLastError() != cudaSuccess) ok = false;
         cudaFree(ge_all); cudaFree(cnt_all);
         if (d_all) cudaFree(d_all);
         if (!ok) { if (rc == S3_OK) { s3_set_error("s3_seed_pair_candidates: a CUDA call failed: %s", cudaGetErrorString(cudaGetLastError())); rc = S3_ECUDA; } goto done; }
-        if (m) { *candReadIDLeft = h[0]; *candPosLeft = h[1]; *candPosRight = h[2]; h[0] = h[1] = h[2] = NULL; }
+        if (m && !onDevice) { *candReadIDLeft = h[0]; *candPosLeft = h[1]; *candPosRight = h[2]; h[0] = h[1] = h[2] = NULL; }
         *numCandidates = m;
     }
 done:
+    clk.lap("frees");
     for (int s = 0; s < 2; ++s) if (side[s].keys) cudaFree(side[s].keys);
     if (d_len) cudaFree(d_len);
     if (d_aux) cudaFree(d_aux);

@@ -9,18 +9,21 @@
 //                        position pairs (decodeMergePositions) -> left window, DP, right window cut by the left hit
 //                        (packLeft / packRight), DP -> DeepDPAlignResult for candidates whose two reads reach their cutoffs
 //
-// Both are orchestration, like the reference's wrappers: every step is one of the library's entries (s3_seed_layout,
-// s3_dp_stage_parameters, s3_seed_search, s3_seed_candidates / s3_seed_pair_candidates, s3_dp_make_windows,
-// s3_dp_align_windows), each verified against its own oracle; host arrays travel between them, as they do between the
-// reference's engine threads.  The batches here are the small remainder of a run (reads the search left unaligned).
+// The stage logic (which reads go on, the rounds, the records) runs on the host like the reference's wrappers; everything
+// between stays on the device: the seeds are cut from the query buffer by a kernel, the seeding driver, the seed merges, the
+// windows, the DP and the CIGAR runs work on device arrays (s3_seed_search_device, s3_seed_candidates_device,
+// s3_seed_pair_candidates_any, s3_stage_align), and what comes back per call is a few small count reads, the candidates'
+// read ids and the alignments' scores, positions and runs.  Stream-ordered allocations (cudaMallocAsync) hold the intermediates.
 #include "s3_common.cuh"
 #include "s3_windows.cuh"
+#include <cub/cub.cuh>
 #include "../../include/soap3dp_b200.h"
 
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include <chrono>
+#include <map>
 #include <vector>
 
 // ---- device side of the stages: seeds cut from the query buffer, windows of the candidates ---------------------------------
@@ -74,6 +77,34 @@ __global__ void s3_stage_win_single_kernel(S3WinParams w, uint32_t m, const uint
     s3_stage_win_store(o, c, c, x);
 }
 
+// packLeft for every candidate (readIDLeft | estimated left start | estimated right start)
+__global__ void s3_stage_win_left_kernel(S3WinParams w, uint32_t m, const uint32_t *__restrict__ cand, const uint32_t *__restrict__ lenByRead, S3StageWin o)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    S3Window x;
+    const uint32_t id = cand[c];
+    s3_win_pair_left(w, id, cand[m + c], lenByRead[id], x);
+    s3_stage_win_store(o, c, c, x);
+}
+
+// packRight: only for candidates whose left read reached its cutoff; window cut by the left hit.  COUNT / FILL
+template <bool FILL>
+__global__ void s3_stage_win_right_kernel(S3WinParams w, uint32_t m, const uint32_t *__restrict__ cand, const uint32_t *__restrict__ lenByRead,
+                                          const int32_t *__restrict__ leftScore, const uint32_t *__restrict__ leftStart, const uint32_t *__restrict__ leftHit,
+                                          uint32_t *__restrict__ count, const uint32_t *__restrict__ off, S3StageWin o)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= m) return;
+    const uint32_t id = cand[c];
+    const bool go = leftScore[c] >= s3_win_cutoff(w, id, lenByRead[id]);
+    if (!FILL) { count[c] = go ? 1u : 0u; return; }
+    if (!go) return;
+    S3Window x;
+    s3_win_pair_right(w, id, cand[2 * (size_t)m + c], leftStart[c] + leftHit[c], lenByRead[id ^ 1u], x);
+    s3_stage_win_store(o, off[c], c, x);
+}
+
 namespace {
 
 // S3_STAGE_TIMING=1: wall-clock milliseconds of every step of a stage call on stderr (tuning aid)
@@ -90,69 +121,6 @@ struct StageClock {
         t = now;
     }
 };
-
-struct SeedSet {                                   // one side's seeding batch (DV-DPfunctions.cu:2655-2680 / 1057-1080)
-    std::vector<uint32_t> words, lengths, readIDs, offsets, maxHit;
-    uint32_t wordPerSeed = 0;
-    uint64_t n = 0;
-};
-
-// base k of read r in the query buffer: bits 2 (k % 16) of word k / 16 (QueryParser.cpp:1146)
-inline uint32_t read_base(const uint32_t *queries, uint32_t wpq, uint32_t r, uint32_t k)
-{
-    return (queries[(size_t)(r / 32) * 32 * wpq + (size_t)(k >> 4) * 32 + r % 32] >> ((k & 15u) << 1)) & 3u;
-}
-
-void seed_set_reserve(SeedSet &s, uint32_t wordPerSeed, size_t seeds)
-{
-    s.wordPerSeed = wordPerSeed;
-    s.words.assign(((seeds + 31) / 32 * 32 + 32) * wordPerSeed, 0u);
-    s.lengths.assign((seeds + 31) / 32 * 32 + 32, 0u);
-    s.readIDs.clear(); s.offsets.clear(); s.maxHit.clear();
-    s.n = 0;
-}
-
-// `len` bases of read `readID` from base `off` on, 16 per word, as the next seed of the set (word-wise: two source words per word)
-void seed_set_add(SeedSet &s, const uint32_t *queries, uint32_t wpq, uint32_t readID, uint32_t keyID, uint32_t off, uint32_t len, uint32_t maxHit)
-{
-    const uint64_t id = s.n++;
-    uint32_t *dst = s.words.data() + (id / 32) * 32 * s.wordPerSeed + id % 32;
-    const uint32_t *src = queries + (size_t)(readID / 32) * 32 * wpq + readID % 32;
-    for (uint32_t w = 0, done = 0; done < len; ++w, done += 16) {
-        const uint32_t k = off + done, sw = k >> 4, sh = (k & 15u) << 1;
-        uint32_t v = sw < wpq ? src[(size_t)sw * 32] >> sh : 0u;
-        if (sh && sw + 1 < wpq) v |= src[(size_t)(sw + 1) * 32] << (32u - sh);
-        const uint32_t rem = len - done;
-        if (rem < 16) v &= (1u << (2 * rem)) - 1u;
-        dst[(size_t)w * 32] = v;
-    }
-    s.lengths[id] = len;
-    s.readIDs.push_back(keyID); s.offsets.push_back(off); s.maxHit.push_back(maxHit);
-}
-
-struct Windows {
-    std::vector<uint32_t> cand, readID, start, len, clipLt, clipRt, ancL, ancR;
-    std::vector<uint8_t> strand, lor;
-    std::vector<int32_t> cutoff;
-    uint64_t n = 0;
-    void resize(size_t k) { cand.resize(k); readID.resize(k); start.resize(k); len.resize(k); clipLt.resize(k); clipRt.resize(k); ancL.resize(k); ancR.resize(k);
-                            strand.resize(k); lor.resize(k); cutoff.resize(k); }
-};
-
-int make_windows(s3_index *ix, int mode, const s3_window_params &wp, const uint32_t *readLengths, uint64_t numReads, const uint32_t *ids, const uint32_t *pos,
-                 const uint32_t *pos2, const uint8_t *strands, const int32_t *lsc, const uint32_t *lst, const uint32_t *lhit, uint64_t n, Windows &w)
-{
-    w.resize(n ? n : 1);
-    return s3_dp_make_windows(ix, mode, &wp, readLengths, numReads, ids, pos, pos2, strands, lsc, lst, lhit, n, w.cand.data(), w.readID.data(), w.strand.data(),
-                              w.lor.data(), w.start.data(), w.len.data(), w.clipLt.data(), w.clipRt.data(), w.ancL.data(), w.ancR.data(), w.cutoff.data(), &w.n);
-}
-
-int align_windows(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wpq, int uploadQueries, uint32_t maxRead,
-                  uint32_t maxDNA, s3_dp_scores scores, int slot, Windows &w, S3StageAligned &a)
-{
-    return s3_stage_align(ix, queries, readLengths, numReads, wpq, uploadQueries, maxRead, maxDNA, scores, slot, w.n, w.readID.data(), w.strand.data(),
-                          w.start.data(), w.len.data(), w.cutoff.data(), w.clipLt.data(), w.clipRt.data(), w.ancL.data(), w.ancR.data(), NULL, NULL, &a);
-}
 
 uint32_t margin_of(uint32_t len) { return len > 100u ? len >> 2 : 25u; }
 
@@ -185,12 +153,13 @@ namespace {
 // seed plans of a stage by read length, made once per distinct length; entries (read to cut, key id, plan, first seed id)
 struct StagePlans {
     std::vector<S3SeedPlan> table;
-    std::vector<int32_t> ofLen;                 // plan index by read length, -1: not made yet
+    std::map<uint64_t, int> made;               // (read length, mate length, side) -> plan index
     uint32_t maxSeedLen = 1;
     int get(int stage, uint32_t len, uint32_t len2, int side, const s3_stage_params *par, uint32_t *idx)
     {
-        if (len >= ofLen.size()) ofLen.resize(len + 1, -1);
-        if (ofLen[len] < 0) {
+        const uint64_t key = (uint64_t)len | ((uint64_t)len2 << 24) | ((uint64_t)side << 48);
+        auto it = made.find(key);
+        if (it == made.end()) {
             S3SeedPlan p;
             memset(&p, 0, sizeof p);
             std::vector<int32_t> pos(len + 64);
@@ -203,10 +172,10 @@ struct StagePlans {
                                              par->softClipLeft, par->softClipRight, &sp))) return rc;
             p.maxHit = sp.paramRead[side].maxHitNum;
             if ((uint32_t)p.seedLen > maxSeedLen) maxSeedLen = (uint32_t)p.seedLen;
-            ofLen[len] = (int32_t)table.size();
+            it = made.emplace(key, (int)table.size()).first;
             table.push_back(p);
         }
-        *idx = (uint32_t)ofLen[len];
+        *idx = (uint32_t)it->second;
         return S3_OK;
     }
 };
@@ -365,133 +334,153 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
     if (!out) { s3_set_error("s3_deep_dp_align: NULL result"); return S3_EINVAL; }
     memset(out, 0, sizeof *out);
     if (!ix || !queries || !readLengths || !par || (n && !pairReadIDs)) { s3_set_error("s3_deep_dp_align: NULL argument"); return S3_EINVAL; }
+    if (!ix->loc.sa || !ix->loc.text) { s3_set_error("s3_deep_dp_align: the index was uploaded without its suffix array and packed text"); return S3_EINVAL; }
     out->numPairs = n;
     if (n == 0) return S3_OK;
+    if (numReads >= 0xFFFFFFF0ull) { s3_set_error("s3_deep_dp_align: too many reads"); return S3_EINVAL; }
     uint32_t maxLen = 0;
     for (uint64_t k = 0; k < n; ++k) {
         const uint32_t e = pairReadIDs[k];
         if ((e & 1u) || (uint64_t)e + 1 >= numReads) { s3_set_error("s3_deep_dp_align: %u is not the even read id of a pair", e); return S3_EINVAL; }
-        for (int i = 0; i < 2; ++i) if (readLengths[e + i] > maxLen) maxLen = readLengths[e + i];
+        for (int i = 0; i < 2; ++i) {
+            if (readLengths[e + i] > 16u * wordPerQuery) { s3_set_error("s3_deep_dp_align: read %u longer than its query words", e + i); return S3_EINVAL; }
+            if (readLengths[e + i] > maxLen) maxLen = readLengths[e + i];
+        }
     }
     int rc = S3_OK;
     StageClock clk("s3_deep_dp_align");
+    if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_deep_dp_align: cudaSetDevice failed"); return S3_ECUDA; }
+    cudaStream_t st = ix->stream;
     std::vector<uint32_t> candID, candL, candR;                       // readIDLeft, estimated starts: all rounds' candidates
     std::vector<uint32_t> input(pairReadIDs, pairReadIDs + n), next, unseeded;
-    for (int round = 0; round < 2 && !input.empty() && rc == S3_OK; ++round) {
+    std::vector<s3_deep_dp_hit> hits;
+    std::vector<uint32_t> runs;
+    uint32_t *d_len = NULL, *d_c = NULL, *d_wl = NULL, *d_wr = NULL, *d_cnt = NULL;
+    void *d_tmp = NULL;
+    SeedSide side[2];
+    uint32_t *d_pc = NULL;                                              // a round's candidates (base of s3_seed_pair_candidates_any's allocation)
+    S3_TRYS(cudaMallocAsync((void **)&d_len, numReads * 4 + 16, st));
+    S3_TRYS(cudaMemcpyAsync(d_len, readLengths, numReads * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = s3_stage_upload_queries(ix, queries, numReads, wordPerQuery))) goto done;
+    for (int round = 0; round < 2 && !input.empty(); ++round) {
         const int stage = round == 0 ? S3_STAGE_DEEP_DP_ROUND1 : S3_STAGE_DEEP_DP_ROUND2;
-        // ---- seeds of both mates (PairEndSeedingBatch::packSeeds, DV-DPfunctions.cu:2682-2706)
-        SeedSet side[2];
-        // seed layout per read length, hit limits per pair of lengths: made once per distinct value
-        struct Layout { int32_t seedLen, seedNum; std::vector<int32_t> pos; bool made; };
-        std::vector<Layout> layouts(maxLen + 1);
-        for (auto &l : layouts) l.made = false;
-        uint64_t sideSeeds[2] = {0, 0};
-        uint32_t maxSeedLen = 1;
-        for (size_t k = 0; k < input.size() && rc == S3_OK; ++k)
-            for (int i = 0; i < 2; ++i) {
-                Layout &l = layouts[readLengths[input[k] + i]];
-                if (!l.made) {
-                    l.pos.resize(maxLen + 16);
-                    if ((rc = s3_seed_layout(stage, (int32_t)readLengths[input[k] + i], &l.seedLen, l.pos.data(), (int32_t)l.pos.size(), &l.seedNum))) break;
-                    l.made = true;
-                    if ((uint32_t)l.seedLen > maxSeedLen) maxSeedLen = (uint32_t)l.seedLen;
-                }
-                sideSeeds[i] += (uint64_t)l.seedNum;
+        // ---- seeds of both mates (PairEndSeedingBatch::packSeeds, DV-DPfunctions.cu:2682-2706), seeding driver per side
+        StagePlans plans[2];
+        const size_t ni = input.size();
+        std::vector<uint32_t> entries[2];
+        uint64_t total[2] = {0, 0};
+        for (int i = 0; i < 2; ++i) {
+            entries[i].resize(4 * ni);
+            for (size_t k = 0; k < ni; ++k) {
+                const uint32_t e = input[k];
+                uint32_t idx;
+                if ((rc = plans[i].get(stage, readLengths[e + i], readLengths[e + 1 - i], i, par, &idx))) goto done;
+                entries[i][k] = e + i; entries[i][ni + k] = e; entries[i][2 * ni + k] = idx; entries[i][3 * ni + k] = (uint32_t)total[i];
+                total[i] += (uint64_t)plans[i].table[idx].seedNum;
             }
-        if (rc) break;
-        for (int i = 0; i < 2; ++i) seed_set_reserve(side[i], (maxSeedLen + 15) / 16, (size_t)sideSeeds[i]);
-        uint32_t spLen[2] = {0xFFFFFFFFu, 0xFFFFFFFFu};
-        s3_dp_stage_params sp;
-        for (size_t k = 0; k < input.size() && rc == S3_OK; ++k) {
-            const uint32_t e = input[k];
-            if (readLengths[e] != spLen[0] || readLengths[e + 1] != spLen[1]) {
-                if ((rc = s3_dp_stage_parameters(stage, readLengths[e], readLengths[e + 1], par->isDefaultThreshold, par->dpScoreThreshold, par->softClipLeft, par->softClipRight, &sp))) break;
-                spLen[0] = readLengths[e]; spLen[1] = readLengths[e + 1];
-            }
-            for (int i = 0; i < 2; ++i) {
-                Layout &l = layouts[readLengths[e + i]];
-                for (int32_t j = 0; j < l.seedNum; ++j)
-                    seed_set_add(side[i], queries, wordPerQuery, e + i, e, (uint32_t)l.pos[j], (uint32_t)l.seedLen, (uint32_t)sp.paramRead[i].maxHitNum);
+            if ((rc = seed_side_run(ix, entries[i], ni, total[i], plans[i], wordPerQuery, d_len, side[i]))) goto done;
+        }
+        out->numSeeds += total[0] + total[1];
+        clk.lap("seeds + seeding driver x 2");
+        // a pair with a too-many seed on either side is flagged (decodePositions, :2951-2954)
+        std::vector<uint8_t> tooMany(numReads, 0), seeded(numReads, 0);
+        for (int i = 0; i < 2; ++i) {
+            if (!total[i]) continue;
+            std::vector<uint8_t> status(total[i]);
+            S3_TRYS(cudaMemcpyAsync(status.data(), side[i].ranges.d_status, total[i], cudaMemcpyDeviceToHost, st));
+            S3_TRYS(cudaStreamSynchronize(st));
+            for (size_t k = 0; k < ni; ++k) {
+                const uint32_t s0 = entries[i][3 * ni + k], s1 = k + 1 < ni ? entries[i][3 * ni + k + 1] : (uint32_t)total[i];
+                for (uint32_t sd = s0; sd < s1; ++sd) if (status[sd] == 4) { tooMany[input[k]] = 1; break; }
             }
         }
-        if (rc) break;
-        clk.lap("seed packing");
-        out->numSeeds += side[0].n + side[1].n;
-        // ---- seeding driver per side; a pair with a too-many seed on either side is flagged (decodePositions, :2951-2954)
-        s3_seed_search_result sr[2];
-        memset(sr, 0, sizeof sr);
-        std::vector<uint8_t> tooMany(numReads, 0);
-        std::vector<uint32_t> rid[2], off[2], slen[2], rlen[2];
-        std::vector<int32_t> strand[2];
-        for (int i = 0; i < 2 && rc == S3_OK; ++i) {
-            rc = s3_seed_search(ix, side[i].words.data(), side[i].lengths.data(), side[i].n, side[i].wordPerSeed, side[i].maxHit.data(), &sr[i]);
-            if (rc) break;
-            rid[i].resize(sr[i].total); off[i].resize(sr[i].total); slen[i].resize(sr[i].total); rlen[i].resize(sr[i].total); strand[i].resize(sr[i].total);
-            for (uint64_t s = 0; s < side[i].n; ++s) {
-                if (sr[i].status[s] == 4) tooMany[side[i].readIDs[s]] = 1;
-                for (uint64_t g = sr[i].offsets[s]; g < sr[i].offsets[s + 1]; ++g) {
-                    rid[i][g] = side[i].readIDs[s]; off[i][g] = side[i].offsets[s]; slen[i][g] = side[i].lengths[s];
-                    rlen[i][g] = readLengths[side[i].readIDs[s] + i]; strand[i][g] = sr[i].strand[g];
-                }
-            }
-        }
-        clk.lap("s3_seed_search x 2");
         // ---- candidate position pairs (decodeMergePositions, DV-DPfunctions.cu:2963-2999)
-        uint32_t *cID = NULL, *cL = NULL, *cR = NULL;
+        uint32_t *d_id = NULL, *d_l = NULL, *d_r = NULL;
         uint64_t nc = 0;
-        if (rc == S3_OK)
-            rc = s3_seed_pair_candidates(ix, sr[0].saL, sr[0].saR, strand[0].data(), rid[0].data(), off[0].data(), slen[0].data(), rlen[0].data(), sr[0].total,
-                                         sr[1].saL, sr[1].saR, strand[1].data(), rid[1].data(), off[1].data(), slen[1].data(), rlen[1].data(), sr[1].total,
-                                         0xFFFFFFFFu, readLengths, numReads, par->insertLow, par->insertHigh, par->strandLeftLeg, par->strandRightLeg,
-                                         &cID, &cL, &cR, &nc);
-        s3_seed_search_result_free(&sr[0]); s3_seed_search_result_free(&sr[1]);
-        clk.lap("s3_seed_pair_candidates");
-        if (rc) break;
+        {
+            const uint32_t *in[2][7];
+            for (int i = 0; i < 2; ++i) { const uint64_t R = side[i].ranges.numRanges; for (int a = 0; a < 7; ++a) in[i][a] = side[i].ranges.d_buf ? side[i].ranges.d_buf + a * R : NULL; }
+            if ((rc = s3_seed_pair_candidates_any(ix, in[0], side[0].ranges.numRanges, in[1], side[1].ranges.numRanges, 1, 0xFFFFFFFFu, d_len, numReads,
+                                                  par->insertLow, par->insertHigh, par->strandLeftLeg, par->strandRightLeg, &d_id, &d_l, &d_r, &nc))) goto done;
+            d_pc = d_id;
+        }
+        if (nc) {
+            const size_t base = candID.size();
+            candID.resize(base + nc); candL.resize(base + nc); candR.resize(base + nc);
+            S3_TRYS(cudaMemcpyAsync(candID.data() + base, d_id, nc * 4, cudaMemcpyDeviceToHost, st));
+            S3_TRYS(cudaMemcpyAsync(candL.data() + base, d_l, nc * 4, cudaMemcpyDeviceToHost, st));
+            S3_TRYS(cudaMemcpyAsync(candR.data() + base, d_r, nc * 4, cudaMemcpyDeviceToHost, st));
+            S3_TRYS(cudaStreamSynchronize(st));
+            for (size_t c = base; c < base + nc; ++c) seeded[candID[c] & ~1u] = 1;
+        }
+        if (d_pc) { cudaFree(d_pc); d_pc = NULL; }
+        seed_side_free(ix, side[0]); seed_side_free(ix, side[1]);
+        clk.lap("pair candidates");
         // ---- seeded / too many / unseeded pairs (performSeeding, DV-DPfunctions.cu:3105-3125)
-        std::vector<uint8_t> seeded(numReads, 0);
-        for (uint64_t c = 0; c < nc; ++c) { seeded[cID[c] & ~1u] = 1; candID.push_back(cID[c]); candL.push_back(cL[c]); candR.push_back(cR[c]); }
-        s3_free(cID); s3_free(cL); s3_free(cR);
         next.clear();
-        for (size_t k = 0; k < input.size(); ++k) {
+        for (size_t k = 0; k < ni; ++k) {
             const uint32_t e = input[k];
             if (seeded[e]) continue;
             if (round == 0 && tooMany[e]) next.push_back(e); else unseeded.push_back(e);
         }
         input.swap(next);
     }
-    if (rc) return rc;
-    const uint64_t nc = candID.size();
-    out->numCandidates = nc;
-    std::vector<s3_deep_dp_hit> hits;
-    std::vector<uint32_t> runs;
-    if (nc) {
-        // ---- left read, then the right read inside the window the left hit allows (DP2CPUAlgnThread, DV-DPfunctions.cu:3731-3800)
-        const uint32_t maxRead = (maxLen / 4 + 1) * 4, maxDNA = maxRead + 2 * margin_of(maxRead) + 8;
-        s3_window_params wp;
-        memset(&wp, 0, sizeof wp);
-        wp.insertLow = par->insertLow; wp.insertHigh = par->insertHigh; wp.strandLeftLeg = par->strandLeftLeg; wp.strandRightLeg = par->strandRightLeg;
-        wp.softClipLeft = par->softClipLeft; wp.softClipRight = par->softClipRight;
-        wp.cutoffThreshold[0] = wp.cutoffThreshold[1] = par->isDefaultThreshold ? -1 : par->dpScoreThreshold; wp.maxDNALength = maxDNA;
-        Windows wl, wr;
-        S3StageAligned al, ar;
-        clk.lap("round bookkeeping");
-        rc = make_windows(ix, S3_WIN_PAIR_LEFT, wp, readLengths, numReads, candID.data(), candL.data(), NULL, NULL, NULL, NULL, NULL, nc, wl);
-        clk.lap("windows left");
-        if (rc == S3_OK) rc = align_windows(ix, queries, readLengths, numReads, wordPerQuery, 1, maxRead, maxDNA, par->scores, 0, wl, al);
-        clk.lap("align left");
-        if (rc == S3_OK) rc = make_windows(ix, S3_WIN_PAIR_RIGHT, wp, readLengths, numReads, candID.data(), candL.data(), candR.data(), NULL, al.score,
-                                           wl.start.data(), al.hit, nc, wr);
-        if (rc == S3_OK) rc = align_windows(ix, queries, readLengths, numReads, wordPerQuery, 0, maxRead, maxDNA, par->scores, 1, wr, ar);
-        clk.lap("windows right + align right");
-        if (rc == S3_OK)
-            for (uint64_t t = 0; t < wr.n; ++t) {
-                if (ar.score[t] < wr.cutoff[t]) continue;           // the left read reached its cutoff or the candidate has no right window
-                const uint32_t c = wr.cand[t], left = candID[c], readSide = left & 1u;
+    {
+        const uint64_t nc64 = candID.size();
+        out->numCandidates = nc64;
+        if (nc64 >= 0x7FFFFFF0ull) { s3_set_error("s3_deep_dp_align: too many candidates"); rc = S3_EINVAL; goto done; }
+        const uint32_t nc = (uint32_t)nc64;
+        if (nc) {
+            // ---- left read, then the right read inside the window the left hit allows (DP2CPUAlgnThread, DV-DPfunctions.cu:3731-3800)
+            const uint32_t maxRead = (maxLen / 4 + 1) * 4, maxDNA = maxRead + 2 * margin_of(maxRead) + 8;
+            S3WinParams w;
+            memset(&w, 0, sizeof w);
+            w.insertLow = par->insertLow; w.insertHigh = par->insertHigh; w.leftLeg = par->strandLeftLeg; w.rightLeg = par->strandRightLeg;
+            w.softClipLeft = par->softClipLeft; w.softClipRight = par->softClipRight;
+            w.cutoff[0] = w.cutoff[1] = par->isDefaultThreshold ? -1 : par->dpScoreThreshold; w.maxDNALength = maxDNA; w.textLength = ix->textLength;
+            auto win_of = [&](uint32_t *b, size_t m) { S3StageWin o; o.readID = b; o.start = b + m; o.dnaLen = b + 2 * m; o.clipLt = b + 3 * m; o.clipRt = b + 4 * m;
+                                                       o.ancL = b + 5 * m; o.ancR = b + 6 * m; o.cand = b + 7 * m; o.cutoff = (int32_t *)(b + 8 * m); o.strand = (uint8_t *)(b + 9 * m); return o; };
+            size_t scanTemp = 0;
+            cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (uint32_t *)NULL, (uint32_t *)NULL, (int)(nc + 1), st);
+            S3_TRYS(cudaMallocAsync((void **)&d_c, (size_t)nc * 12, st));
+            S3_TRYS(cudaMallocAsync((void **)&d_wl, (size_t)nc * 40 + 64, st));
+            S3_TRYS(cudaMallocAsync((void **)&d_wr, (size_t)nc * 40 + 64, st));
+            S3_TRYS(cudaMallocAsync((void **)&d_cnt, 2 * ((size_t)nc + 1) * 4, st));
+            S3_TRYS(cudaMallocAsync(&d_tmp, scanTemp + 16, st));
+            S3_TRYS(cudaMemcpyAsync(d_c, candID.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+            S3_TRYS(cudaMemcpyAsync(d_c + nc, candL.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+            S3_TRYS(cudaMemcpyAsync(d_c + 2 * (size_t)nc, candR.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+            const S3StageWin ol = win_of(d_wl, nc), orr = win_of(d_wr, nc);
+            const unsigned nb = (nc + 255) / 256;
+            s3_stage_win_left_kernel<<<nb, 256, 0, st>>>(w, nc, d_c, d_len, ol);
+            S3_LAUNCHED(1);
+            S3StageAligned al, ar;
+            memset(&ar, 0, sizeof ar);
+            if ((rc = s3_stage_align(ix, queries, readLengths, numReads, wordPerQuery, 0, maxRead, maxDNA, par->scores, 0, nc, ol.readID, ol.strand, ol.start, ol.dnaLen,
+                                     ol.cutoff, ol.clipLt, ol.clipRt, ol.ancL, ol.ancR, d_len, NULL, &al))) goto done;
+            clk.lap("left windows + DP");
+            uint32_t *d_count = d_cnt, *d_off = d_cnt + nc + 1;
+            S3_TRYS(cudaMemsetAsync(d_count + nc, 0, 4, st));
+            s3_stage_win_right_kernel<false><<<nb, 256, 0, st>>>(w, nc, d_c, d_len, al.d_score, ol.start, al.d_hit, d_count, NULL, orr);
+            S3_TRYS(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_count, d_off, (int)(nc + 1), st));
+            s3_stage_win_right_kernel<true><<<nb, 256, 0, st>>>(w, nc, d_c, d_len, al.d_score, ol.start, al.d_hit, NULL, d_off, orr);
+            S3_LAUNCHED(2);
+            S3_TRYS(cudaGetLastError());
+            uint32_t *h_nr = (uint32_t *)ix->pinnedCount + 12;
+            S3_TRYS(cudaMemcpyAsync(h_nr, d_off + nc, 4, cudaMemcpyDeviceToHost, st));
+            S3_TRYS(cudaStreamSynchronize(st));
+            const uint32_t nr = *h_nr;
+            if (nr && (rc = s3_stage_align(ix, queries, readLengths, numReads, wordPerQuery, 0, maxRead, maxDNA, par->scores, 1, nr, orr.readID, orr.strand, orr.start,
+                                           orr.dnaLen, orr.cutoff, orr.clipLt, orr.clipRt, orr.ancL, orr.ancR, d_len, orr.cand, &ar))) goto done;
+            clk.lap("right windows + DP");
+            for (uint32_t t = 0; t < nr; ++t) {
+                if (ar.score[t] < ar.cutoff[t]) continue;           // (the left read reached its cutoff: only those have a right window)
+                const uint32_t c = ar.cand[t], left = candID[c], readSide = left & 1u;
                 // fields _1 belong to the pair's first read, _2 to its mate, whichever is the left one
                 s3_deep_dp_hit h;
                 memset(&h, 0, sizeof h);
                 h.readID = left - readSide;
-                const uint32_t posLeft = wl.start[c] + al.hit[c], posRight = wr.start[t] + ar.hit[t];
+                const uint32_t posLeft = al.start[c] + al.hit[c], posRight = ar.start[t] + ar.hit[t];
                 uint32_t roL = (uint32_t)runs.size();
                 runs.insert(runs.end(), al.runs + al.runOff[c], al.runs + al.runOff[c + 1]);
                 uint32_t nL = (uint32_t)runs.size() - roL, roR = (uint32_t)runs.size();
@@ -508,8 +497,16 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
                 }
                 hits.push_back(h);
             }
+            clk.lap("records");
+        }
     }
-    clk.lap("records + CIGAR runs");
+done:
+    seed_side_free(ix, side[0]); seed_side_free(ix, side[1]);
+    if (d_pc) cudaFree(d_pc);
+    {
+        void *p[] = {d_len, d_c, d_wl, d_wr, d_cnt, d_tmp};
+        for (void *q : p) if (q) cudaFreeAsync(q, st);
+    }
     if (rc) return rc;
     out->numHits = hits.size(); out->numRuns = runs.size(); out->numUnseeded = unseeded.size();
     out->hits = to_malloc(hits); out->runs = to_malloc(runs); out->unseeded = to_malloc(unseeded);

@@ -706,6 +706,50 @@ int s3_index_read_timing(s3_index *ix, float *msPerSlot, int *launchesPerSlot);
 int s3_dp_set_timing(s3_dp *dp, int on);
 int s3_dp_read_timing(s3_dp *dp, float *msPerSlot, int *launchesPerSlot);
 
+/* ------------------------------------------------------------------------
+ * SAM records (host).  s3_sam_pair_records replaces pairOutputSAMAPI (BGS-IO.cpp:3478-3793) for one read pair: the two
+ * records samwrite would receive -- bam1_t.core fields and bam1_t.data (name, CIGAR, 4-bit bases, qualities, tags RG NM X0 X1
+ * XM XO XG MD XA) byte for byte -- from the pair's valid pairings (PEPairs in list order, bestIndex = the one reported, < 0:
+ * none, both reads come out unmapped), the reads, and the counts hostKernel passes (CPUfunctions.cpp:2281-2380): the optimal /
+ * suboptimal total mismatches (PEStatsPEOutput), X0 / X1 of either read, the number of optimal pairings, whether the reported
+ * ends are best hits of their reads, the number of valid pairings.  Included: position -> chromosome through the translate
+ * table (getChrAndPos, :1746), trimming of an alignment that hangs over a chromosome / segment end (BoundaryCheck, :1779: CIGAR
+ * <a>M<b>S or <a>S<b>M, MAPQ 0, mismatches recounted), the MD string and mean mismatch quality (getMdStr, PE.cpp:374), MAPQ
+ * (s3_mapq_bwa_pair, or s3_mapq_pair_end + s3_mapq_of_pair; 255 unless the report type is all-valid / all-best), the XA:Z list
+ * of the other pairings with the best total (up to peMaxOutputPerPair results).  record.data is malloc'ed
+ * (s3_sam_record_free).  alignmentType: OUTPUT_* of definitions.h:127-130.
+ * ------------------------------------------------------------------------ */
+typedef struct { uint32_t startPos, chrID, correction; } s3_sam_segment;            /* Translate, 2bwt-lib/HSP.h:73-77 */
+typedef struct {
+    const uint32_t *packedDNA; uint32_t dnaLength;                                    /* hsp->packedDNA, dnaLength */
+    const s3_sam_segment *segments; uint32_t numSegments;                             /* hsp->translate, numOfRemovedSegment */
+    const uint32_t *ambiguityMap;                                                     /* hsp->ambiguityMap: per 2^18 positions a segment at or after theirs */
+    const uint32_t *chrEndPos; uint32_t numChr; const char *const *chrNames;          /* hsp->seqOffset[].endPos; header->target_name */
+} s3_sam_genome;
+typedef struct {
+    int32_t alignmentType, bwaLikeScore, dpMatchScore, dpMisMatchScore, isFastq, maxMAPQ, minMAPQ, isPrintMDNM, outputXAZTag;   /* HSPAux.h */
+    uint32_t peMaxOutputPerPair;
+    const char *readGroup;
+} s3_sam_config;
+typedef struct {
+    uint32_t algnmt1, algnmt2;                                                        /* PEPairs, PEAlgnmt.h:164-178 */
+    uint8_t strand1, mismatch1, strand2, mismatch2;
+    int8_t totalMismatchCount; uint8_t pad[3];
+} s3_sam_pairing;
+typedef struct {
+    int32_t tid, pos;                                                                 /* bam1_core_t, samtools-0.1.18/bam.h:169-178 */
+    uint16_t bin; uint8_t qual, l_qname; uint16_t flag, n_cigar;
+    int32_t l_qseq, mtid, mpos, isize;
+    int32_t l_aux, data_len;                                                          /* bam1_t */
+    uint8_t *data;
+} s3_sam_record;
+int s3_sam_pair_records(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_pairing *pairs, uint32_t numPairs, int32_t bestIndex,
+                        const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                        int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2,
+                        int32_t minTotalMismatch, int32_t secMinTotalMismatch, int32_t x0First, int32_t x0Second, int32_t x1First, int32_t x1Second,
+                        int32_t numMinMismatchPair, int32_t isBestHit1, int32_t isBestHit2, uint32_t totalNumValidPairs, s3_sam_record out[2]);
+void s3_sam_record_free(s3_sam_record *record);
+
 #ifdef __cplusplus
 }
 #endif

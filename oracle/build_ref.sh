@@ -22,11 +22,14 @@
 #   libref_cpu_search.so  the reference's own CPU search: ProcessReadDoubleStrand2 (CPUfunctions.cpp:555-622) + BGS-HostAlgnmtAlgo2.cpp,
 #                      SAList.cpp, SRA2BWTMdl.c, SRA2BWTCheckAndExtend.c, BWT.c compiled from where they lie; the CPU arm of bench.py
 #   libref_validate.so validateAlignments (CPUfunctions.cpp:1129-1222) + the packers / popcount distance it calls (PE.cpp:28-60,148-206,287-325)
+#   libref_sam.so      pairOutputSAMAPI (BGS-IO.cpp:3478-3793) and all it calls: BGS-IO.cpp, PE.cpp, SAM.cpp, PEAlgnmt.cpp, SAList.cpp, samtools' bam_aux.c,
+#                      whole; samwrite is the shim's and keeps the bam1_t records
 #   libref_seed.so     the seed-hit radix sorts + singleMerge of single-end DP seeding (DV-DPfunctions.h:60-95, .cu:1101-1141)
 #
-# Two one-line build fixes are applied to *copies* in oracle/_ref/patched/
-# (SURVEY.md §8c): 2bwt-lib/BWT.c:424 pointer comparison, and
-# 2bwt-flex/LTConstruct.c BuildLookupTable falling off the end without return.
+# Three build fixes are applied to *copies* in oracle/_ref/patched/
+# (SURVEY.md §8c): 2bwt-lib/BWT.c:424 pointer comparison,
+# 2bwt-flex/LTConstruct.c BuildLookupTable falling off the end without return, and the same
+# in three helpers of SAM.cpp (libref_sam.so only).
 set -euo pipefail
 REF=${REF:-/root/reference}
 HERE=$(cd "$(dirname "$0")" && pwd)
@@ -164,6 +167,20 @@ echo "[build_ref] libref_params.so OK"
 $CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" \
     "$HERE/ref_shim/ref_validate_host.cpp" -o "$OUT/libref_validate.so"
 echo "[build_ref] libref_validate.so OK"
+
+# ---- the reference's SAM writer of a properly paired read pair, records kept instead of written ------------------------------------
+# SAM.cpp:58,70,80: three int functions fall off their end; g++ then drops the loop exits (undefined behaviour).  `return 0;` is added
+# to a COPY (the third build fix of this kind, see the top of the script); everything else is compiled from where it lies.
+sed -e '58s/^}/    return 0;\n}/' -e '70s/^}/    return 0;\n}/' -e '80s/^}/    return 0;\n}/' "$REF/SAM.cpp" > "$OUT/patched/SAM.cpp"
+sed -n '24,41p' "$REF/samtools-0.1.18/bam_import.c" > "$OUT/patched/sam_nt16.inc"
+sed -n '3014,3019p' "$REF/CPUfunctions.cpp" > "$OUT/patched/sam_bwase.inc"
+for f in BGS-IO PE PEAlgnmt; do $CXX -O1 -fpermissive -w -fPIC -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -c "$REF/$f.cpp" -o "$OUT/obj/sam_$f.o"; done
+$CXX -O1 -fpermissive -w -fPIC -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -c "$OUT/patched/SAM.cpp" -o "$OUT/obj/sam_SAM.o"
+/usr/bin/gcc -O1 -w -fPIC -I"$REF/samtools-0.1.18" -c "$REF/samtools-0.1.18/bam_aux.c" -o "$OUT/obj/sam_bam_aux.o"
+$CXX $CFLAGS -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -c "$REF/SAList.cpp" -o "$OUT/obj/SAList.o"
+$CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" "$HERE/ref_shim/ref_sam_host.cpp" \
+    "$OUT/obj/sam_BGS-IO.o" "$OUT/obj/sam_PE.o" "$OUT/obj/sam_SAM.o" "$OUT/obj/sam_PEAlgnmt.o" "$OUT/obj/SAList.o" "$OUT/obj/sam_bam_aux.o" $BWTOBJ -lm -o "$OUT/libref_sam.so"
+echo "[build_ref] libref_sam.so OK"
 
 # ---- the reference's CPU search path: models, lookup-table + BWT backward / bidirectional search, check-and-extend ------------
 # ProcessReadDoubleStrand2 is cut by line range (CPUfunctions.cpp as a whole needs the aligner around it); the files it calls

@@ -1,0 +1,124 @@
+// TEST INFRASTRUCTURE ONLY (oracle/_ref/libref_sam.so, built by oracle/build_ref.sh).
+// The reference's SAM record of a properly paired read pair: pairOutputSAMAPI (BGS-IO.cpp:3478-3793) with everything it calls --
+// getChrAndPosWithBoundaryCheck / BoundaryCheck / getChrAndPos (:1746-2007), getMdStr + mdStr (PE.cpp), the MAPQ functions,
+// initializeSAMAlgnmt / initializeSAMAlgnmt2 (:2036-2278), samtools' bam_aux_append -- from BGS-IO.cpp, PE.cpp, SAM.cpp, PEAlgnmt.cpp,
+// SAList.cpp and samtools-0.1.18/bam_aux.c compiled whole and unmodified.  samwrite is defined HERE and keeps the record instead of
+// writing it; this file only builds the structs the function reads (SRAQueryInput, HSP, HSPAux, OCC, PEOutput, a header with the
+// chromosome names) from flat arrays.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <stdint.h>
+#include <vector>
+#include "BGS-IO.h"
+#include "PEAlgnmt.h"
+#include "SAM.h"
+#include "HSPAux.h"
+#include "definitions.h"
+
+int bam_verbose = 0;
+#include "sam_nt16.inc"          // bam_nt16_table, samtools-0.1.18/bam_import.c:24-41
+
+void bwase_initialize ( int * g_log_n );     // CPUfunctions.cpp:3014-3019, in mapq-style cut below
+#include "sam_bwase.inc"
+
+struct Kept { bam1_core_t core; int l_aux, data_len; std::vector<uint8_t> data; };
+static std::vector<Kept> g_kept;
+
+extern "C" int samwrite ( samfile_t * fp, const bam1_t * b )
+{
+    Kept k;
+    k.core = b->core; k.l_aux = b->l_aux; k.data_len = b->data_len;
+    k.data.assign ( b->data, b->data + b->data_len );
+    g_kept.push_back ( k );
+    return b->data_len;
+}
+
+extern "C" int ref_sam_pair ( const uint32_t * pac, uint32_t dnaLength, const uint32_t * translate, uint32_t numSeg, const uint32_t * ambiguityMap,
+                              const uint32_t * chrEndPos, uint32_t numChr, const char * const * chrNames,
+                              int alignmentType, int bwaLike, int dpMatch, int dpMismatch, int isFastq, int maxMAPQ, int minMAPQ, int isPrintMDNM,
+                              const char * readGroup, int outputXAZ, uint32_t peMaxOutputPerPair,
+                              const uint32_t * pairs, uint32_t numPairs, int bestIdx,
+                              const uint8_t * query1, const uint8_t * query2, const char * qual1, const char * qual2, int len1, int len2,
+                              const char * name1, const char * name2,
+                              int minTot, int secMinTot, int X0f, int X0s, int X1f, int X1s, int numMin, int best1, int best2, uint32_t totalValid,
+                              int32_t * core, uint8_t * data, int32_t dataCap, int32_t * dataLen )
+{
+    HSP hsp;
+    memset ( &hsp, 0, sizeof ( hsp ) );
+    hsp.dnaLength = dnaLength;
+    hsp.packedDNA = ( unsigned int * ) pac;
+    hsp.numOfRemovedSegment = numSeg;
+    std::vector<Translate> tr ( numSeg );
+    for ( uint32_t i = 0; i < numSeg; i++ ) { tr[i].startPos = translate[3 * i]; tr[i].chrID = translate[3 * i + 1]; tr[i].correction = translate[3 * i + 2]; }
+    hsp.translate = tr.data ();
+    hsp.ambiguityMap = ( unsigned int * ) ambiguityMap;
+    std::vector<SeqOffset> so ( numChr );
+    for ( uint32_t i = 0; i < numChr; i++ ) { memset ( &so[i], 0, sizeof ( SeqOffset ) ); so[i].endPos = chrEndPos[i]; }
+    hsp.seqOffset = so.data ();
+    hsp.numOfSeq = numChr;
+    HSPAux aux;
+    memset ( &aux, 0, sizeof ( aux ) );
+    aux.isFastq = isFastq; aux.dpMatchScore = dpMatch; aux.dpMisMatchScore = dpMismatch; aux.alignmentType = alignmentType;
+    aux.minMAPQ = minMAPQ; aux.maxMAPQ = maxMAPQ; aux.bwaLikeScore = bwaLike; aux.readGroup = ( char * ) readGroup; aux.isPrintMDNM = isPrintMDNM;
+    bwase_initialize ( aux.g_log_n );
+    SRAIndex index;
+    memset ( &index, 0, sizeof ( index ) );
+    index.hsp = &hsp; index.hspaux = &aux;
+    OCC occ;
+    memset ( &occ, 0, sizeof ( occ ) );
+    SAMOccurrenceConstruct ( &occ );
+    bam_header_t header;
+    memset ( &header, 0, sizeof ( header ) );
+    header.n_targets = numChr;
+    header.target_name = ( char ** ) chrNames;
+    samfile_t sf;
+    memset ( &sf, 0, sizeof ( sf ) );
+    sf.header = &header;
+    SRASetting setting;
+    memset ( &setting, 0, sizeof ( setting ) );
+    setting.occ = &occ; setting.SAMOutFilePtr = &sf;
+    SRAQueryInput in;
+    memset ( &in, 0, sizeof ( in ) );
+    in.AlgnmtIndex = &index; in.QuerySetting = &setting;
+    // the pairs as PEMappingOccurrences leaves them: buckets of PE_MAX_BUCKET_SIZE
+    PEOutput out;
+    memset ( &out, 0, sizeof ( out ) );
+    std::vector<PEPairList *> buckets;
+    PEPairs * best = NULL;
+    for ( uint32_t p = 0; p < numPairs || buckets.empty (); p++ )
+    {
+        if ( buckets.empty () || buckets.back ()->pairsCount == PE_MAX_BUCKET_SIZE )
+        {
+            PEPairList * b = ( PEPairList * ) calloc ( 1, sizeof ( PEPairList ) );
+            if ( !buckets.empty () ) { buckets.back ()->next = b; }
+            buckets.push_back ( b );
+        }
+        if ( p >= numPairs ) { break; }
+        PEPairs * x = &buckets.back ()->pairs[buckets.back ()->pairsCount++];
+        x->algnmt_1 = pairs[7 * p]; x->strand_1 = ( char ) pairs[7 * p + 1]; x->mismatch_1 = ( char ) pairs[7 * p + 2];
+        x->algnmt_2 = pairs[7 * p + 3]; x->strand_2 = ( char ) pairs[7 * p + 4]; x->mismatch_2 = ( char ) pairs[7 * p + 5];
+        x->totalMismatchCount = ( char ) pairs[7 * p + 6];
+        if ( ( int ) p == bestIdx ) { best = x; }
+    }
+    out.root = buckets[0]; out.tail = buckets.back ();
+    DynamicUint8Array * xaz = DynamicUint8ArrayConstruct ();
+    g_kept.clear ();
+    pairOutputSAMAPI ( &in, &out, best, ( unsigned char * ) query1, ( unsigned char * ) query2, ( char * ) qual1, ( char * ) qual2, len1, len2,
+                       ( char * ) name1, ( char * ) name2, ( char ) minTot, ( char ) secMinTot, outputXAZ, xaz, peMaxOutputPerPair,
+                       X0f, X0s, X1f, X1s, numMin, ( char ) best1, ( char ) best2, totalValid );
+    int n = ( int ) g_kept.size ();
+    for ( int r = 0; r < n && r < 2; r++ )
+    {
+        const Kept & k = g_kept[r];
+        int32_t * c = core + 12 * r;
+        c[0] = k.core.tid; c[1] = k.core.pos; c[2] = k.core.bin; c[3] = k.core.qual; c[4] = k.core.l_qname; c[5] = k.core.flag; c[6] = k.core.n_cigar;
+        c[7] = k.core.l_qseq; c[8] = k.core.mtid; c[9] = k.core.mpos; c[10] = k.core.isize; c[11] = k.l_aux;
+        dataLen[r] = k.data_len;
+        if ( k.data_len <= dataCap ) { memcpy ( data + ( size_t ) r * dataCap, k.data.data (), k.data_len ); }
+    }
+    DynamicUint8ArrayFree ( xaz );
+    SAMOccurrenceDestruct ( &occ );
+    for ( size_t i = 0; i < buckets.size (); i++ ) { free ( buckets[i] ); }
+    return n;
+}

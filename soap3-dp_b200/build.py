@@ -8,7 +8,7 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libsoap3dp_b200.so")
-SOURCES = ["s3_index.cu", "s3_search.cu", "s3_dp.cu", "s3_seed.cu", "s3_decode.cu", "s3_params.cu", "s3_pair.cu", "s3_chain.cu", "s3_windows.cu", "s3_stages.cu"]
+SOURCES = ["s3_index.cu", "s3_search.cu", "s3_dp.cu", "s3_seed.cu", "s3_decode.cu", "s3_params.cu", "s3_pair.cu", "s3_chain.cu", "s3_windows.cu", "s3_stages.cu", "s3_sam.cu"]
 NVCC = os.environ.get("S3_NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
          "-ccbin", "/usr/bin/g++", "-Xcompiler", "-fPIC", "-Xcompiler", "-Wno-deprecated-declarations",

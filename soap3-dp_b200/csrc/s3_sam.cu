@@ -1,0 +1,275 @@
+// s3_sam.cu -- the SAM record of a properly paired read pair (host code, like the writers it replaces).
+//
+// s3_sam_pair_records replaces pairOutputSAMAPI (BGS-IO.cpp:3478-3793) with what it calls: position -> (chromosome, offset)
+// through the translate table (getChrAndPos, :1746-1776), the boundary check that trims an alignment hanging over a chromosome
+// or segment end into <a>M<b>S / <a>S<b>M (BoundaryCheck / getChrAndPosWithBoundaryCheck, :1779-2007), the MD string of a
+// gap-free alignment (getMdStr + mdStr, PE.cpp:209-285,374-419), the pair's mapping qualities (s3_mapq_bwa_pair or s3_mapq_pair_end +
+// s3_mapq_of_pair), the XA:Z list of the other pairs with the same number of mismatches, flags, mate fields, insert size, and
+// the record body of initializeSAMAlgnmt2 (:2136-2278): name, CIGAR, 4-bit bases (reverse-complemented on the reverse strand),
+// qualities, tags RG NM X0 X1 XM XO XG MD XA in that order -- byte for byte bam1_t.core + bam1_t.data as samwrite receives them.
+// (l_aux is what the reference leaves there: bam_aux_append and initializeSAMAlgnmt2 both add the tags' bytes.)
+#include "s3_common.cuh"
+#include "../../include/soap3dp_b200.h"
+
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+#include <string>
+#include <vector>
+
+namespace {
+
+const char kDnaChar[4] = {'A', 'C', 'G', 'T'};
+// bam_nt16_table of the four letters (samtools-0.1.18/bam_import.c:24-41): A 1, C 2, G 4, T 8
+const uint8_t kNt16[4] = {1, 2, 4, 8};
+
+int write_num(long long num, char *str)                 // writeNumToStr / writeULLToStr (PE.cpp:62-110): no leading zeros, "0" for 0
+{
+    char tmp[24];
+    int n = 0;
+    bool neg = num < 0;
+    unsigned long long v = neg ? (unsigned long long)(-num) : (unsigned long long)num;
+    do { tmp[n++] = (char)('0' + v % 10); v /= 10; } while (v);
+    int k = 0;
+    if (neg) str[k++] = '-';
+    while (n) str[k++] = tmp[--n];
+    return k;
+}
+
+// getChrAndPos: -> end of the segment the position lies in
+uint32_t chr_and_pos(const s3_sam_genome *g, uint32_t ambPos, unsigned long long *tp, uint32_t *chr)
+{
+    uint32_t v = g->ambiguityMap[ambPos >> 18];
+    while (g->segments[v].startPos > ambPos) --v;
+    *tp = (unsigned long long)(uint32_t)(ambPos - g->segments[v].correction);
+    *chr = g->segments[v].chrID;
+    return v < g->numSegments - 1 ? g->segments[v + 1].startPos - 1 : g->dnaLength;
+}
+
+// getChrAndPosWithBoundaryCheck: trimmed bases (> 0 left, < 0 right, 0 none); cigar = the replacement CIGAR when trimmed
+int chr_and_pos_checked(const s3_sam_genome *g, uint32_t readLength, uint32_t ambPos, unsigned long long *tp, uint32_t *chr, std::string &cigar)
+{
+    uint32_t segEnd = chr_and_pos(g, ambPos, tp, chr);
+    const uint32_t chrEnd = g->chrEndPos[*chr - 1];
+    segEnd = chrEnd < segEnd ? chrEnd : segEnd;
+    if (ambPos + readLength <= segEnd + 1) return 0;
+    const int aligned = (int)(segEnd - ambPos + 1);
+    char buf[40];
+    if (aligned >= ((int)readLength + 1) / 2) {
+        snprintf(buf, sizeof buf, "%dM%dS", aligned, (int)readLength - aligned);
+        cigar = buf;
+        return -((int)readLength - aligned);
+    }
+    snprintf(buf, sizeof buf, "%dS%dM", aligned, (int)readLength - aligned);
+    cigar = buf;
+    const uint32_t corrected = segEnd + 1;
+    if (corrected > ambPos) chr_and_pos(g, corrected, tp, chr);
+    return aligned;
+}
+
+inline uint32_t text_base(const uint32_t *pac, unsigned long long p) { return (pac[p >> 4] >> (30 - 2 * (p & 15))) & 3u; }
+
+// getMdStr: MD of the (trimmed) read against the text, the mean quality at the mismatches
+int md_string(const s3_sam_genome *g, const uint8_t *query, const char *qualities, uint32_t len, uint32_t pos, int strand, int mismatchNum, int trim,
+              std::string &md, int *avgQual)
+{
+    if (strand == 1) {
+        if (trim > 0) { query += trim; pos += trim; len -= trim; }
+        else if (trim < 0) len -= -trim;
+    } else {
+        if (trim > 0) { pos += trim; len -= trim; }
+        else if (trim < 0) { query += -trim; len -= -trim; }
+    }
+    *avgQual = 20;                                       // DEFAULT_QUAL_VALUE
+    md.clear();
+    char num[24];
+    if ((char)mismatchNum == 0) { md.assign(num, write_num(len, num)); return (int)md.size(); }
+    double sum = 0.0;
+    int pre = -1;
+    for (uint32_t i = 0; i < len; ++i) {
+        const uint32_t q = strand == 2 ? 3u - query[len - 1 - i] : query[i];
+        const uint32_t t = text_base(g->packedDNA, (unsigned long long)pos + i);
+        if (q == t) continue;
+        md.append(num, write_num((int)i - pre - 1, num));
+        md.push_back(kDnaChar[t]);
+        pre = (int)i;
+        sum += qualities[i];                             // the reference indexes the qualities by alignment column, whatever the strand
+    }
+    md.append(num, write_num((int)len - pre - 1, num));
+    *avgQual = (int)(sum / (char)mismatchNum);
+    return (int)md.size();
+}
+
+void put32(std::vector<uint8_t> &d, uint32_t v) { for (int k = 0; k < 4; ++k) d.push_back((uint8_t)(v >> (8 * k))); }
+void put_tag(std::vector<uint8_t> &d, const char *tag, char type, const void *data, size_t len)
+{
+    d.push_back((uint8_t)tag[0]); d.push_back((uint8_t)tag[1]); d.push_back((uint8_t)type);
+    const uint8_t *p = (const uint8_t *)data;
+    d.insert(d.end(), p, p + len);
+}
+
+// initializeSAMAlgnmt2 (mapped) / initializeSAMAlgnmt (unmapped): the body of the record
+void record_body(s3_sam_record &r, std::vector<uint8_t> &d, int readlen, const char *name, const uint8_t *seq, const char *qual, int strand,
+                 const std::string &xa, const std::string *cigar, bool unmapped, int mismatchNum, int editDist, int x0, int x1, int gapOpen, int gapExt,
+                 const std::string &md, int mapq, const char *readGroup, bool printMDNM)
+{
+    d.clear();
+    r.bin = 0;                                           // bam_reg2bin(0, 0): the end wraps below 0, no level contains the interval
+    r.l_qseq = readlen;
+    r.l_qname = (uint8_t)(strlen(name) + 1);
+    r.qual = unmapped ? 0 : (uint8_t)mapq;
+    d.insert(d.end(), (const uint8_t *)name, (const uint8_t *)name + strlen(name) + 1);
+    r.n_cigar = 0;
+    if (!unmapped) {
+        if (cigar) {
+            // AssignCigarStrToSAMIU (BGS-IO.cpp:177-201)
+            int num = 0;
+            for (char c : *cigar) {
+                if (c >= '0' && c <= '9') num = num * 10 + c - '0';
+                else if (num > 0) { const uint32_t op = c == 'M' ? 0u : c == 'I' ? 1u : c == 'D' ? 2u : 4u; put32(d, ((uint32_t)num << 4) | op); ++r.n_cigar; num = 0; }
+            }
+        } else { r.n_cigar = 1; put32(d, (uint32_t)readlen << 4); }
+    }
+    if (strand == 2) {
+        if (readlen % 2 == 1) {
+            for (int i = (readlen - 1) / 2; i > 0; --i) d.push_back((uint8_t)((kNt16[3 - seq[i * 2]] << 4) | kNt16[3 - seq[i * 2 - 1]]));
+            d.push_back((uint8_t)(kNt16[3 - seq[0]] << 4));
+        } else {
+            for (int i = readlen / 2 - 1; i >= 0; --i) d.push_back((uint8_t)((kNt16[3 - seq[i * 2 + 1]] << 4) | kNt16[3 - seq[i * 2]]));
+        }
+        for (int i = readlen - 1; i >= 0; --i) d.push_back((uint8_t)qual[i]);
+    } else {
+        for (int i = 0; i < readlen / 2; ++i) d.push_back((uint8_t)((kNt16[seq[i * 2]] << 4) | kNt16[seq[i * 2 + 1]]));
+        if (readlen % 2 == 1) d.push_back((uint8_t)(kNt16[seq[readlen - 1]] << 4));
+        for (int i = 0; i < readlen; ++i) d.push_back((uint8_t)qual[i]);
+    }
+    const size_t auxStart = d.size();
+    put_tag(d, "RG", 'Z', readGroup, strlen(readGroup) + 1);
+    if (!unmapped) {
+        if (printMDNM && editDist >= 0) put_tag(d, "NM", 'i', &editDist, 4);
+        if (x0 >= 0) put_tag(d, "X0", 'i', &x0, 4);
+        if (x1 >= 0) put_tag(d, "X1", 'i', &x1, 4);
+        if (mismatchNum >= 0) put_tag(d, "XM", 'i', &mismatchNum, 4);
+        if (gapOpen >= 0) put_tag(d, "XO", 'i', &gapOpen, 4);
+        if (gapExt >= 0) put_tag(d, "XG", 'i', &gapExt, 4);
+        if (printMDNM && !md.empty()) put_tag(d, "MD", 'Z', md.c_str(), md.size() + 1);
+        if (!xa.empty()) put_tag(d, "XA", 'Z', xa.c_str(), xa.size() + 1);
+    }
+    r.l_aux = 2 * (int32_t)(d.size() - auxStart);       // counted by bam_aux_append and again by initializeSAMAlgnmt2 (:2277)
+}
+
+int finish(s3_sam_record &r, const std::vector<uint8_t> &d)
+{
+    r.data_len = (int32_t)d.size();
+    r.data = (uint8_t *)malloc(d.size() ? d.size() : 1);
+    if (!r.data) return S3_ENOMEM;
+    memcpy(r.data, d.data(), d.size());
+    return S3_OK;
+}
+
+}  // namespace
+
+extern "C" void s3_sam_record_free(s3_sam_record *r)
+{
+    if (!r) return;
+    free(r->data);
+    memset(r, 0, sizeof *r);
+}
+
+extern "C" int s3_sam_pair_records(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_pairing *pairs, uint32_t numPairs, int32_t bestIndex,
+                                   const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                                   int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2,
+                                   int32_t minTotalMismatch, int32_t secMinTotalMismatch, int32_t x0First, int32_t x0Second, int32_t x1First, int32_t x1Second,
+                                   int32_t numMinMismatchPair, int32_t isBestHit1, int32_t isBestHit2, uint32_t totalNumValidPairs, s3_sam_record out[2])
+{
+    if (!out) { s3_set_error("s3_sam_pair_records: NULL output"); return S3_EINVAL; }
+    memset(out, 0, 2 * sizeof(s3_sam_record));
+    if (!g || !cfg || !query1 || !query2 || !qualities1 || !qualities2 || !queryName1 || !queryName2 || !cfg->readGroup || (numPairs && !pairs) ||
+        readlen1 <= 0 || readlen2 <= 0 || bestIndex >= (int32_t)numPairs) { s3_set_error("s3_sam_pair_records: bad argument"); return S3_EINVAL; }
+    if (bestIndex >= 0 && (!g->packedDNA || !g->segments || !g->ambiguityMap || !g->chrEndPos || !g->chrNames || g->numSegments == 0)) {
+        s3_set_error("s3_sam_pair_records: incomplete genome description"); return S3_EINVAL;
+    }
+    std::vector<uint8_t> d;
+    const std::string none;
+    int rc;
+    if (bestIndex < 0) {
+        // no pair reported: both reads unmapped (BGS-IO.cpp:3748-3787)
+        for (int k = 0; k < 2; ++k) {
+            s3_sam_record &r = out[k];
+            record_body(r, d, k ? readlen2 : readlen1, k ? queryName2 : queryName1, k ? query2 : query1, k ? qualities2 : qualities1, 1, none, NULL, true,
+                        0, 0, 0, 0, 0, 0, none, 0, cfg->readGroup, false);
+            r.flag = (uint16_t)(1 | (k ? 128 : 64) | 4 | 8);
+            r.tid = r.pos = r.mtid = r.mpos = -1; r.isize = 0;
+            if ((rc = finish(r, d))) { s3_sam_record_free(&out[0]); s3_sam_record_free(&out[1]); s3_set_error("s3_sam_pair_records: out of host memory"); return rc; }
+        }
+        return S3_OK;
+    }
+    const s3_sam_pairing &best = pairs[bestIndex];
+    unsigned long long tp[2];
+    uint32_t chr[2];
+    std::string newCigar[2], md[2];
+    int avgQual[2], bestMismatch[2], mapq[2];
+    const int trim1 = chr_and_pos_checked(g, (uint32_t)readlen1, best.algnmt1, &tp[0], &chr[0], newCigar[0]);
+    const int trim2 = chr_and_pos_checked(g, (uint32_t)readlen2, best.algnmt2, &tp[1], &chr[1], newCigar[1]);
+    md_string(g, query1, qualities1, (uint32_t)readlen1, best.algnmt1, best.strand1, (int8_t)best.mismatch1, trim1, md[0], &avgQual[0]);
+    md_string(g, query2, qualities2, (uint32_t)readlen2, best.algnmt2, best.strand2, (int8_t)best.mismatch2, trim2, md[1], &avgQual[1]);
+    bestMismatch[0] = (int8_t)best.mismatch1; bestMismatch[1] = (int8_t)best.mismatch2;
+    const int trims[2] = {trim1, trim2};
+    for (int k = 0; k < 2; ++k)
+        if (trims[k] && bestMismatch[k]) { bestMismatch[k] = 0; for (char c : md[k]) bestMismatch[k] += c > '9'; }
+    const int8_t minTot = (int8_t)minTotalMismatch, secMinTot = (int8_t)secMinTotalMismatch;
+    if (cfg->alignmentType == 1 || cfg->alignmentType == 2) {           // OUTPUT_ALL_VALID / OUTPUT_ALL_BEST
+        if (cfg->bwaLikeScore) {
+            const int op = (readlen1 + readlen2 - minTot) * cfg->dpMatchScore + minTot * cfg->dpMisMatchScore;
+            const int subop = (readlen1 + readlen2 - secMinTot) * cfg->dpMatchScore + secMinTot * cfg->dpMisMatchScore;
+            // (unsigned arithmetic like the reference: totalNumValidPairs is unsigned there)
+            const int subopNum = (totalNumValidPairs - (uint32_t)numMinMismatchPair) > 0 ? (int)(totalNumValidPairs - (uint32_t)numMinMismatchPair) : 0;
+            s3_mapq_bwa_pair(x0First, x1First, x0Second, x1Second, op, numMinMismatchPair, subop, subopNum, readlen1, readlen2, &mapq[0], &mapq[1]);
+        } else {
+            const int s1 = s3_mapq_pair_end((int8_t)best.mismatch1, cfg->isFastq == 1 ? avgQual[0] : 20, x0First, x1First, (char)isBestHit1, totalNumValidPairs, cfg->maxMAPQ, cfg->minMAPQ);
+            const int s2 = s3_mapq_pair_end((int8_t)best.mismatch2, cfg->isFastq == 1 ? avgQual[1] : 20, x0Second, x1Second, (char)isBestHit2, totalNumValidPairs, cfg->maxMAPQ, cfg->minMAPQ);
+            mapq[0] = mapq[1] = s3_mapq_of_pair(s1, s2);
+        }
+        if (trim1) mapq[0] = 0;
+        if (trim2) mapq[1] = 0;
+    } else mapq[0] = mapq[1] = 255;                                       // SAM_MAPQ_UNAVAILABLE
+    const int readlen[2] = {readlen1, readlen2};
+    for (int k = 0; k < 2; ++k) {
+        // XA:Z: the other pairs with no more mismatches than the best, in list order, up to peMaxOutputPerPair results in all
+        std::string xa;
+        if (cfg->outputXAZTag == 1) {
+            uint32_t total = 1;
+            char num[24];
+            for (uint32_t i = 0; i < numPairs && total < cfg->peMaxOutputPerPair; ++i) {
+                if ((int32_t)i == bestIndex || pairs[i].totalMismatchCount > minTot) continue;
+                unsigned long long t;
+                uint32_t c;
+                chr_and_pos(g, k ? pairs[i].algnmt2 : pairs[i].algnmt1, &t, &c);
+                xa += g->chrNames[c - 1];
+                xa.push_back(',');
+                xa.push_back((k ? pairs[i].strand2 : pairs[i].strand1) == 2 ? '-' : '+');
+                xa.append(num, write_num((long long)t, num));
+                xa.push_back(',');
+                xa.append(num, write_num(readlen[k], num));
+                xa += "M,";
+                xa.append(num, write_num((int)(int8_t)(k ? pairs[i].mismatch2 : pairs[i].mismatch1), num));
+                xa.push_back(';');
+                ++total;
+            }
+        }
+        s3_sam_record &r = out[k];
+        const int strand = k ? best.strand2 : best.strand1, mateStrand = k ? best.strand1 : best.strand2;
+        record_body(r, d, readlen[k], k ? queryName2 : queryName1, k ? query2 : query1, k ? qualities2 : qualities1, strand, xa,
+                    newCigar[k].empty() ? NULL : &newCigar[k], false, bestMismatch[k], bestMismatch[k], k ? x0Second : x0First, k ? x1Second : x1First, 0, 0,
+                    md[k], mapq[k], cfg->readGroup, cfg->isPrintMDNM != 0);
+        r.flag = (uint16_t)(1 | 2 | (k ? 128 : 64) | (strand == 2 ? 16 : 0) | (mateStrand == 2 ? 32 : 0));
+        r.tid = (int32_t)chr[k] - 1; r.pos = (int32_t)(tp[k] - 1);
+        r.mtid = (int32_t)chr[1 - k] - 1; r.mpos = (int32_t)(tp[1 - k] - 1);
+        if (chr[0] == chr[1]) {
+            const unsigned long long me = tp[k], mate = tp[1 - k];
+            r.isize = mate > me ? (int32_t)(mate + (unsigned)readlen[1 - k] - me) : -(int32_t)(me + (unsigned)readlen[k] - mate);
+        } else r.isize = 0;
+        if ((rc = finish(r, d))) { s3_sam_record_free(&out[0]); s3_sam_record_free(&out[1]); s3_set_error("s3_sam_pair_records: out of host memory"); return rc; }
+    }
+    return S3_OK;
+}

@@ -1,0 +1,150 @@
+"""CPU tier: s3_sam_pair_records (host entry) against the reference's own pairOutputSAMAPI and everything it calls, compiled from
+where it lies into oracle/_ref/libref_sam.so with a samwrite that keeps the records (oracle/ref_shim/ref_sam_host.cpp)."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+
+import helpers
+from helpers import ROOT, U32P
+from soap3dp_b200 import api
+
+U8P = C.POINTER(C.c_uint8)
+I32P = C.POINTER(C.c_int32)
+REF = os.path.join(ROOT, "oracle", "_ref", "libref_sam.so")
+
+
+class Segment(C.Structure):
+    _fields_ = [("startPos", C.c_uint32), ("chrID", C.c_uint32), ("correction", C.c_uint32)]
+
+
+class Genome(C.Structure):
+    _fields_ = [("packedDNA", U32P), ("dnaLength", C.c_uint32), ("segments", C.POINTER(Segment)), ("numSegments", C.c_uint32),
+                ("ambiguityMap", U32P), ("chrEndPos", U32P), ("numChr", C.c_uint32), ("chrNames", C.POINTER(C.c_char_p))]
+
+
+class Config(C.Structure):
+    _fields_ = [("alignmentType", C.c_int32), ("bwaLikeScore", C.c_int32), ("dpMatchScore", C.c_int32), ("dpMisMatchScore", C.c_int32),
+                ("isFastq", C.c_int32), ("maxMAPQ", C.c_int32), ("minMAPQ", C.c_int32), ("isPrintMDNM", C.c_int32), ("outputXAZTag", C.c_int32),
+                ("peMaxOutputPerPair", C.c_uint32), ("readGroup", C.c_char_p)]
+
+
+class Pairing(C.Structure):
+    _fields_ = [("algnmt1", C.c_uint32), ("algnmt2", C.c_uint32), ("strand1", C.c_uint8), ("mismatch1", C.c_uint8), ("strand2", C.c_uint8),
+                ("mismatch2", C.c_uint8), ("totalMismatchCount", C.c_int8), ("pad", C.c_uint8 * 3)]
+
+
+class Record(C.Structure):
+    _fields_ = [("tid", C.c_int32), ("pos", C.c_int32), ("bin", C.c_uint16), ("qual", C.c_uint8), ("l_qname", C.c_uint8), ("flag", C.c_uint16),
+                ("n_cigar", C.c_uint16), ("l_qseq", C.c_int32), ("mtid", C.c_int32), ("mpos", C.c_int32), ("isize", C.c_int32), ("l_aux", C.c_int32),
+                ("data_len", C.c_int32), ("data", U8P)]
+
+
+def product_records(lib, gen, cfg, pairs, best, q1, q2, ql1, ql2, n1, n2, counts):
+    arr = (Pairing * max(len(pairs), 1))()
+    for k, p in enumerate(pairs):
+        arr[k] = Pairing(p[0], p[3], p[1], p[2], p[4], p[5], p[6])
+    out = (Record * 2)()
+    lib.s3_sam_pair_records.restype = C.c_int
+    rc = lib.s3_sam_pair_records(C.byref(gen), C.byref(cfg), arr, len(pairs), best, q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P),
+                                 ql1.ctypes.data_as(C.c_char_p), ql2.ctypes.data_as(C.c_char_p), len(q1), len(q2), n1, n2, *counts, out)
+    assert rc == 0, api.last_error() if hasattr(api, "last_error") else rc
+    res = []
+    for r in out:
+        core = (r.tid, r.pos, r.bin, r.qual, r.l_qname, r.flag, r.n_cigar, r.l_qseq, r.mtid, r.mpos, r.isize, r.l_aux)
+        res.append((core, bytes(bytearray(r.data[:r.data_len]))))
+    lib.s3_sam_record_free.restype = None
+    for k in range(2):
+        lib.s3_sam_record_free(C.byref(out[k]))
+    return res
+
+
+def reference_records(ref, g, cfg, pairs, best, q1, q2, ql1, ql2, n1, n2, counts):
+    flat = np.array([x for p in pairs for x in p], np.uint32) if pairs else np.zeros(7, np.uint32)
+    core = np.zeros(24, np.int32)
+    cap = 8192
+    data = np.zeros(2 * cap, np.uint8)
+    dlen = np.zeros(2, np.int32)
+    names = (C.c_char_p * len(g["names"]))(*g["names"])
+    ref.ref_sam_pair.restype = C.c_int
+    n = ref.ref_sam_pair(helpers.u32p(g["pac"]), g["n"], helpers.u32p(g["translate"]), len(g["translate"]) // 3, helpers.u32p(g["amb"]),
+                         helpers.u32p(g["chr_end"]), len(g["chr_end"]), names,
+                         cfg.alignmentType, cfg.bwaLikeScore, cfg.dpMatchScore, cfg.dpMisMatchScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM,
+                         cfg.readGroup, cfg.outputXAZTag, cfg.peMaxOutputPerPair, helpers.u32p(flat), len(pairs), best,
+                         q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p), ql2.ctypes.data_as(C.c_char_p), len(q1), len(q2), n1, n2,
+                         *counts, core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), cap, dlen.ctypes.data_as(I32P))
+    assert n == 2
+    return [(tuple(int(x) for x in core[12 * r:12 * r + 12]), bytes(data[r * cap:r * cap + int(dlen[r])])) for r in range(2)]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_sam.so not built")
+def test_sam_pair_records_match_the_reference_writer():
+    ref = C.CDLL(REF)
+    lib = api.load_library()
+    rng = np.random.default_rng(11)
+    n = 200_000
+    G = rng.integers(0, 4, n).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    # three chromosomes; the second one in two segments (500 ambiguous bases were removed between them)
+    starts = [0, 70_000, 100_000, 150_000]
+    translate = np.array([0, 1, 0xFFFFFFFF,                      # tp = pos + 1
+                          70_000, 2, 70_000 - 1,
+                          100_000, 2, 70_000 - 1 - 500,
+                          150_000, 3, 150_000 - 1], np.uint32)
+    chr_end = np.array([69_999, 149_999, 199_999], np.uint32)
+    amb = np.full(4, 3, np.uint32)
+    names = [b"chr1", b"chrTwo", b"3"]
+    g = dict(pac=pac, n=n, translate=translate, amb=amb, chr_end=chr_end, names=names)
+    segs = (Segment * 4)(*[Segment(int(translate[3 * i]), int(translate[3 * i + 1]), int(translate[3 * i + 2])) for i in range(4)])
+    gen = Genome(helpers.u32p(pac), n, segs, 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, (C.c_char_p * 3)(*names))
+    trimmed = unmapped = with_xa = 0
+    for trial in range(1500):
+        L1, L2 = int(rng.integers(36, 152)), int(rng.integers(36, 152))
+        cfg = Config(int(rng.integers(1, 5)), int(rng.integers(0, 2)), 1, -2, int(rng.integers(0, 2)), 40, 1, int(rng.integers(0, 2)), int(rng.integers(0, 2)),
+                     int(rng.choice([1, 2, 5, 1000])), b"grp%d" % trial)
+        # the reported pairing: positions near ends of chromosomes / segments now and then
+        edges = [70_000, 100_000, 150_000, 200_000]
+        def place(L):
+            if rng.random() < 0.25:
+                e = int(rng.choice(edges))
+                return max(0, min(n - L, e - int(rng.integers(1, L))))
+            return int(rng.integers(0, n - L))
+        p1, p2 = place(L1), place(L2)
+        if rng.random() < 0.6:
+            p2 = max(0, min(n - L2, p1 + int(rng.integers(-400, 400))))
+        s1, s2 = int(rng.integers(1, 3)), int(rng.integers(1, 3))
+
+        def read_at(p, L, s, nm):
+            r = G[p:p + L].copy()
+            for k in rng.choice(L, nm, replace=False):
+                r[k] = (r[k] + int(rng.integers(1, 4))) & 3
+            return np.ascontiguousarray((3 - r[::-1]) if s == 2 else r).astype(np.uint8)
+        m1, m2 = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+        q1, q2 = read_at(p1, L1, s1, m1), read_at(p2, L2, s2, m2)
+        ql1 = np.ascontiguousarray(rng.integers(2, 41, L1 + 1).astype(np.uint8)); ql1[-1] = 0
+        ql2 = np.ascontiguousarray(rng.integers(2, 41, L2 + 1).astype(np.uint8)); ql2[-1] = 0
+        pairs = [(p1, s1, m1, p2, s2, m2, m1 + m2)]
+        for _ in range(int(rng.integers(0, 6))):
+            a, b = int(rng.integers(0, n - L1)), int(rng.integers(0, n - L2))
+            x, y = int(rng.integers(0, 4)), int(rng.integers(0, 4))
+            pairs.append((a, int(rng.integers(1, 3)), x, b, int(rng.integers(1, 3)), y, x + y))
+        order = rng.permutation(len(pairs))
+        pairs = [pairs[k] for k in order]
+        best = int(np.where(order == 0)[0][0])
+        if rng.random() < 0.05:
+            best = -1
+            unmapped += 1
+        tot = sorted(p[6] for p in pairs)
+        min_tot = m1 + m2 if rng.random() < 0.8 else tot[0]
+        sec = [t for t in tot if t > min_tot]
+        counts = (min_tot, sec[0] if sec else 127, int(rng.integers(0, 5)), int(rng.integers(0, 5)), int(rng.integers(0, 300)), int(rng.integers(0, 300)),
+                  int(rng.integers(1, 4)), int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(1, 6)))
+        n1, n2 = b"read%d/1" % trial, b"read%d/2" % trial
+        got = product_records(lib, gen, cfg, pairs, best, q1, q2, ql1, ql2, n1, n2, counts)
+        want = reference_records(ref, g, cfg, pairs, best, q1, q2, ql1, ql2, n1, n2, counts)
+        assert got == want, (trial, got, want)
+        if best >= 0:
+            trimmed += any(b"S" in w[1] or w[0][6] == 2 for w in want)
+            with_xa += any(b"XAZ" in w[1] for w in want)
+    assert trimmed > 20 and unmapped > 20 and with_xa > 100

@@ -865,7 +865,8 @@ class SingleAligner:
         _check(lib.s3_se_create(gpu_index.handle, max_reads, C.byref(par), C.byref(out)), "s3_se_create")
         self.handle = out
 
-    def align(self, queries, read_lengths, num_reads: int, word_per_query: int):
+    def align(self, queries, read_lengths, num_reads: int, word_per_query: int, copy: bool = True):
+        """-> dict of numpy arrays (copies; with copy=False views of the handle's host buffers, valid until the next call)"""
         res = SEResult()
         q = queries.ctypes.data if hasattr(queries, "ctypes") else int(queries)
         l = read_lengths.ctypes.data if hasattr(read_lengths, "ctypes") else int(read_lengths)
@@ -875,7 +876,8 @@ class SingleAligner:
             if not ptr or n == 0:
                 return np.zeros(0, dtype)
             buf = (C.c_char * (n * np.dtype(dtype).itemsize)).from_address(ptr)
-            return np.frombuffer(buf, dtype=dtype, count=n).copy()
+            a = np.frombuffer(buf, dtype=dtype, count=n)
+            return a.copy() if copy else a
         n, t = int(res.numReads), int(res.numOccurrences)
         return {"occ_offsets": view(res.occOffsets, np.uint32, n + 1), "positions": view(res.positions, np.uint32, t),
                 "occ_flags": view(res.occFlags, np.uint8, 2 * t).reshape(-1, 2), "read_flags": view(res.readFlags, np.uint8, n),
@@ -958,7 +960,7 @@ def stage_params(insert_low=200, insert_high=500, left_leg=1, right_leg=2, score
     return StageParams(insert_low, insert_high, left_leg, right_leg, DPScores(*scores), int(default_threshold), threshold, soft_clip_left, soft_clip_right)
 
 
-def _stage_align(fn_name, free_name, dtype, gpu_index, queries, read_lengths, num_reads, word_per_query, ids, params):
+def _stage_align(fn_name, free_name, dtype, gpu_index, queries, read_lengths, num_reads, word_per_query, ids, params, counts_only=False):
     lib = load_library()
     fn, fr = getattr(lib, fn_name), getattr(lib, free_name)
     fn.restype = C.c_int
@@ -974,20 +976,26 @@ def _stage_align(fn_name, free_name, dtype, gpu_index, queries, read_lengths, nu
             return np.zeros(0, dt)
         buf = (C.c_char * (n * np.dtype(dt).itemsize)).from_address(ptr)
         return np.frombuffer(buf, dtype=dt, count=n).copy()
-    out = {"hits": view(res.hits, dtype, int(res.numHits)), "runs": view(res.runs, np.uint32, int(res.numRuns)),
-           "unseeded": view(res.unseeded, np.uint32, int(res.numUnseeded)), "num_seeds": int(res.numSeeds), "num_candidates": int(res.numCandidates)}
+    if counts_only:                    # (timing loops: the C entry has done all its work, the arrays are not copied into numpy)
+        out = {"num_hits": int(res.numHits), "num_runs": int(res.numRuns), "num_unseeded": int(res.numUnseeded), "num_seeds": int(res.numSeeds),
+               "num_candidates": int(res.numCandidates)}
+    else:
+        out = {"hits": view(res.hits, dtype, int(res.numHits)), "runs": view(res.runs, np.uint32, int(res.numRuns)),
+               "unseeded": view(res.unseeded, np.uint32, int(res.numUnseeded)), "num_seeds": int(res.numSeeds), "num_candidates": int(res.numCandidates)}
     fr(C.byref(res))
     return out
 
 
-def single_dp_align(gpu_index: GpuIndex, queries, read_lengths, num_reads: int, word_per_query: int, read_ids, params: StageParams):
+def single_dp_align(gpu_index: GpuIndex, queries, read_lengths, num_reads: int, word_per_query: int, read_ids, params: StageParams, counts_only=False):
     """s3_single_dp_align (DPForUnalignSingle2, DV-DPForSingleReads.cu:155)"""
-    return _stage_align("s3_single_dp_align", "s3_single_dp_result_free", DP_HIT_DTYPE, gpu_index, queries, read_lengths, num_reads, word_per_query, read_ids, params)
+    return _stage_align("s3_single_dp_align", "s3_single_dp_result_free", DP_HIT_DTYPE, gpu_index, queries, read_lengths, num_reads, word_per_query, read_ids, params,
+                        counts_only)
 
 
-def deep_dp_align(gpu_index: GpuIndex, queries, read_lengths, num_reads: int, word_per_query: int, pair_read_ids, params: StageParams):
+def deep_dp_align(gpu_index: GpuIndex, queries, read_lengths, num_reads: int, word_per_query: int, pair_read_ids, params: StageParams, counts_only=False):
     """s3_deep_dp_align (DPForUnalignPairs2, DV-DPForBothUnalign.cu:245)"""
-    return _stage_align("s3_deep_dp_align", "s3_deep_dp_result_free", DEEP_HIT_DTYPE, gpu_index, queries, read_lengths, num_reads, word_per_query, pair_read_ids, params)
+    return _stage_align("s3_deep_dp_align", "s3_deep_dp_result_free", DEEP_HIT_DTYPE, gpu_index, queries, read_lengths, num_reads, word_per_query, pair_read_ids, params,
+                        counts_only)
 
 
 def set_l2_persist(gpu_index: GpuIndex, region: int, window_bytes: int = 0, persist_bytes: int = 0):

@@ -330,7 +330,7 @@ static int s3_pair_side(s3_index *ix, const uint32_t *const in[7], uint64_t n, u
     size_t t1 = 0, t2 = 0;
     s3_u64 total = 0;
     out->keys = NULL; out->len = out->rev = 0;
-    S3_TRY(cudaMalloc(&d_in, 7 * rB + (n + 1) * 8 + 16));
+    S3_TRY(cudaMallocAsync(&d_in, 7 * rB + (n + 1) * 8 + 16, st));
     {
         uint32_t *d[7];
         for (int a = 0; a < 7; ++a) {
@@ -342,28 +342,28 @@ static int s3_pair_side(s3_index *ix, const uint32_t *const in[7], uint64_t n, u
         s3_seed_count_kernel<<<(unsigned)((n + 256) / 256), 256, 0, st>>>(d[0], d[1], n, maxPerRange, d_cnt);
         S3_LAUNCHED(1);
         cub::DeviceScan::ExclusiveSum(NULL, t1, d_cnt, d_cnt, (int)(n + 1), st);
-        S3_TRY(cudaMalloc(&d_tmp, t1));
+        S3_TRY(cudaMallocAsync(&d_tmp, t1, st));
         S3_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, t1, d_cnt, d_cnt, (int)(n + 1), st));
         S3_TRY(cudaMemcpyAsync(&total, d_cnt + n, 8, cudaMemcpyDeviceToHost, st));
         S3_TRY(cudaStreamSynchronize(st));
-        cudaFree(d_tmp); d_tmp = NULL;
+        cudaFreeAsync(d_tmp, st); d_tmp = NULL;
         if (total + 2 >= 0x7FFFFFFFull) { s3_set_error("s3_seed_pair_candidates: %llu positions in one call", total); rc = S3_EINVAL; goto done; }
         const size_t T = (size_t)total + 2;
-        S3_TRY(cudaMalloc(&k0, T * 8)); S3_TRY(cudaMalloc(&k1, T * 8));
+        S3_TRY(cudaMallocAsync(&k0, T * 8, st)); S3_TRY(cudaMallocAsync(&k1, T * 8, st));
         s3_pair_fill_kernel<<<(unsigned)(((n + 1) * 32 + 255) / 256), 256, 0, st>>>(ix->loc.sa, d[0], d[1], (const int32_t *)d[2], d[3], d[4], d[5], d[6],
                                                                                        n, maxPerRange, d_cnt, total, k0);
         S3_LAUNCHED(1);
         cub::DeviceRadixSort::SortKeys(NULL, t2, k0, k1, (int)T, 0, 64, st);
-        S3_TRY(cudaMalloc(&d_tmp, t2));
+        S3_TRY(cudaMallocAsync(&d_tmp, t2, st));
         S3_TRY(cub::DeviceRadixSort::SortKeys(d_tmp, t2, k0, k1, (int)T, 0, 64, st));
         S3_TRY(cudaStreamSynchronize(st));
         out->keys = k1; k1 = NULL; out->len = (uint32_t)T;
     }
 done:
-    if (d_in) cudaFree(d_in);
-    if (d_tmp) cudaFree(d_tmp);
-    if (k0) cudaFree(k0);
-    if (k1) cudaFree(k1);
+    if (d_in) cudaFreeAsync(d_in, st);
+    if (d_tmp) cudaFreeAsync(d_tmp, st);
+    if (k0) cudaFreeAsync(k0, st);
+    if (k1) cudaFreeAsync(k1, st);
     return rc;
 }
 
@@ -405,7 +405,7 @@ extern "C" int s3_seed_pair_candidates(s3_index *ix,
 }
 
 // onDevice: the range arrays and lengthsByReadID are device arrays, and the three output pointers receive device arrays: the first
-// one (*candReadIDLeft) is the base of one allocation the caller returns with cudaFree.
+// one (*candReadIDLeft) is the base of one allocation the caller returns with cudaFreeAsync on the index stream.
 int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint64_t n0, const uint32_t *const in1[7], uint64_t n1, int onDevice,
                                 uint32_t maxPerRange, const uint32_t *lengthsByReadID, uint64_t numReadIDs,
                                 int insertLow, int insertHigh, int peStrandLeftLeg, int peStrandRightLeg,
@@ -426,7 +426,7 @@ int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint
     if ((rc = s3_pair_side(ix, in1, n1, maxPerRange, onDevice, &side[1]))) goto done;
     clk.lap("two sides: gather + sort");
     {
-        S3_TRY(cudaMalloc(&d_len, numReadIDs * 4 + 16));
+        S3_TRY(cudaMallocAsync(&d_len, numReadIDs * 4 + 16, st));
         S3_TRY(cudaMemcpyAsync(d_len, lengthsByReadID, numReadIDs * 4, onDevice ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, st));
         uint32_t *d_rev = d_len + numReadIDs;
         for (int s = 0; s < 2; ++s) s3_pair_revstart_kernel<<<1, 1, 0, st>>>(side[s].keys, side[s].len, d_rev + s);
@@ -435,10 +435,10 @@ int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint
         S3_TRY(cudaStreamSynchronize(st));
         side[0].rev = rev[0]; side[1].rev = rev[1];
         const uint32_t maxLen = side[0].len > side[1].len ? side[0].len : side[1].len;
-        S3_TRY(cudaMalloc(&d_counts, ((size_t)maxLen + 1) * 8));                   // only to size the scan's temporary storage
+        S3_TRY(cudaMallocAsync(&d_counts, ((size_t)maxLen + 1) * 8, st));                   // only to size the scan's temporary storage
         size_t tScan = 0;
         cub::DeviceScan::ExclusiveSum(NULL, tScan, d_counts, d_counts, (int)(maxLen + 1), st);
-        S3_TRY(cudaMalloc(&d_tmp, tScan));
+        S3_TRY(cudaMallocAsync(&d_tmp, tScan, st));
         // segment of an end's array that holds strand index si: [0, rev) or [rev, len)
         auto seg = [&](int s, int si, uint32_t &lo, uint32_t &hi) { lo = si ? side[s].rev : 0u; hi = si ? side[s].len : side[s].rev; };
         // the two calls (DV-DPfunctions.cu:2987-2988): read left / mate right, then mate left / read right.  Counting of
@@ -447,12 +447,12 @@ int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint
         uint32_t *groupEnd[2], *rightStart[2];
         s3_u64 *counts[2] = {NULL, NULL};
         uint32_t *ge_all = NULL;
-        S3_TRY(cudaMalloc(&ge_all, ((size_t)side[0].len + side[1].len) * 8 + 16));
+        S3_TRY(cudaMallocAsync(&ge_all, ((size_t)side[0].len + side[1].len) * 8 + 16, st));
         groupEnd[0] = ge_all; rightStart[0] = ge_all + side[0].len;
         groupEnd[1] = ge_all + 2 * (size_t)side[0].len; rightStart[1] = groupEnd[1] + side[1].len;
         s3_u64 *cnt_all = NULL;
-        cudaError_t e2 = cudaMalloc(&cnt_all, ((size_t)side[0].len + side[1].len + 2) * 8);
-        if (e2 != cudaSuccess) { cudaFree(ge_all); s3_set_error("s3_seed_pair_candidates: %s", cudaGetErrorString(e2)); rc = S3_ECUDA; goto done; }
+        cudaError_t e2 = cudaMallocAsync((void **)&cnt_all, ((size_t)side[0].len + side[1].len + 2) * 8, st);
+        if (e2 != cudaSuccess) { cudaFreeAsync(ge_all, st); s3_set_error("s3_seed_pair_candidates: %s", cudaGetErrorString(e2)); rc = S3_ECUDA; goto done; }
         counts[0] = cnt_all; counts[1] = cnt_all + side[0].len + 1;
         bool ok = true;
         for (int call = 0; call < 2 && ok; ++call) {
@@ -475,7 +475,7 @@ int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint
             if (cudaStreamSynchronize(st) != cudaSuccess) { ok = false; break; }
             if (call == 0) {
                 // room for call 0's candidates now; call 1's are appended after its own count
-                if (tot[0] && cudaMalloc(&d_out, (size_t)tot[0] * 12) != cudaSuccess) { ok = false; break; }
+                if (tot[0] && cudaMallocAsync((void **)&d_out, (size_t)tot[0] * 12, st) != cudaSuccess) { ok = false; break; }
                 if (tot[0]) {
                     s3_pair_join_kernel<true><<<(nL + 1 + 255) / 256, 256, 0, st>>>(side[ls].keys, lo[0], hi[0], side[rs].keys, groupEnd[0], rightStart[0], d_len,
                                                                                    insertLow, insertHigh, 0u, counts[0], d_out, d_out + tot[0], d_out + 2 * tot[0]);
@@ -489,7 +489,7 @@ int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint
         if (ok && m >= 0x7FFFFFFFull) { s3_set_error("s3_seed_pair_candidates: %llu candidates in one call", m); rc = S3_EINVAL; ok = false; }
         if (ok && m) {
             // all candidates in one place: ids | left | right, call 0's first
-            ok = cudaMalloc(&d_all, (size_t)m * 12) == cudaSuccess;
+            ok = cudaMallocAsync((void **)&d_all, (size_t)m * 12, st) == cudaSuccess;
             if (ok && tot[0]) {
                 ok = cudaMemcpyAsync(d_all, d_out, (size_t)tot[0] * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess &&
                      cudaMemcpyAsync(d_all + m, d_out + tot[0], (size_t)tot[0] * 4, cudaMemcpyDeviceToDevice, st) == cudaSuccess &&
@@ -504,12 +504,12 @@ int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint
             // stable sort by readIDLeft (MC_RadixSort_32_16 on candArr, DV-DPfunctions.cu:2997)
             size_t tSort = 0;
             void *d_t2 = NULL;
-            if (ok) ok = cudaMalloc(&d_sorted, (size_t)m * 20) == cudaSuccess;      // ids out | order in | order out | left out | right out
+            if (ok) ok = cudaMallocAsync((void **)&d_sorted, (size_t)m * 20, st) == cudaSuccess;      // ids out | order in | order out | left out | right out
             if (ok) {
                 uint32_t *idsOut = d_sorted, *ordIn = d_sorted + m, *ordOut = d_sorted + 2 * m, *lOut = d_sorted + 3 * m, *rOut = d_sorted + 4 * m;
                 s3_iota_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ordIn, m);
                 cub::DeviceRadixSort::SortPairs(NULL, tSort, d_all, idsOut, ordIn, ordOut, (int)m, 0, 32, st);
-                ok = cudaMalloc(&d_t2, tSort) == cudaSuccess &&
+                ok = cudaMallocAsync((void **)&d_t2, tSort, st) == cudaSuccess &&
                      cub::DeviceRadixSort::SortPairs(d_t2, tSort, d_all, idsOut, ordIn, ordOut, (int)m, 0, 32, st) == cudaSuccess;
                 if (ok) {
                     s3_pair_gather_kernel<<<(unsigned)((m + 255) / 256), 256, 0, st>>>(ordOut, m, d_all + m, d_all + 2 * m, lOut, rOut);
@@ -525,26 +525,26 @@ int s3_seed_pair_candidates_any(s3_index *ix, const uint32_t *const in0[7], uint
                                  cudaMemcpyAsync(h[2], rOut, (size_t)m * 4, cudaMemcpyDeviceToHost, st) == cudaSuccess &&
                                  cudaStreamSynchronize(st) == cudaSuccess;
                 }
-                if (d_t2) cudaFree(d_t2);
+                if (d_t2) cudaFreeAsync(d_t2, st);
             }
         }
         clk.lap("fill + final sort");
         if (ok && cudaGetLastError() != cudaSuccess) ok = false;
-        cudaFree(ge_all); cudaFree(cnt_all);
-        if (d_all) cudaFree(d_all);
+        cudaFreeAsync(ge_all, st); cudaFreeAsync(cnt_all, st);
+        if (d_all) cudaFreeAsync(d_all, st);
         if (!ok) { if (rc == S3_OK) { s3_set_error("s3_seed_pair_candidates: a CUDA call failed: %s", cudaGetErrorString(cudaGetLastError())); rc = S3_ECUDA; } goto done; }
         if (m && !onDevice) { *candReadIDLeft = h[0]; *candPosLeft = h[1]; *candPosRight = h[2]; h[0] = h[1] = h[2] = NULL; }
         *numCandidates = m;
     }
 done:
     clk.lap("frees");
-    for (int s = 0; s < 2; ++s) if (side[s].keys) cudaFree(side[s].keys);
-    if (d_len) cudaFree(d_len);
-    if (d_aux) cudaFree(d_aux);
-    if (d_counts) cudaFree(d_counts);
-    if (d_out) cudaFree(d_out);
-    if (d_sorted) cudaFree(d_sorted);
-    if (d_tmp) cudaFree(d_tmp);
+    for (int s = 0; s < 2; ++s) if (side[s].keys) cudaFreeAsync(side[s].keys, st);
+    if (d_len) cudaFreeAsync(d_len, st);
+    if (d_aux) cudaFreeAsync(d_aux, st);
+    if (d_counts) cudaFreeAsync(d_counts, st);
+    if (d_out) cudaFreeAsync(d_out, st);
+    if (d_sorted) cudaFreeAsync(d_sorted, st);
+    if (d_tmp) cudaFreeAsync(d_tmp, st);
     for (int a = 0; a < 3; ++a) free(h[a]);
     return rc;
 }

@@ -110,9 +110,13 @@ namespace {
 // S3_STAGE_TIMING=1: wall-clock milliseconds of every step of a stage call on stderr (tuning aid)
 struct StageClock {
     bool on;
-    std::chrono::steady_clock::time_point t;
+    std::chrono::steady_clock::time_point t, t0;
     const char *what;
-    explicit StageClock(const char *w) : on(getenv("S3_STAGE_TIMING") != NULL), t(std::chrono::steady_clock::now()), what(w) {}
+    explicit StageClock(const char *w) : on(getenv("S3_STAGE_TIMING") != NULL), t(std::chrono::steady_clock::now()), t0(t), what(w) {}
+    ~StageClock()
+    {
+        if (on) fprintf(stderr, "[%s] %-28s %8.2f ms\n", what, "TOTAL since entry checks", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+    }
     void lap(const char *step)
     {
         if (!on) return;
@@ -413,7 +417,7 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
             S3_TRYS(cudaStreamSynchronize(st));
             for (size_t c = base; c < base + nc; ++c) seeded[candID[c] & ~1u] = 1;
         }
-        if (d_pc) { cudaFree(d_pc); d_pc = NULL; }
+        if (d_pc) { cudaFreeAsync(d_pc, st); d_pc = NULL; }
         seed_side_free(ix, side[0]); seed_side_free(ix, side[1]);
         clk.lap("pair candidates");
         // ---- seeded / too many / unseeded pairs (performSeeding, DV-DPfunctions.cu:3105-3125)
@@ -502,7 +506,7 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
     }
 done:
     seed_side_free(ix, side[0]); seed_side_free(ix, side[1]);
-    if (d_pc) cudaFree(d_pc);
+    if (d_pc) cudaFreeAsync(d_pc, st);
     {
         void *p[] = {d_len, d_c, d_wl, d_wr, d_cnt, d_tmp};
         for (void *q : p) if (q) cudaFreeAsync(q, st);

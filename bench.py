@@ -1100,7 +1100,18 @@ def main():
     if args.impl == "reference" and rank != 0:
         return
     if world > 1 and args.impl == "ours":
-        torch.distributed.init_process_group("nccl", device_id=device)
+        # NCCL announces its version on stdout when the first communicator is made: keep stdout for the one JSON line
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            torch.distributed.init_process_group("nccl", device_id=device)
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     L = args.read_len
     genome, host = get_index(args.genome_bp, 3, device, rank, world if args.impl == "ours" else 1, args.repeat_fraction)
     threads = os.cpu_count() or 1

@@ -749,6 +749,15 @@ int s3_sam_pair_records(const s3_sam_genome *genome, const s3_sam_config *config
                         int32_t minTotalMismatch, int32_t secMinTotalMismatch, int32_t x0First, int32_t x0Second, int32_t x1First, int32_t x1Second,
                         int32_t numMinMismatchPair, int32_t isBestHit1, int32_t isBestHit2, uint32_t totalNumValidPairs, s3_sam_record out[2]);
 void s3_sam_record_free(s3_sam_record *record);
+/* OCCOutputSAMAPI (BGS-IO.cpp:5556-5772): a single read's record from its occurrence list (s3_se_align's results): the first
+ * occurrence with the fewest mismatches is reported (X0 = how many share that count; one that hangs over a chromosome /
+ * segment end gives way to the best one that does not), the others are listed in XA:Z (alignmentType OUTPUT_ALL_BEST: only
+ * those with the best count; never one that would be trimmed), X1 = the listed ones with more mismatches, MAPQ =
+ * s3_mapq_single; numOcc == 0: the unmapped record.  (The reference leaves the XA buffer of the PREVIOUS read in place when the
+ * reported occurrence is trimmed; calls here are independent, the list is empty then.) */
+typedef struct { uint32_t ambPosition; uint8_t strand, mismatchCount, pad[2]; } s3_sam_occurrence;      /* SRAOccurrence, SRACore.h:86-95 */
+int s3_sam_single_record(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_occurrence *occ, uint32_t numOcc,
+                         const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName, s3_sam_record *out);
 
 #ifdef __cplusplus
 }

@@ -273,3 +273,82 @@ extern "C" int s3_sam_pair_records(const s3_sam_genome *g, const s3_sam_config *
     }
     return S3_OK;
 }
+
+// OCCOutputSAMAPI (BGS-IO.cpp:5556-5772): a single read's record from its occurrence list -- the occurrence with the fewest
+// mismatches (the first of them) is reported, X0 = how many share that count; when it hangs over a chromosome / segment end the
+// best occurrence that does not is taken instead (none: the first choice, trimmed); the others go to XA:Z (all of them, or with
+// all-best only those with the best count; never one that would be trimmed), X1 = how many of the listed ones have more
+// mismatches; MAPQ = s3_mapq_single.  No occurrence: the unmapped record.
+extern "C" int s3_sam_single_record(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_occurrence *occ, uint32_t numOcc,
+                                    const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName, s3_sam_record *out)
+{
+    if (!out) { s3_set_error("s3_sam_single_record: NULL output"); return S3_EINVAL; }
+    memset(out, 0, sizeof *out);
+    if (!g || !cfg || !query || !qualities || !queryName || !cfg->readGroup || (numOcc && !occ) || readlen <= 0) { s3_set_error("s3_sam_single_record: bad argument"); return S3_EINVAL; }
+    if (numOcc && (!g->packedDNA || !g->segments || !g->ambiguityMap || !g->chrEndPos || !g->chrNames || g->numSegments == 0)) {
+        s3_set_error("s3_sam_single_record: incomplete genome description"); return S3_EINVAL;
+    }
+    std::vector<uint8_t> d;
+    std::string xa, md, newCigar, scratch;
+    unsigned long long bestTP = 0, tp;
+    uint32_t bestChr = 0, chr;
+    uint32_t bestMism = 0;
+    int best = -1, bestHitNum = 0, secBestHitNum = 0, trim = 0, avgQual = 20, mapq = 0;
+    int strand = 1;
+    if (numOcc) {
+        best = 0; bestMism = occ[0].mismatchCount; bestHitNum = 1;
+        for (uint32_t k = 1; k < numOcc; ++k) {
+            if (occ[k].mismatchCount < bestMism) { best = (int)k; bestMism = occ[k].mismatchCount; bestHitNum = 1; }
+            else if (occ[k].mismatchCount == bestMism) ++bestHitNum;
+        }
+        strand = occ[best].strand;
+        trim = chr_and_pos_checked(g, (uint32_t)readlen, occ[best].ambPosition, &bestTP, &bestChr, scratch);
+        if (trim) {
+            const int stored = best;
+            best = -1; bestMism = 9999; bestHitNum = 0;
+            for (uint32_t k = 0; k < numOcc; ++k) {
+                if (chr_and_pos_checked(g, (uint32_t)readlen, occ[k].ambPosition, &tp, &chr, scratch)) continue;
+                if (occ[k].mismatchCount < bestMism) { best = (int)k; bestMism = occ[k].mismatchCount; bestHitNum = 1; }
+                else if (occ[k].mismatchCount == bestMism) ++bestHitNum;
+            }
+            if (best < 0) { best = stored; bestHitNum = 1; }
+            newCigar.clear();
+            trim = chr_and_pos_checked(g, (uint32_t)readlen, occ[best].ambPosition, &bestTP, &bestChr, newCigar);
+            // (the strand stays that of the first choice, and bestMism what the scan left: 9999 when nothing fits -- as the reference)
+        }
+    }
+    if (numOcc > 1 && !trim) {
+        char num[24];
+        for (uint32_t k = 0; k < numOcc; ++k) {
+            if ((int)k == best) continue;
+            if (cfg->alignmentType == 2 && occ[k].mismatchCount > bestMism) continue;
+            if (chr_and_pos_checked(g, (uint32_t)readlen, occ[k].ambPosition, &tp, &chr, scratch)) continue;
+            xa += g->chrNames[chr - 1];
+            xa.push_back(',');
+            xa.push_back(occ[k].strand == 2 ? '-' : '+');
+            xa.append(num, write_num((long long)tp, num));
+            xa.push_back(',');
+            xa.append(num, write_num(readlen, num));
+            xa += "M,";
+            xa.append(num, write_num((int)occ[k].mismatchCount, num));
+            xa.push_back(';');
+            if (occ[k].mismatchCount > bestMism) ++secBestHitNum;
+        }
+    }
+    if (best >= 0) {
+        md_string(g, query, qualities, (uint32_t)readlen, occ[best].ambPosition, strand, (int)bestMism, trim, md, &avgQual);
+        if (trim && bestMism) { bestMism = 0; for (char c : md) bestMism += c > '9'; }
+        mapq = s3_mapq_single((int)bestMism, cfg->isFastq == 1 ? avgQual : 20, bestHitNum, secBestHitNum, cfg->maxMAPQ, cfg->minMAPQ, cfg->bwaLikeScore);
+    }
+    const std::string none;
+    record_body(*out, d, readlen, queryName, query, qualities, strand, numOcc > 1 ? xa : none, newCigar.empty() ? NULL : &newCigar, numOcc == 0,
+                (int)bestMism, (int)bestMism, bestHitNum, secBestHitNum, 0, 0, md, mapq, cfg->readGroup, cfg->isPrintMDNM != 0);
+    if (best >= 0) {
+        out->flag = (uint16_t)(strand == 2 ? 16 : 0);
+        out->tid = (int32_t)bestChr - 1; out->pos = (int32_t)(bestTP - 1);
+    } else { out->flag = 4; out->tid = -1; out->pos = -1; }
+    out->mtid = -1; out->mpos = -1; out->isize = 0;
+    const int rc = finish(*out, d);
+    if (rc) { s3_set_error("s3_sam_single_record: out of host memory"); }
+    return rc;
+}

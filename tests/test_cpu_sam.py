@@ -148,3 +148,70 @@ def test_sam_pair_records_match_the_reference_writer():
             trimmed += any(b"S" in w[1] or w[0][6] == 2 for w in want)
             with_xa += any(b"XAZ" in w[1] for w in want)
     assert trimmed > 20 and unmapped > 20 and with_xa > 100
+
+
+class Occurrence(C.Structure):
+    _fields_ = [("ambPosition", C.c_uint32), ("strand", C.c_uint8), ("mismatchCount", C.c_uint8), ("pad", C.c_uint8 * 2)]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_sam.so not built")
+def test_sam_single_record_matches_the_reference_writer():
+    """s3_sam_single_record against OCCOutputSAMAPI: best-hit choice, cross-chromosome handling, XA:Z, X0 / X1, MAPQ, unmapped"""
+    ref = C.CDLL(REF)
+    lib = api.load_library()
+    rng = np.random.default_rng(12)
+    n = 200_000
+    G = rng.integers(0, 4, n).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    translate = np.array([0, 1, 0xFFFFFFFF, 70_000, 2, 70_000 - 1, 100_000, 2, 70_000 - 1 - 500, 150_000, 3, 150_000 - 1], np.uint32)
+    chr_end = np.array([69_999, 149_999, 199_999], np.uint32)
+    amb = np.full(4, 3, np.uint32)
+    names = [b"chr1", b"chrTwo", b"3"]
+    segs = (Segment * 4)(*[Segment(int(translate[3 * i]), int(translate[3 * i + 1]), int(translate[3 * i + 2])) for i in range(4)])
+    gen = Genome(helpers.u32p(pac), n, segs, 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, (C.c_char_p * 3)(*names))
+    cnames = (C.c_char_p * 3)(*names)
+    edges = [70_000, 100_000, 150_000, 200_000]
+    trimmed = unmapped = with_xa = 0
+    for trial in range(1500):
+        L = int(rng.integers(36, 152))
+        cfg = Config(int(rng.integers(1, 3)), int(rng.integers(0, 2)), 1, -2, int(rng.integers(0, 2)), 40, 1, int(rng.integers(0, 2)), 1, 1000, b"rg%d" % trial)
+        m = int(rng.choice([0, 1, 1, 2, 3, 6]))
+        occ = []
+        for _ in range(m):
+            if rng.random() < 0.3:
+                e = int(rng.choice(edges))
+                p = max(0, min(n - L, e - int(rng.integers(1, L))))
+            else:
+                p = int(rng.integers(0, n - L))
+            occ.append((p, int(rng.integers(1, 3)), int(rng.integers(0, 4))))
+        p0, s0 = (occ[0][0], occ[0][1]) if occ else (0, 1)
+        r = G[p0:p0 + L].copy()
+        for k in rng.choice(L, int(rng.integers(0, 4)), replace=False):
+            r[k] = (r[k] + 1) & 3
+        q = np.ascontiguousarray((3 - r[::-1]) if s0 == 2 else r).astype(np.uint8)
+        ql = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql[-1] = 0
+        name = b"single%d" % trial
+        arr = (Occurrence * max(m, 1))(*[Occurrence(*o) for o in occ])
+        out = Record()
+        lib.s3_sam_single_record.restype = C.c_int
+        assert lib.s3_sam_single_record(C.byref(gen), C.byref(cfg), arr, m, q.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name, C.byref(out)) == 0
+        got = ((out.tid, out.pos, out.bin, out.qual, out.l_qname, out.flag, out.n_cigar, out.l_qseq, out.mtid, out.mpos, out.isize, out.l_aux),
+               bytes(bytearray(out.data[:out.data_len])))
+        lib.s3_sam_record_free.restype = None
+        lib.s3_sam_record_free(C.byref(out))
+        flat = np.array([x for o in occ for x in o], np.uint32) if occ else np.zeros(3, np.uint32)
+        core = np.zeros(12, np.int32)
+        data = np.zeros(8192, np.uint8)
+        dlen = np.zeros(1, np.int32)
+        ref.ref_sam_single.restype = C.c_int
+        k = ref.ref_sam_single(helpers.u32p(pac), n, helpers.u32p(translate), 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, cnames,
+                               cfg.alignmentType, cfg.bwaLikeScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup,
+                               helpers.u32p(flat), m, q.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name,
+                               core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P))
+        assert k == 1
+        want = (tuple(int(x) for x in core), bytes(data[:int(dlen[0])]))
+        assert got == want, (trial, occ, got, want)
+        unmapped += m == 0
+        trimmed += want[0][6] == 2
+        with_xa += b"XAZ" in want[1]
+    assert unmapped > 100 and trimmed > 30 and with_xa > 300

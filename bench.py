@@ -1302,7 +1302,7 @@ def main():
         h.copy_(t)
         return h
     host_sets = [(pinned(batches[args.warmup + k].queries), pinned(batches[args.warmup + k].lens)) for k in range(args.steps)]
-    pageable_sets = [(q.numpy().copy(), l.numpy().copy()) for q, l in host_sets[:2]]
+    pageable_sets = [(q.numpy().copy(), l.numpy().copy()) for q, l in host_sets[:4]]
 
     def timed(fn):
         barrier()
@@ -1340,7 +1340,8 @@ def main():
     h2d, d2h = last["h2d_bytes"], last["d2h_bytes"]
     e2e_value = world * reads_per_rank / t_e2e
     e2e_steps(pageable_sets[:1])
-    t_page, _ = timed(lambda: e2e_steps(pageable_sets))
+    t_page_one, _ = timed(lambda: e2e_steps(pageable_sets))
+    t_page, _ = timed(lambda: two_threads(lambda: e2e_steps_on(pe, pageable_sets[0::2]), lambda: e2e_steps_on(pe2, pageable_sets[1::2])))
     pageable_value = world * N * len(pageable_sets) / t_page
     # what the link gives: one 256 MiB pinned copy each way, alone
     probe_h = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
@@ -1449,6 +1450,7 @@ def main():
                 "mode": "s3_pe_align (host-pointer C ABI): queries from pinned host memory in, routes + pairings + rescue records + CIGAR runs "
                         "into host memory out, one call per step; the next step's queries are uploaded by s3_pe_prefetch under this step's kernels",
                 "pageable_value": pageable_value, "pageable_ms_per_step": 1e3 * t_page / len(pageable_sets),
+                "pageable_one_thread_value": world * N * len(pageable_sets) / t_page_one,
                 "link": link},
         "gpu_launches": int(launches),
         "roofline": sweep_roof if dominant.startswith("s3_dp") else search_roof,

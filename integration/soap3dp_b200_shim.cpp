@@ -175,3 +175,78 @@ void SemiGlobalAligner::freeMemory ()
     s3_dp_free ( ( s3_dp * ) _DPTable );
     _DPTable = NULL;
 }
+
+// ---- soap3-dp-module.cu:62-181 ------------------------------------------------------------------
+// alignSingleR, the reference's in-memory entry (soap3-dp-module.h:60-74; alignPairR is declared there but "NOT YET IMPLEMENTED" in
+// the reference itself, soap3-dp-module.cu:183): every read's alignments as occRec records in algnResultArrays.  The reference
+// reaches them through soap3_dp_single_align -> hostKernel -> addOCCToArray (CPUfunctions.cpp:1958-1968: readID, position, strand,
+// source 1, score = mismatches; readID = readIDs[r] + accumReadNum with accumReadNum 0 here); this body asks the device-resident
+// single-end chain for the same lists (s3_se_align: search, answer collection, best-hit filter, locate, long-read validation).
+//   outputOption 1 (all valid) / 2 (all best): the occurrences in hostKernel's order, up to maxHitNum per read
+//   outputOption 3 / 4 (unique / random best) are reached in the reference by searching with 0, 1, .. mismatches in turn
+//   (best_single_alignment), whose "first" occurrence depends on that schedule: not offered here.
+//   enableDP == 1: the reads left without an alignment go through s3_single_dp_align (DPForUnalignSingle2); its alignments are
+//   added to the LAST array with source 2 and score = the DP score, as outputDPSingleResult does (OutputDPResult.cpp:1036-1040) --
+//   every candidate that reaches the cutoff, without that function's per-read selection.
+// The records of the search go to algnArrays[0] (the reference spreads them over its host threads' arrays).
+#include "soap3-dp-module.h"
+void alignSingleR ( unsigned int * queries, unsigned int * readLengths, unsigned int * readIDs,
+                    unsigned int wordPerQuery,
+                    unsigned int numQueries, Soap3Index * index,
+                    SingleAlignParam * param,
+                    unsigned long long & numOfAnswer,
+                    unsigned int & numOfAlignedRead,
+                    AlgnResultArrays * algnResultArrays )
+{
+    numOfAnswer = 0; numOfAlignedRead = 0;
+    if ( param->outputOption != 1 && param->outputOption != 2 )
+    { printf ( "alignSingleR FAILED .. outputOption %d is not offered by the B200 shim (1 = all valid, 2 = all best)\n", param->outputOption ); exit ( 1 ); }
+    if ( !algnResultArrays || algnResultArrays->numArrays < 1 ) { printf ( "alignSingleR FAILED .. no result arrays\n" ); exit ( 1 ); }
+    uint * _bwt, * _occ, * _revBwt, * _revOcc;
+    GPUINDEXUpload ( index, &_bwt, &_occ, &_revBwt, &_revOcc );
+    s3_index * ix = ( s3_index * ) _bwt;
+    s3_se_params sp;
+    memset ( &sp, 0, sizeof ( sp ) );
+    sp.numMismatch = ( uint32_t ) param->numMismatch;
+    sp.maxOutputPerRead = param->maxHitNum > 0 ? ( uint32_t ) param->maxHitNum : 0xFFFFFFFFu;
+    sp.reportBest = param->outputOption == 2;
+    sp.longReadMode = param->maxReadLength > LONG_READ_LEN;               // alignment.cu:2475-2491
+    s3_se * se = NULL;
+    if ( s3_se_create ( ix, numQueries, &sp, &se ) != S3_OK ) { s3_die ( "alignSingleR" ); }
+    s3_se_result r;
+    if ( s3_se_align ( se, queries, readLengths, numQueries, wordPerQuery, &r ) != S3_OK ) { s3_die ( "alignSingleR" ); }
+    AlgnResult * first = algnResultArrays->algnArrays[0];
+    std::vector<uint32_t> unaligned;
+    for ( unsigned int q = 0; q < numQueries; q++ )
+    {
+        const uint32_t a = r.occOffsets[q], b = r.occOffsets[q + 1];
+        for ( uint32_t k = a; k < b; k++ )
+        { addOCCToArray ( first, readIDs[q], r.positions[k], r.occFlags[2 * k], 1, ( char ) r.occFlags[2 * k + 1] ); }
+        numOfAnswer += b - a;
+        if ( b > a ) { numOfAlignedRead++; }
+        else if ( !( r.readFlags[q] & 1 ) ) { unaligned.push_back ( q ); }
+    }
+    s3_se_free ( se );
+    if ( param->enableDP == 1 && !unaligned.empty () )
+    {
+        s3_stage_params st;
+        memset ( &st, 0, sizeof ( st ) );
+        st.insertLow = 0; st.insertHigh = 0; st.strandLeftLeg = 1; st.strandRightLeg = 2;
+        st.scores.matchScore = param->scoring.matchScore; st.scores.mismatchScore = param->scoring.mismatchScore;
+        st.scores.gapOpenScore = param->scoring.openGapScore; st.scores.gapExtendScore = param->scoring.extendGapScore;
+        st.isDefaultThreshold = 0; st.dpScoreThreshold = param->scoring.cutoffThreshold;      // setParam, soap3-dp-module.cu:44-46
+        st.softClipLeft = 3; st.softClipRight = 8;                                             // setParam, soap3-dp-module.cu:31-33
+        s3_single_dp_result d;
+        if ( s3_single_dp_align ( ix, queries, readLengths, numQueries, wordPerQuery, unaligned.data (), unaligned.size (), &st, &d ) != S3_OK ) { s3_die ( "alignSingleR (DP)" ); }
+        AlgnResult * last = algnResultArrays->algnArrays[algnResultArrays->numArrays - 1];
+        uint32_t pre = 0xFFFFFFFFu;
+        for ( uint64_t h = 0; h < d.numHits; h++ )
+        {
+            addOCCToArray ( last, readIDs[d.hits[h].readID], d.hits[h].pos, d.hits[h].strand, 2, ( char ) d.hits[h].score );
+            if ( d.hits[h].readID != pre ) { numOfAlignedRead++; pre = d.hits[h].readID; }
+        }
+        numOfAnswer += d.numHits;
+        s3_single_dp_result_free ( &d );
+    }
+    GPUINDEXFree ( _bwt, _occ, _revBwt, _revOcc );
+}

@@ -63,6 +63,20 @@ for case in range(formats.NUM_CASES[k]):
         bl[:nb] = lens[idx2]
         helpers.oracle_launch(olib, hi, case, bq, bl, nb, wpq, a2, np.zeros(formats.ceil32(nb), np.uint8), 1, k, allowed2, wpa2)
     save(f"bad_ans{case}", a2)
+# alignSingleR, outputOption 1 (all valid), maxHitNum 1000: per read what collect_all_answers + transferAllSAToOcc leave
+# (CPUfunctions.cpp:1226-1300, SAList.cpp:392-419), restated in oracle/pe_chain_oracle.collect over the round-1 slots
+sys.path.insert(0, HERE)
+import pe_chain_oracle  # noqa: E402
+views = [formats.answers_view(np.fromfile(os.path.join(out, f"answers{case}.bin"), np.uint32), n, wpa) for case in range(formats.NUM_CASES[k])]
+col = pe_chain_oracle.collect(views, allowed, hi.n, 1000)
+so, sp, sf = [0], [], []
+sa_true = idx.fwd.sa.cpu().numpy()
+for ranges, tot, more in col:
+    for l, r, st, mm in ranges:
+        for i in range(l, r + 1):
+            sp.append(int(sa_true[i])); sf.append(st | (mm << 8))
+    so.append(len(sp))
+save("single_off", np.array(so, np.uint32)); save("single_pos", np.array(sp, np.uint32)); save("single_flags", np.array(sf, np.uint32))
 m = 512
 b = helpers.make_dp_batch(G, m, L, "rescue", seed=13, indel_rate=0.01)
 sc, hit, cnt, pat, _ = helpers.oracle_dp(helpers.load_oracle_dp(), b)

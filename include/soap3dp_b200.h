@@ -64,6 +64,11 @@ int s3_index_upload(const uint32_t *bwt, const uint32_t *occ,
 /* the same two optional arrays when they already live in device memory (copied) */
 int s3_index_set_locate_device(s3_index *ix, const uint32_t *d_sa, const uint32_t *d_packedDNA);
 void s3_index_free(s3_index *ix);
+/* The reference's index files straight from disk (INDEXLoad, IndexHandler.cpp:118-330, for the arrays the device needs):
+ * <prefix>.bwt, .fmv.gpu, .rev.bwt, .rev.fmv.gpu as soap3-dp-builder + BGS-Build write them (5-word header, payload) and, with
+ * withText, .sa (full suffix array: SaValueFreq = 1) and .pac for check-and-extend, locate and the chains.  The files are
+ * mapped, page-locked for the copy when the driver allows it, and handed to s3_index_upload; headers are cross-checked. */
+int s3_index_load(const char *prefix, int withText, int device, s3_index **out);
 /* A second handle on the same device arrays with a stream, work queues and scratch of its own: two batches can then be in
  * flight at once, one host thread per handle (the reference overlaps its search of batch k + 1 with the DP of batch k the
  * same way, alignment.cu:555,1030).  Clones are freed before the handle they were made from. */

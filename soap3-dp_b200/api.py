@@ -40,7 +40,7 @@ EXPORTS = [
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
     "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows", "s3_index_set_l2_persist", "s3_index_clone",
     "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
-    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_validate_alignments", "s3_sam_pair_records", "s3_sam_single_record", "s3_sam_record_free", "s3_seed_search", "s3_seed_search_result_free",
+    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_validate_alignments", "s3_sam_pair_records", "s3_sam_single_record", "s3_sam_record_free", "s3_index_load", "s3_seed_search", "s3_seed_search_result_free",
     "s3_single_dp_align", "s3_single_dp_result_free", "s3_deep_dp_align", "s3_deep_dp_result_free",
 ]
 
@@ -1004,6 +1004,17 @@ def set_l2_persist(gpu_index: GpuIndex, region: int, window_bytes: int = 0, pers
     lib.s3_index_set_l2_persist.restype = C.c_int
     lib.s3_index_set_l2_persist.argtypes = [C.c_void_p, C.c_int, C.c_size_t, C.c_size_t]
     _check(lib.s3_index_set_l2_persist(gpu_index.handle, region, window_bytes, persist_bytes), "s3_index_set_l2_persist")
+
+
+def index_load(prefix: str, with_text: bool = True, device: int = 0) -> GpuIndex:
+    """s3_index_load: the reference's index files (<prefix>.bwt / .fmv.gpu / .rev.bwt / .rev.fmv.gpu [/ .sa / .pac]) straight from disk"""
+    lib = load_library()
+    lib.s3_index_load.restype = C.c_int
+    lib.s3_index_load.argtypes = [C.c_char_p, C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    out = C.c_void_p()
+    _check(lib.s3_index_load(prefix.encode(), int(with_text), device, C.byref(out)), "s3_index_load")
+    n = int(np.fromfile(prefix + ".bwt", dtype=np.uint32, count=5)[4])
+    return GpuIndex(out.value, n)
 
 
 def index_clone(gpu_index: GpuIndex) -> GpuIndex:

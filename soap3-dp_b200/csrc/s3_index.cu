@@ -325,6 +325,96 @@ extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const u
     return S3_OK;
 }
 
+// ---- the reference's index files, straight from disk ------------------------------------------------------------------
+// s3_index_load maps <prefix>.bwt, .fmv.gpu, .rev.bwt, .rev.fmv.gpu (and .sa, .pac for the text side) as soap3-dp-builder +
+// BGS-Build write them -- a 5-word header (inverseSa0, cumulative frequencies of A C G T; 2bwt-lib/BWT.c:170-200,
+// BGS-Build.cpp:139-160), then the payload; .sa: one more word, the sampling interval, which must be 1 (BWT.c:225-285); .pac: four
+// bases per byte in n / 4 + 1 bytes, then one byte = n % 4, the bases the byte before it holds (TextConverter.c:666-720) -- and hands the mappings to
+// s3_index_upload: no copy of the files is made on the host (the packed text, 0.25 byte per base, is the exception: its bytes are
+// turned into the big-endian words of hsp->packedDNA).  The mappings are page-locked for the upload when the driver allows it
+// (cudaHostRegisterReadOnly), so that the copies run at the link's rate.
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <string>
+
+namespace {
+struct S3Mapped {
+    const uint32_t *words; size_t bytes; int registered;
+    S3Mapped() : words(NULL), bytes(0), registered(0) {}
+};
+int map_file(const std::string &path, S3Mapped *m)
+{
+    const int fd = open(path.c_str(), O_RDONLY);
+    if (fd < 0) { s3_set_error("s3_index_load: cannot open %s", path.c_str()); return S3_EINVAL; }
+    struct stat st;
+    if (fstat(fd, &st) != 0 || st.st_size < 20) { close(fd); s3_set_error("s3_index_load: %s is too short", path.c_str()); return S3_EINVAL; }
+    void *p = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    close(fd);
+    if (p == MAP_FAILED) { s3_set_error("s3_index_load: mmap of %s failed", path.c_str()); return S3_ENOMEM; }
+    m->words = (const uint32_t *)p; m->bytes = (size_t)st.st_size;
+    if (cudaHostRegister(p, m->bytes, cudaHostRegisterReadOnly | cudaHostRegisterPortable) == cudaSuccess) m->registered = 1;
+    else cudaGetLastError();
+    return S3_OK;
+}
+void unmap_file(S3Mapped *m)
+{
+    if (!m->words) return;
+    if (m->registered) cudaHostUnregister((void *)m->words);
+    munmap((void *)m->words, m->bytes);
+    *m = S3Mapped();
+}
+}  // namespace
+
+extern "C" int s3_index_load(const char *prefix, int withText, int device, s3_index **out)
+{
+    if (!prefix || !out) { s3_set_error("s3_index_load: NULL argument"); return S3_EINVAL; }
+    *out = NULL;
+    if (device < 0 || device >= s3_device_count()) { s3_set_error("s3_index_load: CUDA device %d not available; there is no CPU fallback", device); return S3_ECUDA; }
+    if (cudaSetDevice(device) != cudaSuccess) { s3_set_error("s3_index_load: cudaSetDevice failed"); return S3_ECUDA; }
+    const std::string pre(prefix);
+    S3Mapped f[6];               // bwt, fmv.gpu, rev.bwt, rev.fmv.gpu, sa, pac
+    const char *ext[6] = {".bwt", ".fmv.gpu", ".rev.bwt", ".rev.fmv.gpu", ".sa", ".pac"};
+    uint32_t *text = NULL;
+    int rc = S3_OK;
+    for (int i = 0; i < (withText ? 6 : 4) && rc == S3_OK; ++i) rc = map_file(pre + ext[i], &f[i]);
+    if (rc == S3_OK) {
+        const uint32_t n = f[0].words[4];
+        const size_t numWords = ((size_t)n + 15) / 16, numOcc = ((size_t)n + 127) / 128 + 1;
+        // the two files of a direction carry the same header; both directions index texts of one length
+        if (memcmp(f[0].words, f[1].words, 20) || memcmp(f[2].words, f[3].words, 20) || f[2].words[4] != n || n == 0) {
+            s3_set_error("s3_index_load: the headers of %s.* do not agree", prefix); rc = S3_EINVAL;
+        } else if (f[0].bytes < 20 + numWords * 4 || f[2].bytes < 20 + numWords * 4 || f[1].bytes < 20 + numOcc * 16 || f[3].bytes < 20 + numOcc * 16) {
+            s3_set_error("s3_index_load: a file of %s.* is shorter than its header says", prefix); rc = S3_EINVAL;
+        }
+        const uint32_t *sa = NULL;
+        if (rc == S3_OK && withText) {
+            if (memcmp(f[4].words, f[0].words, 20) || f[4].bytes < 24 + ((size_t)n + 1) * 4 || f[4].words[5] != 1) {
+                s3_set_error("s3_index_load: %s.sa does not hold the full suffix array of this index (SaValueFreq must be 1)", prefix); rc = S3_EINVAL;
+            } else sa = f[4].words + 6;
+            const uint8_t *pac = (const uint8_t *)f[5].words;
+            const size_t fileLen = f[5].bytes - 1, textLen = fileLen ? (fileLen - 1) * 4 + pac[fileLen] : 0;
+            if (rc == S3_OK && textLen != n) { s3_set_error("s3_index_load: %s.pac holds %zu bases, the index %u", prefix, textLen, n); rc = S3_EINVAL; }
+            if (rc == S3_OK) {
+                text = (uint32_t *)calloc(numWords + 8, 4);
+                if (!text) { s3_set_error("s3_index_load: out of host memory"); rc = S3_ENOMEM; }
+                else for (size_t w = 0; w < numWords; ++w) {
+                    uint32_t v = 0;
+                    for (int b = 0; b < 4; ++b) { const size_t k = 4 * w + b; v = (v << 8) | (k < fileLen ? pac[k] : 0u); }
+                    text[w] = v;
+                }
+            }
+        }
+        if (rc == S3_OK)
+            rc = s3_index_upload(f[0].words + 5, f[1].words + 5, f[2].words + 5, f[3].words + 5, (uint32_t)numOcc, f[0].words[0], f[2].words[0], n,
+                                 withText ? text : NULL, withText ? sa : NULL, device, out);
+    }
+    free(text);
+    for (int i = 0; i < 6; ++i) unmap_file(&f[i]);
+    return rc;
+}
+
 extern "C" int s3_index_set_locate_device(s3_index *ix, const uint32_t *d_sa, const uint32_t *d_packedDNA)
 {
     if (!ix || !d_sa || !d_packedDNA) { s3_set_error("s3_index_set_locate_device: NULL argument"); return S3_EINVAL; }

@@ -804,3 +804,35 @@ def validation_cases(rng, genome, trials):
                 p = p0 + ext if (c < 0.6 and rev) else (int(rng.integers(0, L)) if c < 0.7 else int(rng.integers(0, n)))
             pos.append(p); st.append(s); mm.append(int(rng.integers(0, 3)))
         yield read, seed, pos, st, mm, int(rng.integers(0, 2)), int(rng.integers(0, 3)), int(rng.integers(0, 8)), int(rng.integers(1, 6))
+
+
+# ---- the reference's index files (s3_index_load) --------------------------------------------------------------------------
+def write_reference_files(prefix, idx):
+    """the on-disk formats (2bwt-lib/BWT.c:170-285, BGS-Build.cpp:139-160, TextConverter.c:666-720) from in-memory arrays"""
+    n = idx.text_length
+    for half, tag in ((idx.fwd, ""), (idx.rev, ".rev")):
+        hdr = np.array([half.inverse_sa0] + list(half.cum_freq[1:]), np.uint32)
+        np.concatenate([hdr, half.bwt_words.cpu().numpy().view(np.uint32)[:(n + 15) // 16]]).tofile(prefix + tag + ".bwt")
+        np.concatenate([hdr, half.occ.cpu().numpy().view(np.uint32)]).tofile(prefix + tag + ".fmv.gpu")
+    hdr = np.array([idx.fwd.inverse_sa0] + list(idx.fwd.cum_freq[1:]), np.uint32)
+    np.concatenate([hdr, np.array([1], np.uint32), idx.fwd.sa.cpu().numpy().astype(np.uint32)]).tofile(prefix + ".sa")
+    words = idx.packed_text.cpu().numpy().view(np.uint32)[:(n + 15) // 16]
+    # n / 4 + 1 data bytes (the last one holds the n % 4 bases left over, none when n is a multiple of four), then n % 4
+    data = (words.astype(">u4").tobytes() + b"\0")[:n // 4 + 1]
+    last = n % 4
+    open(prefix + ".pac", "wb").write(data + bytes([last]))
+
+
+def run_reference_builders(G, tmp):
+    """soap3-dp-builder + BGS-Build (oracle/_ref, the reference's own, built by oracle/build_ref.sh) on genome G; returns the index prefix"""
+    import subprocess
+    ref_dir = os.path.join(ROOT, "oracle", "_ref")
+    fa = os.path.join(tmp, "g.fa")
+    seq = "".join(np.array(list("ACGT"))[G.numpy()])
+    with open(fa, "w") as f:
+        f.write(">chr1\n")
+        for i in range(0, len(seq), 60):
+            f.write(seq[i:i + 60] + "\n")
+    subprocess.check_call([os.path.join(ref_dir, "soap3-dp-builder"), fa], stdout=subprocess.DEVNULL, cwd=ref_dir)
+    subprocess.check_call([os.path.join(ref_dir, "BGS-Build"), fa + ".index"], stdout=subprocess.DEVNULL, cwd=ref_dir)
+    return fa + ".index"

@@ -1,6 +1,7 @@
 """CPU tier: the oracle restatements against the reference's own kernels compiled for the
 host (oracle/_ref, built by oracle/build_ref.sh where /root/reference exists).  Skipped
 on boxes where oracle/_ref was not shipped; the golden-fixture tests cover those."""
+import os
 import numpy as np
 import pytest
 
@@ -364,3 +365,22 @@ def test_validate_oracle_matches_the_reference_validation():
         kept += len(a[0])
         changed += a[0] != pos
     assert kept > 1000 and changed > 1000
+
+
+def test_index_file_formats_equal_reference_builders(tmp_path):
+    """the six files s3_index_load maps (.bwt, .fmv.gpu, .rev.bwt, .rev.fmv.gpu, .sa, .pac) written from our builder's arrays ==
+    the files soap3-dp-builder + BGS-Build write for the same genome, byte for byte (headers, payloads, the .pac tail byte)"""
+    import tempfile
+    from helpers import run_reference_builders, write_reference_files
+    from soap3dp_b200 import synth as _synth
+    if not os.path.exists(os.path.join(helpers.ROOT, "oracle", "_ref", "soap3-dp-builder")):
+        pytest.skip("oracle/_ref builders not built")
+    for n in (250_003, 100_000):                       # a length that leaves 3 bases in the last .pac byte, and one that fills it
+        G = _synth.random_genome(n, seed=77)
+        idx = fmindex.build_index(G, keep_sa=True)
+        with tempfile.TemporaryDirectory() as tmp:
+            ref = run_reference_builders(G, tmp)
+            ours = os.path.join(tmp, "ours.index")
+            write_reference_files(ours, idx)
+            for e in (".bwt", ".fmv.gpu", ".rev.bwt", ".rev.fmv.gpu", ".sa", ".pac"):
+                assert open(ref + e, "rb").read() == open(ours + e, "rb").read(), (n, e)

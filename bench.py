@@ -678,13 +678,17 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
         chain = api.PairAligner(gi, N, L, api.pe_params(num_mismatch=K_MISMATCH, insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES,
                                                         read_length=L, max_windows=N // 2))
 
-    # a second handle on the same index with its own chain and stage workspace: two batches in flight, one host thread each
-    gi2 = api.index_clone(gi)
-    if se_mode:
-        chain2 = api.SingleAligner(gi2, N, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True)
-    else:
-        chain2 = api.PairAligner(gi2, N, L, api.pe_params(num_mismatch=K_MISMATCH, insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES,
-                                                          read_length=L, max_windows=N // 2))
+    # more handles on the same index, each with its own chain and stage workspace: T batches in flight, one host thread each
+    T = max(int(os.environ.get("S3_IN_FLIGHT", "2")), 1)
+    handles = [(chain, gi)]
+    for _ in range(T - 1):
+        g2 = api.index_clone(gi)
+        if se_mode:
+            c2 = api.SingleAligner(g2, N, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True)
+        else:
+            c2 = api.PairAligner(g2, N, L, api.pe_params(num_mismatch=K_MISMATCH, insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES,
+                                                         read_length=L, max_windows=N // 2))
+        handles.append((c2, g2))
 
     def step(q, lens, chain=chain, gi=gi):
         # results stay where the C entries put them (the handle's pinned buffers / malloc'ed arrays): no numpy copies in the timed loop
@@ -711,8 +715,8 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
             torch.distributed.barrier()
         torch.cuda.synchronize()
     for s in range(args.warmup):
-        step(sets[s][0], sets[s][1])
-        step(sets[s][0], sets[s][1], chain2, gi2)
+        for ch, g in handles:
+            step(sets[s][0], sets[s][1], ch, g)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -734,9 +738,9 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
 
     def run_half(first, ch, g):
         torch.cuda.set_device(local_rank)
-        for kk in range(first, args.steps, 2):
+        for kk in range(first, args.steps, T):
             step(sets[args.warmup + kk][0], sets[args.warmup + kk][1], ch, g)
-    th = [threading.Thread(target=run_half, args=(0, chain, gi)), threading.Thread(target=run_half, args=(1, chain2, gi2))]
+    th = [threading.Thread(target=run_half, args=(i, ch, g)) for i, (ch, g) in enumerate(handles)]
     barrier()
     t0 = time.perf_counter()
     for t in th:
@@ -766,8 +770,9 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
            "config": {"workload": name, "genome_bp": args.genome_bp, "repeat_fraction": args.repeat_fraction, "reads_per_step_per_gpu": N,
                       "timing": "wall clock over K steps through the host-pointer entries, queries in pinned host memory, every result in host memory "
-                                "(the seeded stages' logic runs on the host between device steps): value == e2e; two batches in flight (even steps on one "
-                                "handle, odd steps on its s3_index_clone, a host thread each); value_one_batch_in_flight and the stage times: the same steps one after the other",
+                                "(the seeded stages' logic runs on the host between device steps): value == e2e; " + str(T) + " batches in flight (step k on handle "
+                                "k mod T: the index handle and its s3_index_clones, a host thread each); value_one_batch_in_flight and the stage times: the same steps one after the other",
+                      "batches_in_flight": T,
                       "l2": "inputs larger than L2: the 56 GB index is touched at random, a different read batch every step",
                       "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"},
            "clocks": sampler.result(),
@@ -863,10 +868,9 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
                                                  "the validation and the seeded DP stage are not included (the reference has no CPU DP)",
                                        "reads_with_a_hit": int((res["counts"][:, 3] > 0).sum())}
     print(json.dumps(out), flush=True)
-    chain2.free()
-    api.GPUINDEXFree(gi2)
-    chain.free()
-    api.GPUINDEXFree(gi)
+    for ch, g in reversed(handles):                               # clones are freed before the handle they were made from
+        ch.free()
+        api.GPUINDEXFree(g)
     if world > 1:
         torch.distributed.destroy_process_group()
 

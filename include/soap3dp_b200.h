@@ -663,6 +663,11 @@ int s3_single_dp_align(s3_index *ix, const uint32_t *queries, const uint32_t *re
 void s3_single_dp_result_free(s3_single_dp_result *r);
 int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
                      const uint32_t *pairReadIDs, uint64_t n, const s3_stage_params *par, s3_deep_dp_result *out);
+/* The same stage for the batch a paired-end chain has just aligned (the call DPForUnalignPairs2 follows semiGlobalDP2 with,
+ * soap3-dp-module.cu / SOAP3-DP.cu main loop): the pairs s3_pe_align[_device] left as S3_PE_NONE are picked on the device and the stage
+ * works on the chain's own query buffer and read lengths -- nothing is uploaded again.  To be called before the next s3_pe_prefetch /
+ * s3_pe_align on the handle.  Results as s3_deep_dp_align (readIDs are the even read ids of the batch); numPairs = the pairs picked. */
+int s3_pe_deep_dp(s3_pe *pe, const s3_stage_params *par, s3_deep_dp_result *out);
 void s3_deep_dp_result_free(s3_deep_dp_result *r);
 
 /* ------------------------------------------------------------------------

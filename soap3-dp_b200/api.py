@@ -40,7 +40,7 @@ EXPORTS = [
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
     "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows", "s3_index_set_l2_persist", "s3_index_clone",
     "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
-    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_validate_alignments", "s3_sam_pair_records", "s3_sam_single_record", "s3_sam_record_free", "s3_index_load", "s3_seed_search", "s3_seed_search_result_free",
+    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_validate_alignments", "s3_sam_pair_records", "s3_sam_single_record", "s3_sam_record_free", "s3_index_load", "s3_pe_deep_dp", "s3_seed_search", "s3_seed_search_result_free",
     "s3_single_dp_align", "s3_single_dp_result_free", "s3_deep_dp_align", "s3_deep_dp_result_free",
 ]
 
@@ -733,6 +733,17 @@ class PairAligner:
         _check(lib.s3_pe_create(gpu_index.handle, max_reads, max_read_length, C.byref(params), C.byref(out)), "s3_pe_create")
         self.handle = out
 
+    def deep_dp(self, params, counts_only: bool = False):
+        """s3_pe_deep_dp: DPForUnalignPairs2 for the both-unaligned pairs of the batch this handle has just aligned (on the device)"""
+        lib = load_library()
+        lib.s3_pe_deep_dp.restype = C.c_int
+        lib.s3_pe_deep_dp.argtypes = [C.c_void_p, C.POINTER(StageParams), C.POINTER(_StageResult)]
+        lib.s3_deep_dp_result_free.restype = None
+        lib.s3_deep_dp_result_free.argtypes = [C.POINTER(_StageResult)]
+        res = _StageResult()
+        _check(lib.s3_pe_deep_dp(self.handle, C.byref(params), C.byref(res)), "s3_pe_deep_dp")
+        return _stage_unpack(res, DEEP_HIT_DTYPE, counts_only, lib.s3_deep_dp_result_free)
+
     def align(self, queries, read_lengths, num_reads: int, word_per_query: int, copy: bool = True):
         """queries / read_lengths: host uint32 arrays (or raw host addresses).  -> dict of numpy arrays (copies unless copy=False)"""
         res = PEResult()
@@ -970,7 +981,10 @@ def _stage_align(fn_name, free_name, dtype, gpu_index, queries, read_lengths, nu
     ids = np.ascontiguousarray(ids, np.uint32)
     res = _StageResult()
     _check(fn(gpu_index.handle, _u32(queries), _u32(read_lengths), num_reads, word_per_query, _u32(ids), len(ids), C.byref(params), C.byref(res)), fn_name)
+    return _stage_unpack(res, dtype, counts_only, fr)
 
+
+def _stage_unpack(res, dtype, counts_only, fr):
     def view(ptr, dt, n):
         if not ptr or n == 0:
             return np.zeros(0, dt)
@@ -978,10 +992,11 @@ def _stage_align(fn_name, free_name, dtype, gpu_index, queries, read_lengths, nu
         return np.frombuffer(buf, dtype=dt, count=n).copy()
     if counts_only:                    # (timing loops: the C entry has done all its work, the arrays are not copied into numpy)
         out = {"num_hits": int(res.numHits), "num_runs": int(res.numRuns), "num_unseeded": int(res.numUnseeded), "num_seeds": int(res.numSeeds),
-               "num_candidates": int(res.numCandidates)}
+               "num_candidates": int(res.numCandidates), "num_input": int(res.numIn)}
     else:
         out = {"hits": view(res.hits, dtype, int(res.numHits)), "runs": view(res.runs, np.uint32, int(res.numRuns)),
-               "unseeded": view(res.unseeded, np.uint32, int(res.numUnseeded)), "num_seeds": int(res.numSeeds), "num_candidates": int(res.numCandidates)}
+               "unseeded": view(res.unseeded, np.uint32, int(res.numUnseeded)), "num_seeds": int(res.numSeeds), "num_candidates": int(res.numCandidates),
+               "num_input": int(res.numIn)}
     fr(C.byref(res))
     return out
 

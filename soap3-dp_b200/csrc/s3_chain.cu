@@ -70,6 +70,8 @@ struct s3_pe {
     uint32_t *d_in[2]; size_t inBytes[2];
     cudaStream_t copyStream; cudaEvent_t pfDone[2];
     struct { const uint32_t *queries; uint64_t reads; uint32_t wpq; } pf[2];     // what has been prefetched into d_in[k] and not aligned yet (queries NULL: nothing)
+    // the batch of the last s3_pe_align[_device] call, still on the device: what s3_pe_deep_dp works on
+    struct { const uint32_t *d_q, *d_len; const uint8_t *d_route; uint32_t N, wpq; } last;
 };
 
 static int pe_input_buffer(s3_pe *pe, int k, size_t bytes, cudaStream_t st)
@@ -699,6 +701,7 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     }
     res->numPairs = P; res->numOccurrences = T; res->numWindows = M; res->numRuns = totalRuns;
     for (int c = 0; c < 16; ++c) res->routeCounts[c] = pe->h_counts[8 + c];
+    pe->last.d_q = d_q; pe->last.d_len = d_len; pe->last.d_route = d_routeFinal; pe->last.N = N; pe->last.wpq = wordPerQuery;
     if (pe->timing) {
         for (int s = 0; s < 7; ++s) { float ms = 0; cudaEventElapsedTime(&ms, pe->ev[s], pe->ev[s + 1]); pe->msStages[s] += ms; }
     }
@@ -732,6 +735,17 @@ extern "C" int s3_pe_align(s3_pe *pe, const uint32_t *queries, const uint32_t *r
 extern "C" int s3_pe_align_device(s3_pe *pe, const uint32_t *d_queries, const uint32_t *d_readLengths, uint64_t numReads, uint32_t wordPerQuery, s3_pe_result *out)
 {
     return pe_run(pe, d_queries, d_readLengths, numReads, wordPerQuery, 1, out);
+}
+
+// DPForUnalignPairs2 for the both-unaligned pairs of the batch this handle has just aligned (s3_stages.cu)
+int s3_stage_deep_dp_of_chain(s3_index *ix, const uint32_t *d_queries, const uint32_t *d_len, uint64_t numReads, uint32_t wordPerQuery, const uint8_t *d_route,
+                              uint8_t wantRoute, const s3_stage_params *par, s3_deep_dp_result *out);
+extern "C" int s3_pe_deep_dp(s3_pe *pe, const s3_stage_params *par, s3_deep_dp_result *out)
+{
+    if (!pe || !par || !out) { s3_set_error("s3_pe_deep_dp: NULL argument"); return S3_EINVAL; }
+    memset(out, 0, sizeof *out);
+    if (!pe->last.d_q) { s3_set_error("s3_pe_deep_dp: no batch has been aligned on this handle"); return S3_EINVAL; }
+    return s3_stage_deep_dp_of_chain(pe->ix, pe->last.d_q, pe->last.d_len, pe->last.N, pe->last.wpq, pe->last.d_route, S3_PE_NONE, par, out);
 }
 
 
@@ -1056,7 +1070,8 @@ extern "C" int s3_se_align_device(s3_se *se, const uint32_t *d_queries, const ui
 // =======================================================================================================================
 struct S3StageWs {
     s3_dp *dp; uint32_t maxRead, maxDNA, cap; s3_dp_scores scores;
-    uint32_t *d_q; size_t qBytes;                 // query buffer + read lengths of the current stage call
+    uint32_t *d_q; size_t qBytes;                 // query buffer of the current stage call when it came from the host
+    const uint32_t *d_qUse;                       // the query buffer the stage works on: d_q, or the caller's device buffer
     S3Arena arena;
     void *pinned[2]; size_t pinnedBytes[2];
 };
@@ -1089,7 +1104,16 @@ static S3StageWs *stage_ws(s3_index *ix)
     return ws;
 }
 
-const uint32_t *s3_stage_queries(s3_index *ix) { S3StageWs *ws = (S3StageWs *)ix->stageWs; return ws ? ws->d_q : NULL; }
+const uint32_t *s3_stage_queries(s3_index *ix) { S3StageWs *ws = (S3StageWs *)ix->stageWs; return ws ? ws->d_qUse : NULL; }
+
+// the stage works on a query buffer that is on the device already (the chain's): nothing is copied
+int s3_stage_use_queries(s3_index *ix, const uint32_t *d_queries)
+{
+    S3StageWs *ws = stage_ws(ix);
+    if (!ws) { s3_set_error("out of host memory"); return S3_ENOMEM; }
+    ws->d_qUse = d_queries;
+    return S3_OK;
+}
 
 int s3_stage_upload_queries(s3_index *ix, const uint32_t *queries, uint64_t numReads, uint32_t wordPerQuery)
 {
@@ -1104,6 +1128,7 @@ int s3_stage_upload_queries(s3_index *ix, const uint32_t *queries, uint64_t numR
         ws->qBytes = qBytes + qBytes / 4;
     }
     S3_TRYC(cudaMemcpyAsync(ws->d_q, queries, qBytes, cudaMemcpyHostToDevice, st));
+    ws->d_qUse = ws->d_q;
     return S3_OK;
 }
 
@@ -1130,7 +1155,7 @@ int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLe
         s3_dp_set_stream(ws->dp, st);
         ws->maxRead = maxRead; ws->maxDNA = maxDNA; ws->cap = cap; ws->scores = scores;
     }
-    if (uploadQueries || !ws->d_q) { if ((rc = s3_stage_upload_queries(ix, queries, numReads, wordPerQuery))) return rc; }
+    if (uploadQueries || !ws->d_qUse) { if ((rc = s3_stage_upload_queries(ix, queries, numReads, wordPerQuery))) return rc; }
     const size_t patLen = s3_dp_pattern_length(ws->dp);
     size_t scanTemp = 0;
     cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (uint32_t *)NULL, (uint32_t *)NULL, (int)(n + 1), st);
@@ -1187,7 +1212,7 @@ int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLe
         S3_TRYC(cudaMemcpyAsync(d_ar, ancR, (size_t)n * 4, cudaMemcpyHostToDevice, st));
         S3_TRYC(cudaMemcpyAsync(d_strand, strand, n, cudaMemcpyHostToDevice, st));
     }
-    if ((rc = s3_dp_align_windows_device(ws->dp, ix, ws->d_q, wordPerQuery, d_readID, d_strand, d_start, d_len, d_rl, d_cut, d_score, d_hit, d_cnt, d_pattern, n,
+    if ((rc = s3_dp_align_windows_device(ws->dp, ix, ws->d_qUse, wordPerQuery, d_readID, d_strand, d_start, d_len, d_rl, d_cut, d_score, d_hit, d_cnt, d_pattern, n,
                                          d_clt, d_crt, d_al, d_ar))) return rc;
     const unsigned nb = (n + 127) / 128;
     S3_TRYC(cudaMemsetAsync(d_runCount + n, 0, 4, st));

@@ -118,6 +118,8 @@ struct S3SeedRangesDev {
     uint32_t *d_buf;             // saL | saR | strand | read id | seed offset | seed length | read length, numRanges words each (cudaFreeAsync)
     uint64_t numRanges;
     uint8_t *d_status;           // per seed: 0 none, 1 kept, 4 too many occurrences (cudaFreeAsync)
+    uint32_t splitSeed;          // in: a seed id (0: none); out: rangesBeforeSplit = the ranges of the seeds below it (ranges come in seed order,
+    uint64_t rangesBeforeSplit;  // so two groups of seeds searched in one call are two stretches of d_buf's columns)
 };
 int s3_seed_search_device(s3_index *ix, const uint32_t *d_seeds, const uint32_t *d_seedLengths, uint32_t numSeeds, uint32_t wordPerSeed,
                           const uint32_t *d_maxHit, const uint32_t *d_seedReadID, const uint32_t *d_seedOffset, const uint32_t *d_seedReadLength,
@@ -153,6 +155,7 @@ int s3_stage_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLe
                    const uint32_t *d_readLengthsByRead, const uint32_t *d_cand, S3StageAligned *out);
 const uint32_t *s3_stage_queries(s3_index *ix);            // device copy of the query buffer of the current stage call (NULL before the first upload)
 int s3_stage_upload_queries(s3_index *ix, const uint32_t *queries, uint64_t numReads, uint32_t wordPerQuery);
+int s3_stage_use_queries(s3_index *ix, const uint32_t *d_queries);   // the stage works on the caller's device buffer instead
 void s3_stage_ws_free(s3_index *ix);
 
 void s3_set_error(const char *fmt, ...);

@@ -711,6 +711,7 @@ int s3_seed_search_device(s3_index *ix, const uint32_t *d_seeds, const uint32_t 
                           const uint32_t *d_maxHit, const uint32_t *d_seedReadID, const uint32_t *d_seedOffset, const uint32_t *d_seedReadLength,
                           S3SeedRangesDev *out)
 {
+    const uint32_t splitSeed = out->splitSeed <= numSeeds ? out->splitSeed : numSeeds;
     memset(out, 0, sizeof *out);
     if (numSeeds == 0) return S3_OK;
     int rc = S3_OK;
@@ -759,8 +760,10 @@ int s3_seed_search_device(s3_index *ix, const uint32_t *d_seeds, const uint32_t 
     S3_LAUNCHED(1);
     S3_TRY(cub::DeviceScan::ExclusiveSum(d_tmp, t2, d_keptCount, d_keptOff, (int)(numSeeds + 1), st));
     S3_TRY(cudaMemcpyAsync(h_cnt, d_keptOff + numSeeds, 4, cudaMemcpyDeviceToHost, st));
+    S3_TRY(cudaMemcpyAsync(h_cnt + 1, d_keptOff + splitSeed, 4, cudaMemcpyDeviceToHost, st));
     S3_TRY(cudaStreamSynchronize(st));
     out->numRanges = h_cnt[0];
+    out->splitSeed = splitSeed; out->rangesBeforeSplit = h_cnt[1];
     if (out->numRanges) {
         S3_TRY(cudaMallocAsync((void **)&out->d_buf, (size_t)out->numRanges * 28, st));
         s3_seedsrch_merge_kernel<true><<<nb, 256, 0, st>>>(numSeeds, d_starts0, d_out0, total0, d_rank, d_starts1, d_out1, total1, d_maxHit, out->d_status,

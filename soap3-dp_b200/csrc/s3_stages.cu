@@ -332,100 +332,104 @@ done:
     return S3_OK;
 }
 
-extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
-                                const uint32_t *pairReadIDs, uint64_t n, const s3_stage_params *par, s3_deep_dp_result *out)
+namespace {
+
+// the pairs with route `want` of a chain's route array, as even read ids, with the two reads' lengths: id | length | mate's length
+__global__ void s3_stage_pick_flag_kernel(uint32_t P, const uint8_t *__restrict__ route, uint8_t want, uint8_t *__restrict__ flags)
 {
-    if (!out) { s3_set_error("s3_deep_dp_align: NULL result"); return S3_EINVAL; }
-    memset(out, 0, sizeof *out);
-    if (!ix || !queries || !readLengths || !par || (n && !pairReadIDs)) { s3_set_error("s3_deep_dp_align: NULL argument"); return S3_EINVAL; }
-    if (!ix->loc.sa || !ix->loc.text) { s3_set_error("s3_deep_dp_align: the index was uploaded without its suffix array and packed text"); return S3_EINVAL; }
-    out->numPairs = n;
-    if (n == 0) return S3_OK;
-    if (numReads >= 0xFFFFFFF0ull) { s3_set_error("s3_deep_dp_align: too many reads"); return S3_EINVAL; }
-    uint32_t maxLen = 0;
-    for (uint64_t k = 0; k < n; ++k) {
-        const uint32_t e = pairReadIDs[k];
-        if ((e & 1u) || (uint64_t)e + 1 >= numReads) { s3_set_error("s3_deep_dp_align: %u is not the even read id of a pair", e); return S3_EINVAL; }
-        for (int i = 0; i < 2; ++i) {
-            if (readLengths[e + i] > 16u * wordPerQuery) { s3_set_error("s3_deep_dp_align: read %u longer than its query words", e + i); return S3_EINVAL; }
-            if (readLengths[e + i] > maxLen) maxLen = readLengths[e + i];
-        }
-    }
+    const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p < P) flags[p] = route[p] == want;
+}
+__global__ void s3_stage_pick_kernel(uint32_t n, const uint32_t *__restrict__ pairs, const uint32_t *__restrict__ lenByRead, uint32_t *__restrict__ out)
+{
+    const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n) return;
+    const uint32_t e = 2u * pairs[k];
+    out[k] = e; out[n + k] = lenByRead[e]; out[2 * (size_t)n + k] = lenByRead[e + 1];
+}
+
+// DPForUnalignPairs2 for the pairs pairIDs[0..n) (even read ids) whose two lengths are pairLens[2k], pairLens[2k + 1].  The query
+// buffer is on the device already (s3_stage_queries(ix)) and so are the read lengths by read id.
+int deep_dp_core(s3_index *ix, const uint32_t *d_len, uint64_t numReads, uint32_t wordPerQuery, const uint32_t *pairIDs, const uint32_t *pairLens, uint64_t n,
+                 const s3_stage_params *par, s3_deep_dp_result *out, StageClock &clk)
+{
     int rc = S3_OK;
-    StageClock clk("s3_deep_dp_align");
-    if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_deep_dp_align: cudaSetDevice failed"); return S3_ECUDA; }
     cudaStream_t st = ix->stream;
-    std::vector<uint32_t> candID, candL, candR;                       // readIDLeft, estimated starts: all rounds' candidates
-    std::vector<uint32_t> input(pairReadIDs, pairReadIDs + n), next, unseeded;
+    uint32_t maxLen = 0;
+    for (uint64_t k = 0; k < 2 * n; ++k) if (pairLens[k] > maxLen) maxLen = pairLens[k];
+    std::vector<uint32_t> candID;                                      // readIDLeft of all rounds' candidates
+    std::vector<uint32_t> input(n), next, unseeded;                     // places in pairIDs
+    std::vector<uint8_t> flags(numReads, 0);                            // by even read id: 1 a seed with too many hits, 2 a candidate
     std::vector<s3_deep_dp_hit> hits;
     std::vector<uint32_t> runs;
-    uint32_t *d_len = NULL, *d_c = NULL, *d_wl = NULL, *d_wr = NULL, *d_cnt = NULL;
+    std::vector<uint32_t> entries;
+    std::vector<uint8_t> status;
+    uint32_t *d_c = NULL, *d_wl = NULL, *d_wr = NULL, *d_cnt = NULL;
     void *d_tmp = NULL;
-    SeedSide side[2];
-    uint32_t *d_pc = NULL;                                              // a round's candidates (base of s3_seed_pair_candidates_any's allocation)
-    S3_TRYS(cudaMallocAsync((void **)&d_len, numReads * 4 + 16, st));
-    S3_TRYS(cudaMemcpyAsync(d_len, readLengths, numReads * 4, cudaMemcpyHostToDevice, st));
-    if ((rc = s3_stage_upload_queries(ix, queries, numReads, wordPerQuery))) goto done;
+    SeedSide side;
+    uint32_t *d_round[2] = {NULL, NULL};                                // a round's candidates: ids | left | right (base of s3_seed_pair_candidates_any's allocation)
+    uint64_t ncRound[2] = {0, 0};
+    for (uint64_t k = 0; k < n; ++k) input[k] = (uint32_t)k;
     for (int round = 0; round < 2 && !input.empty(); ++round) {
         const int stage = round == 0 ? S3_STAGE_DEEP_DP_ROUND1 : S3_STAGE_DEEP_DP_ROUND2;
-        // ---- seeds of both mates (PairEndSeedingBatch::packSeeds, DV-DPfunctions.cu:2682-2706), seeding driver per side
-        StagePlans plans[2];
-        const size_t ni = input.size();
-        std::vector<uint32_t> entries[2];
+        // ---- seeds of both mates (PairEndSeedingBatch::packSeeds, DV-DPfunctions.cu:2682-2706): one seeding call for the two sides,
+        // the first mates' seeds before the second mates' -- the driver returns ranges in seed order, so each side is a stretch of them
+        StagePlans plans;
+        const size_t ni = input.size(), ne = 2 * ni;
+        entries.resize(4 * ne);
         uint64_t total[2] = {0, 0};
         for (int i = 0; i < 2; ++i) {
-            entries[i].resize(4 * ni);
             for (size_t k = 0; k < ni; ++k) {
-                const uint32_t e = input[k];
+                const uint32_t e = pairIDs[input[k]], len = pairLens[2 * (size_t)input[k] + i], len2 = pairLens[2 * (size_t)input[k] + 1 - i];
                 uint32_t idx;
-                if ((rc = plans[i].get(stage, readLengths[e + i], readLengths[e + 1 - i], i, par, &idx))) goto done;
-                entries[i][k] = e + i; entries[i][ni + k] = e; entries[i][2 * ni + k] = idx; entries[i][3 * ni + k] = (uint32_t)total[i];
-                total[i] += (uint64_t)plans[i].table[idx].seedNum;
+                if ((rc = plans.get(stage, len, len2, i, par, &idx))) goto done;
+                const size_t at = (size_t)i * ni + k;
+                entries[at] = e + i; entries[ne + at] = e; entries[2 * ne + at] = idx; entries[3 * ne + at] = (uint32_t)(total[0] + total[1]);
+                total[i] += (uint64_t)plans.table[idx].seedNum;
             }
-            if ((rc = seed_side_run(ix, entries[i], ni, total[i], plans[i], wordPerQuery, d_len, side[i]))) goto done;
         }
+        side.ranges.splitSeed = (uint32_t)total[0];
+        if ((rc = seed_side_run(ix, entries, ne, total[0] + total[1], plans, wordPerQuery, d_len, side))) goto done;
         out->numSeeds += total[0] + total[1];
-        clk.lap("seeds + seeding driver x 2");
+        clk.lap("seeds + seeding driver");
         // a pair with a too-many seed on either side is flagged (decodePositions, :2951-2954)
-        std::vector<uint8_t> tooMany(numReads, 0), seeded(numReads, 0);
-        for (int i = 0; i < 2; ++i) {
-            if (!total[i]) continue;
-            std::vector<uint8_t> status(total[i]);
-            S3_TRYS(cudaMemcpyAsync(status.data(), side[i].ranges.d_status, total[i], cudaMemcpyDeviceToHost, st));
+        for (size_t k = 0; k < ni; ++k) flags[pairIDs[input[k]]] = 0;
+        if (total[0] + total[1]) {
+            status.resize(total[0] + total[1]);
+            S3_TRYS(cudaMemcpyAsync(status.data(), side.ranges.d_status, status.size(), cudaMemcpyDeviceToHost, st));
             S3_TRYS(cudaStreamSynchronize(st));
-            for (size_t k = 0; k < ni; ++k) {
-                const uint32_t s0 = entries[i][3 * ni + k], s1 = k + 1 < ni ? entries[i][3 * ni + k + 1] : (uint32_t)total[i];
-                for (uint32_t sd = s0; sd < s1; ++sd) if (status[sd] == 4) { tooMany[input[k]] = 1; break; }
+            for (size_t at = 0; at < ne; ++at) {
+                const uint32_t s0 = entries[3 * ne + at], s1 = at + 1 < ne ? entries[3 * ne + at + 1] : (uint32_t)status.size();
+                for (uint32_t sd = s0; sd < s1; ++sd) if (status[sd] == 4) { flags[entries[ne + at]] |= 1; break; }
             }
         }
         // ---- candidate position pairs (decodeMergePositions, DV-DPfunctions.cu:2963-2999)
         uint32_t *d_id = NULL, *d_l = NULL, *d_r = NULL;
         uint64_t nc = 0;
         {
+            const uint64_t R = side.ranges.numRanges, R0 = side.ranges.rangesBeforeSplit;
             const uint32_t *in[2][7];
-            for (int i = 0; i < 2; ++i) { const uint64_t R = side[i].ranges.numRanges; for (int a = 0; a < 7; ++a) in[i][a] = side[i].ranges.d_buf ? side[i].ranges.d_buf + a * R : NULL; }
-            if ((rc = s3_seed_pair_candidates_any(ix, in[0], side[0].ranges.numRanges, in[1], side[1].ranges.numRanges, 1, 0xFFFFFFFFu, d_len, numReads,
+            for (int a = 0; a < 7; ++a) { in[0][a] = side.ranges.d_buf ? side.ranges.d_buf + a * R : NULL; in[1][a] = side.ranges.d_buf ? side.ranges.d_buf + a * R + R0 : NULL; }
+            if ((rc = s3_seed_pair_candidates_any(ix, in[0], R0, in[1], R - R0, 1, 0xFFFFFFFFu, d_len, numReads,
                                                   par->insertLow, par->insertHigh, par->strandLeftLeg, par->strandRightLeg, &d_id, &d_l, &d_r, &nc))) goto done;
-            d_pc = d_id;
+            d_round[round] = d_id; ncRound[round] = nc;                     // (d_l = d_id + 3 nc, d_r = d_id + 4 nc: see s3_seed_pair_candidates_any)
+            if (nc && (d_l != d_id + 3 * nc || d_r != d_id + 4 * nc)) { s3_set_error("s3_deep_dp_align: candidate layout"); rc = S3_EINVAL; goto done; }
         }
         if (nc) {
             const size_t base = candID.size();
-            candID.resize(base + nc); candL.resize(base + nc); candR.resize(base + nc);
+            candID.resize(base + nc);
             S3_TRYS(cudaMemcpyAsync(candID.data() + base, d_id, nc * 4, cudaMemcpyDeviceToHost, st));
-            S3_TRYS(cudaMemcpyAsync(candL.data() + base, d_l, nc * 4, cudaMemcpyDeviceToHost, st));
-            S3_TRYS(cudaMemcpyAsync(candR.data() + base, d_r, nc * 4, cudaMemcpyDeviceToHost, st));
             S3_TRYS(cudaStreamSynchronize(st));
-            for (size_t c = base; c < base + nc; ++c) seeded[candID[c] & ~1u] = 1;
+            for (size_t c = base; c < base + nc; ++c) flags[candID[c] & ~1u] |= 2;
         }
-        if (d_pc) { cudaFreeAsync(d_pc, st); d_pc = NULL; }
-        seed_side_free(ix, side[0]); seed_side_free(ix, side[1]);
+        seed_side_free(ix, side);
         clk.lap("pair candidates");
         // ---- seeded / too many / unseeded pairs (performSeeding, DV-DPfunctions.cu:3105-3125)
         next.clear();
         for (size_t k = 0; k < ni; ++k) {
-            const uint32_t e = input[k];
-            if (seeded[e]) continue;
-            if (round == 0 && tooMany[e]) next.push_back(e); else unseeded.push_back(e);
+            const uint32_t e = pairIDs[input[k]];
+            if (flags[e] & 2) continue;
+            if (round == 0 && (flags[e] & 1)) next.push_back(input[k]); else unseeded.push_back(e);
         }
         input.swap(next);
     }
@@ -451,16 +455,21 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
             S3_TRYS(cudaMallocAsync((void **)&d_wr, (size_t)nc * 40 + 64, st));
             S3_TRYS(cudaMallocAsync((void **)&d_cnt, 2 * ((size_t)nc + 1) * 4, st));
             S3_TRYS(cudaMallocAsync(&d_tmp, scanTemp + 16, st));
-            S3_TRYS(cudaMemcpyAsync(d_c, candID.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
-            S3_TRYS(cudaMemcpyAsync(d_c + nc, candL.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
-            S3_TRYS(cudaMemcpyAsync(d_c + 2 * (size_t)nc, candR.data(), (size_t)nc * 4, cudaMemcpyHostToDevice, st));
+            // the rounds' candidates one after the other (they never left the device): ids | left | right
+            for (uint64_t r = 0, base = 0; r < 2; base += ncRound[r], ++r) {
+                if (!ncRound[r]) continue;
+                const uint64_t m = ncRound[r];
+                S3_TRYS(cudaMemcpyAsync(d_c + base, d_round[r], m * 4, cudaMemcpyDeviceToDevice, st));
+                S3_TRYS(cudaMemcpyAsync(d_c + nc + base, d_round[r] + 3 * m, m * 4, cudaMemcpyDeviceToDevice, st));
+                S3_TRYS(cudaMemcpyAsync(d_c + 2 * (size_t)nc + base, d_round[r] + 4 * m, m * 4, cudaMemcpyDeviceToDevice, st));
+            }
             const S3StageWin ol = win_of(d_wl, nc), orr = win_of(d_wr, nc);
             const unsigned nb = (nc + 255) / 256;
             s3_stage_win_left_kernel<<<nb, 256, 0, st>>>(w, nc, d_c, d_len, ol);
             S3_LAUNCHED(1);
             S3StageAligned al, ar;
             memset(&ar, 0, sizeof ar);
-            if ((rc = s3_stage_align(ix, queries, readLengths, numReads, wordPerQuery, 0, maxRead, maxDNA, par->scores, 0, nc, ol.readID, ol.strand, ol.start, ol.dnaLen,
+            if ((rc = s3_stage_align(ix, NULL, NULL, numReads, wordPerQuery, 0, maxRead, maxDNA, par->scores, 0, nc, ol.readID, ol.strand, ol.start, ol.dnaLen,
                                      ol.cutoff, ol.clipLt, ol.clipRt, ol.ancL, ol.ancR, d_len, NULL, &al))) goto done;
             clk.lap("left windows + DP");
             uint32_t *d_count = d_cnt, *d_off = d_cnt + nc + 1;
@@ -474,9 +483,19 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
             S3_TRYS(cudaMemcpyAsync(h_nr, d_off + nc, 4, cudaMemcpyDeviceToHost, st));
             S3_TRYS(cudaStreamSynchronize(st));
             const uint32_t nr = *h_nr;
-            if (nr && (rc = s3_stage_align(ix, queries, readLengths, numReads, wordPerQuery, 0, maxRead, maxDNA, par->scores, 1, nr, orr.readID, orr.strand, orr.start,
+            if (nr && (rc = s3_stage_align(ix, NULL, NULL, numReads, wordPerQuery, 0, maxRead, maxDNA, par->scores, 1, nr, orr.readID, orr.strand, orr.start,
                                            orr.dnaLen, orr.cutoff, orr.clipLt, orr.clipRt, orr.ancL, orr.ancR, d_len, orr.cand, &ar))) goto done;
             clk.lap("right windows + DP");
+            uint32_t nh = 0;
+            uint64_t nruns = 0;
+            for (uint32_t t = 0; t < nr; ++t) {
+                if (ar.score[t] < ar.cutoff[t]) continue;
+                const uint32_t c = ar.cand[t];
+                ++nh; nruns += (al.runOff[c + 1] - al.runOff[c]) + (ar.runOff[t + 1] - ar.runOff[t]);
+            }
+            hits.reserve(nh);
+            runs.resize(nruns);
+            uint32_t at = 0;
             for (uint32_t t = 0; t < nr; ++t) {
                 if (ar.score[t] < ar.cutoff[t]) continue;           // (the left read reached its cutoff: only those have a right window)
                 const uint32_t c = ar.cand[t], left = candID[c], readSide = left & 1u;
@@ -485,11 +504,10 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
                 memset(&h, 0, sizeof h);
                 h.readID = left - readSide;
                 const uint32_t posLeft = al.start[c] + al.hit[c], posRight = ar.start[t] + ar.hit[t];
-                uint32_t roL = (uint32_t)runs.size();
-                runs.insert(runs.end(), al.runs + al.runOff[c], al.runs + al.runOff[c + 1]);
-                uint32_t nL = (uint32_t)runs.size() - roL, roR = (uint32_t)runs.size();
-                runs.insert(runs.end(), ar.runs + ar.runOff[t], ar.runs + ar.runOff[t + 1]);
-                uint32_t nR = (uint32_t)runs.size() - roR;
+                const uint32_t roL = at, nL = al.runOff[c + 1] - al.runOff[c];
+                memcpy(runs.data() + at, al.runs + al.runOff[c], (size_t)nL * 4); at += nL;
+                const uint32_t roR = at, nR = ar.runOff[t + 1] - ar.runOff[t];
+                memcpy(runs.data() + at, ar.runs + ar.runOff[t], (size_t)nR * 4); at += nR;
                 if (readSide == 0) {
                     h.pos1 = posLeft; h.pos2 = posRight; h.score1 = al.score[c]; h.score2 = ar.score[t]; h.numSame1 = al.cnt[c]; h.numSame2 = ar.cnt[t];
                     h.strand1 = (uint8_t)par->strandLeftLeg; h.strand2 = (uint8_t)par->strandRightLeg;
@@ -505,10 +523,9 @@ extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uin
         }
     }
 done:
-    seed_side_free(ix, side[0]); seed_side_free(ix, side[1]);
-    if (d_pc) cudaFreeAsync(d_pc, st);
+    seed_side_free(ix, side);
     {
-        void *p[] = {d_len, d_c, d_wl, d_wr, d_cnt, d_tmp};
+        void *p[] = {d_round[0], d_round[1], d_c, d_wl, d_wr, d_cnt, d_tmp};
         for (void *q : p) if (q) cudaFreeAsync(q, st);
     }
     if (rc) return rc;
@@ -516,4 +533,96 @@ done:
     out->hits = to_malloc(hits); out->runs = to_malloc(runs); out->unseeded = to_malloc(unseeded);
     if (!out->hits || !out->runs || !out->unseeded) { s3_deep_dp_result_free(out); s3_set_error("s3_deep_dp_align: out of host memory"); return S3_ENOMEM; }
     return S3_OK;
+}
+
+}  // namespace
+
+extern "C" int s3_deep_dp_align(s3_index *ix, const uint32_t *queries, const uint32_t *readLengths, uint64_t numReads, uint32_t wordPerQuery,
+                                const uint32_t *pairReadIDs, uint64_t n, const s3_stage_params *par, s3_deep_dp_result *out)
+{
+    if (!out) { s3_set_error("s3_deep_dp_align: NULL result"); return S3_EINVAL; }
+    memset(out, 0, sizeof *out);
+    if (!ix || !queries || !readLengths || !par || (n && !pairReadIDs)) { s3_set_error("s3_deep_dp_align: NULL argument"); return S3_EINVAL; }
+    if (!ix->loc.sa || !ix->loc.text) { s3_set_error("s3_deep_dp_align: the index was uploaded without its suffix array and packed text"); return S3_EINVAL; }
+    out->numPairs = n;
+    if (n == 0) return S3_OK;
+    if (numReads >= 0xFFFFFFF0ull) { s3_set_error("s3_deep_dp_align: too many reads"); return S3_EINVAL; }
+    std::vector<uint32_t> lens(2 * n);
+    for (uint64_t k = 0; k < n; ++k) {
+        const uint32_t e = pairReadIDs[k];
+        if ((e & 1u) || (uint64_t)e + 1 >= numReads) { s3_set_error("s3_deep_dp_align: %u is not the even read id of a pair", e); return S3_EINVAL; }
+        for (int i = 0; i < 2; ++i) {
+            if (readLengths[e + i] > 16u * wordPerQuery) { s3_set_error("s3_deep_dp_align: read %u longer than its query words", e + i); return S3_EINVAL; }
+            lens[2 * k + i] = readLengths[e + i];
+        }
+    }
+    int rc = S3_OK;
+    StageClock clk("s3_deep_dp_align");
+    if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_deep_dp_align: cudaSetDevice failed"); return S3_ECUDA; }
+    cudaStream_t st = ix->stream;
+    uint32_t *d_len = NULL;
+    S3_TRYS(cudaMallocAsync((void **)&d_len, numReads * 4 + 16, st));
+    S3_TRYS(cudaMemcpyAsync(d_len, readLengths, numReads * 4, cudaMemcpyHostToDevice, st));
+    if ((rc = s3_stage_upload_queries(ix, queries, numReads, wordPerQuery))) goto done;
+    clk.lap("uploads");
+    rc = deep_dp_core(ix, d_len, numReads, wordPerQuery, pairReadIDs, lens.data(), n, par, out, clk);
+done:
+    if (d_len) cudaFreeAsync(d_len, st);
+    return rc;
+}
+
+// The same stage for the batch a paired-end chain has just aligned: the pairs it left with no occurrence of either read
+// (route S3_PE_BOTH_UNALIGNED) are picked on the device, and the stage works on the chain's own query buffer and read lengths.
+int s3_stage_deep_dp_of_chain(s3_index *ix, const uint32_t *d_queries, const uint32_t *d_len, uint64_t numReads, uint32_t wordPerQuery, const uint8_t *d_route,
+                              uint8_t wantRoute, const s3_stage_params *par, s3_deep_dp_result *out)
+{
+    memset(out, 0, sizeof *out);
+    if (!ix->loc.sa || !ix->loc.text) { s3_set_error("s3_pe_deep_dp: the index was uploaded without its suffix array and packed text"); return S3_EINVAL; }
+    if (numReads < 2) return S3_OK;
+    int rc = S3_OK;
+    StageClock clk("s3_pe_deep_dp");
+    if (cudaSetDevice(ix->device) != cudaSuccess) { s3_set_error("s3_pe_deep_dp: cudaSetDevice failed"); return S3_ECUDA; }
+    cudaStream_t st = ix->stream;
+    const uint32_t P = (uint32_t)(numReads / 2);
+    uint8_t *d_flags = NULL;
+    uint32_t *d_pairs = NULL, *d_sel = NULL, *d_n = NULL;
+    void *d_tmp = NULL;
+    size_t t1 = 0;
+    uint32_t n = 0;
+    std::vector<uint32_t> sel;
+    uint32_t *h_n = (uint32_t *)ix->pinnedCount + 13;
+    S3_TRYS(cudaMallocAsync((void **)&d_flags, P, st));
+    S3_TRYS(cudaMallocAsync((void **)&d_pairs, (size_t)P * 4 + 16, st));
+    S3_TRYS(cudaMallocAsync((void **)&d_n, 16, st));
+    cub::DeviceSelect::Flagged(NULL, t1, cub::CountingInputIterator<uint32_t>(0), d_flags, d_pairs, d_n, (int)P, st);
+    S3_TRYS(cudaMallocAsync(&d_tmp, t1 + 16, st));
+    s3_stage_pick_flag_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, d_route, wantRoute, d_flags);
+    S3_LAUNCHED(1);
+    S3_TRYS(cub::DeviceSelect::Flagged(d_tmp, t1, cub::CountingInputIterator<uint32_t>(0), d_flags, d_pairs, d_n, (int)P, st));
+    S3_TRYS(cudaMemcpyAsync(h_n, d_n, 4, cudaMemcpyDeviceToHost, st));
+    S3_TRYS(cudaStreamSynchronize(st));
+    n = *h_n;
+    out->numPairs = n;
+    if (n) {
+        S3_TRYS(cudaMallocAsync((void **)&d_sel, (size_t)n * 12, st));
+        s3_stage_pick_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d_pairs, d_len, d_sel);
+        S3_LAUNCHED(1);
+        sel.resize(3 * (size_t)n);
+        S3_TRYS(cudaMemcpyAsync(sel.data(), d_sel, (size_t)n * 12, cudaMemcpyDeviceToHost, st));
+        S3_TRYS(cudaStreamSynchronize(st));
+        std::vector<uint32_t> lens(2 * (size_t)n);
+        for (uint32_t k = 0; k < n; ++k) {
+            lens[2 * (size_t)k] = sel[n + k]; lens[2 * (size_t)k + 1] = sel[2 * (size_t)n + k];
+            if (sel[n + k] > 16u * wordPerQuery || sel[2 * (size_t)n + k] > 16u * wordPerQuery) { s3_set_error("s3_pe_deep_dp: a read longer than its query words"); rc = S3_EINVAL; goto done; }
+        }
+        if ((rc = s3_stage_use_queries(ix, d_queries))) goto done;
+        clk.lap("picking the pairs");
+        rc = deep_dp_core(ix, d_len, numReads, wordPerQuery, sel.data(), lens.data(), n, par, out, clk);
+    }
+done:
+    {
+        void *p[] = {d_flags, d_pairs, d_sel, d_n, d_tmp};
+        for (void *q : p) if (q) cudaFreeAsync(q, st);
+    }
+    return rc;
 }

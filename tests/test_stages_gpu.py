@@ -191,6 +191,49 @@ def test_deep_dp_stage(env):
                 int(h["numSame1"]), int(h["numSame2"]), c1, c2) == w
 
 
+def test_deep_dp_of_the_chain(env):
+    """s3_pe_deep_dp (the both-unaligned pairs picked on the device, the chain's own query buffer) == s3_deep_dp_align of the pairs the
+    chain routed as S3_PE_NONE == the seeding oracle, after s3_pe_align and after s3_pe_align_device"""
+    G, idx, hi, gi = env
+    rng = np.random.default_rng(21)
+    L, pairs = 100, 400
+    m1, m2, _ = synth.simulate_paired_end(G, pairs, L, seed=31, bad_mate_fraction=0.0)
+    raw = torch.stack([m1.reads, m2.reads], dim=1).reshape(2 * pairs, L).cpu().numpy()
+    reads = [r.copy() for r in raw]
+    for p in range(0, pairs, 3):                                    # a third of the pairs: both mates beyond the search, within the seeds' reach
+        for i in range(2):
+            reads[2 * p + i] = mutate(rng, raw[2 * p + i], int(rng.integers(4, 8)), int(rng.integers(0, 2)))
+    for p in range(0, pairs, 30):
+        reads[2 * p] = rng.integers(0, 4, L).astype(np.uint8)
+        reads[2 * p + 1] = rng.integers(0, 4, L).astype(np.uint8)
+    n = 2 * pairs
+    wpq = formats.word_per_query(L)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    q = formats.pack_queries(np.stack(reads), lens[:n], wpq)
+    sp = api.stage_params()
+    pe = api.PairAligner(gi, n, L, api.pe_params(num_mismatch=2, insert_low=200, insert_high=500, scores=(1, -2, -3, -1), read_length=L, max_windows=n))
+    try:
+        got_chain = pe.align(q, lens, n, wpq)
+        ids = (2 * np.nonzero(got_chain["route"] == 0)[0]).astype(np.uint32)
+        assert len(ids) > pairs // 5
+        a = pe.deep_dp(sp)
+        qd, ld = torch.from_numpy(q.view(np.int32)).cuda(), torch.from_numpy(lens.view(np.int32)).cuda()
+        pe.align_device(qd.data_ptr(), ld.data_ptr(), n, wpq)
+        torch.cuda.synchronize()
+        b = pe.deep_dp(sp)
+    finally:
+        pe.free()
+    want = api.deep_dp_align(gi, q, lens, n, wpq, ids, sp)
+    ora = seeding_oracle.deep_dp(OracleEnv(idx, hi), G.cpu().numpy(), reads, ids.tolist(), PAR)
+    assert want["num_seeds"] == ora["seeds"] and want["num_candidates"] == ora["candidates"] and len(want["hits"]) == len(ora["hits"]) > len(ids) // 3
+    for got in (a, b):
+        assert got["num_input"] == len(ids)
+        assert got["num_seeds"] == want["num_seeds"] and got["num_candidates"] == want["num_candidates"]
+        assert got["unseeded"].tolist() == want["unseeded"].tolist()
+        assert got["hits"].tobytes() == want["hits"].tobytes() and np.array_equal(got["runs"], want["runs"])
+
+
 def test_stages_empty_and_bad_args(env):
     G, idx, hi, gi = env
     z = np.zeros(32 * 8, np.uint32)

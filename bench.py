@@ -643,6 +643,55 @@ def pinned_np(t):
     return h.numpy().view(np.uint32)
 
 
+def stage_parity(args, gi, host, genome, L, wpq, reads, sp, se_mode):
+    """a sample at full size through the seeded stage (every read / pair of the sample sent through it) against oracle/seeding_oracle.py"""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import seeding_oracle
+    from test_stages_gpu import OracleEnv, PAR
+    m = min(args.parity_pairs // 16, 2048)
+    m = m - (m & 1)
+    rd = [np.ascontiguousarray(reads[r]) for r in range(m)]
+    lens_m = np.zeros(formats.ceil32(m), np.uint32)
+    lens_m[:m] = L
+    qm = formats.pack_queries(np.stack(rd), lens_m[:m], wpq)
+
+    class HI:
+        pass
+    hi = HI()
+    hi.bwt, hi.occ, hi.rbwt, hi.rocc = host["bwt"], host["occ"], host["rbwt"], host["rocc"]
+    hi.isa0, hi.risa0, hi.n = int(host["meta"][0]), int(host["meta"][1]), int(host["meta"][2])
+    env = OracleEnv(None, hi, sa=host["sa"])
+    gv = _GenomeView(genome)
+    t0 = time.time()
+    if se_mode:
+        ids = np.arange(m, dtype=np.uint32)
+        got = api.single_dp_align(gi, qm, lens_m, m, wpq, ids, sp)
+        want = seeding_oracle.single_dp(env, gv, rd, ids.tolist(), PAR)
+        same = got["num_seeds"] == want["seeds"] and got["num_candidates"] == want["candidates"] and got["unseeded"].tolist() == want["unseeded"] \
+            and len(got["hits"]) == len(want["hits"])
+        if same:
+            for h, w in zip(got["hits"], want["hits"]):
+                cig = api.runs_to_cigar(got["runs"][int(h["runOffset"]):int(h["runOffset"]) + int(h["numRuns"])])
+                same &= (int(h["readID"]), int(h["strand"]), int(h["pos"]), int(h["score"]), int(h["numSameScore"]), cig) == w
+    else:
+        ids = np.arange(0, m, 2, dtype=np.uint32)
+        got = api.deep_dp_align(gi, qm, lens_m, m, wpq, ids, sp)
+        want = seeding_oracle.deep_dp(env, gv, rd, ids.tolist(), PAR)
+        same = got["num_seeds"] == want["seeds"] and got["num_candidates"] == want["candidates"] and got["unseeded"].tolist() == want["unseeded"] \
+            and len(got["hits"]) == len(want["hits"])
+        if same:
+            for h, w in zip(got["hits"], want["hits"]):
+                c1 = api.runs_to_cigar(got["runs"][int(h["runOffset1"]):int(h["runOffset1"]) + int(h["numRuns1"])])
+                c2 = api.runs_to_cigar(got["runs"][int(h["runOffset2"]):int(h["runOffset2"]) + int(h["numRuns2"])])
+                same &= (int(h["readID"]), int(h["strand1"]), int(h["strand2"]), int(h["pos1"]), int(h["pos2"]), int(h["score1"]), int(h["score2"]),
+                         int(h["numSame1"]), int(h["numSame2"]), c1, c2) == w
+    return {("reads" if se_mode else "pairs"): int(m if se_mode else m // 2), "seeds": int(want["seeds"]),
+            "candidates": int(want["candidates"]), "stage_alignments": len(want["hits"]), "stage_bit_exact": bool(same),
+            "seconds": time.time() - t0,
+            "checker": "oracle/seeding_oracle.py (every read of the sample sent through the seeded stage) over the oracle restatements"}, (m, rd, qm, lens_m, hi)
+
+
 def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, threads):
     """BASELINE config 3 (se150_dp) and the deep-DP leg of config 4 (pe100_deep): the search chain followed by the DP stage that
     starts from seeds, for the reads the chain left unaligned.
@@ -702,10 +751,10 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
             t1b = time.perf_counter()
             res = api.single_dp_align(gi, q, lens, N, wpq, ids, sp, counts_only=True)
         else:
-            ids = (2 * np.nonzero(got["route"] == 0)[0]).astype(np.uint32)
-            aligned = int(N // 2 - len(ids))
             t1b = time.perf_counter()
-            res = api.deep_dp_align(gi, q, lens, N, wpq, ids, sp, counts_only=True)
+            res = chain.deep_dp(sp, counts_only=True)               # the pairs the chain left as S3_PE_NONE, picked on the device
+            ids = range(res["num_input"])
+            aligned = int(N // 2 - len(ids))
         t2 = time.perf_counter()
         return got, res, ids, (t1 - t0, t2 - t1b, t1b - t1), aligned
 
@@ -789,50 +838,7 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
     if world == 1 and not args.no_cpu_baseline:
         # parity of a sample at full size: the chain and the seeded stage against the compositions of the oracles
         import helpers
-        import seeding_oracle
-        from test_stages_gpu import OracleEnv, PAR
-        m = min(args.parity_pairs // 16, 2048)
-        q, lens, reads = sets[-1]
-        m = m - (m & 1)
-        rd = [np.ascontiguousarray(reads[r]) for r in range(m)]
-        lens_m = np.zeros(formats.ceil32(m), np.uint32)
-        lens_m[:m] = L
-        qm = formats.pack_queries(np.stack(rd), lens_m[:m], wpq)
-
-        class HI:
-            pass
-        hi = HI()
-        hi.bwt, hi.occ, hi.rbwt, hi.rocc = host["bwt"], host["occ"], host["rbwt"], host["rocc"]
-        hi.isa0, hi.risa0, hi.n = int(host["meta"][0]), int(host["meta"][1]), int(host["meta"][2])
-        env = OracleEnv(None, hi, sa=host["sa"])
-        gv = _GenomeView(genome)
-        t0 = time.time()
-        if se_mode:
-            ids = np.arange(m, dtype=np.uint32)
-            got = api.single_dp_align(gi, qm, lens_m, m, wpq, ids, sp)
-            want = seeding_oracle.single_dp(env, gv, rd, ids.tolist(), PAR)
-            same = got["num_seeds"] == want["seeds"] and got["num_candidates"] == want["candidates"] and got["unseeded"].tolist() == want["unseeded"] \
-                and len(got["hits"]) == len(want["hits"])
-            if same:
-                for h, w in zip(got["hits"], want["hits"]):
-                    cig = api.runs_to_cigar(got["runs"][int(h["runOffset"]):int(h["runOffset"]) + int(h["numRuns"])])
-                    same &= (int(h["readID"]), int(h["strand"]), int(h["pos"]), int(h["score"]), int(h["numSameScore"]), cig) == w
-        else:
-            ids = np.arange(0, m, 2, dtype=np.uint32)
-            got = api.deep_dp_align(gi, qm, lens_m, m, wpq, ids, sp)
-            want = seeding_oracle.deep_dp(env, gv, rd, ids.tolist(), PAR)
-            same = got["num_seeds"] == want["seeds"] and got["num_candidates"] == want["candidates"] and got["unseeded"].tolist() == want["unseeded"] \
-                and len(got["hits"]) == len(want["hits"])
-            if same:
-                for h, w in zip(got["hits"], want["hits"]):
-                    c1 = api.runs_to_cigar(got["runs"][int(h["runOffset1"]):int(h["runOffset1"]) + int(h["numRuns1"])])
-                    c2 = api.runs_to_cigar(got["runs"][int(h["runOffset2"]):int(h["runOffset2"]) + int(h["numRuns2"])])
-                    same &= (int(h["readID"]), int(h["strand1"]), int(h["strand2"]), int(h["pos1"]), int(h["pos2"]), int(h["score1"]), int(h["score2"]),
-                             int(h["numSame1"]), int(h["numSame2"]), c1, c2) == w
-        out["parity_at_full_size"] = {("reads" if se_mode else "pairs"): int(m if se_mode else m // 2), "seeds": int(want["seeds"]),
-                                      "candidates": int(want["candidates"]), "stage_alignments": len(want["hits"]), "stage_bit_exact": bool(same),
-                                      "seconds": time.time() - t0,
-                                      "checker": "oracle/seeding_oracle.py (every read of the sample sent through the seeded stage) over the oracle restatements"}
+        out["parity_at_full_size"], (m, rd, qm, lens_m, hi) = stage_parity(args, gi, host, genome, L, wpq, sets[-1][2], sp, se_mode)
         log("seeded stage parity at full size:", out["parity_at_full_size"])
         if se_mode:
             # and the long-read chain of the same sample against the reference's CPU search of the seeds + the validation oracle
@@ -1085,10 +1091,11 @@ def main():
     ap.add_argument("--parity-pairs", type=int, default=int(os.environ.get("S3_PARITY_PAIRS", 32_768)))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--repeat-fraction", type=float, default=float(os.environ.get("S3_REPEAT_FRACTION", 0.2)))
-    ap.add_argument("--config", default="pe100", choices=["pe100", "se100_k4", "se150_dp", "pe100_deep"],
-                    help="pe100 (default): the BASELINE metric's workload (config 4 shape); se100_k4: config 2, single-end 100 bp, <= 4 mismatches, "
+    ap.add_argument("--config", default="pe100", choices=["pe100", "pe100_deep", "pe100_chain", "se100_k4", "se150_dp"],
+                    help="pe100 (default; pe100_deep is the same): the BASELINE metric's workload, config 4 -- search + mate-rescue DP + deep DP of the "
+                         "both-unaligned pairs; pe100_chain: the same without the deep-DP stage; se100_k4: config 2, single-end 100 bp, <= 4 mismatches, "
                          "search + collect + locate (s3_se_align); se150_dp: config 3, 150 bp reads with indels, long-read search chain + single-read DP from "
-                         "seeds; pe100_deep: the default workload + deep DP of the both-unaligned pairs.  A 45 %%-repeat genome: --repeat-fraction 0.45")
+                         "seeds.  A 45 %%-repeat genome: --repeat-fraction 0.45")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         log("note: the timing rules ask for >= 3 warm-up steps")
@@ -1120,7 +1127,9 @@ def main():
     genome, host = get_index(args.genome_bp, 3, device, rank, world if args.impl == "ours" else 1, args.repeat_fraction)
     threads = os.cpu_count() or 1
     workload = (f"pe_2x{L}bp_insert{INSERT_LO}-{INSERT_HI}_genome{args.genome_bp}bp: per step and GPU {args.pairs} read pairs through k<=2 search "
-                f"(4 cases, both strands, round-1 slots), answer collection, routing, locate, pairing and mate-rescue DP (400 bp windows) with CIGARs")
+                f"(4 cases, both strands, round-1 slots), answer collection, routing, locate, pairing and mate-rescue DP (400 bp windows) with CIGARs"
+                + ("" if args.config == "pe100_chain" else "; then deep DP (DPForUnalignPairs2) of the pairs with no occurrence of either read: seeds of both mates, "
+                   "seeding driver, candidate position pairs, left window + DP, right window + DP, CIGARs"))
 
     if args.impl == "reference":
         vals = []
@@ -1161,7 +1170,7 @@ def main():
         return
     if os.environ.get("S3_L2_REGION"):                        # ncu captures with a window in place (profiles/exp_l2_persist.sh)
         api.set_l2_persist(gi, int(os.environ["S3_L2_REGION"]))
-    if args.config in ("se150_dp", "pe100_deep"):
+    if args.config == "se150_dp":
         return run_stage_config(args, gi, host, genome, device, local_rank, rank, world, threads)
     if args.config == "se100_k4":
         return run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream, L, threads, k=4)
@@ -1171,14 +1180,20 @@ def main():
     par = api.pe_params(num_mismatch=K_MISMATCH, insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES, read_length=L,
                         max_windows=N // 2)
     pe = api.PairAligner(gi, N, L, par)
-    # a second handle on the same index arrays + its own chain: two batches in flight, one host thread each
-    gi2 = api.index_clone(gi)
-    pe2 = api.PairAligner(gi2, N, L, par)
-    stream2 = torch.cuda.ExternalStream(gi2.stream, device=device)
+    # more handles on the same index arrays, each with its own chain and stage workspace: T batches in flight, one host thread each
+    with_deep = args.config != "pe100_chain"
+    T = max(int(os.environ.get("S3_IN_FLIGHT", "4" if with_deep else "2")), 1)
+    sp = api.stage_params(insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES)
+    gis, pes, streams = [gi], [pe], [stream]
+    for _ in range(T - 1):
+        g2 = api.index_clone(gi)
+        gis.append(g2)
+        pes.append(api.PairAligner(g2, N, L, par))
+        streams.append(torch.cuda.ExternalStream(g2.stream, device=device))
     torch.cuda.synchronize()
     log(f"{total} batches of {N} reads prepared in {time.time() - t0:.1f}s")
 
-    def two_threads(fn_a, fn_b):
+    def in_threads(fns):
         errs = []
 
         def run(fn):
@@ -1187,8 +1202,11 @@ def main():
                 fn()
             except Exception as e:                          # noqa: BLE001
                 errs.append(e)
-        ta, tb = threading.Thread(target=run, args=(fn_a,)), threading.Thread(target=run, args=(fn_b,))
-        ta.start(); tb.start(); ta.join(); tb.join()
+        th = [threading.Thread(target=run, args=(fn,)) for fn in fns]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
         if errs:
             raise errs[0]
 
@@ -1198,21 +1216,30 @@ def main():
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def device_step(b):
-        return pe.align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq)
+    deep_stats = []
+
+    def device_step(b, h=0, keep=None):
+        # the chain on queries resident in HBM, then (config 4) deep DP of the pairs it left with no occurrence of either read,
+        # picked on the device from the chain's routes; results stay where the entries put them
+        r = pes[h].align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq)
+        if with_deep:
+            d = pes[h].deep_dp(sp, counts_only=True)
+            if keep is not None:
+                keep.append(d)
+        return r
 
     # ---- device-resident timing: queries in HBM, results left there ---------------------------------------------
     for s in range(args.warmup):
-        device_step(batches[s])
+        for h in range(T):
+            device_step(batches[s], h)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = api.launch_count()
     stats = []
     e0.record(stream)
     for k in range(args.steps):
-        stats.append(device_step(batches[args.warmup + k]))
+        stats.append(device_step(batches[args.warmup + k], 0, deep_stats))
     e1.record(stream)
     stream.synchronize()
     barrier()
@@ -1222,20 +1249,19 @@ def main():
     t_one = float(tt[0])
     reads_per_rank = N * args.steps
     value_one = world * reads_per_rank / t_one
-    # ---- the same K steps with two batches in flight: even steps on one handle, odd steps on its clone ------------
+    # ---- the same K steps with T batches in flight: step k on handle k mod T ---------------------------------------
     timed_batches = [batches[args.warmup + k] for k in range(args.steps)]
-    for s in range(args.warmup):
-        pe2.align_device(batches[s].queries.data_ptr(), batches[s].lens.data_ptr(), N, wpq)
-    two_threads(lambda: [device_step(b) for b in timed_batches[0:2:2]], lambda: [pe2.align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq) for b in timed_batches[1:2:2]])
+    # (warm-up of the threaded shape: with T handles allocating at once the stream-ordered pool reaches its working size here, not in the timed pass)
+    in_threads([(lambda h=h: [device_step(batches[s_], h) for s_ in range(args.warmup)]) for h in range(T)])
     barrier()
     d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = api.launch_count()
     d0.record(stream)
-    two_threads(lambda: [device_step(b) for b in timed_batches[0::2]],
-                lambda: [pe2.align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq) for b in timed_batches[1::2]])
-    fin = torch.cuda.Event()
-    fin.record(stream2)
-    stream.wait_event(fin)
+    in_threads([(lambda h=h: [device_step(b, h) for b in timed_batches[h::T]]) for h in range(T)])
+    for h in range(1, T):
+        fin = torch.cuda.Event()
+        fin.record(streams[h])
+        stream.wait_event(fin)
     d1.record(stream)
     stream.synchronize()
     barrier()
@@ -1257,14 +1283,15 @@ def main():
     api.set_timing(gi.handle, True)
     api.set_timing(pe.dp_handle, True, dp=True)
     pe.set_timing(True)
-    device_step(batches[0])
+    chain_step = lambda b: pe.align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq)
+    chain_step(batches[0])
     barrier()
     api.read_timing(gi.handle)
     api.read_timing(pe.dp_handle, dp=True)
     pe.read_timing()
     st0 = pe.read_timing()
     for k in range(args.steps):
-        device_step(batches[args.warmup + k])
+        chain_step(batches[args.warmup + k])
     barrier()
     ms_search, n_search = api.read_timing(gi.handle)
     ms_dp, n_dp = api.read_timing(pe.dp_handle, dp=True)
@@ -1306,7 +1333,7 @@ def main():
         h.copy_(t)
         return h
     host_sets = [(pinned(batches[args.warmup + k].queries), pinned(batches[args.warmup + k].lens)) for k in range(args.steps)]
-    pageable_sets = [(q.numpy().copy(), l.numpy().copy()) for q, l in host_sets[:4]]
+    pageable_sets = [(q.numpy().copy(), l.numpy().copy()) for q, l in host_sets[:max(4, T)]]
 
     def timed(fn):
         barrier()
@@ -1318,34 +1345,35 @@ def main():
             torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
         return float(t[0]), r
 
-    def e2e_steps(sets):
-        # the next batch's queries go up (s3_pe_prefetch, a copy stream) while this batch is aligned
+    def e2e_steps_on(h, sets, keep=None):
+        # the next batch's queries go up (s3_pe_prefetch, a copy stream) while this batch is aligned; the deep stage works on the
+        # batch's device copy, its records land in host memory
         out = None
         ptr = lambda x: x.data_ptr() if hasattr(x, "data_ptr") else x
         for k, (q, l) in enumerate(sets):
             if k + 1 < len(sets):
-                pe.prefetch(ptr(sets[k + 1][0]), ptr(sets[k + 1][1]), N, wpq)
-            out = pe.align(ptr(q), ptr(l), N, wpq, copy=False)
+                pes[h].prefetch(ptr(sets[k + 1][0]), ptr(sets[k + 1][1]), N, wpq)
+            out = pes[h].align(ptr(q), ptr(l), N, wpq, copy=False)
+            if with_deep:
+                d = pes[h].deep_dp(sp, counts_only=True)
+                if keep is not None:
+                    keep.append(d)
         return out
-    def e2e_steps_on(aligner, sets):
-        out = None
-        ptr = lambda x: x.data_ptr() if hasattr(x, "data_ptr") else x
-        for k, (q, l) in enumerate(sets):
-            if k + 1 < len(sets):
-                aligner.prefetch(ptr(sets[k + 1][0]), ptr(sets[k + 1][1]), N, wpq)
-            out = aligner.align(ptr(q), ptr(l), N, wpq, copy=False)
-        return out
-    for s in range(max(min(args.warmup, len(host_sets)) // 2, 1)):          # warm-up with the prefetch path: both input buffers of both handles get allocated
-        e2e_steps(host_sets[:2])
-        e2e_steps_on(pe2, host_sets[:2])
-    t_e2e_one, last = timed(lambda: e2e_steps(host_sets))
-    # two caller threads, a handle each: the reference's own shape (its main thread searches batch k + 1 while a DP engine thread aligns batch k)
-    t_e2e, _ = timed(lambda: two_threads(lambda: e2e_steps_on(pe, host_sets[0::2]), lambda: e2e_steps_on(pe2, host_sets[1::2])))
+    for s in range(max(min(args.warmup, len(host_sets)) // 2, 1)):          # warm-up with the prefetch path: both input buffers of every handle get allocated
+        for h in range(T):
+            e2e_steps_on(h, host_sets[:2])
+    deep_e2e = []
+    t_e2e_one, last = timed(lambda: e2e_steps_on(0, host_sets, deep_e2e))
+    # T caller threads, a handle each: the reference's own shape (its main thread searches batch k + 1 while a DP engine thread aligns batch k)
+    t_e2e, _ = timed(lambda: in_threads([(lambda h=h: e2e_steps_on(h, host_sets[h::T])) for h in range(T)]))
     h2d, d2h = last["h2d_bytes"], last["d2h_bytes"]
+    if deep_e2e:
+        # the deep stage's records (56 bytes per paired alignment, runs, the pairs without a candidate); its internal count / id reads are not counted
+        d2h += int(np.mean([56 * d["num_hits"] + 4 * d["num_runs"] + 4 * d["num_unseeded"] for d in deep_e2e]))
     e2e_value = world * reads_per_rank / t_e2e
-    e2e_steps(pageable_sets[:1])
-    t_page_one, _ = timed(lambda: e2e_steps(pageable_sets))
-    t_page, _ = timed(lambda: two_threads(lambda: e2e_steps_on(pe, pageable_sets[0::2]), lambda: e2e_steps_on(pe2, pageable_sets[1::2])))
+    e2e_steps_on(0, pageable_sets[:1])
+    t_page_one, _ = timed(lambda: e2e_steps_on(0, pageable_sets))
+    t_page, _ = timed(lambda: in_threads([(lambda h=h: e2e_steps_on(h, pageable_sets[h::T])) for h in range(T)]))
     pageable_value = world * N * len(pageable_sets) / t_page
     # what the link gives: one 256 MiB pinned copy each way, alone
     probe_h = torch.empty(256 << 20, dtype=torch.uint8, pin_memory=True)
@@ -1437,12 +1465,15 @@ def main():
         "value_one_batch_in_flight": value_one, "ms_per_step_one_batch_in_flight": 1e3 * t_one / args.steps,
         "config": {"workload": workload, "genome_bp": args.genome_bp, "repeat_fraction": args.repeat_fraction, "pairs_per_step_per_gpu": args.pairs,
                    "step": "s3_pe_align_device: search -> collect -> route -> locate -> pairing -> rescue windows -> DP -> CIGAR runs, nothing "
-                           "taken from the simulator's truth; reads whose round-1 slot overflowed are reported (route 8), not searched again",
-                   "timing": "value: K steps, queries resident in HBM, results left there, two batches in flight (even steps on one handle, odd "
-                             "steps on its s3_index_clone, one host thread each), CUDA events around the whole; value_one_batch_in_flight: the "
+                           "taken from the simulator's truth; reads whose round-1 slot overflowed are reported (route 8), not searched again"
+                           + ("; then s3_pe_deep_dp on the same handle: the S3_PE_NONE pairs picked on the device, the stage's records into host memory "
+                              "(its logic -- rounds, which pairs go on -- runs on the host between device steps, like the reference's wrapper)" if with_deep else ""),
+                   "batches_in_flight": T,
+                   "timing": f"value: K steps, queries resident in HBM, the chain's results left there, {T} batches in flight (step k on handle k mod {T}: the "
+                             "index handle and its s3_index_clones, one host thread each), CUDA events around the whole; value_one_batch_in_flight: the "
                              "same K steps back to back on one handle (two 4-byte count reads per step are part of the chain); kernels / "
-                             "stages: those K steps once more with the library's timing hooks on; e2e: the K steps through s3_pe_align, queries "
-                             "from pinned host memory, results into host memory, wall clock, two caller threads like value",
+                             "stages: the chain of those K steps once more with the library's timing hooks on; e2e: the K steps through s3_pe_align"
+                             + (" + s3_pe_deep_dp" if with_deep else "") + ", queries from pinned host memory, results into host memory, wall clock, the same caller threads as value",
                    "l2": "inputs larger than L2: 56 GB of index (buckets, seed tables, suffix array, text) touched at random, a different "
                          "32 MiB read batch every step",
                    "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"
@@ -1452,7 +1483,8 @@ def main():
                 "ms_per_step": 1e3 * t_e2e / args.steps,
                 "one_thread_value": world * reads_per_rank / t_e2e_one, "one_thread_ms_per_step": 1e3 * t_e2e_one / args.steps,
                 "mode": "s3_pe_align (host-pointer C ABI): queries from pinned host memory in, routes + pairings + rescue records + CIGAR runs "
-                        "into host memory out, one call per step; the next step's queries are uploaded by s3_pe_prefetch under this step's kernels",
+                        "into host memory out; the next step's queries are uploaded by s3_pe_prefetch under this step's kernels"
+                        + ("; then s3_pe_deep_dp: paired deep-DP alignments + CIGAR runs into host memory" if with_deep else ""),
                 "pageable_value": pageable_value, "pageable_ms_per_step": 1e3 * t_page / len(pageable_sets),
                 "pageable_one_thread_value": world * N * len(pageable_sets) / t_page_one,
                 "link": link},
@@ -1473,6 +1505,14 @@ def main():
         "stages_ms_per_step": stages,
         "kernels": kernels,
     }
+    if with_deep and deep_stats:
+        out["deep_dp"] = {"entry": "s3_pe_deep_dp (DPForUnalignPairs2, DV-DPForBothUnalign.cu:245): per step",
+                          "pairs": float(np.mean([d["num_input"] for d in deep_stats])), "seeds": float(np.mean([d["num_seeds"] for d in deep_stats])),
+                          "candidate_pairs": float(np.mean([d["num_candidates"] for d in deep_stats])),
+                          "paired_alignments": float(np.mean([d["num_hits"] for d in deep_stats])),
+                          "pairs_without_a_candidate": float(np.mean([d["num_unseeded"] for d in deep_stats])),
+                          "ms_per_step_one_batch_in_flight": 1e3 * t_one / args.steps - t_step_hooks,
+                          "note": "ms = the one-in-flight step minus the chain's stages timed by the hooks (wall time of the stage incl. its host side)"}
     if l2_exp is not None:
         out["l2_persistence_experiment"] = l2_exp
     if world == 1 and not args.no_cpu_baseline:
@@ -1487,7 +1527,8 @@ def main():
         out["cpu_baseline"]["search_path"] = cb["search_path"]
         out["cpu_baseline"]["cpu_search"] = cb.get("cpu_search")
         out["cpu_baseline"]["kernel_code"] = cb["kernel_code"]
-        out["cpu_baseline"]["same_config"] = "same workload generator, read length, k, cases, MaxOutputPerRead and rescue fraction as the GPU arm; bounded sample"
+        out["cpu_baseline"]["same_config"] = ("same workload generator, read length, k, cases, MaxOutputPerRead and rescue fraction as the GPU arm; bounded sample"
+                                              + ("; the CPU arm does not run the deep-DP stage of the both-unaligned pairs (the reference has no CPU DP engine): it does less work than the GPU arm" if with_deep else ""))
         if cb.get("gpu_reference_search"):
             out["search"]["reference_cuda_kernels_on_this_gpu"] = cb["gpu_reference_search"]
             if cb["gpu_reference_search"].get("reads_per_s"):
@@ -1511,11 +1552,16 @@ def main():
         except Exception as e:                               # noqa: BLE001
             out["parity_at_full_size"] = {"error": str(e)[:300]}
         out["parity_at_full_size"]["search_vs_reference_cpu_search"] = cpu_parity
+        if with_deep:
+            try:
+                out["parity_at_full_size"]["deep_dp_stage"], _ = stage_parity(args, gi, host, genome, L, wpq, batches[-1].reads.cpu().numpy(), sp, False)
+                log("deep DP stage parity at full size:", out["parity_at_full_size"]["deep_dp_stage"])
+            except Exception as e:                           # noqa: BLE001
+                out["parity_at_full_size"]["deep_dp_stage"] = {"error": str(e)[:300]}
     print(json.dumps(out), flush=True)
-    pe2.free()
-    api.GPUINDEXFree(gi2)
-    pe.free()
-    api.GPUINDEXFree(gi)
+    for h in reversed(range(T)):                                  # clones are freed before the handle they were made from
+        pes[h].free()
+        api.GPUINDEXFree(gis[h])
     if world > 1:
         torch.distributed.destroy_process_group()
 

@@ -103,6 +103,7 @@ struct S3Heavy {
     int32_t budget;                // LF-mapping steps an item may take in one lane before it is split
 };
 
+#define S3_CSR_SLOT 4u                 // ranges per item the counting pass of the capless search keeps
 struct S3SearchArgs {
     const uint32_t *queries;
     const uint32_t *readLengths;
@@ -124,6 +125,7 @@ struct S3SearchArgs {
     // where its ranges start (second pass), and the range arrays
     unsigned long long *csrCount;
     uint32_t *csrL, *csrR, *csrInfo;
+    uint32_t *csrSlot;                   // counting pass: the first S3_CSR_SLOT ranges of every item (L, R, info), so that only items with more are enumerated twice
 };
 
 // DFS frame: a node where substitutions are still allowed, kept in shared memory
@@ -525,6 +527,10 @@ s3_search_kernel(const S3Half fwd, const S3Half rev, const S3Seed seed, const S3
                 const unsigned long long o = args.csrCount[(size_t)q * args.numCases + ci] + saCount;
                 args.csrL[o] = l; args.csrR[o] = r;
                 args.csrInfo[o] = strand | (mm << 1) | ((args.firstCase + ci) << 4);
+            } else if (args.csrSlot && saCount < S3_CSR_SLOT) {
+                const uint32_t ci = curItem / args.numQueries, q = curItem - ci * args.numQueries;
+                uint32_t *slot = args.csrSlot + ((size_t)q * args.numCases + ci) * (3 * S3_CSR_SLOT) + 3 * saCount;
+                slot[0] = l; slot[1] = r; slot[2] = strand | (mm << 1) | ((args.firstCase + ci) << 4);
             }
             ++saCount;                                               // no cap: every range of the item
         } else if (MODE == S3_MODE_ITEMS) {
@@ -1106,12 +1112,31 @@ __global__ void s3_gather_bad_kernel(const uint32_t *__restrict__ queries, const
 // sum, fill.  Order inside a read: case ascending, inside a case the enumeration order of round 1 (first strand =
 // case parity, DV-Kernel.cu:4280-4285), so the reference's slot contents are the first saRangeAllowed entries of a
 // case's run and any order-dependent truncation can be replayed by the caller.
+// After the counting pass and the prefix sum: an item with at most S3_CSR_SLOT ranges takes them from its slot; the others are listed
+// (item id = case * numQueries + read, the enumerator's numbering) for the second pass.
+__global__ void s3_csr_scatter_kernel(uint32_t items, uint32_t numQueries, uint32_t numCases, const unsigned long long *__restrict__ starts,
+                                      const uint32_t *__restrict__ slot, uint32_t *__restrict__ csrL, uint32_t *__restrict__ csrR, uint32_t *__restrict__ csrInfo,
+                                      uint32_t *__restrict__ list)
+{
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;             // = read * numCases + case
+    if (i >= items) return;
+    const unsigned long long a = starts[i], n = starts[i + 1] - a;
+    if (n == 0) return;
+    if (n <= S3_CSR_SLOT) {
+        const uint32_t *src = slot + (size_t)i * (3 * S3_CSR_SLOT);
+        for (uint32_t g = 0; g < (uint32_t)n; ++g) { csrL[a + g] = src[3 * g]; csrR[a + g] = src[3 * g + 1]; csrInfo[a + g] = src[3 * g + 2]; }
+    } else {
+        const uint32_t q = i / numCases, ci = i - q * numCases;
+        list[4 + atomicAdd(list + 1, 1u)] = ci * numQueries + q;
+    }
+}
+
 template <int PASS>
 static int launch_search_csr(s3_index *ix, S3SearchArgs &a, uint32_t numCases)
 {
     a.numCases = numCases;
     a.workCounter = ix->d_workCounter;
-    a.itemList = NULL; a.itemCount = NULL;
+    if (PASS == 1) { a.itemList = NULL; a.itemCount = NULL; }       // (the second pass runs over the list the scatter kernel made)
     memset(&a.heavy, 0, sizeof a.heavy);
     const size_t smem = (size_t)(2 * a.wordPerQuery + S3_MAX_DEPTH * S3_FRAME_WORDS) * S3_THREADS * sizeof(uint32_t);
     S3_CUDA(cudaFuncSetAttribute(s3_search_kernel<false, S3_MODE_ITEMS, PASS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1153,25 +1178,38 @@ int s3_search_csr_device(s3_index *ix, const uint32_t *d_queries, const uint32_t
     void *d_tmp = NULL;
     S3_CUDA(cudaMallocAsync(&d_tmp, scanTemp + 16, st));
     S3_CUDA(cudaMemsetAsync(d_starts, 0, (items + 1) * 8, st));
+    // the counting pass keeps the first S3_CSR_SLOT ranges of every item; the second pass enumerates only the items with more
+    uint32_t *d_slot = NULL, *d_list = NULL;
+    S3_CUDA(cudaMallocAsync((void **)&d_slot, items * (3 * S3_CSR_SLOT) * 4, st));
+    S3_CUDA(cudaMallocAsync((void **)&d_list, (items + 4) * 4, st));
     S3SearchArgs a;
     memset(&a, 0, sizeof a);
     a.queries = d_queries; a.readLengths = d_readLengths; a.numQueries = batchSize; a.wordPerQuery = wordPerQuery;
     a.round = 0; a.numMismatch = numMismatch; a.saRangeAllowed = 0xFFFFFFFFu; a.wordPerAnswer = 0;
     a.firstCase = 0; a.exactNum = isExactNumMismatch ? 1 : 0; a.textLength = ix->textLength;
-    a.csrCount = d_starts;
+    a.csrCount = d_starts; a.csrSlot = d_slot;
     int rc = launch_search_csr<1>(ix, a, numCases);
     if (rc == S3_OK && cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_starts, d_starts, (int)(items + 1), st) != cudaSuccess) { s3_set_error("s3_search: scan failed"); rc = S3_ECUDA; }
     cudaFreeAsync(d_tmp, st);
-    if (rc) return rc;
     unsigned long long *h_total = (unsigned long long *)ix->pinnedCount;
-    S3_CUDA(cudaMemcpyAsync(h_total, d_starts + items, 8, cudaMemcpyDeviceToHost, st));
-    S3_CUDA(cudaStreamSynchronize(st));
-    *total = *h_total;
-    if (*total == 0) return S3_OK;
-    if (*total >= 0x7FFFFFFFull) { s3_set_error("s3_search: %llu ranges in one call", *total); return S3_EINVAL; }
-    S3_CUDA(cudaMallocAsync((void **)d_out, (size_t)*total * 12, st));
-    a.csrL = *d_out; a.csrR = *d_out + *total; a.csrInfo = *d_out + 2 * *total;
-    if ((rc = launch_search_csr<2>(ix, a, numCases))) { cudaFreeAsync(*d_out, st); *d_out = NULL; }
+    if (rc == S3_OK && (cudaMemcpyAsync(h_total, d_starts + items, 8, cudaMemcpyDeviceToHost, st) != cudaSuccess || cudaStreamSynchronize(st) != cudaSuccess)) {
+        s3_set_error("s3_search: reading the total failed"); rc = S3_ECUDA;
+    }
+    if (rc == S3_OK) *total = *h_total;
+    if (rc == S3_OK && *total >= 0x7FFFFFFFull) { s3_set_error("s3_search: %llu ranges in one call", *total); rc = S3_EINVAL; }
+    if (rc == S3_OK && *total) {
+        if (cudaMallocAsync((void **)d_out, (size_t)*total * 12, st) != cudaSuccess) { s3_set_error("s3_search: out of device memory"); rc = S3_ECUDA; }
+        else {
+            a.csrL = *d_out; a.csrR = *d_out + *total; a.csrInfo = *d_out + 2 * *total;
+            // list[0..3] = the second pass's item counters (front count at [1], as the enumerator reads them), item ids from list[4] on
+            cudaMemsetAsync(d_list, 0, 16, st);
+            s3_csr_scatter_kernel<<<(unsigned)((items + 255) / 256), 256, 0, st>>>((uint32_t)items, batchSize, numCases, d_starts, d_slot, a.csrL, a.csrR, a.csrInfo, d_list);
+            S3_LAUNCHED(1);
+            a.itemList = d_list + 4; a.itemCount = d_list; a.itemCap = (uint32_t)items;
+            if ((rc = launch_search_csr<2>(ix, a, numCases))) { cudaFreeAsync(*d_out, st); *d_out = NULL; }
+        }
+    }
+    cudaFreeAsync(d_slot, st); cudaFreeAsync(d_list, st);
     return rc;
 }
 

@@ -728,7 +728,7 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
                                                         read_length=L, max_windows=N // 2))
 
     # more handles on the same index, each with its own chain and stage workspace: T batches in flight, one host thread each
-    T = max(int(os.environ.get("S3_IN_FLIGHT", "2")), 1)
+    T = max(int(os.environ.get("S3_IN_FLIGHT", "4")), 1)
     handles = [(chain, gi)]
     for _ in range(T - 1):
         g2 = api.index_clone(gi)
@@ -1081,7 +1081,7 @@ def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=6)
+    ap.add_argument("--steps", type=int, default=12)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--genome-bp", type=int, default=int(os.environ.get("S3_GENOME_BP", 3_100_000_000)))

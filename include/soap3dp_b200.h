@@ -768,6 +768,17 @@ void s3_sam_record_free(s3_sam_record *record);
 typedef struct { uint32_t ambPosition; uint8_t strand, mismatchCount, pad[2]; } s3_sam_occurrence;      /* SRAOccurrence, SRACore.h:86-95 */
 int s3_sam_single_record(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_occurrence *occ, uint32_t numOcc,
                          const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName, s3_sam_record *out);
+/* SingleDPOutputSAMAPI (BGS-IO.cpp:5857-6118): a single read's record from its DP alignments (the hits of s3_single_dp_align with
+ * the special CIGARs and edit distances of s3_dp_decode): the first alignment with the best score is reported (X0 = how many share
+ * it), its CIGAR through convertToCigarStr, MD / XM / XO / XG / NM through getMisInfoForDP (s3_dp_md), MAPQ = s3_mapq_single_dp with
+ * x1_t1 / x1_t2 = the listed suboptimal alignments at or above / below 0.7 x the best score; the others go to XA:Z (alignmentType
+ * OUTPUT_ALL_VALID / OUTPUT_ALL_BEST; chromosome, strand + position, CIGAR, edit distance).  An alignment with gaps that hangs over
+ * a chromosome / segment end is cut there (BoundaryCheckDP, :1807-1976): the longer side stays, the other becomes a soft clip, and
+ * such a record carries no XA:Z.  numResult == 0 or ambPosition 0xFFFFFFFF in the first entry: the unmapped record. */
+typedef struct { uint32_t ambPosition; uint8_t strand, pad[3]; int32_t score, editdist; const char *cigar; } s3_sam_dp_alignment;   /* SingleAlgnmtResult, PEAlgnmt.h:434-445 */
+int s3_sam_single_dp_record(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_dp_alignment *alignments, uint32_t numResult,
+                            int32_t singleDPcutoffThreshold, const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName,
+                            s3_sam_record *out);
 
 #ifdef __cplusplus
 }

@@ -104,6 +104,9 @@ struct Chunk {
 
 }  // namespace
 
+// convertToCigarStr for the SAM writers of s3_sam.cu
+void s3_special_to_sam(const char *sp, size_t len, std::string &out) { special_to_sam(sp, len, out); }
+
 extern "C" int s3_dp_decode(const uint8_t *pattern, uint32_t patternLength, const int32_t *scores, const uint32_t *readLengths,
                             const int32_t *cutoffThresholds, uint32_t numOfThreads, s3_dp_scores sc,
                             uint64_t *cigarOffsets, char **cigars, uint64_t *samOffsets, char **samCigars,

@@ -352,3 +352,174 @@ extern "C" int s3_sam_single_record(const s3_sam_genome *g, const s3_sam_config 
     if (rc) { s3_set_error("s3_sam_single_record: out of host memory"); }
     return rc;
 }
+
+
+// ---- SingleDPOutputSAMAPI (BGS-IO.cpp:5857-6118): the record of a single read from its DP alignments ---------------------------
+void s3_special_to_sam(const char *sp, size_t len, std::string &out);          // convertToCigarStr (s3_decode.cu)
+
+namespace {
+
+// BoundaryCheckDP + getChrAndPosWithBoundaryCheckDP (BGS-IO.cpp:1807-1976, 2009-2033): an alignment with gaps that hangs over a
+// chromosome / segment end is cut there; the longer side stays, the other becomes a soft clip.  Returns the bases trimmed (> 0 on
+// the left, < 0 on the right, 0: nothing to trim); newCigar (may be NULL) = the special CIGAR of what stays.
+int chr_and_pos_checked_dp(const s3_sam_genome *g, uint32_t readLength, uint32_t ambPos, const char *cigar, unsigned long long *tp, uint32_t *chr,
+                           std::string *newCigar)
+{
+    uint32_t segEnd = chr_and_pos(g, ambPos, tp, chr);
+    const uint32_t chrEnd = g->chrEndPos[*chr - 1];
+    if (ambPos + readLength * 2u <= chrEnd + 1u && ambPos + readLength * 2u <= segEnd + 1u) return 0;
+    segEnd = chrEnd < segEnd ? chrEnd : segEnd;
+    std::string left, right;
+    char buf[48];
+    int leftLen = 0, rightLen = 0, rightOff = 0, leftS = 0, rightS = 0;
+    uint32_t refPos = ambPos;
+    for (const char *c = cigar; *c;) {
+        int num = 0;
+        while (*c && *c <= '9') { num = num * 10 + (*c - '0'); ++c; }
+        if (!*c) break;
+        const char op = *c++;
+        if (op == 'S') {
+            snprintf(buf, sizeof buf, "%dS", num);
+            if (refPos <= segEnd) { left += buf; leftS += num; } else { right += buf; rightS += num; }
+        } else if (op == 'M' || op == 'm') {
+            if (refPos > segEnd) { rightLen += num; snprintf(buf, sizeof buf, "%d%c", num, op); right += buf; }
+            else if (refPos + (uint32_t)num <= segEnd + 1u) { leftLen += num; snprintf(buf, sizeof buf, "%d%c", num, op); left += buf; }
+            else {
+                const int l = (int)(segEnd - refPos + 1u);
+                leftLen += l; snprintf(buf, sizeof buf, "%d%c", l, op); left += buf;
+                rightLen += num - l; snprintf(buf, sizeof buf, "%d%c", num - l, op); right += buf;
+            }
+            refPos += (uint32_t)num;
+        } else if (op == 'D') {
+            snprintf(buf, sizeof buf, "%dD", num);
+            if (refPos > segEnd) { if (right.empty()) rightOff = num; else right += buf; }
+            else if (refPos + (uint32_t)num <= segEnd + 1u) left += buf;
+            else {
+                const int l = (int)(segEnd - refPos + 1u);
+                snprintf(buf, sizeof buf, "%dD", l); left += buf;
+                snprintf(buf, sizeof buf, "%dD", num - l);
+                if (right.empty()) rightOff = num - l; else right += buf;
+            }
+            refPos += (uint32_t)num;
+        } else if (op == 'I') {
+            if (refPos == chrEnd + 1u) { /* exactly at the boundary: on neither side */ }
+            else if (refPos <= segEnd) { leftLen += num; snprintf(buf, sizeof buf, "%dI", num); left += buf; }
+            else { rightLen += num; snprintf(buf, sizeof buf, "%dI", num); right += buf; }
+        }
+    }
+    if (!leftLen || !rightLen) return 0;
+    int ret;
+    uint32_t corrected;
+    if (leftLen >= rightLen) {
+        const int clip = (int)readLength - leftLen - leftS;
+        if (newCigar) { snprintf(buf, sizeof buf, "%dS", clip); *newCigar = left + buf; }
+        corrected = ambPos; ret = -clip;
+    } else {
+        const int clip = (int)readLength - rightLen - rightS;
+        if (newCigar) { snprintf(buf, sizeof buf, "%dS", clip); *newCigar = buf + right; }
+        corrected = segEnd + 1u + (uint32_t)rightOff; ret = clip;
+    }
+    if (ret && corrected > ambPos) chr_and_pos(g, corrected, tp, chr);
+    return ret;
+}
+
+}  // namespace
+
+extern "C" int s3_sam_single_dp_record(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_dp_alignment *algn, uint32_t numResult,
+                                       int32_t singleDPcutoffThreshold, const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName,
+                                       s3_sam_record *out)
+{
+    if (!out) { s3_set_error("s3_sam_single_dp_record: NULL output"); return S3_EINVAL; }
+    memset(out, 0, sizeof *out);
+    if (!g || !cfg || !query || !qualities || !queryName || !cfg->readGroup || (numResult && !algn) || readlen <= 0) { s3_set_error("s3_sam_single_dp_record: bad argument"); return S3_EINVAL; }
+    const bool unaligned = numResult == 0 || algn[0].ambPosition == 0xFFFFFFFFu;
+    if (!unaligned && (!g->packedDNA || !g->segments || !g->ambiguityMap || !g->chrEndPos || !g->chrNames || g->numSegments == 0)) {
+        s3_set_error("s3_sam_single_dp_record: incomplete genome description"); return S3_EINVAL;
+    }
+    for (uint32_t k = 0; k < numResult && !unaligned; ++k) if (!algn[k].cigar) { s3_set_error("s3_sam_single_dp_record: alignment %u without a CIGAR", k); return S3_EINVAL; }
+    std::vector<uint8_t> d;
+    std::string xa, md, cigar, newSp;
+    unsigned long long bestTP = 0, tp;
+    uint32_t bestChr = 0, chr;
+    int strand = 1, bestHitNum = 1, secBestHitNum = 0, mism = 0, gapOpen = 0, gapExt = 0, editDist = 0, avgQual = 20, mapq = 0;
+    const bool lists = numResult > 1 && (cfg->alignmentType == 1 || cfg->alignmentType == 2);      // OUTPUT_ALL_VALID / OUTPUT_ALL_BEST
+    if (!unaligned) {
+        // the reference keeps the scores in unsigned ints (BGS-IO.cpp:5877): comparisons are made that way here too
+        uint32_t best = 0, bestScore = (uint32_t)algn[0].score, secBestScore = 0;
+        for (uint32_t k = 1; k < numResult; ++k) {
+            const uint32_t cur = (uint32_t)algn[k].score;
+            if (cur >= bestScore) {
+                if (cur == bestScore) ++bestHitNum;
+                else { secBestScore = bestScore; bestScore = cur; bestHitNum = 1; best = k; }
+            } else if (cur >= secBestScore) { if (cur != secBestScore) secBestScore = cur; }
+        }
+        int trim = chr_and_pos_checked_dp(g, (uint32_t)readlen, algn[best].ambPosition, algn[best].cigar, &bestTP, &bestChr, NULL);
+        if (trim) {
+            // the best alignment that does not hang over an end, searched from start values of -9998 / -9999 held in unsigned ints:
+            // only a score that is negative as an int can replace them (as the reference)
+            bestScore = (uint32_t)-9998; secBestScore = (uint32_t)-9999;
+            for (uint32_t k = 0; k < numResult; ++k) {
+                if (chr_and_pos_checked_dp(g, (uint32_t)readlen, algn[k].ambPosition, algn[k].cigar, &bestTP, &bestChr, NULL)) continue;
+                const uint32_t cur = (uint32_t)algn[k].score;
+                if (cur >= bestScore) {
+                    if (cur == bestScore) ++bestHitNum;
+                    else { secBestScore = bestScore; bestScore = cur; bestHitNum = 1; best = k; }
+                } else if (cur > secBestScore) secBestScore = cur;
+            }
+            trim = chr_and_pos_checked_dp(g, (uint32_t)readlen, algn[best].ambPosition, algn[best].cigar, &bestTP, &bestChr, NULL);
+        }
+        int x1t1 = 0, x1t2 = 0;
+        if (lists && !trim) {
+            const int thres = (int)(0.7 * bestScore);
+            char num[24];
+            for (uint32_t k = 0; k < numResult; ++k) {
+                if (k == best) continue;
+                const uint32_t cur = (uint32_t)algn[k].score;
+                if (cfg->alignmentType == 2 && cur < bestScore) continue;
+                if (chr_and_pos_checked_dp(g, (uint32_t)readlen, algn[k].ambPosition, algn[k].cigar, &tp, &chr, NULL)) continue;
+                xa += g->chrNames[chr - 1];
+                xa.push_back(',');
+                xa.push_back(algn[k].strand == 2 ? '-' : '+');
+                xa.append(num, write_num((long long)tp, num));
+                xa.push_back(',');
+                s3_special_to_sam(algn[k].cigar, strlen(algn[k].cigar), xa);
+                xa.push_back(',');
+                xa.append(num, write_num(algn[k].editdist, num));
+                xa.push_back(';');
+                if (cur < bestScore) { if (cur >= (uint32_t)thres) ++x1t1; else ++x1t2; }
+            }
+        }
+        secBestHitNum = x1t1 + x1t2;
+        strand = algn[best].strand;
+        trim = chr_and_pos_checked_dp(g, (uint32_t)readlen, algn[best].ambPosition, algn[best].cigar, &bestTP, &bestChr, &newSp);
+        const std::string sp = trim ? newSp : std::string(algn[best].cigar);
+        s3_special_to_sam(sp.c_str(), sp.size(), cigar);
+        // getMisInfoForDP (PE.cpp:499-666): a left trim moves the text position, the qualities stay indexed by read offset
+        {
+            const uint64_t cigOff[2] = {0, sp.size()}, qOff[2] = {0, (uint64_t)readlen};
+            const uint32_t pos = algn[best].ambPosition + (trim > 0 ? (uint32_t)trim : 0u);
+            uint64_t mdOff[2];
+            char *mdBuf = NULL;
+            int32_t nm = 0, go = 0, ge = 0, aq = 20;
+            const int rc = s3_dp_md(g->packedDNA, g->dnaLength, sp.c_str(), cigOff, &pos, 1, (const int8_t *)qualities, qOff, mdOff, &mdBuf, &nm, &go, &ge, &aq);
+            if (rc) return rc;
+            md.assign(mdBuf, (size_t)(mdOff[1] - mdOff[0]));
+            free(mdBuf);
+            mism = nm; gapOpen = go; gapExt = ge; avgQual = aq;
+        }
+        editDist = gapExt + mism;
+        mapq = s3_mapq_single_dp(readlen * cfg->dpMatchScore, cfg->isFastq == 1 ? avgQual : 20, bestHitNum, x1t1, x1t2, (int)bestScore, (int)secBestScore,
+                                 cfg->maxMAPQ, cfg->minMAPQ, singleDPcutoffThreshold, cfg->bwaLikeScore);
+    }
+    const std::string none;
+    record_body(*out, d, readlen, queryName, query, qualities, strand, lists ? xa : none, &cigar, unaligned, mism, editDist, bestHitNum, secBestHitNum,
+                gapOpen, gapExt, md, mapq, cfg->readGroup, cfg->isPrintMDNM != 0);
+    if (!unaligned) {
+        out->flag = (uint16_t)(strand == 2 ? 16 : 0);
+        out->tid = (int32_t)bestChr - 1; out->pos = (int32_t)(bestTP - 1);
+    } else { out->flag = 4; out->tid = -1; out->pos = -1; }
+    out->mtid = -1; out->mpos = -1; out->isize = 0;
+    const int rc = finish(*out, d);
+    if (rc) { s3_set_error("s3_sam_single_dp_record: out of host memory"); }
+    return rc;
+}

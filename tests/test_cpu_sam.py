@@ -215,3 +215,107 @@ def test_sam_single_record_matches_the_reference_writer():
         trimmed += want[0][6] == 2
         with_xa += b"XAZ" in want[1]
     assert unmapped > 100 and trimmed > 30 and with_xa > 300
+
+
+class DpAlignment(C.Structure):
+    _fields_ = [("ambPosition", C.c_uint32), ("strand", C.c_uint8), ("pad", C.c_uint8 * 3), ("score", C.c_int32), ("editdist", C.c_int32),
+                ("cigar", C.c_char_p)]
+
+
+def random_special_cigar(rng, L):
+    """a special CIGAR (M match run, m mismatch run, I, D, S) whose read bases add up to L"""
+    s1 = int(rng.integers(1, 6)) if rng.random() < 0.2 else 0
+    s2 = int(rng.integers(1, 9)) if rng.random() < 0.2 else 0
+    left = L - s1 - s2
+    ops = []
+    if rng.random() < 0.03:
+        ops.append((int(rng.integers(1, 4)), "D"))                  # a leading deletion (convertToCigarStr drops it, its count stays)
+    prev = ""
+    while left > 0:
+        op = "M" if prev != "M" and (not ops or rng.random() < 0.7) else str(rng.choice(["m", "I", "D", "m"]))
+        if op == prev:
+            op = "M"
+        k = int(rng.integers(1, 40)) if op == "M" else int(rng.integers(1, 4))
+        if op != "D":
+            k = min(k, left)
+            left -= k
+        ops.append((k, op))
+        prev = op
+    if rng.random() < 0.03:
+        ops.append((int(rng.integers(1, 4)), "D"))                  # a trailing deletion
+    body = "".join(f"{k}{op}" for k, op in ops)
+    return (f"{s1}S" if s1 else "") + body + (f"{s2}S" if s2 else "")
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_sam.so not built")
+def test_sam_single_dp_record_matches_the_reference_writer():
+    """s3_sam_single_dp_record against SingleDPOutputSAMAPI: best score / X0, XA:Z with CIGARs and edit distances, x1_t1 / x1_t2, MD / XM / XO /
+    XG / NM from the special CIGAR, MAPQ, alignments cut at a chromosome or segment end (BoundaryCheckDP), unmapped"""
+    ref = C.CDLL(REF)
+    lib = api.load_library()
+    rng = np.random.default_rng(33)
+    n = 200_000
+    G = rng.integers(0, 4, n).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    translate = np.array([0, 1, 0xFFFFFFFF, 70_000, 2, 70_000 - 1, 100_000, 2, 70_000 - 1 - 500, 150_000, 3, 150_000 - 1], np.uint32)
+    chr_end = np.array([69_999, 149_999, 199_999], np.uint32)
+    amb = np.full(4, 3, np.uint32)
+    names = [b"chr1", b"chrTwo", b"3"]
+    segs = (Segment * 4)(*[Segment(int(translate[3 * i]), int(translate[3 * i + 1]), int(translate[3 * i + 2])) for i in range(4)])
+    gen = Genome(helpers.u32p(pac), n, segs, 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, (C.c_char_p * 3)(*names))
+    cnames = (C.c_char_p * 3)(*names)
+    edges = [70_000, 100_000, 150_000]
+    trimmed = unmapped = with_xa = 0
+    lib.s3_sam_single_dp_record.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    ref.ref_sam_single_dp.restype = C.c_int
+    for trial in range(1500):
+        L = int(rng.integers(36, 152))
+        cfg = Config(int(rng.integers(1, 4)), int(rng.integers(0, 2)), 1, -2, int(rng.integers(0, 2)), 40, 1, int(rng.integers(0, 2)), 1, 1000, b"rg%d" % trial)
+        cutoff = int(0.3 * L)
+        m = int(rng.choice([0, 1, 1, 2, 3, 6]))
+        algn = []
+        for _ in range(m):
+            if rng.random() < 0.35:
+                e = int(rng.choice(edges))
+                p = max(0, e - int(rng.integers(1, L + 4)))
+            else:
+                p = int(rng.integers(0, n - 2 * L - 8))
+            algn.append((p, int(rng.integers(1, 3)), int(rng.integers(cutoff, L + 1)) if rng.random() < 0.8 else L - 3, int(rng.integers(0, 9)),
+                         random_special_cigar(rng, L).encode()))
+        if m and rng.random() < 0.05:
+            algn[0] = (0xFFFFFFFF,) + algn[0][1:]                    # the unaligned marker
+        q = np.ascontiguousarray(rng.integers(0, 4, L).astype(np.uint8))
+        ql = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql[-1] = 0
+        name = b"dp%d" % trial
+        arr = (DpAlignment * max(m, 1))()
+        for k, a in enumerate(algn):
+            arr[k].ambPosition, arr[k].strand, arr[k].score, arr[k].editdist, arr[k].cigar = a
+        out = Record()
+        rc = lib.s3_sam_single_dp_record(C.byref(gen), C.byref(cfg), arr, m, cutoff, q.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name, C.byref(out))
+        assert rc == 0, (trial, algn)
+        got = ((out.tid, out.pos, out.bin, out.qual, out.l_qname, out.flag, out.n_cigar, out.l_qseq, out.mtid, out.mpos, out.isize, out.l_aux),
+               bytes(bytearray(out.data[:out.data_len])))
+        lib.s3_sam_record_free(C.byref(out))
+        if m == 0:
+            # the reference is never called without a result; its unaligned form is an entry with position 0xFFFFFFFF
+            algn_ref = [(0xFFFFFFFF, 1, 0, 0, b"")]
+        else:
+            algn_ref = algn
+        flat = np.array([[np.int64(a[0]).astype(np.int32) if a[0] > 0x7FFFFFFF else a[0], a[1], a[2], a[3], k] for k, a in enumerate(algn_ref)], np.int64).astype(np.int32).ravel()
+        cig = (C.c_char_p * len(algn_ref))(*[a[4] for a in algn_ref])
+        core = np.zeros(12, np.int32)
+        data = np.zeros(8192, np.uint8)
+        dlen = np.zeros(1, np.int32)
+        k = ref.ref_sam_single_dp(helpers.u32p(pac), n, helpers.u32p(translate), 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, cnames,
+                                  cfg.alignmentType, cfg.bwaLikeScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup,
+                                  cfg.dpMatchScore, cutoff, flat.ctypes.data_as(I32P), len(algn_ref), cig,
+                                  q.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name,
+                                  core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P))
+        assert k == 1
+        want = (tuple(int(x) for x in core), bytes(data[:int(dlen[0])]))
+        assert got == want, (trial, algn, got, want)
+        unmapped += want[0][5] == 4
+        trimmed += m == 1 and algn[0][0] != 0xFFFFFFFF and any(algn[0][0] < e <= algn[0][0] + L - 8 for e in edges)      # hangs over an end
+        with_xa += b"XAZ" in want[1]
+    assert unmapped > 100 and with_xa > 100 and trimmed > 40

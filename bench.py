@@ -789,6 +789,16 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
         torch.cuda.set_device(local_rank)
         for kk in range(first, args.steps, T):
             step(sets[args.warmup + kk][0], sets[args.warmup + kk][1], ch, g)
+    def warm_half(ch, g):
+        torch.cuda.set_device(local_rank)
+        for s_ in range(args.warmup):
+            step(sets[s_][0], sets[s_][1], ch, g)
+    # (warm-up of the threaded shape: with T handles allocating at once the stream-ordered pool reaches its working size here, not in the timed pass)
+    wt = [threading.Thread(target=warm_half, args=(ch, g)) for ch, g in handles]
+    for t in wt:
+        t.start()
+    for t in wt:
+        t.join()
     th = [threading.Thread(target=run_half, args=(i, ch, g)) for i, (ch, g) in enumerate(handles)]
     barrier()
     t0 = time.perf_counter()

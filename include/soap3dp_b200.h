@@ -779,6 +779,24 @@ typedef struct { uint32_t ambPosition; uint8_t strand, pad[3]; int32_t score, ed
 int s3_sam_single_dp_record(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_dp_alignment *alignments, uint32_t numResult,
                             int32_t singleDPcutoffThreshold, const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName,
                             s3_sam_record *out);
+/* pairDeepDPOutputSAMAPI (BGS-IO.cpp:3824-4500): the two records of a read pair from its deep-DP alignments (the hits of
+ * s3_deep_dp_align / s3_pe_deep_dp with the special CIGARs and edit distances of s3_dp_decode; entry bestIndex is the one reported,
+ * < 0: both reads unmapped): per read the CIGAR, MD and XM / XO / XG / NM of its alignment (cut at a chromosome / segment end like
+ * s3_sam_single_dp_record), X0 / X1 from the scores and tie counts of the pair's other alignments and from the counts the search
+ * left for the read (x0 / x1 / mismatch = hspaux->x0_array / x1_array / mismatch_array of the two reads), MAPQ = s3_mapq_bwa_pair or
+ * s3_mapq_pair_end_dp + s3_mapq_of_pair, XA:Z with the other alignments; a pair whose reads run through each other keeps only the
+ * read with fewer mismatches (the other comes out unmapped, MAPQ = s3_mapq_unique_dp).  A reported entry without any alignment
+ * belongs to the writer of improperly paired reads (unproperlypairOutputSAMAPI2), which is not built: S3_EINVAL. */
+typedef struct {
+    int32_t insertSize;                                                               /* DeepDPAlignResult, PEAlgnmt.h:409-429; [0] the pair's first read, [1] its mate */
+    uint32_t ambPosition[2]; uint8_t strand[2], pad[2];
+    int32_t score[2], editdist[2], numSameScore[2];
+    const char *cigar[2];
+} s3_sam_deep_alignment;
+int s3_sam_deep_dp_records(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_deep_alignment *alignments, uint32_t num, int32_t bestIndex,
+                           const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                           int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2,
+                           const int32_t x0[2], const int32_t x1[2], const int32_t mismatch[2], s3_sam_record out[2]);
 
 #ifdef __cplusplus
 }

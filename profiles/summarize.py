@@ -75,7 +75,7 @@ def short(name):
 def main():
     tag = sys.argv[1]
     md = [f"# ncu summary `{tag}`", "",
-          f"Produced by `profiles/gpu_session.sh {tag}` (round 2: `profiles/gpu_session_r2.sh {tag}`) on one B200 (through gpurun) and "
+          f"Produced by `profiles/gpu_session.sh {tag}` (round 2: `profiles/gpu_session_r2.sh {tag}`, `profiles/gpu_session_r2t.sh {tag}`) on one B200 (through gpurun) and "
           f"`profiles/summarize.py {tag}` here.  Launch times under ncu are cold-cache and serialised: "
           "compare SHARES with the CUDA-event numbers of the bench line, not absolutes.", ""]
     bj = os.path.join(OUT, f"{tag}_bench.json")
@@ -97,6 +97,8 @@ def main():
         rows = launches(lc)
         agg = OrderedDict()
         for k, ns in rows:
+            if "at_cuda_detail" in k:                       # torch's own kernels (index build, batch simulation): not part of a step
+                continue
             a = agg.setdefault(short(k), [0, 0.0])
             a[0] += 1
             a[1] += ns
@@ -180,7 +182,12 @@ def main():
                 md.append(f"| {k} | {v['easy_kernel_ms']:.3f} | {v['enumerator_ms']:.3f} | {v['search_launch_ms']:.3f} |")
             md += ["", "No window changes the launch by more than its run-to-run spread: reads are uniform over the genome, the seed tables replace the "
                    "top of the BWT, and nothing in the 56 GB index is touched often enough to be worth a carve-out of the 126 MB L2.", ""]
-    if len(traffic) > 2:
+    # a capture that also holds the deep-DP stage sums launches of different sizes per kernel: not a per-launch figure, bench.py keeps the chain-only one
+    if len(traffic) > 2 and not any("s3_stage" in k or "s3_csr" in k for k in traffic):
+        # measured once on the probe kernel itself (profiles/r2k_probe_ncu.csv): DRAM bytes per independent random 32-byte load; kept across captures
+        old_path = os.path.join(PROF, "ncu_traffic.json")
+        keep = json.load(open(old_path)).get("random_sector_probe_dram_bytes_per_load") if os.path.exists(old_path) else None
+        traffic["random_sector_probe_dram_bytes_per_load"] = keep or 120.6
         json.dump(traffic, open(os.path.join(PROF, "ncu_traffic.json"), "w"), indent=1)      # bench.py's roofline.traffic
     open(os.path.join(PROF, f"{tag}_summary.md"), "w").write("\n".join(md) + "\n")
     print("\n".join(md))

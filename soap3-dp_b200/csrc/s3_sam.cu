@@ -523,3 +523,209 @@ extern "C" int s3_sam_single_dp_record(const s3_sam_genome *g, const s3_sam_conf
     if (rc) { s3_set_error("s3_sam_single_dp_record: out of host memory"); }
     return rc;
 }
+
+
+// ---- pairDeepDPOutputSAMAPI (BGS-IO.cpp:3824-4500): the two records of a read pair from its deep-DP alignments ------------------
+namespace {
+
+// readLengthWithCigar (BGS-IO.cpp:3795-3822): text bases an alignment covers (M, m, D; a deletion as the last op is ignored)
+int cigar_span(const char *cigar)
+{
+    int len = 0, x = 0;
+    char op = ' ';
+    for (const char *p = cigar; *p;) {
+        x = 0;
+        while (*p && *p <= '9') { x = x * 10 + (*p - '0'); ++p; }
+        if (!*p) break;
+        op = *p++;
+        if (op == 'M' || op == 'm' || op == 'D') len += x;
+    }
+    if (op == 'D') len -= x;
+    return len;
+}
+
+struct DpSide {                      // what getMisInfoForDP and convertToCigarStr give for one read's reported alignment
+    std::string cigar, md;
+    int mism = 0, gapOpen = 0, gapExt = 0, avgQual = 20, trim = 0;
+};
+int dp_side(const s3_sam_genome *g, const char *special, uint32_t pos, int readlen, const char *qualities, unsigned long long *tp, uint32_t *chr, DpSide &o)
+{
+    std::string newSp;
+    o.trim = chr_and_pos_checked_dp(g, (uint32_t)readlen, pos, special, tp, chr, &newSp);
+    const std::string sp = o.trim ? newSp : std::string(special);
+    s3_special_to_sam(sp.c_str(), sp.size(), o.cigar);
+    const uint64_t cigOff[2] = {0, sp.size()}, qOff[2] = {0, (uint64_t)readlen};
+    const uint32_t p = pos + (o.trim > 0 ? (uint32_t)o.trim : 0u);
+    uint64_t mdOff[2];
+    char *mdBuf = NULL;
+    int32_t nm = 0, go = 0, ge = 0, aq = 20;
+    const int rc = s3_dp_md(g->packedDNA, g->dnaLength, sp.c_str(), cigOff, &p, 1, (const int8_t *)qualities, qOff, mdOff, &mdBuf, &nm, &go, &ge, &aq);
+    if (rc) return rc;
+    o.md.assign(mdBuf, (size_t)(mdOff[1] - mdOff[0]));
+    free(mdBuf);
+    o.mism = nm; o.gapOpen = go; o.gapExt = ge; o.avgQual = aq;
+    return S3_OK;
+}
+
+}  // namespace
+
+extern "C" int s3_sam_deep_dp_records(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_deep_alignment *algn, uint32_t num, int32_t bestIndex,
+                                      const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                                      int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2,
+                                      const int32_t x0[2], const int32_t x1[2], const int32_t mismatch[2], s3_sam_record out[2])
+{
+    if (!out) { s3_set_error("s3_sam_deep_dp_records: NULL output"); return S3_EINVAL; }
+    memset(out, 0, 2 * sizeof(s3_sam_record));
+    if (!g || !cfg || !query1 || !query2 || !qualities1 || !qualities2 || !queryName1 || !queryName2 || !cfg->readGroup || (num && !algn) || !x0 || !x1 || !mismatch ||
+        readlen1 <= 0 || readlen2 <= 0 || bestIndex >= (int32_t)num) { s3_set_error("s3_sam_deep_dp_records: bad argument"); return S3_EINVAL; }
+    const uint32_t NONE = 0xFFFFFFFFu;
+    const uint8_t *query[2] = {query1, query2};
+    const char *qual[2] = {qualities1, qualities2}, *name[2] = {queryName1, queryName2};
+    const int readlen[2] = {readlen1, readlen2};
+    std::vector<uint8_t> d;
+    const std::string none;
+    int rc;
+    if (bestIndex < 0) {
+        // nothing to report: both reads unmapped, flags 0x41 / 0x81 (BGS-IO.cpp:4463-4494)
+        for (int k = 0; k < 2; ++k) {
+            s3_sam_record &r = out[k];
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], 1, none, NULL, true, 0, 0, 0, 0, 0, 0, none, 0, cfg->readGroup, false);
+            r.flag = (uint16_t)(1 | (k ? 128 : 64));
+            r.tid = r.pos = r.mtid = r.mpos = -1; r.isize = 0;
+            if ((rc = finish(r, d))) { s3_sam_record_free(&out[0]); s3_sam_record_free(&out[1]); s3_set_error("s3_sam_deep_dp_records: out of host memory"); return rc; }
+        }
+        return S3_OK;
+    }
+    if (!g->packedDNA || !g->segments || !g->ambiguityMap || !g->chrEndPos || !g->chrNames || g->numSegments == 0) { s3_set_error("s3_sam_deep_dp_records: incomplete genome description"); return S3_EINVAL; }
+    const s3_sam_deep_alignment &best = algn[bestIndex];
+    uint32_t bpos[2] = {best.ambPosition[0], best.ambPosition[1]};
+    if (bpos[0] == NONE && bpos[1] == NONE) {
+        s3_set_error("s3_sam_deep_dp_records: a pair without any alignment goes through the writer of improperly paired reads (unproperlypairOutputSAMAPI2), which is not built");
+        return S3_EINVAL;
+    }
+    for (uint32_t i = 0; i < num; ++i)
+        for (int k = 0; k < 2; ++k)
+            if (algn[i].ambPosition[k] != NONE && !algn[i].cigar[k]) { s3_set_error("s3_sam_deep_dp_records: alignment %u without a CIGAR", i); return S3_EINVAL; }
+    unsigned long long tp[2] = {0, 0};
+    uint32_t chr[2] = {0, 0};
+    DpSide sd[2];
+    int strand[2] = {1, 1}, span[2] = {readlen1, readlen2};
+    for (int k = 0; k < 2; ++k) {
+        if (bpos[k] == NONE) continue;
+        strand[k] = best.strand[k];
+        if ((rc = dp_side(g, best.cigar[k], bpos[k], readlen[k], qual[k], &tp[k], &chr[k], sd[k]))) return rc;
+        span[k] = cigar_span(best.cigar[k]);
+    }
+    int bestInsert = (bpos[0] != NONE && bpos[1] != NONE) ? best.insertSize : 0;
+    // a pair whose reads run through each other loses the read with more mismatches (:3949-3972)
+    if (bpos[0] != NONE && bpos[1] != NONE) {
+        const unsigned long long a1 = (unsigned long long)bpos[0] + (sd[0].trim > 0 ? sd[0].trim : 0), a2 = (unsigned long long)bpos[1] + (sd[1].trim > 0 ? sd[1].trim : 0);
+        if ((best.strand[0] == 1 && (a1 > a2 || a1 + span[0] > a2 + span[1])) || (best.strand[0] == 2 && (a2 > a1 || a2 + span[1] > a1 + span[0]))) {
+            const int drop = sd[0].mism <= sd[1].mism ? 1 : 0;
+            bpos[drop] = NONE; tp[drop] = 0; chr[drop] = 0;
+            bestInsert = 0;
+        }
+    }
+    const bool both = bpos[0] != NONE && bpos[1] != NONE;
+    int bestPairNum = 0, bestPairScore = 0, secBestPairScore = 0, numSimilar = 0;
+    if (both) {
+        bestPairNum = 1; numSimilar = 1;
+        bestPairScore = best.score[0] + best.score[1];
+        for (uint32_t i = 0; i < num && num > 1; ++i) {
+            if ((int32_t)i == bestIndex) continue;
+            const int sum = algn[i].score[0] + algn[i].score[1];
+            if (sum == bestPairScore) ++bestPairNum;
+            else if (sum > secBestPairScore) secBestPairScore = sum;
+            if (algn[i].score[0] >= best.score[0] + cfg->dpMisMatchScore && algn[i].score[1] >= best.score[1] + cfg->dpMisMatchScore) ++numSimilar;
+        }
+    }
+    int bestHitNum[2] = {0, 0}, secBestHitNum[2] = {0, 0}, bestScore[2] = {0, 0}, secBestScore[2] = {0, 0}, isBestHit[2] = {1, 1};
+    for (int k = 0; k < 2; ++k) {
+        uint32_t bestPos = NONE, secBestPos = NONE;
+        if (bpos[k] != NONE) { bestScore[k] = best.score[k]; bestPos = bpos[k]; bestHitNum[k] = 1; }
+        if (bpos[k] != NONE && num > 1) {
+            for (uint32_t i = 0; i < num; ++i) {
+                if ((int32_t)i == bestIndex) continue;
+                const int sc = algn[i].score[k], same = algn[i].numSameScore[k];
+                const uint32_t pos = algn[i].ambPosition[k];
+                if (sc >= bestScore[k]) {
+                    if (sc == bestScore[k]) { if (pos != bestPos) bestHitNum[k] += same; }
+                    else { secBestScore[k] = bestScore[k]; secBestHitNum[k] = bestHitNum[k]; secBestPos = bestPos; bestScore[k] = sc; bestHitNum[k] = same; bestPos = pos; isBestHit[k] = 0; }
+                } else if (sc >= secBestScore[k]) {
+                    if (sc == secBestScore[k]) { if (pos != secBestPos) secBestHitNum[k] += same; }
+                    else { secBestScore[k] = sc; secBestPos = pos; secBestHitNum[k] = same; }
+                }
+            }
+        }
+        // the counts the search left for the read (hspaux->x0_array / x1_array / mismatch_array; the first read's are used from 1 on, the mate's from 2 on)
+        if (x0[k] > (k ? 1 : 0)) {
+            const int x0Score = mismatch[k] * cfg->dpMisMatchScore + (readlen[k] - mismatch[k]) * cfg->dpMatchScore;
+            if (x0Score >= bestScore[k]) {
+                if (x0[k] > bestHitNum[k]) bestHitNum[k] = x0[k];
+                if (x1[k] > secBestHitNum[k]) secBestHitNum[k] = x1[k];
+                if (x0Score > bestScore[k]) isBestHit[k] = 0;
+            }
+        }
+    }
+    int mapq[2];
+    const bool lists = cfg->alignmentType == 1 || cfg->alignmentType == 2;
+    if (lists) {
+        if (cfg->bwaLikeScore) {
+            s3_mapq_bwa_pair(bestHitNum[0], secBestHitNum[0], bestHitNum[1], secBestHitNum[1], bestPairScore, bestPairNum, secBestPairScore, (int)num - bestPairNum,
+                             readlen1, readlen2, &mapq[0], &mapq[1]);
+        } else {
+            int m[2];
+            for (int k = 0; k < 2; ++k)
+                m[k] = s3_mapq_pair_end_dp(best.score[k], readlen[k] * cfg->dpMatchScore, cfg->isFastq == 1 ? sd[k].avgQual : 20, bestHitNum[k], secBestHitNum[k],
+                                           bestScore[k], secBestScore[k], isBestHit[k], numSimilar, cfg->maxMAPQ, cfg->minMAPQ);
+            mapq[0] = mapq[1] = s3_mapq_of_pair(m[0], m[1]);
+        }
+        for (int k = 0; k < 2; ++k) if (sd[k].trim) mapq[k] = 0;
+    } else mapq[0] = mapq[1] = 255;
+    for (int k = 0; k < 2; ++k) {
+        std::string xa;
+        if (bpos[k] != NONE && num > 1) {
+            char numBuf[24];
+            for (uint32_t i = 0; i < num; ++i) {
+                if ((int32_t)i == bestIndex) continue;
+                if (cfg->alignmentType == 2 && algn[i].score[0] + algn[i].score[1] < bestPairScore) continue;
+                unsigned long long t;
+                uint32_t c;
+                chr_and_pos(g, algn[i].ambPosition[k], &t, &c);
+                xa += g->chrNames[c - 1];
+                xa.push_back(',');
+                xa.push_back(algn[i].strand[k] == 2 ? '-' : '+');
+                xa.append(numBuf, write_num((long long)t, numBuf));
+                xa.push_back(',');
+                s3_special_to_sam(algn[i].cigar[k], strlen(algn[i].cigar[k]), xa);
+                xa.push_back(',');
+                xa.append(numBuf, write_num(algn[i].editdist[k], numBuf));
+                xa.push_back(';');
+            }
+        }
+        if (cfg->alignmentType == 4) { bestHitNum[k] = -1; secBestHitNum[k] = -1; }
+        else if (!lists) secBestHitNum[k] = -1;
+        s3_sam_record &r = out[k];
+        if (bpos[k] != NONE) {
+            if (bpos[1 - k] == NONE) {
+                mapq[k] = s3_mapq_unique_dp(bestHitNum[k], best.score[k], readlen[k] * cfg->dpMatchScore, cfg->isFastq == 1 ? sd[k].avgQual : 20, cfg->maxMAPQ, cfg->minMAPQ);
+                if (sd[k].trim) mapq[k] = 0;
+            }
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], strand[k], xa, &sd[k].cigar, false, sd[k].mism, sd[k].mism + sd[k].gapExt, bestHitNum[k], secBestHitNum[k],
+                        sd[k].gapOpen, sd[k].gapExt, sd[k].md, mapq[k], cfg->readGroup, cfg->isPrintMDNM != 0);
+        } else {
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], strand[k], none, NULL, true, 0, 0, 0, 0, 0, 0, none, 0, cfg->readGroup, false);
+        }
+        r.flag = (uint16_t)(1 | (both ? 2 : 0) | (k ? 128 : 64) | (bpos[k] == NONE ? 4 : 0) | (bpos[1 - k] == NONE ? 8 : 0) |
+                            (bpos[k] != NONE && best.strand[k] == 2 ? 16 : 0) | (bpos[1 - k] != NONE && best.strand[1 - k] == 2 ? 32 : 0));
+        const int m = 1 - k;
+        r.tid = chr[k] == 0 ? (chr[m] == 0 ? -1 : (int32_t)chr[m] - 1) : (int32_t)chr[k] - 1;
+        r.pos = tp[k] == 0 ? (tp[m] == 0 ? -1 : (int32_t)(tp[m] - 1)) : (int32_t)(tp[k] - 1);
+        r.mtid = chr[m] == 0 ? (chr[k] == 0 ? -1 : (int32_t)chr[k] - 1) : (int32_t)chr[m] - 1;
+        r.mpos = tp[m] == 0 ? (tp[k] == 0 ? -1 : (int32_t)(tp[k] - 1)) : (int32_t)(tp[m] - 1);
+        if (bestInsert > 0) r.isize = tp[k] > tp[m] ? -(int32_t)(tp[k] + (unsigned long long)span[k] - tp[m]) : (int32_t)(tp[m] + (unsigned long long)span[m] - tp[k]);
+        else r.isize = 0;
+        if ((rc = finish(r, d))) { s3_sam_record_free(&out[0]); s3_sam_record_free(&out[1]); s3_set_error("s3_sam_deep_dp_records: out of host memory"); return rc; }
+    }
+    return S3_OK;
+}

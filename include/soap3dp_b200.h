@@ -797,6 +797,24 @@ int s3_sam_deep_dp_records(const s3_sam_genome *genome, const s3_sam_config *con
                            const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
                            int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2,
                            const int32_t x0[2], const int32_t x1[2], const int32_t mismatch[2], s3_sam_record out[2]);
+/* pairDPOutputSAMAPI (BGS-IO.cpp:4504-5554): the two records of a read pair from its default-DP (mate rescue) results -- the rescue
+ * records of s3_pe_align with the special CIGARs and edit distances of s3_dp_decode.  In every entry one read comes from the search
+ * (score = its mismatches, ungapped: CIGAR <len>M or the trimmed form, MD by getMdStr, MAPQ leg s3_mapq_pair_end) and the other
+ * from DP (score = DP score; CIGAR, MD, XM / XO / XG by getMisInfoForDP, MAPQ leg s3_mapq_pair_end_dp); whichFromDP says which
+ * (0 the first read, 1 its mate), and only the entries of the reported entry's kind are counted and listed.  X0 / X1 per read from
+ * those entries and the search's counts (x0 / x1 / mismatch), the "second best" pair for s3_mapq_bwa_pair as the reference's scan
+ * leaves it, read-through pairs as in s3_sam_deep_dp_records (the single read left: s3_mapq_unique_dp or s3_mapq_unique). */
+typedef struct {
+    uint8_t whichFromDP, strand[2], pad;                                              /* AlgnmtDPResult, PEAlgnmt.h:384-402; [0] the pair's first read, [1] its mate */
+    int32_t editdist, insertSize, numSameScore;
+    uint32_t ambPosition[2];
+    int32_t score[2];
+    const char *cigar;                                                                /* special CIGAR of the read that came from DP */
+} s3_sam_dp_pairing;
+int s3_sam_pair_dp_records(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_dp_pairing *alignments, uint32_t num, int32_t bestIndex,
+                           const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                           int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2,
+                           const int32_t x0[2], const int32_t x1[2], const int32_t mismatch[2], s3_sam_record out[2]);
 
 #ifdef __cplusplus
 }

@@ -351,3 +351,83 @@ extern "C" int ref_sam_deep_dp ( const uint32_t * pac, uint32_t dnaLength, const
     SAMOccurrenceDestruct ( &occBuf );
     return n;
 }
+
+// pairDPOutputSAMAPI (BGS-IO.cpp:4504-5554): the two records of a pair from its default-DP (mate rescue) results.  results[11 * i] =
+// whichFromDP, edit distance, insert size, tie count, then per read position, strand, score, and last the index of the entry's special
+// CIGAR in cigars[]; counts[6] as ref_sam_deep_dp.
+extern "C" int ref_sam_pair_dp ( const uint32_t * pac, uint32_t dnaLength, const uint32_t * translate, uint32_t numSeg, const uint32_t * ambiguityMap,
+                                 const uint32_t * chrEndPos, uint32_t numChr, const char * const * chrNames,
+                                 int alignmentType, int bwaLike, int isFastq, int maxMAPQ, int minMAPQ, int isPrintMDNM, const char * readGroup,
+                                 int dpMatch, int dpMismatch,
+                                 const int32_t * results, uint32_t num, int bestIdx, const char * const * cigars, const int32_t * counts,
+                                 const uint8_t * query1, const uint8_t * query2, const char * qual1, const char * qual2, int len1, int len2,
+                                 const char * name1, const char * name2,
+                                 int32_t * core, uint8_t * data, int32_t dataCap, int32_t * dataLen )
+{
+    HSP hsp;
+    memset ( &hsp, 0, sizeof ( hsp ) );
+    hsp.dnaLength = dnaLength;
+    hsp.packedDNA = ( unsigned int * ) pac;
+    hsp.numOfRemovedSegment = numSeg;
+    std::vector<Translate> tr ( numSeg );
+    for ( uint32_t i = 0; i < numSeg; i++ ) { tr[i].startPos = translate[3 * i]; tr[i].chrID = translate[3 * i + 1]; tr[i].correction = translate[3 * i + 2]; }
+    hsp.translate = tr.data ();
+    hsp.ambiguityMap = ( unsigned int * ) ambiguityMap;
+    std::vector<SeqOffset> so ( numChr );
+    for ( uint32_t i = 0; i < numChr; i++ ) { memset ( &so[i], 0, sizeof ( SeqOffset ) ); so[i].endPos = chrEndPos[i]; }
+    hsp.seqOffset = so.data ();
+    hsp.numOfSeq = numChr;
+    HSPAux aux;
+    memset ( &aux, 0, sizeof ( aux ) );
+    aux.isFastq = isFastq; aux.alignmentType = alignmentType; aux.minMAPQ = minMAPQ; aux.maxMAPQ = maxMAPQ; aux.bwaLikeScore = bwaLike;
+    aux.readGroup = ( char * ) readGroup; aux.isPrintMDNM = isPrintMDNM; aux.dpMatchScore = dpMatch; aux.dpMisMatchScore = dpMismatch;
+    bwase_initialize ( aux.g_log_n );
+    int x0a[2] = { counts[0], counts[3] }, x1a[2] = { counts[1], counts[4] }, mma[2] = { counts[2], counts[5] };
+    aux.x0_array = x0a; aux.x1_array = x1a; aux.mismatch_array = mma;
+    SRAIndex index;
+    memset ( &index, 0, sizeof ( index ) );
+    index.hsp = &hsp; index.hspaux = &aux;
+    OCC occBuf;
+    memset ( &occBuf, 0, sizeof ( occBuf ) );
+    SAMOccurrenceConstruct ( &occBuf );
+    bam_header_t header;
+    memset ( &header, 0, sizeof ( header ) );
+    header.n_targets = numChr;
+    header.target_name = ( char ** ) chrNames;
+    samfile_t sf;
+    memset ( &sf, 0, sizeof ( sf ) );
+    sf.header = &header;
+    SRASetting setting;
+    memset ( &setting, 0, sizeof ( setting ) );
+    setting.occ = &occBuf; setting.SAMOutFilePtr = &sf;
+    SRAQueryInput in;
+    memset ( &in, 0, sizeof ( in ) );
+    in.AlgnmtIndex = &index; in.QuerySetting = &setting;
+    std::vector<AlgnmtDPResult> res ( num ? num : 1 );
+    memset ( res.data (), 0, res.size () * sizeof ( AlgnmtDPResult ) );
+    for ( uint32_t i = 0; i < num; i++ )
+    {
+        const int32_t * r = results + 11 * i;
+        res[i].readID = 0; res[i].whichFromDP = ( char ) r[0]; res[i].editdist = r[1]; res[i].insertSize = r[2]; res[i].num_sameScore = r[3];
+        res[i].algnmt_1 = ( unsigned int ) r[4]; res[i].strand_1 = ( char ) r[5]; res[i].score_1 = r[6];
+        res[i].algnmt_2 = ( unsigned int ) r[7]; res[i].strand_2 = ( char ) r[8]; res[i].score_2 = r[9];
+        res[i].cigarString = ( char * ) cigars[r[10]];
+    }
+    DynamicUint8Array * xaz = DynamicUint8ArrayConstruct ();
+    g_kept.clear ();
+    pairDPOutputSAMAPI ( &in, res.data (), bestIdx >= 0 ? &res[bestIdx] : NULL, 0, num, ( unsigned char * ) query1, ( unsigned char * ) query2,
+                         ( char * ) qual1, ( char * ) qual2, len1, len2, ( char * ) name1, ( char * ) name2, xaz );
+    int n = ( int ) g_kept.size ();
+    for ( int r = 0; r < n && r < 2; r++ )
+    {
+        const Kept & k = g_kept[r];
+        int32_t * c = core + 12 * r;
+        c[0] = k.core.tid; c[1] = k.core.pos; c[2] = k.core.bin; c[3] = k.core.qual; c[4] = k.core.l_qname; c[5] = k.core.flag; c[6] = k.core.n_cigar;
+        c[7] = k.core.l_qseq; c[8] = k.core.mtid; c[9] = k.core.mpos; c[10] = k.core.isize; c[11] = k.l_aux;
+        dataLen[r] = k.data_len;
+        if ( k.data_len <= dataCap ) { memcpy ( data + ( size_t ) r * dataCap, k.data.data (), k.data_len ); }
+    }
+    DynamicUint8ArrayFree ( xaz );
+    SAMOccurrenceDestruct ( &occBuf );
+    return n;
+}

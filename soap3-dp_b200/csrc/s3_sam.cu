@@ -729,3 +729,214 @@ extern "C" int s3_sam_deep_dp_records(const s3_sam_genome *g, const s3_sam_confi
     }
     return S3_OK;
 }
+
+
+// ---- pairDPOutputSAMAPI (BGS-IO.cpp:4504-5554): the two records of a read pair from its default-DP (mate rescue) results ---------
+// One read of every entry comes from the search (score = its mismatches, ungapped), the other from DP (score = DP score, special
+// CIGAR): whichFromDP says which; only entries of the reported entry's kind count.
+extern "C" int s3_sam_pair_dp_records(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_dp_pairing *algn, uint32_t num, int32_t bestIndex,
+                                      const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                                      int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2,
+                                      const int32_t x0[2], const int32_t x1[2], const int32_t mismatch[2], s3_sam_record out[2])
+{
+    if (!out) { s3_set_error("s3_sam_pair_dp_records: NULL output"); return S3_EINVAL; }
+    memset(out, 0, 2 * sizeof(s3_sam_record));
+    if (!g || !cfg || !query1 || !query2 || !qualities1 || !qualities2 || !queryName1 || !queryName2 || !cfg->readGroup || (num && !algn) || !x0 || !x1 || !mismatch ||
+        readlen1 <= 0 || readlen2 <= 0 || bestIndex >= (int32_t)num) { s3_set_error("s3_sam_pair_dp_records: bad argument"); return S3_EINVAL; }
+    const uint32_t NONE = 0xFFFFFFFFu;
+    const uint8_t *query[2] = {query1, query2};
+    const char *qual[2] = {qualities1, qualities2}, *name[2] = {queryName1, queryName2};
+    const int readlen[2] = {readlen1, readlen2};
+    std::vector<uint8_t> d;
+    const std::string none;
+    int rc;
+    if (bestIndex < 0) {
+        for (int k = 0; k < 2; ++k) {
+            s3_sam_record &r = out[k];
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], 1, none, NULL, true, 0, 0, 0, 0, 0, 0, none, 0, cfg->readGroup, false);
+            r.flag = (uint16_t)(1 | (k ? 128 : 64));
+            r.tid = r.pos = r.mtid = r.mpos = -1; r.isize = 0;
+            if ((rc = finish(r, d))) { s3_sam_record_free(&out[0]); s3_sam_record_free(&out[1]); s3_set_error("s3_sam_pair_dp_records: out of host memory"); return rc; }
+        }
+        return S3_OK;
+    }
+    if (!g->packedDNA || !g->segments || !g->ambiguityMap || !g->chrEndPos || !g->chrNames || g->numSegments == 0) { s3_set_error("s3_sam_pair_dp_records: incomplete genome description"); return S3_EINVAL; }
+    const s3_sam_dp_pairing &best = algn[bestIndex];
+    const int fromDP = best.whichFromDP;                                  // 0: the first read's alignment is the DP one, 1: the mate's, 2: neither
+    for (uint32_t i = 0; i < num; ++i)
+        if (algn[i].whichFromDP <= 1 && algn[i].ambPosition[algn[i].whichFromDP] != NONE && !algn[i].cigar) { s3_set_error("s3_sam_pair_dp_records: entry %u without a CIGAR", i); return S3_EINVAL; }
+    uint32_t bpos[2] = {best.ambPosition[0], best.ambPosition[1]};
+    unsigned long long tp[2] = {0, 0};
+    uint32_t chr[2] = {0, 0};
+    DpSide sd[2];                                                         // (cigar stays empty for the read that came from the search)
+    std::string newCigar[2];
+    int strand[2] = {1, 1}, span[2] = {readlen1, readlen2};
+    for (int k = 0; k < 2; ++k) {
+        if (bpos[k] == NONE) continue;
+        strand[k] = best.strand[k];
+        if (fromDP == k) {
+            if ((rc = dp_side(g, best.cigar, bpos[k], readlen[k], qual[k], &tp[k], &chr[k], sd[k]))) return rc;
+            span[k] = cigar_span(best.cigar);
+        } else {
+            sd[k].trim = chr_and_pos_checked(g, (uint32_t)readlen[k], bpos[k], &tp[k], &chr[k], newCigar[k]);
+            md_string(g, query[k], qual[k], (uint32_t)readlen[k], bpos[k], strand[k], best.score[k], sd[k].trim, sd[k].md, &sd[k].avgQual);
+            sd[k].mism = best.score[k];
+            if (sd[k].trim && sd[k].mism) { sd[k].mism = 0; for (char c : sd[k].md) sd[k].mism += c > '9'; }
+        }
+    }
+    int bestInsert = (bpos[0] != NONE && bpos[1] != NONE) ? best.insertSize : 0;
+    if (bpos[0] != NONE && bpos[1] != NONE) {
+        const unsigned long long a1 = (unsigned long long)bpos[0] + (sd[0].trim > 0 ? sd[0].trim : 0), a2 = (unsigned long long)bpos[1] + (sd[1].trim > 0 ? sd[1].trim : 0);
+        if ((best.strand[0] == 1 && (a1 > a2 || a1 + span[0] > a2 + span[1])) || (best.strand[0] == 2 && (a2 > a1 || a2 + span[1] > a1 + span[0]))) {
+            const int drop = sd[0].mism <= sd[1].mism ? 1 : 0;
+            bpos[drop] = NONE; tp[drop] = 0; chr[drop] = 0;
+            bestInsert = 0;
+        }
+    }
+    const bool both = bpos[0] != NONE && bpos[1] != NONE;
+    // pairs with the reported pair's scores, and the "second best" pair as the reference's scan leaves it (:4700-4777)
+    int bestPairNum = 0, bestPairScore[2] = {0, 0}, secBestPairNum = 0, secBestPairScore[2] = {0, 0}, numSimilar = 0;
+    if (both) {
+        bestPairNum = 1; numSimilar = 1;
+        bestPairScore[0] = best.score[0]; bestPairScore[1] = best.score[1];
+        for (uint32_t i = 0; i < num && num > 1; ++i) {
+            if ((int32_t)i == bestIndex || algn[i].whichFromDP != fromDP) continue;
+            const int s1 = algn[i].score[0], s2 = algn[i].score[1];
+            if (s1 == bestPairScore[0] && s2 == bestPairScore[1]) ++bestPairNum;
+            else if (secBestPairNum == 0) { secBestPairScore[0] = s1; secBestPairScore[1] = s2; secBestPairNum = 1; }
+            else if (fromDP == 0 || fromDP == 1) {
+                const int dp = fromDP, se = 1 - fromDP;                   // the DP read's score: larger is better; the other's mismatches: fewer is better
+                const int sdp = algn[i].score[dp], sse = algn[i].score[se];
+                if (sse < secBestPairScore[se]) { secBestPairScore[0] = s1; secBestPairScore[1] = s2; secBestPairNum = 1; }
+                else if (sse == secBestPairScore[se] && sdp > secBestPairScore[dp]) { secBestPairScore[dp] = sdp; secBestPairNum = 1; }
+                else if (sse == secBestPairScore[se] && sdp == secBestPairScore[dp]) ++secBestPairNum;
+            }
+            // pairs about as good as the reported one (within one mismatch's worth)
+        }
+        for (uint32_t i = 0; i < num && num > 1; ++i) {
+            if ((int32_t)i == bestIndex || algn[i].whichFromDP != fromDP) continue;
+            const int s1 = algn[i].score[0], s2 = algn[i].score[1];
+            bool similar;
+            if (fromDP == 0) similar = s1 >= bestPairScore[0] + cfg->dpMisMatchScore && s2 <= bestPairScore[1] + 1;
+            else if (fromDP == 1) similar = s1 <= bestPairScore[0] + 1 && s2 >= bestPairScore[1] + cfg->dpMisMatchScore;
+            else similar = s1 <= bestPairScore[0] + 1 && s2 <= bestPairScore[1] + 1;
+            if (similar) ++numSimilar;
+        }
+    }
+    int bestHitNum[2] = {0, 0}, secBestHitNum[2] = {0, 0}, bestScore[2] = {0, 0}, secBestScore[2] = {0, 0}, isBestHit[2] = {1, 1};
+    for (int k = 0; k < 2; ++k) {
+        uint32_t bestPos = NONE, secBestPos = NONE;
+        const bool dpRead = fromDP == k;
+        if (bpos[k] != NONE) { bestScore[k] = best.score[k]; bestPos = bpos[k]; bestHitNum[k] = 1; secBestScore[k] = dpRead ? 0 : 999; }
+        if (bpos[k] != NONE && num > 1) {
+            for (uint32_t i = 0; i < num; ++i) {
+                if ((int32_t)i == bestIndex || algn[i].whichFromDP != fromDP) continue;
+                const int sc = algn[i].score[k];
+                const uint32_t pos = algn[i].ambPosition[k];
+                if (!dpRead) {                                            // mismatches: smaller is better, every entry counts once
+                    if (sc <= bestScore[k]) {
+                        if (sc == bestScore[k]) { if (pos != bestPos) ++bestHitNum[k]; }
+                        else { secBestScore[k] = bestScore[k]; secBestHitNum[k] = bestHitNum[k]; secBestPos = bestPos; bestScore[k] = sc; bestHitNum[k] = 1; bestPos = pos; isBestHit[k] = 0; }
+                    } else if (sc <= secBestScore[k]) {
+                        if (sc == secBestScore[k]) { if (pos != secBestPos) ++secBestHitNum[k]; }
+                        else { secBestScore[k] = sc; secBestPos = pos; secBestHitNum[k] = 1; }
+                    }
+                } else {                                                  // DP scores: larger is better, an entry counts with its ties
+                    const int same = algn[i].numSameScore;
+                    if (sc >= bestScore[k]) {
+                        if (sc == bestScore[k]) { if (pos != bestPos) bestHitNum[k] += same; }
+                        else { secBestScore[k] = bestScore[k]; secBestHitNum[k] = bestHitNum[k]; secBestPos = bestPos; bestScore[k] = sc; bestPos = pos; bestHitNum[k] = same; isBestHit[k] = 0; }
+                    } else if (sc >= secBestScore[k]) {
+                        if (sc == secBestScore[k]) { if (pos != secBestPos) secBestHitNum[k] += same; }
+                        else { secBestScore[k] = sc; secBestPos = pos; secBestHitNum[k] = same; }
+                    }
+                }
+            }
+        }
+        if (x0[k] > (k ? 1 : 0)) {
+            if (!dpRead) {                                                // the read came from the search: its own counts
+                bestHitNum[k] = x0[k]; secBestHitNum[k] = x1[k];
+                if (mismatch[k] < best.score[k]) isBestHit[k] = 0;
+            } else {
+                const int x0Score = mismatch[k] * cfg->dpMisMatchScore + (readlen[k] - mismatch[k]) * cfg->dpMatchScore;
+                if (x0Score >= bestScore[k]) {
+                    if (x0[k] > bestHitNum[k]) bestHitNum[k] = x0[k];
+                    if (x1[k] > secBestHitNum[k]) secBestHitNum[k] = x1[k];
+                    if (x0Score > bestScore[k]) isBestHit[k] = 0;
+                }
+            }
+        }
+    }
+    const bool lists = cfg->alignmentType == 1 || cfg->alignmentType == 2;
+    int mapq[2] = {0, 0};
+    if (both) {
+        if (!lists) mapq[0] = mapq[1] = 255;
+        else {
+            if (cfg->bwaLikeScore) {
+                const int dp = fromDP == 0 ? 0 : 1, se = 1 - dp;          // (whichFromDP 2 takes the second form, like the reference)
+                const int op = bestPairScore[se] * cfg->dpMisMatchScore + (readlen[se] - bestPairScore[se]) * cfg->dpMatchScore + bestPairScore[dp];
+                const int subop = secBestPairNum > 0 ? secBestPairScore[se] * cfg->dpMisMatchScore + (readlen[se] - secBestPairScore[se]) * cfg->dpMatchScore + secBestPairScore[dp] : 0;
+                s3_mapq_bwa_pair(bestHitNum[0], secBestHitNum[0], bestHitNum[1], secBestHitNum[1], op, bestPairNum, subop, secBestPairNum, readlen1, readlen2, &mapq[0], &mapq[1]);
+            } else {
+                int m[2];
+                const int dp = fromDP == 0 ? 0 : 1;
+                for (int k = 0; k < 2; ++k) {
+                    const int aq = cfg->isFastq == 1 ? sd[k].avgQual : 20;
+                    m[k] = k == dp ? s3_mapq_pair_end_dp(best.score[k], readlen[k] * cfg->dpMatchScore, aq, bestHitNum[k], secBestHitNum[k], bestScore[k], secBestScore[k], isBestHit[k],
+                                                         numSimilar, cfg->maxMAPQ, cfg->minMAPQ)
+                                   : s3_mapq_pair_end(best.score[k], aq, bestHitNum[k], secBestHitNum[k], isBestHit[k], (uint32_t)numSimilar, cfg->maxMAPQ, cfg->minMAPQ);
+                }
+                mapq[0] = mapq[1] = s3_mapq_of_pair(m[0], m[1]);
+            }
+            for (int k = 0; k < 2; ++k) if (sd[k].trim) mapq[k] = 0;
+        }
+    }
+    for (int k = 0; k < 2; ++k) {
+        std::string xa;
+        if (bpos[k] != NONE && num > 1) {
+            char nb[24];
+            for (uint32_t i = 0; i < num; ++i) {
+                if ((int32_t)i == bestIndex || algn[i].whichFromDP != fromDP) continue;
+                if (cfg->alignmentType == 2 && (algn[i].score[0] != bestPairScore[0] || algn[i].score[1] != bestPairScore[1])) continue;
+                unsigned long long t;
+                uint32_t c;
+                chr_and_pos(g, algn[i].ambPosition[k], &t, &c);
+                xa += g->chrNames[c - 1];
+                xa.push_back(',');
+                xa.push_back(algn[i].strand[k] == 2 ? '-' : '+');
+                xa.append(nb, write_num((long long)t, nb));
+                xa.push_back(',');
+                if (algn[i].whichFromDP != k) { xa.append(nb, write_num(readlen[k], nb)); xa += "M,"; xa.append(nb, write_num(algn[i].score[k], nb)); }
+                else { s3_special_to_sam(algn[i].cigar, strlen(algn[i].cigar), xa); xa.push_back(','); xa.append(nb, write_num(algn[i].editdist, nb)); }
+                xa.push_back(';');
+            }
+        }
+        if (cfg->alignmentType == 4) { bestHitNum[k] = -1; secBestHitNum[k] = -1; }
+        else if (!lists) secBestHitNum[k] = -1;
+        s3_sam_record &r = out[k];
+        if (bpos[k] != NONE) {
+            if (bpos[1 - k] == NONE) {
+                const int aq = cfg->isFastq == 1 ? sd[k].avgQual : 20;
+                mapq[k] = fromDP == k ? s3_mapq_unique_dp(bestHitNum[k], best.score[k], readlen[k] * cfg->dpMatchScore, aq, cfg->maxMAPQ, cfg->minMAPQ)
+                                      : s3_mapq_unique(bestHitNum[k], best.score[k], aq, cfg->maxMAPQ, cfg->minMAPQ);
+                if (sd[k].trim) mapq[k] = 0;
+            }
+            const std::string *cig = !newCigar[k].empty() ? &newCigar[k] : (fromDP == k ? &sd[k].cigar : NULL);
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], strand[k], xa, cig, false, sd[k].mism, sd[k].mism + sd[k].gapExt, bestHitNum[k], secBestHitNum[k],
+                        sd[k].gapOpen, sd[k].gapExt, sd[k].md, mapq[k], cfg->readGroup, cfg->isPrintMDNM != 0);
+        } else {
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], strand[k], none, NULL, true, 0, 0, 0, 0, 0, 0, none, 0, cfg->readGroup, false);
+        }
+        r.flag = (uint16_t)(1 | (both ? 2 : 0) | (k ? 128 : 64) | (bpos[k] == NONE ? 4 : 0) | (bpos[1 - k] == NONE ? 8 : 0) |
+                            (bpos[k] != NONE && best.strand[k] == 2 ? 16 : 0) | (bpos[1 - k] != NONE && best.strand[1 - k] == 2 ? 32 : 0));
+        const int m = 1 - k;
+        r.tid = chr[k] == 0 ? (chr[m] == 0 ? -1 : (int32_t)chr[m] - 1) : (int32_t)chr[k] - 1;
+        r.pos = tp[k] == 0 ? (tp[m] == 0 ? -1 : (int32_t)(tp[m] - 1)) : (int32_t)(tp[k] - 1);
+        r.mtid = chr[m] == 0 ? (chr[k] == 0 ? -1 : (int32_t)chr[k] - 1) : (int32_t)chr[m] - 1;
+        r.mpos = tp[m] == 0 ? (tp[k] == 0 ? -1 : (int32_t)(tp[k] - 1)) : (int32_t)(tp[m] - 1);
+        if (bestInsert > 0) r.isize = tp[k] > tp[m] ? -(int32_t)(tp[k] + (unsigned long long)span[k] - tp[m]) : (int32_t)(tp[m] + (unsigned long long)span[m] - tp[k]);
+        else r.isize = 0;
+        if ((rc = finish(r, d))) { s3_sam_record_free(&out[0]); s3_sam_record_free(&out[1]); s3_set_error("s3_sam_pair_dp_records: out of host memory"); return rc; }
+    }
+    return S3_OK;
+}

@@ -412,3 +412,112 @@ def test_sam_deep_dp_records_match_the_reference_writer():
         demoted += m > 0 and bool((want[0][0][5] | want[1][0][5]) & 4)
         with_xa += b"XAZ" in want[0][1]
     assert none > 100 and demoted > 50 and with_xa > 200
+
+
+class DpPairing(C.Structure):
+    _fields_ = [("whichFromDP", C.c_uint8), ("strand", C.c_uint8 * 2), ("pad", C.c_uint8), ("editdist", C.c_int32), ("insertSize", C.c_int32),
+                ("numSameScore", C.c_int32), ("ambPosition", C.c_uint32 * 2), ("score", C.c_int32 * 2), ("cigar", C.c_char_p)]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_sam.so not built")
+def test_sam_pair_dp_records_match_the_reference_writer():
+    """s3_sam_pair_dp_records against pairDPOutputSAMAPI: one read from the search and one from DP per entry, entries of both kinds mixed,
+    X0 / X1 by mismatches or by DP score, the second-best pair of the BWA-like MAPQ, both MAPQ modes, XA:Z in both forms, read-through
+    pairs, trimmed alignments on either side, no result"""
+    ref = C.CDLL(REF)
+    lib = api.load_library()
+    rng = np.random.default_rng(55)
+    n = 200_000
+    G = rng.integers(0, 4, n).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    translate = np.array([0, 1, 0xFFFFFFFF, 70_000, 2, 70_000 - 1, 100_000, 2, 70_000 - 1 - 500, 150_000, 3, 150_000 - 1], np.uint32)
+    chr_end = np.array([69_999, 149_999, 199_999], np.uint32)
+    amb = np.full(4, 3, np.uint32)
+    names = [b"chr1", b"chrTwo", b"3"]
+    segs = (Segment * 4)(*[Segment(int(translate[3 * i]), int(translate[3 * i + 1]), int(translate[3 * i + 2])) for i in range(4)])
+    gen = Genome(helpers.u32p(pac), n, segs, 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, (C.c_char_p * 3)(*names))
+    cnames = (C.c_char_p * 3)(*names)
+    edges = [70_000, 100_000, 150_000]
+    lib.s3_sam_pair_dp_records.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    ref.ref_sam_pair_dp.restype = C.c_int
+    none = demoted = with_xa = 0
+    for trial in range(2000):
+        L = (int(rng.integers(50, 152)), int(rng.integers(50, 152)))
+        cfg = Config(int(rng.integers(1, 5)), int(rng.integers(0, 2)), 1, -2, int(rng.integers(0, 2)), 40, 1, int(rng.integers(0, 2)), 1, 1000, b"grp%d" % trial)
+        m = int(rng.choice([0, 1, 1, 2, 3, 6]))
+        main_kind = int(rng.integers(0, 2))
+        algn = []
+        for _ in range(m):
+            kind = main_kind if rng.random() < 0.8 else 1 - main_kind
+            if rng.random() < 0.3:
+                e = int(rng.choice(edges))
+                p1 = max(0, e - int(rng.integers(1, L[0] + 4)))
+            else:
+                p1 = int(rng.integers(1000, n - 3000))
+            gap = int(rng.integers(-40, 400))
+            s1 = int(rng.integers(1, 3))
+            p2 = min(max(p1 + gap if s1 == 1 else p1 - gap, 0), n - 2 * L[1] - 8)
+            sc = [0, 0]
+            sc[kind] = int(rng.integers(30, L[kind] + 1))                 # DP score of the read that came from DP
+            sc[1 - kind] = int(rng.integers(0, 4))                         # mismatches of the read that came from the search
+            algn.append((kind, (s1, 3 - s1), int(rng.integers(0, 9)), int(rng.integers(150, 600)), int(rng.integers(1, 4)), (p1, p2), tuple(sc),
+                         random_special_cigar(rng, L[kind]).encode()))
+        if m > 1 and rng.random() < 0.4:                                   # ties with the first entry
+            a = algn[0]
+            algn[1] = (a[0], algn[1][1], algn[1][2], algn[1][3], algn[1][4], (a[5][0], algn[1][5][1]) if rng.random() < 0.5 else algn[1][5], a[6],
+                       random_special_cigar(rng, L[a[0]]).encode())
+        best = int(rng.integers(0, m)) if m else -1
+        counts = np.array([int(rng.integers(0, 4)), int(rng.integers(0, 4)), int(rng.integers(0, 5)),
+                           int(rng.integers(0, 4)), int(rng.integers(0, 4)), int(rng.integers(0, 5))], np.int32)
+        # the reads: where the reported entry's search-side read lies, with a few substitutions, so that its MD string has content
+        q = []
+        for k in range(2):
+            if m and algn[best][0] != k and algn[best][5][k] + L[k] <= n:
+                r = G[algn[best][5][k]:algn[best][5][k] + L[k]].copy()
+                for j in rng.choice(L[k], int(rng.integers(0, 4)), replace=False):
+                    r[j] = (r[j] + 1) & 3
+                q.append(np.ascontiguousarray((3 - r[::-1]) if algn[best][1][k] == 2 else r).astype(np.uint8))
+            else:
+                q.append(np.ascontiguousarray(rng.integers(0, 4, L[k]).astype(np.uint8)))
+        ql = []
+        for k in range(2):
+            x = np.ascontiguousarray(rng.integers(2, 41, L[k] + 1).astype(np.uint8)); x[-1] = 0
+            ql.append(x)
+        n1, n2 = b"pair%d/1" % trial, b"pair%d/2" % trial
+        arr = (DpPairing * max(m, 1))()
+        for k, a in enumerate(algn):
+            arr[k].whichFromDP, arr[k].editdist, arr[k].insertSize, arr[k].numSameScore, arr[k].cigar = a[0], a[2], a[3], a[4], a[7]
+            for i in range(2):
+                arr[k].strand[i], arr[k].ambPosition[i], arr[k].score[i] = a[1][i], a[5][i], a[6][i]
+        x0 = (C.c_int32 * 2)(int(counts[0]), int(counts[3])); x1 = (C.c_int32 * 2)(int(counts[1]), int(counts[4])); mm = (C.c_int32 * 2)(int(counts[2]), int(counts[5]))
+        out = (Record * 2)()
+        rc = lib.s3_sam_pair_dp_records(C.byref(gen), C.byref(cfg), arr, m, best, q[0].ctypes.data_as(U8P), q[1].ctypes.data_as(U8P), ql[0].ctypes.data_as(C.c_char_p),
+                                        ql[1].ctypes.data_as(C.c_char_p), L[0], L[1], n1, n2, x0, x1, mm, out)
+        assert rc == 0, (trial, algn)
+        got = []
+        for r in out:
+            got.append(((r.tid, r.pos, r.bin, r.qual, r.l_qname, r.flag, r.n_cigar, r.l_qseq, r.mtid, r.mpos, r.isize, r.l_aux), bytes(bytearray(r.data[:r.data_len]))))
+        for k in range(2):
+            lib.s3_sam_record_free(C.byref(out[k]))
+        flat = []
+        for k, a in enumerate(algn):
+            flat += [a[0], a[2], a[3], a[4], a[5][0], a[1][0], a[6][0], a[5][1], a[1][1], a[6][1], k]
+        flat = np.array(flat if flat else [0] * 11, np.int64).astype(np.int32)
+        cig = (C.c_char_p * max(m, 1))(*([a[7] for a in algn] or [b""]))
+        core = np.zeros(24, np.int32)
+        cap = 8192
+        data = np.zeros(2 * cap, np.uint8)
+        dlen = np.zeros(2, np.int32)
+        k = ref.ref_sam_pair_dp(helpers.u32p(pac), n, helpers.u32p(translate), 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, cnames,
+                                cfg.alignmentType, cfg.bwaLikeScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup, cfg.dpMatchScore, cfg.dpMisMatchScore,
+                                flat.ctypes.data_as(I32P), m, best, cig, counts.ctypes.data_as(I32P),
+                                q[0].ctypes.data_as(U8P), q[1].ctypes.data_as(U8P), ql[0].ctypes.data_as(C.c_char_p), ql[1].ctypes.data_as(C.c_char_p), L[0], L[1], n1, n2,
+                                core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), cap, dlen.ctypes.data_as(I32P))
+        assert k == 2
+        want = [(tuple(int(x) for x in core[12 * r:12 * r + 12]), bytes(data[r * cap:r * cap + int(dlen[r])])) for r in range(2)]
+        assert got == want, (trial, algn, best, counts.tolist(), got, want)
+        none += m == 0
+        demoted += m > 0 and bool((want[0][0][5] | want[1][0][5]) & 4)
+        with_xa += b"XAZ" in want[0][1]
+    assert none > 100 and demoted > 50 and with_xa > 200

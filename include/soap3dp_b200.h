@@ -815,6 +815,16 @@ int s3_sam_pair_dp_records(const s3_sam_genome *genome, const s3_sam_config *con
                            const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
                            int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2,
                            const int32_t x0[2], const int32_t x1[2], const int32_t mismatch[2], s3_sam_record out[2]);
+/* unproperlypairOutputSAMAPI (BGS-IO.cpp:2582-2930): the two records of a read pair whose reads have occurrences but no valid pairing
+ * (and of pairs where only one read, or neither, has any): each read reported on its own -- the first occurrence with the fewest
+ * mismatches, X0 / X1 = the occurrences with that count / with one more, the others in XA:Z (alignmentType OUTPUT_ALL_VALID /
+ * OUTPUT_ALL_BEST, up to peMaxOutputPerRead results), MAPQ = s3_mapq_single >> 1, at least minMAPQ (255 for the unique / random
+ * report types; OUTPUT_UNIQUE_BEST reports a read only when its best count is held by one occurrence) -- flags without the
+ * proper-pair bit, the mate's chromosome and position in the mate fields, an insert size when both lie on one chromosome. */
+int s3_sam_unpaired_records(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_occurrence *occ1, uint32_t numOcc1,
+                            const s3_sam_occurrence *occ2, uint32_t numOcc2, uint32_t peMaxOutputPerRead,
+                            const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                            int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2, s3_sam_record out[2]);
 
 #ifdef __cplusplus
 }

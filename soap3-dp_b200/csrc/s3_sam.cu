@@ -940,3 +940,102 @@ extern "C" int s3_sam_pair_dp_records(const s3_sam_genome *g, const s3_sam_confi
     }
     return S3_OK;
 }
+
+
+// ---- unproperlypairOutputSAMAPI (BGS-IO.cpp:2582-2930): the two records of a read pair without a valid pairing ---------------------
+// Each read is reported on its own -- the first occurrence with the fewest mismatches, X0 / X1 = the occurrences with that count / one
+// more, the others in XA:Z, MAPQ = half of s3_mapq_single (at least minMAPQ) -- with the mate's position in the mate fields.
+extern "C" int s3_sam_unpaired_records(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_occurrence *occ1, uint32_t numOcc1,
+                                       const s3_sam_occurrence *occ2, uint32_t numOcc2, uint32_t peMaxOutputPerRead,
+                                       const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                                       int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2, s3_sam_record out[2])
+{
+    if (!out) { s3_set_error("s3_sam_unpaired_records: NULL output"); return S3_EINVAL; }
+    memset(out, 0, 2 * sizeof(s3_sam_record));
+    if (!g || !cfg || !query1 || !query2 || !qualities1 || !qualities2 || !queryName1 || !queryName2 || !cfg->readGroup || (numOcc1 && !occ1) || (numOcc2 && !occ2) ||
+        readlen1 <= 0 || readlen2 <= 0) { s3_set_error("s3_sam_unpaired_records: bad argument"); return S3_EINVAL; }
+    if ((numOcc1 || numOcc2) && (!g->packedDNA || !g->segments || !g->ambiguityMap || !g->chrEndPos || !g->chrNames || g->numSegments == 0)) {
+        s3_set_error("s3_sam_unpaired_records: incomplete genome description"); return S3_EINVAL;
+    }
+    const s3_sam_occurrence *occ[2] = {occ1, occ2};
+    const uint32_t numOcc[2] = {numOcc1, numOcc2};
+    const uint8_t *query[2] = {query1, query2};
+    const char *qual[2] = {qualities1, qualities2}, *name[2] = {queryName1, queryName2};
+    const int readlen[2] = {readlen1, readlen2};
+    const int type = cfg->alignmentType;
+    const bool lists = type == 1 || type == 2;
+    int best[2] = {-1, -1}, bestScore[2] = {0, 0}, bestNum[2] = {0, 0}, secNum[2] = {0, 0}, mapq[2] = {0, 0}, avgQual[2] = {20, 20};
+    unsigned long long tp[2] = {0, 0};
+    uint32_t chr[2] = {0, 0};
+    std::string md[2];
+    for (int k = 0; k < 2; ++k) {
+        if (numOcc[k]) {
+            best[k] = 0; bestScore[k] = occ[k][0].mismatchCount; bestNum[k] = 1;
+            for (uint32_t i = 1; i < numOcc[k]; ++i) {
+                const int mm = occ[k][i].mismatchCount;
+                if (mm < bestScore[k]) { secNum[k] = bestScore[k] == mm + 1 ? bestNum[k] : 0; best[k] = (int)i; bestScore[k] = mm; bestNum[k] = 1; }
+                else if (mm == bestScore[k]) ++bestNum[k];
+                else if (mm == bestScore[k] + 1) ++secNum[k];
+            }
+        }
+        if (best[k] >= 0 && (type != 3 || bestNum[k] == 1)) {
+            const s3_sam_occurrence &b = occ[k][best[k]];
+            chr_and_pos(g, b.ambPosition, &tp[k], &chr[k]);
+            md_string(g, query[k], qual[k], (uint32_t)readlen[k], b.ambPosition, b.strand, b.mismatchCount, 0, md[k], &avgQual[k]);
+            if (type == 4 || type == 3) mapq[k] = 255;
+            else {
+                mapq[k] = s3_mapq_single(b.mismatchCount, cfg->isFastq == 1 ? avgQual[k] : 20, bestNum[k], secNum[k], cfg->maxMAPQ, cfg->minMAPQ, cfg->bwaLikeScore) >> 1;
+                if (mapq[k] < cfg->minMAPQ) mapq[k] = cfg->minMAPQ;
+            }
+        } else best[k] = -1;
+    }
+    std::vector<uint8_t> d;
+    const std::string none;
+    int rc;
+    for (int k = 0; k < 2; ++k) {
+        std::string xa;
+        if (lists) {
+            uint32_t total = 1;
+            char nb[24];
+            for (uint32_t i = 0; i < numOcc[k] && total < peMaxOutputPerRead; ++i) {
+                if ((int)i == best[k]) continue;
+                const int mm = occ[k][i].mismatchCount;
+                if (type == 2 && mm > bestScore[k]) continue;
+                unsigned long long t;
+                uint32_t c;
+                chr_and_pos(g, occ[k][i].ambPosition, &t, &c);
+                xa += g->chrNames[c - 1];
+                xa.push_back(',');
+                xa.push_back(occ[k][i].strand == 2 ? '-' : '+');
+                xa.append(nb, write_num((long long)t, nb));
+                xa.push_back(',');
+                xa.append(nb, write_num(readlen[k], nb));
+                xa += "M,";
+                xa.append(nb, write_num(mm, nb));
+                xa.push_back(';');
+                ++total;
+            }
+        }
+        s3_sam_record &r = out[k];
+        const int m = 1 - k;
+        if (best[k] >= 0) {
+            const s3_sam_occurrence &b = occ[k][best[k]];
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], b.strand, xa, NULL, false, b.mismatchCount, b.mismatchCount, type == 4 ? -1 : bestNum[k],
+                        lists ? secNum[k] : -1, 0, 0, md[k], mapq[k], cfg->readGroup, cfg->isPrintMDNM != 0);
+        } else {
+            // (initializeSAMAlgnmt appends a non-empty XA:Z to an unmapped record too)
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], 1, none, NULL, true, 0, 0, 0, 0, 0, 0, none, 0, cfg->readGroup, false);
+            if (!xa.empty()) { d.clear(); s3_set_error("s3_sam_unpaired_records: internal: XA:Z of an unmapped read"); return S3_EINVAL; }
+        }
+        r.flag = (uint16_t)(1 | (best[k] < 0 ? 4 : 0) | (best[m] < 0 ? 8 : 0) | (k ? 128 : 64) | (best[k] >= 0 && occ[k][best[k]].strand == 2 ? 16 : 0) |
+                            (best[m] >= 0 && occ[m][best[m]].strand == 2 ? 32 : 0));
+        r.tid = chr[k] == 0 ? (chr[m] == 0 ? -1 : (int32_t)chr[m] - 1) : (int32_t)chr[k] - 1;
+        r.pos = tp[k] == 0 ? (tp[m] == 0 ? -1 : (int32_t)(tp[m] - 1)) : (int32_t)(tp[k] - 1);
+        r.mtid = chr[m] == 0 ? (chr[k] == 0 ? -1 : (int32_t)chr[k] - 1) : (int32_t)chr[m] - 1;
+        r.mpos = tp[m] == 0 ? (tp[k] == 0 ? -1 : (int32_t)(tp[k] - 1)) : (int32_t)(tp[m] - 1);
+        if (chr[0] > 0 && chr[0] == chr[1]) r.isize = tp[m] > tp[k] ? (int32_t)(tp[m] + (unsigned)readlen[m] - tp[k]) : -(int32_t)(tp[k] + (unsigned)readlen[k] - tp[m]);
+        else r.isize = 0;
+        if ((rc = finish(r, d))) { s3_sam_record_free(&out[0]); s3_sam_record_free(&out[1]); s3_set_error("s3_sam_unpaired_records: out of host memory"); return rc; }
+    }
+    return S3_OK;
+}

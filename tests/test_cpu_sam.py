@@ -521,3 +521,74 @@ def test_sam_pair_dp_records_match_the_reference_writer():
         demoted += m > 0 and bool((want[0][0][5] | want[1][0][5]) & 4)
         with_xa += b"XAZ" in want[0][1]
     assert none > 100 and demoted > 50 and with_xa > 200
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_sam.so not built")
+def test_sam_unpaired_records_match_the_reference_writer():
+    """s3_sam_unpaired_records against unproperlypairOutputSAMAPI: each read on its own (best occurrence, X0 / X1, XA:Z up to the cap,
+    halved MAPQ), all four report types, one or both reads without an occurrence, mate fields and insert sizes"""
+    ref = C.CDLL(REF)
+    lib = api.load_library()
+    rng = np.random.default_rng(66)
+    n = 200_000
+    G = rng.integers(0, 4, n).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    translate = np.array([0, 1, 0xFFFFFFFF, 70_000, 2, 70_000 - 1, 100_000, 2, 70_000 - 1 - 500, 150_000, 3, 150_000 - 1], np.uint32)
+    chr_end = np.array([69_999, 149_999, 199_999], np.uint32)
+    amb = np.full(4, 3, np.uint32)
+    names = [b"chr1", b"chrTwo", b"3"]
+    segs = (Segment * 4)(*[Segment(int(translate[3 * i]), int(translate[3 * i + 1]), int(translate[3 * i + 2])) for i in range(4)])
+    gen = Genome(helpers.u32p(pac), n, segs, 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, (C.c_char_p * 3)(*names))
+    cnames = (C.c_char_p * 3)(*names)
+    lib.s3_sam_unpaired_records.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    ref.ref_sam_unpaired.restype = C.c_int
+    one_sided = neither = with_xa = 0
+    for trial in range(2000):
+        L = (int(rng.integers(36, 152)), int(rng.integers(36, 152)))
+        cfg = Config(int(rng.integers(1, 5)), int(rng.integers(0, 2)), 1, -2, int(rng.integers(0, 2)), 40, 1, int(rng.integers(0, 2)), 1, 1000, b"grp%d" % trial)
+        cap = int(rng.choice([2, 3, 1000]))
+        occs, q = [], []
+        for k in range(2):
+            m = int(rng.choice([0, 1, 1, 2, 4, 7]))
+            lst = [(int(rng.integers(0, n - L[k])), int(rng.integers(1, 3)), int(rng.integers(0, 4))) for _ in range(m)]
+            occs.append(lst)
+            if lst:
+                r = G[lst[0][0]:lst[0][0] + L[k]].copy()
+                for j in rng.choice(L[k], int(rng.integers(0, 4)), replace=False):
+                    r[j] = (r[j] + 1) & 3
+                q.append(np.ascontiguousarray((3 - r[::-1]) if lst[0][1] == 2 else r).astype(np.uint8))
+            else:
+                q.append(np.ascontiguousarray(rng.integers(0, 4, L[k]).astype(np.uint8)))
+        ql = []
+        for k in range(2):
+            x = np.ascontiguousarray(rng.integers(2, 41, L[k] + 1).astype(np.uint8)); x[-1] = 0
+            ql.append(x)
+        n1, n2 = b"u%d/1" % trial, b"u%d/2" % trial
+        arrs = [(Occurrence * max(len(o), 1))(*[Occurrence(*x) for x in o]) for o in occs]
+        out = (Record * 2)()
+        rc = lib.s3_sam_unpaired_records(C.byref(gen), C.byref(cfg), arrs[0], len(occs[0]), arrs[1], len(occs[1]), cap, q[0].ctypes.data_as(U8P), q[1].ctypes.data_as(U8P),
+                                         ql[0].ctypes.data_as(C.c_char_p), ql[1].ctypes.data_as(C.c_char_p), L[0], L[1], n1, n2, out)
+        assert rc == 0, (trial, occs)
+        got = []
+        for r in out:
+            got.append(((r.tid, r.pos, r.bin, r.qual, r.l_qname, r.flag, r.n_cigar, r.l_qseq, r.mtid, r.mpos, r.isize, r.l_aux), bytes(bytearray(r.data[:r.data_len]))))
+        for k in range(2):
+            lib.s3_sam_record_free(C.byref(out[k]))
+        flats = [np.array([x for o in lst for x in o], np.uint32) if lst else np.zeros(3, np.uint32) for lst in occs]
+        core = np.zeros(24, np.int32)
+        dcap = 8192
+        data = np.zeros(2 * dcap, np.uint8)
+        dlen = np.zeros(2, np.int32)
+        k = ref.ref_sam_unpaired(helpers.u32p(pac), n, helpers.u32p(translate), 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, cnames,
+                                 cfg.alignmentType, cfg.bwaLikeScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup,
+                                 helpers.u32p(flats[0]), len(occs[0]), helpers.u32p(flats[1]), len(occs[1]), cap,
+                                 q[0].ctypes.data_as(U8P), q[1].ctypes.data_as(U8P), ql[0].ctypes.data_as(C.c_char_p), ql[1].ctypes.data_as(C.c_char_p), L[0], L[1], n1, n2,
+                                 core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), dcap, dlen.ctypes.data_as(I32P))
+        assert k == 2
+        want = [(tuple(int(x) for x in core[12 * r:12 * r + 12]), bytes(data[r * dcap:r * dcap + int(dlen[r])])) for r in range(2)]
+        assert got == want, (trial, occs, cfg.alignmentType, got, want)
+        one_sided += bool(occs[0]) != bool(occs[1])
+        neither += not occs[0] and not occs[1]
+        with_xa += b"XAZ" in want[0][1]
+    assert one_sided > 300 and neither > 30 and with_xa > 200

@@ -825,6 +825,16 @@ int s3_sam_unpaired_records(const s3_sam_genome *genome, const s3_sam_config *co
                             const s3_sam_occurrence *occ2, uint32_t numOcc2, uint32_t peMaxOutputPerRead,
                             const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
                             int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2, s3_sam_record out[2]);
+/* unproperlypairDPOutputSAMAPI (BGS-IO.cpp:2932-3447): the same for a pair whose reads went through DP without ending up properly
+ * paired -- per read a list of alignments, each from DP (special CIGAR; handled like s3_sam_single_dp_record's) or from the search
+ * (isFromDP 0: editdist = its mismatches, cigar = "<len>M"; handled like an occurrence): the first alignment with the best score is
+ * reported, X0 = how many share it, X1 = the rest (x1_t1 + x1_t2), MAPQ = s3_mapq_single_dp halved unless BWA-like, at least minMAPQ,
+ * 0 when trimmed; XA:Z with CIGARs and edit distances; the insert size discounts a trailing deletion as convertToCigarStr reports it. */
+typedef struct { uint32_t ambPosition; uint8_t strand, isFromDP, pad[2]; int32_t score, editdist; const char *cigar; } s3_sam_read_alignment;   /* Algnmt, PEAlgnmt.h:468-479 */
+int s3_sam_unpaired_dp_records(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_read_alignment *alignments1, uint32_t num1,
+                               const s3_sam_read_alignment *alignments2, uint32_t num2, int32_t singleDPcutoffThreshold,
+                               const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                               int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2, s3_sam_record out[2]);
 
 #ifdef __cplusplus
 }

@@ -506,3 +506,83 @@ extern "C" int ref_sam_unpaired ( const uint32_t * pac, uint32_t dnaLength, cons
     free ( list[0].occ ); free ( list[1].occ );
     return n;
 }
+
+// unproperlypairDPOutputSAMAPI (BGS-IO.cpp:2932-3447): lists[k][6 * i] = position, strand, score, edit distance, isFromDP, index of the CIGAR in cigars[]
+extern "C" int ref_sam_unpaired_dp ( const uint32_t * pac, uint32_t dnaLength, const uint32_t * translate, uint32_t numSeg, const uint32_t * ambiguityMap,
+                                     const uint32_t * chrEndPos, uint32_t numChr, const char * const * chrNames,
+                                     int alignmentType, int bwaLike, int isFastq, int maxMAPQ, int minMAPQ, int isPrintMDNM, const char * readGroup,
+                                     int dpMatch, int singleDPcutoff,
+                                     const int32_t * list1, uint32_t num1, const int32_t * list2, uint32_t num2, const char * const * cigars,
+                                     const uint8_t * query1, const uint8_t * query2, const char * qual1, const char * qual2, int len1, int len2,
+                                     const char * name1, const char * name2,
+                                     int32_t * core, uint8_t * data, int32_t dataCap, int32_t * dataLen )
+{
+    HSP hsp;
+    memset ( &hsp, 0, sizeof ( hsp ) );
+    hsp.dnaLength = dnaLength;
+    hsp.packedDNA = ( unsigned int * ) pac;
+    hsp.numOfRemovedSegment = numSeg;
+    std::vector<Translate> tr ( numSeg );
+    for ( uint32_t i = 0; i < numSeg; i++ ) { tr[i].startPos = translate[3 * i]; tr[i].chrID = translate[3 * i + 1]; tr[i].correction = translate[3 * i + 2]; }
+    hsp.translate = tr.data ();
+    hsp.ambiguityMap = ( unsigned int * ) ambiguityMap;
+    std::vector<SeqOffset> so ( numChr );
+    for ( uint32_t i = 0; i < numChr; i++ ) { memset ( &so[i], 0, sizeof ( SeqOffset ) ); so[i].endPos = chrEndPos[i]; }
+    hsp.seqOffset = so.data ();
+    hsp.numOfSeq = numChr;
+    HSPAux aux;
+    memset ( &aux, 0, sizeof ( aux ) );
+    aux.isFastq = isFastq; aux.alignmentType = alignmentType; aux.minMAPQ = minMAPQ; aux.maxMAPQ = maxMAPQ; aux.bwaLikeScore = bwaLike;
+    aux.readGroup = ( char * ) readGroup; aux.isPrintMDNM = isPrintMDNM; aux.dpMatchScore = dpMatch; aux.singleDPcutoffThreshold = singleDPcutoff;
+    bwase_initialize ( aux.g_log_n );
+    SRAIndex index;
+    memset ( &index, 0, sizeof ( index ) );
+    index.hsp = &hsp; index.hspaux = &aux;
+    OCC occBuf;
+    memset ( &occBuf, 0, sizeof ( occBuf ) );
+    SAMOccurrenceConstruct ( &occBuf );
+    bam_header_t header;
+    memset ( &header, 0, sizeof ( header ) );
+    header.n_targets = numChr;
+    header.target_name = ( char ** ) chrNames;
+    samfile_t sf;
+    memset ( &sf, 0, sizeof ( sf ) );
+    sf.header = &header;
+    SRASetting setting;
+    memset ( &setting, 0, sizeof ( setting ) );
+    setting.occ = &occBuf; setting.SAMOutFilePtr = &sf;
+    SRAQueryInput in;
+    memset ( &in, 0, sizeof ( in ) );
+    in.AlgnmtIndex = &index; in.QuerySetting = &setting;
+    std::vector<Algnmt> lists[2];
+    const int32_t * src[2] = { list1, list2 };
+    const uint32_t cnt[2] = { num1, num2 };
+    for ( int k = 0; k < 2; k++ )
+    {
+        lists[k].resize ( cnt[k] ? cnt[k] : 1 );
+        memset ( lists[k].data (), 0, lists[k].size () * sizeof ( Algnmt ) );
+        for ( uint32_t i = 0; i < cnt[k]; i++ )
+        {
+            const int32_t * r = src[k] + 6 * i;
+            lists[k][i].algnmt = ( unsigned int ) r[0]; lists[k][i].strand = ( char ) r[1]; lists[k][i].score = r[2]; lists[k][i].editdist = r[3];
+            lists[k][i].isFromDP = r[4]; lists[k][i].cigarString = ( char * ) cigars[r[5]]; lists[k][i].num_sameScore = 1;
+        }
+    }
+    DynamicUint8Array * xaz = DynamicUint8ArrayConstruct ();
+    g_kept.clear ();
+    unproperlypairDPOutputSAMAPI ( &in, lists[0].data (), lists[1].data (), ( int ) num1, ( int ) num2, ( unsigned char * ) query1, ( unsigned char * ) query2,
+                                   ( char * ) qual1, ( char * ) qual2, len1, len2, ( char * ) name1, ( char * ) name2, xaz );
+    int n = ( int ) g_kept.size ();
+    for ( int r = 0; r < n && r < 2; r++ )
+    {
+        const Kept & k = g_kept[r];
+        int32_t * c = core + 12 * r;
+        c[0] = k.core.tid; c[1] = k.core.pos; c[2] = k.core.bin; c[3] = k.core.qual; c[4] = k.core.l_qname; c[5] = k.core.flag; c[6] = k.core.n_cigar;
+        c[7] = k.core.l_qseq; c[8] = k.core.mtid; c[9] = k.core.mpos; c[10] = k.core.isize; c[11] = k.l_aux;
+        dataLen[r] = k.data_len;
+        if ( k.data_len <= dataCap ) { memcpy ( data + ( size_t ) r * dataCap, k.data.data (), k.data_len ); }
+    }
+    DynamicUint8ArrayFree ( xaz );
+    SAMOccurrenceDestruct ( &occBuf );
+    return n;
+}

@@ -1039,3 +1039,141 @@ extern "C" int s3_sam_unpaired_records(const s3_sam_genome *g, const s3_sam_conf
     }
     return S3_OK;
 }
+
+
+// ---- unproperlypairDPOutputSAMAPI (BGS-IO.cpp:2932-3447): a pair without a valid pairing, the reads' alignment lists after DP ------
+namespace {
+// what convertToCigarStr (PE.cpp:421-486) reports as deletedEnd: the pending match count when the special CIGAR ends in a deletion
+int deleted_end(const char *sp)
+{
+    const size_t len = strlen(sp);
+    int cur = 0, curM = 0, out = 0;
+    bool written = false;
+    for (size_t i = 0; i < len; ++i) {
+        const char c = sp[i];
+        if (c >= '0' && c <= '9') { cur = cur * 10 + (c - '0'); continue; }
+        switch (c) {
+        case 'M': case 'm': curM += cur; cur = 0; break;
+        case 'D':
+            if ((!written && curM == 0) || i == len - 1) { if (i == len - 1) out = curM; break; }
+            /* fall through */
+        case 'I': case 'S': written = true; curM = 0; cur = 0; break;
+        default: break;
+        }
+    }
+    return out;
+}
+}  // namespace
+
+extern "C" int s3_sam_unpaired_dp_records(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_read_alignment *algn1, uint32_t num1,
+                                          const s3_sam_read_alignment *algn2, uint32_t num2, int32_t singleDPcutoffThreshold,
+                                          const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
+                                          int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2, s3_sam_record out[2])
+{
+    if (!out) { s3_set_error("s3_sam_unpaired_dp_records: NULL output"); return S3_EINVAL; }
+    memset(out, 0, 2 * sizeof(s3_sam_record));
+    if (!g || !cfg || !query1 || !query2 || !qualities1 || !qualities2 || !queryName1 || !queryName2 || !cfg->readGroup || (num1 && !algn1) || (num2 && !algn2) ||
+        readlen1 <= 0 || readlen2 <= 0) { s3_set_error("s3_sam_unpaired_dp_records: bad argument"); return S3_EINVAL; }
+    if ((num1 || num2) && (!g->packedDNA || !g->segments || !g->ambiguityMap || !g->chrEndPos || !g->chrNames || g->numSegments == 0)) {
+        s3_set_error("s3_sam_unpaired_dp_records: incomplete genome description"); return S3_EINVAL;
+    }
+    const s3_sam_read_alignment *algn[2] = {algn1, algn2};
+    const uint32_t num[2] = {num1, num2};
+    for (int k = 0; k < 2; ++k) for (uint32_t i = 0; i < num[k]; ++i) if (!algn[k][i].cigar) { s3_set_error("s3_sam_unpaired_dp_records: alignment %u of read %d without a CIGAR", i, k + 1); return S3_EINVAL; }
+    const uint8_t *query[2] = {query1, query2};
+    const char *qual[2] = {qualities1, qualities2}, *name[2] = {queryName1, queryName2};
+    const int readlen[2] = {readlen1, readlen2};
+    const int type = cfg->alignmentType;
+    const bool lists = type == 1 || type == 2;
+    int best[2] = {-1, -1}, bestScore[2] = {0, 0}, bestNum[2] = {0, 0}, secNum[2] = {0, 0}, mapq[2] = {0, 0}, deletedEnd[2] = {0, 0};
+    unsigned long long tp[2] = {0, 0};
+    uint32_t chr[2] = {0, 0};
+    DpSide sd[2];
+    std::string newCigar[2];
+    int rc;
+    for (int k = 0; k < 2; ++k) {
+        int x1t1 = 0, x1t2 = 0, secondBestScore = -9999;
+        if (num[k]) {
+            best[k] = 0; bestScore[k] = algn[k][0].score; bestNum[k] = 1;
+            for (uint32_t i = 1; i < num[k]; ++i) {
+                if (algn[k][i].score > bestScore[k]) { best[k] = (int)i; bestScore[k] = algn[k][i].score; bestNum[k] = 1; }
+                else if (algn[k][i].score == bestScore[k]) ++bestNum[k];
+            }
+            const int thres = (int)(0.7 * bestScore[k]);
+            for (uint32_t i = 0; i < num[k]; ++i) {
+                const int sc = algn[k][i].score;
+                if (sc >= bestScore[k]) continue;
+                if (sc > secondBestScore) secondBestScore = sc;
+                if (sc >= thres) ++x1t1; else ++x1t2;
+            }
+        }
+        secNum[k] = (type == 4 || type == 3) ? -1 : x1t1 + x1t2;
+        if (best[k] >= 0 && (type != 3 || bestNum[k] == 1)) {
+            const s3_sam_read_alignment &b = algn[k][best[k]];
+            if (b.isFromDP == 1) {
+                if ((rc = dp_side(g, b.cigar, b.ambPosition, readlen[k], qual[k], &tp[k], &chr[k], sd[k]))) return rc;
+                if (!sd[k].trim) deletedEnd[k] = deleted_end(b.cigar);
+            } else {
+                sd[k].trim = chr_and_pos_checked(g, (uint32_t)readlen[k], b.ambPosition, &tp[k], &chr[k], newCigar[k]);
+                md_string(g, query[k], qual[k], (uint32_t)readlen[k], b.ambPosition, b.strand, b.editdist, sd[k].trim, sd[k].md, &sd[k].avgQual);
+                sd[k].mism = 0;
+                for (char c : sd[k].md) sd[k].mism += c > '9';
+            }
+            if (type == 4 || type == 3) { mapq[k] = 255; if (k == 0 && sd[k].trim) mapq[k] = 0; }        // (only the first read's trimmed record loses the 255)
+            else {
+                mapq[k] = s3_mapq_single_dp(readlen[k] * cfg->dpMatchScore, cfg->isFastq == 1 ? sd[k].avgQual : 20, bestNum[k], x1t1, x1t2, bestScore[k], secondBestScore,
+                                            cfg->maxMAPQ, cfg->minMAPQ, singleDPcutoffThreshold, cfg->bwaLikeScore);
+                if (!cfg->bwaLikeScore) mapq[k] >>= 1;
+                if (mapq[k] < cfg->minMAPQ) mapq[k] = cfg->minMAPQ;
+                if (sd[k].trim) mapq[k] = 0;
+            }
+        } else best[k] = -1;
+    }
+    std::vector<uint8_t> d;
+    const std::string none;
+    for (int k = 0; k < 2; ++k) {
+        std::string xa;
+        if (lists) {
+            char nb[24];
+            for (uint32_t i = 0; i < num[k]; ++i) {
+                if ((int)i == best[k]) continue;
+                if (type == 2 && algn[k][i].score < bestScore[k]) continue;
+                unsigned long long t;
+                uint32_t c;
+                chr_and_pos(g, algn[k][i].ambPosition, &t, &c);
+                xa += g->chrNames[c - 1];
+                xa.push_back(',');
+                xa.push_back(algn[k][i].strand == 2 ? '-' : '+');
+                xa.append(nb, write_num((long long)t, nb));
+                xa.push_back(',');
+                s3_special_to_sam(algn[k][i].cigar, strlen(algn[k][i].cigar), xa);
+                xa.push_back(',');
+                xa.append(nb, write_num(algn[k][i].editdist, nb));
+                xa.push_back(';');
+            }
+        }
+        s3_sam_record &r = out[k];
+        const int m = 1 - k;
+        if (best[k] >= 0) {
+            const s3_sam_read_alignment &b = algn[k][best[k]];
+            const std::string *cig = b.isFromDP ? &sd[k].cigar : (newCigar[k].empty() ? NULL : &newCigar[k]);
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], b.strand, xa, cig, false, sd[k].mism, sd[k].mism + sd[k].gapExt, bestNum[k], secNum[k], sd[k].gapOpen, sd[k].gapExt,
+                        sd[k].md, mapq[k], cfg->readGroup, cfg->isPrintMDNM != 0);
+        } else {
+            record_body(r, d, readlen[k], name[k], query[k], qual[k], 1, none, NULL, true, 0, 0, 0, 0, 0, 0, none, 0, cfg->readGroup, false);
+            if (!xa.empty()) { s3_set_error("s3_sam_unpaired_dp_records: internal: XA:Z of an unmapped read"); return S3_EINVAL; }
+        }
+        r.flag = (uint16_t)(1 | (best[k] < 0 ? 4 : 0) | (best[m] < 0 ? 8 : 0) | (k ? 128 : 64) | (best[k] >= 0 && algn[k][best[k]].strand == 2 ? 16 : 0) |
+                            (best[m] >= 0 && algn[m][best[m]].strand == 2 ? 32 : 0));
+        r.tid = chr[k] == 0 ? (chr[m] == 0 ? -1 : (int32_t)chr[m] - 1) : (int32_t)chr[k] - 1;
+        r.pos = tp[k] == 0 ? (tp[m] == 0 ? -1 : (int32_t)(tp[m] - 1)) : (int32_t)(tp[k] - 1);
+        r.mtid = chr[m] == 0 ? (chr[k] == 0 ? -1 : (int32_t)chr[k] - 1) : (int32_t)chr[m] - 1;
+        r.mpos = tp[m] == 0 ? (tp[k] == 0 ? -1 : (int32_t)(tp[k] - 1)) : (int32_t)(tp[m] - 1);
+        if (chr[0] > 0 && chr[0] == chr[1])
+            r.isize = tp[m] > tp[k] ? (int32_t)(tp[m] - (unsigned long long)deletedEnd[m] + (unsigned long long)readlen[m] - tp[k])
+                                    : -(int32_t)(tp[k] - (unsigned long long)deletedEnd[k] + (unsigned long long)readlen[k] - tp[m]);
+        else r.isize = 0;
+        if ((rc = finish(r, d))) { s3_sam_record_free(&out[0]); s3_sam_record_free(&out[1]); s3_set_error("s3_sam_unpaired_dp_records: out of host memory"); return rc; }
+    }
+    return S3_OK;
+}

@@ -592,3 +592,112 @@ def test_sam_unpaired_records_match_the_reference_writer():
         neither += not occs[0] and not occs[1]
         with_xa += b"XAZ" in want[0][1]
     assert one_sided > 300 and neither > 30 and with_xa > 200
+
+
+class ReadAlignment(C.Structure):
+    _fields_ = [("ambPosition", C.c_uint32), ("strand", C.c_uint8), ("isFromDP", C.c_uint8), ("pad", C.c_uint8 * 2), ("score", C.c_int32), ("editdist", C.c_int32),
+                ("cigar", C.c_char_p)]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_sam.so not built")
+def test_sam_unpaired_dp_records_match_the_reference_writer():
+    """s3_sam_unpaired_dp_records against unproperlypairDPOutputSAMAPI: lists that mix DP alignments and search hits, best score / X0 / X1,
+    halved MAPQ (not when BWA-like), trims on either kind, the trailing-deletion term of the insert size, all report types, empty lists"""
+    ref = C.CDLL(REF)
+    lib = api.load_library()
+    rng = np.random.default_rng(77)
+    n = 200_000
+    G = rng.integers(0, 4, n).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    translate = np.array([0, 1, 0xFFFFFFFF, 70_000, 2, 70_000 - 1, 100_000, 2, 70_000 - 1 - 500, 150_000, 3, 150_000 - 1], np.uint32)
+    chr_end = np.array([69_999, 149_999, 199_999], np.uint32)
+    amb = np.full(4, 3, np.uint32)
+    names = [b"chr1", b"chrTwo", b"3"]
+    segs = (Segment * 4)(*[Segment(int(translate[3 * i]), int(translate[3 * i + 1]), int(translate[3 * i + 2])) for i in range(4)])
+    gen = Genome(helpers.u32p(pac), n, segs, 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, (C.c_char_p * 3)(*names))
+    cnames = (C.c_char_p * 3)(*names)
+    edges = [70_000, 100_000, 150_000]
+    lib.s3_sam_unpaired_dp_records.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    ref.ref_sam_unpaired_dp.restype = C.c_int
+    one_sided = with_xa = trailing = 0
+    for trial in range(2000):
+        L = (int(rng.integers(50, 152)), int(rng.integers(50, 152)))
+        cfg = Config(int(rng.integers(1, 5)), int(rng.integers(0, 2)), 1, -2, int(rng.integers(0, 2)), 40, 1, int(rng.integers(0, 2)), 1, 1000, b"grp%d" % trial)
+        cutoff = int(0.3 * min(L))
+        lists, q = [], []
+        near = int(rng.integers(1000, n - 3000))
+        for k in range(2):
+            m = int(rng.choice([0, 1, 1, 2, 4, 6]))
+            lst = []
+            for _ in range(m):
+                r = rng.random()
+                if r < 0.3:
+                    p = max(0, int(rng.choice(edges)) - int(rng.integers(1, L[k] + 4)))
+                elif r < 0.6:
+                    p = min(max(near + int(rng.integers(-300, 300)), 0), n - 2 * L[k] - 8)      # on one chromosome with the mate: insert sizes
+                else:
+                    p = int(rng.integers(0, n - 2 * L[k] - 8))
+                from_dp = int(rng.integers(0, 2))
+                if from_dp:
+                    cg = random_special_cigar(rng, L[k])
+                    if rng.random() < 0.15 and not cg.endswith("D"):
+                        cg += "%dD" % int(rng.integers(1, 4))
+                    lst.append((p, int(rng.integers(1, 3)), int(rng.integers(cutoff, L[k] + 1)), int(rng.integers(0, 9)), 1, cg.encode()))
+                else:
+                    mm = int(rng.integers(0, 4))
+                    lst.append((p, int(rng.integers(1, 3)), L[k] - 3 * mm, mm, 0, b"%dM" % L[k]))
+            if m > 1 and rng.random() < 0.3:
+                lst[1] = lst[1][:2] + (lst[0][2],) + lst[1][3:]                      # a tie in score
+            lists.append(lst)
+            if lst and lst[0][4] == 0 and lst[0][0] + L[k] <= n:
+                r = G[lst[0][0]:lst[0][0] + L[k]].copy()
+                for j in rng.choice(L[k], int(rng.integers(0, 4)), replace=False):
+                    r[j] = (r[j] + 1) & 3
+                q.append(np.ascontiguousarray((3 - r[::-1]) if lst[0][1] == 2 else r).astype(np.uint8))
+            else:
+                q.append(np.ascontiguousarray(rng.integers(0, 4, L[k]).astype(np.uint8)))
+        ql = []
+        for k in range(2):
+            x = np.ascontiguousarray(rng.integers(2, 41, L[k] + 1).astype(np.uint8)); x[-1] = 0
+            ql.append(x)
+        n1, n2 = b"ud%d/1" % trial, b"ud%d/2" % trial
+        arrs = []
+        for lst in lists:
+            a = (ReadAlignment * max(len(lst), 1))()
+            for i, x in enumerate(lst):
+                a[i].ambPosition, a[i].strand, a[i].score, a[i].editdist, a[i].isFromDP, a[i].cigar = x
+            arrs.append(a)
+        out = (Record * 2)()
+        rc = lib.s3_sam_unpaired_dp_records(C.byref(gen), C.byref(cfg), arrs[0], len(lists[0]), arrs[1], len(lists[1]), cutoff, q[0].ctypes.data_as(U8P), q[1].ctypes.data_as(U8P),
+                                            ql[0].ctypes.data_as(C.c_char_p), ql[1].ctypes.data_as(C.c_char_p), L[0], L[1], n1, n2, out)
+        assert rc == 0, (trial, lists)
+        got = []
+        for r in out:
+            got.append(((r.tid, r.pos, r.bin, r.qual, r.l_qname, r.flag, r.n_cigar, r.l_qseq, r.mtid, r.mpos, r.isize, r.l_aux), bytes(bytearray(r.data[:r.data_len]))))
+        for k in range(2):
+            lib.s3_sam_record_free(C.byref(out[k]))
+        cigs, flats = [], []
+        for lst in lists:
+            f = []
+            for x in lst:
+                f += [x[0], x[1], x[2], x[3], x[4], len(cigs)]
+                cigs.append(x[5])
+            flats.append(np.array(f if f else [0] * 6, np.int64).astype(np.int32))
+        cig = (C.c_char_p * max(len(cigs), 1))(*(cigs or [b""]))
+        core = np.zeros(24, np.int32)
+        dcap = 8192
+        data = np.zeros(2 * dcap, np.uint8)
+        dlen = np.zeros(2, np.int32)
+        k = ref.ref_sam_unpaired_dp(helpers.u32p(pac), n, helpers.u32p(translate), 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, cnames,
+                                    cfg.alignmentType, cfg.bwaLikeScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup, cfg.dpMatchScore, cutoff,
+                                    flats[0].ctypes.data_as(I32P), len(lists[0]), flats[1].ctypes.data_as(I32P), len(lists[1]), cig,
+                                    q[0].ctypes.data_as(U8P), q[1].ctypes.data_as(U8P), ql[0].ctypes.data_as(C.c_char_p), ql[1].ctypes.data_as(C.c_char_p), L[0], L[1], n1, n2,
+                                    core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), dcap, dlen.ctypes.data_as(I32P))
+        assert k == 2
+        want = [(tuple(int(x) for x in core[12 * r:12 * r + 12]), bytes(data[r * dcap:r * dcap + int(dlen[r])])) for r in range(2)]
+        assert got == want, (trial, lists, cfg.alignmentType, cfg.bwaLikeScore, got, want)
+        one_sided += bool(lists[0]) != bool(lists[1])
+        with_xa += b"XAZ" in want[0][1]
+        trailing += want[0][0][10] != 0 and any(x[5].endswith(b"D") for lst in lists for x in lst)
+    assert one_sided > 300 and with_xa > 200 and trailing > 20

@@ -835,6 +835,11 @@ int s3_sam_unpaired_dp_records(const s3_sam_genome *genome, const s3_sam_config 
                                const s3_sam_read_alignment *alignments2, uint32_t num2, int32_t singleDPcutoffThreshold,
                                const uint8_t *query1, const uint8_t *query2, const char *qualities1, const char *qualities2,
                                int32_t readlen1, int32_t readlen2, const char *queryName1, const char *queryName2, s3_sam_record out[2]);
+/* SingleAnsOutputSAMAPI (BGS-IO.cpp:5774-5827): a single read reported with ONE alignment (the unique-best / random-best report types):
+ * MD, XM / NM = its mismatches, X0 = bestHitNum (< 0: no X0 tag), no X1, MAPQ = s3_mapq_unique (255 when bestHitNum <= 0), no trimming.
+ * (noAnsOutputSAMAPI, :5829-5855, the read without any alignment, is s3_sam_single_record with numOcc 0.) */
+int s3_sam_single_answer_record(const s3_sam_genome *genome, const s3_sam_config *config, uint32_t ambPosition, int32_t strand, int32_t numMismatch, int32_t bestHitNum,
+                                const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName, s3_sam_record *out);
 
 #ifdef __cplusplus
 }

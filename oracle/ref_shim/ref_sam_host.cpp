@@ -586,3 +586,67 @@ extern "C" int ref_sam_unpaired_dp ( const uint32_t * pac, uint32_t dnaLength, c
     SAMOccurrenceDestruct ( &occBuf );
     return n;
 }
+
+// SingleAnsOutputSAMAPI (BGS-IO.cpp:5774-5827) and, with ambPosition 0xFFFFFFFF, noAnsOutputSAMAPI (:5829-5855)
+extern "C" int ref_sam_single_answer ( const uint32_t * pac, uint32_t dnaLength, const uint32_t * translate, uint32_t numSeg, const uint32_t * ambiguityMap,
+                                       const uint32_t * chrEndPos, uint32_t numChr, const char * const * chrNames,
+                                       int isFastq, int maxMAPQ, int minMAPQ, int isPrintMDNM, const char * readGroup,
+                                       uint32_t ambPosition, int strand, int numMismatch, int bestHitNum,
+                                       const uint8_t * query, const char * qual, int len, const char * name,
+                                       int32_t * core, uint8_t * data, int32_t dataCap, int32_t * dataLen )
+{
+    HSP hsp;
+    memset ( &hsp, 0, sizeof ( hsp ) );
+    hsp.dnaLength = dnaLength;
+    hsp.packedDNA = ( unsigned int * ) pac;
+    hsp.numOfRemovedSegment = numSeg;
+    std::vector<Translate> tr ( numSeg );
+    for ( uint32_t i = 0; i < numSeg; i++ ) { tr[i].startPos = translate[3 * i]; tr[i].chrID = translate[3 * i + 1]; tr[i].correction = translate[3 * i + 2]; }
+    hsp.translate = tr.data ();
+    hsp.ambiguityMap = ( unsigned int * ) ambiguityMap;
+    std::vector<SeqOffset> so ( numChr );
+    for ( uint32_t i = 0; i < numChr; i++ ) { memset ( &so[i], 0, sizeof ( SeqOffset ) ); so[i].endPos = chrEndPos[i]; }
+    hsp.seqOffset = so.data ();
+    hsp.numOfSeq = numChr;
+    HSPAux aux;
+    memset ( &aux, 0, sizeof ( aux ) );
+    aux.isFastq = isFastq; aux.minMAPQ = minMAPQ; aux.maxMAPQ = maxMAPQ; aux.readGroup = ( char * ) readGroup; aux.isPrintMDNM = isPrintMDNM;
+    bwase_initialize ( aux.g_log_n );
+    SRAIndex index;
+    memset ( &index, 0, sizeof ( index ) );
+    index.hsp = &hsp; index.hspaux = &aux;
+    OCC occBuf;
+    memset ( &occBuf, 0, sizeof ( occBuf ) );
+    SAMOccurrenceConstruct ( &occBuf );
+    bam_header_t header;
+    memset ( &header, 0, sizeof ( header ) );
+    header.n_targets = numChr;
+    header.target_name = ( char ** ) chrNames;
+    samfile_t sf;
+    memset ( &sf, 0, sizeof ( sf ) );
+    sf.header = &header;
+    SRASetting setting;
+    memset ( &setting, 0, sizeof ( setting ) );
+    setting.occ = &occBuf; setting.SAMOutFilePtr = &sf;
+    SRAQueryInfo info;
+    memset ( &info, 0, sizeof ( info ) );
+    info.ReadCode = ( unsigned char * ) query; info.ReportingReadCode = ( unsigned char * ) query; info.ReadQuality = ( char * ) qual;
+    info.ReadLength = len; info.ReadName = ( char * ) name; info.ReadStrand = QUERY_POS_STRAND;
+    SRAQueryInput in;
+    memset ( &in, 0, sizeof ( in ) );
+    in.AlgnmtIndex = &index; in.QuerySetting = &setting; in.QueryInfo = &info;
+    g_kept.clear ();
+    if ( ambPosition == 0xFFFFFFFFu ) { noAnsOutputSAMAPI ( &in ); }
+    else { SingleAnsOutputSAMAPI ( &in, ( char ) strand, ambPosition, numMismatch, bestHitNum ); }
+    int n = ( int ) g_kept.size ();
+    if ( n >= 1 )
+    {
+        const Kept & k = g_kept[0];
+        core[0] = k.core.tid; core[1] = k.core.pos; core[2] = k.core.bin; core[3] = k.core.qual; core[4] = k.core.l_qname; core[5] = k.core.flag; core[6] = k.core.n_cigar;
+        core[7] = k.core.l_qseq; core[8] = k.core.mtid; core[9] = k.core.mpos; core[10] = k.core.isize; core[11] = k.l_aux;
+        dataLen[0] = k.data_len;
+        if ( k.data_len <= dataCap ) { memcpy ( data, k.data.data (), k.data_len ); }
+    }
+    SAMOccurrenceDestruct ( &occBuf );
+    return n;
+}

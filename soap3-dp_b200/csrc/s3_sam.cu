@@ -1177,3 +1177,31 @@ extern "C" int s3_sam_unpaired_dp_records(const s3_sam_genome *g, const s3_sam_c
     }
     return S3_OK;
 }
+
+
+// ---- SingleAnsOutputSAMAPI (BGS-IO.cpp:5774-5827): the record of a single read reported with one alignment (unique / random best) ----
+extern "C" int s3_sam_single_answer_record(const s3_sam_genome *g, const s3_sam_config *cfg, uint32_t ambPosition, int32_t strand, int32_t numMismatch, int32_t bestHitNum,
+                                           const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName, s3_sam_record *out)
+{
+    if (!out) { s3_set_error("s3_sam_single_answer_record: NULL output"); return S3_EINVAL; }
+    memset(out, 0, sizeof *out);
+    if (!g || !cfg || !query || !qualities || !queryName || !cfg->readGroup || readlen <= 0 || !g->packedDNA || !g->segments || !g->ambiguityMap || g->numSegments == 0) {
+        s3_set_error("s3_sam_single_answer_record: bad argument"); return S3_EINVAL;
+    }
+    unsigned long long tp;
+    uint32_t chr;
+    chr_and_pos(g, ambPosition, &tp, &chr);
+    std::string md;
+    int avgQual = 20;
+    md_string(g, query, qualities, (uint32_t)readlen, ambPosition, strand, numMismatch, 0, md, &avgQual);
+    const int mapq = bestHitNum > 0 ? s3_mapq_unique(bestHitNum, numMismatch, cfg->isFastq == 1 ? avgQual : 20, cfg->maxMAPQ, cfg->minMAPQ) : 255;
+    std::vector<uint8_t> d;
+    const std::string none;
+    record_body(*out, d, readlen, queryName, query, qualities, strand, none, NULL, false, numMismatch, numMismatch, bestHitNum, -1, 0, 0, md, mapq, cfg->readGroup, cfg->isPrintMDNM != 0);
+    out->flag = (uint16_t)(strand == 2 ? 16 : 0);
+    out->tid = (int32_t)chr - 1; out->pos = (int32_t)(tp - 1);
+    out->mtid = -1; out->mpos = -1; out->isize = 0;
+    const int rc = finish(*out, d);
+    if (rc) s3_set_error("s3_sam_single_answer_record: out of host memory");
+    return rc;
+}

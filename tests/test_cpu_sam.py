@@ -701,3 +701,55 @@ def test_sam_unpaired_dp_records_match_the_reference_writer():
         with_xa += b"XAZ" in want[0][1]
         trailing += want[0][0][10] != 0 and any(x[5].endswith(b"D") for lst in lists for x in lst)
     assert one_sided > 300 and with_xa > 200 and trailing > 20
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_sam.so not built")
+def test_sam_single_answer_and_no_answer_records_match_the_reference_writer():
+    """s3_sam_single_answer_record against SingleAnsOutputSAMAPI, and s3_sam_single_record with no occurrence against noAnsOutputSAMAPI"""
+    ref = C.CDLL(REF)
+    lib = api.load_library()
+    rng = np.random.default_rng(88)
+    n = 200_000
+    G = rng.integers(0, 4, n).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    translate = np.array([0, 1, 0xFFFFFFFF, 70_000, 2, 70_000 - 1, 100_000, 2, 70_000 - 1 - 500, 150_000, 3, 150_000 - 1], np.uint32)
+    chr_end = np.array([69_999, 149_999, 199_999], np.uint32)
+    amb = np.full(4, 3, np.uint32)
+    names = [b"chr1", b"chrTwo", b"3"]
+    segs = (Segment * 4)(*[Segment(int(translate[3 * i]), int(translate[3 * i + 1]), int(translate[3 * i + 2])) for i in range(4)])
+    gen = Genome(helpers.u32p(pac), n, segs, 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, (C.c_char_p * 3)(*names))
+    cnames = (C.c_char_p * 3)(*names)
+    lib.s3_sam_single_answer_record.restype = C.c_int
+    lib.s3_sam_single_record.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    ref.ref_sam_single_answer.restype = C.c_int
+    for trial in range(600):
+        L = int(rng.integers(36, 152))
+        cfg = Config(int(rng.integers(3, 5)), 0, 1, -2, int(rng.integers(0, 2)), 40, 1, int(rng.integers(0, 2)), 1, 1000, b"rg%d" % trial)
+        none = trial % 6 == 0
+        p, strand, hits = int(rng.integers(0, n - L)), int(rng.integers(1, 3)), int(rng.integers(-1, 4))
+        r = G[p:p + L].copy()
+        sub = rng.choice(L, int(rng.integers(0, 4)), replace=False)
+        for j in sub:
+            r[j] = (r[j] + 1) & 3
+        q = np.ascontiguousarray((3 - r[::-1]) if strand == 2 else r).astype(np.uint8)
+        ql = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql[-1] = 0
+        name = b"one%d" % trial
+        out = Record()
+        if none:
+            rc = lib.s3_sam_single_record(C.byref(gen), C.byref(cfg), (Occurrence * 1)(), 0, q.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name, C.byref(out))
+        else:
+            rc = lib.s3_sam_single_answer_record(C.byref(gen), C.byref(cfg), p, strand, len(sub), hits, q.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name, C.byref(out))
+        assert rc == 0
+        got = ((out.tid, out.pos, out.bin, out.qual, out.l_qname, out.flag, out.n_cigar, out.l_qseq, out.mtid, out.mpos, out.isize, out.l_aux),
+               bytes(bytearray(out.data[:out.data_len])))
+        lib.s3_sam_record_free(C.byref(out))
+        core = np.zeros(12, np.int32)
+        data = np.zeros(8192, np.uint8)
+        dlen = np.zeros(1, np.int32)
+        k = ref.ref_sam_single_answer(helpers.u32p(pac), n, helpers.u32p(translate), 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, cnames,
+                                      cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup, 0xFFFFFFFF if none else p, strand, len(sub), hits,
+                                      q.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name, core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P))
+        assert k == 1
+        want = (tuple(int(x) for x in core), bytes(data[:int(dlen[0])]))
+        assert got == want, (trial, none, p, strand, hits, got, want)

@@ -375,6 +375,12 @@ int s3_dp_decode(const uint8_t *pattern, uint32_t patternLength, const int32_t *
                  uint64_t *cigarOffsets, char **cigars, uint64_t *samOffsets, char **samCigars,
                  int32_t *editdist, int32_t *refSpanDelta, uint32_t *opCounts);
 
+/* The same for ONE alignment that is already held as (op, count) runs -- what s3_pe_align, s3_single_dp_align and s3_deep_dp_align /
+ * s3_pe_deep_dp return (length << 8 | op, read order): the special CIGAR string (NUL-terminated, cigarCapacity bytes of room), the
+ * edit distance and the insert-size term D - I - S, i.e. what the SAM writers below take for a DP alignment. */
+int s3_runs_decode(const uint32_t *runs, uint32_t numRuns, uint32_t readLength, int32_t score, s3_dp_scores scores4, char *cigar, uint32_t cigarCapacity,
+                   uint32_t *cigarLength, int32_t *editdist, int32_t *refSpanDelta);
+
 /* MD:Z and the NM pieces of decoded alignments.  Replaces getMisInfoForDP (PE.cpp:499-666, trim 0)
  * for a batch: from the special CIGARs of s3_dp_decode (cigars / cigarOffsets), the alignments'
  * text positions (windowStart + hitLoc) and the packed text (hsp->packedDNA: 16 bases per word,

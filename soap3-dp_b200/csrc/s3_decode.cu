@@ -104,6 +104,37 @@ struct Chunk {
 
 }  // namespace
 
+// The (op, count) runs the chains and the seeded stages return for an alignment (length << 8 | op, read order: what CigarStringEncoder
+// holds) -> what the SAM writers take: the special CIGAR string, the edit distance and the insert-size term of the result loops
+// (DV-DPfunctions.cu:1699-1733,2359-2400,3765-3795), computed as s3_dp_decode computes them from the pattern bytes.
+extern "C" int s3_runs_decode(const uint32_t *runs, uint32_t numRuns, uint32_t readLength, int32_t score, s3_dp_scores sc, char *cigar, uint32_t cigarCapacity,
+                              uint32_t *cigarLength, int32_t *editdist, int32_t *refSpanDelta)
+{
+    if ((numRuns && !runs) || !cigar || cigarCapacity == 0) { s3_set_error("s3_runs_decode: NULL argument"); return S3_EINVAL; }
+    if (sc.matchScore == sc.mismatchScore) { s3_set_error("s3_runs_decode: match and mismatch scores are equal"); return S3_EINVAL; }
+    std::string out;
+    uint32_t ops[5] = {0, 0, 0, 0, 0};
+    int32_t gapPenalty = 0;
+    for (uint32_t i = 0; i < numRuns; ++i) {
+        const int32_t cnt = (int32_t)(runs[i] >> 8);
+        const uint8_t type = (uint8_t)(runs[i] & 0xFFu);
+        const int slot = op_slot(type);
+        if (cnt <= 0 || slot < 0) { s3_set_error("s3_runs_decode: run %u is not one of M m I D S with a positive length", i); return S3_EINVAL; }
+        put_num(out, cnt);
+        out.push_back((char)type);
+        ops[slot] += (uint32_t)cnt;
+        if (type == 'I' || type == 'D') gapPenalty += sc.gapOpenScore + (cnt - 1) * sc.gapExtendScore;
+    }
+    if (out.size() + 1 > cigarCapacity) { s3_set_error("s3_runs_decode: the CIGAR needs %zu bytes", out.size() + 1); return S3_EINVAL; }
+    memcpy(cigar, out.c_str(), out.size() + 1);
+    if (cigarLength) *cigarLength = (uint32_t)out.size();
+    const int32_t L = (int32_t)readLength - (int32_t)ops[2] - (int32_t)ops[4];
+    const int32_t mism = (L * sc.matchScore + gapPenalty - score) / (sc.matchScore - sc.mismatchScore);
+    if (editdist) *editdist = (int32_t)ops[2] + (int32_t)ops[3] + mism;
+    if (refSpanDelta) *refSpanDelta = (int32_t)ops[3] - (int32_t)ops[2] - (int32_t)ops[4];
+    return S3_OK;
+}
+
 // convertToCigarStr for the SAM writers of s3_sam.cu
 void s3_special_to_sam(const char *sp, size_t len, std::string &out) { special_to_sam(sp, len, out); }
 

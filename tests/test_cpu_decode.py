@@ -245,3 +245,32 @@ def test_md_thread_count_does_not_change_the_result(monkeypatch):
     monkeypatch.setenv("S3_DECODE_THREADS", "3")
     with pytest.raises(api.S3Error, match="runs past the text"):
         api.md_strings(packed, len(text), cig + ["5M3m"], pos + [len(text) - 6])
+
+
+def test_runs_decode_equals_the_pattern_decoder():
+    """s3_runs_decode (an alignment held as (op, count) runs, as the chains and the seeded stages return it) == s3_dp_decode on the
+    pattern bytes of the same alignment: special CIGAR, edit distance, insert-size term"""
+    import ctypes as C
+    import re
+    lib = api.load_library()
+    lib.s3_runs_decode.restype = C.c_int
+    done = 0
+    for mode in ("single", "rescue"):
+        for scores4 in SCORES[:2]:
+            b, sc, hit, cnt, pat = dp_oracle_batch(mode, 100, scores4)
+            want = product_decode(pat, b.pat_len, sc, b.read_len, b.cutoff, scores4)
+            for t, (cig, sam, ed, span, ops) in enumerate(want):
+                if not cig:
+                    continue
+                cig_s = cig.decode() if isinstance(cig, bytes) else cig
+                runs = np.array([(int(k) << 8) | ord(op) for k, op in re.findall(r"(\d+)([MmIDS])", cig_s)], np.uint32)
+                buf = C.create_string_buffer(1024)
+                n, e, s = C.c_uint32(), C.c_int32(), C.c_int32()
+                rc = lib.s3_runs_decode(runs.ctypes.data_as(C.POINTER(C.c_uint32)), len(runs), int(b.read_len[t]), int(sc[t]), api.DPScores(*scores4), buf, 1024,
+                                        C.byref(n), C.byref(e), C.byref(s))
+                assert rc == 0
+                assert (buf.value.decode(), n.value, e.value, s.value) == (cig_s, len(cig_s), ed, span), (t, cig_s)
+                done += 1
+    assert done > 800
+    bad = np.array([(5 << 8) | ord("X")], np.uint32)
+    assert lib.s3_runs_decode(bad.ctypes.data_as(C.POINTER(C.c_uint32)), 1, 5, 5, api.DPScores(1, -2, -3, -1), C.create_string_buffer(16), 16, None, None, None) != 0

@@ -1,0 +1,278 @@
+"""End to end: reads -> the CUDA path (chain / seeded stage through the C ABI) -> s3_runs_decode -> the SAM record entries, against
+reads -> the composition of the oracles -> the reference's own SAM writers (oracle/_ref/libref_sam.so).  Every piece has its own
+parity test; this one checks that what the device entries return is what the record writers need -- bam1_t records equal byte for byte."""
+import ctypes as C
+import os
+import re
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+import helpers
+from helpers import HostIndex, ROOT, fmindex, formats
+from soap3dp_b200 import api, synth
+
+sys.path.insert(0, os.path.join(ROOT, "oracle"))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import seeding_oracle  # noqa: E402
+from test_cpu_sam import (Config, DeepAlignment, DpAlignment, Genome, I32P, Occurrence, Record, REF, Segment, U8P)  # noqa: E402
+from test_stages_gpu import OracleEnv, PAR, mutate  # noqa: E402
+
+pytestmark = [pytest.mark.gpu, pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_sam.so not built")]
+SCORES = (1, -2, -3, -1)
+
+
+@pytest.fixture(scope="module")
+def env():
+    G = synth.random_genome(400_000, seed=29)
+    idx = fmindex.build_index(G, keep_sa=True)
+    gi = api.GPUINDEXUpload(idx, device=0, with_text=True, with_sa=True)
+    yield G, idx, HostIndex(idx), gi
+    api.GPUINDEXFree(gi)
+
+
+class OneChromosome:
+    """the genome description of the SAM entries for a text that is one chromosome (hsp->translate, ambiguityMap, seqOffset)"""
+
+    def __init__(self, G):
+        g = G.cpu().numpy().astype(np.uint8)
+        self.n = len(g)
+        self.pac = helpers.pack_text(g)
+        self.translate = np.array([0, 1, 0xFFFFFFFF], np.uint32)            # position p -> 1-based p + 1 on chromosome 1
+        self.chr_end = np.array([self.n - 1], np.uint32)
+        self.amb = np.zeros((self.n >> 18) + 2, np.uint32)
+        self.names = [b"chrSynth"]
+        self.segs = (Segment * 1)(Segment(0, 1, 0xFFFFFFFF))
+        self.cnames = (C.c_char_p * 1)(*self.names)
+        self.gen = Genome(helpers.u32p(self.pac), self.n, self.segs, 1, helpers.u32p(self.amb), helpers.u32p(self.chr_end), 1, self.cnames)
+
+    def ref_args(self):
+        return (helpers.u32p(self.pac), self.n, helpers.u32p(self.translate), 1, helpers.u32p(self.amb), helpers.u32p(self.chr_end), 1, self.cnames)
+
+
+def record_tuple(r):
+    return ((r.tid, r.pos, r.bin, r.qual, r.l_qname, r.flag, r.n_cigar, r.l_qseq, r.mtid, r.mpos, r.isize, r.l_aux), bytes(bytearray(r.data[:r.data_len])))
+
+
+def runs_decode(lib, runs, read_length, score):
+    buf = C.create_string_buffer(2048)
+    e, s = C.c_int32(), C.c_int32()
+    assert lib.s3_runs_decode(np.ascontiguousarray(runs, np.uint32).ctypes.data_as(C.POINTER(C.c_uint32)), len(runs), read_length, score, api.DPScores(*SCORES), buf, 2048,
+                              None, C.byref(e), C.byref(s)) == 0
+    return buf.value, e.value, s.value
+
+
+def oracle_edit(cigar, read_length, score):
+    """edit distance and D - I - S of the reference's result loops (DV-DPfunctions.cu:3788-3794), from the oracle's special CIGAR"""
+    ops = {k: 0 for k in "MmIDS"}
+    gap = 0
+    for k, op in re.findall(r"(\d+)([MmIDS])", cigar):
+        ops[op] += int(k)
+        if op in "ID":
+            gap += SCORES[2] + (int(k) - 1) * SCORES[3]
+    L = read_length - ops["I"] - ops["S"]
+    mism = int((L * SCORES[0] + gap - score) / (SCORES[0] - SCORES[1]))
+    return ops["I"] + ops["D"] + mism, ops["D"] - ops["I"] - ops["S"]
+
+
+def test_single_end_reads_to_sam_records(env):
+    """s3_se_align -> s3_sam_single_record == the oracle chain's occurrences -> OCCOutputSAMAPI"""
+    G, idx, hi, gi = env
+    ref, lib = C.CDLL(REF), api.load_library()
+    ref.ref_sam_single.restype = C.c_int
+    lib.s3_sam_single_record.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    one = OneChromosome(G)
+    n, L, k = 1500, 100, 2
+    rs = synth.simulate_single_end(G, n, L, seed=41, sub_rate=0.015)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    wpq = formats.word_per_query(L)
+    reads = rs.reads.numpy().astype(np.uint8)
+    q = formats.pack_queries(reads, lens[:n], wpq)
+    al = api.SingleAligner(gi, n, num_mismatch=k)
+    got = al.align(q, lens, n, wpq)
+    al.free()
+    # the oracle chain: the search oracle's slots -> collect_all_answers -> transferAllSAToOcc (oracle/pe_chain_oracle.py)
+    import pe_chain_oracle
+    olib = helpers.load_oracle()
+    allowed = formats.SA_RANGES_ROUND1[k]
+    wpa = 2 * allowed
+    bad = np.zeros(formats.ceil32(n), np.uint8)
+    views = []
+    for case in range(formats.NUM_CASES[k]):
+        a_ = np.zeros(formats.ceil32(n) * wpa, np.uint32)
+        helpers.oracle_launch(olib, hi, case, q, lens, n, wpq, a_, bad, 0, k, allowed, wpa)
+        views.append(formats.answers_view(a_, n, wpa))
+    sa = idx.fwd.sa.cpu().numpy()
+    want_occ = [[(int(sa[i]), st, mm) for l, rr, st, mm in ranges for i in range(l, rr + 1)] for ranges, tot, more in pe_chain_oracle.collect(views, allowed, hi.n, 1000)]
+    cfg = Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgE2E")
+    rng = np.random.default_rng(5)
+    mapped = 0
+    for r in range(n):
+        a, b = int(got["occ_offsets"][r]), int(got["occ_offsets"][r + 1])
+        occ = [(int(got["positions"][i]), int(got["occ_flags"][i][0]), int(got["occ_flags"][i][1])) for i in range(a, b)]
+        theirs = want_occ[r]
+        ql = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql[-1] = 0
+        name = b"se%d" % r
+        qr = np.ascontiguousarray(reads[r])
+        arr = (Occurrence * max(len(occ), 1))(*[Occurrence(*o) for o in occ])
+        out = Record()
+        assert lib.s3_sam_single_record(C.byref(one.gen), C.byref(cfg), arr, len(occ), qr.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name, C.byref(out)) == 0
+        mine = record_tuple(out)
+        lib.s3_sam_record_free(C.byref(out))
+        flat = np.array([x for o in theirs for x in o], np.uint32) if theirs else np.zeros(3, np.uint32)
+        core, data, dlen = np.zeros(12, np.int32), np.zeros(8192, np.uint8), np.zeros(1, np.int32)
+        assert ref.ref_sam_single(*one.ref_args(), cfg.alignmentType, cfg.bwaLikeScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup,
+                                  helpers.u32p(flat), len(theirs), qr.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name,
+                                  core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P)) == 1
+        assert mine == (tuple(int(x) for x in core), bytes(data[:int(dlen[0])])), r
+        mapped += bool(occ)
+    assert mapped > n // 2
+
+
+def test_read_pairs_through_deep_dp_to_sam_records(env):
+    """s3_deep_dp_align -> s3_runs_decode -> s3_sam_deep_dp_records == oracle/seeding_oracle.deep_dp -> pairDeepDPOutputSAMAPI, the
+    reported entry = the first one with the largest sum of scores (outputDeepDPResult2, OutputDPResult.cpp:700-760)"""
+    G, idx, hi, gi = env
+    ref, lib = C.CDLL(REF), api.load_library()
+    ref.ref_sam_deep_dp.restype = C.c_int
+    lib.s3_sam_deep_dp_records.restype = C.c_int
+    lib.s3_runs_decode.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    one = OneChromosome(G)
+    rng = np.random.default_rng(13)
+    L, pairs = 100, 240
+    m1, m2, _ = synth.simulate_paired_end(G, pairs, L, seed=17, bad_mate_fraction=0.0)
+    raw = torch.stack([m1.reads, m2.reads], dim=1).reshape(2 * pairs, L).cpu().numpy()
+    reads = [mutate(rng, r, int(rng.integers(3, 8)), int(rng.integers(0, 2))) for r in raw]
+    n = 2 * pairs
+    wpq = formats.word_per_query(L)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    q = formats.pack_queries(np.stack(reads), lens[:n], wpq)
+    ids = 2 * np.arange(pairs, dtype=np.uint32)
+    got = api.deep_dp_align(gi, q, lens, n, wpq, ids, api.stage_params())
+    want = seeding_oracle.deep_dp(OracleEnv(idx, hi), G.cpu().numpy(), reads, ids.tolist(), PAR)
+    assert len(got["hits"]) == len(want["hits"]) > pairs // 3
+    by_pair_got, by_pair_want = {}, {}
+    for h in got["hits"]:
+        by_pair_got.setdefault(int(h["readID"]), []).append(h)
+    for w in want["hits"]:
+        by_pair_want.setdefault(int(w[0]), []).append(w)
+    assert sorted(by_pair_got) == sorted(by_pair_want)
+    cfg = Config(1, 0, SCORES[0], SCORES[1], 1, 40, 1, 1, 1, 1000, b"rgDeep")
+    zeros = (C.c_int32 * 2)(0, 0)
+    counts = np.zeros(6, np.int32)
+    for e in sorted(by_pair_got):
+        q1, q2 = np.ascontiguousarray(reads[e]).astype(np.uint8), np.ascontiguousarray(reads[e + 1]).astype(np.uint8)
+        ql1 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql1[-1] = 0
+        ql2 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql2[-1] = 0
+        n1, n2 = b"p%d/1" % e, b"p%d/2" % e
+        # ---- the CUDA path's hits -> the writer's inputs
+        hs = by_pair_got[e]
+        arr = (DeepAlignment * len(hs))()
+        keep = []
+        for k, h in enumerate(hs):
+            d1 = runs_decode(lib, got["runs"][int(h["runOffset1"]):int(h["runOffset1"]) + int(h["numRuns1"])], L, int(h["score1"]))
+            d2 = runs_decode(lib, got["runs"][int(h["runOffset2"]):int(h["runOffset2"]) + int(h["numRuns2"])], L, int(h["score2"]))
+            keep += [d1[0], d2[0]]
+            p1, p2 = int(h["pos1"]), int(h["pos2"])
+            arr[k].insertSize = (p2 - p1 + L + d2[2]) if p1 < p2 else (p1 - p2 + L + d1[2])              # DV-DPfunctions.cu:3810-3815
+            arr[k].ambPosition[0], arr[k].ambPosition[1] = p1, p2
+            arr[k].strand[0], arr[k].strand[1] = int(h["strand1"]), int(h["strand2"])
+            arr[k].score[0], arr[k].score[1] = int(h["score1"]), int(h["score2"])
+            arr[k].editdist[0], arr[k].editdist[1] = d1[1], d2[1]
+            arr[k].numSameScore[0], arr[k].numSameScore[1] = int(h["numSame1"]), int(h["numSame2"])
+            arr[k].cigar[0], arr[k].cigar[1] = d1[0], d2[0]
+        sums = [int(h["score1"]) + int(h["score2"]) for h in hs]
+        best = sums.index(max(sums))
+        out = (Record * 2)()
+        assert lib.s3_sam_deep_dp_records(C.byref(one.gen), C.byref(cfg), arr, len(hs), best, q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p),
+                                          ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2, zeros, zeros, zeros, out) == 0
+        mine = [record_tuple(r) for r in out]
+        for k in range(2):
+            lib.s3_sam_record_free(C.byref(out[k]))
+        # ---- the oracle's hits -> the reference's writer
+        ws = by_pair_want[e]
+        flat, cigs = [], []
+        for w in ws:
+            _, s1, s2, p1, p2, sc1, sc2, ns1, ns2, c1, c2 = w
+            e1, dis1 = oracle_edit(c1, L, sc1)
+            e2, dis2 = oracle_edit(c2, L, sc2)
+            ins = (p2 - p1 + L + dis2) if p1 < p2 else (p1 - p2 + L + dis1)
+            flat += [ins, p1, s1, sc1, e1, ns1, len(cigs), p2, s2, sc2, e2, ns2, len(cigs) + 1]
+            cigs += [c1.encode(), c2.encode()]
+        wsums = [w[5] + w[6] for w in ws]
+        wbest = wsums.index(max(wsums))
+        flat = np.array(flat, np.int64).astype(np.int32)
+        cig = (C.c_char_p * len(cigs))(*cigs)
+        core, data, dlen = np.zeros(24, np.int32), np.zeros(2 * 8192, np.uint8), np.zeros(2, np.int32)
+        assert ref.ref_sam_deep_dp(*one.ref_args(), cfg.alignmentType, cfg.bwaLikeScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup,
+                                   cfg.dpMatchScore, cfg.dpMisMatchScore, flat.ctypes.data_as(I32P), len(ws), wbest, cig, counts.ctypes.data_as(I32P),
+                                   q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p), ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2,
+                                   core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P)) == 2
+        theirs = [(tuple(int(x) for x in core[12 * r:12 * r + 12]), bytes(data[r * 8192:r * 8192 + int(dlen[r])])) for r in range(2)]
+        assert mine == theirs, (e, mine, theirs)
+
+
+def test_single_reads_through_single_dp_to_sam_records(env):
+    """s3_single_dp_align -> s3_runs_decode -> s3_sam_single_dp_record == oracle/seeding_oracle.single_dp -> SingleDPOutputSAMAPI (150-base reads
+    with indels, every alignment of a read handed to the writer, which picks the one it reports)"""
+    G, idx, hi, gi = env
+    ref, lib = C.CDLL(REF), api.load_library()
+    ref.ref_sam_single_dp.restype = C.c_int
+    lib.s3_sam_single_dp_record.restype = C.c_int
+    lib.s3_runs_decode.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    one = OneChromosome(G)
+    rng = np.random.default_rng(19)
+    L, n = 150, 400
+    rs = synth.simulate_single_end(G, n, L, seed=43, sub_rate=0.0)
+    reads = [mutate(rng, r, int(rng.integers(3, 9)), int(rng.integers(0, 3))) for r in rs.reads.numpy()]
+    wpq = formats.word_per_query(L)
+    lens = np.zeros(formats.ceil32(n), np.uint32)
+    lens[:n] = L
+    q = formats.pack_queries(np.stack(reads), lens[:n], wpq)
+    ids = np.arange(n, dtype=np.uint32)
+    got = api.single_dp_align(gi, q, lens, n, wpq, ids, api.stage_params())
+    want = seeding_oracle.single_dp(OracleEnv(idx, hi), G.cpu().numpy(), reads, ids.tolist(), PAR)
+    assert len(got["hits"]) == len(want["hits"]) > n // 3
+    mine_by, want_by = {}, {}
+    for h in got["hits"]:
+        mine_by.setdefault(int(h["readID"]), []).append(h)
+    for w in want["hits"]:
+        want_by.setdefault(int(w[0]), []).append(w)
+    assert sorted(mine_by) == sorted(want_by)
+    cfg = Config(1, 0, SCORES[0], SCORES[1], 1, 40, 1, 1, 1, 1000, b"rgSDP")
+    cutoff = int(np.ceil(0.3 * L))
+    for r in sorted(mine_by):
+        qr = np.ascontiguousarray(reads[r]).astype(np.uint8)
+        ql = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql[-1] = 0
+        name = b"sdp%d" % r
+        hs = mine_by[r]
+        arr = (DpAlignment * len(hs))()
+        keep = []
+        for k, h in enumerate(hs):
+            d = runs_decode(lib, got["runs"][int(h["runOffset"]):int(h["runOffset"]) + int(h["numRuns"])], L, int(h["score"]))
+            keep.append(d[0])
+            arr[k].ambPosition, arr[k].strand, arr[k].score, arr[k].editdist, arr[k].cigar = int(h["pos"]), int(h["strand"]), int(h["score"]), d[1], d[0]
+        out = Record()
+        assert lib.s3_sam_single_dp_record(C.byref(one.gen), C.byref(cfg), arr, len(hs), cutoff, qr.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name, C.byref(out)) == 0
+        mine = record_tuple(out)
+        lib.s3_sam_record_free(C.byref(out))
+        ws = want_by[r]
+        flat, cigs = [], []
+        for k, w in enumerate(ws):
+            _, st, pos, sc, same, cg = w
+            flat += [pos, st, sc, oracle_edit(cg, L, sc)[0], k]
+            cigs.append(cg.encode())
+        flat = np.array(flat, np.int64).astype(np.int32)
+        cig = (C.c_char_p * len(cigs))(*cigs)
+        core, data, dlen = np.zeros(12, np.int32), np.zeros(8192, np.uint8), np.zeros(1, np.int32)
+        assert ref.ref_sam_single_dp(*one.ref_args(), cfg.alignmentType, cfg.bwaLikeScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup,
+                                     cfg.dpMatchScore, cutoff, flat.ctypes.data_as(I32P), len(ws), cig, qr.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name,
+                                     core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P)) == 1
+        assert mine == (tuple(int(x) for x in core), bytes(data[:int(dlen[0])])), r

@@ -491,6 +491,7 @@ typedef struct {
     int32_t cutoffThreshold;              /* DPScoreThreshold; < 0: DEFAULT = ceil(0.3 * read length) */
     int32_t softClipLeft, softClipRight;  /* MaxFrontLenClipped / MaxEndLenClipped */
     uint32_t maxWindows;                  /* rescue windows per batch the DP workspace is sized for; 0: one per read */
+    int32_t readStats;                    /* 1: also return, per read, the mismatch statistics hostKernel keeps for MAPQ (readStats below) */
 } s3_pe_params;
 typedef struct {
     uint32_t pos1, pos2, insertion;       /* PEPairs algnmt_1, algnmt_2, insertion */
@@ -500,6 +501,10 @@ typedef struct {
     int8_t optimalTotal, suboptimalTotal; /* totalMismatchCount of the two pairs of PEStatsPEPairList; 127: none */
     uint16_t pad;
 } s3_pe_pair_result;
+typedef struct {
+    uint32_t x0, x1;                      /* occurrences with the fewest mismatches / with one more: first_X0 / first_X1 of hostKernel */
+    uint8_t minMismatch, pad[3];          /* previousMinNumMismatch (CPUfunctions.cpp:2061-2141; rOutput->WithError of collect_all_answers); 255: no occurrence */
+} s3_pe_read_stats;
 typedef struct {
     uint32_t dpReadID, alignedPos, dpPos;
     int32_t score;
@@ -513,6 +518,7 @@ typedef struct {
     uint64_t h2dBytes, d2hBytes;          /* what crossed the link for this batch */
     uint8_t *route; s3_pe_pair_result *pairs; s3_pe_dp_result *dp; uint32_t *runs;              /* host (s3_pe_align) */
     uint8_t *d_route; s3_pe_pair_result *d_pairs; s3_pe_dp_result *d_dp; uint32_t *d_runs;      /* device (s3_pe_align_device) */
+    s3_pe_read_stats *readStats, *d_readStats;                                                  /* per read, with params.readStats (host / device) */
 } s3_pe_result;
 /* maxReads (even) reads of up to maxReadLength bases per batch; needs an index uploaded with suffix array and text */
 int s3_pe_create(s3_index *ix, uint32_t maxReads, uint32_t maxReadLength, const s3_pe_params *params, s3_pe **out);

@@ -680,19 +680,21 @@ class PEParams(C.Structure):
                 ("strandLeftLeg", C.c_int32), ("strandRightLeg", C.c_int32), ("maxOutputPerRead", C.c_uint32),
                 ("maxHitNumForDP", C.c_uint32), ("keepSecondBest", C.c_int32), ("scores", DPScores),
                 ("cutoffThreshold", C.c_int32), ("softClipLeft", C.c_int32), ("softClipRight", C.c_int32),
-                ("maxWindows", C.c_uint32)]
+                ("maxWindows", C.c_uint32), ("readStats", C.c_int32)]
 
 
 class PEResult(C.Structure):
     _fields_ = [("numPairs", C.c_uint64), ("numRanges", C.c_uint64), ("numOccurrences", C.c_uint64), ("numWindows", C.c_uint64),
                 ("numRuns", C.c_uint64), ("routeCounts", C.c_uint32 * 16), ("h2dBytes", C.c_uint64), ("d2hBytes", C.c_uint64),
                 ("route", C.c_void_p), ("pairs", C.c_void_p), ("dp", C.c_void_p), ("runs", C.c_void_p),
-                ("d_route", C.c_void_p), ("d_pairs", C.c_void_p), ("d_dp", C.c_void_p), ("d_runs", C.c_void_p)]
+                ("d_route", C.c_void_p), ("d_pairs", C.c_void_p), ("d_dp", C.c_void_p), ("d_runs", C.c_void_p),
+                ("readStats", C.c_void_p), ("d_readStats", C.c_void_p)]
 
 
 PE_PAIR_DTYPE = np.dtype([("pos1", np.uint32), ("pos2", np.uint32), ("insertion", np.uint32), ("strand1", np.uint8), ("mism1", np.uint8),
                           ("strand2", np.uint8), ("mism2", np.uint8), ("numPairs", np.uint32), ("numOptimal", np.uint32),
                           ("numSuboptimal", np.uint32), ("optimalTotal", np.int8), ("suboptimalTotal", np.int8), ("pad", np.uint16)])
+PE_READ_STATS_DTYPE = np.dtype([("x0", np.uint32), ("x1", np.uint32), ("minMismatch", np.uint8), ("pad", np.uint8, (3,))])
 PE_DP_DTYPE = np.dtype([("dpReadID", np.uint32), ("alignedPos", np.uint32), ("dpPos", np.uint32), ("score", np.int32),
                         ("numSameScore", np.uint32), ("runOffset", np.uint32), ("numRuns", np.uint16), ("alignedStrand", np.uint8),
                         ("alignedMismatches", np.uint8), ("dpStrand", np.uint8), ("leftOrRight", np.uint8), ("pad", np.uint8, (2,))])
@@ -700,13 +702,13 @@ PE_DP_DTYPE = np.dtype([("dpReadID", np.uint32), ("alignedPos", np.uint32), ("dp
 
 def pe_params(num_mismatch=2, insert_low=200, insert_high=500, left_leg=1, right_leg=2, max_output_per_read=1000,
               max_hit_num_for_dp=None, keep_second_best=False, scores=(1, -2, -3, -1), cutoff=-1, soft_clip_left=3,
-              soft_clip_right=8, max_windows=0, read_length=100) -> PEParams:
+              soft_clip_right=8, max_windows=0, read_length=100, read_stats=False) -> PEParams:
     """Defaults as soap3_dp_pair_align sees them: Soap3MisMatchAllow 2 with DP (SOAP3-DP.cu:210-213), the ini's MaxOutputPerRead,
     getParameterForDefaultDP's maxHitNum for the read length, clips 3 / 8 (soap3-dp-module.cu:14)."""
     if max_hit_num_for_dp is None:
         max_hit_num_for_dp = getParameterForDP(2, read_length, read_length).paramRead[0].maxHitNum
     return PEParams(num_mismatch, insert_low, insert_high, left_leg, right_leg, max_output_per_read, max_hit_num_for_dp,
-                    int(keep_second_best), DPScores(*scores), cutoff, soft_clip_left, soft_clip_right, max_windows)
+                    int(keep_second_best), DPScores(*scores), cutoff, soft_clip_left, soft_clip_right, max_windows, int(read_stats))
 
 
 class PairAligner:
@@ -778,7 +780,8 @@ class PairAligner:
         P, M, R = int(res.numPairs), int(res.numWindows), int(res.numRuns)
         return {"route": view(res.route, np.uint8, P), "pairs": view(res.pairs, PE_PAIR_DTYPE, P), "dp": view(res.dp, PE_DP_DTYPE, M),
                 "runs": view(res.runs, np.uint32, R), "num_ranges": int(res.numRanges), "num_occurrences": int(res.numOccurrences),
-                "route_counts": list(res.routeCounts), "h2d_bytes": int(res.h2dBytes), "d2h_bytes": int(res.d2hBytes)}
+                "route_counts": list(res.routeCounts), "h2d_bytes": int(res.h2dBytes), "d2h_bytes": int(res.d2hBytes),
+                "read_stats": view(res.readStats, PE_READ_STATS_DTYPE, 2 * P)}
 
     def set_timing(self, on: bool):
         _check(load_library().s3_pe_set_timing(self.handle, int(on)), "s3_pe_set_timing")

@@ -94,12 +94,13 @@ struct S3Collect {
 template <bool FILL>
 __global__ void s3_pe_collect_kernel(const S3Collect c, uint32_t *__restrict__ nRanges, uint32_t *__restrict__ totOcc, uint8_t *__restrict__ readFlags,
                                      const uint32_t *__restrict__ rangeOff, uint32_t *__restrict__ saL, uint32_t *__restrict__ saR,
-                                     uint8_t *__restrict__ saFlags)
+                                     uint8_t *__restrict__ saFlags, s3_pe_read_stats *__restrict__ stats = NULL)
 {
     const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= c.numReads) return;
     const size_t off = (size_t)(r >> 5) * 32 * c.wordPerAns + (r & 31);
     uint32_t n = 0, tot = 0;
+    uint32_t withError[8] = {0, 0, 0, 0, 0, 0, 0, 0};            // rOutput->WithError: occurrences per mismatch count (:1294)
     bool more = false;
     const uint32_t base = FILL ? rangeOff[r] : 0u;
     for (uint32_t w = 0; w < c.numCases; ++w) {
@@ -121,11 +122,21 @@ __global__ void s3_pe_collect_kernel(const S3Collect c, uint32_t *__restrict__ n
                     saFlags[2 * (size_t)(base + n) + 1] = (uint8_t)((a1 >> 24) & 7u);           // mismatches
                 }
                 ++n; tot += rr - l + 1;
+                if (!FILL) withError[(a1 >> 24) & 7u] += rr - l + 1;
             }
             if (tot >= c.maxOutputPerRead) break;
         }
     }
-    if (!FILL) { nRanges[r] = n; totOcc[r] = tot; readFlags[r] = more ? 1 : 0; }
+    if (!FILL) {
+        nRanges[r] = n; totOcc[r] = tot; readFlags[r] = more ? 1 : 0;
+        if (stats) {
+            // what hostKernel keeps of a read for MAPQ (CPUfunctions.cpp:2061-2141): the fewest mismatches, X0 = the occurrences with that
+            // many, X1 = those with one more
+            s3_pe_read_stats o = {0u, 0u, 255u, {0, 0, 0}};
+            for (uint32_t m = 0; m < 8; ++m) if (withError[m]) { o.minMismatch = (uint8_t)m; o.x0 = withError[m]; o.x1 = m < 7 ? withError[m + 1] : 0u; break; }
+            stats[r] = o;
+        }
+    }
 }
 
 // ---- route (CPUfunctions.cpp:2153-2262) ------------------------------------------------------------------------------
@@ -516,7 +527,7 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (uint32_t *)NULL, (uint32_t *)NULL, (int)(N + 1), st);
     size_t needA = arena_need(up * wordPerQuery, 4) + arena_need(up, 4) + C * arena_need(up * wpa, 4) + 6 * arena_need(N + 1, 4) + arena_need(N, 1) +
                    2 * arena_need(maxRanges, 4) + arena_need(maxRanges, 2) + arena_need(maxRanges, 1) + 2 * arena_need(P, 1) + arena_need(P, sizeof(S3PeBest)) +
-                   arena_need(scanTemp, 1) + arena_need(64, 4) + 4096;
+                   arena_need(scanTemp, 1) + arena_need(64, 4) + (pe->par.readStats ? arena_need(N, sizeof(s3_pe_read_stats)) : 0) + 4096;
     if ((rc = arena_reserve(&pe->A, needA, st))) return rc;
     S3Arena *A = &pe->A;
     uint32_t *d_q = const_cast<uint32_t *>(queries), *d_len = const_cast<uint32_t *>(readLengths);
@@ -548,7 +559,8 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     S3PeBest *d_best = arena_take<S3PeBest>(A, P);
     void *d_tmp = arena_take<char>(A, scanTemp);
     uint32_t *d_counters = arena_take<uint32_t>(A, 64);
-    if (!d_counters) { s3_set_error("s3_pe_align: stage buffer accounting"); return S3_ENOMEM; }
+    s3_pe_read_stats *d_stats = pe->par.readStats ? arena_take<s3_pe_read_stats>(A, N) : NULL;
+    if (!d_counters || (pe->par.readStats && !d_stats)) { s3_set_error("s3_pe_align: stage buffer accounting"); return S3_ENOMEM; }
 
     PE_MARK(0);
     if (!queriesOnDevice && !uploaded) {
@@ -565,7 +577,7 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     const unsigned nbR = (N + 255) / 256, nbP = (P + 255) / 256;
     S3_TRYC(cudaMemsetAsync(d_nRanges + N, 0, 4, st));
     S3_TRYC(cudaMemsetAsync(d_counters, 0, 64 * 4, st));
-    s3_pe_collect_kernel<false><<<nbR, 256, 0, st>>>(col, d_nRanges, d_totOcc, d_readFlags, NULL, NULL, NULL, NULL);
+    s3_pe_collect_kernel<false><<<nbR, 256, 0, st>>>(col, d_nRanges, d_totOcc, d_readFlags, NULL, NULL, NULL, NULL, d_stats);
     S3_TRYC(cub::DeviceScan::ExclusiveSum(d_tmp, scanTemp, d_nRanges, d_rangeOff, (int)(N + 1), st));
     s3_pe_collect_kernel<true><<<nbR, 256, 0, st>>>(col, NULL, NULL, NULL, d_rangeOff, d_saL, d_saR, d_saFlags);
     S3_TRYC(cudaMemsetAsync(d_keep, 1, maxRanges, st));
@@ -677,19 +689,22 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
     if (queriesOnDevice) {
         S3_TRYC(cudaStreamSynchronize(st));
         totalRuns = M ? pe->h_counts[3] : 0;
-        res->d_route = d_routeFinal; res->d_pairs = (s3_pe_pair_result *)d_best; res->d_dp = d_res; res->d_runs = d_runs;
+        res->d_route = d_routeFinal; res->d_pairs = (s3_pe_pair_result *)d_best; res->d_dp = d_res; res->d_runs = d_runs; res->d_readStats = d_stats;
     } else {
         // the runs' total is needed to size their copy: everything else goes first
-        const size_t bytes = (size_t)P + 256 + (size_t)P * sizeof(S3PeBest) + 256 + Mm * sizeof(s3_pe_dp_result) + 256 + Mm * (size_t)(pe->maxReadLength + 8) * 4;
+        const size_t statBytes = d_stats ? ((size_t)N * sizeof(s3_pe_read_stats) + 255) / 256 * 256 : 0;
+        const size_t bytes = (size_t)P + 256 + (size_t)P * sizeof(S3PeBest) + 256 + Mm * sizeof(s3_pe_dp_result) + 256 + statBytes + Mm * (size_t)(pe->maxReadLength + 8) * 4;
         if ((rc = pe_pinned(pe, bytes))) return rc;
         char *h = (char *)pe->pinned;
         res->route = (uint8_t *)h; h += ((size_t)P + 255) / 256 * 256;
         res->pairs = (s3_pe_pair_result *)h; h += ((size_t)P * sizeof(S3PeBest) + 255) / 256 * 256;
         res->dp = (s3_pe_dp_result *)h; h += (Mm * sizeof(s3_pe_dp_result) + 255) / 256 * 256;
+        if (d_stats) { res->readStats = (s3_pe_read_stats *)h; h += statBytes; }
         res->runs = (uint32_t *)h;
         S3_TRYC(cudaMemcpyAsync(res->route, d_routeFinal, P, cudaMemcpyDeviceToHost, st));
         S3_TRYC(cudaMemcpyAsync(res->pairs, d_best, (size_t)P * sizeof(S3PeBest), cudaMemcpyDeviceToHost, st));
         if (M) S3_TRYC(cudaMemcpyAsync(res->dp, d_res, (size_t)M * sizeof(s3_pe_dp_result), cudaMemcpyDeviceToHost, st));
+        if (d_stats) S3_TRYC(cudaMemcpyAsync(res->readStats, d_stats, (size_t)N * sizeof(s3_pe_read_stats), cudaMemcpyDeviceToHost, st));
         S3_TRYC(cudaStreamSynchronize(st));
         totalRuns = M ? pe->h_counts[3] : 0;
         if (totalRuns) {
@@ -697,7 +712,7 @@ static int pe_run(s3_pe *pe, const uint32_t *queries, const uint32_t *readLength
             S3_TRYC(cudaStreamSynchronize(st));
         }
         res->h2dBytes = up * wordPerQuery * 4 + (size_t)N * 4;
-        res->d2hBytes = (size_t)P + (size_t)P * sizeof(S3PeBest) + (size_t)M * sizeof(s3_pe_dp_result) + (size_t)totalRuns * 4 + 20 * 4;
+        res->d2hBytes = (size_t)P + (size_t)P * sizeof(S3PeBest) + (size_t)M * sizeof(s3_pe_dp_result) + (size_t)totalRuns * 4 + 20 * 4 + (d_stats ? (size_t)N * sizeof(s3_pe_read_stats) : 0);
     }
     res->numPairs = P; res->numOccurrences = T; res->numWindows = M; res->numRuns = totalRuns;
     for (int c = 0; c < 16; ++c) res->routeCounts[c] = pe->h_counts[8 + c];

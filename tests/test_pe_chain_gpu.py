@@ -38,7 +38,10 @@ def _decode_fn(pat, score, read_length, scores):
     return decode_oracle.decode_one(pat, score, read_length, scores)[0]
 
 
-def _run_both(env, pairs, L, seed, k=2, max_hit=None, keep_second=False, max_output=1000, bad_mate_fraction=0.2, insert=(200, 500)):
+LAST = {}     # the inputs of the last _run_both call (reads, the oracle's answer slots), for tests that go on from its results
+
+
+def _run_both(env, pairs, L, seed, k=2, max_hit=None, keep_second=False, max_output=1000, bad_mate_fraction=0.2, insert=(200, 500), read_stats=False):
     G, idx, hi, gi = env
     m1, m2, _ = synth.simulate_paired_end(G, pairs, L, seed=seed, insert_lo=insert[0], insert_hi=insert[1], bad_mate_fraction=bad_mate_fraction)
     reads = torch.stack([m1.reads, m2.reads], dim=1).reshape(2 * pairs, L).cpu().numpy()
@@ -57,7 +60,7 @@ def _run_both(env, pairs, L, seed, k=2, max_hit=None, keep_second=False, max_out
     lens[:n] = L
     q = formats.pack_queries(reads, lens[:n], wpq)
     par = api.pe_params(num_mismatch=k, insert_low=insert[0], insert_high=insert[1], max_output_per_read=max_output,
-                        max_hit_num_for_dp=max_hit, keep_second_best=keep_second, read_length=L)
+                        max_hit_num_for_dp=max_hit, keep_second_best=keep_second, read_length=L, read_stats=read_stats)
     al = api.PairAligner(gi, n, L, par)
     try:
         got = al.align(q, lens, n, wpq)
@@ -79,6 +82,7 @@ def _run_both(env, pairs, L, seed, k=2, max_hit=None, keep_second=False, max_out
                 keep_second_best=keep_second, cutoff=-1, soft_clip_left=3, soft_clip_right=8, max_read=max_read,
                 max_dna=insert[1] - insert[0] + max_read + 1, scores=(1, -2, -3, -1))
     want = pe_chain_oracle.pe_chain(views, allowed, lens[:n], sa, gen, list(reads), opar, oracle_pair_occurrences, _dp_fn, _decode_fn)
+    LAST.update(reads=reads, views=views, allowed=allowed, max_output=max_output, text_length=hi.n)
     return got, want
 
 
@@ -103,6 +107,31 @@ def _compare(got, want):
         assert cig == w["cigar"], (t, cig, w["cigar"])
         traced += w["cigar"] != ""
     return traced
+
+
+def oracle_read_stats(views, allowed, text_length, max_output):
+    """what hostKernel keeps of a read for MAPQ (CPUfunctions.cpp:2061-2141) from rOutput->WithError of collect_all_answers: (X0, X1, fewest mismatches)"""
+    out = []
+    for ranges, tot, more in pe_chain_oracle.collect(views, allowed, text_length, max_output):
+        with_error = [0] * 9
+        for l, r, st, mm in ranges:
+            with_error[mm] += r - l + 1
+        m = next((i for i in range(8) if with_error[i]), None)
+        out.append((0, 0, 255) if m is None else (with_error[m], with_error[m + 1], m))
+    return out
+
+
+def test_pe_chain_read_stats(env):
+    """params.readStats: X0 / X1 / the fewest mismatches of every read == the restatement over the oracle's answer slots"""
+    got, want = _run_both(env, 1200, 100, 8, read_stats=True)
+    _compare(got, want)
+    stats = oracle_read_stats(LAST["views"], LAST["allowed"], LAST["text_length"], LAST["max_output"])
+    assert len(got["read_stats"]) == len(stats) == 2400
+    mine = [(int(x["x0"]), int(x["x1"]), int(x["minMismatch"])) for x in got["read_stats"]]
+    assert mine == stats
+    assert sum(1 for s_ in stats if s_[2] == 255) > 50 and sum(1 for s_ in stats if s_[0] > 1) > 10
+    plain, _ = _run_both(env, 300, 100, 8)
+    assert len(plain["read_stats"]) == 0
 
 
 @pytest.mark.parametrize("L,pairs,seed", [(100, 1500, 3), (75, 800, 4), (50, 600, 5)])

@@ -276,3 +276,59 @@ def test_single_reads_through_single_dp_to_sam_records(env):
                                      cfg.dpMatchScore, cutoff, flat.ctypes.data_as(I32P), len(ws), cig, qr.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name,
                                      core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P)) == 1
         assert mine == (tuple(int(x) for x in core), bytes(data[:int(dlen[0])])), r
+
+
+def test_read_pairs_through_the_chain_to_sam_records(env):
+    """s3_pe_align (with params.readStats) -> s3_sam_pair_records == the oracle chain + the restated per-read statistics -> pairOutputSAMAPI,
+    for the pairs the chain paired with ONE valid pairing (the chain returns the reported pairing and the counts; with more pairings
+    the XA:Z list needs them all: s3_pair_occurrences)"""
+    import test_pe_chain_gpu as chain
+    from test_cpu_sam import Pairing
+    G, idx, hi, gi = env
+    ref, lib = C.CDLL(REF), api.load_library()
+    ref.ref_sam_pair.restype = C.c_int
+    lib.s3_sam_pair_records.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    one = OneChromosome(G)
+    L, pairs = 100, 700
+    got, want = chain._run_both(env, pairs, L, 51, read_stats=True)
+    chain._compare(got, want)
+    reads = chain.LAST["reads"]
+    ostats = chain.oracle_read_stats(chain.LAST["views"], chain.LAST["allowed"], chain.LAST["text_length"], chain.LAST["max_output"])
+    rng = np.random.default_rng(23)
+    done = 0
+    for mode in ((1, 0), (2, 1)):                                     # (report type, BWA-like MAPQ)
+        cfg = Config(mode[0], mode[1], SCORES[0], SCORES[1], 1, 40, 1, 1, 1, 1000, b"rgPE")
+        for p in range(pairs):
+            g = got["pairs"][p]
+            if int(got["route"][p]) != 1 or int(g["numPairs"]) != 1:
+                continue
+            w = want["pairs"][p]
+            q1, q2 = np.ascontiguousarray(reads[2 * p]).astype(np.uint8), np.ascontiguousarray(reads[2 * p + 1]).astype(np.uint8)
+            ql1 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql1[-1] = 0
+            ql2 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql2[-1] = 0
+            n1, n2 = b"c%d/1" % p, b"c%d/2" % p
+            # ---- the chain's result of the pair -> the writer's inputs
+            s1, s2 = got["read_stats"][2 * p], got["read_stats"][2 * p + 1]
+            arr = (Pairing * 1)(Pairing(int(g["pos1"]), int(g["pos2"]), int(g["strand1"]), int(g["mism1"]), int(g["strand2"]), int(g["mism2"]), int(g["optimalTotal"])))
+            counts = (int(g["optimalTotal"]), int(g["suboptimalTotal"]), int(s1["x0"]), int(s2["x0"]), int(s1["x1"]), int(s2["x1"]), int(g["numOptimal"]),
+                      int(int(s1["minMismatch"]) == int(g["mism1"])), int(int(s2["minMismatch"]) == int(g["mism2"])), int(g["numPairs"]))
+            out = (Record * 2)()
+            assert lib.s3_sam_pair_records(C.byref(one.gen), C.byref(cfg), arr, 1, 0, q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p),
+                                           ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2, *counts, out) == 0
+            mine = [record_tuple(r) for r in out]
+            for k in range(2):
+                lib.s3_sam_record_free(C.byref(out[k]))
+            # ---- the oracle chain's result -> the reference's writer
+            o1, o2 = ostats[2 * p], ostats[2 * p + 1]
+            flat = np.array([w["pos1"], w["strand1"], w["mism1"], w["pos2"], w["strand2"], w["mism2"], w["optimalTotal"] & 0xFF], np.uint32)
+            wcounts = (w["optimalTotal"], w["suboptimalTotal"], o1[0], o2[0], o1[1], o2[1], w["numOptimal"], int(o1[2] == w["mism1"]), int(o2[2] == w["mism2"]), w["numPairs"])
+            core, data, dlen = np.zeros(24, np.int32), np.zeros(2 * 8192, np.uint8), np.zeros(2, np.int32)
+            assert ref.ref_sam_pair(*one.ref_args(), cfg.alignmentType, cfg.bwaLikeScore, cfg.dpMatchScore, cfg.dpMisMatchScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ,
+                                    cfg.isPrintMDNM, cfg.readGroup, cfg.outputXAZTag, cfg.peMaxOutputPerPair, helpers.u32p(flat), 1, 0,
+                                    q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p), ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2,
+                                    *wcounts, core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P)) == 2
+            theirs = [(tuple(int(x) for x in core[12 * r:12 * r + 12]), bytes(data[r * 8192:r * 8192 + int(dlen[r])])) for r in range(2)]
+            assert mine == theirs, (p, mine, theirs)
+            done += 1
+    assert done > pairs // 2

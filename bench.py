@@ -909,15 +909,42 @@ def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream
             torch.distributed.barrier()
         torch.cuda.synchronize()
 
-    def device_step(b):
-        return se.align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq)
+    # more handles on the same index arrays, each with its own chain: T batches in flight, one host thread each (the enumerator of one batch is
+    # latency-bound; the other batches' kernels run beside it)
+    T = max(int(os.environ.get("S3_IN_FLIGHT", "4")), 1)
+    gis, ses, streams = [gi], [se], [stream]
+    for _ in range(T - 1):
+        g2 = api.index_clone(gi)
+        gis.append(g2)
+        ses.append(api.SingleAligner(g2, N, num_mismatch=k, max_output_per_read=1000, report_best=False))
+        streams.append(torch.cuda.ExternalStream(g2.stream, device=device))
+
+    def in_threads(fns):
+        errs = []
+
+        def run(fn):
+            try:
+                torch.cuda.set_device(local_rank)
+                fn()
+            except Exception as e:                          # noqa: BLE001
+                errs.append(e)
+        th = [threading.Thread(target=run, args=(fn,)) for fn in fns]
+        for t_ in th:
+            t_.start()
+        for t_ in th:
+            t_.join()
+        if errs:
+            raise errs[0]
+
+    def device_step(b, h=0):
+        return ses[h].align_device(b.queries.data_ptr(), b.lens.data_ptr(), b.n, b.wpq)
     for s in range(args.warmup):
-        device_step(batches[s])
+        for h in range(T):
+            device_step(batches[s], h)
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    launches0 = api.launch_count()
     stats = []
     e0.record(stream)
     for kk in range(args.steps):
@@ -925,10 +952,29 @@ def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream
     e1.record(stream)
     stream.synchronize()
     barrier()
+    tt = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=device)
+    if world > 1:
+        torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
+    t_one = float(tt[0])
+    # the same K steps with T batches in flight: step k on handle k mod T
+    timed_batches = [batches[args.warmup + kk] for kk in range(args.steps)]
+    in_threads([(lambda h=h: [device_step(batches[s_], h) for s_ in range(args.warmup)]) for h in range(T)])
+    barrier()
+    d0, d1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = api.launch_count()
+    d0.record(stream)
+    in_threads([(lambda h=h: [device_step(b_, h) for b_ in timed_batches[h::T]]) for h in range(T)])
+    for h in range(1, T):
+        fin = torch.cuda.Event()
+        fin.record(streams[h])
+        stream.wait_event(fin)
+    d1.record(stream)
+    stream.synchronize()
+    barrier()
     launches = api.launch_count() - launches0
     sampler.stop_flag = True
     sampler.join()
-    tt = torch.tensor([e0.elapsed_time(e1) / 1e3], dtype=torch.float64, device=device)
+    tt = torch.tensor([d0.elapsed_time(d1) / 1e3], dtype=torch.float64, device=device)
     if world > 1:
         torch.distributed.all_reduce(tt, op=torch.distributed.ReduceOp.MAX)
     t_total = float(tt[0])
@@ -948,15 +994,18 @@ def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream
         h.copy_(t)
         return h
     host_sets = [(pinned(batches[args.warmup + kk].queries), pinned(batches[args.warmup + kk].lens)) for kk in range(args.steps)]
-    for q, l in host_sets[:2]:
-        se.align(q.data_ptr(), l.data_ptr(), N, wpq)
+    lasts = [None] * T
+
+    def e2e_on(h, sets):
+        for q, l in sets:
+            lasts[h] = ses[h].align(q.data_ptr(), l.data_ptr(), N, wpq, copy=False)
+    in_threads([(lambda h=h: e2e_on(h, host_sets[:2])) for h in range(T)])
     barrier()
     t0 = time.perf_counter()
-    last = None
-    for q, l in host_sets:
-        last = se.align(q.data_ptr(), l.data_ptr(), N, wpq)
+    in_threads([(lambda h=h: e2e_on(h, host_sets[h::T])) for h in range(T)])
     barrier()
     te = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+    last = lasts[0]
     if world > 1:
         torch.distributed.all_reduce(te, op=torch.distributed.ReduceOp.MAX)
     t_e2e = float(te[0])
@@ -988,11 +1037,14 @@ def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream
     out = {"metric": f"reads/s searched and located (SE {L} bp, <= {k} mismatches, 3.1 Gbp synth ref)", "value": value, "unit": "reads/s", "n_gpus": world,
            "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / args.steps, "higher_is_better": True, "scaling": "weak",
            "vs_baseline": None, "dtype": "u32", "data": "synthetic",
+           "value_one_batch_in_flight": world * N * args.steps / t_one, "ms_per_step_one_batch_in_flight": 1e3 * t_one / args.steps,
            "config": {"workload": f"se_{L}bp_k{k}_genome{args.genome_bp}bp: per step and GPU {N} reads through <= {k}-mismatch search ({ncases} cases, both "
                                   "strands, round-1 slots), answer collection and locate (s3_se_align)",
                       "genome_bp": args.genome_bp, "repeat_fraction": args.repeat_fraction, "reads_per_step_per_gpu": N,
-                      "timing": "value: K steps back to back, queries resident in HBM (one 8-byte count read per step is part of the chain), CUDA events; "
-                                "e2e: s3_se_align with pinned host queries in, occurrences out, wall clock",
+                      "batches_in_flight": T,
+                      "timing": f"value: K steps, queries resident in HBM (one 8-byte count read per step is part of the chain), {T} batches in flight (step k on "
+                                "handle k mod T: the index handle and its s3_index_clones, a host thread each), CUDA events; value_one_batch_in_flight: the same "
+                                "steps back to back on one handle; e2e: s3_se_align with pinned host queries in, occurrences out, wall clock, the same threads",
                       "l2": "inputs larger than L2: the 56 GB index is touched at random, a different read batch every step",
                       "parallelism": f"reads sharded over {world} GPU(s), index replicated, no collective"},
            "clocks": sampler.result(),
@@ -1082,8 +1134,9 @@ def run_se(args, gi, host, genome, device, local_rank, rank, world, numa, stream
                                       "checker": "oracle/pe_chain_oracle.collect over " + ("the reference's kernels compiled for the host" if ref_s is not None else "the oracle port")}
         out["pipeline"]["reads_with_a_slot_overflow_per_step"] = float(got["read_flags"].mean() * N)
     print(json.dumps(out), flush=True)
-    se.free()
-    api.GPUINDEXFree(gi)
+    for h in reversed(range(T)):                                  # clones are freed before the handle they were made from
+        ses[h].free()
+        api.GPUINDEXFree(gis[h])
     if world > 1:
         torch.distributed.destroy_process_group()
 
@@ -1192,7 +1245,7 @@ def main():
     pe = api.PairAligner(gi, N, L, par)
     # more handles on the same index arrays, each with its own chain and stage workspace: T batches in flight, one host thread each
     with_deep = args.config != "pe100_chain"
-    T = max(int(os.environ.get("S3_IN_FLIGHT", "4" if with_deep else "2")), 1)
+    T = max(int(os.environ.get("S3_IN_FLIGHT", "4")), 1)
     sp = api.stage_params(insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES)
     gis, pes, streams = [gi], [pe], [stream]
     for _ in range(T - 1):

@@ -332,3 +332,122 @@ def test_read_pairs_through_the_chain_to_sam_records(env):
             assert mine == theirs, (p, mine, theirs)
             done += 1
     assert done > pairs // 2
+
+
+def test_rescued_pairs_through_the_chain_to_sam_records(env):
+    """s3_pe_align's rescue records of a pair -> s3_runs_decode -> s3_sam_pair_dp_records == the oracle chain's records -> pairDPOutputSAMAPI.
+    Every record of the pair is an AlgnmtDPResult (DV-DPfunctions.cu:2355-2440): whichFromDP = the DP read's parity (2 when it missed its
+    cutoff), insert size as computed there; the reported entry = fewest mismatches of the aligned read, then the highest DP score
+    (outputDPResult2, OutputDPResult.cpp:296-420)"""
+    import test_pe_chain_gpu as chain
+    from test_cpu_sam import DpPairing
+    G, idx, hi, gi = env
+    ref, lib = C.CDLL(REF), api.load_library()
+    ref.ref_sam_pair_dp.restype = C.c_int
+    lib.s3_sam_pair_dp_records.restype = C.c_int
+    lib.s3_runs_decode.restype = C.c_int
+    lib.s3_sam_record_free.restype = None
+    one = OneChromosome(G)
+    L, pairs = 100, 900
+    got, want = chain._run_both(env, pairs, L, 61, read_stats=True, bad_mate_fraction=0.5)
+    chain._compare(got, want)
+    reads = chain.LAST["reads"]
+    ostats = chain.oracle_read_stats(chain.LAST["views"], chain.LAST["allowed"], chain.LAST["text_length"], chain.LAST["max_output"])
+    NONE = 0xFFFFFFFF
+    mine_by, want_by = {}, {}
+    for t in range(len(got["dp"])):
+        mine_by.setdefault(int(got["dp"][t]["dpReadID"]) >> 1, []).append(t)
+        want_by.setdefault(int(want["dp"][t]["dpReadID"]) >> 1, []).append(t)
+    assert sorted(mine_by) == sorted(want_by) and len(mine_by) > pairs // 5
+
+    def entry(rec, cigar, editdist, dis):
+        """one rescue record as the fields of an AlgnmtDPResult: (whichFromDP, strands, editdist, insertSize, numSameScore, positions, scores)"""
+        dp_read = int(rec["dpReadID"]) & 1
+        al_pos, dp_pos = int(rec["alignedPos"]), int(rec["dpPos"])
+        if cigar:
+            which = dp_read
+            ins = (al_pos - dp_pos + L) if dp_pos < al_pos else (dp_pos - al_pos + L + dis)
+        else:
+            which, dp_pos, ins, editdist = 2, NONE, 0, 0
+        pos, strand, score = [0, 0], [0, 0], [0, 0]
+        pos[dp_read], strand[dp_read], score[dp_read] = dp_pos, int(rec["dpStrand"]), int(rec["score"])
+        pos[1 - dp_read], strand[1 - dp_read], score[1 - dp_read] = al_pos, int(rec["alignedStrand"]), int(rec["alignedMismatches"])
+        return which, strand, editdist, ins, int(rec["numSameScore"]) if cigar else 0, pos, score
+
+    def pick(entries):
+        """outputDPResult2: the reported entry of a pair's records"""
+        best, mn, mx = None, 0, 0
+        for i, (which, strand, ed, ins, same, pos, score) in enumerate(entries):
+            un1, un2 = pos[0] == NONE, pos[1] == NONE
+            if un1 and not un2:
+                cm, cs = score[1], -127
+            elif un2 and not un1:
+                cm, cs = score[0], -127
+            elif not un1 and not un2:
+                cm, cs = (score[0], score[1]) if which == 1 else (score[1], score[0])
+            else:
+                cm, cs = 127, -127
+            if best is None or cm < mn or (cm == mn and cs > mx and not (un1 or un2)):
+                best, mn, mx = i, cm, cs
+        return best
+
+    cfg = Config(1, 0, SCORES[0], SCORES[1], 1, 40, 1, 1, 1, 1000, b"rgRescue")
+    rng = np.random.default_rng(31)
+    done = 0
+    for p in sorted(mine_by):
+        q1, q2 = np.ascontiguousarray(reads[2 * p]).astype(np.uint8), np.ascontiguousarray(reads[2 * p + 1]).astype(np.uint8)
+        ql1 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql1[-1] = 0
+        ql2 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql2[-1] = 0
+        n1, n2 = b"r%d/1" % p, b"r%d/2" % p
+        # ---- the chain's records -> the writer's inputs
+        ents, cigs = [], []
+        for t in mine_by[p]:
+            rec = got["dp"][t]
+            if int(rec["numRuns"]):
+                cg, ed, dis = runs_decode(lib, got["runs"][int(rec["runOffset"]):int(rec["runOffset"]) + int(rec["numRuns"])], L, int(rec["score"]))
+            else:
+                cg, ed, dis = b"", 0, 0
+            ents.append(entry(rec, cg, ed, dis))
+            cigs.append(cg)
+        if all(e[0] == 2 for e in ents):
+            continue                                                  # no rescue succeeded: the pair goes to the writers of improperly paired reads
+        best = pick(ents)
+        arr = (DpPairing * len(ents))()
+        for k, (which, strand, ed, ins, same, pos, score) in enumerate(ents):
+            arr[k].whichFromDP, arr[k].editdist, arr[k].insertSize, arr[k].numSameScore, arr[k].cigar = which, ed, ins, same, cigs[k] or None
+            for i in range(2):
+                arr[k].strand[i], arr[k].ambPosition[i], arr[k].score[i] = strand[i], pos[i], score[i]
+        st = [got["read_stats"][2 * p], got["read_stats"][2 * p + 1]]
+        x0 = (C.c_int32 * 2)(*[int(s_["x0"]) for s_ in st]); x1 = (C.c_int32 * 2)(*[int(s_["x1"]) for s_ in st])
+        mm = (C.c_int32 * 2)(*[int(s_["minMismatch"]) if int(s_["x0"]) else 0 for s_ in st])
+        out = (Record * 2)()
+        assert lib.s3_sam_pair_dp_records(C.byref(one.gen), C.byref(cfg), arr, len(ents), best, q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p),
+                                          ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2, x0, x1, mm, out) == 0, api.load_library().s3_last_error()
+        mine = [record_tuple(r) for r in out]
+        for k in range(2):
+            lib.s3_sam_record_free(C.byref(out[k]))
+        # ---- the oracle chain's records -> the reference's writer
+        wents, wcigs = [], []
+        for t in want_by[p]:
+            w = want["dp"][t]
+            cg = w["cigar"]
+            ed, dis = oracle_edit(cg, L, w["score"]) if cg else (0, 0)
+            wents.append(entry(w, cg, ed, dis))
+            wcigs.append(cg.encode())
+        wbest = pick(wents)
+        flat = []
+        for k, (which, strand, ed, ins, same, pos, score) in enumerate(wents):
+            flat += [which, ed, ins, same, pos[0] if pos[0] != NONE else -1, strand[0], score[0], pos[1] if pos[1] != NONE else -1, strand[1], score[1], k]
+        flat = np.array(flat, np.int64).astype(np.int32)
+        cig = (C.c_char_p * len(wcigs))(*wcigs)
+        o = [ostats[2 * p], ostats[2 * p + 1]]
+        counts = np.array([o[0][0], o[0][1], o[0][2] if o[0][0] else 0, o[1][0], o[1][1], o[1][2] if o[1][0] else 0], np.int32)
+        core, data, dlen = np.zeros(24, np.int32), np.zeros(2 * 8192, np.uint8), np.zeros(2, np.int32)
+        assert ref.ref_sam_pair_dp(*one.ref_args(), cfg.alignmentType, cfg.bwaLikeScore, cfg.isFastq, cfg.maxMAPQ, cfg.minMAPQ, cfg.isPrintMDNM, cfg.readGroup,
+                                   cfg.dpMatchScore, cfg.dpMisMatchScore, flat.ctypes.data_as(I32P), len(wents), wbest, cig, counts.ctypes.data_as(I32P),
+                                   q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p), ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2,
+                                   core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P)) == 2
+        theirs = [(tuple(int(x) for x in core[12 * r:12 * r + 12]), bytes(data[r * 8192:r * 8192 + int(dlen[r])])) for r in range(2)]
+        assert mine == theirs, (p, ents, mine, theirs)
+        done += 1
+    assert done > pairs // 6

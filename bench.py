@@ -1,21 +1,20 @@
 #!/usr/bin/env python
 """bench.py -- reads/s of the SOAP3-dp GPU alignment hot path on B200.
 
-Workload (BASELINE.json metric; config 4 shape at one batch per step):
+Workload (BASELINE.json metric = config 4, one batch per step):
   paired-end 2x100 bp, insert 200-500, FR, against a 3.1 Gbp synthetic genome.
   One STEP = one batch of P pairs (2P reads, default 1,048,576 reads = the reference's
-  NUM_BLOCKS*THREADS_PER_BLOCK launch size, definitions.h:75-77):
-    (1) GPU-2BWT search, <=2 mismatches (Soap3MisMatchAllow=2 when DP is on,
-        SOAP3-DP.cu:210-213): 4 cases x both strands, round-1 answer slots, for all 2P reads;
-    (2) semi-global DP mate rescue (window insert_high-insert_low+len = 400 bp, anchors as
-        HalfEndAlgnBatch::pack, DV-DPfunctions.cu:2027-2110) for every pair in which exactly
-        one mate was found by (1).
-  `value`  : inputs resident in HBM, CUDA-event timed on the library's stream.
-  `e2e`    : the same step through the host-pointer C ABI (s3_search_round1 + s3_dp_align),
-             pinned host buffers, H2D + D2H inside the timed region.
-  `--impl reference` : the reference's own kernel sources compiled for the host
-             (oracle/_ref, OpenMP over reads) -- or the oracle port if oracle/_ref is
-             absent -- timed on a bounded sample of the same workload.
+  NUM_BLOCKS*THREADS_PER_BLOCK launch size, definitions.h:75-77) through
+    (1) the paired-end chain (s3_pe_align[_device]): GPU-2BWT search, <=2 mismatches (Soap3MisMatchAllow=2 when DP is on,
+        SOAP3-DP.cu:210-213; 4 cases x both strands, round-1 slots), answer collection, routing, locate, pairing, mate-rescue
+        windows (HalfEndAlgnBatch::pack), semi-global DP, CIGAR runs -- nothing taken from the simulator's truth;
+    (2) deep DP (s3_pe_deep_dp = DPForUnalignPairs2) of the pairs (1) left with no occurrence of either read.
+  `value`  : queries resident in HBM, CUDA-event timed, S3_IN_FLIGHT (4) batches in flight on handles that share the index.
+  `e2e`    : the same steps through the host-pointer C ABI, queries from pinned host memory, every result into host memory,
+             H2D + D2H inside the timed region; `e2e.pageable_value`: caller buffers from malloc.
+  `--impl reference` : the reference's own CPU search (ProcessReadDoubleStrand2, oracle/_ref) + its DP kernels compiled for the
+             host, on all host threads, on a bounded sample of the same workload.
+  `--config` : pe100_chain (without (2)), se100_k4 (BASELINE config 2), se150_dp (config 3).
 
 Launch:  python bench.py --gpus N --steps K --warmup W
          (N > 1: python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...)
@@ -164,72 +163,6 @@ def make_batch(genome, pairs, L, seed):
     b.lens = lens
     b.queries = packing.pack_queries(reads, lens[:b.n], b.wpq)
     return b
-
-
-def alloc_answers(b, device):
-    allowed = formats.SA_RANGES_ROUND1[K_MISMATCH]
-    wpa = 2 * allowed
-    ncases = formats.NUM_CASES[K_MISMATCH]
-    up = formats.ceil32(b.n)
-    return [torch.empty(up * wpa, dtype=torch.int32, device=device) for _ in range(ncases)], allowed, wpa, ncases
-
-
-def build_rescue_batch(genome, b, answers, wpa, max_read, max_dna):
-    """From the search result: pairs with exactly one mate found -> DP batch that rescues the
-    other mate from the found mate's position (windows/anchors/clips as HalfEndAlgnBatch::pack,
-    DV-DPfunctions.cu:2027-2110; reverse-strand reads are reverse-complemented, :1497-1505)."""
-    dev = genome.device
-    found = torch.zeros(b.n, dtype=torch.bool, device=dev)
-    for a in answers:
-        found |= packing.answers_status(a, b.n, wpa) != formats.ANSWER_NO_HIT
-    f = found.view(-1, 2)
-    need = f[:, 0] ^ f[:, 1]
-    pair_ids = torch.nonzero(need).reshape(-1)
-    aligned = pair_ids * 2 + (~f[pair_ids, 0]).to(torch.int64)      # index of the found mate
-    target = pair_ids * 2 + f[pair_ids, 0].to(torch.int64)          # mate to rescue
-    L = b.L
-    p = b.pos[aligned]
-    left = b.strand[aligned] == 0                                     # found mate is the left (+) read
-    wlen = INSERT_HI - INSERT_LO + L
-    start = torch.where(left, p + INSERT_LO - L, p + L - INSERT_HI).clamp(min=0, max=genome.numel() - wlen - 1)
-    M = pair_ids.numel()
-    ar = torch.arange(wlen, device=dev)
-    dna = torch.empty(M, wlen, dtype=torch.uint8, device=dev)
-    step = 1 << 16
-    for r0 in range(0, M, step):
-        dna[r0:r0 + step] = genome[(start[r0:r0 + step, None] + ar[None, :]).reshape(-1)].reshape(-1, wlen)
-    rd = b.reads[target]
-    rd = torch.where(left[:, None], (3 - torch.flip(rd, dims=[1])).to(torch.uint8), rd)   # mate of a + read is on -
-    d = Batch()
-    d.n = M
-    d.max_read, d.max_dna = max_read, max_dna
-    d.dna = packing.pack_dp_sequences(dna, max_dna)
-    d.read = packing.pack_dp_sequences(rd, max_read)
-    up = formats.ceil32(max(M, 1))
-
-    def full(v, dtype=torch.int32):
-        t = torch.zeros(up, dtype=dtype, device=dev)
-        t[:M] = v
-        return t
-    d.dna_len = full(wlen)
-    d.read_len = full(L)
-    d.cutoff = full(int(np.ceil(0.3 * L)))
-    # the rescued read lies on the opposite strand of the found one; clips 3/8 by strand (soap3-dp-module.cu:14)
-    d.clip_lt = full(torch.where(left, 8, 3))
-    d.clip_rt = full(torch.where(left, 3, 8))
-    d.anchor_l = full(torch.where(left, max_dna, INSERT_HI - INSERT_LO + 1))
-    d.anchor_r = full(torch.where(left, L, 0))
-    d.scores = torch.zeros(up, dtype=torch.int32, device=dev)
-    d.hit = torch.zeros(up, dtype=torch.int32, device=dev)
-    d.cnt = torch.zeros(up, dtype=torch.int32, device=dev)
-    d.pattern = torch.zeros(up * (max_read + max_dna), dtype=torch.uint8, device=dev)
-    d.cells = M * wlen * L
-    # the same batch as the caller of s3_dp_align_windows names it: read ids, strands (2 = reverse-complemented), window starts
-    d.read_ids = full(target.to(torch.int32))
-    d.strand_code = torch.zeros(up, dtype=torch.uint8, device=dev)
-    d.strand_code[:M] = torch.where(left, 2, 1).to(torch.uint8)
-    d.start = full(start.to(torch.int32))
-    return d
 
 
 # ---------------------------------------------------------------------------
@@ -424,63 +357,6 @@ def cpu_arm(host, genome, L, sample_reads, seed, dp_fraction, threads, kernel_co
                 "rank_queries_per_read": nrank / nk, "t_search_s": t_search, "t_dp_s": t_dp,
                 "dp_gcups": dpb.n * 400 * L / t_dp / 1e9})
     return out
-
-
-def pairing_rows(views, allowed, n_reads, L, true_pos, retain_best, locate, pair_occurrences, max_per_range=8):
-    """The steps between the search answers and the paired result, as SOAP3-dp's hostKernel runs them per read pair
-    (CPUfunctions.cpp:1258-1300, 2170-2310): answer slots -> per-read SA-range lists -> best-hit filter (s3_retain_best)
-    -> positions (s3_locate) -> pairing of the two mates' occurrence lists (s3_pair_occurrences).  views: one [n_reads,
-    2 * allowed] array per case; reads 2i / 2i+1 are mates.  The three callables are the library entries (tests pass the
-    oracles).  Returns the measured row for `next_rows`."""
-    rid, sl, sr, mm, st = [], [], [], [], []
-    for v in views:
-        for sidx in range(allowed):
-            l, w = v[:, 2 * sidx], v[:, 2 * sidx + 1]
-            ok = (l < 0xFFFFFFFD) & (w != 0xFFFFFFFF) if sidx == 0 else (l != 0xFFFFFFFF) & (w != 0xFFFFFFFF)
-            ok &= v[:, 0] < 0xFFFFFFFD
-            rid.append(np.nonzero(ok)[0])
-            sl.append(l[ok]); sr.append(l[ok] + (w[ok] & 0xFFFFFF))
-            mm.append((w[ok] >> 24) & 7); st.append(((w[ok] >> 27) & 1) + 1)           # CPUfunctions.cpp:1281-1282
-    rid = np.concatenate(rid)
-    order = np.argsort(rid, kind="stable")
-    rid = rid[order]
-    sl, sr = (np.ascontiguousarray(np.concatenate(x)[order].astype(np.uint32)) for x in (sl, sr))
-    mm, st = (np.ascontiguousarray(np.concatenate(x)[order].astype(np.uint8)) for x in (mm, st))
-    sa_off = np.zeros(n_reads + 1, np.uint64)
-    sa_off[1:] = np.cumsum(np.bincount(rid, minlength=n_reads))
-    z32, z8, zoff = np.zeros(0, np.uint32), np.zeros(0, np.uint8), np.zeros(n_reads + 1, np.uint64)
-    t0 = time.perf_counter()
-    kept = retain_best(0, sl, sr, st, mm, sa_off, z32, z8, z8, zoff)
-    t_retain = time.perf_counter() - t0
-    t0 = time.perf_counter()
-    loc_off, pos = locate(kept["sa_l"], kept["sa_r"], max_per_range)
-    t_locate = time.perf_counter() - t0
-    per_range = np.diff(loc_off).astype(np.int64)
-    range_read = np.repeat(np.arange(n_reads), np.diff(kept["sa_off"]).astype(np.int64))
-    occ_read = np.repeat(range_read, per_range)
-    occ_strand = np.repeat(kept["sa_flags"][:, 0], per_range)
-    occ_mism = np.repeat(kept["sa_flags"][:, 1], per_range)
-    per_read = np.bincount(occ_read, minlength=n_reads)
-    lists = []
-    for parity in (0, 1):
-        sel = (occ_read & 1) == parity
-        off = np.zeros(n_reads // 2 + 1, np.uint64)
-        off[1:] = np.cumsum(per_read[parity::2])
-        lists += [np.ascontiguousarray(pos[sel]), np.ascontiguousarray(occ_strand[sel]), np.ascontiguousarray(occ_mism[sel]), off]
-    n_pairs = n_reads // 2
-    t0 = time.perf_counter()
-    pr = pair_occurrences(*lists, np.full(n_pairs, L, np.uint32), INSERT_LO, INSERT_HI, 1, 2, False)
-    t_pair = time.perf_counter() - t0
-    has = pr["optimal"] != 0xFFFFFFFF
-    best = (pr["offsets"][:-1][has] + pr["optimal"][has]).astype(np.int64)
-    at_truth = int(((pr["pos1"][best] == true_pos[0::2][has]) & (pr["pos2"][best] == true_pos[1::2][has])).sum())
-    both_found = int(((per_read[0::2] > 0) & (per_read[1::2] > 0)).sum())
-    return {"read_pairs": int(n_pairs), "sa_ranges": int(len(sl)), "sa_ranges_kept": int(len(kept["sa_l"])), "positions": int(len(pos)),
-            "pairs_with_both_mates_found": both_found, "pairs_with_a_valid_pairing": int(has.sum()),
-            "optimal_pairing_at_the_true_positions": at_truth, "valid_pairings": int(pr["offsets"][-1]),
-            "ms_retain_best": 1e3 * t_retain, "ms_locate": 1e3 * t_locate, "ms_pair_occurrences": 1e3 * t_pair,
-            "call": "s3_retain_best (all best) -> s3_locate (<= 8 per range) -> s3_pair_occurrences (insert 200-500, FR), pageable host "
-                    "arrays between the calls; numpy glue between them not counted"}
 
 
 # ---------------------------------------------------------------------------
@@ -693,68 +569,45 @@ def stage_parity(args, gi, host, genome, L, wpq, reads, sp, se_mode):
 
 
 def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, threads):
-    """BASELINE config 3 (se150_dp) and the deep-DP leg of config 4 (pe100_deep): the search chain followed by the DP stage that
-    starts from seeds, for the reads the chain left unaligned.
-      se150_dp    150 bp single-end reads with 1 % substitutions and 0.15 % indels: s3_se_align in long-read mode (first 100 bases
-                  searched with <= 2 mismatches, occurrences extended over the read: validateAlignments), then s3_single_dp_align
-                  (DPForUnalignSingle2) for the reads without a valid occurrence
-      pe100_deep  the default workload's pairs: s3_pe_align, then s3_deep_dp_align (DPForUnalignPairs2) for the pairs with no
-                  occurrence of either read
-    The seeded stages are host-orchestrated entries (host arrays in and out), so every number here is end to end: wall clock over
+    """BASELINE config 3 (se150_dp): the search chain followed by the DP stage that starts from seeds, for the reads the chain left
+    unaligned -- 150 bp single-end reads with 1 % substitutions and 0.15 % indels: s3_se_align in long-read mode (first 100 bases searched
+    with <= 2 mismatches, occurrences extended over the read: validateAlignments), then s3_single_dp_align (DPForUnalignSingle2) for the
+    reads without a valid occurrence.  (The deep-DP stage of config 4 is part of the default step, see main.)
+    The seeded stage is a host-orchestrated entry (host arrays in and out), so every number here is end to end: wall clock over
     K steps through the host-pointer C ABI, queries from host memory, results into host memory."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    se_mode = args.config == "se150_dp"
-    L = 150 if se_mode else args.read_len
-    N = args.pairs if se_mode else 2 * args.pairs
+    L = 150
+    N = args.pairs
     total = args.warmup + args.steps
     wpq = formats.word_per_query(L)
     sets = []
     for s in range(total):
-        if se_mode:
-            rs = synth.simulate_single_end(genome, N, L, seed=500 + 1000 * rank + s, sub_rate=0.01, indel_rate=0.0015)
-            lens = torch.zeros(formats.ceil32(N), dtype=torch.int32, device=device)
-            lens[:N] = L
-            q = packing.pack_queries(rs.reads, lens[:N], wpq)
-            sets.append((pinned_np(q), pinned_np(lens), rs.reads.cpu().numpy()))
-        else:
-            b = make_batch(genome, args.pairs, L, seed=100 + 1000 * rank + s)
-            sets.append((pinned_np(b.queries), pinned_np(b.lens), b.reads.cpu().numpy()))
+        rs = synth.simulate_single_end(genome, N, L, seed=500 + 1000 * rank + s, sub_rate=0.01, indel_rate=0.0015)
+        lens = torch.zeros(formats.ceil32(N), dtype=torch.int32, device=device)
+        lens[:N] = L
+        q = packing.pack_queries(rs.reads, lens[:N], wpq)
+        sets.append((pinned_np(q), pinned_np(lens), rs.reads.cpu().numpy()))
     sp = api.stage_params(insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES)
-    if se_mode:
-        chain = api.SingleAligner(gi, N, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True)
-    else:
-        chain = api.PairAligner(gi, N, L, api.pe_params(num_mismatch=K_MISMATCH, insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES,
-                                                        read_length=L, max_windows=N // 2))
+    chain = api.SingleAligner(gi, N, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True)
 
     # more handles on the same index, each with its own chain and stage workspace: T batches in flight, one host thread each
     T = max(int(os.environ.get("S3_IN_FLIGHT", "4")), 1)
     handles = [(chain, gi)]
     for _ in range(T - 1):
         g2 = api.index_clone(gi)
-        if se_mode:
-            c2 = api.SingleAligner(g2, N, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True)
-        else:
-            c2 = api.PairAligner(g2, N, L, api.pe_params(num_mismatch=K_MISMATCH, insert_low=INSERT_LO, insert_high=INSERT_HI, scores=DP_SCORES,
-                                                         read_length=L, max_windows=N // 2))
-        handles.append((c2, g2))
+        handles.append((api.SingleAligner(g2, N, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True), g2))
 
     def step(q, lens, chain=chain, gi=gi):
         # results stay where the C entries put them (the handle's pinned buffers / malloc'ed arrays): no numpy copies in the timed loop
         t0 = time.perf_counter()
         got = chain.align(q, lens, N, wpq, copy=False)
         t1 = time.perf_counter()
-        if se_mode:
-            found = got["occ_offsets"][1:] != got["occ_offsets"][:-1]
-            ids = np.nonzero(~found & (got["read_flags"] == 0))[0].astype(np.uint32)
-            aligned = int(found.sum())
-            t1b = time.perf_counter()
-            res = api.single_dp_align(gi, q, lens, N, wpq, ids, sp, counts_only=True)
-        else:
-            t1b = time.perf_counter()
-            res = chain.deep_dp(sp, counts_only=True)               # the pairs the chain left as S3_PE_NONE, picked on the device
-            ids = range(res["num_input"])
-            aligned = int(N // 2 - len(ids))
+        found = got["occ_offsets"][1:] != got["occ_offsets"][:-1]
+        ids = np.nonzero(~found & (got["read_flags"] == 0))[0].astype(np.uint32)
+        aligned = int(found.sum())
+        t1b = time.perf_counter()
+        res = api.single_dp_align(gi, q, lens, N, wpq, ids, sp, counts_only=True)
         t2 = time.perf_counter()
         return got, res, ids, (t1 - t0, t2 - t1b, t1b - t1), aligned
 
@@ -816,14 +669,11 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
         return
     t_total = float(tt[0])
     K = args.steps
-    unit = "reads" if se_mode else "pairs"
+    unit = "reads"
     value = world * N * K / t_total
     name = (f"se_{L}bp_indels_genome{args.genome_bp}bp: per step and GPU {N} reads (1 % substitutions, 0.15 % indels) through the long-read search chain "
-            "(first 100 bases, k<=2, validateAlignments) and single-read DP from seeds for the rest") if se_mode else \
-           (f"pe_2x{L}bp_insert{INSERT_LO}-{INSERT_HI}_genome{args.genome_bp}bp + deep DP: per step and GPU {args.pairs} read pairs through s3_pe_align and, for the "
-            "pairs with no occurrence of either read, deep DP from seeds (two rounds, left read then right read)")
-    out = {"metric": ("reads/s aligned (SE 150 bp with indels, search + single-read DP, 3.1 Gbp synth ref)" if se_mode else
-                      "reads/s aligned (2x100bp PE + deep DP for both-unaligned pairs, 3.1 Gbp synth ref)"),
+            "(first 100 bases, k<=2, validateAlignments) and single-read DP from seeds for the rest")
+    out = {"metric": "reads/s aligned (SE 150 bp with indels, search + single-read DP, 3.1 Gbp synth ref)",
            "value": value, "unit": "reads/s", "n_gpus": world, "steps": K, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / K,
            "value_one_batch_in_flight": world * N * K / t_one, "ms_per_step_one_batch_in_flight": 1e3 * t_one / K,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32", "data": "synthetic",
@@ -838,9 +688,9 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
            "e2e": {"value": value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d / K), "d2h_bytes_per_step": int(d2h / K), "ms_per_step": 1e3 * t_total / K,
                    "note": "h2d / d2h count the chain's transfers; the seeded stage moves its own seed, candidate and window arrays"},
            "gpu_launches": int(launches),
-           "stages_ms_per_step": {"search chain (s3_se_align long-read mode)" if se_mode else "s3_pe_align": 1e3 * t_chain / K,
+           "stages_ms_per_step": {"search chain (s3_se_align long-read mode)": 1e3 * t_chain / K,
                                   "picking the reads that go on (host, numpy)": 1e3 * t_pick / K,
-                                  "s3_single_dp_align" if se_mode else "s3_deep_dp_align": 1e3 * t_stage / K},
+                                  "s3_single_dp_align": 1e3 * t_stage / K},
            "pipeline": {f"{unit}_aligned_by_the_chain_per_step": n_aligned / K, f"{unit}_sent_to_the_seeded_stage_per_step": n_ids / K,
                         "seeds_per_step": n_seeds / K, "candidates_per_step": n_cand / K, "stage_alignments_per_step": n_hits / K,
                         f"{unit}_without_a_candidate_per_step": n_unseeded / K},
@@ -848,41 +698,40 @@ def run_stage_config(args, gi, host, genome, device, local_rank, rank, world, th
     if world == 1 and not args.no_cpu_baseline:
         # parity of a sample at full size: the chain and the seeded stage against the compositions of the oracles
         import helpers
-        out["parity_at_full_size"], (m, rd, qm, lens_m, hi) = stage_parity(args, gi, host, genome, L, wpq, sets[-1][2], sp, se_mode)
+        out["parity_at_full_size"], (m, rd, qm, lens_m, hi) = stage_parity(args, gi, host, genome, L, wpq, sets[-1][2], sp, True)
         log("seeded stage parity at full size:", out["parity_at_full_size"])
-        if se_mode:
-            # and the long-read chain of the same sample against the reference's CPU search of the seeds + the validation oracle
-            ref_c = ref_cpu_handle(host, threads)
-            if ref_c is not None:
-                seeds = np.ascontiguousarray(np.stack(rd)[:, :100])
-                hits = ref_c.search(seeds, K_MISMATCH, formats.NUM_CASES[K_MISMATCH], MAX_OUTPUT_PER_READ, threads, out_cap=64)["hits"]
-                al = api.SingleAligner(gi, m, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True)
-                g2 = al.align(qm, lens_m, m, wpq)
-                al.free()
-                pac = host["pac"]
-                olib = helpers.load_oracle()
-                ok = cmp = 0
-                for r in range(m):
-                    if len(hits[r]) >= 64 or int(g2["read_flags"][r]):
-                        continue
-                    a, b2 = int(g2["occ_offsets"][r]), int(g2["occ_offsets"][r + 1])
-                    mine = sorted((int(p), int(f[0]), int(f[1])) for p, f in zip(g2["positions"][a:b2], g2["occ_flags"][a:b2]))
-                    hp = [h[0] for h in hits[r]]; hs = [h[1] for h in hits[r]]; hm = [h[2] for h in hits[r]]
-                    vp, vs, vm = helpers.validate_one(olib.s3o_validate_one, pac, hi.n, rd[r], 100, hp, hs, hm, 0, 0, int(np.ceil(0.02 * L)), MAX_OUTPUT_PER_READ)
-                    cmp += 1
-                    ok += mine == sorted(zip(vp, vs, vm))
-                out["parity_at_full_size"]["long_read_chain_vs_reference_cpu_search"] = {"reads_compared": cmp, "equal": ok, "bit_exact": bool(ok == cmp)}
-                log("long-read chain vs the reference's CPU search + validation oracle:", out["parity_at_full_size"]["long_read_chain_vs_reference_cpu_search"])
-                # CPU baseline of this config's search leg: the reference's CPU search of the 100-base seeds
-                nb = min(args.cpu_sample // 2, N)
-                sd = np.ascontiguousarray(sets[0][2][:nb, :100])
-                t0 = time.perf_counter()
-                res = ref_c.search(sd, K_MISMATCH, formats.NUM_CASES[K_MISMATCH], MAX_OUTPUT_PER_READ, threads)
-                tcs = time.perf_counter() - t0
-                out["cpu_baseline"] = {"value": nb / tcs, "unit": "reads/s", "cores": threads, "kind": "reference", "cpu_model": cpu_model(),
-                                       "sample": f"{nb} reads: the reference's CPU search (ProcessReadDoubleStrand2) of the first 100 bases, k<=2, both strands; "
-                                                 "the validation and the seeded DP stage are not included (the reference has no CPU DP)",
-                                       "reads_with_a_hit": int((res["counts"][:, 3] > 0).sum())}
+        # and the long-read chain of the same sample against the reference's CPU search of the seeds + the validation oracle
+        ref_c = ref_cpu_handle(host, threads)
+        if ref_c is not None:
+            seeds = np.ascontiguousarray(np.stack(rd)[:, :100])
+            hits = ref_c.search(seeds, K_MISMATCH, formats.NUM_CASES[K_MISMATCH], MAX_OUTPUT_PER_READ, threads, out_cap=64)["hits"]
+            al = api.SingleAligner(gi, m, num_mismatch=K_MISMATCH, max_output_per_read=MAX_OUTPUT_PER_READ, long_read_mode=True)
+            g2 = al.align(qm, lens_m, m, wpq)
+            al.free()
+            pac = host["pac"]
+            olib = helpers.load_oracle()
+            ok = cmp = 0
+            for r in range(m):
+                if len(hits[r]) >= 64 or int(g2["read_flags"][r]):
+                    continue
+                a, b2 = int(g2["occ_offsets"][r]), int(g2["occ_offsets"][r + 1])
+                mine = sorted((int(p), int(f[0]), int(f[1])) for p, f in zip(g2["positions"][a:b2], g2["occ_flags"][a:b2]))
+                hp = [h[0] for h in hits[r]]; hs = [h[1] for h in hits[r]]; hm = [h[2] for h in hits[r]]
+                vp, vs, vm = helpers.validate_one(olib.s3o_validate_one, pac, hi.n, rd[r], 100, hp, hs, hm, 0, 0, int(np.ceil(0.02 * L)), MAX_OUTPUT_PER_READ)
+                cmp += 1
+                ok += mine == sorted(zip(vp, vs, vm))
+            out["parity_at_full_size"]["long_read_chain_vs_reference_cpu_search"] = {"reads_compared": cmp, "equal": ok, "bit_exact": bool(ok == cmp)}
+            log("long-read chain vs the reference's CPU search + validation oracle:", out["parity_at_full_size"]["long_read_chain_vs_reference_cpu_search"])
+            # CPU baseline of this config's search leg: the reference's CPU search of the 100-base seeds
+            nb = min(args.cpu_sample // 2, N)
+            sd = np.ascontiguousarray(sets[0][2][:nb, :100])
+            t0 = time.perf_counter()
+            res = ref_c.search(sd, K_MISMATCH, formats.NUM_CASES[K_MISMATCH], MAX_OUTPUT_PER_READ, threads)
+            tcs = time.perf_counter() - t0
+            out["cpu_baseline"] = {"value": nb / tcs, "unit": "reads/s", "cores": threads, "kind": "reference", "cpu_model": cpu_model(),
+                                   "sample": f"{nb} reads: the reference's CPU search (ProcessReadDoubleStrand2) of the first 100 bases, k<=2, both strands; "
+                                             "the validation and the seeded DP stage are not included (the reference has no CPU DP)",
+                                   "reads_with_a_hit": int((res["counts"][:, 3] > 0).sum())}
     print(json.dumps(out), flush=True)
     for ch, g in reversed(handles):                               # clones are freed before the handle they were made from
         ch.free()

@@ -188,6 +188,9 @@ def main():
         old_path = os.path.join(PROF, "ncu_traffic.json")
         keep = json.load(open(old_path)).get("random_sector_probe_dram_bytes_per_load") if os.path.exists(old_path) else None
         traffic["random_sector_probe_dram_bytes_per_load"] = keep or 120.6
+        k4 = json.load(open(old_path)).get("search_launch_k4") if os.path.exists(old_path) else None
+        if k4 and "search_launch_k4" not in traffic:
+            traffic["search_launch_k4"] = k4                        # (from the capture of the k <= 4 launch, kept across chain captures)
         json.dump(traffic, open(os.path.join(PROF, "ncu_traffic.json"), "w"), indent=1)      # bench.py's roofline.traffic
     open(os.path.join(PROF, f"{tag}_summary.md"), "w").write("\n".join(md) + "\n")
     print("\n".join(md))

@@ -332,7 +332,7 @@ extern "C" int s3_index_upload(const uint32_t *bwt, const uint32_t *occ, const u
 // bases per byte in n / 4 + 1 bytes, then one byte = n % 4, the bases the byte before it holds (TextConverter.c:666-720) -- and hands the mappings to
 // s3_index_upload: no copy of the files is made on the host (the packed text, 0.25 byte per base, is the exception: its bytes are
 // turned into the big-endian words of hsp->packedDNA).  The mappings are page-locked for the upload when the driver allows it
-// (cudaHostRegisterReadOnly), so that the copies run at the link's rate.
+// (cudaHostRegister of a private mapping), so that the copies run at the link's rate.
 #include <fcntl.h>
 #include <sys/mman.h>
 #include <sys/stat.h>
@@ -350,12 +350,14 @@ int map_file(const std::string &path, S3Mapped *m)
     if (fd < 0) { s3_set_error("s3_index_load: cannot open %s", path.c_str()); return S3_EINVAL; }
     struct stat st;
     if (fstat(fd, &st) != 0 || st.st_size < 20) { close(fd); s3_set_error("s3_index_load: %s is too short", path.c_str()); return S3_EINVAL; }
-    void *p = mmap(NULL, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+    // a private, writable mapping (never written: no page is ever copied): the driver page-locks those, read-only file mappings it refuses
+    void *p = mmap(NULL, (size_t)st.st_size, PROT_READ | PROT_WRITE, MAP_PRIVATE, fd, 0);
     close(fd);
     if (p == MAP_FAILED) { s3_set_error("s3_index_load: mmap of %s failed", path.c_str()); return S3_ENOMEM; }
     m->words = (const uint32_t *)p; m->bytes = (size_t)st.st_size;
-    if (cudaHostRegister(p, m->bytes, cudaHostRegisterReadOnly | cudaHostRegisterPortable) == cudaSuccess) m->registered = 1;
-    else cudaGetLastError();
+    if (cudaHostRegister(p, m->bytes, cudaHostRegisterPortable) == cudaSuccess) m->registered = 1;
+    else cudaGetLastError();                          // not page-locked: the copies still work, staged by the driver
+    if (getenv("S3_INDEX_LOAD_VERBOSE")) fprintf(stderr, "[s3_index_load] %s: %zu bytes mapped, %s\n", path.c_str(), m->bytes, m->registered ? "page-locked" : "not page-locked");
     return S3_OK;
 }
 void unmap_file(S3Mapped *m)

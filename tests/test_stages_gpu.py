@@ -191,12 +191,12 @@ def test_deep_dp_stage(env):
                 int(h["numSame1"]), int(h["numSame2"]), c1, c2) == w
 
 
-def test_deep_dp_of_the_chain(env):
+def deep_dp_of_the_chain(env, pairs=400, seed=21):
     """s3_pe_deep_dp (the both-unaligned pairs picked on the device, the chain's own query buffer) == s3_deep_dp_align of the pairs the
-    chain routed as S3_PE_NONE == the seeding oracle, after s3_pe_align and after s3_pe_align_device"""
+    chain routed as S3_PE_NONE == the seeding oracle, after s3_pe_align and after s3_pe_align_device; -> (pairs picked, paired alignments)"""
     G, idx, hi, gi = env
-    rng = np.random.default_rng(21)
-    L, pairs = 100, 400
+    rng = np.random.default_rng(seed)
+    L = 100
     m1, m2, _ = synth.simulate_paired_end(G, pairs, L, seed=31, bad_mate_fraction=0.0)
     raw = torch.stack([m1.reads, m2.reads], dim=1).reshape(2 * pairs, L).cpu().numpy()
     reads = [r.copy() for r in raw]
@@ -232,6 +232,11 @@ def test_deep_dp_of_the_chain(env):
         assert got["num_seeds"] == want["num_seeds"] and got["num_candidates"] == want["num_candidates"]
         assert got["unseeded"].tolist() == want["unseeded"].tolist()
         assert got["hits"].tobytes() == want["hits"].tobytes() and np.array_equal(got["runs"], want["runs"])
+    return len(ids), len(want["hits"])
+
+
+def test_deep_dp_of_the_chain(env):
+    deep_dp_of_the_chain(env)
 
 
 def test_stages_empty_and_bad_args(env):

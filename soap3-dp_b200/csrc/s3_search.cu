@@ -1176,12 +1176,16 @@ int s3_search_csr_device(s3_index *ix, const uint32_t *d_queries, const uint32_t
     size_t scanTemp = 0;
     cub::DeviceScan::ExclusiveSum(NULL, scanTemp, (unsigned long long *)NULL, (unsigned long long *)NULL, (int)(items + 1), st);
     void *d_tmp = NULL;
-    S3_CUDA(cudaMallocAsync(&d_tmp, scanTemp + 16, st));
-    S3_CUDA(cudaMemsetAsync(d_starts, 0, (items + 1) * 8, st));
     // the counting pass keeps the first S3_CSR_SLOT ranges of every item; the second pass enumerates only the items with more
     uint32_t *d_slot = NULL, *d_list = NULL;
-    S3_CUDA(cudaMallocAsync((void **)&d_slot, items * (3 * S3_CSR_SLOT) * 4, st));
-    S3_CUDA(cudaMallocAsync((void **)&d_list, (items + 4) * 4, st));
+    if (cudaMallocAsync(&d_tmp, scanTemp + 16, st) != cudaSuccess || cudaMallocAsync((void **)&d_slot, items * (3 * S3_CSR_SLOT) * 4, st) != cudaSuccess ||
+        cudaMallocAsync((void **)&d_list, (items + 4) * 4, st) != cudaSuccess || cudaMemsetAsync(d_starts, 0, (items + 1) * 8, st) != cudaSuccess) {
+        s3_set_error("s3_search: scratch for %zu items: %s", items, cudaGetErrorString(cudaGetLastError()));
+        if (d_tmp) cudaFreeAsync(d_tmp, st);
+        if (d_slot) cudaFreeAsync(d_slot, st);
+        if (d_list) cudaFreeAsync(d_list, st);
+        return S3_ECUDA;
+    }
     S3SearchArgs a;
     memset(&a, 0, sizeof a);
     a.queries = d_queries; a.readLengths = d_readLengths; a.numQueries = batchSize; a.wordPerQuery = wordPerQuery;

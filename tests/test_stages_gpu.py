@@ -248,3 +248,9 @@ def test_stages_empty_and_bad_args(env):
         api.deep_dp_align(gi, z, z[:32], 32, 8, np.array([3], np.uint32), api.stage_params())      # odd id
     with pytest.raises(api.S3Error):
         api.single_dp_align(gi, z, z[:32], 32, 8, np.array([40], np.uint32), api.stage_params())
+    pe = api.PairAligner(gi, 64, 100, api.pe_params(read_length=100))
+    try:
+        with pytest.raises(api.S3Error):
+            pe.deep_dp(api.stage_params())                             # no batch has been aligned on the handle
+    finally:
+        pe.free()

@@ -127,55 +127,3 @@ def test_sharded_results_come_back_in_input_order_gloo(tmp_path):
                          env=env, capture_output=True, text=True, timeout=240)
     assert "GLOO_OK" in out.stdout, out.stdout + out.stderr
 
-
-def test_bench_pairing_row_finds_the_simulated_pairs():
-    """bench.py's `pairing` row (answer slots -> s3_retain_best -> s3_locate -> s3_pair_occurrences) run with the oracles
-    standing in for the three library entries: the slot decoding, the strand convention and the CSR glue must bring
-    nearly every simulated FR pair back at its true positions."""
-    import importlib.util
-    import sys
-    import helpers
-    from helpers import HostIndex, load_oracle, oracle_launch
-    from soap3dp_b200 import fmindex, synth
-    spec = importlib.util.spec_from_file_location("bench_mod", os.path.join(helpers.ROOT, "bench.py"))
-    bench = importlib.util.module_from_spec(spec)
-    sys.modules["bench_mod"] = bench
-    spec.loader.exec_module(bench)
-    G = synth.random_genome(300_000, seed=77)
-    idx = fmindex.build_index(G)
-    hi = HostIndex(idx)
-    pairs, L, k = 600, 100, 2
-    m1, m2, _ = synth.simulate_paired_end(G, pairs, L, seed=5, insert_lo=200, insert_hi=500)
-    reads = np.stack([m1.reads.numpy(), m2.reads.numpy()], axis=1).reshape(2 * pairs, L)
-    true_pos = np.stack([m1.pos.numpy(), m2.pos.numpy()], axis=1).reshape(-1).astype(np.uint32)
-    n = 2 * pairs
-    wpq = formats.word_per_query(L)
-    lens = np.zeros(formats.ceil32(n), np.uint32)
-    lens[:n] = L
-    q = formats.pack_queries(reads, lens[:n], wpq)
-    allowed = formats.SA_RANGES_ROUND1[k]
-    wpa = 2 * allowed
-    olib = load_oracle()
-    bad = np.zeros(formats.ceil32(n), np.uint8)
-    views = []
-    for case in range(formats.NUM_CASES[k]):
-        a = np.zeros(formats.ceil32(n) * wpa, np.uint32)
-        oracle_launch(olib, hi, case, q, lens, n, wpq, a, bad, 0, k, allowed, wpa)
-        views.append(formats.answers_view(a, n, wpa))
-    sa = idx.fwd.sa.numpy().astype(np.uint32) if hasattr(idx.fwd.sa, "numpy") else np.asarray(idx.fwd.sa, np.uint32)
-
-    def locate(sa_l, sa_r, cap):
-        cnt = np.minimum(sa_r.astype(np.int64) - sa_l.astype(np.int64) + 1, cap)
-        off = np.zeros(len(sa_l) + 1, np.uint64)
-        off[1:] = np.cumsum(cnt)
-        pos = np.concatenate([sa[int(l):int(l) + int(c)] for l, c in zip(sa_l, cnt)]) if len(sa_l) else np.zeros(0, np.uint32)
-        return off, pos.astype(np.uint32)
-
-    row = bench.pairing_rows(views, allowed, n, L, true_pos,
-                             lambda mode, *a: helpers.oracle_retain_best(a[:9], mode, 0),
-                             locate,
-                             lambda *a: helpers.oracle_pair_occurrences(a[:8], a[8], a[9], a[10], a[11], a[12], a[13]))
-    assert row["read_pairs"] == pairs
-    assert row["pairs_with_both_mates_found"] > 0.55 * pairs          # <= 2 substitutions and no indel in both mates
-    assert row["pairs_with_a_valid_pairing"] > 0.95 * row["pairs_with_both_mates_found"]
-    assert row["optimal_pairing_at_the_true_positions"] > 0.9 * row["pairs_with_a_valid_pairing"]

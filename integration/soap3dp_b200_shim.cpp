@@ -250,3 +250,66 @@ void alignSingleR ( unsigned int * queries, unsigned int * readLengths, unsigned
     }
     GPUINDEXFree ( _bwt, _occ, _revBwt, _revOcc );
 }
+
+// ---- DV-DPForBothUnalign.cu:245 (DPForUnalignPairs2) / DV-DPfunctions.cu:3731-3826 --------------------------------------------
+// The deep-DP stage of a batch as the reference's own result records.  DPForUnalignPairs2 -> DeepDPWrapper::run2 seeds the pairs
+// without any alignment, aligns left read then right read, and DeepDP_Space::DP2CPUAlgnThread turns every candidate whose two reads
+// reach their cutoffs into a DeepDPAlignResult (PEAlgnmt.h:409-429) that outputDeepDPResult2 (OutputDPResult.cpp:564) writes out.
+// deepDPAlignResults runs the stage on the device (s3_deep_dp_align: seeds, seeding driver, candidate pairs, windows, DP, CIGAR runs)
+// and builds exactly those records, in the order the reference's engine emits them: a maintainer calls it from DPForUnalignPairs2
+// in place of deepDPWrapper.run2 () and hands the array to outputDeepDPResult2 unchanged.  cigarString_1 / _2 are malloc'ed like the
+// encoder's (the output code frees them); *unseeded receives the even read ids of the pairs without a candidate (outputUnaligned),
+// malloc'ed.  Returns the number of records.
+#include "PEAlgnmt.h"
+unsigned int deepDPAlignResults ( unsigned int * queries, unsigned int * upkdReadLengths, unsigned int numQueries, unsigned int wordPerQuery,
+                                  const unsigned int * pairReadIDs, unsigned int numPairs,
+                                  int insert_high, int insert_low, int peStrandLeftLeg, int peStrandRightLeg,
+                                  unsigned int * _bwt, DPParameters * dpParameters,
+                                  DeepDPAlignResult ** results, unsigned int ** unseeded, unsigned int * numUnseeded )
+{
+    s3_index * ix = ( s3_index * ) _bwt;
+    s3_stage_params st;
+    memset ( &st, 0, sizeof ( st ) );
+    st.insertLow = insert_low; st.insertHigh = insert_high; st.strandLeftLeg = peStrandLeftLeg; st.strandRightLeg = peStrandRightLeg;
+    st.scores.matchScore = dpParameters->matchScore; st.scores.mismatchScore = dpParameters->mismatchScore;
+    st.scores.gapOpenScore = dpParameters->openGapScore; st.scores.gapExtendScore = dpParameters->extendGapScore;
+    // getParameterForDeepDP (CPUfunctions.cpp:135-148): ceil(0.3 x read length) per read, or the ini's threshold for both reads
+    st.isDefaultThreshold = dpParameters->paramRead[0].cutoffThreshold <= 0;
+    st.dpScoreThreshold = dpParameters->paramRead[0].cutoffThreshold;
+    st.softClipLeft = dpParameters->softClipLeft; st.softClipRight = dpParameters->softClipRight;
+    s3_deep_dp_result d;
+    if ( s3_deep_dp_align ( ix, queries, upkdReadLengths, numQueries, wordPerQuery, pairReadIDs, numPairs, &st, &d ) != S3_OK ) { s3_die ( "DPForUnalignPairs2" ); }
+    DeepDPAlignResult * out = ( DeepDPAlignResult * ) calloc ( d.numHits ? d.numHits : 1, sizeof ( DeepDPAlignResult ) );
+    for ( unsigned long long h = 0; h < d.numHits; h++ )
+    {
+        const s3_deep_dp_hit & x = d.hits[h];
+        DeepDPAlignResult & r = out[h];
+        int32_t ed[2], dis[2];
+        char * cig[2];
+        const uint32_t * runs[2] = { d.runs + x.runOffset1, d.runs + x.runOffset2 };
+        const uint32_t nruns[2] = { x.numRuns1, x.numRuns2 };
+        const int32_t score[2] = { x.score1, x.score2 };
+        for ( int k = 0; k < 2; k++ )
+        {
+            const uint32_t cap = 12 * nruns[k] + 1;
+            cig[k] = ( char * ) malloc ( cap );
+            if ( s3_runs_decode ( runs[k], nruns[k], upkdReadLengths[x.readID + k], score[k], st.scores, cig[k], cap, NULL, &ed[k], &dis[k] ) != S3_OK ) { s3_die ( "DPForUnalignPairs2 (CIGAR)" ); }
+        }
+        r.readID = x.readID;
+        r.algnmt_1 = x.pos1; r.strand_1 = ( char ) x.strand1; r.score_1 = x.score1; r.editdist_1 = ed[0]; r.cigarString_1 = cig[0]; r.num_sameScore_1 = ( int ) x.numSame1;
+        r.algnmt_2 = x.pos2; r.strand_2 = ( char ) x.strand2; r.score_2 = x.score2; r.editdist_2 = ed[1]; r.cigarString_2 = cig[1]; r.num_sameScore_2 = ( int ) x.numSame2;
+        // DV-DPfunctions.cu:3810-3815: the length of the engine's batch entry is that of the left read; with reads of one length, as here
+        r.insertSize = r.algnmt_1 < r.algnmt_2 ? ( int ) ( r.algnmt_2 - r.algnmt_1 + upkdReadLengths[x.readID + 1] + dis[1] )
+                                                : ( int ) ( r.algnmt_1 - r.algnmt_2 + upkdReadLengths[x.readID] + dis[0] );
+    }
+    if ( unseeded )
+    {
+        *unseeded = ( unsigned int * ) malloc ( ( d.numUnseeded ? d.numUnseeded : 1 ) * sizeof ( unsigned int ) );
+        memcpy ( *unseeded, d.unseeded, d.numUnseeded * sizeof ( unsigned int ) );
+    }
+    if ( numUnseeded ) { *numUnseeded = ( unsigned int ) d.numUnseeded; }
+    const unsigned int n = ( unsigned int ) d.numHits;
+    s3_deep_dp_result_free ( &d );
+    *results = out;
+    return n;
+}

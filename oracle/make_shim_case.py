@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY.  Writes the inputs and the oracle's expected outputs for oracle/ref_shim/shim_check.cu (the
 executed check of the drop-in shim, integration/soap3dp_b200_shim.cpp) into oracle/_ref/shim_case/ as raw little-endian
 arrays: a 200 kbp index with close repeats, 2048 reads of 100 bp searched with <= 2 mismatches (round 1, four cases; round 2
-on the reads whose round-1 slot overflowed), and 512 mate-rescue DP alignments.  Run by oracle/build_ref.sh in the container that has /root/reference."""
+on the reads whose round-1 slot overflowed), 512 mate-rescue DP alignments, and 160 read pairs for the deep-DP stage.  Run by oracle/build_ref.sh in the container that has /root/reference."""
 import os
 import sys
 
@@ -83,6 +83,52 @@ sc, hit, cnt, pat, _ = helpers.oracle_dp(helpers.load_oracle_dp(), b)
 for name in ("dna", "dna_len", "read", "read_len", "cutoff", "clip_lt", "clip_rt", "anchor_l", "anchor_r"):
     save("dp_" + name, getattr(b, name))
 save("dp_scores", sc); save("dp_hit", hit); save("dp_cnt", cnt); save("dp_pattern", pat)
+# deepDPAlignResults (the shim's DPForUnalignPairs2 results): pairs whose reads are beyond the search, through oracle/seeding_oracle.deep_dp;
+# per record the DeepDPAlignResult fields as DeepDP_Space::DP2CPUAlgnThread fills them (DV-DPfunctions.cu:3755-3820)
+import re  # noqa: E402
+import torch  # noqa: E402
+import seeding_oracle  # noqa: E402
+from test_stages_gpu import OracleEnv, PAR, mutate  # noqa: E402
+rng = np.random.default_rng(29)
+dpairs = 160
+m1, m2, _ = synth.simulate_paired_end(G, dpairs, L, seed=31, bad_mate_fraction=0.0)
+raw = torch.stack([m1.reads, m2.reads], dim=1).reshape(2 * dpairs, L).cpu().numpy()
+dreads = [mutate(rng, r, int(rng.integers(3, 8)), int(rng.integers(0, 2))) for r in raw]
+dn = 2 * dpairs
+dlens = np.zeros(formats.ceil32(dn), np.uint32)
+dlens[:dn] = L
+save("deep_queries", formats.pack_queries(np.stack(dreads), dlens[:dn], wpq)); save("deep_lengths", dlens)
+dids = 2 * np.arange(dpairs, dtype=np.uint32)
+save("deep_ids", dids)
+want = seeding_oracle.deep_dp(OracleEnv(idx, hi), G.cpu().numpy(), dreads, dids.tolist(), PAR)
+MATCH, MISM, OPEN, EXT = PAR["scores"]
+
+
+def edit(cigar, score):
+    ops = {c: 0 for c in "MmIDS"}
+    gap = 0
+    for cnt, op in re.findall(r"(\d+)([MmIDS])", cigar):
+        ops[op] += int(cnt)
+        if op in "ID":
+            gap += OPEN + (int(cnt) - 1) * EXT
+    mism = int(((L - ops["I"] - ops["S"]) * MATCH + gap - score) / (MATCH - MISM))
+    return ops["I"] + ops["D"] + mism, ops["D"] - ops["I"] - ops["S"]
+
+
+rec, cig, cigoff = [], b"", [0]
+for (rid, s1, s2, p1, p2, sc1, sc2, ns1, ns2, c1, c2) in want["hits"]:
+    e1, d1 = edit(c1, sc1)
+    e2, d2 = edit(c2, sc2)
+    ins = (p2 - p1 + L + d2) if p1 < p2 else (p1 - p2 + L + d1)
+    rec.append([rid, ins, p1, s1, sc1, e1, ns1, p2, s2, sc2, e2, ns2])
+    for c in (c1, c2):
+        cig += c.encode()
+        cigoff.append(len(cig))
+save("deep_records", np.array(rec, np.int64).astype(np.int32)); save("deep_cigars", np.frombuffer(cig, np.uint8)); save("deep_cigar_off", np.array(cigoff, np.uint32))
+save("deep_unseeded", np.array(want["unseeded"], np.uint32))
+with open(os.path.join(out, "deep_meta.txt"), "w") as f:
+    f.write(f"{dn} {dpairs} {len(rec)} {len(want['unseeded'])}\n")
+print(f"[make_shim_case] deep DP: {dpairs} pairs -> {len(rec)} DeepDPAlignResult records, {len(want['unseeded'])} pairs without a candidate")
 with open(os.path.join(out, "meta.txt"), "w") as f:
     f.write(f"{hi.n} {hi.isa0} {hi.risa0} {len(hi.bwt)} {len(hi.occ)} {n} {wpq} {k} {formats.NUM_CASES[k]} {allowed} {wpa} "
             f"{m} {b.max_read} {b.max_dna} {b.pat_len} {allowed2} {wpa2}\n")

@@ -13,6 +13,12 @@
 #include "alignment.h"
 #include "DV-DPfunctions.h"
 #include "soap3-dp-module.h"
+#include "PEAlgnmt.h"
+
+/* defined by the shim (integration/soap3dp_b200_shim.cpp): the results of the deep-DP stage as the reference's own records */
+unsigned int deepDPAlignResults ( unsigned int * queries, unsigned int * upkdReadLengths, unsigned int numQueries, unsigned int wordPerQuery,
+                                  const unsigned int * pairReadIDs, unsigned int numPairs, int insert_high, int insert_low, int peStrandLeftLeg, int peStrandRightLeg,
+                                  unsigned int * _bwt, DPParameters * dpParameters, DeepDPAlignResult ** results, unsigned int ** unseeded, unsigned int * numUnseeded );
 
 template <class T> static std::vector<T> load(const std::string &dir, const char *name)
 {
@@ -190,6 +196,41 @@ int main(int argc, char **argv)
                bad ? "FAIL" : "PASS", n, aligned, overflow, res->occTotalNum, numOfAnswer, numOfAlignedRead, bad);
         fails += bad != 0;
         resultArraysFree(arr);
+    }
+    /* deepDPAlignResults (the shim's results of DPForUnalignPairs2, DV-DPForBothUnalign.cu:245): DeepDPAlignResult records as the reference's
+       engine builds them, against oracle/seeding_oracle.deep_dp */
+    {
+        unsigned dn = 0, dpairs = 0, nrec = 0, nuns = 0;
+        FILE *f = fopen((dir + "/deep_meta.txt").c_str(), "r");
+        if (!f || fscanf(f, "%u %u %u %u", &dn, &dpairs, &nrec, &nuns) != 4) { printf("FAIL deep_meta.txt\n"); return 2; }
+        fclose(f);
+        std::vector<uint> dq = load<uint>(dir, "deep_queries"), dl = load<uint>(dir, "deep_lengths"), ids = load<uint>(dir, "deep_ids");
+        std::vector<int> rec = load<int>(dir, "deep_records");
+        std::vector<uchar> cig = load<uchar>(dir, "deep_cigars");
+        std::vector<uint> coff = load<uint>(dir, "deep_cigar_off"), wuns = load<uint>(dir, "deep_unseeded");
+        uint *_b, *_o, *_rb, *_ro;
+        GPUINDEXUpload(&index, &_b, &_o, &_rb, &_ro);
+        DPParameters dpp; memset(&dpp, 0, sizeof dpp);
+        dpp.matchScore = 1; dpp.mismatchScore = -2; dpp.openGapScore = -3; dpp.extendGapScore = -1; dpp.softClipLeft = 3; dpp.softClipRight = 8;
+        dpp.paramRead[0].cutoffThreshold = dpp.paramRead[1].cutoffThreshold = 0;          /* default: ceil(0.3 x read length) */
+        DeepDPAlignResult *res = NULL; unsigned int *uns = NULL, gotUns = 0;
+        unsigned int got = deepDPAlignResults(dq.data(), dl.data(), dn, wpq, ids.data(), dpairs, 500, 200, 1, 2, _b, &dpp, &res, &uns, &gotUns);
+        size_t bad = (got != nrec) + (gotUns != nuns);
+        for (unsigned h = 0; h < got && h < nrec; ++h) {
+            const int *w = rec.data() + 12 * (size_t)h;
+            const DeepDPAlignResult &r = res[h];
+            const std::string c1((const char *)cig.data() + coff[2 * h], coff[2 * h + 1] - coff[2 * h]), c2((const char *)cig.data() + coff[2 * h + 1], coff[2 * h + 2] - coff[2 * h + 1]);
+            bad += (int)r.readID != w[0] || r.insertSize != w[1] || (int)r.algnmt_1 != w[2] || r.strand_1 != w[3] || r.score_1 != w[4] || r.editdist_1 != w[5] || r.num_sameScore_1 != w[6] ||
+                   (int)r.algnmt_2 != w[7] || r.strand_2 != w[8] || r.score_2 != w[9] || r.editdist_2 != w[10] || r.num_sameScore_2 != w[11] ||
+                   c1 != r.cigarString_1 || c2 != r.cigarString_2;
+        }
+        for (unsigned u = 0; u < gotUns && u < nuns; ++u) bad += uns[u] != wuns[u];
+        printf("%s deepDPAlignResults (DPForUnalignPairs2): %u pairs, %u DeepDPAlignResult records (position, strand, score, edit distance, ties, CIGAR of both reads, insert size), "
+               "%u pairs without a candidate, %zu differences\n", bad ? "FAIL" : "PASS", dpairs, got, gotUns, bad);
+        fails += bad != 0;
+        for (unsigned h = 0; h < got; ++h) { free(res[h].cigarString_1); free(res[h].cigarString_2); }
+        free(res); free(uns);
+        GPUINDEXFree(_b, _o, _rb, _ro);
     }
     printf("%s drop-in shim executed through the reference's declarations\n", fails ? "FAIL" : "PASS");
     return fails ? 1 : 0;

@@ -313,3 +313,48 @@ unsigned int deepDPAlignResults ( unsigned int * queries, unsigned int * upkdRea
     *results = out;
     return n;
 }
+
+// ---- DV-DPForSingleReads.cu:155 (DPForUnalignSingle2) / DV-DPfunctions.cu:1682-1740 -------------------------------------------
+// The single-read DP stage of a batch as the reference's own result records: SingleDP_Space::algnmtCPUThread turns every candidate
+// that reaches the cutoff into a SingleAlgnmtResult (PEAlgnmt.h:434-445) for outputDPSingleResult2 (OutputDPResult.cpp:937).
+// singleDPAlignResults runs the stage on the device (s3_single_dp_align) and builds those records in the engine's order; a
+// maintainer calls it from DPForUnalignSingle2 in place of singleDPWrapper.run ().  cigarString is malloc'ed like the encoder's;
+// *unseeded receives the ids of the reads without a candidate, malloc'ed.  Returns the number of records.
+unsigned int singleDPAlignResults ( unsigned int * queries, unsigned int * upkdReadLengths, unsigned int numQueries, unsigned int wordPerQuery,
+                                    const unsigned int * readIDs, unsigned int numReads,
+                                    unsigned int * _bwt, DPParameters * dpParameters,
+                                    SingleAlgnmtResult ** results, unsigned int ** unseeded, unsigned int * numUnseeded )
+{
+    s3_index * ix = ( s3_index * ) _bwt;
+    s3_stage_params st;
+    memset ( &st, 0, sizeof ( st ) );
+    st.strandLeftLeg = 1; st.strandRightLeg = 2;
+    st.scores.matchScore = dpParameters->matchScore; st.scores.mismatchScore = dpParameters->mismatchScore;
+    st.scores.gapOpenScore = dpParameters->openGapScore; st.scores.gapExtendScore = dpParameters->extendGapScore;
+    st.isDefaultThreshold = dpParameters->paramRead[0].cutoffThreshold <= 0;                  // getParameterForSingleDP, CPUfunctions.cpp:190-260
+    st.dpScoreThreshold = dpParameters->paramRead[0].cutoffThreshold;
+    st.softClipLeft = dpParameters->softClipLeft; st.softClipRight = dpParameters->softClipRight;
+    s3_single_dp_result d;
+    if ( s3_single_dp_align ( ix, queries, upkdReadLengths, numQueries, wordPerQuery, readIDs, numReads, &st, &d ) != S3_OK ) { s3_die ( "DPForUnalignSingle2" ); }
+    SingleAlgnmtResult * out = ( SingleAlgnmtResult * ) calloc ( d.numHits ? d.numHits : 1, sizeof ( SingleAlgnmtResult ) );
+    for ( unsigned long long h = 0; h < d.numHits; h++ )
+    {
+        const s3_dp_hit & x = d.hits[h];
+        SingleAlgnmtResult & r = out[h];
+        int32_t ed = 0;
+        const uint32_t cap = 12 * x.numRuns + 1;
+        char * cig = ( char * ) malloc ( cap );
+        if ( s3_runs_decode ( d.runs + x.runOffset, x.numRuns, upkdReadLengths[x.readID], x.score, st.scores, cig, cap, NULL, &ed, NULL ) != S3_OK ) { s3_die ( "DPForUnalignSingle2 (CIGAR)" ); }
+        r.readID = x.readID; r.strand = ( char ) x.strand; r.algnmt = x.pos; r.score = x.score; r.cigarString = cig; r.editdist = ed; r.num_sameScore = ( int ) x.numSameScore;
+    }
+    if ( unseeded )
+    {
+        *unseeded = ( unsigned int * ) malloc ( ( d.numUnseeded ? d.numUnseeded : 1 ) * sizeof ( unsigned int ) );
+        memcpy ( *unseeded, d.unseeded, d.numUnseeded * sizeof ( unsigned int ) );
+    }
+    if ( numUnseeded ) { *numUnseeded = ( unsigned int ) d.numUnseeded; }
+    const unsigned int n = ( unsigned int ) d.numHits;
+    s3_single_dp_result_free ( &d );
+    *results = out;
+    return n;
+}

@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY.  Writes the inputs and the oracle's expected outputs for oracle/ref_shim/shim_check.cu (the
 executed check of the drop-in shim, integration/soap3dp_b200_shim.cpp) into oracle/_ref/shim_case/ as raw little-endian
 arrays: a 200 kbp index with close repeats, 2048 reads of 100 bp searched with <= 2 mismatches (round 1, four cases; round 2
-on the reads whose round-1 slot overflowed), 512 mate-rescue DP alignments, and 160 read pairs for the deep-DP stage.  Run by oracle/build_ref.sh in the container that has /root/reference."""
+on the reads whose round-1 slot overflowed), 512 mate-rescue DP alignments, 160 read pairs for the deep-DP stage and 300 reads of 150 bases for the single-read DP stage.  Run by oracle/build_ref.sh in the container that has /root/reference."""
 import os
 import sys
 
@@ -129,6 +129,34 @@ save("deep_unseeded", np.array(want["unseeded"], np.uint32))
 with open(os.path.join(out, "deep_meta.txt"), "w") as f:
     f.write(f"{dn} {dpairs} {len(rec)} {len(want['unseeded'])}\n")
 print(f"[make_shim_case] deep DP: {dpairs} pairs -> {len(rec)} DeepDPAlignResult records, {len(want['unseeded'])} pairs without a candidate")
+# singleDPAlignResults (the shim's DPForUnalignSingle2 results): 150-base reads with indels through oracle/seeding_oracle.single_dp;
+# per record the SingleAlgnmtResult fields as SingleDP_Space::algnmtCPUThread fills them (DV-DPfunctions.cu:1699-1733)
+SL, sn = 150, 300
+srs = synth.simulate_single_end(G, sn, SL, seed=37, sub_rate=0.0)
+sreads = [mutate(rng, r, int(rng.integers(3, 9)), int(rng.integers(0, 3))) for r in srs.reads.numpy()]
+swpq = formats.word_per_query(SL)
+slens = np.zeros(formats.ceil32(sn), np.uint32)
+slens[:sn] = SL
+save("sdp_queries", formats.pack_queries(np.stack(sreads), slens[:sn], swpq)); save("sdp_lengths", slens)
+sids = np.arange(sn, dtype=np.uint32)
+swant = seeding_oracle.single_dp(OracleEnv(idx, hi), G.cpu().numpy(), sreads, sids.tolist(), PAR)
+srec, scig, scoff = [], b"", [0]
+for (rid, st_, pos, sc_, same, cg) in swant["hits"]:
+    ops = {c: 0 for c in "MmIDS"}
+    gap = 0
+    for cnt, op in re.findall(r"(\d+)([MmIDS])", cg):
+        ops[op] += int(cnt)
+        if op in "ID":
+            gap += OPEN + (int(cnt) - 1) * EXT
+    mism = int(((SL - ops["I"] - ops["S"]) * MATCH + gap - sc_) / (MATCH - MISM))
+    srec.append([rid, st_, pos, sc_, ops["I"] + ops["D"] + mism, same])
+    scig += cg.encode()
+    scoff.append(len(scig))
+save("sdp_records", np.array(srec, np.int64).astype(np.int32)); save("sdp_cigars", np.frombuffer(scig, np.uint8)); save("sdp_cigar_off", np.array(scoff, np.uint32))
+save("sdp_unseeded", np.array(swant["unseeded"], np.uint32))
+with open(os.path.join(out, "sdp_meta.txt"), "w") as f:
+    f.write(f"{sn} {swpq} {len(srec)} {len(swant['unseeded'])}\n")
+print(f"[make_shim_case] single-read DP: {sn} reads of {SL} bases -> {len(srec)} SingleAlgnmtResult records, {len(swant['unseeded'])} reads without a candidate")
 with open(os.path.join(out, "meta.txt"), "w") as f:
     f.write(f"{hi.n} {hi.isa0} {hi.risa0} {len(hi.bwt)} {len(hi.occ)} {n} {wpq} {k} {formats.NUM_CASES[k]} {allowed} {wpa} "
             f"{m} {b.max_read} {b.max_dna} {b.pat_len} {allowed2} {wpa2}\n")

@@ -15,7 +15,10 @@
 #include "soap3-dp-module.h"
 #include "PEAlgnmt.h"
 
-/* defined by the shim (integration/soap3dp_b200_shim.cpp): the results of the deep-DP stage as the reference's own records */
+/* defined by the shim (integration/soap3dp_b200_shim.cpp): the results of the two seeded DP stages as the reference's own records */
+unsigned int singleDPAlignResults ( unsigned int * queries, unsigned int * upkdReadLengths, unsigned int numQueries, unsigned int wordPerQuery,
+                                    const unsigned int * readIDs, unsigned int numReads, unsigned int * _bwt, DPParameters * dpParameters,
+                                    SingleAlgnmtResult ** results, unsigned int ** unseeded, unsigned int * numUnseeded );
 unsigned int deepDPAlignResults ( unsigned int * queries, unsigned int * upkdReadLengths, unsigned int numQueries, unsigned int wordPerQuery,
                                   const unsigned int * pairReadIDs, unsigned int numPairs, int insert_high, int insert_low, int peStrandLeftLeg, int peStrandRightLeg,
                                   unsigned int * _bwt, DPParameters * dpParameters, DeepDPAlignResult ** results, unsigned int ** unseeded, unsigned int * numUnseeded );
@@ -229,6 +232,40 @@ int main(int argc, char **argv)
                "%u pairs without a candidate, %zu differences\n", bad ? "FAIL" : "PASS", dpairs, got, gotUns, bad);
         fails += bad != 0;
         for (unsigned h = 0; h < got; ++h) { free(res[h].cigarString_1); free(res[h].cigarString_2); }
+        free(res); free(uns);
+        GPUINDEXFree(_b, _o, _rb, _ro);
+    }
+    /* singleDPAlignResults (the shim's results of DPForUnalignSingle2, DV-DPForSingleReads.cu:155): SingleAlgnmtResult records as the reference's
+       engine builds them, against oracle/seeding_oracle.single_dp */
+    {
+        unsigned sn = 0, swpq = 0, nrec = 0, nuns = 0;
+        FILE *f = fopen((dir + "/sdp_meta.txt").c_str(), "r");
+        if (!f || fscanf(f, "%u %u %u %u", &sn, &swpq, &nrec, &nuns) != 4) { printf("FAIL sdp_meta.txt\n"); return 2; }
+        fclose(f);
+        std::vector<uint> sq = load<uint>(dir, "sdp_queries"), sl = load<uint>(dir, "sdp_lengths");
+        std::vector<int> rec = load<int>(dir, "sdp_records");
+        std::vector<uchar> cig = load<uchar>(dir, "sdp_cigars");
+        std::vector<uint> coff = load<uint>(dir, "sdp_cigar_off"), wuns = load<uint>(dir, "sdp_unseeded");
+        std::vector<uint> ids(sn);
+        for (unsigned q = 0; q < sn; ++q) ids[q] = q;
+        uint *_b, *_o, *_rb, *_ro;
+        GPUINDEXUpload(&index, &_b, &_o, &_rb, &_ro);
+        DPParameters dpp; memset(&dpp, 0, sizeof dpp);
+        dpp.matchScore = 1; dpp.mismatchScore = -2; dpp.openGapScore = -3; dpp.extendGapScore = -1; dpp.softClipLeft = 3; dpp.softClipRight = 8;
+        SingleAlgnmtResult *res = NULL; unsigned int *uns = NULL, gotUns = 0;
+        unsigned int got = singleDPAlignResults(sq.data(), sl.data(), sn, swpq, ids.data(), sn, _b, &dpp, &res, &uns, &gotUns);
+        size_t bad = (got != nrec) + (gotUns != nuns);
+        for (unsigned h = 0; h < got && h < nrec; ++h) {
+            const int *w = rec.data() + 6 * (size_t)h;
+            const SingleAlgnmtResult &r = res[h];
+            const std::string c((const char *)cig.data() + coff[h], coff[h + 1] - coff[h]);
+            bad += (int)r.readID != w[0] || r.strand != w[1] || (int)r.algnmt != w[2] || r.score != w[3] || r.editdist != w[4] || r.num_sameScore != w[5] || c != r.cigarString;
+        }
+        for (unsigned u = 0; u < gotUns && u < nuns; ++u) bad += uns[u] != wuns[u];
+        printf("%s singleDPAlignResults (DPForUnalignSingle2): %u reads, %u SingleAlgnmtResult records (position, strand, score, edit distance, ties, CIGAR), "
+               "%u reads without a candidate, %zu differences\n", bad ? "FAIL" : "PASS", sn, got, gotUns, bad);
+        fails += bad != 0;
+        for (unsigned h = 0; h < got; ++h) free(res[h].cigarString);
         free(res); free(uns);
         GPUINDEXFree(_b, _o, _rb, _ro);
     }

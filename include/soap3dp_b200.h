@@ -10,8 +10,16 @@
  *
  * There is no CPU fallback: if no CUDA device is usable the calls fail.  A few
  * entries replace code that runs on the host in the reference as well and are
- * host code here too (no device involved): s3_dp_decode, s3_dp_md,
- * s3_seed_layout, s3_dp_stage_parameters, s3_mapq_*.
+ * host code here too (no device involved): s3_dp_decode, s3_runs_decode,
+ * s3_dp_md, s3_seed_layout, s3_dp_stage_parameters, s3_mapq_*, s3_sam_*.
+ *
+ * Sections, in the order of a batch's way through the aligner: index
+ * (s3_index_upload / _load / _clone), search (s3_search_round1 / round2,
+ * the capless s3_search, the seeding driver s3_seed_search), locate and the
+ * seed-hit merges, DP (s3_dp_*, window selection), decoders, the chains
+ * (s3_pe_* = alignPairR with s3_pe_deep_dp, s3_se_* = alignSingleR), the
+ * seeded DP stages (s3_single_dp_align, s3_deep_dp_align), stage tables,
+ * mapping qualities, measurement hooks, SAM records.
  */
 #ifndef SOAP3DP_B200_H
 #define SOAP3DP_B200_H

@@ -860,6 +860,10 @@ int s3_sam_unpaired_dp_records(const s3_sam_genome *genome, const s3_sam_config 
  * (noAnsOutputSAMAPI, :5829-5855, the read without any alignment, is s3_sam_single_record with numOcc 0.) */
 int s3_sam_single_answer_record(const s3_sam_genome *genome, const s3_sam_config *config, uint32_t ambPosition, int32_t strand, int32_t numMismatch, int32_t bestHitNum,
                                 const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName, s3_sam_record *out);
+/* The text line samwrite prints for a record in a SAM file: bam_format1 (samtools-0.1.18/bam.c:243-329) -- QNAME FLAG RNAME POS MAPQ CIGAR
+ * RNEXT ('=' on the same chromosome) PNEXT TLEN SEQ QUAL (+ 33) and the tags as TAG:TYPE:VALUE, tab-separated, no newline.  *line is
+ * malloc'ed (s3_free). */
+int s3_sam_format_line(const s3_sam_record *record, const char *const *chrNames, uint32_t numChr, char **line);
 
 #ifdef __cplusplus
 }

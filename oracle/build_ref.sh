@@ -174,12 +174,15 @@ echo "[build_ref] libref_validate.so OK"
 sed -e '58s/^}/    return 0;\n}/' -e '70s/^}/    return 0;\n}/' -e '80s/^}/    return 0;\n}/' "$REF/SAM.cpp" > "$OUT/patched/SAM.cpp"
 sed -n '24,41p' "$REF/samtools-0.1.18/bam_import.c" > "$OUT/patched/sam_nt16.inc"
 sed -n '3014,3019p' "$REF/CPUfunctions.cpp" > "$OUT/patched/sam_bwase.inc"
+# the text formatter of a record (what samwrite prints into a SAM file): bam_format1_core cut by line range, with samtools' own kstring
+sed -n '243,324p' "$REF/samtools-0.1.18/bam.c" > "$OUT/patched/sam_format.inc"
+/usr/bin/gcc -O1 -w -fPIC -I"$REF/samtools-0.1.18" -c "$REF/samtools-0.1.18/kstring.c" -o "$OUT/obj/sam_kstring.o"
 for f in BGS-IO PE PEAlgnmt; do $CXX -O1 -fpermissive -w -fPIC -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -c "$REF/$f.cpp" -o "$OUT/obj/sam_$f.o"; done
 $CXX -O1 -fpermissive -w -fPIC -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -c "$OUT/patched/SAM.cpp" -o "$OUT/obj/sam_SAM.o"
 /usr/bin/gcc -O1 -w -fPIC -I"$REF/samtools-0.1.18" -c "$REF/samtools-0.1.18/bam_aux.c" -o "$OUT/obj/sam_bam_aux.o"
 $CXX $CFLAGS -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -c "$REF/SAList.cpp" -o "$OUT/obj/SAList.o"
-$CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" "$HERE/ref_shim/ref_sam_host.cpp" \
-    "$OUT/obj/sam_BGS-IO.o" "$OUT/obj/sam_PE.o" "$OUT/obj/sam_SAM.o" "$OUT/obj/sam_PEAlgnmt.o" "$OUT/obj/SAList.o" "$OUT/obj/sam_bam_aux.o" $BWTOBJ -lm -o "$OUT/libref_sam.so"
+$CXX -O1 -fpermissive -w -fPIC -shared -I"$OUT/patched" -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -I"$REF/samtools-0.1.18" "$HERE/ref_shim/ref_sam_host.cpp" \
+    "$OUT/obj/sam_BGS-IO.o" "$OUT/obj/sam_PE.o" "$OUT/obj/sam_SAM.o" "$OUT/obj/sam_PEAlgnmt.o" "$OUT/obj/SAList.o" "$OUT/obj/sam_bam_aux.o" "$OUT/obj/sam_kstring.o" $BWTOBJ -lm -o "$OUT/libref_sam.so"
 echo "[build_ref] libref_sam.so OK"
 
 # ---- the reference's CPU search path: models, lookup-table + BWT backward / bidirectional search, check-and-extend ------------

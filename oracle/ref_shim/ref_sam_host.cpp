@@ -650,3 +650,27 @@ extern "C" int ref_sam_single_answer ( const uint32_t * pac, uint32_t dnaLength,
     SAMOccurrenceDestruct ( &occBuf );
     return n;
 }
+
+// the text line of a record: samtools' own bam_format1_core (samtools-0.1.18/bam.c:243-324, cut by line range; kstring.c compiled whole)
+extern "C" {
+#include "kstring.h"
+}
+char * bam_flag2char_table = ( char * ) "pPuUrR12sfd\0\0\0\0\0";        // bam.c:11
+char * bam_nt16_rev_table = ( char * ) "=ACMGRSVTWYHKDBN";               // bam_import.c:62
+#include "sam_format.inc"
+extern "C" int ref_sam_format ( const int32_t * core, const uint8_t * data, int32_t dataLen, const char * const * chrNames, int numChr, char * out, int cap )
+{
+    bam1_t b;
+    memset ( &b, 0, sizeof ( b ) );
+    b.core.tid = core[0]; b.core.pos = core[1]; b.core.bin = core[2]; b.core.qual = core[3]; b.core.l_qname = core[4]; b.core.flag = core[5]; b.core.n_cigar = core[6];
+    b.core.l_qseq = core[7]; b.core.mtid = core[8]; b.core.mpos = core[9]; b.core.isize = core[10];
+    b.l_aux = core[11]; b.data_len = dataLen; b.m_data = dataLen; b.data = ( uint8_t * ) data;
+    bam_header_t header;
+    memset ( &header, 0, sizeof ( header ) );
+    header.n_targets = numChr; header.target_name = ( char ** ) chrNames;
+    char * s = bam_format1_core ( &header, &b, BAM_OFDEC );
+    int n = ( int ) strlen ( s );
+    if ( n < cap ) { memcpy ( out, s, n + 1 ); }
+    free ( s );
+    return n;
+}

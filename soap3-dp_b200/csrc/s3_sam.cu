@@ -1205,3 +1205,55 @@ extern "C" int s3_sam_single_answer_record(const s3_sam_genome *g, const s3_sam_
     if (rc) s3_set_error("s3_sam_single_answer_record: out of host memory");
     return rc;
 }
+
+// ---- the SAM text line of a record: bam_format1 (samtools-0.1.18/bam.c:243-329, what samwrite prints for a text file) ----------
+extern "C" int s3_sam_format_line(const s3_sam_record *r, const char *const *chrNames, uint32_t numChr, char **line)
+{
+    if (!r || !line || !r->data) { s3_set_error("s3_sam_format_line: NULL argument"); return S3_EINVAL; }
+    *line = NULL;
+    if ((r->tid >= 0 || r->mtid >= 0) && !chrNames) { s3_set_error("s3_sam_format_line: chromosome names needed"); return S3_EINVAL; }
+    if (r->tid >= (int32_t)numChr || r->mtid >= (int32_t)numChr) { s3_set_error("s3_sam_format_line: chromosome id out of range"); return S3_EINVAL; }
+    const size_t seqBytes = ((size_t)r->l_qseq + 1) / 2, fixed = (size_t)r->l_qname + 4 * (size_t)r->n_cigar + seqBytes + (size_t)r->l_qseq;
+    if (r->l_qname == 0 || fixed > (size_t)r->data_len) { s3_set_error("s3_sam_format_line: the record's data is shorter than its fields"); return S3_EINVAL; }
+    static const char nt16[] = "=ACMGRSVTWYHKDBN";                       // bam_nt16_rev_table
+    const uint8_t *d = r->data, *cig = d + r->l_qname, *seq = cig + 4 * (size_t)r->n_cigar, *qual = seq + seqBytes, *aux = qual + r->l_qseq, *end = d + r->data_len;
+    std::string s;
+    char nb[24];
+    auto num = [&](long long v) { s.append(nb, write_num(v, nb)); };
+    s.append((const char *)d, (size_t)r->l_qname - 1); s.push_back('\t');
+    num(r->flag); s.push_back('\t');
+    if (r->tid < 0) s += "*\t"; else { s += chrNames[r->tid]; s.push_back('\t'); }
+    num((long long)r->pos + 1); s.push_back('\t'); num(r->qual); s.push_back('\t');
+    if (r->n_cigar == 0) s.push_back('*');
+    else for (uint32_t i = 0; i < r->n_cigar; ++i) {
+        uint32_t c;
+        memcpy(&c, cig + 4 * (size_t)i, 4);
+        num(c >> 4); s.push_back("MIDNSHP=X"[c & 15u]);
+    }
+    s.push_back('\t');
+    if (r->mtid < 0) s += "*\t"; else if (r->mtid == r->tid) s += "=\t"; else { s += chrNames[r->mtid]; s.push_back('\t'); }
+    num((long long)r->mpos + 1); s.push_back('\t'); num(r->isize); s.push_back('\t');
+    if (r->l_qseq) {
+        for (int32_t i = 0; i < r->l_qseq; ++i) s.push_back(nt16[(seq[i >> 1] >> ((~i & 1) << 2)) & 0xF]);
+        s.push_back('\t');
+        if (qual[0] == 0xFF) s.push_back('*'); else for (int32_t i = 0; i < r->l_qseq; ++i) s.push_back((char)(qual[i] + 33));
+    } else s += "*\t*";
+    for (const uint8_t *p = aux; p + 3 <= end;) {
+        const char type = (char)p[2];
+        s.push_back('\t'); s.push_back((char)p[0]); s.push_back((char)p[1]); s.push_back(':');
+        p += 3;
+        if (type == 'A') { s += "A:"; s.push_back((char)*p); ++p; }
+        else if (type == 'C') { s += "i:"; num(*p); ++p; }
+        else if (type == 'c') { s += "i:"; num((int8_t)*p); ++p; }
+        else if (type == 'S') { uint16_t v; memcpy(&v, p, 2); s += "i:"; num(v); p += 2; }
+        else if (type == 's') { int16_t v; memcpy(&v, p, 2); s += "i:"; num(v); p += 2; }
+        else if (type == 'I') { uint32_t v; memcpy(&v, p, 4); s += "i:"; num(v); p += 4; }
+        else if (type == 'i') { int32_t v; memcpy(&v, p, 4); s += "i:"; num(v); p += 4; }
+        else if (type == 'Z' || type == 'H') { s.push_back(type); s.push_back(':'); while (p < end && *p) s.push_back((char)*p++); ++p; }
+        else { s3_set_error("s3_sam_format_line: tag type '%c' is not one the record writers produce", type); return S3_EINVAL; }
+    }
+    *line = (char *)malloc(s.size() + 1);
+    if (!*line) { s3_set_error("s3_sam_format_line: out of host memory"); return S3_ENOMEM; }
+    memcpy(*line, s.c_str(), s.size() + 1);
+    return S3_OK;
+}

@@ -753,3 +753,74 @@ def test_sam_single_answer_and_no_answer_records_match_the_reference_writer():
         assert k == 1
         want = (tuple(int(x) for x in core), bytes(data[:int(dlen[0])]))
         assert got == want, (trial, none, p, strand, hits, got, want)
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="oracle/_ref/libref_sam.so not built")
+def test_sam_text_lines_match_samtools_formatter():
+    """s3_sam_format_line against samtools' own bam_format1 (what samwrite prints into a SAM file), on records of the writers: mapped with
+    gapped CIGARs, soft clips, MD / XA:Z tags, reverse strand, mates on the same and on other chromosomes, unmapped"""
+    ref = C.CDLL(REF)
+    lib = api.load_library()
+    rng = np.random.default_rng(99)
+    n = 200_000
+    G = rng.integers(0, 4, n).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    translate = np.array([0, 1, 0xFFFFFFFF, 70_000, 2, 70_000 - 1, 100_000, 2, 70_000 - 1 - 500, 150_000, 3, 150_000 - 1], np.uint32)
+    chr_end = np.array([69_999, 149_999, 199_999], np.uint32)
+    amb = np.full(4, 3, np.uint32)
+    names = [b"chr1", b"chrTwo", b"3"]
+    segs = (Segment * 4)(*[Segment(int(translate[3 * i]), int(translate[3 * i + 1]), int(translate[3 * i + 2])) for i in range(4)])
+    gen = Genome(helpers.u32p(pac), n, segs, 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, (C.c_char_p * 3)(*names))
+    cnames = (C.c_char_p * 3)(*names)
+    lib.s3_sam_single_dp_record.restype = C.c_int
+    lib.s3_sam_unpaired_records.restype = C.c_int
+    lib.s3_sam_format_line.restype = C.c_int
+    lib.s3_sam_format_line.argtypes = [C.POINTER(Record), C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    lib.s3_sam_record_free.restype = None
+    ref.ref_sam_format.restype = C.c_int
+    checked = 0
+
+    def check(rec):
+        nonlocal checked
+        line = C.c_void_p()
+        assert lib.s3_sam_format_line(C.byref(rec), cnames, 3, C.byref(line)) == 0
+        mine = C.string_at(line.value)
+        lib.s3_free(line)
+        core = np.array([rec.tid, rec.pos, rec.bin, rec.qual, rec.l_qname, rec.flag, rec.n_cigar, rec.l_qseq, rec.mtid, rec.mpos, rec.isize, rec.l_aux], np.int32)
+        data = np.frombuffer(bytes(bytearray(rec.data[:rec.data_len])), np.uint8)
+        out = C.create_string_buffer(16384)
+        k = ref.ref_sam_format(core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), rec.data_len, cnames, 3, out, 16384)
+        assert 0 < k < 16384 and mine == out.value, (mine, out.value)
+        assert mine.count(b"\t") >= 11 and mine.split(b"\t")[0] == bytes(bytearray(rec.data[:rec.l_qname - 1]))
+        checked += 1
+
+    for trial in range(400):
+        L = int(rng.integers(36, 152))
+        cfg = Config(int(rng.integers(1, 3)), int(rng.integers(0, 2)), 1, -2, 1, 40, 1, 1, 1, 1000, b"grp%d" % trial)
+        q = np.ascontiguousarray(rng.integers(0, 4, L).astype(np.uint8))
+        ql = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql[-1] = 0
+        m = int(rng.choice([0, 1, 2, 4]))
+        arr = (DpAlignment * max(m, 1))()
+        keep = []
+        for k in range(m):
+            cg = random_special_cigar(rng, L).encode()
+            keep.append(cg)
+            arr[k].ambPosition, arr[k].strand, arr[k].score, arr[k].editdist, arr[k].cigar = int(rng.integers(0, n - 2 * L - 8)), int(rng.integers(1, 3)), int(rng.integers(30, L + 1)), int(rng.integers(0, 9)), cg
+        out = Record()
+        assert lib.s3_sam_single_dp_record(C.byref(gen), C.byref(cfg), arr, m, int(0.3 * L), q.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, b"txt%d" % trial, C.byref(out)) == 0
+        check(out)
+        lib.s3_sam_record_free(C.byref(out))
+        # a pair reported read by read: mate fields, '=' / other chromosome / unmapped mate
+        occs = []
+        for k in range(2):
+            occs.append([(int(rng.integers(0, n - L)), int(rng.integers(1, 3)), int(rng.integers(0, 4))) for _ in range(int(rng.choice([0, 1, 3])))])
+        arrs = [(Occurrence * max(len(o), 1))(*[Occurrence(*x) for x in o]) for o in occs]
+        out2 = (Record * 2)()
+        assert lib.s3_sam_unpaired_records(C.byref(gen), C.byref(cfg), arrs[0], len(occs[0]), arrs[1], len(occs[1]), 1000, q.ctypes.data_as(U8P), q.ctypes.data_as(U8P),
+                                           ql.ctypes.data_as(C.c_char_p), ql.ctypes.data_as(C.c_char_p), L, L, b"u%d/1" % trial, b"u%d/2" % trial, out2) == 0
+        for k in range(2):
+            check(out2[k])
+            lib.s3_sam_record_free(C.byref(out2[k]))
+    assert checked == 1200

@@ -860,6 +860,11 @@ int s3_sam_unpaired_dp_records(const s3_sam_genome *genome, const s3_sam_config 
  * (noAnsOutputSAMAPI, :5829-5855, the read without any alignment, is s3_sam_single_record with numOcc 0.) */
 int s3_sam_single_answer_record(const s3_sam_genome *genome, const s3_sam_config *config, uint32_t ambPosition, int32_t strand, int32_t numMismatch, int32_t bestHitNum,
                                 const uint8_t *query, const char *qualities, int32_t readlen, const char *queryName, s3_sam_record *out);
+/* Which entry of a pair's results the reference reports (bestIndex of the two entries above): the scans of outputDeepDPResult2
+ * (OutputDPResult.cpp:590-760: the first entry with the largest score1 + score2) and outputDPResult2 (:263-350: the fewest mismatches of
+ * the read that came from the search, then the highest DP score, the first of equals).  -1 for an empty list. */
+int32_t s3_sam_pick_deep_dp(const s3_sam_deep_alignment *alignments, uint32_t num);
+int32_t s3_sam_pick_pair_dp(const s3_sam_dp_pairing *alignments, uint32_t num);
 /* The text line samwrite prints for a record in a SAM file: bam_format1 (samtools-0.1.18/bam.c:243-329) -- QNAME FLAG RNAME POS MAPQ CIGAR
  * RNEXT ('=' on the same chromosome) PNEXT TLEN SEQ QUAL (+ 33) and the tags as TAG:TYPE:VALUE, tab-separated, no newline.  *line is
  * malloc'ed (s3_free). */

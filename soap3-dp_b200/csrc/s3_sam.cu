@@ -1257,3 +1257,46 @@ extern "C" int s3_sam_format_line(const s3_sam_record *r, const char *const *chr
     memcpy(*line, s.c_str(), s.size() + 1);
     return S3_OK;
 }
+
+// ---- which entry of a pair's results is reported: the scans of outputDeepDPResult2 / outputDPResult2 (OutputDPResult.cpp) ---------
+// Deep DP (:590-760): the first entry sets the score to beat -- score1 + score2, or the aligned read's score when the other is unaligned,
+// -127 when neither is -- and a later entry takes over when its own is strictly larger.
+extern "C" int32_t s3_sam_pick_deep_dp(const s3_sam_deep_alignment *algn, uint32_t num)
+{
+    if (!algn || num == 0) return -1;
+    const uint32_t NONE = 0xFFFFFFFFu;
+    auto own = [&](const s3_sam_deep_alignment &a, bool *any) {
+        const bool u1 = a.ambPosition[0] == NONE, u2 = a.ambPosition[1] == NONE;
+        *any = !(u1 && u2);
+        return u1 && !u2 ? a.score[1] : (u2 && !u1 ? a.score[0] : (!u1 && !u2 ? a.score[0] + a.score[1] : -127));
+    };
+    bool any;
+    int32_t best = 0, maxScore = own(algn[0], &any);
+    for (uint32_t i = 1; i < num; ++i) {
+        const int32_t s = own(algn[i], &any);
+        if (any && s > maxScore) { best = (int32_t)i; maxScore = s; }
+    }
+    return best;
+}
+
+// Default DP / mate rescue (:263-350): the fewest mismatches of the read that came from the search, then the highest DP score of the
+// other; an entry whose DP read missed its cutoff (position 0xFFFFFFFF) competes with its mismatches alone.  (An entry with neither
+// read aligned leaves the reference's running values as they were; here it neither sets nor beats anything.)
+extern "C" int32_t s3_sam_pick_pair_dp(const s3_sam_dp_pairing *algn, uint32_t num)
+{
+    if (!algn || num == 0) return -1;
+    const uint32_t NONE = 0xFFFFFFFFu;
+    int32_t best = 0, minMismatch = 0x7FFFFFFF, maxScore = -127;
+    for (uint32_t i = 0; i < num; ++i) {
+        const s3_sam_dp_pairing &a = algn[i];
+        const bool u1 = a.ambPosition[0] == NONE, u2 = a.ambPosition[1] == NONE;
+        int32_t cm, cs;
+        if (u1 && !u2) { cm = a.score[1]; cs = -127; }
+        else if (u2 && !u1) { cm = a.score[0]; cs = -127; }
+        else if (!u1 && !u2) { cm = a.whichFromDP == 1 ? a.score[0] : a.score[1]; cs = a.whichFromDP == 1 ? a.score[1] : a.score[0]; }
+        else continue;
+        const bool paired = !u1 && !u2;
+        if (i == 0 || cm < minMismatch || (paired && cm == minMismatch && cs > maxScore)) { best = (int32_t)i; minMismatch = cm; maxScore = cs; }
+    }
+    return best;
+}

@@ -824,3 +824,41 @@ def test_sam_text_lines_match_samtools_formatter():
             check(out2[k])
             lib.s3_sam_record_free(C.byref(out2[k]))
     assert checked == 1200
+
+
+def test_sam_pick_reported_entry():
+    """s3_sam_pick_deep_dp / s3_sam_pick_pair_dp == the scans of outputDeepDPResult2 / outputDPResult2 restated (OutputDPResult.cpp:263-350,
+    590-760; the functions themselves need the whole aligner around them: unpinned restatement, used by tests/test_sam_e2e_gpu.py too)"""
+    lib = api.load_library()
+    lib.s3_sam_pick_deep_dp.restype = C.c_int32
+    lib.s3_sam_pick_pair_dp.restype = C.c_int32
+    rng = np.random.default_rng(111)
+    NONE = 0xFFFFFFFF
+    assert lib.s3_sam_pick_deep_dp(None, 0) == -1 and lib.s3_sam_pick_pair_dp(None, 0) == -1
+    for trial in range(2000):
+        m = int(rng.integers(1, 8))
+        deep = (DeepAlignment * m)()
+        want, mx = 0, None
+        for k in range(m):
+            u = int(rng.choice([0, 0, 0, 1, 2]))
+            deep[k].ambPosition[0] = NONE if u == 1 else int(rng.integers(0, 1000))
+            deep[k].ambPosition[1] = NONE if u == 2 else int(rng.integers(0, 1000))
+            deep[k].score[0], deep[k].score[1] = int(rng.integers(30, 40)), int(rng.integers(30, 40))
+            s = deep[k].score[1] if u == 1 else deep[k].score[0] if u == 2 else deep[k].score[0] + deep[k].score[1]
+            if mx is None or s > mx:
+                want, mx = k, s
+        assert lib.s3_sam_pick_deep_dp(deep, m) == want
+        pd = (DpPairing * m)()
+        want, mn, mx = None, 0, 0
+        for k in range(m):
+            which = int(rng.integers(0, 2))
+            failed = rng.random() < 0.2
+            pd[k].whichFromDP = 2 if failed else which
+            pd[k].ambPosition[which] = NONE if failed else int(rng.integers(0, 1000))
+            pd[k].ambPosition[1 - which] = int(rng.integers(0, 1000))
+            pd[k].score[which], pd[k].score[1 - which] = int(rng.integers(30, 36)), int(rng.integers(0, 3))
+            cm = pd[k].score[1 - which]
+            cs = -127 if failed else pd[k].score[which]
+            if want is None or cm < mn or (not failed and cm == mn and cs > mx):
+                want, mn, mx = k, cm, cs
+        assert lib.s3_sam_pick_pair_dp(pd, m) == want, trial

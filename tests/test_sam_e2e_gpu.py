@@ -140,6 +140,7 @@ def test_read_pairs_through_deep_dp_to_sam_records(env):
     ref, lib = C.CDLL(REF), api.load_library()
     ref.ref_sam_deep_dp.restype = C.c_int
     lib.s3_sam_deep_dp_records.restype = C.c_int
+    lib.s3_sam_pick_deep_dp.restype = C.c_int32
     lib.s3_runs_decode.restype = C.c_int
     lib.s3_sam_record_free.restype = None
     one = OneChromosome(G)
@@ -187,8 +188,7 @@ def test_read_pairs_through_deep_dp_to_sam_records(env):
             arr[k].editdist[0], arr[k].editdist[1] = d1[1], d2[1]
             arr[k].numSameScore[0], arr[k].numSameScore[1] = int(h["numSame1"]), int(h["numSame2"])
             arr[k].cigar[0], arr[k].cigar[1] = d1[0], d2[0]
-        sums = [int(h["score1"]) + int(h["score2"]) for h in hs]
-        best = sums.index(max(sums))
+        best = lib.s3_sam_pick_deep_dp(arr, len(hs))                # outputDeepDPResult2's choice
         out = (Record * 2)()
         assert lib.s3_sam_deep_dp_records(C.byref(one.gen), C.byref(cfg), arr, len(hs), best, q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p),
                                           ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2, zeros, zeros, zeros, out) == 0
@@ -345,6 +345,7 @@ def test_rescued_pairs_through_the_chain_to_sam_records(env):
     ref, lib = C.CDLL(REF), api.load_library()
     ref.ref_sam_pair_dp.restype = C.c_int
     lib.s3_sam_pair_dp_records.restype = C.c_int
+    lib.s3_sam_pick_pair_dp.restype = C.c_int32
     lib.s3_runs_decode.restype = C.c_int
     lib.s3_sam_record_free.restype = None
     one = OneChromosome(G)
@@ -411,12 +412,13 @@ def test_rescued_pairs_through_the_chain_to_sam_records(env):
             cigs.append(cg)
         if all(e[0] == 2 for e in ents):
             continue                                                  # no rescue succeeded: the pair goes to the writers of improperly paired reads
-        best = pick(ents)
         arr = (DpPairing * len(ents))()
         for k, (which, strand, ed, ins, same, pos, score) in enumerate(ents):
             arr[k].whichFromDP, arr[k].editdist, arr[k].insertSize, arr[k].numSameScore, arr[k].cigar = which, ed, ins, same, cigs[k] or None
             for i in range(2):
                 arr[k].strand[i], arr[k].ambPosition[i], arr[k].score[i] = strand[i], pos[i], score[i]
+        best = lib.s3_sam_pick_pair_dp(arr, len(ents))              # outputDPResult2's choice
+        assert best == pick(ents)
         st = [got["read_stats"][2 * p], got["read_stats"][2 * p + 1]]
         x0 = (C.c_int32 * 2)(*[int(s_["x0"]) for s_ in st]); x1 = (C.c_int32 * 2)(*[int(s_["x1"]) for s_ in st])
         mm = (C.c_int32 * 2)(*[int(s_["minMismatch"]) if int(s_["x0"]) else 0 for s_ in st])

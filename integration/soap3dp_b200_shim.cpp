@@ -358,3 +358,65 @@ unsigned int singleDPAlignResults ( unsigned int * queries, unsigned int * upkdR
     *results = out;
     return n;
 }
+
+// ---- DV-SemiDP.cu (semiGlobalDP2) / DV-DPfunctions.cu:2329-2440 (DP_Space::algnmtCPUThread) -------------------------------------
+// Mate rescue of a batch of read pairs as the reference's own result records.  semiGlobalDP2 aligns, for every pair of which one
+// read (or both, without a valid pairing) has occurrences, the mate inside the window each occurrence allows, and
+// DP_Space::algnmtCPUThread turns EVERY window into an AlgnmtDPResult (PEAlgnmt.h:384-402; whichFromDP 2 and position 0xFFFFFFFF when
+// the mate missed its cutoff) for outputDPResult2 (OutputDPResult.cpp:240).  rescueDPAlignResults runs the whole paired-end chain on
+// the device (s3_pe_align: search, answer collection, routing, locate, pairing, windows, DP, CIGAR runs) and builds those records in
+// the order the reference's occurrence stream visits the windows.  cigarString is malloc'ed like the encoder's (NULL for a miss).
+unsigned int rescueDPAlignResults ( unsigned int * queries, unsigned int * upkdReadLengths, unsigned int numQueries, unsigned int wordPerQuery,
+                                    unsigned int maxReadLength, int insert_high, int insert_low, int peStrandLeftLeg, int peStrandRightLeg,
+                                    unsigned int numMismatch, unsigned int maxOutputPerRead, unsigned int maxHitNumForDP,
+                                    unsigned int * _bwt, DPParameters * dpParameters, AlgnmtDPResult ** results )
+{
+    s3_index * ix = ( s3_index * ) _bwt;
+    s3_pe_params par;
+    memset ( &par, 0, sizeof ( par ) );
+    par.numMismatch = numMismatch; par.insertLow = insert_low; par.insertHigh = insert_high;
+    par.strandLeftLeg = peStrandLeftLeg; par.strandRightLeg = peStrandRightLeg;
+    par.maxOutputPerRead = maxOutputPerRead; par.maxHitNumForDP = maxHitNumForDP; par.keepSecondBest = 0;
+    par.scores.matchScore = dpParameters->matchScore; par.scores.mismatchScore = dpParameters->mismatchScore;
+    par.scores.gapOpenScore = dpParameters->openGapScore; par.scores.gapExtendScore = dpParameters->extendGapScore;
+    par.cutoffThreshold = dpParameters->paramRead[0].cutoffThreshold > 0 ? dpParameters->paramRead[0].cutoffThreshold : -1;      // getParameterForDefaultDP, CPUfunctions.cpp:59-86
+    par.softClipLeft = dpParameters->softClipLeft; par.softClipRight = dpParameters->softClipRight;
+    s3_pe * pe = NULL;
+    if ( s3_pe_create ( ix, numQueries, maxReadLength, &par, &pe ) != S3_OK ) { s3_die ( "semiGlobalDP2" ); }
+    s3_pe_result r;
+    if ( s3_pe_align ( pe, queries, upkdReadLengths, numQueries, wordPerQuery, &r ) != S3_OK ) { s3_die ( "semiGlobalDP2" ); }
+    const unsigned int n = ( unsigned int ) r.numWindows;
+    AlgnmtDPResult * out = ( AlgnmtDPResult * ) calloc ( n ? n : 1, sizeof ( AlgnmtDPResult ) );
+    for ( unsigned int t = 0; t < n; t++ )
+    {
+        const s3_pe_dp_result & x = r.dp[t];
+        AlgnmtDPResult & a = out[t];
+        const unsigned int alignedID = x.dpReadID ^ 1u, alignedIsReadOrMate = alignedID & 1u;
+        a.readID = alignedID - alignedIsReadOrMate;
+        unsigned int dpPos = 0xFFFFFFFFu;
+        if ( x.numRuns )
+        {
+            int32_t ed = 0, dis = 0;
+            const uint32_t cap = 12 * x.numRuns + 1;
+            char * cig = ( char * ) malloc ( cap );
+            if ( s3_runs_decode ( r.runs + x.runOffset, x.numRuns, upkdReadLengths[x.dpReadID], x.score, par.scores, cig, cap, NULL, &ed, &dis ) != S3_OK ) { s3_die ( "semiGlobalDP2 (CIGAR)" ); }
+            a.cigarString = cig; a.editdist = ed; a.whichFromDP = ( char ) ( 1 - alignedIsReadOrMate ); a.num_sameScore = ( int ) x.numSameScore;
+            dpPos = x.dpPos;
+            a.insertSize = dpPos < x.alignedPos ? ( int ) ( x.alignedPos - dpPos + upkdReadLengths[alignedID] )                     // DV-DPfunctions.cu:2388-2400
+                                                : ( int ) ( dpPos - x.alignedPos + upkdReadLengths[x.dpReadID] + dis );
+        }
+        else { a.cigarString = NULL; a.whichFromDP = 2; }
+        const char dpStrand = ( char ) ( x.leftOrRight == 0 ? peStrandLeftLeg : peStrandRightLeg );
+        if ( alignedIsReadOrMate == 0 )
+        {
+            a.algnmt_1 = x.alignedPos; a.algnmt_2 = dpPos; a.score_1 = x.alignedMismatches; a.score_2 = x.score; a.strand_1 = ( char ) x.alignedStrand; a.strand_2 = dpStrand;
+        }
+        else
+        {
+            a.algnmt_1 = dpPos; a.algnmt_2 = x.alignedPos; a.score_1 = x.score; a.score_2 = x.alignedMismatches; a.strand_1 = dpStrand; a.strand_2 = ( char ) x.alignedStrand;
+        }
+    }
+    s3_pe_free ( pe );
+    *results = out;
+    return n;
+}

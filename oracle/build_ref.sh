@@ -216,7 +216,7 @@ if [ -x "$NVCC" ]; then
   for sym in _Z14GPUINDEXUploadP10Soap3IndexPPjS2_S2_S2_ _Z24perform_round1_alignmentPjS_PA10_S_jjjjjbijyP10Soap3IndexS_S_S_S_ \
              _ZN17SemiGlobalAligner16performAlignmentEPjS0_S0_S0_PiS1_S0_S0_PhiS0_S0_S0_S0_ \
              _Z12alignSingleRPjS_S_jjP10Soap3IndexP16SingleAlignParamRyRjP16AlgnResultArrays \
-             deepDPAlignResults singleDPAlignResults; do
+             deepDPAlignResults singleDPAlignResults rescueDPAlignResults; do
     nm "$OUT/obj/soap3dp_b200_shim.o" > "$OUT/obj/soap3dp_b200_shim.nm"          # (not piped: grep -q would end nm early under pipefail)
     grep -q " T .*$sym" "$OUT/obj/soap3dp_b200_shim.nm" || { echo "[build_ref] shim lacks $sym" >&2; exit 1; }
   done
@@ -228,7 +228,7 @@ if [ -x "$NVCC" ]; then
     $CXX $CFLAGS -I"$REF" -I"$REF/2bwt-lib" -I"$REF/2bwt-flex" -c "$REF/global_arrays.cpp" -o "$OUT/obj/global_arrays.o"      # addOCCToArray, resultArraysConstruct
     $NVCC -Wno-deprecated-gpu-targets -ccbin "$CXX" -o "$OUT/shim_check" "$OUT/obj/shim_check.o" "$OUT/obj/soap3dp_b200_shim.o" "$OUT/obj/global_arrays.o" \
         -L"$LIBDIR" -lsoap3dp_b200 -Xlinker -rpath -Xlinker '$ORIGIN/../../soap3-dp_b200' -lcudart
-    if [ ! -f "$OUT/shim_case/meta.txt" ] || [ ! -f "$OUT/shim_case/single_off.bin" ] || [ ! -f "$OUT/shim_case/deep_meta.txt" ] || [ ! -f "$OUT/shim_case/sdp_meta.txt" ]; then python "$HERE/make_shim_case.py"; fi
+    if [ ! -f "$OUT/shim_case/meta.txt" ] || [ ! -f "$OUT/shim_case/single_off.bin" ] || [ ! -f "$OUT/shim_case/deep_meta.txt" ] || [ ! -f "$OUT/shim_case/sdp_meta.txt" ] || [ ! -f "$OUT/shim_case/rescue_meta.txt" ]; then python "$HERE/make_shim_case.py"; fi
     echo "[build_ref] shim_check OK"
   fi
 fi

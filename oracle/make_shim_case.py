@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY.  Writes the inputs and the oracle's expected outputs for oracle/ref_shim/shim_check.cu (the
 executed check of the drop-in shim, integration/soap3dp_b200_shim.cpp) into oracle/_ref/shim_case/ as raw little-endian
 arrays: a 200 kbp index with close repeats, 2048 reads of 100 bp searched with <= 2 mismatches (round 1, four cases; round 2
-on the reads whose round-1 slot overflowed), 512 mate-rescue DP alignments, 160 read pairs for the deep-DP stage and 300 reads of 150 bases for the single-read DP stage.  Run by oracle/build_ref.sh in the container that has /root/reference."""
+on the reads whose round-1 slot overflowed), 512 mate-rescue DP alignments, 160 read pairs for the deep-DP stage 300 reads of 150 bases for the single-read DP stage and 300 read pairs for mate rescue through the whole chain.  Run by oracle/build_ref.sh in the container that has /root/reference."""
 import os
 import sys
 
@@ -157,6 +157,59 @@ save("sdp_unseeded", np.array(swant["unseeded"], np.uint32))
 with open(os.path.join(out, "sdp_meta.txt"), "w") as f:
     f.write(f"{sn} {swpq} {len(srec)} {len(swant['unseeded'])}\n")
 print(f"[make_shim_case] single-read DP: {sn} reads of {SL} bases -> {len(srec)} SingleAlgnmtResult records, {len(swant['unseeded'])} reads without a candidate")
+# rescueDPAlignResults (the shim's mate-rescue results through the whole paired-end chain): oracle/pe_chain_oracle.pe_chain over the search
+# oracle's slots; per window the AlgnmtDPResult fields as DP_Space::algnmtCPUThread fills them (DV-DPfunctions.cu:2355-2432)
+import pe_chain_oracle  # noqa: E402,F811
+from test_pe_chain_gpu import _decode_fn, _dp_fn  # noqa: E402
+rpairs = 300
+r1, r2, _ = synth.simulate_paired_end(G, rpairs, L, seed=43, insert_lo=200, insert_hi=500, bad_mate_fraction=0.4)
+rreads = torch.stack([r1.reads, r2.reads], dim=1).reshape(2 * rpairs, L).cpu().numpy()
+rn = 2 * rpairs
+rlens = np.zeros(formats.ceil32(rn), np.uint32)
+rlens[:rn] = L
+rq = formats.pack_queries(rreads, rlens[:rn], wpq)
+save("rescue_queries", rq); save("rescue_lengths", rlens)
+rbad = np.zeros(formats.ceil32(rn), np.uint8)
+rviews = []
+for case in range(formats.NUM_CASES[k]):
+    a = np.zeros(formats.ceil32(rn) * wpa, np.uint32)
+    helpers.oracle_launch(olib, hi, case, rq, rlens, rn, wpq, a, rbad, 0, k, allowed, wpa)
+    rviews.append(formats.answers_view(a, rn, wpa))
+from soap3dp_b200 import api as _api  # noqa: E402  (only the parameter table: getParameterForDefaultDP's maxHitNum)
+max_hit = _api.getParameterForDP(2, L, L).paramRead[0].maxHitNum
+max_read = (L // 4 + 1) * 4
+opar = dict(insert_low=200, insert_high=500, left_leg=1, right_leg=2, max_output_per_read=1000, max_hit=max_hit, keep_second_best=False, cutoff=-1,
+            soft_clip_left=3, soft_clip_right=8, max_read=max_read, max_dna=500 - 200 + max_read + 1, scores=(MATCH, MISM, OPEN, EXT))
+rwant = pe_chain_oracle.pe_chain(rviews, allowed, rlens[:rn], sa_true, G.cpu().numpy(), list(rreads), opar, helpers.oracle_pair_occurrences, _dp_fn, _decode_fn)
+rrec, rcig, rcoff = [], b"", [0]
+for w in rwant["dp"]:
+    dp_read = w["dpReadID"]
+    aligned = dp_read ^ 1
+    side = aligned & 1
+    cg = w["cigar"]
+    if cg:
+        ops = {c: 0 for c in "MmIDS"}
+        gap = 0
+        for cnt, op in re.findall(r"(\d+)([MmIDS])", cg):
+            ops[op] += int(cnt)
+            if op in "ID":
+                gap += OPEN + (int(cnt) - 1) * EXT
+        mism = int(((L - ops["I"] - ops["S"]) * MATCH + gap - w["score"]) / (MATCH - MISM))
+        ed, dis, which, dp_pos, same = ops["I"] + ops["D"] + mism, ops["D"] - ops["I"] - ops["S"], 1 - side, w["dpPos"], w["numSameScore"]
+        ins = (w["alignedPos"] - dp_pos + L) if dp_pos < w["alignedPos"] else (dp_pos - w["alignedPos"] + L + dis)
+    else:
+        ed, which, dp_pos, same, ins = 0, 2, 0xFFFFFFFF, 0, 0
+    if side == 0:
+        f = [w["alignedPos"], dp_pos, w["alignedStrand"], w["dpStrand"], w["alignedMismatches"], w["score"]]
+    else:
+        f = [dp_pos, w["alignedPos"], w["dpStrand"], w["alignedStrand"], w["score"], w["alignedMismatches"]]
+    rrec.append([aligned - side, which] + f + [ed, ins, same])
+    rcig += cg.encode()
+    rcoff.append(len(rcig))
+save("rescue_records", np.array(rrec, np.int64).astype(np.int32).reshape(-1, 11)); save("rescue_cigars", np.frombuffer(rcig, np.uint8)); save("rescue_cigar_off", np.array(rcoff, np.uint32))
+with open(os.path.join(out, "rescue_meta.txt"), "w") as f:
+    f.write(f"{rn} {len(rrec)} {max_hit}\n")
+print(f"[make_shim_case] mate rescue: {rpairs} pairs -> {len(rrec)} AlgnmtDPResult records ({sum(1 for x in rrec if x[1] != 2)} with a CIGAR), routes {np.bincount(rwant['route'], minlength=9).tolist()}")
 with open(os.path.join(out, "meta.txt"), "w") as f:
     f.write(f"{hi.n} {hi.isa0} {hi.risa0} {len(hi.bwt)} {len(hi.occ)} {n} {wpq} {k} {formats.NUM_CASES[k]} {allowed} {wpa} "
             f"{m} {b.max_read} {b.max_dna} {b.pat_len} {allowed2} {wpa2}\n")

@@ -16,6 +16,10 @@
 #include "PEAlgnmt.h"
 
 /* defined by the shim (integration/soap3dp_b200_shim.cpp): the results of the two seeded DP stages as the reference's own records */
+unsigned int rescueDPAlignResults ( unsigned int * queries, unsigned int * upkdReadLengths, unsigned int numQueries, unsigned int wordPerQuery,
+                                    unsigned int maxReadLength, int insert_high, int insert_low, int peStrandLeftLeg, int peStrandRightLeg,
+                                    unsigned int numMismatch, unsigned int maxOutputPerRead, unsigned int maxHitNumForDP,
+                                    unsigned int * _bwt, DPParameters * dpParameters, AlgnmtDPResult ** results );
 unsigned int singleDPAlignResults ( unsigned int * queries, unsigned int * upkdReadLengths, unsigned int numQueries, unsigned int wordPerQuery,
                                     const unsigned int * readIDs, unsigned int numReads, unsigned int * _bwt, DPParameters * dpParameters,
                                     SingleAlgnmtResult ** results, unsigned int ** unseeded, unsigned int * numUnseeded );
@@ -267,6 +271,42 @@ int main(int argc, char **argv)
         fails += bad != 0;
         for (unsigned h = 0; h < got; ++h) free(res[h].cigarString);
         free(res); free(uns);
+        GPUINDEXFree(_b, _o, _rb, _ro);
+    }
+    /* rescueDPAlignResults (the shim's results of semiGlobalDP2 through the whole paired-end chain): AlgnmtDPResult records as DP_Space::algnmtCPUThread
+       builds them, one per rescue window, against oracle/pe_chain_oracle.pe_chain */
+    {
+        unsigned rn = 0, nrec = 0, maxHit = 0;
+        FILE *f = fopen((dir + "/rescue_meta.txt").c_str(), "r");
+        if (!f || fscanf(f, "%u %u %u", &rn, &nrec, &maxHit) != 3) { printf("FAIL rescue_meta.txt\n"); return 2; }
+        fclose(f);
+        std::vector<uint> rq = load<uint>(dir, "rescue_queries"), rl = load<uint>(dir, "rescue_lengths");
+        std::vector<int> rec = load<int>(dir, "rescue_records");
+        std::vector<uchar> cig = load<uchar>(dir, "rescue_cigars");
+        std::vector<uint> coff = load<uint>(dir, "rescue_cigar_off");
+        uint *_b, *_o, *_rb, *_ro;
+        GPUINDEXUpload(&index, &_b, &_o, &_rb, &_ro);
+        DPParameters dpp; memset(&dpp, 0, sizeof dpp);
+        dpp.matchScore = 1; dpp.mismatchScore = -2; dpp.openGapScore = -3; dpp.extendGapScore = -1; dpp.softClipLeft = 3; dpp.softClipRight = 8;
+        AlgnmtDPResult *res = NULL;
+        unsigned int got = rescueDPAlignResults(rq.data(), rl.data(), rn, wpq, 100, 500, 200, 1, 2, k, 1000, maxHit, _b, &dpp, &res);
+        size_t bad = got != nrec, traced = 0;
+        for (unsigned t = 0; t < got && t < nrec; ++t) {
+            const int *w = rec.data() + 11 * (size_t)t;
+            const AlgnmtDPResult &r = res[t];
+            bad += (int)r.readID != w[0] || r.whichFromDP != w[1] || (int)r.algnmt_1 != w[2] || (int)r.algnmt_2 != w[3] || r.strand_1 != w[4] || r.strand_2 != w[5] ||
+                   r.score_1 != w[6] || r.score_2 != w[7];
+            if (w[1] != 2) {       /* (the reference leaves edit distance, insert size and tie count of a miss unset) */
+                const std::string c((const char *)cig.data() + coff[t], coff[t + 1] - coff[t]);
+                bad += r.editdist != w[8] || r.insertSize != w[9] || r.num_sameScore != w[10] || !r.cigarString || c != r.cigarString;
+                ++traced;
+            } else bad += r.cigarString != NULL;
+        }
+        printf("%s rescueDPAlignResults (semiGlobalDP2 through the paired-end chain): %u reads, %u AlgnmtDPResult records (%zu with a CIGAR), %zu differences\n",
+               bad ? "FAIL" : "PASS", rn, got, traced, bad);
+        fails += bad != 0;
+        for (unsigned t = 0; t < got; ++t) free(res[t].cigarString);
+        free(res);
         GPUINDEXFree(_b, _o, _rb, _ro);
     }
     printf("%s drop-in shim executed through the reference's declarations\n", fails ? "FAIL" : "PASS");

@@ -1046,7 +1046,7 @@ def main():
     if args.impl == "reference":
         vals = []
         info = None
-        per_step = max(args.cpu_sample // 4, 4096)
+        per_step = min(2 * args.pairs, max(args.cpu_sample // 2, 4096))        # the GPU arm's reads per step (1,048,576), about 4 s of CPU work
         for s in range(args.warmup + args.steps):
             info = cpu_arm(host, genome, L, per_step, 1000 + s, RESCUE_FRACTION_HINT, threads, kernel_code_reads=32768, gpu_legs=False)
             if s >= args.warmup:

@@ -869,6 +869,31 @@ int32_t s3_sam_pick_pair_dp(const s3_sam_dp_pairing *alignments, uint32_t num);
  * RNEXT ('=' on the same chromosome) PNEXT TLEN SEQ QUAL (+ 33) and the tags as TAG:TYPE:VALUE, tab-separated, no newline.  *line is
  * malloc'ed (s3_free). */
 int s3_sam_format_line(const s3_sam_record *record, const char *const *chrNames, uint32_t numChr, char **line);
+/* Whole batches as SAM text: the loops the reference's output threads run around the record writers, one record per read, printed as
+ * s3_sam_format_line prints it, one line (+ '\n') per record in read order; *text is malloc'ed (s3_free), NUL-terminated, *textBytes
+ * without the NUL.  Reads are independent: numThreads host threads (0: all of the machine) each take a slice of the batch.
+ *   s3_sam_single_batch_text     the results of s3_se_align (occOffsets / positions / occFlags of s3_se_result) -> s3_sam_single_record per
+ *                                read, the unmapped record for a read without an occurrence (hostKernel's SAM branch for single reads,
+ *                                CPUfunctions.cpp:1887-1905 -> OCCOutputSAMAPI / noAnsOutputSAMAPI): BASELINE config 2 from reads to text
+ *   s3_sam_single_dp_batch_text  the results of s3_single_dp_align (hits in candidate order, the candidates of a read next to each
+ *                                other; runs) -> s3_runs_decode -> s3_sam_single_dp_record per read that has a hit
+ *                                (outputDPSingleResult2, OutputDPResult.cpp:938-1058, with hspaux->singleDPcutoffThreshold,
+ *                                alignment.cu:2360); reads without a hit are the caller's (the reference reports them after its last
+ *                                stage).  Where the reference's DP batches cut a read's candidates in two, its loop writes the read
+ *                                twice; there are no batch borders here. */
+typedef struct {
+    const uint8_t *bases;                 /* numReads rows of rowBytes: one base code (0..3) per byte, the read as sequenced */
+    const char *qualities;                /* numReads rows of rowBytes: Phred values */
+    uint32_t rowBytes;
+    const uint32_t *readLengths;
+    const char *const *names;
+} s3_sam_reads;
+int s3_sam_single_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
+                             const uint32_t *occOffsets, const uint32_t *positions, const uint8_t *occFlags, uint32_t numThreads,
+                             char **text, uint64_t *textBytes);
+int s3_sam_single_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
+                                const s3_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
+                                int32_t singleDPcutoffThreshold, uint32_t numThreads, char **text, uint64_t *textBytes);
 
 #ifdef __cplusplus
 }

@@ -12,6 +12,9 @@
 #include "../../include/soap3dp_b200.h"
 
 #include <math.h>
+#include <algorithm>
+#include <atomic>
+#include <thread>
 #include <stdlib.h>
 #include <string.h>
 #include <string>
@@ -1299,4 +1302,125 @@ extern "C" int32_t s3_sam_pick_pair_dp(const s3_sam_dp_pairing *algn, uint32_t n
         if (i == 0 || cm < minMismatch || (paired && cm == minMismatch && cs > maxScore)) { best = (int32_t)i; minMismatch = cm; maxScore = cs; }
     }
     return best;
+}
+
+// ---- whole batches as SAM text -------------------------------------------------------------------------------------------------
+// The loops around the record writers that the reference's output threads run per read (hostKernel -> OCCOutputSAMAPI,
+// CPUfunctions.cpp:1887-1905; outputDPSingleResult2 -> SingleDPOutputSAMAPI, OutputDPResult.cpp:938-1058): one record per read through
+// the entries above, printed by s3_sam_format_line, lines in read order.  Reads are independent, so the batch is cut into contiguous
+// slices, one per host thread, and the slices' text is concatenated.
+namespace {
+struct BatchError { std::atomic<int> rc{0}; char msg[512]; };
+
+void batch_fail(BatchError &e, int rc)
+{
+    int expected = 0;
+    if (e.rc.compare_exchange_strong(expected, rc)) { strncpy(e.msg, s3_last_error(), sizeof e.msg - 1); e.msg[sizeof e.msg - 1] = 0; }
+}
+
+// runs `one(r, text)` for r in [0, n) on numThreads host threads and joins the slices' text
+template <typename F>
+int batch_text(const char *what, uint64_t n, uint32_t numThreads, char **text, uint64_t *textBytes, F one)
+{
+    if (!text || !textBytes) { s3_set_error("%s: NULL output", what); return S3_EINVAL; }
+    *text = NULL; *textBytes = 0;
+    uint32_t T = numThreads ? numThreads : std::max(1u, std::thread::hardware_concurrency());
+    if ((uint64_t)T > n) T = (uint32_t)std::max<uint64_t>(n, 1);
+    std::vector<std::string> part(T);
+    BatchError err;
+    auto work = [&](uint32_t t) {
+        const uint64_t a = n * t / T, b = n * (t + 1) / T;
+        for (uint64_t r = a; r < b && err.rc.load(std::memory_order_relaxed) == 0; ++r) {
+            const int rc = one(r, part[t]);
+            if (rc) { batch_fail(err, rc); return; }
+        }
+    };
+    std::vector<std::thread> th;
+    for (uint32_t t = 1; t < T; ++t) th.emplace_back(work, t);
+    work(0);
+    for (auto &x : th) x.join();
+    if (err.rc) { s3_set_error("%s", err.msg); return err.rc; }
+    size_t total = 0;
+    for (auto &p : part) total += p.size();
+    char *out = (char *)malloc(total + 1);
+    if (!out) { s3_set_error("%s: out of host memory", what); return S3_ENOMEM; }
+    size_t at = 0;
+    for (auto &p : part) { memcpy(out + at, p.data(), p.size()); at += p.size(); }
+    out[total] = 0;
+    *text = out; *textBytes = total;
+    return S3_OK;
+}
+
+int append_line(const s3_sam_genome *g, s3_sam_record *rec, std::string &text)
+{
+    char *line = NULL;
+    const int rc = s3_sam_format_line(rec, g->chrNames, g->numChr, &line);
+    s3_sam_record_free(rec);
+    if (rc) return rc;
+    text += line; text.push_back('\n');
+    free(line);
+    return S3_OK;
+}
+
+bool reads_ok(const s3_sam_reads *rd) { return rd && rd->bases && rd->qualities && rd->readLengths && rd->names && rd->rowBytes; }
+}  // namespace
+
+extern "C" int s3_sam_single_batch_text(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_reads *reads, uint64_t numReads,
+                                        const uint32_t *occOffsets, const uint32_t *positions, const uint8_t *occFlags, uint32_t numThreads,
+                                        char **text, uint64_t *textBytes)
+{
+    if (text) *text = NULL;
+    if (textBytes) *textBytes = 0;
+    if (!g || !cfg || !reads_ok(reads) || !occOffsets || (numReads && occOffsets[numReads] && (!positions || !occFlags))) { s3_set_error("s3_sam_single_batch_text: NULL argument"); return S3_EINVAL; }
+    for (uint64_t r = 0; r < numReads; ++r) {
+        if (occOffsets[r + 1] < occOffsets[r]) { s3_set_error("s3_sam_single_batch_text: occOffsets decrease at read %llu", (unsigned long long)r); return S3_EINVAL; }
+        if (reads->readLengths[r] == 0 || reads->readLengths[r] > reads->rowBytes) { s3_set_error("s3_sam_single_batch_text: read %llu has length %u (rows of %u)", (unsigned long long)r, reads->readLengths[r], reads->rowBytes); return S3_EINVAL; }
+    }
+    return batch_text("s3_sam_single_batch_text", numReads, numThreads, text, textBytes, [&](uint64_t r, std::string &out) {
+        const uint32_t a = occOffsets[r], n = occOffsets[r + 1] - a;
+        std::vector<s3_sam_occurrence> occ(n);
+        for (uint32_t k = 0; k < n; ++k) { occ[k].ambPosition = positions[a + k]; occ[k].strand = occFlags[2 * (size_t)(a + k)]; occ[k].mismatchCount = occFlags[2 * (size_t)(a + k) + 1]; occ[k].pad[0] = occ[k].pad[1] = 0; }
+        s3_sam_record rec;
+        const int rc = s3_sam_single_record(g, cfg, occ.data(), n, reads->bases + r * reads->rowBytes, reads->qualities + r * reads->rowBytes, (int32_t)reads->readLengths[r], reads->names[r], &rec);
+        return rc ? rc : append_line(g, &rec, out);
+    });
+}
+
+// The hits of s3_single_dp_align are in candidate order, the candidates of a read next to each other; a record is written for every read
+// that has a hit (reads without one are reported by the caller's last stage: s3_sam_single_record with no occurrence).  Where the
+// reference's DP batches cut a read's candidates in two its writer sees two groups; there are no batch borders here.
+extern "C" int s3_sam_single_dp_batch_text(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_reads *reads, uint64_t numReads,
+                                           const s3_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
+                                           int32_t singleDPcutoffThreshold, uint32_t numThreads, char **text, uint64_t *textBytes)
+{
+    if (text) *text = NULL;
+    if (textBytes) *textBytes = 0;
+    if (!g || !cfg || !reads_ok(reads) || (numHits && (!hits || !runs))) { s3_set_error("s3_sam_single_dp_batch_text: NULL argument"); return S3_EINVAL; }
+    std::vector<uint64_t> first;                                          // the first hit of every group of equal read ids
+    for (uint64_t i = 0; i < numHits; ++i) {
+        const s3_dp_hit &h = hits[i];
+        if (h.readID >= numReads || (uint64_t)h.runOffset + h.numRuns > numRuns) { s3_set_error("s3_sam_single_dp_batch_text: hit %llu points outside the batch", (unsigned long long)i); return S3_EINVAL; }
+        if (reads->readLengths[h.readID] == 0 || reads->readLengths[h.readID] > reads->rowBytes) { s3_set_error("s3_sam_single_dp_batch_text: read %u has length %u (rows of %u)", h.readID, reads->readLengths[h.readID], reads->rowBytes); return S3_EINVAL; }
+        if (i == 0 || h.readID != hits[i - 1].readID) first.push_back(i);
+    }
+    first.push_back(numHits);
+    return batch_text("s3_sam_single_dp_batch_text", first.size() - 1, numThreads, text, textBytes, [&](uint64_t grp, std::string &out) {
+        const uint64_t a = first[grp], n = first[grp + 1] - a;
+        const uint32_t r = hits[a].readID, len = reads->readLengths[r];
+        std::vector<s3_sam_dp_alignment> al(n);
+        std::vector<std::string> cig(n);
+        for (uint64_t k = 0; k < n; ++k) {
+            const s3_dp_hit &h = hits[a + k];
+            cig[k].resize(10 * (size_t)h.numRuns + 16);
+            uint32_t clen = 0; int32_t edit = 0, span = 0;
+            const int rc = s3_runs_decode(runs + h.runOffset, h.numRuns, len, h.score, scores, &cig[k][0], (uint32_t)cig[k].size(), &clen, &edit, &span);
+            if (rc) return rc;
+            memset(&al[k], 0, sizeof al[k]);
+            al[k].ambPosition = h.pos; al[k].strand = h.strand; al[k].score = h.score; al[k].editdist = edit; al[k].cigar = cig[k].c_str();
+        }
+        s3_sam_record rec;
+        const int rc = s3_sam_single_dp_record(g, cfg, al.data(), (uint32_t)n, singleDPcutoffThreshold, reads->bases + (size_t)r * reads->rowBytes, reads->qualities + (size_t)r * reads->rowBytes,
+                                               (int32_t)len, reads->names[r], &rec);
+        return rc ? rc : append_line(g, &rec, out);
+    });
 }

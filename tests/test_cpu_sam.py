@@ -862,3 +862,160 @@ def test_sam_pick_reported_entry():
             if want is None or cm < mn or (not failed and cm == mn and cs > mx):
                 want, mn, mx = k, cm, cs
         assert lib.s3_sam_pick_pair_dp(pd, m) == want, trial
+
+
+class SamReads(C.Structure):
+    _fields_ = [("bases", U8P), ("qualities", C.c_char_p), ("rowBytes", C.c_uint32), ("readLengths", C.POINTER(C.c_uint32)), ("names", C.POINTER(C.c_char_p))]
+
+
+def _batch_genome(rng):
+    n = 200_000
+    G = rng.integers(0, 4, n).astype(np.uint8)
+    pac = helpers.pack_text(G)
+    translate = np.array([0, 1, 0xFFFFFFFF, 70_000, 2, 70_000 - 1, 100_000, 2, 70_000 - 1 - 500, 150_000, 3, 150_000 - 1], np.uint32)
+    chr_end = np.array([69_999, 149_999, 199_999], np.uint32)
+    amb = np.full(4, 3, np.uint32)
+    cnames = (C.c_char_p * 3)(b"chr1", b"chrTwo", b"3")
+    segs = (Segment * 4)(*[Segment(int(translate[3 * i]), int(translate[3 * i + 1]), int(translate[3 * i + 2])) for i in range(4)])
+    gen = Genome(helpers.u32p(pac), n, segs, 4, helpers.u32p(amb), helpers.u32p(chr_end), 3, cnames)
+    return n, G, gen, cnames, (pac, chr_end, amb, segs)
+
+
+def _line_of(lib, rec, cnames):
+    line = C.c_void_p()
+    assert lib.s3_sam_format_line(C.byref(rec), cnames, 3, C.byref(line)) == 0
+    text = C.string_at(line.value)
+    lib.s3_free(line)
+    lib.s3_sam_record_free(C.byref(rec))
+    return text
+
+
+def _batch_lib():
+    lib = api.load_library()
+    lib.s3_sam_format_line.restype = C.c_int
+    lib.s3_sam_format_line.argtypes = [C.POINTER(Record), C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    lib.s3_sam_record_free.restype = None
+    for f in (lib.s3_sam_single_record, lib.s3_sam_single_dp_record, lib.s3_sam_single_batch_text, lib.s3_sam_single_dp_batch_text, lib.s3_runs_decode):
+        f.restype = C.c_int
+    return lib
+
+
+def _batch_reads(rng, num, row):
+    lens = rng.integers(36, 152, num).astype(np.uint32)
+    bases = np.ascontiguousarray(rng.integers(0, 4, (num, row)).astype(np.uint8))
+    quals = np.ascontiguousarray(rng.integers(2, 41, (num, row)).astype(np.uint8))
+    names = (C.c_char_p * num)(*[b"batch%d" % r for r in range(num)])
+    rd = SamReads(bases.ctypes.data_as(U8P), C.cast(quals.ctypes.data, C.c_char_p), row, lens.ctypes.data_as(C.POINTER(C.c_uint32)), names)
+    return lens, bases, quals, names, rd
+
+
+def test_sam_single_batch_text_is_the_reads_records_in_order():
+    """s3_sam_single_batch_text == s3_sam_single_record + s3_sam_format_line per read (each pinned to the reference above), whatever the
+    number of host threads; reads without an occurrence come out as unmapped records; bad arguments are refused"""
+    lib = _batch_lib()
+    rng = np.random.default_rng(314)
+    n, G, gen, cnames, keep = _batch_genome(rng)
+    num, row = 700, 160
+    lens, bases, quals, names, rd = _batch_reads(rng, num, row)
+    counts = rng.choice([0, 1, 1, 2, 3, 7], num)
+    off = np.zeros(num + 1, np.uint32)
+    off[1:] = np.cumsum(counts)
+    tot = int(off[-1])
+    pos = rng.integers(0, n - 160, tot).astype(np.uint32)
+    edge = rng.random(tot) < 0.2
+    pos[edge] = (rng.choice([70_000, 100_000, 150_000], int(edge.sum())) - rng.integers(1, 36, int(edge.sum()))).astype(np.uint32)
+    flags = np.ascontiguousarray(np.stack([rng.integers(1, 3, tot), rng.integers(0, 4, tot)], 1).astype(np.uint8))
+    for cfg in (Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), Config(2, 1, 1, -2, 0, 40, 1, 0, 1, 1000, b"rgB")):
+        want = []
+        for r in range(num):
+            a, b = int(off[r]), int(off[r + 1])
+            arr = (Occurrence * max(b - a, 1))(*[Occurrence(int(pos[i]), int(flags[i][0]), int(flags[i][1])) for i in range(a, b)])
+            out = Record()
+            assert lib.s3_sam_single_record(C.byref(gen), C.byref(cfg), arr, b - a, bases[r].ctypes.data_as(U8P), C.cast(quals[r].ctypes.data, C.c_char_p), int(lens[r]), names[r],
+                                            C.byref(out)) == 0
+            want.append(_line_of(lib, out, cnames))
+        want = b"".join(x + b"\n" for x in want)
+        assert want.count(b"\t4\t*\t0\t0\t*") >= 50                       # unmapped reads are in the batch
+        for threads in (1, 5, 0):
+            text, size = C.c_void_p(), C.c_uint64()
+            rc = lib.s3_sam_single_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P), threads,
+                                              C.byref(text), C.byref(size))
+            assert rc == 0, lib.s3_last_error()
+            got = C.string_at(text.value, size.value)
+            lib.s3_free(text)
+            assert got == want
+    # an empty batch is an empty text; decreasing offsets and a read longer than its row are refused
+    cfg = Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA")
+    text, size = C.c_void_p(), C.c_uint64(7)
+    assert lib.s3_sam_single_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(0), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P), 3, C.byref(text), C.byref(size)) == 0
+    assert size.value == 0 and C.string_at(text.value) == b""
+    lib.s3_free(text)
+    bad = off.copy(); bad[5] = bad[4] - 1 if bad[4] else 0xFFFFFFFF
+    assert lib.s3_sam_single_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(bad), helpers.u32p(pos), flags.ctypes.data_as(U8P), 2, C.byref(text), C.byref(size)) != 0
+    long_lens = lens.copy(); long_lens[9] = row + 1
+    rd2 = SamReads(rd.bases, rd.qualities, row, long_lens.ctypes.data_as(C.POINTER(C.c_uint32)), names)
+    assert lib.s3_sam_single_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd2), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P), 2, C.byref(text), C.byref(size)) != 0
+    assert text.value is None
+
+
+def test_sam_single_dp_batch_text_groups_the_hits_of_a_read():
+    """s3_sam_single_dp_batch_text == per read s3_runs_decode -> s3_sam_single_dp_record -> s3_sam_format_line over the read's hits (the
+    grouping of outputDPSingleResult2, OutputDPResult.cpp:938-1058), whatever the number of host threads"""
+    import re
+    lib = _batch_lib()
+    rng = np.random.default_rng(2718)
+    n, G, gen, cnames, keep = _batch_genome(rng)
+    num, row = 500, 160
+    lens, bases, quals, names, rd = _batch_reads(rng, num, row)
+    scores = api.DPScores(1, -2, -3, -1)
+    hits, runs, per_read = [], [], {}
+    for r in range(num):
+        if rng.random() < 0.25:
+            continue                                                      # a read without a hit: no record
+        L = int(lens[r])
+        for _ in range(int(rng.choice([1, 1, 2, 4]))):
+            cg = random_special_cigar(rng, L)
+            mine = [(int(k) << 8) | ord(op) for k, op in re.findall(r"(\d+)([MmIDS])", cg)]
+            p = int(rng.choice([70_000, 100_000, 150_000])) - int(rng.integers(1, L)) if rng.random() < 0.2 else int(rng.integers(0, n - 2 * L - 8))
+            h = (r, p, int(rng.integers(int(0.3 * L), L + 1)), int(rng.integers(1, 3)), len(runs), len(mine), int(rng.integers(1, 3)), 0)
+            runs += mine
+            hits.append(h)
+            per_read.setdefault(r, []).append(h)
+    harr = np.array(hits, api.DP_HIT_DTYPE)
+    rarr = np.array(runs, np.uint32)
+    cutoff = 30
+    for cfg in (Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), Config(3, 1, 1, -2, 0, 40, 1, 1, 1, 1000, b"rgB")):
+        want = []
+        for r in sorted(per_read):
+            L = int(lens[r])
+            hs = per_read[r]
+            arr = (DpAlignment * len(hs))()
+            held = []
+            for k, h in enumerate(hs):
+                buf = C.create_string_buffer(4096)
+                e, s = C.c_int32(), C.c_int32()
+                sub = np.ascontiguousarray(rarr[h[4]:h[4] + h[5]])
+                assert lib.s3_runs_decode(helpers.u32p(sub), h[5], L, h[2], scores, buf, 4096, None, C.byref(e), C.byref(s)) == 0
+                held.append(buf.value)
+                arr[k].ambPosition, arr[k].strand, arr[k].score, arr[k].editdist, arr[k].cigar = h[1], h[6], h[2], e.value, held[-1]
+            out = Record()
+            assert lib.s3_sam_single_dp_record(C.byref(gen), C.byref(cfg), arr, len(hs), cutoff, bases[r].ctypes.data_as(U8P), C.cast(quals[r].ctypes.data, C.c_char_p), L, names[r],
+                                               C.byref(out)) == 0
+            want.append(_line_of(lib, out, cnames))
+        want = b"".join(x + b"\n" for x in want)
+        for threads in (1, 4, 0):
+            text, size = C.c_void_p(), C.c_uint64()
+            rc = lib.s3_sam_single_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), harr.ctypes.data_as(C.c_void_p), C.c_uint64(len(harr)),
+                                                 helpers.u32p(rarr), C.c_uint64(len(rarr)), scores, cutoff, threads, C.byref(text), C.byref(size))
+            assert rc == 0, lib.s3_last_error()
+            got = C.string_at(text.value, size.value)
+            lib.s3_free(text)
+            assert got == want and got.count(b"\n") == len(per_read)
+    # a hit whose runs lie outside the run array is refused
+    cfg = Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA")
+    bad = harr.copy(); bad[3]["runOffset"] = len(rarr)
+    text, size = C.c_void_p(), C.c_uint64()
+    assert lib.s3_sam_single_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), bad.ctypes.data_as(C.c_void_p), C.c_uint64(len(bad)),
+                                           helpers.u32p(rarr), C.c_uint64(len(rarr)), scores, cutoff, 2, C.byref(text), C.byref(size)) != 0

@@ -64,6 +64,27 @@ def runs_decode(lib, runs, read_length, score):
     return buf.value, e.value, s.value
 
 
+def line_of(lib, one, rec):
+    """the record's SAM text line (s3_sam_format_line); the record stays the caller's"""
+    lib.s3_sam_format_line.restype = C.c_int
+    lib.s3_sam_format_line.argtypes = [C.POINTER(Record), C.POINTER(C.c_char_p), C.c_uint32, C.POINTER(C.c_void_p)]
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    line = C.c_void_p()
+    assert lib.s3_sam_format_line(C.byref(rec), one.cnames, 1, C.byref(line)) == 0
+    text = C.string_at(line.value)
+    lib.s3_free(line)
+    return text
+
+
+def batch_reads(reads, quals, lens, names):
+    """s3_sam_reads over rows of equal width"""
+    from test_cpu_sam import SamReads
+    keep = (np.ascontiguousarray(reads, np.uint8), np.ascontiguousarray(quals, np.uint8), np.ascontiguousarray(lens, np.uint32), (C.c_char_p * len(names))(*names))
+    assert keep[0].shape == keep[1].shape
+    return SamReads(keep[0].ctypes.data_as(U8P), C.cast(keep[1].ctypes.data, C.c_char_p), keep[0].shape[1], keep[2].ctypes.data_as(C.POINTER(C.c_uint32)), keep[3]), keep
+
+
 def oracle_edit(cigar, read_length, score):
     """edit distance and D - I - S of the reference's result loops (DV-DPfunctions.cu:3788-3794), from the oracle's special CIGAR"""
     ops = {k: 0 for k in "MmIDS"}
@@ -111,17 +132,20 @@ def test_single_end_reads_to_sam_records(env):
     cfg = Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgE2E")
     rng = np.random.default_rng(5)
     mapped = 0
+    quals = np.ascontiguousarray(rng.integers(2, 41, (n, L + 1)).astype(np.uint8)); quals[:, -1] = 0
+    lines = []
     for r in range(n):
         a, b = int(got["occ_offsets"][r]), int(got["occ_offsets"][r + 1])
         occ = [(int(got["positions"][i]), int(got["occ_flags"][i][0]), int(got["occ_flags"][i][1])) for i in range(a, b)]
         theirs = want_occ[r]
-        ql = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql[-1] = 0
+        ql = quals[r]
         name = b"se%d" % r
         qr = np.ascontiguousarray(reads[r])
         arr = (Occurrence * max(len(occ), 1))(*[Occurrence(*o) for o in occ])
         out = Record()
         assert lib.s3_sam_single_record(C.byref(one.gen), C.byref(cfg), arr, len(occ), qr.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name, C.byref(out)) == 0
         mine = record_tuple(out)
+        lines.append(line_of(lib, one, out) + b"\n")
         lib.s3_sam_record_free(C.byref(out))
         flat = np.array([x for o in theirs for x in o], np.uint32) if theirs else np.zeros(3, np.uint32)
         core, data, dlen = np.zeros(12, np.int32), np.zeros(8192, np.uint8), np.zeros(1, np.int32)
@@ -131,6 +155,16 @@ def test_single_end_reads_to_sam_records(env):
         assert mine == (tuple(int(x) for x in core), bytes(data[:int(dlen[0])])), r
         mapped += bool(occ)
     assert mapped > n // 2
+    # the whole batch as SAM text (s3_sam_single_batch_text over the chain's arrays) == those records' lines in read order
+    padded = np.zeros((n, L + 1), np.uint8); padded[:, :L] = reads
+    rd, keep = batch_reads(padded, quals, lens[:n], [b"se%d" % r for r in range(n)])
+    lib.s3_sam_single_batch_text.restype = C.c_int
+    text, size = C.c_void_p(), C.c_uint64()
+    off, pos, fl = (np.ascontiguousarray(got["occ_offsets"], np.uint32), np.ascontiguousarray(got["positions"], np.uint32), np.ascontiguousarray(got["occ_flags"], np.uint8))
+    assert lib.s3_sam_single_batch_text(C.byref(one.gen), C.byref(cfg), C.byref(rd), C.c_uint64(n), helpers.u32p(off), helpers.u32p(pos), fl.ctypes.data_as(U8P), 4,
+                                        C.byref(text), C.byref(size)) == 0, lib.s3_last_error()
+    assert C.string_at(text.value, size.value) == b"".join(lines)
+    lib.s3_free(text)
 
 
 def test_read_pairs_through_deep_dp_to_sam_records(env):
@@ -248,9 +282,11 @@ def test_single_reads_through_single_dp_to_sam_records(env):
     assert sorted(mine_by) == sorted(want_by)
     cfg = Config(1, 0, SCORES[0], SCORES[1], 1, 40, 1, 1, 1, 1000, b"rgSDP")
     cutoff = int(np.ceil(0.3 * L))
+    quals = np.ascontiguousarray(rng.integers(2, 41, (n, L + 1)).astype(np.uint8)); quals[:, -1] = 0
+    lines = []
     for r in sorted(mine_by):
         qr = np.ascontiguousarray(reads[r]).astype(np.uint8)
-        ql = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql[-1] = 0
+        ql = quals[r]
         name = b"sdp%d" % r
         hs = mine_by[r]
         arr = (DpAlignment * len(hs))()
@@ -262,6 +298,7 @@ def test_single_reads_through_single_dp_to_sam_records(env):
         out = Record()
         assert lib.s3_sam_single_dp_record(C.byref(one.gen), C.byref(cfg), arr, len(hs), cutoff, qr.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name, C.byref(out)) == 0
         mine = record_tuple(out)
+        lines.append(line_of(lib, one, out) + b"\n")
         lib.s3_sam_record_free(C.byref(out))
         ws = want_by[r]
         flat, cigs = [], []
@@ -276,6 +313,16 @@ def test_single_reads_through_single_dp_to_sam_records(env):
                                      cfg.dpMatchScore, cutoff, flat.ctypes.data_as(I32P), len(ws), cig, qr.ctypes.data_as(U8P), ql.ctypes.data_as(C.c_char_p), L, name,
                                      core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P)) == 1
         assert mine == (tuple(int(x) for x in core), bytes(data[:int(dlen[0])])), r
+    # the stage's whole result as SAM text (s3_sam_single_dp_batch_text over hits + runs) == those records' lines, reads in hit order
+    padded = np.zeros((n, L + 1), np.uint8); padded[:, :L] = np.stack(reads)
+    rd, keep = batch_reads(padded, quals, lens[:n], [b"sdp%d" % r for r in range(n)])
+    lib.s3_sam_single_dp_batch_text.restype = C.c_int
+    text, size = C.c_void_p(), C.c_uint64()
+    hits, runs = np.ascontiguousarray(got["hits"]), np.ascontiguousarray(got["runs"], np.uint32)
+    assert lib.s3_sam_single_dp_batch_text(C.byref(one.gen), C.byref(cfg), C.byref(rd), C.c_uint64(n), hits.ctypes.data_as(C.c_void_p), C.c_uint64(len(hits)), helpers.u32p(runs),
+                                           C.c_uint64(len(runs)), api.DPScores(*SCORES), cutoff, 4, C.byref(text), C.byref(size)) == 0, lib.s3_last_error()
+    assert C.string_at(text.value, size.value) == b"".join(lines)
+    lib.s3_free(text)
 
 
 def test_read_pairs_through_the_chain_to_sam_records(env):

@@ -894,6 +894,24 @@ int s3_sam_single_batch_text(const s3_sam_genome *genome, const s3_sam_config *c
 int s3_sam_single_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
                                 const s3_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
                                 int32_t singleDPcutoffThreshold, uint32_t numThreads, char **text, uint64_t *textBytes);
+/* The same for the DP results of read pairs: two lines per pair (the first read's, then its mate's), pairs in the order of their results;
+ * readStats (s3_pe_result.readStats of the chain that aligned the batch, indexed by read id; NULL: zeros) gives the x0 / x1 / mismatch
+ * counts the writers take from the search (hspaux->x0_array / x1_array / mismatch_array).
+ *   s3_sam_deep_dp_batch_text    the hits of s3_deep_dp_align / s3_pe_deep_dp (the hits of a pair next to each other) -> per hit the
+ *                                DeepDPAlignResult fields the engine derives (s3_runs_decode; insert size, DV-DPfunctions.cu:3810-3815) ->
+ *                                s3_sam_pick_deep_dp -> s3_sam_deep_dp_records (outputDeepDPResult2, OutputDPResult.cpp:590-760)
+ *   s3_sam_pair_dp_batch_text    the rescue records of s3_pe_align (dp / runs of s3_pe_result; the records of a pair next to each other)
+ *                                -> per record the AlgnmtDPResult the default-DP engine builds (DV-DPfunctions.cu:2355-2440: whichFromDP =
+ *                                the DP read's parity, or 2 with an unaligned DP side when it missed its cutoff; insert size :2388-2400) ->
+ *                                s3_sam_pick_pair_dp -> s3_sam_pair_dp_records (outputDPResult2, OutputDPResult.cpp:263-420).  A pair none
+ *                                of whose rescues succeeded gets no lines: it belongs to the writers of improperly paired reads
+ *                                (s3_sam_unpaired_records over the reads' occurrence lists). */
+int s3_sam_deep_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
+                              const s3_deep_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
+                              const s3_pe_read_stats *readStats, uint32_t numThreads, char **text, uint64_t *textBytes);
+int s3_sam_pair_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
+                              const s3_pe_dp_result *dp, uint64_t numRecords, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
+                              const s3_pe_read_stats *readStats, uint32_t numThreads, char **text, uint64_t *textBytes);
 
 #ifdef __cplusplus
 }

@@ -1424,3 +1424,142 @@ extern "C" int s3_sam_single_dp_batch_text(const s3_sam_genome *g, const s3_sam_
         return rc ? rc : append_line(g, &rec, out);
     });
 }
+
+namespace {
+// x0 / x1 / mismatch of the two reads of a pair as the DP writers take them (hspaux->x0_array / x1_array / mismatch_array, filled by
+// hostKernel, CPUfunctions.cpp:2061-2141): the chain's per-read statistics, zeros for a read without an occurrence or without statistics
+void pair_counts(const s3_pe_read_stats *st, uint32_t evenRead, int32_t x0[2], int32_t x1[2], int32_t mm[2])
+{
+    for (int k = 0; k < 2; ++k) {
+        if (!st) { x0[k] = x1[k] = mm[k] = 0; continue; }
+        const s3_pe_read_stats &s = st[evenRead + k];
+        x0[k] = (int32_t)s.x0; x1[k] = (int32_t)s.x1; mm[k] = s.x0 ? (int32_t)s.minMismatch : 0;
+    }
+}
+
+int decode_runs(const uint32_t *runs, uint32_t numRuns, uint32_t readLength, int32_t score, s3_dp_scores sc, std::string &cigar, int32_t *edit, int32_t *span)
+{
+    cigar.assign(10 * (size_t)numRuns + 16, '\0');
+    uint32_t len = 0;
+    const int rc = s3_runs_decode(runs, numRuns, readLength, score, sc, &cigar[0], (uint32_t)cigar.size(), &len, edit, span);
+    if (rc == S3_OK) cigar.resize(len);
+    return rc;
+}
+
+int append_pair(const s3_sam_genome *g, s3_sam_record rec[2], std::string &text)
+{
+    const int a = append_line(g, &rec[0], text), b = append_line(g, &rec[1], text);
+    return a ? a : b;
+}
+}  // namespace
+
+// outputDeepDPResult2 (OutputDPResult.cpp:590-760) over the hits of s3_deep_dp_align / s3_pe_deep_dp: the hits of a pair are next to each
+// other; the DeepDPAlignResult fields the engine derives (edit distances, insert size: DV-DPfunctions.cu:3765-3815) come from the runs.
+extern "C" int s3_sam_deep_dp_batch_text(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_reads *reads, uint64_t numReads,
+                                         const s3_deep_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
+                                         const s3_pe_read_stats *readStats, uint32_t numThreads, char **text, uint64_t *textBytes)
+{
+    if (text) *text = NULL;
+    if (textBytes) *textBytes = 0;
+    if (!g || !cfg || !reads_ok(reads) || (numHits && (!hits || !runs))) { s3_set_error("s3_sam_deep_dp_batch_text: NULL argument"); return S3_EINVAL; }
+    std::vector<uint64_t> first;
+    for (uint64_t i = 0; i < numHits; ++i) {
+        const s3_deep_dp_hit &h = hits[i];
+        if ((h.readID & 1u) || (uint64_t)h.readID + 1 >= numReads || (uint64_t)h.runOffset1 + h.numRuns1 > numRuns || (uint64_t)h.runOffset2 + h.numRuns2 > numRuns) {
+            s3_set_error("s3_sam_deep_dp_batch_text: hit %llu points outside the batch", (unsigned long long)i); return S3_EINVAL;
+        }
+        for (int k = 0; k < 2; ++k) if (reads->readLengths[h.readID + k] == 0 || reads->readLengths[h.readID + k] > reads->rowBytes) {
+            s3_set_error("s3_sam_deep_dp_batch_text: read %u has length %u (rows of %u)", h.readID + k, reads->readLengths[h.readID + k], reads->rowBytes); return S3_EINVAL;
+        }
+        if (i == 0 || h.readID != hits[i - 1].readID) first.push_back(i);
+    }
+    first.push_back(numHits);
+    return batch_text("s3_sam_deep_dp_batch_text", first.size() - 1, numThreads, text, textBytes, [&](uint64_t grp, std::string &out) {
+        const uint64_t a = first[grp], n = first[grp + 1] - a;
+        const uint32_t r = hits[a].readID, len1 = reads->readLengths[r], len2 = reads->readLengths[r + 1];
+        std::vector<s3_sam_deep_alignment> al(n);
+        std::vector<std::string> cig(2 * n);
+        for (uint64_t k = 0; k < n; ++k) {
+            const s3_deep_dp_hit &h = hits[a + k];
+            int32_t ed[2], span[2];
+            int rc = decode_runs(runs + h.runOffset1, h.numRuns1, len1, h.score1, scores, cig[2 * k], &ed[0], &span[0]);
+            if (!rc) rc = decode_runs(runs + h.runOffset2, h.numRuns2, len2, h.score2, scores, cig[2 * k + 1], &ed[1], &span[1]);
+            if (rc) return rc;
+            s3_sam_deep_alignment &x = al[k];
+            memset(&x, 0, sizeof x);
+            x.insertSize = h.pos1 < h.pos2 ? (int32_t)(h.pos2 - h.pos1 + len2) + span[1] : (int32_t)(h.pos1 - h.pos2 + len1) + span[0];
+            x.ambPosition[0] = h.pos1; x.ambPosition[1] = h.pos2; x.strand[0] = h.strand1; x.strand[1] = h.strand2;
+            x.score[0] = h.score1; x.score[1] = h.score2; x.editdist[0] = ed[0]; x.editdist[1] = ed[1];
+            x.numSameScore[0] = (int32_t)h.numSame1; x.numSameScore[1] = (int32_t)h.numSame2;
+            x.cigar[0] = cig[2 * k].c_str(); x.cigar[1] = cig[2 * k + 1].c_str();
+        }
+        int32_t x0[2], x1[2], mm[2];
+        pair_counts(readStats, r, x0, x1, mm);
+        s3_sam_record rec[2];
+        const int rc = s3_sam_deep_dp_records(g, cfg, al.data(), (uint32_t)n, s3_sam_pick_deep_dp(al.data(), (uint32_t)n),
+                                              reads->bases + (size_t)r * reads->rowBytes, reads->bases + (size_t)(r + 1) * reads->rowBytes,
+                                              reads->qualities + (size_t)r * reads->rowBytes, reads->qualities + (size_t)(r + 1) * reads->rowBytes,
+                                              (int32_t)len1, (int32_t)len2, reads->names[r], reads->names[r + 1], x0, x1, mm, rec);
+        return rc ? rc : append_pair(g, rec, out);
+    });
+}
+
+// outputDPResult2 (OutputDPResult.cpp:263-420) over the rescue records of s3_pe_align: every record of a pair becomes an AlgnmtDPResult as
+// the default-DP engine builds it (DV-DPfunctions.cu:2355-2440: whichFromDP = the DP read's parity, 2 with an unaligned DP side when it
+// missed its cutoff; insert size :2388-2400).  A pair none of whose rescues succeeded has no record here: it belongs to the writers of
+// improperly paired reads (s3_sam_unpaired_records over the reads' occurrence lists).
+extern "C" int s3_sam_pair_dp_batch_text(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_reads *reads, uint64_t numReads,
+                                         const s3_pe_dp_result *dp, uint64_t numRecords, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
+                                         const s3_pe_read_stats *readStats, uint32_t numThreads, char **text, uint64_t *textBytes)
+{
+    if (text) *text = NULL;
+    if (textBytes) *textBytes = 0;
+    if (!g || !cfg || !reads_ok(reads) || (numRecords && !dp)) { s3_set_error("s3_sam_pair_dp_batch_text: NULL argument"); return S3_EINVAL; }
+    std::vector<uint64_t> first;
+    for (uint64_t i = 0; i < numRecords; ++i) {
+        const s3_pe_dp_result &x = dp[i];
+        if ((uint64_t)(x.dpReadID | 1u) >= numReads || (x.numRuns && (!runs || (uint64_t)x.runOffset + x.numRuns > numRuns))) {
+            s3_set_error("s3_sam_pair_dp_batch_text: record %llu points outside the batch", (unsigned long long)i); return S3_EINVAL;
+        }
+        for (uint32_t k = x.dpReadID & ~1u; k <= (x.dpReadID | 1u); ++k) if (reads->readLengths[k] == 0 || reads->readLengths[k] > reads->rowBytes) {
+            s3_set_error("s3_sam_pair_dp_batch_text: read %u has length %u (rows of %u)", k, reads->readLengths[k], reads->rowBytes); return S3_EINVAL;
+        }
+        if (i == 0 || (x.dpReadID >> 1) != (dp[i - 1].dpReadID >> 1)) first.push_back(i);
+    }
+    first.push_back(numRecords);
+    return batch_text("s3_sam_pair_dp_batch_text", first.size() - 1, numThreads, text, textBytes, [&](uint64_t grp, std::string &out) {
+        const uint64_t a = first[grp], n = first[grp + 1] - a;
+        const uint32_t r = dp[a].dpReadID & ~1u;
+        std::vector<s3_sam_dp_pairing> al(n);
+        std::vector<std::string> cig(n);
+        bool any = false;
+        for (uint64_t k = 0; k < n; ++k) {
+            const s3_pe_dp_result &x = dp[a + k];
+            const uint32_t dpSide = x.dpReadID & 1u, alignedID = x.dpReadID ^ 1u;
+            s3_sam_dp_pairing &e = al[k];
+            memset(&e, 0, sizeof e);
+            uint32_t dpPos = 0xFFFFFFFFu;
+            if (x.numRuns) {
+                int32_t ed = 0, span = 0;
+                const int rc = decode_runs(runs + x.runOffset, x.numRuns, reads->readLengths[x.dpReadID], x.score, scores, cig[k], &ed, &span);
+                if (rc) return rc;
+                dpPos = x.dpPos;
+                e.whichFromDP = (uint8_t)dpSide; e.editdist = ed; e.numSameScore = (int32_t)x.numSameScore; e.cigar = cig[k].c_str();
+                e.insertSize = dpPos < x.alignedPos ? (int32_t)(x.alignedPos - dpPos + reads->readLengths[alignedID])
+                                                    : (int32_t)(dpPos - x.alignedPos + reads->readLengths[x.dpReadID]) + span;
+                any = true;
+            } else e.whichFromDP = 2;
+            e.ambPosition[dpSide] = dpPos; e.strand[dpSide] = x.dpStrand; e.score[dpSide] = x.score;
+            e.ambPosition[1 - dpSide] = x.alignedPos; e.strand[1 - dpSide] = x.alignedStrand; e.score[1 - dpSide] = x.alignedMismatches;
+        }
+        if (!any) return (int)S3_OK;
+        int32_t x0[2], x1[2], mm[2];
+        pair_counts(readStats, r, x0, x1, mm);
+        s3_sam_record rec[2];
+        const int rc = s3_sam_pair_dp_records(g, cfg, al.data(), (uint32_t)n, s3_sam_pick_pair_dp(al.data(), (uint32_t)n),
+                                              reads->bases + (size_t)r * reads->rowBytes, reads->bases + (size_t)(r + 1) * reads->rowBytes,
+                                              reads->qualities + (size_t)r * reads->rowBytes, reads->qualities + (size_t)(r + 1) * reads->rowBytes,
+                                              (int32_t)reads->readLengths[r], (int32_t)reads->readLengths[r + 1], reads->names[r], reads->names[r + 1], x0, x1, mm, rec);
+        return rc ? rc : append_pair(g, rec, out);
+    });
+}

@@ -1019,3 +1019,177 @@ def test_sam_single_dp_batch_text_groups_the_hits_of_a_read():
     text, size = C.c_void_p(), C.c_uint64()
     assert lib.s3_sam_single_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), bad.ctypes.data_as(C.c_void_p), C.c_uint64(len(bad)),
                                            helpers.u32p(rarr), C.c_uint64(len(rarr)), scores, cutoff, 2, C.byref(text), C.byref(size)) != 0
+
+
+def _cigar_runs(cg):
+    import re
+    return [(int(k) << 8) | ord(op) for k, op in re.findall(r"(\d+)([MmIDS])", cg)]
+
+
+def _decode(lib, runs, L, score, scores):
+    buf = C.create_string_buffer(4096)
+    e, s = C.c_int32(), C.c_int32()
+    sub = np.ascontiguousarray(runs, np.uint32)
+    assert lib.s3_runs_decode(helpers.u32p(sub), len(sub), L, score, scores, buf, 4096, None, C.byref(e), C.byref(s)) == 0
+    return buf.value, e.value, s.value
+
+
+def _stats(rng, num):
+    st = np.zeros(num, api.PE_READ_STATS_DTYPE)
+    st["x0"] = rng.integers(0, 4, num)
+    st["x1"] = rng.integers(0, 4, num)
+    st["minMismatch"] = np.where(st["x0"] > 0, rng.integers(0, 4, num), 255)
+    return st
+
+
+def _counts(st, r):
+    x0 = (C.c_int32 * 2)(*[int(st[r + k]["x0"]) for k in range(2)])
+    x1 = (C.c_int32 * 2)(*[int(st[r + k]["x1"]) for k in range(2)])
+    mm = (C.c_int32 * 2)(*[int(st[r + k]["minMismatch"]) if int(st[r + k]["x0"]) else 0 for k in range(2)])
+    return x0, x1, mm
+
+
+def test_sam_deep_dp_batch_text_is_the_pairs_records_in_order():
+    """s3_sam_deep_dp_batch_text == per pair: the hits' runs -> s3_runs_decode, insert size (DV-DPfunctions.cu:3810-3815), s3_sam_pick_deep_dp,
+    s3_sam_deep_dp_records, s3_sam_format_line -- with and without the search's per-read statistics, whatever the number of host threads"""
+    lib = _batch_lib()
+    lib.s3_sam_deep_dp_records.restype = C.c_int
+    lib.s3_sam_deep_dp_batch_text.restype = C.c_int
+    lib.s3_sam_pick_deep_dp.restype = C.c_int32
+    rng = np.random.default_rng(1618)
+    n, G, gen, cnames, keep = _batch_genome(rng)
+    num, row = 600, 160
+    lens, bases, quals, names, rd = _batch_reads(rng, num, row)
+    scores = api.DPScores(1, -2, -3, -1)
+    st = _stats(rng, num)
+    hits, runs, per_pair = [], [], {}
+    for r in range(0, num, 2):
+        if rng.random() < 0.3:
+            continue
+        L1, L2 = int(lens[r]), int(lens[r + 1])
+        for _ in range(int(rng.choice([1, 1, 2, 4]))):
+            r1, r2 = _cigar_runs(random_special_cigar(rng, L1)), _cigar_runs(random_special_cigar(rng, L2))
+            p1 = int(rng.choice([70_000, 100_000, 150_000])) - int(rng.integers(1, L1)) if rng.random() < 0.2 else int(rng.integers(1000, n - 3000))
+            s1 = int(rng.integers(1, 3))
+            gap = int(rng.integers(-30, 400))
+            p2 = min(max(p1 + gap if s1 == 1 else p1 - gap, 0), n - 2 * L2 - 8)
+            h = (r, p1, p2, int(rng.integers(30, L1 + 1)), int(rng.integers(30, L2 + 1)), int(rng.integers(1, 3)), int(rng.integers(1, 3)), len(runs), len(runs) + len(r1),
+                 len(r1), len(r2), s1, 3 - s1, (0, 0))
+            runs += r1 + r2
+            hits.append(h)
+            per_pair.setdefault(r, []).append(h)
+    harr = np.array(hits, api.DEEP_HIT_DTYPE)
+    rarr = np.array(runs, np.uint32)
+    for cfg, stats in ((Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), st), (Config(2, 1, 1, -2, 0, 40, 1, 1, 1, 1000, b"rgB"), None)):
+        want = []
+        for r in sorted(per_pair):
+            L1, L2 = int(lens[r]), int(lens[r + 1])
+            hs = per_pair[r]
+            arr = (DeepAlignment * len(hs))()
+            held = []
+            for k, h in enumerate(hs):
+                d1 = _decode(lib, rarr[h[7]:h[7] + h[9]], L1, h[3], scores)
+                d2 = _decode(lib, rarr[h[8]:h[8] + h[10]], L2, h[4], scores)
+                held += [d1[0], d2[0]]
+                arr[k].insertSize = (h[2] - h[1] + L2 + d2[2]) if h[1] < h[2] else (h[1] - h[2] + L1 + d1[2])
+                arr[k].ambPosition[0], arr[k].ambPosition[1] = h[1], h[2]
+                arr[k].strand[0], arr[k].strand[1] = h[11], h[12]
+                arr[k].score[0], arr[k].score[1] = h[3], h[4]
+                arr[k].editdist[0], arr[k].editdist[1] = d1[1], d2[1]
+                arr[k].numSameScore[0], arr[k].numSameScore[1] = h[5], h[6]
+                arr[k].cigar[0], arr[k].cigar[1] = d1[0], d2[0]
+            x0, x1, mm = _counts(stats, r) if stats is not None else ((C.c_int32 * 2)(0, 0),) * 3
+            out = (Record * 2)()
+            assert lib.s3_sam_deep_dp_records(C.byref(gen), C.byref(cfg), arr, len(hs), lib.s3_sam_pick_deep_dp(arr, len(hs)), bases[r].ctypes.data_as(U8P), bases[r + 1].ctypes.data_as(U8P),
+                                              C.cast(quals[r].ctypes.data, C.c_char_p), C.cast(quals[r + 1].ctypes.data, C.c_char_p), L1, L2, names[r], names[r + 1], x0, x1, mm, out) == 0
+            want += [_line_of(lib, out[0], cnames), _line_of(lib, out[1], cnames)]
+        want = b"".join(x + b"\n" for x in want)
+        for threads in (1, 6, 0):
+            text, size = C.c_void_p(), C.c_uint64()
+            rc = lib.s3_sam_deep_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), harr.ctypes.data_as(C.c_void_p), C.c_uint64(len(harr)), helpers.u32p(rarr),
+                                               C.c_uint64(len(rarr)), scores, stats.ctypes.data_as(C.c_void_p) if stats is not None else None, threads, C.byref(text), C.byref(size))
+            assert rc == 0, lib.s3_last_error()
+            got = C.string_at(text.value, size.value)
+            lib.s3_free(text)
+            assert got == want and got.count(b"\n") == 2 * len(per_pair)
+    bad = harr.copy(); bad[2]["readID"] += 1                                # an odd read id is not a pair's
+    text, size = C.c_void_p(), C.c_uint64()
+    assert lib.s3_sam_deep_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), bad.ctypes.data_as(C.c_void_p), C.c_uint64(len(bad)), helpers.u32p(rarr),
+                                         C.c_uint64(len(rarr)), scores, None, 2, C.byref(text), C.byref(size)) != 0
+
+
+def test_sam_pair_dp_batch_text_is_the_rescued_pairs_records_in_order():
+    """s3_sam_pair_dp_batch_text == per pair: every rescue record as the AlgnmtDPResult of the default-DP engine (whichFromDP, insert size,
+    the unaligned form of a DP side under its cutoff), s3_sam_pick_pair_dp, s3_sam_pair_dp_records, s3_sam_format_line; pairs none of whose
+    rescues succeeded get no lines"""
+    lib = _batch_lib()
+    lib.s3_sam_pair_dp_records.restype = C.c_int
+    lib.s3_sam_pair_dp_batch_text.restype = C.c_int
+    lib.s3_sam_pick_pair_dp.restype = C.c_int32
+    rng = np.random.default_rng(5772)
+    n, G, gen, cnames, keep = _batch_genome(rng)
+    num, row = 600, 160
+    lens, bases, quals, names, rd = _batch_reads(rng, num, row)
+    scores = api.DPScores(1, -2, -3, -1)
+    st = _stats(rng, num)
+    NONE = 0xFFFFFFFF
+    recs, runs, per_pair = [], [], {}
+    for r in range(0, num, 2):
+        if rng.random() < 0.3:
+            continue
+        main = int(rng.integers(0, 2))
+        for _ in range(int(rng.choice([1, 1, 2, 4]))):
+            dp_side = main if rng.random() < 0.8 else 1 - main
+            Ld = int(lens[r + dp_side])
+            ok = rng.random() < 0.75
+            mine = _cigar_runs(random_special_cigar(rng, Ld)) if ok else []
+            pa = int(rng.choice([70_000, 100_000, 150_000])) - int(rng.integers(1, 36)) if rng.random() < 0.15 else int(rng.integers(1000, n - 3000))
+            sa = int(rng.integers(1, 3))
+            gap = int(rng.integers(-30, 400))
+            pd = min(max(pa + gap if sa == 1 else pa - gap, 0), n - 2 * Ld - 8)
+            x = (r + dp_side, pa, pd if ok else 0, int(rng.integers(30, Ld + 1)) if ok else int(rng.integers(0, 29)), int(rng.integers(1, 3)), len(runs), len(mine),
+                 sa, int(rng.integers(0, 4)), 3 - sa, int(rng.integers(0, 2)), (0, 0))
+            runs += mine
+            recs.append(x)
+            per_pair.setdefault(r, []).append(x)
+    darr = np.array(recs, api.PE_DP_DTYPE)
+    rarr = np.array(runs, np.uint32)
+    silent = 0
+    for cfg in (Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), Config(2, 1, 1, -2, 0, 40, 1, 1, 1, 1000, b"rgB")):
+        want = []
+        silent = 0
+        for r in sorted(per_pair):
+            xs = per_pair[r]
+            arr = (DpPairing * len(xs))()
+            held = []
+            for k, x in enumerate(xs):
+                side = x[0] & 1
+                if x[6]:
+                    cg, ed, dis = _decode(lib, rarr[x[5]:x[5] + x[6]], int(lens[x[0]]), x[3], scores)
+                    held.append(cg)
+                    arr[k].whichFromDP, arr[k].editdist, arr[k].numSameScore, arr[k].cigar = side, ed, x[4], cg
+                    arr[k].insertSize = (x[1] - x[2] + int(lens[x[0] ^ 1])) if x[2] < x[1] else (x[2] - x[1] + int(lens[x[0]]) + dis)
+                    dp_pos = x[2]
+                else:
+                    arr[k].whichFromDP, dp_pos = 2, NONE
+                arr[k].ambPosition[side], arr[k].strand[side], arr[k].score[side] = dp_pos, x[9], x[3]
+                arr[k].ambPosition[1 - side], arr[k].strand[1 - side], arr[k].score[1 - side] = x[1], x[7], x[8]
+            if all(a.whichFromDP == 2 for a in arr):
+                silent += 1
+                continue
+            x0, x1, mm = _counts(st, r)
+            out = (Record * 2)()
+            assert lib.s3_sam_pair_dp_records(C.byref(gen), C.byref(cfg), arr, len(xs), lib.s3_sam_pick_pair_dp(arr, len(xs)), bases[r].ctypes.data_as(U8P), bases[r + 1].ctypes.data_as(U8P),
+                                              C.cast(quals[r].ctypes.data, C.c_char_p), C.cast(quals[r + 1].ctypes.data, C.c_char_p), int(lens[r]), int(lens[r + 1]), names[r], names[r + 1],
+                                              x0, x1, mm, out) == 0, lib.s3_last_error()
+            want += [_line_of(lib, out[0], cnames), _line_of(lib, out[1], cnames)]
+        want = b"".join(x + b"\n" for x in want)
+        for threads in (1, 6, 0):
+            text, size = C.c_void_p(), C.c_uint64()
+            rc = lib.s3_sam_pair_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), darr.ctypes.data_as(C.c_void_p), C.c_uint64(len(darr)), helpers.u32p(rarr),
+                                               C.c_uint64(len(rarr)), scores, st.ctypes.data_as(C.c_void_p), threads, C.byref(text), C.byref(size))
+            assert rc == 0, lib.s3_last_error()
+            got = C.string_at(text.value, size.value)
+            lib.s3_free(text)
+            assert got == want
+    assert silent > 10

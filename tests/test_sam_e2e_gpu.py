@@ -201,10 +201,11 @@ def test_read_pairs_through_deep_dp_to_sam_records(env):
     cfg = Config(1, 0, SCORES[0], SCORES[1], 1, 40, 1, 1, 1, 1000, b"rgDeep")
     zeros = (C.c_int32 * 2)(0, 0)
     counts = np.zeros(6, np.int32)
+    quals = np.ascontiguousarray(rng.integers(2, 41, (n, L + 1)).astype(np.uint8)); quals[:, -1] = 0
+    lines = []
     for e in sorted(by_pair_got):
         q1, q2 = np.ascontiguousarray(reads[e]).astype(np.uint8), np.ascontiguousarray(reads[e + 1]).astype(np.uint8)
-        ql1 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql1[-1] = 0
-        ql2 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql2[-1] = 0
+        ql1, ql2 = quals[e], quals[e + 1]
         n1, n2 = b"p%d/1" % e, b"p%d/2" % e
         # ---- the CUDA path's hits -> the writer's inputs
         hs = by_pair_got[e]
@@ -227,6 +228,7 @@ def test_read_pairs_through_deep_dp_to_sam_records(env):
         assert lib.s3_sam_deep_dp_records(C.byref(one.gen), C.byref(cfg), arr, len(hs), best, q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p),
                                           ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2, zeros, zeros, zeros, out) == 0
         mine = [record_tuple(r) for r in out]
+        lines += [line_of(lib, one, out[0]) + b"\n", line_of(lib, one, out[1]) + b"\n"]
         for k in range(2):
             lib.s3_sam_record_free(C.byref(out[k]))
         # ---- the oracle's hits -> the reference's writer
@@ -250,6 +252,16 @@ def test_read_pairs_through_deep_dp_to_sam_records(env):
                                    core.ctypes.data_as(I32P), data.ctypes.data_as(U8P), 8192, dlen.ctypes.data_as(I32P)) == 2
         theirs = [(tuple(int(x) for x in core[12 * r:12 * r + 12]), bytes(data[r * 8192:r * 8192 + int(dlen[r])])) for r in range(2)]
         assert mine == theirs, (e, mine, theirs)
+    # the stage's whole result as SAM text (s3_sam_deep_dp_batch_text over hits + runs) == those records' lines, pairs in hit order
+    padded = np.zeros((n, L + 1), np.uint8); padded[:, :L] = np.stack(reads)
+    rd, keep = batch_reads(padded, quals, lens[:n], [b"p%d/%d" % (r & ~1, 1 + (r & 1)) for r in range(n)])
+    lib.s3_sam_deep_dp_batch_text.restype = C.c_int
+    text, size = C.c_void_p(), C.c_uint64()
+    hits, runs = np.ascontiguousarray(got["hits"]), np.ascontiguousarray(got["runs"], np.uint32)
+    assert lib.s3_sam_deep_dp_batch_text(C.byref(one.gen), C.byref(cfg), C.byref(rd), C.c_uint64(n), hits.ctypes.data_as(C.c_void_p), C.c_uint64(len(hits)), helpers.u32p(runs),
+                                         C.c_uint64(len(runs)), api.DPScores(*SCORES), None, 4, C.byref(text), C.byref(size)) == 0, lib.s3_last_error()
+    assert C.string_at(text.value, size.value) == b"".join(lines) and len(lines) == 2 * len(by_pair_got)
+    lib.s3_free(text)
 
 
 def test_single_reads_through_single_dp_to_sam_records(env):
@@ -442,10 +454,11 @@ def test_rescued_pairs_through_the_chain_to_sam_records(env):
     cfg = Config(1, 0, SCORES[0], SCORES[1], 1, 40, 1, 1, 1, 1000, b"rgRescue")
     rng = np.random.default_rng(31)
     done = 0
+    quals = np.ascontiguousarray(rng.integers(2, 41, (2 * pairs, L + 1)).astype(np.uint8)); quals[:, -1] = 0
+    lines = []
     for p in sorted(mine_by):
         q1, q2 = np.ascontiguousarray(reads[2 * p]).astype(np.uint8), np.ascontiguousarray(reads[2 * p + 1]).astype(np.uint8)
-        ql1 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql1[-1] = 0
-        ql2 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql2[-1] = 0
+        ql1, ql2 = quals[2 * p], quals[2 * p + 1]
         n1, n2 = b"r%d/1" % p, b"r%d/2" % p
         # ---- the chain's records -> the writer's inputs
         ents, cigs = [], []
@@ -473,6 +486,7 @@ def test_rescued_pairs_through_the_chain_to_sam_records(env):
         assert lib.s3_sam_pair_dp_records(C.byref(one.gen), C.byref(cfg), arr, len(ents), best, q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p),
                                           ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2, x0, x1, mm, out) == 0, api.load_library().s3_last_error()
         mine = [record_tuple(r) for r in out]
+        lines += [line_of(lib, one, out[0]) + b"\n", line_of(lib, one, out[1]) + b"\n"]
         for k in range(2):
             lib.s3_sam_record_free(C.byref(out[k]))
         # ---- the oracle chain's records -> the reference's writer
@@ -500,3 +514,13 @@ def test_rescued_pairs_through_the_chain_to_sam_records(env):
         assert mine == theirs, (p, ents, mine, theirs)
         done += 1
     assert done > pairs // 6
+    # the chain's rescue records of the whole batch as SAM text (s3_sam_pair_dp_batch_text) == those records' lines, pairs in record order
+    padded = np.zeros((2 * pairs, L + 1), np.uint8); padded[:, :L] = np.asarray(reads)[:2 * pairs]
+    rd, keep = batch_reads(padded, quals, np.full(2 * pairs, L, np.uint32), [b"r%d/%d" % (r >> 1, 1 + (r & 1)) for r in range(2 * pairs)])
+    lib.s3_sam_pair_dp_batch_text.restype = C.c_int
+    text, size = C.c_void_p(), C.c_uint64()
+    dp, runs, stats = np.ascontiguousarray(got["dp"]), np.ascontiguousarray(got["runs"], np.uint32), np.ascontiguousarray(got["read_stats"])
+    assert lib.s3_sam_pair_dp_batch_text(C.byref(one.gen), C.byref(cfg), C.byref(rd), C.c_uint64(2 * pairs), dp.ctypes.data_as(C.c_void_p), C.c_uint64(len(dp)), helpers.u32p(runs),
+                                         C.c_uint64(len(runs)), api.DPScores(*SCORES), stats.ctypes.data_as(C.c_void_p), 4, C.byref(text), C.byref(size)) == 0, lib.s3_last_error()
+    assert C.string_at(text.value, size.value) == b"".join(lines) and len(lines) == 2 * done
+    lib.s3_free(text)

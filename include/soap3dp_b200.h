@@ -823,7 +823,9 @@ int s3_sam_deep_dp_records(const s3_sam_genome *genome, const s3_sam_config *con
  * from DP (score = DP score; CIGAR, MD, XM / XO / XG by getMisInfoForDP, MAPQ leg s3_mapq_pair_end_dp); whichFromDP says which
  * (0 the first read, 1 its mate), and only the entries of the reported entry's kind are counted and listed.  X0 / X1 per read from
  * those entries and the search's counts (x0 / x1 / mismatch), the "second best" pair for s3_mapq_bwa_pair as the reference's scan
- * leaves it, read-through pairs as in s3_sam_deep_dp_records (the single read left: s3_mapq_unique_dp or s3_mapq_unique). */
+ * leaves it, read-through pairs as in s3_sam_deep_dp_records (the single read left: s3_mapq_unique_dp or s3_mapq_unique).  With a
+ * reported entry whose DP side missed its cutoff (whichFromDP 2) the other entries of that kind are listed in XA:Z only where they
+ * have a position for the read (the reference translates 0xFFFFFFFF through tables that do not reach it there). */
 typedef struct {
     uint8_t whichFromDP, strand[2], pad;                                              /* AlgnmtDPResult, PEAlgnmt.h:384-402; [0] the pair's first read, [1] its mate */
     int32_t editdist, insertSize, numSameScore;

@@ -692,6 +692,7 @@ extern "C" int s3_sam_deep_dp_records(const s3_sam_genome *g, const s3_sam_confi
             for (uint32_t i = 0; i < num; ++i) {
                 if ((int32_t)i == bestIndex) continue;
                 if (cfg->alignmentType == 2 && algn[i].score[0] + algn[i].score[1] < bestPairScore) continue;
+                if (algn[i].ambPosition[k] == NONE) continue;             // no position to translate (the stage's hits always have both)
                 unsigned long long t;
                 uint32_t c;
                 chr_and_pos(g, algn[i].ambPosition[k], &t, &c);
@@ -901,6 +902,9 @@ extern "C" int s3_sam_pair_dp_records(const s3_sam_genome *g, const s3_sam_confi
             for (uint32_t i = 0; i < num; ++i) {
                 if ((int32_t)i == bestIndex || algn[i].whichFromDP != fromDP) continue;
                 if (cfg->alignmentType == 2 && (algn[i].score[0] != bestPairScore[0] || algn[i].score[1] != bestPairScore[1])) continue;
+                // an entry whose DP side missed its cutoff (whichFromDP 2) has no position for that read: with a reported entry of that kind the
+                // reference translates 0xFFFFFFFF through tables that do not reach it; nothing is listed here
+                if (algn[i].ambPosition[k] == NONE) continue;
                 unsigned long long t;
                 uint32_t c;
                 chr_and_pos(g, algn[i].ambPosition[k], &t, &c);

@@ -117,6 +117,7 @@ void record_body(s3_sam_record &r, std::vector<uint8_t> &d, int readlen, const c
                  const std::string &md, int mapq, const char *readGroup, bool printMDNM)
 {
     d.clear();
+    d.reserve(2 * (size_t)readlen + xa.size() + md.size() + 192);
     r.bin = 0;                                           // bam_reg2bin(0, 0): the end wraps below 0, no level contains the interval
     r.l_qseq = readlen;
     r.l_qname = (uint8_t)(strlen(name) + 1);
@@ -133,18 +134,23 @@ void record_body(s3_sam_record &r, std::vector<uint8_t> &d, int readlen, const c
             }
         } else { r.n_cigar = 1; put32(d, (uint32_t)readlen << 4); }
     }
-    if (strand == 2) {
-        if (readlen % 2 == 1) {
-            for (int i = (readlen - 1) / 2; i > 0; --i) d.push_back((uint8_t)((kNt16[3 - seq[i * 2]] << 4) | kNt16[3 - seq[i * 2 - 1]]));
-            d.push_back((uint8_t)(kNt16[3 - seq[0]] << 4));
+    {
+        const size_t at = d.size(), half = ((size_t)readlen + 1) / 2;
+        d.resize(at + half + (size_t)readlen);
+        uint8_t *p = d.data() + at, *pq = p + half;
+        if (strand == 2) {
+            if (readlen % 2 == 1) {
+                for (int i = (readlen - 1) / 2; i > 0; --i) *p++ = (uint8_t)((kNt16[3 - seq[i * 2]] << 4) | kNt16[3 - seq[i * 2 - 1]]);
+                *p++ = (uint8_t)(kNt16[3 - seq[0]] << 4);
+            } else {
+                for (int i = readlen / 2 - 1; i >= 0; --i) *p++ = (uint8_t)((kNt16[3 - seq[i * 2 + 1]] << 4) | kNt16[3 - seq[i * 2]]);
+            }
+            for (int i = readlen - 1; i >= 0; --i) *pq++ = (uint8_t)qual[i];
         } else {
-            for (int i = readlen / 2 - 1; i >= 0; --i) d.push_back((uint8_t)((kNt16[3 - seq[i * 2 + 1]] << 4) | kNt16[3 - seq[i * 2]]));
+            for (int i = 0; i < readlen / 2; ++i) *p++ = (uint8_t)((kNt16[seq[i * 2]] << 4) | kNt16[seq[i * 2 + 1]]);
+            if (readlen % 2 == 1) *p++ = (uint8_t)(kNt16[seq[readlen - 1]] << 4);
+            memcpy(pq, qual, (size_t)readlen);
         }
-        for (int i = readlen - 1; i >= 0; --i) d.push_back((uint8_t)qual[i]);
-    } else {
-        for (int i = 0; i < readlen / 2; ++i) d.push_back((uint8_t)((kNt16[seq[i * 2]] << 4) | kNt16[seq[i * 2 + 1]]));
-        if (readlen % 2 == 1) d.push_back((uint8_t)(kNt16[seq[readlen - 1]] << 4));
-        for (int i = 0; i < readlen; ++i) d.push_back((uint8_t)qual[i]);
     }
     const size_t auxStart = d.size();
     put_tag(d, "RG", 'Z', readGroup, strlen(readGroup) + 1);
@@ -1214,17 +1220,17 @@ extern "C" int s3_sam_single_answer_record(const s3_sam_genome *g, const s3_sam_
 }
 
 // ---- the SAM text line of a record: bam_format1 (samtools-0.1.18/bam.c:243-329, what samwrite prints for a text file) ----------
-extern "C" int s3_sam_format_line(const s3_sam_record *r, const char *const *chrNames, uint32_t numChr, char **line)
+static int format_line_into(const s3_sam_record *r, const char *const *chrNames, uint32_t numChr, std::string &s)      // appends the line to s
 {
-    if (!r || !line || !r->data) { s3_set_error("s3_sam_format_line: NULL argument"); return S3_EINVAL; }
-    *line = NULL;
+    if (!r || !r->data) { s3_set_error("s3_sam_format_line: NULL argument"); return S3_EINVAL; }
     if ((r->tid >= 0 || r->mtid >= 0) && !chrNames) { s3_set_error("s3_sam_format_line: chromosome names needed"); return S3_EINVAL; }
     if (r->tid >= (int32_t)numChr || r->mtid >= (int32_t)numChr) { s3_set_error("s3_sam_format_line: chromosome id out of range"); return S3_EINVAL; }
     const size_t seqBytes = ((size_t)r->l_qseq + 1) / 2, fixed = (size_t)r->l_qname + 4 * (size_t)r->n_cigar + seqBytes + (size_t)r->l_qseq;
     if (r->l_qname == 0 || fixed > (size_t)r->data_len) { s3_set_error("s3_sam_format_line: the record's data is shorter than its fields"); return S3_EINVAL; }
     static const char nt16[] = "=ACMGRSVTWYHKDBN";                       // bam_nt16_rev_table
     const uint8_t *d = r->data, *cig = d + r->l_qname, *seq = cig + 4 * (size_t)r->n_cigar, *qual = seq + seqBytes, *aux = qual + r->l_qseq, *end = d + r->data_len;
-    std::string s;
+    const size_t room = 2 * (size_t)r->data_len + 96;                       // a hint; growth stays geometric when lines are appended to one text
+    if (s.capacity() - s.size() < room) s.reserve(std::max(2 * s.capacity(), s.size() + room));
     char nb[24];
     auto num = [&](long long v) { s.append(nb, write_num(v, nb)); };
     s.append((const char *)d, (size_t)r->l_qname - 1); s.push_back('\t');
@@ -1241,9 +1247,13 @@ extern "C" int s3_sam_format_line(const s3_sam_record *r, const char *const *chr
     if (r->mtid < 0) s += "*\t"; else if (r->mtid == r->tid) s += "=\t"; else { s += chrNames[r->mtid]; s.push_back('\t'); }
     num((long long)r->mpos + 1); s.push_back('\t'); num(r->isize); s.push_back('\t');
     if (r->l_qseq) {
-        for (int32_t i = 0; i < r->l_qseq; ++i) s.push_back(nt16[(seq[i >> 1] >> ((~i & 1) << 2)) & 0xF]);
-        s.push_back('\t');
-        if (qual[0] == 0xFF) s.push_back('*'); else for (int32_t i = 0; i < r->l_qseq; ++i) s.push_back((char)(qual[i] + 33));
+        const size_t at = s.size(), n = (size_t)r->l_qseq;
+        const bool noQual = qual[0] == 0xFF;
+        s.resize(at + n + 1 + (noQual ? 1 : n));
+        char *p = &s[at];
+        for (size_t i = 0; i < n; ++i) p[i] = nt16[(seq[i >> 1] >> ((~i & 1) << 2)) & 0xF];
+        p[n] = '\t';
+        if (noQual) p[n + 1] = '*'; else for (size_t i = 0; i < n; ++i) p[n + 1 + i] = (char)(qual[i] + 33);
     } else s += "*\t*";
     for (const uint8_t *p = aux; p + 3 <= end;) {
         const char type = (char)p[2];
@@ -1259,6 +1269,16 @@ extern "C" int s3_sam_format_line(const s3_sam_record *r, const char *const *chr
         else if (type == 'Z' || type == 'H') { s.push_back(type); s.push_back(':'); while (p < end && *p) s.push_back((char)*p++); ++p; }
         else { s3_set_error("s3_sam_format_line: tag type '%c' is not one the record writers produce", type); return S3_EINVAL; }
     }
+    return S3_OK;
+}
+
+extern "C" int s3_sam_format_line(const s3_sam_record *r, const char *const *chrNames, uint32_t numChr, char **line)
+{
+    if (!line) { s3_set_error("s3_sam_format_line: NULL argument"); return S3_EINVAL; }
+    *line = NULL;
+    std::string s;
+    const int rc = format_line_into(r, chrNames, numChr, s);
+    if (rc) return rc;
     *line = (char *)malloc(s.size() + 1);
     if (!*line) { s3_set_error("s3_sam_format_line: out of host memory"); return S3_ENOMEM; }
     memcpy(*line, s.c_str(), s.size() + 1);
@@ -1357,12 +1377,11 @@ int batch_text(const char *what, uint64_t n, uint32_t numThreads, char **text, u
 
 int append_line(const s3_sam_genome *g, s3_sam_record *rec, std::string &text)
 {
-    char *line = NULL;
-    const int rc = s3_sam_format_line(rec, g->chrNames, g->numChr, &line);
+    const size_t at = text.size();
+    const int rc = format_line_into(rec, g->chrNames, g->numChr, text);
     s3_sam_record_free(rec);
-    if (rc) return rc;
-    text += line; text.push_back('\n');
-    free(line);
+    if (rc) { text.resize(at); return rc; }
+    text.push_back('\n');
     return S3_OK;
 }
 

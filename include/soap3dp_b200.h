@@ -908,6 +908,13 @@ int s3_sam_single_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config
  *                                s3_sam_pick_pair_dp -> s3_sam_pair_dp_records (outputDPResult2, OutputDPResult.cpp:263-420).  A pair none
  *                                of whose rescues succeeded gets no lines: it belongs to the writers of improperly paired reads
  *                                (s3_sam_unpaired_records over the reads' occurrence lists). */
+/*   s3_sam_paired_batch_text     the pairs s3_pe_align paired (route S3_PE_PAIRED) with ONE valid pairing -> s3_sam_pair_records with the
+ *                                chain's reported pairing, totals and per-read statistics (hostKernel's SAM branch, CPUfunctions.cpp:2281-2380
+ *                                -> pairOutputSAMAPI); readStats is required.  Pairs with more valid pairings need the whole list for XA:Z
+ *                                (s3_pair_occurrences) and get no lines here. */
+int s3_sam_paired_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
+                             const uint8_t *route, const s3_pe_pair_result *pairs, uint64_t numPairs, const s3_pe_read_stats *readStats,
+                             uint32_t numThreads, char **text, uint64_t *textBytes);
 int s3_sam_deep_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
                               const s3_deep_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
                               const s3_pe_read_stats *readStats, uint32_t numThreads, char **text, uint64_t *textBytes);

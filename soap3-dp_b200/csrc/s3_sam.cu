@@ -1586,3 +1586,40 @@ extern "C" int s3_sam_pair_dp_batch_text(const s3_sam_genome *g, const s3_sam_co
         return rc ? rc : append_pair(g, rec, out);
     });
 }
+
+// hostKernel's SAM branch for a pair the search paired (CPUfunctions.cpp:2281-2380 -> pairOutputSAMAPI) over the paired-end chain's result:
+// the pairs with route S3_PE_PAIRED and ONE valid pairing -- the chain returns the reported pairing, the totals and (params.readStats) the
+// per-read counts, which is all the writer takes then.  Pairs with more valid pairings need the whole list for XA:Z (s3_pair_occurrences)
+// and are left to the caller, like every other route.
+extern "C" int s3_sam_paired_batch_text(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_reads *reads, uint64_t numReads,
+                                        const uint8_t *route, const s3_pe_pair_result *pairs, uint64_t numPairs, const s3_pe_read_stats *readStats,
+                                        uint32_t numThreads, char **text, uint64_t *textBytes)
+{
+    if (text) *text = NULL;
+    if (textBytes) *textBytes = 0;
+    if (!g || !cfg || !reads_ok(reads) || (numPairs && (!route || !pairs || !readStats))) { s3_set_error("s3_sam_paired_batch_text: NULL argument (the chain's readStats are needed)"); return S3_EINVAL; }
+    if (2 * numPairs > numReads) { s3_set_error("s3_sam_paired_batch_text: %llu pairs of %llu reads", (unsigned long long)numPairs, (unsigned long long)numReads); return S3_EINVAL; }
+    std::vector<uint64_t> pick;
+    for (uint64_t p = 0; p < numPairs; ++p) {
+        if (route[p] != S3_PE_PAIRED || pairs[p].numPairs != 1) continue;
+        for (uint64_t r = 2 * p; r < 2 * p + 2; ++r) if (reads->readLengths[r] == 0 || reads->readLengths[r] > reads->rowBytes) {
+            s3_set_error("s3_sam_paired_batch_text: read %llu has length %u (rows of %u)", (unsigned long long)r, reads->readLengths[r], reads->rowBytes); return S3_EINVAL;
+        }
+        pick.push_back(p);
+    }
+    return batch_text("s3_sam_paired_batch_text", pick.size(), numThreads, text, textBytes, [&](uint64_t i, std::string &out) {
+        const uint64_t p = pick[i], r = 2 * p;
+        const s3_pe_pair_result &x = pairs[p];
+        const s3_pe_read_stats &s1 = readStats[r], &s2 = readStats[r + 1];
+        s3_sam_pairing pr;
+        memset(&pr, 0, sizeof pr);
+        pr.algnmt1 = x.pos1; pr.algnmt2 = x.pos2; pr.strand1 = x.strand1; pr.mismatch1 = x.mism1; pr.strand2 = x.strand2; pr.mismatch2 = x.mism2; pr.totalMismatchCount = x.optimalTotal;
+        s3_sam_record rec[2];
+        const int rc = s3_sam_pair_records(g, cfg, &pr, 1, 0, reads->bases + r * reads->rowBytes, reads->bases + (r + 1) * reads->rowBytes,
+                                           reads->qualities + r * reads->rowBytes, reads->qualities + (r + 1) * reads->rowBytes,
+                                           (int32_t)reads->readLengths[r], (int32_t)reads->readLengths[r + 1], reads->names[r], reads->names[r + 1],
+                                           x.optimalTotal, x.suboptimalTotal, (int32_t)s1.x0, (int32_t)s2.x0, (int32_t)s1.x1, (int32_t)s2.x1, (int32_t)x.numOptimal,
+                                           s1.minMismatch == x.mism1, s2.minMismatch == x.mism2, x.numPairs, rec);
+        return rc ? rc : append_pair(g, rec, out);
+    });
+}

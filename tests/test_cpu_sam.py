@@ -1193,3 +1193,65 @@ def test_sam_pair_dp_batch_text_is_the_rescued_pairs_records_in_order():
             lib.s3_free(text)
             assert got == want
     assert silent > 10
+
+
+def test_sam_paired_batch_text_is_the_paired_reads_records_in_order():
+    """s3_sam_paired_batch_text == s3_sam_pair_records + s3_sam_format_line for the pairs with route 1 and one valid pairing (the chain's
+    reported pairing, totals and per-read statistics as the writer's counts); other routes and pairs with more pairings get no lines"""
+    lib = _batch_lib()
+    lib.s3_sam_pair_records.restype = C.c_int
+    lib.s3_sam_paired_batch_text.restype = C.c_int
+    rng = np.random.default_rng(8128)
+    n, G, gen, cnames, keep = _batch_genome(rng)
+    num, row = 800, 160
+    lens, bases, quals, names, rd = _batch_reads(rng, num, row)
+    P = num // 2
+    st = _stats(rng, num)
+    st["x0"] = np.maximum(st["x0"], 1)
+    st["minMismatch"] = rng.integers(0, 3, num)
+    route = rng.choice([1, 1, 1, 2, 4, 0], P).astype(np.uint8)
+    pr = np.zeros(P, api.PE_PAIR_DTYPE)
+    for p in range(P):
+        L1, L2 = int(lens[2 * p]), int(lens[2 * p + 1])
+        p1 = int(rng.choice([70_000, 100_000, 150_000])) - int(rng.integers(1, L1)) if rng.random() < 0.15 else int(rng.integers(1000, n - 3000))
+        s1 = int(rng.integers(1, 3))
+        gap = int(rng.integers(50, 400))
+        p2 = min(max(p1 + gap if s1 == 1 else p1 - gap, 0), n - L2)
+        # the reads: the text at the pairing's positions with a few substitutions, so that MD and the mismatch counts have content
+        for k, (pos, sd, L) in enumerate(((p1, s1, L1), (p2, 3 - s1, L2))):
+            r = G[pos:pos + L].copy()
+            for j in rng.choice(L, int(rng.integers(0, 3)), replace=False):
+                r[j] = (r[j] + 1) & 3
+            bases[2 * p + k, :L] = (3 - r[::-1]) if sd == 2 else r
+        m1, m2 = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+        pr[p] = (p1, p2, abs(p2 - p1) + L2, s1, m1, 3 - s1, m2, int(rng.choice([1, 1, 1, 2])), int(rng.integers(1, 3)), int(rng.integers(0, 3)), m1 + m2,
+                 int(rng.choice([127, m1 + m2 + 1])), 0)
+    for cfg in (Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), Config(2, 1, 1, -2, 0, 40, 1, 1, 1, 1000, b"rgB")):
+        want, done = [], 0
+        for p in range(P):
+            x = pr[p]
+            if int(route[p]) != 1 or int(x["numPairs"]) != 1:
+                continue
+            arr = (Pairing * 1)(Pairing(int(x["pos1"]), int(x["pos2"]), int(x["strand1"]), int(x["mism1"]), int(x["strand2"]), int(x["mism2"]), int(x["optimalTotal"])))
+            s1, s2 = st[2 * p], st[2 * p + 1]
+            counts = (int(x["optimalTotal"]), int(x["suboptimalTotal"]), int(s1["x0"]), int(s2["x0"]), int(s1["x1"]), int(s2["x1"]), int(x["numOptimal"]),
+                      int(int(s1["minMismatch"]) == int(x["mism1"])), int(int(s2["minMismatch"]) == int(x["mism2"])), int(x["numPairs"]))
+            out = (Record * 2)()
+            assert lib.s3_sam_pair_records(C.byref(gen), C.byref(cfg), arr, 1, 0, bases[2 * p].ctypes.data_as(U8P), bases[2 * p + 1].ctypes.data_as(U8P),
+                                           C.cast(quals[2 * p].ctypes.data, C.c_char_p), C.cast(quals[2 * p + 1].ctypes.data, C.c_char_p), int(lens[2 * p]), int(lens[2 * p + 1]),
+                                           names[2 * p], names[2 * p + 1], *counts, out) == 0, lib.s3_last_error()
+            want += [_line_of(lib, out[0], cnames), _line_of(lib, out[1], cnames)]
+            done += 1
+        want = b"".join(x + b"\n" for x in want)
+        assert 100 < done < P
+        for threads in (1, 6, 0):
+            text, size = C.c_void_p(), C.c_uint64()
+            rc = lib.s3_sam_paired_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), route.ctypes.data_as(U8P), pr.ctypes.data_as(C.c_void_p), C.c_uint64(P),
+                                              st.ctypes.data_as(C.c_void_p), threads, C.byref(text), C.byref(size))
+            assert rc == 0, lib.s3_last_error()
+            got = C.string_at(text.value, size.value)
+            lib.s3_free(text)
+            assert got == want
+    text, size = C.c_void_p(), C.c_uint64()
+    assert lib.s3_sam_paired_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), route.ctypes.data_as(U8P), pr.ctypes.data_as(C.c_void_p), C.c_uint64(P),
+                                        None, 2, C.byref(text), C.byref(size)) != 0                   # no statistics, no counts for the writer

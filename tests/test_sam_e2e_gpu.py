@@ -356,16 +356,20 @@ def test_read_pairs_through_the_chain_to_sam_records(env):
     ostats = chain.oracle_read_stats(chain.LAST["views"], chain.LAST["allowed"], chain.LAST["text_length"], chain.LAST["max_output"])
     rng = np.random.default_rng(23)
     done = 0
+    quals = np.ascontiguousarray(rng.integers(2, 41, (2 * pairs, L + 1)).astype(np.uint8)); quals[:, -1] = 0
+    padded = np.zeros((2 * pairs, L + 1), np.uint8); padded[:, :L] = np.asarray(reads)[:2 * pairs]
+    rd, keep = batch_reads(padded, quals, np.full(2 * pairs, L, np.uint32), [b"c%d/%d" % (r >> 1, 1 + (r & 1)) for r in range(2 * pairs)])
+    lib.s3_sam_paired_batch_text.restype = C.c_int
     for mode in ((1, 0), (2, 1)):                                     # (report type, BWA-like MAPQ)
         cfg = Config(mode[0], mode[1], SCORES[0], SCORES[1], 1, 40, 1, 1, 1, 1000, b"rgPE")
+        lines = []
         for p in range(pairs):
             g = got["pairs"][p]
             if int(got["route"][p]) != 1 or int(g["numPairs"]) != 1:
                 continue
             w = want["pairs"][p]
             q1, q2 = np.ascontiguousarray(reads[2 * p]).astype(np.uint8), np.ascontiguousarray(reads[2 * p + 1]).astype(np.uint8)
-            ql1 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql1[-1] = 0
-            ql2 = np.ascontiguousarray(rng.integers(2, 41, L + 1).astype(np.uint8)); ql2[-1] = 0
+            ql1, ql2 = quals[2 * p], quals[2 * p + 1]
             n1, n2 = b"c%d/1" % p, b"c%d/2" % p
             # ---- the chain's result of the pair -> the writer's inputs
             s1, s2 = got["read_stats"][2 * p], got["read_stats"][2 * p + 1]
@@ -376,6 +380,7 @@ def test_read_pairs_through_the_chain_to_sam_records(env):
             assert lib.s3_sam_pair_records(C.byref(one.gen), C.byref(cfg), arr, 1, 0, q1.ctypes.data_as(U8P), q2.ctypes.data_as(U8P), ql1.ctypes.data_as(C.c_char_p),
                                            ql2.ctypes.data_as(C.c_char_p), L, L, n1, n2, *counts, out) == 0
             mine = [record_tuple(r) for r in out]
+            lines += [line_of(lib, one, out[0]) + b"\n", line_of(lib, one, out[1]) + b"\n"]
             for k in range(2):
                 lib.s3_sam_record_free(C.byref(out[k]))
             # ---- the oracle chain's result -> the reference's writer
@@ -390,6 +395,13 @@ def test_read_pairs_through_the_chain_to_sam_records(env):
             theirs = [(tuple(int(x) for x in core[12 * r:12 * r + 12]), bytes(data[r * 8192:r * 8192 + int(dlen[r])])) for r in range(2)]
             assert mine == theirs, (p, mine, theirs)
             done += 1
+        # the chain's result of the whole batch as SAM text (s3_sam_paired_batch_text) == those records' lines, pairs in order
+        text, size = C.c_void_p(), C.c_uint64()
+        rt, pr, stats = np.ascontiguousarray(got["route"], np.uint8), np.ascontiguousarray(got["pairs"]), np.ascontiguousarray(got["read_stats"])
+        assert lib.s3_sam_paired_batch_text(C.byref(one.gen), C.byref(cfg), C.byref(rd), C.c_uint64(2 * pairs), rt.ctypes.data_as(U8P), pr.ctypes.data_as(C.c_void_p), C.c_uint64(pairs),
+                                            stats.ctypes.data_as(C.c_void_p), 4, C.byref(text), C.byref(size)) == 0, lib.s3_last_error()
+        assert C.string_at(text.value, size.value) == b"".join(lines) and len(lines) > pairs // 2
+        lib.s3_free(text)
     assert done > pairs // 2
 
 

@@ -1354,14 +1354,18 @@ int batch_text(const char *what, uint64_t n, uint32_t numThreads, char **text, u
     BatchError err;
     auto work = [&](uint32_t t) {
         const uint64_t a = n * t / T, b = n * (t + 1) / T;
-        for (uint64_t r = a; r < b && err.rc.load(std::memory_order_relaxed) == 0; ++r) {
-            const int rc = one(r, part[t]);
-            if (rc) { batch_fail(err, rc); return; }
-        }
+        try {
+            for (uint64_t r = a; r < b && err.rc.load(std::memory_order_relaxed) == 0; ++r) {
+                const int rc = one(r, part[t]);
+                if (rc) { batch_fail(err, rc); return; }
+            }
+        } catch (...) { s3_set_error("%s: out of host memory", what); batch_fail(err, S3_ENOMEM); }
     };
     std::vector<std::thread> th;
-    for (uint32_t t = 1; t < T; ++t) th.emplace_back(work, t);
+    uint32_t started = 1;
+    try { for (; started < T; ++started) th.emplace_back(work, started); } catch (...) { }
     work(0);
+    for (uint32_t t = started; t < T; ++t) work(t);                       // slices whose thread could not be started run here
     for (auto &x : th) x.join();
     if (err.rc) { s3_set_error("%s", err.msg); return err.rc; }
     size_t total = 0;

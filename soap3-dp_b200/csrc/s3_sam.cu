@@ -1355,6 +1355,7 @@ int batch_text(const char *what, uint64_t n, uint32_t numThreads, char **text, u
     auto work = [&](uint32_t t) {
         const uint64_t a = n * t / T, b = n * (t + 1) / T;
         try {
+            part[t].reserve((size_t)(b - a) * 352 + 4096);                 // about a line of a 100-base read each; growth stays geometric beyond it
             for (uint64_t r = a; r < b && err.rc.load(std::memory_order_relaxed) == 0; ++r) {
                 const int rc = one(r, part[t]);
                 if (rc) { batch_fail(err, rc); return; }
@@ -1372,8 +1373,15 @@ int batch_text(const char *what, uint64_t n, uint32_t numThreads, char **text, u
     for (auto &p : part) total += p.size();
     char *out = (char *)malloc(total + 1);
     if (!out) { s3_set_error("%s: out of host memory", what); return S3_ENOMEM; }
-    size_t at = 0;
-    for (auto &p : part) { memcpy(out + at, p.data(), p.size()); at += p.size(); }
+    std::vector<size_t> at(T + 1, 0);
+    for (uint32_t t = 0; t < T; ++t) at[t + 1] = at[t] + part[t].size();
+    auto copy = [&](uint32_t t) { memcpy(out + at[t], part[t].data(), part[t].size()); std::string().swap(part[t]); };
+    th.clear();
+    started = 1;
+    try { for (; started < T; ++started) th.emplace_back(copy, started); } catch (...) { }
+    copy(0);
+    for (uint32_t t = started; t < T; ++t) copy(t);
+    for (auto &x : th) x.join();
     out[total] = 0;
     *text = out; *textBytes = total;
     return S3_OK;

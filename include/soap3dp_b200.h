@@ -915,6 +915,14 @@ int s3_sam_single_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config
 int s3_sam_paired_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
                              const uint8_t *route, const s3_pe_pair_result *pairs, uint64_t numPairs, const s3_pe_read_stats *readStats,
                              uint32_t numThreads, char **text, uint64_t *textBytes);
+/*   s3_sam_unpaired_batch_text   pairs without a valid pairing, each read on its own from its occurrence list -> s3_sam_unpaired_records
+ *                                (hostKernel's SAM branch, CPUfunctions.cpp:2546-2557 -> unproperlypairOutputSAMAPI, for runs without the DP stages).  The lists are a CSR over
+ *                                ALL reads of the batch -- what s3_se_align returns for the same queries -- and pairIDs names the pairs to
+ *                                write (pair p = reads 2p and 2p + 1), e.g. those of the chain's routes without a DP result. */
+int s3_sam_unpaired_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
+                               const uint32_t *occOffsets, const uint32_t *positions, const uint8_t *occFlags,
+                               const uint32_t *pairIDs, uint64_t numPairs, uint32_t peMaxOutputPerRead, uint32_t numThreads,
+                               char **text, uint64_t *textBytes);
 int s3_sam_deep_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
                               const s3_deep_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
                               const s3_pe_read_stats *readStats, uint32_t numThreads, char **text, uint64_t *textBytes);

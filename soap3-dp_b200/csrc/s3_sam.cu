@@ -1635,3 +1635,41 @@ extern "C" int s3_sam_paired_batch_text(const s3_sam_genome *g, const s3_sam_con
         return rc ? rc : append_pair(g, rec, out);
     });
 }
+
+// hostKernel's SAM branch for a pair without a valid pairing (CPUfunctions.cpp:2546-2557 -> unproperlypairOutputSAMAPI, for runs without the DP stages): each read reported
+// on its own from its occurrence list.  The lists are a CSR over all reads of the batch -- what s3_se_align returns for the same queries
+// (the paired-end chain keeps its occurrences on the device) -- and pairIDs names the pairs to write (pair p = reads 2p, 2p + 1).
+extern "C" int s3_sam_unpaired_batch_text(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_reads *reads, uint64_t numReads,
+                                          const uint32_t *occOffsets, const uint32_t *positions, const uint8_t *occFlags,
+                                          const uint32_t *pairIDs, uint64_t numPairs, uint32_t peMaxOutputPerRead, uint32_t numThreads,
+                                          char **text, uint64_t *textBytes)
+{
+    if (text) *text = NULL;
+    if (textBytes) *textBytes = 0;
+    if (!g || !cfg || !reads_ok(reads) || !occOffsets || (numPairs && !pairIDs) || (numReads && occOffsets[numReads] && (!positions || !occFlags))) {
+        s3_set_error("s3_sam_unpaired_batch_text: NULL argument"); return S3_EINVAL;
+    }
+    for (uint64_t i = 0; i < numPairs; ++i) {
+        const uint64_t r = 2 * (uint64_t)pairIDs[i];
+        if (r + 1 >= numReads) { s3_set_error("s3_sam_unpaired_batch_text: pair %u lies outside the batch", pairIDs[i]); return S3_EINVAL; }
+        for (uint64_t k = r; k < r + 2; ++k) {
+            if (occOffsets[k + 1] < occOffsets[k]) { s3_set_error("s3_sam_unpaired_batch_text: occOffsets decrease at read %llu", (unsigned long long)k); return S3_EINVAL; }
+            if (reads->readLengths[k] == 0 || reads->readLengths[k] > reads->rowBytes) { s3_set_error("s3_sam_unpaired_batch_text: read %llu has length %u (rows of %u)", (unsigned long long)k, reads->readLengths[k], reads->rowBytes); return S3_EINVAL; }
+        }
+    }
+    return batch_text("s3_sam_unpaired_batch_text", numPairs, numThreads, text, textBytes, [&](uint64_t i, std::string &out) {
+        const uint64_t r = 2 * (uint64_t)pairIDs[i];
+        std::vector<s3_sam_occurrence> occ[2];
+        for (int k = 0; k < 2; ++k) {
+            const uint32_t a = occOffsets[r + k], n = occOffsets[r + k + 1] - a;
+            occ[k].resize(n);
+            for (uint32_t j = 0; j < n; ++j) { occ[k][j].ambPosition = positions[a + j]; occ[k][j].strand = occFlags[2 * (size_t)(a + j)]; occ[k][j].mismatchCount = occFlags[2 * (size_t)(a + j) + 1]; occ[k][j].pad[0] = occ[k][j].pad[1] = 0; }
+        }
+        s3_sam_record rec[2];
+        const int rc = s3_sam_unpaired_records(g, cfg, occ[0].data(), (uint32_t)occ[0].size(), occ[1].data(), (uint32_t)occ[1].size(), peMaxOutputPerRead,
+                                               reads->bases + r * reads->rowBytes, reads->bases + (r + 1) * reads->rowBytes,
+                                               reads->qualities + r * reads->rowBytes, reads->qualities + (r + 1) * reads->rowBytes,
+                                               (int32_t)reads->readLengths[r], (int32_t)reads->readLengths[r + 1], reads->names[r], reads->names[r + 1], rec);
+        return rc ? rc : append_pair(g, rec, out);
+    });
+}

@@ -1255,3 +1255,48 @@ def test_sam_paired_batch_text_is_the_paired_reads_records_in_order():
     text, size = C.c_void_p(), C.c_uint64()
     assert lib.s3_sam_paired_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), route.ctypes.data_as(U8P), pr.ctypes.data_as(C.c_void_p), C.c_uint64(P),
                                         None, 2, C.byref(text), C.byref(size)) != 0                   # no statistics, no counts for the writer
+
+
+def test_sam_unpaired_batch_text_is_the_named_pairs_records_in_order():
+    """s3_sam_unpaired_batch_text == s3_sam_unpaired_records + s3_sam_format_line for the pairs named, from a CSR of occurrences over all
+    reads of the batch (s3_se_align's arrays); pairs with one or both reads without an occurrence included"""
+    lib = _batch_lib()
+    lib.s3_sam_unpaired_records.restype = C.c_int
+    lib.s3_sam_unpaired_batch_text.restype = C.c_int
+    rng = np.random.default_rng(4669)
+    n, G, gen, cnames, keep = _batch_genome(rng)
+    num, row = 600, 160
+    lens, bases, quals, names, rd = _batch_reads(rng, num, row)
+    counts = rng.choice([0, 1, 1, 2, 4, 7], num)
+    off = np.zeros(num + 1, np.uint32)
+    off[1:] = np.cumsum(counts)
+    tot = int(off[-1])
+    pos = rng.integers(0, n - 160, tot).astype(np.uint32)
+    flags = np.ascontiguousarray(np.stack([rng.integers(1, 3, tot), rng.integers(0, 4, tot)], 1).astype(np.uint8))
+    ids = np.sort(rng.choice(num // 2, 180, replace=False)).astype(np.uint32)
+    for cfg, cap in ((Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), 1000), (Config(2, 1, 1, -2, 0, 40, 1, 1, 1, 1000, b"rgB"), 3), (Config(4, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgC"), 1000)):
+        want = []
+        for p in ids.tolist():
+            arrs, ns = [], []
+            for r in (2 * p, 2 * p + 1):
+                a, b = int(off[r]), int(off[r + 1])
+                arrs.append((Occurrence * max(b - a, 1))(*[Occurrence(int(pos[i]), int(flags[i][0]), int(flags[i][1])) for i in range(a, b)]))
+                ns.append(b - a)
+            out = (Record * 2)()
+            assert lib.s3_sam_unpaired_records(C.byref(gen), C.byref(cfg), arrs[0], ns[0], arrs[1], ns[1], cap, bases[2 * p].ctypes.data_as(U8P), bases[2 * p + 1].ctypes.data_as(U8P),
+                                               C.cast(quals[2 * p].ctypes.data, C.c_char_p), C.cast(quals[2 * p + 1].ctypes.data, C.c_char_p), int(lens[2 * p]), int(lens[2 * p + 1]),
+                                               names[2 * p], names[2 * p + 1], out) == 0, lib.s3_last_error()
+            want += [_line_of(lib, out[0], cnames), _line_of(lib, out[1], cnames)]
+        want = b"".join(x + b"\n" for x in want)
+        for threads in (1, 5, 0):
+            text, size = C.c_void_p(), C.c_uint64()
+            rc = lib.s3_sam_unpaired_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P),
+                                                helpers.u32p(ids), C.c_uint64(len(ids)), cap, threads, C.byref(text), C.byref(size))
+            assert rc == 0, lib.s3_last_error()
+            got = C.string_at(text.value, size.value)
+            lib.s3_free(text)
+            assert got == want and got.count(b"\n") == 2 * len(ids)
+    bad = ids.copy(); bad[0] = num // 2                                      # a pair beyond the batch
+    text, size = C.c_void_p(), C.c_uint64()
+    assert lib.s3_sam_unpaired_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P),
+                                          helpers.u32p(bad), C.c_uint64(len(bad)), 1000, 2, C.byref(text), C.byref(size)) != 0

@@ -923,6 +923,15 @@ int s3_sam_unpaired_batch_text(const s3_sam_genome *genome, const s3_sam_config 
                                const uint32_t *occOffsets, const uint32_t *positions, const uint8_t *occFlags,
                                const uint32_t *pairIDs, uint64_t numPairs, uint32_t peMaxOutputPerRead, uint32_t numThreads,
                                char **text, uint64_t *textBytes);
+/*   s3_sam_unpaired_dp_batch_text  the pairs no stage paired, after DP: per read ONE list as the reference's AllHits holds it (PEAlgnmt.cpp:1033-1260) --
+ *                                the read's hits of s3_single_dp_align when it has any (isFromDP 1; s3_runs_decode), else its occurrences from the
+ *                                search (CSR as above; isFromDP 0, score = len x match + mismatches x mismatch score, CIGAR <len>M) -- and
+ *                                s3_sam_unpaired_dp_records for the two lists (outputSingleResultForPairEnds, OutputDPResult.cpp:1062-1150). */
+int s3_sam_unpaired_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
+                                  const uint32_t *occOffsets, const uint32_t *positions, const uint8_t *occFlags,
+                                  const s3_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
+                                  int32_t singleDPcutoffThreshold, const uint32_t *pairIDs, uint64_t numPairs, uint32_t numThreads,
+                                  char **text, uint64_t *textBytes);
 int s3_sam_deep_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
                               const s3_deep_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
                               const s3_pe_read_stats *readStats, uint32_t numThreads, char **text, uint64_t *textBytes);

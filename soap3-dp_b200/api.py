@@ -40,7 +40,7 @@ EXPORTS = [
     "s3_dp_create", "s3_dp_free", "s3_dp_stream", "s3_dp_pattern_length", "s3_dp_align", "s3_dp_align_device",
     "s3_dp_align_windows_device", "s3_random_sector_probe", "s3_dp_make_windows", "s3_index_set_l2_persist", "s3_index_clone",
     "s3_pe_create", "s3_pe_free", "s3_pe_prefetch", "s3_pe_align", "s3_pe_align_device", "s3_pe_set_timing", "s3_pe_read_timing", "s3_pe_dp",
-    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_validate_alignments", "s3_sam_pair_records", "s3_sam_single_record", "s3_sam_single_dp_record", "s3_sam_deep_dp_records", "s3_sam_pair_dp_records", "s3_sam_unpaired_records", "s3_sam_unpaired_dp_records", "s3_sam_single_answer_record", "s3_sam_format_line", "s3_sam_pick_deep_dp", "s3_sam_pick_pair_dp", "s3_sam_single_batch_text", "s3_sam_single_dp_batch_text", "s3_sam_deep_dp_batch_text", "s3_sam_pair_dp_batch_text", "s3_sam_paired_batch_text", "s3_sam_unpaired_batch_text", "s3_runs_decode", "s3_sam_record_free", "s3_index_load", "s3_pe_deep_dp", "s3_seed_search", "s3_seed_search_result_free",
+    "s3_se_create", "s3_se_free", "s3_se_align", "s3_se_align_device", "s3_validate_alignments", "s3_sam_pair_records", "s3_sam_single_record", "s3_sam_single_dp_record", "s3_sam_deep_dp_records", "s3_sam_pair_dp_records", "s3_sam_unpaired_records", "s3_sam_unpaired_dp_records", "s3_sam_single_answer_record", "s3_sam_format_line", "s3_sam_pick_deep_dp", "s3_sam_pick_pair_dp", "s3_sam_single_batch_text", "s3_sam_single_dp_batch_text", "s3_sam_deep_dp_batch_text", "s3_sam_pair_dp_batch_text", "s3_sam_paired_batch_text", "s3_sam_unpaired_batch_text", "s3_sam_unpaired_dp_batch_text", "s3_runs_decode", "s3_sam_record_free", "s3_index_load", "s3_pe_deep_dp", "s3_seed_search", "s3_seed_search_result_free",
     "s3_single_dp_align", "s3_single_dp_result_free", "s3_deep_dp_align", "s3_deep_dp_result_free",
 ]
 

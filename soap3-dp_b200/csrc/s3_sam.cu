@@ -1673,3 +1673,75 @@ extern "C" int s3_sam_unpaired_batch_text(const s3_sam_genome *g, const s3_sam_c
         return rc ? rc : append_pair(g, rec, out);
     });
 }
+
+// outputSingleResultForPairEnds (OutputDPResult.cpp:1062-1150) over what the stages left for the pairs that never became properly paired: per
+// read ONE list (AllHits, PEAlgnmt.cpp:1033-1260) -- the hits of the single-read DP stage when the read has any (inputAlgnmtsToArray: isFromDP 1),
+// else its occurrences from the search (inputSoap3AnsToArray: isFromDP 0, score = len x match + mismatches x mismatch score, CIGAR <len>M,
+// edit distance = the mismatches), else nothing -- and unproperlypairDPOutputSAMAPI for the two lists.
+extern "C" int s3_sam_unpaired_dp_batch_text(const s3_sam_genome *g, const s3_sam_config *cfg, const s3_sam_reads *reads, uint64_t numReads,
+                                             const uint32_t *occOffsets, const uint32_t *positions, const uint8_t *occFlags,
+                                             const s3_dp_hit *hits, uint64_t numHits, const uint32_t *runs, uint64_t numRuns, s3_dp_scores scores,
+                                             int32_t singleDPcutoffThreshold, const uint32_t *pairIDs, uint64_t numPairs, uint32_t numThreads,
+                                             char **text, uint64_t *textBytes)
+{
+    if (text) *text = NULL;
+    if (textBytes) *textBytes = 0;
+    if (!g || !cfg || !reads_ok(reads) || !occOffsets || (numPairs && !pairIDs) || (numHits && (!hits || !runs)) ||
+        (numReads && occOffsets[numReads] && (!positions || !occFlags))) { s3_set_error("s3_sam_unpaired_dp_batch_text: NULL argument"); return S3_EINVAL; }
+    // the hits of a read are next to each other (candidate order): first hit and count per read
+    std::vector<uint64_t> firstHit(numReads, 0);
+    std::vector<uint32_t> hitCount(numReads, 0);
+    for (uint64_t i = 0; i < numHits; ++i) {
+        const s3_dp_hit &h = hits[i];
+        if (h.readID >= numReads || (uint64_t)h.runOffset + h.numRuns > numRuns) { s3_set_error("s3_sam_unpaired_dp_batch_text: hit %llu points outside the batch", (unsigned long long)i); return S3_EINVAL; }
+        if (hitCount[h.readID] && hits[i - 1].readID != h.readID) { s3_set_error("s3_sam_unpaired_dp_batch_text: the hits of read %u are not next to each other", h.readID); return S3_EINVAL; }
+        if (!hitCount[h.readID]) firstHit[h.readID] = i;
+        ++hitCount[h.readID];
+    }
+    for (uint64_t i = 0; i < numPairs; ++i) {
+        const uint64_t r = 2 * (uint64_t)pairIDs[i];
+        if (r + 1 >= numReads) { s3_set_error("s3_sam_unpaired_dp_batch_text: pair %u lies outside the batch", pairIDs[i]); return S3_EINVAL; }
+        for (uint64_t k = r; k < r + 2; ++k) {
+            if (occOffsets[k + 1] < occOffsets[k]) { s3_set_error("s3_sam_unpaired_dp_batch_text: occOffsets decrease at read %llu", (unsigned long long)k); return S3_EINVAL; }
+            if (reads->readLengths[k] == 0 || reads->readLengths[k] > reads->rowBytes) { s3_set_error("s3_sam_unpaired_dp_batch_text: read %llu has length %u (rows of %u)", (unsigned long long)k, reads->readLengths[k], reads->rowBytes); return S3_EINVAL; }
+        }
+    }
+    return batch_text("s3_sam_unpaired_dp_batch_text", numPairs, numThreads, text, textBytes, [&](uint64_t i, std::string &out) {
+        const uint64_t r = 2 * (uint64_t)pairIDs[i];
+        std::vector<s3_sam_read_alignment> al[2];
+        std::vector<std::string> cig[2];
+        for (int k = 0; k < 2; ++k) {
+            const uint64_t id = r + k;
+            const uint32_t len = reads->readLengths[id];
+            if (hitCount[id]) {
+                al[k].resize(hitCount[id]); cig[k].resize(hitCount[id]);
+                for (uint32_t j = 0; j < hitCount[id]; ++j) {
+                    const s3_dp_hit &h = hits[firstHit[id] + j];
+                    int32_t ed = 0, span = 0;
+                    const int rc = decode_runs(runs + h.runOffset, h.numRuns, len, h.score, scores, cig[k][j], &ed, &span);
+                    if (rc) return rc;
+                    s3_sam_read_alignment &a = al[k][j];
+                    memset(&a, 0, sizeof a);
+                    a.ambPosition = h.pos; a.strand = h.strand; a.isFromDP = 1; a.score = h.score; a.editdist = ed; a.cigar = cig[k][j].c_str();
+                }
+            } else {
+                const uint32_t a0 = occOffsets[id], n = occOffsets[id + 1] - a0;
+                al[k].resize(n); cig[k].resize(n ? 1 : 0);
+                if (n) { char nb[24]; cig[k][0].assign(nb, write_num(len, nb)); cig[k][0].push_back('M'); }
+                for (uint32_t j = 0; j < n; ++j) {
+                    s3_sam_read_alignment &a = al[k][j];
+                    memset(&a, 0, sizeof a);
+                    const int32_t mism = occFlags[2 * (size_t)(a0 + j) + 1];
+                    a.ambPosition = positions[a0 + j]; a.strand = occFlags[2 * (size_t)(a0 + j)]; a.isFromDP = 0;
+                    a.score = (int32_t)len * cfg->dpMatchScore + mism * cfg->dpMisMatchScore; a.editdist = mism; a.cigar = cig[k][0].c_str();
+                }
+            }
+        }
+        s3_sam_record rec[2];
+        const int rc = s3_sam_unpaired_dp_records(g, cfg, al[0].data(), (uint32_t)al[0].size(), al[1].data(), (uint32_t)al[1].size(), singleDPcutoffThreshold,
+                                                  reads->bases + r * reads->rowBytes, reads->bases + (r + 1) * reads->rowBytes,
+                                                  reads->qualities + r * reads->rowBytes, reads->qualities + (r + 1) * reads->rowBytes,
+                                                  (int32_t)reads->readLengths[r], (int32_t)reads->readLengths[r + 1], reads->names[r], reads->names[r + 1], rec);
+        return rc ? rc : append_pair(g, rec, out);
+    });
+}

@@ -1300,3 +1300,93 @@ def test_sam_unpaired_batch_text_is_the_named_pairs_records_in_order():
     text, size = C.c_void_p(), C.c_uint64()
     assert lib.s3_sam_unpaired_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P),
                                           helpers.u32p(bad), C.c_uint64(len(bad)), 1000, 2, C.byref(text), C.byref(size)) != 0
+
+
+def test_sam_unpaired_dp_batch_text_builds_one_list_per_read():
+    """s3_sam_unpaired_dp_batch_text == per named pair: each read's list as the reference's AllHits holds it (its single-read DP hits when it
+    has any, else its occurrences from the search with score = len x match + mismatches x mismatch score and CIGAR <len>M, else nothing)
+    -> s3_sam_unpaired_dp_records -> s3_sam_format_line"""
+    lib = _batch_lib()
+    lib.s3_sam_unpaired_dp_records.restype = C.c_int
+    lib.s3_sam_unpaired_dp_batch_text.restype = C.c_int
+    rng = np.random.default_rng(1729)
+    n, G, gen, cnames, keep = _batch_genome(rng)
+    num, row = 600, 160
+    lens, bases, quals, names, rd = _batch_reads(rng, num, row)
+    scores = api.DPScores(1, -2, -3, -1)
+    kind = rng.choice([0, 1, 2], num, p=[0.2, 0.4, 0.4])                      # nothing / search occurrences / DP hits (a few of these also have occurrences: DP wins)
+    counts = np.where(kind == 1, rng.choice([1, 1, 2, 5], num), np.where((kind == 2) & (rng.random(num) < 0.2), 1, 0))
+    off = np.zeros(num + 1, np.uint32)
+    off[1:] = np.cumsum(counts)
+    tot = int(off[-1])
+    near = rng.integers(1000, n - 3000, num // 2)
+    pos = rng.integers(0, n - 400, tot).astype(np.uint32)
+    flags = np.ascontiguousarray(np.stack([rng.integers(1, 3, tot), rng.integers(0, 4, tot)], 1).astype(np.uint8))
+    hits, runs, per_read = [], [], {}
+    for r in range(num):
+        if kind[r] != 2:
+            continue
+        L = int(lens[r])
+        for _ in range(int(rng.choice([1, 1, 2, 4]))):
+            cg = random_special_cigar(rng, L)
+            mine = _cigar_runs(cg)
+            p = int(near[r // 2]) + int(rng.integers(-300, 300)) if rng.random() < 0.5 else int(rng.integers(0, n - 2 * L - 8))
+            h = (r, p, int(rng.integers(int(0.3 * L), L + 1)), int(rng.integers(1, 3)), len(runs), len(mine), int(rng.integers(1, 3)), 0)
+            runs += mine
+            hits.append(h)
+            per_read.setdefault(r, []).append(h)
+    # mates of reads with DP hits often lie near them (insert sizes on one chromosome)
+    for r in range(num):
+        if kind[r] == 1 and rng.random() < 0.5:
+            pos[int(off[r])] = int(near[r // 2]) + int(rng.integers(-300, 300))
+    harr = np.array(hits, api.DP_HIT_DTYPE)
+    rarr = np.array(runs, np.uint32)
+    ids = np.sort(rng.choice(num // 2, 200, replace=False)).astype(np.uint32)
+    cutoff = 30
+    for cfg in (Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), Config(2, 1, 1, -2, 0, 40, 1, 1, 1, 1000, b"rgB"), Config(3, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgC")):
+        want = []
+        mixed = 0
+        for p in ids.tolist():
+            arrs, ns, held = [], [], []
+            for r in (2 * p, 2 * p + 1):
+                L = int(lens[r])
+                if r in per_read:
+                    hs = per_read[r]
+                    a = (ReadAlignment * len(hs))()
+                    for k, h in enumerate(hs):
+                        cg, ed, _ = _decode(lib, rarr[h[4]:h[4] + h[5]], L, h[2], scores)
+                        held.append(cg)
+                        a[k].ambPosition, a[k].strand, a[k].score, a[k].editdist, a[k].isFromDP, a[k].cigar = h[1], h[6], h[2], ed, 1, cg
+                    arrs.append(a); ns.append(len(hs))
+                else:
+                    lo, hi = int(off[r]), int(off[r + 1])
+                    a = (ReadAlignment * max(hi - lo, 1))()
+                    cg = b"%dM" % L
+                    held.append(cg)
+                    for k, i in enumerate(range(lo, hi)):
+                        mm = int(flags[i][1])
+                        a[k].ambPosition, a[k].strand, a[k].score, a[k].editdist, a[k].isFromDP, a[k].cigar = int(pos[i]), int(flags[i][0]), L * cfg.dpMatchScore + mm * cfg.dpMisMatchScore, mm, 0, cg
+                    arrs.append(a); ns.append(hi - lo)
+            mixed += (2 * p in per_read) != (2 * p + 1 in per_read)
+            out = (Record * 2)()
+            assert lib.s3_sam_unpaired_dp_records(C.byref(gen), C.byref(cfg), arrs[0], ns[0], arrs[1], ns[1], cutoff, bases[2 * p].ctypes.data_as(U8P), bases[2 * p + 1].ctypes.data_as(U8P),
+                                                  C.cast(quals[2 * p].ctypes.data, C.c_char_p), C.cast(quals[2 * p + 1].ctypes.data, C.c_char_p), int(lens[2 * p]), int(lens[2 * p + 1]),
+                                                  names[2 * p], names[2 * p + 1], out) == 0, lib.s3_last_error()
+            want += [_line_of(lib, out[0], cnames), _line_of(lib, out[1], cnames)]
+        want = b"".join(x + b"\n" for x in want)
+        assert mixed > 40
+        for threads in (1, 5, 0):
+            text, size = C.c_void_p(), C.c_uint64()
+            rc = lib.s3_sam_unpaired_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P),
+                                                   harr.ctypes.data_as(C.c_void_p), C.c_uint64(len(harr)), helpers.u32p(rarr), C.c_uint64(len(rarr)), scores, cutoff,
+                                                   helpers.u32p(ids), C.c_uint64(len(ids)), threads, C.byref(text), C.byref(size))
+            assert rc == 0, lib.s3_last_error()
+            got = C.string_at(text.value, size.value)
+            lib.s3_free(text)
+            assert got == want and got.count(b"\n") == 2 * len(ids)
+    # hits of a read that are not next to each other are refused
+    bad = np.concatenate([harr, harr[:1]])
+    text, size = C.c_void_p(), C.c_uint64()
+    assert lib.s3_sam_unpaired_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P),
+                                             bad.ctypes.data_as(C.c_void_p), C.c_uint64(len(bad)), helpers.u32p(rarr), C.c_uint64(len(rarr)), scores, cutoff,
+                                             helpers.u32p(ids), C.c_uint64(len(ids)), 2, C.byref(text), C.byref(size)) != 0

@@ -1043,3 +1043,133 @@ def index_clone(gpu_index: GpuIndex) -> GpuIndex:
     out = C.c_void_p()
     _check(lib.s3_index_clone(gpu_index.handle, C.byref(out)), "s3_index_clone")
     return GpuIndex(out.value, gpu_index.text_length)
+
+
+# ---- SAM text of whole batches (s3_sam_*_batch_text): the structs of include/soap3dp_b200.h and one wrapper per entry ----------------
+class SamSegment(C.Structure):
+    _fields_ = [("startPos", C.c_uint32), ("chrID", C.c_uint32), ("correction", C.c_uint32)]
+
+
+class SamGenome(C.Structure):
+    _fields_ = [("packedDNA", C.POINTER(C.c_uint32)), ("dnaLength", C.c_uint32), ("segments", C.POINTER(SamSegment)), ("numSegments", C.c_uint32),
+                ("ambiguityMap", C.POINTER(C.c_uint32)), ("chrEndPos", C.POINTER(C.c_uint32)), ("numChr", C.c_uint32), ("chrNames", C.POINTER(C.c_char_p))]
+
+
+class SamConfig(C.Structure):
+    _fields_ = [("alignmentType", C.c_int32), ("bwaLikeScore", C.c_int32), ("dpMatchScore", C.c_int32), ("dpMisMatchScore", C.c_int32),
+                ("isFastq", C.c_int32), ("maxMAPQ", C.c_int32), ("minMAPQ", C.c_int32), ("isPrintMDNM", C.c_int32), ("outputXAZTag", C.c_int32),
+                ("peMaxOutputPerPair", C.c_uint32), ("readGroup", C.c_char_p)]
+
+
+class SamReadsStruct(C.Structure):
+    _fields_ = [("bases", C.POINTER(C.c_uint8)), ("qualities", C.c_char_p), ("rowBytes", C.c_uint32), ("readLengths", C.POINTER(C.c_uint32)),
+                ("names", C.POINTER(C.c_char_p))]
+
+
+def _u32(a):
+    return np.ascontiguousarray(a, np.uint32)
+
+
+class SamGenomeDesc:
+    """s3_sam_genome over numpy arrays (kept alive here): packed text (hsp->packedDNA), the translate table as rows (startPos, chrID, correction),
+    the ambiguity map, the chromosomes' last positions and names"""
+
+    def __init__(self, packed_dna, dna_length: int, segments, ambiguity_map, chr_end_pos, chr_names):
+        self.pac, self.amb, self.end = _u32(packed_dna), _u32(ambiguity_map), _u32(chr_end_pos)
+        seg = np.asarray(segments, np.int64).reshape(-1, 3)
+        self.segs = (SamSegment * len(seg))(*[SamSegment(int(a) & 0xFFFFFFFF, int(b), int(c) & 0xFFFFFFFF) for a, b, c in seg])
+        self.names = (C.c_char_p * len(chr_names))(*[n if isinstance(n, bytes) else n.encode() for n in chr_names])
+        p = C.POINTER(C.c_uint32)
+        self.struct = SamGenome(self.pac.ctypes.data_as(p), dna_length, self.segs, len(seg), self.amb.ctypes.data_as(p), self.end.ctypes.data_as(p), len(chr_names), self.names)
+
+
+class SamReads:
+    """s3_sam_reads: bases (one code per byte) and Phred qualities as (numReads, rowBytes) uint8 arrays, read lengths, names"""
+
+    def __init__(self, bases, qualities, read_lengths, names):
+        self.bases, self.quals, self.lens = np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(qualities, np.uint8), _u32(read_lengths)
+        if self.bases.ndim != 2 or self.bases.shape != self.quals.shape or len(self.lens) != len(self.bases) or len(names) != len(self.bases):
+            raise ValueError("SamReads: bases and qualities must be (numReads, rowBytes) arrays with one length and one name per read")
+        self.names = (C.c_char_p * len(names))(*[n if isinstance(n, bytes) else n.encode() for n in names])
+        self.num = len(self.bases)
+        self.struct = SamReadsStruct(self.bases.ctypes.data_as(C.POINTER(C.c_uint8)), C.cast(self.quals.ctypes.data, C.c_char_p), self.bases.shape[1],
+                                     self.lens.ctypes.data_as(C.POINTER(C.c_uint32)), self.names)
+
+
+def _sam_text(name: str, genome: SamGenomeDesc, config: SamConfig, reads: SamReads, args, num_threads: int) -> bytes:
+    lib = load_library()
+    fn = getattr(lib, name)
+    fn.restype = C.c_int
+    lib.s3_free.restype = None
+    lib.s3_free.argtypes = [C.c_void_p]
+    text, size = C.c_void_p(), C.c_uint64()
+    _check(fn(C.byref(genome.struct), C.byref(config), C.byref(reads.struct), C.c_uint64(reads.num), *args, C.c_uint32(num_threads), C.byref(text), C.byref(size)), name)
+    out = C.string_at(text.value, size.value)
+    lib.s3_free(text)
+    return out
+
+
+def _csr(occ_offsets, positions, occ_flags):
+    off, pos, fl = _u32(occ_offsets), _u32(positions), np.ascontiguousarray(occ_flags, np.uint8)
+    p = C.POINTER(C.c_uint32)
+    return (off, pos, fl), [off.ctypes.data_as(p), pos.ctypes.data_as(p), fl.ctypes.data_as(C.POINTER(C.c_uint8))]
+
+
+def _hits(hits, dtype, runs):
+    h, r = np.ascontiguousarray(hits, dtype), _u32(runs)
+    return (h, r), [h.ctypes.data_as(C.c_void_p), C.c_uint64(len(h)), r.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(len(r))]
+
+
+def _stats(read_stats):
+    if read_stats is None:
+        return None, None
+    s = np.ascontiguousarray(read_stats, PE_READ_STATS_DTYPE)
+    return s, s.ctypes.data_as(C.c_void_p)
+
+
+def sam_single_batch_text(genome, config, reads, occ_offsets, positions, occ_flags, num_threads=0) -> bytes:
+    """s3_sam_single_batch_text over the arrays SingleAligner.align returns: one SAM line per read, unmapped ones included"""
+    keep, a = _csr(occ_offsets, positions, occ_flags)
+    return _sam_text("s3_sam_single_batch_text", genome, config, reads, a, num_threads)
+
+
+def sam_single_dp_batch_text(genome, config, reads, hits, runs, scores: DPScores, cutoff: int, num_threads=0) -> bytes:
+    """s3_sam_single_dp_batch_text over single_dp_align's hits + runs: one line per read that has a hit"""
+    keep, a = _hits(hits, DP_HIT_DTYPE, runs)
+    return _sam_text("s3_sam_single_dp_batch_text", genome, config, reads, a + [scores, C.c_int32(cutoff)], num_threads)
+
+
+def sam_paired_batch_text(genome, config, reads, route, pairs, read_stats, num_threads=0) -> bytes:
+    """s3_sam_paired_batch_text over PairAligner.align's route / pairs / read_stats: two lines per paired pair with one valid pairing"""
+    rt, pr = np.ascontiguousarray(route, np.uint8), np.ascontiguousarray(pairs, PE_PAIR_DTYPE)
+    keep, st = _stats(read_stats)
+    return _sam_text("s3_sam_paired_batch_text", genome, config, reads, [rt.ctypes.data_as(C.POINTER(C.c_uint8)), pr.ctypes.data_as(C.c_void_p), C.c_uint64(len(pr)), st], num_threads)
+
+
+def sam_pair_dp_batch_text(genome, config, reads, dp, runs, scores: DPScores, read_stats=None, num_threads=0) -> bytes:
+    """s3_sam_pair_dp_batch_text over PairAligner.align's rescue records + runs: two lines per pair with a successful rescue"""
+    keep, a = _hits(dp, PE_DP_DTYPE, runs)
+    keep2, st = _stats(read_stats)
+    return _sam_text("s3_sam_pair_dp_batch_text", genome, config, reads, a + [scores, st], num_threads)
+
+
+def sam_deep_dp_batch_text(genome, config, reads, hits, runs, scores: DPScores, read_stats=None, num_threads=0) -> bytes:
+    """s3_sam_deep_dp_batch_text over deep_dp_align / PairAligner.deep_dp hits + runs: two lines per pair with a hit"""
+    keep, a = _hits(hits, DEEP_HIT_DTYPE, runs)
+    keep2, st = _stats(read_stats)
+    return _sam_text("s3_sam_deep_dp_batch_text", genome, config, reads, a + [scores, st], num_threads)
+
+
+def sam_unpaired_batch_text(genome, config, reads, occ_offsets, positions, occ_flags, pair_ids, max_output_per_read=1000, num_threads=0) -> bytes:
+    """s3_sam_unpaired_batch_text: the named pairs, each read on its own from a CSR of occurrences over all reads of the batch"""
+    keep, a = _csr(occ_offsets, positions, occ_flags)
+    ids = _u32(pair_ids)
+    return _sam_text("s3_sam_unpaired_batch_text", genome, config, reads, a + [ids.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(len(ids)), C.c_uint32(max_output_per_read)], num_threads)
+
+
+def sam_unpaired_dp_batch_text(genome, config, reads, occ_offsets, positions, occ_flags, hits, runs, scores: DPScores, cutoff: int, pair_ids, num_threads=0) -> bytes:
+    """s3_sam_unpaired_dp_batch_text: the named pairs after DP, per read its single-read DP hits when it has any, else its occurrences"""
+    keep, a = _csr(occ_offsets, positions, occ_flags)
+    keep2, b = _hits(hits, DP_HIT_DTYPE, runs)
+    ids = _u32(pair_ids)
+    return _sam_text("s3_sam_unpaired_dp_batch_text", genome, config, reads, a + b + [scores, C.c_int32(cutoff), ids.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(len(ids))], num_threads)

@@ -911,6 +911,15 @@ def _batch_reads(rng, num, row):
     return lens, bases, quals, names, rd
 
 
+def _api_handles(n, keep, cfg, bases, quals, lens, num):
+    """the same genome / config / reads as soap3dp_b200.api's objects"""
+    pac, chr_end, amb, segs = keep
+    g2 = api.SamGenomeDesc(pac, n, [(0, 1, 0xFFFFFFFF), (70_000, 2, 70_000 - 1), (100_000, 2, 70_000 - 1 - 500), (150_000, 3, 150_000 - 1)], amb, chr_end, [b"chr1", b"chrTwo", b"3"])
+    c2 = api.SamConfig(*[getattr(cfg, f[0]) for f in Config._fields_])
+    r2 = api.SamReads(bases, quals, lens, [b"batch%d" % r for r in range(num)])
+    return g2, c2, r2
+
+
 def test_sam_single_batch_text_is_the_reads_records_in_order():
     """s3_sam_single_batch_text == s3_sam_single_record + s3_sam_format_line per read (each pinned to the reference above), whatever the
     number of host threads; reads without an occurrence come out as unmapped records; bad arguments are refused"""
@@ -1013,6 +1022,8 @@ def test_sam_single_dp_batch_text_groups_the_hits_of_a_read():
             got = C.string_at(text.value, size.value)
             lib.s3_free(text)
             assert got == want and got.count(b"\n") == len(per_read)
+        g2, c2, r2 = _api_handles(n, keep, cfg, bases, quals, lens, num)
+        assert api.sam_single_dp_batch_text(g2, c2, r2, harr, rarr, scores, cutoff, num_threads=3) == want
     # a hit whose runs lie outside the run array is refused
     cfg = Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA")
     bad = harr.copy(); bad[3]["runOffset"] = len(rarr)
@@ -1112,6 +1123,8 @@ def test_sam_deep_dp_batch_text_is_the_pairs_records_in_order():
             got = C.string_at(text.value, size.value)
             lib.s3_free(text)
             assert got == want and got.count(b"\n") == 2 * len(per_pair)
+        g2, c2, r2 = _api_handles(n, keep, cfg, bases, quals, lens, num)
+        assert api.sam_deep_dp_batch_text(g2, c2, r2, harr, rarr, scores, stats, num_threads=3) == want
     bad = harr.copy(); bad[2]["readID"] += 1                                # an odd read id is not a pair's
     text, size = C.c_void_p(), C.c_uint64()
     assert lib.s3_sam_deep_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), bad.ctypes.data_as(C.c_void_p), C.c_uint64(len(bad)), helpers.u32p(rarr),
@@ -1192,6 +1205,8 @@ def test_sam_pair_dp_batch_text_is_the_rescued_pairs_records_in_order():
             got = C.string_at(text.value, size.value)
             lib.s3_free(text)
             assert got == want
+        g2, c2, r2 = _api_handles(n, keep, cfg, bases, quals, lens, num)
+        assert api.sam_pair_dp_batch_text(g2, c2, r2, darr, rarr, scores, st, num_threads=3) == want
     assert silent > 10
 
 
@@ -1252,6 +1267,8 @@ def test_sam_paired_batch_text_is_the_paired_reads_records_in_order():
             got = C.string_at(text.value, size.value)
             lib.s3_free(text)
             assert got == want
+        g2, c2, r2 = _api_handles(n, keep, cfg, bases, quals, lens, num)
+        assert api.sam_paired_batch_text(g2, c2, r2, route, pr, st, num_threads=3) == want
     text, size = C.c_void_p(), C.c_uint64()
     assert lib.s3_sam_paired_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), route.ctypes.data_as(U8P), pr.ctypes.data_as(C.c_void_p), C.c_uint64(P),
                                         None, 2, C.byref(text), C.byref(size)) != 0                   # no statistics, no counts for the writer
@@ -1384,9 +1401,47 @@ def test_sam_unpaired_dp_batch_text_builds_one_list_per_read():
             got = C.string_at(text.value, size.value)
             lib.s3_free(text)
             assert got == want and got.count(b"\n") == 2 * len(ids)
+        g2, c2, r2 = _api_handles(n, keep, cfg, bases, quals, lens, num)
+        assert api.sam_unpaired_dp_batch_text(g2, c2, r2, off, pos, flags, harr, rarr, scores, cutoff, ids, num_threads=3) == want
     # hits of a read that are not next to each other are refused
     bad = np.concatenate([harr, harr[:1]])
     text, size = C.c_void_p(), C.c_uint64()
     assert lib.s3_sam_unpaired_dp_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P),
                                              bad.ctypes.data_as(C.c_void_p), C.c_uint64(len(bad)), helpers.u32p(rarr), C.c_uint64(len(rarr)), scores, cutoff,
                                              helpers.u32p(ids), C.c_uint64(len(ids)), 2, C.byref(text), C.byref(size)) != 0
+
+
+def test_api_mirror_of_the_batch_text_entries():
+    """soap3dp_b200.api's wrappers of the batch entries give the text the raw C calls give (single reads and unpaired pairs; the other
+    wrappers share their marshalling)"""
+    lib = _batch_lib()
+    rng = np.random.default_rng(999)
+    n, G, gen, cnames, (pac, chr_end, amb, segs) = _batch_genome(rng)
+    num, row = 300, 160
+    lens, bases, quals, names, rd = _batch_reads(rng, num, row)
+    counts = rng.choice([0, 1, 2, 5], num)
+    off = np.zeros(num + 1, np.uint32)
+    off[1:] = np.cumsum(counts)
+    tot = int(off[-1])
+    pos = rng.integers(0, n - 160, tot).astype(np.uint32)
+    flags = np.ascontiguousarray(np.stack([rng.integers(1, 3, tot), rng.integers(0, 4, tot)], 1).astype(np.uint8))
+    cfg = Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA")
+    text, size = C.c_void_p(), C.c_uint64()
+    assert lib.s3_sam_single_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P), 3,
+                                        C.byref(text), C.byref(size)) == 0
+    want_single = C.string_at(text.value, size.value)
+    lib.s3_free(text)
+    ids = np.arange(0, num // 2, 3, dtype=np.uint32)
+    assert lib.s3_sam_unpaired_batch_text(C.byref(gen), C.byref(cfg), C.byref(rd), C.c_uint64(num), helpers.u32p(off), helpers.u32p(pos), flags.ctypes.data_as(U8P),
+                                          helpers.u32p(ids), C.c_uint64(len(ids)), 1000, 3, C.byref(text), C.byref(size)) == 0
+    want_unpaired = C.string_at(text.value, size.value)
+    lib.s3_free(text)
+    g2 = api.SamGenomeDesc(pac, n, [(0, 1, 0xFFFFFFFF), (70_000, 2, 70_000 - 1), (100_000, 2, 70_000 - 1 - 500), (150_000, 3, 150_000 - 1)], amb, chr_end, [b"chr1", "chrTwo", b"3"])
+    c2 = api.SamConfig(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA")
+    r2 = api.SamReads(bases, quals, lens, [b"batch%d" % r for r in range(num)])
+    assert api.sam_single_batch_text(g2, c2, r2, off, pos, flags, num_threads=2) == want_single
+    assert api.sam_unpaired_batch_text(g2, c2, r2, off, pos, flags, ids) == want_unpaired
+    with pytest.raises(api.S3Error):
+        api.sam_paired_batch_text(g2, c2, r2, np.ones(num // 2, np.uint8), np.zeros(num // 2, api.PE_PAIR_DTYPE), None)      # the chain's statistics are required
+    with pytest.raises(ValueError):
+        api.SamReads(bases, quals[:, :10], lens, [b"x"] * num)

@@ -1066,7 +1066,7 @@ class SamReadsStruct(C.Structure):
                 ("names", C.POINTER(C.c_char_p))]
 
 
-def _u32(a):
+def _as_u32(a):
     return np.ascontiguousarray(a, np.uint32)
 
 
@@ -1075,7 +1075,7 @@ class SamGenomeDesc:
     the ambiguity map, the chromosomes' last positions and names"""
 
     def __init__(self, packed_dna, dna_length: int, segments, ambiguity_map, chr_end_pos, chr_names):
-        self.pac, self.amb, self.end = _u32(packed_dna), _u32(ambiguity_map), _u32(chr_end_pos)
+        self.pac, self.amb, self.end = _as_u32(packed_dna), _as_u32(ambiguity_map), _as_u32(chr_end_pos)
         seg = np.asarray(segments, np.int64).reshape(-1, 3)
         self.segs = (SamSegment * len(seg))(*[SamSegment(int(a) & 0xFFFFFFFF, int(b), int(c) & 0xFFFFFFFF) for a, b, c in seg])
         self.names = (C.c_char_p * len(chr_names))(*[n if isinstance(n, bytes) else n.encode() for n in chr_names])
@@ -1087,7 +1087,7 @@ class SamReads:
     """s3_sam_reads: bases (one code per byte) and Phred qualities as (numReads, rowBytes) uint8 arrays, read lengths, names"""
 
     def __init__(self, bases, qualities, read_lengths, names):
-        self.bases, self.quals, self.lens = np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(qualities, np.uint8), _u32(read_lengths)
+        self.bases, self.quals, self.lens = np.ascontiguousarray(bases, np.uint8), np.ascontiguousarray(qualities, np.uint8), _as_u32(read_lengths)
         if self.bases.ndim != 2 or self.bases.shape != self.quals.shape or len(self.lens) != len(self.bases) or len(names) != len(self.bases):
             raise ValueError("SamReads: bases and qualities must be (numReads, rowBytes) arrays with one length and one name per read")
         self.names = (C.c_char_p * len(names))(*[n if isinstance(n, bytes) else n.encode() for n in names])
@@ -1110,13 +1110,13 @@ def _sam_text(name: str, genome: SamGenomeDesc, config: SamConfig, reads: SamRea
 
 
 def _csr(occ_offsets, positions, occ_flags):
-    off, pos, fl = _u32(occ_offsets), _u32(positions), np.ascontiguousarray(occ_flags, np.uint8)
+    off, pos, fl = _as_u32(occ_offsets), _as_u32(positions), np.ascontiguousarray(occ_flags, np.uint8)
     p = C.POINTER(C.c_uint32)
     return (off, pos, fl), [off.ctypes.data_as(p), pos.ctypes.data_as(p), fl.ctypes.data_as(C.POINTER(C.c_uint8))]
 
 
 def _hits(hits, dtype, runs):
-    h, r = np.ascontiguousarray(hits, dtype), _u32(runs)
+    h, r = np.ascontiguousarray(hits, dtype), _as_u32(runs)
     return (h, r), [h.ctypes.data_as(C.c_void_p), C.c_uint64(len(h)), r.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(len(r))]
 
 
@@ -1163,7 +1163,7 @@ def sam_deep_dp_batch_text(genome, config, reads, hits, runs, scores: DPScores, 
 def sam_unpaired_batch_text(genome, config, reads, occ_offsets, positions, occ_flags, pair_ids, max_output_per_read=1000, num_threads=0) -> bytes:
     """s3_sam_unpaired_batch_text: the named pairs, each read on its own from a CSR of occurrences over all reads of the batch"""
     keep, a = _csr(occ_offsets, positions, occ_flags)
-    ids = _u32(pair_ids)
+    ids = _as_u32(pair_ids)
     return _sam_text("s3_sam_unpaired_batch_text", genome, config, reads, a + [ids.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(len(ids)), C.c_uint32(max_output_per_read)], num_threads)
 
 
@@ -1171,5 +1171,5 @@ def sam_unpaired_dp_batch_text(genome, config, reads, occ_offsets, positions, oc
     """s3_sam_unpaired_dp_batch_text: the named pairs after DP, per read its single-read DP hits when it has any, else its occurrences"""
     keep, a = _csr(occ_offsets, positions, occ_flags)
     keep2, b = _hits(hits, DP_HIT_DTYPE, runs)
-    ids = _u32(pair_ids)
+    ids = _as_u32(pair_ids)
     return _sam_text("s3_sam_unpaired_dp_batch_text", genome, config, reads, a + b + [scores, C.c_int32(cutoff), ids.ctypes.data_as(C.POINTER(C.c_uint32)), C.c_uint64(len(ids))], num_threads)

@@ -876,7 +876,10 @@ int s3_sam_format_line(const s3_sam_record *record, const char *const *chrNames,
  * without the NUL.  Reads are independent: numThreads host threads (0: all of the machine) each take a slice of the batch.
  *   s3_sam_single_batch_text     the results of s3_se_align (occOffsets / positions / occFlags of s3_se_result) -> s3_sam_single_record per
  *                                read, the unmapped record for a read without an occurrence (hostKernel's SAM branch for single reads,
- *                                CPUfunctions.cpp:1887-1905 -> OCCOutputSAMAPI / noAnsOutputSAMAPI): BASELINE config 2 from reads to text
+ *                                CPUfunctions.cpp:1862-1941 -> OCCOutputSAMAPI / noAnsOutputSAMAPI; with alignmentType OUTPUT_UNIQUE_BEST /
+ *                                OUTPUT_RANDOM_BEST the first occurrence alone through s3_sam_single_answer_record, unique-best only when it
+ *                                is the read's one occurrence): BASELINE config 2 from reads to text.  The reference writes the reads without
+ *                                an occurrence after its last stage; here every read has its line in input order.
  *   s3_sam_single_dp_batch_text  the results of s3_single_dp_align (hits in candidate order, the candidates of a read next to each
  *                                other; runs) -> s3_runs_decode -> s3_sam_single_dp_record per read that has a hit
  *                                (outputDPSingleResult2, OutputDPResult.cpp:938-1058, with hspaux->singleDPcutoffThreshold,

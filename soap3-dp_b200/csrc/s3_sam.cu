@@ -1416,7 +1416,16 @@ extern "C" int s3_sam_single_batch_text(const s3_sam_genome *g, const s3_sam_con
         std::vector<s3_sam_occurrence> occ(n);
         for (uint32_t k = 0; k < n; ++k) { occ[k].ambPosition = positions[a + k]; occ[k].strand = occFlags[2 * (size_t)(a + k)]; occ[k].mismatchCount = occFlags[2 * (size_t)(a + k) + 1]; occ[k].pad[0] = occ[k].pad[1] = 0; }
         s3_sam_record rec;
-        const int rc = s3_sam_single_record(g, cfg, occ.data(), n, reads->bases + r * reads->rowBytes, reads->qualities + r * reads->rowBytes, (int32_t)reads->readLengths[r], reads->names[r], &rec);
+        const uint8_t *q = reads->bases + r * reads->rowBytes;
+        const char *ql = reads->qualities + r * reads->rowBytes;
+        const int32_t len = (int32_t)reads->readLengths[r];
+        int rc;
+        // the unique-best / random-best report types write the first occurrence alone (SingleAnsOutputSAMAPI with bestHitNum 1, CPUfunctions.cpp:1862-1925);
+        // unique-best reports nothing for a read with more than one occurrence (noAnsOutputSAMAPI)
+        if (cfg->alignmentType == 3 || cfg->alignmentType == 4) {
+            if (n == 1 || (n > 1 && cfg->alignmentType == 4)) rc = s3_sam_single_answer_record(g, cfg, occ[0].ambPosition, occ[0].strand, occ[0].mismatchCount, 1, q, ql, len, reads->names[r], &rec);
+            else rc = s3_sam_single_record(g, cfg, NULL, 0, q, ql, len, reads->names[r], &rec);
+        } else rc = s3_sam_single_record(g, cfg, occ.data(), n, q, ql, len, reads->names[r], &rec);
         return rc ? rc : append_line(g, &rec, out);
     });
 }

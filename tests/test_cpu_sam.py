@@ -936,14 +936,23 @@ def test_sam_single_batch_text_is_the_reads_records_in_order():
     edge = rng.random(tot) < 0.2
     pos[edge] = (rng.choice([70_000, 100_000, 150_000], int(edge.sum())) - rng.integers(1, 36, int(edge.sum()))).astype(np.uint32)
     flags = np.ascontiguousarray(np.stack([rng.integers(1, 3, tot), rng.integers(0, 4, tot)], 1).astype(np.uint8))
-    for cfg in (Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), Config(2, 1, 1, -2, 0, 40, 1, 0, 1, 1000, b"rgB")):
+    lib.s3_sam_single_answer_record.restype = C.c_int
+    for cfg in (Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), Config(2, 1, 1, -2, 0, 40, 1, 0, 1, 1000, b"rgB"), Config(3, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgC"),
+                Config(4, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgD")):
         want = []
         for r in range(num):
             a, b = int(off[r]), int(off[r + 1])
             arr = (Occurrence * max(b - a, 1))(*[Occurrence(int(pos[i]), int(flags[i][0]), int(flags[i][1])) for i in range(a, b)])
             out = Record()
-            assert lib.s3_sam_single_record(C.byref(gen), C.byref(cfg), arr, b - a, bases[r].ctypes.data_as(U8P), C.cast(quals[r].ctypes.data, C.c_char_p), int(lens[r]), names[r],
-                                            C.byref(out)) == 0
+            args = (bases[r].ctypes.data_as(U8P), C.cast(quals[r].ctypes.data, C.c_char_p), int(lens[r]), names[r], C.byref(out))
+            if cfg.alignmentType in (3, 4):
+                # unique best: the read's one occurrence or nothing; random best: the first one (hostKernel, CPUfunctions.cpp:1862-1925)
+                if b - a == 1 or (b - a > 1 and cfg.alignmentType == 4):
+                    assert lib.s3_sam_single_answer_record(C.byref(gen), C.byref(cfg), int(pos[a]), int(flags[a][0]), int(flags[a][1]), 1, *args) == 0
+                else:
+                    assert lib.s3_sam_single_record(C.byref(gen), C.byref(cfg), arr, 0, *args) == 0
+            else:
+                assert lib.s3_sam_single_record(C.byref(gen), C.byref(cfg), arr, b - a, *args) == 0
             want.append(_line_of(lib, out, cnames))
         want = b"".join(x + b"\n" for x in want)
         assert want.count(b"\t4\t*\t0\t0\t*") >= 50                       # unmapped reads are in the batch

@@ -1635,11 +1635,16 @@ extern "C" int s3_sam_paired_batch_text(const s3_sam_genome *g, const s3_sam_con
         s3_sam_pairing pr;
         memset(&pr, 0, sizeof pr);
         pr.algnmt1 = x.pos1; pr.algnmt2 = x.pos2; pr.strand1 = x.strand1; pr.mismatch1 = x.mism1; pr.strand2 = x.strand2; pr.mismatch2 = x.mism2; pr.totalMismatchCount = x.optimalTotal;
+        // X0 / X1 as hostKernel passes them per report type (CPUfunctions.cpp:2326-2362): the reads' counts for all-valid / all-best, 1 and none
+        // for unique-best (one optimal pairing here), none for random-best
+        int32_t x0[2] = {(int32_t)s1.x0, (int32_t)s2.x0}, x1[2] = {(int32_t)s1.x1, (int32_t)s2.x1};
+        if (cfg->alignmentType == 3) { x0[0] = x0[1] = 1; x1[0] = x1[1] = -1; }
+        else if (cfg->alignmentType == 4) { x0[0] = x0[1] = x1[0] = x1[1] = -1; }
         s3_sam_record rec[2];
         const int rc = s3_sam_pair_records(g, cfg, &pr, 1, 0, reads->bases + r * reads->rowBytes, reads->bases + (r + 1) * reads->rowBytes,
                                            reads->qualities + r * reads->rowBytes, reads->qualities + (r + 1) * reads->rowBytes,
                                            (int32_t)reads->readLengths[r], (int32_t)reads->readLengths[r + 1], reads->names[r], reads->names[r + 1],
-                                           x.optimalTotal, x.suboptimalTotal, (int32_t)s1.x0, (int32_t)s2.x0, (int32_t)s1.x1, (int32_t)s2.x1, (int32_t)x.numOptimal,
+                                           x.optimalTotal, x.suboptimalTotal, x0[0], x0[1], x1[0], x1[1], (int32_t)x.numOptimal,
                                            s1.minMismatch == x.mism1, s2.minMismatch == x.mism2, x.numPairs, rec);
         return rc ? rc : append_pair(g, rec, out);
     });

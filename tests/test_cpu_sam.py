@@ -140,6 +140,8 @@ def test_sam_pair_records_match_the_reference_writer():
         sec = [t for t in tot if t > min_tot]
         counts = (min_tot, sec[0] if sec else 127, int(rng.integers(0, 5)), int(rng.integers(0, 5)), int(rng.integers(0, 300)), int(rng.integers(0, 300)),
                   int(rng.integers(1, 4)), int(rng.integers(0, 2)), int(rng.integers(0, 2)), int(rng.integers(1, 6)))
+        if cfg.alignmentType >= 3 and trial % 2:                       # hostKernel's X0 / X1 of the unique-best / random-best report types (CPUfunctions.cpp:2326-2349;
+            counts = counts[:2] + ((1, 1, -1, -1) if cfg.alignmentType == 3 else (-1, -1, -1, -1)) + counts[6:]      # with MAPQ computed, -1 indexes before g_log_n there)
         n1, n2 = b"read%d/1" % trial, b"read%d/2" % trial
         got = product_records(lib, gen, cfg, pairs, best, q1, q2, ql1, ql2, n1, n2, counts)
         want = reference_records(ref, g, cfg, pairs, best, q1, q2, ql1, ql2, n1, n2, counts)
@@ -1250,7 +1252,8 @@ def test_sam_paired_batch_text_is_the_paired_reads_records_in_order():
         m1, m2 = int(rng.integers(0, 3)), int(rng.integers(0, 3))
         pr[p] = (p1, p2, abs(p2 - p1) + L2, s1, m1, 3 - s1, m2, int(rng.choice([1, 1, 1, 2])), int(rng.integers(1, 3)), int(rng.integers(0, 3)), m1 + m2,
                  int(rng.choice([127, m1 + m2 + 1])), 0)
-    for cfg in (Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), Config(2, 1, 1, -2, 0, 40, 1, 1, 1, 1000, b"rgB")):
+    for cfg in (Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgA"), Config(2, 1, 1, -2, 0, 40, 1, 1, 1, 1000, b"rgB"), Config(3, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgC"),
+                Config(4, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgD")):
         want, done = [], 0
         for p in range(P):
             x = pr[p]
@@ -1258,7 +1261,9 @@ def test_sam_paired_batch_text_is_the_paired_reads_records_in_order():
                 continue
             arr = (Pairing * 1)(Pairing(int(x["pos1"]), int(x["pos2"]), int(x["strand1"]), int(x["mism1"]), int(x["strand2"]), int(x["mism2"]), int(x["optimalTotal"])))
             s1, s2 = st[2 * p], st[2 * p + 1]
-            counts = (int(x["optimalTotal"]), int(x["suboptimalTotal"]), int(s1["x0"]), int(s2["x0"]), int(s1["x1"]), int(s2["x1"]), int(x["numOptimal"]),
+            # X0 / X1 per report type as hostKernel passes them (CPUfunctions.cpp:2326-2362)
+            xs = {3: (1, 1, -1, -1), 4: (-1, -1, -1, -1)}.get(cfg.alignmentType, (int(s1["x0"]), int(s2["x0"]), int(s1["x1"]), int(s2["x1"])))
+            counts = (int(x["optimalTotal"]), int(x["suboptimalTotal"]), *xs, int(x["numOptimal"]),
                       int(int(s1["minMismatch"]) == int(x["mism1"])), int(int(s2["minMismatch"]) == int(x["mism2"])), int(x["numPairs"]))
             out = (Record * 2)()
             assert lib.s3_sam_pair_records(C.byref(gen), C.byref(cfg), arr, 1, 0, bases[2 * p].ctypes.data_as(U8P), bases[2 * p + 1].ctypes.data_as(U8P),

@@ -913,7 +913,8 @@ int s3_sam_single_dp_batch_text(const s3_sam_genome *genome, const s3_sam_config
  *                                (s3_sam_unpaired_records over the reads' occurrence lists). */
 /*   s3_sam_paired_batch_text     the pairs s3_pe_align paired (route S3_PE_PAIRED) with ONE valid pairing -> s3_sam_pair_records with the
  *                                chain's reported pairing, totals and per-read statistics (hostKernel's SAM branch, CPUfunctions.cpp:2281-2380
- *                                -> pairOutputSAMAPI); readStats is required.  Pairs with more valid pairings need the whole list for XA:Z
+ *                                -> pairOutputSAMAPI; X0 / X1 per report type as hostKernel passes them: the reads' counts for all-valid /
+ *                                all-best, 1 / none for unique-best, none for random-best); readStats is required.  Pairs with more valid pairings need the whole list for XA:Z
  *                                (s3_pair_occurrences) and get no lines here. */
 int s3_sam_paired_batch_text(const s3_sam_genome *genome, const s3_sam_config *config, const s3_sam_reads *reads, uint64_t numReads,
                              const uint8_t *route, const s3_pe_pair_result *pairs, uint64_t numPairs, const s3_pe_read_stats *readStats,

@@ -1459,3 +1459,32 @@ def test_api_mirror_of_the_batch_text_entries():
         api.sam_paired_batch_text(g2, c2, r2, np.ones(num // 2, np.uint8), np.zeros(num // 2, api.PE_PAIR_DTYPE), None)      # the chain's statistics are required
     with pytest.raises(ValueError):
         api.SamReads(bases, quals[:, :10], lens, [b"x"] * num)
+
+
+def test_sam_batch_text_edge_sizes():
+    """more host threads than items, one item, no item: the same text as one thread gives; empty results give an empty text"""
+    lib = _batch_lib()
+    rng = np.random.default_rng(77)
+    n, G, gen, cnames, keep = _batch_genome(rng)
+    num, row = 6, 160
+    lens, bases, quals, names, rd = _batch_reads(rng, num, row)
+    off = np.array([0, 1, 1, 3, 3, 4, 6], np.uint32)
+    pos = rng.integers(0, n - 160, 6).astype(np.uint32)
+    flags = np.ascontiguousarray(np.stack([rng.integers(1, 3, 6), rng.integers(0, 3, 6)], 1).astype(np.uint8))
+    g2, c2, r2 = _api_handles(n, keep, Config(1, 0, 1, -2, 1, 40, 1, 1, 1, 1000, b"rgE"), bases, quals, lens, num)
+    one = api.sam_single_batch_text(g2, c2, r2, off, pos, flags, num_threads=1)
+    assert one.count(b"\n") == num
+    for t in (2, 6, 7, 64):
+        assert api.sam_single_batch_text(g2, c2, r2, off, pos, flags, num_threads=t) == one
+    ids = np.array([1], np.uint32)
+    a = api.sam_unpaired_batch_text(g2, c2, r2, off, pos, flags, ids, num_threads=1)
+    assert a.count(b"\n") == 2 and api.sam_unpaired_batch_text(g2, c2, r2, off, pos, flags, ids, num_threads=32) == a
+    scores = api.DPScores(1, -2, -3, -1)
+    none_hits, none_runs = np.zeros(0, api.DP_HIT_DTYPE), np.zeros(0, np.uint32)
+    assert api.sam_single_dp_batch_text(g2, c2, r2, none_hits, none_runs, scores, 30, num_threads=8) == b""
+    assert api.sam_deep_dp_batch_text(g2, c2, r2, np.zeros(0, api.DEEP_HIT_DTYPE), none_runs, scores) == b""
+    assert api.sam_pair_dp_batch_text(g2, c2, r2, np.zeros(0, api.PE_DP_DTYPE), none_runs, scores) == b""
+    assert api.sam_unpaired_batch_text(g2, c2, r2, off, pos, flags, np.zeros(0, np.uint32)) == b""
+    # without DP hits the after-DP writer of unpaired reads works from the occurrences alone
+    b = api.sam_unpaired_dp_batch_text(g2, c2, r2, off, pos, flags, none_hits, none_runs, scores, 30, ids, num_threads=3)
+    assert b.count(b"\n") == 2
